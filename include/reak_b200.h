@@ -1,0 +1,185 @@
+/*
+ * reak_b200.h — C-ABI of the B200 batched KTE-chain propagator.
+ *
+ * This is the drop-in boundary for ONE path of ReaK: evaluating and integrating a serial
+ * Kinetostatic-Transmission-Element chain over a batch of independent states.  Every entry
+ * point names the reference interface it replaces (paths relative to the ReaK source tree):
+ *
+ *   rkb_chain_create      <- model assembly: kte_map_chain::operator<<  (ctrl/mbd_kte/kte_map_chain.hpp:98-102),
+ *                            mass_matrix_calc::operator<<               (ctrl/mbd_kte/mass_matrix_calculator.cpp:30-78),
+ *                            kte_nl_system public members               (ctrl/ctrl_sys/kte_nl_system.hpp:70-78)
+ *   rkb_eval              <- kte_nl_system::get_state_derivative        (ctrl/ctrl_sys/kte_nl_system.hpp:238-346)
+ *   rkb_rollout_rk4       <- runge_kutta4_integrator<double>::integrate (core/integrators/fixed_step_integrators.hpp:256-293)
+ *                            driven through num_int_dtnl_sys::get_next_state (ctrl/ctrl_sys/num_int_dtnl_system.hpp:166-180)
+ *   rkb_mass_matrix       <- mass_matrix_calc::getMassMatrix / getMassMatrixAndDerivative
+ *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
+ *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
+ *   rkb_steer_batch       <- the inner loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561),
+ *                            many (start, goal, control) tuples per call
+ *
+ * Conventions
+ *   - All arithmetic is IEEE double, like the reference.
+ *   - State per sample: 2n doubles interleaved (q0, qd0, q1, qd1, ...) — kte_nl_system.hpp:189-193.
+ *     Input per sample: one double per driving_actuator_gen, in input-index order.
+ *   - Buffers are caller-owned.  RKB_MEM_DEVICE pointers must be valid on `device`;
+ *     RKB_MEM_HOST pointers are staged through device memory by the library
+ *     (pinned host memory makes the copies asynchronous up to the final sync).
+ *   - RKB_LAYOUT_AOS is the reference layout [N][dim]; RKB_LAYOUT_SOA is [dim][N].
+ *   - No exception crosses this boundary.  Return 0 = ok, negative = error (rkb_strerror).
+ *     Per-sample `status` words mirror the reference's exceptions:
+ *       bit 0 (RKB_STATUS_SINGULAR)  Cholesky pivot < 1e-8, where linsolve_Cholesky throws
+ *                                    singularity_error (core/lin_alg/mat_cholesky.hpp:80-82, 546)
+ *       bit 1 (RKB_STATUS_NONFINITE) a non-finite state derivative was produced
+ *   - There is no CPU fallback: every compute entry point fails with RKB_ERR_CUDA when no
+ *     usable sm_100 device is present.
+ */
+#ifndef REAK_B200_H
+#define REAK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RKB_VERSION 100
+
+/* ---- element kinds (one per in-scope kte_map subclass) ------------------------------------ */
+enum rkb_kind {
+  RKB_REVOLUTE_3D       = 1,  /* revolute_joint_3D   (revolute_joint.cpp:121-213)  p[0..2] = axis                   */
+  RKB_PRISMATIC_3D      = 2,  /* prismatic_joint_3D  (prismatic_joint.cpp:129-222) p[0..2] = axis                   */
+  RKB_FREE_3D           = 3,  /* free_joint_3D       (free_joints.cpp:123-208)     reserved, not accepted yet       */
+  RKB_RIGID_LINK_3D     = 4,  /* rigid_link_3D       (rigid_link.cpp:152-185)      p[0..2] = offset, p[3..6] = quat (w,x,y,z) */
+  RKB_INERTIA_3D        = 5,  /* inertia_3D          (inertia.cpp:111-121)         p[0] = mass, p[1..6] = Ixx Ixy Ixz Iyy Iyz Izz */
+  RKB_INERTIA_GEN       = 6,  /* inertia_gen         (inertia.cpp:47-53)           p[0] = mass (jacobian_gen_gen(1,0))          */
+  RKB_ACTUATOR_GEN      = 7,  /* driving_actuator_gen (driving_actuator.cpp:31-38) aux = input index, frame_b = joint element index */
+  RKB_TORSION_SPRING_3D = 8,  /* torsion_spring_3D   (torsion_spring.cpp:106-129)  p[0] = stiffness, p[1] = saturation */
+  RKB_TORSION_DAMPER_3D = 9,  /* torsion_damper_3D   (torsion_damper.cpp:93-104)   p[0] = damping                    */
+  RKB_SPRING_3D         = 10, /* spring_3D           (spring.cpp:178-207)          p[0] = rest length, p[1] = stiffness, p[2] = saturation */
+  RKB_DAMPER_3D         = 11, /* damper_3D           (damper.cpp:136-149)          p[0] = damping                    */
+  RKB_REVOLUTE_2D       = 17, /* revolute_joint_2D   (revolute_joint.cpp:32-116)                                     */
+  RKB_PRISMATIC_2D      = 18, /* prismatic_joint_2D  (prismatic_joint.cpp:33-123)  p[0..1] = axis                    */
+  RKB_RIGID_LINK_2D     = 20, /* rigid_link_2D       (rigid_link.cpp:87-139)       p[0..1] = offset, p[2] = angle    */
+  RKB_INERTIA_2D        = 21, /* inertia_2D          (inertia.cpp:77-86)           p[0] = mass, p[1] = moment of inertia */
+  RKB_TORSION_SPRING_2D = 24, /* torsion_spring_2D   (torsion_spring.cpp:50-71)    p[0] = stiffness, p[1] = saturation */
+  RKB_TORSION_DAMPER_2D = 25, /* torsion_damper_2D   (torsion_damper.cpp:49-58)    p[0] = damping                    */
+  RKB_SPRING_2D         = 26, /* spring_2D           (spring.cpp:116-143)          as RKB_SPRING_3D                  */
+  RKB_DAMPER_2D         = 27  /* damper_2D           (damper.cpp:88-102)           p[0] = damping                    */
+};
+
+#define RKB_MAX_COORDS 16 /* largest number of generalized coordinates one chain may carry */
+
+/* One KTE of the chain, in kte_map_chain order (doMotion order; doForce runs it reversed). */
+typedef struct rkb_element {
+  int32_t  kind;      /* enum rkb_kind */
+  int32_t  frame_a;   /* joint/link: base frame; spring/damper: anchor 1; inertia_2D/3D: CoM frame; else -1 */
+  int32_t  frame_b;   /* joint/link: end frame;  spring/damper: anchor 2; actuator: index of the reacting joint element; else -1 */
+  int32_t  coord;     /* generalized coordinate (joints, inertia_gen, actuator); else -1 */
+  int32_t  aux;       /* actuator: input index; else 0 */
+  int32_t  reserved;
+  uint64_t upstream;  /* inertias: bit c set <=> coordinate c is in mUpStreamJoints (jacobian_joint_map.hpp:252-331) */
+  double   p[12];     /* parameters, see enum rkb_kind */
+} rkb_element;
+
+/* Kinematics of the un-driven root frame (robot_base in CRS_A465_models.cpp:298-301). */
+typedef struct rkb_base_frame {
+  double position[3];
+  double quat[4];          /* (w,x,y,z); 2D chains: rotation angle in quat[0] */
+  double velocity[3];
+  double ang_velocity[3];  /* 2D chains: scalar in [0] */
+  double acceleration[3];  /* gravity enters as an upward base acceleration */
+  double ang_acceleration[3];
+} rkb_base_frame;
+
+typedef struct rkb_chain_desc {
+  int32_t dim;          /* 2 or 3: all frames of a chain are frame_2D or frame_3D */
+  int32_t n_elements;
+  int32_t n_frames;     /* frame ids are 0..n_frames-1; base_frame is never written by doMotion */
+  int32_t n_coords;     /* = kte_nl_system::dofs_gen.size(); state index j <-> coordinate j   */
+  int32_t n_inputs;     /* = kte_nl_system::get_input_dimensions()                            */
+  int32_t base_frame;
+  rkb_base_frame base;
+  const rkb_element* elements;
+} rkb_chain_desc;
+
+typedef struct rkb_chain rkb_chain; /* opaque */
+
+/* ---- flags ---------------------------------------------------------------------------------- */
+#define RKB_MEM_HOST    0u
+#define RKB_MEM_DEVICE  1u
+#define RKB_LAYOUT_AOS  0u
+#define RKB_LAYOUT_SOA  2u
+
+#define RKB_STATUS_SINGULAR  1
+#define RKB_STATUS_NONFINITE 2
+
+/* ---- error codes ---------------------------------------------------------------------------- */
+#define RKB_OK                 0
+#define RKB_ERR_INVALID       -1  /* null pointer / bad argument / malformed descriptor        */
+#define RKB_ERR_UNSUPPORTED   -2  /* chain topology or element outside the compiled path       */
+#define RKB_ERR_DIMENSION     -3  /* std::range_error of kte_nl_system::apply_states_and_inputs */
+#define RKB_ERR_CUDA          -4  /* CUDA runtime failure or no usable device                  */
+#define RKB_ERR_NOMEM         -5
+#define RKB_ERR_INTEGRATION   -6  /* impossible_integration (dt == 0, n_steps < 0)             */
+
+int         rkb_version(void);
+const char* rkb_strerror(int code);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* rkb_last_cuda_error(void);
+
+/* Validate `desc`, lower it to the device program and return a handle.  The descriptor is
+ * copied; the caller may free it afterwards. */
+int  rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out);
+void rkb_chain_destroy(rkb_chain* chain);
+
+int  rkb_chain_state_dim(const rkb_chain* chain);  /* kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147 */
+int  rkb_chain_input_dim(const rkb_chain* chain);  /* kte_nl_system::get_input_dimensions, kte_nl_system.hpp:153-158 */
+int  rkb_chain_dof(const rkb_chain* chain);
+
+/* xdot[i] = get_state_derivative(x[i], u[i]).  x: N x 2n, u: N x n_inputs, xdot: N x 2n,
+ * status: N (nullable).  `stream` is a cudaStream_t (NULL = default stream). */
+int rkb_eval(rkb_chain* chain, int device, size_t n_samples,
+             const double* x, const double* u, double* xdot, int32_t* status,
+             unsigned flags, void* stream);
+
+/* x_out[i] = state after exactly n_steps RK4 steps of size dt from x0[i] with u[i] held
+ * constant (zero-order hold, num_int_dtnl_system.hpp:166-180).  The step COUNT is explicit:
+ * the reference's time-driven loop would take one step more or less depending on rounding. */
+int rkb_rollout_rk4(rkb_chain* chain, int device, size_t n_samples,
+                    const double* x0, const double* u, double dt, int n_steps,
+                    double* x_out, int32_t* status, unsigned flags, void* stream);
+
+/* Generalised force gen_coord::f after doMotion/clearForce/doForce with q_ddot = 0
+ * (tau - h(q,qd) in ReaK's convention).  f: N x n. */
+int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,
+                   const double* x, const double* u, double* f,
+                   unsigned flags, void* stream);
+
+/* M[i] (n x n, full symmetric storage, row-major) and, if Mdot != NULL, its time
+ * derivative at state x[i].  AOS: [N][n][n]; SOA: [n*n][N]. */
+int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
+                    const double* x, double* M, double* Mdot,
+                    unsigned flags, void* stream);
+
+/* For each of n_pairs (start, goal) pairs roll out n_rollouts constant controls for n_steps
+ * RK4 steps and keep the rollout whose end state is closest to the goal (Euclidean norm over
+ * the 2n state components).  x0, goal: P x 2n; u: P x R x n_inputs (AOS) or [n_inputs][P*R] (SOA);
+ * best_idx: P; best_x: P x 2n; best_cost: P (nullable); status: P x R (nullable). */
+int rkb_steer_batch(rkb_chain* chain, int device, size_t n_pairs, size_t n_rollouts,
+                    const double* x0, const double* goal, const double* u,
+                    double dt, int n_steps,
+                    int32_t* best_idx, double* best_x, double* best_cost, int32_t* status,
+                    unsigned flags, void* stream);
+
+/* Device-side timing of the last compute launch issued through `chain` on the calling
+ * thread, in milliseconds (CUDA events on the launch stream); < 0 if none. Blocks until
+ * that launch has finished. */
+double rkb_last_kernel_ms(rkb_chain* chain);
+/* Number of kernels launched through this handle since creation. */
+uint64_t rkb_launch_count(const rkb_chain* chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REAK_B200_H */

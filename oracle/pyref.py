@@ -1,0 +1,117 @@
+"""ctypes access to the two checkers (see oracle/__init__.py).  numpy in, numpy out, AoS layout."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libreak_ref.so")
+ORACLE_SO = os.path.join(_HERE, "libkte_oracle.so")
+
+
+def build(which=("oracle", "ref")):
+    """Run oracle/Makefile (gcc only).  `ref` is a no-op where /root/reference is absent."""
+    for target in which:
+        subprocess.check_call(["make", "-s", "-C", _HERE, target])
+
+
+def have_ref():
+    return os.path.isfile(REF_SO)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _Checker(object):
+    """Common driver for a library exporting <prefix>_{create,destroy,eval,gen_forces,mass,rk4,frames}."""
+
+    def __init__(self, so_path, prefix, compiled):
+        if not os.path.isfile(so_path):
+            raise RuntimeError("%s is not built (make -C oracle)" % so_path)
+        self.lib = C.CDLL(so_path)
+        self.compiled = compiled  # keeps the descriptor arrays alive
+        self.n, self.nu, self.nx = compiled.n_coords, compiled.n_inputs, 2 * compiled.n_coords
+        g = lambda name: getattr(self.lib, prefix + name)
+        self._create, self._destroy = g("create"), g("destroy")
+        self._eval, self._forces, self._mass, self._rk4, self._frames = g("eval"), g("gen_forces"), g("mass"), g("rk4"), g("frames")
+        self._create.restype = C.c_void_p
+        self._create.argtypes = [C.c_void_p]
+        self._destroy.argtypes = [C.c_void_p]
+        self._eval.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+        self._forces.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3
+        self._mass.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3
+        self._rk4.restype = C.c_double
+        self._rk4.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_int]
+        self._frames.argtypes = [C.c_void_p] * 4
+        self.h = self._create(C.byref(compiled.desc))
+        if not self.h:
+            raise RuntimeError("checker could not build the model from the descriptor")
+
+    def close(self):
+        if self.h:
+            self._destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _xu(self, x, u):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        if u is None:
+            u = np.zeros((N, self.nu))
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(N, self.nu)
+        return x, u, N
+
+    def eval(self, x, u=None):
+        x, u, N = self._xu(x, u)
+        xd, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        self._eval(self.h, N, _dp(x), _dp(u), _dp(xd), _dp(st))
+        return xd, st
+
+    def gen_forces(self, x, u=None):
+        x, u, N = self._xu(x, u)
+        f = np.empty((N, self.n))
+        self._forces(self.h, N, _dp(x), _dp(u), _dp(f))
+        return f
+
+    def mass(self, x, with_dot=True):
+        x, _, N = self._xu(x, None)
+        M = np.empty((N, self.n, self.n))
+        Md = np.empty((N, self.n, self.n)) if with_dot else None
+        self._mass(self.h, N, _dp(x), _dp(M), _dp(Md))
+        return (M, Md) if with_dot else M
+
+    def rk4(self, x0, u, dt, n_steps, n_workers=1):
+        """Returns (x_out, status, seconds)."""
+        x, u, N = self._xu(x0, u)
+        out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        secs = self._rk4(self.h, N, _dp(x), _dp(u), float(dt), int(n_steps), _dp(out), _dp(st), int(n_workers))
+        return out, st, secs
+
+    def frames(self, x, u=None):
+        """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""
+        x, u, _ = self._xu(x, u)
+        out = np.zeros((self.compiled.desc.n_frames, 25))
+        self._frames(self.h, _dp(x[0].copy()), _dp(u[0].copy()), _dp(out))
+        return out
+
+
+class Reference(_Checker):
+    """The real ReaK code (kte_nl_system + runge_kutta4_integrator)."""
+
+    def __init__(self, compiled):
+        _Checker.__init__(self, REF_SO, "rkref_", compiled)
+
+
+class Oracle(_Checker):
+    """The plain-C restatement oracle/kte_oracle.c."""
+
+    def __init__(self, compiled):
+        _Checker.__init__(self, ORACLE_SO, "kto_", compiled)

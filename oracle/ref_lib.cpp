@@ -1,0 +1,410 @@
+// ref_lib.cpp — TEST INFRASTRUCTURE.  Wraps the UNMODIFIED ReaK sources (read where they lie,
+// under /root/reference/src) behind a small C interface so the parity tests and the
+// cpu_baseline leg of bench.py can run the reference itself.  Nothing in the product path
+// links or loads this file.  Built by oracle/Makefile into oracle/_ref/libreak_ref.so.
+//
+// The model is assembled from the same flat descriptor (include/reak_b200.h) the CUDA
+// library consumes, using the reference's own classes exactly the way
+// examples/robot_airship/old/CRS_A465_models.cpp:260-822 and ctrl/mbd_kte/test_bm.cpp:46-72 do,
+// evaluated with ctrl/ctrl_sys/kte_nl_system.hpp and integrated with
+// core/integrators/fixed_step_integrators.hpp (runge_kutta4_integrator<double>).
+
+#include <ReaK/core/base/defs.hpp>
+#include <ReaK/core/lin_alg/mat_alg.hpp>
+#include <ReaK/core/lin_alg/vect_alg.hpp>
+#include <ReaK/core/lin_alg/mat_num_exceptions.hpp>
+#include <ReaK/core/kinetostatics/kinetostatics.hpp>
+#include <ReaK/core/kinetostatics/motion_jacobians.hpp>
+#include <ReaK/core/integrators/fixed_step_integrators.hpp>
+
+#include <ReaK/ctrl/mbd_kte/kte_map_chain.hpp>
+#include <ReaK/ctrl/mbd_kte/revolute_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/prismatic_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/rigid_link.hpp>
+#include <ReaK/ctrl/mbd_kte/inertia.hpp>
+#include <ReaK/ctrl/mbd_kte/spring.hpp>
+#include <ReaK/ctrl/mbd_kte/damper.hpp>
+#include <ReaK/ctrl/mbd_kte/torsion_spring.hpp>
+#include <ReaK/ctrl/mbd_kte/torsion_damper.hpp>
+#include <ReaK/ctrl/mbd_kte/driving_actuator.hpp>
+#include <ReaK/ctrl/mbd_kte/jacobian_joint_map.hpp>
+#include <ReaK/ctrl/mbd_kte/mass_matrix_calculator.hpp>
+#include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
+
+#include "../include/reak_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <vector>
+
+using namespace ReaK;
+
+namespace {
+
+struct ref_model {
+  std::vector<shared_ptr<frame_3D<double> > > f3;
+  std::vector<shared_ptr<frame_2D<double> > > f2;
+  std::vector<shared_ptr<gen_coord<double> > > coords;
+  std::vector<shared_ptr<jacobian_gen_3D<double> > > jac3;
+  std::vector<shared_ptr<jacobian_gen_2D<double> > > jac2;
+  std::vector<shared_ptr<kte::kte_map> > elems;
+  shared_ptr<kte::kte_map_chain> chain;
+  shared_ptr<kte::mass_matrix_calc> mcalc;
+  ctrl::kte_nl_system sys;
+  int n, nu;
+};
+
+struct ref_handle {
+  rkb_chain_desc desc;
+  std::vector<rkb_element> elements;
+  ref_model* proto;
+};
+
+ref_model* build_model(const rkb_chain_desc& d) {
+  ref_model* m = new ref_model();
+  m->n = d.n_coords;
+  m->nu = d.n_inputs;
+  const bool is3 = (d.dim == 3);
+  for (int i = 0; i < d.n_frames; ++i) {
+    if (is3) m->f3.push_back(shared_ptr<frame_3D<double> >(new frame_3D<double>()));
+    else     m->f2.push_back(shared_ptr<frame_2D<double> >(new frame_2D<double>()));
+  }
+  for (int i = 0; i < d.n_coords; ++i) {
+    m->coords.push_back(shared_ptr<gen_coord<double> >(new gen_coord<double>()));
+    if (is3) m->jac3.push_back(shared_ptr<jacobian_gen_3D<double> >(new jacobian_gen_3D<double>()));
+    else     m->jac2.push_back(shared_ptr<jacobian_gen_2D<double> >(new jacobian_gen_2D<double>()));
+  }
+  const rkb_base_frame& b = d.base;
+  if (is3) {
+    frame_3D<double>& B = *m->f3[d.base_frame];
+    B.Position = vect<double,3>(b.position[0], b.position[1], b.position[2]);
+    B.Quat = quaternion<double>(vect<double,4>(b.quat[0], b.quat[1], b.quat[2], b.quat[3]));
+    B.Velocity = vect<double,3>(b.velocity[0], b.velocity[1], b.velocity[2]);
+    B.AngVelocity = vect<double,3>(b.ang_velocity[0], b.ang_velocity[1], b.ang_velocity[2]);
+    B.Acceleration = vect<double,3>(b.acceleration[0], b.acceleration[1], b.acceleration[2]);
+    B.AngAcceleration = vect<double,3>(b.ang_acceleration[0], b.ang_acceleration[1], b.ang_acceleration[2]);
+  } else {
+    frame_2D<double>& B = *m->f2[d.base_frame];
+    B.Position = vect<double,2>(b.position[0], b.position[1]);
+    B.Rotation = rot_mat_2D<double>(b.quat[0]);
+    B.Velocity = vect<double,2>(b.velocity[0], b.velocity[1]);
+    B.AngVelocity = b.ang_velocity[0];
+    B.Acceleration = vect<double,2>(b.acceleration[0], b.acceleration[1]);
+    B.AngAcceleration = b.ang_acceleration[0];
+  }
+
+  m->chain = shared_ptr<kte::kte_map_chain>(new kte::kte_map_chain("chain"));
+  m->mcalc = shared_ptr<kte::mass_matrix_calc>(new kte::mass_matrix_calc("mcalc"));
+  std::vector<shared_ptr<kte::reacting_kte_gen> > joint_of_elem(d.n_elements);
+  std::vector<shared_ptr<kte::inertia_gen> > gen_inertias;
+  std::vector<shared_ptr<kte::driving_actuator_gen> > actuators(d.n_inputs);
+
+  // Pass 1: joints (an actuator precedes the joint it drives in the CRS chain order,
+  // CRS_A465_models.cpp:748-788, and needs the joint object at construction).
+  for (int e = 0; e < d.n_elements; ++e) {
+    const rkb_element& E = d.elements[e];
+    const std::string nm = "e" + std::to_string(e);
+    switch (E.kind) {
+      case RKB_REVOLUTE_3D:
+        joint_of_elem[e] = shared_ptr<kte::reacting_kte_gen>(new kte::revolute_joint_3D(nm, m->coords[E.coord],
+            vect<double,3>(E.p[0], E.p[1], E.p[2]), m->f3[E.frame_a], m->f3[E.frame_b], m->jac3[E.coord]));
+        break;
+      case RKB_PRISMATIC_3D:
+        joint_of_elem[e] = shared_ptr<kte::reacting_kte_gen>(new kte::prismatic_joint_3D(nm, m->coords[E.coord],
+            vect<double,3>(E.p[0], E.p[1], E.p[2]), m->f3[E.frame_a], m->f3[E.frame_b], m->jac3[E.coord]));
+        break;
+      case RKB_REVOLUTE_2D:
+        joint_of_elem[e] = shared_ptr<kte::reacting_kte_gen>(new kte::revolute_joint_2D(nm, m->coords[E.coord],
+            m->f2[E.frame_a], m->f2[E.frame_b], m->jac2[E.coord]));
+        break;
+      case RKB_PRISMATIC_2D:
+        joint_of_elem[e] = shared_ptr<kte::reacting_kte_gen>(new kte::prismatic_joint_2D(nm, m->coords[E.coord],
+            vect<double,2>(E.p[0], E.p[1]), m->f2[E.frame_a], m->f2[E.frame_b], m->jac2[E.coord]));
+        break;
+      default: break;
+    }
+  }
+
+  for (int e = 0; e < d.n_elements; ++e) {
+    const rkb_element& E = d.elements[e];
+    const std::string nm = "e" + std::to_string(e);
+    shared_ptr<kte::kte_map> k;
+    switch (E.kind) {
+      case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
+        k = joint_of_elem[e]; break;
+      case RKB_RIGID_LINK_3D: {
+        pose_3D<double> off(weak_ptr<pose_3D<double> >(), vect<double,3>(E.p[0], E.p[1], E.p[2]),
+                            quaternion<double>(vect<double,4>(E.p[3], E.p[4], E.p[5], E.p[6])));
+        k = shared_ptr<kte::kte_map>(new kte::rigid_link_3D(nm, m->f3[E.frame_a], m->f3[E.frame_b], off));
+        break; }
+      case RKB_INERTIA_3D: {
+        shared_ptr<kte::joint_dependent_frame_3D> dep(new kte::joint_dependent_frame_3D(m->f3[E.frame_a]));
+        for (int c = 0; c < d.n_coords; ++c)
+          if ((E.upstream >> c) & 1u) dep->add_joint(m->coords[c], m->jac3[c]);
+        shared_ptr<kte::inertia_3D> in(new kte::inertia_3D(nm, dep, E.p[0],
+            mat<double,mat_structure::symmetric>(E.p[1], E.p[2], E.p[3], E.p[4], E.p[5], E.p[6])));
+        *m->mcalc << in; k = in; break; }
+      case RKB_INERTIA_GEN: {
+        shared_ptr<kte::joint_dependent_gen_coord> dep(new kte::joint_dependent_gen_coord(m->coords[E.coord]));
+        dep->add_joint(m->coords[E.coord], shared_ptr<jacobian_gen_gen<double> >(new jacobian_gen_gen<double>(1.0, 0.0)));
+        shared_ptr<kte::inertia_gen> in(new kte::inertia_gen(nm, dep, E.p[0]));
+        gen_inertias.push_back(in); k = in; break; }
+      case RKB_ACTUATOR_GEN: {
+        if (E.frame_b < 0 || E.frame_b >= d.n_elements || !joint_of_elem[E.frame_b]) { delete m; return NULL; }
+        shared_ptr<kte::driving_actuator_gen> a(new kte::driving_actuator_gen(nm, m->coords[E.coord], joint_of_elem[E.frame_b]));
+        actuators.at(E.aux) = a; k = a; break; }
+      case RKB_TORSION_SPRING_3D:
+        k = shared_ptr<kte::kte_map>(new kte::torsion_spring_3D(nm, m->f3[E.frame_a], m->f3[E.frame_b], E.p[0], E.p[1])); break;
+      case RKB_TORSION_DAMPER_3D:
+        k = shared_ptr<kte::kte_map>(new kte::torsion_damper_3D(nm, m->f3[E.frame_a], m->f3[E.frame_b], E.p[0])); break;
+      case RKB_SPRING_3D:
+        k = shared_ptr<kte::kte_map>(new kte::spring_3D(nm, m->f3[E.frame_a], m->f3[E.frame_b], E.p[0], E.p[1], E.p[2])); break;
+      case RKB_DAMPER_3D:
+        k = shared_ptr<kte::kte_map>(new kte::damper_3D(nm, m->f3[E.frame_a], m->f3[E.frame_b], E.p[0])); break;
+      case RKB_RIGID_LINK_2D: {
+        pose_2D<double> off(weak_ptr<pose_2D<double> >(), vect<double,2>(E.p[0], E.p[1]), rot_mat_2D<double>(E.p[2]));
+        k = shared_ptr<kte::kte_map>(new kte::rigid_link_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], off));
+        break; }
+      case RKB_INERTIA_2D: {
+        kte::jacobian_joint_map_2D jm;
+        for (int c = 0; c < d.n_coords; ++c)
+          if ((E.upstream >> c) & 1u) jm[m->coords[c]] = m->jac2[c];
+        shared_ptr<kte::joint_dependent_frame_2D> dep(new kte::joint_dependent_frame_2D(m->f2[E.frame_a], jm));
+        shared_ptr<kte::inertia_2D> in(new kte::inertia_2D(nm, dep, E.p[0], E.p[1]));
+        *m->mcalc << in; k = in; break; }
+      case RKB_TORSION_SPRING_2D:
+        k = shared_ptr<kte::kte_map>(new kte::torsion_spring_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], E.p[0], E.p[1])); break;
+      case RKB_TORSION_DAMPER_2D:
+        k = shared_ptr<kte::kte_map>(new kte::torsion_damper_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], E.p[0])); break;
+      case RKB_SPRING_2D:
+        k = shared_ptr<kte::kte_map>(new kte::spring_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], E.p[0], E.p[1], E.p[2])); break;
+      case RKB_DAMPER_2D:
+        k = shared_ptr<kte::kte_map>(new kte::damper_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], E.p[0])); break;
+      default:
+        delete m; return NULL;
+    }
+    m->elems.push_back(k);
+    *m->chain << k;
+  }
+  // CRS_A465_models.cpp:791-822: link inertias, then motor inertias, then the coordinates.
+  for (std::size_t i = 0; i < gen_inertias.size(); ++i) *m->mcalc << gen_inertias[i];
+  for (int c = 0; c < d.n_coords; ++c) *m->mcalc << m->coords[c];
+
+  m->sys.dofs_gen = m->coords;
+  for (int i = 0; i < d.n_inputs; ++i) {
+    if (!actuators[i]) { delete m; return NULL; }
+    m->sys.inputs.push_back(actuators[i]);
+  }
+  m->sys.chain = m->chain;
+  m->sys.mass_calc = m->mcalc;
+  return m;
+}
+
+// Same wrapper as num_int_dtnl_sys::rate_function_impl (num_int_dtnl_system.hpp:85-99).
+class rate_fn : public state_rate_function<double> {
+ public:
+  const ctrl::kte_nl_system* sys;
+  vect_n<double> u;
+  rate_fn(const ctrl::kte_nl_system* s, const vect_n<double>& aU) : sys(s), u(aU) {}
+  virtual void RK_CALL computeStateRate(double t, const vect_n<double>& x, vect_n<double>& xd) {
+    xd = sys->get_state_derivative(*sys, x, u, t);
+  }
+};
+
+void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, const double* u,
+               double dt, int n_steps, double* xout, int32_t* status) {
+  const int nx = 2 * m->n, nu = m->nu;
+  for (std::size_t i = i0; i < i1; ++i) {
+    vect_n<double> x(nx), uu(nu);
+    for (int k = 0; k < nx; ++k) x[k] = x0[i * nx + k];
+    for (int k = 0; k < nu; ++k) uu[k] = u[i * nu + k];
+    int32_t st = 0;
+    if (n_steps > 0) {
+      shared_ptr<state_rate_function<double> > fn(new rate_fn(&m->sys, uu));
+      runge_kutta4_integrator<double> integ("rk4", x, 0.0, dt, fn);
+      try {
+        // The loop of fixed_step_integrators.hpp:275 is time-driven; an end time half a step
+        // short of n_steps*dt makes it run exactly n_steps steps.
+        integ.integrate((double(n_steps) - 0.5) * dt);
+      } catch (singularity_error&) { st |= RKB_STATUS_SINGULAR; }
+      int k = 0;
+      for (std::vector<double>::const_iterator it = integ.getStateBegin(); it != integ.getStateEnd(); ++it, ++k)
+        xout[i * nx + k] = *it;
+    } else {
+      for (int k = 0; k < nx; ++k) xout[i * nx + k] = x[k];
+    }
+    for (int k = 0; k < nx; ++k) if (!std::isfinite(xout[i * nx + k])) st |= RKB_STATUS_NONFINITE;
+    if (status) status[i] = st;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* rkref_create(const rkb_chain_desc* d) {
+  if (!d || !d->elements) return NULL;
+  ref_handle* h = new ref_handle();
+  h->desc = *d;
+  h->elements.assign(d->elements, d->elements + d->n_elements);
+  h->desc.elements = h->elements.data();
+  try { h->proto = build_model(h->desc); } catch (...) { h->proto = NULL; }
+  if (!h->proto) { delete h; return NULL; }
+  return h;
+}
+
+void rkref_destroy(void* hv) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  if (!h) return;
+  delete h->proto;
+  delete h;
+}
+
+int rkref_eval(void* hv, std::size_t N, const double* x, const double* u, double* xdot, int32_t* status) {
+  ref_model* m = static_cast<ref_handle*>(hv)->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  vect_n<double> p(nx), uu(nu);
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    for (int k = 0; k < nu; ++k) uu[k] = u[i * nu + k];
+    int32_t st = 0;
+    try {
+      vect_n<double> pd = m->sys.get_state_derivative(m->sys, p, uu, 0.0);
+      for (int k = 0; k < nx; ++k) xdot[i * nx + k] = pd[k];
+    } catch (singularity_error&) {
+      st |= RKB_STATUS_SINGULAR;
+      for (int k = 0; k < nx; ++k) xdot[i * nx + k] = std::nan("");
+    }
+    if (status) status[i] = st;
+  }
+  return 0;
+}
+
+// gen_coord::f after doMotion/clearForce/doForce with q_ddot = 0 (kte_nl_system.hpp:240-253).
+int rkref_gen_forces(void* hv, std::size_t N, const double* x, const double* u, double* f) {
+  ref_model* m = static_cast<ref_handle*>(hv)->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  vect_n<double> p(nx), uu(nu);
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    for (int k = 0; k < nu; ++k) uu[k] = u[i * nu + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    m->chain->clearForce();
+    m->chain->doForce();
+    for (int k = 0; k < m->n; ++k) f[i * m->n + k] = m->coords[k]->f;
+  }
+  return 0;
+}
+
+// M (and Mdot) row-major n x n per sample (mass_matrix_calculator.cpp:80-98).
+int rkref_mass(void* hv, std::size_t N, const double* x, double* M, double* Mdot) {
+  ref_model* m = static_cast<ref_handle*>(hv)->proto;
+  const int nx = 2 * m->n, nu = m->nu, n = m->n;
+  vect_n<double> p(nx), uu(nu, 0.0);
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    mat<double,mat_structure::symmetric> Ms(n);
+    mat<double,mat_structure::square> Md(n);
+    if (Mdot) m->mcalc->getMassMatrixAndDerivative(Ms, Md);
+    else      m->mcalc->getMassMatrix(Ms);
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) {
+        M[(i * n + r) * n + c] = Ms(r, c);
+        if (Mdot) Mdot[(i * n + r) * n + c] = Md(r, c);
+      }
+  }
+  return 0;
+}
+
+// World-frame kinematics of every frame after doMotion, for debugging the restatement:
+// per frame 19 doubles: Position3, Quat4, Velocity3, AngVelocity3, Acceleration3, AngAcceleration3
+// (2D: Position2, (cos,sin), Velocity2, AngVelocity, Acceleration2, AngAcceleration, rest 0).
+int rkref_frames(void* hv, const double* x, const double* u, double* out) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  vect_n<double> p(nx), uu(nu);
+  for (int k = 0; k < nx; ++k) p[k] = x[k];
+  for (int k = 0; k < nu; ++k) uu[k] = u[k];
+  m->sys.apply_states_and_inputs(p, uu);
+  m->chain->doMotion();
+  m->chain->clearForce();
+  m->chain->doForce();
+  for (int i = 0; i < h->desc.n_frames; ++i) {
+    double* o = out + 25 * i;
+    for (int k = 0; k < 25; ++k) o[k] = 0.0;
+    if (h->desc.dim == 3) {
+      const frame_3D<double>& F = *m->f3[i];
+      for (int k = 0; k < 3; ++k) { o[k] = F.Position[k]; o[7 + k] = F.Velocity[k]; o[10 + k] = F.AngVelocity[k];
+                                    o[13 + k] = F.Acceleration[k]; o[16 + k] = F.AngAcceleration[k];
+                                    o[19 + k] = F.Force[k]; o[22 + k] = F.Torque[k]; }
+      for (int k = 0; k < 4; ++k) o[3 + k] = F.Quat[k];
+    } else {
+      const frame_2D<double>& F = *m->f2[i];
+      for (int k = 0; k < 2; ++k) { o[k] = F.Position[k]; o[3 + k] = F.Rotation[k]; o[7 + k] = F.Velocity[k];
+                                    o[13 + k] = F.Acceleration[k]; o[19 + k] = F.Force[k]; }
+      o[10] = F.AngVelocity; o[16] = F.AngAcceleration; o[22] = F.Torque;
+    }
+  }
+  return 0;
+}
+
+// n_workers > 1: the samples are block-partitioned over forked worker processes.  Threads do
+// not scale here: every rk_dynamic_ptr_cast in the reference bumps the atomic reference count
+// of shared static type descriptors, so threads serialise on those cache lines (measured:
+// 8 threads = 1.04x, 8 processes = 3.7x on the 8-vCPU build container).  A forked child owns a
+// copy-on-write image of the whole model, which is the "one model instance per worker" the
+// non-re-entrant KTE objects need.  Results come back through a shared anonymous mapping.
+// Returns wall seconds of the integration (< 0 on failure).
+double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, double dt, int n_steps,
+                 double* xout, int32_t* status, int n_workers) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n;
+  if (n_workers < 1) n_workers = 1;
+  if (std::size_t(n_workers) > N && N > 0) n_workers = int(N);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (n_workers == 1 || N == 0) {
+    rk4_range(m, 0, N, x0, u, dt, n_steps, xout, status);
+  } else {
+    const std::size_t bytes_x = N * nx * sizeof(double), bytes_s = N * sizeof(int32_t);
+    void* shm = mmap(NULL, bytes_x + bytes_s, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (shm == MAP_FAILED) return -1.0;
+    double* sx = static_cast<double*>(shm);
+    int32_t* ss = reinterpret_cast<int32_t*>(static_cast<char*>(shm) + bytes_x);
+    std::vector<pid_t> pids;
+    bool ok = true;
+    for (int t = 0; t < n_workers; ++t) {
+      std::size_t i0 = N * t / n_workers, i1 = N * (t + 1) / n_workers;
+      pid_t pid = fork();
+      if (pid == 0) {
+        rk4_range(m, i0, i1, x0, u, dt, n_steps, sx, ss);
+        _exit(0);
+      }
+      if (pid < 0) { ok = false; break; }
+      pids.push_back(pid);
+    }
+    for (std::size_t i = 0; i < pids.size(); ++i) {
+      int wst = 0;
+      if (waitpid(pids[i], &wst, 0) < 0 || !WIFEXITED(wst) || WEXITSTATUS(wst) != 0) ok = false;
+    }
+    if (ok) {
+      std::memcpy(xout, sx, bytes_x);
+      if (status) std::memcpy(status, ss, bytes_s);
+    }
+    munmap(shm, bytes_x + bytes_s);
+    if (!ok) return -1.0;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+"""ctypes view of include/reak_b200.h (the C-ABI of libreak_b200.so).
+
+The structures below mirror `rkb_element`, `rkb_base_frame` and `rkb_chain_desc` field by
+field.  `load_library()` fails loudly when the CUDA library has not been built: there is no
+CPU fallback behind this package.
+"""
+import ctypes as C
+import os
+
+RKB_MAX_COORDS = 16
+
+# enum rkb_kind
+REVOLUTE_3D, PRISMATIC_3D, FREE_3D, RIGID_LINK_3D, INERTIA_3D, INERTIA_GEN, ACTUATOR_GEN = 1, 2, 3, 4, 5, 6, 7
+TORSION_SPRING_3D, TORSION_DAMPER_3D, SPRING_3D, DAMPER_3D = 8, 9, 10, 11
+REVOLUTE_2D, PRISMATIC_2D, RIGID_LINK_2D, INERTIA_2D = 17, 18, 20, 21
+TORSION_SPRING_2D, TORSION_DAMPER_2D, SPRING_2D, DAMPER_2D = 24, 25, 26, 27
+
+MEM_HOST, MEM_DEVICE = 0, 1
+LAYOUT_AOS, LAYOUT_SOA = 0, 2
+STATUS_SINGULAR, STATUS_NONFINITE = 1, 2
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_DIMENSION, ERR_CUDA, ERR_NOMEM, ERR_INTEGRATION = 0, -1, -2, -3, -4, -5, -6
+
+
+class rkb_element(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("frame_a", C.c_int32), ("frame_b", C.c_int32),
+                ("coord", C.c_int32), ("aux", C.c_int32), ("reserved", C.c_int32),
+                ("upstream", C.c_uint64), ("p", C.c_double * 12)]
+
+
+class rkb_base_frame(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("quat", C.c_double * 4), ("velocity", C.c_double * 3),
+                ("ang_velocity", C.c_double * 3), ("acceleration", C.c_double * 3),
+                ("ang_acceleration", C.c_double * 3)]
+
+
+class rkb_chain_desc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_elements", C.c_int32), ("n_frames", C.c_int32),
+                ("n_coords", C.c_int32), ("n_inputs", C.c_int32), ("base_frame", C.c_int32),
+                ("base", rkb_base_frame), ("elements", C.POINTER(rkb_element))]
+
+
+assert C.sizeof(rkb_element) == 128, C.sizeof(rkb_element)
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libreak_b200.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); every symbol include/reak_b200.h declares
+SYMBOLS = {
+    "rkb_version": (C.c_int, []),
+    "rkb_strerror": (C.c_char_p, [C.c_int]),
+    "rkb_last_cuda_error": (C.c_char_p, []),
+    "rkb_chain_create": (C.c_int, [C.POINTER(rkb_chain_desc), C.POINTER(C.c_void_p)]),
+    "rkb_chain_destroy": (None, [C.c_void_p]),
+    "rkb_chain_state_dim": (C.c_int, [C.c_void_p]),
+    "rkb_chain_input_dim": (C.c_int, [C.c_void_p]),
+    "rkb_chain_dof": (C.c_int, [C.c_void_p]),
+    "rkb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_uint, C.c_void_p]),
+    "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_gen_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_uint, C.c_void_p]),
+    "rkb_mass_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_uint, C.c_void_p]),
+    "rkb_steer_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_uint, C.c_void_p]),
+    "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
+}
+
+
+def load_library(path=None):
+    """dlopen libreak_b200.so and bind every declared symbol.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise RuntimeError(
+            "reak_b200: CUDA library %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C reak_b200/csrc`). There is no CPU fallback." % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class RkbError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        lib = load_library()
+        msg = lib.rkb_strerror(code).decode()
+        cu = lib.rkb_last_cuda_error().decode()
+        RuntimeError.__init__(self, "%s%s (code %d)%s" % (what + ": " if what else "", msg, code,
+                                                          " [cuda: %s]" % cu if cu and code == ERR_CUDA else ""))
+
+
+def check(code, what=""):
+    if code != 0:
+        raise RkbError(code, what)

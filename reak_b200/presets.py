@@ -1,0 +1,176 @@
+"""The chains BASELINE.json's configs name, written with the mirrored ReaK::kte API.
+
+Geometry follows the reference's own model code: the CRS A465 preset of
+examples/robot_airship/old/CRS_A465_models.cpp:260-822 (axes z,-y,-y,z,-y,z; link z-offsets
+0.3302, 0.3048, 0.1500, 0.1802, 0.0762, 0; unit masses and inertias; gravity as an upward base
+acceleration, :299) and the pendulum of ctrl/mbd_kte/test_bm.cpp:46-72.
+"""
+import math
+
+from . import kte
+
+
+class kte_system(object):
+    """The public data members of ctrl::kte_nl_system (kte_nl_system.hpp:70-78)."""
+
+    def __init__(self, name=""):
+        self.name = name
+        self.dofs_gen, self.inputs = [], []
+        self.chain = kte.kte_map_chain(name + "_chain")
+        self.mass_calc = kte.mass_matrix_calc(name + "_mcalc")
+
+    def get_state_dimensions(self):
+        return 2 * len(self.dofs_gen)
+
+    def get_input_dimensions(self):
+        return sum(a.getInputCount() for a in self.inputs)
+
+
+CRS_AXES = [(0.0, 0.0, 1.0), (0.0, -1.0, 0.0), (0.0, -1.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0), (0.0, 0.0, 1.0)]
+CRS_LINK_Z = [0.3302, 0.3048, 0.1500, 0.1802, 0.0762, 0.0]
+PHYS_MASS = [5.0, 4.0, 3.0, 2.0, 1.0, 0.5]
+PHYS_INERTIA = [(0.2, 0.15, 0.1), (0.12, 0.2, 0.08), (0.06, 0.09, 0.05), (0.03, 0.02, 0.04), (0.02, 0.015, 0.01), (0.01, 0.012, 0.011)]
+
+
+def crs_chain(n_revolute=6, track=False, springs=False, physical=False, actuated=True,
+              stiffness=10.0, damping=0.5, saturation=0.0, link_rotation=False):
+    """CRS-A465-style serial arm.  `track` prepends the prismatic x-axis joint (cfg 4);
+    `springs` inserts a torsion_spring_3D + torsion_damper_3D across every revolute joint
+    (cfg 3); `physical` uses graded masses / anisotropic inertias instead of the preset's
+    unit placeholders; `link_rotation` gives the links a fixed twist (exercises R_o != I)."""
+    s = kte_system("crs")
+    base = kte.frame_3D()
+    base.Acceleration = [0.0, 0.0, 9.81]
+    base.Position = [0.0, -3.3, 0.3]
+    base.Quat = kte.axis_angle_quat(math.pi * 0.5, (0.0, 0.0, 1.0))
+    cur = base
+    upstream = []  # (coord, jacobian) of every joint met so far
+
+    def stage(idx, joint_kind, axis, link_pos, mass, tensor, with_spring):
+        nonlocal cur
+        coord, jac, end, nxt = kte.gen_coord(), kte.jacobian_gen_3D(), kte.frame_3D(), kte.frame_3D()
+        if joint_kind == "P":
+            joint = kte.prismatic_joint_3D("joint_%d" % idx, coord, axis, cur, end, jac)
+        else:
+            joint = kte.revolute_joint_3D("joint_%d" % idx, coord, axis, cur, end, jac)
+        dep = kte.joint_dependent_gen_coord(coord)
+        dep.add_joint(coord, kte.jacobian_gen_gen(1.0, 0.0))
+        rotor = kte.inertia_gen("joint_%d_inertia" % idx, dep, 1.0)
+        if actuated:
+            act = kte.driving_actuator_gen("joint_%d_actuator" % idx, coord, joint)
+            s.chain << act
+            s.inputs.append(act)
+        s.chain << rotor << joint
+        if with_spring:
+            s.chain << kte.torsion_spring_3D("spring_%d" % idx, cur, end, stiffness, saturation)
+            s.chain << kte.torsion_damper_3D("damper_%d" % idx, cur, end, damping)
+        q_off = kte.axis_angle_quat(0.3 + 0.1 * idx, (1.0, 2.0, -1.0)) if link_rotation else (1.0, 0.0, 0.0, 0.0)
+        link = kte.rigid_link_3D("link_%d" % idx, end, nxt, kte.pose_3D(link_pos, q_off))
+        upstream.append((coord, jac))
+        depf = kte.joint_dependent_frame_3D(nxt)
+        for c, j in upstream:
+            depf.add_joint(c, j)
+        inertia = kte.inertia_3D("link_%d_inertia" % idx, depf, mass, tensor)
+        s.chain << link << inertia
+        s.dofs_gen.append(coord)
+        s.mass_calc << inertia
+        gen_inertias.append(rotor)
+        cur = nxt
+
+    gen_inertias = []
+    idx = 0
+    if track:
+        stage(idx, "P", (1.0, 0.0, 0.0), (0.0, 0.0, 0.0), 1.0, (1.0, 0.0, 0.0, 1.0, 0.0, 1.0), False)
+        idx += 1
+    for k in range(n_revolute):
+        if physical:
+            ix, iy, iz = PHYS_INERTIA[k % 6]
+            mass, tensor = PHYS_MASS[k % 6], (ix, 0.01 * (k + 1), -0.005, iy, 0.002 * (k + 1), iz)
+        else:
+            mass, tensor = 1.0, (1.0, 0.0, 0.0, 1.0, 0.0, 1.0)
+        stage(idx, "R", CRS_AXES[k % 6], (0.0, 0.0, CRS_LINK_Z[k % 6]), mass, tensor, springs)
+        idx += 1
+    for g in gen_inertias:
+        s.mass_calc << g
+    for c in s.dofs_gen:
+        s.mass_calc << c
+    return s
+
+
+def planar_chain(lengths=(0.5, 0.4), masses=(1.0, 0.8), moments=(0.1, 0.05), actuated=False,
+                 springs=False, stiffness=10.0, damping=0.5):
+    """cfg 1: revolute_joint_2D -> rigid_link_2D -> inertia_2D per link; base accel (0, 9.81)."""
+    s = kte_system("planar")
+    base = kte.frame_2D()
+    base.Acceleration = [0.0, 9.81]
+    cur, upstream, acts = base, {}, []
+    for k, (L, m, J) in enumerate(zip(lengths, masses, moments)):
+        coord, jac, end, nxt = kte.gen_coord(), kte.jacobian_gen_2D(), kte.frame_2D(), kte.frame_2D()
+        joint = kte.revolute_joint_2D("joint_%d" % k, coord, cur, end, jac)
+        if actuated:
+            act = kte.driving_actuator_gen("actuator_%d" % k, coord, joint)
+            s.chain << act
+            s.inputs.append(act)
+        s.chain << joint
+        if springs:
+            s.chain << kte.torsion_spring_2D("spring_%d" % k, cur, end, stiffness)
+            s.chain << kte.torsion_damper_2D("damper_%d" % k, cur, end, damping)
+        link = kte.rigid_link_2D("link_%d" % k, end, nxt, kte.pose_2D((L, 0.0), 0.0))
+        upstream[coord] = jac
+        inertia = kte.inertia_2D("mass_%d" % k, kte.joint_dependent_frame_2D(nxt, upstream), m, J)
+        s.chain << link << inertia
+        s.dofs_gen.append(coord)
+        s.mass_calc << inertia
+        cur = nxt
+    for c in s.dofs_gen:
+        s.mass_calc << c
+    return s
+
+
+def pendulum_chain():
+    """ctrl/mbd_kte/test_bm.cpp:46-72: 0.5 m massless rod, 1 kg point mass, gravity (0, 9.81)."""
+    return planar_chain(lengths=(0.5,), masses=(1.0,), moments=(0.0,))
+
+
+def torsion_1dof_chain():
+    """BASELINE.md known answer: one revolute_joint_3D about -y with torsion_spring_3D k=10 and
+    torsion_damper_3D c=0.5, 2 kg at 0.3 m along z, I = diag(0.1,0.2,0.3); base at the origin."""
+    s = kte_system("torsion1")
+    base, end, tip = kte.frame_3D(), kte.frame_3D(), kte.frame_3D()
+    base.Acceleration = [0.0, 0.0, 9.81]
+    coord, jac = kte.gen_coord(), kte.jacobian_gen_3D()
+    joint = kte.revolute_joint_3D("joint", coord, (0.0, -1.0, 0.0), base, end, jac)
+    s.chain << joint
+    s.chain << kte.torsion_spring_3D("spring", base, end, 10.0)
+    s.chain << kte.torsion_damper_3D("damper", base, end, 0.5)
+    s.chain << kte.rigid_link_3D("link", end, tip, kte.pose_3D((0.0, 0.0, 0.3)))
+    dep = kte.joint_dependent_frame_3D(tip)
+    dep.add_joint(coord, jac)
+    inertia = kte.inertia_3D("mass", dep, 2.0, (0.1, 0.0, 0.0, 0.2, 0.0, 0.3))
+    s.chain << inertia
+    s.dofs_gen.append(coord)
+    s.mass_calc << inertia << coord
+    return s
+
+
+PRESETS = {
+    "pendulum": pendulum_chain,
+    "planar2": planar_chain,                                          # cfg 1
+    "planar2_act": lambda: planar_chain(actuated=True),
+    "planar3_sd": lambda: planar_chain(lengths=(0.5, 0.4, 0.3), masses=(1.0, 0.8, 0.5),
+                                       moments=(0.1, 0.05, 0.02), actuated=True, springs=True),
+    "crs6": crs_chain,                                                # cfg 2 / 5
+    "crs6_phys": lambda: crs_chain(physical=True),
+    "crs6_sd": lambda: crs_chain(springs=True),                       # cfg 3
+    "crs6_sd_sat": lambda: crs_chain(springs=True, saturation=3.0),
+    "crs6_twist": lambda: crs_chain(physical=True, link_rotation=True),
+    "crs7": lambda: crs_chain(track=True),                            # cfg 4
+    "crs7_phys_sd": lambda: crs_chain(track=True, physical=True, springs=True),
+    "torsion1": torsion_1dof_chain,
+    "crs3": lambda: crs_chain(n_revolute=3),
+    "crs6_passive": lambda: crs_chain(actuated=False),
+}
+
+
+def make(name):
+    return PRESETS[name]()

@@ -1,0 +1,222 @@
+"""kte_batch_propagator — the batched counterpart of ctrl::kte_nl_system + num_int_dtnl_sys.
+
+It is constructed from the same members kte_nl_system holds (chain, mass_calc, dofs_gen, inputs;
+ctrl/ctrl_sys/kte_nl_system.hpp:70-78).  The single-sample methods keep the reference's
+state-space-system signatures (SSSystemConcept, ctrl/ctrl_sys/state_space_sys_concept.hpp:111-137;
+DiscreteSSSConcept, ctrl/ctrl_sys/discrete_sss_concept.hpp:40-141) and raise the reference's
+errors; the batched methods are additive.  All numerics run in libreak_b200.so on the GPU —
+this module only moves pointers.  numpy arrays are treated as HOST buffers (staged by the
+library), torch CUDA tensors as DEVICE buffers (zero-copy).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, kte
+
+
+class singularity_error(ArithmeticError):
+    """core/lin_alg/mat_num_exceptions.hpp:45-56 — thrown by linsolve_Cholesky on a pivot < 1e-8."""
+
+
+class impossible_integration(ValueError):
+    """core/integrators/integration_exceptions.hpp:38."""
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class kte_batch_propagator(object):
+    def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3):
+        if mass_calc is None and hasattr(chain, "chain"):  # a kte_system / kte_nl_system-like object
+            sys_ = chain
+            chain, mass_calc, dofs_gen, inputs = sys_.chain, sys_.mass_calc, sys_.dofs_gen, sys_.inputs
+        self.chain, self.mass_calc, self.dofs_gen, self.inputs = chain, mass_calc, list(dofs_gen), list(inputs)
+        self.compiled = kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs)
+        self.device = int(device)
+        self.dt = float(time_step)
+        self._lib = _abi.load_library()
+        h = C.c_void_p()
+        _abi.check(self._lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(h)), "rkb_chain_create")
+        self._h = h
+        self.n = self._lib.rkb_chain_dof(h)
+        self.nx = self._lib.rkb_chain_state_dim(h)
+        self.nu = self._lib.rkb_chain_input_dim(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rkb_chain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- SSSystemConcept / DiscreteSSSConcept (single sample) ---------------------------
+    def get_state_dimensions(self):
+        return self.nx
+
+    def get_input_dimensions(self):
+        return self.nu
+
+    def get_output_dimensions(self):
+        return 0
+
+    def get_time_step(self):
+        return self.dt
+
+    def set_time_step(self, dt):
+        self.dt = float(dt)
+
+    def get_state_derivative(self, space, p, u, t=0.0):
+        """kte_nl_system::get_state_derivative (kte_nl_system.hpp:238-346) for one state."""
+        p = np.asarray(p, dtype=np.float64).ravel()
+        u = np.asarray(u, dtype=np.float64).ravel()
+        if p.size != self.nx:
+            raise IndexError("State vector dimension mismatch!")  # std::range_error, :181-185
+        if u.size != self.nu:
+            raise IndexError("Input vector dimension mismatch!")  # std::range_error, :186-187
+        xd, st = self.get_state_derivatives(p[None, :], u[None, :])
+        if st[0] & _abi.STATUS_SINGULAR:
+            raise singularity_error("Cholesky pivot below 1e-8")
+        return xd[0]
+
+    def get_next_state(self, space, p, u, t=0.0):
+        """num_int_dtnl_sys::get_next_state (num_int_dtnl_system.hpp:166-180): one RK4 step of get_time_step()."""
+        p = np.asarray(p, dtype=np.float64).ravel()
+        u = np.asarray(u, dtype=np.float64).ravel()
+        if p.size != self.nx:
+            raise IndexError("State vector dimension mismatch!")
+        if u.size != self.nu:
+            raise IndexError("Input vector dimension mismatch!")
+        x, st = self.get_next_states(p[None, :], u[None, :], self.dt, 1)
+        if st[0] & _abi.STATUS_SINGULAR:
+            raise singularity_error("Cholesky pivot below 1e-8")
+        return x[0]
+
+    # ---- buffer plumbing --------------------------------------------------------------------
+    def _prep(self, arrs, soa):
+        """Returns (flags, stream, n_samples-agnostic pointers); all buffers must live in one space."""
+        kinds = set(_is_torch(a) for a in arrs if a is not None)
+        if len(kinds) != 1:
+            raise TypeError("mix of numpy (host) and torch (device) buffers")
+        flags = _abi.LAYOUT_SOA if soa else _abi.LAYOUT_AOS
+        if kinds.pop():
+            import torch
+            for a in arrs:
+                if a is None:
+                    continue
+                if not a.is_cuda or a.device.index != self.device:
+                    raise TypeError("torch buffers must be CUDA tensors on device %d" % self.device)
+                if not a.is_contiguous():
+                    raise TypeError("buffers must be contiguous")
+            flags |= _abi.MEM_DEVICE
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            ptr = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
+        else:
+            stream = None
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        return flags, stream, ptr
+
+    def _in(self, a, cols, dtype, soa=False, rows=None):
+        if _is_torch(a):
+            import torch
+            want = torch.float64 if dtype == np.float64 else torch.int32
+            if a.dtype != want:
+                raise TypeError("expected %s tensor" % want)
+            a = a.contiguous()
+            shape = tuple(a.shape)
+        else:
+            a = np.ascontiguousarray(a, dtype=dtype)
+            shape = a.shape
+        if len(shape) != 2:
+            raise IndexError("expected a 2-D batch buffer")
+        n, c = (shape[1], shape[0]) if soa else shape
+        if c != cols or (rows is not None and n != rows):
+            raise IndexError("State vector dimension mismatch!" if cols == self.nx else "Input vector dimension mismatch!")
+        return a, n
+
+    def _like(self, ref, shape, dtype=np.float64):
+        if _is_torch(ref):
+            import torch
+            return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, device=ref.device)
+        return np.empty(shape, dtype=dtype)
+
+    def _u_default(self, x, N, soa):
+        if self.nu:
+            raise IndexError("Input vector dimension mismatch!")
+        return self._like(x, (0, N) if soa else (N, 0))
+
+    # ---- batched API ------------------------------------------------------------------------
+    def get_state_derivatives(self, x, u=None, soa=False, out=None, status=None):
+        x, N = self._in(x, self.nx, np.float64, soa)
+        u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]
+        xd = out if out is not None else self._like(x, x.shape)
+        st = status if status is not None else self._like(x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, u if self.nu else None, xd, st], soa)
+        _abi.check(self._lib.rkb_eval(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
+                                      ptr(xd), ptr(st), flags, stream), "rkb_eval")
+        return xd, st
+
+    def get_next_states(self, x, u=None, dt=None, n_steps=1, soa=False, out=None, status=None):
+        x, N = self._in(x, self.nx, np.float64, soa)
+        u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]
+        dt = self.dt if dt is None else float(dt)
+        if dt == 0.0 or n_steps < 0:
+            raise impossible_integration("dt == 0 or negative step count")
+        xo = out if out is not None else self._like(x, x.shape)
+        st = status if status is not None else self._like(x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, u if self.nu else None, xo, st], soa)
+        _abi.check(self._lib.rkb_rollout_rk4(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
+                                             dt, int(n_steps), ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4")
+        return xo, st
+
+    def get_gen_forces(self, x, u=None, soa=False):
+        x, N = self._in(x, self.nx, np.float64, soa)
+        u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]
+        f = self._like(x, (self.n, N) if soa else (N, self.n))
+        flags, stream, ptr = self._prep([x, u if self.nu else None, f], soa)
+        _abi.check(self._lib.rkb_gen_forces(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
+                                            ptr(f), flags, stream), "rkb_gen_forces")
+        return f
+
+    def get_mass_matrices(self, x, with_derivative=False, soa=False):
+        x, N = self._in(x, self.nx, np.float64, soa)
+        shape = (self.n * self.n, N) if soa else (N, self.n, self.n)
+        M = self._like(x, shape)
+        Md = self._like(x, shape) if with_derivative else None
+        flags, stream, ptr = self._prep([x, M, Md], soa)
+        _abi.check(self._lib.rkb_mass_matrix(self._h, self.device, N, ptr(x), ptr(M), ptr(Md), flags, stream),
+                   "rkb_mass_matrix")
+        return (M, Md) if with_derivative else M
+
+    def steer_batch(self, x0, goal, u, dt=None, n_steps=10, want_status=False):
+        """x0, goal: [P][nx]; u: [P][R][nu].  Returns (best_idx[P], best_x[P][nx], best_cost[P])."""
+        x0, P = self._in(x0, self.nx, np.float64)
+        goal, _ = self._in(goal, self.nx, np.float64, rows=P)
+        if _is_torch(u):
+            u = u.contiguous()
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+        if len(u.shape) != 3 or u.shape[0] != P or u.shape[2] != self.nu:
+            raise IndexError("Input vector dimension mismatch!")
+        R = u.shape[1]
+        dt = self.dt if dt is None else float(dt)
+        idx = self._like(x0, (P,), np.int32)
+        bx = self._like(x0, (P, self.nx))
+        bc = self._like(x0, (P,))
+        st = self._like(x0, (P, R), np.int32) if want_status else None
+        flags, stream, ptr = self._prep([x0, goal, u, idx, bx, bc, st], False)
+        _abi.check(self._lib.rkb_steer_batch(self._h, self.device, P, R, ptr(x0), ptr(goal), ptr(u), dt, int(n_steps),
+                                             ptr(idx), ptr(bx), ptr(bc), ptr(st), flags, stream), "rkb_steer_batch")
+        return (idx, bx, bc, st) if want_status else (idx, bx, bc)
+
+    # ---- instrumentation ----------------------------------------------------------------------
+    def last_kernel_ms(self):
+        return self._lib.rkb_last_kernel_ms(self._h)
+
+    def launch_count(self):
+        return int(self._lib.rkb_launch_count(self._h))
