@@ -1,0 +1,34 @@
+/* kte_oracle.h — TEST INFRASTRUCTURE.  Plain-C restatement of ReaK's KTE-chain forward-dynamics
+ * path (see kte_oracle.c).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load libkte_oracle.so; nothing in reak_b200/ links or calls it. */
+#ifndef KTE_ORACLE_H
+#define KTE_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/reak_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void*  kto_create(const rkb_chain_desc* desc);
+void   kto_destroy(void* h);
+int    kto_eval(void* h, size_t n, const double* x, const double* u, double* xdot, int32_t* status);
+int    kto_gen_forces(void* h, size_t n, const double* x, const double* u, double* f);
+int    kto_mass(void* h, size_t n, const double* x, double* M, double* Mdot);
+int    kto_frames(void* h, const double* x, const double* u, double* out);
+/* returns wall seconds (< 0 on failure); n_workers > 1 forks worker processes */
+double kto_rk4(void* h, size_t n, const double* x0, const double* u, double dt, int n_steps,
+               double* xout, int32_t* status, int n_workers);
+/* raw twist-shaping matrices of mass_matrix_calc::get_TMT_TdMT for one state: Tcm, Tcm_dot are
+ * m x n row-major, Mcm m x m; returns m (rows) or < 0.  Pass NULL to query m only. */
+int    kto_tmt(void* h, const double* x, double* Tcm, double* Mcm, double* Tcm_dot);
+/* core/lin_alg/mat_cholesky.hpp pieces on a dense row-major n x n matrix (known-answer tests) */
+int    kto_cholesky_solve(int n, const double* A, double* b, int nrhs, double tol);
+int    kto_ldl_solve(int n, const double* A, double* b, int nrhs, double tol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
