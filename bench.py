@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — batched 6-DOF KTE-chain RK4 forward dynamics on B200 (BASELINE.json config 2).
+
+One "step" = one pass of the hot path over one batch: rkb_rollout_rk4 on 2^20 independent states
+of the 6-DOF CRS-A465-style chain, 100 RK4 steps of 1 ms each with the torques held constant.
+metric = state-steps/s (samples x RK4 steps per second), whole job over all ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [...]                         the reference's CPU path (oracle/_ref)
+
+N > 1 runs under torchrun (one rank per GPU, NCCL): the batch is sharded by sample index, every
+rank integrates its own 2^20 states (weak scaling), no data-path collective; the final
+all-gather of the end states the north star names is timed separately (gather_ms).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rk4_state_steps_per_s"
+UNIT = "state-steps/s"
+PRESET = "crs6"
+N_SAMPLES = 1 << 20
+RK4_STEPS = 100
+DT = 1e-3
+# algorithmic FP64 flops of one RK4 state-step of the 6-DOF chain and
+# algorithmic bytes of one sample per call (read 2n + n doubles, write 2n doubles + status).
+FLOP_PER_STATE_STEP = 2.26e4
+BYTES_PER_SAMPLE = (12 + 6) * 8 + 12 * 8 + 4
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index, period=0.2):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.period = index, period
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        nv = self.nv
+        self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.sample()
+            except Exception:
+                break
+            self.stop_flag.wait(self.period)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(timeout=2.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": []}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+def make_inputs(n, nx, nu, seed):
+    """BASELINE config 2 inputs: q, qd, tau ~ U(-1, 1)."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, (n, nx)), rng.uniform(-1.0, 1.0, (n, nu))
+
+
+def cpu_reference_run(compiled, x, u, workers):
+    """Times the reference's own CPU path (kte_nl_system + runge_kutta4_integrator compiled from
+    the unmodified sources, oracle/_ref) on `workers` forked processes; falls back to the C port."""
+    from oracle import pyref
+    if pyref.have_ref():
+        chk, kind = pyref.Reference(compiled), "reference"
+    else:
+        if not os.path.isfile(pyref.ORACLE_SO):
+            pyref.build(("oracle",))
+        chk, kind = pyref.Oracle(compiled), "port"
+    out, st, secs = chk.rk4(x, u, DT, RK4_STEPS, n_workers=workers)
+    if secs <= 0:
+        raise RuntimeError("CPU baseline run failed")
+    return out, secs, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from reak_b200 import kte, presets
+    s = presets.make(PRESET)
+    compiled = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    cores = os.cpu_count() or 1
+    per_core = 96  # ~1.5-2 s per step at ~5-7 k state-steps/s/core
+    n = per_core * cores
+    x, u = make_inputs(n, 12, 6, 12346)
+    kind = "reference"
+    for _ in range(args.warmup):
+        _, _, kind = cpu_reference_run(compiled, x[: 8 * cores], u[: 8 * cores], cores)
+    total = 0.0
+    for _ in range(args.steps):
+        _, secs, kind = cpu_reference_run(compiled, x, u, cores)
+        total += secs
+    value = n * RK4_STEPS * args.steps / total
+    sample = "%d samples x %d RK4 steps per step (%d per core) of the same workload" % (n, RK4_STEPS, per_core)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "6-DOF CRS-A465-style kte_map_chain, %d RK4 steps dt=1ms, constant torques; CPU: %s" % (RK4_STEPS, sample),
+                   "preset": PRESET, "rk4_steps": RK4_STEPS, "dt": DT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from reak_b200 import kte_batch_propagator, presets, _abi
+    prop = kte_batch_propagator(presets.make(PRESET), device=local)
+    assert prop.is_serial(), "bench chain must run on the serial-chain kernels"
+    nx, nu = prop.nx, prop.nu
+    n = N_SAMPLES
+    x_h, u_h = make_inputs(n, nx, nu, 12346 + rank)
+
+    # pinned host buffers for the end-to-end leg
+    px = torch.empty((n, nx), dtype=torch.float64).pin_memory()
+    pu = torch.empty((n, nu), dtype=torch.float64).pin_memory()
+    po = torch.empty((n, nx), dtype=torch.float64).pin_memory()
+    ps = torch.empty((n,), dtype=torch.int32).pin_memory()
+    px.numpy()[:] = x_h
+    pu.numpy()[:] = u_h
+    # device-resident buffers for the kernel leg (151 MB of input per step: larger than the 126 MB L2)
+    dx, du = px.cuda(), pu.cuda()
+    dout = torch.empty_like(dx)
+    dst = torch.empty((n,), dtype=torch.int32, device=dx.device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        prop.get_next_states(dx, du, DT, RK4_STEPS, out=dout, status=dst)
+
+    def e2e_step():
+        prop.get_next_states(px.numpy(), pu.numpy(), DT, RK4_STEPS, out=po.numpy(), status=ps.numpy())
+
+    # ---- kernel-only leg -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    launches0 = prop.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+        kernel_ms.append(prop.last_kernel_ms())  # CUDA events recorded around the kernel on its launch stream
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.result()
+    launches = prop.launch_count() - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    assert int(dst.max().item()) == 0, "status word set in the timed region"
+
+    # ---- end-to-end leg: pinned host buffers through the public API -------------------------
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    assert np.array_equal(po.numpy(), dout.cpu().numpy()), "host and device legs disagree"
+
+    # ---- final gather of the end states (north star: NCCL used only for this) ---------------
+    gather_ms = None
+    if world > 1:
+        gathered = torch.empty((world * n, nx), dtype=torch.float64, device=dx.device)
+        dist.all_gather_into_tensor(gathered, dout)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gathered, dout)
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    state_steps_per_step = float(world) * n * RK4_STEPS
+    value = state_steps_per_step * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = state_steps_per_step * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (serial_rollout_kernel<6,0>), this rank --------------
+    peaks, peaks_src = load_peaks()
+    tf = C.c_double(0.0)
+    clk = C.c_double(0.0)
+    _abi.check(_abi.load_library().rkb_measure_fp64_peak(local, 1.0, C.byref(tf), C.byref(clk)), "rkb_measure_fp64_peak")
+    k_ms = float(np.mean(kernel_ms))
+    achieved_tf = FLOP_PER_STATE_STEP * n * RK4_STEPS / (k_ms * 1e-3) / 1e12
+    achieved_gbs = BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
+                "traffic": None, "kernel": "serial_rollout_kernel<6,0>", "kernel_ms": k_ms,
+                "peak_source": "DFMA loop measured in this run (rkb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "flop_per_state_step": FLOP_PER_STATE_STEP}
+    roofline_hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": achieved_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src, "bytes_per_sample": BYTES_PER_SAMPLE}
+
+    # ---- CPU baseline: the reference itself on the host cores, bounded sample (N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        per_core = 128
+        m = min(n, per_core * cores)
+        ref_out, secs, kind = cpu_reference_run(prop.compiled, x_h[:m], u_h[:m], cores)
+        err = float(np.max(np.abs(po.numpy()[:m] - ref_out) / np.maximum(1.0, np.abs(ref_out))))
+        cpu = {"value": m * RK4_STEPS / secs, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "first %d of the %d samples x %d RK4 steps, %d forked workers" % (m, n, RK4_STEPS, cores),
+               "max_rel_err_vs_gpu": err, "tolerance": 1e-8}
+        assert err < 1e-8, "GPU result disagrees with the reference on the CPU sample: %g" % err
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "6-DOF CRS-A465-style kte_map_chain (BASELINE config 2): 2^20 states x 100 RK4 steps dt=1ms per GPU, constant torques",
+                   "preset": PRESET, "samples_per_gpu": n, "rk4_steps": RK4_STEPS, "dt": DT, "parallelism": "sample-sharded x%d" % world,
+                   "l2": "inputs (151 MB per step) exceed the 126 MB L2; no flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(world * n * (nx + nu) * 8), "d2h_bytes_per_step": int(world * n * (nx * 8 + 4))},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_hbm": roofline_hbm,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if gather_ms is not None:
+        line["gather_ms"] = gather_ms
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        args.steps = 1
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

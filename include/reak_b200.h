@@ -45,6 +45,12 @@ extern "C" {
 
 #define RKB_VERSION 100
 
+#if defined(__GNUC__)
+#define RKB_API __attribute__((visibility("default")))
+#else
+#define RKB_API
+#endif
+
 /* ---- element kinds (one per in-scope kte_map subclass) ------------------------------------ */
 enum rkb_kind {
   RKB_REVOLUTE_3D       = 1,  /* revolute_joint_3D   (revolute_joint.cpp:121-213)  p[0..2] = axis                   */
@@ -123,42 +129,45 @@ typedef struct rkb_chain rkb_chain; /* opaque */
 #define RKB_ERR_NOMEM         -5
 #define RKB_ERR_INTEGRATION   -6  /* impossible_integration (dt == 0, n_steps < 0)             */
 
-int         rkb_version(void);
-const char* rkb_strerror(int code);
+RKB_API int         rkb_version(void);
+RKB_API const char* rkb_strerror(int code);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
-const char* rkb_last_cuda_error(void);
+RKB_API const char* rkb_last_cuda_error(void);
 
 /* Validate `desc`, lower it to the device program and return a handle.  The descriptor is
  * copied; the caller may free it afterwards. */
-int  rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out);
-void rkb_chain_destroy(rkb_chain* chain);
+RKB_API int  rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out);
+RKB_API void rkb_chain_destroy(rkb_chain* chain);
 
-int  rkb_chain_state_dim(const rkb_chain* chain);  /* kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147 */
-int  rkb_chain_input_dim(const rkb_chain* chain);  /* kte_nl_system::get_input_dimensions, kte_nl_system.hpp:153-158 */
-int  rkb_chain_dof(const rkb_chain* chain);
+RKB_API int  rkb_chain_state_dim(const rkb_chain* chain);  /* kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147 */
+RKB_API int  rkb_chain_input_dim(const rkb_chain* chain);  /* kte_nl_system::get_input_dimensions, kte_nl_system.hpp:153-158 */
+RKB_API int  rkb_chain_dof(const rkb_chain* chain);
+/* 1 when the chain was lowered to the register-resident serial-chain kernels, 0 when it runs on
+ * the interpreter kernels (any element order, 2D frames, two-anchor springs/dampers). */
+RKB_API int  rkb_chain_is_serial(const rkb_chain* chain);
 
 /* xdot[i] = get_state_derivative(x[i], u[i]).  x: N x 2n, u: N x n_inputs, xdot: N x 2n,
  * status: N (nullable).  `stream` is a cudaStream_t (NULL = default stream). */
-int rkb_eval(rkb_chain* chain, int device, size_t n_samples,
+RKB_API int rkb_eval(rkb_chain* chain, int device, size_t n_samples,
              const double* x, const double* u, double* xdot, int32_t* status,
              unsigned flags, void* stream);
 
 /* x_out[i] = state after exactly n_steps RK4 steps of size dt from x0[i] with u[i] held
  * constant (zero-order hold, num_int_dtnl_system.hpp:166-180).  The step COUNT is explicit:
  * the reference's time-driven loop would take one step more or less depending on rounding. */
-int rkb_rollout_rk4(rkb_chain* chain, int device, size_t n_samples,
+RKB_API int rkb_rollout_rk4(rkb_chain* chain, int device, size_t n_samples,
                     const double* x0, const double* u, double dt, int n_steps,
                     double* x_out, int32_t* status, unsigned flags, void* stream);
 
 /* Generalised force gen_coord::f after doMotion/clearForce/doForce with q_ddot = 0
  * (tau - h(q,qd) in ReaK's convention).  f: N x n. */
-int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,
+RKB_API int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,
                    const double* x, const double* u, double* f,
                    unsigned flags, void* stream);
 
 /* M[i] (n x n, full symmetric storage, row-major) and, if Mdot != NULL, its time
  * derivative at state x[i].  AOS: [N][n][n]; SOA: [n*n][N]. */
-int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
+RKB_API int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
                     const double* x, double* M, double* Mdot,
                     unsigned flags, void* stream);
 
@@ -166,7 +175,7 @@ int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
  * RK4 steps and keep the rollout whose end state is closest to the goal (Euclidean norm over
  * the 2n state components).  x0, goal: P x 2n; u: P x R x n_inputs (AOS) or [n_inputs][P*R] (SOA);
  * best_idx: P; best_x: P x 2n; best_cost: P (nullable); status: P x R (nullable). */
-int rkb_steer_batch(rkb_chain* chain, int device, size_t n_pairs, size_t n_rollouts,
+RKB_API int rkb_steer_batch(rkb_chain* chain, int device, size_t n_pairs, size_t n_rollouts,
                     const double* x0, const double* goal, const double* u,
                     double dt, int n_steps,
                     int32_t* best_idx, double* best_x, double* best_cost, int32_t* status,
@@ -175,9 +184,13 @@ int rkb_steer_batch(rkb_chain* chain, int device, size_t n_pairs, size_t n_rollo
 /* Device-side timing of the last compute launch issued through `chain` on the calling
  * thread, in milliseconds (CUDA events on the launch stream); < 0 if none. Blocks until
  * that launch has finished. */
-double rkb_last_kernel_ms(rkb_chain* chain);
+RKB_API double rkb_last_kernel_ms(rkb_chain* chain);
 /* Number of kernels launched through this handle since creation. */
-uint64_t rkb_launch_count(const rkb_chain* chain);
+RKB_API uint64_t rkb_launch_count(const rkb_chain* chain);
+
+/* Instrumentation: best-of-runs throughput of a pure DFMA loop on `device` for about `seconds`
+ * (TFLOP/s, 2 flops per DFMA) — the FP64 roofline denominator bench.py reports against. */
+RKB_API int rkb_measure_fp64_peak(int device, double seconds, double* tflops_out, double* sm_clock_mhz_out);
 
 #ifdef __cplusplus
 }

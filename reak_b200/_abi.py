@@ -59,6 +59,7 @@ SYMBOLS = {
     "rkb_chain_state_dim": (C.c_int, [C.c_void_p]),
     "rkb_chain_input_dim": (C.c_int, [C.c_void_p]),
     "rkb_chain_dof": (C.c_int, [C.c_void_p]),
+    "rkb_chain_is_serial": (C.c_int, [C.c_void_p]),
     "rkb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
@@ -72,6 +73,7 @@ SYMBOLS = {
                                   C.c_uint, C.c_void_p]),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rkb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 

@@ -1,0 +1,762 @@
+// kte_generic.cu — interpreter kernels: any chain the descriptor can express (2D and 3D frames,
+// any element order, two-anchor springs/dampers, partial upstream-joint sets).  One thread per
+// sample; the frames live in per-thread local memory, the element list is read from a
+// GenericProgram in global memory (uniform loads).  This is the compatibility path — canonical
+// serial chains run on the register-resident kernels of kte_serial.cuh instead.
+//
+// Reference semantics followed (paths relative to ReaK's source tree):
+//   doMotion / clearForce / doForce      ctrl/mbd_kte/kte_map_chain.hpp:71-89 and the element .cpp files
+//   mass matrix                           ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98,100-287 with the
+//                                         Jacobian columns of core/kinetostatics/motion_jacobians.hpp:139-147,
+//                                         238-251 written in closed form from the world-frame kinematics
+//   solve                                 core/lin_alg/mat_cholesky.hpp:63-84,160-179
+//   RK4                                   core/integrators/fixed_step_integrators.hpp:256-293
+#include <cuda_runtime.h>
+#include <math.h>
+#include "rkb_internal.h"
+
+namespace {
+
+#define GD __device__ __forceinline__
+#define MAXC RKB_MAX_COORDS
+
+struct V3 { double x, y, z; };
+GD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+GD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+GD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+GD V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+GD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+GD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+GD V3 ldv(const double* p) { return v3(p[0], p[1], p[2]); }
+
+struct Q4 { double w, x, y, z; };
+GD Q4 qmul(Q4 a, Q4 b) {  // rotations_3D.hpp:1093-1098
+  Q4 r;
+  r.w = b.w * a.w - b.x * a.x - b.y * a.y - b.z * a.z;
+  r.x = b.w * a.x + b.z * a.y - b.y * a.z + b.x * a.w;
+  r.y = b.w * a.y - b.z * a.x + b.x * a.z + b.y * a.w;
+  r.z = b.w * a.z + b.y * a.x - b.x * a.y + b.z * a.w;
+  return r;
+}
+GD Q4 qconj(Q4 a) { Q4 r; r.w = a.w; r.x = -a.x; r.y = -a.y; r.z = -a.z; return r; }
+struct M3 { double m[9]; };  // row-major, v_parent = R v_local
+GD M3 qrot(Q4 q) {  // quaternion::getRotMat, rotations_3D.hpp:986-1000
+  const double t01 = 2.0 * q.w * q.x, t02 = 2.0 * q.w * q.y, t03 = 2.0 * q.w * q.z;
+  const double t11 = 2.0 * q.x * q.x, t12 = 2.0 * q.x * q.y, t13 = 2.0 * q.x * q.z;
+  const double t22 = 2.0 * q.y * q.y, t23 = 2.0 * q.y * q.z, t33 = 2.0 * q.z * q.z;
+  M3 R;
+  R.m[0] = 1.0 - t22 - t33; R.m[1] = t12 - t03; R.m[2] = t02 + t13;
+  R.m[3] = t12 + t03; R.m[4] = 1.0 - t11 - t33; R.m[5] = t23 - t01;
+  R.m[6] = t13 - t02; R.m[7] = t01 + t23; R.m[8] = 1.0 - t11 - t22;
+  return R;
+}
+GD V3 mul(const M3& R, V3 v) {
+  return v3(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z, R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+GD V3 tmul(const M3& R, V3 v) {
+  return v3(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z, R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+GD V3 unit_axis(V3 a) {  // axis_angle ctor, rotations_3D.hpp:1962-1974
+  const double n = sqrt(dot(a, a));
+  if (n > 0.0000001) return v3(a.x / n, a.y / n, a.z / n);
+  return v3(1.0, 0.0, 0.0);
+}
+GD M3 aa_rot(double angle, V3 a) {  // axis_angle::getRotMat, rotations_3D.hpp:2159-2178 (a normalised)
+  double sa, ca;
+  sincos(angle, &sa, &ca);
+  const double omc = 1.0 - ca;
+  const double t12 = omc * a.x * a.y, t13 = omc * a.x * a.z, t23 = omc * a.y * a.z;
+  const double t01 = sa * a.x, t02 = sa * a.y, t03 = sa * a.z;
+  M3 R;
+  R.m[0] = ca + omc * a.x * a.x; R.m[1] = t12 - t03; R.m[2] = t13 + t02;
+  R.m[3] = t12 + t03; R.m[4] = ca + omc * a.y * a.y; R.m[5] = t23 - t01;
+  R.m[6] = t13 - t02; R.m[7] = t23 + t01; R.m[8] = ca + omc * a.z * a.z;
+  return R;
+}
+
+struct Fr3 { V3 p; Q4 q; V3 v, w, a, al, F, T; };
+struct V2 { double x, y; };
+GD V2 v2(double x, double y) { V2 r; r.x = x; r.y = y; return r; }
+GD V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+GD V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+GD V2 operator*(double s, V2 a) { return v2(s * a.x, s * a.y); }
+GD double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+GD double cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }   // vect_alg.hpp:1142
+GD V2 crs(double s, V2 v) { return v2(-v.y * s, v.x * s); }     // vect_alg.hpp:1171
+struct R2 { double c, s; };
+GD V2 rmul(R2 R, V2 v) { return v2(v.x * R.c - v.y * R.s, v.x * R.s + v.y * R.c); }    // rotations_2D.hpp:292
+GD V2 rtmul(R2 R, V2 v) { return v2(v.x * R.c + v.y * R.s, v.y * R.c - v.x * R.s); }   // rotations_2D.hpp:300 (v * R)
+GD R2 rr(R2 a, R2 b) { R2 r; r.c = a.c * b.c - a.s * b.s; r.s = a.s * b.c + a.c * b.s; return r; }
+struct Fr2 { V2 p; R2 R; V2 v; double w; V2 a; double al; V2 F; double T; };
+
+template <int DIM> struct FrameOf;
+template <> struct FrameOf<3> { typedef Fr3 type; };
+template <> struct FrameOf<2> { typedef Fr2 type; };
+
+template <int DIM, int MAXF>
+struct Work {
+  typename FrameOf<DIM>::type fr[MAXF];
+  double q[MAXC], qd[MAXC], f[MAXC], u[MAXC];
+};
+
+GD void set_base(const GenericProgram* G, Fr3& B) {
+  const double* b = G->base;
+  B.p = ldv(b); B.q.w = b[3]; B.q.x = b[4]; B.q.y = b[5]; B.q.z = b[6];
+  B.v = ldv(b + 7); B.w = ldv(b + 10); B.a = ldv(b + 13); B.al = ldv(b + 16);
+}
+GD void set_base(const GenericProgram* G, Fr2& B) {
+  const double* b = G->base;
+  B.p = v2(b[0], b[1]); B.R.c = b[3]; B.R.s = b[4];
+  B.v = v2(b[7], b[8]); B.w = b[10]; B.a = v2(b[13], b[14]); B.al = b[16];
+}
+
+// ---- doMotion ---------------------------------------------------------------------------------
+template <int MAXF>
+GD void motion(const GenericProgram* G, Work<3, MAXF>& W) {
+  set_base(G, W.fr[G->base_frame]);
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-152 (q_ddot = 0)
+      const Fr3 B = W.fr[E.fa];
+      Fr3& N = W.fr[E.fb];
+      const V3 ax = ldv(E.p), an = unit_axis(ax);
+      double sh, ch;
+      sincos(0.5 * W.q[E.coord], &sh, &ch);
+      Q4 tq; tq.w = ch; tq.x = an.x * sh; tq.y = an.y * sh; tq.z = an.z * sh;
+      const M3 R = qrot(tq);
+      const V3 wt = tmul(R, B.w), qda = W.qd[E.coord] * ax;
+      N.p = B.p; N.v = B.v; N.a = B.a;
+      N.q = qmul(B.q, tq);
+      N.w = wt + qda;
+      N.al = tmul(R, B.al) + cross(wt, qda);
+    } else if (E.kind == RKB_PRISMATIC_3D) {  // prismatic_joint.cpp:129-161
+      const Fr3 B = W.fr[E.fa];
+      Fr3& N = W.fr[E.fb];
+      const V3 ax = ldv(E.p);
+      const M3 R = qrot(B.q);
+      const V3 tp = W.q[E.coord] * ax, tv = W.qd[E.coord] * ax;
+      N.p = B.p + mul(R, tp);
+      N.v = B.v + mul(R, cross(B.w, tp) + tv);
+      N.a = B.a + mul(R, cross(B.w, cross(B.w, tp)) + 2.0 * cross(B.w, tv) + cross(B.al, tp));
+      N.q = B.q; N.w = B.w; N.al = B.al;
+    } else if (E.kind == RKB_RIGID_LINK_3D) {  // rigid_link.cpp:156 -> frame_3D.hpp:236-251
+      const Fr3 B = W.fr[E.fa];
+      Fr3& N = W.fr[E.fb];
+      const V3 po = ldv(E.p);
+      Q4 qo; qo.w = E.p[3]; qo.x = E.p[4]; qo.y = E.p[5]; qo.z = E.p[6];
+      const M3 R = qrot(B.q), Ro = qrot(qo);
+      N.p = B.p + mul(R, po);
+      N.v = B.v + mul(R, cross(B.w, po));
+      N.a = B.a + mul(R, cross(B.w, cross(B.w, po)) + cross(B.al, po));
+      N.q = qmul(B.q, qo);
+      N.al = tmul(Ro, B.al);
+      N.w = tmul(Ro, B.w);
+    }
+  }
+}
+template <int MAXF>
+GD void motion(const GenericProgram* G, Work<2, MAXF>& W) {
+  set_base(G, W.fr[G->base_frame]);
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_REVOLUTE_2D) {  // revolute_joint.cpp:32-58
+      const Fr2 B = W.fr[E.fa];
+      Fr2& N = W.fr[E.fb];
+      R2 rq;
+      sincos(W.q[E.coord], &rq.s, &rq.c);
+      N.p = B.p; N.v = B.v; N.a = B.a;
+      N.R = rr(B.R, rq);
+      N.w = B.w + W.qd[E.coord];
+      N.al = B.al;
+    } else if (E.kind == RKB_PRISMATIC_2D) {  // prismatic_joint.cpp:33-67
+      const Fr2 B = W.fr[E.fa];
+      Fr2& N = W.fr[E.fb];
+      const V2 ax = v2(E.p[0], E.p[1]);
+      const V2 tp = W.q[E.coord] * ax, tv = W.qd[E.coord] * ax;
+      N.p = B.p + rmul(B.R, tp);
+      N.v = B.v + rmul(B.R, crs(B.w, tp) + tv);
+      N.a = B.a + rmul(B.R, (-B.w * B.w) * tp + crs(2.0 * B.w, tv) + crs(B.al, tp));
+      N.R = B.R; N.w = B.w; N.al = B.al;
+    } else if (E.kind == RKB_RIGID_LINK_2D) {  // rigid_link.cpp:87-99
+      const Fr2 B = W.fr[E.fa];
+      Fr2& N = W.fr[E.fb];
+      const V2 po = v2(E.p[0], E.p[1]);
+      R2 ro; ro.c = E.p[3]; ro.s = E.p[4];
+      N.p = B.p + rmul(B.R, po);
+      N.v = B.v + rmul(B.R, crs(B.w, po));
+      N.a = B.a + rmul(B.R, (-B.w * B.w) * po + crs(B.al, po));
+      N.R = rr(B.R, ro);
+      N.w = B.w; N.al = B.al;
+    }
+  }
+}
+
+// ---- clearForce + doForce ------------------------------------------------------------------------
+template <int MAXF>
+GD void force(const GenericProgram* G, Work<3, MAXF>& W) {
+  for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v3(0, 0, 0); W.fr[i].T = v3(0, 0, 0); }
+  for (int i = 0; i < G->n_coords; ++i) W.f[i] = 0.0;
+  for (int e = G->n_elements - 1; e >= 0; --e) {
+    const GenericElement& E = G->el[e];
+    switch (E.kind) {
+      case RKB_REVOLUTE_3D: {  // revolute_joint.cpp:172-184
+        const Fr3& N = W.fr[E.fb];
+        Fr3& B = W.fr[E.fa];
+        const V3 ax = ldv(E.p);
+        const M3 R = aa_rot(W.q[E.coord], unit_axis(ax));
+        const double ta = dot(N.T, ax);
+        B.F = B.F + mul(R, N.F);
+        W.f[E.coord] += ta;
+        B.T = B.T + mul(R, N.T - ta * ax);
+        break;
+      }
+      case RKB_PRISMATIC_3D: {  // prismatic_joint.cpp:181-193
+        const Fr3& N = W.fr[E.fb];
+        Fr3& B = W.fr[E.fa];
+        const V3 ax = ldv(E.p);
+        const double tf = dot(N.F, ax);
+        W.f[E.coord] += tf;
+        B.F = B.F + (N.F - tf * ax);
+        B.T = B.T + (N.T + cross(W.q[E.coord] * ax, N.F));
+        break;
+      }
+      case RKB_RIGID_LINK_3D: {  // rigid_link.cpp:170-177
+        const Fr3& N = W.fr[E.fb];
+        Fr3& B = W.fr[E.fa];
+        Q4 qo; qo.w = E.p[3]; qo.x = E.p[4]; qo.y = E.p[5]; qo.z = E.p[6];
+        const M3 Ro = qrot(qo);
+        const V3 tf = mul(Ro, N.F);
+        B.F = B.F + tf;
+        B.T = B.T + (mul(Ro, N.T) + cross(ldv(E.p), tf));
+        break;
+      }
+      case RKB_INERTIA_3D: {  // inertia.cpp:111-121
+        Fr3& Gf = W.fr[E.fa];
+        const double* I = &E.p[1];
+        const V3 Ial = v3(I[0] * Gf.al.x + I[1] * Gf.al.y + I[2] * Gf.al.z, I[1] * Gf.al.x + I[3] * Gf.al.y + I[4] * Gf.al.z,
+                          I[2] * Gf.al.x + I[4] * Gf.al.y + I[5] * Gf.al.z);
+        const V3 Iw = v3(I[0] * Gf.w.x + I[1] * Gf.w.y + I[2] * Gf.w.z, I[1] * Gf.w.x + I[3] * Gf.w.y + I[4] * Gf.w.z,
+                         I[2] * Gf.w.x + I[4] * Gf.w.y + I[5] * Gf.w.z);
+        Gf.F = Gf.F - E.p[0] * tmul(qrot(Gf.q), Gf.a);
+        Gf.T = Gf.T - (Ial + cross(Gf.w, Iw));
+        break;
+      }
+      case RKB_ACTUATOR_GEN: {  // driving_actuator.cpp:31-38 + applyReactionForce
+        const GenericElement& J = G->el[E.fb];
+        const double drive = W.u[E.aux];
+        W.f[E.coord] += drive;
+        Fr3& B = W.fr[J.fa];
+        if (J.kind == RKB_REVOLUTE_3D) B.T = B.T - drive * ldv(J.p);        // revolute_joint.cpp:210-213
+        else if (J.kind == RKB_PRISMATIC_3D) B.F = B.F - drive * ldv(J.p);  // prismatic_joint.cpp:219-222
+        break;
+      }
+      case RKB_TORSION_SPRING_3D: {  // torsion_spring.cpp:106-129, axis_angle(quaternion) rotations_3D.hpp:1985-2010
+        Fr3& A1 = W.fr[E.fa];
+        Fr3& A2 = W.fr[E.fb];
+        Q4 d = qmul(qconj(A1.q), A2.q);
+        const double nq = sqrt(d.w * d.w + d.x * d.x + d.y * d.y + d.z * d.z);
+        d.w /= nq; d.x /= nq; d.y /= nq; d.z /= nq;
+        const double tmp = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        V3 ax = v3(1.0, 0.0, 0.0);
+        double angle = 0.0;
+        if (tmp > 0.0000001) {
+          ax = v3(d.x / tmp, d.y / tmp, d.z / tmp);
+          // 2 acos(|w|) is ill-conditioned near w = 1; 2 atan2(|v|, |w|) is the same angle, well-conditioned
+          angle = 2.0 * atan2(tmp, fabs(d.w));
+          if (d.w < 0.0) ax = v3(-ax.x, -ax.y, -ax.z);
+        }
+        const double mag = E.p[0] * angle, sat = E.p[1];
+        V3 t = mag * ax;
+        if (sat > 0.0 && fabs(mag) > sat) t = (mag > 0.0 ? sat : -sat) * ax;
+        A1.T = A1.T + t;
+        A2.T = A2.T - t;
+        break;
+      }
+      case RKB_TORSION_DAMPER_3D: {  // torsion_damper.cpp:93-104
+        Fr3& A1 = W.fr[E.fa];
+        Fr3& A2 = W.fr[E.fb];
+        const M3 R1 = qrot(A1.q), R2_ = qrot(A2.q);
+        const V3 diff = E.p[0] * (mul(R1, A1.w) - mul(R2_, A2.w));
+        A1.T = A1.T - tmul(R1, diff);
+        A2.T = A2.T + tmul(R2_, diff);
+        break;
+      }
+      case RKB_SPRING_3D: {  // spring.cpp:178-207
+        Fr3& A1 = W.fr[E.fa];
+        Fr3& A2 = W.fr[E.fb];
+        V3 diff = A1.p - A2.p;
+        const double mag = sqrt(dot(diff, diff));
+        if (mag > 1E-7) {
+          const double fm = (mag - E.p[0]) * E.p[1], sat = E.p[2];
+          double sc = fm / mag;
+          if (sat > 0.0 && fabs(fm) > sat) sc = (fm > 0.0 ? sat : -sat) / mag;
+          diff = sc * diff;
+          A1.F = A1.F - tmul(qrot(A1.q), diff);
+          A2.F = A2.F + tmul(qrot(A2.q), diff);
+        }
+        break;
+      }
+      case RKB_DAMPER_3D: {  // damper.cpp:136-149
+        Fr3& A1 = W.fr[E.fa];
+        Fr3& A2 = W.fr[E.fb];
+        V3 diff = A1.p - A2.p;
+        const double sq = dot(diff, diff);
+        if (sq > 1E-7) {
+          diff = (dot(A1.v - A2.v, diff) * E.p[0] / sq) * diff;
+          A1.F = A1.F - tmul(qrot(A1.q), diff);
+          A2.F = A2.F + tmul(qrot(A2.q), diff);
+        }
+        break;
+      }
+      default: break;  // inertia_gen: f -= q_ddot * m with q_ddot = 0
+    }
+  }
+}
+template <int MAXF>
+GD void force(const GenericProgram* G, Work<2, MAXF>& W) {
+  for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v2(0, 0); W.fr[i].T = 0.0; }
+  for (int i = 0; i < G->n_coords; ++i) W.f[i] = 0.0;
+  for (int e = G->n_elements - 1; e >= 0; --e) {
+    const GenericElement& E = G->el[e];
+    switch (E.kind) {
+      case RKB_REVOLUTE_2D: {  // revolute_joint.cpp:78-90 (torque is not passed to the base)
+        const Fr2& N = W.fr[E.fb];
+        Fr2& B = W.fr[E.fa];
+        R2 rq;
+        sincos(W.q[E.coord], &rq.s, &rq.c);
+        B.F = B.F + rmul(rq, N.F);
+        W.f[E.coord] += N.T;
+        break;
+      }
+      case RKB_PRISMATIC_2D: {  // prismatic_joint.cpp:83-95
+        const Fr2& N = W.fr[E.fb];
+        Fr2& B = W.fr[E.fa];
+        const V2 ax = v2(E.p[0], E.p[1]);
+        const double tf = dot(N.F, ax);
+        W.f[E.coord] += tf;
+        B.F = B.F + (N.F - tf * ax);
+        B.T += N.T + cross(W.q[E.coord] * ax, N.F);
+        break;
+      }
+      case RKB_RIGID_LINK_2D: {  // rigid_link.cpp:117-125
+        const Fr2& N = W.fr[E.fb];
+        Fr2& B = W.fr[E.fa];
+        R2 ro; ro.c = E.p[3]; ro.s = E.p[4];
+        const V2 tf = rmul(ro, N.F);
+        B.F = B.F + tf;
+        B.T += N.T + cross(v2(E.p[0], E.p[1]), tf);
+        break;
+      }
+      case RKB_INERTIA_2D: {  // inertia.cpp:77-86
+        Fr2& Gf = W.fr[E.fa];
+        Gf.F = Gf.F - E.p[0] * rtmul(Gf.R, Gf.a);
+        Gf.T -= E.p[1] * Gf.al;
+        break;
+      }
+      case RKB_ACTUATOR_GEN: {
+        const GenericElement& J = G->el[E.fb];
+        const double drive = W.u[E.aux];
+        W.f[E.coord] += drive;
+        Fr2& B = W.fr[J.fa];
+        if (J.kind == RKB_REVOLUTE_2D) B.T -= drive;                                 // revolute_joint.cpp:113-116
+        else if (J.kind == RKB_PRISMATIC_2D) B.F = B.F - drive * v2(J.p[0], J.p[1]); // prismatic_joint.cpp:120-123
+        break;
+      }
+      case RKB_TORSION_SPRING_2D: {  // torsion_spring.cpp:50-71
+        Fr2& A1 = W.fr[E.fa];
+        Fr2& A2 = W.fr[E.fb];
+        R2 inv; inv.c = A1.R.c; inv.s = -A1.R.s;
+        const R2 rel = rr(inv, A2.R);
+        const double ad = atan2(rel.s, rel.c) * E.p[0], sat = E.p[1];
+        double t = ad;
+        if (sat > 0.0 && fabs(ad) > sat) t = ad > 0.0 ? sat : -sat;
+        A1.T += t; A2.T -= t;
+        break;
+      }
+      case RKB_TORSION_DAMPER_2D: {  // torsion_damper.cpp:49-58
+        Fr2& A1 = W.fr[E.fa];
+        Fr2& A2 = W.fr[E.fb];
+        const double tm = (A1.w - A2.w) * E.p[0];
+        A1.T -= tm; A2.T += tm;
+        break;
+      }
+      case RKB_SPRING_2D: {  // spring.cpp:116-143
+        Fr2& A1 = W.fr[E.fa];
+        Fr2& A2 = W.fr[E.fb];
+        V2 diff = A1.p - A2.p;
+        const double mag = sqrt(dot(diff, diff));
+        if (mag > 1E-7) {
+          const double fm = (mag - E.p[0]) * E.p[1], sat = E.p[2];
+          double sc = fm / mag;
+          if (sat > 0.0 && fabs(fm) > sat) sc = (fm > 0.0 ? sat : -sat) / mag;
+          diff = sc * diff;
+          A1.F = A1.F - rtmul(A1.R, diff);
+          A2.F = A2.F + rtmul(A2.R, diff);
+        }
+        break;
+      }
+      case RKB_DAMPER_2D: {  // damper.cpp:88-102
+        Fr2& A1 = W.fr[E.fa];
+        Fr2& A2 = W.fr[E.fb];
+        V2 diff = A1.p - A2.p;
+        const double sq = dot(diff, diff);
+        if (sq > 1E-7) {
+          diff = (dot(A1.v - A2.v, diff) * E.p[0] / sq) * diff;
+          A1.F = A1.F - rtmul(A1.R, diff);
+          A2.F = A2.F + rtmul(A2.R, diff);
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+}
+
+// ---- mass matrix ---------------------------------------------------------------------------------
+// Column of the twist-shaping matrix (and of its time derivative) of coordinate `c` seen from the
+// inertia frame F: jacobian_gen_3D::get_jac_relative_to (motion_jacobians.hpp:238-251) with
+// f2 = (~E) * F (frame_3D.hpp:183-188, 219-234, 376-388) written out in world-frame quantities:
+//   a_g = R_E a,  dp = p_F - p_E,  dv = v_F - v_E,  adot_g = (R_E w_E) x a_g
+//   revolute : Tv = R_F^T (a_g x dp), Tw = R_F^T a_g,
+//              Tvd = R_F^T (adot_g x dp + a_g x dv) - w_F x Tv,  Twd = R_F^T adot_g - w_F x Tw
+//   prismatic: Tv = R_F^T a_g, Tw = 0,  Tvd = R_F^T adot_g - w_F x Tv, Twd = 0
+template <int MAXF>
+GD void jac_col(const GenericProgram* G, const Work<3, MAXF>& W, int c, const Fr3& F, const M3& RF, double* T, double* Td, bool want_dot) {
+  const GenericElement& J = G->el[G->jelem[c]];
+  const Fr3& E = W.fr[J.fb];
+  const M3 RE = qrot(E.q);
+  const V3 ag = mul(RE, ldv(J.p));
+  const V3 adg = cross(mul(RE, E.w), ag);
+  V3 Tv, Tw, Tvd = v3(0, 0, 0), Twd = v3(0, 0, 0);
+  if (J.kind == RKB_REVOLUTE_3D) {
+    const V3 dp = F.p - E.p;
+    Tv = tmul(RF, cross(ag, dp));
+    Tw = tmul(RF, ag);
+    if (want_dot) {
+      const V3 dv = F.v - E.v;
+      Tvd = tmul(RF, cross(adg, dp) + cross(ag, dv)) - cross(F.w, Tv);
+      Twd = tmul(RF, adg) - cross(F.w, Tw);
+    }
+  } else {
+    Tv = tmul(RF, ag);
+    Tw = v3(0, 0, 0);
+    if (want_dot) Tvd = tmul(RF, adg) - cross(F.w, Tv);
+  }
+  T[0] = Tv.x; T[1] = Tv.y; T[2] = Tv.z; T[3] = Tw.x; T[4] = Tw.y; T[5] = Tw.z;
+  Td[0] = Tvd.x; Td[1] = Tvd.y; Td[2] = Tvd.z; Td[3] = Twd.x; Td[4] = Twd.y; Td[5] = Twd.z;
+}
+
+// M and (optionally) S with Mdot = S + S^T; both n x n row-major in local memory.
+template <int MAXF>
+GD void mass(const GenericProgram* G, const Work<3, MAXF>& W, double* M, double* S, bool want_dot) {
+  const int n = G->n_coords;
+  for (int i = 0; i < n * n; ++i) { M[i] = 0.0; if (want_dot) S[i] = 0.0; }
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_INERTIA_GEN) {
+      M[E.coord * n + E.coord] += E.p[0];  // jacobian_gen_gen(1, 0): Tcm = 1, Tcm_dot = 0
+    } else if (E.kind == RKB_INERTIA_3D) {
+      const Fr3& F = W.fr[E.fa];
+      const M3 RF = qrot(F.q);
+      const double m = E.p[0];
+      const double* I = &E.p[1];
+      double T[MAXC][6], Td[MAXC][6], MT[MAXC][6];
+      for (int c = 0; c < n; ++c) {
+        if (!((E.upstream >> c) & 1u)) continue;
+        jac_col(G, W, c, F, RF, T[c], Td[c], want_dot);
+        MT[c][0] = m * T[c][0]; MT[c][1] = m * T[c][1]; MT[c][2] = m * T[c][2];
+        MT[c][3] = I[0] * T[c][3] + I[1] * T[c][4] + I[2] * T[c][5];
+        MT[c][4] = I[1] * T[c][3] + I[3] * T[c][4] + I[4] * T[c][5];
+        MT[c][5] = I[2] * T[c][3] + I[4] * T[c][4] + I[5] * T[c][5];
+      }
+      for (int a = 0; a < n; ++a) {
+        if (!((E.upstream >> a) & 1u)) continue;
+        for (int b = 0; b < n; ++b) {
+          if (!((E.upstream >> b) & 1u)) continue;
+          double s = 0.0, sd = 0.0;
+          for (int k = 0; k < 6; ++k) { s += T[a][k] * MT[b][k]; if (want_dot) sd += Td[a][k] * MT[b][k]; }
+          M[a * n + b] += s;
+          if (want_dot) S[a * n + b] += sd;
+        }
+      }
+    }
+  }
+}
+// 2D: jacobian_gen_2D::get_jac_relative_to (motion_jacobians.hpp:139-147) with f2 = (~E) * F
+// (frame_2D.hpp:288-300, 350-360): f2.p = R_E^T dp, f2.R = R_E^T R_F, f2.w = w_F - w_E,
+// f2.v = R_E^T (dv - w_E % dp).
+template <int MAXF>
+GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double* S, bool want_dot) {
+  const int n = G->n_coords;
+  for (int i = 0; i < n * n; ++i) { M[i] = 0.0; if (want_dot) S[i] = 0.0; }
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_INERTIA_GEN) {
+      M[E.coord * n + E.coord] += E.p[0];
+    } else if (E.kind == RKB_INERTIA_2D) {
+      const Fr2& F = W.fr[E.fa];
+      double T[MAXC][3], Td[MAXC][3];
+      for (int c = 0; c < n; ++c) {
+        if (!((E.upstream >> c) & 1u)) continue;
+        const GenericElement& J = G->el[G->jelem[c]];
+        const Fr2& Ej = W.fr[J.fb];
+        const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
+        const double wrel = F.w - Ej.w;
+        V2 Tv, Tvd;
+        double Tw;
+        if (J.kind == RKB_REVOLUTE_2D) {
+          Tv = rtmul(F.R, crs(1.0, dp));
+          Tw = 1.0;
+          Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
+        } else {
+          Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
+          Tw = 0.0;
+          Tvd = v2(0, 0) - crs(wrel, Tv);
+        }
+        T[c][0] = Tv.x; T[c][1] = Tv.y; T[c][2] = Tw;
+        Td[c][0] = Tvd.x; Td[c][1] = Tvd.y; Td[c][2] = 0.0;
+      }
+      const double mc[3] = {E.p[0], E.p[0], E.p[1]};
+      for (int a = 0; a < n; ++a) {
+        if (!((E.upstream >> a) & 1u)) continue;
+        for (int b = 0; b < n; ++b) {
+          if (!((E.upstream >> b) & 1u)) continue;
+          double s = 0.0, sd = 0.0;
+          for (int k = 0; k < 3; ++k) { s += T[a][k] * mc[k] * T[b][k]; if (want_dot) sd += Td[a][k] * mc[k] * T[b][k]; }
+          M[a * n + b] += s;
+          if (want_dot) S[a * n + b] += sd;
+        }
+      }
+    }
+  }
+}
+
+// linsolve_Cholesky (mat_cholesky.hpp:63-84, 160-179) on a row-major n x n matrix, in place
+GD int cholesky_solve(int n, double* A, double* b) {
+  int st = 0;
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < i; ++j) {
+      double s = A[i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / A[j * n + j];
+    }
+    double d = A[i * n + i];
+    for (int k = 0; k < i; ++k) d -= A[i * n + k] * A[i * n + k];
+    if (!(d >= 1.0e-8)) st = RKB_STATUS_SINGULAR;
+    A[i * n + i] = sqrt(d);
+  }
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[i * n + k] * b[k];
+    b[i] = s / A[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = n - 1; k > i; --k) s -= A[k * n + i] * b[k];
+    b[i] = s / A[i * n + i];
+  }
+  return st;
+}
+
+// q_ddot into W.f; returns status
+template <int DIM, int MAXF>
+GD int accel(const GenericProgram* G, Work<DIM, MAXF>& W) {
+  double M[MAXC * MAXC];
+  motion(G, W);
+  force(G, W);
+  mass(G, W, M, (double*)0, false);
+  return cholesky_solve(G->n_coords, M, W.f);
+}
+
+template <int DIM, int MAXF>
+GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& x, const ConstBatchView& u, long long ix, long long iu, bool with_u) {
+  for (int c = 0; c < G->n_coords; ++c) {
+    W.q[c] = x.p[ix * x.si + (2 * c) * x.sk];
+    W.qd[c] = x.p[ix * x.si + (2 * c + 1) * x.sk];
+  }
+  for (int k = 0; k < G->n_inputs; ++k) W.u[k] = with_u ? u.p[iu * u.si + k * u.sk] : 0.0;
+}
+
+#define GEN_BLOCK 128
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_eval_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, true);
+  int st = accel(G, W);
+  bool finite = true;
+  for (int c = 0; c < G->n_coords; ++c) {
+    A.out.p[i * A.out.si + (2 * c) * A.out.sk] = W.qd[c];
+    A.out.p[i * A.out.si + (2 * c + 1) * A.out.sk] = W.f[c];
+    finite = finite && isfinite(W.f[c]) && isfinite(W.qd[c]);
+  }
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
+}
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_forces_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, true);
+  motion(G, W);
+  force(G, W);
+  for (int c = 0; c < G->n_coords; ++c) A.out.p[i * A.out.si + c * A.out.sk] = W.f[c];
+}
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, false);
+  motion(G, W);
+  double M[MAXC * MAXC], S[MAXC * MAXC];
+  const bool want_dot = A.out2.p != (double*)0;
+  mass(G, W, M, S, want_dot);
+  const int n = G->n_coords;
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      // mat<symmetric> converting ctor averages the two halves (mat_alg_symmetric.hpp:171-200)
+      const double m = (a == b) ? M[a * n + a] : 0.5 * (M[a * n + b] + M[b * n + a]);
+      A.out.p[i * A.out.si + (long long)(a * n + b) * A.out.sk] = m;
+      if (want_dot) A.out2.p[i * A.out2.si + (long long)(a * n + b) * A.out2.sk] = S[a * n + b] + S[b * n + a];
+    }
+}
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const GenericProgram* __restrict__ G, const RolloutArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
+  load(G, W, A.x0, A.u, i0, i, true);
+  const int n = G->n_coords;
+  const double dt = A.dt;
+  double w[2 * MAXC], acc[2 * MAXC], k3[2 * MAXC];
+  int st = 0;
+  for (int step = 0; step < A.n_steps; ++step) {
+    // fixed_step_integrators.hpp:277-289
+    st |= accel(G, W);
+    for (int c = 0; c < n; ++c) {
+      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+      w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c];
+      acc[2 * c] = kq; acc[2 * c + 1] = kv;
+      W.q[c] += kq * 0.5; W.qd[c] += kv * 0.5;
+    }
+    st |= accel(G, W);
+    for (int c = 0; c < n; ++c) {
+      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+      acc[2 * c] += kq * 2.0; acc[2 * c + 1] += kv * 2.0;
+      W.q[c] = w[2 * c] + kq * 0.5; W.qd[c] = w[2 * c + 1] + kv * 0.5;
+    }
+    st |= accel(G, W);
+    for (int c = 0; c < n; ++c) {
+      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+      k3[2 * c] = kq; k3[2 * c + 1] = kv;
+      W.q[c] = w[2 * c] + kq; W.qd[c] = w[2 * c + 1] + kv;
+    }
+    st |= accel(G, W);
+    for (int c = 0; c < n; ++c) {
+      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+      W.q[c] += (acc[2 * c] + kq) / 6.0 - k3[2 * c] * (2.0 / 3.0);
+      W.qd[c] += (acc[2 * c + 1] + kv) / 6.0 - k3[2 * c + 1] * (2.0 / 3.0);
+    }
+  }
+  bool finite = true;
+  for (int c = 0; c < n; ++c) {
+    A.xout.p[i * A.xout.si + (2 * c) * A.xout.sk] = W.q[c];
+    A.xout.p[i * A.xout.si + (2 * c + 1) * A.xout.sk] = W.qd[c];
+    finite = finite && isfinite(W.q[c]) && isfinite(W.qd[c]);
+  }
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
+}
+
+unsigned grid_of(long long n) { return (unsigned)((n + GEN_BLOCK - 1) / GEN_BLOCK); }
+
+#define DISPATCH(kernel, host, ...)                                                              \
+  do {                                                                                           \
+    if ((host).dim == 3) {                                                                       \
+      if ((host).n_frames <= 16) kernel<3, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);     \
+      else kernel<3, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);           \
+    } else {                                                                                     \
+      if ((host).n_frames <= 16) kernel<2, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);     \
+      else kernel<2, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);           \
+    }                                                                                            \
+  } while (0)
+
+// ---- steer: per-pair arg-min over the rollout end states -------------------------------------------
+// One CTA per pair.  cost = || x_end - goal ||_2 over the 2n state components; the lowest
+// rollout index wins ties.
+__global__ void __launch_bounds__(256) steer_reduce_kernel(int nx, long long n_rollouts, const double* __restrict__ xend,
+                                                            const double* __restrict__ goal, int32_t* best_idx,
+                                                            double* best_x, double* best_cost) {
+  __shared__ double s_cost[256];
+  __shared__ long long s_idx[256];
+  const long long pair = blockIdx.x;
+  double best = INFINITY;
+  long long bi = -1;
+  for (long long r = threadIdx.x; r < n_rollouts; r += blockDim.x) {
+    const double* xe = xend + (pair * n_rollouts + r) * nx;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) { const double d = xe[k] - goal[pair * nx + k]; s += d * d; }
+    const double c = sqrt(s);
+    if (c < best || (bi < 0 && !(c > best))) { best = c; bi = r; }  // NaN costs never win over a finite one
+  }
+  s_cost[threadIdx.x] = best;
+  s_idx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const double c2 = s_cost[threadIdx.x + off];
+      const long long i2 = s_idx[threadIdx.x + off];
+      const double c1 = s_cost[threadIdx.x];
+      const long long i1 = s_idx[threadIdx.x];
+      if (i2 >= 0 && (i1 < 0 || c2 < c1 || (c2 == c1 && i2 < i1))) { s_cost[threadIdx.x] = c2; s_idx[threadIdx.x] = i2; }
+    }
+    __syncthreads();
+  }
+  const long long win = s_idx[0] < 0 ? 0 : s_idx[0];
+  if (threadIdx.x == 0) {
+    best_idx[pair] = (int32_t)win;
+    if (best_cost) best_cost[pair] = s_cost[0];
+  }
+  for (int k = threadIdx.x; k < nx; k += blockDim.x) best_x[pair * nx + k] = xend[(pair * n_rollouts + win) * nx + k];
+}
+
+}  // namespace
+
+cudaError_t rkb_generic_eval(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_eval_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_forces_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_mass_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_rollout_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, const double* xend, const double* goal,
+                             int32_t* best_idx, double* best_x, double* best_cost, cudaStream_t s) {
+  if (n_pairs <= 0) return cudaSuccess;
+  steer_reduce_kernel<<<(unsigned)n_pairs, 256, 0, s>>>(nx, n_rollouts, xend, goal, best_idx, best_x, best_cost);
+  return cudaGetLastError();
+}

@@ -1,0 +1,436 @@
+// kte_serial.cuh — register-resident FP64 kernels for canonical serial KTE chains (sm_100a).
+//
+// One thread integrates one sample.  All per-sample quantities live in registers (plus a
+// per-thread shared-memory column for the few arrays that must survive between sweeps); every
+// chain constant is read from the __grid_constant__ SerialParams kernel parameter, i.e. it is
+// a constant-bank operand of the DFMA/DMUL that uses it and costs no register.  The stage
+// loops are fully unrolled at compile time (template<int N>).
+//
+// What is computed is exactly what ReaK's kte_nl_system::get_state_derivative computes
+// (ctrl/ctrl_sys/kte_nl_system.hpp:238-346) for a chain of
+//   [driving_actuator_gen] [inertia_gen] joint [torsion_spring_3D] [torsion_damper_3D]
+//   [rigid_link_3D] [inertia_3D]
+// stages — but formulated in link-local coordinates so that no global frame is ever built:
+//
+//  sweep 1 (doMotion, kte_map_chain.hpp:71-76):  w, al (local angular velocity/acceleration)
+//      and a (linear acceleration rotated into the local frame) are pushed through each joint
+//      (revolute_joint.cpp:121-152 / prismatic_joint.cpp:129-161) and link
+//      (rigid_link.cpp:156 -> frame_3D.hpp:236-251); the d'Alembert wrench of the stage's
+//      inertia_3D (inertia.cpp:111-121) is formed on the spot and parked in shared memory.
+//  sweep 2 (doForce, kte_map_chain.hpp:78-83, reverse order): wrenches are shifted back through
+//      links (rigid_link.cpp:170-177) and joints (revolute_joint.cpp:172-184,
+//      prismatic_joint.cpp:181-193) INCLUDING the reference's removal of the axial component
+//      and the actuator reaction (driving_actuator.cpp:31-38, revolute_joint.cpp:210-213),
+//      which makes gen_coord::f differ from the textbook tau - h whenever joint axes are not
+//      orthogonal; torsion springs/dampers across a joint (torsion_spring.cpp:106-129,
+//      torsion_damper.cpp:93-104) reduce to scalars along the joint axis.
+//  sweep 3 (mass_matrix_calc::getMassMatrix, mass_matrix_calculator.cpp:80-87,100-287): the
+//      twist-shaping columns (jacobian_gen_3D::get_jac_relative_to, motion_jacobians.hpp:238-251)
+//      of all upstream joints are carried outward along the chain — rotate at the joint, shift at
+//      the link — instead of being re-derived from relative frames per (joint, inertia) pair;
+//      M += T^T diag(m, I) T per inertia; rotor inertias (inertia_gen) land on the diagonal.
+//  solve  (linsolve_Cholesky, core/lin_alg/mat_cholesky.hpp:63-84,160-179) with the reference's
+//      "pivot < 1e-8 before the square root" singularity test reported in the status word.
+//  RK4    (runge_kutta4_integrator<T>::integrate, core/integrators/fixed_step_integrators.hpp:256-293),
+//      constant input over the rollout (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
+#ifndef RKB_KTE_SERIAL_CUH
+#define RKB_KTE_SERIAL_CUH
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include "rkb_types.h"
+
+namespace rkb {
+
+#define RKB_DEV __device__ __forceinline__
+
+struct vec3 { double x, y, z; };
+
+RKB_DEV vec3 mk(double x, double y, double z) { vec3 r; r.x = x; r.y = y; r.z = z; return r; }
+RKB_DEV vec3 operator+(vec3 a, vec3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+RKB_DEV vec3 operator-(vec3 a, vec3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+RKB_DEV vec3 operator*(double s, vec3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+RKB_DEV double dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RKB_DEV vec3 cross(vec3 a, vec3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RKB_DEV vec3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+// 3x3 rotation held row-major: v_parent = R v_child
+struct mat3 { double m[9]; };
+RKB_DEV vec3 mul(const mat3& R, vec3 v) {
+  return mk(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z,
+            R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
+            R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+RKB_DEV vec3 tmul(const mat3& R, vec3 v) {  // R^T v
+  return mk(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z,
+            R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
+            R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+RKB_DEV vec3 mulc(const double* R, vec3 v) {  // constant-bank matrix (row-major) times v
+  return mk(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z);
+}
+RKB_DEV vec3 tmulc(const double* R, vec3 v) {
+  return mk(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z);
+}
+RKB_DEV vec3 symmul(const double* I, vec3 v) {  // I = xx xy xz yy yz zz
+  return mk(I[0] * v.x + I[1] * v.y + I[2] * v.z, I[1] * v.x + I[3] * v.y + I[4] * v.z, I[2] * v.x + I[4] * v.y + I[5] * v.z);
+}
+
+// axis_angle(q, axis).getRotMat(), rotations_3D.hpp:2159-2178, from cos/sin of the joint angle
+RKB_DEV mat3 rodrigues(const SerialStage& S, double c, double s) {
+  const double omc = 1.0 - c;
+  const double t12 = omc * S.aa[3], t13 = omc * S.aa[4], t23 = omc * S.aa[5];
+  const double t01 = s * S.an[0], t02 = s * S.an[1], t03 = s * S.an[2];
+  mat3 R;
+  R.m[0] = c + omc * S.aa[0]; R.m[1] = t12 - t03;         R.m[2] = t13 + t02;
+  R.m[3] = t12 + t03;         R.m[4] = c + omc * S.aa[1]; R.m[5] = t23 - t01;
+  R.m[6] = t13 - t02;         R.m[7] = t23 + t01;         R.m[8] = c + omc * S.aa[2];
+  return R;
+}
+
+// Angle of axis_angle(conj(Q_base) * Q_end) times its axis, expressed as a signed scalar along the
+// normalised joint axis (rotations_3D.hpp:1985-2010): the angle wrapped to (-pi, pi], zero inside
+// the reference's |sin(q/2)| <= 1e-7 dead zone.
+RKB_DEV double wrapped_angle(double q) {
+  const double two_pi = 6.283185307179586476925286766559;
+  double r = q - two_pi * rint(q * 0.15915494309189533576888376337251);
+  if (fabs(r) <= 2.0e-7) r = 0.0;
+  return r;
+}
+
+template <int N>
+struct SerialState {
+  double q[N], qd[N], u[N];
+};
+
+// The evaluation proper.  `sm` is this thread's shared-memory column (stride SMS doubles
+// between consecutive slots); slots [0, 6N) hold the parked inertia wrenches.
+// Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
+// Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
+template <int N, int FL, int SMS, bool WANT_F, bool WANT_M>
+RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
+                           double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
+  // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const SerialStage& S = P.st[k];
+    const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+    if (!prismatic) sincos(X.q[k], &sn[k], &cs[k]);
+    else { sn[k] = 0.0; cs[k] = 1.0; }
+  }
+  if (WANT_F) {
+    vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const SerialStage& S = P.st[k];
+      const vec3 ax = ld3(S.ax);
+      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+      if (!prismatic) {
+        const mat3 R2 = rodrigues(S, cs[k], sn[k]);
+        const vec3 wt = tmul(R2, w);
+        const vec3 qda = X.qd[k] * ax;
+        al = tmul(R2, al) + cross(wt, qda);  // + q_ddot * axis, zero in this pass (kte_nl_system.hpp:192)
+        w = wt + qda;
+        a = tmul(R2, a);
+      } else {
+        const vec3 r = X.q[k] * ax, rd = X.qd[k] * ax;
+        a = a + cross(w, cross(w, r)) + 2.0 * cross(w, rd) + cross(al, r);
+      }
+      if (S.flags & RKB_ST_LINK) {
+        const vec3 po = ld3(S.po);
+        a = a + cross(w, cross(w, po)) + cross(al, po);
+        if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) {
+          a = tmulc(S.Ro, a); w = tmulc(S.Ro, w); al = tmulc(S.Ro, al);
+        }
+      }
+      // inertia_3D::doForce: F -= m * (R^T a_global) ; T -= I al + w x (I w)
+      vec3 Fk = mk(0, 0, 0), Tk = mk(0, 0, 0);
+      if (S.flags & RKB_ST_INERTIA) {
+        Fk = (-S.m) * a;
+        const vec3 Iw = symmul(S.I, w);
+        Tk = mk(0, 0, 0) - (symmul(S.I, al) + cross(w, Iw));
+      }
+      sm[(6 * k + 0) * SMS] = Fk.x; sm[(6 * k + 1) * SMS] = Fk.y; sm[(6 * k + 2) * SMS] = Fk.z;
+      sm[(6 * k + 3) * SMS] = Tk.x; sm[(6 * k + 4) * SMS] = Tk.y; sm[(6 * k + 5) * SMS] = Tk.z;
+    }
+    // ---- sweep 2: wrenches inward -----------------------------------------------------------
+    vec3 F = mk(0, 0, 0), T = mk(0, 0, 0);
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+      const SerialStage& S = P.st[k];
+      const vec3 ax = ld3(S.ax);
+      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+      F = F + mk(sm[(6 * k + 0) * SMS], sm[(6 * k + 1) * SMS], sm[(6 * k + 2) * SMS]);
+      T = T + mk(sm[(6 * k + 3) * SMS], sm[(6 * k + 4) * SMS], sm[(6 * k + 5) * SMS]);
+      if (S.flags & RKB_ST_LINK) {
+        if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) { F = mulc(S.Ro, F); T = mulc(S.Ro, T); }
+        T = T + cross(ld3(S.po), F);
+      }
+      if (!prismatic) {
+        // torsion spring / damper between the joint's base and end frames act along the axis
+        vec3 tsd = mk(0, 0, 0);
+        if (FL & RKB_FL_SPRINGS) {
+          if (S.flags & RKB_ST_SPRING) {
+            const double r = wrapped_angle(X.q[k]);
+            double mag = S.ks * fabs(r);  // stiffness * angle_diff.angle(), angle >= 0
+            if (S.sat > 0.0 && fabs(mag) > S.sat) mag = (mag > 0.0) ? S.sat : -S.sat;
+            tsd = (r < 0.0 ? -mag : mag) * ld3(S.an);
+          }
+          if (S.flags & RKB_ST_DAMPER) tsd = tsd + (S.cd * X.qd[k]) * ax;
+          T = T - tsd;
+        }
+        const double ta = dot(T, ax);
+        f[k] = ta + X.u[k];
+        const mat3 R = rodrigues(S, cs[k], sn[k]);
+        F = mul(R, F);
+        T = mul(R, T - ta * ax) - X.u[k] * ax;  // actuator reaction on the joint base
+        if (FL & RKB_FL_SPRINGS) T = T + tsd;
+      } else {
+        const double fa = dot(F, ax);
+        f[k] = fa + X.u[k];
+        T = T + cross(X.q[k] * ax, F);
+        F = F - fa * ax - X.u[k] * ax;
+      }
+    }
+  }
+  // ---- sweep 3: twist-shaping columns outward, M accumulated per inertia ---------------------
+  if (WANT_M) {
+    vec3 Tv[N], Tw[N];
+#pragma unroll
+    for (int i = 0; i < N * (N + 1) / 2; ++i) Mp[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const SerialStage& S = P.st[k];
+      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+      if (!prismatic) {
+        const mat3 R2 = rodrigues(S, cs[k], sn[k]);
+#pragma unroll
+        for (int i = 0; i < k; ++i) { Tv[i] = tmul(R2, Tv[i]); Tw[i] = tmul(R2, Tw[i]); }
+        Tv[k] = mk(0, 0, 0); Tw[k] = ld3(S.ax);
+      } else {
+        const vec3 r = X.q[k] * ld3(S.ax);
+#pragma unroll
+        for (int i = 0; i < k; ++i) Tv[i] = Tv[i] + cross(Tw[i], r);
+        Tv[k] = ld3(S.ax); Tw[k] = mk(0, 0, 0);
+      }
+      if (S.flags & RKB_ST_LINK) {
+        const vec3 po = ld3(S.po);
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+          Tv[i] = Tv[i] + cross(Tw[i], po);
+          if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) { Tv[i] = tmulc(S.Ro, Tv[i]); Tw[i] = tmulc(S.Ro, Tw[i]); }
+        }
+      }
+      if (S.flags & RKB_ST_INERTIA) {
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+          const vec3 mv = S.m * Tv[i];
+          const vec3 Iw = symmul(S.I, Tw[i]);
+#pragma unroll
+          for (int j = 0; j <= i; ++j) Mp[i * (i + 1) / 2 + j] += dot(Tv[j], mv) + dot(Tw[j], Iw);
+        }
+      }
+      Mp[k * (k + 1) / 2 + k] += S.rotor;
+    }
+  }
+}
+
+// linsolve_Cholesky on the packed matrix; b is overwritten with the solution.
+// Returns RKB_STATUS_SINGULAR where the reference throws singularity_error.
+template <int N>
+RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N]) {
+  int st = 0;
+  double inv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      double s = Mp[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= Mp[i * (i + 1) / 2 + k] * Mp[j * (j + 1) / 2 + k];
+      Mp[i * (i + 1) / 2 + j] = s * inv[j];
+    }
+    double d = Mp[i * (i + 1) / 2 + i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) d -= Mp[i * (i + 1) / 2 + k] * Mp[i * (i + 1) / 2 + k];
+    if (!(d >= 1.0e-8)) st = RKB_STATUS_SINGULAR;
+    const double l = sqrt(d);
+    Mp[i * (i + 1) / 2 + i] = l;
+    inv[i] = 1.0 / l;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= Mp[i * (i + 1) / 2 + k] * b[k];
+    b[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = N - 1; k > i; --k) s -= Mp[k * (k + 1) / 2 + i] * b[k];
+    b[i] = s * inv[i];
+  }
+  return st;
+}
+
+// q_ddot = M^-1 f for the state in X; returns the status bits.
+template <int N, int FL, int SMS>
+RKB_DEV int serial_accel(const SerialParams& P, const SerialState<N>& X, double (&qdd)[N], double* sm) {
+  double cs[N], sn[N], Mp[N * (N + 1) / 2];
+  serial_sweeps<N, FL, SMS, true, true>(P, X, cs, sn, qdd, Mp, sm);
+  return cholesky_solve_packed<N>(Mp, qdd);
+}
+
+template <int N>
+RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const ConstBatchView& u, long long i, SerialState<N>& X) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = P.st[k].coord;
+    X.q[k] = x.p[i * x.si + (2 * c) * x.sk];
+    X.qd[k] = x.p[i * x.si + (2 * c + 1) * x.sk];
+    const int in = P.st[k].input;
+    X.u[k] = (in >= 0) ? u.p[i * u.si + in * u.sk] : 0.0;
+  }
+}
+
+#ifndef RKB_BLOCK
+#define RKB_BLOCK 128
+#endif
+
+// ---- kernels ---------------------------------------------------------------------------------
+// xdot = get_state_derivative(x, u)
+template <int N, int FL>
+__global__ void __launch_bounds__(RKB_BLOCK) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+  extern __shared__ double smem[];
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  SerialState<N> X;
+  load_state<N>(P, A.x, A.u, i, X);
+  double qdd[N];
+  int st = serial_accel<N, FL, RKB_BLOCK>(P, X, qdd, smem + threadIdx.x);
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = P.st[k].coord;
+    A.out.p[i * A.out.si + (2 * c) * A.out.sk] = X.qd[k];
+    A.out.p[i * A.out.si + (2 * c + 1) * A.out.sk] = qdd[k];
+    finite = finite && isfinite(qdd[k]) && isfinite(X.qd[k]);
+  }
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
+}
+
+// f = gen_coord::f after doMotion / clearForce / doForce with q_ddot = 0
+template <int N, int FL>
+__global__ void __launch_bounds__(RKB_BLOCK) serial_forces_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+  extern __shared__ double smem[];
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  SerialState<N> X;
+  load_state<N>(P, A.x, A.u, i, X);
+  double cs[N], sn[N], f[N], Mp[N * (N + 1) / 2];
+  serial_sweeps<N, FL, RKB_BLOCK, true, false>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
+#pragma unroll
+  for (int k = 0; k < N; ++k) A.out.p[i * A.out.si + P.st[k].coord * A.out.sk] = f[k];
+}
+
+// M = getMassMatrix (full symmetric n x n, row-major per sample in AoS)
+template <int N, int FL>
+__global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+  extern __shared__ double smem[];
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  SerialState<N> X;
+  ConstBatchView nou = A.x;
+  load_state<N>(P, A.x, nou, i, X);
+  double cs[N], sn[N], f[N], Mp[N * (N + 1) / 2];
+  serial_sweeps<N, FL, RKB_BLOCK, false, true>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
+#pragma unroll
+  for (int a = 0; a < N; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const int ca = P.st[a].coord, cb = P.st[b].coord;
+      const double v = Mp[a * (a + 1) / 2 + b];
+      A.out.p[i * A.out.si + (long long)(ca * N + cb) * A.out.sk] = v;
+      A.out.p[i * A.out.si + (long long)(cb * N + ca) * A.out.sk] = v;
+    }
+}
+
+// n_steps of fixed-step RK4 with the input held constant.
+// Per-thread shared-memory column: [0,6N) wrenches, then w (2N), acc (2N), k3 (2N).
+template <int N, int FL>
+__global__ void __launch_bounds__(RKB_BLOCK) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  double* sm = smem + threadIdx.x;
+  double* sw = sm + 6 * N * SMS;    // state at the start of the step (w)
+  double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
+  double* s3 = sa + 2 * N * SMS;    // k3
+  SerialState<N> X;
+  {
+    const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
+    ConstBatchView xv = A.x0;
+    xv.p += i0 * xv.si - i * xv.si;  // rows of x0 are shared by x0_div consecutive samples (steer batch)
+    load_state<N>(P, xv, A.u, i, X);
+  }
+  const double dt = A.dt;
+  int st = 0;
+  const int total = 4 * A.n_steps;
+#pragma unroll 1
+  for (int it = 0; it < total; ++it) {
+    double qdd[N];
+    st |= serial_accel<N, FL, SMS>(P, X, qdd, sm);
+    const int stage = it & 3;
+    // state derivative f = (qd, qdd) interleaved; the four stages of fixed_step_integrators.hpp:277-289
+    if (stage == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double k1q = X.qd[k] * dt, k1v = qdd[k] * dt;
+        sw[(2 * k) * SMS] = X.q[k]; sw[(2 * k + 1) * SMS] = X.qd[k];
+        sa[(2 * k) * SMS] = k1q;    sa[(2 * k + 1) * SMS] = k1v;
+        X.q[k] += k1q * 0.5; X.qd[k] += k1v * 0.5;
+      }
+    } else if (stage == 1) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double k2q = X.qd[k] * dt, k2v = qdd[k] * dt;
+        sa[(2 * k) * SMS] += k2q * 2.0; sa[(2 * k + 1) * SMS] += k2v * 2.0;
+        X.q[k] = sw[(2 * k) * SMS] + k2q * 0.5; X.qd[k] = sw[(2 * k + 1) * SMS] + k2v * 0.5;
+      }
+    } else if (stage == 2) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double k3q = X.qd[k] * dt, k3v = qdd[k] * dt;
+        s3[(2 * k) * SMS] = k3q; s3[(2 * k + 1) * SMS] = k3v;
+        X.q[k] = sw[(2 * k) * SMS] + k3q; X.qd[k] = sw[(2 * k + 1) * SMS] + k3v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double k4q = X.qd[k] * dt, k4v = qdd[k] * dt;
+        X.q[k] += (sa[(2 * k) * SMS] + k4q) / 6.0 - s3[(2 * k) * SMS] * (2.0 / 3.0);
+        X.qd[k] += (sa[(2 * k + 1) * SMS] + k4v) / 6.0 - s3[(2 * k + 1) * SMS] * (2.0 / 3.0);
+      }
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = P.st[k].coord;
+    A.xout.p[i * A.xout.si + (2 * c) * A.xout.sk] = X.q[k];
+    A.xout.p[i * A.xout.si + (2 * c + 1) * A.xout.sk] = X.qd[k];
+    finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+  }
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
+}
+
+template <int N>
+constexpr int serial_smem_doubles_per_thread(bool rollout) { return 6 * N + (rollout ? 6 * N : 0); }
+
+}  // namespace rkb
+#endif

@@ -1,0 +1,691 @@
+// rkb_api.cu — the C-ABI of include/reak_b200.h: descriptor validation and lowering, buffer
+// staging, kernel dispatch.  No numerics happen on the host and there is no CPU fallback: every
+// compute entry point needs a usable sm_100 device and fails with RKB_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/reak_b200.h"
+#include "rkb_internal.h"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
+  std::snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", where, cudaGetErrorString(e));
+  cudaGetLastError();  // clear the sticky-less error state
+  return RKB_ERR_CUDA;
+}
+#define CU(call)                                          \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); return RKB_ERR_NOMEM; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceCtx {
+  int device = -1;
+  bool checked = false;
+  GenericProgram* d_prog = nullptr;
+  DevBuf in_x, in_u, out_a, out_b, st, scratch_x, scratch_u, scratch_o, scratch_s, in_goal, out_idx, out_cost;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  bool prepared = false;
+};
+
+}  // namespace
+
+struct rkb_chain {
+  rkb_chain_desc desc;
+  std::vector<rkb_element> elements;
+  int n = 0, nu = 0;
+  bool serial_ok = false;
+  int serial_fl = 0;
+  SerialParams sp;
+  const SerialKernels* sk = nullptr;
+  bool generic_ok = false;
+  GenericProgram gp;
+  std::vector<DeviceCtx*> ctx;  // one per device used
+  std::mutex mu;
+  uint64_t launches = 0;
+  DeviceCtx* last = nullptr;
+};
+
+namespace {
+
+// ---- small host-side algebra used only to lower constants -------------------------------------
+void quat_to_rowmajor(const double* q, double* R) {  // quaternion::getRotMat, rotations_3D.hpp:986-1000
+  const double t01 = 2.0 * q[0] * q[1], t02 = 2.0 * q[0] * q[2], t03 = 2.0 * q[0] * q[3];
+  const double t11 = 2.0 * q[1] * q[1], t12 = 2.0 * q[1] * q[2], t13 = 2.0 * q[1] * q[3];
+  const double t22 = 2.0 * q[2] * q[2], t23 = 2.0 * q[2] * q[3], t33 = 2.0 * q[3] * q[3];
+  R[0] = 1.0 - t22 - t33; R[1] = t12 - t03; R[2] = t02 + t13;
+  R[3] = t12 + t03; R[4] = 1.0 - t11 - t33; R[5] = t23 - t01;
+  R[6] = t13 - t02; R[7] = t01 + t23; R[8] = 1.0 - t11 - t22;
+}
+void unit_quat(const double* in, double* out) {  // explicit quaternion(Vector), rotations_3D.hpp:917-920
+  const double n = std::sqrt(in[0] * in[0] + in[1] * in[1] + in[2] * in[2] + in[3] * in[3]);
+  for (int i = 0; i < 4; ++i) out[i] = in[i] / n;
+}
+void tmul3(const double* R, const double* v, double* o) {
+  for (int i = 0; i < 3; ++i) o[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+}
+void cross3(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+bool is_identity_quat(const double* q) { return q[0] == 1.0 && q[1] == 0.0 && q[2] == 0.0 && q[3] == 0.0; }
+
+bool finite_all(const double* p, int n) {
+  for (int i = 0; i < n; ++i) if (!std::isfinite(p[i])) return false;
+  return true;
+}
+
+int validate(const rkb_chain_desc* d) {
+  if (!d || (!d->elements && d->n_elements > 0)) return RKB_ERR_INVALID;
+  if (d->dim != 2 && d->dim != 3) return RKB_ERR_INVALID;
+  if (d->n_elements < 0 || d->n_frames < 1 || d->n_coords < 0 || d->n_inputs < 0) return RKB_ERR_INVALID;
+  if (d->n_coords > RKB_MAX_COORDS) return RKB_ERR_UNSUPPORTED;
+  if (d->base_frame < 0 || d->base_frame >= d->n_frames) return RKB_ERR_INVALID;
+  if (!finite_all(d->base.position, 3) || !finite_all(d->base.quat, 4) || !finite_all(d->base.velocity, 3) ||
+      !finite_all(d->base.ang_velocity, 3) || !finite_all(d->base.acceleration, 3) || !finite_all(d->base.ang_acceleration, 3))
+    return RKB_ERR_INVALID;
+  std::vector<int> coord_joint(d->n_coords, 0), input_used(d->n_inputs, 0), written(d->n_frames, 0);
+  for (int e = 0; e < d->n_elements; ++e) {
+    const rkb_element& E = d->elements[e];
+    if (!finite_all(E.p, 12)) return RKB_ERR_INVALID;
+    const bool is3 = E.kind < 16;
+    auto frame_ok = [&](int f) { return f >= 0 && f < d->n_frames; };
+    auto coord_ok = [&](int c) { return c >= 0 && c < d->n_coords; };
+    switch (E.kind) {
+      case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
+        if (!frame_ok(E.frame_a) || !frame_ok(E.frame_b) || !coord_ok(E.coord) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
+        if ((d->dim == 3) != is3) return RKB_ERR_INVALID;
+        if (coord_joint[E.coord]++) return RKB_ERR_UNSUPPORTED;  // one joint per coordinate
+        if (written[E.frame_b]++ || E.frame_b == d->base_frame) return RKB_ERR_INVALID;
+        break;
+      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D:
+        if (!frame_ok(E.frame_a) || !frame_ok(E.frame_b) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
+        if ((d->dim == 3) != is3) return RKB_ERR_INVALID;
+        if (written[E.frame_b]++ || E.frame_b == d->base_frame) return RKB_ERR_INVALID;
+        if (E.kind == RKB_RIGID_LINK_3D) {
+          const double n2 = E.p[3] * E.p[3] + E.p[4] * E.p[4] + E.p[5] * E.p[5] + E.p[6] * E.p[6];
+          if (!(n2 > 0.0)) return RKB_ERR_INVALID;
+        }
+        break;
+      case RKB_INERTIA_3D: case RKB_INERTIA_2D:
+        if (!frame_ok(E.frame_a) || (d->dim == 3) != is3) return RKB_ERR_INVALID;
+        if (d->n_coords < 64 && (E.upstream >> d->n_coords)) return RKB_ERR_INVALID;
+        break;
+      case RKB_INERTIA_GEN:
+        if (!coord_ok(E.coord)) return RKB_ERR_INVALID;
+        if (E.upstream != (1ull << E.coord)) return RKB_ERR_UNSUPPORTED;
+        break;
+      case RKB_ACTUATOR_GEN: {
+        if (!coord_ok(E.coord) || E.aux < 0 || E.aux >= d->n_inputs) return RKB_ERR_INVALID;
+        if (E.frame_b < 0 || E.frame_b >= d->n_elements) return RKB_ERR_INVALID;
+        const int jk = d->elements[E.frame_b].kind;
+        if (jk != RKB_REVOLUTE_3D && jk != RKB_PRISMATIC_3D && jk != RKB_REVOLUTE_2D && jk != RKB_PRISMATIC_2D) return RKB_ERR_INVALID;
+        if (input_used[E.aux]++) return RKB_ERR_INVALID;
+        break;
+      }
+      case RKB_TORSION_SPRING_3D: case RKB_TORSION_DAMPER_3D: case RKB_SPRING_3D: case RKB_DAMPER_3D:
+      case RKB_TORSION_SPRING_2D: case RKB_TORSION_DAMPER_2D: case RKB_SPRING_2D: case RKB_DAMPER_2D:
+        if (!frame_ok(E.frame_a) || !frame_ok(E.frame_b) || (d->dim == 3) != is3) return RKB_ERR_INVALID;
+        break;
+      case RKB_FREE_3D:
+        return RKB_ERR_UNSUPPORTED;
+      default:
+        return RKB_ERR_INVALID;
+    }
+  }
+  for (int c = 0; c < d->n_coords; ++c) if (coord_joint[c] != 1) return RKB_ERR_UNSUPPORTED;
+  for (int i = 0; i < d->n_inputs; ++i) if (input_used[i] != 1) return RKB_ERR_INVALID;
+  // every frame must be reachable: doMotion must write a frame before an element reads it
+  std::vector<int> ready(d->n_frames, 0);
+  ready[d->base_frame] = 1;
+  for (int e = 0; e < d->n_elements; ++e) {
+    const rkb_element& E = d->elements[e];
+    switch (E.kind) {
+      case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
+      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D:
+        if (!ready[E.frame_a]) return RKB_ERR_UNSUPPORTED;
+        ready[E.frame_b] = 1;
+        break;
+      default: break;
+    }
+  }
+  for (int f = 0; f < d->n_frames; ++f) if (!ready[f]) return RKB_ERR_UNSUPPORTED;
+  return RKB_OK;
+}
+
+// Try to express the chain as joint/link/inertia stages (see rkb_types.h).  Returns false when
+// the chain needs the generic interpreter.
+bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl) {
+  if (d.dim != 3 || d.n_coords < 1 || d.n_coords > RKB_SERIAL_MAX_DOF) return false;
+  std::memset(&P, 0, sizeof P);
+  P.n = d.n_coords;
+  P.n_inputs = d.n_inputs;
+  fl = 0;
+  // base frame in its own coordinates
+  double q0[4], R0[9];
+  unit_quat(d.base.quat, q0);
+  quat_to_rowmajor(q0, R0);
+  double w[3] = {d.base.ang_velocity[0], d.base.ang_velocity[1], d.base.ang_velocity[2]};
+  double al[3] = {d.base.ang_acceleration[0], d.base.ang_acceleration[1], d.base.ang_acceleration[2]};
+  double a[3];
+  tmul3(R0, d.base.acceleration, a);
+
+  std::vector<double> rotor(d.n_coords, 0.0);
+  std::vector<int> input_of(d.n_coords, -1);
+  int cur = d.base_frame, k = -1;
+  int joint_base = -1, joint_end = -1;
+  uint64_t mask = 0;
+  bool stage_has_link = false, stage_has_inertia = false;
+  for (int e = 0; e < d.n_elements; ++e) {
+    const rkb_element& E = d.elements[e];
+    switch (E.kind) {
+      case RKB_ACTUATOR_GEN: {
+        const rkb_element& J = d.elements[E.frame_b];
+        if (J.coord != E.coord || input_of[E.coord] >= 0) return false;
+        input_of[E.coord] = E.aux;
+        break;
+      }
+      case RKB_INERTIA_GEN:
+        rotor[E.coord] += E.p[0];
+        break;
+      case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: {
+        if (E.frame_a != cur) return false;
+        if (++k >= RKB_SERIAL_MAX_DOF) return false;
+        SerialStage& S = P.st[k];
+        S.coord = E.coord;
+        S.input = -1;
+        const double nrm = std::sqrt(E.p[0] * E.p[0] + E.p[1] * E.p[1] + E.p[2] * E.p[2]);
+        for (int i = 0; i < 3; ++i) S.ax[i] = E.p[i];
+        if (nrm > 0.0000001) for (int i = 0; i < 3; ++i) S.an[i] = E.p[i] / nrm;  // rotations_3D.hpp:1962-1974
+        else { S.an[0] = 1.0; S.an[1] = 0.0; S.an[2] = 0.0; }
+        S.aa[0] = S.an[0] * S.an[0]; S.aa[1] = S.an[1] * S.an[1]; S.aa[2] = S.an[2] * S.an[2];
+        S.aa[3] = S.an[0] * S.an[1]; S.aa[4] = S.an[0] * S.an[2]; S.aa[5] = S.an[1] * S.an[2];
+        S.Ro[0] = S.Ro[4] = S.Ro[8] = 1.0;
+        if (E.kind == RKB_PRISMATIC_3D) { S.flags |= RKB_ST_PRISMATIC; fl |= RKB_FL_PRISMATIC; }
+        else if (nrm <= 0.0000001) return false;  // degenerate revolute axis: leave it to the interpreter
+        joint_base = E.frame_a; joint_end = E.frame_b; cur = E.frame_b;
+        mask |= 1ull << E.coord;
+        stage_has_link = stage_has_inertia = false;
+        break;
+      }
+      case RKB_RIGID_LINK_3D: {
+        if (E.frame_a != cur) return false;
+        double q[4], R[9];
+        unit_quat(&E.p[3], q);
+        quat_to_rowmajor(q, R);
+        if (k < 0) {
+          // a link ahead of the first joint only re-bases the root frame (frame_3D.hpp:236-251)
+          double t1[3], t2[3], t3[3], acc[3];
+          cross3(w, E.p, t1); cross3(w, t1, t2); cross3(al, E.p, t3);
+          for (int i = 0; i < 3; ++i) acc[i] = a[i] + t2[i] + t3[i];
+          double wn[3], aln[3];
+          tmul3(R, acc, a); tmul3(R, w, wn); tmul3(R, al, aln);
+          std::memcpy(w, wn, sizeof w); std::memcpy(al, aln, sizeof al);
+        } else {
+          if (stage_has_link || stage_has_inertia) return false;
+          SerialStage& S = P.st[k];
+          S.flags |= RKB_ST_LINK;
+          for (int i = 0; i < 3; ++i) S.po[i] = E.p[i];
+          std::memcpy(S.Ro, R, sizeof R);
+          if (!is_identity_quat(q)) { S.flags |= RKB_ST_LINKROT; fl |= RKB_FL_LINKROT; }
+          stage_has_link = true;
+        }
+        cur = E.frame_b;
+        break;
+      }
+      case RKB_INERTIA_3D: {
+        if (k < 0) { if (E.upstream != 0) return false; break; }  // rides on the fixed root: no generalised force
+        if (E.frame_a != cur || E.upstream != mask) return false;
+        SerialStage& S = P.st[k];
+        S.flags |= RKB_ST_INERTIA;
+        S.m += E.p[0];
+        for (int i = 0; i < 6; ++i) S.I[i] += E.p[1 + i];
+        stage_has_inertia = true;
+        break;
+      }
+      case RKB_TORSION_SPRING_3D: case RKB_TORSION_DAMPER_3D: {
+        if (k < 0 || E.frame_a != joint_base || E.frame_b != joint_end) return false;
+        SerialStage& S = P.st[k];
+        if (S.flags & RKB_ST_PRISMATIC) break;  // no relative rotation across a prismatic joint: zero torque
+        if (E.kind == RKB_TORSION_SPRING_3D) {
+          if (S.flags & RKB_ST_SPRING) return false;
+          S.flags |= RKB_ST_SPRING; S.ks = E.p[0]; S.sat = E.p[1];
+        } else {
+          S.flags |= RKB_ST_DAMPER; S.cd += E.p[0];
+        }
+        fl |= RKB_FL_SPRINGS;
+        break;
+      }
+      default:
+        return false;
+    }
+  }
+  if (k + 1 != d.n_coords) return false;
+  for (int s = 0; s <= k; ++s) {
+    P.st[s].rotor = rotor[P.st[s].coord];
+    P.st[s].input = input_of[P.st[s].coord];
+  }
+  for (int i = 0; i < 3; ++i) { P.w0[i] = w[i]; P.al0[i] = al[i]; P.a0[i] = a[i]; }
+  return true;
+}
+
+bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
+  if (d.n_elements > RKB_GEN_MAX_ELEMENTS || d.n_frames > RKB_GEN_MAX_FRAMES) return false;
+  std::memset(&G, 0, sizeof G);
+  G.dim = d.dim; G.n_elements = d.n_elements; G.n_frames = d.n_frames;
+  G.n_coords = d.n_coords; G.n_inputs = d.n_inputs; G.base_frame = d.base_frame;
+  if (d.dim == 3) {
+    double q[4];
+    unit_quat(d.base.quat, q);
+    for (int i = 0; i < 3; ++i) {
+      G.base[i] = d.base.position[i]; G.base[7 + i] = d.base.velocity[i]; G.base[10 + i] = d.base.ang_velocity[i];
+      G.base[13 + i] = d.base.acceleration[i]; G.base[16 + i] = d.base.ang_acceleration[i];
+    }
+    for (int i = 0; i < 4; ++i) G.base[3 + i] = q[i];
+  } else {
+    G.base[0] = d.base.position[0]; G.base[1] = d.base.position[1];
+    G.base[3] = std::cos(d.base.quat[0]); G.base[4] = std::sin(d.base.quat[0]);  // rot_mat_2D(angle), rotations_2D.hpp:108-112
+    G.base[7] = d.base.velocity[0]; G.base[8] = d.base.velocity[1];
+    G.base[10] = d.base.ang_velocity[0];
+    G.base[13] = d.base.acceleration[0]; G.base[14] = d.base.acceleration[1];
+    G.base[16] = d.base.ang_acceleration[0];
+  }
+  int row_gen = 0, row_2d = 0, row_3d = 0;
+  for (int e = 0; e < d.n_elements; ++e) {
+    const rkb_element& E = d.elements[e];
+    if (E.kind == RKB_INERTIA_GEN) row_2d += 1;
+  }
+  row_3d = row_2d;
+  for (int e = 0; e < d.n_elements; ++e) if (d.elements[e].kind == RKB_INERTIA_2D) row_3d += 3;
+  for (int e = 0; e < d.n_elements; ++e) {
+    const rkb_element& E = d.elements[e];
+    GenericElement& g = G.el[e];
+    g.kind = E.kind; g.fa = E.frame_a; g.fb = E.frame_b; g.coord = E.coord; g.aux = E.aux;
+    g.upstream = (uint32_t)E.upstream;
+    std::memcpy(g.p, E.p, sizeof g.p);
+    if (E.kind == RKB_RIGID_LINK_3D) unit_quat(&E.p[3], &g.p[3]);
+    if (E.kind == RKB_RIGID_LINK_2D) { g.p[3] = std::cos(E.p[2]); g.p[4] = std::sin(E.p[2]); }
+    if (E.kind == RKB_INERTIA_GEN) { g.row = row_gen; row_gen += 1; }
+    if (E.kind == RKB_INERTIA_2D) { g.row = row_2d; row_2d += 3; }
+    if (E.kind == RKB_INERTIA_3D) { g.row = row_3d; row_3d += 6; }
+    if (E.kind == RKB_REVOLUTE_3D || E.kind == RKB_PRISMATIC_3D || E.kind == RKB_REVOLUTE_2D || E.kind == RKB_PRISMATIC_2D)
+      G.jelem[E.coord] = e;
+  }
+  return true;
+}
+
+const SerialKernels* find_serial(int n, int fl) {
+  int count = 0;
+  const SerialKernels* t = nullptr;
+  switch (n) {
+    case 1: t = rkb_serial_table_1(&count); break;
+    case 2: t = rkb_serial_table_2(&count); break;
+    case 3: t = rkb_serial_table_3(&count); break;
+    case 4: t = rkb_serial_table_4(&count); break;
+    case 5: t = rkb_serial_table_5(&count); break;
+    case 6: t = rkb_serial_table_6(&count); break;
+    case 7: t = rkb_serial_table_7(&count); break;
+    case 8: t = rkb_serial_table_8(&count); break;
+    default: return nullptr;
+  }
+  const SerialKernels* best = nullptr;
+  for (int i = 0; i < count; ++i)
+    if ((t[i].fl & fl) == fl && (!best || __builtin_popcount(t[i].fl) < __builtin_popcount(best->fl))) best = &t[i];
+  return best;
+}
+
+// RAII: switch to `device`, restore on exit
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    ok = cudaSetDevice(device) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int get_ctx(rkb_chain* c, int device, DeviceCtx** out) {
+  for (DeviceCtx* x : c->ctx) if (x->device == device) { *out = x; return 0; }
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    std::snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major, prop.minor);
+    return RKB_ERR_CUDA;
+  }
+  DeviceCtx* x = new (std::nothrow) DeviceCtx();
+  if (!x) return RKB_ERR_NOMEM;
+  x->device = device;
+  if (c->generic_ok) {
+    e = cudaMalloc(&x->d_prog, sizeof(GenericProgram));
+    if (e != cudaSuccess) { delete x; return cuda_fail(e, "cudaMalloc(program)"); }
+    e = cudaMemcpy(x->d_prog, &c->gp, sizeof(GenericProgram), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(x->d_prog); delete x; return cuda_fail(e, "cudaMemcpy(program)"); }
+  }
+  if (c->sk) {
+    e = c->sk->prepare();
+    if (e != cudaSuccess) { if (x->d_prog) cudaFree(x->d_prog); delete x; return cuda_fail(e, "cudaFuncSetAttribute"); }
+  }
+  e = cudaEventCreate(&x->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&x->ev1);
+  if (e != cudaSuccess) { delete x; return cuda_fail(e, "cudaEventCreate"); }
+  c->ctx.push_back(x);
+  *out = x;
+  return 0;
+}
+
+struct Layout {
+  bool device, soa;
+};
+Layout parse_flags(unsigned flags) { return Layout{(flags & RKB_MEM_DEVICE) != 0, (flags & RKB_LAYOUT_SOA) != 0}; }
+
+ConstBatchView cview(const double* p, long long n, int dim, bool soa) { return ConstBatchView{p, soa ? 1 : dim, soa ? n : 1}; }
+BatchView view(double* p, long long n, int dim, bool soa) { return BatchView{p, soa ? 1 : dim, soa ? n : 1}; }
+
+// Stage a host input on the device (or pass a device pointer through).
+int stage_in(DevBuf& buf, const void* src, size_t bytes, bool on_device, cudaStream_t s, const void** out) {
+  if (on_device || bytes == 0) { *out = src; return 0; }
+  int rc = buf.ensure(bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s));
+  *out = buf.p;
+  return 0;
+}
+int stage_out(DevBuf& buf, void* dst, size_t bytes, bool on_device, void** out) {
+  if (on_device || bytes == 0 || !dst) { *out = dst; return 0; }
+  int rc = buf.ensure(bytes);
+  if (rc) return rc;
+  *out = buf.p;
+  return 0;
+}
+int unstage_out(void* dev, void* dst, size_t bytes, bool on_device, cudaStream_t s) {
+  if (on_device || bytes == 0 || !dst) return 0;
+  CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+enum Op { OP_EVAL, OP_FORCES, OP_MASS };
+
+int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, const double* u, double* out, double* out2,
+                  int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  if (!x || !out || (c->nu > 0 && !u && op != OP_MASS)) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int n = c->n, nx = 2 * n, nu = c->nu;
+  const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : n * n;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx = nullptr, *du = nullptr;
+  void *dout = nullptr, *dout2 = nullptr, *dst = nullptr;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if (op != OP_MASS && nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc; }
+  if ((rc = stage_out(ctx->out_a, out, N * out_dim * sizeof(double), L.device, &dout))) return rc;
+  if ((rc = stage_out(ctx->out_b, out2, N * out_dim * sizeof(double), L.device, &dout2))) return rc;
+  if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
+  EvalArgs A;
+  A.x = cview((const double*)dx, (long long)N, nx, L.soa);
+  A.u = cview((const double*)(du ? du : dx), (long long)N, nu > 0 ? nu : 1, L.soa);
+  A.out = view((double*)dout, (long long)N, out_dim, L.soa);
+  A.out2 = view((double*)dout2, (long long)N, out_dim, L.soa);
+  A.status = (int32_t*)dst;
+  A.n_samples = (long long)N;
+  CU(cudaEventRecord(ctx->ev0, s));
+  cudaError_t e;
+  const bool use_serial = c->serial_ok && c->sk && !(op == OP_MASS && out2);
+  if (use_serial) {
+    e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
+  } else if (c->generic_ok) {
+    e = op == OP_EVAL ? rkb_generic_eval(ctx->d_prog, c->gp, A, s)
+        : op == OP_FORCES ? rkb_generic_forces(ctx->d_prog, c->gp, A, s) : rkb_generic_mass(ctx->d_prog, c->gp, A, s);
+  } else {
+    return RKB_ERR_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  c->launches += 1;
+  if ((rc = unstage_out(dout, out, N * out_dim * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dout2, out2, N * out_dim * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
+// rollout on device-resident views; used by rkb_rollout_rk4 and rkb_steer_batch
+int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, cudaStream_t s) {
+  cudaError_t e;
+  if (c->serial_ok && c->sk) e = c->sk->rollout(c->sp, A, s);
+  else if (c->generic_ok) e = rkb_generic_rollout(ctx->d_prog, c->gp, A, s);
+  else return RKB_ERR_UNSUPPORTED;
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  c->launches += 1;
+  return RKB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rkb_version(void) { return RKB_VERSION; }
+
+const char* rkb_strerror(int code) {
+  switch (code) {
+    case RKB_OK: return "ok";
+    case RKB_ERR_INVALID: return "invalid argument or malformed chain descriptor";
+    case RKB_ERR_UNSUPPORTED: return "chain or element outside the compiled path";
+    case RKB_ERR_DIMENSION: return "state or input vector dimension mismatch";
+    case RKB_ERR_CUDA: return "CUDA failure or no usable sm_100 device (there is no CPU fallback)";
+    case RKB_ERR_NOMEM: return "out of memory";
+    case RKB_ERR_INTEGRATION: return "impossible integration (zero step or negative step count)";
+    default: return "unknown error";
+  }
+}
+
+const char* rkb_last_cuda_error(void) { return g_cuda_err; }
+
+int rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out) {
+  if (!out) return RKB_ERR_INVALID;
+  *out = nullptr;
+  int rc = validate(desc);
+  if (rc) return rc;
+  rkb_chain* c = new (std::nothrow) rkb_chain();
+  if (!c) return RKB_ERR_NOMEM;
+  c->desc = *desc;
+  c->elements.assign(desc->elements, desc->elements + desc->n_elements);
+  c->desc.elements = c->elements.data();
+  c->n = desc->n_coords;
+  c->nu = desc->n_inputs;
+  c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl);
+  if (c->serial_ok) {
+    c->sk = find_serial(c->n, c->serial_fl);
+    if (!c->sk) c->serial_ok = false;
+  }
+  const char* force = std::getenv("RKB_FORCE_GENERIC");
+  c->generic_ok = lower_generic(c->desc, c->gp);
+  if (force && force[0] == '1' && c->generic_ok) { c->serial_ok = false; c->sk = nullptr; }
+  if (!c->serial_ok && !c->generic_ok) { delete c; return RKB_ERR_UNSUPPORTED; }
+  *out = c;
+  return RKB_OK;
+}
+
+void rkb_chain_destroy(rkb_chain* c) {
+  if (!c) return;
+  for (DeviceCtx* x : c->ctx) {
+    DeviceGuard g(x->device);
+    if (x->d_prog) cudaFree(x->d_prog);
+    DevBuf* bufs[] = {&x->in_x, &x->in_u, &x->out_a, &x->out_b, &x->st, &x->scratch_x, &x->scratch_u, &x->scratch_o,
+                      &x->scratch_s, &x->in_goal, &x->out_idx, &x->out_cost};
+    for (DevBuf* b : bufs) b->release();
+    if (x->ev0) cudaEventDestroy(x->ev0);
+    if (x->ev1) cudaEventDestroy(x->ev1);
+    delete x;
+  }
+  delete c;
+}
+
+int rkb_chain_state_dim(const rkb_chain* c) { return c ? 2 * c->n : RKB_ERR_INVALID; }
+int rkb_chain_input_dim(const rkb_chain* c) { return c ? c->nu : RKB_ERR_INVALID; }
+int rkb_chain_dof(const rkb_chain* c) { return c ? c->n : RKB_ERR_INVALID; }
+/* 1 when the chain runs on the register-resident serial kernels, 0 on the interpreter */
+int rkb_chain_is_serial(const rkb_chain* c) { return c ? (c->serial_ok ? 1 : 0) : RKB_ERR_INVALID; }
+
+int rkb_eval(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* xdot, int32_t* status,
+             unsigned flags, void* stream) {
+  return run_eval_like(c, OP_EVAL, device, N, x, u, xdot, nullptr, status, flags, stream);
+}
+
+int rkb_gen_forces(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* f, unsigned flags, void* stream) {
+  return run_eval_like(c, OP_FORCES, device, N, x, u, f, nullptr, nullptr, flags, stream);
+}
+
+int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double* M, double* Mdot, unsigned flags, void* stream) {
+  return run_eval_like(c, OP_MASS, device, N, x, nullptr, M, Mdot, nullptr, flags, stream);
+}
+
+int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                    double* x_out, int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;  // fixed_step_integrators.hpp:258-266
+  if (N == 0) return RKB_OK;
+  if (!x0 || !x_out || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n, nu = c->nu;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx = nullptr, *du = nullptr;
+  void *dout = nullptr, *dst = nullptr;
+  if ((rc = stage_in(ctx->in_x, x0, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if (nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc; }
+  if ((rc = stage_out(ctx->out_a, x_out, N * nx * sizeof(double), L.device, &dout))) return rc;
+  if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
+  RolloutArgs A;
+  A.x0 = cview((const double*)dx, (long long)N, nx, L.soa);
+  A.u = cview((const double*)(du ? du : dx), (long long)N, nu > 0 ? nu : 1, L.soa);
+  A.xout = view((double*)dout, (long long)N, nx, L.soa);
+  A.status = (int32_t*)dst;
+  A.n_samples = (long long)N;
+  A.x0_div = 1;
+  A.dt = dt;
+  A.n_steps = n_steps;
+  CU(cudaEventRecord(ctx->ev0, s));
+  if ((rc = launch_rollout(c, ctx, A, s))) return rc;
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(dout, x_out, N * nx * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
+int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* x0, const double* goal, const double* u,
+                    double dt, int n_steps, int32_t* best_idx, double* best_x, double* best_cost, int32_t* status,
+                    unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
+  if (P == 0) return RKB_OK;
+  if (R == 0) return RKB_ERR_INVALID;
+  if (!x0 || !goal || !best_idx || !best_x || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n, nu = c->nu;
+  const size_t T = P * R;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx0 = nullptr, *dgoal = nullptr, *du = nullptr;
+  void *didx = nullptr, *dbx = nullptr, *dbc = nullptr, *dst = nullptr;
+  if ((rc = stage_in(ctx->in_x, x0, P * nx * sizeof(double), L.device, s, &dx0))) return rc;
+  if ((rc = stage_in(ctx->in_goal, goal, P * nx * sizeof(double), L.device, s, &dgoal))) return rc;
+  if (nu > 0) { if ((rc = stage_in(ctx->in_u, u, T * nu * sizeof(double), L.device, s, &du))) return rc; }
+  if ((rc = stage_out(ctx->out_idx, best_idx, P * sizeof(int32_t), L.device, &didx))) return rc;
+  if ((rc = stage_out(ctx->out_a, best_x, P * nx * sizeof(double), L.device, &dbx))) return rc;
+  if ((rc = ctx->out_cost.ensure(P * sizeof(double)))) return rc;
+  dbc = (L.device && best_cost) ? (void*)best_cost : ctx->out_cost.p;
+  if ((rc = stage_out(ctx->st, status, T * sizeof(int32_t), L.device, &dst))) return rc;
+  // every rollout of a pair starts from the pair's state (x0_div = R); end states go to a
+  // [P*R][nx] scratch that the per-pair arg-min reads.
+  if ((rc = ctx->scratch_o.ensure(T * nx * sizeof(double)))) return rc;
+  CU(cudaEventRecord(ctx->ev0, s));
+  cudaError_t e;
+  RolloutArgs A;
+  A.x0 = cview((const double*)dx0, (long long)P, nx, false);
+  A.u = (L.soa && nu > 0) ? cview((const double*)du, (long long)T, nu, true) : cview((const double*)(du ? du : dx0), (long long)T, nu > 0 ? nu : 1, false);
+  A.xout = view((double*)ctx->scratch_o.p, (long long)T, nx, false);
+  A.status = (int32_t*)dst;
+  A.n_samples = (long long)T;
+  A.x0_div = (long long)R;
+  A.dt = dt;
+  A.n_steps = n_steps;
+  if ((rc = launch_rollout(c, ctx, A, s))) return rc;
+  e = rkb_steer_reduce(nx, (long long)P, (long long)R, (const double*)ctx->scratch_o.p, (const double*)dgoal, (int32_t*)didx,
+                       (double*)dbx, (double*)dbc, s);
+  if (e != cudaSuccess) return cuda_fail(e, "steer reduce");
+  c->launches += 1;
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(didx, best_idx, P * sizeof(int32_t), L.device, s))) return rc;
+  if ((rc = unstage_out(dbx, best_x, P * nx * sizeof(double), L.device, s))) return rc;
+  if (!L.device && best_cost) CU(cudaMemcpyAsync(best_cost, dbc, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if ((rc = unstage_out(dst, status, T * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
+double rkb_last_kernel_ms(rkb_chain* c) {
+  if (!c) return -1.0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!c->last || !c->last->timed) return -1.0;
+  DeviceGuard guard(c->last->device);
+  float ms = -1.0f;
+  if (cudaEventSynchronize(c->last->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  if (cudaEventElapsedTime(&ms, c->last->ev0, c->last->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  return (double)ms;
+}
+
+uint64_t rkb_launch_count(const rkb_chain* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

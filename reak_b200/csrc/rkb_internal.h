@@ -1,0 +1,36 @@
+// rkb_internal.h — host-side glue between rkb_api.cu and the kernel translation units.
+#ifndef RKB_INTERNAL_H
+#define RKB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include "rkb_types.h"
+
+// One entry per compiled (N, feature-mask) instantiation of the serial kernels.
+struct SerialKernels {
+  int n, fl;
+  int smem_eval, smem_rollout;  // dynamic shared memory per CTA, bytes
+  int block;
+  cudaError_t (*prepare)(void);  // opt in to > 48 KB dynamic shared memory
+  cudaError_t (*eval)(const SerialParams&, const EvalArgs&, cudaStream_t);
+  cudaError_t (*forces)(const SerialParams&, const EvalArgs&, cudaStream_t);
+  cudaError_t (*mass)(const SerialParams&, const EvalArgs&, cudaStream_t);
+  cudaError_t (*rollout)(const SerialParams&, const RolloutArgs&, cudaStream_t);
+};
+
+// defined in rkb_serial_n.cu, compiled once per N with -DRKB_N=<n>
+#define RKB_DECL_TABLE(n) extern "C" const SerialKernels* rkb_serial_table_##n(int* count)
+RKB_DECL_TABLE(1); RKB_DECL_TABLE(2); RKB_DECL_TABLE(3); RKB_DECL_TABLE(4);
+RKB_DECL_TABLE(5); RKB_DECL_TABLE(6); RKB_DECL_TABLE(7); RKB_DECL_TABLE(8);
+
+// generic interpreter (kte_generic.cu); `prog` is a device pointer to a GenericProgram
+cudaError_t rkb_generic_eval(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
+cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
+cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
+cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, cudaStream_t s);
+
+// steer helpers (rkb_steer.cu): cost of every rollout end state against its pair's goal, then
+// per-pair arg-min (first index wins ties) and gather of the winning end state.
+cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, const double* xend, const double* goal,
+                             int32_t* best_idx, double* best_x, double* best_cost, cudaStream_t s);
+
+#endif

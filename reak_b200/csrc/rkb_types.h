@@ -1,0 +1,104 @@
+// rkb_types.h — internal structures shared by the host lowering (rkb_api.cu) and the kernels.
+//
+// A descriptor (include/reak_b200.h) is lowered once, at rkb_chain_create, into one or both of
+//   * SerialParams  — the canonical serial-chain form consumed by the register-resident
+//                     kernels in kte_serial.cuh (joint -> link -> inertia stages), passed BY VALUE
+//                     as a __grid_constant__ kernel parameter so that every chain constant is a
+//                     constant-bank operand of the FP64 instructions, and
+//   * GenericProgram — the element list as is, consumed by the interpreter kernels in
+//                     kte_generic.cuh (any element order, 2D chains, two-anchor springs/dampers).
+#ifndef RKB_TYPES_H
+#define RKB_TYPES_H
+
+#include <stdint.h>
+#include "../../include/reak_b200.h"
+
+#define RKB_SERIAL_MAX_DOF 8
+
+// stage flags (uniform across the grid, so branching on them never diverges)
+#define RKB_ST_PRISMATIC 1u  // joint is prismatic_joint_3D instead of revolute_joint_3D
+#define RKB_ST_LINKROT   2u  // rigid link carries a rotation (Ro != I)
+#define RKB_ST_SPRING    4u  // torsion_spring_3D across the joint (anchors: joint base, joint end)
+#define RKB_ST_DAMPER    8u  // torsion_damper_3D across the joint
+#define RKB_ST_INERTIA   16u // an inertia_3D sits on the link end frame
+#define RKB_ST_LINK      32u // a rigid_link_3D follows the joint (else end frame == joint end)
+
+// kernel-template feature mask: which optional code is compiled in
+#define RKB_FL_PRISMATIC 1
+#define RKB_FL_LINKROT   2
+#define RKB_FL_SPRINGS   4
+#define RKB_FL_ALL       7
+
+struct SerialStage {
+  double ax[3];    // joint axis as stored (mAxis): used for angular/linear velocity terms and force projection
+  double an[3];    // normalised axis (axis_angle ctor, rotations_3D.hpp:1962-1974): used for the rotation
+  double aa[6];    // an an^T: xx, yy, zz, xy, xz, yz
+  double po[3];    // rigid link offset position
+  double Ro[9];    // rigid link offset rotation, row-major, v_base = Ro v_end
+  double m;        // inertia_3D mass
+  double I[6];     // inertia tensor xx, xy, xz, yy, yz, zz
+  double rotor;    // sum of inertia_gen masses on this coordinate (diagonal of M)
+  double ks, sat;  // torsion spring stiffness / saturation
+  double cd;       // torsion damper coefficient
+  uint32_t flags;
+  int32_t  coord;  // state slot of this joint's coordinate (q at 2*coord, qd at 2*coord+1)
+  int32_t  input;  // input index of the driving_actuator_gen on this joint, -1 if none
+  int32_t  pad;
+};
+
+struct SerialParams {
+  int32_t n;            // number of stages == number of coordinates
+  int32_t n_inputs;
+  double  w0[3];        // base frame AngVelocity (local)
+  double  al0[3];       // base frame AngAcceleration (local)
+  double  a0[3];        // base frame Acceleration rotated into base-local coordinates
+  SerialStage st[RKB_SERIAL_MAX_DOF];
+};
+
+// strided view of a batch buffer: element k of sample i lives at p[i * si + k * sk]
+struct BatchView {
+  double*  p;
+  long long si, sk;
+};
+struct ConstBatchView {
+  const double* p;
+  long long si, sk;
+};
+
+struct RolloutArgs {
+  ConstBatchView x0, u;
+  BatchView      xout;
+  int32_t*       status;   // nullable
+  long long      n_samples;
+  long long      x0_div;   // sample i starts from row i / x0_div of x0 (steer batch: rollouts per pair; else 1)
+  double         dt;
+  int32_t        n_steps;
+};
+
+struct EvalArgs {
+  ConstBatchView x, u;
+  BatchView      out;      // xdot (2n), f (n) or M (n*n) depending on the kernel
+  BatchView      out2;     // Mdot (n*n) for the mass kernel, else unused
+  int32_t*       status;   // nullable
+  long long      n_samples;
+};
+
+// ---- generic interpreter program ------------------------------------------------------------
+#define RKB_GEN_MAX_FRAMES 40
+#define RKB_GEN_MAX_ELEMENTS 96
+
+struct GenericElement {
+  int32_t kind, fa, fb, coord, aux, pad;
+  uint32_t upstream;
+  int32_t  row;      // first row of this inertia in the twist-shaping matrix (unused by the kernel)
+  double   p[12];    // as rkb_element::p; rigid_link_3D: p[3..6] normalised quaternion
+};
+
+struct GenericProgram {
+  int32_t dim, n_elements, n_frames, n_coords, n_inputs, base_frame;
+  double  base[19];  // p3 q4 v3 w3 a3 al3 (2D: p2, -, cos, sin, -, -, v2, -, w, -, -, a2, -, al)
+  int32_t jelem[RKB_MAX_COORDS];  // element index of the joint that owns each coordinate
+  GenericElement el[RKB_GEN_MAX_ELEMENTS];
+};
+
+#endif

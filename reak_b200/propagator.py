@@ -55,6 +55,10 @@ class kte_batch_propagator(object):
         except Exception:
             pass
 
+    def is_serial(self):
+        """True when the chain runs on the register-resident serial-chain kernels."""
+        return bool(self._lib.rkb_chain_is_serial(self._h))
+
     # ---- SSSystemConcept / DiscreteSSSConcept (single sample) ---------------------------
     def get_state_dimensions(self):
         return self.nx

@@ -1,0 +1,186 @@
+"""GPU parity: libreak_b200.so (through the C-ABI / kte_batch_propagator) against the oracle.
+
+Tolerances are BASELINE.json's: 1e-10 relative per step, 1e-8 after 1000 steps, relative error
+taken per component as |a-b| / max(1, |b|).  Evaluation outputs (xdot, f, M, Mdot) are held to
+1e-10 as well.  Every chain is run on the kernels the library picks for it and, where that is
+the register-resident serial path, once more on the interpreter kernels (RKB_FORCE_GENERIC=1).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import random_batch, rel_err
+from reak_b200 import kte, presets
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-10
+TOL_LONG = 1e-8
+ALL = sorted(presets.PRESETS)
+
+
+def _make(name, generic=False):
+    from reak_b200 import kte_batch_propagator
+    s = presets.make(name)
+    old = os.environ.get("RKB_FORCE_GENERIC")
+    os.environ["RKB_FORCE_GENERIC"] = "1" if generic else "0"
+    try:
+        p = kte_batch_propagator(s)
+    finally:
+        if old is None:
+            os.environ.pop("RKB_FORCE_GENERIC", None)
+        else:
+            os.environ["RKB_FORCE_GENERIC"] = old
+    return p
+
+
+def _variants(name):
+    p = _make(name)
+    out = [("auto", p)]
+    if p.is_serial():
+        out.append(("generic", _make(name, generic=True)))
+    return out
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_eval_forces_mass(name, oracle_built):
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        x, u = random_batch(p.compiled, 257, seed=11, q_range=3.0)
+        xd, st = p.get_state_derivatives(x, u)
+        xd_o, st_o = O.eval(x, u)
+        assert not st.any() and not st_o.any()
+        assert rel_err(xd, xd_o) < TOL_STEP, (name, label)
+        assert rel_err(p.get_gen_forces(x, u), O.gen_forces(x, u)) < TOL_STEP, (name, label)
+        M, Md = p.get_mass_matrices(x, with_derivative=True)
+        M_o, Md_o = O.mass(x)
+        assert rel_err(M, M_o) < TOL_STEP and rel_err(Md, Md_o) < TOL_STEP, (name, label)
+        assert rel_err(p.get_mass_matrices(x), M_o) < TOL_STEP, (name, label)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_rk4_one_and_many_steps(name, oracle_built):
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        x, u = random_batch(p.compiled, 96, seed=5)
+        for steps, tol in ((1, TOL_STEP), (100, TOL_LONG)):
+            xo, st = p.get_next_states(x, u, 1e-3, steps)
+            xr, sr, _ = O.rk4(x, u, 1e-3, steps)
+            assert not st.any() and not sr.any()
+            assert rel_err(xo, xr) < tol, (name, label, steps)
+
+
+def test_cfg1_planar_1024x1000(oracle_built):
+    """BASELINE config 1: 2-link planar arm, 1024 random states, 1000 RK4 steps of 1 ms."""
+    p = _make("planar2")
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 1024, seed=12345, q_range=np.pi, qd_range=2.0)
+    xo, st = p.get_next_states(x, None, 1e-3, 1000)
+    xr, sr, _ = O.rk4(x, None, 1e-3, 1000, n_workers=os.cpu_count() or 1)
+    assert not st.any() and not sr.any()
+    assert rel_err(xo, xr) < TOL_LONG
+
+
+def test_cfg2_crs6_1000_steps(oracle_built):
+    p = _make("crs6")
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 64, seed=12346)
+    xo, st = p.get_next_states(x, u, 1e-3, 1000)
+    xr, sr, _ = O.rk4(x, u, 1e-3, 1000, n_workers=min(8, os.cpu_count() or 1))
+    assert not st.any() and not sr.any()
+    assert rel_err(xo, xr) < TOL_LONG
+
+
+def test_layouts_and_device_buffers(oracle_built):
+    import torch
+    p = _make("crs6_sd")
+    x, u = random_batch(p.compiled, 1000, seed=3)
+    ref, _ = p.get_next_states(x, u, 1e-3, 7)
+    # SoA host
+    xs, st = p.get_next_states(np.ascontiguousarray(x.T), np.ascontiguousarray(u.T), 1e-3, 7, soa=True)
+    assert np.array_equal(xs.T, ref)
+    # device AoS / SoA (torch tensors are passed zero-copy)
+    xt, ut = torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda()
+    xo, st = p.get_next_states(xt, ut, 1e-3, 7)
+    torch.cuda.synchronize()
+    assert np.array_equal(xo.cpu().numpy(), ref) and not st.any().item()
+    xo, st = p.get_next_states(xt.t().contiguous(), ut.t().contiguous(), 1e-3, 7, soa=True)
+    assert np.array_equal(xo.t().cpu().numpy(), ref)
+    # zero steps is the identity, n = 0 is a no-op
+    same, _ = p.get_next_states(x, u, 1e-3, 0)
+    assert np.array_equal(same, x)
+    e, _ = p.get_next_states(x[:0], u[:0], 1e-3, 3)
+    assert e.shape == (0, p.nx)
+    assert p.launch_count() > 0 and p.last_kernel_ms() >= 0.0
+
+
+def test_single_sample_concept_api(oracle_built):
+    from reak_b200.propagator import singularity_error  # noqa: F401
+    p = _make("crs6")
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 1, seed=9)
+    xd = p.get_state_derivative(None, x[0], u[0], 0.0)
+    assert rel_err(xd, O.eval(x, u)[0][0]) < TOL_STEP
+    p.set_time_step(2e-3)
+    xn = p.get_next_state(None, x[0], u[0], 0.0)
+    assert rel_err(xn, O.rk4(x, u, 2e-3, 1)[0][0]) < TOL_STEP
+    with pytest.raises(IndexError):
+        p.get_state_derivative(None, x[0][:-1], u[0])
+    with pytest.raises(IndexError):
+        p.get_state_derivative(None, x[0], u[0][:-1])
+
+
+def test_singular_mass_matrix_sets_status():
+    """A massless chain has a singular M: the reference throws singularity_error
+    (mat_cholesky.hpp:80-82); the batch path reports it per sample."""
+    s = presets.crs_chain(n_revolute=2)
+    for k in s.chain.getKTEs():
+        if isinstance(k, kte.inertia_gen):
+            k.mMass = 0.0
+        if isinstance(k, kte.inertia_3D):
+            k.mMass, k.mInertiaTensor = 0.0, [0.0] * 6
+    from reak_b200 import kte_batch_propagator, _abi
+    p = kte_batch_propagator(s)
+    x, u = random_batch(p.compiled, 5, seed=1)
+    _, st = p.get_state_derivatives(x, u)
+    assert (st & _abi.STATUS_SINGULAR).all()
+    from reak_b200.propagator import singularity_error
+    with pytest.raises(singularity_error):
+        p.get_state_derivative(None, x[0], u[0])
+
+
+def test_steer_batch(oracle_built):
+    p = _make("crs6")
+    O = oracle_built.Oracle(p.compiled)
+    rng = np.random.default_rng(77)
+    P, R, K = 6, 37, 10
+    x0, _ = random_batch(p.compiled, P, seed=21)
+    goal, _ = random_batch(p.compiled, P, seed=22)
+    u = rng.uniform(-5, 5, (P, R, p.nu))
+    idx, bx, bc, st = p.steer_batch(x0, goal, u, 1e-3, K, want_status=True)
+    xe, _, _ = O.rk4(np.repeat(x0, R, axis=0), u.reshape(P * R, -1), 1e-3, K)
+    cost = np.linalg.norm(xe.reshape(P, R, -1) - goal[:, None, :], axis=2)
+    assert np.array_equal(idx, cost.argmin(axis=1))
+    assert rel_err(bx, xe.reshape(P, R, -1)[np.arange(P), idx]) < TOL_STEP
+    assert rel_err(bc, cost.min(axis=1)) < TOL_STEP
+    assert st.shape == (P, R) and not st.any()
+
+
+def test_full_size_properties():
+    """At BASELINE config 2's size (2^20 states) the oracle cannot follow; check size-independent
+    properties instead: a strided sub-batch reproduces the big batch bit for bit, two half-length
+    rollouts compose to the full one bit for bit, and integrating back with -dt returns to the start."""
+    p = _make("crs6")
+    N = 1 << 20
+    x, u = random_batch(p.compiled, N, seed=12346)
+    full, st = p.get_next_states(x, u, 1e-3, 20)
+    assert not st.any() and np.isfinite(full).all()
+    sel = np.arange(0, N, 4099)
+    sub, _ = p.get_next_states(x[sel], u[sel], 1e-3, 20)
+    assert np.array_equal(sub, full[sel])
+    half, _ = p.get_next_states(x, u, 1e-3, 10)
+    two, _ = p.get_next_states(half, u, 1e-3, 10)
+    assert np.array_equal(two, full)
+    back, _ = p.get_next_states(full, u, -1e-3, 20)
+    assert rel_err(back, x) < 1e-9
