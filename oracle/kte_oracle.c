@@ -900,6 +900,18 @@ int kto_gen_forces(void* h, size_t N, const double* x, const double* u, double* 
   return 0;
 }
 
+/* doMotion / clearForce / doForce with caller-chosen q_ddot (the demo of ctrl/mbd_kte/test_bm.cpp:103-121
+ * evaluates the chain at q_ddot = 0 and q_ddot = 1 to read the mass matrix off the force difference) */
+int kto_gen_forces_qdd(void* h, const double* x, const double* u, const double* qdd, double* f) {
+  model* m = (model*)h;
+  int k;
+  apply_states_and_inputs(m, x, u);
+  for (k = 0; k < m->n; ++k) m->c[k].qdd = qdd[k];
+  do_motion(m); clear_force(m); do_force(m);
+  for (k = 0; k < m->n; ++k) f[k] = m->c[k].f;
+  return 0;
+}
+
 int kto_mass(void* h, size_t N, const double* x, double* M, double* Mdot) {
   model* m = (model*)h;
   const int nx = 2 * m->n, nn = m->n * m->n;

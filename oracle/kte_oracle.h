@@ -16,6 +16,7 @@ void*  kto_create(const rkb_chain_desc* desc);
 void   kto_destroy(void* h);
 int    kto_eval(void* h, size_t n, const double* x, const double* u, double* xdot, int32_t* status);
 int    kto_gen_forces(void* h, size_t n, const double* x, const double* u, double* f);
+int    kto_gen_forces_qdd(void* h, const double* x, const double* u, const double* qdd, double* f);
 int    kto_mass(void* h, size_t n, const double* x, double* M, double* Mdot);
 int    kto_frames(void* h, const double* x, const double* u, double* out);
 /* returns wall seconds (< 0 on failure); n_workers > 1 forks worker processes */

@@ -115,3 +115,33 @@ class Oracle(_Checker):
 
     def __init__(self, compiled):
         _Checker.__init__(self, ORACLE_SO, "kto_", compiled)
+        self.lib.kto_gen_forces_qdd.argtypes = [C.c_void_p] * 5
+        self.lib.kto_tmt.argtypes = [C.c_void_p] * 5
+
+    def gen_forces_qdd(self, x, u, qdd):
+        """gen_coord::f of one state with a caller-chosen q_ddot (test_bm.cpp:103-121)."""
+        x, u, _ = self._xu(x, u)
+        qdd = np.ascontiguousarray(qdd, dtype=np.float64).reshape(self.n)
+        f = np.empty(self.n)
+        self.lib.kto_gen_forces_qdd(self.h, _dp(x[0].copy()), _dp(u[0].copy()), _dp(qdd), _dp(f))
+        return f
+
+    def tmt(self, x):
+        """(Tcm, Mcm, Tcm_dot) of mass_matrix_calc::get_TMT_TdMT for one state."""
+        x, _, _ = self._xu(x, None)
+        rows = self.lib.kto_tmt(self.h, _dp(x[0].copy()), None, None, None)
+        T, Mc, Td = np.zeros((rows, self.n)), np.zeros((rows, rows)), np.zeros((rows, self.n))
+        self.lib.kto_tmt(self.h, _dp(x[0].copy()), _dp(T), _dp(Mc), _dp(Td))
+        return T, Mc, Td
+
+
+def cholesky_solve(A, b, tol=1e-8, ldl=False):
+    """linsolve_Cholesky / the LDL variant of core/lin_alg/mat_cholesky.hpp on a dense system; returns (x, singular)."""
+    lib = C.CDLL(ORACLE_SO)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.array(b, dtype=np.float64)
+    b2 = np.ascontiguousarray(b.reshape(A.shape[0], -1)).copy()
+    fn = lib.kto_ldl_solve if ldl else lib.kto_cholesky_solve
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    rc = fn(A.shape[0], _dp(A), _dp(b2), b2.shape[1], float(tol))
+    return b2.reshape(b.shape), rc

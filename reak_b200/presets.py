@@ -153,6 +153,56 @@ def torsion_1dof_chain():
     return s
 
 
+def crs_linear_spring_chain():
+    """6-DOF arm with two-anchor linear elements (spring.cpp:178-207, damper.cpp:136-149): a spring
+    from the robot base to the end of link 3, a saturating spring between links 1 and 5 and a
+    damper between the ends of links 2 and 6.  Exercises the interpreter kernels."""
+    s = crs_chain(physical=True)
+    ends = [k.mEnd for k in s.chain.getKTEs() if isinstance(k, kte.rigid_link_3D)]
+    base = s.chain.getKTEs()[2].mBase  # base frame of joint_0 (chain order: actuator, rotor, joint, ...)
+    s.chain << kte.spring_3D("spring_a", base, ends[2], 0.3, 50.0)
+    s.chain << kte.spring_3D("spring_b", ends[0], ends[4], 0.1, 400.0, 20.0)
+    s.chain << kte.damper_3D("damper_a", ends[1], ends[5], 2.0)
+    return s
+
+
+def planar_linear_spring_chain():
+    """3-link planar arm with spring_2D / damper_2D between the base and the tip and a saturating
+    spring between link ends (spring.cpp:116-143, damper.cpp:88-102)."""
+    s = planar_chain(lengths=(0.5, 0.4, 0.3), masses=(1.0, 0.8, 0.5), moments=(0.1, 0.05, 0.02), actuated=True)
+    ends = [k.mEnd for k in s.chain.getKTEs() if isinstance(k, kte.rigid_link_2D)]
+    base = [k for k in s.chain.getKTEs() if isinstance(k, kte.revolute_joint_2D)][0].mBase
+    s.chain << kte.spring_2D("spring_a", base, ends[2], 0.4, 30.0)
+    s.chain << kte.spring_2D("spring_b", ends[0], ends[2], 0.2, 500.0, 15.0)
+    s.chain << kte.damper_2D("damper_a", base, ends[1], 1.5)
+    return s
+
+
+def planar_prismatic_revolute_chain():
+    """prismatic_joint_2D (axis x) -> link -> inertia_2D -> revolute_joint_2D -> link -> inertia_2D,
+    both actuated, base tilted by 0.3 rad (prismatic_joint.cpp:33-123)."""
+    s = kte_system("planar_pr")
+    base = kte.frame_2D()
+    base.Acceleration = [0.0, 9.81]
+    base.Rotation = 0.3
+    c0, j0, e0, f0 = kte.gen_coord(), kte.jacobian_gen_2D(), kte.frame_2D(), kte.frame_2D()
+    slide = kte.prismatic_joint_2D("slide", c0, (1.0, 0.0), base, e0, j0)
+    a0 = kte.driving_actuator_gen("slide_act", c0, slide)
+    s.chain << a0 << slide << kte.rigid_link_2D("cart", e0, f0, kte.pose_2D((0.0, 0.1), 0.2))
+    m0 = kte.inertia_2D("cart_mass", kte.joint_dependent_frame_2D(f0, {c0: j0}), 2.0, 0.3)
+    s.chain << m0
+    c1, j1, e1, f1 = kte.gen_coord(), kte.jacobian_gen_2D(), kte.frame_2D(), kte.frame_2D()
+    pin = kte.revolute_joint_2D("pin", c1, f0, e1, j1)
+    a1 = kte.driving_actuator_gen("pin_act", c1, pin)
+    s.chain << a1 << pin << kte.rigid_link_2D("rod", e1, f1, kte.pose_2D((0.6, 0.0), 0.0))
+    m1 = kte.inertia_2D("bob", kte.joint_dependent_frame_2D(f1, {c0: j0, c1: j1}), 0.7, 0.04)
+    s.chain << m1
+    s.dofs_gen += [c0, c1]
+    s.inputs += [a0, a1]
+    s.mass_calc << m0 << m1 << c0 << c1
+    return s
+
+
 PRESETS = {
     "pendulum": pendulum_chain,
     "planar2": planar_chain,                                          # cfg 1
@@ -169,6 +219,9 @@ PRESETS = {
     "torsion1": torsion_1dof_chain,
     "crs3": lambda: crs_chain(n_revolute=3),
     "crs6_passive": lambda: crs_chain(actuated=False),
+    "crs6_lin_sd": crs_linear_spring_chain,
+    "planar2_lin_sd": planar_linear_spring_chain,
+    "planar_pr": planar_prismatic_revolute_chain,
 }
 
 

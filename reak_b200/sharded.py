@@ -1,0 +1,90 @@
+"""Sample-sharded propagation over the GPUs of one box: one process per GPU (torch.distributed),
+contiguous block partition by sample index (pairs, for the steer batch), NO communication while
+integrating, and one all-gather of the end states at the end — NCCL over NVLink/NVSwitch on GPUs,
+gloo in the CPU tests.  The reference has no counterpart (it is single-threaded); the semantics
+per sample are those of kte_batch_propagator.get_next_states / steer_batch.
+"""
+import numpy as np
+
+
+def shard_bounds(n, rank, world):
+    """[lo, hi) of the contiguous block of `n` samples owned by `rank` (sizes differ by at most 1)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _all_gather_rows(local, n_total, group=None):
+    """All-gather row blocks of unequal length (block partition of n_total rows) into the full array.
+    `local` is a torch tensor [rows_of_this_rank, ...] on the device the backend communicates from."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+    assert local.shape[0] == sizes[rank]
+    cap = max(sizes) if sizes else 0
+    tail = tuple(local.shape[1:])
+    if min(sizes) == cap:
+        out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    padded = torch.zeros((cap,) + tail, dtype=local.dtype, device=local.device)
+    padded[: sizes[rank]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class sharded_propagator(object):
+    """Wraps one kte_batch_propagator per rank.  Every rank passes the same full-batch arrays (or
+    only its own block with `local_input=True`); results come back as the full batch on every rank."""
+
+    def __init__(self, propagator, group=None, comm_device=None):
+        self.prop, self.group = propagator, group
+        dist = _dist()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.comm_device = comm_device  # torch device the collective runs from (cuda:k for NCCL, cpu for gloo)
+
+    def _to_comm(self, a, dtype):
+        import torch
+        if type(a).__module__.startswith("torch"):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        t = t.to(dtype)
+        return t.to(self.comm_device) if self.comm_device is not None else t
+
+    def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None):
+        """Returns (x_out[n_total][nx], status[n_total]) gathered on every rank (torch tensors on the
+        communication device).  `compute(x_block, u_block, dt, n_steps) -> (x_out, status)` defaults to
+        the wrapped propagator's GPU rollout."""
+        import torch
+        compute = compute or self.prop.get_next_states
+        if local_input:
+            if n_total is None:
+                raise ValueError("n_total is required with local_input")
+            xb, ub = x, u
+        else:
+            n_total = x.shape[0]
+            lo, hi = shard_bounds(n_total, self.rank, self.world)
+            xb, ub = x[lo:hi], (u[lo:hi] if u is not None else None)
+        xo, st = compute(xb, ub, dt, n_steps)
+        xo_t, st_t = self._to_comm(xo, torch.float64), self._to_comm(st, torch.int32)
+        return _all_gather_rows(xo_t, n_total, self.group), _all_gather_rows(st_t, n_total, self.group)
+
+    def steer_batch(self, x0, goal, u, dt, n_steps, compute=None):
+        """Pairs are never split across ranks, so the per-pair arg-min stays on one device; only
+        (best_idx, best_x, best_cost) per pair travel."""
+        import torch
+        compute = compute or self.prop.steer_batch
+        P = x0.shape[0]
+        lo, hi = shard_bounds(P, self.rank, self.world)
+        idx, bx, bc = compute(x0[lo:hi], goal[lo:hi], u[lo:hi], dt, n_steps)[:3]
+        return (_all_gather_rows(self._to_comm(idx, torch.int32), P, self.group),
+                _all_gather_rows(self._to_comm(bx, torch.float64), P, self.group),
+                _all_gather_rows(self._to_comm(bc, torch.float64), P, self.group))

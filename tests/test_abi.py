@@ -1,0 +1,120 @@
+"""CPU tests of the drop-in boundary: libreak_b200.so loads, exports every symbol include/reak_b200.h
+declares, validates/lower descriptors on the host, and refuses to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from reak_b200 import _abi, kte, presets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "reak_b200.h")).read()
+    return sorted(set(re.findall(r"RKB_API[^;(]*?\b(rkb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _abi.SYMBOLS, "ctypes table misses %s" % n
+    assert lib.rkb_version() == 100
+    assert lib.rkb_strerror(0) == b"ok" and b"CPU fallback" in lib.rkb_strerror(_abi.ERR_CUDA)
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_abi.rkb_element) == 128
+    assert C.sizeof(_abi.rkb_base_frame) == 19 * 8
+    assert _abi.rkb_chain_desc.elements.offset == 24 + 19 * 8
+
+
+def _create(desc):
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    rc = lib.rkb_chain_create(C.byref(desc), C.byref(h))
+    return rc, h
+
+
+SERIAL = {"crs6", "crs6_phys", "crs6_sd", "crs6_sd_sat", "crs6_twist", "crs7", "crs7_phys_sd", "torsion1", "crs3", "crs6_passive"}
+
+
+@pytest.mark.parametrize("name", sorted(presets.PRESETS))
+def test_chain_create_and_lowering(name):
+    lib = _abi.load_library()
+    s = presets.make(name)
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    rc, h = _create(c.desc)
+    assert rc == 0
+    assert lib.rkb_chain_dof(h) == c.n_coords
+    assert lib.rkb_chain_state_dim(h) == 2 * c.n_coords
+    assert lib.rkb_chain_input_dim(h) == c.n_inputs
+    assert lib.rkb_chain_is_serial(h) == (1 if name in SERIAL else 0)
+    lib.rkb_chain_destroy(h)
+
+
+def test_malformed_descriptors_are_rejected():
+    lib = _abi.load_library()
+    s = presets.make("crs3")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    assert lib.rkb_chain_create(None, C.byref(C.c_void_p())) == _abi.ERR_INVALID
+    saved = c.desc.n_frames
+    c.desc.n_frames = 2  # frame ids out of range
+    assert _create(c.desc)[0] == _abi.ERR_INVALID
+    c.desc.n_frames = saved
+    kind = c.elements[3].kind
+    c.elements[3].kind = 99
+    assert _create(c.desc)[0] == _abi.ERR_INVALID
+    c.elements[3].kind = _abi.FREE_3D  # free joints are reserved, not compiled
+    assert _create(c.desc)[0] == _abi.ERR_UNSUPPORTED
+    c.elements[3].kind = kind
+    c.elements[2].p[0] = float("nan")
+    assert _create(c.desc)[0] == _abi.ERR_INVALID
+    c.elements[2].p[0] = 0.0
+    c.desc.n_inputs = c.desc.n_inputs + 1  # an input nobody drives
+    assert _create(c.desc)[0] == _abi.ERR_INVALID
+    c.desc.n_inputs -= 1
+    assert _create(c.desc)[0] == 0
+
+
+def test_argument_errors_without_touching_the_gpu():
+    lib = _abi.load_library()
+    s = presets.make("crs3")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    rc, h = _create(c.desc)
+    x = np.zeros((4, 6)); u = np.zeros((4, 3)); o = np.zeros((4, 6))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.rkb_rollout_rk4(h, 0, 4, p(x), p(u), 0.0, 3, p(o), None, 0, None) == _abi.ERR_INTEGRATION
+    assert lib.rkb_rollout_rk4(h, 0, 4, p(x), p(u), 1e-3, -1, p(o), None, 0, None) == _abi.ERR_INTEGRATION
+    assert lib.rkb_rollout_rk4(h, 0, 4, None, p(u), 1e-3, 1, p(o), None, 0, None) == _abi.ERR_INVALID
+    assert lib.rkb_rollout_rk4(h, 0, 0, None, None, 1e-3, 1, None, None, 0, None) == 0  # empty batch is a no-op
+    assert lib.rkb_eval(None, 0, 4, p(x), p(u), p(o), None, 0, None) == _abi.ERR_INVALID
+    assert lib.rkb_launch_count(h) == 0 and lib.rkb_last_kernel_ms(h) < 0
+    lib.rkb_chain_destroy(h)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from reak_b200 import kte_batch_propagator
+    p = kte_batch_propagator(presets.make("crs6"))
+    with pytest.raises(_abi.RkbError) as e:
+        p.get_state_derivatives(np.zeros((2, 12)), np.zeros((2, 6)))
+    assert e.value.code == _abi.ERR_CUDA
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "reak_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) :
+                text = open(os.path.join(dirpath, f)).read()
+                for line in text.splitlines():
+                    code = line.split("#")[0].split("//")[0]
+                    assert "oracle" not in code.lower() or "import" not in code and "include" not in code, (f, line)

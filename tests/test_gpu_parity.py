@@ -59,6 +59,26 @@ def test_eval_forces_mass(name, oracle_built):
         assert rel_err(p.get_mass_matrices(x), M_o) < TOL_STEP, (name, label)
 
 
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_against_golden_reference_vectors(name):
+    """tests/golden/*.npz hold outputs of the unmodified reference (see tests/golden/make_golden.py)."""
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    if not os.path.isfile(path):
+        pytest.skip("no fixture for " + name)
+    g = np.load(path)
+    for label, p in _variants(name):
+        xd, st = p.get_state_derivatives(g["x"], g["u"])
+        assert not st.any() and rel_err(xd, g["xdot"]) < TOL_STEP, (name, label)
+        assert rel_err(p.get_gen_forces(g["x"], g["u"]), g["f"]) < TOL_STEP, (name, label)
+        M, Md = p.get_mass_matrices(g["x"], with_derivative=True)
+        assert rel_err(M, g["M"]) < TOL_STEP and rel_err(Md, g["Mdot"]) < TOL_STEP, (name, label)
+        assert rel_err(p.get_next_states(g["x"], g["u"], 1e-3, 1)[0], g["x1"]) < TOL_STEP, (name, label)
+        assert rel_err(p.get_next_states(g["x"], g["u"], 1e-3, 25)[0], g["x25"]) < TOL_LONG, (name, label)
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_rk4_one_and_many_steps(name, oracle_built):
     for label, p in _variants(name):

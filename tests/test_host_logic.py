@@ -1,0 +1,71 @@
+"""CPU tests of the host-side mirror of the ReaK::kte modelling API and its chain compiler."""
+import numpy as np
+import pytest
+
+from reak_b200 import _abi, kte, presets
+
+
+def test_crs_descriptor_shape():
+    s = presets.make("crs6")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    assert (c.dim, c.n_coords, c.n_inputs) == (3, 6, 6)
+    kinds = [e.kind for e in c.elements]
+    # CRS_A465_models.cpp:748-788 chain order: actuator, rotor inertia, joint, link, link inertia
+    assert kinds[:5] == [_abi.ACTUATOR_GEN, _abi.INERTIA_GEN, _abi.REVOLUTE_3D, _abi.RIGID_LINK_3D, _abi.INERTIA_3D]
+    inertias = [e for e in c.elements if e.kind == _abi.INERTIA_3D]
+    assert [e.upstream for e in inertias] == [(1 << (k + 1)) - 1 for k in range(6)]
+    acts = [e for e in c.elements if e.kind == _abi.ACTUATOR_GEN]
+    assert [a.aux for a in acts] == list(range(6))
+    assert all(c.elements[a.frame_b].kind == _abi.REVOLUTE_3D and c.elements[a.frame_b].coord == a.coord for a in acts)
+    assert abs(c.desc.base.acceleration[2] - 9.81) < 1e-15 and c.desc.base.position[1] == -3.3
+
+
+def test_state_layout_follows_dofs_order():
+    s = presets.make("crs3")
+    s.dofs_gen.reverse()
+    s.mass_calc.mCoords.reverse()
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    joints = [e for e in c.elements if e.kind == _abi.REVOLUTE_3D]
+    assert [j.coord for j in joints] == [2, 1, 0]
+
+
+def test_unsupported_chains_raise():
+    s = presets.make("crs3")
+    with pytest.raises(kte.UnsupportedChain):
+        kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen[:-1], s.inputs)
+    with pytest.raises(kte.UnsupportedChain):
+        kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs[:-1])
+    s2 = presets.make("crs3")
+    s2.chain << kte.kte_map("mystery")
+    with pytest.raises(kte.UnsupportedChain):
+        kte.compile_chain(s2.chain, s2.mass_calc, s2.dofs_gen, s2.inputs)
+    s3 = presets.make("crs3")
+    s3.chain << kte.rigid_link_2D("flat", kte.frame_2D(), kte.frame_2D(), kte.pose_2D())
+    with pytest.raises(kte.UnsupportedChain):
+        kte.compile_chain(s3.chain, s3.mass_calc, s3.dofs_gen, s3.inputs)
+    with pytest.raises(TypeError):
+        kte.mass_matrix_calc() << kte.frame_3D()
+
+
+def test_axis_angle_quaternion():
+    """core/kinetostatics/unit_test_rotations.cpp:257-330: 45 degrees about z."""
+    q = kte.axis_angle_quat(np.pi / 4, (0.0, 0.0, 2.0))
+    assert np.allclose(q, [np.cos(np.pi / 8), 0.0, 0.0, np.sin(np.pi / 8)], atol=1e-16)
+
+
+def test_propagator_argument_checks():
+    from reak_b200 import kte_batch_propagator
+    p = kte_batch_propagator(presets.make("crs6"))
+    assert (p.get_state_dimensions(), p.get_input_dimensions(), p.get_output_dimensions()) == (12, 6, 0)
+    assert p.is_serial()
+    with pytest.raises(IndexError):
+        p.get_state_derivatives(np.zeros((3, 11)), np.zeros((3, 6)))
+    with pytest.raises(IndexError):
+        p.get_state_derivatives(np.zeros((3, 12)), np.zeros((2, 6)))
+    with pytest.raises(IndexError):
+        p.get_state_derivatives(np.zeros((3, 12)))  # inputs are required when the chain has actuators
+    from reak_b200.propagator import impossible_integration
+    with pytest.raises(impossible_integration):
+        p.get_next_states(np.zeros((3, 12)), np.zeros((3, 6)), 0.0, 1)
+    with pytest.raises(IndexError):
+        p.steer_batch(np.zeros((2, 12)), np.zeros((2, 12)), np.zeros((2, 5, 4)))

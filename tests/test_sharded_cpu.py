@@ -1,0 +1,93 @@
+"""world_size-2 gloo test of the N > 1 path: block partition by sample index, no data-path
+collective, one all-gather of the end states.  The per-rank compute is injected (the oracle
+stands in for the GPU rollout here: this test covers the host-side sharding logic only)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import pyref
+    from reak_b200 import kte, presets
+    from reak_b200.sharded import shard_bounds, sharded_propagator
+    from conftest import random_batch
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    s = presets.make("crs3")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    O = pyref.Oracle(c)
+    x, u = random_batch(c, n_total, seed=31)
+
+    def compute(xb, ub, dt, k):
+        xo, st, _ = O.rk4(xb, ub, dt, k)
+        return xo, st
+
+    sp = sharded_propagator(None, comm_device=None)
+    full, st = sp.get_next_states(x, u, 1e-3, 5, compute=compute)
+    lo, hi = shard_bounds(n_total, rank, world)
+    loc, st2 = sp.get_next_states(x[lo:hi], u[lo:hi], 1e-3, 5, local_input=True, n_total=n_total, compute=compute)
+    assert np.array_equal(full.numpy(), loc.numpy()) and np.array_equal(st.numpy(), st2.numpy())
+
+    # steer: pairs are sharded, rollouts of a pair stay together
+    P, R = 5, 7
+    rng = np.random.default_rng(5)
+    x0, goal, uu = x[:P], x[P:2 * P], rng.uniform(-2, 2, (P, R, c.n_inputs))
+
+    def steer(x0b, gb, ub, dt, k):
+        p = x0b.shape[0]
+        xe, _, _ = O.rk4(np.repeat(x0b, R, axis=0), ub.reshape(p * R, -1), dt, k)
+        cost = np.linalg.norm(xe.reshape(p, R, -1) - gb[:, None, :], axis=2)
+        idx = cost.argmin(axis=1).astype(np.int32)
+        return idx, xe.reshape(p, R, -1)[np.arange(p), idx], cost.min(axis=1)
+
+    idx, bx, bc = sp.steer_batch(x0, goal, uu, 1e-3, 3, compute=steer)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), full=full.numpy(), st=st.numpy(), idx=idx.numpy(), bx=bx.numpy(), bc=bc.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [64, 37])
+def test_two_rank_gloo_gather(n_total, tmp_path, oracle_built):
+    import torch.multiprocessing as mp
+    from oracle import pyref
+    from reak_b200 import kte, presets
+    from conftest import random_batch
+
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    s = presets.make("crs3")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    x, u = random_batch(c, n_total, seed=31)
+    want, st, _ = pyref.Oracle(c).rk4(x, u, 1e-3, 5)
+    got = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    for g in got:
+        assert np.array_equal(g["full"], want) and not g["st"].any()
+    assert np.array_equal(got[0]["idx"], got[1]["idx"]) and np.array_equal(got[0]["bx"], got[1]["bx"])
+    assert got[0]["idx"].shape == (5,) and got[0]["bx"].shape == (5, 6)
+
+
+def test_shard_bounds_cover_everything():
+    from reak_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 64, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
