@@ -145,6 +145,10 @@ RKB_API int  rkb_chain_dof(const rkb_chain* chain);
 /* 1 when the chain was lowered to the register-resident serial-chain kernels, 0 when it runs on
  * the interpreter kernels (any element order, 2D frames, two-anchor springs/dampers). */
 RKB_API int  rkb_chain_is_serial(const rkb_chain* chain);
+/* Structure found in the descriptor (axis-aligned joints, axis-aligned unrotated links, diagonal
+ * inertia tensors; 8 bits per stage) and the part of it the selected kernels are specialised on. */
+RKB_API unsigned long long rkb_chain_shape(const rkb_chain* chain);
+RKB_API unsigned long long rkb_chain_kernel_shape(const rkb_chain* chain);
 
 /* xdot[i] = get_state_derivative(x[i], u[i]).  x: N x 2n, u: N x n_inputs, xdot: N x 2n,
  * status: N (nullable).  `stream` is a cudaStream_t (NULL = default stream). */

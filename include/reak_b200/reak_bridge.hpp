@@ -1,0 +1,293 @@
+// reak_bridge.hpp — the reference-side binding: turns LIVE ReaK objects into the flat chain
+// descriptor of reak_b200.h and wraps the GPU propagator in a class that models ReaK's
+// state-space-system concepts with ReaK's own types.  Needs the ReaK headers on the include path
+// (this is the one header of the repo that does); it uses public accessors only, so it compiles
+// against an unmodified ReaK tree.
+//
+//   reak_b200::compile_kte_system(sys)   walks kte_nl_system::chain->getKTEs()
+//                                        (ctrl/mbd_kte/kte_map_chain.hpp:59) the way
+//                                        ctrl/mbd_kte/kte_chain_visitation.hpp:39-84 does, reading
+//                                        joints, links, inertias (+ their mUpStreamJoints maps,
+//                                        jacobian_joint_map.hpp:76-331), springs, dampers and
+//                                        driving actuators through their accessors.
+//   ReaK::ctrl::kte_batch_system         SSSystemConcept + DiscreteSSSConcept on vect_n<double>,
+//                                        drop-in where kte_nl_system / num_int_dtnl_sys are used
+//                                        (e.g. runge_kutta4_integrate_impl, sys_integrators/
+//                                        runge_kutta4_integrator_sys.hpp:50-97), plus the batched calls.
+#ifndef REAK_B200_REAK_BRIDGE_HPP
+#define REAK_B200_REAK_BRIDGE_HPP
+
+#include <map>
+#include <stdexcept>
+#include <vector>
+
+#include <ReaK/core/lin_alg/vect_alg.hpp>
+#include <ReaK/core/lin_alg/mat_num_exceptions.hpp>
+#include <ReaK/core/kinetostatics/kinetostatics.hpp>
+#include <ReaK/ctrl/mbd_kte/kte_map_chain.hpp>
+#include <ReaK/ctrl/mbd_kte/revolute_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/prismatic_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/rigid_link.hpp>
+#include <ReaK/ctrl/mbd_kte/inertia.hpp>
+#include <ReaK/ctrl/mbd_kte/spring.hpp>
+#include <ReaK/ctrl/mbd_kte/damper.hpp>
+#include <ReaK/ctrl/mbd_kte/torsion_spring.hpp>
+#include <ReaK/ctrl/mbd_kte/torsion_damper.hpp>
+#include <ReaK/ctrl/mbd_kte/driving_actuator.hpp>
+#include <ReaK/ctrl/mbd_kte/mass_matrix_calculator.hpp>
+#include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
+
+#include "kte_batch_propagator.hpp"
+
+namespace reak_b200 {
+
+class unsupported_chain : public std::runtime_error {
+ public:
+  explicit unsupported_chain(const std::string& what) : std::runtime_error("reak_b200: " + what) {}
+};
+
+namespace detail {
+
+struct id_map {
+  std::map<const void*, int> ids;
+  int lookup(const void* p) const {
+    std::map<const void*, int>::const_iterator it = ids.find(p);
+    return it == ids.end() ? -1 : it->second;
+  }
+};
+
+template <typename JointMap>
+std::uint64_t upstream_mask(const JointMap& m, const id_map& coords) {
+  std::uint64_t mask = 0;
+  for (typename JointMap::const_iterator it = m.begin(); it != m.end(); ++it) {
+    int c = coords.lookup(it->first.get());
+    if (c < 0) throw unsupported_chain("an inertia depends on a coordinate that is not a system dof");
+    mask |= std::uint64_t(1) << c;
+  }
+  return mask;
+}
+
+}  // namespace detail
+
+/// Flatten (chain, mass_calc, dofs_gen, inputs) — the public members of kte_nl_system
+/// (kte_nl_system.hpp:70-78) — into a chain_builder.  State slot j <-> dofs_gen[j]
+/// (kte_nl_system.hpp:189-193); input k <-> inputs[k] (kte_nl_system.hpp:221-224).
+inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
+  using namespace ReaK;
+  using namespace ReaK::kte;
+  using ReaK::rtti::rk_dynamic_ptr_cast;
+  if (!sys.chain || !sys.mass_calc) throw unsupported_chain("kte_nl_system without chain or mass_calc");
+  if (!sys.dofs_2D.empty() || !sys.dofs_3D.empty()) throw unsupported_chain("free-frame dofs are outside the compiled path");
+  if (sys.mass_calc->Coords().size() != sys.dofs_gen.size()) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
+  detail::id_map coords, inputs, frames, elems;
+  for (std::size_t i = 0; i < sys.dofs_gen.size(); ++i) {
+    if (sys.mass_calc->Coords()[i] != sys.dofs_gen[i]) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
+    coords.ids[sys.dofs_gen[i].get()] = static_cast<int>(i);
+  }
+  int n_inputs = 0;
+  for (std::size_t i = 0; i < sys.inputs.size(); ++i) {
+    if (sys.inputs[i]->getInputCount() != 1) throw unsupported_chain("only single-input driving_actuator_gen inputs are compiled");
+    inputs.ids[sys.inputs[i].get()] = n_inputs++;
+  }
+  const std::vector<shared_ptr<kte_map> >& ktes = sys.chain->getKTEs();
+  int dim = 0;
+  for (std::size_t e = 0; e < ktes.size() && !dim; ++e) {
+    if (rk_dynamic_ptr_cast<revolute_joint_3D>(ktes[e]) || rk_dynamic_ptr_cast<prismatic_joint_3D>(ktes[e]) ||
+        rk_dynamic_ptr_cast<rigid_link_3D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_3D>(ktes[e])) dim = 3;
+    else if (rk_dynamic_ptr_cast<revolute_joint_2D>(ktes[e]) || rk_dynamic_ptr_cast<prismatic_joint_2D>(ktes[e]) ||
+             rk_dynamic_ptr_cast<rigid_link_2D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_2D>(ktes[e])) dim = 2;
+  }
+  if (!dim) throw unsupported_chain("chain has no 2D or 3D element");
+  chain_builder b(dim);
+  for (std::size_t i = 0; i < sys.dofs_gen.size(); ++i) b.add_coord();
+  std::map<int, int> written;  // frame id -> 1 when some element's doMotion writes it
+  struct local {
+    static int fid(chain_builder& bb, detail::id_map& fr, const void* p) {
+      if (!p) throw unsupported_chain("element with a null frame");
+      int id = fr.lookup(p);
+      if (id < 0) { id = bb.add_frame(); fr.ids[p] = id; }
+      return id;
+    }
+    static int cid(const detail::id_map& co, const void* p) {
+      int id = co.lookup(p);
+      if (id < 0) throw unsupported_chain("element refers to a coordinate that is not a system dof");
+      return id;
+    }
+  };
+  std::vector<std::pair<int, const void*> > pending_actuators;  // (element index, joint object)
+  const void* base3 = NULL;
+  std::map<int, const void*> frame_obj;
+  for (std::size_t e = 0; e < ktes.size(); ++e) {
+    const shared_ptr<kte_map>& k = ktes[e];
+    int idx = -1;
+    if (shared_ptr<revolute_joint_3D> j = rk_dynamic_ptr_cast<revolute_joint_3D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      vect<double, 3> a = j->Axis();
+      idx = b.revolute_joint_3D(local::cid(coords, j->Angle().get()), a[0], a[1], a[2], fa, fb);
+    } else if (shared_ptr<prismatic_joint_3D> j = rk_dynamic_ptr_cast<prismatic_joint_3D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      vect<double, 3> a = j->Axis();
+      idx = b.prismatic_joint_3D(local::cid(coords, j->Coord().get()), a[0], a[1], a[2], fa, fb);
+    } else if (shared_ptr<revolute_joint_2D> j = rk_dynamic_ptr_cast<revolute_joint_2D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      idx = b.revolute_joint_2D(local::cid(coords, j->Angle().get()), fa, fb);
+    } else if (shared_ptr<prismatic_joint_2D> j = rk_dynamic_ptr_cast<prismatic_joint_2D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      vect<double, 2> a = j->Axis();
+      idx = b.prismatic_joint_2D(local::cid(coords, j->Coord().get()), a[0], a[1], fa, fb);
+    } else if (shared_ptr<rigid_link_3D> l = rk_dynamic_ptr_cast<rigid_link_3D>(k)) {
+      int fa = local::fid(b, frames, l->BaseFrame().get()), fb = local::fid(b, frames, l->EndFrame().get());
+      frame_obj[fa] = l->BaseFrame().get(); written[fb] = 1;
+      pose_3D<double> o = l->PoseOffset();
+      double p[3] = {o.Position[0], o.Position[1], o.Position[2]};
+      double q[4] = {o.Quat[0], o.Quat[1], o.Quat[2], o.Quat[3]};
+      idx = b.rigid_link_3D(fa, fb, p, q);
+    } else if (shared_ptr<rigid_link_2D> l = rk_dynamic_ptr_cast<rigid_link_2D>(k)) {
+      int fa = local::fid(b, frames, l->BaseFrame().get()), fb = local::fid(b, frames, l->EndFrame().get());
+      frame_obj[fa] = l->BaseFrame().get(); written[fb] = 1;
+      pose_2D<double> o = l->PoseOffset();
+      idx = b.rigid_link_2D(fa, fb, o.Position[0], o.Position[1], o.Rotation.getAngle());
+    } else if (shared_ptr<inertia_3D> in = rk_dynamic_ptr_cast<inertia_3D>(k)) {
+      int f = local::fid(b, frames, in->CenterOfMass()->mFrame.get());
+      frame_obj[f] = in->CenterOfMass()->mFrame.get();
+      mat<double, mat_structure::symmetric> I = in->InertiaTensor();
+      double t[6] = {I(0, 0), I(0, 1), I(0, 2), I(1, 1), I(1, 2), I(2, 2)};
+      idx = b.inertia_3D(f, in->Mass(), t, detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords));
+    } else if (shared_ptr<inertia_2D> in = rk_dynamic_ptr_cast<inertia_2D>(k)) {
+      int f = local::fid(b, frames, in->CenterOfMass()->mFrame.get());
+      frame_obj[f] = in->CenterOfMass()->mFrame.get();
+      idx = b.inertia_2D(f, in->Mass(), in->MomentOfInertia(), detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords));
+    } else if (shared_ptr<inertia_gen> in = rk_dynamic_ptr_cast<inertia_gen>(k)) {
+      int c = local::cid(coords, in->CenterOfMass()->mFrame.get());
+      if (detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords) != (std::uint64_t(1) << c))
+        throw unsupported_chain("inertia_gen must depend on its own coordinate only");
+      idx = b.inertia_gen(c, in->Mass());
+    } else if (shared_ptr<driving_actuator_gen> a = rk_dynamic_ptr_cast<driving_actuator_gen>(k)) {
+      int in = inputs.lookup(static_cast<system_input*>(a.get()));
+      if (in < 0) throw unsupported_chain("a driving actuator of the chain is not listed in the system inputs");
+      idx = b.driving_actuator_gen(local::cid(coords, a->Frame().get()), -1, in);
+      pending_actuators.push_back(std::make_pair(idx, static_cast<const void*>(a->Joint().get())));
+    } else if (shared_ptr<torsion_spring_3D> s = rk_dynamic_ptr_cast<torsion_spring_3D>(k)) {
+      idx = b.torsion_spring(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Stiffness(), s->Saturation());
+    } else if (shared_ptr<torsion_spring_2D> s = rk_dynamic_ptr_cast<torsion_spring_2D>(k)) {
+      idx = b.torsion_spring(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Stiffness(), s->Saturation());
+    } else if (shared_ptr<torsion_damper_3D> s = rk_dynamic_ptr_cast<torsion_damper_3D>(k)) {
+      idx = b.torsion_damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
+    } else if (shared_ptr<torsion_damper_2D> s = rk_dynamic_ptr_cast<torsion_damper_2D>(k)) {
+      idx = b.torsion_damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
+    } else if (shared_ptr<spring_3D> s = rk_dynamic_ptr_cast<spring_3D>(k)) {
+      idx = b.spring(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->RestLength(), s->Stiffness(), s->Saturation());
+    } else if (shared_ptr<spring_2D> s = rk_dynamic_ptr_cast<spring_2D>(k)) {
+      idx = b.spring(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->RestLength(), s->Stiffness(), s->Saturation());
+    } else if (shared_ptr<damper_3D> s = rk_dynamic_ptr_cast<damper_3D>(k)) {
+      idx = b.damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
+    } else if (shared_ptr<damper_2D> s = rk_dynamic_ptr_cast<damper_2D>(k)) {
+      idx = b.damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
+    } else {
+      throw unsupported_chain("KTE '" + k->getName() + "' is outside the compiled element set");
+    }
+    elems.ids[k.get()] = idx;
+  }
+  for (std::size_t i = 0; i < pending_actuators.size(); ++i) {
+    // the joint is addressed through its reacting_kte_gen base: find the chain element that is the same object
+    int j = -1;
+    for (std::size_t e = 0; e < ktes.size(); ++e)
+      if (static_cast<const void*>(rk_dynamic_ptr_cast<reacting_kte_gen>(ktes[e]).get()) == pending_actuators[i].second &&
+          pending_actuators[i].second)
+        j = elems.lookup(ktes[e].get());
+    if (j < 0) throw unsupported_chain("an actuator drives a joint that is not in the chain");
+    b.set_actuator_joint(pending_actuators[i].first, j);
+  }
+  // the root: the one frame no element writes
+  int root = -1, n_roots = 0;
+  for (std::map<const void*, int>::const_iterator it = frames.ids.begin(); it != frames.ids.end(); ++it)
+    if (!written.count(it->second)) { root = it->second; base3 = it->first; ++n_roots; }
+  if (n_roots != 1) throw unsupported_chain("the chain must have exactly one un-driven base frame");
+  rkb_base_frame bf = rkb_base_frame();
+  if (dim == 3) {
+    const frame_3D<double>* B = static_cast<const frame_3D<double>*>(base3);
+    for (int i = 0; i < 3; ++i) {
+      bf.position[i] = B->Position[i]; bf.velocity[i] = B->Velocity[i]; bf.ang_velocity[i] = B->AngVelocity[i];
+      bf.acceleration[i] = B->Acceleration[i]; bf.ang_acceleration[i] = B->AngAcceleration[i];
+    }
+    for (int i = 0; i < 4; ++i) bf.quat[i] = B->Quat[i];
+  } else {
+    const frame_2D<double>* B = static_cast<const frame_2D<double>*>(base3);
+    for (int i = 0; i < 2; ++i) { bf.position[i] = B->Position[i]; bf.velocity[i] = B->Velocity[i]; bf.acceleration[i] = B->Acceleration[i]; }
+    bf.quat[0] = B->Rotation.getAngle();
+    bf.ang_velocity[0] = B->AngVelocity;
+    bf.ang_acceleration[0] = B->AngAcceleration;
+  }
+  b.set_base(root, bf);
+  return b;
+}
+
+}  // namespace reak_b200
+
+namespace ReaK {
+namespace ctrl {
+
+/// Batched, GPU-backed counterpart of kte_nl_system (+ num_int_dtnl_sys with RK4).  Models
+/// SSSystemConcept and DiscreteSSSConcept on the same point/input types as kte_nl_system.
+class kte_batch_system {
+ public:
+  typedef vect_n<double> point_type;
+  typedef vect_n<double> point_difference_type;
+  typedef vect_n<double> point_derivative_type;
+  typedef double time_type;
+  typedef double time_difference_type;
+  typedef vect_n<double> input_type;
+  typedef vect_n<double> output_type;
+  typedef std::size_t size_type;
+  BOOST_STATIC_CONSTANT(std::size_t, dimensions = 0);
+  BOOST_STATIC_CONSTANT(std::size_t, input_dimensions = 0);
+  BOOST_STATIC_CONSTANT(std::size_t, output_dimensions = 0);
+
+  explicit kte_batch_system(const kte_nl_system& sys, int device = 0, double time_step = 1e-3)
+      : mBuilder(reak_b200::compile_kte_system(sys)), mProp(mBuilder, device, time_step) {}
+
+  size_type get_state_dimensions() const { return mProp.get_state_dimensions(); }
+  size_type get_input_dimensions() const { return mProp.get_input_dimensions(); }
+  size_type get_output_dimensions() const { return 0; }
+  time_difference_type get_time_step() const { return mProp.get_time_step(); }
+
+  template <typename StateSpaceType>
+  point_derivative_type get_state_derivative(const StateSpaceType& space, const point_type& p, const input_type& u, const time_type& t = 0) const {
+    return to_vect(translate_errors_derivative(space, p, u, t));
+  }
+  template <typename StateSpaceType>
+  point_type get_next_state(const StateSpaceType& space, const point_type& p, const input_type& u, const time_type& t = 0) const {
+    try {
+      return to_vect(mProp.get_next_state(space, p, u, t));
+    } catch (reak_b200::singularity_error&) { throw singularity_error("A"); }
+  }
+  template <typename StateSpaceType>
+  output_type get_output(const StateSpaceType&, const point_type&, const input_type&, const time_type& = 0) const { return output_type(); }
+
+  const reak_b200::kte_batch_propagator& batch() const { return mProp; }
+  const reak_b200::chain_builder& descriptor() const { return mBuilder; }
+
+ private:
+  template <typename StateSpaceType>
+  std::vector<double> translate_errors_derivative(const StateSpaceType& space, const point_type& p, const input_type& u, const time_type& t) const {
+    try {
+      return mProp.get_state_derivative(space, p, u, t);
+    } catch (reak_b200::singularity_error&) { throw singularity_error("A"); }
+  }
+  static vect_n<double> to_vect(const std::vector<double>& v) {
+    vect_n<double> r(v.size());
+    for (std::size_t i = 0; i < v.size(); ++i) r[i] = v[i];
+    return r;
+  }
+  reak_b200::chain_builder mBuilder;
+  reak_b200::kte_batch_propagator mProp;
+};
+
+}  // namespace ctrl
+}  // namespace ReaK
+
+#endif

@@ -43,7 +43,7 @@ class rkb_chain_desc(C.Structure):
 assert C.sizeof(rkb_element) == 128, C.sizeof(rkb_element)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libreak_b200.so")
+LIB_PATH = os.environ.get("RKB_LIB_PATH") or os.path.join(_PKG_DIR, "lib", "libreak_b200.so")
 _lib = None
 
 _dp = C.POINTER(C.c_double)
@@ -60,6 +60,8 @@ SYMBOLS = {
     "rkb_chain_input_dim": (C.c_int, [C.c_void_p]),
     "rkb_chain_dof": (C.c_int, [C.c_void_p]),
     "rkb_chain_is_serial": (C.c_int, [C.c_void_p]),
+    "rkb_chain_shape": (C.c_uint64, [C.c_void_p]),
+    "rkb_chain_kernel_shape": (C.c_uint64, [C.c_void_p]),
     "rkb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,

@@ -33,6 +33,13 @@
 //      "pivot < 1e-8 before the square root" singularity test reported in the status word.
 //  RK4    (runge_kutta4_integrator<T>::integrate, core/integrators/fixed_step_integrators.hpp:256-293),
 //      constant input over the rollout (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
+//
+// Structural specialisation.  The third template argument SHAPE carries 8 bits per stage
+// (rkb_types.h, RKB_SHAPE_*) that promise structure the lowering found in the descriptor: a
+// revolute axis that is +-e_x/e_y/e_z, a link offset along one coordinate axis without rotation,
+// a diagonal inertia tensor.  A promised stage uses the 4-multiply planar rotation, the
+// 2-multiply axis cross products and the 3-multiply tensor product instead of the dense 3x3
+// forms; SHAPE = 0 is the fully general code.  Results are the same up to rounding.
 #ifndef RKB_KTE_SERIAL_CUH
 #define RKB_KTE_SERIAL_CUH
 
@@ -44,37 +51,45 @@ namespace rkb {
 
 #define RKB_DEV __device__ __forceinline__
 
-struct vec3 { double x, y, z; };
+typedef unsigned long long shape_t;
 
-RKB_DEV vec3 mk(double x, double y, double z) { vec3 r; r.x = x; r.y = y; r.z = z; return r; }
-RKB_DEV vec3 operator+(vec3 a, vec3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-RKB_DEV vec3 operator-(vec3 a, vec3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-RKB_DEV vec3 operator*(double s, vec3 a) { return mk(s * a.x, s * a.y, s * a.z); }
-RKB_DEV double dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-RKB_DEV vec3 cross(vec3 a, vec3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+struct vec3 { double c[3]; };
+
+RKB_DEV vec3 mk(double x, double y, double z) { vec3 r; r.c[0] = x; r.c[1] = y; r.c[2] = z; return r; }
+RKB_DEV vec3 operator+(vec3 a, vec3 b) { return mk(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+RKB_DEV vec3 operator-(vec3 a, vec3 b) { return mk(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
+RKB_DEV vec3 operator*(double s, vec3 a) { return mk(s * a.c[0], s * a.c[1], s * a.c[2]); }
+RKB_DEV double dot(vec3 a, vec3 b) { return a.c[0] * b.c[0] + a.c[1] * b.c[1] + a.c[2] * b.c[2]; }
+RKB_DEV vec3 cross(vec3 a, vec3 b) {
+  return mk(a.c[1] * b.c[2] - a.c[2] * b.c[1], a.c[2] * b.c[0] - a.c[0] * b.c[2], a.c[0] * b.c[1] - a.c[1] * b.c[0]);
+}
 RKB_DEV vec3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
 // 3x3 rotation held row-major: v_parent = R v_child
 struct mat3 { double m[9]; };
 RKB_DEV vec3 mul(const mat3& R, vec3 v) {
-  return mk(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z,
-            R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
-            R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+  return mk(R.m[0] * v.c[0] + R.m[1] * v.c[1] + R.m[2] * v.c[2],
+            R.m[3] * v.c[0] + R.m[4] * v.c[1] + R.m[5] * v.c[2],
+            R.m[6] * v.c[0] + R.m[7] * v.c[1] + R.m[8] * v.c[2]);
 }
 RKB_DEV vec3 tmul(const mat3& R, vec3 v) {  // R^T v
-  return mk(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z,
-            R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
-            R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+  return mk(R.m[0] * v.c[0] + R.m[3] * v.c[1] + R.m[6] * v.c[2],
+            R.m[1] * v.c[0] + R.m[4] * v.c[1] + R.m[7] * v.c[2],
+            R.m[2] * v.c[0] + R.m[5] * v.c[1] + R.m[8] * v.c[2]);
 }
 RKB_DEV vec3 mulc(const double* R, vec3 v) {  // constant-bank matrix (row-major) times v
-  return mk(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z);
+  return mk(R[0] * v.c[0] + R[1] * v.c[1] + R[2] * v.c[2], R[3] * v.c[0] + R[4] * v.c[1] + R[5] * v.c[2],
+            R[6] * v.c[0] + R[7] * v.c[1] + R[8] * v.c[2]);
 }
 RKB_DEV vec3 tmulc(const double* R, vec3 v) {
-  return mk(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z);
+  return mk(R[0] * v.c[0] + R[3] * v.c[1] + R[6] * v.c[2], R[1] * v.c[0] + R[4] * v.c[1] + R[7] * v.c[2],
+            R[2] * v.c[0] + R[5] * v.c[1] + R[8] * v.c[2]);
 }
 RKB_DEV vec3 symmul(const double* I, vec3 v) {  // I = xx xy xz yy yz zz
-  return mk(I[0] * v.x + I[1] * v.y + I[2] * v.z, I[1] * v.x + I[3] * v.y + I[4] * v.z, I[2] * v.x + I[4] * v.y + I[5] * v.z);
+  return mk(I[0] * v.c[0] + I[1] * v.c[1] + I[2] * v.c[2], I[1] * v.c[0] + I[3] * v.c[1] + I[4] * v.c[2],
+            I[2] * v.c[0] + I[4] * v.c[1] + I[5] * v.c[2]);
 }
+RKB_DEV vec3 diagmul(const double* I, vec3 v) { return mk(I[0] * v.c[0], I[3] * v.c[1], I[5] * v.c[2]); }
 
 // axis_angle(q, axis).getRotMat(), rotations_3D.hpp:2159-2178, from cos/sin of the joint angle
 RKB_DEV mat3 rodrigues(const SerialStage& S, double c, double s) {
@@ -88,6 +103,27 @@ RKB_DEV mat3 rodrigues(const SerialStage& S, double c, double s) {
   return R;
 }
 
+// Rotation by (c, s) about coordinate axis D (0 = x, 1 = y, 2 = z); D1, D2 follow D cyclically.
+// R_D v and R_D^T v touch only the two off-axis components: 4 multiplies instead of 9.
+template <int D>
+RKB_DEV vec3 rot_axis(double c, double s, vec3 v) {
+  constexpr int D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+  vec3 r;
+  r.c[D] = v.c[D];
+  r.c[D1] = c * v.c[D1] - s * v.c[D2];
+  r.c[D2] = s * v.c[D1] + c * v.c[D2];
+  return r;
+}
+template <int D>
+RKB_DEV vec3 rotT_axis(double c, double s, vec3 v) {
+  constexpr int D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+  vec3 r;
+  r.c[D] = v.c[D];
+  r.c[D1] = c * v.c[D1] + s * v.c[D2];
+  r.c[D2] = c * v.c[D2] - s * v.c[D1];
+  return r;
+}
+
 // Angle of axis_angle(conj(Q_base) * Q_end) times its axis, expressed as a signed scalar along the
 // normalised joint axis (rotations_3D.hpp:1985-2010): the angle wrapped to (-pi, pi], zero inside
 // the reference's |sin(q/2)| <= 1e-7 dead zone.
@@ -98,45 +134,85 @@ RKB_DEV double wrapped_angle(double q) {
   return r;
 }
 
+// torsion spring (+ saturation) and damper across a revolute joint, as a signed scalar along the axis
+RKB_DEV double spring_scalar(const SerialStage& S, double q) {
+  const double r = wrapped_angle(q);
+  double mag = S.ks * fabs(r);  // stiffness * angle_diff.angle(), angle >= 0
+  if (S.sat > 0.0 && fabs(mag) > S.sat) mag = (mag > 0.0) ? S.sat : -S.sat;
+  return r < 0.0 ? -mag : mag;
+}
+
 template <int N>
 struct SerialState {
   double q[N], qd[N], u[N];
 };
 
+__host__ __device__ constexpr int shape_ax(shape_t s, int k) { return (int)((s >> (8 * k)) & 7u); }         // 0 general, 1..3 revolute about x,y,z
+__host__ __device__ constexpr int shape_lk(shape_t s, int k) { return (int)((s >> (8 * k + 3)) & 3u); }     // 0 general, 1..3 offset along x,y,z, no rotation
+__host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 3u); }     // 0 general, 1 diagonal tensor present
+
 // The evaluation proper.  `sm` is this thread's shared-memory column (stride SMS doubles
 // between consecutive slots); slots [0, 6N) hold the parked inertia wrenches.
 // Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
 // Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
-template <int N, int FL, int SMS, bool WANT_F, bool WANT_M>
+template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M>
 RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
                            double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
-  // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const SerialStage& S = P.st[k];
-    const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-    if (!prismatic) sincos(X.q[k], &sn[k], &cs[k]);
-    else { sn[k] = 0.0; cs[k] = 1.0; }
+    constexpr shape_t SH = SHAPE;
+    const int AX = shape_ax(SH, k);
+    const bool prismatic = AX == 0 && (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+    if (!prismatic) {
+      sincos(X.q[k], &sn[k], &cs[k]);
+      if (AX != 0) sn[k] *= S.ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
+    } else { sn[k] = 0.0; cs[k] = 1.0; }
   }
+  // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
   if (WANT_F) {
     vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const SerialStage& S = P.st[k];
-      const vec3 ax = ld3(S.ax);
-      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-      if (!prismatic) {
-        const mat3 R2 = rodrigues(S, cs[k], sn[k]);
-        const vec3 wt = tmul(R2, w);
-        const vec3 qda = X.qd[k] * ax;
-        al = tmul(R2, al) + cross(wt, qda);  // + q_ddot * axis, zero in this pass (kte_nl_system.hpp:192)
-        w = wt + qda;
-        a = tmul(R2, a);
+      constexpr shape_t SH = SHAPE;
+      const int AX = shape_ax(SH, k), LK = shape_lk(SH, k), IN = shape_in(SH, k);
+      if (AX != 0) {
+        // revolute about +-e_D (revolute_joint.cpp:121-152)
+        const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double g = S.ax[D] * X.qd[k];  // q_dot * axis has the single component g
+        vec3 wt, alt, at;
+        if (D == 0) { wt = rotT_axis<0>(cs[k], sn[k], w); alt = rotT_axis<0>(cs[k], sn[k], al); at = rotT_axis<0>(cs[k], sn[k], a); }
+        else if (D == 1) { wt = rotT_axis<1>(cs[k], sn[k], w); alt = rotT_axis<1>(cs[k], sn[k], al); at = rotT_axis<1>(cs[k], sn[k], a); }
+        else { wt = rotT_axis<2>(cs[k], sn[k], w); alt = rotT_axis<2>(cs[k], sn[k], al); at = rotT_axis<2>(cs[k], sn[k], a); }
+        // al = R^T al + wt x (g e_D): (v x e_D)[D1] = v[D2], (v x e_D)[D2] = -v[D1]
+        alt.c[D1] += wt.c[D2] * g;
+        alt.c[D2] -= wt.c[D1] * g;
+        wt.c[D] += g;
+        w = wt; al = alt; a = at;
       } else {
-        const vec3 r = X.q[k] * ax, rd = X.qd[k] * ax;
-        a = a + cross(w, cross(w, r)) + 2.0 * cross(w, rd) + cross(al, r);
+        const vec3 ax = ld3(S.ax);
+        const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+        if (!prismatic) {
+          const mat3 R2 = rodrigues(S, cs[k], sn[k]);
+          const vec3 wt = tmul(R2, w);
+          const vec3 qda = X.qd[k] * ax;
+          al = tmul(R2, al) + cross(wt, qda);  // + q_ddot * axis, zero in this pass (kte_nl_system.hpp:192)
+          w = wt + qda;
+          a = tmul(R2, a);
+        } else {
+          const vec3 r = X.q[k] * ax, rd = X.qd[k] * ax;
+          a = a + cross(w, cross(w, r)) + 2.0 * cross(w, rd) + cross(al, r);
+        }
       }
-      if (S.flags & RKB_ST_LINK) {
+      if (LK != 0) {
+        // link offset L e_D, no rotation: a += w x (w x po) + al x po = L (w_D w - |w|^2 e_D + al x e_D)
+        const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double L = S.po[D];
+        a.c[D] -= L * (w.c[D1] * w.c[D1] + w.c[D2] * w.c[D2]);
+        a.c[D1] += L * (w.c[D] * w.c[D1] + al.c[D2]);
+        a.c[D2] += L * (w.c[D] * w.c[D2] - al.c[D1]);
+      } else if (S.flags & RKB_ST_LINK) {
         const vec3 po = ld3(S.po);
         a = a + cross(w, cross(w, po)) + cross(al, po);
         if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) {
@@ -145,51 +221,74 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       }
       // inertia_3D::doForce: F -= m * (R^T a_global) ; T -= I al + w x (I w)
       vec3 Fk = mk(0, 0, 0), Tk = mk(0, 0, 0);
-      if (S.flags & RKB_ST_INERTIA) {
+      if (IN == 1) {
+        Fk = (-S.m) * a;
+        const vec3 Iw = diagmul(S.I, w);
+        Tk = mk(0, 0, 0) - (diagmul(S.I, al) + cross(w, Iw));
+      } else if (S.flags & RKB_ST_INERTIA) {
         Fk = (-S.m) * a;
         const vec3 Iw = symmul(S.I, w);
         Tk = mk(0, 0, 0) - (symmul(S.I, al) + cross(w, Iw));
       }
-      sm[(6 * k + 0) * SMS] = Fk.x; sm[(6 * k + 1) * SMS] = Fk.y; sm[(6 * k + 2) * SMS] = Fk.z;
-      sm[(6 * k + 3) * SMS] = Tk.x; sm[(6 * k + 4) * SMS] = Tk.y; sm[(6 * k + 5) * SMS] = Tk.z;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { sm[(6 * k + d) * SMS] = Fk.c[d]; sm[(6 * k + 3 + d) * SMS] = Tk.c[d]; }
     }
     // ---- sweep 2: wrenches inward -----------------------------------------------------------
     vec3 F = mk(0, 0, 0), T = mk(0, 0, 0);
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       const SerialStage& S = P.st[k];
-      const vec3 ax = ld3(S.ax);
-      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-      F = F + mk(sm[(6 * k + 0) * SMS], sm[(6 * k + 1) * SMS], sm[(6 * k + 2) * SMS]);
-      T = T + mk(sm[(6 * k + 3) * SMS], sm[(6 * k + 4) * SMS], sm[(6 * k + 5) * SMS]);
-      if (S.flags & RKB_ST_LINK) {
+      constexpr shape_t SH = SHAPE;
+      const int AX = shape_ax(SH, k), LK = shape_lk(SH, k);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { F.c[d] += sm[(6 * k + d) * SMS]; T.c[d] += sm[(6 * k + 3 + d) * SMS]; }
+      if (LK != 0) {
+        // T += po x F = L (e_D x F): [D1] -= L F[D2], [D2] += L F[D1]   (rigid_link.cpp:170-177, Ro = I)
+        const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double L = S.po[D];
+        T.c[D1] -= L * F.c[D2];
+        T.c[D2] += L * F.c[D1];
+      } else if (S.flags & RKB_ST_LINK) {
         if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) { F = mulc(S.Ro, F); T = mulc(S.Ro, T); }
         T = T + cross(ld3(S.po), F);
       }
-      if (!prismatic) {
-        // torsion spring / damper between the joint's base and end frames act along the axis
-        vec3 tsd = mk(0, 0, 0);
+      if (AX != 0) {
+        // revolute about +-e_D (revolute_joint.cpp:172-184 + actuator reaction :210-213)
+        const int D = AX - 1;
+        const double sg = S.ax[D];
+        double tsd = 0.0;  // spring + damper torque along e_D
         if (FL & RKB_FL_SPRINGS) {
-          if (S.flags & RKB_ST_SPRING) {
-            const double r = wrapped_angle(X.q[k]);
-            double mag = S.ks * fabs(r);  // stiffness * angle_diff.angle(), angle >= 0
-            if (S.sat > 0.0 && fabs(mag) > S.sat) mag = (mag > 0.0) ? S.sat : -S.sat;
-            tsd = (r < 0.0 ? -mag : mag) * ld3(S.an);
-          }
-          if (S.flags & RKB_ST_DAMPER) tsd = tsd + (S.cd * X.qd[k]) * ax;
-          T = T - tsd;
+          if (S.flags & RKB_ST_SPRING) tsd = sg * spring_scalar(S, X.q[k]);
+          if (S.flags & RKB_ST_DAMPER) tsd += sg * (S.cd * X.qd[k]);
         }
-        const double ta = dot(T, ax);
-        f[k] = ta + X.u[k];
-        const mat3 R = rodrigues(S, cs[k], sn[k]);
-        F = mul(R, F);
-        T = mul(R, T - ta * ax) - X.u[k] * ax;  // actuator reaction on the joint base
-        if (FL & RKB_FL_SPRINGS) T = T + tsd;
+        f[k] = sg * (T.c[D] - tsd) + X.u[k];
+        T.c[D] = tsd - sg * X.u[k];  // axial part removed, reaction and spring/damper on the base side added
+        if (D == 0) { F = rot_axis<0>(cs[k], sn[k], F); T = rot_axis<0>(cs[k], sn[k], T); }
+        else if (D == 1) { F = rot_axis<1>(cs[k], sn[k], F); T = rot_axis<1>(cs[k], sn[k], T); }
+        else { F = rot_axis<2>(cs[k], sn[k], F); T = rot_axis<2>(cs[k], sn[k], T); }
       } else {
-        const double fa = dot(F, ax);
-        f[k] = fa + X.u[k];
-        T = T + cross(X.q[k] * ax, F);
-        F = F - fa * ax - X.u[k] * ax;
+        const vec3 ax = ld3(S.ax);
+        const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+        if (!prismatic) {
+          // torsion spring / damper between the joint's base and end frames act along the axis
+          vec3 tsd = mk(0, 0, 0);
+          if (FL & RKB_FL_SPRINGS) {
+            if (S.flags & RKB_ST_SPRING) tsd = spring_scalar(S, X.q[k]) * ld3(S.an);
+            if (S.flags & RKB_ST_DAMPER) tsd = tsd + (S.cd * X.qd[k]) * ax;
+            T = T - tsd;
+          }
+          const double ta = dot(T, ax);
+          f[k] = ta + X.u[k];
+          const mat3 R = rodrigues(S, cs[k], sn[k]);
+          F = mul(R, F);
+          T = mul(R, T - ta * ax) - X.u[k] * ax;  // actuator reaction on the joint base
+          if (FL & RKB_FL_SPRINGS) T = T + tsd;
+        } else {
+          const double fa = dot(F, ax);
+          f[k] = fa + X.u[k];
+          T = T + cross(X.q[k] * ax, F);
+          F = F - fa * ax - X.u[k] * ax;
+        }
       }
     }
   }
@@ -201,19 +300,41 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const SerialStage& S = P.st[k];
-      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-      if (!prismatic) {
-        const mat3 R2 = rodrigues(S, cs[k], sn[k]);
+      constexpr shape_t SH = SHAPE;
+      const int AX = shape_ax(SH, k), LK = shape_lk(SH, k), IN = shape_in(SH, k);
+      if (AX != 0) {
+        const int D = AX - 1;
 #pragma unroll
-        for (int i = 0; i < k; ++i) { Tv[i] = tmul(R2, Tv[i]); Tw[i] = tmul(R2, Tw[i]); }
+        for (int i = 0; i < k; ++i) {
+          if (D == 0) { Tv[i] = rotT_axis<0>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<0>(cs[k], sn[k], Tw[i]); }
+          else if (D == 1) { Tv[i] = rotT_axis<1>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<1>(cs[k], sn[k], Tw[i]); }
+          else { Tv[i] = rotT_axis<2>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<2>(cs[k], sn[k], Tw[i]); }
+        }
         Tv[k] = mk(0, 0, 0); Tw[k] = ld3(S.ax);
       } else {
-        const vec3 r = X.q[k] * ld3(S.ax);
+        const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+        if (!prismatic) {
+          const mat3 R2 = rodrigues(S, cs[k], sn[k]);
 #pragma unroll
-        for (int i = 0; i < k; ++i) Tv[i] = Tv[i] + cross(Tw[i], r);
-        Tv[k] = ld3(S.ax); Tw[k] = mk(0, 0, 0);
+          for (int i = 0; i < k; ++i) { Tv[i] = tmul(R2, Tv[i]); Tw[i] = tmul(R2, Tw[i]); }
+          Tv[k] = mk(0, 0, 0); Tw[k] = ld3(S.ax);
+        } else {
+          const vec3 r = X.q[k] * ld3(S.ax);
+#pragma unroll
+          for (int i = 0; i < k; ++i) Tv[i] = Tv[i] + cross(Tw[i], r);
+          Tv[k] = ld3(S.ax); Tw[k] = mk(0, 0, 0);
+        }
       }
-      if (S.flags & RKB_ST_LINK) {
+      if (LK != 0) {
+        // Tv += Tw x po = L (Tw x e_D)
+        const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double L = S.po[D];
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+          Tv[i].c[D1] += L * Tw[i].c[D2];
+          Tv[i].c[D2] -= L * Tw[i].c[D1];
+        }
+      } else if (S.flags & RKB_ST_LINK) {
         const vec3 po = ld3(S.po);
 #pragma unroll
         for (int i = 0; i <= k; ++i) {
@@ -221,11 +342,11 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
           if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) { Tv[i] = tmulc(S.Ro, Tv[i]); Tw[i] = tmulc(S.Ro, Tw[i]); }
         }
       }
-      if (S.flags & RKB_ST_INERTIA) {
+      if (IN == 1 || (S.flags & RKB_ST_INERTIA)) {
 #pragma unroll
         for (int i = 0; i <= k; ++i) {
           const vec3 mv = S.m * Tv[i];
-          const vec3 Iw = symmul(S.I, Tw[i]);
+          const vec3 Iw = (IN == 1) ? diagmul(S.I, Tw[i]) : symmul(S.I, Tw[i]);
 #pragma unroll
           for (int j = 0; j <= i; ++j) Mp[i * (i + 1) / 2 + j] += dot(Tv[j], mv) + dot(Tw[j], Iw);
         }
@@ -235,7 +356,8 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
   }
 }
 
-// linsolve_Cholesky on the packed matrix; b is overwritten with the solution.
+// linsolve_Cholesky on the packed matrix; b is overwritten with the solution.  Only the
+// reciprocals 1/L(i,i) are ever needed: one rsqrt per pivot, no sqrt and no division.
 // Returns RKB_STATUS_SINGULAR where the reference throws singularity_error.
 template <int N>
 RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N]) {
@@ -254,9 +376,7 @@ RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N])
 #pragma unroll
     for (int k = 0; k < i; ++k) d -= Mp[i * (i + 1) / 2 + k] * Mp[i * (i + 1) / 2 + k];
     if (!(d >= 1.0e-8)) st = RKB_STATUS_SINGULAR;
-    const double l = sqrt(d);
-    Mp[i * (i + 1) / 2 + i] = l;
-    inv[i] = 1.0 / l;
+    inv[i] = rsqrt(d);
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -276,10 +396,10 @@ RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N])
 }
 
 // q_ddot = M^-1 f for the state in X; returns the status bits.
-template <int N, int FL, int SMS>
+template <int N, int FL, shape_t SHAPE, int SMS>
 RKB_DEV int serial_accel(const SerialParams& P, const SerialState<N>& X, double (&qdd)[N], double* sm) {
   double cs[N], sn[N], Mp[N * (N + 1) / 2];
-  serial_sweeps<N, FL, SMS, true, true>(P, X, cs, sn, qdd, Mp, sm);
+  serial_sweeps<N, FL, SHAPE, SMS, true, true>(P, X, cs, sn, qdd, Mp, sm);
   return cholesky_solve_packed<N>(Mp, qdd);
 }
 
@@ -298,18 +418,21 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #ifndef RKB_BLOCK
 #define RKB_BLOCK 128
 #endif
+#ifndef RKB_MINBLOCKS
+#define RKB_MINBLOCKS 1
+#endif
 
 // ---- kernels ---------------------------------------------------------------------------------
 // xdot = get_state_derivative(x, u)
-template <int N, int FL>
-__global__ void __launch_bounds__(RKB_BLOCK) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
   SerialState<N> X;
   load_state<N>(P, A.x, A.u, i, X);
   double qdd[N];
-  int st = serial_accel<N, FL, RKB_BLOCK>(P, X, qdd, smem + threadIdx.x);
+  int st = serial_accel<N, FL, SHAPE, RKB_BLOCK>(P, X, qdd, smem + threadIdx.x);
   bool finite = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -323,7 +446,7 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_eval_kernel(const __grid_con
 }
 
 // f = gen_coord::f after doMotion / clearForce / doForce with q_ddot = 0
-template <int N, int FL>
+template <int N, int FL, shape_t SHAPE>
 __global__ void __launch_bounds__(RKB_BLOCK) serial_forces_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
@@ -331,13 +454,13 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_forces_kernel(const __grid_c
   SerialState<N> X;
   load_state<N>(P, A.x, A.u, i, X);
   double cs[N], sn[N], f[N], Mp[N * (N + 1) / 2];
-  serial_sweeps<N, FL, RKB_BLOCK, true, false>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
+  serial_sweeps<N, FL, SHAPE, RKB_BLOCK, true, false>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
 #pragma unroll
   for (int k = 0; k < N; ++k) A.out.p[i * A.out.si + P.st[k].coord * A.out.sk] = f[k];
 }
 
 // M = getMassMatrix (full symmetric n x n, row-major per sample in AoS)
-template <int N, int FL>
+template <int N, int FL, shape_t SHAPE>
 __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
@@ -346,7 +469,7 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
   ConstBatchView nou = A.x;
   load_state<N>(P, A.x, nou, i, X);
   double cs[N], sn[N], f[N], Mp[N * (N + 1) / 2];
-  serial_sweeps<N, FL, RKB_BLOCK, false, true>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
+  serial_sweeps<N, FL, SHAPE, RKB_BLOCK, false, true>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
 #pragma unroll
   for (int a = 0; a < N; ++a)
 #pragma unroll
@@ -360,8 +483,8 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
 
 // n_steps of fixed-step RK4 with the input held constant.
 // Per-thread shared-memory column: [0,6N) wrenches, then w (2N), acc (2N), k3 (2N).
-template <int N, int FL>
-__global__ void __launch_bounds__(RKB_BLOCK) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
@@ -378,12 +501,13 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_rollout_kernel(const __grid_
     load_state<N>(P, xv, A.u, i, X);
   }
   const double dt = A.dt;
+  const double sixth = 1.0 / 6.0;
   int st = 0;
   const int total = 4 * A.n_steps;
 #pragma unroll 1
   for (int it = 0; it < total; ++it) {
     double qdd[N];
-    st |= serial_accel<N, FL, SMS>(P, X, qdd, sm);
+    st |= serial_accel<N, FL, SHAPE, SMS>(P, X, qdd, sm);
     const int stage = it & 3;
     // state derivative f = (qd, qdd) interleaved; the four stages of fixed_step_integrators.hpp:277-289
     if (stage == 0) {
@@ -409,11 +533,12 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_rollout_kernel(const __grid_
         X.q[k] = sw[(2 * k) * SMS] + k3q; X.qd[k] = sw[(2 * k + 1) * SMS] + k3v;
       }
     } else {
+      // x += (k1 + 2 k2 + k4) / 6 - k3 (2/3), with the division by 6 as a multiplication
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double k4q = X.qd[k] * dt, k4v = qdd[k] * dt;
-        X.q[k] += (sa[(2 * k) * SMS] + k4q) / 6.0 - s3[(2 * k) * SMS] * (2.0 / 3.0);
-        X.qd[k] += (sa[(2 * k + 1) * SMS] + k4v) / 6.0 - s3[(2 * k + 1) * SMS] * (2.0 / 3.0);
+        X.q[k] += (sa[(2 * k) * SMS] + k4q) * sixth - s3[(2 * k) * SMS] * (2.0 / 3.0);
+        X.qd[k] += (sa[(2 * k + 1) * SMS] + k4v) * sixth - s3[(2 * k + 1) * SMS] * (2.0 / 3.0);
       }
     }
   }
@@ -428,9 +553,6 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_rollout_kernel(const __grid_
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = st;
 }
-
-template <int N>
-constexpr int serial_smem_doubles_per_thread(bool rollout) { return 6 * N + (rollout ? 6 * N : 0); }
 
 }  // namespace rkb
 #endif

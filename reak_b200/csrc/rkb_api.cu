@@ -62,6 +62,7 @@ struct rkb_chain {
   int n = 0, nu = 0;
   bool serial_ok = false;
   int serial_fl = 0;
+  unsigned long long serial_shape = 0;  // structure found in the descriptor (RKB_SHAPE_*)
   SerialParams sp;
   const SerialKernels* sk = nullptr;
   bool generic_ok = false;
@@ -180,7 +181,7 @@ int validate(const rkb_chain_desc* d) {
 
 // Try to express the chain as joint/link/inertia stages (see rkb_types.h).  Returns false when
 // the chain needs the generic interpreter.
-bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl) {
+bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl, unsigned long long& shape) {
   if (d.dim != 3 || d.n_coords < 1 || d.n_coords > RKB_SERIAL_MAX_DOF) return false;
   std::memset(&P, 0, sizeof P);
   P.n = d.n_coords;
@@ -291,6 +292,25 @@ bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl) {
     P.st[s].input = input_of[P.st[s].coord];
   }
   for (int i = 0; i < 3; ++i) { P.w0[i] = w[i]; P.al0[i] = al[i]; P.a0[i] = a[i]; }
+  // structure the specialised kernels may rely on
+  shape = 0;
+  for (int s = 0; s <= k; ++s) {
+    const SerialStage& S = P.st[s];
+    unsigned ax = 0, lk = 0, in = 0;
+    if (!(S.flags & RKB_ST_PRISMATIC)) {
+      for (int dd = 0; dd < 3; ++dd) {
+        const int d1 = (dd + 1) % 3, d2 = (dd + 2) % 3;
+        if ((S.ax[dd] == 1.0 || S.ax[dd] == -1.0) && S.ax[d1] == 0.0 && S.ax[d2] == 0.0) ax = dd + 1;
+      }
+    }
+    if (!(S.flags & RKB_ST_LINKROT)) {  // no link at all counts as a zero offset along z
+      int nz = 0, which = 2;
+      for (int dd = 0; dd < 3; ++dd) if (S.po[dd] != 0.0) { ++nz; which = dd; }
+      if (nz <= 1) lk = which + 1;
+    }
+    if ((S.flags & RKB_ST_INERTIA) && S.I[1] == 0.0 && S.I[2] == 0.0 && S.I[4] == 0.0) in = 1;
+    shape |= RKB_SHAPE_AT(RKB_SHAPE_STAGE(ax, lk, in), s);
+  }
   return true;
 }
 
@@ -339,7 +359,25 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
   return true;
 }
 
-const SerialKernels* find_serial(int n, int fl) {
+// every promise of `have` (8 bits per stage, three fields) is either absent or kept by `chain`
+bool shape_compatible(unsigned long long have, unsigned long long chain, int n) {
+  for (int k = 0; k < n; ++k) {
+    const unsigned h = (unsigned)((have >> (8 * k)) & 0xffu), c = (unsigned)((chain >> (8 * k)) & 0xffu);
+    const unsigned hf[3] = {h & 7u, (h >> 3) & 3u, (h >> 5) & 3u}, cf[3] = {c & 7u, (c >> 3) & 3u, (c >> 5) & 3u};
+    for (int i = 0; i < 3; ++i) if (hf[i] != 0 && hf[i] != cf[i]) return false;
+  }
+  return (n >= 8) || (have >> (8 * n)) == 0;
+}
+int shape_score(unsigned long long have, int n) {
+  int sc = 0;
+  for (int k = 0; k < n; ++k) {
+    const unsigned h = (unsigned)((have >> (8 * k)) & 0xffu);
+    sc += ((h & 7u) ? 3 : 0) + (((h >> 3) & 3u) ? 1 : 0) + (((h >> 5) & 3u) ? 1 : 0);
+  }
+  return sc;
+}
+
+const SerialKernels* find_serial(int n, int fl, unsigned long long shape) {
   int count = 0;
   const SerialKernels* t = nullptr;
   switch (n) {
@@ -353,9 +391,15 @@ const SerialKernels* find_serial(int n, int fl) {
     case 8: t = rkb_serial_table_8(&count); break;
     default: return nullptr;
   }
+  const bool no_special = std::getenv("RKB_NO_SPECIALIZE") && std::getenv("RKB_NO_SPECIALIZE")[0] == '1';
   const SerialKernels* best = nullptr;
-  for (int i = 0; i < count; ++i)
-    if ((t[i].fl & fl) == fl && (!best || __builtin_popcount(t[i].fl) < __builtin_popcount(best->fl))) best = &t[i];
+  for (int i = 0; i < count; ++i) {
+    if ((t[i].fl & fl) != fl || !shape_compatible(t[i].shape, shape, n)) continue;
+    if (no_special && t[i].shape != 0) continue;
+    if (!best) { best = &t[i]; continue; }
+    const int sa = shape_score(t[i].shape, n), sb = shape_score(best->shape, n);
+    if (sa > sb || (sa == sb && __builtin_popcount(t[i].fl) < __builtin_popcount(best->fl))) best = &t[i];
+  }
   return best;
 }
 
@@ -529,9 +573,9 @@ int rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out) {
   c->desc.elements = c->elements.data();
   c->n = desc->n_coords;
   c->nu = desc->n_inputs;
-  c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl);
+  c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl, c->serial_shape);
   if (c->serial_ok) {
-    c->sk = find_serial(c->n, c->serial_fl);
+    c->sk = find_serial(c->n, c->serial_fl, c->serial_shape);
     if (!c->sk) c->serial_ok = false;
   }
   const char* force = std::getenv("RKB_FORCE_GENERIC");
@@ -562,6 +606,9 @@ int rkb_chain_input_dim(const rkb_chain* c) { return c ? c->nu : RKB_ERR_INVALID
 int rkb_chain_dof(const rkb_chain* c) { return c ? c->n : RKB_ERR_INVALID; }
 /* 1 when the chain runs on the register-resident serial kernels, 0 on the interpreter */
 int rkb_chain_is_serial(const rkb_chain* c) { return c ? (c->serial_ok ? 1 : 0) : RKB_ERR_INVALID; }
+/* structural promises of the kernels picked for this chain (0 = general code) and those the chain would allow */
+unsigned long long rkb_chain_kernel_shape(const rkb_chain* c) { return (c && c->sk) ? c->sk->shape : 0ull; }
+unsigned long long rkb_chain_shape(const rkb_chain* c) { return c ? c->serial_shape : 0ull; }
 
 int rkb_eval(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* xdot, int32_t* status,
              unsigned flags, void* stream) {

@@ -8,6 +8,7 @@
 // One entry per compiled (N, feature-mask) instantiation of the serial kernels.
 struct SerialKernels {
   int n, fl;
+  unsigned long long shape;     // structural promises compiled in (0 = none)
   int smem_eval, smem_rollout;  // dynamic shared memory per CTA, bytes
   int block;
   cudaError_t (*prepare)(void);  // opt in to > 48 KB dynamic shared memory

@@ -10,43 +10,43 @@ namespace {
 
 using namespace rkb;
 
-template <int N, int FL>
+template <int N, int FL, shape_t SHAPE>
 struct Launch {
   static constexpr int kSmemEval = 6 * N * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemRollout = 12 * N * RKB_BLOCK * (int)sizeof(double);
   static unsigned grid(long long n) { return (unsigned)((n + RKB_BLOCK - 1) / RKB_BLOCK); }
   static cudaError_t prepare() {
-    cudaError_t e = cudaFuncSetAttribute(serial_rollout_kernel<N, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
+    cudaError_t e = cudaFuncSetAttribute(serial_rollout_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(serial_eval_kernel<N, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
+    e = cudaFuncSetAttribute(serial_eval_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(serial_forces_kernel<N, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
+    e = cudaFuncSetAttribute(serial_forces_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(serial_mass_kernel<N, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
+    return cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
   }
   static cudaError_t eval(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_eval_kernel<N, FL><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
+    serial_eval_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t forces(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_forces_kernel<N, FL><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
+    serial_forces_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t mass(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_mass_kernel<N, FL><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
+    serial_mass_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t rollout(const SerialParams& P, const RolloutArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_rollout_kernel<N, FL><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
+    serial_rollout_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
     return cudaGetLastError();
   }
   static SerialKernels entry() {
     SerialKernels k;
-    k.n = N; k.fl = FL; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
+    k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
     k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout;
     return k;
   }
@@ -57,11 +57,32 @@ struct Launch {
 #define RKB_CAT2(a, b) a##b
 #define RKB_CAT(a, b) RKB_CAT2(a, b)
 
+// Structural shapes compiled ahead of time besides the general code (shape 0).  The lowering
+// (rkb_api.cu) picks the most specialised entry whose promises the chain keeps.
+//   Z/Y/X: revolute about that axis, link offset along z (or none), diagonal inertia tensor —
+//   the anthropomorphic-arm-with-spherical-wrist pattern z,y,y,z,y,z of the CRS A465 preset
+//   (examples/robot_airship/old/CRS_A465_models.cpp:304-640) and its prefixes.
+constexpr int kArmAxis[6] = {3, 2, 2, 3, 2, 3};
+constexpr shape_t arm_shape(int n, int first, int inertia = 1) {
+  shape_t s = 0;
+  for (int k = 0; k < n; ++k) s |= RKB_SHAPE_AT(RKB_SHAPE_STAGE(kArmAxis[k % 6], 3, inertia), k + first);
+  return s;
+}
+// general joint (prismatic track) with a z-aligned link and a diagonal tensor, then the arm
+constexpr shape_t track_arm_shape(int n) { return RKB_SHAPE_AT(RKB_SHAPE_STAGE(0, 3, 1), 0) | arm_shape(n - 1, 1); }
+
 extern "C" const SerialKernels* RKB_CAT(rkb_serial_table_, RKB_N)(int* count) {
   static const SerialKernels table[] = {
-      Launch<RKB_N, 0>::entry(),
-      Launch<RKB_N, RKB_FL_SPRINGS>::entry(),
-      Launch<RKB_N, RKB_FL_ALL>::entry(),
+      Launch<RKB_N, 0, 0>::entry(),
+      Launch<RKB_N, RKB_FL_SPRINGS, 0>::entry(),
+      Launch<RKB_N, RKB_FL_ALL, 0>::entry(),
+      Launch<RKB_N, 0, arm_shape(RKB_N, 0)>::entry(),
+      Launch<RKB_N, RKB_FL_SPRINGS, arm_shape(RKB_N, 0)>::entry(),
+      Launch<RKB_N, RKB_FL_SPRINGS, arm_shape(RKB_N, 0, 0)>::entry(),  // same arm, full inertia tensors
+#if RKB_N >= 2
+      Launch<RKB_N, RKB_FL_PRISMATIC, track_arm_shape(RKB_N)>::entry(),
+      Launch<RKB_N, RKB_FL_PRISMATIC | RKB_FL_SPRINGS, track_arm_shape(RKB_N)>::entry(),
+#endif
   };
   *count = (int)(sizeof(table) / sizeof(table[0]));
   return table;

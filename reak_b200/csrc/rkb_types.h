@@ -29,6 +29,13 @@
 #define RKB_FL_SPRINGS   4
 #define RKB_FL_ALL       7
 
+// Structural promises, 8 bits per stage (stage k at bits [8k, 8k+8)): see kte_serial.cuh
+//   bits 0-2  axis   0 = general (revolute with any axis, or prismatic), 1/2/3 = revolute about +-e_x/e_y/e_z
+//   bits 3-4  link   0 = general (none / any offset / rotated), 1/2/3 = offset along e_x/e_y/e_z, no rotation
+//   bits 5-6  inertia 0 = general (none / full tensor), 1 = present with a diagonal tensor
+#define RKB_SHAPE_STAGE(ax, lk, in) ((unsigned long long)((ax) | ((lk) << 3) | ((in) << 5)))
+#define RKB_SHAPE_AT(code, k) ((unsigned long long)(code) << (8 * (k)))
+
 struct SerialStage {
   double ax[3];    // joint axis as stored (mAxis): used for angular/linear velocity terms and force projection
   double an[3];    // normalised axis (axis_angle ctor, rotations_3D.hpp:1962-1974): used for the rotation
