@@ -103,10 +103,18 @@ class _Checker(object):
         return out
 
 
+_PRODUCT_SO = os.path.join(os.path.dirname(_HERE), "reak_b200", "lib", "libreak_b200.so")
+_preloaded = []
+
+
 class Reference(_Checker):
     """The real ReaK code (kte_nl_system + runge_kutta4_integrator)."""
 
     def __init__(self, compiled):
+        # rkref_bridge_gpu_check (the C++ drop-in check) calls into the product library: make its
+        # symbols visible before libreak_ref.so binds its weak references to them.
+        if not _preloaded and os.path.isfile(os.environ.get("RKB_LIB_PATH") or _PRODUCT_SO):
+            _preloaded.append(C.CDLL(os.environ.get("RKB_LIB_PATH") or _PRODUCT_SO, mode=C.RTLD_GLOBAL))
         _Checker.__init__(self, REF_SO, "rkref_", compiled)
 
 

@@ -32,7 +32,24 @@
 #include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
 
 #include "../include/reak_b200.h"
+// libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
+// checker library still loads (RTLD_NOW) where the product library is not loaded.
+#pragma weak rkb_chain_create
+#pragma weak rkb_chain_destroy
+#pragma weak rkb_chain_input_dim
+#pragma weak rkb_chain_state_dim
+#pragma weak rkb_chain_is_serial
+#pragma weak rkb_eval
+#pragma weak rkb_gen_forces
+#pragma weak rkb_mass_matrix
+#pragma weak rkb_steer_batch
+#pragma weak rkb_last_kernel_ms
+#pragma weak rkb_last_cuda_error
+#pragma weak rkb_rollout_rk4
+#pragma weak rkb_strerror
+#include "../include/reak_b200/reak_bridge.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -355,6 +372,70 @@ int rkref_frames(void* hv, const double* x, const double* u, double* out) {
     }
   }
   return 0;
+}
+
+// Runs include/reak_b200/reak_bridge.hpp on the LIVE ReaK objects of this model (built by
+// build_model above from the descriptor) and hands the descriptor it derives back, so that a test
+// can check that descriptor -> ReaK objects -> descriptor is the identity.  Returns the number of
+// elements, or -1 (and the message in `err`) when the bridge rejects the chain.
+int rkref_bridge_desc(void* hv, rkb_chain_desc* out, rkb_element* elems, int max_elems, char* err, int err_len) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  try {
+    reak_b200::chain_builder b = reak_b200::compile_kte_system(h->proto->sys);
+    rkb_chain_desc d = b.desc();
+    if (d.n_elements > max_elems) return -2;
+    for (int i = 0; i < d.n_elements; ++i) elems[i] = b.element(i);
+    *out = d;
+    out->elements = elems;
+    return d.n_elements;
+  } catch (std::exception& e) {
+    if (err && err_len > 0) { std::strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+    return -1;
+  }
+}
+
+// GPU drop-in check, all in C++ with ReaK's own types: a ReaK::ctrl::kte_batch_system is built
+// from the live kte_nl_system through the bridge and compared, sample by sample, with that
+// kte_nl_system (state derivative) and with runge_kutta4_integrator<double> driven by it (one
+// step through get_next_state, n_steps through the batched call).  err[0..2] receive the max
+// relative errors |a-b| / max(1,|b|).  Needs libreak_b200.so loaded first (RTLD_GLOBAL) and a GPU.
+// Returns 0, or -1 with the exception text in `msg`.
+int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const double* u, double dt, int n_steps,
+                           double* err, char* msg, int msg_len) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  try {
+    if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
+    ctrl::kte_batch_system bs(m->sys, 0, dt);
+    err[0] = err[1] = err[2] = 0.0;
+    std::vector<double> ref_n(N * nx), got_n(N * nx);
+    std::vector<int32_t> st(N);
+    rk4_range(m, 0, N, x, u, dt, n_steps, ref_n.data(), NULL);
+    bs.batch().get_next_states(N, x, u, n_steps, dt, got_n.data(), st.data());
+    for (std::size_t i = 0; i < N * nx; ++i)
+      err[2] = std::max(err[2], std::fabs(got_n[i] - ref_n[i]) / std::max(1.0, std::fabs(ref_n[i])));
+    std::vector<double> ref_1(nx);
+    for (std::size_t i = 0; i < N && i < 16; ++i) {
+      vect_n<double> p(nx), uu(nu);
+      for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+      for (int k = 0; k < nu; ++k) uu[k] = u[i * nu + k];
+      vect_n<double> a = bs.get_state_derivative(m->sys, p, uu, 0.0);
+      vect_n<double> b = m->sys.get_state_derivative(m->sys, p, uu, 0.0);
+      for (int k = 0; k < nx; ++k) err[0] = std::max(err[0], std::fabs(a[k] - b[k]) / std::max(1.0, std::fabs(b[k])));
+      vect_n<double> nxt = bs.get_next_state(m->sys, p, uu, 0.0);
+      rk4_range(m, i, i + 1, x, u, dt, 1, ref_1.data() - i * nx, NULL);
+      for (int k = 0; k < nx; ++k) err[1] = std::max(err[1], std::fabs(nxt[k] - ref_1[k]) / std::max(1.0, std::fabs(ref_1[k])));
+    }
+    // dimension errors surface as the reference's std::range_error
+    bool threw = false;
+    try { bs.get_state_derivative(m->sys, vect_n<double>(nx + 1), vect_n<double>(nu), 0.0); } catch (std::range_error&) { threw = true; }
+    if (!threw) throw std::runtime_error("size mismatch did not raise std::range_error");
+    return 0;
+  } catch (std::exception& e) {
+    if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
+    return -1;
+  }
 }
 
 // n_workers > 1: the samples are block-partitioned over forked worker processes.  Threads do

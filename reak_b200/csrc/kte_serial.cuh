@@ -348,7 +348,14 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
           const vec3 mv = S.m * Tv[i];
           const vec3 Iw = (IN == 1) ? diagmul(S.I, Tw[i]) : symmul(S.I, Tw[i]);
 #pragma unroll
-          for (int j = 0; j <= i; ++j) Mp[i * (i + 1) / 2 + j] += dot(Tv[j], mv) + dot(Tw[j], Iw);
+          for (int j = 0; j <= i; ++j) {  // one chain of six DFMAs per entry
+            double acc = Mp[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) acc = fma(Tv[j].c[d], mv.c[d], acc);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) acc = fma(Tw[j].c[d], Iw.c[d], acc);
+            Mp[i * (i + 1) / 2 + j] = acc;
+          }
         }
       }
       Mp[k * (k + 1) / 2 + k] += S.rotor;
@@ -418,14 +425,18 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #ifndef RKB_BLOCK
 #define RKB_BLOCK 128
 #endif
+// Resident CTAs per SM the compiler must leave room for.  The structurally specialised code fits
+// 168 registers without spilling (3 CTAs of 128 threads = 3 warps per scheduler); the general
+// code needs the full 255 and would spill at that budget.
 #ifndef RKB_MINBLOCKS
-#define RKB_MINBLOCKS 1
+#define RKB_MINBLOCKS(shape, smem_doubles_per_thread) \
+  (((shape) != 0 && 3 * (smem_doubles_per_thread) * RKB_BLOCK * 8 <= 227 * 1024) ? 3 : 1)
 #endif
 
 // ---- kernels ---------------------------------------------------------------------------------
 // xdot = get_state_derivative(x, u)
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 6 * N)) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
 // n_steps of fixed-step RK4 with the input held constant.
 // Per-thread shared-memory column: [0,6N) wrenches, then w (2N), acc (2N), k3 (2N).
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 12 * N)) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;

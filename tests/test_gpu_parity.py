@@ -204,3 +204,26 @@ def test_full_size_properties():
     assert np.array_equal(two, full)
     back, _ = p.get_next_states(full, u, -1e-3, 20)
     assert rel_err(back, x) < 1e-9
+
+
+def test_reak_bridge_cpp_drop_in(oracle_built):
+    """ReaK::ctrl::kte_batch_system (include/reak_b200/reak_bridge.hpp) built from a LIVE kte_nl_system,
+    compared in C++ against that kte_nl_system and ReaK's own runge_kutta4_integrator — the code is
+    compiled against the unmodified reference headers inside oracle/_ref/libreak_ref.so."""
+    import ctypes as C
+    from reak_b200 import _abi
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built")
+    C.CDLL(_abi.LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name in ("crs6", "crs7_phys_sd", "planar2_lin_sd"):
+        s = presets.make(name)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        R = oracle_built.Reference(c)
+        fn = R.lib.rkref_bridge_gpu_check
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+        x, u = random_batch(c, 64, seed=17)
+        err = np.zeros(3)
+        msg = C.create_string_buffer(512)
+        rc = fn(R.h, 64, x.ctypes.data, u.ctypes.data, 1e-3, 20, err.ctypes.data, msg, 512)
+        assert rc == 0, msg.value
+        assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] < TOL_LONG, (name, err)

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Developer tool: condense an .ncu-rep (ncu --set full) into the few numbers DESIGN.md / bench.py quote.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [units_per_launch] > profiles/<name>.md
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__block_size", "launch__grid_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained",
+    "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+]
+STALLS = "smsp__average_warps_issue_stalled_"
+
+
+def main():
+    rep = sys.argv[1]
+    units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, unit = rows[0], rows[1]
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals))
+        u = dict(zip(hdr, unit))
+        print("## %s" % d.get("Kernel Name", "?"))
+        print("")
+        print("source: `%s` (ncu --set full --clock-control none)" % rep)
+        print("")
+        print("| metric | value | unit |")
+        print("|---|---|---|")
+        for k in KEYS:
+            if k in d:
+                print("| %s | %s | %s |" % (k, d[k], u.get(k, "")))
+        st = sorted(((float(d[k]), k) for k in d if k.startswith(STALLS) and k.endswith("per_issue_active.ratio") and d[k] not in ("", "n/a")), reverse=True)
+        for v, k in st[:8]:
+            print("| stall: %s | %.3f | warps per issue |" % (k[len(STALLS):].replace("_per_issue_active.ratio", ""), v))
+        try:
+            g = lambda k: float(d[k].replace(",", ""))
+            cyc = g("sm__cycles_elapsed.avg")
+            fma, mul, add = (g("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % o) for o in ("dfma", "dmul", "dadd"))
+            peak = g("sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained")
+            print("")
+            print("derived: FP64 thread-instructions per cycle %.1f of %.0f peak = %.1f %% of the DFMA issue rate"
+                  % (fma + mul + add, peak, 100.0 * (fma + mul + add) / peak))
+            if units:
+                print("derived: per unit (%.0f units/launch): %.0f FP64 instructions, %.0f FP64 flops (DFMA = 2)"
+                      % (units, (fma + mul + add) * cyc / units, (2 * fma + mul + add) * cyc / units))
+            print("derived: DRAM traffic %.1f MB per launch" % (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")))
+        except Exception as e:  # metric missing in a reduced set
+            print("derived: n/a (%s)" % e)
+        print("")
+
+
+if __name__ == "__main__":
+    main()
