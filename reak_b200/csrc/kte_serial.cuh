@@ -24,11 +24,13 @@
 //      which makes gen_coord::f differ from the textbook tau - h whenever joint axes are not
 //      orthogonal; torsion springs/dampers across a joint (torsion_spring.cpp:106-129,
 //      torsion_damper.cpp:93-104) reduce to scalars along the joint axis.
-//  sweep 3 (mass_matrix_calc::getMassMatrix, mass_matrix_calculator.cpp:80-87,100-287): the
-//      twist-shaping columns (jacobian_gen_3D::get_jac_relative_to, motion_jacobians.hpp:238-251)
-//      of all upstream joints are carried outward along the chain — rotate at the joint, shift at
-//      the link — instead of being re-derived from relative frames per (joint, inertia) pair;
-//      M += T^T diag(m, I) T per inertia; rotor inertias (inertia_gen) land on the diagonal.
+//  sweep 3 (mass_matrix_calc::getMassMatrix, mass_matrix_calculator.cpp:80-87,100-287):
+//      M = Tcm^T Mcm Tcm, whose twist-shaping columns the reference re-derives from relative
+//      frames per (joint, inertia) pair (jacobian_gen_3D::get_jac_relative_to,
+//      motion_jacobians.hpp:238-251), is regrouped by composite inertias: one inward pass carries
+//      the composite (mass, first moment, tensor) of everything beyond a joint, and each column
+//      C_k S_k is carried inward and projected on the axes below; rotor inertias (inertia_gen)
+//      land on the diagonal.  Same matrix, O(n^2) small-vector work instead of O(n^2) frame algebra.
 //  solve  (linsolve_Cholesky, core/lin_alg/mat_cholesky.hpp:63-84,160-179) with the reference's
 //      "pivot < 1e-8 before the square root" singularity test reported in the status word.
 //  RK4    (runge_kutta4_integrator<T>::integrate, core/integrators/fixed_step_integrators.hpp:256-293),
@@ -140,6 +142,52 @@ RKB_DEV double spring_scalar(const SerialStage& S, double q) {
   double mag = S.ks * fabs(r);  // stiffness * angle_diff.angle(), angle >= 0
   if (S.sat > 0.0 && fabs(mag) > S.sat) mag = (mag > 0.0) ? S.sat : -S.sat;
   return r < 0.0 ? -mag : mag;
+}
+
+// ---- symmetric 3x3 tensors held as xx xy xz yy yz zz ---------------------------------------------
+__host__ __device__ constexpr int sym_idx(int i, int j) {
+  return (i <= j) ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : (j == 0 ? i : (j == 1 ? 2 + i : 5));
+}
+// I <- R I R^T for a rotation by (c, s) about coordinate axis D: 18 multiplies
+template <int D>
+RKB_DEV void sym_rotate_axis(double c, double s, double (&I)[6]) {
+  constexpr int p = (D + 1) % 3, q = (D + 2) % 3;
+  const double ipr = I[sym_idx(p, D)], iqr = I[sym_idx(q, D)];
+  I[sym_idx(p, D)] = c * ipr - s * iqr;
+  I[sym_idx(q, D)] = s * ipr + c * iqr;
+  const double ipp = I[sym_idx(p, p)], ipq = I[sym_idx(p, q)], iqq = I[sym_idx(q, q)];
+  const double app = c * ipp - s * ipq, apq = c * ipq - s * iqq;  // A = R I (2x2 block)
+  const double aqp = s * ipp + c * ipq, aqq = s * ipq + c * iqq;
+  I[sym_idx(p, p)] = c * app - s * apq;
+  I[sym_idx(p, q)] = s * app + c * apq;
+  I[sym_idx(q, q)] = s * aqp + c * aqq;
+}
+// I <- R I R^T for a general rotation
+RKB_DEV void sym_rotate(const mat3& R, double (&I)[6]) {
+  double A[9];  // A = R I
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      A[3 * i + j] = R.m[3 * i] * I[sym_idx(0, j)] + R.m[3 * i + 1] * I[sym_idx(1, j)] + R.m[3 * i + 2] * I[sym_idx(2, j)];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      I[sym_idx(i, j)] = A[3 * i] * R.m[3 * j] + A[3 * i + 1] * R.m[3 * j + 1] + A[3 * i + 2] * R.m[3 * j + 2];
+}
+// Parallel-axis move of a composite (mass mc, first moment h, tensor I): every mass point goes from
+// r to r + p.  mcp = mc * p.  With w = h + mcp / 2:  I += 2 (w.p) 1 - w p^T - p w^T,  h += mcp.
+RKB_DEV void sym_shift(vec3 p, vec3 mcp, vec3& h, double (&I)[6]) {
+  const vec3 w = mk(fma(0.5, mcp.c[0], h.c[0]), fma(0.5, mcp.c[1], h.c[1]), fma(0.5, mcp.c[2], h.c[2]));
+  const double d = 2.0 * dot(w, p);
+  I[0] += d - 2.0 * (w.c[0] * p.c[0]);
+  I[3] += d - 2.0 * (w.c[1] * p.c[1]);
+  I[5] += d - 2.0 * (w.c[2] * p.c[2]);
+  I[1] -= w.c[0] * p.c[1] + p.c[0] * w.c[1];
+  I[2] -= w.c[0] * p.c[2] + p.c[0] * w.c[2];
+  I[4] -= w.c[1] * p.c[2] + p.c[1] * w.c[2];
+  h = h + mcp;
 }
 
 template <int N>
@@ -292,73 +340,118 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       }
     }
   }
-  // ---- sweep 3: twist-shaping columns outward, M accumulated per inertia ---------------------
+  // ---- sweep 3: mass matrix by composite inertias, inward -------------------------------------
+  // M = Tcm^T Mcm Tcm (mass_matrix_calculator.cpp:80-87) regrouped: with C_k the composite inertia
+  // (mass mc, first moment h, tensor I about the frame origin) of all inertias at or beyond stage k,
+  // column k of M is S_j^T X_{j<-k} (C_k S_k) for j <= k.  The composite walks inward once
+  // (rotate at the joint, parallel-axis shift at the link); each new column (f, n) = C_k S_k is then
+  // carried inward through the joints below it and projected on their axes.
   if (WANT_M) {
-    vec3 Tv[N], Tw[N];
+    vec3 h = mk(0, 0, 0);
+    double I[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
 #pragma unroll
-    for (int i = 0; i < N * (N + 1) / 2; ++i) Mp[i] = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
+    for (int k = N - 1; k >= 0; --k) {
       const SerialStage& S = P.st[k];
       constexpr shape_t SH = SHAPE;
       const int AX = shape_ax(SH, k), LK = shape_lk(SH, k), IN = shape_in(SH, k);
-      if (AX != 0) {
-        const int D = AX - 1;
+      // [1] the stage's own inertia_3D sits at the link end frame, centre of mass on its origin
+      if (IN == 1) { I[0] += S.I[0]; I[3] += S.I[3]; I[5] += S.I[5]; }
+      else if (S.flags & RKB_ST_INERTIA) {
 #pragma unroll
-        for (int i = 0; i < k; ++i) {
-          if (D == 0) { Tv[i] = rotT_axis<0>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<0>(cs[k], sn[k], Tw[i]); }
-          else if (D == 1) { Tv[i] = rotT_axis<1>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<1>(cs[k], sn[k], Tw[i]); }
-          else { Tv[i] = rotT_axis<2>(cs[k], sn[k], Tv[i]); Tw[i] = rotT_axis<2>(cs[k], sn[k], Tw[i]); }
-        }
-        Tv[k] = mk(0, 0, 0); Tw[k] = ld3(S.ax);
-      } else {
-        const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-        if (!prismatic) {
-          const mat3 R2 = rodrigues(S, cs[k], sn[k]);
-#pragma unroll
-          for (int i = 0; i < k; ++i) { Tv[i] = tmul(R2, Tv[i]); Tw[i] = tmul(R2, Tw[i]); }
-          Tv[k] = mk(0, 0, 0); Tw[k] = ld3(S.ax);
-        } else {
-          const vec3 r = X.q[k] * ld3(S.ax);
-#pragma unroll
-          for (int i = 0; i < k; ++i) Tv[i] = Tv[i] + cross(Tw[i], r);
-          Tv[k] = ld3(S.ax); Tw[k] = mk(0, 0, 0);
-        }
+        for (int d = 0; d < 6; ++d) I[d] += S.I[d];
       }
+      // [2] link end frame -> joint end frame
       if (LK != 0) {
-        // Tv += Tw x po = L (Tw x e_D)
+        // offset L e_D: w = h + mc po / 2, I += 2 (w.po) 1 - w po^T - po w^T, h += mc po
         const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
         const double L = S.po[D];
-#pragma unroll
-        for (int i = 0; i <= k; ++i) {
-          Tv[i].c[D1] += L * Tw[i].c[D2];
-          Tv[i].c[D2] -= L * Tw[i].c[D1];
-        }
+        const double dd = L * (2.0 * h.c[D] + S.mcpo[D]);
+        I[sym_idx(D1, D1)] += dd;
+        I[sym_idx(D2, D2)] += dd;
+        I[sym_idx(D1, D)] -= L * h.c[D1];
+        I[sym_idx(D2, D)] -= L * h.c[D2];
+        h.c[D] += S.mcpo[D];
       } else if (S.flags & RKB_ST_LINK) {
-        const vec3 po = ld3(S.po);
+        if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) {
+          mat3 Ro;
 #pragma unroll
-        for (int i = 0; i <= k; ++i) {
-          Tv[i] = Tv[i] + cross(Tw[i], po);
-          if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) { Tv[i] = tmulc(S.Ro, Tv[i]); Tw[i] = tmulc(S.Ro, Tw[i]); }
+          for (int d = 0; d < 9; ++d) Ro.m[d] = S.Ro[d];
+          h = mul(Ro, h);
+          sym_rotate(Ro, I);
+        }
+        sym_shift(ld3(S.po), ld3(S.mcpo), h, I);
+      }
+      // [3] column k at the joint end frame, then inward
+      vec3 f, n;
+      const bool prismatic_k = AX == 0 && (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+      if (AX != 0) {
+        // revolute about sg e_D: n = I a, f = a x h
+        const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double sg = S.ax[D];
+        n.c[0] = sg * I[sym_idx(0, D)]; n.c[1] = sg * I[sym_idx(1, D)]; n.c[2] = sg * I[sym_idx(2, D)];
+        f.c[D] = 0.0; f.c[D1] = -sg * h.c[D2]; f.c[D2] = sg * h.c[D1];
+        Mp[k * (k + 1) / 2 + k] = I[sym_idx(D, D)] + S.rotor;
+      } else if (!prismatic_k) {
+        const vec3 ax = ld3(S.ax);
+        n = symmul(I, ax);
+        f = cross(ax, h);
+        Mp[k * (k + 1) / 2 + k] = dot(ax, n) + S.rotor;
+      } else {
+        const vec3 ax = ld3(S.ax);
+        f = S.mc * ax;
+        n = cross(h, ax);
+        Mp[k * (k + 1) / 2 + k] = dot(ax, f) + S.rotor;
+      }
+#pragma unroll
+      for (int j = k; j >= 1; --j) {
+        // joint j: end frame -> base frame (= link end frame of stage j-1)
+        const SerialStage& Sj = P.st[j];
+        const int AXj = shape_ax(SH, j);
+        if (AXj != 0) {
+          const int D = AXj - 1;
+          if (D == 0) { f = rot_axis<0>(cs[j], sn[j], f); n = rot_axis<0>(cs[j], sn[j], n); }
+          else if (D == 1) { f = rot_axis<1>(cs[j], sn[j], f); n = rot_axis<1>(cs[j], sn[j], n); }
+          else { f = rot_axis<2>(cs[j], sn[j], f); n = rot_axis<2>(cs[j], sn[j], n); }
+        } else if (!((FL & RKB_FL_PRISMATIC) && (Sj.flags & RKB_ST_PRISMATIC))) {
+          const mat3 R = rodrigues(Sj, cs[j], sn[j]);
+          f = mul(R, f); n = mul(R, n);
+        } else {
+          n = n + cross(X.q[j] * ld3(Sj.ax), f);
+        }
+        // link j-1: end frame -> joint end frame, then project on joint j-1
+        const SerialStage& Si = P.st[j - 1];
+        const int AXi = shape_ax(SH, j - 1), LKi = shape_lk(SH, j - 1);
+        if (LKi != 0) {
+          const int D = LKi - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+          const double L = Si.po[D];
+          n.c[D1] -= L * f.c[D2];
+          n.c[D2] += L * f.c[D1];
+        } else if (Si.flags & RKB_ST_LINK) {
+          if ((FL & RKB_FL_LINKROT) && (Si.flags & RKB_ST_LINKROT)) { f = mulc(Si.Ro, f); n = mulc(Si.Ro, n); }
+          n = n + cross(ld3(Si.po), f);
+        }
+        double mjk;
+        if (AXi != 0) mjk = Si.ax[AXi - 1] * n.c[AXi - 1];
+        else if (!((FL & RKB_FL_PRISMATIC) && (Si.flags & RKB_ST_PRISMATIC))) mjk = dot(ld3(Si.ax), n);
+        else mjk = dot(ld3(Si.ax), f);
+        Mp[k * (k + 1) / 2 + (j - 1)] = mjk;
+      }
+      // [4] composite: joint end frame -> joint base frame
+      if (k > 0) {
+        if (AX != 0) {
+          const int D = AX - 1;
+          if (D == 0) { h = rot_axis<0>(cs[k], sn[k], h); sym_rotate_axis<0>(cs[k], sn[k], I); }
+          else if (D == 1) { h = rot_axis<1>(cs[k], sn[k], h); sym_rotate_axis<1>(cs[k], sn[k], I); }
+          else { h = rot_axis<2>(cs[k], sn[k], h); sym_rotate_axis<2>(cs[k], sn[k], I); }
+        } else if (!prismatic_k) {
+          const mat3 R = rodrigues(S, cs[k], sn[k]);
+          h = mul(R, h);
+          sym_rotate(R, I);
+        } else {
+          const vec3 r = X.q[k] * ld3(S.ax);
+          sym_shift(r, S.mc * r, h, I);
         }
       }
-      if (IN == 1 || (S.flags & RKB_ST_INERTIA)) {
-#pragma unroll
-        for (int i = 0; i <= k; ++i) {
-          const vec3 mv = S.m * Tv[i];
-          const vec3 Iw = (IN == 1) ? diagmul(S.I, Tw[i]) : symmul(S.I, Tw[i]);
-#pragma unroll
-          for (int j = 0; j <= i; ++j) {  // one chain of six DFMAs per entry
-            double acc = Mp[i * (i + 1) / 2 + j];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) acc = fma(Tv[j].c[d], mv.c[d], acc);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) acc = fma(Tw[j].c[d], Iw.c[d], acc);
-            Mp[i * (i + 1) / 2 + j] = acc;
-          }
-        }
-      }
-      Mp[k * (k + 1) / 2 + k] += S.rotor;
     }
   }
 }

@@ -292,6 +292,12 @@ bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl, unsigned lo
     P.st[s].input = input_of[P.st[s].coord];
   }
   for (int i = 0; i < 3; ++i) { P.w0[i] = w[i]; P.al0[i] = al[i]; P.a0[i] = a[i]; }
+  double mc = 0.0;  // composite masses for the inward mass-matrix pass
+  for (int s = k; s >= 0; --s) {
+    mc += P.st[s].m;
+    P.st[s].mc = mc;
+    for (int i = 0; i < 3; ++i) P.st[s].mcpo[i] = mc * P.st[s].po[i];
+  }
   // structure the specialised kernels may rely on
   shape = 0;
   for (int s = 0; s <= k; ++s) {

@@ -45,6 +45,8 @@ struct SerialStage {
   double m;        // inertia_3D mass
   double I[6];     // inertia tensor xx, xy, xz, yy, yz, zz
   double rotor;    // sum of inertia_gen masses on this coordinate (diagonal of M)
+  double mc;       // composite mass: sum of the inertia_3D masses of this and all later stages
+  double mcpo[3];  // mc * po
   double ks, sat;  // torsion spring stiffness / saturation
   double cd;       // torsion damper coefficient
   uint32_t flags;
