@@ -456,41 +456,56 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
   }
 }
 
-// linsolve_Cholesky on the packed matrix; b is overwritten with the solution.  Only the
-// reciprocals 1/L(i,i) are ever needed: one rsqrt per pivot, no sqrt and no division.
-// Returns RKB_STATUS_SINGULAR where the reference throws singularity_error.
+// 1/d for a pivot d >= 1e-8 (anything else has already raised the singular status): the 2^-23
+// hardware seed (MUFU.RCP64H) and two Newton steps, relative error ~2^-52, no slow path.
+RKB_DEV double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
+// M q_ddot = f on the packed matrix; b is overwritten with the solution.  The factorisation is the
+// square-root-free L D L^T of core/lin_alg/mat_cholesky.hpp:134-157 (same pivots as the Cholesky
+// of :63-84: D(i) = L_chol(i,i)^2), so the reference's "pivot < 1e-8 -> singularity_error" test
+// (:80-82) is applied to D(i) unchanged, and only one reciprocal per pivot is needed — no sqrt.
+// Row i keeps W(i,k) = L(i,k) D(k) in a scratch row while L(i,k) overwrites the matrix.
 template <int N>
 RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N]) {
   int st = 0;
   double inv[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
+    double W[N];
 #pragma unroll
     for (int j = 0; j < i; ++j) {
       double s = Mp[i * (i + 1) / 2 + j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= Mp[i * (i + 1) / 2 + k] * Mp[j * (j + 1) / 2 + k];
-      Mp[i * (i + 1) / 2 + j] = s * inv[j];
+      for (int k = 0; k < j; ++k) s = fma(-W[k], Mp[j * (j + 1) / 2 + k], s);
+      W[j] = s;                              // L(i,j) D(j)
+      Mp[i * (i + 1) / 2 + j] = s * inv[j];  // L(i,j)
     }
     double d = Mp[i * (i + 1) / 2 + i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) d -= Mp[i * (i + 1) / 2 + k] * Mp[i * (i + 1) / 2 + k];
+    for (int k = 0; k < i; ++k) d = fma(-W[k], Mp[i * (i + 1) / 2 + k], d);
     if (!(d >= 1.0e-8)) st = RKB_STATUS_SINGULAR;
-    inv[i] = rsqrt(d);
+    inv[i] = fast_rcp(d);
   }
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
+  for (int i = 0; i < N; ++i) {  // L y = b
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= Mp[i * (i + 1) / 2 + k] * b[k];
-    b[i] = s * inv[i];
+    for (int k = 0; k < i; ++k) s = fma(-Mp[i * (i + 1) / 2 + k], b[k], s);
+    b[i] = s;
   }
 #pragma unroll
-  for (int i = N - 1; i >= 0; --i) {
-    double s = b[i];
+  for (int i = N - 1; i >= 0; --i) {  // D L^T x = y
+    double s = b[i] * inv[i];
 #pragma unroll
-    for (int k = N - 1; k > i; --k) s -= Mp[k * (k + 1) / 2 + i] * b[k];
-    b[i] = s * inv[i];
+    for (int k = N - 1; k > i; --k) s = fma(-Mp[k * (k + 1) / 2 + i], b[k], s);
+    b[i] = s;
   }
   return st;
 }

@@ -50,6 +50,9 @@ struct DeviceCtx {
   GenericProgram* d_prog = nullptr;
   DevBuf in_x, in_u, out_a, out_b, st, scratch_x, scratch_u, scratch_o, scratch_s, in_goal, out_idx, out_cost;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-buffer pipeline: copy-in, two alternating compute streams, copy-out
+  cudaStream_t s_in = nullptr, s_k[2] = {nullptr, nullptr}, s_out = nullptr;
+  cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_join = nullptr;
   bool timed = false;
   bool prepared = false;
 };
@@ -602,6 +605,11 @@ void rkb_chain_destroy(rkb_chain* c) {
     for (DevBuf* b : bufs) b->release();
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
+    if (x->s_in) {
+      cudaStreamDestroy(x->s_in); cudaStreamDestroy(x->s_k[0]); cudaStreamDestroy(x->s_k[1]); cudaStreamDestroy(x->s_out);
+      for (int i = 0; i < 16; ++i) { if (x->ev_in[i]) cudaEventDestroy(x->ev_in[i]); if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]); }
+      if (x->ev_join) cudaEventDestroy(x->ev_join);
+    }
     delete x;
   }
   delete c;
@@ -629,6 +637,94 @@ int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double*
   return run_eval_like(c, OP_MASS, device, N, x, nullptr, M, Mdot, nullptr, flags, stream);
 }
 
+}  // extern "C"
+
+namespace {
+
+constexpr int kPipeChunks = 8;
+constexpr size_t kPipeMinSamples = 1u << 16;
+
+int ensure_pipe(DeviceCtx* ctx) {
+  if (ctx->s_in) return 0;
+  CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->s_k[0], cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->s_k[1], cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < kPipeChunks; ++i) {
+    CU(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  return 0;
+}
+
+// Host AoS buffers, large batch: the batch is cut into chunks whose host->device copy, rollout
+// kernel and device->host copy overlap (copy-in stream, two alternating compute streams so that
+// one chunk's tail wave overlaps the next chunk's head, copy-out stream).  Only the first copy-in
+// and the last copy-out stay exposed.  Pinned host memory is what makes the copies asynchronous.
+int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                           double* x_out, int32_t* status, cudaStream_t s) {
+  const int nx = 2 * c->n, nu = c->nu;
+  int rc;
+  if ((rc = ensure_pipe(ctx))) return rc;
+  if ((rc = ctx->in_x.ensure(N * nx * sizeof(double)))) return rc;
+  if (nu > 0 && (rc = ctx->in_u.ensure(N * nu * sizeof(double)))) return rc;
+  if ((rc = ctx->out_a.ensure(N * nx * sizeof(double)))) return rc;
+  if ((rc = ctx->st.ensure(N * sizeof(int32_t)))) return rc;
+  double* dx = (double*)ctx->in_x.p;
+  double* du = (double*)ctx->in_u.p;
+  double* dout = (double*)ctx->out_a.p;
+  int32_t* dst = (int32_t*)ctx->st.p;
+  // order after whatever the caller queued on its stream
+  CU(cudaEventRecord(ctx->ev_join, s));
+  CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_join, 0));
+  CU(cudaStreamWaitEvent(ctx->s_k[0], ctx->ev_join, 0));
+  CU(cudaEventRecord(ctx->ev0, ctx->s_k[0]));
+  const size_t per = ((N + kPipeChunks - 1) / kPipeChunks + 127) / 128 * 128;
+  int last_k = 0;
+  for (int i = 0; i < kPipeChunks; ++i) {
+    const size_t lo = per * i;
+    if (lo >= N) break;
+    const size_t m = (lo + per <= N) ? per : N - lo;
+    CU(cudaMemcpyAsync(dx + lo * nx, x0 + lo * nx, m * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->s_in));
+    if (nu > 0) CU(cudaMemcpyAsync(du + lo * nu, u + lo * nu, m * nu * sizeof(double), cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+    cudaStream_t sk = ctx->s_k[i & 1];
+    CU(cudaStreamWaitEvent(sk, ctx->ev_in[i], 0));
+    RolloutArgs A;
+    A.x0 = cview(dx + lo * nx, (long long)m, nx, false);
+    A.u = cview(nu > 0 ? du + lo * nu : dx, (long long)m, nu > 0 ? nu : 1, false);
+    A.xout = view(dout + lo * nx, (long long)m, nx, false);
+    A.status = dst + lo;
+    A.n_samples = (long long)m;
+    A.x0_div = 1;
+    A.dt = dt;
+    A.n_steps = n_steps;
+    if ((rc = launch_rollout(c, ctx, A, sk))) return rc;
+    CU(cudaEventRecord(ctx->ev_k[i], sk));
+    CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[i], 0));
+    CU(cudaMemcpyAsync(x_out + lo * nx, dout + lo * nx, m * nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+    if (status) CU(cudaMemcpyAsync(status + lo, dst + lo, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+    last_k = i;
+  }
+  // ev1 closes the timed span on the stream that ran the last kernel, after the other one joined it
+  cudaStream_t sl = ctx->s_k[last_k & 1];
+  if (last_k > 0) CU(cudaStreamWaitEvent(sl, ctx->ev_k[last_k - 1], 0));
+  CU(cudaEventRecord(ctx->ev1, sl));
+  ctx->timed = true;
+  c->last = ctx;
+  CU(cudaStreamSynchronize(ctx->s_out));
+  CU(cudaStreamSynchronize(sl));
+  // let the caller's stream observe completion as well
+  CU(cudaEventRecord(ctx->ev_join, ctx->s_out));
+  CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  return RKB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const double* u, double dt, int n_steps,
                     double* x_out, int32_t* status, unsigned flags, void* stream) {
   if (!c) return RKB_ERR_INVALID;
@@ -644,6 +740,8 @@ int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const 
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if (!L.device && !L.soa && N >= kPipeMinSamples && n_steps > 0 && !(std::getenv("RKB_NO_PIPELINE") && std::getenv("RKB_NO_PIPELINE")[0] == '1'))
+    return rollout_host_pipelined(c, ctx, N, x0, u, dt, n_steps, x_out, status, s);
   const void *dx = nullptr, *du = nullptr;
   void *dout = nullptr, *dst = nullptr;
   if ((rc = stage_in(ctx->in_x, x0, N * nx * sizeof(double), L.device, s, &dx))) return rc;
