@@ -220,6 +220,7 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
   // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
   if (WANT_F) {
     vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
+    vec3 F = mk(0, 0, 0), T = mk(0, 0, 0);  // running wrench of sweep 2
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const SerialStage& S = P.st[k];
@@ -279,17 +280,21 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
         Tk = mk(0, 0, 0) - (symmul(S.I, al) + cross(w, Iw));
       }
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { sm[(6 * k + d) * SMS] = Fk.c[d]; sm[(6 * k + 3 + d) * SMS] = Tk.c[d]; }
+      for (int d = 0; d < 3; ++d) {
+        if (k == N - 1) { F.c[d] = Fk.c[d]; T.c[d] = Tk.c[d]; }  // the outermost wrench is consumed first: keep it in registers
+        else { sm[(6 * k + d) * SMS] = Fk.c[d]; sm[(6 * k + 3 + d) * SMS] = Tk.c[d]; }
+      }
     }
     // ---- sweep 2: wrenches inward -----------------------------------------------------------
-    vec3 F = mk(0, 0, 0), T = mk(0, 0, 0);
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       const SerialStage& S = P.st[k];
       constexpr shape_t SH = SHAPE;
       const int AX = shape_ax(SH, k), LK = shape_lk(SH, k);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { F.c[d] += sm[(6 * k + d) * SMS]; T.c[d] += sm[(6 * k + 3 + d) * SMS]; }
+      for (int d = 0; d < 3; ++d) {
+        if (k < N - 1) { F.c[d] += sm[(6 * k + d) * SMS]; T.c[d] += sm[(6 * k + 3 + d) * SMS]; }
+      }
       if (LK != 0) {
         // T += po x F = L (e_D x F): [D1] -= L F[D2], [D2] += L F[D1]   (rigid_link.cpp:170-177, Ro = I)
         const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
@@ -533,18 +538,28 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #ifndef RKB_BLOCK
 #define RKB_BLOCK 128
 #endif
-// Resident CTAs per SM the compiler must leave room for.  The structurally specialised code fits
-// 168 registers without spilling (3 CTAs of 128 threads = 3 warps per scheduler); the general
-// code needs the full 255 and would spill at that budget.
+// per-thread shared-memory doubles: parked wrenches of stages 0..N-2, and for the rollout the
+// state at the start of the step (w) and k1 + 2 k2.  k3 is not stored: the stage-4 update starts
+// from x = w + k3, so k3 is recovered as x - w (exact up to one rounding of x, i.e. ~1e-16 |x|).
+#define RKB_SMEM_EVAL(n) (6 * ((n) - 1) + 1)
+#define RKB_SMEM_ROLLOUT(n) (6 * ((n) - 1) + 4 * (n))
+// Resident CTAs per SM the compiler must leave room for.  The structurally specialised code runs
+// best with 4 CTAs of 128 threads (128 registers, 4 warps per scheduler; measured 25.4 ms vs
+// 26.1 ms at 3 CTAs and 27.0 ms at 2 for the 6-DOF rollout) when 4 columns of shared memory fit,
+// else 3; the general code needs the full 255 registers and loses 10 % when squeezed.
+#ifdef RKB_FORCE_MINBLOCKS
+#define RKB_MINBLOCKS(shape, smem_doubles_per_thread) (RKB_FORCE_MINBLOCKS)
+#endif
 #ifndef RKB_MINBLOCKS
+#define RKB_FITS(blocks, smem_doubles_per_thread) ((blocks) * ((smem_doubles_per_thread) * RKB_BLOCK * 8 + 1024) <= 227 * 1024)
 #define RKB_MINBLOCKS(shape, smem_doubles_per_thread) \
-  (((shape) != 0 && 3 * (smem_doubles_per_thread) * RKB_BLOCK * 8 <= 227 * 1024) ? 3 : 1)
+  ((shape) == 0 ? 1 : (RKB_FITS(4, smem_doubles_per_thread) ? 4 : (RKB_FITS(3, smem_doubles_per_thread) ? 3 : 1)))
 #endif
 
 // ---- kernels ---------------------------------------------------------------------------------
 // xdot = get_state_derivative(x, u)
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 6 * N)) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_EVAL(N))) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
@@ -601,17 +616,16 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
 }
 
 // n_steps of fixed-step RK4 with the input held constant.
-// Per-thread shared-memory column: [0,6N) wrenches, then w (2N), acc (2N), k3 (2N).
+// Per-thread shared-memory column: [0, 6(N-1)) wrenches, then w (2N) and k1 + 2 k2 (2N).
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 12 * N)) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
   double* sm = smem + threadIdx.x;
-  double* sw = sm + 6 * N * SMS;    // state at the start of the step (w)
+  double* sw = sm + 6 * (N - 1) * SMS;  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
-  double* s3 = sa + 2 * N * SMS;    // k3
   SerialState<N> X;
   {
     const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
@@ -648,7 +662,6 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 12 * N)) seria
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double k3q = X.qd[k] * dt, k3v = qdd[k] * dt;
-        s3[(2 * k) * SMS] = k3q; s3[(2 * k + 1) * SMS] = k3v;
         X.q[k] = sw[(2 * k) * SMS] + k3q; X.qd[k] = sw[(2 * k + 1) * SMS] + k3v;
       }
     } else {
@@ -656,8 +669,9 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, 12 * N)) seria
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double k4q = X.qd[k] * dt, k4v = qdd[k] * dt;
-        X.q[k] += (sa[(2 * k) * SMS] + k4q) * sixth - s3[(2 * k) * SMS] * (2.0 / 3.0);
-        X.qd[k] += (sa[(2 * k + 1) * SMS] + k4v) * sixth - s3[(2 * k + 1) * SMS] * (2.0 / 3.0);
+        const double k3q = X.q[k] - sw[(2 * k) * SMS], k3v = X.qd[k] - sw[(2 * k + 1) * SMS];
+        X.q[k] += (sa[(2 * k) * SMS] + k4q) * sixth - k3q * (2.0 / 3.0);
+        X.qd[k] += (sa[(2 * k + 1) * SMS] + k4v) * sixth - k3v * (2.0 / 3.0);
       }
     }
   }

@@ -12,8 +12,8 @@ using namespace rkb;
 
 template <int N, int FL, shape_t SHAPE>
 struct Launch {
-  static constexpr int kSmemEval = 6 * N * RKB_BLOCK * (int)sizeof(double);
-  static constexpr int kSmemRollout = 12 * N * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemEval = RKB_SMEM_EVAL(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemRollout = RKB_SMEM_ROLLOUT(N) * RKB_BLOCK * (int)sizeof(double);
   static unsigned grid(long long n) { return (unsigned)((n + RKB_BLOCK - 1) / RKB_BLOCK); }
   static cudaError_t prepare() {
     cudaError_t e = cudaFuncSetAttribute(serial_rollout_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
