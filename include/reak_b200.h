@@ -163,6 +163,13 @@ RKB_API int rkb_rollout_rk4(rkb_chain* chain, int device, size_t n_samples,
                     const double* x0, const double* u, double dt, int n_steps,
                     double* x_out, int32_t* status, unsigned flags, void* stream);
 
+/* rkb_rollout_rk4 on HOST buffers (AoS), sharded over `n_devices` GPUs of this box from one
+ * process: contiguous blocks of samples, one copy/compute pipeline per device, no inter-GPU
+ * communication (the reference has no counterpart; per sample the semantics are unchanged). */
+RKB_API int rkb_rollout_rk4_multi(rkb_chain* chain, int n_devices, const int* devices, size_t n_samples,
+                                  const double* x0, const double* u, double dt, int n_steps,
+                                  double* x_out, int32_t* status);
+
 /* Generalised force gen_coord::f after doMotion/clearForce/doForce with q_ddot = 0
  * (tau - h(q,qd) in ReaK's convention).  f: N x n. */
 RKB_API int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,

@@ -224,6 +224,15 @@ class kte_batch_propagator {
     if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step or negative step count");
     check(rc, "rkb_rollout_rk4");
   }
+  /// Host (AoS) buffers sharded over several GPUs of this box from one process: contiguous blocks of
+  /// samples, one copy/compute pipeline per device, no inter-GPU communication.
+  void get_next_states_multi(const std::vector<int>& devices, std::size_t n, const double* x, const double* u, int n_steps,
+                             double dt, double* x_out, int32_t* status = NULL) const {
+    int rc = rkb_rollout_rk4_multi(mChain, static_cast<int>(devices.size()), devices.empty() ? NULL : &devices[0], n, x, u, dt,
+                                   n_steps, x_out, status);
+    if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step or negative step count");
+    check(rc, "rkb_rollout_rk4_multi");
+  }
   void get_gen_forces(std::size_t n, const double* x, const double* u, double* f, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_gen_forces(mChain, mDevice, n, x, u, f, flags, stream), "rkb_gen_forces");
   }

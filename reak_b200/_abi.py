@@ -66,6 +66,8 @@ SYMBOLS = {
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_rollout_rk4_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_int, C.c_void_p, C.c_void_p]),
     "rkb_gen_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_uint, C.c_void_p]),
     "rkb_mass_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,

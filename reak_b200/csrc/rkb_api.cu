@@ -3,6 +3,7 @@
 // compute entry point needs a usable sm_100 device and fails with RKB_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -662,8 +663,8 @@ int ensure_pipe(DeviceCtx* ctx) {
 // kernel and device->host copy overlap (copy-in stream, two alternating compute streams so that
 // one chunk's tail wave overlaps the next chunk's head, copy-out stream).  Only the first copy-in
 // and the last copy-out stay exposed.  Pinned host memory is what makes the copies asynchronous.
-int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
-                           double* x_out, int32_t* status, cudaStream_t s) {
+int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                       double* x_out, int32_t* status, cudaStream_t s, bool join_caller) {
   const int nx = 2 * c->n, nu = c->nu;
   int rc;
   if ((rc = ensure_pipe(ctx))) return rc;
@@ -675,10 +676,11 @@ int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double*
   double* du = (double*)ctx->in_u.p;
   double* dout = (double*)ctx->out_a.p;
   int32_t* dst = (int32_t*)ctx->st.p;
-  // order after whatever the caller queued on its stream
-  CU(cudaEventRecord(ctx->ev_join, s));
-  CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_join, 0));
-  CU(cudaStreamWaitEvent(ctx->s_k[0], ctx->ev_join, 0));
+  if (join_caller) {  // order after whatever the caller queued on its stream
+    CU(cudaEventRecord(ctx->ev_join, s));
+    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_join, 0));
+    CU(cudaStreamWaitEvent(ctx->s_k[0], ctx->ev_join, 0));
+  }
   CU(cudaEventRecord(ctx->ev0, ctx->s_k[0]));
   const size_t per = ((N + kPipeChunks - 1) / kPipeChunks + 127) / 128 * 128;
   int last_k = 0;
@@ -713,8 +715,21 @@ int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double*
   CU(cudaEventRecord(ctx->ev1, sl));
   ctx->timed = true;
   c->last = ctx;
+  return RKB_OK;
+}
+
+int rollout_host_wait(DeviceCtx* ctx) {
   CU(cudaStreamSynchronize(ctx->s_out));
-  CU(cudaStreamSynchronize(sl));
+  CU(cudaStreamSynchronize(ctx->s_k[0]));
+  CU(cudaStreamSynchronize(ctx->s_k[1]));
+  return RKB_OK;
+}
+
+int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                           double* x_out, int32_t* status, cudaStream_t s) {
+  int rc = rollout_host_issue(c, ctx, N, x0, u, dt, n_steps, x_out, status, s, true);
+  if (rc) return rc;
+  if ((rc = rollout_host_wait(ctx))) return rc;
   // let the caller's stream observe completion as well
   CU(cudaEventRecord(ctx->ev_join, ctx->s_out));
   CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -766,6 +781,48 @@ int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const 
   if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
   if (!L.device) CU(cudaStreamSynchronize(s));
   return RKB_OK;
+}
+
+/* Host-buffer rollout sharded over several GPUs of one box from one process: contiguous block
+ * partition by sample index (sizes differ by at most one 128-sample tile), every device runs its
+ * own copy-in / compute / copy-out pipeline concurrently, no inter-GPU communication — the
+ * "gather" is the device->host copies landing in the caller's output buffer. */
+int rkb_rollout_rk4_multi(rkb_chain* c, int n_devices, const int* devices, size_t N, const double* x0, const double* u,
+                          double dt, int n_steps, double* x_out, int32_t* status) {
+  if (!c || n_devices < 1 || !devices) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
+  if (N == 0) return RKB_OK;
+  if (!x0 || !x_out || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
+  const int nx = 2 * c->n, nu = c->nu;
+  std::lock_guard<std::mutex> lock(c->mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  std::vector<DeviceCtx*> used(n_devices, nullptr);
+  const size_t tiles = (N + 127) / 128;
+  int rc = RKB_OK;
+  for (int g = 0; g < n_devices && rc == RKB_OK; ++g) {
+    const size_t lo = std::min(N, (tiles * g / n_devices) * 128), hi = std::min(N, (tiles * (g + 1) / n_devices) * 128);
+    if (hi <= lo) continue;
+    if (cudaSetDevice(devices[g]) != cudaSuccess) { cudaGetLastError(); rc = RKB_ERR_CUDA; break; }
+    DeviceCtx* ctx = nullptr;
+    if ((rc = get_ctx(c, devices[g], &ctx))) break;
+    if (n_steps == 0) {
+      std::memcpy(x_out + lo * nx, x0 + lo * nx, (hi - lo) * nx * sizeof(double));
+      if (status) std::memset(status + lo, 0, (hi - lo) * sizeof(int32_t));
+      continue;
+    }
+    rc = rollout_host_issue(c, ctx, hi - lo, x0 + lo * nx, nu > 0 ? u + lo * nu : nullptr, dt, n_steps, x_out + lo * nx,
+                            status ? status + lo : nullptr, nullptr, false);
+    used[g] = ctx;
+  }
+  for (int g = 0; g < n_devices; ++g) {
+    if (!used[g]) continue;
+    cudaSetDevice(devices[g]);
+    const int w = rollout_host_wait(used[g]);
+    if (rc == RKB_OK) rc = w;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
 }
 
 int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* x0, const double* goal, const double* u,

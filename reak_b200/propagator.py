@@ -178,6 +178,23 @@ class kte_batch_propagator(object):
                                              dt, int(n_steps), ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4")
         return xo, st
 
+    def get_next_states_multi(self, x, u=None, dt=None, n_steps=1, devices=(0,), out=None, status=None):
+        """Host (numpy, AoS) buffers sharded over several GPUs from this one process (rkb_rollout_rk4_multi)."""
+        x, N = self._in(x, self.nx, np.float64)
+        u = self._u_default(x, N, False) if u is None else self._in(u, self.nu, np.float64, False, N)[0]
+        if _is_torch(x) or _is_torch(u):
+            raise TypeError("get_next_states_multi takes host (numpy) buffers")
+        dt = self.dt if dt is None else float(dt)
+        if dt == 0.0 or n_steps < 0:
+            raise impossible_integration("dt == 0 or negative step count")
+        xo = out if out is not None else np.empty_like(x)
+        st = status if status is not None else np.empty((N,), dtype=np.int32)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _abi.check(self._lib.rkb_rollout_rk4_multi(self._h, len(devices), devs, N, p(x), p(u) if self.nu else None, dt, int(n_steps),
+                                                   p(xo), p(st)), "rkb_rollout_rk4_multi")
+        return xo, st
+
     def get_gen_forces(self, x, u=None, soa=False):
         x, N = self._in(x, self.nx, np.float64, soa)
         u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]

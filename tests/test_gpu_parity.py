@@ -227,3 +227,45 @@ def test_reak_bridge_cpp_drop_in(oracle_built):
         rc = fn(R.h, 64, x.ctypes.data, u.ctypes.data, 1e-3, 20, err.ctypes.data, msg, 512)
         assert rc == 0, msg.value
         assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] < TOL_LONG, (name, err)
+
+
+def test_multi_device_host_rollout():
+    """rkb_rollout_rk4_multi: block partition over every visible GPU from one process; bit-identical
+    to the single-device result (runs with one device when only one is visible)."""
+    import torch
+    p = _make("crs6")
+    n_dev = torch.cuda.device_count()
+    x, u = random_batch(p.compiled, 200003, seed=41)
+    ref, st0 = p.get_next_states(x, u, 1e-3, 6)
+    for devs in ([0], list(range(n_dev)), [0] * 3):
+        got, st = p.get_next_states_multi(x, u, 1e-3, 6, devices=devs)
+        assert np.array_equal(got, ref) and np.array_equal(st, st0), devs
+    same, st = p.get_next_states_multi(x[:1000], u[:1000], 1e-3, 0, devices=[0])
+    assert np.array_equal(same, x[:1000]) and not st.any()
+
+
+def test_ragged_sizes_and_permuted_dofs(oracle_built):
+    """Batch sizes around the 128-thread tile and the 65536-sample pipeline threshold; a chain whose
+    state order is not the chain order."""
+    p = _make("crs6_sd")
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 66000, seed=19)
+    full, _ = p.get_next_states(x, u, 1e-3, 3)
+    for n in (1, 2, 127, 128, 129, 65535, 65536, 65537):
+        got, st = p.get_next_states(x[:n], u[:n], 1e-3, 3)
+        assert np.array_equal(got, full[:n]) and not st.any(), n
+    assert rel_err(full[:64], O.rk4(x[:64], u[:64], 1e-3, 3)[0]) < TOL_STEP
+    from reak_b200 import kte_batch_propagator
+    s = presets.make("crs6_phys")
+    perm = [3, 0, 5, 1, 4, 2]
+    s.dofs_gen = [s.dofs_gen[i] for i in perm]
+    s.mass_calc.mCoords = list(s.dofs_gen)
+    s.inputs = [s.inputs[i] for i in (5, 4, 3, 2, 1, 0)]
+    q = kte_batch_propagator(s)
+    assert q.is_serial()
+    Oq = oracle_built.Oracle(q.compiled)
+    x, u = random_batch(q.compiled, 77, seed=23)
+    assert rel_err(q.get_state_derivatives(x, u)[0], Oq.eval(x, u)[0]) < TOL_STEP
+    assert rel_err(q.get_mass_matrices(x), Oq.mass(x, with_dot=False)) < TOL_STEP
+    assert rel_err(q.get_gen_forces(x, u), Oq.gen_forces(x, u)) < TOL_STEP
+    assert rel_err(q.get_next_states(x, u, 1e-3, 20)[0], Oq.rk4(x, u, 1e-3, 20)[0]) < TOL_LONG
