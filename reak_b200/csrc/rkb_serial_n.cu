@@ -12,7 +12,9 @@ using namespace rkb;
 
 template <int N, int FL, shape_t SHAPE>
 struct Launch {
-  static constexpr int kSmemEval = RKB_SMEM_EVAL(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemEval = RKB_SMEM_EVAL_K(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemForces = RKB_SMEM_FORCES_K(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemMass = RKB_SMEM_MASS_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemRollout = RKB_SMEM_ROLLOUT(N) * RKB_BLOCK * (int)sizeof(double);
   static unsigned grid(long long n) { return (unsigned)((n + RKB_BLOCK - 1) / RKB_BLOCK); }
   static cudaError_t prepare() {
@@ -20,9 +22,9 @@ struct Launch {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_eval_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(serial_forces_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
+    e = cudaFuncSetAttribute(serial_forces_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemForces);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
+    return cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMass);
   }
   static cudaError_t eval(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
@@ -31,12 +33,12 @@ struct Launch {
   }
   static cudaError_t forces(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_forces_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
+    serial_forces_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemForces, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t mass(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_mass_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemEval, s>>>(P, A);
+    serial_mass_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemMass, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t rollout(const SerialParams& P, const RolloutArgs& A, cudaStream_t s) {
