@@ -32,19 +32,22 @@ N_SAMPLES = 1 << 20
 RK4_STEPS = 100
 DT = 1e-3
 # Algorithmic work of one RK4 state-step of the 6-DOF chain:
-#   * FP64 flops and FP64 instructions the structure-specialised kernel executes per state-step —
-#     counted from the SASS instruction mix of serial_rollout_kernel<6,0,arm> (DFMA = 2 flops) and
-#     cross-checked against ncu's smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on
-#     (profiles/r1_rollout_spec_v2.md).  SURVEY.md 8(d)'s 2.26e4 flop figure is the count for the dense,
-#     general-axis formulation; the specialised kernel does the same mathematics with the structural
-#     zeros removed, so that figure would read as 1.7x the DFMA peak and is reported separately.
+#   * FP64 flops and FP64 instructions the structure-specialised kernel executes per state-step (DFMA = 2
+#     flops), taken from ncu's smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on of the committed
+#     capture: tools/ncu_summary.py writes them, with the DRAM traffic of that launch, to
+#     profiles/roofline_constants.json, so the numbers always belong to the kernel that was profiled.
+#     SURVEY.md 8(d)'s 2.26e4 flop figure is the count for the dense, general-axis formulation; the
+#     specialised kernel does the same mathematics with the structural zeros removed, so that figure
+#     would read as more than the DFMA peak and is reported separately (survey_frac).
 #   * bytes of one sample per call: read 2n + n doubles, write 2n doubles + status word.
-FLOP_PER_STATE_STEP = 8.08e3
-FP64_INSTR_PER_STATE_STEP = 4.90e3
 SURVEY_FLOP_PER_STATE_STEP = 2.26e4
 BYTES_PER_SAMPLE = (12 + 6) * 8 + 12 * 8 + 4
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 samples), ncu --set full, profiles/r1_rollout_spec_v2.md
-DRAM_TRAFFIC_BYTES = 225.4e6
+
+
+def load_roofline_constants():
+    with open(os.path.join(ROOT, "profiles", "roofline_constants.json")) as f:
+        c = json.load(f)
+    return c
 
 
 def load_peaks():
@@ -298,6 +301,9 @@ def run_ours(args):
     clk = C.c_double(0.0)
     _abi.check(_abi.load_library().rkb_measure_fp64_peak(local, 1.0, C.byref(tf), C.byref(clk)), "rkb_measure_fp64_peak")
     k_ms = float(np.mean(kernel_ms))
+    rc = load_roofline_constants()
+    FLOP_PER_STATE_STEP, FP64_INSTR_PER_STATE_STEP = rc["flop_per_state_step"], rc["fp64_instr_per_state_step"]
+    DRAM_TRAFFIC_BYTES = rc["dram_traffic_bytes_per_launch"]
     achieved_tf = FLOP_PER_STATE_STEP * n * RK4_STEPS / (k_ms * 1e-3) / 1e12
     achieved_gbs = BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     instr_rate = FP64_INSTR_PER_STATE_STEP * n * RK4_STEPS / (k_ms * 1e-3)
@@ -307,6 +313,7 @@ def run_ours(args):
                 "survey_flop_per_state_step": SURVEY_FLOP_PER_STATE_STEP,
                 "survey_frac": SURVEY_FLOP_PER_STATE_STEP * n * RK4_STEPS / (k_ms * 1e-3) / 1e12 / tf.value,
                 "traffic": DRAM_TRAFFIC_BYTES, "kernel": "serial_rollout_kernel<6,0,arm>", "kernel_ms": k_ms,
+                "constants_source": "profiles/roofline_constants.json <- " + str(rc.get("source")),
                 "peak_source": "DFMA loop measured in this run (rkb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flop_per_state_step": FLOP_PER_STATE_STEP}
     roofline_hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

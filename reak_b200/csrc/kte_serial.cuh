@@ -190,6 +190,64 @@ RKB_DEV void sym_shift(vec3 p, vec3 mcp, vec3& h, double (&I)[6]) {
   h = h + mcp;
 }
 
+// ---- sine and cosine of the joint angles ---------------------------------------------------------
+// The CUDA library's sincos() spends more issue slots on loading its polynomial coefficients
+// (two UMOV per 64-bit immediate), on F2I/I2F and on its slow-path branch than on arithmetic, and the
+// branch keeps the compiler from interleaving the six independent evaluations: ncu attributed 29 % of
+// the rollout kernel's stall samples to it.  This version has the same structure — three-term
+// Cody-Waite reduction by pi/2 (exact for |q| < 2^30), degree-13/12 polynomials on [-pi/4, pi/4],
+// error below 1.6 ulp — but rounds with the 1.5*2^52 trick instead of F2I/I2F and has no branch,
+// so the six evaluations of a stage interleave.  Arguments outside the reduction's range (and NaN)
+// are left to sincos() by the caller.
+// sin(r) = r + r z (S1 + z (S2 + ... z S6)),  cos(r) = 1 - z/2 + z^2 (C1 + z (C2 + ... z C6)),  z = r^2, |r| <= pi/4.
+// The coefficients are literals on purpose: FP64 instructions take constants only through uniform
+// registers, of which there are 63; a table would be hoisted out of the rollout loop into 32 of them
+// and push chain constants out (R2UR.FILL traffic), whereas literals are re-materialised by UMOVs on
+// the uniform datapath, which costs no issue slot of the vector pipes.
+#define RKB_S1 -1.66666666666666324348e-01
+#define RKB_S2 8.33333333332248946124e-03
+#define RKB_S3 -1.98412698298579493134e-04
+#define RKB_S4 2.75573137070700676789e-06
+#define RKB_S5 -2.50507602534068634195e-08
+#define RKB_S6 1.58969099521155010221e-10
+#define RKB_C1 4.16666666666666019037e-02
+#define RKB_C2 -1.38888888888741095749e-03
+#define RKB_C3 2.48015872894767294178e-05
+#define RKB_C4 -2.75573143513906633035e-07
+#define RKB_C5 2.08757232129817482790e-09
+#define RKB_C6 -1.13596475577881948265e-11
+#define RKB_2_OVER_PI 6.36619772367581382433e-01
+#define RKB_PIO2_HI 1.570796326794896557999e+00   // pi/2 split in three doubles
+#define RKB_PIO2_MID 6.123233995736766035869e-17
+#define RKB_PIO2_LO -1.497384904859169832944e-33
+
+#define RKB_SINCOS_MAX 1.0e9  // |q| below this: k = rint(q 2/pi) fits 31 bits and the reduction is accurate
+
+RKB_DEV void sincos_reduced(double q, double& sn, double& cs) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+  const double t = fma(q, RKB_2_OVER_PI, magic);
+  const int k = __double2loint(t);          // low mantissa word = the integer, two's complement
+  const double kd = t - magic;
+  double r = fma(-kd, RKB_PIO2_HI, q);
+  r = fma(-kd, RKB_PIO2_MID, r);
+  r = fma(-kd, RKB_PIO2_LO, r);
+  const double z = r * r;
+  double ps = fma(z, RKB_S6, RKB_S5);
+  double pc = fma(z, RKB_C6, RKB_C5);
+  ps = fma(z, ps, RKB_S4); pc = fma(z, pc, RKB_C4);
+  ps = fma(z, ps, RKB_S3); pc = fma(z, pc, RKB_C3);
+  ps = fma(z, ps, RKB_S2); pc = fma(z, pc, RKB_C2);
+  ps = fma(z, ps, RKB_S1); pc = fma(z, pc, RKB_C1);
+  const double s0 = fma(r * z, ps, r);
+  const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+  // quadrant k mod 4: (sin, cos) = (s0, c0), (c0, -s0), (-s0, -c0), (-c0, s0)
+  double s = (k & 1) ? c0 : s0;
+  double c = (k & 1) ? s0 : c0;
+  if (k & 2) s = -s;
+  if ((k + 1) & 2) c = -c;
+  sn = s; cs = c;
+}
+
 template <int N>
 struct SerialState {
   double q[N], qd[N], u[N];
@@ -199,13 +257,14 @@ __host__ __device__ constexpr int shape_ax(shape_t s, int k) { return (int)((s >
 __host__ __device__ constexpr int shape_lk(shape_t s, int k) { return (int)((s >> (8 * k + 3)) & 3u); }     // 0 general, 1..3 offset along x,y,z, no rotation
 __host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 3u); }     // 0 general, 1 diagonal tensor present
 
-// The evaluation proper.  `sm` is this thread's shared-memory column (stride SMS doubles
-// between consecutive slots); slots [0, 6N) hold the parked inertia wrenches.
+// The evaluation proper.  (`sm`, this thread's shared-memory column with stride SMS, is no longer
+// used by the sweeps; the rollout kernel keeps its RK4 state there.)
 // Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
 // Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
 template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M>
 RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
                            double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
+  bool in_range = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const SerialStage& S = P.st[k];
@@ -213,14 +272,32 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
     const int AX = shape_ax(SH, k);
     const bool prismatic = AX == 0 && (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
     if (!prismatic) {
-      sincos(X.q[k], &sn[k], &cs[k]);
-      if (AX != 0) sn[k] *= S.ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
+      sincos_reduced(X.q[k], sn[k], cs[k]);
+      in_range = in_range && (fabs(X.q[k]) < RKB_SINCOS_MAX);
     } else { sn[k] = 0.0; cs[k] = 1.0; }
+  }
+  if (!in_range) {  // a huge or non-finite angle somewhere in this sample: library path, never taken in practice
+#pragma unroll
+    for (int k = 0; k < N; ++k) {  // (static indices: a rolled loop would push q, sn, cs into local memory)
+      const bool prismatic = (FL & RKB_FL_PRISMATIC) && (P.st[k].flags & RKB_ST_PRISMATIC);
+      if (!prismatic) sincos(X.q[k], &sn[k], &cs[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    constexpr shape_t SH = SHAPE;
+    const int AX = shape_ax(SH, k);
+    if (AX != 0) sn[k] *= P.st[k].ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
   }
   // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
   if (WANT_F) {
     vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
     vec3 F = mk(0, 0, 0), T = mk(0, 0, 0);  // running wrench of sweep 2
+    // d'Alembert wrenches of stages 0..N-2, held until sweep 2 picks them up.  (They used to be parked
+    // in shared memory; the compiler forwarded every store to its load and kept the values in
+    // registers anyway, so the stores were 30 dead STS per evaluation.  It now decides itself which of
+    // them to keep and which to spill.)
+    double park[6 * (N > 1 ? N - 1 : 1)];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const SerialStage& S = P.st[k];
@@ -282,7 +359,7 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         if (k == N - 1) { F.c[d] = Fk.c[d]; T.c[d] = Tk.c[d]; }  // the outermost wrench is consumed first: keep it in registers
-        else { sm[(6 * k + d) * SMS] = Fk.c[d]; sm[(6 * k + 3 + d) * SMS] = Tk.c[d]; }
+        else { park[6 * k + d] = Fk.c[d]; park[6 * k + 3 + d] = Tk.c[d]; }
       }
     }
     // ---- sweep 2: wrenches inward -----------------------------------------------------------
@@ -293,7 +370,7 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       const int AX = shape_ax(SH, k), LK = shape_lk(SH, k);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        if (k < N - 1) { F.c[d] += sm[(6 * k + d) * SMS]; T.c[d] += sm[(6 * k + 3 + d) * SMS]; }
+        if (k < N - 1) { F.c[d] += park[6 * k + d]; T.c[d] += park[6 * k + 3 + d]; }
       }
       if (LK != 0) {
         // T += po x F = L (e_D x F): [D1] -= L F[D2], [D2] += L F[D1]   (rigid_link.cpp:170-177, Ro = I)
@@ -538,11 +615,11 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #ifndef RKB_BLOCK
 #define RKB_BLOCK 128
 #endif
-// per-thread shared-memory doubles: parked wrenches of stages 0..N-2, and for the rollout the
+// per-thread shared-memory doubles: for the rollout the
 // state at the start of the step (w) and k1 + 2 k2.  k3 is not stored: the stage-4 update starts
 // from x = w + k3, so k3 is recovered as x - w (exact up to one rounding of x, i.e. ~1e-16 |x|).
-#define RKB_SMEM_EVAL(n) (6 * ((n) - 1) + 1)
-#define RKB_SMEM_ROLLOUT(n) (6 * ((n) - 1) + 4 * (n))
+#define RKB_SMEM_EVAL(n) 1
+#define RKB_SMEM_ROLLOUT(n) (4 * (n))
 // Resident CTAs per SM the compiler must leave room for.  The structurally specialised code runs
 // best with 4 CTAs of 128 threads (128 registers, 4 warps per scheduler; measured 25.4 ms vs
 // 26.1 ms at 3 CTAs and 27.0 ms at 2 for the 6-DOF rollout) when 4 columns of shared memory fit,
@@ -726,7 +803,7 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
 }
 
 // n_steps of fixed-step RK4 with the input held constant.
-// Per-thread shared-memory column: [0, 6(N-1)) wrenches, then w (2N) and k1 + 2 k2 (2N).
+// Per-thread shared-memory column: w (2N) and k1 + 2 k2 (2N).
 template <int N, int FL, shape_t SHAPE>
 __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
   extern __shared__ double smem[];
@@ -734,7 +811,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
   double* sm = smem + threadIdx.x;
-  double* sw = sm + 6 * (N - 1) * SMS;  // state at the start of the step (w)
+  double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
   SerialState<N> X;
   {

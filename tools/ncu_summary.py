@@ -1,10 +1,14 @@
 #!/usr/bin/env python
 """Developer tool: condense an .ncu-rep (ncu --set full) into the few numbers DESIGN.md / bench.py quote.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [units_per_launch] > profiles/<name>.md
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [units_per_launch [constants.json]] > profiles/<name>.md
+
+With a third argument the per-unit FP64 instruction / flop counts and the DRAM traffic of the FIRST kernel
+in the report are also written as JSON (profiles/roofline_constants.json is what bench.py reads).
 """
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -26,6 +30,7 @@ STALLS = "smsp__average_warps_issue_stalled_"
 def main():
     rep = sys.argv[1]
     units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    json_out = sys.argv[3] if len(sys.argv) > 3 else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, unit = rows[0], rows[1]
@@ -55,7 +60,19 @@ def main():
             if units:
                 print("derived: per unit (%.0f units/launch): %.0f FP64 instructions, %.0f FP64 flops (DFMA = 2)"
                       % (units, (fma + mul + add) * cyc / units, (2 * fma + mul + add) * cyc / units))
-            print("derived: DRAM traffic %.1f MB per launch" % (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")))
+            mb = lambda k: g(k) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(u.get(k, "byte"), 1.0)
+            traffic = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+            print("derived: DRAM traffic %.1f MB per launch" % (traffic / 1e6))
+            if json_out and units:
+                with open(json_out, "w") as f:
+                    json.dump({"kernel": d.get("Kernel Name", "?"), "source": rep, "units_per_launch": units,
+                               "fp64_instr_per_state_step": (fma + mul + add) * cyc / units,
+                               "flop_per_state_step": (2 * fma + mul + add) * cyc / units,
+                               "dram_traffic_bytes_per_launch": traffic,
+                               "fp64_pipe_active_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                               "kernel_ms_under_ncu": g("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u.get("gpu__time_duration.sum", "ms"), 1.0)},
+                              f, indent=1)
+                json_out = None
         except Exception as e:  # metric missing in a reduced set
             print("derived: n/a (%s)" % e)
         print("")
