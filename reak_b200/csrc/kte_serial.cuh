@@ -148,48 +148,6 @@ RKB_DEV double spring_scalar(const SerialStage& S, double q) {
 __host__ __device__ constexpr int sym_idx(int i, int j) {
   return (i <= j) ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : (j == 0 ? i : (j == 1 ? 2 + i : 5));
 }
-// I <- R I R^T for a rotation by (c, s) about coordinate axis D: 18 multiplies
-template <int D>
-RKB_DEV void sym_rotate_axis(double c, double s, double (&I)[6]) {
-  constexpr int p = (D + 1) % 3, q = (D + 2) % 3;
-  const double ipr = I[sym_idx(p, D)], iqr = I[sym_idx(q, D)];
-  I[sym_idx(p, D)] = c * ipr - s * iqr;
-  I[sym_idx(q, D)] = s * ipr + c * iqr;
-  const double ipp = I[sym_idx(p, p)], ipq = I[sym_idx(p, q)], iqq = I[sym_idx(q, q)];
-  const double app = c * ipp - s * ipq, apq = c * ipq - s * iqq;  // A = R I (2x2 block)
-  const double aqp = s * ipp + c * ipq, aqq = s * ipq + c * iqq;
-  I[sym_idx(p, p)] = c * app - s * apq;
-  I[sym_idx(p, q)] = s * app + c * apq;
-  I[sym_idx(q, q)] = s * aqp + c * aqq;
-}
-// I <- R I R^T for a general rotation
-RKB_DEV void sym_rotate(const mat3& R, double (&I)[6]) {
-  double A[9];  // A = R I
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      A[3 * i + j] = R.m[3 * i] * I[sym_idx(0, j)] + R.m[3 * i + 1] * I[sym_idx(1, j)] + R.m[3 * i + 2] * I[sym_idx(2, j)];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = i; j < 3; ++j)
-      I[sym_idx(i, j)] = A[3 * i] * R.m[3 * j] + A[3 * i + 1] * R.m[3 * j + 1] + A[3 * i + 2] * R.m[3 * j + 2];
-}
-// Parallel-axis move of a composite (mass mc, first moment h, tensor I): every mass point goes from
-// r to r + p.  mcp = mc * p.  With w = h + mcp / 2:  I += 2 (w.p) 1 - w p^T - p w^T,  h += mcp.
-RKB_DEV void sym_shift(vec3 p, vec3 mcp, vec3& h, double (&I)[6]) {
-  const vec3 w = mk(fma(0.5, mcp.c[0], h.c[0]), fma(0.5, mcp.c[1], h.c[1]), fma(0.5, mcp.c[2], h.c[2]));
-  const double d = 2.0 * dot(w, p);
-  I[0] += d - 2.0 * (w.c[0] * p.c[0]);
-  I[3] += d - 2.0 * (w.c[1] * p.c[1]);
-  I[5] += d - 2.0 * (w.c[2] * p.c[2]);
-  I[1] -= w.c[0] * p.c[1] + p.c[0] * w.c[1];
-  I[2] -= w.c[0] * p.c[2] + p.c[0] * w.c[2];
-  I[4] -= w.c[1] * p.c[2] + p.c[1] * w.c[2];
-  h = h + mcp;
-}
-
 // ---- sine and cosine of the joint angles ---------------------------------------------------------
 // The CUDA library's sincos() spends more issue slots on loading its polynomial coefficients
 // (two UMOV per 64-bit immediate), on F2I/I2F and on its slow-path branch than on arithmetic, and the
@@ -248,6 +206,152 @@ RKB_DEV void sincos_reduced(double q, double& sn, double& cs) {
   sn = s; cs = c;
 }
 
+// ---- forward-mode scalars for the mass-matrix sweep ------------------------------------------------
+// mass_sweep<..., T> below runs on T = double (M only) or T = dual (value and time derivative: M and
+// Mdot = d/dt M along q_dot, what mass_matrix_calc::getMassMatrixAndDerivative assembles from Tcm_dot,
+// mass_matrix_calculator.cpp:89-98).  Chain constants stay plain doubles, so a constant times a dual
+// costs two multiplies, not three.
+struct dual { double v, d; };
+RKB_DEV dual mkd(double v, double d) { dual r; r.v = v; r.d = d; return r; }
+RKB_DEV dual operator+(dual a, dual b) { return mkd(a.v + b.v, a.d + b.d); }
+RKB_DEV dual operator-(dual a, dual b) { return mkd(a.v - b.v, a.d - b.d); }
+RKB_DEV dual operator-(dual a) { return mkd(-a.v, -a.d); }
+RKB_DEV dual operator*(dual a, dual b) { return mkd(a.v * b.v, a.v * b.d + a.d * b.v); }
+RKB_DEV dual operator*(double a, dual b) { return mkd(a * b.v, a * b.d); }
+RKB_DEV dual operator*(dual a, double b) { return mkd(a.v * b, a.d * b); }
+RKB_DEV dual operator+(dual a, double b) { return mkd(a.v + b, a.d); }
+RKB_DEV dual operator+(double a, dual b) { return mkd(a + b.v, b.d); }
+RKB_DEV dual operator-(dual a, double b) { return mkd(a.v - b, a.d); }
+RKB_DEV dual operator-(double a, dual b) { return mkd(a - b.v, -b.d); }
+RKB_DEV dual& operator+=(dual& a, dual b) { a = a + b; return a; }
+RKB_DEV dual& operator-=(dual& a, dual b) { a = a - b; return a; }
+RKB_DEV dual& operator+=(dual& a, double b) { a.v += b; return a; }
+RKB_DEV double value_of(double a) { return a; }
+RKB_DEV double value_of(dual a) { return a.v; }
+RKB_DEV double deriv_of(double) { return 0.0; }
+RKB_DEV double deriv_of(dual a) { return a.d; }
+template <class T> RKB_DEV T zero_of();
+template <> RKB_DEV double zero_of<double>() { return 0.0; }
+template <> RKB_DEV dual zero_of<dual>() { return mkd(0.0, 0.0); }
+
+template <class T> struct vec3t { T c[3]; };
+template <class T> RKB_DEV vec3t<T> mkt(T x, T y, T z) { vec3t<T> r; r.c[0] = x; r.c[1] = y; r.c[2] = z; return r; }
+template <class T> RKB_DEV vec3t<T> operator+(vec3t<T> a, vec3t<T> b) { return mkt<T>(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+template <class T> RKB_DEV vec3t<T> cross_cv(vec3 a, vec3t<T> b) {  // constant x variable
+  return mkt<T>(a.c[1] * b.c[2] - a.c[2] * b.c[1], a.c[2] * b.c[0] - a.c[0] * b.c[2], a.c[0] * b.c[1] - a.c[1] * b.c[0]);
+}
+template <class T> RKB_DEV vec3t<T> cross_vc(vec3t<T> a, vec3 b) {  // variable x constant
+  return mkt<T>(a.c[1] * b.c[2] - a.c[2] * b.c[1], a.c[2] * b.c[0] - a.c[0] * b.c[2], a.c[0] * b.c[1] - a.c[1] * b.c[0]);
+}
+template <class T> RKB_DEV vec3t<T> cross_vv(vec3t<T> a, vec3t<T> b) {
+  return mkt<T>(a.c[1] * b.c[2] - a.c[2] * b.c[1], a.c[2] * b.c[0] - a.c[0] * b.c[2], a.c[0] * b.c[1] - a.c[1] * b.c[0]);
+}
+template <class T> RKB_DEV T dot_cv(vec3 a, vec3t<T> b) { return a.c[0] * b.c[0] + a.c[1] * b.c[1] + a.c[2] * b.c[2]; }
+template <class T> RKB_DEV T dot_vv(vec3t<T> a, vec3t<T> b) { return a.c[0] * b.c[0] + a.c[1] * b.c[1] + a.c[2] * b.c[2]; }
+template <class T> struct mat3t { T m[9]; };
+template <class T> RKB_DEV vec3t<T> mul(const mat3t<T>& R, vec3t<T> v) {
+  return mkt<T>(R.m[0] * v.c[0] + R.m[1] * v.c[1] + R.m[2] * v.c[2], R.m[3] * v.c[0] + R.m[4] * v.c[1] + R.m[5] * v.c[2],
+                R.m[6] * v.c[0] + R.m[7] * v.c[1] + R.m[8] * v.c[2]);
+}
+template <class T> RKB_DEV vec3t<T> mulc_t(const double* R, vec3t<T> v) {
+  return mkt<T>(R[0] * v.c[0] + R[1] * v.c[1] + R[2] * v.c[2], R[3] * v.c[0] + R[4] * v.c[1] + R[5] * v.c[2],
+                R[6] * v.c[0] + R[7] * v.c[1] + R[8] * v.c[2]);
+}
+template <class T> RKB_DEV vec3t<T> symmul_vc(const T (&I)[6], vec3 v) {  // variable tensor times constant vector
+  return mkt<T>(I[0] * v.c[0] + I[1] * v.c[1] + I[2] * v.c[2], I[1] * v.c[0] + I[3] * v.c[1] + I[4] * v.c[2],
+                I[2] * v.c[0] + I[4] * v.c[1] + I[5] * v.c[2]);
+}
+template <class T> RKB_DEV mat3t<T> rodrigues_t(const SerialStage& S, T c, T s) {
+  const T omc = 1.0 - c;
+  const T t12 = omc * S.aa[3], t13 = omc * S.aa[4], t23 = omc * S.aa[5];
+  const T t01 = s * S.an[0], t02 = s * S.an[1], t03 = s * S.an[2];
+  mat3t<T> R;
+  R.m[0] = c + omc * S.aa[0]; R.m[1] = t12 - t03;         R.m[2] = t13 + t02;
+  R.m[3] = t12 + t03;         R.m[4] = c + omc * S.aa[1]; R.m[5] = t23 - t01;
+  R.m[6] = t13 - t02;         R.m[7] = t23 + t01;         R.m[8] = c + omc * S.aa[2];
+  return R;
+}
+template <int D, class T>
+RKB_DEV vec3t<T> rot_axis_t(T c, T s, vec3t<T> v) {
+  constexpr int D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+  vec3t<T> r;
+  r.c[D] = v.c[D];
+  r.c[D1] = c * v.c[D1] - s * v.c[D2];
+  r.c[D2] = s * v.c[D1] + c * v.c[D2];
+  return r;
+}
+// I <- R I R^T for a rotation by (c, s) about coordinate axis D: 18 multiplies
+template <int D, class T>
+RKB_DEV void sym_rotate_axis_t(T c, T s, T (&I)[6]) {
+  constexpr int p = (D + 1) % 3, q = (D + 2) % 3;
+  const T ipr = I[sym_idx(p, D)], iqr = I[sym_idx(q, D)];
+  I[sym_idx(p, D)] = c * ipr - s * iqr;
+  I[sym_idx(q, D)] = s * ipr + c * iqr;
+  const T ipp = I[sym_idx(p, p)], ipq = I[sym_idx(p, q)], iqq = I[sym_idx(q, q)];
+  const T app = c * ipp - s * ipq, apq = c * ipq - s * iqq;  // A = R I (2x2 block)
+  const T aqp = s * ipp + c * ipq, aqq = s * ipq + c * iqq;
+  I[sym_idx(p, p)] = c * app - s * apq;
+  I[sym_idx(p, q)] = s * app + c * apq;
+  I[sym_idx(q, q)] = s * aqp + c * aqq;
+}
+// I <- R I R^T for a general rotation
+template <class T>
+RKB_DEV void sym_rotate_t(const mat3t<T>& R, T (&I)[6]) {
+  T A[9];  // A = R I
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      A[3 * i + j] = R.m[3 * i] * I[sym_idx(0, j)] + R.m[3 * i + 1] * I[sym_idx(1, j)] + R.m[3 * i + 2] * I[sym_idx(2, j)];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      I[sym_idx(i, j)] = A[3 * i] * R.m[3 * j] + A[3 * i + 1] * R.m[3 * j + 1] + A[3 * i + 2] * R.m[3 * j + 2];
+}
+template <class T>
+RKB_DEV void sym_rotate_c(const double* R, T (&I)[6]) {  // constant rotation (row-major)
+  T A[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      A[3 * i + j] = R[3 * i] * I[sym_idx(0, j)] + R[3 * i + 1] * I[sym_idx(1, j)] + R[3 * i + 2] * I[sym_idx(2, j)];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      I[sym_idx(i, j)] = A[3 * i] * R[3 * j] + A[3 * i + 1] * R[3 * j + 1] + A[3 * i + 2] * R[3 * j + 2];
+}
+// Parallel-axis move of a composite (mass mc, first moment h, tensor I): every mass point goes from
+// r to r + p, p constant, mcp = mc * p.  With w = h + mcp / 2:  I += 2 (w.p) 1 - w p^T - p w^T,  h += mcp.
+template <class T>
+RKB_DEV void sym_shift_c(vec3 p, vec3 mcp, vec3t<T>& h, T (&I)[6]) {
+  const vec3t<T> w = mkt<T>(h.c[0] + 0.5 * mcp.c[0], h.c[1] + 0.5 * mcp.c[1], h.c[2] + 0.5 * mcp.c[2]);
+  const T d = 2.0 * dot_cv(p, w);
+  I[0] += d - 2.0 * (w.c[0] * p.c[0]);
+  I[3] += d - 2.0 * (w.c[1] * p.c[1]);
+  I[5] += d - 2.0 * (w.c[2] * p.c[2]);
+  I[1] -= w.c[0] * p.c[1] + w.c[1] * p.c[0];
+  I[2] -= w.c[0] * p.c[2] + w.c[2] * p.c[0];
+  I[4] -= w.c[1] * p.c[2] + w.c[2] * p.c[1];
+  h.c[0] += mcp.c[0]; h.c[1] += mcp.c[1]; h.c[2] += mcp.c[2];
+}
+// ... and by a variable offset r = q * axis of a prismatic joint (mc constant)
+template <class T>
+RKB_DEV void sym_shift_v(vec3t<T> p, double mc, vec3t<T>& h, T (&I)[6]) {
+  const vec3t<T> mcp = mkt<T>(mc * p.c[0], mc * p.c[1], mc * p.c[2]);
+  const vec3t<T> w = mkt<T>(h.c[0] + 0.5 * mcp.c[0], h.c[1] + 0.5 * mcp.c[1], h.c[2] + 0.5 * mcp.c[2]);
+  const T d = 2.0 * dot_vv(w, p);
+  I[0] += d - 2.0 * (w.c[0] * p.c[0]);
+  I[3] += d - 2.0 * (w.c[1] * p.c[1]);
+  I[5] += d - 2.0 * (w.c[2] * p.c[2]);
+  I[1] -= w.c[0] * p.c[1] + p.c[0] * w.c[1];
+  I[2] -= w.c[0] * p.c[2] + p.c[0] * w.c[2];
+  I[4] -= w.c[1] * p.c[2] + p.c[1] * w.c[2];
+  h = h + mcp;
+}
+
 template <int N>
 struct SerialState {
   double q[N], qd[N], u[N];
@@ -257,13 +361,10 @@ __host__ __device__ constexpr int shape_ax(shape_t s, int k) { return (int)((s >
 __host__ __device__ constexpr int shape_lk(shape_t s, int k) { return (int)((s >> (8 * k + 3)) & 3u); }     // 0 general, 1..3 offset along x,y,z, no rotation
 __host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 3u); }     // 0 general, 1 diagonal tensor present
 
-// The evaluation proper.  (`sm`, this thread's shared-memory column with stride SMS, is no longer
-// used by the sweeps; the rollout kernel keeps its RK4 state there.)
-// Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
-// Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
-template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M>
-RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
-                           double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
+// cos and sin of every revolute joint angle (1, 0 for a prismatic joint); the sign of an axis-aligned
+// joint's axis is folded into the sine, which is all the specialised rotations need.
+template <int N, int FL, shape_t SHAPE>
+RKB_DEV void serial_trig(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N]) {
   bool in_range = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -289,6 +390,136 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
     const int AX = shape_ax(SH, k);
     if (AX != 0) sn[k] *= P.st[k].ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
   }
+}
+
+// ---- sweep 3: mass matrix by composite inertias, inward -------------------------------------------
+// M = Tcm^T Mcm Tcm (mass_matrix_calculator.cpp:80-87) regrouped: with C_k the composite inertia
+// (mass mc, first moment h, tensor I about the frame origin) of all inertias at or beyond stage k,
+// column k of M is S_j^T X_{j<-k} (C_k S_k) for j <= k.  The composite walks inward once
+// (rotate at the joint, parallel-axis shift at the link); each new column (f, n) = C_k S_k is then
+// carried inward through the joints below it and projected on their axes.  Rotor inertias
+// (inertia_gen) land on the diagonal.
+// T = double gives M; T = dual carries d/dt alongside (cs, sn and the prismatic displacements have
+// derivatives -sin q q_dot, cos q q_dot and q_dot), which yields Mdot in the same pass.
+// Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
+template <int N, int FL, shape_t SHAPE, class T>
+RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N], const T (&qp)[N], T (&Mp)[N * (N + 1) / 2]) {
+  vec3t<T> h = mkt<T>(zero_of<T>(), zero_of<T>(), zero_of<T>());
+  T I[6];  // xx xy xz yy yz zz
+#pragma unroll
+  for (int d = 0; d < 6; ++d) I[d] = zero_of<T>();
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    const SerialStage& S = P.st[k];
+    constexpr shape_t SH = SHAPE;
+    const int AX = shape_ax(SH, k), LK = shape_lk(SH, k), IN = shape_in(SH, k);
+    // [1] the stage's own inertia_3D sits at the link end frame, centre of mass on its origin
+    if (IN == 1) { I[0] += S.I[0]; I[3] += S.I[3]; I[5] += S.I[5]; }
+    else if (S.flags & RKB_ST_INERTIA) {
+#pragma unroll
+      for (int d = 0; d < 6; ++d) I[d] += S.I[d];
+    }
+    // [2] link end frame -> joint end frame
+    if (LK != 0) {
+      // offset L e_D: w = h + mc po / 2, I += 2 (w.po) 1 - w po^T - po w^T, h += mc po
+      const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+      const double L = S.po[D];
+      const T dd = L * (2.0 * h.c[D] + S.mcpo[D]);
+      I[sym_idx(D1, D1)] += dd;
+      I[sym_idx(D2, D2)] += dd;
+      I[sym_idx(D1, D)] -= L * h.c[D1];
+      I[sym_idx(D2, D)] -= L * h.c[D2];
+      h.c[D] += S.mcpo[D];
+    } else if (S.flags & RKB_ST_LINK) {
+      if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) {
+        h = mulc_t<T>(S.Ro, h);
+        sym_rotate_c<T>(S.Ro, I);
+      }
+      sym_shift_c<T>(ld3(S.po), ld3(S.mcpo), h, I);
+    }
+    // [3] column k at the joint end frame, then inward
+    vec3t<T> f, n;
+    const bool prismatic_k = AX == 0 && (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
+    if (AX != 0) {
+      // revolute about sg e_D: n = I a, f = a x h
+      const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+      const double sg = S.ax[D];
+      n.c[0] = sg * I[sym_idx(0, D)]; n.c[1] = sg * I[sym_idx(1, D)]; n.c[2] = sg * I[sym_idx(2, D)];
+      f.c[D] = zero_of<T>(); f.c[D1] = (-sg) * h.c[D2]; f.c[D2] = sg * h.c[D1];
+      Mp[k * (k + 1) / 2 + k] = I[sym_idx(D, D)] + S.rotor;
+    } else if (!prismatic_k) {
+      const vec3 ax = ld3(S.ax);
+      n = symmul_vc<T>(I, ax);
+      f = cross_cv<T>(ax, h);
+      Mp[k * (k + 1) / 2 + k] = dot_cv<T>(ax, n) + S.rotor;
+    } else {
+      const vec3 ax = ld3(S.ax);
+      f = mkt<T>(zero_of<T>() + S.mc * ax.c[0], zero_of<T>() + S.mc * ax.c[1], zero_of<T>() + S.mc * ax.c[2]);
+      n = cross_vc<T>(h, ax);
+      Mp[k * (k + 1) / 2 + k] = dot_cv<T>(ax, f) + S.rotor;
+    }
+#pragma unroll
+    for (int j = k; j >= 1; --j) {
+      // joint j: end frame -> base frame (= link end frame of stage j-1)
+      const SerialStage& Sj = P.st[j];
+      const int AXj = shape_ax(SH, j);
+      if (AXj != 0) {
+        const int D = AXj - 1;
+        if (D == 0) { f = rot_axis_t<0, T>(cs[j], sn[j], f); n = rot_axis_t<0, T>(cs[j], sn[j], n); }
+        else if (D == 1) { f = rot_axis_t<1, T>(cs[j], sn[j], f); n = rot_axis_t<1, T>(cs[j], sn[j], n); }
+        else { f = rot_axis_t<2, T>(cs[j], sn[j], f); n = rot_axis_t<2, T>(cs[j], sn[j], n); }
+      } else if (!((FL & RKB_FL_PRISMATIC) && (Sj.flags & RKB_ST_PRISMATIC))) {
+        const mat3t<T> R = rodrigues_t<T>(Sj, cs[j], sn[j]);
+        f = mul(R, f); n = mul(R, n);
+      } else {
+        const vec3 ax = ld3(Sj.ax);
+        n = n + cross_vv<T>(mkt<T>(qp[j] * ax.c[0], qp[j] * ax.c[1], qp[j] * ax.c[2]), f);
+      }
+      // link j-1: end frame -> joint end frame, then project on joint j-1
+      const SerialStage& Si = P.st[j - 1];
+      const int AXi = shape_ax(SH, j - 1), LKi = shape_lk(SH, j - 1);
+      if (LKi != 0) {
+        const int D = LKi - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double L = Si.po[D];
+        n.c[D1] -= L * f.c[D2];
+        n.c[D2] += L * f.c[D1];
+      } else if (Si.flags & RKB_ST_LINK) {
+        if ((FL & RKB_FL_LINKROT) && (Si.flags & RKB_ST_LINKROT)) { f = mulc_t<T>(Si.Ro, f); n = mulc_t<T>(Si.Ro, n); }
+        n = n + cross_cv<T>(ld3(Si.po), f);
+      }
+      T mjk;
+      if (AXi != 0) mjk = Si.ax[AXi - 1] * n.c[AXi - 1];
+      else if (!((FL & RKB_FL_PRISMATIC) && (Si.flags & RKB_ST_PRISMATIC))) mjk = dot_cv<T>(ld3(Si.ax), n);
+      else mjk = dot_cv<T>(ld3(Si.ax), f);
+      Mp[k * (k + 1) / 2 + (j - 1)] = mjk;
+    }
+    // [4] composite: joint end frame -> joint base frame
+    if (k > 0) {
+      if (AX != 0) {
+        const int D = AX - 1;
+        if (D == 0) { h = rot_axis_t<0, T>(cs[k], sn[k], h); sym_rotate_axis_t<0, T>(cs[k], sn[k], I); }
+        else if (D == 1) { h = rot_axis_t<1, T>(cs[k], sn[k], h); sym_rotate_axis_t<1, T>(cs[k], sn[k], I); }
+        else { h = rot_axis_t<2, T>(cs[k], sn[k], h); sym_rotate_axis_t<2, T>(cs[k], sn[k], I); }
+      } else if (!prismatic_k) {
+        const mat3t<T> R = rodrigues_t<T>(S, cs[k], sn[k]);
+        h = mul(R, h);
+        sym_rotate_t<T>(R, I);
+      } else {
+        const vec3 ax = ld3(S.ax);
+        sym_shift_v<T>(mkt<T>(qp[k] * ax.c[0], qp[k] * ax.c[1], qp[k] * ax.c[2]), S.mc, h, I);
+      }
+    }
+  }
+}
+
+// The evaluation proper.  (`sm`, this thread's shared-memory column with stride SMS, is no longer
+// used by the sweeps; the rollout kernel keeps its RK4 state there.)
+// Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
+// Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
+template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M>
+RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
+                           double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
+  serial_trig<N, FL, SHAPE>(P, X, cs, sn);
   // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
   if (WANT_F) {
     vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
@@ -422,120 +653,8 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       }
     }
   }
-  // ---- sweep 3: mass matrix by composite inertias, inward -------------------------------------
-  // M = Tcm^T Mcm Tcm (mass_matrix_calculator.cpp:80-87) regrouped: with C_k the composite inertia
-  // (mass mc, first moment h, tensor I about the frame origin) of all inertias at or beyond stage k,
-  // column k of M is S_j^T X_{j<-k} (C_k S_k) for j <= k.  The composite walks inward once
-  // (rotate at the joint, parallel-axis shift at the link); each new column (f, n) = C_k S_k is then
-  // carried inward through the joints below it and projected on their axes.
-  if (WANT_M) {
-    vec3 h = mk(0, 0, 0);
-    double I[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-      const SerialStage& S = P.st[k];
-      constexpr shape_t SH = SHAPE;
-      const int AX = shape_ax(SH, k), LK = shape_lk(SH, k), IN = shape_in(SH, k);
-      // [1] the stage's own inertia_3D sits at the link end frame, centre of mass on its origin
-      if (IN == 1) { I[0] += S.I[0]; I[3] += S.I[3]; I[5] += S.I[5]; }
-      else if (S.flags & RKB_ST_INERTIA) {
-#pragma unroll
-        for (int d = 0; d < 6; ++d) I[d] += S.I[d];
-      }
-      // [2] link end frame -> joint end frame
-      if (LK != 0) {
-        // offset L e_D: w = h + mc po / 2, I += 2 (w.po) 1 - w po^T - po w^T, h += mc po
-        const int D = LK - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
-        const double L = S.po[D];
-        const double dd = L * (2.0 * h.c[D] + S.mcpo[D]);
-        I[sym_idx(D1, D1)] += dd;
-        I[sym_idx(D2, D2)] += dd;
-        I[sym_idx(D1, D)] -= L * h.c[D1];
-        I[sym_idx(D2, D)] -= L * h.c[D2];
-        h.c[D] += S.mcpo[D];
-      } else if (S.flags & RKB_ST_LINK) {
-        if ((FL & RKB_FL_LINKROT) && (S.flags & RKB_ST_LINKROT)) {
-          mat3 Ro;
-#pragma unroll
-          for (int d = 0; d < 9; ++d) Ro.m[d] = S.Ro[d];
-          h = mul(Ro, h);
-          sym_rotate(Ro, I);
-        }
-        sym_shift(ld3(S.po), ld3(S.mcpo), h, I);
-      }
-      // [3] column k at the joint end frame, then inward
-      vec3 f, n;
-      const bool prismatic_k = AX == 0 && (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
-      if (AX != 0) {
-        // revolute about sg e_D: n = I a, f = a x h
-        const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
-        const double sg = S.ax[D];
-        n.c[0] = sg * I[sym_idx(0, D)]; n.c[1] = sg * I[sym_idx(1, D)]; n.c[2] = sg * I[sym_idx(2, D)];
-        f.c[D] = 0.0; f.c[D1] = -sg * h.c[D2]; f.c[D2] = sg * h.c[D1];
-        Mp[k * (k + 1) / 2 + k] = I[sym_idx(D, D)] + S.rotor;
-      } else if (!prismatic_k) {
-        const vec3 ax = ld3(S.ax);
-        n = symmul(I, ax);
-        f = cross(ax, h);
-        Mp[k * (k + 1) / 2 + k] = dot(ax, n) + S.rotor;
-      } else {
-        const vec3 ax = ld3(S.ax);
-        f = S.mc * ax;
-        n = cross(h, ax);
-        Mp[k * (k + 1) / 2 + k] = dot(ax, f) + S.rotor;
-      }
-#pragma unroll
-      for (int j = k; j >= 1; --j) {
-        // joint j: end frame -> base frame (= link end frame of stage j-1)
-        const SerialStage& Sj = P.st[j];
-        const int AXj = shape_ax(SH, j);
-        if (AXj != 0) {
-          const int D = AXj - 1;
-          if (D == 0) { f = rot_axis<0>(cs[j], sn[j], f); n = rot_axis<0>(cs[j], sn[j], n); }
-          else if (D == 1) { f = rot_axis<1>(cs[j], sn[j], f); n = rot_axis<1>(cs[j], sn[j], n); }
-          else { f = rot_axis<2>(cs[j], sn[j], f); n = rot_axis<2>(cs[j], sn[j], n); }
-        } else if (!((FL & RKB_FL_PRISMATIC) && (Sj.flags & RKB_ST_PRISMATIC))) {
-          const mat3 R = rodrigues(Sj, cs[j], sn[j]);
-          f = mul(R, f); n = mul(R, n);
-        } else {
-          n = n + cross(X.q[j] * ld3(Sj.ax), f);
-        }
-        // link j-1: end frame -> joint end frame, then project on joint j-1
-        const SerialStage& Si = P.st[j - 1];
-        const int AXi = shape_ax(SH, j - 1), LKi = shape_lk(SH, j - 1);
-        if (LKi != 0) {
-          const int D = LKi - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
-          const double L = Si.po[D];
-          n.c[D1] -= L * f.c[D2];
-          n.c[D2] += L * f.c[D1];
-        } else if (Si.flags & RKB_ST_LINK) {
-          if ((FL & RKB_FL_LINKROT) && (Si.flags & RKB_ST_LINKROT)) { f = mulc(Si.Ro, f); n = mulc(Si.Ro, n); }
-          n = n + cross(ld3(Si.po), f);
-        }
-        double mjk;
-        if (AXi != 0) mjk = Si.ax[AXi - 1] * n.c[AXi - 1];
-        else if (!((FL & RKB_FL_PRISMATIC) && (Si.flags & RKB_ST_PRISMATIC))) mjk = dot(ld3(Si.ax), n);
-        else mjk = dot(ld3(Si.ax), f);
-        Mp[k * (k + 1) / 2 + (j - 1)] = mjk;
-      }
-      // [4] composite: joint end frame -> joint base frame
-      if (k > 0) {
-        if (AX != 0) {
-          const int D = AX - 1;
-          if (D == 0) { h = rot_axis<0>(cs[k], sn[k], h); sym_rotate_axis<0>(cs[k], sn[k], I); }
-          else if (D == 1) { h = rot_axis<1>(cs[k], sn[k], h); sym_rotate_axis<1>(cs[k], sn[k], I); }
-          else { h = rot_axis<2>(cs[k], sn[k], h); sym_rotate_axis<2>(cs[k], sn[k], I); }
-        } else if (!prismatic_k) {
-          const mat3 R = rodrigues(S, cs[k], sn[k]);
-          h = mul(R, h);
-          sym_rotate(R, I);
-        } else {
-          const vec3 r = X.q[k] * ld3(S.ax);
-          sym_shift(r, S.mc * r, h, I);
-        }
-      }
-    }
-  }
+  // ---- sweep 3: mass matrix -----------------------------------------------------------------------
+  if (WANT_M) mass_sweep<N, FL, SHAPE, double>(P, cs, sn, X.q, Mp);
 }
 
 // 1/d for a pivot d >= 1e-8 (anything else has already raised the singular status): the 2^-23
@@ -757,32 +876,22 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_forces_kernel(const __grid_c
   }
 }
 
-// M = getMassMatrix (full symmetric n x n, row-major per sample in AoS)
-template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
-  extern __shared__ double smem[];
-  const long long tile_first = (long long)blockIdx.x * RKB_BLOCK;
-  const long long i = tile_first + threadIdx.x;
-  const bool active = i < A.n_samples;
-  const bool staged = tile_is_aos<N * N>(A.out);
-  double Mp[N * (N + 1) / 2];
-  if (active) {
-    SerialState<N> X;
-    ConstBatchView nou = A.x;
-    load_state<N>(P, A.x, nou, i, X);
-    double cs[N], sn[N], f[N];
-    serial_sweeps<N, FL, SHAPE, RKB_BLOCK, false, true>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
-    if (!staged) {
+// M = getMassMatrix (full symmetric n x n, row-major per sample in AoS) and, with WANT_DOT, its time
+// derivative Mdot = getMassMatrixAndDerivative's second result (mass_matrix_calculator.cpp:89-98) from
+// the same sweep run on forward-mode scalars.
+template <int N, int DIMS>
+RKB_DEV void store_sym(const double (&Mp)[N * (N + 1) / 2], const SerialParams& P, const BatchView& o, long long i, bool staged, bool active,
+                       double* smem, long long tile_first, long long n_samples) {
+  if (active && !staged) {
 #pragma unroll
-      for (int a = 0; a < N; ++a)
+    for (int a = 0; a < N; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) {
-          const int ca = P.st[a].coord, cb = P.st[b].coord;
-          const double v = Mp[a * (a + 1) / 2 + b];
-          A.out.p[i * A.out.si + (long long)(ca * N + cb) * A.out.sk] = v;
-          A.out.p[i * A.out.si + (long long)(cb * N + ca) * A.out.sk] = v;
-        }
-    }
+      for (int b = 0; b <= a; ++b) {
+        const int ca = P.st[a].coord, cb = P.st[b].coord;
+        const double v = Mp[a * (a + 1) / 2 + b];
+        o.p[i * o.si + (long long)(ca * N + cb) * o.sk] = v;
+        o.p[i * o.si + (long long)(cb * N + ca) * o.sk] = v;
+      }
   }
   if (staged) {
     __syncthreads();
@@ -798,7 +907,50 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
         }
     }
     __syncthreads();
-    tile_write_back<N * N>(smem, A.out, tile_first, A.n_samples);
+    tile_write_back<N * N>(smem, o, tile_first, n_samples);
+  }
+}
+
+template <int N, int FL, shape_t SHAPE, bool WANT_DOT>
+__global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+  extern __shared__ double smem[];
+  const long long tile_first = (long long)blockIdx.x * RKB_BLOCK;
+  const long long i = tile_first + threadIdx.x;
+  const bool active = i < A.n_samples;
+  double Mp[N * (N + 1) / 2], Mdp[WANT_DOT ? N * (N + 1) / 2 : 1];
+  if (active) {
+    SerialState<N> X;
+    ConstBatchView nou = A.x;
+    load_state<N>(P, A.x, nou, i, X);
+    double cs[N], sn[N], f[N];
+    if (!WANT_DOT) {
+      serial_sweeps<N, FL, SHAPE, RKB_BLOCK, false, true>(P, X, cs, sn, f, Mp, smem + threadIdx.x);
+    } else {
+      serial_trig<N, FL, SHAPE>(P, X, cs, sn);
+      dual dcs[N], dsn[N], dq[N], Md[N * (N + 1) / 2];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        constexpr shape_t SH = SHAPE;
+        const int AX = shape_ax(SH, k);
+        const bool prismatic = AX == 0 && (FL & RKB_FL_PRISMATIC) && (P.st[k].flags & RKB_ST_PRISMATIC);
+        // d/dt cos q = -sin q q_dot, d/dt sin q = cos q q_dot; with the axis sign sg = +-1 folded in,
+        // sn = sg sin q: d/dt sn = sg cos q q_dot and sin q = sg sn
+        const double sg = (AX != 0) ? P.st[k].ax[AX - 1] : 1.0;
+        if (!prismatic) {
+          dcs[k] = mkd(cs[k], -(sg * sn[k]) * X.qd[k]);
+          dsn[k] = mkd(sn[k], (sg * cs[k]) * X.qd[k]);
+        } else { dcs[k] = mkd(1.0, 0.0); dsn[k] = mkd(0.0, 0.0); }
+        dq[k] = mkd(X.q[k], X.qd[k]);
+      }
+      mass_sweep<N, FL, SHAPE, dual>(P, dcs, dsn, dq, Md);
+#pragma unroll
+      for (int e = 0; e < N * (N + 1) / 2; ++e) { Mp[e] = Md[e].v; Mdp[e] = Md[e].d; }
+    }
+  }
+  store_sym<N, N * N>(Mp, P, A.out, i, tile_is_aos<N * N>(A.out), active, smem, tile_first, A.n_samples);
+  if (WANT_DOT) {
+    double (&Mdq)[N * (N + 1) / 2] = reinterpret_cast<double (&)[N * (N + 1) / 2]>(Mdp);
+    store_sym<N, N * N>(Mdq, P, A.out2, i, tile_is_aos<N * N>(A.out2), active, smem, tile_first, A.n_samples);
   }
 }
 

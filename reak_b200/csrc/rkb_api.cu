@@ -518,7 +518,7 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   A.n_samples = (long long)N;
   CU(cudaEventRecord(ctx->ev0, s));
   cudaError_t e;
-  const bool use_serial = c->serial_ok && c->sk && !(op == OP_MASS && out2);
+  const bool use_serial = c->serial_ok && c->sk;
   if (use_serial) {
     e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
   } else if (c->generic_ok) {

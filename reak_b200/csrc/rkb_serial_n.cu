@@ -24,7 +24,9 @@ struct Launch {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_forces_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemForces);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMass);
+    e = cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMass);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(serial_mass_kernel<N, FL, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMass);
   }
   static cudaError_t eval(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
@@ -38,7 +40,8 @@ struct Launch {
   }
   static cudaError_t mass(const SerialParams& P, const EvalArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
-    serial_mass_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemMass, s>>>(P, A);
+    if (A.out2.p) serial_mass_kernel<N, FL, SHAPE, true><<<grid(A.n_samples), RKB_BLOCK, kSmemMass, s>>>(P, A);
+    else serial_mass_kernel<N, FL, SHAPE, false><<<grid(A.n_samples), RKB_BLOCK, kSmemMass, s>>>(P, A);
     return cudaGetLastError();
   }
   static cudaError_t rollout(const SerialParams& P, const RolloutArgs& A, cudaStream_t s) {
