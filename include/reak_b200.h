@@ -11,6 +11,8 @@
  *   rkb_eval              <- kte_nl_system::get_state_derivative        (ctrl/ctrl_sys/kte_nl_system.hpp:238-346)
  *   rkb_rollout_rk4       <- runge_kutta4_integrator<double>::integrate (core/integrators/fixed_step_integrators.hpp:256-293)
  *                            driven through num_int_dtnl_sys::get_next_state (ctrl/ctrl_sys/num_int_dtnl_system.hpp:166-180)
+ *   rkb_rollout           <- the same with euler / midpoint / runge_kutta4 / runge_kutta5 integrators
+ *                            (fixed_step_integrators.hpp:60-399) over a sequence of control intervals
  *   rkb_mass_matrix       <- mass_matrix_calc::getMassMatrix / getMassMatrixAndDerivative
  *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
  *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
@@ -162,6 +164,35 @@ RKB_API int rkb_eval(rkb_chain* chain, int device, size_t n_samples,
 RKB_API int rkb_rollout_rk4(rkb_chain* chain, int device, size_t n_samples,
                     const double* x0, const double* u, double dt, int n_steps,
                     double* x_out, int32_t* status, unsigned flags, void* stream);
+
+/* ---- general fixed-step rollout ----------------------------------------------------------------
+ * The fixed-step schemes of core/integrators/fixed_step_integrators.hpp, driven the way a planner
+ * drives them: n_intervals control intervals, the input constant within an interval
+ * (num_int_dtnl_sys::get_next_state once per interval, ctrl/ctrl_sys/num_int_dtnl_system.hpp:166-180;
+ * steer_with_constant_control's inner loop, examples/misc/MEAQR_topology.hpp:539-547), and
+ * steps_per_interval integrator steps of size dt per interval. */
+enum rkb_scheme {
+  RKB_SCHEME_EULER    = 1,  /* euler_integrator<T>::integrate          fixed_step_integrators.hpp:64-84   */
+  RKB_SCHEME_MIDPOINT = 2,  /* midpoint_integrator<T>::integrate       fixed_step_integrators.hpp:177-202 */
+  RKB_SCHEME_RK4      = 4,  /* runge_kutta4_integrator<T>::integrate   fixed_step_integrators.hpp:257-293 */
+  RKB_SCHEME_RK5      = 5   /* runge_kutta5_integrator<T>::integrate   fixed_step_integrators.hpp:351-399 */
+};
+
+typedef struct rkb_rollout_opts {
+  int32_t scheme;              /* enum rkb_scheme */
+  int32_t n_intervals;         /* >= 1 */
+  int32_t steps_per_interval;  /* >= 0 */
+  int32_t reserved;            /* must be 0 */
+  double  dt;                  /* integrator step, != 0 (negative integrates backwards) */
+} rkb_rollout_opts;
+
+/* x0: N x 2n.  u: one input vector per sample and interval — AOS [N][n_intervals][n_inputs],
+ * SOA [n_intervals][n_inputs][N].  x_out: N x 2n, the state after the last interval.
+ * x_traj (nullable): the state at the end of every interval — AOS [N][n_intervals][2n],
+ * SOA [n_intervals][2n][N].  status: N (nullable), bits OR-ed over the whole rollout. */
+RKB_API int rkb_rollout(rkb_chain* chain, int device, size_t n_samples,
+                        const double* x0, const double* u, const rkb_rollout_opts* opts,
+                        double* x_out, double* x_traj, int32_t* status, unsigned flags, void* stream);
 
 /* rkb_rollout_rk4 on HOST buffers (AoS), sharded over `n_devices` GPUs of this box from one
  * process: contiguous blocks of samples, one copy/compute pipeline per device, no inter-GPU

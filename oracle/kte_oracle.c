@@ -998,10 +998,82 @@ static void rk4_range(model* m, size_t i0, size_t i1, const double* x0, const do
   }
 }
 
+/* euler_integrator<T>::integrate (fixed_step_integrators.hpp:64-84), midpoint_integrator<T>::integrate
+ * (:177-202) and runge_kutta5_integrator<T>::integrate (:351-399), same conventions as rk4_range:
+ * explicit step count, input held constant, the trailing rate evaluation kept for the status only. */
+static void scheme_range(model* m, int scheme, size_t i0, size_t i1, const double* x0, const double* u, double dt, int n_steps,
+                         double* xout, int32_t* status) {
+  const int nx = 2 * m->n;
+  double x[2 * RKB_MAX_COORDS], w[2 * RKB_MAX_COORDS], f[2 * RKB_MAX_COORDS];
+  double k1[2 * RKB_MAX_COORDS], k2[2 * RKB_MAX_COORDS], k3[2 * RKB_MAX_COORDS], k4[2 * RKB_MAX_COORDS], k5[2 * RKB_MAX_COORDS];
+  size_t i;
+  int s, k;
+  if (scheme == RKB_SCHEME_RK4) { rk4_range(m, i0, i1, x0, u, dt, n_steps, xout, status); return; }
+  for (i = i0; i < i1; ++i) {
+    const double* ui = u ? u + i * m->nu : NULL;
+    int st = 0;
+    for (k = 0; k < nx; ++k) x[k] = x0[i * nx + k];
+    if (n_steps > 0) {
+      st |= state_derivative(m, x, ui, f);
+      for (s = 0; s < n_steps && !st; ++s) {
+        if (scheme == RKB_SCHEME_EULER) {
+          for (k = 0; k < nx; ++k) x[k] += f[k] * dt;                                   /* :78 */
+          st |= state_derivative(m, x, ui, f);                                          /* :82 */
+        } else if (scheme == RKB_SCHEME_MIDPOINT) {
+          for (k = 0; k < nx; ++k) w[k] = x[k] + f[k] * (dt * 0.5);                     /* :193 */
+          st |= state_derivative(m, w, ui, f);                                          /* :195 */
+          if (st) break;
+          for (k = 0; k < nx; ++k) x[k] += f[k] * dt;                                   /* :197 */
+          st |= state_derivative(m, x, ui, f);                                          /* :199 */
+        } else {
+          for (k = 0; k < nx; ++k) { w[k] = x[k]; k1[k] = f[k] * dt; x[k] += k1[k] * 0.25; }              /* :367-368 */
+          st |= state_derivative(m, x, ui, f);
+          if (st) break;
+          for (k = 0; k < nx; ++k) { k2[k] = f[k] * dt; x[k] += (k2[k] * 9.0 - k1[k] * 5.0) / 32.0; }    /* :372 */
+          st |= state_derivative(m, x, ui, f);
+          if (st) break;
+          for (k = 0; k < nx; ++k) {                                                                     /* :376 */
+            k3[k] = f[k] * dt;
+            x[k] += (k1[k] * 276165.0 - k2[k] * 1250865.0 + k3[k] * 1167360.0) / 351520.0;
+          }
+          st |= state_derivative(m, x, ui, f);
+          if (st) break;
+          for (k = 0; k < nx; ++k) {                                                                     /* :380 */
+            k4[k] = f[k] * dt;
+            x[k] = w[k] + k1[k] * (439.0 / 216.0) - k2[k] * 8.0 + k3[k] * (3680.0 / 513.0) - k4[k] * (845.0 / 4104.0);
+          }
+          st |= state_derivative(m, x, ui, f);
+          if (st) break;
+          for (k = 0; k < nx; ++k) {                                                                     /* :384 */
+            k5[k] = f[k] * dt;
+            x[k] = w[k] - k1[k] * (8.0 / 27.0) + k2[k] * 2.0 - k3[k] * (3544.0 / 2565.0) + k4[k] * (1859.0 / 4104.0) - k5[k] * (11.0 / 40.0);
+          }
+          st |= state_derivative(m, x, ui, f);
+          if (st) break;
+          for (k = 0; k < nx; ++k)                                                                       /* :388 */
+            x[k] = w[k] + k1[k] * (16.0 / 135.0) + k3[k] * (6656.0 / 12825.0) + k4[k] * (28561.0 / 56430.0) - k5[k] * (9.0 / 50.0)
+                   + f[k] * (2.0 * dt / 55.0);
+          st |= state_derivative(m, x, ui, f);                                                           /* :391 */
+        }
+      }
+    }
+    for (k = 0; k < nx; ++k) {
+      xout[i * nx + k] = x[k];
+      if (!isfinite(x[k])) st |= RKB_STATUS_NONFINITE;
+    }
+    if (status) status[i] = st;
+  }
+}
+
 static model* model_clone(const model* m) { return (model*)kto_create(&m->d); }
 
 double kto_rk4(void* h, size_t N, const double* x0, const double* u, double dt, int n_steps,
                double* xout, int32_t* status, int n_workers) {
+  return kto_integrate(h, N, x0, u, RKB_SCHEME_RK4, dt, n_steps, xout, status, n_workers);
+}
+
+double kto_integrate(void* h, size_t N, const double* x0, const double* u, int scheme, double dt, int n_steps,
+                     double* xout, int32_t* status, int n_workers) {
   model* m = (model*)h;
   const int nx = 2 * m->n;
   struct timespec t0, t1;
@@ -1009,7 +1081,7 @@ double kto_rk4(void* h, size_t N, const double* x0, const double* u, double dt, 
   if ((size_t)n_workers > N && N > 0) n_workers = (int)N;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   if (n_workers == 1 || N == 0) {
-    rk4_range(m, 0, N, x0, u, dt, n_steps, xout, status);
+    scheme_range(m, scheme, 0, N, x0, u, dt, n_steps, xout, status);
   } else {
     /* one forked worker per block of samples; results come back through a shared mapping */
     size_t bx = N * (size_t)nx * sizeof(double), bs = N * sizeof(int32_t);
@@ -1027,7 +1099,7 @@ double kto_rk4(void* h, size_t N, const double* x0, const double* u, double dt, 
       pid_t pid = fork();
       if (pid == 0) {
         model* mine = model_clone(m);
-        rk4_range(mine, i0, i1, x0, u, dt, n_steps, sx, ss);
+        scheme_range(mine, scheme, i0, i1, x0, u, dt, n_steps, sx, ss);
         _exit(0);
       }
       if (pid < 0) { ok = 0; break; }

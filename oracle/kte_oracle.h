@@ -22,6 +22,9 @@ int    kto_frames(void* h, const double* x, const double* u, double* out);
 /* returns wall seconds (< 0 on failure); n_workers > 1 forks worker processes */
 double kto_rk4(void* h, size_t n, const double* x0, const double* u, double dt, int n_steps,
                double* xout, int32_t* status, int n_workers);
+/* the same for any scheme of enum rkb_scheme (euler, midpoint, runge_kutta4, runge_kutta5) */
+double kto_integrate(void* h, size_t n, const double* x0, const double* u, int scheme, double dt, int n_steps,
+                     double* xout, int32_t* status, int n_workers);
 /* raw twist-shaping matrices of mass_matrix_calc::get_TMT_TdMT for one state: Tcm, Tcm_dot are
  * m x n row-major, Mcm m x m; returns m (rows) or < 0.  Pass NULL to query m only. */
 int    kto_tmt(void* h, const double* x, double* Tcm, double* Mcm, double* Tcm_dot);

@@ -45,6 +45,10 @@ class _Checker(object):
         self._rk4.restype = C.c_double
         self._rk4.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_int]
+        self._integrate = g("integrate")
+        self._integrate.restype = C.c_double
+        self._integrate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_int]
         self._frames.argtypes = [C.c_void_p] * 4
         self.h = self._create(C.byref(compiled.desc))
         if not self.h:
@@ -94,6 +98,29 @@ class _Checker(object):
         out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
         secs = self._rk4(self.h, N, _dp(x), _dp(u), float(dt), int(n_steps), _dp(out), _dp(st), int(n_workers))
         return out, st, secs
+
+    def integrate(self, x0, u, scheme, dt, n_steps, n_workers=1):
+        """n_steps of euler (1) / midpoint (2) / runge_kutta4 (4) / runge_kutta5 (5); returns (x_out, status, seconds)."""
+        x, u, N = self._xu(x0, u)
+        out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        secs = self._integrate(self.h, N, _dp(x), _dp(u), int(scheme), float(dt), int(n_steps), _dp(out), _dp(st), int(n_workers))
+        return out, st, secs
+
+    def rollout(self, x0, u_seq, scheme, dt, steps_per_interval, n_workers=1):
+        """The planner-side loop: one get_next_state per control interval (num_int_dtnl_system.hpp:166-180).
+        u_seq: [N][n_intervals][nu].  Returns (x_out, x_traj [N][n_intervals][nx], status)."""
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        u_seq = np.asarray(u_seq, dtype=np.float64)
+        J = u_seq.shape[1]
+        u_seq = u_seq.reshape(N, J, self.nu)
+        traj = np.empty((N, J, self.nx))
+        st = np.zeros(N, dtype=np.int32)
+        for j in range(J):
+            x, sj, _ = self.integrate(x, np.ascontiguousarray(u_seq[:, j, :]), scheme, dt, steps_per_interval, n_workers)
+            traj[:, j, :] = x
+            st |= sj
+        return x, traj, st
 
     def frames(self, x, u=None):
         """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""

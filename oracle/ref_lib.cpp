@@ -233,8 +233,18 @@ class rate_fn : public state_rate_function<double> {
   }
 };
 
+// scheme: enum rkb_scheme (1 euler, 2 midpoint, 4 runge_kutta4, 5 runge_kutta5)
+integrator<double>* make_integrator(int scheme, const vect_n<double>& x, double dt, const shared_ptr<state_rate_function<double> >& fn) {
+  switch (scheme) {
+    case RKB_SCHEME_EULER: return new euler_integrator<double>("euler", x, 0.0, dt, fn);
+    case RKB_SCHEME_MIDPOINT: return new midpoint_integrator<double>("midpoint", x, 0.0, dt, fn);
+    case RKB_SCHEME_RK5: return new runge_kutta5_integrator<double>("rk5", x, 0.0, dt, fn);
+    default: return new runge_kutta4_integrator<double>("rk4", x, 0.0, dt, fn);
+  }
+}
+
 void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, const double* u,
-               double dt, int n_steps, double* xout, int32_t* status) {
+               double dt, int n_steps, double* xout, int32_t* status, int scheme = RKB_SCHEME_RK4) {
   const int nx = 2 * m->n, nu = m->nu;
   for (std::size_t i = i0; i < i1; ++i) {
     vect_n<double> x(nx), uu(nu);
@@ -243,15 +253,17 @@ void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, c
     int32_t st = 0;
     if (n_steps > 0) {
       shared_ptr<state_rate_function<double> > fn(new rate_fn(&m->sys, uu));
-      runge_kutta4_integrator<double> integ("rk4", x, 0.0, dt, fn);
+      integrator<double>* integ = make_integrator(scheme, x, dt, fn);
       try {
-        // The loop of fixed_step_integrators.hpp:275 is time-driven; an end time half a step
-        // short of n_steps*dt makes it run exactly n_steps steps.
-        integ.integrate((double(n_steps) - 0.5) * dt);
+        // The loops of fixed_step_integrators.hpp (:76, :191, :275, :365) are time-driven; an end time
+        // half a step short of n_steps*dt makes them run exactly n_steps steps.  (runge_kutta5 moves
+        // its clock back and forth within a step, :392-397, but ends each step at t + dt.)
+        integ->integrate((double(n_steps) - 0.5) * dt);
       } catch (singularity_error&) { st |= RKB_STATUS_SINGULAR; }
       int k = 0;
-      for (std::vector<double>::const_iterator it = integ.getStateBegin(); it != integ.getStateEnd(); ++it, ++k)
+      for (std::vector<double>::const_iterator it = integ->getStateBegin(); it != integ->getStateEnd(); ++it, ++k)
         xout[i * nx + k] = *it;
+      delete integ;
     } else {
       for (int k = 0; k < nx; ++k) xout[i * nx + k] = x[k];
     }
@@ -445,8 +457,15 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
 // copy-on-write image of the whole model, which is the "one model instance per worker" the
 // non-re-entrant KTE objects need.  Results come back through a shared anonymous mapping.
 // Returns wall seconds of the integration (< 0 on failure).
+double rkref_integrate(void* hv, std::size_t N, const double* x0, const double* u, int scheme, double dt, int n_steps,
+                       double* xout, int32_t* status, int n_workers);
 double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, double dt, int n_steps,
                  double* xout, int32_t* status, int n_workers) {
+  return rkref_integrate(hv, N, x0, u, RKB_SCHEME_RK4, dt, n_steps, xout, status, n_workers);
+}
+
+double rkref_integrate(void* hv, std::size_t N, const double* x0, const double* u, int scheme, double dt, int n_steps,
+                       double* xout, int32_t* status, int n_workers) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
   const int nx = 2 * m->n;
@@ -454,7 +473,7 @@ double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, dou
   if (std::size_t(n_workers) > N && N > 0) n_workers = int(N);
   const auto t0 = std::chrono::steady_clock::now();
   if (n_workers == 1 || N == 0) {
-    rk4_range(m, 0, N, x0, u, dt, n_steps, xout, status);
+    rk4_range(m, 0, N, x0, u, dt, n_steps, xout, status, scheme);
   } else {
     const std::size_t bytes_x = N * nx * sizeof(double), bytes_s = N * sizeof(int32_t);
     void* shm = mmap(NULL, bytes_x + bytes_s, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
@@ -467,7 +486,7 @@ double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, dou
       std::size_t i0 = N * t / n_workers, i1 = N * (t + 1) / n_workers;
       pid_t pid = fork();
       if (pid == 0) {
-        rk4_range(m, i0, i1, x0, u, dt, n_steps, sx, ss);
+        rk4_range(m, i0, i1, x0, u, dt, n_steps, sx, ss, scheme);
         _exit(0);
       }
       if (pid < 0) { ok = false; break; }

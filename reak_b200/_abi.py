@@ -42,6 +42,16 @@ class rkb_chain_desc(C.Structure):
 
 assert C.sizeof(rkb_element) == 128, C.sizeof(rkb_element)
 
+
+class rkb_rollout_opts(C.Structure):
+    _fields_ = [("scheme", C.c_int32), ("n_intervals", C.c_int32), ("steps_per_interval", C.c_int32),
+                ("reserved", C.c_int32), ("dt", C.c_double)]
+
+
+SCHEME_EULER, SCHEME_MIDPOINT, SCHEME_RK4, SCHEME_RK5 = 1, 2, 4, 5
+SCHEMES = {"euler": SCHEME_EULER, "midpoint": SCHEME_MIDPOINT, "rk4": SCHEME_RK4, "runge_kutta4": SCHEME_RK4,
+           "rk5": SCHEME_RK5, "runge_kutta5": SCHEME_RK5}
+
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RKB_LIB_PATH") or os.path.join(_PKG_DIR, "lib", "libreak_b200.so")
 _lib = None
@@ -66,6 +76,8 @@ SYMBOLS = {
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(rkb_rollout_opts),
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "rkb_gen_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,

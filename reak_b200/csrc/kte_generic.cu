@@ -628,7 +628,17 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
 }
 
 template <int DIM, int MAXF>
-__global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const GenericProgram* __restrict__ G, const RolloutArgs A) {
+GD void store_state(const GenericProgram* G, const Work<DIM, MAXF>& W, const BatchView& o, long long off) {
+  for (int c = 0; c < G->n_coords; ++c) {
+    o.p[off + (2 * c) * o.sk] = W.q[c];
+    o.p[off + (2 * c + 1) * o.sk] = W.qd[c];
+  }
+}
+
+// n_steps RK4 steps (fixed_step_integrators.hpp:277-289, the reference's own operation order) with
+// the input held constant; TABLE selects the table-driven form for the other schemes.
+template <int DIM, int MAXF, bool TABLE>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const GenericProgram* __restrict__ G, const RolloutArgs A, const RkTable T) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
   Work<DIM, MAXF> W;
@@ -637,43 +647,56 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
   const int n = G->n_coords;
   const double dt = A.dt;
   double w[2 * MAXC], acc[2 * MAXC], k3[2 * MAXC];
+  double ks[TABLE ? RKB_RK_MAX_STAGES : 1][2 * MAXC];
   int st = 0;
-  for (int step = 0; step < A.n_steps; ++step) {
-    // fixed_step_integrators.hpp:277-289
-    st |= accel(G, W);
-    for (int c = 0; c < n; ++c) {
-      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-      w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c];
-      acc[2 * c] = kq; acc[2 * c + 1] = kv;
-      W.q[c] += kq * 0.5; W.qd[c] += kv * 0.5;
-    }
-    st |= accel(G, W);
-    for (int c = 0; c < n; ++c) {
-      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-      acc[2 * c] += kq * 2.0; acc[2 * c + 1] += kv * 2.0;
-      W.q[c] = w[2 * c] + kq * 0.5; W.qd[c] = w[2 * c + 1] + kv * 0.5;
-    }
-    st |= accel(G, W);
-    for (int c = 0; c < n; ++c) {
-      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-      k3[2 * c] = kq; k3[2 * c + 1] = kv;
-      W.q[c] = w[2 * c] + kq; W.qd[c] = w[2 * c + 1] + kv;
-    }
-    st |= accel(G, W);
-    for (int c = 0; c < n; ++c) {
-      const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-      W.q[c] += (acc[2 * c] + kq) / 6.0 - k3[2 * c] * (2.0 / 3.0);
-      W.qd[c] += (acc[2 * c + 1] + kv) / 6.0 - k3[2 * c + 1] * (2.0 / 3.0);
+  {
+    for (int step = 0; step < A.n_steps; ++step) {
+      if (TABLE) {
+        for (int c = 0; c < n; ++c) { w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c]; }
+        for (int s = 0; s < T.stages; ++s) {
+          st |= accel(G, W);
+          for (int c = 0; c < n; ++c) { ks[s][2 * c] = W.qd[c] * dt; ks[s][2 * c + 1] = W.f[c] * dt; }
+          for (int c = 0; c < n; ++c) {
+            double q = w[2 * c], qd = w[2 * c + 1];
+            for (int j = 0; j <= s; ++j) { q = fma(T.c[s][j], ks[j][2 * c], q); qd = fma(T.c[s][j], ks[j][2 * c + 1], qd); }
+            W.q[c] = q; W.qd[c] = qd;
+          }
+        }
+        continue;
+      }
+      st |= accel(G, W);
+      for (int c = 0; c < n; ++c) {
+        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+        w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c];
+        acc[2 * c] = kq; acc[2 * c + 1] = kv;
+        W.q[c] += kq * 0.5; W.qd[c] += kv * 0.5;
+      }
+      st |= accel(G, W);
+      for (int c = 0; c < n; ++c) {
+        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+        acc[2 * c] += kq * 2.0; acc[2 * c + 1] += kv * 2.0;
+        W.q[c] = w[2 * c] + kq * 0.5; W.qd[c] = w[2 * c + 1] + kv * 0.5;
+      }
+      st |= accel(G, W);
+      for (int c = 0; c < n; ++c) {
+        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+        k3[2 * c] = kq; k3[2 * c + 1] = kv;
+        W.q[c] = w[2 * c] + kq; W.qd[c] = w[2 * c + 1] + kv;
+      }
+      st |= accel(G, W);
+      for (int c = 0; c < n; ++c) {
+        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
+        W.q[c] += (acc[2 * c] + kq) / 6.0 - k3[2 * c] * (2.0 / 3.0);
+        W.qd[c] += (acc[2 * c + 1] + kv) / 6.0 - k3[2 * c + 1] * (2.0 / 3.0);
+      }
     }
   }
   bool finite = true;
-  for (int c = 0; c < n; ++c) {
-    A.xout.p[i * A.xout.si + (2 * c) * A.xout.sk] = W.q[c];
-    A.xout.p[i * A.xout.si + (2 * c + 1) * A.xout.sk] = W.qd[c];
-    finite = finite && isfinite(W.q[c]) && isfinite(W.qd[c]);
-  }
+  for (int c = 0; c < n; ++c) finite = finite && isfinite(W.q[c]) && isfinite(W.qd[c]);
+  store_state(G, W, A.xout, i * A.xout.si);
+  if (A.traj.p) store_state(G, W, A.traj, i * A.traj.si);
   if (!finite) st |= RKB_STATUS_NONFINITE;
-  if (A.status) A.status[i] = st;
+  if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }
 
 unsigned grid_of(long long n) { return (unsigned)((n + GEN_BLOCK - 1) / GEN_BLOCK); }
@@ -687,6 +710,17 @@ unsigned grid_of(long long n) { return (unsigned)((n + GEN_BLOCK - 1) / GEN_BLOC
       if ((host).n_frames <= 16) kernel<2, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);     \
       else kernel<2, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);           \
     }                                                                                            \
+  } while (0)
+
+#define DISPATCH2(kernel, flag, host, ...)                                                             \
+  do {                                                                                                 \
+    if ((host).dim == 3) {                                                                             \
+      if ((host).n_frames <= 16) kernel<3, 16, flag><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);     \
+      else kernel<3, RKB_GEN_MAX_FRAMES, flag><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);           \
+    } else {                                                                                           \
+      if ((host).n_frames <= 16) kernel<2, 16, flag><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);     \
+      else kernel<2, RKB_GEN_MAX_FRAMES, flag><<<grid_of(n), GEN_BLOCK, 0, s>>>(__VA_ARGS__);           \
+    }                                                                                                  \
   } while (0)
 
 // ---- steer: per-pair arg-min over the rollout end states -------------------------------------------
@@ -748,10 +782,14 @@ cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& h
   DISPATCH(generic_mass_kernel, host, prog, a);
   return cudaGetLastError();
 }
-cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, cudaStream_t s) {
+cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,
+                                cudaStream_t s) {
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
-  DISPATCH(generic_rollout_kernel, host, prog, a);
+  RkTable none;
+  none.stages = 0;
+  if (table) DISPATCH2(generic_rollout_kernel, true, host, prog, a, *table);
+  else DISPATCH2(generic_rollout_kernel, false, host, prog, a, none);
   return cudaGetLastError();
 }
 cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, const double* xend, const double* goal,

@@ -954,7 +954,18 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
   }
 }
 
-// n_steps of fixed-step RK4 with the input held constant.
+template <int N>
+RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long off, const SerialState<N>& X) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = P.st[k].coord;
+    o.p[off + (2 * c) * o.sk] = X.q[k];
+    o.p[off + (2 * c + 1) * o.sk] = X.qd[k];
+  }
+}
+
+// n_steps of fixed-step RK4 (runge_kutta4_integrator<T>::integrate, fixed_step_integrators.hpp:256-293)
+// with the input held constant (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
 // Per-thread shared-memory column: w (2N) and k1 + 2 k2 (2N).
 template <int N, int FL, shape_t SHAPE>
 __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
@@ -1016,14 +1027,67 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   }
   bool finite = true;
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const int c = P.st[k].coord;
-    A.xout.p[i * A.xout.si + (2 * c) * A.xout.sk] = X.q[k];
-    A.xout.p[i * A.xout.si + (2 * c + 1) * A.xout.sk] = X.qd[k];
-    finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
-  }
+  for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+  store_state<N>(P, A.xout, i * A.xout.si, X);
+  if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si, X);
   if (!finite) st |= RKB_STATUS_NONFINITE;
-  if (A.status) A.status[i] = st;
+  if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
+}
+
+// Any explicit one-step scheme given as an RkTable (Euler, midpoint, RK5 — and RK4, which the kernel
+// above does faster).  Per-thread shared-memory column: w (2N), then k_0 .. k_{stages-1} (2N each).
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_rk_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A,
+                                                                                                       const __grid_constant__ RkTable T) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  double* sm = smem + threadIdx.x;
+  double* sw = sm;
+  double* sk = sw + 2 * N * SMS;
+  SerialState<N> X;
+  {
+    const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
+    ConstBatchView xv = A.x0;
+    xv.p += i0 * xv.si - i * xv.si;
+    load_state<N>(P, xv, A.u, i, X);
+  }
+  const double dt = A.dt;
+  int st = 0;
+#pragma unroll 1
+  for (int step = 0; step < A.n_steps; ++step) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) { sw[(2 * k) * SMS] = X.q[k]; sw[(2 * k + 1) * SMS] = X.qd[k]; }
+#pragma unroll 1
+    for (int s = 0; s < T.stages; ++s) {
+      double qdd[N];
+      st |= serial_accel<N, FL, SHAPE, SMS>(P, X, qdd, sm);
+      double* ks = sk + s * (2 * N * SMS);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        ks[(2 * k) * SMS] = X.qd[k] * dt; ks[(2 * k + 1) * SMS] = qdd[k] * dt;
+        X.q[k] = sw[(2 * k) * SMS]; X.qd[k] = sw[(2 * k + 1) * SMS];
+      }
+#pragma unroll 1
+      for (int j = 0; j <= s; ++j) {
+        const double c = T.c[s][j];
+        const double* kj = sk + j * (2 * N * SMS);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          X.q[k] = fma(c, kj[(2 * k) * SMS], X.q[k]);
+          X.qd[k] = fma(c, kj[(2 * k + 1) * SMS], X.qd[k]);
+        }
+      }
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+  store_state<N>(P, A.xout, i * A.xout.si, X);
+  if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si, X);
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }
 
 }  // namespace rkb

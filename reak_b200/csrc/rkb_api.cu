@@ -540,10 +540,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
 }
 
 // rollout on device-resident views; used by rkb_rollout_rk4 and rkb_steer_batch
-int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, cudaStream_t s) {
+// table == nullptr: the dedicated RK4 kernels (the fast path)
+int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, const RkTable* table, cudaStream_t s) {
   cudaError_t e;
-  if (c->serial_ok && c->sk) e = c->sk->rollout(c->sp, A, s);
-  else if (c->generic_ok) e = rkb_generic_rollout(ctx->d_prog, c->gp, A, s);
+  if (c->serial_ok && c->sk) e = table ? c->sk->rollout_rk(c->sp, A, *table, s) : c->sk->rollout(c->sp, A, s);
+  else if (c->generic_ok) e = rkb_generic_rollout(ctx->d_prog, c->gp, A, table, s);
   else return RKB_ERR_UNSUPPORTED;
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   c->launches += 1;
@@ -642,6 +643,69 @@ int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double*
 
 namespace {
 
+// What to integrate: scheme (table == false: the dedicated RK4 kernels), step, steps per control
+// interval, number of intervals.
+struct RolloutPlan {
+  bool use_table = false;
+  RkTable table;
+  double dt = 0.0;
+  int n_steps = 0, n_intervals = 1;
+};
+
+// The schemes of fixed_step_integrators.hpp rewritten as "start of step + weighted increments"
+// (the reference updates the state incrementally; the weights below are those sums in closed form).
+int make_plan(const rkb_rollout_opts* o, RolloutPlan& pl) {
+  if (!o || o->reserved != 0) return RKB_ERR_INVALID;
+  if (o->dt == 0.0 || !std::isfinite(o->dt) || o->steps_per_interval < 0 || o->n_intervals < 1) return RKB_ERR_INTEGRATION;
+  pl.dt = o->dt; pl.n_steps = o->steps_per_interval; pl.n_intervals = o->n_intervals;
+  std::memset(&pl.table, 0, sizeof pl.table);
+  double (*c)[RKB_RK_MAX_STAGES] = pl.table.c;
+  switch (o->scheme) {
+    case RKB_SCHEME_RK4: pl.use_table = false; return RKB_OK;
+    case RKB_SCHEME_EULER:  // :78  x += f dt
+      pl.table.stages = 1; c[0][0] = 1.0; break;
+    case RKB_SCHEME_MIDPOINT:  // :193-199  w = x + f dt/2 ; x += f(w) dt
+      pl.table.stages = 2; c[0][0] = 0.5; c[1][1] = 1.0; break;
+    case RKB_SCHEME_RK5:  // :368-395
+      pl.table.stages = 6;
+      c[0][0] = 0.25;
+      c[1][0] = 0.25 - 5.0 / 32.0; c[1][1] = 9.0 / 32.0;
+      c[2][0] = c[1][0] + 276165.0 / 351520.0; c[2][1] = c[1][1] - 1250865.0 / 351520.0; c[2][2] = 1167360.0 / 351520.0;
+      c[3][0] = 439.0 / 216.0; c[3][1] = -8.0; c[3][2] = 3680.0 / 513.0; c[3][3] = -845.0 / 4104.0;
+      c[4][0] = -8.0 / 27.0; c[4][1] = 2.0; c[4][2] = -3544.0 / 2565.0; c[4][3] = 1859.0 / 4104.0; c[4][4] = -11.0 / 40.0;
+      c[5][0] = 16.0 / 135.0; c[5][2] = 6656.0 / 12825.0; c[5][3] = 28561.0 / 56430.0; c[5][4] = -9.0 / 50.0; c[5][5] = 2.0 / 55.0;
+      break;
+    default: return RKB_ERR_INVALID;
+  }
+  pl.use_table = true;
+  return RKB_OK;
+}
+
+// One launch per control interval over device-resident AoS/SoA views.  Interval 0 reads x0 and every
+// later one the previous end state, in place in xout; the end state of interval j also goes to slot j
+// of the trajectory when one is wanted; status bits accumulate.
+//   u:    input k of interval j of sample i at u.p[i * u.si + j * u_sj + k * u.sk]
+//   traj: likewise with traj_sj
+int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long long n, ConstBatchView x0, ConstBatchView u, long long u_sj,
+                     BatchView xout, BatchView traj, long long traj_sj, int32_t* status, cudaStream_t s) {
+  for (int j = 0; j < pl.n_intervals; ++j) {
+    RolloutArgs A;
+    A.x0 = j == 0 ? x0 : ConstBatchView{xout.p, xout.si, xout.sk};
+    A.u = ConstBatchView{u.p + j * u_sj, u.si, u.sk};
+    A.xout = xout;
+    A.traj = traj.p ? BatchView{traj.p + j * traj_sj, traj.si, traj.sk} : BatchView{nullptr, 0, 0};
+    A.status = status;
+    A.n_samples = n;
+    A.x0_div = 1;
+    A.dt = pl.dt;
+    A.n_steps = pl.n_steps;
+    A.status_or = j > 0;
+    const int rc = launch_rollout(c, ctx, A, pl.use_table ? &pl.table : nullptr, s);
+    if (rc) return rc;
+  }
+  return RKB_OK;
+}
+
 constexpr int kPipeChunks = 8;
 constexpr size_t kPipeMinSamples = 1u << 16;
 
@@ -663,18 +727,22 @@ int ensure_pipe(DeviceCtx* ctx) {
 // kernel and device->host copy overlap (copy-in stream, two alternating compute streams so that
 // one chunk's tail wave overlaps the next chunk's head, copy-out stream).  Only the first copy-in
 // and the last copy-out stay exposed.  Pinned host memory is what makes the copies asynchronous.
-int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
-                       double* x_out, int32_t* status, cudaStream_t s, bool join_caller) {
-  const int nx = 2 * c->n, nu = c->nu;
+int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
+                       double* x_out, double* x_traj, int32_t* status, cudaStream_t s, bool join_caller) {
+  const int nx = 2 * c->n;
+  const size_t nu = (size_t)c->nu * pl.n_intervals;  // doubles of input per sample
+  const size_t nt = (size_t)nx * pl.n_intervals;     // doubles of trajectory per sample
   int rc;
   if ((rc = ensure_pipe(ctx))) return rc;
   if ((rc = ctx->in_x.ensure(N * nx * sizeof(double)))) return rc;
   if (nu > 0 && (rc = ctx->in_u.ensure(N * nu * sizeof(double)))) return rc;
   if ((rc = ctx->out_a.ensure(N * nx * sizeof(double)))) return rc;
+  if (x_traj && (rc = ctx->out_b.ensure(N * nt * sizeof(double)))) return rc;
   if ((rc = ctx->st.ensure(N * sizeof(int32_t)))) return rc;
   double* dx = (double*)ctx->in_x.p;
   double* du = (double*)ctx->in_u.p;
   double* dout = (double*)ctx->out_a.p;
+  double* dtraj = x_traj ? (double*)ctx->out_b.p : nullptr;
   int32_t* dst = (int32_t*)ctx->st.p;
   if (join_caller) {  // order after whatever the caller queued on its stream
     CU(cudaEventRecord(ctx->ev_join, s));
@@ -693,19 +761,15 @@ int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0,
     CU(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
     cudaStream_t sk = ctx->s_k[i & 1];
     CU(cudaStreamWaitEvent(sk, ctx->ev_in[i], 0));
-    RolloutArgs A;
-    A.x0 = cview(dx + lo * nx, (long long)m, nx, false);
-    A.u = cview(nu > 0 ? du + lo * nu : dx, (long long)m, nu > 0 ? nu : 1, false);
-    A.xout = view(dout + lo * nx, (long long)m, nx, false);
-    A.status = dst + lo;
-    A.n_samples = (long long)m;
-    A.x0_div = 1;
-    A.dt = dt;
-    A.n_steps = n_steps;
-    if ((rc = launch_rollout(c, ctx, A, sk))) return rc;
+    if ((rc = launch_intervals(c, ctx, pl, (long long)m, cview(dx + lo * nx, (long long)m, nx, false),
+                               ConstBatchView{nu > 0 ? du + lo * nu : dx, (long long)(nu > 0 ? nu : 1), 1}, c->nu,
+                               view(dout + lo * nx, (long long)m, nx, false),
+                               BatchView{dtraj ? dtraj + lo * nt : nullptr, (long long)nt, 1}, nx, dst + lo, sk)))
+      return rc;
     CU(cudaEventRecord(ctx->ev_k[i], sk));
     CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[i], 0));
     CU(cudaMemcpyAsync(x_out + lo * nx, dout + lo * nx, m * nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+    if (x_traj) CU(cudaMemcpyAsync(x_traj + lo * nt, dtraj + lo * nt, m * nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
     if (status) CU(cudaMemcpyAsync(status + lo, dst + lo, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
     last_k = i;
   }
@@ -725,9 +789,9 @@ int rollout_host_wait(DeviceCtx* ctx) {
   return RKB_OK;
 }
 
-int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, double dt, int n_steps,
-                           double* x_out, int32_t* status, cudaStream_t s) {
-  int rc = rollout_host_issue(c, ctx, N, x0, u, dt, n_steps, x_out, status, s, true);
+int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
+                           double* x_out, double* x_traj, int32_t* status, cudaStream_t s) {
+  int rc = rollout_host_issue(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, true);
   if (rc) return rc;
   if ((rc = rollout_host_wait(ctx))) return rc;
   // let the caller's stream observe completion as well
@@ -740,14 +804,12 @@ int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double*
 
 extern "C" {
 
-int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const double* u, double dt, int n_steps,
-                    double* x_out, int32_t* status, unsigned flags, void* stream) {
-  if (!c) return RKB_ERR_INVALID;
-  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;  // fixed_step_integrators.hpp:258-266
+static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
+                      double* x_out, double* x_traj, int32_t* status, unsigned flags, void* stream) {
   if (N == 0) return RKB_OK;
   if (!x0 || !x_out || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n, nu = c->nu;
+  const int nx = 2 * c->n, nu = c->nu, J = pl.n_intervals;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -755,32 +817,50 @@ int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const 
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!L.device && !L.soa && N >= kPipeMinSamples && n_steps > 0 && !(std::getenv("RKB_NO_PIPELINE") && std::getenv("RKB_NO_PIPELINE")[0] == '1'))
-    return rollout_host_pipelined(c, ctx, N, x0, u, dt, n_steps, x_out, status, s);
+  if (!L.device && !L.soa && N >= kPipeMinSamples && pl.n_steps > 0 && !(std::getenv("RKB_NO_PIPELINE") && std::getenv("RKB_NO_PIPELINE")[0] == '1'))
+    return rollout_host_pipelined(c, ctx, N, x0, u, pl, x_out, x_traj, status, s);
   const void *dx = nullptr, *du = nullptr;
-  void *dout = nullptr, *dst = nullptr;
+  void *dout = nullptr, *dtraj = nullptr, *dst = nullptr;
   if ((rc = stage_in(ctx->in_x, x0, N * nx * sizeof(double), L.device, s, &dx))) return rc;
-  if (nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc; }
+  if (nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * J * sizeof(double), L.device, s, &du))) return rc; }
   if ((rc = stage_out(ctx->out_a, x_out, N * nx * sizeof(double), L.device, &dout))) return rc;
+  if ((rc = stage_out(ctx->out_b, x_traj, N * nx * J * sizeof(double), L.device, &dtraj))) return rc;
   if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
-  RolloutArgs A;
-  A.x0 = cview((const double*)dx, (long long)N, nx, L.soa);
-  A.u = cview((const double*)(du ? du : dx), (long long)N, nu > 0 ? nu : 1, L.soa);
-  A.xout = view((double*)dout, (long long)N, nx, L.soa);
-  A.status = (int32_t*)dst;
-  A.n_samples = (long long)N;
-  A.x0_div = 1;
-  A.dt = dt;
-  A.n_steps = n_steps;
+  // AoS [N][J][nu]: sample stride J nu, interval stride nu; SoA [J][nu][N]: sample stride 1, interval stride nu N
+  const ConstBatchView uv = L.soa ? ConstBatchView{(const double*)(du ? du : dx), 1, (long long)N}
+                                  : ConstBatchView{(const double*)(du ? du : dx), (long long)(nu > 0 ? nu * J : 1), 1};
+  const BatchView tv = L.soa ? BatchView{(double*)dtraj, 1, (long long)N} : BatchView{(double*)dtraj, (long long)nx * J, 1};
   CU(cudaEventRecord(ctx->ev0, s));
-  if ((rc = launch_rollout(c, ctx, A, s))) return rc;
+  if ((rc = launch_intervals(c, ctx, pl, (long long)N, cview((const double*)dx, (long long)N, nx, L.soa), uv,
+                             L.soa ? (long long)nu * (long long)N : (long long)nu, view((double*)dout, (long long)N, nx, L.soa), tv,
+                             L.soa ? (long long)nx * (long long)N : (long long)nx, (int32_t*)dst, s)))
+    return rc;
   CU(cudaEventRecord(ctx->ev1, s));
   ctx->timed = true;
   c->last = ctx;
   if ((rc = unstage_out(dout, x_out, N * nx * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dtraj, x_traj, N * nx * J * sizeof(double), L.device, s))) return rc;
   if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
   if (!L.device) CU(cudaStreamSynchronize(s));
   return RKB_OK;
+}
+
+int rkb_rollout_rk4(rkb_chain* c, int device, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                    double* x_out, int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;  // fixed_step_integrators.hpp:258-266
+  RolloutPlan pl;
+  pl.dt = dt; pl.n_steps = n_steps; pl.n_intervals = 1;
+  return do_rollout(c, device, N, x0, u, pl, x_out, nullptr, status, flags, stream);
+}
+
+int rkb_rollout(rkb_chain* c, int device, size_t N, const double* x0, const double* u, const rkb_rollout_opts* opts,
+                double* x_out, double* x_traj, int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  RolloutPlan pl;
+  const int rc = make_plan(opts, pl);
+  if (rc) return rc;
+  return do_rollout(c, device, N, x0, u, pl, x_out, x_traj, status, flags, stream);
 }
 
 /* Host-buffer rollout sharded over several GPUs of one box from one process: contiguous block
@@ -811,7 +891,9 @@ int rkb_rollout_rk4_multi(rkb_chain* c, int n_devices, const int* devices, size_
       if (status) std::memset(status + lo, 0, (hi - lo) * sizeof(int32_t));
       continue;
     }
-    rc = rollout_host_issue(c, ctx, hi - lo, x0 + lo * nx, nu > 0 ? u + lo * nu : nullptr, dt, n_steps, x_out + lo * nx,
+    RolloutPlan pl;
+    pl.dt = dt; pl.n_steps = n_steps; pl.n_intervals = 1;
+    rc = rollout_host_issue(c, ctx, hi - lo, x0 + lo * nx, nu > 0 ? u + lo * nu : nullptr, pl, x_out + lo * nx, nullptr,
                             status ? status + lo : nullptr, nullptr, false);
     used[g] = ctx;
   }
@@ -865,9 +947,11 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   A.status = (int32_t*)dst;
   A.n_samples = (long long)T;
   A.x0_div = (long long)R;
+  A.traj = BatchView{nullptr, 0, 0};
   A.dt = dt;
   A.n_steps = n_steps;
-  if ((rc = launch_rollout(c, ctx, A, s))) return rc;
+  A.status_or = 0;
+  if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
   e = rkb_steer_reduce(nx, (long long)P, (long long)R, (const double*)ctx->scratch_o.p, (const double*)dgoal, (int32_t*)didx,
                        (double*)dbx, (double*)dbc, s);
   if (e != cudaSuccess) return cuda_fail(e, "steer reduce");

@@ -15,7 +15,8 @@ struct SerialKernels {
   cudaError_t (*eval)(const SerialParams&, const EvalArgs&, cudaStream_t);
   cudaError_t (*forces)(const SerialParams&, const EvalArgs&, cudaStream_t);
   cudaError_t (*mass)(const SerialParams&, const EvalArgs&, cudaStream_t);
-  cudaError_t (*rollout)(const SerialParams&, const RolloutArgs&, cudaStream_t);
+  cudaError_t (*rollout)(const SerialParams&, const RolloutArgs&, cudaStream_t);                     // RK4
+  cudaError_t (*rollout_rk)(const SerialParams&, const RolloutArgs&, const RkTable&, cudaStream_t);  // any explicit scheme
 };
 
 // defined in rkb_serial_n.cu, compiled once per N with -DRKB_N=<n>
@@ -27,7 +28,8 @@ RKB_DECL_TABLE(5); RKB_DECL_TABLE(6); RKB_DECL_TABLE(7); RKB_DECL_TABLE(8);
 cudaError_t rkb_generic_eval(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
-cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, cudaStream_t s);
+cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,
+                                cudaStream_t s);  // table == NULL: the reference's RK4 arithmetic
 
 // steer helpers (rkb_steer.cu): cost of every rollout end state against its pair's goal, then
 // per-pair arg-min (first index wins ties) and gather of the winning end state.

@@ -16,9 +16,12 @@ struct Launch {
   static constexpr int kSmemForces = RKB_SMEM_FORCES_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemMass = RKB_SMEM_MASS_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemRollout = RKB_SMEM_ROLLOUT(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int smem_rk(int stages) { return (2 * N + 2 * N * stages) * RKB_BLOCK * (int)sizeof(double); }
   static unsigned grid(long long n) { return (unsigned)((n + RKB_BLOCK - 1) / RKB_BLOCK); }
   static cudaError_t prepare() {
     cudaError_t e = cudaFuncSetAttribute(serial_rollout_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(serial_rollout_rk_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rk(RKB_RK_MAX_STAGES));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_eval_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
     if (e != cudaSuccess) return e;
@@ -49,10 +52,15 @@ struct Launch {
     serial_rollout_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
     return cudaGetLastError();
   }
+  static cudaError_t rollout_rk(const SerialParams& P, const RolloutArgs& A, const RkTable& T, cudaStream_t s) {
+    if (A.n_samples <= 0) return cudaSuccess;
+    serial_rollout_rk_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, smem_rk(T.stages), s>>>(P, A, T);
+    return cudaGetLastError();
+  }
   static SerialKernels entry() {
     SerialKernels k;
     k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
-    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout;
+    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk;
     return k;
   }
 };

@@ -74,14 +74,31 @@ struct ConstBatchView {
   long long si, sk;
 };
 
+// Explicit one-step scheme in "start of step plus weighted increments" form: after evaluation s
+// (k_s = dt f(X_s)) the next evaluation point — or, for s = stages - 1, the end of the step — is
+// w + sum_{j <= s} c[s][j] k_j.  Filled by the host from the formulas of
+// core/integrators/fixed_step_integrators.hpp (euler :64-84, midpoint :177-202, runge_kutta4 :257-293,
+// runge_kutta5 :351-399).
+#define RKB_RK_MAX_STAGES 6
+struct RkTable {
+  int32_t stages;
+  int32_t pad;
+  double  c[RKB_RK_MAX_STAGES][RKB_RK_MAX_STAGES];
+};
+
+// One control interval: n_steps integrator steps with the input held constant.  A sequence of
+// intervals is a sequence of launches (the state makes one round trip through HBM per interval,
+// 2 x 16 n bytes per sample against >= 4 evaluations of the chain).
 struct RolloutArgs {
   ConstBatchView x0, u;
-  BatchView      xout;
+  BatchView      xout;     // may alias x0 (each thread reads its own row before it writes it)
+  BatchView      traj;     // nullable (p == 0): a second copy of the end state (the interval's slot of x_traj)
   int32_t*       status;   // nullable
   long long      n_samples;
   long long      x0_div;   // sample i starts from row i / x0_div of x0 (steer batch: rollouts per pair; else 1)
   double         dt;
   int32_t        n_steps;
+  int32_t        status_or;  // != 0: OR the status bits into status[i] instead of overwriting it
 };
 
 struct EvalArgs {

@@ -178,6 +178,33 @@ class kte_batch_propagator(object):
                                              dt, int(n_steps), ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4")
         return xo, st
 
+    def rollout(self, x, u_seq, dt=None, steps_per_interval=1, scheme="rk4", want_traj=False, out=None, status=None):
+        """n_intervals = u_seq.shape[1] control intervals, the input constant within each (one
+        num_int_dtnl_sys::get_next_state per interval), steps_per_interval steps of `scheme`
+        (euler / midpoint / rk4 / rk5, core/integrators/fixed_step_integrators.hpp) per interval.
+        x: [N][nx]; u_seq: [N][n_intervals][nu].  Returns (x_out, status) or, with want_traj,
+        (x_out, x_traj [N][n_intervals][nx], status)."""
+        x, N = self._in(x, self.nx, np.float64)
+        if _is_torch(u_seq):
+            u_seq = u_seq.contiguous()
+        else:
+            u_seq = np.ascontiguousarray(u_seq, dtype=np.float64)
+        if len(u_seq.shape) != 3 or u_seq.shape[0] != N or u_seq.shape[2] != self.nu or u_seq.shape[1] < 1:
+            raise IndexError("Input vector dimension mismatch!")
+        J = int(u_seq.shape[1])
+        dt = self.dt if dt is None else float(dt)
+        if dt == 0.0 or steps_per_interval < 0:
+            raise impossible_integration("dt == 0 or negative step count")
+        code = _abi.SCHEMES[scheme] if isinstance(scheme, str) else int(scheme)
+        opts = _abi.rkb_rollout_opts(code, J, int(steps_per_interval), 0, dt)
+        xo = out if out is not None else self._like(x, x.shape)
+        tr = self._like(x, (N, J, self.nx)) if want_traj else None
+        st = status if status is not None else self._like(x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, u_seq if self.nu else None, xo, tr, st], False)
+        _abi.check(self._lib.rkb_rollout(self._h, self.device, N, ptr(x), ptr(u_seq) if self.nu else None, C.byref(opts),
+                                         ptr(xo), ptr(tr), ptr(st), flags, stream), "rkb_rollout")
+        return (xo, tr, st) if want_traj else (xo, st)
+
     def get_next_states_multi(self, x, u=None, dt=None, n_steps=1, devices=(0,), out=None, status=None):
         """Host (numpy, AoS) buffers sharded over several GPUs from this one process (rkb_rollout_rk4_multi)."""
         x, N = self._in(x, self.nx, np.float64)

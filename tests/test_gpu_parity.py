@@ -269,3 +269,107 @@ def test_ragged_sizes_and_permuted_dofs(oracle_built):
     assert rel_err(q.get_mass_matrices(x), Oq.mass(x, with_dot=False)) < TOL_STEP
     assert rel_err(q.get_gen_forces(x, u), Oq.gen_forces(x, u)) < TOL_STEP
     assert rel_err(q.get_next_states(x, u, 1e-3, 20)[0], Oq.rk4(x, u, 1e-3, 20)[0]) < TOL_LONG
+
+
+# ---- rkb_rollout: every fixed-step scheme, control sequences, interval trajectories ---------------
+SCHEME_CODES = {"euler": 1, "midpoint": 2, "rk4": 4, "rk5": 5}
+SCHEME_DIR = os.path.join(GOLDEN_DIR, "schemes")
+
+
+@pytest.mark.parametrize("name", ["planar2_act", "crs6", "crs6_sd", "crs7", "crs6_twist"])
+def test_rollout_schemes_against_golden_reference_trajectories(name):
+    """tests/golden/schemes/*.npz: trajectories of the unmodified reference driven one control interval
+    at a time (tests/golden/make_golden_schemes.py)."""
+    g = np.load(os.path.join(SCHEME_DIR, name + ".npz"))
+    for label, p in _variants(name):
+        for sname in SCHEME_CODES:
+            xo, traj, st = p.rollout(g["x"], g["u_seq"], float(g["dt"]), int(g["steps_per_interval"]), scheme=sname, want_traj=True)
+            assert not st.any()
+            assert rel_err(traj, g["traj_" + sname]) < TOL_STEP, (name, label, sname)
+            assert np.array_equal(xo, traj[:, -1, :])
+
+
+@pytest.mark.parametrize("name", ["planar2", "planar_pr", "crs3", "crs6_phys", "crs6_sd_sat", "crs7_phys_sd", "crs6_lin_sd"])
+def test_rollout_schemes_vs_oracle(name, oracle_built):
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        x, _ = random_batch(p.compiled, 130, seed=21)
+        rng = np.random.default_rng(22)
+        u_seq = rng.uniform(-1.5, 1.5, (130, 3, p.nu))
+        for sname, code in SCHEME_CODES.items():
+            xo, traj, st = p.rollout(x, u_seq, 2e-3, 6, scheme=sname, want_traj=True)
+            xr, tr, sr = O.rollout(x, u_seq, code, 2e-3, 6)
+            assert not st.any() and not sr.any()
+            assert rel_err(traj, tr) < TOL_STEP and rel_err(xo, xr) < TOL_STEP, (name, label, sname)
+            # without the trajectory the end state is the same, bit for bit
+            xo2, st2 = p.rollout(x, u_seq, 2e-3, 6, scheme=sname)
+            assert np.array_equal(xo2, xo)
+
+
+def test_rollout_rk4_single_interval_is_get_next_states():
+    import torch
+    p = _make("crs6")
+    x, u = random_batch(p.compiled, 3000, seed=4)
+    ref, _ = p.get_next_states(x, u, 1e-3, 9)
+    xo, st = p.rollout(x, u[:, None, :], 1e-3, 9, scheme="rk4")
+    assert np.array_equal(xo, ref) and not st.any()
+    # a constant sequence equals one long interval; device buffers give the same bits as host buffers
+    u_seq = np.ascontiguousarray(np.repeat(u[:, None, :], 3, axis=1))
+    xo3, tr3, _ = p.rollout(x, u_seq, 1e-3, 3, scheme="rk4", want_traj=True)
+    assert np.array_equal(xo3, ref)
+    xt, ut = torch.from_numpy(x).cuda(), torch.from_numpy(u_seq).cuda()
+    xd, trd, _ = p.rollout(xt, ut, 1e-3, 3, scheme="rk4", want_traj=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), ref) and np.array_equal(trd.cpu().numpy(), tr3)
+
+
+def test_rollout_large_host_batch_is_pipelined_and_consistent():
+    """Above 2^16 samples host buffers go through the chunked copy/compute pipeline, trajectory included."""
+    p = _make("crs6")
+    n = (1 << 16) + 777
+    x, _ = random_batch(p.compiled, n, seed=6)
+    u_seq = np.random.default_rng(7).uniform(-1, 1, (n, 2, p.nu))
+    xo, tr, st = p.rollout(x, u_seq, 1e-3, 2, scheme="rk4", want_traj=True)
+    m = 500
+    xs, ts, _ = p.rollout(x[-m:], u_seq[-m:], 1e-3, 2, scheme="rk4", want_traj=True)
+    assert not st.any() and np.array_equal(xo[-m:], xs) and np.array_equal(tr[-m:], ts)
+    xe, te, _ = p.rollout(x, u_seq, 1e-3, 2, scheme="midpoint", want_traj=True)
+    xs, ts, _ = p.rollout(x[:m], u_seq[:m], 1e-3, 2, scheme="midpoint", want_traj=True)
+    assert np.array_equal(xe[:m], xs) and np.array_equal(te[:m], ts)
+
+
+def test_rollout_soa_through_the_c_abi():
+    """SOA layout of rkb_rollout: u [n_intervals][nu][N], x_traj [n_intervals][2n][N]."""
+    import ctypes as C
+    from reak_b200 import _abi
+    p = _make("crs6_sd")
+    n, J = 257, 4
+    x, _ = random_batch(p.compiled, n, seed=8)
+    u_seq = np.random.default_rng(9).uniform(-1, 1, (n, J, p.nu))
+    xo, tr, _ = p.rollout(x, u_seq, 1e-3, 3, scheme="rk5", want_traj=True)
+    xs = np.ascontiguousarray(x.T)
+    us = np.ascontiguousarray(u_seq.transpose(1, 2, 0))
+    xo_s, tr_s, st = np.empty_like(xs), np.empty((J, p.nx, n)), np.zeros(n, dtype=np.int32)
+    opts = _abi.rkb_rollout_opts(_abi.SCHEME_RK5, J, 3, 0, 1e-3)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _abi.check(_abi.load_library().rkb_rollout(p._h, 0, n, vp(xs), vp(us), C.byref(opts), vp(xo_s), vp(tr_s), vp(st),
+                                               _abi.LAYOUT_SOA, None))
+    assert np.array_equal(xo_s.T, xo) and np.array_equal(tr_s.transpose(2, 0, 1), tr) and not st.any()
+
+
+def test_rollout_argument_errors():
+    import ctypes as C
+    from reak_b200 import _abi
+    p = _make("crs3")
+    x, u = random_batch(p.compiled, 4, seed=1)
+    lib = _abi.load_library()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = np.empty_like(x)
+    call = lambda o: lib.rkb_rollout(p._h, 0, 4, vp(x), vp(u), C.byref(o) if o is not None else None, vp(out), None, None, 0, None)
+    assert call(None) == _abi.ERR_INVALID
+    assert call(_abi.rkb_rollout_opts(3, 1, 1, 0, 1e-3)) == _abi.ERR_INVALID        # no such scheme
+    assert call(_abi.rkb_rollout_opts(4, 1, 1, 7, 1e-3)) == _abi.ERR_INVALID        # reserved != 0
+    assert call(_abi.rkb_rollout_opts(4, 0, 1, 0, 1e-3)) == _abi.ERR_INTEGRATION    # no interval
+    assert call(_abi.rkb_rollout_opts(4, 1, -1, 0, 1e-3)) == _abi.ERR_INTEGRATION
+    assert call(_abi.rkb_rollout_opts(4, 1, 1, 0, 0.0)) == _abi.ERR_INTEGRATION     # impossible_integration
+    assert call(_abi.rkb_rollout_opts(5, 1, 2, 0, -1e-3)) == 0                      # backwards is allowed
