@@ -224,6 +224,17 @@ class kte_batch_propagator {
     if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step or negative step count");
     check(rc, "rkb_rollout_rk4");
   }
+  /// Any fixed-step scheme of fixed_step_integrators.hpp (scheme = RKB_SCHEME_*) over n_intervals control
+  /// intervals with the input constant within each — what a planner gets by calling get_next_state once
+  /// per interval.  u: [n][n_intervals][n_inputs]; x_traj (nullable): [n][n_intervals][2 dof] (AoS).
+  void rollout(std::size_t n, const double* x, const double* u, int scheme, int n_intervals, int steps_per_interval, double dt,
+               double* x_out, double* x_traj = NULL, int32_t* status = NULL, unsigned flags = 0, void* stream = NULL) const {
+    rkb_rollout_opts o = rkb_rollout_opts();
+    o.scheme = scheme; o.n_intervals = n_intervals; o.steps_per_interval = steps_per_interval; o.dt = dt;
+    int rc = rkb_rollout(mChain, mDevice, n, x, u, &o, x_out, x_traj, status, flags, stream);
+    if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step, negative step count or no interval");
+    check(rc, "rkb_rollout");
+  }
   /// Host (AoS) buffers sharded over several GPUs of this box from one process: contiguous blocks of
   /// samples, one copy/compute pipeline per device, no inter-GPU communication.
   void get_next_states_multi(const std::vector<int>& devices, std::size_t n, const double* x, const double* u, int n_steps,

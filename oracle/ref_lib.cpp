@@ -46,6 +46,7 @@
 #pragma weak rkb_last_kernel_ms
 #pragma weak rkb_last_cuda_error
 #pragma weak rkb_rollout_rk4
+#pragma weak rkb_rollout
 #pragma weak rkb_strerror
 #include "../include/reak_b200/reak_bridge.hpp"
 
