@@ -18,6 +18,8 @@
  *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
  *   rkb_steer_batch       <- the inner loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561),
  *                            many (start, goal, control) tuples per call
+ *   rkb_steer_feedback    <- that loop whole — state feedback, get_bounded_input (examples/misc/IHAQR_topology.hpp:304-327),
+ *                            one RK4 control interval, goal-proximity stop, steer record — for many tuples per call
  *
  * Conventions
  *   - All arithmetic is IEEE double, like the reference.
@@ -222,6 +224,46 @@ RKB_API int rkb_steer_batch(rkb_chain* chain, int device, size_t n_pairs, size_t
                     double dt, int n_steps,
                     int32_t* best_idx, double* best_x, double* best_cost, int32_t* status,
                     unsigned flags, void* stream);
+
+/* ---- closed-loop steering ------------------------------------------------------------------------
+ * The loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) and of
+ * IHAQR_topology::move_position_toward_impl (examples/misc/IHAQR_topology.hpp:349-378) for N independent
+ * (start, goal, gains) tuples at once, collision checking off:
+ *
+ *   while (k < max_intervals && ||x - x_goal||_2 > goal_proximity) {
+ *     correction = -gain (x - x_goal)                       // -K H^-1 (x - x_goal) resp. -K (x - x_goal)
+ *     u = (k == 0 && !saturate_first) ? u_bias + correction // MEAQR_topology.hpp:521-522
+ *                                     : get_bounded_input(u_prev, u_bias, correction)  // IHAQR_topology.hpp:304-327
+ *     x = `substeps` RK4 steps of `dt` with u held          // runge_kutta4_integrate_impl, one control interval
+ *     u_prev = u;  ++k;  record x                           // the steer record
+ *   }
+ *
+ * get_bounded_input clamps u_bias to the input box, bisects the correction (10 halvings) until the sum
+ * is inside the box, and limits the rate (u - u_prev) / time_step to the rate box; a NULL box is unbounded. */
+typedef struct rkb_steer_opts {
+  double  time_step;        /* control interval T of the rate limit (m_time_step), > 0                      */
+  double  dt;               /* RK4 step inside an interval (MEAQR: T / 10, IHAQR: T / 100), != 0             */
+  double  goal_proximity;   /* m_goal_proximity_threshold                                                   */
+  int32_t substeps;         /* RK4 steps per interval, >= 1                                                 */
+  int32_t max_intervals;    /* the time limit, in intervals, >= 0                                           */
+  int32_t saturate_first;   /* 0: the first interval is not saturated (MEAQR); 1: every interval is (IHAQR) */
+  int32_t reserved;         /* must be 0                                                                    */
+  const double* u_lower;    /* n_inputs doubles in HOST memory, or NULL; lower < upper component-wise      */
+  const double* u_upper;
+  const double* du_lower;   /* input-rate box, likewise                                                     */
+  const double* du_upper;
+} rkb_steer_opts;
+
+/* x0, x_goal: N x 2n.  u_bias: N x n_inputs.  gain: N x n_inputs x 2n (row-major per sample).
+ * u_prev: N x n_inputs, in: the input applied before the steer, out: the last input applied.
+ * x_out: N x 2n.  n_done: N, intervals performed.  x_traj (nullable): N x max_intervals x 2n, slot j of
+ * sample i holds the state after interval j for j < n_done[i]; later slots are unspecified.
+ * AOS only (RKB_LAYOUT_SOA -> RKB_ERR_UNSUPPORTED); RKB_MEM_HOST or RKB_MEM_DEVICE. */
+RKB_API int rkb_steer_feedback(rkb_chain* chain, int device, size_t n_samples,
+                               const double* x0, const double* x_goal, const double* u_bias, const double* gain,
+                               double* u_prev, const rkb_steer_opts* opts,
+                               double* x_out, int32_t* n_done, double* x_traj, int32_t* status,
+                               unsigned flags, void* stream);
 
 /* Device-side timing of the last compute launch issued through `chain` on the calling
  * thread, in milliseconds (CUDA events on the launch stream); < 0 if none. Blocks until

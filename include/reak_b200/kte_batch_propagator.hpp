@@ -257,6 +257,16 @@ class kte_batch_propagator {
     if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step or negative step count");
     check(rc, "rkb_steer_batch");
   }
+  /// The whole loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) /
+  /// IHAQR_topology::move_position_toward_impl (examples/misc/IHAQR_topology.hpp:349-378) for n tuples:
+  /// state feedback, get_bounded_input, one RK4 control interval, goal-proximity stop, steer record.
+  void steer_feedback(std::size_t n, const double* x0, const double* x_goal, const double* u_bias, const double* gain, double* u_prev,
+                      const rkb_steer_opts& opts, double* x_out, int32_t* n_done, double* x_traj = NULL, int32_t* status = NULL,
+                      unsigned flags = 0, void* stream = NULL) const {
+    int rc = rkb_steer_feedback(mChain, mDevice, n, x0, x_goal, u_bias, gain, u_prev, &opts, x_out, n_done, x_traj, status, flags, stream);
+    if (rc == RKB_ERR_INTEGRATION) throw impossible_integration("Integration is impossible: zero step, no substep or negative time limit");
+    check(rc, "rkb_steer_feedback");
+  }
   double last_kernel_ms() const { return rkb_last_kernel_ms(mChain); }
   rkb_chain* handle() const { return mChain; }
 

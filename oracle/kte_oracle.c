@@ -1065,6 +1065,43 @@ static void scheme_range(model* m, int scheme, size_t i0, size_t i1, const doubl
   }
 }
 
+#include "steer_law.h"
+
+/* The steering loop of MEAQR_topology.hpp:503-561 / IHAQR_topology.hpp:349-378 for each sample (see
+ * steer_law.h for the feedback law); one control interval = `substeps` RK4 steps of `dt`. */
+int kto_steer_feedback(void* h, size_t N, const double* x0, const double* goal, const double* u_bias, const double* gain,
+                       double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,
+                       const double* lo, const double* hi, const double* dlo, const double* dhi,
+                       double* x_out, int32_t* n_done, double* traj, int32_t* status) {
+  model* m = (model*)h;
+  const int nx = 2 * m->n, nu = m->nu;
+  size_t i;
+  if (nu > STEER_MAX_INPUTS) return -1;
+  for (i = 0; i < N; ++i) {
+    double x[2 * RKB_MAX_COORDS], xn[2 * RKB_MAX_COORDS], u[STEER_MAX_INPUTS], up[STEER_MAX_INPUTS];
+    int k = 0, j, st = 0;
+    for (j = 0; j < nx; ++j) x[j] = x0[i * nx + j];
+    for (j = 0; j < nu; ++j) up[j] = u_prev[i * nu + j];
+    while (k < max_intervals) {
+      int32_t s1 = 0;
+      if (!steer_next_input(nx, nu, T, proximity, (!saturate_first && k == 0), lo, hi, dlo, dhi, x, goal + i * nx,
+                            u_bias + i * nu, gain + i * (size_t)nu * nx, up, u))
+        break;
+      rk4_range(m, 0, 1, x, u, dt, substeps, xn, &s1);
+      st |= s1;
+      for (j = 0; j < nx; ++j) x[j] = xn[j];
+      for (j = 0; j < nu; ++j) up[j] = u[j];
+      if (traj) for (j = 0; j < nx; ++j) traj[(i * (size_t)max_intervals + k) * nx + j] = x[j];
+      ++k;
+    }
+    for (j = 0; j < nx; ++j) x_out[i * nx + j] = x[j];
+    for (j = 0; j < nu; ++j) u_prev[i * nu + j] = up[j];
+    if (n_done) n_done[i] = k;
+    if (status) status[i] = st;
+  }
+  return 0;
+}
+
 static model* model_clone(const model* m) { return (model*)kto_create(&m->d); }
 
 double kto_rk4(void* h, size_t N, const double* x0, const double* u, double dt, int n_steps,

@@ -25,6 +25,11 @@ double kto_rk4(void* h, size_t n, const double* x0, const double* u, double dt, 
 /* the same for any scheme of enum rkb_scheme (euler, midpoint, runge_kutta4, runge_kutta5) */
 double kto_integrate(void* h, size_t n, const double* x0, const double* u, int scheme, double dt, int n_steps,
                      double* xout, int32_t* status, int n_workers);
+/* closed-loop steering (oracle/steer_law.h); lo/hi/dlo/dhi may be NULL */
+int    kto_steer_feedback(void* h, size_t n, const double* x0, const double* goal, const double* u_bias, const double* gain,
+                          double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,
+                          const double* lo, const double* hi, const double* dlo, const double* dhi,
+                          double* x_out, int32_t* n_done, double* traj, int32_t* status);
 /* raw twist-shaping matrices of mass_matrix_calc::get_TMT_TdMT for one state: Tcm, Tcm_dot are
  * m x n row-major, Mcm m x m; returns m (rows) or < 0.  Pass NULL to query m only. */
 int    kto_tmt(void* h, const double* x, double* Tcm, double* Mcm, double* Tcm_dot);

@@ -31,6 +31,7 @@ class _Checker(object):
         if not os.path.isfile(so_path):
             raise RuntimeError("%s is not built (make -C oracle)" % so_path)
         self.lib = C.CDLL(so_path)
+        self._prefix = prefix
         self.compiled = compiled  # keeps the descriptor arrays alive
         self.n, self.nu, self.nx = compiled.n_coords, compiled.n_inputs, 2 * compiled.n_coords
         g = lambda name: getattr(self.lib, prefix + name)
@@ -121,6 +122,32 @@ class _Checker(object):
             traj[:, j, :] = x
             st |= sj
         return x, traj, st
+
+    def steer_feedback(self, x0, goal, u_bias, gain, u_prev, T, dt, substeps, max_intervals, proximity,
+                       saturate_first=False, bounds=None, rate_bounds=None):
+        """The steering loop of MEAQR_topology.hpp:503-561 (oracle/steer_law.h).  bounds / rate_bounds: (lo, hi) or None.
+        Returns (x_out, u_last, n_done, traj [N][max_intervals][nx] (NaN where not written), status)."""
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(N, self.nx)
+        u_bias = np.ascontiguousarray(u_bias, dtype=np.float64).reshape(N, self.nu)
+        gain = np.ascontiguousarray(gain, dtype=np.float64).reshape(N, self.nu, self.nx)
+        up = np.array(u_prev, dtype=np.float64).reshape(N, self.nu).copy()
+        arr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(self.nu)
+        lo, hi = (arr(bounds[0]), arr(bounds[1])) if bounds is not None else (None, None)
+        dlo, dhi = (arr(rate_bounds[0]), arr(rate_bounds[1])) if rate_bounds is not None else (None, None)
+        xo, nd = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        traj = np.full((N, max(int(max_intervals), 1), self.nx), np.nan)
+        st = np.zeros(N, dtype=np.int32)
+        fn = getattr(self.lib, self._prefix + "steer_feedback")
+        fn.restype = C.c_int
+        fn.argtypes = ([C.c_void_p, C.c_size_t] + [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
+                       + [C.c_void_p] * 8)
+        rc = fn(self.h, N, _dp(x), _dp(goal), _dp(u_bias), _dp(gain), _dp(up), float(T), float(dt), int(substeps), int(max_intervals),
+                float(proximity), int(bool(saturate_first)), _dp(lo), _dp(hi), _dp(dlo), _dp(dhi), _dp(xo), _dp(nd), _dp(traj), _dp(st))
+        if rc != 0:
+            raise RuntimeError("steer_feedback failed")
+        return xo, up, nd, traj[:, :int(max_intervals), :], st
 
     def frames(self, x, u=None):
         """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""

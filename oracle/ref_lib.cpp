@@ -47,8 +47,10 @@
 #pragma weak rkb_last_cuda_error
 #pragma weak rkb_rollout_rk4
 #pragma weak rkb_rollout
+#pragma weak rkb_steer_feedback
 #pragma weak rkb_strerror
 #include "../include/reak_b200/reak_bridge.hpp"
+#include "steer_law.h"
 
 #include <algorithm>
 #include <chrono>
@@ -460,6 +462,40 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
 // Returns wall seconds of the integration (< 0 on failure).
 double rkref_integrate(void* hv, std::size_t N, const double* x0, const double* u, int scheme, double dt, int n_steps,
                        double* xout, int32_t* status, int n_workers);
+
+// The steering loop with the reference's own dynamics and runge_kutta4_integrator inside; the feedback
+// law is the restatement of oracle/steer_law.h (the topologies that own it cannot be instantiated here).
+int rkref_steer_feedback(void* hv, std::size_t N, const double* x0, const double* goal, const double* u_bias, const double* gain,
+                         double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,
+                         const double* lo, const double* hi, const double* dlo, const double* dhi,
+                         double* x_out, int32_t* n_done, double* traj, int32_t* status) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  if (nu > STEER_MAX_INPUTS) return -1;
+  for (std::size_t i = 0; i < N; ++i) {
+    std::vector<double> x(x0 + i * nx, x0 + (i + 1) * nx), xn(nx), u(nu ? nu : 1), up(nu ? nu : 1);
+    for (int j = 0; j < nu; ++j) up[j] = u_prev[i * nu + j];
+    int k = 0, st = 0;
+    while (k < max_intervals) {
+      int32_t s1 = 0;
+      if (!steer_next_input(nx, nu, T, proximity, (!saturate_first && k == 0), lo, hi, dlo, dhi, &x[0], goal + i * nx,
+                            u_bias + i * nu, gain + i * std::size_t(nu) * nx, &up[0], &u[0]))
+        break;
+      rk4_range(m, 0, 1, &x[0], &u[0], dt, substeps, &xn[0], &s1);
+      st |= s1;
+      x = xn;
+      for (int j = 0; j < nu; ++j) up[j] = u[j];
+      if (traj) for (int j = 0; j < nx; ++j) traj[(i * std::size_t(max_intervals) + k) * nx + j] = x[j];
+      ++k;
+    }
+    for (int j = 0; j < nx; ++j) x_out[i * nx + j] = x[j];
+    for (int j = 0; j < nu; ++j) u_prev[i * nu + j] = up[j];
+    if (n_done) n_done[i] = k;
+    if (status) status[i] = st;
+  }
+  return 0;
+}
 double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, double dt, int n_steps,
                  double* xout, int32_t* status, int n_workers) {
   return rkref_integrate(hv, N, x0, u, RKB_SCHEME_RK4, dt, n_steps, xout, status, n_workers);

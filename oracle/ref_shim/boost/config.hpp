@@ -9,4 +9,7 @@
 #define BOOST_NOEXCEPT_OR_NOTHROW noexcept
 #define BOOST_NOEXCEPT noexcept
 #define BOOST_CONSTEXPR constexpr
+#define BOOST_USING_STD_MIN() using std::min
+#define BOOST_USING_STD_MAX() using std::max
+#define BOOST_PREVENT_MACRO_SUBSTITUTION
 #endif

@@ -48,6 +48,12 @@ class rkb_rollout_opts(C.Structure):
                 ("reserved", C.c_int32), ("dt", C.c_double)]
 
 
+class rkb_steer_opts(C.Structure):
+    _fields_ = [("time_step", C.c_double), ("dt", C.c_double), ("goal_proximity", C.c_double), ("substeps", C.c_int32),
+                ("max_intervals", C.c_int32), ("saturate_first", C.c_int32), ("reserved", C.c_int32),
+                ("u_lower", C.c_void_p), ("u_upper", C.c_void_p), ("du_lower", C.c_void_p), ("du_upper", C.c_void_p)]
+
+
 SCHEME_EULER, SCHEME_MIDPOINT, SCHEME_RK4, SCHEME_RK5 = 1, 2, 4, 5
 SCHEMES = {"euler": SCHEME_EULER, "midpoint": SCHEME_MIDPOINT, "rk4": SCHEME_RK4, "runge_kutta4": SCHEME_RK4,
            "rk5": SCHEME_RK5, "runge_kutta5": SCHEME_RK5}
@@ -87,6 +93,8 @@ SYMBOLS = {
     "rkb_steer_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_uint, C.c_void_p]),
+    "rkb_steer_feedback": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(rkb_steer_opts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
     "rkb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -641,6 +641,7 @@ template <int DIM, int MAXF, bool TABLE>
 __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const GenericProgram* __restrict__ G, const RolloutArgs A, const RkTable T) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
+  if (A.active && !A.active[i]) return;
   Work<DIM, MAXF> W;
   const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
   load(G, W, A.x0, A.u, i0, i, true);

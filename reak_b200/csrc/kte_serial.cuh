@@ -973,6 +973,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
+  if (A.active && !A.active[i]) return;
   double* sm = smem + threadIdx.x;
   double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
@@ -1043,6 +1044,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
+  if (A.active && !A.active[i]) return;
   double* sm = smem + threadIdx.x;
   double* sw = sm;
   double* sk = sw + 2 * N * SMS;

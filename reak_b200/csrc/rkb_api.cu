@@ -50,6 +50,7 @@ struct DeviceCtx {
   bool checked = false;
   GenericProgram* d_prog = nullptr;
   DevBuf in_x, in_u, out_a, out_b, st, scratch_x, scratch_u, scratch_o, scratch_s, in_goal, out_idx, out_cost;
+  DevBuf in_bias, in_gain, io_uprev, out_ndone, act;  // closed-loop steering
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-buffer pipeline: copy-in, two alternating compute streams, copy-out
   cudaStream_t s_in = nullptr, s_k[2] = {nullptr, nullptr}, s_out = nullptr;
@@ -603,7 +604,8 @@ void rkb_chain_destroy(rkb_chain* c) {
     DeviceGuard g(x->device);
     if (x->d_prog) cudaFree(x->d_prog);
     DevBuf* bufs[] = {&x->in_x, &x->in_u, &x->out_a, &x->out_b, &x->st, &x->scratch_x, &x->scratch_u, &x->scratch_o,
-                      &x->scratch_s, &x->in_goal, &x->out_idx, &x->out_cost};
+                      &x->scratch_s, &x->in_goal, &x->out_idx, &x->out_cost, &x->in_bias, &x->in_gain, &x->io_uprev,
+                      &x->out_ndone, &x->act};
     for (DevBuf* b : bufs) b->release();
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
@@ -700,6 +702,7 @@ int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long l
     A.dt = pl.dt;
     A.n_steps = pl.n_steps;
     A.status_or = j > 0;
+    A.active = nullptr;
     const int rc = launch_rollout(c, ctx, A, pl.use_table ? &pl.table : nullptr, s);
     if (rc) return rc;
   }
@@ -951,6 +954,7 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   A.dt = dt;
   A.n_steps = n_steps;
   A.status_or = 0;
+  A.active = nullptr;
   if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
   e = rkb_steer_reduce(nx, (long long)P, (long long)R, (const double*)ctx->scratch_o.p, (const double*)dgoal, (int32_t*)didx,
                        (double*)dbx, (double*)dbc, s);
@@ -963,6 +967,95 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   if ((rc = unstage_out(dbx, best_x, P * nx * sizeof(double), L.device, s))) return rc;
   if (!L.device && best_cost) CU(cudaMemcpyAsync(best_cost, dbc, P * sizeof(double), cudaMemcpyDeviceToHost, s));
   if ((rc = unstage_out(dst, status, T * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
+int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
+                       const double* gain, double* u_prev, const rkb_steer_opts* o, double* x_out, int32_t* n_done,
+                       double* x_traj, int32_t* status, unsigned flags, void* stream) {
+  if (!c || !o || o->reserved != 0) return RKB_ERR_INVALID;
+  if (o->dt == 0.0 || !std::isfinite(o->dt) || o->substeps < 1 || o->max_intervals < 0) return RKB_ERR_INTEGRATION;
+  if (!(o->time_step > 0.0) || !std::isfinite(o->time_step) || !std::isfinite(o->goal_proximity)) return RKB_ERR_INVALID;
+  if ((o->u_lower == nullptr) != (o->u_upper == nullptr) || (o->du_lower == nullptr) != (o->du_upper == nullptr)) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  if (L.soa) return RKB_ERR_UNSUPPORTED;
+  if (N == 0) return RKB_OK;
+  const int nx = 2 * c->n, nu = c->nu;
+  if (!x0 || !x_goal || !x_out || !n_done || (nu > 0 && (!u_bias || !gain || !u_prev))) return RKB_ERR_INVALID;
+  for (int r = 0; r < nu; ++r) {
+    if (o->u_lower && !(o->u_lower[r] < o->u_upper[r])) return RKB_ERR_INVALID;
+    if (o->du_lower && !(o->du_lower[r] < o->du_upper[r])) return RKB_ERR_INVALID;
+  }
+  const int J = o->max_intervals;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx0 = nullptr, *dgoal = nullptr, *dbias = nullptr, *dgain = nullptr, *dup_in = nullptr;
+  void *dxo = nullptr, *dnd = nullptr, *dtraj = nullptr, *dst = nullptr;
+  const size_t bx = N * nx * sizeof(double), bu = N * (size_t)nu * sizeof(double);
+  if ((rc = stage_in(ctx->in_x, x0, bx, L.device, s, &dx0))) return rc;
+  if ((rc = stage_in(ctx->in_goal, x_goal, bx, L.device, s, &dgoal))) return rc;
+  if (nu > 0) {
+    if ((rc = stage_in(ctx->in_bias, u_bias, bu, L.device, s, &dbias))) return rc;
+    if ((rc = stage_in(ctx->in_gain, gain, bu * nx, L.device, s, &dgain))) return rc;
+    if ((rc = stage_in(ctx->io_uprev, u_prev, bu, L.device, s, &dup_in))) return rc;
+  }
+  if ((rc = stage_out(ctx->out_a, x_out, bx, L.device, &dxo))) return rc;
+  if ((rc = stage_out(ctx->out_ndone, n_done, N * sizeof(int32_t), L.device, &dnd))) return rc;
+  if ((rc = stage_out(ctx->out_b, x_traj, bx * (size_t)(J > 0 ? J : 1), L.device, &dtraj))) return rc;
+  if ((rc = ctx->st.ensure(N * sizeof(int32_t)))) return rc;  // status is accumulated on the device even if not wanted
+  dst = (L.device && status) ? (void*)status : ctx->st.p;
+  if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
+  CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
+  SteerLawArgs W;
+  W.x0 = (const double*)dx0; W.x = (double*)dxo; W.goal = (const double*)dgoal;
+  W.u_bias = (const double*)dbias; W.gain = (const double*)dgain;
+  W.u_prev = (double*)dup_in;  // device memory: updated in place (the caller's buffer, or the staging copy)
+  W.n_done = (int32_t*)dnd; W.active = (int32_t*)ctx->act.p;
+  W.n_samples = (long long)N; W.nx = nx; W.nu = nu; W.saturate_first = o->saturate_first ? 1 : 0;
+  W.have_u_box = o->u_lower ? 1 : 0; W.have_du_box = o->du_lower ? 1 : 0;
+  W.time_step = o->time_step; W.proximity = o->goal_proximity;
+  for (int r = 0; r < RKB_MAX_COORDS; ++r) {
+    W.u_lo[r] = (o->u_lower && r < nu) ? o->u_lower[r] : 0.0; W.u_hi[r] = (o->u_upper && r < nu) ? o->u_upper[r] : 0.0;
+    W.du_lo[r] = (o->du_lower && r < nu) ? o->du_lower[r] : 0.0; W.du_hi[r] = (o->du_upper && r < nu) ? o->du_upper[r] : 0.0;
+  }
+  CU(cudaEventRecord(ctx->ev0, s));
+  if (J == 0) {  // the reference loop would not run at all
+    if (dxo != dx0) CU(cudaMemcpyAsync(dxo, dx0, bx, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemsetAsync(dnd, 0, N * sizeof(int32_t), s));
+  }
+  for (int k = 0; k < J; ++k) {
+    W.interval = k;
+    cudaError_t e = rkb_steer_law(W, s);
+    if (e != cudaSuccess) return cuda_fail(e, "steer law");
+    c->launches += 1;
+    RolloutArgs A;
+    A.x0 = cview((const double*)dxo, (long long)N, nx, false);
+    A.u = cview((const double*)(nu > 0 ? dup_in : dxo), (long long)N, nu > 0 ? nu : 1, false);
+    A.xout = view((double*)dxo, (long long)N, nx, false);
+    A.traj = dtraj ? BatchView{(double*)dtraj + (size_t)k * nx, (long long)nx * J, 1} : BatchView{nullptr, 0, 0};
+    A.status = (int32_t*)dst;
+    A.n_samples = (long long)N;
+    A.x0_div = 1;
+    A.dt = o->dt;
+    A.n_steps = o->substeps;
+    A.status_or = 1;
+    A.active = (const int32_t*)ctx->act.p;
+    if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(dxo, x_out, bx, L.device, s))) return rc;
+  if ((rc = unstage_out(dnd, n_done, N * sizeof(int32_t), L.device, s))) return rc;
+  if ((rc = unstage_out(dtraj, x_traj, bx * (size_t)(J > 0 ? J : 1), L.device, s))) return rc;
+  if (!L.device && nu > 0) CU(cudaMemcpyAsync(u_prev, dup_in, bu, cudaMemcpyDeviceToHost, s));
+  if (!L.device && status) CU(cudaMemcpyAsync(status, dst, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   if (!L.device) CU(cudaStreamSynchronize(s));
   return RKB_OK;
 }

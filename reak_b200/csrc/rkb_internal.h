@@ -36,4 +36,7 @@ cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram
 cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, const double* xend, const double* goal,
                              int32_t* best_idx, double* best_x, double* best_cost, cudaStream_t s);
 
+// steering law between two control intervals (rkb_steer.cu)
+cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s);
+
 #endif

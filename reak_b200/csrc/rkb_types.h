@@ -99,6 +99,23 @@ struct RolloutArgs {
   double         dt;
   int32_t        n_steps;
   int32_t        status_or;  // != 0: OR the status bits into status[i] instead of overwriting it
+  const int32_t* active;     // nullable: samples with active[i] == 0 are left untouched (closed-loop steering)
+};
+
+// One pass of the steering loop head (rkb_steer.cu), all buffers device-resident AoS
+struct SteerLawArgs {
+  const double* x0;      // [N][nx] start states (read at interval 0)
+  double*       x;       // [N][nx] working state, advanced in place by the rollout kernel
+  const double* goal;    // [N][nx]
+  const double* u_bias;  // [N][nu]
+  const double* gain;    // [N][nu][nx]
+  double*       u_prev;  // [N][nu] in: previous input; out: input of the next interval
+  int32_t*      n_done;  // [N] intervals performed so far
+  int32_t*      active;  // [N] 1 when the next interval is to be integrated
+  long long     n_samples;
+  int32_t       nx, nu, interval, saturate_first, have_u_box, have_du_box;
+  double        time_step, proximity;
+  double        u_lo[RKB_MAX_COORDS], u_hi[RKB_MAX_COORDS], du_lo[RKB_MAX_COORDS], du_hi[RKB_MAX_COORDS];
 };
 
 struct EvalArgs {

@@ -262,6 +262,47 @@ class kte_batch_propagator(object):
                                              ptr(idx), ptr(bx), ptr(bc), ptr(st), flags, stream), "rkb_steer_batch")
         return (idx, bx, bc, st) if want_status else (idx, bx, bc)
 
+    def steer_feedback(self, x0, goal, u_bias, gain, u_prev, time_step, dt, substeps, max_intervals, goal_proximity,
+                       saturate_first=False, bounds=None, rate_bounds=None, want_traj=False):
+        """The loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) for N tuples:
+        u = bounded(u_prev, u_bias, -gain (x - goal)), one RK4 control interval, stop within goal_proximity.
+        x0, goal: [N][nx]; u_bias, u_prev: [N][nu]; gain: [N][nu][nx]; bounds / rate_bounds: (lo, hi) or None.
+        Returns (x_out, u_last, n_done[, x_traj [N][max_intervals][nx]], status); u_prev is not modified."""
+        x0, N = self._in(x0, self.nx, np.float64)
+        goal, _ = self._in(goal, self.nx, np.float64, rows=N)
+        u_bias, _ = self._in(u_bias, self.nu, np.float64, rows=N)
+        up, _ = self._in(u_prev, self.nu, np.float64, rows=N)
+        up = up.clone() if _is_torch(up) else up.copy()
+        gain = gain.contiguous() if _is_torch(gain) else np.ascontiguousarray(gain, dtype=np.float64)
+        if tuple(gain.shape) != (N, self.nu, self.nx):
+            raise IndexError("Input vector dimension mismatch!")
+        keep = []
+
+        def box(b):
+            if b is None:
+                return None, None
+            lo = np.ascontiguousarray(b[0], dtype=np.float64).reshape(self.nu)
+            hi = np.ascontiguousarray(b[1], dtype=np.float64).reshape(self.nu)
+            keep.extend([lo, hi])
+            return lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)
+
+        lo, hi = box(bounds)
+        dlo, dhi = box(rate_bounds)
+        opts = _abi.rkb_steer_opts(float(time_step), float(dt), float(goal_proximity), int(substeps), int(max_intervals),
+                                   int(bool(saturate_first)), 0, lo, hi, dlo, dhi)
+        xo = self._like(x0, (N, self.nx))
+        nd = self._like(x0, (N,), np.int32)
+        tr = self._like(x0, (N, max(int(max_intervals), 1), self.nx)) if want_traj else None
+        st = self._like(x0, (N,), np.int32)
+        flags, stream, ptr = self._prep([x0, goal, u_bias if self.nu else None, gain if self.nu else None, up if self.nu else None,
+                                         xo, nd, tr, st], False)
+        _abi.check(self._lib.rkb_steer_feedback(self._h, self.device, N, ptr(x0), ptr(goal), ptr(u_bias) if self.nu else None,
+                                                ptr(gain) if self.nu else None, ptr(up) if self.nu else None, C.byref(opts),
+                                                ptr(xo), ptr(nd), ptr(tr), ptr(st), flags, stream), "rkb_steer_feedback")
+        if want_traj:
+            return xo, up, nd, tr[:, :int(max_intervals)], st
+        return xo, up, nd, st
+
     # ---- instrumentation ----------------------------------------------------------------------
     def last_kernel_ms(self):
         return self._lib.rkb_last_kernel_ms(self._h)

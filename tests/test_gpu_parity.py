@@ -373,3 +373,78 @@ def test_rollout_argument_errors():
     assert call(_abi.rkb_rollout_opts(4, 1, -1, 0, 1e-3)) == _abi.ERR_INTEGRATION
     assert call(_abi.rkb_rollout_opts(4, 1, 1, 0, 0.0)) == _abi.ERR_INTEGRATION     # impossible_integration
     assert call(_abi.rkb_rollout_opts(5, 1, 2, 0, -1e-3)) == 0                      # backwards is allowed
+
+
+# ---- rkb_steer_feedback: the closed-loop steering loop ------------------------------------------------
+def _steer_case(p, n, seed, gain_scale=4.0):
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-0.5, 0.5, (n, p.nx))
+    goal = x0 + rng.uniform(-0.3, 0.3, (n, p.nx))
+    u_bias = rng.uniform(-1.0, 1.0, (n, p.nu))
+    gain = rng.uniform(-gain_scale, gain_scale, (n, p.nu, p.nx))
+    u_prev = rng.uniform(-0.5, 0.5, (n, p.nu))
+    return x0, goal, u_bias, gain, u_prev
+
+
+@pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7", "planar2_act"])
+@pytest.mark.parametrize("saturate_first", [False, True])
+def test_steer_feedback_vs_oracle(name, saturate_first, oracle_built):
+    """Loop of MEAQR_topology.hpp:503-561 (saturate_first = False) and IHAQR_topology.hpp:349-378 (True)."""
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        n = 300
+        x0, goal, u_bias, gain, u_prev = _steer_case(p, n, seed=41)
+        goal[:7] = x0[:7]  # already at the goal: the loop must not start for these
+        kw = dict(bounds=(-2 * np.ones(p.nu), 2 * np.ones(p.nu)), rate_bounds=(-60 * np.ones(p.nu), 60 * np.ones(p.nu)))
+        args = (x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 6, 0.25)
+        xo, ul, nd, tr, st = p.steer_feedback(*args, saturate_first=saturate_first, want_traj=True, **kw)
+        xr, ur, nr, trr, sr = O.steer_feedback(*args, saturate_first=saturate_first, **kw)
+        assert not st.any() and not sr.any()
+        assert np.array_equal(nd, nr), (name, label)
+        assert nd[:7].max() == 0 and 0 < nd.max() <= 6 and len(set(nd.tolist())) > 1  # mixed stopping times
+        assert rel_err(xo, xr) < TOL_STEP and rel_err(ul, ur) < TOL_STEP, (name, label)
+        for i in range(n):
+            assert rel_err(tr[i, :nd[i]], trr[i, :nr[i]]) < TOL_STEP, (name, label, i)
+        assert np.array_equal(xo[:7], x0[:7]) and np.array_equal(ul[:7], u_prev[:7])
+        # without boxes, without the trajectory
+        xo2, ul2, nd2, st2 = p.steer_feedback(*args, saturate_first=saturate_first)
+        xr2, ur2, nr2, _, _ = O.steer_feedback(*args, saturate_first=saturate_first)
+        assert np.array_equal(nd2, nr2) and rel_err(xo2, xr2) < TOL_STEP and rel_err(ul2, ur2) < TOL_STEP
+
+
+def test_steer_feedback_device_buffers_and_limits():
+    import ctypes as C
+    import torch
+    from reak_b200 import _abi
+    p = _make("crs6")
+    x0, goal, u_bias, gain, u_prev = _steer_case(p, 2000, seed=43)
+    args = (1e-2, 1e-3, 10, 4, 0.25)
+    ref = p.steer_feedback(x0, goal, u_bias, gain, u_prev, *args, want_traj=True)
+    t = lambda a: torch.from_numpy(a).cuda()
+    dev = p.steer_feedback(t(x0), t(goal), t(u_bias), t(gain), t(u_prev), *args, want_traj=True)
+    torch.cuda.synchronize()
+    nd = ref[2]
+    assert np.array_equal(dev[2].cpu().numpy(), nd)
+    assert np.array_equal(dev[0].cpu().numpy(), ref[0]) and np.array_equal(dev[1].cpu().numpy(), ref[1])
+    trd = dev[3].cpu().numpy()
+    for i in range(0, 2000, 37):
+        assert np.array_equal(trd[i, :nd[i]], ref[3][i, :nd[i]])
+    # a zero time limit leaves everything as it was
+    xo, ul, n0, st = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 0, 0.25)
+    assert np.array_equal(xo, x0) and np.array_equal(ul, u_prev) and not n0.any()
+    # argument errors
+    lib = _abi.load_library()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    out, n_done = np.empty_like(x0), np.zeros(2000, dtype=np.int32)
+    up = u_prev.copy()
+    bad_lo, bad_hi = np.ones(p.nu), -np.ones(p.nu)
+
+    def call(o, flags=0):
+        return lib.rkb_steer_feedback(p._h, 0, 2000, vp(x0), vp(goal), vp(u_bias), vp(gain), vp(up), C.byref(o), vp(out), vp(n_done),
+                                      None, None, flags, None)
+
+    assert call(_abi.rkb_steer_opts(1e-2, 0.0, 0.1, 10, 4, 0, 0, None, None, None, None)) == _abi.ERR_INTEGRATION
+    assert call(_abi.rkb_steer_opts(1e-2, 1e-3, 0.1, 0, 4, 0, 0, None, None, None, None)) == _abi.ERR_INTEGRATION
+    assert call(_abi.rkb_steer_opts(0.0, 1e-3, 0.1, 10, 4, 0, 0, None, None, None, None)) == _abi.ERR_INVALID
+    assert call(_abi.rkb_steer_opts(1e-2, 1e-3, 0.1, 10, 4, 0, 0, vp(bad_lo), vp(bad_hi), None, None)) == _abi.ERR_INVALID
+    assert call(_abi.rkb_steer_opts(1e-2, 1e-3, 0.1, 10, 4, 0, 0, None, None, None, None), _abi.LAYOUT_SOA) == _abi.ERR_UNSUPPORTED

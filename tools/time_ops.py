@@ -42,6 +42,22 @@ def main():
     uu = torch.from_numpy(rng.uniform(-5, 5, (P, R, p.nu))).cuda()
     t = timed(lambda: p.steer_batch(x0, goal, uu, 1e-3, K), reps=3)
     print("%s steer_batch P=%d R=%d K=%d  %.3f ms  %.3g state-steps/s" % (name, P, R, K, t, P * R * K / t * 1e3))
+    # closed-loop steering: 2^18 tuples, 20 control intervals of 10 RK4 steps (MEAQR's interval = 10 steps)
+    m, J = 1 << 18, 20
+    g = torch.from_numpy(rng.uniform(-4, 4, (m, p.nu, p.nx))).cuda()
+    xs = dx[:m].contiguous() * 0.5
+    goal = xs + torch.from_numpy(rng.uniform(-0.3, 0.3, (m, p.nx))).cuda()
+    ub, up = du[:m].contiguous(), du[m:2 * m].contiguous() * 0.5
+    lo, hi = -2 * np.ones(p.nu), 2 * np.ones(p.nu)
+    nd = [None]
+
+    def steer():
+        nd[0] = p.steer_feedback(xs, goal, ub, g, up, 1e-2, 1e-3, 10, J, 0.25, bounds=(lo, hi), rate_bounds=(-60 * hi, 60 * hi))[2]
+
+    t = timed(steer, reps=3)
+    done = int(nd[0].sum().item())
+    print("%s steer_feedback N=%d J<=%d x10 steps  %.3f ms  %.3g state-steps/s (%.1f intervals/sample on average)"
+          % (name, m, J, t, done * 10 / t * 1e3, done / m))
 
 
 if __name__ == "__main__":
