@@ -364,7 +364,7 @@ __host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >
 // cos and sin of every revolute joint angle (1, 0 for a prismatic joint); the sign of an axis-aligned
 // joint's axis is folded into the sine, which is all the specialised rotations need.
 template <int N, int FL, shape_t SHAPE>
-RKB_DEV void serial_trig(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N]) {
+RKB_DEV void serial_trig_raw(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N]) {
   bool in_range = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -384,12 +384,37 @@ RKB_DEV void serial_trig(const SerialParams& P, const SerialState<N>& X, double 
       if (!prismatic) sincos(X.q[k], &sn[k], &cs[k]);
     }
   }
+}
+template <int N, int FL, shape_t SHAPE>
+RKB_DEV void serial_trig_fold(const SerialParams& P, double (&sn)[N]) {
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     constexpr shape_t SH = SHAPE;
     const int AX = shape_ax(SH, k);
     if (AX != 0) sn[k] *= P.st[k].ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
   }
+}
+template <int N, int FL, shape_t SHAPE>
+RKB_DEV void serial_trig(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N]) {
+  serial_trig_raw<N, FL, SHAPE>(P, X, cs, sn);
+  serial_trig_fold<N, FL, SHAPE>(P, sn);
+}
+
+// sin and cos of w + d from those of w for a small d (|d| < 2^-5): sin d and cos d - 1 from their Taylor
+// polynomials (truncation below 3e-17 relative), then the angle-sum formulas written as corrections to
+// the base values.  14 FP64 instructions and nothing else, against 21 plus the quadrant logic of a full
+// evaluation; the RK4 stages 2-4 of a step differ from its start by dt q_dot / 2 or dt q_dot.
+#define RKB_SMALL_ANGLE 0.03125
+RKB_DEV void sincos_shift(double d, double sw, double cw, double& sn, double& cs) {
+  const double z = d * d;
+  double ps = fma(z, -1.98412698412698412698e-04, 8.33333333333333333333e-03);
+  ps = fma(z, ps, -1.66666666666666666667e-01);
+  const double sd = fma(d * z, ps, d);                      // sin d
+  double pc = fma(z, -1.38888888888888888889e-03, 4.16666666666666666667e-02);
+  pc = fma(z, pc, -0.5);
+  const double cm = z * pc;                                 // cos d - 1
+  sn = sw + fma(cw, sd, sw * cm);
+  cs = cw + fma(-sw, sd, cw * cm);
 }
 
 // ---- sweep 3: mass matrix by composite inertias, inward -------------------------------------------
@@ -516,10 +541,11 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
 // used by the sweeps; the rollout kernel keeps its RK4 state there.)
 // Returns f (generalised forces, gen_coord::f) and, if WANT_M, the packed upper triangle
 // Mp[i*(i+1)/2 + j] = M(j,i), j <= i, in stage order.
-template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M>
+// With HAVE_TRIG the caller has filled cs / sn (sign-folded, see serial_trig).
+template <int N, int FL, shape_t SHAPE, int SMS, bool WANT_F, bool WANT_M, bool HAVE_TRIG = false>
 RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N],
                            double (&f)[N], double (&Mp)[N * (N + 1) / 2], double* sm) {
-  serial_trig<N, FL, SHAPE>(P, X, cs, sn);
+  if (!HAVE_TRIG) serial_trig<N, FL, SHAPE>(P, X, cs, sn);
   // ---- sweep 1: kinematics outward, inertia wrenches parked --------------------------------
   if (WANT_F) {
     vec3 w = ld3(P.w0), al = ld3(P.al0), a = ld3(P.a0);
@@ -718,6 +744,13 @@ RKB_DEV int serial_accel(const SerialParams& P, const SerialState<N>& X, double 
   serial_sweeps<N, FL, SHAPE, SMS, true, true>(P, X, cs, sn, qdd, Mp, sm);
   return cholesky_solve_packed<N>(Mp, qdd);
 }
+// ... with cos / sin supplied by the caller
+template <int N, int FL, shape_t SHAPE, int SMS>
+RKB_DEV int serial_accel_trig(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N], double (&qdd)[N], double* sm) {
+  double Mp[N * (N + 1) / 2];
+  serial_sweeps<N, FL, SHAPE, SMS, true, true, true>(P, X, cs, sn, qdd, Mp, sm);
+  return cholesky_solve_packed<N>(Mp, qdd);
+}
 
 template <int N>
 RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const ConstBatchView& u, long long i, SerialState<N>& X) {
@@ -735,21 +768,23 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #define RKB_BLOCK 128
 #endif
 // per-thread shared-memory doubles: for the rollout the
-// state at the start of the step (w) and k1 + 2 k2.  k3 is not stored: the stage-4 update starts
+// state at the start of the step (w), k1 + 2 k2, and cos / sin of the joint angles at the start of the step.  k3 is not stored: the stage-4 update starts
 // from x = w + k3, so k3 is recovered as x - w (exact up to one rounding of x, i.e. ~1e-16 |x|).
 #define RKB_SMEM_EVAL(n) 1
-#define RKB_SMEM_ROLLOUT(n) (4 * (n))
-// Resident CTAs per SM the compiler must leave room for.  The structurally specialised code runs
-// best with 4 CTAs of 128 threads (128 registers, 4 warps per scheduler; measured 25.4 ms vs
-// 26.1 ms at 3 CTAs and 27.0 ms at 2 for the 6-DOF rollout) when 4 columns of shared memory fit,
-// else 3; the general code needs the full 255 registers and loses 10 % when squeezed.
+#define RKB_SMEM_ROLLOUT(n) (6 * (n))
+// Resident CTAs per SM the compiler must leave room for.  The kernels are bound by register-file
+// reads and the FP64 pipe, not by latency (tools/issue_model.py), so occupancy only matters through
+// the spills a tighter register budget causes: up to 6 coordinates the specialised code is equally
+// fast at 4 CTAs (128 registers) and 3 CTAs (168) per SM and keeps 4; from 7 coordinates on 3 CTAs
+// are 5 % faster (7-DOF rollout 3.24 vs 3.41 ms).  The general code needs the full 255 registers and
+// loses 10 % when squeezed.
 #ifdef RKB_FORCE_MINBLOCKS
-#define RKB_MINBLOCKS(shape, smem_doubles_per_thread) (RKB_FORCE_MINBLOCKS)
+#define RKB_MINBLOCKS(shape, n, smem_doubles_per_thread) (RKB_FORCE_MINBLOCKS)
 #endif
 #ifndef RKB_MINBLOCKS
 #define RKB_FITS(blocks, smem_doubles_per_thread) ((blocks) * ((smem_doubles_per_thread) * RKB_BLOCK * 8 + 1024) <= 227 * 1024)
-#define RKB_MINBLOCKS(shape, smem_doubles_per_thread) \
-  ((shape) == 0 ? 1 : (RKB_FITS(4, smem_doubles_per_thread) ? 4 : (RKB_FITS(3, smem_doubles_per_thread) ? 3 : 1)))
+#define RKB_MINBLOCKS(shape, n, smem_doubles_per_thread) \
+  ((shape) == 0 ? 1 : (((n) <= 6 && RKB_FITS(4, smem_doubles_per_thread)) ? 4 : (RKB_FITS(3, smem_doubles_per_thread) ? 3 : 1)))
 #endif
 
 // ---- coalesced result write-back ------------------------------------------------------------------
@@ -800,7 +835,7 @@ RKB_DEV void tile_write_back(double* smem, const BatchView& o, long long tile_fi
 // ---- kernels ---------------------------------------------------------------------------------
 // xdot = get_state_derivative(x, u)
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_EVAL_K(N))) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_EVAL_K(N))) serial_eval_kernel(const __grid_constant__ SerialParams P, const EvalArgs A) {
   extern __shared__ double smem[];
   const long long tile_first = (long long)blockIdx.x * RKB_BLOCK;
   const long long i = tile_first + threadIdx.x;
@@ -968,7 +1003,7 @@ RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long of
 // with the input held constant (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
 // Per-thread shared-memory column: w (2N) and k1 + 2 k2 (2N).
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
   const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
@@ -977,6 +1012,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   double* sm = smem + threadIdx.x;
   double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
+  double* sb = sa + 2 * N * SMS;    // cos, sin of the joint angles at the start of the step
   SerialState<N> X;
   {
     const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
@@ -990,9 +1026,36 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
   const int total = 4 * A.n_steps;
 #pragma unroll 1
   for (int it = 0; it < total; ++it) {
-    double qdd[N];
-    st |= serial_accel<N, FL, SHAPE, SMS>(P, X, qdd, sm);
     const int stage = it & 3;
+    double qdd[N], cs[N], sn[N];
+    {
+      // Stage 1 evaluates sin / cos in full and keeps them; stages 2-4 sit at w + d with d = dt q_dot / 2
+      // or dt q_dot, and get theirs by sincos_shift unless some |d| is not small (or not finite).
+      double d[N];
+      bool full = stage == 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        d[k] = X.q[k] - sw[(2 * k) * SMS];  // (stage 1 reads the previous step's w: unused, `full` is already set)
+        const bool prismatic = shape_ax(SHAPE, k) == 0 && (FL & RKB_FL_PRISMATIC) && (P.st[k].flags & RKB_ST_PRISMATIC);
+        if (!prismatic) full = full || !(fabs(d[k]) < RKB_SMALL_ANGLE);
+      }
+      if (full) {
+        serial_trig_raw<N, FL, SHAPE>(P, X, cs, sn);
+        if (stage == 0) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) { sb[(2 * k) * SMS] = cs[k]; sb[(2 * k + 1) * SMS] = sn[k]; }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const bool prismatic = shape_ax(SHAPE, k) == 0 && (FL & RKB_FL_PRISMATIC) && (P.st[k].flags & RKB_ST_PRISMATIC);
+          if (!prismatic) sincos_shift(d[k], sb[(2 * k + 1) * SMS], sb[(2 * k) * SMS], sn[k], cs[k]);
+          else { sn[k] = 0.0; cs[k] = 1.0; }
+        }
+      }
+      serial_trig_fold<N, FL, SHAPE>(P, sn);
+    }
+    st |= serial_accel_trig<N, FL, SHAPE, SMS>(P, X, cs, sn, qdd, sm);
     // state derivative f = (qd, qdd) interleaved; the four stages of fixed_step_integrators.hpp:277-289
     if (stage == 0) {
 #pragma unroll
@@ -1038,7 +1101,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLO
 // Any explicit one-step scheme given as an RkTable (Euler, midpoint, RK5 — and RK4, which the kernel
 // above does faster).  Per-thread shared-memory column: w (2N), then k_0 .. k_{stages-1} (2N each).
 template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, RKB_SMEM_ROLLOUT(N))) serial_rollout_rk_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A,
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_rollout_rk_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A,
                                                                                                        const __grid_constant__ RkTable T) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
