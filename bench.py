@@ -180,6 +180,56 @@ def run_reference(args):
     return 0
 
 
+def other_configs(torch, presets, kte_batch_propagator, local, world):
+    """BASELINE configs 3-5 on this rank's shard (device-resident buffers, kernel time from CUDA events on
+    the launch stream, best of 3).  Parity of these paths is the job of tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(777)
+    out = []
+
+    def best(fn, prop, reps=3):
+        fn()
+        ms = []
+        for _ in range(reps):
+            fn()
+            ms.append(prop.last_kernel_ms())
+        return min(ms)
+
+    # cfg 3: 6-DOF + torsion springs/dampers, 100 RK4 steps, then M and Mdot at the final state (2^24 / 8 per GPU)
+    p3 = kte_batch_propagator(presets.make("crs6_sd"), device=local)
+    n3 = 1 << 21
+    x3 = torch.from_numpy(rng.uniform(-1, 1, (n3, p3.nx))).cuda(local)
+    u3 = torch.from_numpy(rng.uniform(-1, 1, (n3, p3.nu))).cuda(local)
+    o3 = torch.empty_like(x3)
+    s3 = torch.empty((n3,), dtype=torch.int32, device=x3.device)
+    t_roll = best(lambda: p3.get_next_states(x3, u3, DT, RK4_STEPS, out=o3, status=s3), p3)
+    t_mass = best(lambda: p3.get_mass_matrices(o3, with_derivative=True), p3)
+    out.append({"config": 3, "workload": "6-DOF + torsion springs/dampers: %d states x %d RK4 steps per GPU, then M and Mdot" % (n3, RK4_STEPS),
+                "rollout_ms": t_roll, "mass_and_derivative_ms": t_mass, "serial_kernels": bool(p3.is_serial()),
+                "state_steps_per_s": world * n3 * RK4_STEPS / ((t_roll + t_mass) * 1e-3)})
+    del x3, u3, o3, s3
+    # cfg 4: 7-DOF with prismatic track, 10 RK4 steps per extension (2^26 / 8 per GPU)
+    p4 = kte_batch_propagator(presets.make("crs7"), device=local)
+    n4 = 1 << 23
+    x4 = torch.from_numpy(rng.uniform(-1, 1, (n4, p4.nx))).cuda(local)
+    u4 = torch.from_numpy(rng.uniform(-1, 1, (n4, p4.nu))).cuda(local)
+    o4 = torch.empty_like(x4)
+    s4 = torch.empty((n4,), dtype=torch.int32, device=x4.device)
+    t4 = best(lambda: p4.get_next_states(x4, u4, DT, 10, out=o4, status=s4), p4)
+    out.append({"config": 4, "workload": "7-DOF with prismatic track: %d RRT extensions x 10 RK4 steps per GPU" % n4, "rollout_ms": t4,
+                "serial_kernels": bool(p4.is_serial()), "state_steps_per_s": world * n4 * 10 / (t4 * 1e-3)})
+    del x4, u4, o4, s4
+    # cfg 5: steer batch, 4096 pairs x 256 controls x 100 steps over all GPUs, pairs sharded
+    p5 = kte_batch_propagator(presets.make(PRESET), device=local)
+    P, R = max(1, 4096 // world), 256
+    x0 = torch.from_numpy(rng.uniform(-1, 1, (P, p5.nx))).cuda(local)
+    goal = torch.from_numpy(rng.uniform(-1, 1, (P, p5.nx))).cuda(local)
+    uu = torch.from_numpy(rng.uniform(-5, 5, (P, R, p5.nu))).cuda(local)
+    t5 = best(lambda: p5.steer_batch(x0, goal, uu, DT, RK4_STEPS), p5)
+    out.append({"config": 5, "workload": "steer batch: %d pairs x %d controls x %d RK4 steps per GPU, arg-min per pair" % (P, R, RK4_STEPS),
+                "steer_ms": t5, "state_steps_per_s": world * P * R * RK4_STEPS / (t5 * 1e-3)})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -332,6 +382,11 @@ def run_ours(args):
                "max_rel_err_vs_gpu": err, "tolerance": 1e-8}
         assert err < 1e-8, "GPU result disagrees with the reference on the CPU sample: %g" % err
 
+    # ---- the other BASELINE configs, one short device-resident measurement each (this rank's share) ----
+    others = None
+    if not args.no_other_configs:
+        others = other_configs(torch, presets, kte_batch_propagator, local, world)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -350,6 +405,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if gather_ms is not None:
         line["gather_ms"] = gather_ms
+    if others is not None:
+        line["other_configs"] = others
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -363,6 +420,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.steps < 1:
         args.steps = 1

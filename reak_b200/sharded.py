@@ -77,6 +77,29 @@ class sharded_propagator(object):
         xo_t, st_t = self._to_comm(xo, torch.float64), self._to_comm(st, torch.int32)
         return _all_gather_rows(xo_t, n_total, self.group), _all_gather_rows(st_t, n_total, self.group)
 
+    def rollout(self, x, u_seq, dt, steps_per_interval, scheme="rk4", compute=None):
+        """kte_batch_propagator.rollout sharded by sample: returns (x_out[N][nx], x_traj[N][J][nx], status[N])
+        gathered on every rank.  `compute(x, u_seq, dt, steps, scheme) -> (x_out, x_traj, status)`."""
+        import torch
+        compute = compute or (lambda xb, ub, d, k, sc: self.prop.rollout(xb, ub, d, k, scheme=sc, want_traj=True))
+        n_total = x.shape[0]
+        lo, hi = shard_bounds(n_total, self.rank, self.world)
+        xo, tr, st = compute(x[lo:hi], u_seq[lo:hi], dt, steps_per_interval, scheme)
+        return (_all_gather_rows(self._to_comm(xo, torch.float64), n_total, self.group),
+                _all_gather_rows(self._to_comm(tr, torch.float64), n_total, self.group),
+                _all_gather_rows(self._to_comm(st, torch.int32), n_total, self.group))
+
+    def steer_feedback(self, x0, goal, u_bias, gain, u_prev, *args, compute=None, **kw):
+        """kte_batch_propagator.steer_feedback sharded by tuple: returns (x_out, u_last, n_done, status)
+        gathered on every rank; positional and keyword arguments after u_prev are passed through."""
+        import torch
+        compute = compute or self.prop.steer_feedback
+        n_total = x0.shape[0]
+        lo, hi = shard_bounds(n_total, self.rank, self.world)
+        xo, ul, nd, st = compute(x0[lo:hi], goal[lo:hi], u_bias[lo:hi], gain[lo:hi], u_prev[lo:hi], *args, **kw)
+        g = lambda a, dt: _all_gather_rows(self._to_comm(a, dt), n_total, self.group)
+        return g(xo, torch.float64), g(ul, torch.float64), g(nd, torch.int32), g(st, torch.int32)
+
     def steer_batch(self, x0, goal, u, dt, n_steps, compute=None):
         """Pairs are never split across ranks, so the per-pair arg-min stays on one device; only
         (best_idx, best_x, best_cost) per pair travel."""

@@ -57,7 +57,19 @@ def _worker(rank, world, port, n_total, out_dir):
         return idx, xe.reshape(p, R, -1)[np.arange(p), idx], cost.min(axis=1)
 
     idx, bx, bc = sp.steer_batch(x0, goal, uu, 1e-3, 3, compute=steer)
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), full=full.numpy(), st=st.numpy(), idx=idx.numpy(), bx=bx.numpy(), bc=bc.numpy())
+    # control sequences and closed-loop steering shard the same way
+    u_seq = rng.uniform(-1, 1, (n_total, 3, c.n_inputs))
+    rx, rtr, rst = sp.rollout(x, u_seq, 1e-3, 2, scheme="rk5", compute=lambda xb, ub, d, k, sc: O.rollout(xb, ub, 5, d, k))
+    goal_all = x + rng.uniform(-0.3, 0.3, x.shape)
+    gain = rng.uniform(-3, 3, (n_total, c.n_inputs, 2 * c.n_coords))
+
+    def feedback(x0b, gb, ubb, gnb, upb, *a, **k):
+        xo, ul, nd, _, s2 = O.steer_feedback(x0b, gb, ubb, gnb, upb, *a, **k)
+        return xo, ul, nd, s2
+
+    fx, fu, fn, fs = sp.steer_feedback(x, goal_all, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, compute=feedback)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), full=full.numpy(), st=st.numpy(), idx=idx.numpy(), bx=bx.numpy(), bc=bc.numpy(),
+             rx=rx.numpy(), rtr=rtr.numpy(), fx=fx.numpy(), fu=fu.numpy(), fn=fn.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,6 +92,18 @@ def test_two_rank_gloo_gather(n_total, tmp_path, oracle_built):
         assert np.array_equal(g["full"], want) and not g["st"].any()
     assert np.array_equal(got[0]["idx"], got[1]["idx"]) and np.array_equal(got[0]["bx"], got[1]["bx"])
     assert got[0]["idx"].shape == (5,) and got[0]["bx"].shape == (5, 6)
+    # sharded control-sequence rollout and closed-loop steering equal the unsharded oracle run
+    O = pyref.Oracle(c)
+    rng = np.random.default_rng(5)
+    rng.uniform(-2, 2, (5, 7, c.n_inputs))  # same stream as the workers
+    u_seq = rng.uniform(-1, 1, (n_total, 3, c.n_inputs))
+    wx, wtr, _ = O.rollout(x, u_seq, 5, 1e-3, 2)
+    goal_all = x + rng.uniform(-0.3, 0.3, x.shape)
+    gain = rng.uniform(-3, 3, (n_total, c.n_inputs, 2 * c.n_coords))
+    fx, fu, fn, _, _ = O.steer_feedback(x, goal_all, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2)
+    for g in got:
+        assert np.array_equal(g["rx"], wx) and np.array_equal(g["rtr"], wtr)
+        assert np.array_equal(g["fx"], fx) and np.array_equal(g["fu"], fu) and np.array_equal(g["fn"], fn)
 
 
 def test_shard_bounds_cover_everything():

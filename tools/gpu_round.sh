@@ -22,10 +22,10 @@ timeout 300 python tools/time_rollout.py planar2 1024 1000 3 2>&1 | tail -1
 if [ "$2" != "noprof" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/ncu_launch_$tag.log 2>&1
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-configs > $out/ncu_launch_$tag.log 2>&1
 echo "rc=$?"
 echo "== ncu --set full, rollout kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:serial_rollout -s 3 -c 1 -f -o $out/prof_$tag \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_full_$tag.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs > $out/ncu_full_$tag.log 2>&1
 echo "rc=$?"
 fi
