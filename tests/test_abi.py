@@ -118,3 +118,25 @@ def test_product_does_not_import_the_oracle():
                 for line in text.splitlines():
                     code = line.split("#")[0].split("//")[0]
                     assert "oracle" not in code.lower() or "import" not in code and "include" not in code, (f, line)
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "c_abi_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + os.path.dirname(_abi.LIB_PATH), "-lreak_b200", "-lm",
+                           "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_abi.LIB_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return exe, env
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/c_abi_demo.c is C99 against include/reak_b200.h only.  Without a CUDA device the first
+    compute call must come back as RKB_ERR_CUDA: there is no CPU fallback behind the C-ABI."""
+    import subprocess
+    import torch
+    exe, env = _build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    assert r.returncode == 1 and "-> -4" in r.stderr, (r.returncode, r.stdout, r.stderr)

@@ -448,3 +448,12 @@ def test_steer_feedback_device_buffers_and_limits():
     assert call(_abi.rkb_steer_opts(0.0, 1e-3, 0.1, 10, 4, 0, 0, None, None, None, None)) == _abi.ERR_INVALID
     assert call(_abi.rkb_steer_opts(1e-2, 1e-3, 0.1, 10, 4, 0, 0, vp(bad_lo), vp(bad_hi), None, None)) == _abi.ERR_INVALID
     assert call(_abi.rkb_steer_opts(1e-2, 1e-3, 0.1, 10, 4, 0, 0, None, None, None, None), _abi.LAYOUT_SOA) == _abi.ERR_UNSUPPORTED
+
+
+def test_plain_c_client(tmp_path):
+    """examples/c_abi_demo.c: C99 against the C-ABI, closed-form pendulum answers, no Python in the loop."""
+    import subprocess
+    from test_abi import _build_c_demo
+    exe, env = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith(")") and "ok (library version" in r.stdout, (r.stdout, r.stderr)
