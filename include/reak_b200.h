@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define RKB_VERSION 100
+#define RKB_VERSION 110
 
 #if defined(__GNUC__)
 #define RKB_API __attribute__((visibility("default")))

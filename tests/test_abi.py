@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _abi.SYMBOLS, "ctypes table misses %s" % n
-    assert lib.rkb_version() == 100
+    assert lib.rkb_version() == 110
     assert lib.rkb_strerror(0) == b"ok" and b"CPU fallback" in lib.rkb_strerror(_abi.ERR_CUDA)
 
 
@@ -32,6 +32,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_abi.rkb_element) == 128
     assert C.sizeof(_abi.rkb_base_frame) == 19 * 8
     assert _abi.rkb_chain_desc.elements.offset == 24 + 19 * 8
+    assert C.sizeof(_abi.rkb_rollout_opts) == 24 and _abi.rkb_rollout_opts.dt.offset == 16
+    assert C.sizeof(_abi.rkb_steer_opts) == 72 and _abi.rkb_steer_opts.u_lower.offset == 40
 
 
 def _create(desc):
