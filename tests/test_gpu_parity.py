@@ -457,3 +457,37 @@ def test_plain_c_client(tmp_path):
     exe, env = _build_c_demo(tmp_path)
     r = subprocess.run([exe], env=env, capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith(")") and "ok (library version" in r.stdout, (r.stdout, r.stderr)
+
+
+# ---- maximum sizes -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_rev,track,springs,serial", [(8, False, True, True), (7, True, True, True), (12, False, True, False),
+                                                        (16, False, False, False)])
+def test_long_chains(n_rev, track, springs, serial, oracle_built):
+    """8 coordinates: the largest register-resident instance; 9..16 (RKB_MAX_COORDS): interpreter kernels
+    (at most 96 elements, so 16 stages without the spring / damper pairs)."""
+    from reak_b200 import kte_batch_propagator
+    s = presets.crs_chain(n_revolute=n_rev, track=track, physical=True, springs=springs)
+    p = kte_batch_propagator(s)
+    assert p.is_serial() == serial
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 70, seed=15)
+    xd, st = p.get_state_derivatives(x, u)
+    assert not st.any() and rel_err(xd, O.eval(x, u)[0]) < TOL_STEP
+    M, Md = p.get_mass_matrices(x, with_derivative=True)
+    Mo, Mdo = O.mass(x)
+    assert rel_err(M, Mo) < TOL_STEP and rel_err(Md, Mdo) < TOL_STEP
+    assert rel_err(p.get_gen_forces(x, u), O.gen_forces(x, u)) < TOL_STEP
+    xo, st = p.get_next_states(x, u, 1e-3, 20)
+    assert not st.any() and rel_err(xo, O.rk4(x, u, 1e-3, 20)[0]) < TOL_LONG
+    for scheme, code in (("euler", 1), ("rk5", 5)):
+        xs, st = p.rollout(x, u[:, None, :], 1e-3, 4, scheme=scheme)
+        assert rel_err(xs, O.integrate(x, u, code, 1e-3, 4)[0]) < TOL_STEP
+
+
+def test_chains_beyond_the_limits_are_rejected():
+    from reak_b200 import _abi, kte_batch_propagator
+    with pytest.raises(kte.UnsupportedChain):
+        kte_batch_propagator(presets.crs_chain(n_revolute=17))           # RKB_MAX_COORDS = 16
+    with pytest.raises(_abi.RkbError) as e:
+        kte_batch_propagator(presets.crs_chain(n_revolute=16, springs=True))  # 112 elements > 96
+    assert e.value.code == _abi.ERR_UNSUPPORTED
