@@ -8,7 +8,9 @@
  *   rkb_chain_create      <- model assembly: kte_map_chain::operator<<  (ctrl/mbd_kte/kte_map_chain.hpp:98-102),
  *                            mass_matrix_calc::operator<<               (ctrl/mbd_kte/mass_matrix_calculator.cpp:30-78),
  *                            kte_nl_system public members               (ctrl/ctrl_sys/kte_nl_system.hpp:70-78)
- *   rkb_eval              <- kte_nl_system::get_state_derivative        (ctrl/ctrl_sys/kte_nl_system.hpp:238-346)
+ *   rkb_eval              <- kte_nl_system::get_state_derivative        (ctrl/ctrl_sys/kte_nl_system.hpp:238-346);
+ *                            with RKB_LAYOUT_BLOCKED: manipulator_dynamics_model::computeStateRate
+ *                            (ctrl/mbd_kte/manipulator_model.cpp:292-355), the state_rate_function of the legacy models
  *   rkb_rollout_rk4       <- runge_kutta4_integrator<double>::integrate (core/integrators/fixed_step_integrators.hpp:256-293)
  *                            driven through num_int_dtnl_sys::get_next_state (ctrl/ctrl_sys/num_int_dtnl_system.hpp:166-180)
  *   rkb_rollout           <- the same with euler / midpoint / runge_kutta4 / runge_kutta5 integrators
@@ -28,7 +30,8 @@
  *   - Buffers are caller-owned.  RKB_MEM_DEVICE pointers must be valid on `device`;
  *     RKB_MEM_HOST pointers are staged through device memory by the library
  *     (pinned host memory makes the copies asynchronous up to the final sync).
- *   - RKB_LAYOUT_AOS is the reference layout [N][dim]; RKB_LAYOUT_SOA is [dim][N].
+ *   - RKB_LAYOUT_AOS is the reference layout [N][dim]; RKB_LAYOUT_SOA is [dim][N];
+ *     RKB_LAYOUT_BLOCKED orders a state as (q..., qd...) like manipulator_dynamics_model::computeStateRate.
  *   - No exception crosses this boundary.  Return 0 = ok, negative = error (rkb_strerror).
  *     Per-sample `status` words mirror the reference's exceptions:
  *       bit 0 (RKB_STATUS_SINGULAR)  Cholesky pivot < 1e-8, where linsolve_Cholesky throws
@@ -120,6 +123,11 @@ typedef struct rkb_chain rkb_chain; /* opaque */
 #define RKB_MEM_DEVICE  1u
 #define RKB_LAYOUT_AOS  0u
 #define RKB_LAYOUT_SOA  2u
+/* State vectors as manipulator_dynamics_model keeps them (ctrl/mbd_kte/manipulator_model.cpp:292-355):
+ * all positions, then all velocities — (q0 .. qn-1, qd0 .. qdn-1) — instead of kte_nl_system's
+ * interleaved pairs.  Applies to every state-shaped buffer of a call (x, xdot, x_out, x_traj, goal,
+ * best_x); combines with AOS / SOA.  The gain columns of rkb_steer_feedback follow the same order. */
+#define RKB_LAYOUT_BLOCKED 4u
 
 #define RKB_STATUS_SINGULAR  1
 #define RKB_STATUS_NONFINITE 2

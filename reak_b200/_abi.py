@@ -16,7 +16,7 @@ REVOLUTE_2D, PRISMATIC_2D, RIGID_LINK_2D, INERTIA_2D = 17, 18, 20, 21
 TORSION_SPRING_2D, TORSION_DAMPER_2D, SPRING_2D, DAMPER_2D = 24, 25, 26, 27
 
 MEM_HOST, MEM_DEVICE = 0, 1
-LAYOUT_AOS, LAYOUT_SOA = 0, 2
+LAYOUT_AOS, LAYOUT_SOA, LAYOUT_BLOCKED = 0, 2, 4
 STATUS_SINGULAR, STATUS_NONFINITE = 1, 2
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_DIMENSION, ERR_CUDA, ERR_NOMEM, ERR_INTEGRATION = 0, -1, -2, -3, -4, -5, -6

@@ -571,8 +571,8 @@ GD int accel(const GenericProgram* G, Work<DIM, MAXF>& W) {
 template <int DIM, int MAXF>
 GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& x, const ConstBatchView& u, long long ix, long long iu, bool with_u) {
   for (int c = 0; c < G->n_coords; ++c) {
-    W.q[c] = x.p[ix * x.si + (2 * c) * x.sk];
-    W.qd[c] = x.p[ix * x.si + (2 * c + 1) * x.sk];
+    W.q[c] = x.p[ix * x.si + rkb_state_q(x.blocked, G->n_coords, c) * x.sk];
+    W.qd[c] = x.p[ix * x.si + rkb_state_qd(x.blocked, G->n_coords, c) * x.sk];
   }
   for (int k = 0; k < G->n_inputs; ++k) W.u[k] = with_u ? u.p[iu * u.si + k * u.sk] : 0.0;
 }
@@ -588,8 +588,8 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_eval_kernel(const GenericPr
   int st = accel(G, W);
   bool finite = true;
   for (int c = 0; c < G->n_coords; ++c) {
-    A.out.p[i * A.out.si + (2 * c) * A.out.sk] = W.qd[c];
-    A.out.p[i * A.out.si + (2 * c + 1) * A.out.sk] = W.f[c];
+    A.out.p[i * A.out.si + rkb_state_q(A.out.blocked, G->n_coords, c) * A.out.sk] = W.qd[c];
+    A.out.p[i * A.out.si + rkb_state_qd(A.out.blocked, G->n_coords, c) * A.out.sk] = W.f[c];
     finite = finite && isfinite(W.f[c]) && isfinite(W.qd[c]);
   }
   if (!finite) st |= RKB_STATUS_NONFINITE;
@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
 template <int DIM, int MAXF>
 GD void store_state(const GenericProgram* G, const Work<DIM, MAXF>& W, const BatchView& o, long long off) {
   for (int c = 0; c < G->n_coords; ++c) {
-    o.p[off + (2 * c) * o.sk] = W.q[c];
-    o.p[off + (2 * c + 1) * o.sk] = W.qd[c];
+    o.p[off + rkb_state_q(o.blocked, G->n_coords, c) * o.sk] = W.q[c];
+    o.p[off + rkb_state_qd(o.blocked, G->n_coords, c) * o.sk] = W.qd[c];
   }
 }
 

@@ -757,8 +757,8 @@ RKB_DEV void load_state(const SerialParams& P, const ConstBatchView& x, const Co
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const int c = P.st[k].coord;
-    X.q[k] = x.p[i * x.si + (2 * c) * x.sk];
-    X.qd[k] = x.p[i * x.si + (2 * c + 1) * x.sk];
+    X.q[k] = x.p[i * x.si + rkb_state_q(x.blocked, N, c) * x.sk];
+    X.qd[k] = x.p[i * x.si + rkb_state_qd(x.blocked, N, c) * x.sk];
     const int in = P.st[k].input;
     X.u[k] = (in >= 0) ? u.p[i * u.si + in * u.sk] : 0.0;
   }
@@ -861,8 +861,8 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_EV
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const int c = P.st[k].coord;
-        A.out.p[i * A.out.si + (2 * c) * A.out.sk] = xd[2 * k];
-        A.out.p[i * A.out.si + (2 * c + 1) * A.out.sk] = xd[2 * k + 1];
+        A.out.p[i * A.out.si + rkb_state_q(A.out.blocked, N, c) * A.out.sk] = xd[2 * k];
+        A.out.p[i * A.out.si + rkb_state_qd(A.out.blocked, N, c) * A.out.sk] = xd[2 * k + 1];
       }
     }
   }
@@ -872,8 +872,8 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_EV
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const int c = P.st[k].coord;
-        smem[threadIdx.x * (2 * N + 1) + 2 * c] = xd[2 * k];
-        smem[threadIdx.x * (2 * N + 1) + 2 * c + 1] = xd[2 * k + 1];
+        smem[threadIdx.x * (2 * N + 1) + rkb_state_q(A.out.blocked, N, c)] = xd[2 * k];
+        smem[threadIdx.x * (2 * N + 1) + rkb_state_qd(A.out.blocked, N, c)] = xd[2 * k + 1];
       }
     }
     __syncthreads();
@@ -994,8 +994,8 @@ RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long of
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const int c = P.st[k].coord;
-    o.p[off + (2 * c) * o.sk] = X.q[k];
-    o.p[off + (2 * c + 1) * o.sk] = X.qd[k];
+    o.p[off + rkb_state_q(o.blocked, N, c) * o.sk] = X.q[k];
+    o.p[off + rkb_state_qd(o.blocked, N, c) * o.sk] = X.qd[k];
   }
 }
 

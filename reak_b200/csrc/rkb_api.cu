@@ -457,12 +457,19 @@ int get_ctx(rkb_chain* c, int device, DeviceCtx** out) {
 }
 
 struct Layout {
-  bool device, soa;
+  bool device, soa, blocked;
 };
-Layout parse_flags(unsigned flags) { return Layout{(flags & RKB_MEM_DEVICE) != 0, (flags & RKB_LAYOUT_SOA) != 0}; }
+Layout parse_flags(unsigned flags) {
+  return Layout{(flags & RKB_MEM_DEVICE) != 0, (flags & RKB_LAYOUT_SOA) != 0, (flags & RKB_LAYOUT_BLOCKED) != 0};
+}
 
-ConstBatchView cview(const double* p, long long n, int dim, bool soa) { return ConstBatchView{p, soa ? 1 : dim, soa ? n : 1}; }
-BatchView view(double* p, long long n, int dim, bool soa) { return BatchView{p, soa ? 1 : dim, soa ? n : 1}; }
+// `blocked` only matters for state buffers ((q, q_dot) interleaved per coordinate, or all q then all q_dot)
+ConstBatchView cview(const double* p, long long n, int dim, bool soa, bool blocked = false) {
+  return ConstBatchView{p, soa ? 1 : dim, soa ? n : 1, blocked ? 1 : 0};
+}
+BatchView view(double* p, long long n, int dim, bool soa, bool blocked = false) {
+  return BatchView{p, soa ? 1 : dim, soa ? n : 1, blocked ? 1 : 0};
+}
 
 // Stage a host input on the device (or pass a device pointer through).
 int stage_in(DevBuf& buf, const void* src, size_t bytes, bool on_device, cudaStream_t s, const void** out) {
@@ -511,9 +518,9 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   if ((rc = stage_out(ctx->out_b, out2, N * out_dim * sizeof(double), L.device, &dout2))) return rc;
   if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
   EvalArgs A;
-  A.x = cview((const double*)dx, (long long)N, nx, L.soa);
+  A.x = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked);
   A.u = cview((const double*)(du ? du : dx), (long long)N, nu > 0 ? nu : 1, L.soa);
-  A.out = view((double*)dout, (long long)N, out_dim, L.soa);
+  A.out = view((double*)dout, (long long)N, out_dim, L.soa, L.blocked && op == OP_EVAL);
   A.out2 = view((double*)dout2, (long long)N, out_dim, L.soa);
   A.status = (int32_t*)dst;
   A.n_samples = (long long)N;
@@ -692,10 +699,10 @@ int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long l
                      BatchView xout, BatchView traj, long long traj_sj, int32_t* status, cudaStream_t s) {
   for (int j = 0; j < pl.n_intervals; ++j) {
     RolloutArgs A;
-    A.x0 = j == 0 ? x0 : ConstBatchView{xout.p, xout.si, xout.sk};
+    A.x0 = j == 0 ? x0 : ConstBatchView{xout.p, xout.si, xout.sk, xout.blocked};
     A.u = ConstBatchView{u.p + j * u_sj, u.si, u.sk};
     A.xout = xout;
-    A.traj = traj.p ? BatchView{traj.p + j * traj_sj, traj.si, traj.sk} : BatchView{nullptr, 0, 0};
+    A.traj = traj.p ? BatchView{traj.p + j * traj_sj, traj.si, traj.sk, traj.blocked} : BatchView{nullptr, 0, 0, 0};
     A.status = status;
     A.n_samples = n;
     A.x0_div = 1;
@@ -731,7 +738,7 @@ int ensure_pipe(DeviceCtx* ctx) {
 // one chunk's tail wave overlaps the next chunk's head, copy-out stream).  Only the first copy-in
 // and the last copy-out stay exposed.  Pinned host memory is what makes the copies asynchronous.
 int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
-                       double* x_out, double* x_traj, int32_t* status, cudaStream_t s, bool join_caller) {
+                       double* x_out, double* x_traj, int32_t* status, cudaStream_t s, bool join_caller, bool blocked = false) {
   const int nx = 2 * c->n;
   const size_t nu = (size_t)c->nu * pl.n_intervals;  // doubles of input per sample
   const size_t nt = (size_t)nx * pl.n_intervals;     // doubles of trajectory per sample
@@ -764,10 +771,10 @@ int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0,
     CU(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
     cudaStream_t sk = ctx->s_k[i & 1];
     CU(cudaStreamWaitEvent(sk, ctx->ev_in[i], 0));
-    if ((rc = launch_intervals(c, ctx, pl, (long long)m, cview(dx + lo * nx, (long long)m, nx, false),
-                               ConstBatchView{nu > 0 ? du + lo * nu : dx, (long long)(nu > 0 ? nu : 1), 1}, c->nu,
-                               view(dout + lo * nx, (long long)m, nx, false),
-                               BatchView{dtraj ? dtraj + lo * nt : nullptr, (long long)nt, 1}, nx, dst + lo, sk)))
+    if ((rc = launch_intervals(c, ctx, pl, (long long)m, cview(dx + lo * nx, (long long)m, nx, false, blocked),
+                               ConstBatchView{nu > 0 ? du + lo * nu : dx, (long long)(nu > 0 ? nu : 1), 1, 0}, c->nu,
+                               view(dout + lo * nx, (long long)m, nx, false, blocked),
+                               BatchView{dtraj ? dtraj + lo * nt : nullptr, (long long)nt, 1, blocked ? 1 : 0}, nx, dst + lo, sk)))
       return rc;
     CU(cudaEventRecord(ctx->ev_k[i], sk));
     CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[i], 0));
@@ -793,8 +800,8 @@ int rollout_host_wait(DeviceCtx* ctx) {
 }
 
 int rollout_host_pipelined(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
-                           double* x_out, double* x_traj, int32_t* status, cudaStream_t s) {
-  int rc = rollout_host_issue(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, true);
+                           double* x_out, double* x_traj, int32_t* status, cudaStream_t s, bool blocked) {
+  int rc = rollout_host_issue(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, true, blocked);
   if (rc) return rc;
   if ((rc = rollout_host_wait(ctx))) return rc;
   // let the caller's stream observe completion as well
@@ -821,7 +828,7 @@ static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, cons
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (!L.device && !L.soa && N >= kPipeMinSamples && pl.n_steps > 0 && !(std::getenv("RKB_NO_PIPELINE") && std::getenv("RKB_NO_PIPELINE")[0] == '1'))
-    return rollout_host_pipelined(c, ctx, N, x0, u, pl, x_out, x_traj, status, s);
+    return rollout_host_pipelined(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, L.blocked);
   const void *dx = nullptr, *du = nullptr;
   void *dout = nullptr, *dtraj = nullptr, *dst = nullptr;
   if ((rc = stage_in(ctx->in_x, x0, N * nx * sizeof(double), L.device, s, &dx))) return rc;
@@ -832,10 +839,11 @@ static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, cons
   // AoS [N][J][nu]: sample stride J nu, interval stride nu; SoA [J][nu][N]: sample stride 1, interval stride nu N
   const ConstBatchView uv = L.soa ? ConstBatchView{(const double*)(du ? du : dx), 1, (long long)N}
                                   : ConstBatchView{(const double*)(du ? du : dx), (long long)(nu > 0 ? nu * J : 1), 1};
-  const BatchView tv = L.soa ? BatchView{(double*)dtraj, 1, (long long)N} : BatchView{(double*)dtraj, (long long)nx * J, 1};
+  const BatchView tv = L.soa ? BatchView{(double*)dtraj, 1, (long long)N, L.blocked ? 1 : 0}
+                             : BatchView{(double*)dtraj, (long long)nx * J, 1, L.blocked ? 1 : 0};
   CU(cudaEventRecord(ctx->ev0, s));
-  if ((rc = launch_intervals(c, ctx, pl, (long long)N, cview((const double*)dx, (long long)N, nx, L.soa), uv,
-                             L.soa ? (long long)nu * (long long)N : (long long)nu, view((double*)dout, (long long)N, nx, L.soa), tv,
+  if ((rc = launch_intervals(c, ctx, pl, (long long)N, cview((const double*)dx, (long long)N, nx, L.soa, L.blocked), uv,
+                             L.soa ? (long long)nu * (long long)N : (long long)nu, view((double*)dout, (long long)N, nx, L.soa, L.blocked), tv,
                              L.soa ? (long long)nx * (long long)N : (long long)nx, (int32_t*)dst, s)))
     return rc;
   CU(cudaEventRecord(ctx->ev1, s));
@@ -944,13 +952,13 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   CU(cudaEventRecord(ctx->ev0, s));
   cudaError_t e;
   RolloutArgs A;
-  A.x0 = cview((const double*)dx0, (long long)P, nx, false);
+  A.x0 = cview((const double*)dx0, (long long)P, nx, false, L.blocked);
   A.u = (L.soa && nu > 0) ? cview((const double*)du, (long long)T, nu, true) : cview((const double*)(du ? du : dx0), (long long)T, nu > 0 ? nu : 1, false);
-  A.xout = view((double*)ctx->scratch_o.p, (long long)T, nx, false);
+  A.xout = view((double*)ctx->scratch_o.p, (long long)T, nx, false, L.blocked);  // rows in the caller's component order
   A.status = (int32_t*)dst;
   A.n_samples = (long long)T;
   A.x0_div = (long long)R;
-  A.traj = BatchView{nullptr, 0, 0};
+  A.traj = BatchView{nullptr, 0, 0, 0};
   A.dt = dt;
   A.n_steps = n_steps;
   A.status_or = 0;
@@ -1035,10 +1043,10 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
     if (e != cudaSuccess) return cuda_fail(e, "steer law");
     c->launches += 1;
     RolloutArgs A;
-    A.x0 = cview((const double*)dxo, (long long)N, nx, false);
+    A.x0 = cview((const double*)dxo, (long long)N, nx, false, L.blocked);
     A.u = cview((const double*)(nu > 0 ? dup_in : dxo), (long long)N, nu > 0 ? nu : 1, false);
-    A.xout = view((double*)dxo, (long long)N, nx, false);
-    A.traj = dtraj ? BatchView{(double*)dtraj + (size_t)k * nx, (long long)nx * J, 1} : BatchView{nullptr, 0, 0};
+    A.xout = view((double*)dxo, (long long)N, nx, false, L.blocked);
+    A.traj = dtraj ? BatchView{(double*)dtraj + (size_t)k * nx, (long long)nx * J, 1, L.blocked ? 1 : 0} : BatchView{nullptr, 0, 0, 0};
     A.status = (int32_t*)dst;
     A.n_samples = (long long)N;
     A.x0_div = 1;

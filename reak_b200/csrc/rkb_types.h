@@ -64,15 +64,28 @@ struct SerialParams {
   SerialStage st[RKB_SERIAL_MAX_DOF];
 };
 
-// strided view of a batch buffer: element k of sample i lives at p[i * si + k * sk]
+// strided view of a batch buffer: element k of sample i lives at p[i * si + k * sk].
+// State buffers hold (q, q_dot) of coordinate c of an n-coordinate chain at elements 2c, 2c + 1
+// (interleaved, kte_nl_system.hpp:189-193) or, when `blocked`, at elements c, n + c
+// (manipulator_dynamics_model::computeStateRate, ctrl/mbd_kte/manipulator_model.cpp:292-355).
 struct BatchView {
   double*  p;
   long long si, sk;
+  int blocked;
 };
 struct ConstBatchView {
   const double* p;
   long long si, sk;
+  int blocked;
 };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline long long rkb_state_q(int blocked, int n, int c) { (void)n; return blocked ? c : 2 * c; }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline long long rkb_state_qd(int blocked, int n, int c) { return blocked ? n + c : 2 * c + 1; }
 
 // Explicit one-step scheme in "start of step plus weighted increments" form: after evaluation s
 // (k_s = dt f(X_s)) the next evaluation point — or, for s = stages - 1, the end of the step — is

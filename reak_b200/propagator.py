@@ -28,7 +28,7 @@ def _is_torch(a):
 
 
 class kte_batch_propagator(object):
-    def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3):
+    def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3, blocked=False):
         if mass_calc is None and hasattr(chain, "chain"):  # a kte_system / kte_nl_system-like object
             sys_ = chain
             chain, mass_calc, dofs_gen, inputs = sys_.chain, sys_.mass_calc, sys_.dofs_gen, sys_.inputs
@@ -36,6 +36,9 @@ class kte_batch_propagator(object):
         self.compiled = kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs)
         self.device = int(device)
         self.dt = float(time_step)
+        # True: every state-shaped buffer is (q..., qd...) like manipulator_dynamics_model::computeStateRate
+        # (ctrl/mbd_kte/manipulator_model.cpp:292-355) instead of kte_nl_system's interleaved (q, qd) pairs
+        self.blocked = bool(blocked)
         self._lib = _abi.load_library()
         h = C.c_void_p()
         _abi.check(self._lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(h)), "rkb_chain_create")
@@ -107,7 +110,7 @@ class kte_batch_propagator(object):
         kinds = set(_is_torch(a) for a in arrs if a is not None)
         if len(kinds) != 1:
             raise TypeError("mix of numpy (host) and torch (device) buffers")
-        flags = _abi.LAYOUT_SOA if soa else _abi.LAYOUT_AOS
+        flags = (_abi.LAYOUT_SOA if soa else _abi.LAYOUT_AOS) | (_abi.LAYOUT_BLOCKED if self.blocked else 0)
         if kinds.pop():
             import torch
             for a in arrs:

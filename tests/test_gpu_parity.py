@@ -491,3 +491,51 @@ def test_chains_beyond_the_limits_are_rejected():
     with pytest.raises(_abi.RkbError) as e:
         kte_batch_propagator(presets.crs_chain(n_revolute=16, springs=True))  # 112 elements > 96
     assert e.value.code == _abi.ERR_UNSUPPORTED
+
+
+# ---- RKB_LAYOUT_BLOCKED: the state order of manipulator_dynamics_model::computeStateRate -----------------
+def _to_blocked(x):
+    """[..., 2n] interleaved (q0, qd0, q1, qd1, ...) -> (q0 .. qn-1, qd0 .. qdn-1)."""
+    return np.ascontiguousarray(np.concatenate([x[..., 0::2], x[..., 1::2]], axis=-1))
+
+
+@pytest.mark.parametrize("name", ["crs6_sd", "crs7", "planar2_act", "crs6_lin_sd"])
+def test_blocked_state_layout(name):
+    """Every entry point gives, in blocked order, exactly the bits it gives in interleaved order."""
+    import torch
+    from reak_b200 import kte_batch_propagator
+    s = presets.make(name)
+    p, pb = kte_batch_propagator(s), kte_batch_propagator(s, blocked=True)
+    n = 777
+    x, u = random_batch(p.compiled, n, seed=51)
+    xb = _to_blocked(x)
+    assert np.array_equal(pb.get_state_derivatives(xb, u)[0], _to_blocked(p.get_state_derivatives(x, u)[0]))
+    assert np.array_equal(pb.get_gen_forces(xb, u), p.get_gen_forces(x, u))
+    Mb, Mdb = pb.get_mass_matrices(xb, with_derivative=True)
+    M, Md = p.get_mass_matrices(x, with_derivative=True)
+    assert np.array_equal(Mb, M) and np.array_equal(Mdb, Md)
+    assert np.array_equal(pb.get_next_states(xb, u, 1e-3, 7)[0], _to_blocked(p.get_next_states(x, u, 1e-3, 7)[0]))
+    # SoA + blocked, device buffers
+    xs = pb.get_next_states(torch.from_numpy(np.ascontiguousarray(xb.T)).cuda(), torch.from_numpy(np.ascontiguousarray(u.T)).cuda(),
+                            1e-3, 7, soa=True)[0]
+    assert np.array_equal(xs.t().cpu().numpy(), _to_blocked(p.get_next_states(x, u, 1e-3, 7)[0]))
+    u_seq = np.random.default_rng(52).uniform(-1, 1, (n, 3, p.nu))
+    for scheme in ("rk4", "midpoint"):
+        xo, tr, _ = p.rollout(x, u_seq, 1e-3, 2, scheme=scheme, want_traj=True)
+        xob, trb, _ = pb.rollout(xb, u_seq, 1e-3, 2, scheme=scheme, want_traj=True)
+        assert np.array_equal(xob, _to_blocked(xo)) and np.array_equal(trb, _to_blocked(tr))
+    if p.nu:
+        rng = np.random.default_rng(53)
+        P, R = 9, 16
+        uu = rng.uniform(-3, 3, (P, R, p.nu))
+        i1, b1, c1 = p.steer_batch(x[:P], x[P:2 * P], uu, 1e-3, 5)
+        i2, b2, c2 = pb.steer_batch(xb[:P], xb[P:2 * P], uu, 1e-3, 5)
+        assert np.array_equal(i1, i2) and np.array_equal(b2, _to_blocked(b1)) and np.allclose(c1, c2, rtol=1e-14)
+        goal = x + rng.uniform(-0.3, 0.3, x.shape)
+        gain = rng.uniform(-3, 3, (n, p.nu, p.nx))
+        gain_b = np.ascontiguousarray(np.concatenate([gain[:, :, 0::2], gain[:, :, 1::2]], axis=2))
+        a = p.steer_feedback(x, goal, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, want_traj=True)
+        b = pb.steer_feedback(xb, _to_blocked(goal), u, gain_b, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, want_traj=True)
+        assert np.array_equal(a[2], b[2])
+        # the law sums gain * (x - goal) in storage order, so the two layouts may differ in the last bits
+        assert rel_err(b[0], _to_blocked(a[0])) < 1e-12 and rel_err(b[1], a[1]) < 1e-12
