@@ -10,6 +10,9 @@
 //                                        joints, links, inertias (+ their mUpStreamJoints maps,
 //                                        jacobian_joint_map.hpp:76-331), springs, dampers and
 //                                        driving actuators through their accessors.
+//   ReaK::pp::kte_steer_space            a steerable space (steer_position_toward of SteerableSpaceConcept,
+//                                        ctrl/topologies/steerable_space_concept.hpp:60-85) whose steering runs on
+//                                        the batched propagator, single pairs and whole planner iterations.
 //   ReaK::ctrl::kte_batch_system         SSSystemConcept + DiscreteSSSConcept on vect_n<double>,
 //                                        drop-in where kte_nl_system / num_int_dtnl_sys are used
 //                                        (e.g. runge_kutta4_integrate_impl, sys_integrators/
@@ -17,8 +20,11 @@
 #ifndef REAK_B200_REAK_BRIDGE_HPP
 #define REAK_B200_REAK_BRIDGE_HPP
 
+#include <cmath>
 #include <map>
+#include <random>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 #include <ReaK/core/lin_alg/vect_alg.hpp>
@@ -288,6 +294,111 @@ class kte_batch_system {
 };
 
 }  // namespace ctrl
+
+namespace pp {
+
+/// A steerable state space over a KTE chain whose steering is served by the batched GPU propagator
+/// (SURVEY 8(f) rank 1).  It offers the valid expression of SteerableSpaceConcept
+/// (ctrl/topologies/steerable_space_concept.hpp:60-85),
+///     tie(p, st_rec) = space.steer_position_toward(p1, d, p3);
+/// next to the metric-space members a planner uses on vect_n states (distance, difference, adjust,
+/// origin), and a batched form that steers all candidate extensions of a planner iteration in one call.
+///
+/// Steering rule — the sampling one of kinodynamic RRT, with the rollouts of steer_with_constant_control
+/// (examples/misc/MEAQR_topology.hpp:539-547: one RK4 control interval after the other, input held):
+/// n_controls constant inputs are drawn uniformly from the input box, each is rolled out from p1 for
+/// n_intervals intervals of steps_per_interval RK4 steps, and the rollout whose end state is nearest
+/// (Euclidean) to the target p1 + d (p3 - p1) wins; its state after every interval is the steer record.
+class kte_steer_space {
+ public:
+  typedef vect_n<double> point_type;
+  typedef vect_n<double> point_difference_type;
+  typedef std::vector<point_type> steer_record_type;
+  BOOST_STATIC_CONSTANT(std::size_t, dimensions = 0);
+
+  kte_steer_space(const ctrl::kte_nl_system& sys, const vect_n<double>& u_lower, const vect_n<double>& u_upper,
+                  std::size_t n_controls, int n_intervals, int steps_per_interval, double dt, unsigned long long seed = 0,
+                  int device = 0)
+      : mSys(sys, device, dt), mLo(u_lower), mHi(u_upper), mControls(n_controls), mIntervals(n_intervals),
+        mSteps(steps_per_interval), mDt(dt), mRng(seed) {
+    if (mLo.size() != mSys.get_input_dimensions() || mHi.size() != mLo.size()) throw std::range_error("Input vector dimension mismatch!");
+    if (n_controls < 1 || n_intervals < 1 || steps_per_interval < 1) throw std::range_error("steering needs at least one control, interval and step");
+  }
+
+  // ---- the metric-space side, on plain vectors ---------------------------------------------------
+  double distance(const point_type& a, const point_type& b) const { return norm_2(difference(b, a)); }
+  double norm(const point_difference_type& d) const { return norm_2(d); }
+  point_difference_type difference(const point_type& a, const point_type& b) const { return a - b; }
+  point_type adjust(const point_type& a, const point_difference_type& d) const { return a + d; }
+  point_type origin() const { return point_type(mSys.get_state_dimensions(), 0.0); }
+  point_type move_position_toward(const point_type& a, double fraction, const point_type& b) const { return a + fraction * (b - a); }
+
+  void reseed(unsigned long long seed) { mRng.seed(seed); }
+  /// The inputs tried by the last steering call, [pairs][n_controls][n_inputs], and the winners' indices.
+  const std::vector<double>& last_controls() const { return mU; }
+  const std::vector<int32_t>& last_choice() const { return mBest; }
+  const ctrl::kte_batch_system& system() const { return mSys; }
+
+  /// SteerableSpaceConcept: steer a fraction d of the way from p1 towards p3.
+  std::pair<point_type, steer_record_type> steer_position_toward(const point_type& p1, double d, const point_type& p3) const {
+    std::vector<point_type> a(1, p1), b(1, p3), res;
+    std::vector<steer_record_type> rec;
+    steer_positions_toward(a, d, b, res, &rec);
+    return std::make_pair(res[0], rec[0]);
+  }
+
+  /// All candidate extensions of one planner iteration: pair i steers from a[i] towards b[i].
+  void steer_positions_toward(const std::vector<point_type>& a, double fraction, const std::vector<point_type>& b,
+                              std::vector<point_type>& result, std::vector<steer_record_type>* records = NULL) const {
+    const std::size_t P = a.size(), nx = mSys.get_state_dimensions(), nu = mSys.get_input_dimensions(), R = mControls;
+    if (b.size() != P) throw std::range_error("as many goals as starts are needed");
+    std::vector<double> x0(P * nx), goal(P * nx), bx(P * nx), cost(P);
+    for (std::size_t i = 0; i < P; ++i) {
+      if (a[i].size() != nx || b[i].size() != nx) throw std::range_error("State vector dimension mismatch!");
+      for (std::size_t k = 0; k < nx; ++k) { x0[i * nx + k] = a[i][k]; goal[i * nx + k] = a[i][k] + fraction * (b[i][k] - a[i][k]); }
+    }
+    mU.assign(P * R * (nu ? nu : 1), 0.0);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    for (std::size_t i = 0; i < P * R; ++i)
+      for (std::size_t k = 0; k < nu; ++k) mU[i * nu + k] = mLo[k] + (mHi[k] - mLo[k]) * uni(mRng);
+    mBest.assign(P, 0);
+    try {
+      mSys.batch().steer_batch(P, R, &x0[0], &goal[0], &mU[0], mIntervals * mSteps, mDt, &mBest[0], &bx[0], &cost[0]);
+      result.assign(P, point_type(nx));
+      for (std::size_t i = 0; i < P; ++i)
+        for (std::size_t k = 0; k < nx; ++k) result[i][k] = bx[i * nx + k];
+      if (records) {
+        // the winners once more, this time keeping the state after every control interval
+        std::vector<double> useq(P * mIntervals * (nu ? nu : 1)), xe(P * nx), traj(P * mIntervals * nx);
+        for (std::size_t i = 0; i < P; ++i)
+          for (int j = 0; j < mIntervals; ++j)
+            for (std::size_t k = 0; k < nu; ++k) useq[(i * mIntervals + j) * nu + k] = mU[(i * R + mBest[i]) * nu + k];
+        mSys.batch().rollout(P, &x0[0], &useq[0], RKB_SCHEME_RK4, mIntervals, mSteps, mDt, &xe[0], &traj[0]);
+        records->assign(P, steer_record_type());
+        for (std::size_t i = 0; i < P; ++i) {
+          (*records)[i].push_back(a[i]);  // the record starts at the start point (MEAQR_topology.hpp:607-608)
+          for (int j = 0; j < mIntervals; ++j) {
+            point_type w(nx);
+            for (std::size_t k = 0; k < nx; ++k) w[k] = traj[(i * mIntervals + j) * nx + k];
+            (*records)[i].push_back(w);
+          }
+        }
+      }
+    } catch (reak_b200::singularity_error&) { throw singularity_error("A"); }
+  }
+
+ private:
+  ctrl::kte_batch_system mSys;
+  vect_n<double> mLo, mHi;
+  std::size_t mControls;
+  int mIntervals, mSteps;
+  double mDt;
+  mutable std::mt19937_64 mRng;
+  mutable std::vector<double> mU;
+  mutable std::vector<int32_t> mBest;
+};
+
+}  // namespace pp
 }  // namespace ReaK
 
 #endif

@@ -453,6 +453,68 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
   }
 }
 
+// GPU drop-in check of ReaK::pp::kte_steer_space (reak_bridge.hpp): P pairs steered in one batched call
+// and again one by one; every claim is re-derived with the reference on the CPU — all n_controls
+// candidates of every pair are integrated with runge_kutta4_integrator, the winner must be the arg-min
+// of the distance to the target, the returned point its end state, the steer record its state after
+// every control interval.  err[0] point, err[1] record, err[2] single-vs-batched.  Returns 0 / -1 (msg).
+int rkref_steer_space_check(void* hv, std::size_t P, const double* a, const double* b, double fraction, const double* u_lo,
+                            const double* u_hi, int n_controls, int n_intervals, int steps, double dt, double* err, char* msg,
+                            int msg_len) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  try {
+    if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
+    vect_n<double> lo(nu), hi(nu);
+    for (int k = 0; k < nu; ++k) { lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
+    pp::kte_steer_space space(m->sys, lo, hi, n_controls, n_intervals, steps, dt, 1234ull);
+    std::vector<vect_n<double> > A(P, vect_n<double>(nx)), B(P, vect_n<double>(nx)), res;
+    for (std::size_t i = 0; i < P; ++i)
+      for (int k = 0; k < nx; ++k) { A[i][k] = a[i * nx + k]; B[i][k] = b[i * nx + k]; }
+    std::vector<pp::kte_steer_space::steer_record_type> rec;
+    space.steer_positions_toward(A, fraction, B, res, &rec);
+    const std::vector<double> U = space.last_controls();
+    const std::vector<int32_t> best = space.last_choice();
+    err[0] = err[1] = err[2] = 0.0;
+    std::vector<double> x0(n_controls * nx), xe(n_controls * nx), xw(nx);
+    for (std::size_t i = 0; i < P; ++i) {
+      for (int r = 0; r < n_controls; ++r)
+        for (int k = 0; k < nx; ++k) x0[r * nx + k] = A[i][k];
+      rk4_range(m, 0, n_controls, x0.data(), U.data() + i * n_controls * nu, dt, n_intervals * steps, xe.data(), NULL);
+      int arg = 0;
+      double dmin = 1e300;
+      for (int r = 0; r < n_controls; ++r) {
+        double d2 = 0.0;
+        for (int k = 0; k < nx; ++k) {
+          const double g = A[i][k] + fraction * (B[i][k] - A[i][k]);
+          d2 += (xe[r * nx + k] - g) * (xe[r * nx + k] - g);
+        }
+        if (std::sqrt(d2) < dmin) { dmin = std::sqrt(d2); arg = r; }
+      }
+      if (arg != best[i]) throw std::runtime_error("the chosen control is not the arg-min of the reference rollouts");
+      for (int k = 0; k < nx; ++k)
+        err[0] = std::max(err[0], std::fabs(res[i][k] - xe[arg * nx + k]) / std::max(1.0, std::fabs(xe[arg * nx + k])));
+      if ((int)rec[i].size() != n_intervals + 1) throw std::runtime_error("steer record has the wrong length");
+      for (int k = 0; k < nx; ++k) if (rec[i][0][k] != A[i][k]) throw std::runtime_error("steer record does not start at the start point");
+      for (int j = 1; j <= n_intervals; ++j) {
+        rk4_range(m, 0, 1, &A[i][0], U.data() + (i * n_controls + arg) * nu, dt, j * steps, xw.data(), NULL);
+        for (int k = 0; k < nx; ++k) err[1] = std::max(err[1], std::fabs(rec[i][j][k] - xw[k]) / std::max(1.0, std::fabs(xw[k])));
+      }
+    }
+    // the concept's single-pair expression draws the same controls after the same reseed
+    space.reseed(1234ull);
+    std::pair<vect_n<double>, pp::kte_steer_space::steer_record_type> one = space.steer_position_toward(A[0], fraction, B[0]);
+    for (int k = 0; k < nx; ++k) err[2] = std::max(err[2], std::fabs(one.first[k] - res[0][k]));
+    if (one.second.size() != rec[0].size()) throw std::runtime_error("single and batched steer records differ in length");
+    if (std::fabs(space.distance(A[0], B[0]) - norm_2(A[0] - B[0])) > 0.0) throw std::runtime_error("distance is not the Euclidean one");
+    return 0;
+  } catch (std::exception& e) {
+    if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
+    return -1;
+  }
+}
+
 // n_workers > 1: the samples are block-partitioned over forked worker processes.  Threads do
 // not scale here: every rk_dynamic_ptr_cast in the reference bumps the atomic reference count
 // of shared static type descriptors, so threads serialise on those cache lines (measured:

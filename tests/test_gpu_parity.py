@@ -539,3 +539,31 @@ def test_blocked_state_layout(name):
         assert np.array_equal(a[2], b[2])
         # the law sums gain * (x - goal) in storage order, so the two layouts may differ in the last bits
         assert rel_err(b[0], _to_blocked(a[0])) < 1e-12 and rel_err(b[1], a[1]) < 1e-12
+
+
+def test_reak_steer_space_cpp(oracle_built):
+    """ReaK::pp::kte_steer_space (reak_bridge.hpp): steer_position_toward of SteerableSpaceConcept served by the
+    batched propagator, checked in C++ against the unmodified reference — every candidate control is
+    re-integrated with runge_kutta4_integrator, the winner must be the arg-min, the returned point its end
+    state and the steer record its state after every control interval."""
+    import ctypes as C
+    from reak_b200 import _abi
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built")
+    C.CDLL(_abi.LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name in ("crs6", "crs7_phys_sd", "planar2_act"):
+        s = presets.make(name)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        R = oracle_built.Reference(c)
+        fn = R.lib.rkref_steer_space_check
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                       C.c_double, C.c_void_p, C.c_char_p, C.c_int]
+        P = 5
+        a, _ = random_batch(c, P, seed=61)
+        b, _ = random_batch(c, P, seed=62)
+        lo, hi = -3.0 * np.ones(c.n_inputs), 3.0 * np.ones(c.n_inputs)
+        err = np.zeros(3)
+        msg = C.create_string_buffer(512)
+        rc = fn(R.h, P, a.ctypes.data, b.ctypes.data, 0.3, lo.ctypes.data, hi.ctypes.data, 24, 3, 5, 1e-3, err.ctypes.data, msg, 512)
+        assert rc == 0, (name, msg.value)
+        assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] == 0.0, (name, err)
