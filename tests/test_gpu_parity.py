@@ -567,3 +567,52 @@ def test_reak_steer_space_cpp(oracle_built):
         rc = fn(R.h, P, a.ctypes.data, b.ctypes.data, 0.3, lo.ctypes.data, hi.ctypes.data, 24, 3, 5, 1e-3, err.ctypes.data, msg, 512)
         assert rc == 0, (name, msg.value)
         assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] == 0.0, (name, err)
+
+
+# ---- the trigonometric paths of the serial kernels -------------------------------------------------------
+@pytest.mark.parametrize("name", ["crs6", "crs7"])
+def test_large_angles_and_fast_joints(name, oracle_built):
+    """sincos_reduced serves |q| < 1e9 (Cody-Waite by pi/2), the library sincos anything beyond; RK4 stages 2-4
+    use the small-angle shift only while |dt q_dot| < 2^-5 and evaluate in full otherwise.  All of them against
+    the oracle, on the rollout and the evaluation kernels."""
+    p = _make(name)
+    O = oracle_built.Oracle(p.compiled)
+    rng = np.random.default_rng(71)
+    n = 96
+    x, u = random_batch(p.compiled, n, seed=72)
+    rev = [2 * k for k in range(p.n)] if name == "crs6" else [2 * k for k in range(1, p.n)]  # crs7: coordinate 0 is the track
+    cases = {}
+    big = x.copy()
+    big[:, rev] = rng.uniform(-1.0, 1.0, (n, len(rev))) * 10.0 ** rng.integers(0, 9, (n, len(rev)))  # up to 1e8 rad
+    cases["angles up to 1e8"] = (big, 1e-3, 1e-10)
+    huge = x.copy()
+    huge[:, rev[0]] = rng.uniform(2e9, 1e12, n)          # beyond the reduction's range: library path
+    cases["angles beyond 1e9"] = (huge, 1e-3, 1e-10)
+    fast = x.copy()
+    fast[:, [k + 1 for k in rev]] = rng.uniform(-80.0, 80.0, (n, len(rev)))  # |dt q_dot| up to 0.08 > 2^-5
+    cases["fast joints"] = (fast, 1e-3, 1e-10)
+    mixed = x.copy()
+    mixed[::2, rev[1] + 1] = 40.0                        # every other sample leaves the small-angle path: divergent warps
+    cases["mixed"] = (mixed, 1e-3, 1e-10)
+    for label, (xx, dt, tol) in cases.items():
+        xd, st = p.get_state_derivatives(xx, u)
+        assert not st.any() and rel_err(xd, O.eval(xx, u)[0]) < tol, (name, label)
+        xo, st = p.get_next_states(xx, u, dt, 3)
+        xr, sr, _ = O.rk4(xx, u, dt, 3)
+        # a state component of 1e8..1e12 carries an absolute rounding error of its own ulp: compare relative to its size
+        err = float(np.max(np.abs(xo - xr) / np.maximum(1.0, np.abs(xr))))
+        assert not st.any() and not sr.any() and err < tol, (name, label, err)
+
+
+def test_non_finite_states_raise_the_status_bit():
+    p = _make("crs6")
+    x, u = random_batch(p.compiled, 64, seed=73)
+    x[5, 0] = np.nan
+    x[9, 3] = np.inf
+    xd, st = p.get_state_derivatives(x, u)
+    xo, st2 = p.get_next_states(x, u, 1e-3, 2)
+    from reak_b200 import _abi
+    for s in (st, st2):
+        assert s[5] & _abi.STATUS_NONFINITE and s[9] & _abi.STATUS_NONFINITE
+        assert not np.delete(s, [5, 9]).any()
+    assert np.isfinite(np.delete(xo, [5, 9], axis=0)).all()
