@@ -136,9 +136,17 @@ RKB_DEV double wrapped_angle(double q) {
   return r;
 }
 
-// torsion spring (+ saturation) and damper across a revolute joint, as a signed scalar along the axis
+// torsion spring (+ saturation) and damper across a revolute joint, as a signed scalar along the axis.
+// torsion_spring_3D goes through axis_angle (dead zone, torsion_spring.cpp:106-129); torsion_spring_2D takes
+// the angle of the relative rotation as it is (atan2, torsion_spring.cpp:50-71).
 RKB_DEV double spring_scalar(const SerialStage& S, double q) {
-  const double r = wrapped_angle(q);
+  double r;
+  if (S.flags & RKB_ST_SPRING_2D) {
+    const double two_pi = 6.283185307179586476925286766559;
+    r = q - two_pi * rint(q * 0.15915494309189533576888376337251);
+  } else {
+    r = wrapped_angle(q);
+  }
   double mag = S.ks * fabs(r);  // stiffness * angle_diff.angle(), angle >= 0
   if (S.sat > 0.0 && fabs(mag) > S.sat) mag = (mag > 0.0) ? S.sat : -S.sat;
   return r < 0.0 ? -mag : mag;

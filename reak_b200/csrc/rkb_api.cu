@@ -186,7 +186,48 @@ int validate(const rkb_chain_desc* d) {
 
 // Try to express the chain as joint/link/inertia stages (see rkb_types.h).  Returns false when
 // the chain needs the generic interpreter.
-bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl, unsigned long long& shape) {
+// A planar chain is the 3D chain it describes when drawn in the x-y plane: revolute_joint_2D turns about
+// e_z (revolute_joint.cpp:32-116 against :121-213 — the torque left on the base is zero in both, the axial
+// part being all there is), prismatic_joint_2D / rigid_link_2D carry planar vectors (prismatic_joint.cpp:33-123,
+// rigid_link.cpp:87-139), inertia_2D is a diagonal tensor whose zz entry is the moment of inertia (no
+// gyroscopic torque for a rotation about a principal axis, inertia.cpp:77-86 against :111-121), and the base
+// frame rotates about e_z.  Two-anchor spring_2D / damper_2D stay with the interpreter.
+bool embed_planar(const rkb_chain_desc& d, rkb_chain_desc& out, std::vector<rkb_element>& el) {
+  out = d;
+  out.dim = 3;
+  el.assign(d.elements, d.elements + d.n_elements);
+  for (rkb_element& E : el) {
+    double p[12];
+    std::memcpy(p, E.p, sizeof p);
+    std::memset(E.p, 0, sizeof E.p);
+    E.reserved = 0;
+    switch (E.kind) {
+      case RKB_REVOLUTE_2D: E.kind = RKB_REVOLUTE_3D; E.p[2] = 1.0; break;
+      case RKB_PRISMATIC_2D: E.kind = RKB_PRISMATIC_3D; E.p[0] = p[0]; E.p[1] = p[1]; break;
+      case RKB_RIGID_LINK_2D:
+        E.kind = RKB_RIGID_LINK_3D; E.p[0] = p[0]; E.p[1] = p[1];
+        if (p[2] == 0.0) { E.p[3] = 1.0; } else { E.p[3] = std::cos(0.5 * p[2]); E.p[6] = std::sin(0.5 * p[2]); }
+        break;
+      case RKB_INERTIA_2D: E.kind = RKB_INERTIA_3D; E.p[0] = p[0]; E.p[6] = p[1]; break;
+      case RKB_TORSION_SPRING_2D: E.kind = RKB_TORSION_SPRING_3D; E.p[0] = p[0]; E.p[1] = p[1]; E.reserved = 1; break;
+      case RKB_TORSION_DAMPER_2D: E.kind = RKB_TORSION_DAMPER_3D; E.p[0] = p[0]; break;
+      case RKB_INERTIA_GEN: case RKB_ACTUATOR_GEN: std::memcpy(E.p, p, sizeof p); break;
+      default: return false;
+    }
+  }
+  out.elements = el.data();
+  const double a = d.base.quat[0];
+  out.base.position[2] = 0.0; out.base.velocity[2] = 0.0; out.base.acceleration[2] = 0.0;
+  out.base.quat[0] = std::cos(0.5 * a); out.base.quat[1] = 0.0; out.base.quat[2] = 0.0; out.base.quat[3] = std::sin(0.5 * a);
+  out.base.ang_velocity[2] = d.base.ang_velocity[0]; out.base.ang_velocity[0] = out.base.ang_velocity[1] = 0.0;
+  out.base.ang_acceleration[2] = d.base.ang_acceleration[0]; out.base.ang_acceleration[0] = out.base.ang_acceleration[1] = 0.0;
+  return true;
+}
+
+bool lower_serial(const rkb_chain_desc& d_in, SerialParams& P, int& fl, unsigned long long& shape) {
+  rkb_chain_desc d = d_in;
+  std::vector<rkb_element> embedded;
+  if (d_in.dim == 2 && !embed_planar(d_in, d, embedded)) return false;
   if (d.dim != 3 || d.n_coords < 1 || d.n_coords > RKB_SERIAL_MAX_DOF) return false;
   std::memset(&P, 0, sizeof P);
   P.n = d.n_coords;
@@ -281,6 +322,7 @@ bool lower_serial(const rkb_chain_desc& d, SerialParams& P, int& fl, unsigned lo
         if (E.kind == RKB_TORSION_SPRING_3D) {
           if (S.flags & RKB_ST_SPRING) return false;
           S.flags |= RKB_ST_SPRING; S.ks = E.p[0]; S.sat = E.p[1];
+          if (d_in.dim == 2 && E.reserved == 1) S.flags |= RKB_ST_SPRING_2D;  // marked by embed_planar
         } else {
           S.flags |= RKB_ST_DAMPER; S.cd += E.p[0];
         }

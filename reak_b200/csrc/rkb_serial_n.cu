@@ -84,6 +84,16 @@ constexpr shape_t arm_shape(int n, int first, int inertia = 1) {
 // general joint (prismatic track) with a z-aligned link and a diagonal tensor, then the arm
 constexpr shape_t track_arm_shape(int n) { return RKB_SHAPE_AT(RKB_SHAPE_STAGE(0, 3, 1), 0) | arm_shape(n - 1, 1); }
 
+// planar chains embedded in the x-y plane (rkb_api.cu: embed_planar): every joint about z, links along x,
+// diagonal tensors — cfg 1 and the 2D analog of the CRS arm (examples/robot_airship/old/CRS_A465_2D_analog.cpp);
+// with the prismatic track of that model in front, whose link has no offset
+constexpr shape_t planar_shape(int n, int first = 0) {
+  shape_t s = 0;
+  for (int k = 0; k < n; ++k) s |= RKB_SHAPE_AT(RKB_SHAPE_STAGE(3, 1, 1), k + first);
+  return s;
+}
+constexpr shape_t track_planar_shape(int n) { return RKB_SHAPE_AT(RKB_SHAPE_STAGE(0, 3, 1), 0) | planar_shape(n - 1, 1); }
+
 extern "C" const SerialKernels* RKB_CAT(rkb_serial_table_, RKB_N)(int* count) {
   static const SerialKernels table[] = {
       Launch<RKB_N, 0, 0>::entry(),
@@ -95,6 +105,12 @@ extern "C" const SerialKernels* RKB_CAT(rkb_serial_table_, RKB_N)(int* count) {
 #if RKB_N >= 2
       Launch<RKB_N, RKB_FL_PRISMATIC, track_arm_shape(RKB_N)>::entry(),
       Launch<RKB_N, RKB_FL_PRISMATIC | RKB_FL_SPRINGS, track_arm_shape(RKB_N)>::entry(),
+#endif
+#if RKB_N <= 4
+      Launch<RKB_N, RKB_FL_SPRINGS, planar_shape(RKB_N)>::entry(),
+#if RKB_N >= 2
+      Launch<RKB_N, RKB_FL_PRISMATIC | RKB_FL_SPRINGS, track_planar_shape(RKB_N)>::entry(),
+#endif
 #endif
   };
   *count = (int)(sizeof(table) / sizeof(table[0]));

@@ -22,6 +22,7 @@
 #define RKB_ST_DAMPER    8u  // torsion_damper_3D across the joint
 #define RKB_ST_INERTIA   16u // an inertia_3D sits on the link end frame
 #define RKB_ST_LINK      32u // a rigid_link_3D follows the joint (else end frame == joint end)
+#define RKB_ST_SPRING_2D 64u // the spring is a torsion_spring_2D: plain wrapped angle, no axis_angle dead zone
 
 // kernel-template feature mask: which optional code is compiled in
 #define RKB_FL_PRISMATIC 1
