@@ -203,6 +203,40 @@ def planar_prismatic_revolute_chain():
     return s
 
 
+def crs_2d_analog_chain():
+    """The planar analog of the CRS A465 on its track, examples/robot_airship/old/CRS_A465_2D_analog.cpp:139-330
+    and :462-512: prismatic_joint_2D along x, then three revolute_joint_2D with links of 0.3048, 0.3302 and
+    0.0762 m along x; every joint carries a driving_actuator_gen and a unit rotor inertia_gen, every link end a
+    unit inertia_2D (m = 1, J = 1); no gravity (the base acceleration is commented out there, :139)."""
+    s = kte_system("crs2d")
+    cur = kte.frame_2D()
+    upstream, rotors = {}, []
+    for k, L in enumerate((0.0, 0.3048, 0.3302, 0.0762)):
+        coord, jac, end, nxt = kte.gen_coord(), kte.jacobian_gen_2D(), kte.frame_2D(), kte.frame_2D()
+        if k == 0:
+            joint = kte.prismatic_joint_2D("track_joint", coord, (1.0, 0.0), cur, end, jac)
+        else:
+            joint = kte.revolute_joint_2D("arm_joint_%d" % k, coord, cur, end, jac)
+        act = kte.driving_actuator_gen("actuator_%d" % k, coord, joint)
+        dep = kte.joint_dependent_gen_coord(coord)
+        dep.add_joint(coord, kte.jacobian_gen_gen(1.0, 0.0))
+        rotor = kte.inertia_gen("joint_%d_inertia" % k, dep, 1.0)
+        link = kte.rigid_link_2D("link_%d" % k, end, nxt, kte.pose_2D((L, 0.0), 0.0))
+        upstream[coord] = jac
+        inertia = kte.inertia_2D("link_%d_inertia" % k, kte.joint_dependent_frame_2D(nxt, dict(upstream)), 1.0, 1.0)
+        s.chain << act << rotor << joint << link << inertia
+        s.inputs.append(act)
+        s.dofs_gen.append(coord)
+        s.mass_calc << inertia
+        rotors.append(rotor)
+        cur = nxt
+    for r in rotors:
+        s.mass_calc << r
+    for c in s.dofs_gen:
+        s.mass_calc << c
+    return s
+
+
 PRESETS = {
     "pendulum": pendulum_chain,
     "planar2": planar_chain,                                          # cfg 1
@@ -222,6 +256,7 @@ PRESETS = {
     "crs6_lin_sd": crs_linear_spring_chain,
     "planar2_lin_sd": planar_linear_spring_chain,
     "planar_pr": planar_prismatic_revolute_chain,
+    "crs2d": crs_2d_analog_chain,                                     # the reference's own planar dynamic model
 }
 
 

@@ -22,7 +22,7 @@ from reak_b200 import kte, presets  # noqa: E402
 
 N = 16
 CASES = ["pendulum", "planar2", "planar3_sd", "torsion1", "crs3", "crs6", "crs6_phys", "crs6_sd", "crs6_sd_sat",
-         "crs6_twist", "crs7", "crs7_phys_sd", "crs6_passive", "planar2_act", "crs6_lin_sd", "planar2_lin_sd", "planar_pr"]
+         "crs6_twist", "crs7", "crs7_phys_sd", "crs6_passive", "planar2_act", "crs6_lin_sd", "planar2_lin_sd", "planar_pr", "crs2d"]
 
 
 def main():

@@ -45,7 +45,7 @@ def _create(desc):
 
 # planar chains are embedded in the x-y plane and run on the same kernels; two-anchor springs / dampers need the interpreter
 SERIAL = {"crs6", "crs6_phys", "crs6_sd", "crs6_sd_sat", "crs6_twist", "crs7", "crs7_phys_sd", "torsion1", "crs3", "crs6_passive",
-          "pendulum", "planar2", "planar2_act", "planar3_sd", "planar_pr"}
+          "pendulum", "planar2", "planar2_act", "planar3_sd", "planar_pr", "crs2d"}
 
 
 @pytest.mark.parametrize("name", sorted(presets.PRESETS))
