@@ -17,6 +17,7 @@
  *                            (fixed_step_integrators.hpp:60-399) over a sequence of control intervals
  *   rkb_mass_matrix       <- mass_matrix_calc::getMassMatrix / getMassMatrixAndDerivative
  *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
+ *   rkb_twist_shaping     <- mass_matrix_calc::get_TMT_TdMT             (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287)
  *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
  *   rkb_steer_batch       <- the inner loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561),
  *                            many (start, goal, control) tuples per call
@@ -222,6 +223,18 @@ RKB_API int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,
 RKB_API int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
                     const double* x, double* M, double* Mdot,
                     unsigned flags, void* stream);
+
+/* Twist-shaping matrix Tcm and its time derivative Tcm_dot of mass_matrix_calc::get_TMT_TdMT
+ * (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287) at state x[i].  Rows: one per inertia_gen, then three per
+ * inertia_2D (v2, w), then six per inertia_3D (v3, w3: jacobian_gen_3D::get_jac_relative_to,
+ * core/kinetostatics/motion_jacobians.hpp:238-279), each group in chain order; columns: the coordinates.
+ * M = Tcm^T Mcm Tcm and Mdot = Tcm_dot^T Mcm Tcm + transpose.  Tcm, Tcm_dot (nullable): AOS [N][rows][n],
+ * SOA [rows * n][N].  Mcm is constant: rkb_twist_shaping_mcm writes it (rows x rows, row-major, host memory).
+ * Always evaluated by the interpreter kernels (the serial kernels never form Tcm). */
+RKB_API int rkb_twist_shaping_rows(const rkb_chain* chain);
+RKB_API int rkb_twist_shaping_mcm(const rkb_chain* chain, double* Mcm);
+RKB_API int rkb_twist_shaping(rkb_chain* chain, int device, size_t n_samples,
+                              const double* x, double* Tcm, double* Tcm_dot, unsigned flags, void* stream);
 
 /* For each of n_pairs (start, goal) pairs roll out n_rollouts constant controls for n_steps
  * RK4 steps and keep the rollout whose end state is closest to the goal (Euclidean norm over

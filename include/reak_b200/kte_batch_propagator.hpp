@@ -250,6 +250,13 @@ class kte_batch_propagator {
   void get_mass_matrices(std::size_t n, const double* x, double* M, double* Mdot = NULL, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_mass_matrix(mChain, mDevice, n, x, M, Mdot, flags, stream), "rkb_mass_matrix");
   }
+  /// mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm and (nullable) Tcm_dot, [n][rows][dof];
+  /// twist_shaping_rows() and twist_shaping_mcm(Mcm) give the row count and the constant rows x rows Mcm.
+  int twist_shaping_rows() const { return rkb_twist_shaping_rows(mChain); }
+  void twist_shaping_mcm(double* Mcm) const { check(rkb_twist_shaping_mcm(mChain, Mcm), "rkb_twist_shaping_mcm"); }
+  void get_twist_shaping(std::size_t n, const double* x, double* Tcm, double* Tcm_dot = NULL, unsigned flags = 0, void* stream = NULL) const {
+    check(rkb_twist_shaping(mChain, mDevice, n, x, Tcm, Tcm_dot, flags, stream), "rkb_twist_shaping");
+  }
   void steer_batch(std::size_t n_pairs, std::size_t n_rollouts, const double* x0, const double* goal, const double* u, int n_steps,
                    double dt, int32_t* best_idx, double* best_x, double* best_cost = NULL, int32_t* status = NULL,
                    unsigned flags = 0, void* stream = NULL) const {

@@ -149,6 +149,18 @@ class _Checker(object):
             raise RuntimeError("steer_feedback failed")
         return xo, up, nd, traj[:, :int(max_intervals), :], st
 
+    def tmt(self, x):
+        """(Tcm, Mcm, Tcm_dot) of mass_matrix_calc::get_TMT_TdMT for one state."""
+        x, _, _ = self._xu(x, None)
+        fn = getattr(self.lib, self._prefix + "tmt")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 5
+        x0 = x[0].copy()
+        rows = fn(self.h, _dp(x0), None, None, None)
+        T, Mc, Td = np.zeros((rows, self.n)), np.zeros((rows, rows)), np.zeros((rows, self.n))
+        fn(self.h, _dp(x0), _dp(T), _dp(Mc), _dp(Td))
+        return T, Mc, Td
+
     def frames(self, x, u=None):
         """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""
         x, u, _ = self._xu(x, u)
@@ -178,7 +190,6 @@ class Oracle(_Checker):
     def __init__(self, compiled):
         _Checker.__init__(self, ORACLE_SO, "kto_", compiled)
         self.lib.kto_gen_forces_qdd.argtypes = [C.c_void_p] * 5
-        self.lib.kto_tmt.argtypes = [C.c_void_p] * 5
 
     def gen_forces_qdd(self, x, u, qdd):
         """gen_coord::f of one state with a caller-chosen q_ddot (test_bm.cpp:103-121)."""
@@ -187,15 +198,6 @@ class Oracle(_Checker):
         f = np.empty(self.n)
         self.lib.kto_gen_forces_qdd(self.h, _dp(x[0].copy()), _dp(u[0].copy()), _dp(qdd), _dp(f))
         return f
-
-    def tmt(self, x):
-        """(Tcm, Mcm, Tcm_dot) of mass_matrix_calc::get_TMT_TdMT for one state."""
-        x, _, _ = self._xu(x, None)
-        rows = self.lib.kto_tmt(self.h, _dp(x[0].copy()), None, None, None)
-        T, Mc, Td = np.zeros((rows, self.n)), np.zeros((rows, rows)), np.zeros((rows, self.n))
-        self.lib.kto_tmt(self.h, _dp(x[0].copy()), _dp(T), _dp(Mc), _dp(Td))
-        return T, Mc, Td
-
 
 def cholesky_solve(A, b, tol=1e-8, ldl=False):
     """linsolve_Cholesky / the LDL variant of core/lin_alg/mat_cholesky.hpp on a dense system; returns (x, singular)."""

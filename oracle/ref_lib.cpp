@@ -42,6 +42,9 @@
 #pragma weak rkb_eval
 #pragma weak rkb_gen_forces
 #pragma weak rkb_mass_matrix
+#pragma weak rkb_twist_shaping
+#pragma weak rkb_twist_shaping_rows
+#pragma weak rkb_twist_shaping_mcm
 #pragma weak rkb_steer_batch
 #pragma weak rkb_last_kernel_ms
 #pragma weak rkb_last_cuda_error
@@ -451,6 +454,28 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
     if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
     return -1;
   }
+}
+
+// mass_matrix_calc::get_TMT_TdMT of the live model at state x (one sample): Tcm, Tcm_dot rows x n row-major,
+// Mcm rows x rows.  Pass NULL pointers to query the row count.
+int rkref_tmt(void* hv, const double* x, double* Tcm, double* Mcm, double* Tcm_dot) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  vect_n<double> p(nx), u(nu, 0.0);
+  for (int k = 0; k < nx; ++k) p[k] = x[k];
+  m->sys.apply_states_and_inputs(p, u);
+  m->chain->doMotion();
+  mat<double, mat_structure::rectangular> T, Td;
+  mat<double, mat_structure::symmetric> Mc;
+  m->mcalc->get_TMT_TdMT(T, Mc, Td);
+  const int rows = int(T.get_row_count()), n = int(T.get_col_count());
+  if (!Tcm || !Mcm || !Tcm_dot) return rows;
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < n; ++c) { Tcm[r * n + c] = T(r, c); Tcm_dot[r * n + c] = Td(r, c); }
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < rows; ++c) Mcm[r * rows + c] = Mc(r, c);
+  return rows;
 }
 
 // GPU drop-in check of ReaK::pp::kte_steer_space (reak_bridge.hpp): P pairs steered in one batched call

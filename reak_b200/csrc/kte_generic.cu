@@ -531,6 +531,78 @@ GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double*
   }
 }
 
+// Tcm / Tcm_dot of mass_matrix_calc::get_TMT_TdMT written out (rows x n per sample; `row` of every inertia was
+// fixed at lowering: gen inertias, then 2D, then 3D).  Entries of coordinates outside an inertia's upstream
+// set stay zero.
+template <int MAXF>
+GD void tmt(const GenericProgram* G, const Work<3, MAXF>& W, const BatchView& T, const BatchView& Td, long long i) {
+  const int n = G->n_coords;
+  const bool want_dot = Td.p != (double*)0;
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_INERTIA_GEN) {
+      for (int c = 0; c < n; ++c) {
+        const long long k = (long long)E.row * n + c;
+        T.p[i * T.si + k * T.sk] = ((E.upstream >> c) & 1u) ? 1.0 : 0.0;
+        if (want_dot) Td.p[i * Td.si + k * Td.sk] = 0.0;
+      }
+    } else if (E.kind == RKB_INERTIA_3D) {
+      const Fr3& F = W.fr[E.fa];
+      const M3 RF = qrot(F.q);
+      for (int c = 0; c < n; ++c) {
+        double col[6] = {0, 0, 0, 0, 0, 0}, cold[6] = {0, 0, 0, 0, 0, 0};
+        if ((E.upstream >> c) & 1u) jac_col(G, W, c, F, RF, col, cold, want_dot);
+        for (int r = 0; r < 6; ++r) {
+          const long long k = (long long)(E.row + r) * n + c;
+          T.p[i * T.si + k * T.sk] = col[r];
+          if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
+        }
+      }
+    }
+  }
+}
+template <int MAXF>
+GD void tmt(const GenericProgram* G, const Work<2, MAXF>& W, const BatchView& T, const BatchView& Td, long long i) {
+  const int n = G->n_coords;
+  const bool want_dot = Td.p != (double*)0;
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_INERTIA_GEN) {
+      for (int c = 0; c < n; ++c) {
+        const long long k = (long long)E.row * n + c;
+        T.p[i * T.si + k * T.sk] = ((E.upstream >> c) & 1u) ? 1.0 : 0.0;
+        if (want_dot) Td.p[i * Td.si + k * Td.sk] = 0.0;
+      }
+    } else if (E.kind == RKB_INERTIA_2D) {
+      const Fr2& F = W.fr[E.fa];
+      for (int c = 0; c < n; ++c) {
+        double col[3] = {0, 0, 0}, cold[3] = {0, 0, 0};
+        if ((E.upstream >> c) & 1u) {
+          const GenericElement& J = G->el[G->jelem[c]];
+          const Fr2& Ej = W.fr[J.fb];
+          const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
+          const double wrel = F.w - Ej.w;
+          V2 Tv, Tvd;
+          if (J.kind == RKB_REVOLUTE_2D) {
+            Tv = rtmul(F.R, crs(1.0, dp));
+            col[2] = 1.0;
+            Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
+          } else {
+            Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
+            Tvd = v2(0, 0) - crs(wrel, Tv);
+          }
+          col[0] = Tv.x; col[1] = Tv.y; cold[0] = Tvd.x; cold[1] = Tvd.y;
+        }
+        for (int r = 0; r < 3; ++r) {
+          const long long k = (long long)(E.row + r) * n + c;
+          T.p[i * T.si + k * T.sk] = col[r];
+          if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
+        }
+      }
+    }
+  }
+}
+
 // linsolve_Cholesky (mat_cholesky.hpp:63-84, 160-179) on a row-major n x n matrix, in place
 GD int cholesky_solve(int n, double* A, double* b) {
   int st = 0;
@@ -625,6 +697,16 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
       A.out.p[i * A.out.si + (long long)(a * n + b) * A.out.sk] = m;
       if (want_dot) A.out2.p[i * A.out2.si + (long long)(a * n + b) * A.out2.sk] = S[a * n + b] + S[b * n + a];
     }
+}
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, false);
+  motion(G, W);
+  tmt(G, W, A.out, A.out2, i);
 }
 
 template <int DIM, int MAXF>
@@ -781,6 +863,12 @@ cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& h
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   DISPATCH(generic_mass_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_tmt_kernel, host, prog, a);
   return cudaGetLastError();
 }
 cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,

@@ -535,16 +535,27 @@ int unstage_out(void* dev, void* dst, size_t bytes, bool on_device, cudaStream_t
   return 0;
 }
 
-enum Op { OP_EVAL, OP_FORCES, OP_MASS };
+enum Op { OP_EVAL, OP_FORCES, OP_MASS, OP_TMT };
+
+int tmt_rows(const rkb_chain_desc& d) {
+  int rows = 0;
+  for (int e = 0; e < d.n_elements; ++e) {
+    const int k = d.elements[e].kind;
+    rows += k == RKB_INERTIA_GEN ? 1 : k == RKB_INERTIA_2D ? 3 : k == RKB_INERTIA_3D ? 6 : 0;
+  }
+  return rows;
+}
 
 int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, const double* u, double* out, double* out2,
                   int32_t* status, unsigned flags, void* stream) {
   if (!c) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
-  if (!x || !out || (c->nu > 0 && !u && op != OP_MASS)) return RKB_ERR_INVALID;
+  if (!x || !out || (c->nu > 0 && !u && op != OP_MASS && op != OP_TMT)) return RKB_ERR_INVALID;
+  if (op == OP_TMT && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
   const Layout L = parse_flags(flags);
   const int n = c->n, nx = 2 * n, nu = c->nu;
-  const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : n * n;
+  const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : op == OP_MASS ? n * n : tmt_rows(c->desc) * n;
+  if (out_dim == 0) return RKB_OK;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -555,7 +566,7 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   const void *dx = nullptr, *du = nullptr;
   void *dout = nullptr, *dout2 = nullptr, *dst = nullptr;
   if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
-  if (op != OP_MASS && nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc; }
+  if (op != OP_MASS && op != OP_TMT && nu > 0) { if ((rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc; }
   if ((rc = stage_out(ctx->out_a, out, N * out_dim * sizeof(double), L.device, &dout))) return rc;
   if ((rc = stage_out(ctx->out_b, out2, N * out_dim * sizeof(double), L.device, &dout2))) return rc;
   if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
@@ -568,8 +579,10 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   A.n_samples = (long long)N;
   CU(cudaEventRecord(ctx->ev0, s));
   cudaError_t e;
-  const bool use_serial = c->serial_ok && c->sk;
-  if (use_serial) {
+  const bool use_serial = c->serial_ok && c->sk && op != OP_TMT;
+  if (op == OP_TMT) {
+    e = rkb_generic_tmt(ctx->d_prog, c->gp, A, s);
+  } else if (use_serial) {
     e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
   } else if (c->generic_ok) {
     e = op == OP_EVAL ? rkb_generic_eval(ctx->d_prog, c->gp, A, s)
@@ -688,6 +701,38 @@ int rkb_gen_forces(rkb_chain* c, int device, size_t N, const double* x, const do
 
 int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double* M, double* Mdot, unsigned flags, void* stream) {
   return run_eval_like(c, OP_MASS, device, N, x, nullptr, M, Mdot, nullptr, flags, stream);
+}
+
+int rkb_twist_shaping_rows(const rkb_chain* c) { return c ? tmt_rows(c->desc) : RKB_ERR_INVALID; }
+
+/* Mcm of get_TMT_TdMT (mass_matrix_calculator.cpp:265-285): block diagonal, the masses and the tensors */
+int rkb_twist_shaping_mcm(const rkb_chain* c, double* Mcm) {
+  if (!c || !Mcm) return RKB_ERR_INVALID;
+  const int rows = tmt_rows(c->desc);
+  std::memset(Mcm, 0, sizeof(double) * (size_t)rows * (size_t)rows);
+  int row = 0;
+  for (int pass = 0; pass < 3; ++pass)
+    for (int e = 0; e < c->desc.n_elements; ++e) {
+      const rkb_element& E = c->elements[e];
+      if (pass == 0 && E.kind == RKB_INERTIA_GEN) { Mcm[row * rows + row] = E.p[0]; row += 1; }
+      else if (pass == 1 && E.kind == RKB_INERTIA_2D) {
+        Mcm[row * rows + row] = Mcm[(row + 1) * rows + row + 1] = E.p[0];
+        Mcm[(row + 2) * rows + row + 2] = E.p[1];
+        row += 3;
+      } else if (pass == 2 && E.kind == RKB_INERTIA_3D) {
+        for (int k = 0; k < 3; ++k) Mcm[(row + k) * rows + row + k] = E.p[0];
+        const double* I = &E.p[1];
+        const int r = row + 3;
+        const double t[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) Mcm[(r + a) * rows + r + b] = t[3 * a + b];
+        row += 6;
+      }
+    }
+  return RKB_OK;
+}
+
+int rkb_twist_shaping(rkb_chain* c, int device, size_t N, const double* x, double* Tcm, double* Tcm_dot, unsigned flags, void* stream) {
+  return run_eval_like(c, OP_TMT, device, N, x, nullptr, Tcm, Tcm_dot, nullptr, flags, stream);
 }
 
 }  // extern "C"

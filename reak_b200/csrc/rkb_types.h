@@ -147,7 +147,7 @@ struct EvalArgs {
 struct GenericElement {
   int32_t kind, fa, fb, coord, aux, pad;
   uint32_t upstream;
-  int32_t  row;      // first row of this inertia in the twist-shaping matrix (unused by the kernel)
+  int32_t  row;      // first row of this inertia in the twist-shaping matrix (rkb_twist_shaping)
   double   p[12];    // as rkb_element::p; rigid_link_3D: p[3..6] normalised quaternion
 };
 

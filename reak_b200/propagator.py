@@ -244,6 +244,19 @@ class kte_batch_propagator(object):
                    "rkb_mass_matrix")
         return (M, Md) if with_derivative else M
 
+    def get_twist_shaping(self, x, with_derivative=True):
+        """mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm [N][rows][n], Mcm [rows][rows]
+        (constant) and, with_derivative, Tcm_dot [N][rows][n]."""
+        x, N = self._in(x, self.nx, np.float64)
+        rows = self._lib.rkb_twist_shaping_rows(self._h)
+        T = self._like(x, (N, rows, self.n))
+        Td = self._like(x, (N, rows, self.n)) if with_derivative else None
+        Mc = np.zeros((rows, rows))
+        _abi.check(self._lib.rkb_twist_shaping_mcm(self._h, Mc.ctypes.data_as(C.c_void_p)), "rkb_twist_shaping_mcm")
+        flags, stream, ptr = self._prep([x, T, Td], False)
+        _abi.check(self._lib.rkb_twist_shaping(self._h, self.device, N, ptr(x), ptr(T), ptr(Td), flags, stream), "rkb_twist_shaping")
+        return (T, Mc, Td) if with_derivative else (T, Mc)
+
     def steer_batch(self, x0, goal, u, dt=None, n_steps=10, want_status=False):
         """x0, goal: [P][nx]; u: [P][R][nu].  Returns (best_idx[P], best_x[P][nx], best_cost[P])."""
         x0, P = self._in(x0, self.nx, np.float64)

@@ -616,3 +616,24 @@ def test_non_finite_states_raise_the_status_bit():
         assert s[5] & _abi.STATUS_NONFINITE and s[9] & _abi.STATUS_NONFINITE
         assert not np.delete(s, [5, 9]).any()
     assert np.isfinite(np.delete(xo, [5, 9], axis=0)).all()
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_twist_shaping_matrices(name, oracle_built):
+    """rkb_twist_shaping = mass_matrix_calc::get_TMT_TdMT: Tcm, Mcm, Tcm_dot against the oracle, and
+    M = Tcm^T Mcm Tcm, Mdot = Tcm_dot^T Mcm Tcm + transpose against rkb_mass_matrix (serial kernels where they apply)."""
+    p = _make(name)
+    O = oracle_built.Oracle(p.compiled)
+    x, _ = random_batch(p.compiled, 40, seed=23, q_range=2.0)
+    T, Mc, Td = p.get_twist_shaping(x)
+    for i in (0, 7, 39):
+        To, Mo, Tdo = O.tmt(x[i:i + 1])
+        assert np.array_equal(Mc, Mo)
+        assert rel_err(T[i], To) < TOL_STEP and rel_err(Td[i], Tdo) < TOL_STEP, (name, i)
+    M, Md = p.get_mass_matrices(x, with_derivative=True)
+    MT = np.einsum("rs,nsc->nrc", Mc, T)
+    M2 = np.einsum("nra,nrb->nab", T, MT)
+    S = np.einsum("nra,nrb->nab", Td, MT)
+    assert rel_err(M, 0.5 * (M2 + M2.transpose(0, 2, 1))) < TOL_STEP and rel_err(Md, S + S.transpose(0, 2, 1)) < TOL_STEP
+    only_T, _ = p.get_twist_shaping(x, with_derivative=False)
+    assert np.array_equal(only_T, T)
