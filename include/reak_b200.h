@@ -18,6 +18,7 @@
  *   rkb_mass_matrix       <- mass_matrix_calc::getMassMatrix / getMassMatrixAndDerivative
  *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
  *   rkb_twist_shaping     <- mass_matrix_calc::get_TMT_TdMT             (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287)
+ *   rkb_frames            <- kte_map_chain::doMotion / doForce as seen on the frames (frame_3D / frame_2D members)
  *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
  *   rkb_steer_batch       <- the inner loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561),
  *                            many (start, goal, control) tuples per call
@@ -223,6 +224,20 @@ RKB_API int rkb_gen_forces(rkb_chain* chain, int device, size_t n_samples,
 RKB_API int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
                     const double* x, double* M, double* Mdot,
                     unsigned flags, void* stream);
+
+/* Every frame of the chain after doMotion / clearForce / doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89) at
+ * state x[i], input u[i], q_ddot = 0 — the direct kinematics (poses, velocities, accelerations) a collision
+ * check or a measurement model reads, and the wrenches the elements left on the frames.  25 doubles per frame:
+ *   frame_3D  Position 0-2, Quat (w,x,y,z) 3-6, Velocity 7-9, AngVelocity 10-12, Acceleration 13-15,
+ *             AngAcceleration 16-18, Force 19-21, Torque 22-24   (conventions of frame_3D.hpp:69-78)
+ *   frame_2D  Position 0-1, Rotation (cos, sin) 3-4, Velocity 7-8, AngVelocity 10, Acceleration 13-14,
+ *             AngAcceleration 16, Force 19-20, Torque 22; the other slots are zero
+ * frames: AOS [N][n_frames][25], SOA [n_frames * 25][N].  Interpreter kernels (the serial kernels work in
+ * link-local coordinates and never build these frames). */
+#define RKB_FRAME_DOUBLES 25
+RKB_API int rkb_chain_frame_count(const rkb_chain* chain);
+RKB_API int rkb_frames(rkb_chain* chain, int device, size_t n_samples,
+                       const double* x, const double* u, double* frames, unsigned flags, void* stream);
 
 /* Twist-shaping matrix Tcm and its time derivative Tcm_dot of mass_matrix_calc::get_TMT_TdMT
  * (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287) at state x[i].  Rows: one per inertia_gen, then three per

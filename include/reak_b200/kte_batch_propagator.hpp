@@ -250,6 +250,11 @@ class kte_batch_propagator {
   void get_mass_matrices(std::size_t n, const double* x, double* M, double* Mdot = NULL, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_mass_matrix(mChain, mDevice, n, x, M, Mdot, flags, stream), "rkb_mass_matrix");
   }
+  /// Every frame after doMotion / clearForce / doForce: [n][frame_count()][RKB_FRAME_DOUBLES], layout in reak_b200.h.
+  int frame_count() const { return rkb_chain_frame_count(mChain); }
+  void get_frames(std::size_t n, const double* x, const double* u, double* frames, unsigned flags = 0, void* stream = NULL) const {
+    check(rkb_frames(mChain, mDevice, n, x, u, frames, flags, stream), "rkb_frames");
+  }
   /// mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm and (nullable) Tcm_dot, [n][rows][dof];
   /// twist_shaping_rows() and twist_shaping_mcm(Mcm) give the row count and the constant rows x rows Mcm.
   int twist_shaping_rows() const { return rkb_twist_shaping_rows(mChain); }

@@ -42,6 +42,8 @@
 #pragma weak rkb_eval
 #pragma weak rkb_gen_forces
 #pragma weak rkb_mass_matrix
+#pragma weak rkb_frames
+#pragma weak rkb_chain_frame_count
 #pragma weak rkb_twist_shaping
 #pragma weak rkb_twist_shaping_rows
 #pragma weak rkb_twist_shaping_mcm

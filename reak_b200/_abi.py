@@ -90,6 +90,8 @@ SYMBOLS = {
                                  C.c_uint, C.c_void_p]),
     "rkb_mass_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_uint, C.c_void_p]),
+    "rkb_chain_frame_count": (C.c_int, [C.c_void_p]),
+    "rkb_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_twist_shaping_rows": (C.c_int, [C.c_void_p]),
     "rkb_twist_shaping_mcm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rkb_twist_shaping": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),

@@ -699,6 +699,27 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
     }
 }
 
+GD void put_frame(const Fr3& F, const BatchView& o, long long base) {
+  const double v[25] = {F.p.x, F.p.y, F.p.z, F.q.w, F.q.x, F.q.y, F.q.z, F.v.x, F.v.y, F.v.z, F.w.x, F.w.y, F.w.z,
+                        F.a.x, F.a.y, F.a.z, F.al.x, F.al.y, F.al.z, F.F.x, F.F.y, F.F.z, F.T.x, F.T.y, F.T.z};
+  for (int k = 0; k < 25; ++k) o.p[base + k * o.sk] = v[k];
+}
+GD void put_frame(const Fr2& F, const BatchView& o, long long base) {
+  const double v[25] = {F.p.x, F.p.y, 0, F.R.c, F.R.s, 0, 0, F.v.x, F.v.y, 0, F.w, 0, 0, F.a.x, F.a.y, 0, F.al, 0, 0, F.F.x, F.F.y, 0, F.T, 0, 0};
+  for (int k = 0; k < 25; ++k) o.p[base + k * o.sk] = v[k];
+}
+
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_frames_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, true);
+  motion(G, W);
+  force(G, W);
+  for (int f = 0; f < G->n_frames; ++f) put_frame(W.fr[f], A.out, i * A.out.si + (long long)(25 * f) * A.out.sk);
+}
+
 template <int DIM, int MAXF>
 __global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
@@ -863,6 +884,12 @@ cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& h
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   DISPATCH(generic_mass_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_frames_kernel, host, prog, a);
   return cudaGetLastError();
 }
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {

@@ -535,7 +535,7 @@ int unstage_out(void* dev, void* dst, size_t bytes, bool on_device, cudaStream_t
   return 0;
 }
 
-enum Op { OP_EVAL, OP_FORCES, OP_MASS, OP_TMT };
+enum Op { OP_EVAL, OP_FORCES, OP_MASS, OP_TMT, OP_FRAMES };
 
 int tmt_rows(const rkb_chain_desc& d) {
   int rows = 0;
@@ -551,10 +551,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   if (!c) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
   if (!x || !out || (c->nu > 0 && !u && op != OP_MASS && op != OP_TMT)) return RKB_ERR_INVALID;
-  if (op == OP_TMT && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  if ((op == OP_TMT || op == OP_FRAMES) && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
   const Layout L = parse_flags(flags);
   const int n = c->n, nx = 2 * n, nu = c->nu;
-  const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : op == OP_MASS ? n * n : tmt_rows(c->desc) * n;
+  const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : op == OP_MASS ? n * n : op == OP_TMT ? tmt_rows(c->desc) * n
+                                                                                           : RKB_FRAME_DOUBLES * c->desc.n_frames;
   if (out_dim == 0) return RKB_OK;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
@@ -579,9 +580,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   A.n_samples = (long long)N;
   CU(cudaEventRecord(ctx->ev0, s));
   cudaError_t e;
-  const bool use_serial = c->serial_ok && c->sk && op != OP_TMT;
+  const bool use_serial = c->serial_ok && c->sk && op != OP_TMT && op != OP_FRAMES;
   if (op == OP_TMT) {
     e = rkb_generic_tmt(ctx->d_prog, c->gp, A, s);
+  } else if (op == OP_FRAMES) {
+    e = rkb_generic_frames(ctx->d_prog, c->gp, A, s);
   } else if (use_serial) {
     e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
   } else if (c->generic_ok) {
@@ -701,6 +704,12 @@ int rkb_gen_forces(rkb_chain* c, int device, size_t N, const double* x, const do
 
 int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double* M, double* Mdot, unsigned flags, void* stream) {
   return run_eval_like(c, OP_MASS, device, N, x, nullptr, M, Mdot, nullptr, flags, stream);
+}
+
+int rkb_chain_frame_count(const rkb_chain* c) { return c ? c->desc.n_frames : RKB_ERR_INVALID; }
+
+int rkb_frames(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* frames, unsigned flags, void* stream) {
+  return run_eval_like(c, OP_FRAMES, device, N, x, u, frames, nullptr, nullptr, flags, stream);
 }
 
 int rkb_twist_shaping_rows(const rkb_chain* c) { return c ? tmt_rows(c->desc) : RKB_ERR_INVALID; }

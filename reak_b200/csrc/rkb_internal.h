@@ -27,6 +27,7 @@ RKB_DECL_TABLE(5); RKB_DECL_TABLE(6); RKB_DECL_TABLE(7); RKB_DECL_TABLE(8);
 // generic interpreter (kte_generic.cu); `prog` is a device pointer to a GenericProgram
 cudaError_t rkb_generic_eval(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
+cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,

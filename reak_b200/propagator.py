@@ -244,6 +244,16 @@ class kte_batch_propagator(object):
                    "rkb_mass_matrix")
         return (M, Md) if with_derivative else M
 
+    def get_frames(self, x, u=None):
+        """Every frame after doMotion / clearForce / doForce: [N][n_frames][25] (layout in include/reak_b200.h)."""
+        x, N = self._in(x, self.nx, np.float64)
+        u = self._u_default(x, N, False) if u is None else self._in(u, self.nu, np.float64, False, N)[0]
+        nf = self._lib.rkb_chain_frame_count(self._h)
+        fr = self._like(x, (N, nf, 25))
+        flags, stream, ptr = self._prep([x, u if self.nu else None, fr], False)
+        _abi.check(self._lib.rkb_frames(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None, ptr(fr), flags, stream), "rkb_frames")
+        return fr
+
     def get_twist_shaping(self, x, with_derivative=True):
         """mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm [N][rows][n], Mcm [rows][rows]
         (constant) and, with_derivative, Tcm_dot [N][rows][n]."""

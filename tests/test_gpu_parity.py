@@ -637,3 +637,16 @@ def test_twist_shaping_matrices(name, oracle_built):
     assert rel_err(M, 0.5 * (M2 + M2.transpose(0, 2, 1))) < TOL_STEP and rel_err(Md, S + S.transpose(0, 2, 1)) < TOL_STEP
     only_T, _ = p.get_twist_shaping(x, with_derivative=False)
     assert np.array_equal(only_T, T)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_frames_after_motion_and_force(name, oracle_built):
+    """rkb_frames: kinematics and wrenches of every frame after doMotion / clearForce / doForce, against the oracle
+    (which matches the live reference frame by frame, tests/test_oracle.py)."""
+    p = _make(name)
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 33, seed=27, q_range=2.0)
+    fr = p.get_frames(x, u)
+    assert fr.shape == (33, p.compiled.desc.n_frames, 25)
+    for i in (0, 16, 32):
+        assert rel_err(fr[i], O.frames(x[i:i + 1], u[i:i + 1])) < TOL_STEP, (name, i)
