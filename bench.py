@@ -182,7 +182,8 @@ def run_reference(args):
 
 def other_configs(torch, presets, kte_batch_propagator, local, world):
     """BASELINE configs 3-5 on this rank's shard (device-resident buffers, kernel time from CUDA events on
-    the launch stream, best of 3).  Parity of these paths is the job of tests/test_gpu_parity.py."""
+    the launch stream, best of 3; run_ours takes the maximum over ranks).  Parity of these paths is the job
+    of tests/test_gpu_parity.py."""
     rng = np.random.default_rng(777)
     out = []
 
@@ -205,7 +206,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world):
     t_mass = best(lambda: p3.get_mass_matrices(o3, with_derivative=True), p3)
     out.append({"config": 3, "workload": "6-DOF + torsion springs/dampers: %d states x %d RK4 steps per GPU, then M and Mdot" % (n3, RK4_STEPS),
                 "rollout_ms": t_roll, "mass_and_derivative_ms": t_mass, "serial_kernels": bool(p3.is_serial()),
-                "state_steps_per_s": world * n3 * RK4_STEPS / ((t_roll + t_mass) * 1e-3)})
+                "units_per_gpu": n3 * RK4_STEPS})
     del x3, u3, o3, s3
     # cfg 4: 7-DOF with prismatic track, 10 RK4 steps per extension (2^26 / 8 per GPU)
     p4 = kte_batch_propagator(presets.make("crs7"), device=local)
@@ -216,7 +217,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world):
     s4 = torch.empty((n4,), dtype=torch.int32, device=x4.device)
     t4 = best(lambda: p4.get_next_states(x4, u4, DT, 10, out=o4, status=s4), p4)
     out.append({"config": 4, "workload": "7-DOF with prismatic track: %d RRT extensions x 10 RK4 steps per GPU" % n4, "rollout_ms": t4,
-                "serial_kernels": bool(p4.is_serial()), "state_steps_per_s": world * n4 * 10 / (t4 * 1e-3)})
+                "serial_kernels": bool(p4.is_serial()), "units_per_gpu": n4 * 10})
     del x4, u4, o4, s4
     # cfg 5: steer batch, 4096 pairs x 256 controls x 100 steps over all GPUs, pairs sharded
     p5 = kte_batch_propagator(presets.make(PRESET), device=local)
@@ -226,7 +227,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world):
     uu = torch.from_numpy(rng.uniform(-5, 5, (P, R, p5.nu))).cuda(local)
     t5 = best(lambda: p5.steer_batch(x0, goal, uu, DT, RK4_STEPS), p5)
     out.append({"config": 5, "workload": "steer batch: %d pairs x %d controls x %d RK4 steps per GPU, arg-min per pair" % (P, R, RK4_STEPS),
-                "steer_ms": t5, "state_steps_per_s": world * P * R * RK4_STEPS / (t5 * 1e-3)})
+                "steer_ms": t5, "units_per_gpu": P * R * RK4_STEPS})
     return out
 
 
@@ -336,6 +337,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gather_ms = float(t.item())
 
+    # ---- the other BASELINE configs: every rank measures its shard, the slowest rank counts ----------
+    others = None
+    if not args.no_other_configs:
+        others = other_configs(torch, presets, kte_batch_propagator, local, world)
+        keys = [(i, k) for i, o in enumerate(others) for k in sorted(o) if k.endswith("_ms")]
+        t = torch.tensor([others[i][k] for i, k in keys], dtype=torch.float64, device=dx.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for (i, k), v in zip(keys, t.tolist()):
+            others[i][k] = v
+        for o in others:
+            o["state_steps_per_s"] = world * o.pop("units_per_gpu") / (sum(v for k, v in o.items() if k.endswith("_ms")) * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -381,11 +395,6 @@ def run_ours(args):
                "sample": "first %d of the %d samples x %d RK4 steps, %d forked workers" % (m, n, RK4_STEPS, cores),
                "max_rel_err_vs_gpu": err, "tolerance": 1e-8}
         assert err < 1e-8, "GPU result disagrees with the reference on the CPU sample: %g" % err
-
-    # ---- the other BASELINE configs, one short device-resident measurement each (this rank's share) ----
-    others = None
-    if not args.no_other_configs:
-        others = other_configs(torch, presets, kte_batch_propagator, local, world)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
