@@ -144,3 +144,25 @@ def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
         pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
     r = subprocess.run([exe], env=env, capture_output=True, text=True)
     assert r.returncode == 1 and "-> -4" in r.stderr, (r.returncode, r.stdout, r.stderr)
+
+
+def _build_cpp_demo(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "cpp_host_demo")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cpp_host_demo.cpp"), "-L" + os.path.dirname(_abi.LIB_PATH), "-lreak_b200",
+                           "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_abi.LIB_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return exe, env
+
+
+def test_cpp_host_class_is_standalone_cxx11(tmp_path):
+    """include/reak_b200/kte_batch_propagator.hpp needs neither ReaK nor Boost nor CUDA headers: C++11, -pedantic -Werror.
+    Without a GPU the propagator raises propagator_error (RKB_ERR_CUDA)."""
+    import subprocess
+    import torch
+    exe, env = _build_cpp_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)

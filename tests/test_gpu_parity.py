@@ -650,3 +650,30 @@ def test_frames_after_motion_and_force(name, oracle_built):
     assert fr.shape == (33, p.compiled.desc.n_frames, 25)
     for i in (0, 16, 32):
         assert rel_err(fr[i], O.frames(x[i:i + 1], u[i:i + 1])) < TOL_STEP, (name, i)
+
+
+def test_cpp_host_class_builds_the_same_chain(tmp_path):
+    """examples/cpp_host_demo.cpp assembles the 6-DOF CRS arm with reak_b200::chain_builder and runs it through
+    kte_batch_propagator (C++11, no ReaK); the Python mirror of the same model must give the same bits."""
+    import subprocess
+    from test_abi import _build_cpp_demo
+    exe, env = _build_cpp_demo(tmp_path)
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    lines = r.stdout.split("\n")
+    vals = np.array([[float(t) for t in l.split()] for l in lines if l and not l.startswith("M")])
+    Mrow = np.array([float(l.split()[1]) for l in lines if l.startswith("M")])
+    N = 64
+    s = 88172645463325252
+    raw = []
+    for _ in range(N * 18):
+        s ^= (s << 13) & 0xFFFFFFFFFFFFFFFF
+        s ^= s >> 7
+        s ^= (s << 17) & 0xFFFFFFFFFFFFFFFF
+        raw.append((s >> 11) / 9007199254740992.0 * 2.0 - 1.0)
+    x, u = np.array(raw[:N * 12]).reshape(N, 12), np.array(raw[N * 12:]).reshape(N, 6)
+    p = _make("crs6")
+    xd, _ = p.get_state_derivatives(x, u)
+    xo, _ = p.get_next_states(x, u, 1e-3, 25)
+    assert np.array_equal(vals[:, 0].reshape(N, 12), xd) and np.array_equal(vals[:, 1].reshape(N, 12), xo)
+    assert np.array_equal(Mrow.reshape(6, 6), p.get_mass_matrices(x[:1])[0])
