@@ -677,3 +677,37 @@ def test_cpp_host_class_builds_the_same_chain(tmp_path):
     xo, _ = p.get_next_states(x, u, 1e-3, 25)
     assert np.array_equal(vals[:, 0].reshape(N, 12), xd) and np.array_equal(vals[:, 1].reshape(N, 12), xo)
     assert np.array_equal(Mrow.reshape(6, 6), p.get_mass_matrices(x[:1])[0])
+
+
+def test_streams_and_threads():
+    """Device buffers run on the caller's CUDA stream; one handle may be shared by threads (its calls are
+    serialised), two handles run concurrently.  Everything must reproduce the default-stream result."""
+    import threading
+    import torch
+    p, p2 = _make("crs6"), _make("crs6")
+    x, u = random_batch(p.compiled, 20000, seed=81)
+    ref, _ = p.get_next_states(x, u, 1e-3, 8)
+    xt, ut = torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        a, _ = p.get_next_states(xt, ut, 1e-3, 4)
+        b, _ = p.get_next_states(a, ut, 1e-3, 4)      # ordered after `a` on the same stream
+    side.synchronize()
+    assert np.array_equal(b.cpu().numpy(), ref)
+    results, errors = {}, []
+
+    def work(tag, prop, lo, hi):
+        try:
+            for _ in range(5):
+                results[tag] = prop.get_next_states(x[lo:hi], u[lo:hi], 1e-3, 8)[0]
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=("s0", p, 0, 10000)), threading.Thread(target=work, args=("s1", p, 10000, 20000)),
+               threading.Thread(target=work, args=("o0", p2, 0, 20000))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    assert np.array_equal(np.concatenate([results["s0"], results["s1"]]), ref) and np.array_equal(results["o0"], ref)
