@@ -1007,31 +1007,16 @@ RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long of
   }
 }
 
-// n_steps of fixed-step RK4 (runge_kutta4_integrator<T>::integrate, fixed_step_integrators.hpp:256-293)
-// with the input held constant (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
-// Per-thread shared-memory column: w (2N) and k1 + 2 k2 (2N).
-template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
-  extern __shared__ double smem[];
-  constexpr int SMS = RKB_BLOCK;
-  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
-  if (i >= A.n_samples) return;
-  if (A.active && !A.active[i]) return;
-  double* sm = smem + threadIdx.x;
+// n_steps RK4 steps of size dt on the state in X with the inputs X.u held; returns the status bits.
+// sm is this thread's shared-memory column: w (2N), k1 + 2 k2 (2N), cos / sin at the start of the step (2N).
+template <int N, int FL, shape_t SHAPE, int SMS>
+RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n_steps, double* sm) {
   double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
   double* sb = sa + 2 * N * SMS;    // cos, sin of the joint angles at the start of the step
-  SerialState<N> X;
-  {
-    const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
-    ConstBatchView xv = A.x0;
-    xv.p += i0 * xv.si - i * xv.si;  // rows of x0 are shared by x0_div consecutive samples (steer batch)
-    load_state<N>(P, xv, A.u, i, X);
-  }
-  const double dt = A.dt;
   const double sixth = 1.0 / 6.0;
   int st = 0;
-  const int total = 4 * A.n_steps;
+  const int total = 4 * n_steps;
 #pragma unroll 1
   for (int it = 0; it < total; ++it) {
     const int stage = it & 3;
@@ -1097,6 +1082,28 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
       }
     }
   }
+  return st;
+}
+
+// n_steps of fixed-step RK4 (runge_kutta4_integrator<T>::integrate, fixed_step_integrators.hpp:256-293)
+// with the input held constant (num_int_dtnl_sys::get_next_state, num_int_dtnl_system.hpp:166-180).
+// Per-thread shared-memory column: w (2N) and k1 + 2 k2 (2N).
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_rollout_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  if (A.active && !A.active[i]) return;
+  double* sm = smem + threadIdx.x;
+  SerialState<N> X;
+  {
+    const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
+    ConstBatchView xv = A.x0;
+    xv.p += i0 * xv.si - i * xv.si;  // rows of x0 are shared by x0_div consecutive samples (steer batch)
+    load_state<N>(P, xv, A.u, i, X);
+  }
+  int st = rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, sm);
   bool finite = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
@@ -1104,6 +1111,128 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
   if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si, X);
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
+}
+
+// The closed-loop steering loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) /
+// IHAQR_topology::move_position_toward_impl (examples/misc/IHAQR_topology.hpp:349-378) in ONE launch: per
+// control interval the goal-proximity test, the state feedback u = u_bias - G (x - x_goal) through
+// get_bounded_input (IHAQR_topology.hpp:304-327, see rkb_steer.cu for the same law as a separate pass), then
+// `substeps` RK4 steps with that input.  A sample whose loop has ended leaves; its warp carries on.
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_steer_kernel(const __grid_constant__ SerialParams P, const __grid_constant__ SteerArgs A) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  constexpr int NX = 2 * N;
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  double* sm = smem + threadIdx.x;
+  const int nu = A.nu;
+  SerialState<N> X;
+  {
+    const ConstBatchView xv = {A.x0, NX, 1, A.blocked};
+    const ConstBatchView uv = {A.x0, 1, 1, 0};
+    load_state<N>(P, xv, uv, i, X);  // (X.u is set by the law below)
+  }
+  const double T = A.time_step;
+  // the input applied last, per stage (stages without a driving actuator carry 0 and are skipped)
+  double up[N];
+  bool act[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    const int in = P.st[s].input;
+    act[s] = in >= 0 && in < nu;
+    up[s] = act[s] ? A.u_prev[i * nu + in] : 0.0;
+  }
+  int st = 0, k = 0;
+#pragma unroll 1
+  for (; k < A.max_intervals; ++k) {
+    // ---- the law: x - x_goal, distance, correction -G (x - x_goal), get_bounded_input ----------------------
+    double dx[NX];
+    double d2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      const int c = P.st[s].coord;
+      const double dq = X.q[s] - A.goal[i * NX + rkb_state_q(A.blocked, N, c)];
+      const double dd = X.qd[s] - A.goal[i * NX + rkb_state_qd(A.blocked, N, c)];
+      dx[2 * s] = dq; dx[2 * s + 1] = dd;
+      d2 = fma(dq, dq, d2); d2 = fma(dd, dd, d2);
+    }
+    if (!(sqrt(d2) > A.proximity)) break;  // MEAQR_topology.hpp:513-514
+    double bias[N], corr[N], cur[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      bias[s] = corr[s] = cur[s] = 0.0;
+      if (!act[s]) continue;
+      const int in = P.st[s].input;
+      const double* G = A.gain + (i * nu + in) * NX;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < N; ++t) {
+        const int c = P.st[t].coord;
+        acc = fma(G[rkb_state_q(A.blocked, N, c)], dx[2 * t], acc);
+        acc = fma(G[rkb_state_qd(A.blocked, N, c)], dx[2 * t + 1], acc);
+      }
+      corr[s] = -acc;
+      bias[s] = A.u_bias[i * nu + in];
+    }
+    if (k == 0 && !A.saturate_first) {  // MEAQR_topology.hpp:521-522: the first interval is not saturated
+#pragma unroll
+      for (int s = 0; s < N; ++s) if (act[s]) up[s] = bias[s] + corr[s];
+    } else {                            // IHAQR_topology.hpp:304-327
+      bool inside = true;
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        if (!act[s]) continue;
+        const int in = P.st[s].input;
+        if (A.have_u_box) { if (bias[s] < A.u_lo[in]) bias[s] = A.u_lo[in]; else if (bias[s] > A.u_hi[in]) bias[s] = A.u_hi[in]; }
+        cur[s] = bias[s] + corr[s];
+        if (A.have_u_box && ((cur[s] < A.u_lo[in]) || (cur[s] > A.u_hi[in]))) inside = false;
+      }
+      if (!inside) {
+#pragma unroll 1
+        for (int j = 0; j < 10; ++j) {
+          bool ok = true;
+#pragma unroll
+          for (int s = 0; s < N; ++s) {
+            if (!act[s]) continue;
+            const int in = P.st[s].input;
+            corr[s] *= 0.5; cur[s] -= corr[s];
+            if ((cur[s] < A.u_lo[in]) || (cur[s] > A.u_hi[in])) ok = false;
+          }
+          if (ok) {
+#pragma unroll
+            for (int s = 0; s < N; ++s) { bias[s] = cur[s]; cur[s] += corr[s]; }
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        if (!act[s]) continue;
+        const int in = P.st[s].input;
+        double du = ((inside ? cur[s] : bias[s]) - up[s]) * (1.0 / T);
+        if (A.have_du_box) { if (du < A.du_lo[in]) du = A.du_lo[in]; else if (du > A.du_hi[in]) du = A.du_hi[in]; }
+        up[s] = up[s] + T * du;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < N; ++s) X.u[s] = up[s];
+    // ---- one control interval -----------------------------------------------------------------------------
+    st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.substeps, sm);
+    if (A.traj) {
+      const BatchView tv = {A.traj + (long long)k * NX, (long long)NX * A.max_intervals, 1, A.blocked};
+      store_state<N>(P, tv, i * tv.si, X);
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int s = 0; s < N; ++s) finite = finite && isfinite(X.q[s]) && isfinite(X.qd[s]);
+  const BatchView ov = {A.xout, NX, 1, A.blocked};
+  store_state<N>(P, ov, i * NX, X);
+#pragma unroll
+  for (int s = 0; s < N; ++s) if (act[s]) A.u_prev[i * nu + P.st[s].input] = up[s];  // u_prev = u_current (MEAQR_topology.hpp:553)
+  A.n_done[i] = k;
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
 }
 
 // Any explicit one-step scheme given as an RkTable (Euler, midpoint, RK5 — and RK4, which the kernel

@@ -1116,6 +1116,25 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
   dst = (L.device && status) ? (void*)status : ctx->st.p;
   if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
   CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
+  const bool fused = c->serial_ok && c->sk && !(std::getenv("RKB_STEER_UNFUSED") && std::getenv("RKB_STEER_UNFUSED")[0] == '1');
+  if (fused) {
+    // serial chains: the whole loop in one launch
+    SteerArgs F;
+    F.x0 = (const double*)dx0; F.goal = (const double*)dgoal; F.u_bias = (const double*)dbias; F.gain = (const double*)dgain;
+    F.u_prev = (double*)dup_in; F.xout = (double*)dxo; F.traj = (double*)dtraj; F.n_done = (int32_t*)dnd;
+    F.status = (int32_t*)dst;
+    F.n_samples = (long long)N; F.nu = nu; F.max_intervals = J; F.substeps = o->substeps; F.saturate_first = o->saturate_first ? 1 : 0;
+    F.have_u_box = o->u_lower ? 1 : 0; F.have_du_box = o->du_lower ? 1 : 0; F.blocked = L.blocked ? 1 : 0; F.pad = 0;
+    F.time_step = o->time_step; F.dt = o->dt; F.proximity = o->goal_proximity;
+    for (int r = 0; r < RKB_MAX_COORDS; ++r) {
+      F.u_lo[r] = (o->u_lower && r < nu) ? o->u_lower[r] : 0.0; F.u_hi[r] = (o->u_upper && r < nu) ? o->u_upper[r] : 0.0;
+      F.du_lo[r] = (o->du_lower && r < nu) ? o->du_lower[r] : 0.0; F.du_hi[r] = (o->du_upper && r < nu) ? o->du_upper[r] : 0.0;
+    }
+    CU(cudaEventRecord(ctx->ev0, s));
+    cudaError_t e = c->sk->steer(c->sp, F, s);
+    if (e != cudaSuccess) return cuda_fail(e, "steer kernel");
+    c->launches += 1;
+  } else {
   SteerLawArgs W;
   W.x0 = (const double*)dx0; W.x = (double*)dxo; W.goal = (const double*)dgoal;
   W.u_bias = (const double*)dbias; W.gain = (const double*)dgain;
@@ -1151,6 +1170,7 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
     A.status_or = 1;
     A.active = (const int32_t*)ctx->act.p;
     if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
+  }
   }
   CU(cudaEventRecord(ctx->ev1, s));
   ctx->timed = true;

@@ -17,6 +17,7 @@ struct SerialKernels {
   cudaError_t (*mass)(const SerialParams&, const EvalArgs&, cudaStream_t);
   cudaError_t (*rollout)(const SerialParams&, const RolloutArgs&, cudaStream_t);                     // RK4
   cudaError_t (*rollout_rk)(const SerialParams&, const RolloutArgs&, const RkTable&, cudaStream_t);  // any explicit scheme
+  cudaError_t (*steer)(const SerialParams&, const SteerArgs&, cudaStream_t);                         // the whole steering loop
 };
 
 // defined in rkb_serial_n.cu, compiled once per N with -DRKB_N=<n>

@@ -23,6 +23,8 @@ struct Launch {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_rollout_rk_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rk(RKB_RK_MAX_STAGES));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(serial_steer_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_eval_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_forces_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemForces);
@@ -57,10 +59,15 @@ struct Launch {
     serial_rollout_rk_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, smem_rk(T.stages), s>>>(P, A, T);
     return cudaGetLastError();
   }
+  static cudaError_t steer(const SerialParams& P, const SteerArgs& A, cudaStream_t s) {
+    if (A.n_samples <= 0) return cudaSuccess;
+    serial_steer_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
+    return cudaGetLastError();
+  }
   static SerialKernels entry() {
     SerialKernels k;
     k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
-    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk;
+    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk; k.steer = &steer;
     return k;
   }
 };

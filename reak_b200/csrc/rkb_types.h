@@ -116,6 +116,23 @@ struct RolloutArgs {
   const int32_t* active;     // nullable: samples with active[i] == 0 are left untouched (closed-loop steering)
 };
 
+// The whole steering loop in one launch (serial kernels), all buffers device-resident AoS
+struct SteerArgs {
+  const double* x0;      // [N][nx]
+  const double* goal;    // [N][nx]
+  const double* u_bias;  // [N][nu]
+  const double* gain;    // [N][nu][nx]
+  double*       u_prev;  // [N][nu] in / out
+  double*       xout;    // [N][nx]
+  double*       traj;    // nullable, [N][max_intervals][nx]
+  int32_t*      n_done;  // [N]
+  int32_t*      status;  // nullable
+  long long     n_samples;
+  int32_t       nu, max_intervals, substeps, saturate_first, have_u_box, have_du_box, blocked, pad;
+  double        time_step, dt, proximity;
+  double        u_lo[RKB_MAX_COORDS], u_hi[RKB_MAX_COORDS], du_lo[RKB_MAX_COORDS], du_hi[RKB_MAX_COORDS];
+};
+
 // One pass of the steering loop head (rkb_steer.cu), all buffers device-resident AoS
 struct SteerLawArgs {
   const double* x0;      // [N][nx] start states (read at interval 0)

@@ -711,3 +711,23 @@ def test_streams_and_threads():
         t.join()
     assert not errors
     assert np.array_equal(np.concatenate([results["s0"], results["s1"]]), ref) and np.array_equal(results["o0"], ref)
+
+
+def test_steer_feedback_fused_kernel_equals_the_launch_per_interval_path():
+    """Serial chains run the whole steering loop in one launch; RKB_STEER_UNFUSED=1 selects the law-kernel +
+    rollout-per-interval path the interpreter chains use.  Same decisions, results within rounding."""
+    p = _make("crs6_sd")
+    x0, goal, u_bias, gain, u_prev = _steer_case(p, 500, seed=91)
+    goal[:5] = x0[:5]                                         # these never start
+    goal[5:60] = x0[5:60] + 0.62 / np.sqrt(p.nx)               # these start just outside the proximity ball
+    kw = dict(bounds=(-2 * np.ones(p.nu), 2 * np.ones(p.nu)), rate_bounds=(-60 * np.ones(p.nu), 60 * np.ones(p.nu)), want_traj=True)
+    a = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 7, 0.6, **kw)
+    os.environ["RKB_STEER_UNFUSED"] = "1"
+    try:
+        b = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 7, 0.6, **kw)
+    finally:
+        os.environ.pop("RKB_STEER_UNFUSED", None)
+    assert np.array_equal(a[2], b[2]) and len(set(a[2].tolist())) > 1
+    assert rel_err(a[0], b[0]) < 1e-12 and rel_err(a[1], b[1]) < 1e-12
+    for i in range(500):
+        assert rel_err(a[3][i, :a[2][i]], b[3][i, :b[2][i]]) < 1e-12
