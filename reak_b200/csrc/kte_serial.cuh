@@ -1113,6 +1113,40 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
   if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }
 
+// A piecewise-constant control sequence in one launch: interval j integrates n_steps RK4 steps with the
+// j-th input of the sample (num_int_dtnl_sys::get_next_state once per interval) and leaves its end state in
+// slot j of the trajectory.  Kept apart from serial_rollout_kernel: the interval loop around the RK4 loop
+// costs that kernel 0.8 % through extra spills.
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_rollout_seq_kernel(const __grid_constant__ SerialParams P, const RolloutSeqArgs A) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  const long long i = (long long)blockIdx.x * RKB_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  double* sm = smem + threadIdx.x;
+  SerialState<N> X;
+  load_state<N>(P, A.x0, A.u, i, X);
+  int st = 0;
+#pragma unroll 1
+  for (int j = 0; j < A.n_intervals; ++j) {
+    if (j > 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int in = P.st[k].input;
+        X.u[k] = (in >= 0) ? A.u.p[i * A.u.si + j * A.u_sj + in * A.u.sk] : 0.0;
+      }
+    }
+    st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, sm);
+    if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si + j * A.traj_sj, X);
+  }
+  bool finite = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+  store_state<N>(P, A.xout, i * A.xout.si, X);
+  if (!finite) st |= RKB_STATUS_NONFINITE;
+  if (A.status) A.status[i] = st;
+}
+
 // The closed-loop steering loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) /
 // IHAQR_topology::move_position_toward_impl (examples/misc/IHAQR_topology.hpp:349-378) in ONE launch: per
 // control interval the goal-proximity test, the state feedback u = u_bias - G (x - x_goal) through

@@ -793,6 +793,16 @@ int make_plan(const rkb_rollout_opts* o, RolloutPlan& pl) {
 //   traj: likewise with traj_sj
 int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long long n, ConstBatchView x0, ConstBatchView u, long long u_sj,
                      BatchView xout, BatchView traj, long long traj_sj, int32_t* status, cudaStream_t s) {
+  if (pl.n_intervals > 1 && !pl.use_table && c->serial_ok && c->sk &&
+      !(std::getenv("RKB_ROLLOUT_UNFUSED") && std::getenv("RKB_ROLLOUT_UNFUSED")[0] == '1')) {
+    RolloutSeqArgs A;  // RK4 on the serial kernels: the whole sequence in one launch
+    A.x0 = x0; A.u = u; A.xout = xout; A.traj = traj; A.status = status;
+    A.n_samples = n; A.u_sj = u_sj; A.traj_sj = traj_sj; A.dt = pl.dt; A.n_steps = pl.n_steps; A.n_intervals = pl.n_intervals;
+    cudaError_t e = c->sk->rollout_seq(c->sp, A, s);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    c->launches += 1;
+    return RKB_OK;
+  }
   for (int j = 0; j < pl.n_intervals; ++j) {
     RolloutArgs A;
     A.x0 = j == 0 ? x0 : ConstBatchView{xout.p, xout.si, xout.sk, xout.blocked};

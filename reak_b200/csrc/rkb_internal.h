@@ -17,6 +17,7 @@ struct SerialKernels {
   cudaError_t (*mass)(const SerialParams&, const EvalArgs&, cudaStream_t);
   cudaError_t (*rollout)(const SerialParams&, const RolloutArgs&, cudaStream_t);                     // RK4
   cudaError_t (*rollout_rk)(const SerialParams&, const RolloutArgs&, const RkTable&, cudaStream_t);  // any explicit scheme
+  cudaError_t (*rollout_seq)(const SerialParams&, const RolloutSeqArgs&, cudaStream_t);              // RK4, control sequence
   cudaError_t (*steer)(const SerialParams&, const SteerArgs&, cudaStream_t);                         // the whole steering loop
 };
 

@@ -23,6 +23,8 @@ struct Launch {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_rollout_rk_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rk(RKB_RK_MAX_STAGES));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(serial_rollout_seq_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_steer_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_eval_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEval);
@@ -59,6 +61,11 @@ struct Launch {
     serial_rollout_rk_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, smem_rk(T.stages), s>>>(P, A, T);
     return cudaGetLastError();
   }
+  static cudaError_t rollout_seq(const SerialParams& P, const RolloutSeqArgs& A, cudaStream_t s) {
+    if (A.n_samples <= 0) return cudaSuccess;
+    serial_rollout_seq_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
+    return cudaGetLastError();
+  }
   static cudaError_t steer(const SerialParams& P, const SteerArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
     serial_steer_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
@@ -67,7 +74,7 @@ struct Launch {
   static SerialKernels entry() {
     SerialKernels k;
     k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
-    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk; k.steer = &steer;
+    k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk; k.rollout_seq = &rollout_seq; k.steer = &steer;
     return k;
   }
 };

@@ -116,6 +116,17 @@ struct RolloutArgs {
   const int32_t* active;     // nullable: samples with active[i] == 0 are left untouched (closed-loop steering)
 };
 
+// A control sequence in one launch (serial kernels, RK4): n_intervals intervals of n_steps steps
+struct RolloutSeqArgs {
+  ConstBatchView x0, u;    // input k of interval j of sample i: u.p[i * u.si + j * u_sj + k * u.sk]
+  BatchView      xout;
+  BatchView      traj;     // nullable; slot j of sample i at traj.p + i * traj.si + j * traj_sj
+  int32_t*       status;   // nullable
+  long long      n_samples, u_sj, traj_sj;
+  double         dt;
+  int32_t        n_steps, n_intervals;
+};
+
 // The whole steering loop in one launch (serial kernels), all buffers device-resident AoS
 struct SteerArgs {
   const double* x0;      // [N][nx]

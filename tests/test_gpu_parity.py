@@ -731,3 +731,18 @@ def test_steer_feedback_fused_kernel_equals_the_launch_per_interval_path():
     assert rel_err(a[0], b[0]) < 1e-12 and rel_err(a[1], b[1]) < 1e-12
     for i in range(500):
         assert rel_err(a[3][i, :a[2][i]], b[3][i, :b[2][i]]) < 1e-12
+
+
+def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
+    """RK4 control sequences on the serial kernels run in one launch; RKB_ROLLOUT_UNFUSED=1 selects one launch
+    per interval (what the other schemes and the interpreter chains use).  Bit-identical."""
+    p = _make("crs7")
+    x, _ = random_batch(p.compiled, 3000, seed=93)
+    u_seq = np.random.default_rng(94).uniform(-2, 2, (3000, 6, p.nu))
+    a = p.rollout(x, u_seq, 1e-3, 5, scheme="rk4", want_traj=True)
+    os.environ["RKB_ROLLOUT_UNFUSED"] = "1"
+    try:
+        b = p.rollout(x, u_seq, 1e-3, 5, scheme="rk4", want_traj=True)
+    finally:
+        os.environ.pop("RKB_ROLLOUT_UNFUSED", None)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
