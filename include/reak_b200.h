@@ -164,6 +164,15 @@ RKB_API int  rkb_chain_is_serial(const rkb_chain* chain);
 RKB_API unsigned long long rkb_chain_shape(const rkb_chain* chain);
 RKB_API unsigned long long rkb_chain_kernel_shape(const rkb_chain* chain);
 
+/* Run-time specialisation.  The library ships the general serial kernels and those specialised for the shapes of
+ * the reference's own models; rkb_chain_specialize compiles the same kernel source for exactly this chain's
+ * structure (NVRTC: a few seconds, cached per structure for the life of the process) and routes every later
+ * launch of this handle to the result — about twice the speed of the general code for a chain with
+ * axis-aligned joints that is not among the shipped shapes.  Results are those of the general code up to rounding.
+ * RKB_ERR_UNSUPPORTED: the chain runs on the interpreter kernels, or libnvrtc.so.12 is not installed. */
+RKB_API int rkb_chain_specialize(rkb_chain* chain, int device);
+RKB_API int rkb_chain_is_specialized(const rkb_chain* chain);
+
 /* xdot[i] = get_state_derivative(x[i], u[i]).  x: N x 2n, u: N x n_inputs, xdot: N x 2n,
  * status: N (nullable).  `stream` is a cudaStream_t (NULL = default stream). */
 RKB_API int rkb_eval(rkb_chain* chain, int device, size_t n_samples,

@@ -182,6 +182,9 @@ class kte_batch_propagator {
   time_difference_type get_time_step() const { return mDt; }
   void set_time_step(time_difference_type dt) { mDt = dt; }
   bool is_serial() const { return rkb_chain_is_serial(mChain) == 1; }
+  /// Compile the kernels for this chain's own structure at run time (NVRTC; a few seconds, cached per structure).
+  void specialize() { check(rkb_chain_specialize(mChain, mDevice), "rkb_chain_specialize"); }
+  bool is_specialized() const { return rkb_chain_is_specialized(mChain) == 1; }
 
   /// kte_nl_system::get_state_derivative (kte_nl_system.hpp:238-346) for one state.
   template <typename StateSpaceType, typename Point, typename Input>

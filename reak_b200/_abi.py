@@ -78,6 +78,8 @@ SYMBOLS = {
     "rkb_chain_is_serial": (C.c_int, [C.c_void_p]),
     "rkb_chain_shape": (C.c_uint64, [C.c_void_p]),
     "rkb_chain_kernel_shape": (C.c_uint64, [C.c_void_p]),
+    "rkb_chain_specialize": (C.c_int, [C.c_void_p, C.c_int]),
+    "rkb_chain_is_specialized": (C.c_int, [C.c_void_p]),
     "rkb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,

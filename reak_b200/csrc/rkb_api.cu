@@ -70,6 +70,7 @@ struct rkb_chain {
   unsigned long long serial_shape = 0;  // structure found in the descriptor (RKB_SHAPE_*)
   SerialParams sp;
   const SerialKernels* sk = nullptr;
+  const JitKernels* jit = nullptr;  // set by rkb_chain_specialize: kernels compiled at run time for this chain's exact shape
   bool generic_ok = false;
   GenericProgram gp;
   std::vector<DeviceCtx*> ctx;  // one per device used
@@ -586,7 +587,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   } else if (op == OP_FRAMES) {
     e = rkb_generic_frames(ctx->d_prog, c->gp, A, s);
   } else if (use_serial) {
-    e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
+    if (c->jit)
+      e = rkb_jit_launch(*c->jit, op == OP_EVAL ? RKB_JIT_EVAL : op == OP_FORCES ? RKB_JIT_FORCES : (A.out2.p ? RKB_JIT_MASSDOT : RKB_JIT_MASS),
+                         c->sp, &A, nullptr, A.n_samples, 0, s);
+    else
+      e = op == OP_EVAL ? c->sk->eval(c->sp, A, s) : op == OP_FORCES ? c->sk->forces(c->sp, A, s) : c->sk->mass(c->sp, A, s);
   } else if (c->generic_ok) {
     e = op == OP_EVAL ? rkb_generic_eval(ctx->d_prog, c->gp, A, s)
         : op == OP_FORCES ? rkb_generic_forces(ctx->d_prog, c->gp, A, s) : rkb_generic_mass(ctx->d_prog, c->gp, A, s);
@@ -609,7 +614,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
 // table == nullptr: the dedicated RK4 kernels (the fast path)
 int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, const RkTable* table, cudaStream_t s) {
   cudaError_t e;
-  if (c->serial_ok && c->sk) e = table ? c->sk->rollout_rk(c->sp, A, *table, s) : c->sk->rollout(c->sp, A, s);
+  if (c->serial_ok && c->jit)
+    e = table ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_RK, c->sp, &A, table, A.n_samples,
+                               (2 * c->n + 2 * c->n * table->stages) * 128 * (int)sizeof(double), s)
+              : rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT, c->sp, &A, nullptr, A.n_samples, 0, s);
+  else if (c->serial_ok && c->sk) e = table ? c->sk->rollout_rk(c->sp, A, *table, s) : c->sk->rollout(c->sp, A, s);
   else if (c->generic_ok) e = rkb_generic_rollout(ctx->d_prog, c->gp, A, table, s);
   else return RKB_ERR_UNSUPPORTED;
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -690,7 +699,27 @@ int rkb_chain_dof(const rkb_chain* c) { return c ? c->n : RKB_ERR_INVALID; }
 /* 1 when the chain runs on the register-resident serial kernels, 0 on the interpreter */
 int rkb_chain_is_serial(const rkb_chain* c) { return c ? (c->serial_ok ? 1 : 0) : RKB_ERR_INVALID; }
 /* structural promises of the kernels picked for this chain (0 = general code) and those the chain would allow */
-unsigned long long rkb_chain_kernel_shape(const rkb_chain* c) { return (c && c->sk) ? c->sk->shape : 0ull; }
+unsigned long long rkb_chain_kernel_shape(const rkb_chain* c) { return !c ? 0ull : c->jit ? c->jit->shape : c->sk ? c->sk->shape : 0ull; }
+
+/* Compile the serial kernels for exactly this chain's structure (NVRTC, a few seconds, cached per shape in the
+ * process) and route the handle's launches to them.  RKB_ERR_UNSUPPORTED: the chain is not serial or
+ * libnvrtc is not installed; RKB_ERR_CUDA: compilation or loading failed (text in rkb_last_cuda_error). */
+int rkb_chain_specialize(rkb_chain* c, int device) {
+  if (!c) return RKB_ERR_INVALID;
+  if (!c->serial_ok || !c->sk) return RKB_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  const JitKernels* J = nullptr;
+  rc = rkb_jit_get(c->n, c->serial_fl, c->serial_shape, &J);
+  if (rc) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "%.250s", rkb_jit_log()); return rc; }
+  c->jit = J;
+  return RKB_OK;
+}
+int rkb_chain_is_specialized(const rkb_chain* c) { return c ? (c->jit ? 1 : 0) : RKB_ERR_INVALID; }
 unsigned long long rkb_chain_shape(const rkb_chain* c) { return c ? c->serial_shape : 0ull; }
 
 int rkb_eval(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* xdot, int32_t* status,
@@ -798,7 +827,7 @@ int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long l
     RolloutSeqArgs A;  // RK4 on the serial kernels: the whole sequence in one launch
     A.x0 = x0; A.u = u; A.xout = xout; A.traj = traj; A.status = status;
     A.n_samples = n; A.u_sj = u_sj; A.traj_sj = traj_sj; A.dt = pl.dt; A.n_steps = pl.n_steps; A.n_intervals = pl.n_intervals;
-    cudaError_t e = c->sk->rollout_seq(c->sp, A, s);
+    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_SEQ, c->sp, &A, nullptr, A.n_samples, 0, s) : c->sk->rollout_seq(c->sp, A, s);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     c->launches += 1;
     return RKB_OK;
@@ -1141,7 +1170,7 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
       F.du_lo[r] = (o->du_lower && r < nu) ? o->du_lower[r] : 0.0; F.du_hi[r] = (o->du_upper && r < nu) ? o->du_upper[r] : 0.0;
     }
     CU(cudaEventRecord(ctx->ev0, s));
-    cudaError_t e = c->sk->steer(c->sp, F, s);
+    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_STEER, c->sp, &F, nullptr, F.n_samples, 0, s) : c->sk->steer(c->sp, F, s);
     if (e != cudaSuccess) return cuda_fail(e, "steer kernel");
     c->launches += 1;
   } else {

@@ -40,6 +40,22 @@ cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram
 cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, const double* xend, const double* goal,
                              int32_t* best_idx, double* best_x, double* best_cost, cudaStream_t s);
 
+// run-time specialised kernels (rkb_jit.cu): the same templates compiled with NVRTC for one (n, fl, shape)
+enum { RKB_JIT_EVAL, RKB_JIT_FORCES, RKB_JIT_MASS, RKB_JIT_MASSDOT, RKB_JIT_ROLLOUT, RKB_JIT_ROLLOUT_RK, RKB_JIT_ROLLOUT_SEQ, RKB_JIT_STEER,
+       RKB_JIT_COUNT };
+struct JitKernels {
+  int n, fl;
+  unsigned long long shape;
+  void* library;                      // cudaLibrary_t
+  const void* kernel[RKB_JIT_COUNT];  // cudaKernel_t, launchable through cudaLaunchKernel
+  int smem[RKB_JIT_COUNT];
+};
+int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out);  // compiles on first use, cached per process
+const char* rkb_jit_log();                                                         // NVRTC log / error text of the calling thread
+// args: the kernel's second parameter (EvalArgs, RolloutArgs, ...); extra: its third (RkTable) or NULL
+cudaError_t rkb_jit_launch(const JitKernels& J, int which, const SerialParams& P, const void* args, const void* extra, long long n_samples,
+                           int smem_override, cudaStream_t s);
+
 // steering law between two control intervals (rkb_steer.cu)
 cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s);
 

@@ -33,11 +33,15 @@ PHYS_INERTIA = [(0.2, 0.15, 0.1), (0.12, 0.2, 0.08), (0.06, 0.09, 0.05), (0.03, 
 
 
 def crs_chain(n_revolute=6, track=False, springs=False, physical=False, actuated=True,
-              stiffness=10.0, damping=0.5, saturation=0.0, link_rotation=False):
+              stiffness=10.0, damping=0.5, saturation=0.0, link_rotation=False, axes=None, link_offsets=None):
     """CRS-A465-style serial arm.  `track` prepends the prismatic x-axis joint (cfg 4);
     `springs` inserts a torsion_spring_3D + torsion_damper_3D across every revolute joint
     (cfg 3); `physical` uses graded masses / anisotropic inertias instead of the preset's
-    unit placeholders; `link_rotation` gives the links a fixed twist (exercises R_o != I)."""
+    unit placeholders; `link_rotation` gives the links a fixed twist (exercises R_o != I); `axes` /
+    `link_offsets` replace the CRS joint axes / link offsets (other arms of the same build, e.g. the ERA
+    and SSRMS geometries of ctrl/kte_models/manip_ERA_arm.cpp:101-227, manip_SSRMS_arm.cpp:105-252)."""
+    axes = list(axes) if axes is not None else CRS_AXES
+    link_offsets = list(link_offsets) if link_offsets is not None else [(0.0, 0.0, z) for z in CRS_LINK_Z]
     s = kte_system("crs")
     base = kte.frame_3D()
     base.Acceleration = [0.0, 0.0, 9.81]
@@ -88,13 +92,21 @@ def crs_chain(n_revolute=6, track=False, springs=False, physical=False, actuated
             mass, tensor = PHYS_MASS[k % 6], (ix, 0.01 * (k + 1), -0.005, iy, 0.002 * (k + 1), iz)
         else:
             mass, tensor = 1.0, (1.0, 0.0, 0.0, 1.0, 0.0, 1.0)
-        stage(idx, "R", CRS_AXES[k % 6], (0.0, 0.0, CRS_LINK_Z[k % 6]), mass, tensor, springs)
+        stage(idx, "R", axes[k % len(axes)], link_offsets[k % len(link_offsets)], mass, tensor, springs)
         idx += 1
     for g in gen_inertias:
         s.mass_calc << g
     for c in s.dofs_gen:
         s.mass_calc << c
     return s
+
+
+# joint axes and link offsets of the reference's ERA and SSRMS arm geometries (kinematic models there;
+# used here with the CRS build of rotors, actuators and link inertias to exercise run-time specialisation)
+ERA_AXES = [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)]
+ERA_LINKS = [(0.0, 0.0, L) for L in (0.35, 0.30, 4.1, 4.1, 0.30, 0.35, 0.2)]
+SSRMS_AXES = [(0.0, 0.0, 1.0), (0.0, -1.0, 0.0), (0.0, 0.0, 1.0), (0.0, 0.0, 1.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0), (0.0, 0.0, 1.0)]
+SSRMS_LINKS = [(0.38, -0.635, 0.0), (0.504, 0.0, 0.38), (6.85, 0.0, 0.504), (6.85, 0.0, 0.504), (0.38, 0.0, 0.0), (0.504, -0.635, 0.0), (0.0, 0.0, 0.38)]
 
 
 def planar_chain(lengths=(0.5, 0.4), masses=(1.0, 0.8), moments=(0.1, 0.05), actuated=False,

@@ -62,6 +62,17 @@ class kte_batch_propagator(object):
         """True when the chain runs on the register-resident serial-chain kernels."""
         return bool(self._lib.rkb_chain_is_serial(self._h))
 
+    def specialize(self):
+        """Compile the serial kernels for exactly this chain's structure (NVRTC) and use them from now on."""
+        _abi.check(self._lib.rkb_chain_specialize(self._h, self.device), "rkb_chain_specialize")
+        return self
+
+    def is_specialized(self):
+        return bool(self._lib.rkb_chain_is_specialized(self._h))
+
+    def kernel_shape(self):
+        return int(self._lib.rkb_chain_kernel_shape(self._h))
+
     # ---- SSSystemConcept / DiscreteSSSConcept (single sample) ---------------------------
     def get_state_dimensions(self):
         return self.nx

@@ -166,3 +166,16 @@ def test_cpp_host_class_is_standalone_cxx11(tmp_path):
         pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
     r = subprocess.run([exe], env=env, capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_specialize_needs_a_gpu_and_a_serial_chain():
+    lib = _abi.load_library()
+    for name, want in (("crs6", _abi.ERR_CUDA), ("planar2_lin_sd", _abi.ERR_UNSUPPORTED)):
+        s = presets.make(name)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        rc, h = _create(c.desc)
+        assert rc == 0 and lib.rkb_chain_is_specialized(h) == 0
+        import torch
+        if not torch.cuda.is_available() or want == _abi.ERR_UNSUPPORTED:
+            assert lib.rkb_chain_specialize(h, 0) == want
+        lib.rkb_chain_destroy(h)

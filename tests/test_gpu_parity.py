@@ -746,3 +746,54 @@ def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
     finally:
         os.environ.pop("RKB_ROLLOUT_UNFUSED", None)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
+
+
+# ---- run-time specialisation (NVRTC) ---------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["era", "ssrms", "crs6_sd"])
+def test_runtime_specialised_kernels(which, oracle_built):
+    """rkb_chain_specialize compiles the serial kernels for the chain's own structure.  The ERA / SSRMS joint
+    layouts are not among the shipped shapes (general code until specialised); every entry point must agree
+    with the oracle before and after, and the two sets of kernels with each other."""
+    from reak_b200 import kte_batch_propagator
+    if which == "era":
+        s = presets.crs_chain(n_revolute=7, axes=presets.ERA_AXES, link_offsets=presets.ERA_LINKS, physical=True, springs=True)
+    elif which == "ssrms":
+        s = presets.crs_chain(n_revolute=7, axes=presets.SSRMS_AXES, link_offsets=presets.SSRMS_LINKS)
+    else:
+        s = presets.make("crs6_sd")
+    p = kte_batch_propagator(s)
+    assert p.is_serial() and not p.is_specialized()
+    if which != "crs6_sd":
+        assert p.kernel_shape() == 0  # general code
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 300, seed=97)
+    u_seq = np.random.default_rng(98).uniform(-1, 1, (300, 3, p.nu))
+
+    def everything():
+        xd, st = p.get_state_derivatives(x, u)
+        f = p.get_gen_forces(x, u)
+        M, Md = p.get_mass_matrices(x, with_derivative=True)
+        M1 = p.get_mass_matrices(x)
+        xo, st2 = p.get_next_states(x, u, 1e-3, 12)
+        xs, tr, _ = p.rollout(x, u_seq, 1e-3, 4, scheme="rk4", want_traj=True)
+        xe, _ = p.rollout(x, u_seq, 1e-3, 4, scheme="rk5")
+        sf = p.steer_feedback(x, x + 0.2, u, np.ones((300, p.nu, p.nx)) * 0.3, 0.5 * u, 1e-2, 1e-3, 5, 3, 0.1,
+                              bounds=(-2 * np.ones(p.nu), 2 * np.ones(p.nu)))
+        assert not st.any() and not st2.any()
+        return [xd, f, M, Md, M1, xo, xs, tr, xe, sf[0], sf[1]]
+
+    before = everything()
+    p.specialize()
+    assert p.is_specialized() and p.kernel_shape() != 0
+    after = everything()
+    for a, b in zip(before, after):
+        assert rel_err(a, b) < 1e-11
+    assert rel_err(after[0], O.eval(x, u)[0]) < TOL_STEP and rel_err(after[1], O.gen_forces(x, u)) < TOL_STEP
+    Mo, Mdo = O.mass(x)
+    assert rel_err(after[2], Mo) < TOL_STEP and rel_err(after[3], Mdo) < TOL_STEP
+    assert rel_err(after[5], O.rk4(x, u, 1e-3, 12)[0]) < TOL_LONG
+    xr, trr, _ = O.rollout(x, u_seq, 4, 1e-3, 4)
+    assert rel_err(after[6], xr) < TOL_STEP and rel_err(after[7], trr) < TOL_STEP
+    # a second handle of the same structure reuses the compiled kernels
+    p2 = kte_batch_propagator(s).specialize()
+    assert np.array_equal(p2.get_next_states(x, u, 1e-3, 12)[0], after[5])
