@@ -489,6 +489,7 @@ int get_ctx(rkb_chain* c, int device, DeviceCtx** out) {
   }
   if (c->sk) {
     e = c->sk->prepare();
+    if (e == cudaSuccess && c->jit) e = rkb_jit_prepare(*c->jit);
     if (e != cudaSuccess) { if (x->d_prog) cudaFree(x->d_prog); delete x; return cuda_fail(e, "cudaFuncSetAttribute"); }
   }
   e = cudaEventCreate(&x->ev0);
@@ -716,6 +717,11 @@ int rkb_chain_specialize(rkb_chain* c, int device) {
   const JitKernels* J = nullptr;
   rc = rkb_jit_get(c->n, c->serial_fl, c->serial_shape, &J);
   if (rc) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "%.250s", rkb_jit_log()); return rc; }
+  for (DeviceCtx* x : c->ctx) {  // every device this handle has been used on so far; later ones are prepared in get_ctx
+    DeviceGuard g(x->device);
+    const cudaError_t e = rkb_jit_prepare(*J);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  }
   c->jit = J;
   return RKB_OK;
 }

@@ -51,6 +51,7 @@ struct JitKernels {
   int smem[RKB_JIT_COUNT];
 };
 int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out);  // compiles on first use, cached per process
+cudaError_t rkb_jit_prepare(const JitKernels& J);                                  // per-device kernel attributes (current device)
 const char* rkb_jit_log();                                                         // NVRTC log / error text of the calling thread
 // args: the kernel's second parameter (EvalArgs, RolloutArgs, ...); extra: its third (RkTable) or NULL
 cudaError_t rkb_jit_launch(const JitKernels& J, int which, const SerialParams& P, const void* args, const void* extra, long long n_samples,

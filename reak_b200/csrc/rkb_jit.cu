@@ -61,6 +61,15 @@ const char* kKernelNames[RKB_JIT_COUNT] = {"serial_eval_kernel", "serial_forces_
 
 const char* rkb_jit_log() { return g_log.c_str(); }
 
+// the opt-in to more than 48 KB of dynamic shared memory is per device: call with the device current
+cudaError_t rkb_jit_prepare(const JitKernels& J) {
+  for (int k = 0; k < RKB_JIT_COUNT; ++k) {
+    const cudaError_t e = cudaFuncSetAttribute(J.kernel[k], cudaFuncAttributeMaxDynamicSharedMemorySize, J.smem[k]);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out) {
   std::lock_guard<std::mutex> lock(g_mu);
   const auto key = std::make_tuple(n, fl, shape);
@@ -121,10 +130,8 @@ int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out)
   J->smem[RKB_JIT_MASS] = J->smem[RKB_JIT_MASSDOT] = (n * n + 1) * B;
   J->smem[RKB_JIT_ROLLOUT] = J->smem[RKB_JIT_ROLLOUT_SEQ] = J->smem[RKB_JIT_STEER] = RKB_SMEM_ROLLOUT(n) * B;
   J->smem[RKB_JIT_ROLLOUT_RK] = (2 * n + 2 * n * RKB_RK_MAX_STAGES) * B;
-  for (int k = 0; k < RKB_JIT_COUNT; ++k) {
-    e = cudaFuncSetAttribute(J->kernel[k], cudaFuncAttributeMaxDynamicSharedMemorySize, J->smem[k]);
-    if (e != cudaSuccess) { g_log = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaGetLastError(); delete J; return RKB_ERR_CUDA; }
-  }
+  e = rkb_jit_prepare(*J);
+  if (e != cudaSuccess) { g_log = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaGetLastError(); delete J; return RKB_ERR_CUDA; }
   g_cache[key] = J;
   *out = J;
   return RKB_OK;

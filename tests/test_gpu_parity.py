@@ -797,3 +797,20 @@ def test_runtime_specialised_kernels(which, oracle_built):
     # a second handle of the same structure reuses the compiled kernels
     p2 = kte_batch_propagator(s).specialize()
     assert np.array_equal(p2.get_next_states(x, u, 1e-3, 12)[0], after[5])
+
+
+def test_specialised_kernels_on_every_device():
+    """An 8-joint chain needs more than 48 KB of dynamic shared memory per CTA: the opt-in is per device, so the
+    run-time specialised kernels must be prepared on every device the handle touches (all visible GPUs)."""
+    import torch
+    from reak_b200 import kte_batch_propagator
+    s = presets.crs_chain(n_revolute=8, axes=presets.ERA_AXES, link_offsets=presets.ERA_LINKS)
+    p = kte_batch_propagator(s)
+    x, u = random_batch(p.compiled, 70001, seed=99)
+    ref, _ = p.get_next_states(x, u, 1e-3, 3)
+    Mref = p.get_mass_matrices(x[:500])
+    p.specialize()
+    n_dev = torch.cuda.device_count()
+    got, st = p.get_next_states_multi(x, u, 1e-3, 3, devices=list(range(n_dev)))
+    assert not st.any() and rel_err(got, ref) < 1e-11
+    assert rel_err(p.get_mass_matrices(x[:500]), Mref) < 1e-11
