@@ -814,3 +814,24 @@ def test_specialised_kernels_on_every_device():
     got, st = p.get_next_states_multi(x, u, 1e-3, 3, devices=list(range(n_dev)))
     assert not st.any() and rel_err(got, ref) < 1e-11
     assert rel_err(p.get_mass_matrices(x[:500]), Mref) < 1e-11
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_every_serial_preset_specialises(name, oracle_built):
+    """Run-time specialisation over every preset the serial kernels take (1 to 7 coordinates, planar chains,
+    prismatic joints, springs, full tensors, twisted links): same results as the shipped kernels, parity with the oracle."""
+    p = _make(name)
+    if not p.is_serial():
+        from reak_b200 import _abi
+        with pytest.raises(_abi.RkbError) as e:
+            p.specialize()
+        assert e.value.code == _abi.ERR_UNSUPPORTED
+        return
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 200, seed=101)
+    before = (p.get_state_derivatives(x, u)[0], p.get_next_states(x, u, 1e-3, 10)[0], p.get_mass_matrices(x, with_derivative=True)[1])
+    p.specialize()
+    after = (p.get_state_derivatives(x, u)[0], p.get_next_states(x, u, 1e-3, 10)[0], p.get_mass_matrices(x, with_derivative=True)[1])
+    for a, b in zip(before, after):
+        assert rel_err(a, b) < 1e-11, name
+    assert rel_err(after[0], O.eval(x, u)[0]) < TOL_STEP and rel_err(after[1], O.rk4(x, u, 1e-3, 10)[0]) < TOL_STEP
