@@ -367,7 +367,10 @@ struct SerialState {
 
 __host__ __device__ constexpr int shape_ax(shape_t s, int k) { return (int)((s >> (8 * k)) & 7u); }         // 0 general, 1..3 revolute about x,y,z
 __host__ __device__ constexpr int shape_lk(shape_t s, int k) { return (int)((s >> (8 * k + 3)) & 3u); }     // 0 general, 1..3 offset along x,y,z, no rotation
-__host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 3u); }     // 0 general, 1 diagonal tensor present
+__host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 1u); }     // 0 general, 1 diagonal tensor present
+__host__ __device__ constexpr int shape_sign(shape_t s, int k) { return (int)((s >> (8 * k + 6)) & 3u); }   // 0 read the sign at run time, 1 axis = +e_D, 3 axis = -e_D
+// sign of an axis-aligned joint axis: a literal when the shape promises it (the multiplications by it fold away)
+#define RKB_AXIS_SIGN(SH, k, runtime) (shape_sign(SH, k) == 1 ? 1.0 : (shape_sign(SH, k) == 3 ? -1.0 : (runtime)))
 
 // cos and sin of every revolute joint angle (1, 0 for a prismatic joint); the sign of an axis-aligned
 // joint's axis is folded into the sine, which is all the specialised rotations need.
@@ -399,7 +402,7 @@ RKB_DEV void serial_trig_fold(const SerialParams& P, double (&sn)[N]) {
   for (int k = 0; k < N; ++k) {
     constexpr shape_t SH = SHAPE;
     const int AX = shape_ax(SH, k);
-    if (AX != 0) sn[k] *= P.st[k].ax[AX - 1];  // axis = +-e_D: fold the sign into the sine
+    if (AX != 0) sn[k] *= RKB_AXIS_SIGN(SH, k, P.st[k].ax[AX - 1]);  // axis = +-e_D: fold the sign into the sine
   }
 }
 template <int N, int FL, shape_t SHAPE>
@@ -476,7 +479,7 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
     if (AX != 0) {
       // revolute about sg e_D: n = I a, f = a x h
       const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
-      const double sg = S.ax[D];
+      const double sg = RKB_AXIS_SIGN(SH, k, S.ax[D]);
       n.c[0] = sg * I[sym_idx(0, D)]; n.c[1] = sg * I[sym_idx(1, D)]; n.c[2] = sg * I[sym_idx(2, D)];
       f.c[D] = zero_of<T>(); f.c[D1] = (-sg) * h.c[D2]; f.c[D2] = sg * h.c[D1];
       Mp[k * (k + 1) / 2 + k] = I[sym_idx(D, D)] + S.rotor;
@@ -521,7 +524,7 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
         n = n + cross_cv<T>(ld3(Si.po), f);
       }
       T mjk;
-      if (AXi != 0) mjk = Si.ax[AXi - 1] * n.c[AXi - 1];
+      if (AXi != 0) mjk = RKB_AXIS_SIGN(SH, j - 1, Si.ax[AXi - 1]) * n.c[AXi - 1];
       else if (!((FL & RKB_FL_PRISMATIC) && (Si.flags & RKB_ST_PRISMATIC))) mjk = dot_cv<T>(ld3(Si.ax), n);
       else mjk = dot_cv<T>(ld3(Si.ax), f);
       Mp[k * (k + 1) / 2 + (j - 1)] = mjk;
@@ -571,7 +574,7 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       if (AX != 0) {
         // revolute about +-e_D (revolute_joint.cpp:121-152)
         const int D = AX - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
-        const double g = S.ax[D] * X.qd[k];  // q_dot * axis has the single component g
+        const double g = RKB_AXIS_SIGN(SH, k, S.ax[D]) * X.qd[k];  // q_dot * axis has the single component g
         vec3 wt, alt, at;
         if (D == 0) { wt = rotT_axis<0>(cs[k], sn[k], w); alt = rotT_axis<0>(cs[k], sn[k], al); at = rotT_axis<0>(cs[k], sn[k], a); }
         else if (D == 1) { wt = rotT_axis<1>(cs[k], sn[k], w); alt = rotT_axis<1>(cs[k], sn[k], al); at = rotT_axis<1>(cs[k], sn[k], a); }
@@ -650,7 +653,7 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
       if (AX != 0) {
         // revolute about +-e_D (revolute_joint.cpp:172-184 + actuator reaction :210-213)
         const int D = AX - 1;
-        const double sg = S.ax[D];
+        const double sg = RKB_AXIS_SIGN(SH, k, S.ax[D]);
         double tsd = 0.0;  // spring + damper torque along e_D
         if (FL & RKB_FL_SPRINGS) {
           if (S.flags & RKB_ST_SPRING) tsd = sg * spring_scalar(S, X.q[k]);
@@ -978,7 +981,7 @@ __global__ void __launch_bounds__(RKB_BLOCK) serial_mass_kernel(const __grid_con
         const bool prismatic = AX == 0 && (FL & RKB_FL_PRISMATIC) && (P.st[k].flags & RKB_ST_PRISMATIC);
         // d/dt cos q = -sin q q_dot, d/dt sin q = cos q q_dot; with the axis sign sg = +-1 folded in,
         // sn = sg sin q: d/dt sn = sg cos q q_dot and sin q = sg sn
-        const double sg = (AX != 0) ? P.st[k].ax[AX - 1] : 1.0;
+        const double sg = (AX != 0) ? RKB_AXIS_SIGN(SH, k, P.st[k].ax[AX - 1]) : 1.0;
         if (!prismatic) {
           dcs[k] = mkd(cs[k], -(sg * sn[k]) * X.qd[k]);
           dsn[k] = mkd(sn[k], (sg * cs[k]) * X.qd[k]);

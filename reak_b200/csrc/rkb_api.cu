@@ -350,11 +350,11 @@ bool lower_serial(const rkb_chain_desc& d_in, SerialParams& P, int& fl, unsigned
   shape = 0;
   for (int s = 0; s <= k; ++s) {
     const SerialStage& S = P.st[s];
-    unsigned ax = 0, lk = 0, in = 0;
+    unsigned ax = 0, lk = 0, in = 0, sign = 0;
     if (!(S.flags & RKB_ST_PRISMATIC)) {
       for (int dd = 0; dd < 3; ++dd) {
         const int d1 = (dd + 1) % 3, d2 = (dd + 2) % 3;
-        if ((S.ax[dd] == 1.0 || S.ax[dd] == -1.0) && S.ax[d1] == 0.0 && S.ax[d2] == 0.0) ax = dd + 1;
+        if ((S.ax[dd] == 1.0 || S.ax[dd] == -1.0) && S.ax[d1] == 0.0 && S.ax[d2] == 0.0) { ax = dd + 1; sign = S.ax[dd] > 0.0 ? 1u : 3u; }
       }
     }
     if (!(S.flags & RKB_ST_LINKROT)) {  // no link at all counts as a zero offset along z
@@ -363,7 +363,7 @@ bool lower_serial(const rkb_chain_desc& d_in, SerialParams& P, int& fl, unsigned
       if (nz <= 1) lk = which + 1;
     }
     if ((S.flags & RKB_ST_INERTIA) && S.I[1] == 0.0 && S.I[2] == 0.0 && S.I[4] == 0.0) in = 1;
-    shape |= RKB_SHAPE_AT(RKB_SHAPE_STAGE(ax, lk, in), s);
+    shape |= RKB_SHAPE_AT(RKB_SHAPE_STAGE_SIGNED(ax, lk, in, sign), s);
   }
   return true;
 }
@@ -417,8 +417,8 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
 bool shape_compatible(unsigned long long have, unsigned long long chain, int n) {
   for (int k = 0; k < n; ++k) {
     const unsigned h = (unsigned)((have >> (8 * k)) & 0xffu), c = (unsigned)((chain >> (8 * k)) & 0xffu);
-    const unsigned hf[3] = {h & 7u, (h >> 3) & 3u, (h >> 5) & 3u}, cf[3] = {c & 7u, (c >> 3) & 3u, (c >> 5) & 3u};
-    for (int i = 0; i < 3; ++i) if (hf[i] != 0 && hf[i] != cf[i]) return false;
+    const unsigned hf[4] = {h & 7u, (h >> 3) & 3u, (h >> 5) & 1u, (h >> 6) & 3u}, cf[4] = {c & 7u, (c >> 3) & 3u, (c >> 5) & 1u, (c >> 6) & 3u};
+    for (int i = 0; i < 4; ++i) if (hf[i] != 0 && hf[i] != cf[i]) return false;
   }
   return (n >= 8) || (have >> (8 * n)) == 0;
 }
@@ -426,7 +426,7 @@ int shape_score(unsigned long long have, int n) {
   int sc = 0;
   for (int k = 0; k < n; ++k) {
     const unsigned h = (unsigned)((have >> (8 * k)) & 0xffu);
-    sc += ((h & 7u) ? 3 : 0) + (((h >> 3) & 3u) ? 1 : 0) + (((h >> 5) & 3u) ? 1 : 0);
+    sc += ((h & 7u) ? 3 : 0) + (((h >> 3) & 3u) ? 1 : 0) + (((h >> 5) & 1u) ? 1 : 0) + (((h >> 6) & 3u) ? 1 : 0);
   }
   return sc;
 }

@@ -33,8 +33,10 @@
 // Structural promises, 8 bits per stage (stage k at bits [8k, 8k+8)): see kte_serial.cuh
 //   bits 0-2  axis   0 = general (revolute with any axis, or prismatic), 1/2/3 = revolute about +-e_x/e_y/e_z
 //   bits 3-4  link   0 = general (none / any offset / rotated), 1/2/3 = offset along e_x/e_y/e_z, no rotation
-//   bits 5-6  inertia 0 = general (none / full tensor), 1 = present with a diagonal tensor
+//   bit  5    inertia 0 = general (none / full tensor), 1 = present with a diagonal tensor
+//   bits 6-7  sign of an axis-aligned joint axis: 0 = read at run time, 1 = +e_D, 3 = -e_D
 #define RKB_SHAPE_STAGE(ax, lk, in) ((unsigned long long)((ax) | ((lk) << 3) | ((in) << 5)))
+#define RKB_SHAPE_STAGE_SIGNED(ax, lk, in, sign) (RKB_SHAPE_STAGE(ax, lk, in) | ((unsigned long long)(sign) << 6))
 #define RKB_SHAPE_AT(code, k) ((unsigned long long)(code) << (8 * (k)))
 
 struct SerialStage {
