@@ -365,7 +365,9 @@ struct SerialState {
   double q[N], qd[N], u[N];
 };
 
-__host__ __device__ constexpr int shape_ax(shape_t s, int k) { return (int)((s >> (8 * k)) & 7u); }         // 0 general, 1..3 revolute about x,y,z
+__host__ __device__ constexpr int shape_axraw(shape_t s, int k) { return (int)((s >> (8 * k)) & 7u); }      // 0 general, 1..3 revolute about x,y,z, 5..7 prismatic along x,y,z
+__host__ __device__ constexpr int shape_ax(shape_t s, int k) { return shape_axraw(s, k) <= 3 ? shape_axraw(s, k) : 0; }      // revolute about e_D: D + 1, else 0
+__host__ __device__ constexpr int shape_px(shape_t s, int k) { return shape_axraw(s, k) >= 5 ? shape_axraw(s, k) - 4 : 0; }  // prismatic along e_D: D + 1, else 0
 __host__ __device__ constexpr int shape_lk(shape_t s, int k) { return (int)((s >> (8 * k + 3)) & 3u); }     // 0 general, 1..3 offset along x,y,z, no rotation
 __host__ __device__ constexpr int shape_in(shape_t s, int k) { return (int)((s >> (8 * k + 5)) & 1u); }     // 0 general, 1 diagonal tensor present
 __host__ __device__ constexpr int shape_sign(shape_t s, int k) { return (int)((s >> (8 * k + 6)) & 3u); }   // 0 read the sign at run time, 1 axis = +e_D, 3 axis = -e_D
@@ -483,6 +485,13 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
       n.c[0] = sg * I[sym_idx(0, D)]; n.c[1] = sg * I[sym_idx(1, D)]; n.c[2] = sg * I[sym_idx(2, D)];
       f.c[D] = zero_of<T>(); f.c[D1] = (-sg) * h.c[D2]; f.c[D2] = sg * h.c[D1];
       Mp[k * (k + 1) / 2 + k] = I[sym_idx(D, D)] + S.rotor;
+    } else if (shape_px(SH, k) != 0) {
+      // prismatic along sg e_D: f = mc sg e_D, n = h x (sg e_D), M(k,k) = mc + rotor
+      const int D = shape_px(SH, k) - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+      const double sg = RKB_AXIS_SIGN(SH, k, S.ax[D]);
+      f.c[D] = zero_of<T>() + sg * S.mc; f.c[D1] = zero_of<T>(); f.c[D2] = zero_of<T>();
+      n.c[D] = zero_of<T>(); n.c[D1] = sg * h.c[D2]; n.c[D2] = (-sg) * h.c[D1];
+      Mp[k * (k + 1) / 2 + k] = zero_of<T>() + (S.mc + S.rotor);
     } else if (!prismatic_k) {
       const vec3 ax = ld3(S.ax);
       n = symmul_vc<T>(I, ax);
@@ -504,6 +513,12 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
         if (D == 0) { f = rot_axis_t<0, T>(cs[j], sn[j], f); n = rot_axis_t<0, T>(cs[j], sn[j], n); }
         else if (D == 1) { f = rot_axis_t<1, T>(cs[j], sn[j], f); n = rot_axis_t<1, T>(cs[j], sn[j], n); }
         else { f = rot_axis_t<2, T>(cs[j], sn[j], f); n = rot_axis_t<2, T>(cs[j], sn[j], n); }
+      } else if (shape_px(SH, j) != 0) {
+        // n += (L e_D) x f, L = sg q
+        const int D = shape_px(SH, j) - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const T L = RKB_AXIS_SIGN(SH, j, Sj.ax[D]) * qp[j];
+        n.c[D1] -= L * f.c[D2];
+        n.c[D2] += L * f.c[D1];
       } else if (!((FL & RKB_FL_PRISMATIC) && (Sj.flags & RKB_ST_PRISMATIC))) {
         const mat3t<T> R = rodrigues_t<T>(Sj, cs[j], sn[j]);
         f = mul(R, f); n = mul(R, n);
@@ -525,6 +540,7 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
       }
       T mjk;
       if (AXi != 0) mjk = RKB_AXIS_SIGN(SH, j - 1, Si.ax[AXi - 1]) * n.c[AXi - 1];
+      else if (shape_px(SH, j - 1) != 0) mjk = RKB_AXIS_SIGN(SH, j - 1, Si.ax[shape_px(SH, j - 1) - 1]) * f.c[shape_px(SH, j - 1) - 1];
       else if (!((FL & RKB_FL_PRISMATIC) && (Si.flags & RKB_ST_PRISMATIC))) mjk = dot_cv<T>(ld3(Si.ax), n);
       else mjk = dot_cv<T>(ld3(Si.ax), f);
       Mp[k * (k + 1) / 2 + (j - 1)] = mjk;
@@ -536,6 +552,17 @@ RKB_DEV void mass_sweep(const SerialParams& P, const T (&cs)[N], const T (&sn)[N
         if (D == 0) { h = rot_axis_t<0, T>(cs[k], sn[k], h); sym_rotate_axis_t<0, T>(cs[k], sn[k], I); }
         else if (D == 1) { h = rot_axis_t<1, T>(cs[k], sn[k], h); sym_rotate_axis_t<1, T>(cs[k], sn[k], I); }
         else { h = rot_axis_t<2, T>(cs[k], sn[k], h); sym_rotate_axis_t<2, T>(cs[k], sn[k], I); }
+      } else if (shape_px(SH, k) != 0) {
+        // parallel-axis move by L e_D, L = sg q (the link-offset formulas with a variable offset)
+        const int D = shape_px(SH, k) - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const T L = RKB_AXIS_SIGN(SH, k, S.ax[D]) * qp[k];
+        const T mcL = S.mc * L;
+        const T dd = L * (2.0 * h.c[D] + mcL);
+        I[sym_idx(D1, D1)] += dd;
+        I[sym_idx(D2, D2)] += dd;
+        I[sym_idx(D1, D)] -= L * h.c[D1];
+        I[sym_idx(D2, D)] -= L * h.c[D2];
+        h.c[D] += mcL;
       } else if (!prismatic_k) {
         const mat3t<T> R = rodrigues_t<T>(S, cs[k], sn[k]);
         h = mul(R, h);
@@ -584,6 +611,15 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
         alt.c[D2] -= wt.c[D1] * g;
         wt.c[D] += g;
         w = wt; al = alt; a = at;
+      } else if (shape_px(SH, k) != 0) {
+        // prismatic along sg e_D (prismatic_joint.cpp:129-161): r = L e_D, r_dot = Ld e_D;
+        // a += w x (w x r) + 2 w x r_dot + al x r, with (v x e_D)[D1] = v[D2], (v x e_D)[D2] = -v[D1]
+        const int D = shape_px(SH, k) - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double sg = RKB_AXIS_SIGN(SH, k, S.ax[D]);
+        const double L = sg * X.q[k], Ld2 = 2.0 * (sg * X.qd[k]);
+        a.c[D] -= L * (w.c[D1] * w.c[D1] + w.c[D2] * w.c[D2]);
+        a.c[D1] += L * (w.c[D] * w.c[D1] + al.c[D2]) + Ld2 * w.c[D2];
+        a.c[D2] += L * (w.c[D] * w.c[D2] - al.c[D1]) - Ld2 * w.c[D1];
       } else {
         const vec3 ax = ld3(S.ax);
         const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);
@@ -664,6 +700,16 @@ RKB_DEV void serial_sweeps(const SerialParams& P, const SerialState<N>& X, doubl
         if (D == 0) { F = rot_axis<0>(cs[k], sn[k], F); T = rot_axis<0>(cs[k], sn[k], T); }
         else if (D == 1) { F = rot_axis<1>(cs[k], sn[k], F); T = rot_axis<1>(cs[k], sn[k], T); }
         else { F = rot_axis<2>(cs[k], sn[k], F); T = rot_axis<2>(cs[k], sn[k], T); }
+      } else if (shape_px(SH, k) != 0) {
+        // prismatic along sg e_D (prismatic_joint.cpp:181-193 + reaction :219-222): f = F.a + u,
+        // T += (q a) x F, F -= (F.a) a + u a  ->  F_D = -sg u
+        const int D = shape_px(SH, k) - 1, D1 = (D + 1) % 3, D2 = (D + 2) % 3;
+        const double sg = RKB_AXIS_SIGN(SH, k, S.ax[D]);
+        const double L = sg * X.q[k];
+        f[k] = sg * F.c[D] + X.u[k];
+        T.c[D1] -= L * F.c[D2];
+        T.c[D2] += L * F.c[D1];
+        F.c[D] = -(sg * X.u[k]);
       } else {
         const vec3 ax = ld3(S.ax);
         const bool prismatic = (FL & RKB_FL_PRISMATIC) && (S.flags & RKB_ST_PRISMATIC);

@@ -351,10 +351,11 @@ bool lower_serial(const rkb_chain_desc& d_in, SerialParams& P, int& fl, unsigned
   for (int s = 0; s <= k; ++s) {
     const SerialStage& S = P.st[s];
     unsigned ax = 0, lk = 0, in = 0, sign = 0;
-    if (!(S.flags & RKB_ST_PRISMATIC)) {
-      for (int dd = 0; dd < 3; ++dd) {
-        const int d1 = (dd + 1) % 3, d2 = (dd + 2) % 3;
-        if ((S.ax[dd] == 1.0 || S.ax[dd] == -1.0) && S.ax[d1] == 0.0 && S.ax[d2] == 0.0) { ax = dd + 1; sign = S.ax[dd] > 0.0 ? 1u : 3u; }
+    for (int dd = 0; dd < 3; ++dd) {  // revolute about / prismatic along +-e_dd
+      const int d1 = (dd + 1) % 3, d2 = (dd + 2) % 3;
+      if ((S.ax[dd] == 1.0 || S.ax[dd] == -1.0) && S.ax[d1] == 0.0 && S.ax[d2] == 0.0) {
+        ax = ((S.flags & RKB_ST_PRISMATIC) ? 4 : 0) + dd + 1;
+        sign = S.ax[dd] > 0.0 ? 1u : 3u;
       }
     }
     if (!(S.flags & RKB_ST_LINKROT)) {  // no link at all counts as a zero offset along z

@@ -100,8 +100,9 @@ constexpr shape_t arm_shape(int n, int first, int inertia = 1, bool signed_axes 
   return s;
 }
 // general joint (prismatic track) with a z-aligned link and a diagonal tensor, then the arm
+// (signed: the track runs along +e_x, CRS_A465_models.cpp:304-347)
 constexpr shape_t track_arm_shape(int n, bool signed_axes = false) {
-  return RKB_SHAPE_AT(RKB_SHAPE_STAGE(0, 3, 1), 0) | arm_shape(n - 1, 1, 1, signed_axes);
+  return RKB_SHAPE_AT(signed_axes ? RKB_SHAPE_STAGE_SIGNED(5, 3, 1, 1) : RKB_SHAPE_STAGE(0, 3, 1), 0) | arm_shape(n - 1, 1, 1, signed_axes);
 }
 
 // planar chains embedded in the x-y plane (rkb_api.cu: embed_planar): every joint about z, links along x,
@@ -112,7 +113,7 @@ constexpr shape_t planar_shape(int n, int first = 0) {
   for (int k = 0; k < n; ++k) s |= RKB_SHAPE_AT(RKB_SHAPE_STAGE_SIGNED(3, 1, 1, 1), k + first);  // revolute_joint_2D turns about +e_z
   return s;
 }
-constexpr shape_t track_planar_shape(int n) { return RKB_SHAPE_AT(RKB_SHAPE_STAGE(0, 3, 1), 0) | planar_shape(n - 1, 1); }
+constexpr shape_t track_planar_shape(int n) { return RKB_SHAPE_AT(RKB_SHAPE_STAGE_SIGNED(5, 3, 1, 1), 0) | planar_shape(n - 1, 1); }
 
 extern "C" const SerialKernels* RKB_CAT(rkb_serial_table_, RKB_N)(int* count) {
   static const SerialKernels table[] = {

@@ -31,7 +31,8 @@
 #define RKB_FL_ALL       7
 
 // Structural promises, 8 bits per stage (stage k at bits [8k, 8k+8)): see kte_serial.cuh
-//   bits 0-2  axis   0 = general (revolute with any axis, or prismatic), 1/2/3 = revolute about +-e_x/e_y/e_z
+//   bits 0-2  axis   0 = general (revolute with any axis, or prismatic), 1/2/3 = revolute about +-e_x/e_y/e_z,
+//                    5/6/7 = prismatic along +-e_x/e_y/e_z
 //   bits 3-4  link   0 = general (none / any offset / rotated), 1/2/3 = offset along e_x/e_y/e_z, no rotation
 //   bit  5    inertia 0 = general (none / full tensor), 1 = present with a diagonal tensor
 //   bits 6-7  sign of an axis-aligned joint axis: 0 = read at run time, 1 = +e_D, 3 = -e_D
