@@ -19,6 +19,9 @@
  *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
  *   rkb_twist_shaping     <- mass_matrix_calc::get_TMT_TdMT             (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287)
  *   rkb_frames            <- kte_map_chain::doMotion / doForce as seen on the frames (frame_3D / frame_2D members)
+ *   rkb_min_distance      <- proxy_query_pair_3D::findMinimumDistance (geometry/proximity/proxy_query_model.cpp:388-412)
+ *                            with the pair finders of geometry/proximity/prox_*_*.cpp: the is_free test of
+ *                            ctrl/topologies/manip_free_workspace.hpp:77-99 on every propagated state
  *   rkb_gen_forces        <- kte_map_chain::doMotion/clearForce/doForce (ctrl/mbd_kte/kte_map_chain.hpp:71-89); returns gen_coord::f
  *   rkb_steer_batch       <- the inner loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561),
  *                            many (start, goal, control) tuples per call
@@ -52,7 +55,7 @@
 extern "C" {
 #endif
 
-#define RKB_VERSION 110
+#define RKB_VERSION 120
 
 #if defined(__GNUC__)
 #define RKB_API __attribute__((visibility("default")))
@@ -247,6 +250,53 @@ RKB_API int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
 RKB_API int rkb_chain_frame_count(const rkb_chain* chain);
 RKB_API int rkb_frames(rkb_chain* chain, int device, size_t n_samples,
                        const double* x, const double* u, double* frames, unsigned flags, void* stream);
+
+/* ---- proximity queries on the propagated states ---------------------------------------
+ * A proximity model is a list of primitive shapes (geometry/shapes/{plane,sphere,capped_cylinder,cylinder,box}.hpp),
+ * each riding on a frame of the chain (geometry_3D::mAnchor) or fixed in the world, with its own pose relative to
+ * that anchor (geometry_3D::mPose).  rkb_proxy pairs two models the way proxy_query_pair_3D does
+ * (geometry/proximity/proxy_query_model.hpp): one finder per (shape of model 1, shape of model 2) the reference has
+ * a finder for, in createProxFinderList order (proxy_query_model.cpp:212-384).  3D chains only. */
+enum rkb_shape_kind {
+  RKB_SHAPE_PLANE     = 1,   /* dims: x, y extents (only the culling test looks at them)  plane.hpp      */
+  RKB_SHAPE_SPHERE    = 2,   /* dims: radius                                              sphere.hpp     */
+  RKB_SHAPE_CCYLINDER = 3,   /* dims: length, radius; axis = local z                      capped_cylinder.hpp */
+  RKB_SHAPE_CYLINDER  = 4,   /* dims: length, radius; axis = local z                      cylinder.hpp   */
+  RKB_SHAPE_BOX       = 5    /* dims: x, y, z extents                                     box.hpp        */
+};
+typedef struct rkb_shape {
+  int32_t kind;          /* rkb_shape_kind */
+  int32_t anchor;        /* frame id of the chain descriptor the shape rides on, -1 = world */
+  double  position[3];   /* mPose.Position, in the anchor's coordinates */
+  double  quat[4];       /* mPose.Quat (w,x,y,z) */
+  double  dims[3];
+} rkb_shape;
+#define RKB_PROXY_MAX_SHAPES 16   /* per model */
+typedef struct rkb_proxy rkb_proxy;
+
+RKB_API int  rkb_proxy_create(const rkb_chain* chain, const rkb_shape* model1, int n1,
+                              const rkb_shape* model2, int n2, rkb_proxy** out);
+RKB_API void rkb_proxy_destroy(rkb_proxy* proxy);
+/* number of finders; finder k pairs shape *i1 of model 1 with shape *i2 of model 2 */
+RKB_API int  rkb_proxy_finder_count(const rkb_proxy* proxy);
+RKB_API int  rkb_proxy_finder(const rkb_proxy* proxy, int k, int* i1, int* i2);
+
+/* diagnostic: copies the lowered device program (an opaque blob: normalised poses, bounding radii) into out;
+ * returns its size in bytes, or RKB_ERR_INVALID when `size` is too small.  tests/host_build uses it to run the
+ * device source of the finders on the host against the compiled reference. */
+RKB_API int  rkb_proxy_program(const rkb_proxy* proxy, void* out, size_t size);
+
+/* proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) after the chain's doMotion at state
+ * x[i], including its bounding-sphere culling, for every sample:
+ *   distance[i]  mLastResult.mDistance of the finder it returns (+inf when the pair has no finder);
+ *                the state is free in the sense of manip_dk_proxy_env_impl::is_free
+ *                (ctrl/topologies/manip_free_workspace.hpp:77-99) iff distance[i] >= 0 for every proxy pair
+ *   finder[i]    index of that finder (-1 when there is none), nullable
+ *   points[i]    mPoint1, mPoint2 of its record (6 doubles, world coordinates), nullable
+ * x as in rkb_eval (only the positions matter).  flags: RKB_LAYOUT_* as everywhere. */
+RKB_API int rkb_min_distance(rkb_chain* chain, const rkb_proxy* proxy, int device, size_t n_samples,
+                             const double* x, double* distance, int32_t* finder, double* points,
+                             unsigned flags, void* stream);
 
 /* Twist-shaping matrix Tcm and its time derivative Tcm_dot of mass_matrix_calc::get_TMT_TdMT
  * (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287) at state x[i].  Rows: one per inertia_gen, then three per

@@ -161,6 +161,26 @@ class _Checker(object):
         fn(self.h, _dp(x0), _dp(T), _dp(Mc), _dp(Td))
         return T, Mc, Td
 
+    def min_distance(self, pair, x):
+        """proxy_query_pair_3D::findMinimumDistance of the live reference after doMotion at every state:
+        (distance [N], finder index [N], points [N][6]).  Reference checker only."""
+        if self._prefix != "rkref_":
+            raise NotImplementedError("proximity is checked against the compiled reference only")
+        x, _, N = self._xu(x, None)
+        m1, n1 = pair.model1.to_c(self.compiled.frames)
+        m2, n2 = pair.model2.to_c(self.compiled.frames)
+        d = np.zeros(N)
+        f = np.zeros(N, dtype=np.int32)
+        pts = np.zeros((N, 6))
+        fn = self.lib.rkref_min_distance
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        xc = np.ascontiguousarray(x)
+        rc = fn(self.h, N, _dp(xc), C.cast(m1, C.c_void_p), n1, C.cast(m2, C.c_void_p), n2, _dp(d), _dp(f), _dp(pts))
+        if rc < 0:
+            raise RuntimeError("rkref_min_distance failed")
+        return d, f, pts
+
     def frames(self, x, u=None):
         """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""
         x, u, _ = self._xu(x, u)

@@ -30,6 +30,12 @@
 #include <ReaK/ctrl/mbd_kte/jacobian_joint_map.hpp>
 #include <ReaK/ctrl/mbd_kte/mass_matrix_calculator.hpp>
 #include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
+#include <ReaK/geometry/shapes/plane.hpp>
+#include <ReaK/geometry/shapes/sphere.hpp>
+#include <ReaK/geometry/shapes/capped_cylinder.hpp>
+#include <ReaK/geometry/shapes/cylinder.hpp>
+#include <ReaK/geometry/shapes/box.hpp>
+#include <ReaK/geometry/proximity/proxy_query_model.hpp>
 
 #include "../include/reak_b200.h"
 // libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
@@ -61,6 +67,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -392,6 +399,79 @@ int rkref_frames(void* hv, const double* x, const double* u, double* out) {
     }
   }
   return 0;
+}
+
+// proxy_query_pair_3D::findMinimumDistance of the live reference (geometry/proximity/proxy_query_model.cpp)
+// for two proximity models given as rkb_shape lists, the shapes of either riding on frames of this model
+// (anchor = frame id) or fixed in the world (-1), after kte_map_chain::doMotion at each state x[i].
+// finder[i] = index of the returned finder in createProxFinderList order, found through its two shapes.
+int rkref_min_distance(void* hv, std::size_t N, const double* x, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2,
+                       double* dist, int32_t* finder, double* points) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  if (h->desc.dim != 3) return -1;
+  const int nx = 2 * m->n, nu = m->nu;
+  std::vector<shared_ptr<geom::shape_3D> > shapes;
+  shared_ptr<geom::proxy_query_model_3D> mdl[2];
+  mdl[0] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("model1"));
+  mdl[1] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("model2"));
+  for (int k = 0; k < n1 + n2; ++k) {
+    const rkb_shape& s = k < n1 ? m1[k] : m2[k - n1];
+    shared_ptr<pose_3D<double> > anchor;
+    if (s.anchor >= 0) anchor = m->f3[s.anchor];
+    const pose_3D<double> pose(weak_ptr<pose_3D<double> >(), vect<double,3>(s.position[0], s.position[1], s.position[2]),
+                               quaternion<double>(vect<double,4>(s.quat[0], s.quat[1], s.quat[2], s.quat[3])));
+    shared_ptr<geom::shape_3D> sh;
+    switch (s.kind) {
+      case RKB_SHAPE_PLANE: sh = shared_ptr<geom::shape_3D>(new geom::plane("p", anchor, pose, vect<double,2>(s.dims[0], s.dims[1]))); break;
+      case RKB_SHAPE_SPHERE: sh = shared_ptr<geom::shape_3D>(new geom::sphere("s", anchor, pose, s.dims[0])); break;
+      case RKB_SHAPE_CCYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::capped_cylinder("cc", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_CYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::cylinder("cy", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_BOX: sh = shared_ptr<geom::shape_3D>(new geom::box("b", anchor, pose, vect<double,3>(s.dims[0], s.dims[1], s.dims[2]))); break;
+      default: return -1;
+    }
+    shapes.push_back(sh);
+    mdl[k < n1 ? 0 : 1]->addShape(sh);
+  }
+  geom::proxy_query_pair_3D pair("pair", mdl[0], mdl[1]);
+  // finder order, restated only to turn the returned finder into an index: one finder per pair the
+  // reference creates one for (proxy_query_model.cpp:212-384)
+  std::vector<std::pair<int, int> > order;
+  for (int a = 0; a < n1; ++a)
+    for (int b = 0; b < n2; ++b) {
+      const int ka = m1[a].kind, kb = m2[b].kind, lo = std::min(ka, kb), hi = std::max(ka, kb);
+      const bool has = lo == RKB_SHAPE_PLANE || lo == RKB_SHAPE_SPHERE ||
+                       (lo == RKB_SHAPE_CCYLINDER && (hi == RKB_SHAPE_CCYLINDER || hi == RKB_SHAPE_BOX));
+      if (has) order.push_back(std::make_pair(a, b));
+    }
+  vect_n<double> p(nx), uu(nu);
+  for (int k = 0; k < nu; ++k) uu[k] = 0.0;
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    shared_ptr<geom::proximity_finder_3D> f = pair.findMinimumDistance();
+    if (!f) {
+      dist[i] = std::numeric_limits<double>::infinity();
+      if (finder) finder[i] = -1;
+      if (points) for (int k = 0; k < 6; ++k) points[6 * i + k] = 0.0;
+      continue;
+    }
+    const geom::proximity_record_3D r = f->getLastResult();
+    dist[i] = r.mDistance;
+    if (points) for (int k = 0; k < 3; ++k) { points[6 * i + k] = r.mPoint1[k]; points[6 * i + 3 + k] = r.mPoint2[k]; }
+    if (finder) {
+      finder[i] = -2;
+      const geom::shape_3D* s1 = f->getShape1().get();
+      const geom::shape_3D* s2 = f->getShape2().get();
+      for (std::size_t q = 0; q < order.size(); ++q) {
+        const geom::shape_3D* a = shapes[order[q].first].get();
+        const geom::shape_3D* b = shapes[n1 + order[q].second].get();
+        if ((a == s1 && b == s2) || (a == s2 && b == s1)) { finder[i] = (int32_t)q; break; }
+      }
+    }
+  }
+  return (int)order.size();
 }
 
 // Runs include/reak_b200/reak_bridge.hpp on the LIVE ReaK objects of this model (built by

@@ -43,6 +43,15 @@ class rkb_chain_desc(C.Structure):
 assert C.sizeof(rkb_element) == 128, C.sizeof(rkb_element)
 
 
+class rkb_shape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("anchor", C.c_int32), ("position", C.c_double * 3), ("quat", C.c_double * 4),
+                ("dims", C.c_double * 3)]
+
+
+SHAPE_PLANE, SHAPE_SPHERE, SHAPE_CCYLINDER, SHAPE_CYLINDER, SHAPE_BOX = 1, 2, 3, 4, 5
+PROXY_MAX_SHAPES = 16
+
+
 class rkb_rollout_opts(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("n_intervals", C.c_int32), ("steps_per_interval", C.c_int32),
                 ("reserved", C.c_int32), ("dt", C.c_double)]
@@ -94,6 +103,13 @@ SYMBOLS = {
                                   C.c_uint, C.c_void_p]),
     "rkb_chain_frame_count": (C.c_int, [C.c_void_p]),
     "rkb_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_proxy_create": (C.c_int, [C.c_void_p, C.POINTER(rkb_shape), C.c_int, C.POINTER(rkb_shape), C.c_int, C.POINTER(C.c_void_p)]),
+    "rkb_proxy_destroy": (None, [C.c_void_p]),
+    "rkb_proxy_finder_count": (C.c_int, [C.c_void_p]),
+    "rkb_proxy_finder": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rkb_proxy_program": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rkb_min_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_uint, C.c_void_p]),
     "rkb_twist_shaping_rows": (C.c_int, [C.c_void_p]),
     "rkb_twist_shaping_mcm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rkb_twist_shaping": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),

@@ -720,6 +720,36 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_frames_kernel(const Generic
   for (int f = 0; f < G->n_frames; ++f) put_frame(W.fr[f], A.out, i * A.out.si + (long long)(25 * f) * A.out.sk);
 }
 
+#include "kte_proximity.cuh"
+
+// proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) at the chain's pose for
+// state x[i]: distance, the index of the finder that gave it and its two points.
+template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_proximity_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
+                                                                       const __grid_constant__ ProxProgram P) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<3, MAXF> W;
+  load(G, W, A.x, A.u, i, i, false);
+  motion(G, W);
+  Pose pose[2 * RKB_PROX_MAX_SHAPES];
+  const int ns = P.n1 + P.n2;
+  for (int k = 0; k < ns; ++k) {
+    const ProxShape& S = P.s[k];
+    const int fa = S.anchor >= 0 ? S.anchor : 0;
+    pose[k] = prox_shape_pose(S, S.anchor >= 0, W.fr[fa].p, W.fr[fa].q);
+  }
+  ProxRecord bestR;
+  const int best = prox_min_distance(P, pose, bestR);
+  const double min_d = bestR.d;
+  A.out.p[i * A.out.si] = min_d;
+  if (A.status) A.status[i] = best;
+  if (A.out2.p) {
+    const double v[6] = {bestR.p1.x, bestR.p1.y, bestR.p1.z, bestR.p2.x, bestR.p2.y, bestR.p2.z};
+    for (int k = 0; k < 6; ++k) A.out2.p[i * A.out2.si + k * A.out2.sk] = v[k];
+  }
+}
+
 template <int DIM, int MAXF>
 __global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
@@ -890,6 +920,14 @@ cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram&
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   DISPATCH(generic_frames_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  if (host.dim != 3) return cudaErrorInvalidValue;
+  if (host.n_frames <= 16) generic_proximity_kernel<3, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+  else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   return cudaGetLastError();
 }
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {

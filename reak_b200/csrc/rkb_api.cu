@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/reak_b200.h"
@@ -746,6 +747,133 @@ int rkb_chain_frame_count(const rkb_chain* c) { return c ? c->desc.n_frames : RK
 
 int rkb_frames(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* frames, unsigned flags, void* stream) {
   return run_eval_like(c, OP_FRAMES, device, N, x, u, frames, nullptr, nullptr, flags, stream);
+}
+
+/* ---- proximity (kte_proximity.cuh) ---------------------------------------------------------------- */
+}  // extern "C"
+
+struct rkb_proxy {
+  ProxProgram prog;
+  std::vector<std::pair<int, int> > finders;
+  int n_frames;
+};
+
+namespace {
+bool prox_pair_has_finder(int ka, int kb) {  // proxy_query_model.cpp:212-384
+  const int lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
+  if (lo == RKB_SHAPE_PLANE || lo == RKB_SHAPE_SPHERE) return true;
+  if (lo == RKB_SHAPE_CCYLINDER) return hi == RKB_SHAPE_CCYLINDER || hi == RKB_SHAPE_BOX;
+  return false;
+}
+bool lower_shape(const rkb_shape& in, int n_frames, ProxShape* out) {
+  if (in.kind < RKB_SHAPE_PLANE || in.kind > RKB_SHAPE_BOX) return false;
+  if (in.anchor < -1 || in.anchor >= n_frames) return false;
+  const int nd = in.kind == RKB_SHAPE_SPHERE ? 1 : in.kind == RKB_SHAPE_BOX ? 3 : 2;
+  for (int k = 0; k < nd; ++k)
+    if (!(in.dims[k] > 0.0) || !std::isfinite(in.dims[k])) return false;
+  double qn = 0.0;
+  for (int k = 0; k < 4; ++k) { if (!std::isfinite(in.quat[k])) return false; qn += in.quat[k] * in.quat[k]; }
+  if (std::fabs(qn - 1.0) > 1e-6) return false;
+  for (int k = 0; k < 3; ++k) if (!std::isfinite(in.position[k])) return false;
+  out->kind = in.kind;
+  out->anchor = in.anchor;
+  for (int k = 0; k < 3; ++k) { out->pos[k] = in.position[k]; out->dims[k] = k < nd ? in.dims[k] : 0.0; }
+  // quaternion(const Vector&) normalises what it is given (rotations_3D.hpp:917-920)
+  for (int k = 0; k < 4; ++k) out->quat[k] = in.quat[k] / std::sqrt(qn);
+  const double* d = out->dims;
+  // getBoundingRadius: plane.cpp:32, sphere.cpp:31, capped_cylinder.cpp:30, cylinder.cpp:33, box.cpp:31
+  switch (in.kind) {
+    case RKB_SHAPE_PLANE: out->brad = std::sqrt(d[0] * d[0] + d[1] * d[1]) * 0.5; break;
+    case RKB_SHAPE_SPHERE: out->brad = d[0]; break;
+    case RKB_SHAPE_CCYLINDER: out->brad = d[0] * 0.5 + d[1]; break;
+    case RKB_SHAPE_CYLINDER: out->brad = std::sqrt(d[1] * d[1] + 0.25 * d[0] * d[0]); break;
+    default: out->brad = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) * 0.5; break;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2, rkb_proxy** out) {
+  if (!c || !out || n1 < 0 || n2 < 0 || (n1 > 0 && !m1) || (n2 > 0 && !m2)) return RKB_ERR_INVALID;
+  if (n1 > RKB_PROX_MAX_SHAPES || n2 > RKB_PROX_MAX_SHAPES) return RKB_ERR_UNSUPPORTED;
+  if (c->desc.dim != 3 || !c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  rkb_proxy* p = new (std::nothrow) rkb_proxy();
+  if (!p) return RKB_ERR_NOMEM;
+  std::memset(&p->prog, 0, sizeof p->prog);
+  p->prog.n1 = n1;
+  p->prog.n2 = n2;
+  p->n_frames = c->desc.n_frames;
+  for (int k = 0; k < n1 + n2; ++k) {
+    const rkb_shape& in = k < n1 ? m1[k] : m2[k - n1];
+    if (!lower_shape(in, c->desc.n_frames, &p->prog.s[k])) { delete p; return RKB_ERR_INVALID; }
+  }
+  for (int a = 0; a < n1; ++a)
+    for (int b = 0; b < n2; ++b)
+      if (prox_pair_has_finder(m1[a].kind, m2[b].kind)) p->finders.push_back(std::make_pair(a, b));
+  *out = p;
+  return RKB_OK;
+}
+
+void rkb_proxy_destroy(rkb_proxy* p) { delete p; }
+
+int rkb_proxy_finder_count(const rkb_proxy* p) { return p ? (int)p->finders.size() : RKB_ERR_INVALID; }
+
+int rkb_proxy_finder(const rkb_proxy* p, int k, int* i1, int* i2) {
+  if (!p || k < 0 || k >= (int)p->finders.size()) return RKB_ERR_INVALID;
+  if (i1) *i1 = p->finders[k].first;
+  if (i2) *i2 = p->finders[k].second;
+  return RKB_OK;
+}
+
+int rkb_proxy_program(const rkb_proxy* p, void* out, size_t size) {
+  if (!p || !out || size < sizeof(ProxProgram)) return RKB_ERR_INVALID;
+  std::memcpy(out, &p->prog, sizeof(ProxProgram));
+  return (int)sizeof(ProxProgram);
+}
+
+int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, const double* x, double* distance, int32_t* finder,
+                     double* points, unsigned flags, void* stream) {
+  if (!c || !p) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  if (!x || !distance) return RKB_ERR_INVALID;
+  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  if (p->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* dx = nullptr;
+  void *dd = nullptr, *dp = nullptr, *df = nullptr;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if ((rc = stage_out(ctx->out_a, distance, N * sizeof(double), L.device, &dd))) return rc;
+  if ((rc = stage_out(ctx->out_b, points, N * 6 * sizeof(double), L.device, &dp))) return rc;
+  if ((rc = stage_out(ctx->st, finder, N * sizeof(int32_t), L.device, &df))) return rc;
+  EvalArgs A;
+  A.x = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked);
+  A.u = cview((const double*)dx, (long long)N, 1, L.soa);
+  A.out = view((double*)dd, (long long)N, 1, L.soa);
+  A.out2 = view((double*)dp, (long long)N, 6, L.soa);
+  A.status = (int32_t*)df;
+  A.n_samples = (long long)N;
+  CU(cudaEventRecord(ctx->ev0, s));
+  const cudaError_t e = rkb_generic_proximity(ctx->d_prog, c->gp, A, p->prog, s);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  c->launches += 1;
+  if ((rc = unstage_out(dd, distance, N * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dp, points, N * 6 * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(df, finder, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
 }
 
 int rkb_twist_shaping_rows(const rkb_chain* c) { return c ? tmt_rows(c->desc) : RKB_ERR_INVALID; }

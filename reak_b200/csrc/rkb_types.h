@@ -171,6 +171,20 @@ struct EvalArgs {
   long long      n_samples;
 };
 
+// ---- proximity models (kte_proximity.cuh) ------------------------------------------------------
+#define RKB_PROX_MAX_SHAPES 16   // per model
+struct ProxShape {
+  int32_t kind;      // rkb_shape_kind
+  int32_t anchor;    // chain frame id, -1 = world
+  double  pos[3], quat[4];
+  double  dims[3];
+  double  brad;      // shape_3D::getBoundingRadius
+};
+struct ProxProgram {
+  int32_t   n1, n2;
+  ProxShape s[2 * RKB_PROX_MAX_SHAPES];  // model 1 then model 2
+};
+
 // ---- generic interpreter program ------------------------------------------------------------
 #define RKB_GEN_MAX_FRAMES 40
 #define RKB_GEN_MAX_ELEMENTS 96

@@ -43,6 +43,7 @@ def crs_chain(n_revolute=6, track=False, springs=False, physical=False, actuated
     axes = list(axes) if axes is not None else CRS_AXES
     link_offsets = list(link_offsets) if link_offsets is not None else [(0.0, 0.0, z) for z in CRS_LINK_Z]
     s = kte_system("crs")
+    s.joint_end_frames, s.link_end_frames = [], []  # what a proximity model anchors its shapes to
     base = kte.frame_3D()
     base.Acceleration = [0.0, 0.0, 9.81]
     base.Position = [0.0, -3.3, 0.3]
@@ -79,6 +80,8 @@ def crs_chain(n_revolute=6, track=False, springs=False, physical=False, actuated
         s.dofs_gen.append(coord)
         s.mass_calc << inertia
         gen_inertias.append(rotor)
+        s.joint_end_frames.append(end)
+        s.link_end_frames.append(nxt)
         cur = nxt
 
     gen_inertias = []
@@ -274,3 +277,27 @@ PRESETS = {
 
 def make(name):
     return PRESETS[name]()
+
+
+def crs_proxy_models(system, track=False):
+    """(robot, lab) proximity models of the CRS A465 in the MD148 lab: the shapes of
+    examples/robot_airship/old/CRS_A465_geom_model.cpp:88-148 (joint2 / link2 / link3 / link5 capsules and the
+    end-effector sphere, each on its joint's end frame) and of examples/robot_airship/build_MD148_lab.cpp:103-149
+    (floor, north and west walls, the two capsules along the track).  `system` is a crs_chain(...) with at least
+    six revolute joints; `track` says whether joint 0 is the prismatic track."""
+    from . import proximity as px
+    je = system.joint_end_frames[1:] if track else system.joint_end_frames
+    half_pi = math.pi * 0.5
+    robot = px.proxy_query_model_3D("CRS_A465_model_proxy")
+    robot.addShape(px.capped_cylinder("joint2_cyl", je[0], px.pose_3D.axis_angle(half_pi, (1.0, 0.0, 0.0), (0.0, 0.0, 0.3302)), 0.34, 0.09))
+    robot.addShape(px.capped_cylinder("link2_cyl", je[1], px.pose_3D((0.0, 0.0, 0.15)), 0.3, 0.07))
+    robot.addShape(px.capped_cylinder("link3_cyl", je[2], px.pose_3D((0.0, 0.0, 0.165)), 0.33, 0.07))
+    robot.addShape(px.capped_cylinder("link5_cyl", je[4], px.pose_3D((0.0, 0.0, 0.0381)), 0.0762, 0.05))
+    robot.addShape(px.sphere("EE_sphere", je[5], px.pose_3D((-0.04, 0.0, 0.05)), 0.11))
+    lab = px.proxy_query_model_3D("MD148_basic_lab_proxy")
+    lab.addShape(px.plane("MD148_floor", None, px.pose_3D((-0.8, -1.0, 0.0)), (4.0, 6.0)))
+    lab.addShape(px.plane("MD148_north_wall", None, px.pose_3D.axis_angle(half_pi, (0.0, -1.0, 0.0), (1.2, -1.0, 1.5)), (3.0, 6.0)))
+    lab.addShape(px.plane("MD148_west_wall", None, px.pose_3D.axis_angle(half_pi, (1.0, 0.0, 0.0), (-0.8, 2.0, 1.5)), (4.0, 3.0)))
+    lab.addShape(px.capped_cylinder("MD148_robot_track_left", None, px.pose_3D.axis_angle(half_pi, (1.0, 0.0, 0.0), (0.1, -1.71, 0.15)), 3.42, 0.18))
+    lab.addShape(px.capped_cylinder("MD148_robot_track_right", None, px.pose_3D.axis_angle(half_pi, (1.0, 0.0, 0.0), (-0.1, -1.71, 0.15)), 3.42, 0.18))
+    return robot, lab

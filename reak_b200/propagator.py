@@ -265,6 +265,34 @@ class kte_batch_propagator(object):
         _abi.check(self._lib.rkb_frames(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None, ptr(fr), flags, stream), "rkb_frames")
         return fr
 
+    def get_min_distances(self, pair, x, with_points=True):
+        """proxy_query_pair_3D::findMinimumDistance at every state (rkb_min_distance): distance [N], finder index [N]
+        and, with_points, (mPoint1, mPoint2) [N][6].  `pair` is a reak_b200.proximity.proxy_query_pair_3D; its device
+        program is built once and cached on the pair."""
+        from . import proximity
+        h = getattr(pair, "_rkb_handle", None)
+        if h is None or getattr(pair, "_rkb_owner", None) is not self:
+            h = proximity.ProxyHandle(self._lib, self._h, pair, self.compiled.frames)
+            pair._rkb_handle, pair._rkb_owner = h, self
+        x, N = self._in(x, self.nx, np.float64)
+        d = self._like(x, (N,))
+        f = self._like(x, (N,), np.int32)
+        pts = self._like(x, (N, 6)) if with_points else None
+        flags, stream, ptr = self._prep([x, d, f, pts], False)
+        _abi.check(self._lib.rkb_min_distance(self._h, h._h, self.device, N, ptr(x), ptr(d), ptr(f), ptr(pts), flags, stream),
+                   "rkb_min_distance")
+        return (d, f, pts) if with_points else (d, f)
+
+    def is_free(self, pairs, x):
+        """manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99): no proxy pair reports
+        a negative minimum distance.  Returns a bool array [N]."""
+        free = None
+        for pair in pairs:
+            d, _ = self.get_min_distances(pair, x, with_points=False)
+            ok = ~(d < 0.0)
+            free = ok if free is None else (free & ok)
+        return free
+
     def get_twist_shaping(self, x, with_derivative=True):
         """mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm [N][rows][n], Mcm [rows][rows]
         (constant) and, with_derivative, Tcm_dot [N][rows][n]."""

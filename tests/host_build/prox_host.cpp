@@ -1,0 +1,53 @@
+// Test infrastructure (never shipped, never loaded by the product): compiles the DEVICE source
+// reak_b200/csrc/kte_proximity.cuh for the host, so that the CPU suite can hold the finders the GPU
+// runs against the compiled reference (oracle/_ref) without a GPU.  Built by tests/test_proximity.py
+// into a temporary directory with g++.
+#include <cmath>
+#include <cstdint>
+#include "../../include/reak_b200.h"
+#include "../../reak_b200/csrc/rkb_types.h"
+
+#define GD static inline
+// the helpers kte_generic.cu defines ahead of including the header
+struct V3 { double x, y, z; };
+GD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+GD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+GD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+GD V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+GD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+struct Q4 { double w, x, y, z; };
+GD Q4 qmul(Q4 a, Q4 b) {
+  Q4 r;
+  r.w = b.w * a.w - b.x * a.x - b.y * a.y - b.z * a.z;
+  r.x = b.w * a.x + b.z * a.y - b.y * a.z + b.x * a.w;
+  r.y = b.w * a.y - b.z * a.x + b.x * a.z + b.y * a.w;
+  r.z = b.w * a.z + b.y * a.x - b.x * a.y + b.z * a.w;
+  return r;
+}
+GD Q4 qconj(Q4 a) { Q4 r; r.w = a.w; r.x = -a.x; r.y = -a.y; r.z = -a.z; return r; }
+using std::fabs;
+using std::sqrt;
+#include "../../reak_b200/csrc/kte_proximity.cuh"
+
+// program: the ProxProgram rkb_proxy_create lowers (read back through rkb_proxy_program, a test hook of the
+// product library); frames: [n_frames][7] world position + quaternion of the chain frames.
+extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames, double* dist, double* pts) {
+  Pose pose[2 * RKB_PROX_MAX_SHAPES];
+  for (int k = 0; k < P->n1 + P->n2; ++k) {
+    const ProxShape& S = P->s[k];
+    V3 fp = v3(0, 0, 0);
+    Q4 fq; fq.w = 1; fq.x = fq.y = fq.z = 0;
+    if (S.anchor >= 0) {
+      const double* f = frames + 7 * S.anchor;
+      fp = v3(f[0], f[1], f[2]);
+      fq.w = f[3]; fq.x = f[4]; fq.y = f[5]; fq.z = f[6];
+    }
+    pose[k] = prox_shape_pose(S, S.anchor >= 0, fp, fq);
+  }
+  ProxRecord R;
+  const int best = prox_min_distance(*P, pose, R);
+  *dist = R.d;
+  pts[0] = R.p1.x; pts[1] = R.p1.y; pts[2] = R.p1.z; pts[3] = R.p2.x; pts[4] = R.p2.y; pts[5] = R.p2.z;
+  return best;
+}
+extern "C" int prox_host_program_size(void) { return (int)sizeof(ProxProgram); }

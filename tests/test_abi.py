@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _abi.SYMBOLS, "ctypes table misses %s" % n
-    assert lib.rkb_version() == 110
+    assert lib.rkb_version() == 120
     assert lib.rkb_strerror(0) == b"ok" and b"CPU fallback" in lib.rkb_strerror(_abi.ERR_CUDA)
 
 

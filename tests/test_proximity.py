@@ -1,0 +1,387 @@
+"""Proximity queries (rkb_min_distance) against the compiled reference.
+
+CPU (`-m "not gpu"`): the DEVICE source of the finders (reak_b200/csrc/kte_proximity.cuh) is compiled for the
+host by tests/host_build/prox_host.cpp and fed the program rkb_proxy_create lowered (host-only code of the
+product library, no GPU needed); its answers are held against
+  (a) the live reference, proxy_query_pair_3D::findMinimumDistance of oracle/_ref/libreak_ref.so, and
+  (b) tests/golden/proximity/proximity.npz, outputs of that library committed with their generator.
+GPU (`-m gpu`): the same comparisons through the C-ABI on the device.
+
+Tolerance: distances and points are O(1) lengths in metres; 1e-10 absolute (the finders are a few dozen
+double operations after the chain's forward kinematics).  ccylinder-box runs a golden-section search whose
+comparisons can flip on rounding differences: its distance is only defined to the search tolerance, and
+gets 1e-6.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import random_batch
+from reak_b200 import _abi, kte, presets
+from reak_b200 import proximity as px
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "proximity", "proximity.npz")
+KINDS = {"plane": px.plane, "sphere": px.sphere, "ccylinder": px.capped_cylinder, "cylinder": px.cylinder, "box": px.box}
+TOL = 1e-10
+TOL_SEARCH = 1e-6
+
+
+def random_pose(rng, spread=1.2):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return px.pose_3D(rng.uniform(-spread, spread, size=3), q)
+
+
+def random_shape(rng, kind, anchor=None, spread=1.2):
+    pose = random_pose(rng, spread)
+    if kind == "plane":
+        return px.plane("pl", anchor, pose, rng.uniform(0.5, 3.0, size=2))
+    if kind == "sphere":
+        return px.sphere("sp", anchor, pose, rng.uniform(0.05, 0.6))
+    if kind == "ccylinder":
+        return px.capped_cylinder("cc", anchor, pose, rng.uniform(0.1, 1.5), rng.uniform(0.03, 0.4))
+    if kind == "cylinder":
+        return px.cylinder("cy", anchor, pose, rng.uniform(0.1, 1.5), rng.uniform(0.03, 0.4))
+    return px.box("bx", anchor, pose, rng.uniform(0.1, 1.5, size=3))
+
+
+def has_search(pair):
+    kinds = {s.kind for s in pair.model1.mShapeList} | {s.kind for s in pair.model2.mShapeList}
+    return _abi.SHAPE_CCYLINDER in kinds and _abi.SHAPE_BOX in kinds
+
+
+def agree(got, want, tol):
+    """(distance, finder, points) triples; a different finder is accepted only on a tie."""
+    d, f, p = got
+    dr, fr, pr = want
+    fin = np.isfinite(dr)
+    assert np.array_equal(np.isfinite(d), fin)
+    assert np.all(d[~fin] == dr[~fin])
+    assert np.max(np.abs(d[fin] - dr[fin]), initial=0.0) < tol
+    same = f == fr
+    assert np.all(np.abs(d[~same] - dr[~same]) < tol), "different finder without a tie"
+    ok = fin & same
+    assert np.max(np.abs(p[ok] - pr[ok]), initial=0.0) < max(tol, 1e-9) * (1e3 if tol > TOL else 1.0)
+
+
+# ---- the host build of the device source --------------------------------------------------------
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("prox_host") / "libprox_host.so")
+    src = os.path.join(HERE, "host_build", "prox_host.cpp")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src], check=True)
+    lib = C.CDLL(out)
+    lib.prox_host_min_distance.restype = C.c_int
+    lib.prox_host_min_distance.argtypes = [C.c_void_p] * 4
+    return lib
+
+
+class HostProximity(object):
+    """chain + proxy lowered by the product library (host code), finders run by the host build."""
+
+    def __init__(self, host_lib, system, pair):
+        self.compiled = kte.compile_chain(system.chain, system.mass_calc, system.dofs_gen, system.inputs)
+        self.lib = _abi.load_library()
+        self.h = C.c_void_p()
+        _abi.check(self.lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(self.h)), "rkb_chain_create")
+        self.proxy = px.ProxyHandle(self.lib, self.h, pair, self.compiled.frames)
+        size = host_lib.prox_host_program_size()
+        self.blob = C.create_string_buffer(size)
+        assert self.lib.rkb_proxy_program(self.proxy._h, self.blob, size) == size
+        self.host = host_lib
+
+    def min_distance(self, frames):
+        """frames [N][n_frames][>=7] world poses -> (distance, finder, points)."""
+        N = frames.shape[0]
+        d, f, p = np.zeros(N), np.zeros(N, dtype=np.int32), np.zeros((N, 6))
+        for i in range(N):
+            fr = np.ascontiguousarray(frames[i][:, :7])
+            di = C.c_double()
+            f[i] = self.host.prox_host_min_distance(self.blob, fr.ctypes.data_as(C.c_void_p), C.byref(di), p[i].ctypes.data_as(C.c_void_p))
+            d[i] = di.value
+        return d, f, p
+
+    def close(self):
+        self.proxy.close()
+        self.lib.rkb_chain_destroy(self.h)
+
+
+def ref_frames(R, x):
+    return np.stack([R.frames(x[i:i + 1]) for i in range(x.shape[0])])
+
+
+def need_ref(oracle_built):
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("k2", sorted(KINDS))
+@pytest.mark.parametrize("k1", sorted(KINDS))
+def test_single_finder_host_vs_reference(k1, k2, host_lib, oracle_built):
+    """every (kind, kind) combination, both model orders: one shape fixed in the world, one on the arm"""
+    need_ref(oracle_built)
+    rng = np.random.default_rng(sum(ord(c) for c in k1) * 131 + sum(ord(c) for c in k2))
+    s = presets.make("crs6")
+    for trial in range(24):
+        a = random_shape(rng, k1, s.joint_end_frames[trial % 6] if trial % 2 else None, spread=0.8 if trial % 2 else 1.2)
+        b = random_shape(rng, k2, None)
+        if trial % 2 == 0:
+            b.pose.position = tuple(np.array(b.pose.position) + np.array([0.0, -3.3, 0.8]))  # near the arm
+        pair = px.proxy_query_pair_3D("t", px.proxy_query_model_3D("a").addShape(a), px.proxy_query_model_3D("b").addShape(b))
+        H = HostProximity(host_lib, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 4, seed=trial, q_range=3.0)
+        want = R.min_distance(pair, x)
+        got = H.min_distance(ref_frames(R, x))
+        if not pair.finder_pairs():
+            assert np.all(np.isinf(got[0])) and np.all(got[1] == -1) and np.all(np.isinf(want[0]))
+        else:
+            agree(got, want, TOL_SEARCH if has_search(pair) else TOL)
+        H.close()
+
+
+def special_pairs():
+    """configurations that land in the finders' special branches"""
+    I = px.pose_3D()
+    out = []
+    # parallel capsules (the always-true overlap branch), overlapping and far apart along the axis
+    out.append(("cc_parallel", px.capped_cylinder("a", None, px.pose_3D((0, 0, 0)), 1.0, 0.1), px.capped_cylinder("b", None, px.pose_3D((0.5, 0.2, 0.3)), 0.6, 0.2)))
+    out.append(("cc_parallel_far", px.capped_cylinder("a", None, px.pose_3D((0, 0, 0)), 1.0, 0.1), px.capped_cylinder("b", None, px.pose_3D((0.5, 0.2, 3.0)), 0.6, 0.2)))
+    # capsule and cylinder lying flat on a plane, cylinder standing on its end
+    flat = px.pose_3D.axis_angle(np.pi / 2, (1, 0, 0), (0.2, 0.1, 0.5))
+    out.append(("plane_cc_flat", px.plane("p", None, I, (2, 2)), px.capped_cylinder("b", None, flat, 0.8, 0.1)))
+    out.append(("plane_cy_flat", px.plane("p", None, I, (2, 2)), px.cylinder("b", None, flat, 0.8, 0.1)))
+    out.append(("plane_cy_end", px.plane("p", None, I, (2, 2)), px.cylinder("b", None, px.pose_3D((0.2, 0.1, 0.9)), 0.8, 0.1)))
+    out.append(("plane_cc_below", px.plane("p", None, I, (2, 2)), px.capped_cylinder("b", None, px.pose_3D.axis_angle(0.4, (0, 1, 0), (0.2, 0.1, -0.2)), 0.8, 0.1)))
+    # sphere inside a box (each nearest face), outside a corner, above a cylinder's end, beside its rim
+    for k, c in enumerate([(0.4, 0.0, 0.0), (0.0, -0.4, 0.1), (0.1, 0.0, 0.2), (1.0, 1.0, 1.0)]):
+        out.append(("sphere_box_%d" % k, px.sphere("s", None, px.pose_3D(c), 0.05), px.box("b", None, I, (1.0, 1.0, 0.5))))
+    out.append(("sphere_cy_top", px.sphere("s", None, px.pose_3D((0.05, 0.02, 0.9)), 0.1), px.cylinder("c", None, I, 1.0, 0.3)))
+    out.append(("sphere_cy_rim", px.sphere("s", None, px.pose_3D((0.6, 0.2, 0.9)), 0.1), px.cylinder("c", None, I, 1.0, 0.3)))
+    out.append(("sphere_cy_side", px.sphere("s", None, px.pose_3D((0.6, 0.2, 0.1)), 0.1), px.cylinder("c", None, I, 1.0, 0.3)))
+    out.append(("sphere_cc_cap", px.sphere("s", None, px.pose_3D((0.2, 0.1, -1.2)), 0.1), px.capped_cylinder("c", None, I, 1.0, 0.3)))
+    # penetrations
+    out.append(("sphere_sphere_in", px.sphere("s", None, px.pose_3D((0.1, 0, 0)), 0.3), px.sphere("t", None, px.pose_3D((0.3, 0.1, 0)), 0.2)))
+    out.append(("cc_box_in", px.capped_cylinder("c", None, px.pose_3D.axis_angle(0.3, (1, 1, 0), (0.1, 0.1, 0.1)), 0.5, 0.05), px.box("b", None, I, (1.0, 1.0, 1.0))))
+    out.append(("plane_box", px.plane("p", None, I, (2, 2)), px.box("b", None, px.pose_3D.axis_angle(0.7, (1, 2, 3), (0.1, 0.2, 0.9)), (0.3, 0.5, 0.7))))
+    out.append(("plane_plane", px.plane("p", None, I, (2, 2)), px.plane("q", None, px.pose_3D.axis_angle(0.7, (1, 2, 3), (0.1, 0.2, 0.9)), (1.0, 3.0))))
+    out.append(("plane_plane_side", px.plane("p", None, I, (2, 2)), px.plane("q", None, px.pose_3D.axis_angle(1.2, (1, 0, 0), (3.0, 0.2, 0.4)), (1.0, 1.0))))
+    return out
+
+
+@pytest.mark.parametrize("case", special_pairs(), ids=[c[0] for c in special_pairs()])
+def test_special_branches_host_vs_reference(case, host_lib, oracle_built):
+    need_ref(oracle_built)
+    _, a, b = case
+    s = presets.make("crs6")
+    for first, second in ((a, b), (b, a)):
+        pair = px.proxy_query_pair_3D("t", px.proxy_query_model_3D("a").addShape(first), px.proxy_query_model_3D("b").addShape(second))
+        H = HostProximity(host_lib, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 1, seed=1)
+        agree(H.min_distance(ref_frames(R, x)), R.min_distance(pair, x), TOL_SEARCH if has_search(pair) else TOL)
+        H.close()
+
+
+def mixed_models(s, rng, n1=6, n2=7):
+    kinds = sorted(KINDS)
+    m1, m2 = px.proxy_query_model_3D("robot"), px.proxy_query_model_3D("world")
+    for k in range(n1):
+        m1.addShape(random_shape(rng, kinds[k % 5], s.joint_end_frames[k % len(s.joint_end_frames)], spread=0.3))
+    for k in range(n2):
+        sh = random_shape(rng, kinds[(k + 2) % 5], None, spread=1.0)
+        sh.pose.position = tuple(np.array(sh.pose.position) + np.array([0.0, -3.3, 0.8]))
+        m2.addShape(sh)
+    return px.proxy_query_pair_3D("mixed", m1, m2)
+
+
+def test_crs_lab_host_vs_reference(host_lib, oracle_built):
+    """the CRS arm's proximity model against the MD148 lab, shapes riding on the joint end frames"""
+    need_ref(oracle_built)
+    s = presets.make("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    assert len(pair.finder_pairs()) == 25
+    H = HostProximity(host_lib, s, pair)
+    assert H.proxy.n_finders == 25 and H.proxy.finder(7) == pair.finder_pairs()[7]
+    R = oracle_built.Reference(H.compiled)
+    x, _ = random_batch(H.compiled, 256, seed=11, q_range=3.1)
+    want = R.min_distance(pair, x)
+    agree(H.min_distance(ref_frames(R, x)), want, TOL)
+    assert (want[0] < 0).any() and (want[0] > 0).any()  # both colliding and free states in the sample
+    assert len(set(want[1].tolist())) >= 3                # and more than one finder wins
+    H.close()
+
+
+def test_mixed_models_host_vs_reference(host_lib, oracle_built):
+    """every shape kind on both sides, including pairs without a finder and the culling test"""
+    need_ref(oracle_built)
+    s = presets.make("crs7")
+    for seed in range(4):
+        pair = mixed_models(s, np.random.default_rng(100 + seed))
+        H = HostProximity(host_lib, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 64, seed=seed, q_range=2.0)
+        agree(H.min_distance(ref_frames(R, x)), R.min_distance(pair, x), TOL_SEARCH)
+        H.close()
+
+
+def golden_pair(s, g):
+    m = [px.proxy_query_model_3D("m1"), px.proxy_query_model_3D("m2")]
+    ctor = {1: "plane", 2: "sphere", 3: "ccylinder", 4: "cylinder", 5: "box"}
+    for which, key in enumerate(("shapes1", "shapes2")):
+        for row in g[key]:
+            kind, anchor = int(row[0]), int(row[1])
+            sh = px.shape_3D("g", None if anchor < 0 else anchor, px.pose_3D(row[2:5], row[5:9]), row[9:12])
+            sh.kind = kind
+            assert ctor[kind]
+            m[which].addShape(sh)
+    return px.proxy_query_pair_3D("golden", m[0], m[1])
+
+
+def test_host_vs_golden(host_lib):
+    """committed outputs of the reference (tests/golden/proximity/make_golden_proximity.py); runs without oracle/_ref"""
+    g = np.load(GOLDEN)
+    for tag, preset in (("crs_lab", "crs6"), ("mixed", "crs7")):
+        s = presets.make(preset)
+        sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        pair = golden_pair(s, sub)
+        H = HostProximity(host_lib, s, pair)
+        got = H.min_distance(sub["frames"])
+        agree(got, (sub["distance"], sub["finder"], sub["points"]), TOL_SEARCH if tag == "mixed" else TOL)
+        H.close()
+
+
+def test_proxy_create_rejects():
+    lib = _abi.load_library()
+    s = presets.make("crs6")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    h = C.c_void_p()
+    _abi.check(lib.rkb_chain_create(C.byref(c.desc), C.byref(h)), "rkb_chain_create")
+
+    def create(shape, n=1):
+        arr = (_abi.rkb_shape * max(n, 1))()
+        for k in range(n):
+            arr[k] = shape.to_c(c.frames)
+        out = C.c_void_p()
+        rc = lib.rkb_proxy_create(h, arr, n, arr, n, C.byref(out))
+        if rc == 0:
+            lib.rkb_proxy_destroy(out)
+        return rc
+
+    assert create(px.sphere("s", None, None, 0.1)) == 0
+    assert create(px.sphere("s", None, None, -0.1)) == _abi.ERR_INVALID             # non-positive size
+    assert create(px.sphere("s", 999, None, 0.1)) == _abi.ERR_INVALID               # anchor out of range
+    assert create(px.sphere("s", None, px.pose_3D(quat=(2, 0, 0, 0)), 0.1)) == _abi.ERR_INVALID  # not a rotation
+    bad = px.sphere("s", None, None, 0.1)
+    bad.kind = 9
+    assert create(bad) == _abi.ERR_INVALID
+    assert create(px.sphere("s", None, None, 0.1), n=_abi.PROXY_MAX_SHAPES + 1) == _abi.ERR_UNSUPPORTED
+    lib.rkb_chain_destroy(h)
+    # planar chains have no 3D frames to anchor to
+    s2 = presets.make("planar2")
+    c2 = kte.compile_chain(s2.chain, s2.mass_calc, s2.dofs_gen, s2.inputs)
+    h2 = C.c_void_p()
+    _abi.check(lib.rkb_chain_create(C.byref(c2.desc), C.byref(h2)), "rkb_chain_create")
+    arr = (_abi.rkb_shape * 1)()
+    arr[0] = px.sphere("s", None, None, 0.1).to_c()
+    out = C.c_void_p()
+    assert lib.rkb_proxy_create(h2, arr, 1, arr, 1, C.byref(out)) == _abi.ERR_UNSUPPORTED
+    lib.rkb_chain_destroy(h2)
+
+
+# ---- GPU ------------------------------------------------------------------------------------------
+def _gpu_prop(preset):
+    from reak_b200.propagator import KteBatchPropagator
+    s = presets.make(preset)
+    return s, KteBatchPropagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+
+
+@pytest.mark.gpu
+def test_gpu_crs_lab_vs_reference(oracle_built):
+    need_ref(oracle_built)
+    s, P = _gpu_prop("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 4096, seed=5, q_range=3.1)
+    want = R.min_distance(pair, x)
+    got = P.get_min_distances(pair, x)
+    agree(got, want, TOL)
+    free = P.is_free([pair], x)
+    assert np.array_equal(free, ~(want[0] < 0.0)) and free.any() and (~free).any()
+
+
+@pytest.mark.gpu
+def test_gpu_track_arm_vs_reference(oracle_built):
+    need_ref(oracle_built)
+    s, P = _gpu_prop("crs7")
+    robot, lab = presets.crs_proxy_models(s, track=True)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 2048, seed=6, q_range=2.5)
+    agree(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_gpu_mixed_models_vs_reference(seed, oracle_built):
+    need_ref(oracle_built)
+    s, P = _gpu_prop("crs7")
+    pair = mixed_models(s, np.random.default_rng(100 + seed))
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 1024, seed=seed, q_range=2.0)
+    agree(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL_SEARCH)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", special_pairs(), ids=[c[0] for c in special_pairs()])
+def test_gpu_special_branches_vs_reference(case, oracle_built):
+    need_ref(oracle_built)
+    _, a, b = case
+    s, P = _gpu_prop("crs6")
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 3, seed=1)
+    for first, second in ((a, b), (b, a)):
+        pair = px.proxy_query_pair_3D("t", px.proxy_query_model_3D("a").addShape(first), px.proxy_query_model_3D("b").addShape(second))
+        agree(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL_SEARCH if has_search(pair) else TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_vs_golden():
+    g = np.load(GOLDEN)
+    for tag, preset in (("crs_lab", "crs6"), ("mixed", "crs7")):
+        s, P = _gpu_prop(preset)
+        sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        pair = golden_pair(s, sub)
+        agree(P.get_min_distances(pair, sub["x"]), (sub["distance"], sub["finder"], sub["points"]), TOL_SEARCH if tag == "mixed" else TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_properties():
+    """2^20 device-resident states: the answer of a sample does not depend on its place in the batch, ragged
+    tails are handled, a pair without finders reports +inf / -1, and no distance is non-finite."""
+    import torch
+    s, P = _gpu_prop("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    N = (1 << 20) + 37
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.rand((N, P.nx), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1) * 3.0
+    d, f, pts = P.get_min_distances(pair, x)
+    assert torch.isfinite(d).all() and ((f >= 0) & (f < 25)).all()
+    perm = torch.randperm(N, device="cuda", generator=gen)
+    d2, f2, pts2 = P.get_min_distances(pair, x[perm].contiguous())
+    assert torch.equal(d2, d[perm]) and torch.equal(f2, f[perm]) and torch.equal(pts2, pts[perm])
+    # outside contact the segment between the two points has the reported length (every finder of this pair)
+    sel = d > 1e-3
+    seg = (pts[sel, 3:] - pts[sel, :3]).norm(dim=1)
+    assert sel.any() and (seg - d[sel]).abs().max().item() < 1e-9
+    none = px.proxy_query_pair_3D("none", px.proxy_query_model_3D("a").addShape(px.box("b", None, None, (1, 1, 1))),
+                                  px.proxy_query_model_3D("b").addShape(px.box("c", None, None, (1, 1, 1))))
+    dn, fn = P.get_min_distances(none, x[:100].contiguous(), with_points=False)
+    assert torch.isinf(dn).all() and (fn == -1).all()

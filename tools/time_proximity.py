@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Developer tool: time rkb_min_distance (CRS arm against the MD148 lab, device-resident states) and the
+reference's findMinimumDistance on one host core for the same states."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    from reak_b200 import kte_batch_propagator, presets
+    from reak_b200 import proximity as px
+    name = sys.argv[1] if len(sys.argv) > 1 else "crs6"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+    s = presets.make(name)
+    p = kte_batch_propagator(s)
+    robot, lab = presets.crs_proxy_models(s, track=(name == "crs7"))
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-3, 3, (n, p.nx))
+    dx = torch.from_numpy(x).cuda()
+    ms = []
+    for k in range(7):
+        d, f = p.get_min_distances(pair, dx, with_points=False)
+        ms.append(p.last_kernel_ms())
+    t = min(ms[2:])
+    print("%s min_distance (25 finders) n=%d  %.3f ms  %.3g states/s  colliding %.1f %%" % (name, n, t, n / t * 1e3, 100.0 * (d < 0).double().mean().item()))
+    d, f, pts = p.get_min_distances(pair, dx)
+    print("%s with points               n=%d  %.3f ms" % (name, n, p.last_kernel_ms()))
+    t0 = time.perf_counter()
+    d, f, pts = p.get_min_distances(pair, x)
+    print("%s host buffers (pageable)   n=%d  %.3f ms end to end" % (name, n, (time.perf_counter() - t0) * 1e3))
+    fr = p.get_frames(dx[: n // 4].contiguous(), torch.zeros((n // 4, p.nu), dtype=torch.float64, device="cuda"))
+    print("%s rkb_frames alone          n=%d  %.3f ms" % (name, n // 4, p.last_kernel_ms()))
+    try:
+        from oracle import pyref
+        if pyref.have_ref():
+            R = pyref.Reference(p.compiled)
+            m = 4096
+            t0 = time.perf_counter()
+            dr, _, _ = R.min_distance(pair, x[:m])
+            dt = time.perf_counter() - t0
+            print("reference, 1 core: %d states in %.3f s = %.3g states/s; max |d - d_ref| = %.2e" % (m, dt, m / dt, np.abs(dr - d[:m]).max()))
+    except Exception as e:  # the checker is optional for this tool
+        print("reference not timed:", e)
+
+
+if __name__ == "__main__":
+    main()
