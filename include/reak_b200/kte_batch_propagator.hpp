@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../reak_b200.h"
@@ -62,6 +63,9 @@ class chain_builder {
   }
 
   int add_frame() { return mFrames++; }
+  /// frame object of the host model (e.g. a ReaK frame_3D) -> frame id; filled by reak_bridge.hpp so that
+  /// proximity shapes can be anchored to the frames they ride on
+  std::map<const void*, int> frame_ids;
   int add_coord() { return mCoords++; }  ///< state slot j <-> kte_nl_system::dofs_gen[j]
 
   /// The un-driven root frame (robot_base in CRS_A465_models.cpp:298-301); gravity is an upward Acceleration.
@@ -257,6 +261,30 @@ class kte_batch_propagator {
   int frame_count() const { return rkb_chain_frame_count(mChain); }
   void get_frames(std::size_t n, const double* x, const double* u, double* frames, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_frames(mChain, mDevice, n, x, u, frames, flags, stream), "rkb_frames");
+  }
+  /// proxy_query_pair_3D (geometry/proximity/proxy_query_model.hpp): two shape lists, the shapes anchored to frames
+  /// of this chain or fixed in the world.  The caller owns the handle: rkb_proxy_destroy.
+  rkb_proxy* make_proxy_pair(const std::vector<rkb_shape>& model1, const std::vector<rkb_shape>& model2) const {
+    rkb_proxy* p = NULL;
+    check(rkb_proxy_create(mChain, model1.empty() ? NULL : &model1[0], static_cast<int>(model1.size()),
+                           model2.empty() ? NULL : &model2[0], static_cast<int>(model2.size()), &p), "rkb_proxy_create");
+    return p;
+  }
+  /// proxy_query_pair_3D::findMinimumDistance at every state (proxy_query_model.cpp:388-412): mDistance [n], finder
+  /// index [n] (nullable), mPoint1 / mPoint2 [n][6] (nullable).
+  void get_min_distances(const rkb_proxy* pair, std::size_t n, const double* x, double* distance, int32_t* finder = NULL,
+                         double* points = NULL, unsigned flags = 0, void* stream = NULL) const {
+    check(rkb_min_distance(mChain, pair, mDevice, n, x, distance, finder, points, flags, stream), "rkb_min_distance");
+  }
+  /// manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99) for one state
+  bool is_free(const std::vector<const rkb_proxy*>& pairs, const point_type& p) const {
+    if (p.size() != get_state_dimensions()) throw std::range_error("State vector dimension mismatch!");
+    for (std::size_t k = 0; k < pairs.size(); ++k) {
+      double d = 0.0;
+      get_min_distances(pairs[k], 1, &p[0], &d);
+      if (d < 0.0) return false;
+    }
+    return true;
   }
   /// mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm and (nullable) Tcm_dot, [n][rows][dof];
   /// twist_shaping_rows() and twist_shaping_mcm(Mcm) give the row count and the constant rows x rows Mcm.

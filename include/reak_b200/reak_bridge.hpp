@@ -42,6 +42,12 @@
 #include <ReaK/ctrl/mbd_kte/driving_actuator.hpp>
 #include <ReaK/ctrl/mbd_kte/mass_matrix_calculator.hpp>
 #include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
+#include <ReaK/geometry/shapes/plane.hpp>
+#include <ReaK/geometry/shapes/sphere.hpp>
+#include <ReaK/geometry/shapes/capped_cylinder.hpp>
+#include <ReaK/geometry/shapes/cylinder.hpp>
+#include <ReaK/geometry/shapes/box.hpp>
+#include <ReaK/geometry/proximity/proxy_query_model.hpp>
 
 #include "kte_batch_propagator.hpp"
 
@@ -229,7 +235,54 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
     bf.ang_acceleration[0] = B->AngAcceleration;
   }
   b.set_base(root, bf);
+  b.frame_ids = frames.ids;
   return b;
+}
+
+/// Flatten a proximity model (geometry/proximity/proxy_query_model.hpp:153-182) into the shape list of
+/// rkb_proxy_create.  Public accessors only: shape_3D::getAnchor() / getPose(), the shapes' getDimensions() /
+/// getRadius() / getLength().  A shape must ride on a frame of the compiled chain (looked up in
+/// builder.frame_ids) or have no anchor; a shape whose anchor is some other pose, or whose pose chain goes
+/// deeper, is refused.
+inline std::vector<rkb_shape> compile_proxy_model(const ReaK::geom::proxy_query_model_3D& mdl, const chain_builder& builder) {
+  using namespace ReaK;
+  using ReaK::rtti::rk_dynamic_ptr_cast;
+  std::vector<rkb_shape> out;
+  for (std::size_t i = 0; i < mdl.mShapeList.size(); ++i) {
+    const shared_ptr<geom::shape_3D>& sh = mdl.mShapeList[i];
+    if (!sh) continue;  // createProxFinderList skips null shapes (proxy_query_model.cpp:219-220)
+    rkb_shape s = rkb_shape();
+    if (shared_ptr<geom::plane> p = rk_dynamic_ptr_cast<geom::plane>(sh)) {
+      s.kind = RKB_SHAPE_PLANE; s.dims[0] = p->getDimensions()[0]; s.dims[1] = p->getDimensions()[1];
+    } else if (shared_ptr<geom::sphere> p = rk_dynamic_ptr_cast<geom::sphere>(sh)) {
+      s.kind = RKB_SHAPE_SPHERE; s.dims[0] = p->getRadius();
+    } else if (shared_ptr<geom::capped_cylinder> p = rk_dynamic_ptr_cast<geom::capped_cylinder>(sh)) {
+      s.kind = RKB_SHAPE_CCYLINDER; s.dims[0] = p->getLength(); s.dims[1] = p->getRadius();
+    } else if (shared_ptr<geom::cylinder> p = rk_dynamic_ptr_cast<geom::cylinder>(sh)) {
+      s.kind = RKB_SHAPE_CYLINDER; s.dims[0] = p->getLength(); s.dims[1] = p->getRadius();
+    } else if (shared_ptr<geom::box> p = rk_dynamic_ptr_cast<geom::box>(sh)) {
+      s.kind = RKB_SHAPE_BOX; for (int k = 0; k < 3; ++k) s.dims[k] = p->getDimensions()[k];
+    } else {
+      throw unsupported_chain("proximity shape outside plane / sphere / capped_cylinder / cylinder / box");
+    }
+    const shared_ptr<pose_3D<double> >& anchor = sh->getAnchor();
+    if (!anchor) s.anchor = -1;
+    else {
+      std::map<const void*, int>::const_iterator it = builder.frame_ids.find(static_cast<const void*>(anchor.get()));
+      if (it == builder.frame_ids.end()) {
+        // frame_3D derives from pose_3D: the same object may be reached through a different base sub-object
+        for (it = builder.frame_ids.begin(); it != builder.frame_ids.end(); ++it)
+          if (static_cast<const pose_3D<double>*>(static_cast<const frame_3D<double>*>(it->first)) == anchor.get()) break;
+      }
+      if (it == builder.frame_ids.end()) throw unsupported_chain("proximity shape anchored to a pose that is not a frame of the chain");
+      s.anchor = it->second;
+    }
+    const pose_3D<double>& P = sh->getPose();
+    for (int k = 0; k < 3; ++k) s.position[k] = P.Position[k];
+    for (int k = 0; k < 4; ++k) s.quat[k] = P.Quat[k];
+    out.push_back(s);
+  }
+  return out;
 }
 
 }  // namespace reak_b200
@@ -275,6 +328,14 @@ class kte_batch_system {
   output_type get_output(const StateSpaceType&, const point_type&, const input_type&, const time_type& = 0) const { return output_type(); }
 
   const reak_b200::kte_batch_propagator& batch() const { return mProp; }
+
+  /// The batched counterpart of a proxy_query_pair_3D(aModel1, aModel2) whose shapes ride on this system's frames:
+  /// batch().get_min_distances(pair, ...) is findMinimumDistance at every state, batch().is_free(...) the test of
+  /// manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99).  Owned by the caller
+  /// (rkb_proxy_destroy).
+  rkb_proxy* make_proxy_pair(const geom::proxy_query_model_3D& aModel1, const geom::proxy_query_model_3D& aModel2) const {
+    return mProp.make_proxy_pair(reak_b200::compile_proxy_model(aModel1, mBuilder), reak_b200::compile_proxy_model(aModel2, mBuilder));
+  }
   const reak_b200::chain_builder& descriptor() const { return mBuilder; }
 
  private:

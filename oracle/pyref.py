@@ -181,6 +181,22 @@ class _Checker(object):
             raise RuntimeError("rkref_min_distance failed")
         return d, f, pts
 
+    def bridge_proxy(self, model):
+        """include/reak_b200/reak_bridge.hpp's compile_proxy_model on live geom:: shapes built from `model`:
+        returns the rkb_shape array it derives and, per shape, the anchor translated back to this descriptor's
+        frame numbering."""
+        arr, n = model.to_c(self.compiled.frames)
+        out = type(arr)()
+        anchors = (C.c_int * max(n, 1))()
+        err = C.create_string_buffer(256)
+        fn = self.lib.rkref_bridge_proxy
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        rc = fn(self.h, C.cast(arr, C.c_void_p), n, C.cast(out, C.c_void_p), C.cast(anchors, C.c_void_p), err, 256)
+        if rc < 0:
+            raise RuntimeError("bridge rejected the model: " + err.value.decode())
+        return arr, out, list(anchors)[:n]
+
     def frames(self, x, u=None):
         """[n_frames][25]: Position3 Quat4 Velocity3 AngVelocity3 Acceleration3 AngAcceleration3 Force3 Torque3."""
         x, u, _ = self._xu(x, u)

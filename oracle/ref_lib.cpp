@@ -60,6 +60,9 @@
 #pragma weak rkb_rollout
 #pragma weak rkb_steer_feedback
 #pragma weak rkb_strerror
+#pragma weak rkb_proxy_create
+#pragma weak rkb_proxy_destroy
+#pragma weak rkb_min_distance
 #include "../include/reak_b200/reak_bridge.hpp"
 #include "steer_law.h"
 
@@ -472,6 +475,49 @@ int rkref_min_distance(void* hv, std::size_t N, const double* x, const rkb_shape
     }
   }
   return (int)order.size();
+}
+
+// reak_bridge.hpp's compile_proxy_model on live geom:: shapes riding on this model's frames: builds the shapes
+// from `in` (as rkref_min_distance does), compiles the system and the model through the bridge and hands the
+// shape list it derives back, so that a test can check rkb_shape -> ReaK shapes -> rkb_shape is the identity
+// (anchors included: the bridge numbers frames its own way, the test compares through the frame order).
+int rkref_bridge_proxy(void* hv, const rkb_shape* in, int n, rkb_shape* out, int* anchor_frame_of_desc, char* err, int err_len) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  try {
+    geom::proxy_query_model_3D mdl("m");
+    for (int k = 0; k < n; ++k) {
+      const rkb_shape& s = in[k];
+      shared_ptr<pose_3D<double> > anchor;
+      if (s.anchor >= 0) anchor = m->f3[s.anchor];
+      const pose_3D<double> pose(weak_ptr<pose_3D<double> >(), vect<double,3>(s.position[0], s.position[1], s.position[2]),
+                                 quaternion<double>(vect<double,4>(s.quat[0], s.quat[1], s.quat[2], s.quat[3])));
+      switch (s.kind) {
+        case RKB_SHAPE_PLANE: mdl.addShape(shared_ptr<geom::shape_3D>(new geom::plane("p", anchor, pose, vect<double,2>(s.dims[0], s.dims[1])))); break;
+        case RKB_SHAPE_SPHERE: mdl.addShape(shared_ptr<geom::shape_3D>(new geom::sphere("s", anchor, pose, s.dims[0]))); break;
+        case RKB_SHAPE_CCYLINDER: mdl.addShape(shared_ptr<geom::shape_3D>(new geom::capped_cylinder("cc", anchor, pose, s.dims[0], s.dims[1]))); break;
+        case RKB_SHAPE_CYLINDER: mdl.addShape(shared_ptr<geom::shape_3D>(new geom::cylinder("cy", anchor, pose, s.dims[0], s.dims[1]))); break;
+        default: mdl.addShape(shared_ptr<geom::shape_3D>(new geom::box("b", anchor, pose, vect<double,3>(s.dims[0], s.dims[1], s.dims[2])))); break;
+      }
+    }
+    reak_b200::chain_builder b = reak_b200::compile_kte_system(m->sys);
+    std::vector<rkb_shape> shapes = reak_b200::compile_proxy_model(mdl, b);
+    if ((int)shapes.size() != n) throw std::runtime_error("shape count differs");
+    for (int k = 0; k < n; ++k) {
+      out[k] = shapes[k];
+      // translate the bridge's frame id back to this descriptor's numbering through the frame object
+      anchor_frame_of_desc[k] = -1;
+      if (shapes[k].anchor >= 0)
+        for (std::size_t f = 0; f < m->f3.size(); ++f) {
+          std::map<const void*, int>::const_iterator it = b.frame_ids.find(static_cast<const void*>(m->f3[f].get()));
+          if (it != b.frame_ids.end() && it->second == shapes[k].anchor) anchor_frame_of_desc[k] = (int)f;
+        }
+    }
+    return n;
+  } catch (std::exception& e) {
+    if (err && err_len > 0) { std::strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+    return -1;
+  }
 }
 
 // Runs include/reak_b200/reak_bridge.hpp on the LIVE ReaK objects of this model (built by

@@ -256,6 +256,23 @@ def test_host_vs_golden(host_lib):
         H.close()
 
 
+def test_reference_side_binding_round_trip(oracle_built):
+    """reak_bridge.hpp's compile_proxy_model, run on live geom:: shapes riding on live ReaK frames, hands back
+    the shape list those shapes were built from"""
+    need_ref(oracle_built)
+    s = presets.make("crs7")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    R = oracle_built.Reference(c)
+    robot, lab = presets.crs_proxy_models(s, track=True)
+    for model in (robot, lab, mixed_models(s, np.random.default_rng(5)).model1):
+        src, out, anchors = R.bridge_proxy(model)
+        for k in range(len(model.mShapeList)):
+            assert out[k].kind == src[k].kind and anchors[k] == src[k].anchor
+            assert np.allclose(list(out[k].position), list(src[k].position), rtol=0, atol=0)
+            assert np.allclose(list(out[k].quat), list(src[k].quat), rtol=0, atol=1e-15)
+            assert np.allclose(list(out[k].dims), list(src[k].dims), rtol=0, atol=0)
+
+
 def test_proxy_create_rejects():
     lib = _abi.load_library()
     s = presets.make("crs6")
@@ -296,9 +313,9 @@ def test_proxy_create_rejects():
 
 # ---- GPU ------------------------------------------------------------------------------------------
 def _gpu_prop(preset):
-    from reak_b200.propagator import KteBatchPropagator
+    from reak_b200.propagator import kte_batch_propagator
     s = presets.make(preset)
-    return s, KteBatchPropagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    return s, kte_batch_propagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
 
 
 @pytest.mark.gpu
