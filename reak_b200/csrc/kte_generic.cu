@@ -722,6 +722,38 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_frames_kernel(const Generic
 
 #include "kte_proximity.cuh"
 
+// doMotion at position level only (the poses are all a proximity query reads): the Position / Quat lines of
+// motion() above, operation for operation.
+template <int MAXF>
+GD void motion_pose(const GenericProgram* G, const double* q, Pose (&fr)[MAXF]) {
+  {
+    const double* b = G->base;
+    Pose& B = fr[G->base_frame];
+    B.p = ldv(b); B.q.w = b[3]; B.q.x = b[4]; B.q.y = b[5]; B.q.z = b[6];
+  }
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-131
+      const Pose B = fr[E.fa];
+      const V3 an = unit_axis(ldv(E.p));
+      double sh, ch;
+      sincos(0.5 * q[E.coord], &sh, &ch);
+      Q4 tq; tq.w = ch; tq.x = an.x * sh; tq.y = an.y * sh; tq.z = an.z * sh;
+      fr[E.fb].p = B.p;
+      fr[E.fb].q = qmul(B.q, tq);
+    } else if (E.kind == RKB_PRISMATIC_3D) {  // prismatic_joint.cpp:129-140
+      const Pose B = fr[E.fa];
+      fr[E.fb].p = B.p + mul(qrot(B.q), q[E.coord] * ldv(E.p));
+      fr[E.fb].q = B.q;
+    } else if (E.kind == RKB_RIGID_LINK_3D) {  // rigid_link.cpp:156 -> pose_3D::addBefore
+      const Pose B = fr[E.fa];
+      Q4 qo; qo.w = E.p[3]; qo.x = E.p[4]; qo.y = E.p[5]; qo.z = E.p[6];
+      fr[E.fb].p = B.p + mul(qrot(B.q), ldv(E.p));
+      fr[E.fb].q = qmul(B.q, qo);
+    }
+  }
+}
+
 // proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) at the chain's pose for
 // state x[i]: distance, the index of the finder that gave it and its two points.
 template <int DIM, int MAXF>
@@ -729,20 +761,13 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_proximity_kernel(const Gene
                                                                        const __grid_constant__ ProxProgram P) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
-  Work<3, MAXF> W;
-  load(G, W, A.x, A.u, i, i, false);
-  motion(G, W);
-  Pose pose[2 * RKB_PROX_MAX_SHAPES];
-  const int ns = P.n1 + P.n2;
-  for (int k = 0; k < ns; ++k) {
-    const ProxShape& S = P.s[k];
-    const int fa = S.anchor >= 0 ? S.anchor : 0;
-    pose[k] = prox_shape_pose(S, S.anchor >= 0, W.fr[fa].p, W.fr[fa].q);
-  }
+  double q[MAXC];
+  for (int c = 0; c < G->n_coords; ++c) q[c] = A.x.p[i * A.x.si + rkb_state_q(A.x.blocked, G->n_coords, c) * A.x.sk];
+  Pose fr[MAXF];
+  motion_pose(G, q, fr);
   ProxRecord bestR;
-  const int best = prox_min_distance(P, pose, bestR);
-  const double min_d = bestR.d;
-  A.out.p[i * A.out.si] = min_d;
+  const int best = prox_min_distance(P, fr, bestR);
+  A.out.p[i * A.out.si] = bestR.d;
   if (A.status) A.status[i] = best;
   if (A.out2.p) {
     const double v[6] = {bestR.p1.x, bestR.p1.y, bestR.p1.z, bestR.p2.x, bestR.p2.y, bestR.p2.z};

@@ -375,36 +375,40 @@ GD ProxRecord prox_compute(const ProxShape& a, const Pose& Pa, const ProxShape& 
   return prox_ccylinder_box(P1, d1.x, d1.y, P2, d2);
 }
 
+// world pose of a shape riding on a frame with pose F: pose_3D::getGlobalPose, pose_3D.hpp:102-110
+GD Pose prox_shape_pose(const ProxShape& S, const Pose* frames) {
+  Pose L;
+  L.p = v3(S.pos[0], S.pos[1], S.pos[2]);
+  L.q.w = S.quat[0]; L.q.x = S.quat[1]; L.q.y = S.quat[2]; L.q.z = S.quat[3];
+  if (S.anchor < 0) return L;
+  const Pose F = frames[S.anchor];
+  Pose G;
+  G.p = F.p + qrotv(F.q, L.p);
+  G.q = qmul(F.q, L.q);
+  return G;
+}
+
 // proxy_query_pair_3D::findMinimumDistance, proxy_query_model.cpp:388-412: the first finder is always
 // evaluated; a later one is skipped when the distance between the two shape origins minus the two
 // bounding radii exceeds the running minimum (for planes that radius is the half diagonal of the
 // extents although their finders treat the plane as unbounded — followed as is).
-// pose[k]: world pose of shape k (model 1 then model 2).  Returns the finder index, -1 without finders.
-GD int prox_min_distance(const ProxProgram& P, const Pose* pose, ProxRecord& bestR) {
+// frames[f]: world pose of chain frame f.  Returns the finder index, -1 without finders.
+GD int prox_min_distance(const ProxProgram& P, const Pose* frames, ProxRecord& bestR) {
   int f = 0, best = -1;
   double min_d = INFINITY;
   bestR.p1 = v3(0, 0, 0); bestR.p2 = v3(0, 0, 0); bestR.d = INFINITY;
-  for (int a = 0; a < P.n1; ++a)
+  for (int a = 0; a < P.n1; ++a) {
+    const ProxShape& Sa = P.s[a];
+    const Pose Pa = prox_shape_pose(Sa, frames);
     for (int b = 0; b < P.n2; ++b) {
-      const ProxShape& Sa = P.s[a];
       const ProxShape& Sb = P.s[P.n1 + b];
       if (!prox_has_finder(Sa.kind, Sb.kind)) continue;
-      if (f > 0 && norm3(pose[P.n1 + b].p - pose[a].p) - Sa.brad - Sb.brad > min_d) { ++f; continue; }
-      const ProxRecord R = prox_compute(Sa, pose[a], Sb, pose[P.n1 + b]);
+      const Pose Pb = prox_shape_pose(Sb, frames);
+      if (f > 0 && norm3(Pb.p - Pa.p) - Sa.brad - Sb.brad > min_d) { ++f; continue; }
+      const ProxRecord R = prox_compute(Sa, Pa, Sb, Pb);
       if (f == 0 || min_d > R.d) { best = f; min_d = R.d; bestR = R; }
       ++f;
     }
+  }
   return best;
-}
-
-// world pose of a shape riding on a frame with pose (fp, fq): pose_3D::getGlobalPose, pose_3D.hpp:102-110
-GD Pose prox_shape_pose(const ProxShape& S, bool anchored, V3 fp, Q4 fq) {
-  Pose L;
-  L.p = v3(S.pos[0], S.pos[1], S.pos[2]);
-  L.q.w = S.quat[0]; L.q.x = S.quat[1]; L.q.y = S.quat[2]; L.q.z = S.quat[3];
-  if (!anchored) return L;
-  Pose G;
-  G.p = fp + qrotv(fq, L.p);
-  G.q = qmul(fq, L.q);
-  return G;
 }

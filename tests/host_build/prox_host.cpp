@@ -31,21 +31,15 @@ using std::sqrt;
 
 // program: the ProxProgram rkb_proxy_create lowers (read back through rkb_proxy_program, a test hook of the
 // product library); frames: [n_frames][7] world position + quaternion of the chain frames.
-extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames, double* dist, double* pts) {
-  Pose pose[2 * RKB_PROX_MAX_SHAPES];
-  for (int k = 0; k < P->n1 + P->n2; ++k) {
-    const ProxShape& S = P->s[k];
-    V3 fp = v3(0, 0, 0);
-    Q4 fq; fq.w = 1; fq.x = fq.y = fq.z = 0;
-    if (S.anchor >= 0) {
-      const double* f = frames + 7 * S.anchor;
-      fp = v3(f[0], f[1], f[2]);
-      fq.w = f[3]; fq.x = f[4]; fq.y = f[5]; fq.z = f[6];
-    }
-    pose[k] = prox_shape_pose(S, S.anchor >= 0, fp, fq);
+extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames, int n_frames, double* dist, double* pts) {
+  Pose fr[RKB_GEN_MAX_FRAMES];
+  for (int f = 0; f < n_frames && f < RKB_GEN_MAX_FRAMES; ++f) {
+    const double* v = frames + 7 * f;
+    fr[f].p = v3(v[0], v[1], v[2]);
+    fr[f].q.w = v[3]; fr[f].q.x = v[4]; fr[f].q.y = v[5]; fr[f].q.z = v[6];
   }
   ProxRecord R;
-  const int best = prox_min_distance(*P, pose, R);
+  const int best = prox_min_distance(*P, fr, R);
   *dist = R.d;
   pts[0] = R.p1.x; pts[1] = R.p1.y; pts[2] = R.p1.z; pts[3] = R.p2.x; pts[4] = R.p2.y; pts[5] = R.p2.z;
   return best;

@@ -76,7 +76,7 @@ def host_lib(tmp_path_factory):
     subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src], check=True)
     lib = C.CDLL(out)
     lib.prox_host_min_distance.restype = C.c_int
-    lib.prox_host_min_distance.argtypes = [C.c_void_p] * 4
+    lib.prox_host_min_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -101,7 +101,7 @@ class HostProximity(object):
         for i in range(N):
             fr = np.ascontiguousarray(frames[i][:, :7])
             di = C.c_double()
-            f[i] = self.host.prox_host_min_distance(self.blob, fr.ctypes.data_as(C.c_void_p), C.byref(di), p[i].ctypes.data_as(C.c_void_p))
+            f[i] = self.host.prox_host_min_distance(self.blob, fr.ctypes.data_as(C.c_void_p), fr.shape[0], C.byref(di), p[i].ctypes.data_as(C.c_void_p))
             d[i] = di.value
         return d, f, p
 
