@@ -19,6 +19,7 @@
  *                                                                       (ctrl/mbd_kte/mass_matrix_calculator.cpp:80-98)
  *   rkb_twist_shaping     <- mass_matrix_calc::get_TMT_TdMT             (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287)
  *   rkb_frames            <- kte_map_chain::doMotion / doForce as seen on the frames (frame_3D / frame_2D members)
+ *   rkb_steer_feedback_checked <- the same loops with with_collision_check = true (is_free_impl after every interval)
  *   rkb_min_distance      <- proxy_query_pair_3D::findMinimumDistance (geometry/proximity/proxy_query_model.cpp:388-412)
  *                            with the pair finders of geometry/proximity/prox_*_*.cpp: the is_free test of
  *                            ctrl/topologies/manip_free_workspace.hpp:77-99 on every propagated state
@@ -359,6 +360,20 @@ RKB_API int rkb_steer_feedback(rkb_chain* chain, int device, size_t n_samples,
                                double* u_prev, const rkb_steer_opts* opts,
                                double* x_out, int32_t* n_done, double* x_traj, int32_t* status,
                                unsigned flags, void* stream);
+
+/* rkb_steer_feedback with with_collision_check = true: after every control interval the state it ended on is
+ * tested like is_free_impl (examples/misc/MEAQR_topology.hpp:921-940: no proxy pair reports a negative
+ * findMinimumDistance); a state that is not free is NOT accepted — the loop of that sample stops on the last free
+ * state, u_prev keeps the last accepted input, no waypoint is recorded (MEAQR_topology.hpp:550-559,
+ * IHAQR_topology.hpp:369-375) — and collided[i] = 1 (was_collision_free == false), else 0.
+ * pairs: n_pairs >= 1 handles of rkb_proxy_create made for `chain`.  Runs interval by interval (control law,
+ * rollout into a scratch state, one proximity launch per pair, acceptance). */
+RKB_API int rkb_steer_feedback_checked(rkb_chain* chain, int device, size_t n_samples,
+                                       const double* x0, const double* x_goal, const double* u_bias, const double* gain,
+                                       double* u_prev, const rkb_steer_opts* opts,
+                                       const rkb_proxy* const* pairs, int n_pairs,
+                                       double* x_out, int32_t* n_done, int32_t* collided, double* x_traj, int32_t* status,
+                                       unsigned flags, void* stream);
 
 /* Device-side timing of the last compute launch issued through `chain` on the calling
  * thread, in milliseconds (CUDA events on the launch stream); < 0 if none. Blocks until

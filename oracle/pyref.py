@@ -124,9 +124,10 @@ class _Checker(object):
         return x, traj, st
 
     def steer_feedback(self, x0, goal, u_bias, gain, u_prev, T, dt, substeps, max_intervals, proximity,
-                       saturate_first=False, bounds=None, rate_bounds=None):
+                       saturate_first=False, bounds=None, rate_bounds=None, proxy_pairs=None):
         """The steering loop of MEAQR_topology.hpp:503-561 (oracle/steer_law.h).  bounds / rate_bounds: (lo, hi) or None.
-        Returns (x_out, u_last, n_done, traj [N][max_intervals][nx] (NaN where not written), status)."""
+        Returns (x_out, u_last, n_done, traj [N][max_intervals][nx] (NaN where not written), status); with
+        proxy_pairs (reference checker only) the loop runs with its collision test on and `collided` is appended."""
         x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
         N = x.shape[0]
         goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(N, self.nx)
@@ -139,6 +140,26 @@ class _Checker(object):
         xo, nd = np.empty_like(x), np.zeros(N, dtype=np.int32)
         traj = np.full((N, max(int(max_intervals), 1), self.nx), np.nan)
         st = np.zeros(N, dtype=np.int32)
+        if proxy_pairs:
+            if self._prefix != "rkref_":
+                raise NotImplementedError("the collision test is checked against the compiled reference only")
+            P = len(proxy_pairs)
+            keep = [(p.model1.to_c(self.compiled.frames), p.model2.to_c(self.compiled.frames)) for p in proxy_pairs]
+            m1s = (C.c_void_p * P)(*[C.cast(k[0][0], C.c_void_p) for k in keep])
+            m2s = (C.c_void_p * P)(*[C.cast(k[1][0], C.c_void_p) for k in keep])
+            n1s = (C.c_int * P)(*[k[0][1] for k in keep])
+            n2s = (C.c_int * P)(*[k[1][1] for k in keep])
+            col = np.zeros(N, dtype=np.int32)
+            fn = self.lib.rkref_steer_feedback_checked
+            fn.restype = C.c_int
+            fn.argtypes = ([C.c_void_p, C.c_size_t] + [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
+                           + [C.c_void_p] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5)
+            rc = fn(self.h, N, _dp(x), _dp(goal), _dp(u_bias), _dp(gain), _dp(up), float(T), float(dt), int(substeps), int(max_intervals),
+                    float(proximity), int(bool(saturate_first)), _dp(lo), _dp(hi), _dp(dlo), _dp(dhi), m1s, n1s, m2s, n2s, P,
+                    _dp(xo), _dp(nd), _dp(col), _dp(traj), _dp(st))
+            if rc != 0:
+                raise RuntimeError("steer_feedback_checked failed")
+            return xo, up, nd, traj[:, :int(max_intervals), :], st, col
         fn = getattr(self.lib, self._prefix + "steer_feedback")
         fn.restype = C.c_int
         fn.argtypes = ([C.c_void_p, C.c_size_t] + [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]

@@ -711,6 +711,80 @@ int rkref_steer_feedback(void* hv, std::size_t N, const double* x0, const double
   }
   return 0;
 }
+// rkref_steer_feedback with with_collision_check = true: after every interval the live proxy pairs are queried at
+// x_next (kte_map_chain::doMotion + proxy_query_pair_3D::findMinimumDistance, the body of is_free_impl,
+// MEAQR_topology.hpp:921-940); a state that is not free is not accepted and ends the loop
+// (MEAQR_topology.hpp:550-559).  Pair p is (m1s[p][0..n1s[p]), m2s[p][0..n2s[p])).
+int rkref_steer_feedback_checked(void* hv, std::size_t N, const double* x0, const double* goal, const double* u_bias, const double* gain,
+                                 double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,
+                                 const double* lo, const double* hi, const double* dlo, const double* dhi,
+                                 const rkb_shape* const* m1s, const int* n1s, const rkb_shape* const* m2s, const int* n2s, int n_pairs,
+                                 double* x_out, int32_t* n_done, int32_t* collided, double* traj, int32_t* status) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  if (nu > STEER_MAX_INPUTS || h->desc.dim != 3) return -1;
+  std::vector<shared_ptr<geom::proxy_query_pair_3D> > pairs;
+  for (int p = 0; p < n_pairs; ++p) {
+    shared_ptr<geom::proxy_query_model_3D> mdl[2];
+    for (int w = 0; w < 2; ++w) {
+      mdl[w] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("m"));
+      const rkb_shape* sh = w == 0 ? m1s[p] : m2s[p];
+      const int n = w == 0 ? n1s[p] : n2s[p];
+      for (int k = 0; k < n; ++k) {
+        const rkb_shape& s = sh[k];
+        shared_ptr<pose_3D<double> > anchor;
+        if (s.anchor >= 0) anchor = m->f3[s.anchor];
+        const pose_3D<double> pose(weak_ptr<pose_3D<double> >(), vect<double,3>(s.position[0], s.position[1], s.position[2]),
+                                   quaternion<double>(vect<double,4>(s.quat[0], s.quat[1], s.quat[2], s.quat[3])));
+        switch (s.kind) {
+          case RKB_SHAPE_PLANE: mdl[w]->addShape(shared_ptr<geom::shape_3D>(new geom::plane("p", anchor, pose, vect<double,2>(s.dims[0], s.dims[1])))); break;
+          case RKB_SHAPE_SPHERE: mdl[w]->addShape(shared_ptr<geom::shape_3D>(new geom::sphere("s", anchor, pose, s.dims[0]))); break;
+          case RKB_SHAPE_CCYLINDER: mdl[w]->addShape(shared_ptr<geom::shape_3D>(new geom::capped_cylinder("cc", anchor, pose, s.dims[0], s.dims[1]))); break;
+          case RKB_SHAPE_CYLINDER: mdl[w]->addShape(shared_ptr<geom::shape_3D>(new geom::cylinder("cy", anchor, pose, s.dims[0], s.dims[1]))); break;
+          case RKB_SHAPE_BOX: mdl[w]->addShape(shared_ptr<geom::shape_3D>(new geom::box("b", anchor, pose, vect<double,3>(s.dims[0], s.dims[1], s.dims[2])))); break;
+          default: return -1;
+        }
+      }
+    }
+    pairs.push_back(shared_ptr<geom::proxy_query_pair_3D>(new geom::proxy_query_pair_3D("pair", mdl[0], mdl[1])));
+  }
+  vect_n<double> pv(nx), uv(nu);
+  for (int j = 0; j < nu; ++j) uv[j] = 0.0;
+  for (std::size_t i = 0; i < N; ++i) {
+    std::vector<double> x(x0 + i * nx, x0 + (i + 1) * nx), xn(nx), u(nu ? nu : 1), up(nu ? nu : 1);
+    for (int j = 0; j < nu; ++j) up[j] = u_prev[i * nu + j];
+    int k = 0, st = 0, hit = 0;
+    while (k < max_intervals) {
+      int32_t s1 = 0;
+      if (!steer_next_input(nx, nu, T, proximity, (!saturate_first && k == 0), lo, hi, dlo, dhi, &x[0], goal + i * nx,
+                            u_bias + i * nu, gain + i * std::size_t(nu) * nx, &up[0], &u[0]))
+        break;
+      rk4_range(m, 0, 1, &x[0], &u[0], dt, substeps, &xn[0], &s1);
+      st |= s1;
+      // is_free_impl(x_next)
+      for (int j = 0; j < nx; ++j) pv[j] = xn[j];
+      m->sys.apply_states_and_inputs(pv, uv);
+      m->chain->doMotion();
+      bool is_free = true;
+      for (std::size_t p = 0; p < pairs.size() && is_free; ++p) {
+        shared_ptr<geom::proximity_finder_3D> f = pairs[p]->findMinimumDistance();
+        if (f && f->getLastResult().mDistance < 0.0) is_free = false;
+      }
+      if (!is_free) { hit = 1; break; }
+      x = xn;
+      for (int j = 0; j < nu; ++j) up[j] = u[j];
+      if (traj) for (int j = 0; j < nx; ++j) traj[(i * std::size_t(max_intervals) + k) * nx + j] = x[j];
+      ++k;
+    }
+    for (int j = 0; j < nx; ++j) x_out[i * nx + j] = x[j];
+    for (int j = 0; j < nu; ++j) u_prev[i * nu + j] = up[j];
+    if (n_done) n_done[i] = k;
+    if (collided) collided[i] = hit;
+    if (status) status[i] = st;
+  }
+  return 0;
+}
 double rkref_rk4(void* hv, std::size_t N, const double* x0, const double* u, double dt, int n_steps,
                  double* xout, int32_t* status, int n_workers) {
   return rkref_integrate(hv, N, x0, u, RKB_SCHEME_RK4, dt, n_steps, xout, status, n_workers);

@@ -118,6 +118,9 @@ SYMBOLS = {
                                   C.c_uint, C.c_void_p]),
     "rkb_steer_feedback": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(rkb_steer_opts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_steer_feedback_checked": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(rkb_steer_opts), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
     "rkb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

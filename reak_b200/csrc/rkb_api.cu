@@ -1249,10 +1249,19 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   return RKB_OK;
 }
 
-int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
-                       const double* gain, double* u_prev, const rkb_steer_opts* o, double* x_out, int32_t* n_done,
-                       double* x_traj, int32_t* status, unsigned flags, void* stream) {
+}  // extern "C"
+
+namespace {
+int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
+                        const double* gain, double* u_prev, const rkb_steer_opts* o, const rkb_proxy* const* pairs, int n_pairs,
+                        double* x_out, int32_t* n_done, int32_t* collided, double* x_traj, int32_t* status, unsigned flags,
+                        void* stream) {
   if (!c || !o || o->reserved != 0) return RKB_ERR_INVALID;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !collided))) return RKB_ERR_INVALID;
+  for (int p = 0; p < n_pairs; ++p) {
+    if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+    if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  }
   if (o->dt == 0.0 || !std::isfinite(o->dt) || o->substeps < 1 || o->max_intervals < 0) return RKB_ERR_INTEGRATION;
   if (!(o->time_step > 0.0) || !std::isfinite(o->time_step) || !std::isfinite(o->goal_proximity)) return RKB_ERR_INVALID;
   if ((o->u_lower == nullptr) != (o->u_upper == nullptr) || (o->du_lower == nullptr) != (o->du_upper == nullptr)) return RKB_ERR_INVALID;
@@ -1290,7 +1299,19 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
   dst = (L.device && status) ? (void*)status : ctx->st.p;
   if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
   CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
-  const bool fused = c->serial_ok && c->sk && !(std::getenv("RKB_STEER_UNFUSED") && std::getenv("RKB_STEER_UNFUSED")[0] == '1');
+  const bool fused = n_pairs == 0 && c->serial_ok && c->sk &&
+                     !(std::getenv("RKB_STEER_UNFUSED") && std::getenv("RKB_STEER_UNFUSED")[0] == '1');
+  void *dcol = nullptr, *dxn = nullptr, *dun = nullptr, *ddist = nullptr;
+  if (n_pairs > 0) {
+    // the interval is integrated into x_next, tested, and only then accepted (MEAQR_topology.hpp:550-559)
+    if ((rc = stage_out(ctx->out_idx, collided, N * sizeof(int32_t), L.device, &dcol))) return rc;
+    if ((rc = ctx->scratch_x.ensure(bx))) return rc;
+    if ((rc = ctx->scratch_u.ensure(bu > 0 ? bu : sizeof(double)))) return rc;
+    if ((rc = ctx->scratch_o.ensure(N * sizeof(double) * (size_t)n_pairs))) return rc;
+    dxn = ctx->scratch_x.p; dun = ctx->scratch_u.p; ddist = ctx->scratch_o.p;
+    CU(cudaMemsetAsync(dcol, 0, N * sizeof(int32_t), s));
+    CU(cudaMemsetAsync(dxn, 0, bx, s));
+  }
   if (fused) {
     // serial chains: the whole loop in one launch
     SteerArgs F;
@@ -1313,6 +1334,7 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
   W.x0 = (const double*)dx0; W.x = (double*)dxo; W.goal = (const double*)dgoal;
   W.u_bias = (const double*)dbias; W.gain = (const double*)dgain;
   W.u_prev = (double*)dup_in;  // device memory: updated in place (the caller's buffer, or the staging copy)
+  W.u_next = n_pairs > 0 ? (double*)dun : nullptr;
   W.n_done = (int32_t*)dnd; W.active = (int32_t*)ctx->act.p;
   W.n_samples = (long long)N; W.nx = nx; W.nu = nu; W.saturate_first = o->saturate_first ? 1 : 0;
   W.have_u_box = o->u_lower ? 1 : 0; W.have_du_box = o->du_lower ? 1 : 0;
@@ -1333,9 +1355,10 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
     c->launches += 1;
     RolloutArgs A;
     A.x0 = cview((const double*)dxo, (long long)N, nx, false, L.blocked);
-    A.u = cview((const double*)(nu > 0 ? dup_in : dxo), (long long)N, nu > 0 ? nu : 1, false);
-    A.xout = view((double*)dxo, (long long)N, nx, false, L.blocked);
-    A.traj = dtraj ? BatchView{(double*)dtraj + (size_t)k * nx, (long long)nx * J, 1, L.blocked ? 1 : 0} : BatchView{nullptr, 0, 0, 0};
+    A.u = cview((const double*)(nu > 0 ? (n_pairs > 0 ? dun : (void*)dup_in) : dxo), (long long)N, nu > 0 ? nu : 1, false);
+    A.xout = view((double*)(n_pairs > 0 ? dxn : dxo), (long long)N, nx, false, L.blocked);
+    A.traj = (dtraj && n_pairs == 0) ? BatchView{(double*)dtraj + (size_t)k * nx, (long long)nx * J, 1, L.blocked ? 1 : 0}
+                                     : BatchView{nullptr, 0, 0, 0};
     A.status = (int32_t*)dst;
     A.n_samples = (long long)N;
     A.x0_div = 1;
@@ -1344,6 +1367,28 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
     A.status_or = 1;
     A.active = (const int32_t*)ctx->act.p;
     if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
+    if (n_pairs > 0) {
+      for (int p = 0; p < n_pairs; ++p) {
+        EvalArgs E;
+        E.x = cview((const double*)dxn, (long long)N, nx, false, L.blocked);
+        E.u = cview((const double*)dxn, (long long)N, 1, false);
+        E.out = view((double*)ddist + (size_t)p * N, (long long)N, 1, false);
+        E.out2 = view((double*)nullptr, (long long)N, 6, false);
+        E.status = nullptr;
+        E.n_samples = (long long)N;
+        const cudaError_t pe = rkb_generic_proximity(ctx->d_prog, c->gp, E, pairs[p]->prog, s);
+        if (pe != cudaSuccess) return cuda_fail(pe, "proximity kernel");
+        c->launches += 1;
+      }
+      SteerCommitArgs K;
+      K.x = (double*)dxo; K.x_next = (const double*)dxn; K.u_prev = (double*)dup_in; K.u_next = (const double*)dun;
+      K.traj = (double*)dtraj; K.dist = (const double*)ddist; K.n_done = (int32_t*)dnd; K.active = (int32_t*)ctx->act.p;
+      K.collided = (int32_t*)dcol; K.n_samples = (long long)N; K.nx = nx; K.nu = nu; K.interval = k; K.max_intervals = J;
+      K.n_pairs = n_pairs; K.pad = 0;
+      const cudaError_t ke = rkb_steer_commit(K, s);
+      if (ke != cudaSuccess) return cuda_fail(ke, "steer commit");
+      c->launches += 1;
+    }
   }
   }
   CU(cudaEventRecord(ctx->ev1, s));
@@ -1352,10 +1397,30 @@ int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, con
   if ((rc = unstage_out(dxo, x_out, bx, L.device, s))) return rc;
   if ((rc = unstage_out(dnd, n_done, N * sizeof(int32_t), L.device, s))) return rc;
   if ((rc = unstage_out(dtraj, x_traj, bx * (size_t)(J > 0 ? J : 1), L.device, s))) return rc;
+  if (n_pairs > 0 && (rc = unstage_out(dcol, collided, N * sizeof(int32_t), L.device, s))) return rc;
   if (!L.device && nu > 0) CU(cudaMemcpyAsync(u_prev, dup_in, bu, cudaMemcpyDeviceToHost, s));
   if (!L.device && status) CU(cudaMemcpyAsync(status, dst, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   if (!L.device) CU(cudaStreamSynchronize(s));
   return RKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rkb_steer_feedback(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
+                       const double* gain, double* u_prev, const rkb_steer_opts* o, double* x_out, int32_t* n_done,
+                       double* x_traj, int32_t* status, unsigned flags, void* stream) {
+  return steer_feedback_impl(c, device, N, x0, x_goal, u_bias, gain, u_prev, o, nullptr, 0, x_out, n_done, nullptr, x_traj, status,
+                             flags, stream);
+}
+
+int rkb_steer_feedback_checked(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
+                               const double* gain, double* u_prev, const rkb_steer_opts* o, const rkb_proxy* const* pairs,
+                               int n_pairs, double* x_out, int32_t* n_done, int32_t* collided, double* x_traj, int32_t* status,
+                               unsigned flags, void* stream) {
+  if (n_pairs <= 0) return RKB_ERR_INVALID;
+  return steer_feedback_impl(c, device, N, x0, x_goal, u_bias, gain, u_prev, o, pairs, n_pairs, x_out, n_done, collided, x_traj,
+                             status, flags, stream);
 }
 
 double rkb_last_kernel_ms(rkb_chain* c) {

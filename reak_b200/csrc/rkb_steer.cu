@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(STEER_BLOCK) steer_law_kernel(const SteerLawAr
     u_prev[r] = A.u_prev[i * nu + r];
   }
   const double T = A.time_step;
-  double* u_out = A.u_prev + i * nu;  // u_prev = u_current once the interval is accepted (MEAQR_topology.hpp:553)
+  // u_prev = u_current once the interval is accepted (MEAQR_topology.hpp:553); with a collision test the
+  // acceptance comes later (steer_commit_kernel) and the input waits in u_next
+  double* u_out = (A.u_next ? A.u_next : A.u_prev) + i * nu;
   if (k == 0 && !A.saturate_first) {  // MEAQR_topology.hpp:521-522
     for (int r = 0; r < nu; ++r) u_out[r] = u_bias[r] + corr[r];
   } else {
@@ -97,7 +99,37 @@ __global__ void __launch_bounds__(STEER_BLOCK) steer_law_kernel(const SteerLawAr
   A.n_done[i] = k + 1;
 }
 
+// `if((!with_collision_check) || is_free_impl(x_next)) { accept } else { was_collision_free = false; break; }`
+// (MEAQR_topology.hpp:550-559, IHAQR_topology.hpp:369-375): is_free = no proxy pair reports a negative minimum
+// distance (MEAQR_topology.hpp:921-940).
+__global__ void __launch_bounds__(STEER_BLOCK) steer_commit_kernel(const SteerCommitArgs A) {
+  const long long i = (long long)blockIdx.x * STEER_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  if (!A.active[i]) return;
+  bool is_free = true;
+  for (int p = 0; p < A.n_pairs; ++p)
+    if (A.dist[(long long)p * A.n_samples + i] < 0.0) is_free = false;
+  if (is_free) {
+    for (int c = 0; c < A.nx; ++c) {
+      const double v = A.x_next[i * A.nx + c];
+      A.x[i * A.nx + c] = v;
+      if (A.traj) A.traj[(i * A.max_intervals + A.interval) * A.nx + c] = v;
+    }
+    for (int r = 0; r < A.nu; ++r) A.u_prev[i * A.nu + r] = A.u_next[i * A.nu + r];
+  } else {
+    A.n_done[i] = A.interval;  // the law kernel counted this interval in advance
+    A.active[i] = 0;
+    A.collided[i] = 1;
+  }
+}
+
 }  // namespace
+
+cudaError_t rkb_steer_commit(const SteerCommitArgs& a, cudaStream_t s) {
+  if (a.n_samples <= 0) return cudaSuccess;
+  steer_commit_kernel<<<(unsigned)((a.n_samples + STEER_BLOCK - 1) / STEER_BLOCK), STEER_BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s) {
   if (a.n_samples <= 0) return cudaSuccess;

@@ -161,6 +161,22 @@ struct SteerLawArgs {
   int32_t       nx, nu, interval, saturate_first, have_u_box, have_du_box;
   double        time_step, proximity;
   double        u_lo[RKB_MAX_COORDS], u_hi[RKB_MAX_COORDS], du_lo[RKB_MAX_COORDS], du_hi[RKB_MAX_COORDS];
+  double*       u_next;  // nullable: where the interval's input goes when acceptance is decided later (collision check)
+};
+
+// acceptance of a control interval after its collision test (MEAQR_topology.hpp:550-559)
+struct SteerCommitArgs {
+  double*       x;        // [N][nx] accepted state
+  const double* x_next;   // [N][nx] state the interval ended on
+  double*       u_prev;   // [N][nu]
+  const double* u_next;   // [N][nu] input the interval was integrated with
+  double*       traj;     // nullable: steer record, [N][J][nx]
+  const double* dist;     // [n_pairs][N] minimum distance of every proxy pair at x_next
+  int32_t*      n_done;
+  int32_t*      active;
+  int32_t*      collided; // [N] set when the loop ended on a state that was not free
+  long long     n_samples;
+  int32_t       nx, nu, interval, max_intervals, n_pairs, pad;
 };
 
 struct EvalArgs {

@@ -328,11 +328,13 @@ class kte_batch_propagator(object):
         return (idx, bx, bc, st) if want_status else (idx, bx, bc)
 
     def steer_feedback(self, x0, goal, u_bias, gain, u_prev, time_step, dt, substeps, max_intervals, goal_proximity,
-                       saturate_first=False, bounds=None, rate_bounds=None, want_traj=False):
+                       saturate_first=False, bounds=None, rate_bounds=None, want_traj=False, proxy_pairs=None):
         """The loop of steer_with_constant_control (examples/misc/MEAQR_topology.hpp:503-561) for N tuples:
         u = bounded(u_prev, u_bias, -gain (x - goal)), one RK4 control interval, stop within goal_proximity.
         x0, goal: [N][nx]; u_bias, u_prev: [N][nu]; gain: [N][nu][nx]; bounds / rate_bounds: (lo, hi) or None.
-        Returns (x_out, u_last, n_done[, x_traj [N][max_intervals][nx]], status); u_prev is not modified."""
+        Returns (x_out, u_last, n_done[, x_traj [N][max_intervals][nx]], status); u_prev is not modified.
+        proxy_pairs: a list of reak_b200.proximity.proxy_query_pair_3D turns the collision test of the loop on
+        (rkb_steer_feedback_checked); the tuple then ends with `collided` [N]."""
         x0, N = self._in(x0, self.nx, np.float64)
         goal, _ = self._in(goal, self.nx, np.float64, rows=N)
         u_bias, _ = self._in(u_bias, self.nu, np.float64, rows=N)
@@ -361,6 +363,26 @@ class kte_batch_propagator(object):
         st = self._like(x0, (N,), np.int32)
         flags, stream, ptr = self._prep([x0, goal, u_bias if self.nu else None, gain if self.nu else None, up if self.nu else None,
                                          xo, nd, tr, st], False)
+        if proxy_pairs:
+            from . import proximity
+            hs = []
+            for pair in proxy_pairs:
+                h = getattr(pair, "_rkb_handle", None)
+                if h is None or getattr(pair, "_rkb_owner", None) is not self:
+                    h = proximity.ProxyHandle(self._lib, self._h, pair, self.compiled.frames)
+                    pair._rkb_handle, pair._rkb_owner = h, self
+                hs.append(h._h)
+            arr = (C.c_void_p * len(hs))(*hs)
+            col = self._like(x0, (N,), np.int32)
+            flags, stream, ptr = self._prep([x0, goal, u_bias if self.nu else None, gain if self.nu else None, up if self.nu else None,
+                                             xo, nd, tr, st, col], False)
+            _abi.check(self._lib.rkb_steer_feedback_checked(self._h, self.device, N, ptr(x0), ptr(goal), ptr(u_bias) if self.nu else None,
+                                                            ptr(gain) if self.nu else None, ptr(up) if self.nu else None, C.byref(opts),
+                                                            arr, len(hs), ptr(xo), ptr(nd), ptr(col), ptr(tr), ptr(st), flags, stream),
+                       "rkb_steer_feedback_checked")
+            if want_traj:
+                return xo, up, nd, tr[:, :int(max_intervals)], st, col
+            return xo, up, nd, st, col
         _abi.check(self._lib.rkb_steer_feedback(self._h, self.device, N, ptr(x0), ptr(goal), ptr(u_bias) if self.nu else None,
                                                 ptr(gain) if self.nu else None, ptr(up) if self.nu else None, C.byref(opts),
                                                 ptr(xo), ptr(nd), ptr(tr), ptr(st), flags, stream), "rkb_steer_feedback")

@@ -402,3 +402,85 @@ def test_gpu_full_size_properties():
                                   px.proxy_query_model_3D("b").addShape(px.box("c", None, None, (1, 1, 1))))
     dn, fn = P.get_min_distances(none, x[:100].contiguous(), with_points=False)
     assert torch.isinf(dn).all() and (fn == -1).all()
+
+
+# ---- the steering loop with its collision test (rkb_steer_feedback_checked) ---------------------------
+def _steer_case(P, n, seed):
+    rng = np.random.default_rng(seed)
+    x0 = np.concatenate([rng.uniform(-3.0, 3.0, (n, P.n)), rng.uniform(-4.0, 4.0, (n, P.n))], axis=1)
+    if not P.blocked:  # interleaved (q0, qd0, q1, qd1, ...)
+        x0 = np.stack([x0[:, :P.n], x0[:, P.n:]], axis=2).reshape(n, P.nx)
+    goal = x0 + rng.uniform(-1.0, 1.0, (n, P.nx))
+    u_bias = rng.uniform(-1.0, 1.0, (n, P.nu))
+    gain = rng.uniform(-2.0, 2.0, (n, P.nu, P.nx))
+    u_prev = rng.uniform(-0.5, 0.5, (n, P.nu))
+    return x0, goal, u_bias, gain, u_prev
+
+
+def _same_loop(got, want, J):
+    xo, ul, nd, tr, st, col = got
+    xr, ur, nr, trr, sr, colr = want
+    assert np.array_equal(nd, nr) and np.array_equal(col, colr)
+    assert np.max(np.abs(xo - xr)) < 1e-9 and np.max(np.abs(ul - ur)) < 1e-9
+    for i in range(len(nd)):
+        assert np.max(np.abs(tr[i, :nd[i]] - trr[i, :nr[i]]), initial=0.0) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True)])
+def test_gpu_steer_feedback_checked_vs_reference(preset, track, oracle_built):
+    """loops of MEAQR_topology.hpp:503-561 / IHAQR_topology.hpp:349-378 with with_collision_check = true: the live
+    reference integrates, queries its proxy pairs at x_next and accepts or stops"""
+    need_ref(oracle_built)
+    s, P = _gpu_prop(preset)
+    robot, lab = presets.crs_proxy_models(s, track=track)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    je = s.joint_end_frames
+    extra = px.proxy_query_pair_3D("tool-obstacle", px.proxy_query_model_3D("tool").addShape(px.sphere("tool", je[-1], None, 0.12)),
+                                   px.proxy_query_model_3D("obstacle").addShape(px.box("crate", None, px.pose_3D((0.3, -3.0, 0.9)), (0.5, 0.5, 0.5))))
+    R = oracle_built.Reference(P.compiled)
+    n, J = 500, 8
+    x0, goal, u_bias, gain, u_prev = _steer_case(P, n, seed=9)
+    kw = dict(bounds=(-2 * np.ones(P.nu), 2 * np.ones(P.nu)), rate_bounds=(-60 * np.ones(P.nu), 60 * np.ones(P.nu)))
+    args = (x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, J, 0.25)
+    for pairs in ([pair], [pair, extra]):
+        got = P.steer_feedback(*args, want_traj=True, proxy_pairs=pairs, **kw)
+        want = R.steer_feedback(*args, proxy_pairs=pairs, **kw)
+        _same_loop(got, want, J)
+        nd, col = got[2], got[5]
+        assert (col == 1).any() and (col == 0).any()
+        assert ((col == 1) & (nd > 0)).any(), "no loop stopped on a collision after its first interval"
+        assert np.all(nd[col == 1] < J)
+    # a pair without finders never rejects: the checked loop equals the unchecked (fused) one
+    none = px.proxy_query_pair_3D("none", px.proxy_query_model_3D("a").addShape(px.box("b", None, None, (1, 1, 1))),
+                                  px.proxy_query_model_3D("b").addShape(px.box("c", None, None, (1, 1, 1))))
+    a = P.steer_feedback(*args, want_traj=True, proxy_pairs=[none], **kw)
+    b = P.steer_feedback(*args, want_traj=True, **kw)
+    assert not a[5].any() and np.array_equal(a[2], b[2])
+    assert np.max(np.abs(a[0] - b[0])) < 1e-10 and np.max(np.abs(a[1] - b[1])) < 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_steer_feedback_checked_device_buffers():
+    import torch
+    s, P = _gpu_prop("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    n, J = 4099, 5
+    case = _steer_case(P, n, seed=2)
+    args_h = case + (1e-2, 1e-3, 10, J, 0.25)
+    args_d = tuple(torch.from_numpy(a).cuda() for a in case) + (1e-2, 1e-3, 10, J, 0.25)
+    h = P.steer_feedback(*args_h, want_traj=True, proxy_pairs=[pair])
+    d = P.steer_feedback(*args_d, want_traj=True, proxy_pairs=[pair])
+    for a, b in zip(h, d):
+        b = b.cpu().numpy()
+        if a.ndim == 3:  # the steer record is only defined below n_done
+            for i in range(n):
+                assert np.array_equal(a[i, :h[2][i]], b[i, :h[2][i]])
+        else:
+            assert np.array_equal(a, b)
+    # the end state is free whenever an interval was accepted, and a rejected sample sits on its last accepted state
+    dist, _ = P.get_min_distances(pair, h[0], with_points=False)
+    assert np.all(dist[h[2] > 0] >= 0.0)
+    stuck = (h[5] == 1) & (h[2] == 0)
+    assert stuck.any() and np.array_equal(h[0][stuck], case[0][stuck])
