@@ -228,6 +228,33 @@ def other_configs(torch, presets, kte_batch_propagator, local, world):
     t5 = best(lambda: p5.steer_batch(x0, goal, uu, DT, RK4_STEPS), p5)
     out.append({"config": 5, "workload": "steer batch: %d pairs x %d controls x %d RK4 steps per GPU, arg-min per pair" % (P, R, RK4_STEPS),
                 "steer_ms": t5, "units_per_gpu": P * R * RK4_STEPS})
+    del x0, goal, uu
+    # the collision test of the steering loops on propagated states (CRS arm's proximity model
+    # against the MD148 lab, 25 finders), alone and inside the closed-loop steering
+    from reak_b200 import proximity as px
+    s6 = presets.make(PRESET)
+    p6 = kte_batch_propagator(s6, device=local)
+    robot, lab = presets.crs_proxy_models(s6)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    n6 = 1 << 20
+    x6 = torch.from_numpy(rng.uniform(-3, 3, (n6, p6.nx))).cuda(local)
+    t6 = best(lambda: p6.get_min_distances(pair, x6, with_points=False), p6)
+    out.append({"config": "proximity", "workload": "findMinimumDistance, CRS arm vs MD148 lab (25 finders): %d states per GPU" % n6,
+                "min_distance_ms": t6, "states_per_gpu": n6})
+    m6, J6 = 1 << 18, 10
+    g6 = torch.from_numpy(rng.uniform(-2, 2, (m6, p6.nu, p6.nx))).cuda(local)
+    xs = x6[:m6].contiguous() * 0.3
+    gl = xs + torch.from_numpy(rng.uniform(-1, 1, (m6, p6.nx))).cuda(local)
+    ub = torch.from_numpy(rng.uniform(-1, 1, (m6, p6.nu))).cuda(local)
+    up = torch.zeros_like(ub)
+    done = [None]
+
+    def steer():
+        done[0] = p6.steer_feedback(xs, gl, ub, g6, up, 1e-2, DT, 10, J6, 0.25, proxy_pairs=[pair])[2]
+
+    t7 = best(steer, p6)
+    out.append({"config": "steer_checked", "workload": "closed-loop steering with collision test: %d tuples x <= %d intervals x 10 RK4 steps per GPU"
+                % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": int(done[0].sum().item()) * 10})
     return out
 
 
@@ -348,7 +375,11 @@ def run_ours(args):
         for (i, k), v in zip(keys, t.tolist()):
             others[i][k] = v
         for o in others:
-            o["state_steps_per_s"] = world * o.pop("units_per_gpu") / (sum(v for k, v in o.items() if k.endswith("_ms")) * 1e-3)
+            ms = sum(v for k, v in o.items() if k.endswith("_ms"))
+            if "states_per_gpu" in o:
+                o["states_per_s"] = world * o.pop("states_per_gpu") / (ms * 1e-3)
+            else:
+                o["state_steps_per_s"] = world * o.pop("units_per_gpu") / (ms * 1e-3)
 
     if rank != 0:
         if world > 1:

@@ -13,6 +13,7 @@
 //   RK4                                   core/integrators/fixed_step_integrators.hpp:256-293
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdlib>
 #include "rkb_internal.h"
 
 namespace {
@@ -756,8 +757,8 @@ GD void motion_pose(const GenericProgram* G, const double* q, Pose (&fr)[MAXF]) 
 
 // proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) at the chain's pose for
 // state x[i]: distance, the index of the finder that gave it and its two points.
-template <int DIM, int MAXF>
-__global__ void __launch_bounds__(GEN_BLOCK) generic_proximity_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
+template <int DIM, int MAXF, int MINB>
+__global__ void __launch_bounds__(GEN_BLOCK, MINB) generic_proximity_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
                                                                        const __grid_constant__ ProxProgram P) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
@@ -951,8 +952,9 @@ cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgr
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   if (host.dim != 3) return cudaErrorInvalidValue;
-  if (host.n_frames <= 16) generic_proximity_kernel<3, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
-  else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+  // 5 resident CTAs per SM (96 registers): measured best of 3 / 4 / 5 / 6 / 8
+  if (host.n_frames <= 16) generic_proximity_kernel<3, 16, 5><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+  else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES, 4><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   return cudaGetLastError();
 }
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
