@@ -22,8 +22,10 @@ int main() {
   base.acceleration[2] = 9.81;
   b.set_base(cur, base);
   std::uint64_t upstream = 0;
+  int joint_end[6];
   for (int k = 0; k < 6; ++k) {
     const int coord = b.add_coord(), end = b.add_frame(), nxt = b.add_frame();
+    joint_end[k] = end;
     const int act = b.driving_actuator_gen(coord, -1, k);
     b.inertia_gen(coord, 1.0);
     const int joint = b.revolute_joint_3D(coord, axes[k][0], axes[k][1], axes[k][2], cur, end);
@@ -60,6 +62,42 @@ int main() {
     if (!threw) return 5;
     for (std::size_t i = 0; i < N * 12; ++i) std::printf("%.17g %.17g\n", xd[i], xo[i]);
     for (std::size_t i = 0; i < 36; ++i) std::printf("M %.17g\n", M[i]);
+    // the arm's proximity model against the lab (CRS_A465_geom_model.cpp:88-148, build_MD148_lab.cpp:103-149):
+    // findMinimumDistance at the propagated states, and the planner's is_free on one of them
+    const double h = 0.70710678118654757;  // axis_angle(pi/2, x).getQuaternion() = (cos pi/4, sin pi/4, 0, 0)
+    struct local {
+      static rkb_shape shape(int kind, int anchor, double px, double py, double pz, double qw, double qx, double qy, double qz,
+                             double d0, double d1, double d2) {
+        rkb_shape s = rkb_shape();
+        s.kind = kind; s.anchor = anchor;
+        s.position[0] = px; s.position[1] = py; s.position[2] = pz;
+        s.quat[0] = qw; s.quat[1] = qx; s.quat[2] = qy; s.quat[3] = qz;
+        s.dims[0] = d0; s.dims[1] = d1; s.dims[2] = d2;
+        return s;
+      }
+    };
+    std::vector<rkb_shape> robot, lab;
+    robot.push_back(local::shape(RKB_SHAPE_CCYLINDER, joint_end[0], 0, 0, 0.3302, h, h, 0, 0, 0.34, 0.09, 0));
+    robot.push_back(local::shape(RKB_SHAPE_CCYLINDER, joint_end[1], 0, 0, 0.15, 1, 0, 0, 0, 0.3, 0.07, 0));
+    robot.push_back(local::shape(RKB_SHAPE_CCYLINDER, joint_end[2], 0, 0, 0.165, 1, 0, 0, 0, 0.33, 0.07, 0));
+    robot.push_back(local::shape(RKB_SHAPE_CCYLINDER, joint_end[4], 0, 0, 0.0381, 1, 0, 0, 0, 0.0762, 0.05, 0));
+    robot.push_back(local::shape(RKB_SHAPE_SPHERE, joint_end[5], -0.04, 0, 0.05, 1, 0, 0, 0, 0.11, 0, 0));
+    lab.push_back(local::shape(RKB_SHAPE_PLANE, -1, -0.8, -1.0, 0.0, 1, 0, 0, 0, 4.0, 6.0, 0));
+    lab.push_back(local::shape(RKB_SHAPE_PLANE, -1, 1.2, -1.0, 1.5, h, 0, -h, 0, 3.0, 6.0, 0));
+    lab.push_back(local::shape(RKB_SHAPE_PLANE, -1, -0.8, 2.0, 1.5, h, h, 0, 0, 4.0, 3.0, 0));
+    lab.push_back(local::shape(RKB_SHAPE_CCYLINDER, -1, 0.1, -1.71, 0.15, h, h, 0, 0, 3.42, 0.18, 0));
+    lab.push_back(local::shape(RKB_SHAPE_CCYLINDER, -1, -0.1, -1.71, 0.15, h, h, 0, 0, 3.42, 0.18, 0));
+    rkb_proxy* pair = prop.make_proxy_pair(robot, lab);
+    if (rkb_proxy_finder_count(pair) != 25) return 6;
+    std::vector<double> dist(N);
+    std::vector<int32_t> finder(N);
+    for (std::size_t i = 0; i < x.size(); ++i) x[i] *= 3.0;
+    prop.get_min_distances(pair, N, &x[0], &dist[0], &finder[0]);
+    std::vector<const rkb_proxy*> pairs(1, pair);
+    std::vector<double> p1(x.begin(), x.begin() + 12);
+    if (prop.is_free(pairs, p1) != !(dist[0] < 0.0)) return 7;
+    for (std::size_t i = 0; i < N; ++i) std::printf("D %.17g %d\n", dist[i], (int)finder[i]);
+    rkb_proxy_destroy(pair);
   } catch (std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());
     return 1;

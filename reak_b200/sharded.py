@@ -90,15 +90,27 @@ class sharded_propagator(object):
                 _all_gather_rows(self._to_comm(st, torch.int32), n_total, self.group))
 
     def steer_feedback(self, x0, goal, u_bias, gain, u_prev, *args, compute=None, **kw):
-        """kte_batch_propagator.steer_feedback sharded by tuple: returns (x_out, u_last, n_done, status)
-        gathered on every rank; positional and keyword arguments after u_prev are passed through."""
+        """kte_batch_propagator.steer_feedback sharded by tuple: returns (x_out, u_last, n_done, status[, collided])
+        gathered on every rank; positional and keyword arguments after u_prev (proxy_pairs=... included) are passed through."""
         import torch
         compute = compute or self.prop.steer_feedback
         n_total = x0.shape[0]
         lo, hi = shard_bounds(n_total, self.rank, self.world)
-        xo, ul, nd, st = compute(x0[lo:hi], goal[lo:hi], u_bias[lo:hi], gain[lo:hi], u_prev[lo:hi], *args, **kw)
+        outs = compute(x0[lo:hi], goal[lo:hi], u_bias[lo:hi], gain[lo:hi], u_prev[lo:hi], *args, **kw)
         g = lambda a, dt: _all_gather_rows(self._to_comm(a, dt), n_total, self.group)
-        return g(xo, torch.float64), g(ul, torch.float64), g(nd, torch.int32), g(st, torch.int32)
+        # (x_out, u_last, n_done, status) and, with proxy_pairs=..., collided: states and inputs are doubles, the rest int32
+        return tuple(g(a, torch.float64 if k < 2 else torch.int32) for k, a in enumerate(outs))
+
+    def get_min_distances(self, pair, x, compute=None):
+        """kte_batch_propagator.get_min_distances sharded by state: (distance[N], finder[N]) gathered on every rank.
+        `compute(pair, x_block) -> (distance, finder)`."""
+        import torch
+        compute = compute or (lambda pr, xb: self.prop.get_min_distances(pr, xb, with_points=False))
+        n_total = x.shape[0]
+        lo, hi = shard_bounds(n_total, self.rank, self.world)
+        d, f = compute(pair, x[lo:hi])[:2]
+        return (_all_gather_rows(self._to_comm(d, torch.float64), n_total, self.group),
+                _all_gather_rows(self._to_comm(f, torch.int32), n_total, self.group))
 
     def steer_batch(self, x0, goal, u, dt, n_steps, compute=None):
         """Pairs are never split across ranks, so the per-pair arg-min stays on one device; only

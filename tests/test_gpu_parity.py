@@ -661,7 +661,8 @@ def test_cpp_host_class_builds_the_same_chain(tmp_path):
     r = subprocess.run([exe], env=env, capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
     lines = r.stdout.split("\n")
-    vals = np.array([[float(t) for t in l.split()] for l in lines if l and not l.startswith("M")])
+    vals = np.array([[float(t) for t in l.split()] for l in lines if l and not l.startswith("M") and not l.startswith("D")])
+    prox = np.array([[float(t) for t in l.split()[1:]] for l in lines if l.startswith("D")])
     Mrow = np.array([float(l.split()[1]) for l in lines if l.startswith("M")])
     N = 64
     s = 88172645463325252
@@ -677,6 +678,15 @@ def test_cpp_host_class_builds_the_same_chain(tmp_path):
     xo, _ = p.get_next_states(x, u, 1e-3, 25)
     assert np.array_equal(vals[:, 0].reshape(N, 12), xd) and np.array_equal(vals[:, 1].reshape(N, 12), xo)
     assert np.array_equal(Mrow.reshape(6, 6), p.get_mass_matrices(x[:1])[0])
+    # the proximity models the demo writes down as rkb_shape literals are those of presets.crs_proxy_models
+    from reak_b200 import proximity as px
+    sys6 = presets.make("crs6")
+    from reak_b200.propagator import kte_batch_propagator
+    p6 = kte_batch_propagator(sys6)
+    robot, lab = presets.crs_proxy_models(sys6)
+    d, f = p6.get_min_distances(px.proxy_query_pair_3D("robot-lab", robot, lab), 3.0 * x, with_points=False)
+    assert prox.shape == (N, 2) and np.array_equal(prox[:, 1].astype(np.int32), f)
+    assert np.max(np.abs(prox[:, 0] - d)) < 1e-12  # the quaternion literals differ from axis_angle's in the last bit
 
 
 def test_streams_and_threads():

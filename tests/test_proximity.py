@@ -484,3 +484,17 @@ def test_gpu_steer_feedback_checked_device_buffers():
     assert np.all(dist[h[2] > 0] >= 0.0)
     stuck = (h[5] == 1) & (h[2] == 0)
     assert stuck.any() and np.array_equal(h[0][stuck], case[0][stuck])
+
+
+@pytest.mark.gpu
+def test_gpu_many_frames_vs_reference(oracle_built):
+    """a 9-joint arm has 19 frames: the kernel instance for more than 16 frames"""
+    need_ref(oracle_built)
+    from reak_b200.propagator import kte_batch_propagator
+    s = presets.crs_chain(n_revolute=9)
+    P = kte_batch_propagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    assert P.compiled.desc.n_frames > 16
+    pair = mixed_models(s, np.random.default_rng(77), n1=9, n2=6)
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 512, seed=4, q_range=2.5)
+    agree(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL_SEARCH)

@@ -19,6 +19,16 @@ def _free_port():
     return p
 
 
+def _test_pair(system, px):
+    """a capsule and a sphere on the last two joints of the arm against a floor and a crate"""
+    je = system.joint_end_frames
+    robot = px.proxy_query_model_3D("robot").addShape(px.capped_cylinder("l", je[-2], px.pose_3D((0, 0, 0.1)), 0.2, 0.05)) \
+        .addShape(px.sphere("t", je[-1], None, 0.08))
+    world = px.proxy_query_model_3D("world").addShape(px.plane("floor", None, px.pose_3D((0, -3.3, 0.45)), (4, 4))) \
+        .addShape(px.box("crate", None, px.pose_3D((0.2, -3.2, 0.9)), (0.3, 0.3, 0.3)))
+    return px.proxy_query_pair_3D("robot-world", robot, world)
+
+
 def _worker(rank, world, port, n_total, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -68,8 +78,22 @@ def _worker(rank, world, port, n_total, out_dir):
         return xo, ul, nd, s2
 
     fx, fu, fn, fs = sp.steer_feedback(x, goal_all, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, compute=feedback)
+    extra = {}
+    if pyref.have_ref():
+        # proximity queries and the checked steering loop shard by state / tuple too (live reference as the compute)
+        from reak_b200 import proximity as px
+        R = pyref.Reference(c)
+        pair = _test_pair(s, px)
+        pd, pf = sp.get_min_distances(pair, x, compute=lambda pr, xb: R.min_distance(pr, xb)[:2])
+
+        def checked(x0b, gb, ubb, gnb, upb, *a, **k):
+            xo, ul, nd, _, s2, col = R.steer_feedback(x0b, gb, ubb, gnb, upb, *a, proxy_pairs=[pair], **k)
+            return xo, ul, nd, s2, col
+
+        cx, cu, cn, cs, cc = sp.steer_feedback(x, goal_all, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, compute=checked)
+        extra = dict(pd=pd.numpy(), pf=pf.numpy(), cx=cx.numpy(), cn=cn.numpy(), cc=cc.numpy())
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), full=full.numpy(), st=st.numpy(), idx=idx.numpy(), bx=bx.numpy(), bc=bc.numpy(),
-             rx=rx.numpy(), rtr=rtr.numpy(), fx=fx.numpy(), fu=fu.numpy(), fn=fn.numpy())
+             rx=rx.numpy(), rtr=rtr.numpy(), fx=fx.numpy(), fu=fu.numpy(), fn=fn.numpy(), **extra)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -104,6 +128,16 @@ def test_two_rank_gloo_gather(n_total, tmp_path, oracle_built):
     for g in got:
         assert np.array_equal(g["rx"], wx) and np.array_equal(g["rtr"], wtr)
         assert np.array_equal(g["fx"], fx) and np.array_equal(g["fu"], fu) and np.array_equal(g["fn"], fn)
+    if pyref.have_ref():
+        from reak_b200 import proximity as px
+        R = pyref.Reference(c)
+        pair = _test_pair(s, px)
+        wd, wf, _ = R.min_distance(pair, x)
+        cx, _, cn, _, _, cc = R.steer_feedback(x, goal_all, u, gain, 0.5 * u, 1e-2, 1e-3, 10, 3, 0.2, proxy_pairs=[pair])
+        assert (wd < 0).any() and (wd > 0).any()
+        for g in got:
+            assert np.array_equal(g["pd"], wd) and np.array_equal(g["pf"], wf)
+            assert np.array_equal(g["cx"], cx) and np.array_equal(g["cn"], cn) and np.array_equal(g["cc"], cc)
 
 
 def test_shard_bounds_cover_everything():
