@@ -685,8 +685,11 @@ def test_cpp_host_class_builds_the_same_chain(tmp_path):
     p6 = kte_batch_propagator(sys6)
     robot, lab = presets.crs_proxy_models(sys6)
     d, f = p6.get_min_distances(px.proxy_query_pair_3D("robot-lab", robot, lab), 3.0 * x, with_points=False)
-    assert prox.shape == (N, 2) and np.array_equal(prox[:, 1].astype(np.int32), f)
-    assert np.max(np.abs(prox[:, 0] - d)) < 1e-12  # the quaternion literals differ from axis_angle's in the last bit
+    # the quaternion literals of the demo differ from axis_angle's in the last bit, and the arm's first capsule sits
+    # exactly between the two track capsules (lab shapes 3 and 4): which of the two wins that tie is rounding
+    pf = prox[:, 1].astype(np.int32)
+    assert prox.shape == (N, 2) and np.max(np.abs(prox[:, 0] - d)) < 1e-12
+    assert np.all((pf == f) | ((pf // 5 == f // 5) & (pf % 5 >= 3) & (f % 5 >= 3))) and np.mean(pf == f) > 0.8
 
 
 def test_streams_and_threads():
