@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(GEN_BLOCK, MINB) generic_proximity_kernel(cons
   Pose fr[MAXF];
   motion_pose(G, q, fr);
   ProxRecord bestR;
-  const int best = prox_min_distance(P, fr, bestR);
+  const int best = prox_min_distance(P, fr, A.out2.p != (double*)0, bestR);
   A.out.p[i * A.out.si] = bestR.d;
   if (A.status) A.status[i] = best;
   if (A.out2.p) {

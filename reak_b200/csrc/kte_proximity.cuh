@@ -23,37 +23,64 @@ GD V3 qrotv(Q4 Q, V3 V) {  // quaternion * vect, rotations_3D.hpp:1137-1151
             2.0 * ((t2 + t4) * V.x + (t3 + t8) * V.y + (t7 - t0) * V.z) + V.y,
             2.0 * ((t5 - t1) * V.x + (t0 + t7) * V.y + (t3 + t6) * V.z) + V.z);
 }
-GD V3 to_global(const Pose& P, V3 v) { return P.p + qrotv(P.q, v); }                 // pose_3D.hpp:175-184
-GD V3 from_global(const Pose& P, V3 v) { return qrotv(qconj(P.q), v - P.p); }        // pose_3D.hpp:189-198
-GD V3 rot_to_global(const Pose& P, V3 v) { return qrotv(P.q, v); }
-GD V3 rot_from_global(const Pose& P, V3 v) { return qrotv(qconj(P.q), v); }
+// World pose of a shape.  A finder rotates with the same quaternion five to ten times, so the nine sums of
+// products that quaternion * vect forms first (rotations_3D.hpp:1139-1150) are kept: m = (t6+t8, t4-t2, t1+t5;
+// t2+t4, t3+t8, t7-t0; t5-t1, t0+t7, t3+t6).  For invert(Q) = (w, -x, -y, -z) the t0..t2 change sign and the
+// sums become the transposed set, bit for bit — so both directions come from one table and the results
+// are the ones qrotv gives.
+struct SPose { V3 p; double m[9]; };
+GD void rot_table(Q4 Q, double* m) {
+  const double t0 = Q.w * Q.x, t1 = Q.w * Q.y, t2 = Q.w * Q.z, t3 = -Q.x * Q.x, t4 = Q.x * Q.y, t5 = Q.x * Q.z, t6 = -Q.y * Q.y,
+               t7 = Q.y * Q.z, t8 = -Q.z * Q.z;
+  m[0] = t6 + t8; m[1] = t4 - t2; m[2] = t1 + t5;
+  m[3] = t2 + t4; m[4] = t3 + t8; m[5] = t7 - t0;
+  m[6] = t5 - t1; m[7] = t0 + t7; m[8] = t3 + t6;
+}
+GD V3 rot_fwd(const double* m, V3 V) {
+  return v3(2.0 * (m[0] * V.x + m[1] * V.y + m[2] * V.z) + V.x, 2.0 * (m[3] * V.x + m[4] * V.y + m[5] * V.z) + V.y,
+            2.0 * (m[6] * V.x + m[7] * V.y + m[8] * V.z) + V.z);
+}
+GD V3 rot_inv(const double* m, V3 V) {
+  return v3(2.0 * (m[0] * V.x + m[3] * V.y + m[6] * V.z) + V.x, 2.0 * (m[1] * V.x + m[4] * V.y + m[7] * V.z) + V.y,
+            2.0 * (m[2] * V.x + m[5] * V.y + m[8] * V.z) + V.z);
+}
+GD V3 to_global(const SPose& P, V3 v) { return P.p + rot_fwd(P.m, v); }              // pose_3D.hpp:175-184
+GD V3 from_global(const SPose& P, V3 v) { return rot_inv(P.m, v - P.p); }            // pose_3D.hpp:189-198
+GD V3 rot_to_global(const SPose& P, V3 v) { return rot_fwd(P.m, v); }
+GD V3 rot_from_global(const SPose& P, V3 v) { return rot_inv(P.m, v); }
 GD double norm3(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 GD V3 neg(V3 a) { return v3(-a.x, -a.y, -a.z); }
 
 struct ProxRecord { V3 p1, p2; double d; };
 
 // prox_sphere_sphere.cpp:50-66
-GD ProxRecord prox_sphere_sphere(const Pose& S1, double r1, const Pose& S2, double r2) {
+template <bool PTS>
+GD ProxRecord prox_sphere_sphere(const SPose& S1, double r1, const SPose& S2, double r2) {
   ProxRecord R;
   const V3 c1 = S1.p, c2 = S2.p;
   const V3 diff = c2 - c1;
   const double dist = norm3(diff);
   R.d = dist - r1 - r2;
-  R.p1 = c1 + (r1 / dist) * diff;
-  R.p2 = c2 - (r2 / dist) * diff;
+  if (PTS) {
+    R.p1 = c1 + (r1 / dist) * diff;
+    R.p2 = c2 - (r2 / dist) * diff;
+  }
   return R;
 }
 
 // prox_sphere_ccylinder.cpp:50-88
-GD ProxRecord prox_sphere_ccylinder(const Pose& S, double rs, const Pose& C, double len, double rc) {
+template <bool PTS>
+GD ProxRecord prox_sphere_ccylinder(const SPose& S, double rs, const SPose& C, double len, double rc) {
   ProxRecord R;
   const V3 sp_c = S.p;
   const V3 rel = from_global(C, sp_c);
   if (fabs(rel.z) <= 0.5 * len) {
     const V3 proj = v3(rel.x, rel.y, 0.0);
     const double pd = norm3(proj);
-    R.p2 = to_global(C, v3(0.0, 0.0, rel.z) + (rc / pd) * proj);
-    R.p1 = to_global(C, rel - (rs / pd) * proj);
+    if (PTS) {
+      R.p2 = to_global(C, v3(0.0, 0.0, rel.z) + (rc / pd) * proj);
+      R.p1 = to_global(C, rel - (rs / pd) * proj);
+    }
     R.d = pd - rs - rc;
   } else {
     const double fact = rel.z < 0.0 ? -1.0 : 1.0;
@@ -61,14 +88,17 @@ GD ProxRecord prox_sphere_ccylinder(const Pose& S, double rs, const Pose& C, dou
     const V3 diff = c2 - sp_c;
     const double dist = norm3(diff);
     R.d = dist - rs - rc;
-    R.p1 = sp_c + (rs / dist) * diff;
-    R.p2 = c2 - (rc / dist) * diff;
+    if (PTS) {
+      R.p1 = sp_c + (rs / dist) * diff;
+      R.p2 = c2 - (rc / dist) * diff;
+    }
   }
   return R;
 }
 
 // prox_sphere_cylinder.cpp:50-103
-GD ProxRecord prox_sphere_cylinder(const Pose& S, double rs, const Pose& C, double len, double rc) {
+template <bool PTS>
+GD ProxRecord prox_sphere_cylinder(const SPose& S, double rs, const SPose& C, double len, double rc) {
   ProxRecord R;
   const V3 sp_c = S.p;
   const V3 rel = from_global(C, sp_c);
@@ -76,13 +106,17 @@ GD ProxRecord prox_sphere_cylinder(const Pose& S, double rs, const Pose& C, doub
   if (fabs(rel.z) <= 0.5 * len) {
     const V3 proj = v3(rel.x, rel.y, 0.0);
     const double pd = norm3(proj);
-    R.p2 = to_global(C, v3(0.0, 0.0, rel.z) + (rc / pd) * proj);
-    R.p1 = to_global(C, rel - (rs / pd) * proj);
+    if (PTS) {
+      R.p2 = to_global(C, v3(0.0, 0.0, rel.z) + (rc / pd) * proj);
+      R.p1 = to_global(C, rel - (rs / pd) * proj);
+    }
     R.d = pd - rs - rc;
   } else if (rad < rc) {
     const double fact = rel.z < 0.0 ? -1.0 : 1.0;
-    R.p2 = to_global(C, v3(rel.x, rel.y, fact * 0.5 * len));
-    R.p1 = to_global(C, v3(rel.x, rel.y, rel.z - fact * rs));
+    if (PTS) {
+      R.p2 = to_global(C, v3(rel.x, rel.y, fact * 0.5 * len));
+      R.p1 = to_global(C, v3(rel.x, rel.y, rel.z - fact * rs));
+    }
     R.d = fact * rel.z - 0.5 * len - rs;
   } else {
     V3 proj = v3(rel.x, rel.y, 0.0);
@@ -92,55 +126,68 @@ GD ProxRecord prox_sphere_cylinder(const Pose& S, double rs, const Pose& C, doub
     R.p2 = to_global(C, rim);
     proj = R.p2 - sp_c;
     pd = norm3(proj);
-    R.p1 = sp_c + (rs / pd) * proj;
+    if (PTS) R.p1 = sp_c + (rs / pd) * proj;
     R.d = pd - rs;
   }
   return R;
 }
 
 // prox_plane_sphere.cpp:128-144 (the live definition; the bounded-plane variant above it is commented out)
-GD ProxRecord prox_plane_sphere(const Pose& PL, const Pose& S, double rs) {
+template <bool PTS>
+GD ProxRecord prox_plane_sphere(const SPose& PL, const SPose& S, double rs) {
   ProxRecord R;
   const V3 rel = from_global(PL, S.p);
-  R.p1 = to_global(PL, v3(rel.x, rel.y, 0.0));
-  R.p2 = to_global(PL, v3(rel.x, rel.y, rel.z - rs));
+  if (PTS) {
+    R.p1 = to_global(PL, v3(rel.x, rel.y, 0.0));
+    R.p2 = to_global(PL, v3(rel.x, rel.y, rel.z - rs));
+  }
   R.d = rel.z - rs;
   return R;
 }
 
 // prox_plane_ccylinder.cpp:51-81
-GD ProxRecord prox_plane_ccylinder(const Pose& PL, const Pose& C, double len, double rc) {
+template <bool PTS>
+GD ProxRecord prox_plane_ccylinder(const SPose& PL, const SPose& C, double len, double rc) {
   ProxRecord R;
   const V3 cy_t = rot_to_global(C, v3(0.0, 0.0, 1.0));
   const V3 c_rel = from_global(PL, C.p);
   V3 t_rel = rot_from_global(PL, cy_t);
   if (fabs(t_rel.z) < 1e-6) {
-    R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
-    R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - rc));
+    if (PTS) {
+      R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
+      R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - rc));
+    }
     R.d = c_rel.z - rc;
   } else {
     if (t_rel.z > 0.0) t_rel = neg(t_rel);
     const V3 pt = c_rel + (0.5 * len) * t_rel + v3(0.0, 0.0, -rc);
-    R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
-    R.p2 = to_global(PL, pt);
+    if (PTS) {
+      R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
+      R.p2 = to_global(PL, pt);
+    }
     R.d = pt.z;
   }
   return R;
 }
 
 // prox_plane_cylinder.cpp:51-88
-GD ProxRecord prox_plane_cylinder(const Pose& PL, const Pose& C, double len, double rc) {
+template <bool PTS>
+GD ProxRecord prox_plane_cylinder(const SPose& PL, const SPose& C, double len, double rc) {
   ProxRecord R;
   const V3 cy_t = rot_to_global(C, v3(0.0, 0.0, 1.0));
   const V3 c_rel = from_global(PL, C.p);
   V3 t_rel = rot_from_global(PL, cy_t);
   if (fabs(t_rel.z) < 1e-6) {
-    R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
-    R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - rc));
+    if (PTS) {
+      R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
+      R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - rc));
+    }
     R.d = c_rel.z - rc;
   } else if (sqrt(t_rel.x * t_rel.x + t_rel.y * t_rel.y) < 1e-6) {
-    R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
-    R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - 0.5 * len));
+    if (PTS) {
+      R.p1 = to_global(PL, v3(c_rel.x, c_rel.y, 0.0));
+      R.p2 = to_global(PL, v3(c_rel.x, c_rel.y, c_rel.z - 0.5 * len));
+    }
     R.d = c_rel.z - 0.5 * len;
   } else {
     if (t_rel.z > 0.0) t_rel = neg(t_rel);
@@ -149,28 +196,33 @@ GD ProxRecord prox_plane_cylinder(const Pose& PL, const Pose& C, double len, dou
     const double rn = norm3(r_rel);
     r_rel = v3(r_rel.x / rn, r_rel.y / rn, r_rel.z / rn);
     const V3 pt = c_rel + (0.5 * len) * t_rel + rc * r_rel;
-    R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
-    R.p2 = to_global(PL, pt);
+    if (PTS) {
+      R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
+      R.p2 = to_global(PL, pt);
+    }
     R.d = pt.z;
   }
   return R;
 }
 
 // prox_plane_box.cpp:51-79 — bx_x, bx_y and bx_z are all the image of the box's x axis
-GD ProxRecord prox_plane_box(const Pose& PL, const Pose& B, V3 dims) {
+template <bool PTS>
+GD ProxRecord prox_plane_box(const SPose& PL, const SPose& B, V3 dims) {
   ProxRecord R;
   V3 bx = rot_from_global(PL, rot_to_global(B, v3(1.0, 0.0, 0.0)));
   if (bx.z > 0.0) bx = neg(bx);
   const V3 c_rel = from_global(PL, B.p);
   const V3 pt = c_rel + 0.5 * (dims.x * bx + dims.y * bx + dims.z * bx);
-  R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
-  R.p2 = to_global(PL, pt);
+  if (PTS) {
+    R.p1 = to_global(PL, v3(pt.x, pt.y, 0.0));
+    R.p2 = to_global(PL, pt);
+  }
   R.d = pt.z;
   return R;
 }
 
 // prox_plane_plane.cpp:44-96
-GD void plane_point(const Pose& PL, V3 dims, V3 pt, V3& rec, double& dist) {
+GD void plane_point(const SPose& PL, V3 dims, V3 pt, V3& rec, double& dist) {
   const V3 rel = from_global(PL, pt);
   const bool in_x = rel.x > -0.5 * dims.x && rel.x < 0.5 * dims.x;
   const bool in_y = rel.y > -0.5 * dims.y && rel.y < 0.5 * dims.y;
@@ -193,12 +245,13 @@ GD void plane_point(const Pose& PL, V3 dims, V3 pt, V3& rec, double& dist) {
 }
 
 // prox_plane_plane.cpp:99-197: the four corners of plane 2 against plane 1, then of plane 1 against plane 2
-GD ProxRecord prox_plane_plane(const Pose& P1, V3 d1, const Pose& P2, V3 d2) {
+template <bool PTS>
+GD ProxRecord prox_plane_plane(const SPose& P1, V3 d1, const SPose& P2, V3 d2) {
   ProxRecord R;
   R.d = INFINITY; R.p1 = v3(0, 0, 0); R.p2 = v3(0, 0, 0);
   for (int side = 0; side < 2; ++side) {
-    const Pose& own = side == 0 ? P2 : P1;
-    const Pose& other = side == 0 ? P1 : P2;
+    const SPose& own = side == 0 ? P2 : P1;
+    const SPose& other = side == 0 ? P1 : P2;
     const V3 od = side == 0 ? d2 : d1, pd = side == 0 ? d1 : d2;
     V3 corner = v3(0.5 * od.x, 0.5 * od.y, 0.0);
     for (int c = 0; c < 4; ++c) {
@@ -217,7 +270,8 @@ GD ProxRecord prox_plane_plane(const Pose& P1, V3 d1, const Pose& P2, V3 d2) {
 }
 
 // findProximityBoxToPoint, prox_fundamentals_3D.cpp:35-83: p1 on the box, p2 the point
-GD ProxRecord box_point(const Pose& B, V3 dims, V3 pt) {
+template <bool PTS>
+GD ProxRecord box_point(const SPose& B, V3 dims, V3 pt) {
   const V3 rel = from_global(B, pt);
   bool in_x = rel.x > -0.5 * dims.x && rel.x < 0.5 * dims.x;
   bool in_y = rel.y > -0.5 * dims.y && rel.y < 0.5 * dims.y;
@@ -234,7 +288,7 @@ GD ProxRecord box_point(const Pose& B, V3 dims, V3 pt) {
   if (in_y) corner.y = rel.y; else if (rel.y < 0.0) corner.y = -corner.y;
   if (in_z) corner.z = rel.z; else if (rel.z < 0.0) corner.z = -corner.z;
   ProxRecord R;
-  R.p1 = to_global(B, corner);
+  if (PTS) R.p1 = to_global(B, corner);
   const double dd = norm3(corner - rel);
   R.p2 = pt;
   R.d = inside ? -dd : dd;
@@ -242,14 +296,17 @@ GD ProxRecord box_point(const Pose& B, V3 dims, V3 pt) {
 }
 
 // prox_sphere_box.cpp:50-73
-GD ProxRecord prox_sphere_box(const Pose& S, double rs, const Pose& B, V3 dims) {
-  const ProxRecord b = box_point(B, dims, S.p);
+template <bool PTS>
+GD ProxRecord prox_sphere_box(const SPose& S, double rs, const SPose& B, V3 dims) {
+  const ProxRecord b = box_point<PTS>(B, dims, S.p);
   ProxRecord R;
-  const V3 diff = b.p1 - b.p2;
-  const double dd = norm3(diff);
-  if (b.d < 0.0) R.p1 = b.p2 - (rs / dd) * diff;
-  else R.p1 = b.p2 + (rs / dd) * diff;
-  R.p2 = b.p1;
+  if (PTS) {
+    const V3 diff = b.p1 - b.p2;
+    const double dd = norm3(diff);
+    if (b.d < 0.0) R.p1 = b.p2 - (rs / dd) * diff;
+    else R.p1 = b.p2 + (rs / dd) * diff;
+    R.p2 = b.p1;
+  }
   R.d = b.d - rs;
   return R;
 }
@@ -257,39 +314,44 @@ GD ProxRecord prox_sphere_box(const Pose& S, double rs, const Pose& B, V3 dims) 
 // findProximityBoxToLine, prox_fundamentals_3D.cpp:110-118, with golden_section_search_impl of
 // core/optimization/line_search.hpp:71-95 (the bracket flips direction when the probe is not better;
 // the record returned is the one of the last evaluation, at the middle of the final bracket).
-GD ProxRecord box_line(const Pose& B, V3 dims, V3 centre, V3 tangent, double half) {
+template <bool PTS>
+GD ProxRecord box_line(const SPose& B, V3 dims, V3 centre, V3 tangent, double half) {
   const double phi = 1.618033988;
   double lo = -half, hi = half;
   const double tol = 1e-3 * half;
   double mid = lo + (hi - lo) / phi;
-  ProxRecord R = box_point(B, dims, centre + mid * tangent);
+  ProxRecord R = box_point<false>(B, dims, centre + mid * tangent);
   double mid_cost = R.d;
   for (int guard = 0; guard < 200; ++guard) {
     if (fabs(lo - hi) < tol) break;
     const double test = mid + (hi - mid) / phi;
-    R = box_point(B, dims, centre + test * tangent);
+    R = box_point<false>(B, dims, centre + test * tangent);
     if (R.d < mid_cost) { lo = mid; mid = test; mid_cost = R.d; }
     else { hi = lo; lo = test; }
   }
-  return box_point(B, dims, centre + ((lo + hi) * 0.5) * tangent);
+  return box_point<PTS>(B, dims, centre + ((lo + hi) * 0.5) * tangent);
 }
 
 // prox_ccylinder_box.cpp:51-75
-GD ProxRecord prox_ccylinder_box(const Pose& C, double len, double rc, const Pose& B, V3 dims) {
+template <bool PTS>
+GD ProxRecord prox_ccylinder_box(const SPose& C, double len, double rc, const SPose& B, V3 dims) {
   const V3 cy_t = rot_to_global(C, v3(0.0, 0.0, 1.0));
-  const ProxRecord b = box_line(B, dims, C.p, cy_t, 0.5 * len);
+  const ProxRecord b = box_line<PTS>(B, dims, C.p, cy_t, 0.5 * len);
   ProxRecord R;
-  const V3 diff = b.p1 - b.p2;
-  const double dd = norm3(diff);
-  if (b.d < 0.0) R.p1 = b.p2 - (rc / dd) * diff;
-  else R.p1 = b.p2 + (rc / dd) * diff;
-  R.p2 = b.p1;
+  if (PTS) {
+    const V3 diff = b.p1 - b.p2;
+    const double dd = norm3(diff);
+    if (b.d < 0.0) R.p1 = b.p2 - (rc / dd) * diff;
+    else R.p1 = b.p2 + (rc / dd) * diff;
+    R.p2 = b.p1;
+  }
   R.d = b.d - rc;
   return R;
 }
 
 // prox_ccylinder_ccylinder.cpp:43-129
-GD ProxRecord prox_ccylinder_ccylinder(const Pose& C1, double len1, double r1, const Pose& C2, double len2, double r2) {
+template <bool PTS>
+GD ProxRecord prox_ccylinder_ccylinder(const SPose& C1, double len1, double r1, const SPose& C2, double len2, double r2) {
   ProxRecord R;
   const V3 c2 = C2.p;
   const V3 t2 = rot_to_global(C2, v3(0.0, 0.0, 1.0));
@@ -305,8 +367,10 @@ GD ProxRecord prox_ccylinder_ccylinder(const Pose& C1, double len1, double r1, c
       V3 rr = v3(c.x, c.y, 0.0);
       const double rn = norm3(rr);
       rr = v3(rr.x / rn, rr.y / rn, rr.z / rn);
-      R.p1 = to_global(C1, v3(r1 * rr.x, r1 * rr.y, avg_z));
-      R.p2 = to_global(C1, v3(c.x - r2 * rr.x, c.y - r2 * rr.y, avg_z));
+      if (PTS) {
+        R.p1 = to_global(C1, v3(r1 * rr.x, r1 * rr.y, avg_z));
+        R.p2 = to_global(C1, v3(c.x - r2 * rr.x, c.y - r2 * rr.y, avg_z));
+      }
       R.d = sqrt(c.x * c.x + c.y * c.y) - r1 - r2;
       return R;
     }
@@ -315,8 +379,10 @@ GD ProxRecord prox_ccylinder_ccylinder(const Pose& C1, double len1, double r1, c
     else { s1.z += 0.5 * len1; s2.z -= 0.5 * len2; }
     const V3 diff = s2 - s1;
     const double dist = norm3(diff);
-    R.p1 = to_global(C1, s1 + (r1 / dist) * diff);
-    R.p2 = to_global(C1, s2 - (r2 / dist) * diff);
+    if (PTS) {
+      R.p1 = to_global(C1, s1 + (r1 / dist) * diff);
+      R.p2 = to_global(C1, s2 - (r2 / dist) * diff);
+    }
     R.d = dist - r1 - r2;
     return R;
   }
@@ -334,8 +400,10 @@ GD ProxRecord prox_ccylinder_ccylinder(const Pose& C1, double len1, double r1, c
   const V3 p2c = c + s_c * t;
   const V3 diff = p2c - p1c;
   const double dist = norm3(diff);
-  R.p1 = to_global(C1, p1c + (r1 / dist) * diff);
-  R.p2 = to_global(C1, p2c - (r2 / dist) * diff);
+  if (PTS) {
+    R.p1 = to_global(C1, p1c + (r1 / dist) * diff);
+    R.p2 = to_global(C1, p2c - (r2 / dist) * diff);
+  }
   R.d = dist - r1 - r2;
   return R;
 }
@@ -350,41 +418,46 @@ GD bool prox_has_finder(int ka, int kb) {
   return false;
 }
 
-GD ProxRecord prox_compute(const ProxShape& a, const Pose& Pa, const ProxShape& b, const Pose& Pb) {
+template <bool PTS>
+GD ProxRecord prox_compute(const ProxShape& a, const SPose& Pa, const ProxShape& b, const SPose& Pb) {
   // first = the shape whose kind is listed first; on equal kinds model 1's shape
   const bool swap = b.kind < a.kind;
   const ProxShape& s1 = swap ? b : a;
   const ProxShape& s2 = swap ? a : b;
-  const Pose& P1 = swap ? Pb : Pa;
-  const Pose& P2 = swap ? Pa : Pb;
+  const SPose& P1 = swap ? Pb : Pa;
+  const SPose& P2 = swap ? Pa : Pb;
   const V3 d1 = v3(s1.dims[0], s1.dims[1], s1.dims[2]), d2 = v3(s2.dims[0], s2.dims[1], s2.dims[2]);
   if (s1.kind == RKB_SHAPE_PLANE) {
-    if (s2.kind == RKB_SHAPE_PLANE) return prox_plane_plane(P1, d1, P2, d2);
-    if (s2.kind == RKB_SHAPE_SPHERE) return prox_plane_sphere(P1, P2, d2.x);
-    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_plane_ccylinder(P1, P2, d2.x, d2.y);
-    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_plane_cylinder(P1, P2, d2.x, d2.y);
-    return prox_plane_box(P1, P2, d2);
+    if (s2.kind == RKB_SHAPE_PLANE) return prox_plane_plane<PTS>(P1, d1, P2, d2);
+    if (s2.kind == RKB_SHAPE_SPHERE) return prox_plane_sphere<PTS>(P1, P2, d2.x);
+    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_plane_ccylinder<PTS>(P1, P2, d2.x, d2.y);
+    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_plane_cylinder<PTS>(P1, P2, d2.x, d2.y);
+    return prox_plane_box<PTS>(P1, P2, d2);
   }
   if (s1.kind == RKB_SHAPE_SPHERE) {
-    if (s2.kind == RKB_SHAPE_SPHERE) return prox_sphere_sphere(P1, d1.x, P2, d2.x);
-    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_sphere_ccylinder(P1, d1.x, P2, d2.x, d2.y);
-    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_sphere_cylinder(P1, d1.x, P2, d2.x, d2.y);
-    return prox_sphere_box(P1, d1.x, P2, d2);
+    if (s2.kind == RKB_SHAPE_SPHERE) return prox_sphere_sphere<PTS>(P1, d1.x, P2, d2.x);
+    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_sphere_ccylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
+    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_sphere_cylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
+    return prox_sphere_box<PTS>(P1, d1.x, P2, d2);
   }
-  if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_ccylinder_ccylinder(P1, d1.x, d1.y, P2, d2.x, d2.y);
-  return prox_ccylinder_box(P1, d1.x, d1.y, P2, d2);
+  if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_ccylinder_ccylinder<PTS>(P1, d1.x, d1.y, P2, d2.x, d2.y);
+  return prox_ccylinder_box<PTS>(P1, d1.x, d1.y, P2, d2);
 }
 
 // world pose of a shape riding on a frame with pose F: pose_3D::getGlobalPose, pose_3D.hpp:102-110
-GD Pose prox_shape_pose(const ProxShape& S, const Pose* frames) {
-  Pose L;
-  L.p = v3(S.pos[0], S.pos[1], S.pos[2]);
-  L.q.w = S.quat[0]; L.q.x = S.quat[1]; L.q.y = S.quat[2]; L.q.z = S.quat[3];
-  if (S.anchor < 0) return L;
-  const Pose F = frames[S.anchor];
-  Pose G;
-  G.p = F.p + qrotv(F.q, L.p);
-  G.q = qmul(F.q, L.q);
+GD SPose prox_shape_pose(const ProxShape& S, const Pose* frames) {
+  const V3 lp = v3(S.pos[0], S.pos[1], S.pos[2]);
+  Q4 lq;
+  lq.w = S.quat[0]; lq.x = S.quat[1]; lq.y = S.quat[2]; lq.z = S.quat[3];
+  SPose G;
+  if (S.anchor < 0) {
+    G.p = lp;
+    rot_table(lq, G.m);
+  } else {
+    const Pose F = frames[S.anchor];
+    G.p = F.p + qrotv(F.q, lp);
+    rot_table(qmul(F.q, lq), G.m);
+  }
   return G;
 }
 
@@ -392,23 +465,30 @@ GD Pose prox_shape_pose(const ProxShape& S, const Pose* frames) {
 // evaluated; a later one is skipped when the distance between the two shape origins minus the two
 // bounding radii exceeds the running minimum (for planes that radius is the half diagonal of the
 // extents although their finders treat the plane as unbounded — followed as is).
-// frames[f]: world pose of chain frame f.  Returns the finder index, -1 without finders.
-GD int prox_min_distance(const ProxProgram& P, const Pose* frames, ProxRecord& bestR) {
-  int f = 0, best = -1;
+// frames[f]: world pose of chain frame f.  Returns the finder index, -1 without finders.  The search itself
+// only forms distances; the record of the winner (its two points) is evaluated once at the end when wanted.
+GD int prox_min_distance(const ProxProgram& P, const Pose* frames, bool want_points, ProxRecord& bestR) {
+  int f = 0, best = -1, best_a = 0, best_b = 0;
   double min_d = INFINITY;
   bestR.p1 = v3(0, 0, 0); bestR.p2 = v3(0, 0, 0); bestR.d = INFINITY;
   for (int a = 0; a < P.n1; ++a) {
     const ProxShape& Sa = P.s[a];
-    const Pose Pa = prox_shape_pose(Sa, frames);
+    const SPose Pa = prox_shape_pose(Sa, frames);
     for (int b = 0; b < P.n2; ++b) {
       const ProxShape& Sb = P.s[P.n1 + b];
       if (!prox_has_finder(Sa.kind, Sb.kind)) continue;
-      const Pose Pb = prox_shape_pose(Sb, frames);
+      const SPose Pb = prox_shape_pose(Sb, frames);
       if (f > 0 && norm3(Pb.p - Pa.p) - Sa.brad - Sb.brad > min_d) { ++f; continue; }
-      const ProxRecord R = prox_compute(Sa, Pa, Sb, Pb);
-      if (f == 0 || min_d > R.d) { best = f; min_d = R.d; bestR = R; }
+      const double d = prox_compute<false>(Sa, Pa, Sb, Pb).d;
+      if (f == 0 || min_d > d) { best = f; min_d = d; best_a = a; best_b = b; }
       ++f;
     }
+  }
+  bestR.d = min_d;
+  if (best >= 0 && want_points) {
+    const ProxShape& Sa = P.s[best_a];
+    const ProxShape& Sb = P.s[P.n1 + best_b];
+    bestR = prox_compute<true>(Sa, prox_shape_pose(Sa, frames), Sb, prox_shape_pose(Sb, frames));
   }
   return best;
 }

@@ -39,7 +39,7 @@ extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames
     fr[f].q.w = v[3]; fr[f].q.x = v[4]; fr[f].q.y = v[5]; fr[f].q.z = v[6];
   }
   ProxRecord R;
-  const int best = prox_min_distance(*P, fr, R);
+  const int best = prox_min_distance(*P, fr, true, R);
   *dist = R.d;
   pts[0] = R.p1.x; pts[1] = R.p1.y; pts[2] = R.p1.z; pts[3] = R.p2.x; pts[4] = R.p2.y; pts[5] = R.p2.z;
   return best;
