@@ -952,8 +952,8 @@ cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgr
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   if (host.dim != 3) return cudaErrorInvalidValue;
-  // 5 resident CTAs per SM (96 registers): measured best of 3 / 4 / 5 / 6 / 8
-  if (host.n_frames <= 16) generic_proximity_kernel<3, 16, 5><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+  // 6 resident CTAs per SM (80 registers): measured best of 3 / 4 / 5 / 6
+  if (host.n_frames <= 16) generic_proximity_kernel<3, 16, 6><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES, 4><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   return cudaGetLastError();
 }

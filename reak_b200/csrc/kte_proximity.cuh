@@ -452,7 +452,7 @@ GD SPose prox_shape_pose(const ProxShape& S, const Pose* frames) {
   SPose G;
   if (S.anchor < 0) {
     G.p = lp;
-    rot_table(lq, G.m);
+    for (int k = 0; k < 9; ++k) G.m[k] = S.rot[k];
   } else {
     const Pose F = frames[S.anchor];
     G.p = F.p + qrotv(F.q, lp);

@@ -780,6 +780,14 @@ bool lower_shape(const rkb_shape& in, int n_frames, ProxShape* out) {
   for (int k = 0; k < 3; ++k) { out->pos[k] = in.position[k]; out->dims[k] = k < nd ? in.dims[k] : 0.0; }
   // quaternion(const Vector&) normalises what it is given (rotations_3D.hpp:917-920)
   for (int k = 0; k < 4; ++k) out->quat[k] = in.quat[k] / std::sqrt(qn);
+  {  // quaternion * vect forms these nine sums first (rotations_3D.hpp:1139-1150); see rot_table in kte_proximity.cuh
+    const double w = out->quat[0], x = out->quat[1], y = out->quat[2], z = out->quat[3];
+    const double t0 = w * x, t1 = w * y, t2 = w * z, t3 = -x * x, t4 = x * y, t5 = x * z, t6 = -y * y, t7 = y * z, t8 = -z * z;
+    double* m = out->rot;
+    m[0] = t6 + t8; m[1] = t4 - t2; m[2] = t1 + t5;
+    m[3] = t2 + t4; m[4] = t3 + t8; m[5] = t7 - t0;
+    m[6] = t5 - t1; m[7] = t0 + t7; m[8] = t3 + t6;
+  }
   const double* d = out->dims;
   // getBoundingRadius: plane.cpp:32, sphere.cpp:31, capped_cylinder.cpp:30, cylinder.cpp:33, box.cpp:31
   switch (in.kind) {

@@ -195,6 +195,7 @@ struct ProxShape {
   double  pos[3], quat[4];
   double  dims[3];
   double  brad;      // shape_3D::getBoundingRadius
+  double  rot[9];    // world-fixed shapes (anchor < 0): the rotation table of kte_proximity.cuh, formed once on the host
 };
 struct ProxProgram {
   int32_t   n1, n2;
