@@ -272,6 +272,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION and up) to stdout by default: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from reak_b200 import kte_batch_propagator, presets, _abi

@@ -34,8 +34,6 @@ def main():
     t0 = time.perf_counter()
     d, f, pts = p.get_min_distances(pair, x)
     print("%s host buffers (pageable)   n=%d  %.3f ms end to end" % (name, n, (time.perf_counter() - t0) * 1e3))
-    fr = p.get_frames(dx[: n // 4].contiguous(), torch.zeros((n // 4, p.nu), dtype=torch.float64, device="cuda"))
-    print("%s rkb_frames alone          n=%d  %.3f ms" % (name, n // 4, p.last_kernel_ms()))
     try:
         from oracle import pyref
         if pyref.have_ref():
