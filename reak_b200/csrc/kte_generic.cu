@@ -724,48 +724,53 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_frames_kernel(const Generic
 #include "kte_proximity.cuh"
 
 // doMotion at position level only (the poses are all a proximity query reads): the Position / Quat lines of
-// motion() above, operation for operation.
-template <int MAXF>
-GD void motion_pose(const GenericProgram* G, const double* q, Pose (&fr)[MAXF]) {
+// motion() above, operation for operation.  The frame being built lives in registers; only the frames the
+// program marks (ProxProgram::slot_of) are written to the thread's local array.
+template <int MAXS>
+GD void motion_pose(const GenericProgram* G, const ProxProgram& P, const double* q, Pose (&slots)[MAXS]) {
+  Pose cur;
   {
     const double* b = G->base;
-    Pose& B = fr[G->base_frame];
-    B.p = ldv(b); B.q.w = b[3]; B.q.x = b[4]; B.q.y = b[5]; B.q.z = b[6];
+    cur.p = ldv(b); cur.q.w = b[3]; cur.q.x = b[4]; cur.q.y = b[5]; cur.q.z = b[6];
   }
+  int last = G->base_frame;
+  if (P.slot_of[last] >= 0) slots[P.slot_of[last]] = cur;
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
+    if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D) continue;
+    Pose B = cur;
+    if (E.fa != last) B = slots[P.slot_of[E.fa]];
     if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-131
-      const Pose B = fr[E.fa];
       const V3 an = unit_axis(ldv(E.p));
       double sh, ch;
       sincos(0.5 * q[E.coord], &sh, &ch);
       Q4 tq; tq.w = ch; tq.x = an.x * sh; tq.y = an.y * sh; tq.z = an.z * sh;
-      fr[E.fb].p = B.p;
-      fr[E.fb].q = qmul(B.q, tq);
+      cur.p = B.p;
+      cur.q = qmul(B.q, tq);
     } else if (E.kind == RKB_PRISMATIC_3D) {  // prismatic_joint.cpp:129-140
-      const Pose B = fr[E.fa];
-      fr[E.fb].p = B.p + mul(qrot(B.q), q[E.coord] * ldv(E.p));
-      fr[E.fb].q = B.q;
-    } else if (E.kind == RKB_RIGID_LINK_3D) {  // rigid_link.cpp:156 -> pose_3D::addBefore
-      const Pose B = fr[E.fa];
+      cur.p = B.p + mul(qrot(B.q), q[E.coord] * ldv(E.p));
+      cur.q = B.q;
+    } else {  // rigid_link.cpp:156 -> pose_3D::addBefore
       Q4 qo; qo.w = E.p[3]; qo.x = E.p[4]; qo.y = E.p[5]; qo.z = E.p[6];
-      fr[E.fb].p = B.p + mul(qrot(B.q), ldv(E.p));
-      fr[E.fb].q = qmul(B.q, qo);
+      cur.p = B.p + mul(qrot(B.q), ldv(E.p));
+      cur.q = qmul(B.q, qo);
     }
+    last = E.fb;
+    if (P.slot_of[last] >= 0) slots[P.slot_of[last]] = cur;
   }
 }
 
 // proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) at the chain's pose for
 // state x[i]: distance, the index of the finder that gave it and its two points.
-template <int DIM, int MAXF, int MINB>
+template <int DIM, int MAXS, int MINB>
 __global__ void __launch_bounds__(GEN_BLOCK, MINB) generic_proximity_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
                                                                        const __grid_constant__ ProxProgram P) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
   if (i >= A.n_samples) return;
   double q[MAXC];
   for (int c = 0; c < G->n_coords; ++c) q[c] = A.x.p[i * A.x.si + rkb_state_q(A.x.blocked, G->n_coords, c) * A.x.sk];
-  Pose fr[MAXF];
-  motion_pose(G, q, fr);
+  Pose fr[MAXS];
+  motion_pose(G, P, q, fr);
   ProxRecord bestR;
   const int best = prox_min_distance(P, fr, A.out2.p != (double*)0, bestR);
   A.out.p[i * A.out.si] = bestR.d;
@@ -953,7 +958,7 @@ cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgr
   if (n <= 0) return cudaSuccess;
   if (host.dim != 3) return cudaErrorInvalidValue;
   // 6 resident CTAs per SM (80 registers): measured best of 3 / 4 / 5 / 6
-  if (host.n_frames <= 16) generic_proximity_kernel<3, 16, 6><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+  if (pp.n_slots <= 8) generic_proximity_kernel<3, 8, 6><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES, 4><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   return cudaGetLastError();
 }

@@ -445,7 +445,7 @@ GD ProxRecord prox_compute(const ProxShape& a, const SPose& Pa, const ProxShape&
 }
 
 // world pose of a shape riding on a frame with pose F: pose_3D::getGlobalPose, pose_3D.hpp:102-110
-GD SPose prox_shape_pose(const ProxShape& S, const Pose* frames) {
+GD SPose prox_shape_pose(const ProxProgram& P, const ProxShape& S, const Pose* slots) {
   const V3 lp = v3(S.pos[0], S.pos[1], S.pos[2]);
   Q4 lq;
   lq.w = S.quat[0]; lq.x = S.quat[1]; lq.y = S.quat[2]; lq.z = S.quat[3];
@@ -454,7 +454,7 @@ GD SPose prox_shape_pose(const ProxShape& S, const Pose* frames) {
     G.p = lp;
     for (int k = 0; k < 9; ++k) G.m[k] = S.rot[k];
   } else {
-    const Pose F = frames[S.anchor];
+    const Pose F = slots[P.slot_of[S.anchor]];
     G.p = F.p + qrotv(F.q, lp);
     rot_table(qmul(F.q, lq), G.m);
   }
@@ -465,19 +465,19 @@ GD SPose prox_shape_pose(const ProxShape& S, const Pose* frames) {
 // evaluated; a later one is skipped when the distance between the two shape origins minus the two
 // bounding radii exceeds the running minimum (for planes that radius is the half diagonal of the
 // extents although their finders treat the plane as unbounded — followed as is).
-// frames[f]: world pose of chain frame f.  Returns the finder index, -1 without finders.  The search itself
+// slots[P.slot_of[f]]: world pose of chain frame f (for the frames shapes ride on).  Returns the finder index, -1 without finders.  The search itself
 // only forms distances; the record of the winner (its two points) is evaluated once at the end when wanted.
-GD int prox_min_distance(const ProxProgram& P, const Pose* frames, bool want_points, ProxRecord& bestR) {
+GD int prox_min_distance(const ProxProgram& P, const Pose* slots, bool want_points, ProxRecord& bestR) {
   int f = 0, best = -1, best_a = 0, best_b = 0;
   double min_d = INFINITY;
   bestR.p1 = v3(0, 0, 0); bestR.p2 = v3(0, 0, 0); bestR.d = INFINITY;
   for (int a = 0; a < P.n1; ++a) {
     const ProxShape& Sa = P.s[a];
-    const SPose Pa = prox_shape_pose(Sa, frames);
+    const SPose Pa = prox_shape_pose(P, Sa, slots);
     for (int b = 0; b < P.n2; ++b) {
       const ProxShape& Sb = P.s[P.n1 + b];
       if (!prox_has_finder(Sa.kind, Sb.kind)) continue;
-      const SPose Pb = prox_shape_pose(Sb, frames);
+      const SPose Pb = prox_shape_pose(P, Sb, slots);
       if (f > 0 && norm3(Pb.p - Pa.p) - Sa.brad - Sb.brad > min_d) { ++f; continue; }
       const double d = prox_compute<false>(Sa, Pa, Sb, Pb).d;
       if (f == 0 || min_d > d) { best = f; min_d = d; best_a = a; best_b = b; }
@@ -488,7 +488,7 @@ GD int prox_min_distance(const ProxProgram& P, const Pose* frames, bool want_poi
   if (best >= 0 && want_points) {
     const ProxShape& Sa = P.s[best_a];
     const ProxShape& Sb = P.s[P.n1 + best_b];
-    bestR = prox_compute<true>(Sa, prox_shape_pose(Sa, frames), Sb, prox_shape_pose(Sb, frames));
+    bestR = prox_compute<true>(Sa, prox_shape_pose(P, Sa, slots), Sb, prox_shape_pose(P, Sb, slots));
   }
   return best;
 }

@@ -820,6 +820,21 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
   for (int a = 0; a < n1; ++a)
     for (int b = 0; b < n2; ++b)
       if (prox_pair_has_finder(m1[a].kind, m2[b].kind)) p->finders.push_back(std::make_pair(a, b));
+  {  // which frames outlive the element after their writer (motion_pose in kte_generic.cu walks the same loop)
+    bool keep[RKB_GEN_MAX_FRAMES] = {};
+    for (int k = 0; k < n1 + n2; ++k)
+      if (p->prog.s[k].anchor >= 0) keep[p->prog.s[k].anchor] = true;
+    int last = c->gp.base_frame;
+    for (int e = 0; e < c->gp.n_elements; ++e) {
+      const GenericElement& E = c->gp.el[e];
+      if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D) continue;
+      if (E.fa != last) keep[E.fa] = true;
+      last = E.fb;
+    }
+    p->prog.n_slots = 0;
+    for (int f = 0; f < RKB_GEN_MAX_FRAMES; ++f)
+      p->prog.slot_of[f] = (f < c->desc.n_frames && keep[f]) ? (int8_t)p->prog.n_slots++ : (int8_t)-1;
+  }
   *out = p;
   return RKB_OK;
 }

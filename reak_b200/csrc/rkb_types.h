@@ -199,6 +199,11 @@ struct ProxShape {
 };
 struct ProxProgram {
   int32_t   n1, n2;
+  // Frames the kernel has to keep after the forward kinematics has moved on: those a shape rides on and those an
+  // element reads that is not the one right after their writer.  All other frames only ever live in registers.
+  int32_t   n_slots;
+  int8_t    slot_of[40];                 // per chain frame (RKB_GEN_MAX_FRAMES): storage slot, -1 = never stored
+  int32_t   pad;
   ProxShape s[2 * RKB_PROX_MAX_SHAPES];  // model 1 then model 2
 };
 

@@ -32,11 +32,13 @@ using std::sqrt;
 // program: the ProxProgram rkb_proxy_create lowers (read back through rkb_proxy_program, a test hook of the
 // product library); frames: [n_frames][7] world position + quaternion of the chain frames.
 extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames, int n_frames, double* dist, double* pts) {
-  Pose fr[RKB_GEN_MAX_FRAMES];
+  Pose fr[RKB_GEN_MAX_FRAMES];  // the kernel's slot array: only the frames the program asks to keep
   for (int f = 0; f < n_frames && f < RKB_GEN_MAX_FRAMES; ++f) {
+    if (P->slot_of[f] < 0) continue;
     const double* v = frames + 7 * f;
-    fr[f].p = v3(v[0], v[1], v[2]);
-    fr[f].q.w = v[3]; fr[f].q.x = v[4]; fr[f].q.y = v[5]; fr[f].q.z = v[6];
+    Pose& S = fr[P->slot_of[f]];
+    S.p = v3(v[0], v[1], v[2]);
+    S.q.w = v[3]; S.q.x = v[4]; S.q.y = v[5]; S.q.z = v[6];
   }
   ProxRecord R;
   const int best = prox_min_distance(*P, fr, true, R);
