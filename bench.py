@@ -426,6 +426,24 @@ def run_ours(args):
                "sample": "first %d of the %d samples x %d RK4 steps, %d forked workers" % (m, n, RK4_STEPS, cores),
                "max_rel_err_vs_gpu": err, "tolerance": 1e-8}
         assert err < 1e-8, "GPU result disagrees with the reference on the CPU sample: %g" % err
+        # the same for the proximity entry: the reference's findMinimumDistance on one host core, checked against the GPU
+        prox = [o for o in (others or []) if o.get("config") == "proximity"]
+        if prox and kind == "reference":
+            from oracle import pyref
+            from reak_b200 import proximity as px
+            s6 = presets.make(PRESET)
+            p6 = kte_batch_propagator(s6, device=local)
+            robot, lab = presets.crs_proxy_models(s6)
+            pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+            xs = 3.0 * np.ascontiguousarray(x_h[:8192])
+            t0 = time.perf_counter()
+            dr, _, _ = pyref.Reference(p6.compiled).min_distance(pair, xs)
+            secs_p = time.perf_counter() - t0
+            dg, _ = p6.get_min_distances(pair, xs, with_points=False)
+            errp = float(np.max(np.abs(dg - dr)))
+            assert errp < 1e-10, "GPU minimum distances disagree with the reference: %g" % errp
+            prox[0]["cpu_baseline"] = {"value": xs.shape[0] / secs_p, "unit": "states/s", "cores": 1, "kind": "reference",
+                                       "sample": "%d states" % xs.shape[0], "max_abs_err_vs_gpu": errp}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Developer tool: time rkb_min_distance (CRS arm against the MD148 lab, device-resident states) and the
-reference's findMinimumDistance on one host core for the same states."""
+"""Developer tool: time rkb_min_distance (CRS arm against the MD148 lab, device-resident states).  The reference's
+findMinimumDistance on a host core is timed by bench.py's cpu_baseline leg (other_configs / proximity)."""
 import os
 import sys
 import time
@@ -34,17 +34,6 @@ def main():
     t0 = time.perf_counter()
     d, f, pts = p.get_min_distances(pair, x)
     print("%s host buffers (pageable)   n=%d  %.3f ms end to end" % (name, n, (time.perf_counter() - t0) * 1e3))
-    try:
-        from oracle import pyref
-        if pyref.have_ref():
-            R = pyref.Reference(p.compiled)
-            m = 4096
-            t0 = time.perf_counter()
-            dr, _, _ = R.min_distance(pair, x[:m])
-            dt = time.perf_counter() - t0
-            print("reference, 1 core: %d states in %.3f s = %.3g states/s; max |d - d_ref| = %.2e" % (m, dt, m / dt, np.abs(dr - d[:m]).max()))
-    except Exception as e:  # the checker is optional for this tool
-        print("reference not timed:", e)
 
 
 if __name__ == "__main__":
