@@ -20,6 +20,7 @@
  *   rkb_twist_shaping     <- mass_matrix_calc::get_TMT_TdMT             (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287)
  *   rkb_frames            <- kte_map_chain::doMotion / doForce as seen on the frames (frame_3D / frame_2D members)
  *   rkb_steer_feedback_checked <- the same loops with with_collision_check = true (is_free_impl after every interval)
+ *   rkb_is_free           <- manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99)
  *   rkb_min_distance      <- proxy_query_pair_3D::findMinimumDistance (geometry/proximity/proxy_query_model.cpp:388-412)
  *                            with the pair finders of geometry/proximity/prox_*_*.cpp: the is_free test of
  *                            ctrl/topologies/manip_free_workspace.hpp:77-99 on every propagated state
@@ -298,6 +299,14 @@ RKB_API int  rkb_proxy_program(const rkb_proxy* proxy, void* out, size_t size);
 RKB_API int rkb_min_distance(rkb_chain* chain, const rkb_proxy* proxy, int device, size_t n_samples,
                              const double* x, double* distance, int32_t* finder, double* points,
                              unsigned flags, void* stream);
+
+/* manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99) and the is_free_impl of the
+ * steering topologies (examples/misc/MEAQR_topology.hpp:921-940) for every state: is_free[i] = 1 unless some proxy
+ * pair's findMinimumDistance reports a negative distance at x[i] (a pair without finders never objects), else 0.
+ * pairs: n_pairs >= 1 handles made for `chain`.  One proximity launch per pair and one combining launch. */
+RKB_API int rkb_is_free(rkb_chain* chain, int device, size_t n_samples, const double* x,
+                        const rkb_proxy* const* pairs, int n_pairs, int32_t* is_free,
+                        unsigned flags, void* stream);
 
 /* Twist-shaping matrix Tcm and its time derivative Tcm_dot of mass_matrix_calc::get_TMT_TdMT
  * (ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287) at state x[i].  Rows: one per inertia_gen, then three per

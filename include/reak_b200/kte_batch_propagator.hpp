@@ -276,15 +276,19 @@ class kte_batch_propagator {
                          double* points = NULL, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_min_distance(mChain, pair, mDevice, n, x, distance, finder, points, flags, stream), "rkb_min_distance");
   }
+  /// manip_dk_proxy_env_impl::is_free for every state: is_free[i] = 1 unless some pair reports a negative distance
+  void get_is_free(const std::vector<const rkb_proxy*>& pairs, std::size_t n, const double* x, int32_t* is_free,
+                   unsigned flags = 0, void* stream = NULL) const {
+    check(rkb_is_free(mChain, mDevice, n, x, pairs.empty() ? NULL : &pairs[0], static_cast<int>(pairs.size()), is_free, flags, stream),
+          "rkb_is_free");
+  }
   /// manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99) for one state
   bool is_free(const std::vector<const rkb_proxy*>& pairs, const point_type& p) const {
     if (p.size() != get_state_dimensions()) throw std::range_error("State vector dimension mismatch!");
-    for (std::size_t k = 0; k < pairs.size(); ++k) {
-      double d = 0.0;
-      get_min_distances(pairs[k], 1, &p[0], &d);
-      if (d < 0.0) return false;
-    }
-    return true;
+    if (pairs.empty()) return true;
+    int32_t ok = 1;
+    get_is_free(pairs, 1, &p[0], &ok);
+    return ok != 0;
   }
   /// mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm and (nullable) Tcm_dot, [n][rows][dof];
   /// twist_shaping_rows() and twist_shaping_mcm(Mcm) give the row count and the constant rows x rows Mcm.

@@ -899,6 +899,52 @@ int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, con
   return RKB_OK;
 }
 
+int rkb_is_free(rkb_chain* c, int device, size_t N, const double* x, const rkb_proxy* const* pairs, int n_pairs, int32_t* is_free,
+                unsigned flags, void* stream) {
+  if (!c || n_pairs < 1 || !pairs) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  if (!x || !is_free) return RKB_ERR_INVALID;
+  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  for (int p = 0; p < n_pairs; ++p)
+    if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* dx = nullptr;
+  void* dfree = nullptr;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if ((rc = stage_out(ctx->st, is_free, N * sizeof(int32_t), L.device, &dfree))) return rc;
+  if ((rc = ctx->scratch_o.ensure(N * sizeof(double) * (size_t)n_pairs))) return rc;
+  CU(cudaEventRecord(ctx->ev0, s));
+  for (int p = 0; p < n_pairs; ++p) {
+    EvalArgs E;
+    E.x = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked);
+    E.u = cview((const double*)dx, (long long)N, 1, L.soa);
+    E.out = view((double*)ctx->scratch_o.p + (size_t)p * N, (long long)N, 1, false);
+    E.out2 = view((double*)nullptr, (long long)N, 6, false);
+    E.status = nullptr;
+    E.n_samples = (long long)N;
+    const cudaError_t e = rkb_generic_proximity(ctx->d_prog, c->gp, E, pairs[p]->prog, s);
+    if (e != cudaSuccess) return cuda_fail(e, "proximity kernel");
+    c->launches += 1;
+  }
+  const cudaError_t e = rkb_free_combine((const double*)ctx->scratch_o.p, n_pairs, (long long)N, (int32_t*)dfree, s);
+  if (e != cudaSuccess) return cuda_fail(e, "free combine");
+  c->launches += 1;
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(dfree, is_free, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
 int rkb_twist_shaping_rows(const rkb_chain* c) { return c ? tmt_rows(c->desc) : RKB_ERR_INVALID; }
 
 /* Mcm of get_TMT_TdMT (mass_matrix_calculator.cpp:265-285): block diagonal, the masses and the tensors */

@@ -61,5 +61,6 @@ cudaError_t rkb_jit_launch(const JitKernels& J, int which, const SerialParams& P
 // steering law between two control intervals (rkb_steer.cu)
 cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s);
 cudaError_t rkb_steer_commit(const SteerCommitArgs& a, cudaStream_t s);
+cudaError_t rkb_free_combine(const double* dist, int n_pairs, long long n, int32_t* out, cudaStream_t s);
 
 #endif

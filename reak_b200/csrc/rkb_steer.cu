@@ -123,7 +123,23 @@ __global__ void __launch_bounds__(STEER_BLOCK) steer_commit_kernel(const SteerCo
   }
 }
 
+// is_free: no pair with a negative minimum distance (manip_free_workspace.hpp:84-97)
+__global__ void __launch_bounds__(STEER_BLOCK) free_combine_kernel(const double* __restrict__ dist, int n_pairs, long long n, int32_t* out) {
+  const long long i = (long long)blockIdx.x * STEER_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  int ok = 1;
+  for (int p = 0; p < n_pairs; ++p)
+    if (dist[(long long)p * n + i] < 0.0) ok = 0;
+  out[i] = ok;
+}
+
 }  // namespace
+
+cudaError_t rkb_free_combine(const double* dist, int n_pairs, long long n, int32_t* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  free_combine_kernel<<<(unsigned)((n + STEER_BLOCK - 1) / STEER_BLOCK), STEER_BLOCK, 0, s>>>(dist, n_pairs, n, out);
+  return cudaGetLastError();
+}
 
 cudaError_t rkb_steer_commit(const SteerCommitArgs& a, cudaStream_t s) {
   if (a.n_samples <= 0) return cudaSuccess;

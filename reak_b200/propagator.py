@@ -286,12 +286,20 @@ class kte_batch_propagator(object):
     def is_free(self, pairs, x):
         """manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99): no proxy pair reports
         a negative minimum distance.  Returns a bool array [N]."""
-        free = None
+        from . import proximity
+        hs = []
         for pair in pairs:
-            d, _ = self.get_min_distances(pair, x, with_points=False)
-            ok = ~(d < 0.0)
-            free = ok if free is None else (free & ok)
-        return free
+            h = getattr(pair, "_rkb_handle", None)
+            if h is None or getattr(pair, "_rkb_owner", None) is not self:
+                h = proximity.ProxyHandle(self._lib, self._h, pair, self.compiled.frames)
+                pair._rkb_handle, pair._rkb_owner = h, self
+            hs.append(h._h)
+        arr = (C.c_void_p * len(hs))(*hs)
+        x, N = self._in(x, self.nx, np.float64)
+        free = self._like(x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, free], False)
+        _abi.check(self._lib.rkb_is_free(self._h, self.device, N, ptr(x), arr, len(hs), ptr(free), flags, stream), "rkb_is_free")
+        return free != 0
 
     def get_twist_shaping(self, x, with_derivative=True):
         """mass_matrix_calc::get_TMT_TdMT (mass_matrix_calculator.cpp:100-287): Tcm [N][rows][n], Mcm [rows][rows]

@@ -587,3 +587,27 @@ def test_gpu_branched_chain_vs_reference(oracle_built):
     # and the dynamics of the same branched chain, for good measure
     xd, st = P.get_state_derivatives(x, u)
     assert not st.any() and np.max(np.abs(xd - R.eval(x, u)[0]) / np.maximum(1.0, np.abs(xd))) < 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_is_free_two_pairs_vs_reference(oracle_built):
+    """rkb_is_free = manip_dk_proxy_env_impl::is_free: no pair with a negative findMinimumDistance"""
+    need_ref(oracle_built)
+    import torch
+    s, P = _gpu_prop("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    extra = px.proxy_query_pair_3D("tool-obstacle", px.proxy_query_model_3D("tool").addShape(px.sphere("tool", s.joint_end_frames[-1], None, 0.12)),
+                                   px.proxy_query_model_3D("obstacle").addShape(px.box("crate", None, px.pose_3D((0.3, -3.0, 0.9)), (0.5, 0.5, 0.5))))
+    none = px.proxy_query_pair_3D("none", px.proxy_query_model_3D("a").addShape(px.box("b", None, None, (1, 1, 1))),
+                                  px.proxy_query_model_3D("b").addShape(px.box("c", None, None, (1, 1, 1))))
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 3001, seed=8, q_range=3.1)
+    d1, d2 = R.min_distance(pair, x)[0], R.min_distance(extra, x)[0]
+    want = ~((d1 < 0) | (d2 < 0))
+    got = P.is_free([pair, extra, none], x)
+    assert np.array_equal(got, want) and want.any() and (~want).any()
+    assert ((d1 >= 0) & (d2 < 0)).any(), "the second pair never decides"
+    assert np.array_equal(P.is_free([pair], x), ~(d1 < 0)) and P.is_free([none], x).all()
+    got_d = P.is_free([pair, extra, none], torch.from_numpy(x).cuda())
+    assert np.array_equal(got_d.cpu().numpy(), want)
