@@ -149,6 +149,8 @@ typedef struct rkb_chain rkb_chain; /* opaque */
 #define RKB_ERR_INTEGRATION   -6  /* impossible_integration (dt == 0, n_steps < 0)             */
 
 RKB_API int         rkb_version(void);
+/* 16 hex digits: a hash over the sources this binary was built from (profiles and benches name the build they measured). */
+RKB_API const char* rkb_build_id(void);
 RKB_API const char* rkb_strerror(int code);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
 RKB_API const char* rkb_last_cuda_error(void);
@@ -390,6 +392,16 @@ RKB_API int rkb_steer_feedback_checked(rkb_chain* chain, int device, size_t n_sa
 RKB_API double rkb_last_kernel_ms(rkb_chain* chain);
 /* Number of kernels launched through this handle since creation. */
 RKB_API uint64_t rkb_launch_count(const rkb_chain* chain);
+
+/* Host buffers.  RKB_MEM_HOST pointers may be pageable (a std::vector's storage): the library then pays the
+ * driver's synchronous staged copy.  rkb_host_pin page-locks a caller-owned range once (cudaHostRegister,
+ * portable across devices) so that every later call on it copies by DMA, overlapped with the kernels;
+ * rkb_host_unpin undoes it (before the memory is freed).  Pinning twice / unpinning unpinned memory is not an error.
+ * Threading: a handle serialises its calls (internal mutex); RKB_MEM_DEVICE calls return without synchronising and
+ * use per-handle scratch buffers, so a handle may have work in flight on ONE stream at a time — make a second
+ * handle (rkb_chain_create is cheap) for a second concurrent stream. */
+RKB_API int rkb_host_pin(void* ptr, size_t bytes);
+RKB_API int rkb_host_unpin(void* ptr);
 
 /* Instrumentation: best-of-runs throughput of a pure DFMA loop on `device` for about `seconds`
  * (TFLOP/s, 2 flops per DFMA) — the FP64 roofline denominator bench.py reports against. */

@@ -230,14 +230,22 @@ _PRODUCT_SO = os.path.join(os.path.dirname(_HERE), "reak_b200", "lib", "libreak_
 _preloaded = []
 
 
+def preload_product():
+    """For the tests that drive the C++ drop-in checks (rkref_bridge_gpu_check, rkref_steer_space_check, ...):
+    those call INTO the product library from code compiled against the reference, through weak references that
+    are bound when libreak_ref.so is mapped.  The product's symbols must be visible before that, so the test
+    session (tests/conftest.py) calls this once, before any Reference exists.  Nothing else does: in
+    particular `bench.py --impl reference` and the cpu_baseline leg never map the product library through here."""
+    path = os.environ.get("RKB_LIB_PATH") or _PRODUCT_SO
+    if not _preloaded and os.path.isfile(path):
+        _preloaded.append(C.CDLL(path, mode=C.RTLD_GLOBAL))
+    return bool(_preloaded)
+
+
 class Reference(_Checker):
     """The real ReaK code (kte_nl_system + runge_kutta4_integrator)."""
 
     def __init__(self, compiled):
-        # rkref_bridge_gpu_check (the C++ drop-in check) calls into the product library: make its
-        # symbols visible before libreak_ref.so binds its weak references to them.
-        if not _preloaded and os.path.isfile(os.environ.get("RKB_LIB_PATH") or _PRODUCT_SO):
-            _preloaded.append(C.CDLL(os.environ.get("RKB_LIB_PATH") or _PRODUCT_SO, mode=C.RTLD_GLOBAL))
         _Checker.__init__(self, REF_SO, "rkref_", compiled)
 
 

@@ -77,6 +77,7 @@ _ip = C.POINTER(C.c_int32)
 # name -> (restype, argtypes); every symbol include/reak_b200.h declares
 SYMBOLS = {
     "rkb_version": (C.c_int, []),
+    "rkb_build_id": (C.c_char_p, []),
     "rkb_strerror": (C.c_char_p, [C.c_int]),
     "rkb_last_cuda_error": (C.c_char_p, []),
     "rkb_chain_create": (C.c_int, [C.POINTER(rkb_chain_desc), C.POINTER(C.c_void_p)]),
@@ -124,6 +125,8 @@ SYMBOLS = {
                                              C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rkb_host_pin": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "rkb_host_unpin": (C.c_int, [C.c_void_p]),
     "rkb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -903,8 +903,9 @@ __global__ void __launch_bounds__(256) steer_reduce_kernel(int nx, long long n_r
     const double* xe = xend + (pair * n_rollouts + r) * nx;
     double s = 0.0;
     for (int k = 0; k < nx; ++k) { const double d = xe[k] - goal[pair * nx + k]; s += d * d; }
-    const double c = sqrt(s);
-    if (c < best || (bi < 0 && !(c > best))) { best = c; bi = r; }  // NaN costs never win over a finite one
+    double c = sqrt(s);
+    if (!isfinite(c)) c = INFINITY;  // a diverged rollout (NaN / inf end state) never beats a finite one; all diverged: index 0, cost +inf
+    if (bi < 0 || c < best) { best = c; bi = r; }
   }
   s_cost[threadIdx.x] = best;
   s_idx[threadIdx.x] = bi;

@@ -15,6 +15,7 @@
 
 #include "../../include/reak_b200.h"
 #include "rkb_internal.h"
+#include "build_id.h"
 
 namespace {
 
@@ -460,11 +461,14 @@ const SerialKernels* find_serial(int n, int fl, unsigned long long shape) {
 }
 
 // RAII: switch to `device`, restore on exit
+// (cudaGetDevice reports 0 for a thread that never chose a device; restoring that would create a context on
+// GPU 0 in every rank of a one-process-per-GPU job, so the previous device is only restored when it differs.)
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
   explicit DeviceGuard(int device) {
     if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev == device) { prev = -1; ok = true; return; }
     ok = cudaSetDevice(device) == cudaSuccess;
     if (!ok) cudaGetLastError();
   }
@@ -634,6 +638,8 @@ int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, const RkT
 extern "C" {
 
 int rkb_version(void) { return RKB_VERSION; }
+
+const char* rkb_build_id(void) { return RKB_BUILD_ID; }
 
 const char* rkb_strerror(int code) {
   switch (code) {
@@ -1363,7 +1369,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   }
   if ((rc = stage_out(ctx->out_a, x_out, bx, L.device, &dxo))) return rc;
   if ((rc = stage_out(ctx->out_ndone, n_done, N * sizeof(int32_t), L.device, &dnd))) return rc;
-  if ((rc = stage_out(ctx->out_b, x_traj, bx * (size_t)(J > 0 ? J : 1), L.device, &dtraj))) return rc;
+  if ((rc = stage_out(ctx->out_b, x_traj, bx * (size_t)J, L.device, &dtraj))) return rc;  // J == 0: x_traj holds nothing, nothing is staged
   if ((rc = ctx->st.ensure(N * sizeof(int32_t)))) return rc;  // status is accumulated on the device even if not wanted
   dst = (L.device && status) ? (void*)status : ctx->st.p;
   if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
@@ -1465,7 +1471,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   c->last = ctx;
   if ((rc = unstage_out(dxo, x_out, bx, L.device, s))) return rc;
   if ((rc = unstage_out(dnd, n_done, N * sizeof(int32_t), L.device, s))) return rc;
-  if ((rc = unstage_out(dtraj, x_traj, bx * (size_t)(J > 0 ? J : 1), L.device, s))) return rc;
+  if ((rc = unstage_out(dtraj, x_traj, bx * (size_t)J, L.device, s))) return rc;
   if (n_pairs > 0 && (rc = unstage_out(dcol, collided, N * sizeof(int32_t), L.device, s))) return rc;
   if (!L.device && nu > 0) CU(cudaMemcpyAsync(u_prev, dup_in, bu, cudaMemcpyDeviceToHost, s));
   if (!L.device && status) CU(cudaMemcpyAsync(status, dst, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -1504,5 +1510,22 @@ double rkb_last_kernel_ms(rkb_chain* c) {
 }
 
 uint64_t rkb_launch_count(const rkb_chain* c) { return c ? c->launches : 0; }
+
+/* A ReaK caller holds its states in pageable std::vectors: cudaMemcpyAsync from those is a synchronous staged copy.
+ * Pinning the buffer once (cudaHostRegister) makes every later RKB_MEM_HOST call on it a plain DMA. */
+int rkb_host_pin(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return RKB_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RKB_OK; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+  return RKB_OK;
+}
+int rkb_host_unpin(void* ptr) {
+  if (!ptr) return RKB_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return RKB_OK; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+  return RKB_OK;
+}
 
 }  // extern "C"

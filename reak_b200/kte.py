@@ -404,6 +404,13 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
         else:
             raise UnsupportedChain("KTE %r (%s) is outside the compiled element set" % (k, type(k).__name__))
 
+    # the converse: M comes from mass_calc (kte_nl_system.hpp:271) and the forces from the chain, so an inertia
+    # registered with mass_calc but absent from the chain would enter the reference's M and be dropped here
+    seen = set(id(k) for k in chain.getKTEs())
+    for x in mass_calc.mGenInertias + mass_calc.m2DInertias + mass_calc.m3DInertias:
+        if id(x) not in seen:
+            raise UnsupportedChain("inertia %s is registered with the mass_matrix_calc but is not in the chain" % x.name)
+
     for i, joint in actuator_joint.items():  # resolve actuator -> joint element index
         j = elem_index.get(id(joint))
         if j is None:

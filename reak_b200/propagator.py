@@ -157,6 +157,29 @@ class kte_batch_propagator(object):
             raise IndexError("State vector dimension mismatch!" if cols == self.nx else "Input vector dimension mismatch!")
         return a, n
 
+    def _out(self, buf, ref, shape, dtype=np.float64):
+        """A caller-supplied result buffer goes to the C-ABI by raw pointer: it must have exactly the shape and
+        dtype the call writes, be C-contiguous and live in the same memory space as the inputs; None allocates."""
+        if buf is None:
+            return self._like(ref, shape, dtype)
+        if _is_torch(buf) != _is_torch(ref):
+            raise TypeError("mix of numpy (host) and torch (device) buffers")
+        if _is_torch(buf):
+            import torch
+            want = torch.float64 if dtype == np.float64 else torch.int32
+            ok_type, contiguous = buf.dtype == want, buf.is_contiguous()
+        else:
+            if not isinstance(buf, np.ndarray):
+                raise TypeError("result buffers must be numpy arrays or torch tensors")
+            ok_type, contiguous = buf.dtype == np.dtype(dtype), buf.flags["C_CONTIGUOUS"] and buf.flags["WRITEABLE"]
+        if not ok_type:
+            raise TypeError("result buffer must be %s" % np.dtype(dtype).name)
+        if tuple(buf.shape) != tuple(shape):
+            raise IndexError("result buffer has shape %s, the call writes %s" % (tuple(buf.shape), tuple(shape)))
+        if not contiguous:
+            raise TypeError("result buffers must be C-contiguous and writeable")
+        return buf
+
     def _like(self, ref, shape, dtype=np.float64):
         if _is_torch(ref):
             import torch
@@ -172,8 +195,8 @@ class kte_batch_propagator(object):
     def get_state_derivatives(self, x, u=None, soa=False, out=None, status=None):
         x, N = self._in(x, self.nx, np.float64, soa)
         u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]
-        xd = out if out is not None else self._like(x, x.shape)
-        st = status if status is not None else self._like(x, (N,), np.int32)
+        xd = self._out(out, x, x.shape)
+        st = self._out(status, x, (N,), np.int32)
         flags, stream, ptr = self._prep([x, u if self.nu else None, xd, st], soa)
         _abi.check(self._lib.rkb_eval(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
                                       ptr(xd), ptr(st), flags, stream), "rkb_eval")
@@ -185,8 +208,8 @@ class kte_batch_propagator(object):
         dt = self.dt if dt is None else float(dt)
         if dt == 0.0 or n_steps < 0:
             raise impossible_integration("dt == 0 or negative step count")
-        xo = out if out is not None else self._like(x, x.shape)
-        st = status if status is not None else self._like(x, (N,), np.int32)
+        xo = self._out(out, x, x.shape)
+        st = self._out(status, x, (N,), np.int32)
         flags, stream, ptr = self._prep([x, u if self.nu else None, xo, st], soa)
         _abi.check(self._lib.rkb_rollout_rk4(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
                                              dt, int(n_steps), ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4")
@@ -211,9 +234,9 @@ class kte_batch_propagator(object):
             raise impossible_integration("dt == 0 or negative step count")
         code = _abi.SCHEMES[scheme] if isinstance(scheme, str) else int(scheme)
         opts = _abi.rkb_rollout_opts(code, J, int(steps_per_interval), 0, dt)
-        xo = out if out is not None else self._like(x, x.shape)
+        xo = self._out(out, x, x.shape)
         tr = self._like(x, (N, J, self.nx)) if want_traj else None
-        st = status if status is not None else self._like(x, (N,), np.int32)
+        st = self._out(status, x, (N,), np.int32)
         flags, stream, ptr = self._prep([x, u_seq if self.nu else None, xo, tr, st], False)
         _abi.check(self._lib.rkb_rollout(self._h, self.device, N, ptr(x), ptr(u_seq) if self.nu else None, C.byref(opts),
                                          ptr(xo), ptr(tr), ptr(st), flags, stream), "rkb_rollout")
@@ -228,8 +251,8 @@ class kte_batch_propagator(object):
         dt = self.dt if dt is None else float(dt)
         if dt == 0.0 or n_steps < 0:
             raise impossible_integration("dt == 0 or negative step count")
-        xo = out if out is not None else np.empty_like(x)
-        st = status if status is not None else np.empty((N,), dtype=np.int32)
+        xo = self._out(out, x, x.shape)
+        st = self._out(status, x, (N,), np.int32)
         devs = (C.c_int * len(devices))(*[int(d) for d in devices])
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         _abi.check(self._lib.rkb_rollout_rk4_multi(self._h, len(devices), devs, N, p(x), p(u) if self.nu else None, dt, int(n_steps),

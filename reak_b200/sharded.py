@@ -59,10 +59,15 @@ class sharded_propagator(object):
         t = t.to(dtype)
         return t.to(self.comm_device) if self.comm_device is not None else t
 
-    def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None):
+    def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None, chunks=1, out=None, status=None):
         """Returns (x_out[n_total][nx], status[n_total]) gathered on every rank (torch tensors on the
         communication device).  `compute(x_block, u_block, dt, n_steps) -> (x_out, status)` defaults to
-        the wrapped propagator's GPU rollout."""
+        the wrapped propagator's GPU rollout.
+
+        chunks > 1 (and n_total divisible by world * chunks): the rank's block is integrated in `chunks` pieces and
+        the all-gather of piece c is issued asynchronously right behind its rollout, so that it travels while piece
+        c + 1 integrates — only the last piece's gather is exposed.  out / status: preallocated
+        result tensors on the communication device ([n_total][nx] float64, [n_total] int32)."""
         import torch
         compute = compute or self.prop.get_next_states
         if local_input:
@@ -73,9 +78,39 @@ class sharded_propagator(object):
             n_total = x.shape[0]
             lo, hi = shard_bounds(n_total, self.rank, self.world)
             xb, ub = x[lo:hi], (u[lo:hi] if u is not None else None)
+        if chunks > 1 and n_total > 0 and n_total % (self.world * chunks) == 0:
+            return self._get_next_states_chunked(xb, ub, dt, n_steps, n_total, compute, chunks, out, status)
         xo, st = compute(xb, ub, dt, n_steps)
         xo_t, st_t = self._to_comm(xo, torch.float64), self._to_comm(st, torch.int32)
-        return _all_gather_rows(xo_t, n_total, self.group), _all_gather_rows(st_t, n_total, self.group)
+        full, full_st = _all_gather_rows(xo_t, n_total, self.group), _all_gather_rows(st_t, n_total, self.group)
+        if out is not None:
+            out.copy_(full); full = out
+        if status is not None:
+            status.copy_(full_st); full_st = status
+        return full, full_st
+
+    def _get_next_states_chunked(self, xb, ub, dt, n_steps, n_total, compute, chunks, out, status):
+        import torch
+        dist = _dist()
+        n_loc = n_total // self.world
+        m = n_loc // chunks
+        assert xb.shape[0] == n_loc
+        full, st_loc, works = out, [], []
+        for c in range(chunks):
+            xo, st = compute(xb[c * m:(c + 1) * m], ub[c * m:(c + 1) * m] if ub is not None else None, dt, n_steps)
+            xo_t = self._to_comm(xo, torch.float64).contiguous()
+            st_loc.append(self._to_comm(st, torch.int32))
+            if full is None:
+                full = torch.empty((n_total,) + tuple(xo_t.shape[1:]), dtype=torch.float64, device=xo_t.device)
+            # rank r's piece c lands where the block partition puts it: rows r n_loc + c m ...
+            dst = [full[r * n_loc + c * m: r * n_loc + (c + 1) * m] for r in range(self.world)]
+            works.append(dist.all_gather(dst, xo_t, group=self.group, async_op=True))
+        st_t = torch.cat(st_loc, dim=0).contiguous()
+        full_st = status if status is not None else torch.empty((n_total,), dtype=torch.int32, device=st_t.device)
+        works.append(dist.all_gather_into_tensor(full_st, st_t, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        return full, full_st
 
     def rollout(self, x, u_seq, dt, steps_per_interval, scheme="rk4", compute=None):
         """kte_batch_propagator.rollout sharded by sample: returns (x_out[N][nx], x_traj[N][J][nx], status[N])

@@ -11,6 +11,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C++ drop-in checks inside oracle/_ref call into the product library through weak references: its
+    # symbols must be visible before libreak_ref.so is mapped (oracle/pyref.py: preload_product)
+    from oracle import pyref
+    pyref.preload_product()
 
 
 def rel_err(a, b):

@@ -187,6 +187,79 @@ def test_steer_batch(oracle_built):
     assert st.shape == (P, R) and not st.any()
 
 
+def test_steer_batch_diverged_rollouts_never_win():
+    """A rollout whose end state is NaN / inf has no distance to the goal: it must lose against any finite one, also
+    when it sits at index 0 (where a plain `<` comparison would keep it), and a pair whose rollouts all diverged
+    reports index 0 with an infinite cost."""
+    p = _make("crs6")
+    rng = np.random.default_rng(78)
+    P, R, K = 5, 300, 5          # R > 256: several rollouts per thread of the arg-min kernel
+    x0, _ = random_batch(p.compiled, P, seed=24)
+    goal, _ = random_batch(p.compiled, P, seed=25)
+    u = rng.uniform(-5, 5, (P, R, p.nu))
+    clean = p.steer_batch(x0, goal, u, 1e-3, K)
+    bad = u.copy()
+    bad[0, 0, :] = np.nan                      # pair 0: rollout 0 diverges
+    bad[1, int(clean[0][1]), 2] = np.inf       # pair 1: the former winner diverges
+    bad[2, :, 0] = np.nan                      # pair 2: every rollout diverges
+    bad[3, 0:256, 1] = np.nan                  # pair 3: the first rollout of every thread diverges
+    idx, bx, bc, st = p.steer_batch(x0, goal, bad, 1e-3, K, want_status=True)
+    from reak_b200 import _abi
+    assert st[0, 0] & _abi.STATUS_NONFINITE and st[2].all()
+    assert idx[0] != 0 and np.isfinite(bc[0]) and np.isfinite(bx[0]).all()
+    assert idx[1] != clean[0][1] and np.isfinite(bc[1]) and bc[1] >= clean[2][1]
+    assert idx[2] == 0 and np.isinf(bc[2])
+    assert idx[3] >= 256 and np.isfinite(bc[3])
+    assert idx[4] == clean[0][4] and bc[4] == clean[2][4]
+    if idx[0] == clean[0][0]:
+        assert bc[0] == clean[2][0]
+
+
+def test_steer_feedback_zero_intervals_writes_nothing_into_x_traj():
+    """max_intervals = 0 is allowed; x_traj is then a zero-length buffer and the library must not touch it
+    (plain C-ABI call with a canary right behind the pointer; host and device buffers)."""
+    import ctypes as C
+    import torch
+    from reak_b200 import _abi
+    p = _make("crs6")
+    lib = _abi.load_library()
+    N = 300
+    x0, goal, u_bias, gain, u_prev = _steer_case(p, N, seed=44)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for checked in (False, True):
+        canary = np.full(N * p.nx + 64, 1234.5)
+        out, nd, col = np.empty_like(x0), np.full(N, -1, dtype=np.int32), np.zeros(N, dtype=np.int32)
+        up = u_prev.copy()
+        o = _abi.rkb_steer_opts(1e-2, 1e-3, 0.25, 10, 0, 0, 0, None, None, None, None)
+        if checked:
+            from reak_b200 import kte_batch_propagator, proximity
+            system = presets.make("crs6")
+            robot, lab = presets.crs_proxy_models(system)
+            pp = kte_batch_propagator(system)
+            pair = proximity.proxy_query_pair_3D("robot-lab", robot, lab)
+            h = proximity.ProxyHandle(lib, pp._h, pair, pp.compiled.frames)
+            arr = (C.c_void_p * 1)(h._h)
+            rc = lib.rkb_steer_feedback_checked(pp._h, 0, N, vp(x0), vp(goal), vp(u_bias), vp(gain), vp(up), C.byref(o), arr, 1,
+                                                vp(out), vp(nd), vp(col), vp(canary), None, 0, None)
+        else:
+            rc = lib.rkb_steer_feedback(p._h, 0, N, vp(x0), vp(goal), vp(u_bias), vp(gain), vp(up), C.byref(o), vp(out), vp(nd),
+                                        vp(canary), None, 0, None)
+        assert rc == 0
+        assert np.all(canary == 1234.5), "x_traj was written with max_intervals == 0"
+        assert np.array_equal(out, x0) and not nd.any() and np.array_equal(up, u_prev)
+    # device buffers
+    t = lambda a: torch.from_numpy(a).cuda()
+    canary = torch.full((N * p.nx + 64,), 1234.5, dtype=torch.float64, device="cuda")
+    dx0, dg, db, dgn, dup = t(x0), t(goal), t(u_bias), t(gain), t(u_prev)
+    dout, dnd = torch.empty_like(dx0), torch.full((N,), -1, dtype=torch.int32, device="cuda")
+    o = _abi.rkb_steer_opts(1e-2, 1e-3, 0.25, 10, 0, 0, 0, None, None, None, None)
+    dp = lambda a: C.c_void_p(a.data_ptr())
+    rc = lib.rkb_steer_feedback(p._h, 0, N, dp(dx0), dp(dg), dp(db), dp(dgn), dp(dup), C.byref(o), dp(dout), dp(dnd), dp(canary), None,
+                                _abi.MEM_DEVICE, None)
+    torch.cuda.synchronize()
+    assert rc == 0 and bool((canary == 1234.5).all()) and torch.equal(dout, dx0) and not bool(dnd.any())
+
+
 def test_full_size_properties():
     """At BASELINE config 2's size (2^20 states) the oracle cannot follow; check size-independent
     properties instead: a strided sub-batch reproduces the big batch bit for bit, two half-length
@@ -602,6 +675,77 @@ def test_large_angles_and_fast_joints(name, oracle_built):
         # a state component of 1e8..1e12 carries an absolute rounding error of its own ulp: compare relative to its size
         err = float(np.max(np.abs(xo - xr) / np.maximum(1.0, np.abs(xr))))
         assert not st.any() and not sr.any() and err < tol, (name, label, err)
+
+
+# ---- torsion springs where the kernels differ from the reference by construction -----------------------------
+# The reference takes axis_angle(conj(Q1) Q2): angle 2 acos(w) with a dead zone |sin(q/2)| <= 1e-7, the axis flipped
+# for w < 0 (rotations_3D.hpp:1985-2010, torsion_spring.cpp:106-129).  The serial kernels use the wrapped joint
+# angle, the interpreter 2 atan2(|v|, |w|).  acos is ill-conditioned at w -> 1: the reference's OWN angle carries an
+# absolute error of about eps / |sin(q/2)| there (measured on the oracle: 8e-11 rad at q = 2e-7, 4e-11 at 1e-6),
+# which the kernels do not reproduce; the tolerance below allows exactly that, per spring, and is 1e-10 elsewhere.
+EDGE_ANGLES = [0.0, 1e-8, -1e-8, 2e-7 - 1e-12, -(2e-7 - 1e-12), 2e-7 + 1e-12, -(2e-7 + 1e-12), 1e-6, -1e-5,
+               np.pi - 1e-9, np.pi + 1e-9, -np.pi + 1e-9, -np.pi - 1e-9, 2 * np.pi + 1e-8, 2 * np.pi + 1e-6,
+               -2 * np.pi - 3e-7, 40.0, -40.0, 12 * np.pi, 12 * np.pi + 1e-8, 39.0 * np.pi - 1e-9]
+
+
+def _spring_tolerance(p, x):
+    """per sample: 1e-10 + sum over torsion_spring_3D of stiffness * 4.5e-16 / |sin(q/2)| outside the dead zone"""
+    from reak_b200 import _abi
+    d = p.compiled.desc
+    tol = np.full(x.shape[0], TOL_STEP)
+    joint_of_end = {}
+    for e in range(d.n_elements):
+        E = d.elements[e]
+        if E.kind in (_abi.REVOLUTE_3D,):
+            joint_of_end[E.frame_b] = E.coord
+    for e in range(d.n_elements):
+        E = d.elements[e]
+        if E.kind == _abi.TORSION_SPRING_3D and E.frame_b in joint_of_end:
+            s = np.abs(np.sin(0.5 * x[:, 2 * joint_of_end[E.frame_b]]))
+            tol += np.where(s > 1e-7, abs(E.p[0]) * 4.5e-16 / np.maximum(s, 1e-7), 0.0)
+    return tol
+
+
+@pytest.mark.parametrize("name", ["crs6_sd", "crs6_sd_sat", "crs7_phys_sd", "planar3_sd", "torsion1"])
+def test_torsion_spring_edges(name, oracle_built):
+    """Dead zone, its two edges, q = +-pi from both sides, whole turns plus a hair, |q| up to 40 rad, with and
+    without saturation, 3D and 2D springs — serial kernels and interpreter against the oracle (= the reference)."""
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        n = p.n
+        first = 1 if name.startswith("crs7") else 0  # crs7: coordinate 0 is the prismatic track
+        rng = np.random.default_rng(81)
+        rows = []
+        for a in EDGE_ANGLES:            # every revolute joint at the edge angle, velocities random
+            r = rng.uniform(-1.0, 1.0, 2 * n)
+            r[2 * first::2] = a
+            rows.append(r)
+        for a in EDGE_ANGLES:            # one joint at the edge, the others anywhere in +-40 rad
+            for k in range(first, n):
+                r = rng.uniform(-1.0, 1.0, 2 * n)
+                r[2 * first::2] = rng.uniform(-40.0, 40.0, n - first)
+                r[2 * k] = a
+                rows.append(r)
+        x = np.array(rows)
+        u = rng.uniform(-1.0, 1.0, (x.shape[0], p.nu))
+        tol = _spring_tolerance(p, x)
+        f, f_o = p.get_gen_forces(x, u), O.gen_forces(x, u)
+        err = np.max(np.abs(f - f_o) / np.maximum(1.0, np.abs(f_o)), axis=1)
+        assert np.all(err < tol), (name, label, "f", float(np.max(err / tol)), x[np.argmax(err / tol)])
+        xd, st = p.get_state_derivatives(x, u)
+        xd_o, st_o = O.eval(x, u)
+        err = np.max(np.abs(xd - xd_o) / np.maximum(1.0, np.abs(xd_o)), axis=1)
+        assert not st.any() and not st_o.any() and np.all(err < tol), (name, label, "xdot", float(np.max(err / tol)))
+        # rollouts that start far from the discontinuities: |q| up to 40 rad, saturation active where configured
+        xr = rng.uniform(-1.0, 1.0, (64, 2 * n))
+        xr[:, 2 * first::2] = rng.uniform(-40.0, 40.0, (64, n - first))
+        w = xr[:, 2 * first::2] - 2 * np.pi * np.rint(xr[:, 2 * first::2] / (2 * np.pi))
+        keep = np.all((np.abs(w) > 0.05) & (np.abs(np.abs(w) - np.pi) > 0.05), axis=1)
+        xr, ur = xr[keep], rng.uniform(-1.0, 1.0, (int(keep.sum()), p.nu))
+        assert xr.shape[0] >= 16
+        xo, st = p.get_next_states(xr, ur, 1e-3, 20)
+        xo_o, st_o, _ = O.rk4(xr, ur, 1e-3, 20)
+        assert not st.any() and not st_o.any() and rel_err(xo, xo_o) < TOL_LONG, (name, label, "rk4")
 
 
 def test_non_finite_states_raise_the_status_bit():

@@ -69,3 +69,40 @@ def test_propagator_argument_checks():
         p.get_next_states(np.zeros((3, 12)), np.zeros((3, 6)), 0.0, 1)
     with pytest.raises(IndexError):
         p.steer_batch(np.zeros((2, 12)), np.zeros((2, 12)), np.zeros((2, 5, 4)))
+
+
+def test_caller_supplied_result_buffers_are_validated():
+    """out= / status= go to the C-ABI by raw pointer: a wrong dtype, shape or layout must be refused on the host
+    (the checks run before the library is called, so no device is needed)."""
+    from reak_b200 import kte_batch_propagator
+    p = kte_batch_propagator(presets.make("crs6"))
+    x, u = np.zeros((8, 12)), np.zeros((8, 6))
+    for call in (lambda **k: p.get_state_derivatives(x, u, **k), lambda **k: p.get_next_states(x, u, 1e-3, 1, **k),
+                 lambda **k: p.get_next_states_multi(x, u, 1e-3, 1, **k),
+                 lambda **k: p.rollout(x, np.zeros((8, 2, 6)), 1e-3, 1, **k)):
+        with pytest.raises(TypeError):
+            call(out=np.zeros((8, 12), dtype=np.float32))
+        with pytest.raises(IndexError):
+            call(out=np.zeros((7, 12)))
+        with pytest.raises(IndexError):
+            call(out=np.zeros((8, 13)))
+        with pytest.raises(TypeError):
+            call(out=np.zeros((12, 8)).T)                      # right shape, not C-contiguous
+        with pytest.raises(TypeError):
+            call(out=np.zeros((8, 24))[:, ::2])                # strided view
+        with pytest.raises(TypeError):
+            call(status=np.zeros(8, dtype=np.int64))
+        with pytest.raises(IndexError):
+            call(status=np.zeros(9, dtype=np.int32))
+        with pytest.raises(TypeError):
+            call(out=[[0.0] * 12] * 8)                         # not an array at all
+
+
+def test_inertia_registered_with_mass_calc_but_missing_from_the_chain_is_refused():
+    """M comes from mass_calc (kte_nl_system.hpp:271), the forces from the chain: an inertia only mass_calc knows
+    would change the reference's M and silently vanish here."""
+    s = presets.make("crs3")
+    ghost_frame = kte.joint_dependent_frame_3D(kte.frame_3D())
+    s.mass_calc << kte.inertia_3D("ghost", ghost_frame, 2.0, (0.1, 0.0, 0.0, 0.1, 0.0, 0.1))
+    with pytest.raises(kte.UnsupportedChain, match="not in the chain"):
+        kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)

@@ -53,6 +53,13 @@ def _worker(rank, world, port, n_total, out_dir):
     lo, hi = shard_bounds(n_total, rank, world)
     loc, st2 = sp.get_next_states(x[lo:hi], u[lo:hi], 1e-3, 5, local_input=True, n_total=n_total, compute=compute)
     assert np.array_equal(full.numpy(), loc.numpy()) and np.array_equal(st.numpy(), st2.numpy())
+    # the pipelined variant (piece c is gathered while piece c + 1 integrates) lands every piece in block-partition order;
+    # with a size that does not divide it falls back to the single gather
+    import torch
+    pre, pre_st = torch.full((n_total, x.shape[1]), np.nan, dtype=torch.float64), torch.full((n_total,), -1, dtype=torch.int32)
+    ch, st3 = sp.get_next_states(x, u, 1e-3, 5, compute=compute, chunks=4, out=pre, status=pre_st)
+    assert ch is pre and st3 is pre_st
+    assert np.array_equal(full.numpy(), ch.numpy()) and np.array_equal(st.numpy(), st3.numpy())
 
     # steer: pairs are sharded, rollouts of a pair stay together
     P, R = 5, 7

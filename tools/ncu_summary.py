@@ -27,6 +27,17 @@ KEYS = [
 STALLS = "smsp__average_warps_issue_stalled_"
 
 
+def build_id():
+    """rkb_build_id() of the library in the tree: the capture is only meaningful for the build it was taken from"""
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    try:
+        from reak_b200 import _abi
+        return _abi.load_library().rkb_build_id().decode()
+    except Exception as e:
+        return "unknown (%s)" % e
+
+
 def main():
     rep = sys.argv[1]
     units = float(sys.argv[2]) if len(sys.argv) > 2 else None
@@ -65,7 +76,7 @@ def main():
             print("derived: DRAM traffic %.1f MB per launch" % (traffic / 1e6))
             if json_out and units:
                 with open(json_out, "w") as f:
-                    json.dump({"kernel": d.get("Kernel Name", "?"), "source": rep, "units_per_launch": units,
+                    json.dump({"kernel": d.get("Kernel Name", "?"), "source": rep, "units_per_launch": units, "build_id": build_id(),
                                "fp64_instr_per_state_step": (fma + mul + add) * cyc / units,
                                "flop_per_state_step": (2 * fma + mul + add) * cyc / units,
                                "dram_traffic_bytes_per_launch": traffic,
