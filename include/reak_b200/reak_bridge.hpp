@@ -48,6 +48,11 @@
 #include <ReaK/geometry/shapes/cylinder.hpp>
 #include <ReaK/geometry/shapes/box.hpp>
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
+#include <ReaK/ctrl/topologies/metric_space_concept.hpp>
+#include <ReaK/ctrl/topologies/subspace_concept.hpp>
+#include <ReaK/ctrl/topologies/random_sampler_concept.hpp>
+#include <ReaK/ctrl/topologies/default_random_sampler.hpp>
+#include <ReaK/ctrl/topologies/steerable_space_concept.hpp>
 
 #include "kte_batch_propagator.hpp"
 
@@ -375,6 +380,12 @@ class kte_steer_space {
   typedef vect_n<double> point_type;
   typedef vect_n<double> point_difference_type;
   typedef std::vector<point_type> steer_record_type;
+  // what the planners' traits read: metric_space_traits (metric_space_concept.hpp:188-191), point_distribution_traits
+  // (random_sampler_concept.hpp:75-78), subspace_traits (subspace_concept.hpp:50-54).  The space is its own super-space:
+  // planning_visitor measures edges with get(distance_metric, space.get_super_space()) (planning_visitors.hpp:259).
+  typedef default_distance_metric distance_metric_type;
+  typedef default_random_sampler random_sampler_type;
+  typedef kte_steer_space super_space_type;
   BOOST_STATIC_CONSTANT(std::size_t, dimensions = 0);
 
   kte_steer_space(const ctrl::kte_nl_system& sys, const vect_n<double>& u_lower, const vect_n<double>& u_upper,
@@ -393,6 +404,52 @@ class kte_steer_space {
   point_type adjust(const point_type& a, const point_difference_type& d) const { return a + d; }
   point_type origin() const { return point_type(mSys.get_state_dimensions(), 0.0); }
   point_type move_position_toward(const point_type& a, double fraction, const point_type& b) const { return a + fraction * (b - a); }
+
+  // ---- what planning_visitor asks of its space besides steering ----------------------------------------
+  const super_space_type& get_super_space() const { return *this; }  // SubSpaceConcept (subspace_concept.hpp:63-73)
+  /// The box random_point() samples (and nothing else: steering may leave it, like the reference's dynamic spaces).
+  void set_state_bounds(const point_type& lower, const point_type& upper) {
+    if (lower.size() != mSys.get_state_dimensions() || upper.size() != lower.size()) throw std::range_error("State vector dimension mismatch!");
+    mXLo = lower; mXHi = upper;
+  }
+  /// default_random_sampler (default_random_sampler.hpp:63-66) calls this: uniform in the state box.
+  point_type random_point() const {
+    const std::size_t nx = mSys.get_state_dimensions();
+    if (mXLo.size() != nx) throw std::logic_error("kte_steer_space::random_point needs set_state_bounds first");
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    point_type p(nx);
+    for (std::size_t k = 0; k < nx; ++k) p[k] = mXLo[k] + (mXHi[k] - mXLo[k]) * uni(mRng);
+    return p;
+  }
+  /// Collision environment: the proxy pairs manip_dk_proxy_env_impl keeps (manip_free_workspace.hpp:60-99), lowered once.
+  void add_proxy_pair(const geom::proxy_query_model_3D& aModel1, const geom::proxy_query_model_3D& aModel2) {
+    mPairs.push_back(mSys.make_proxy_pair(aModel1, aModel2));
+  }
+  /// is_free of the planners (planning_visitors.hpp:242; manip_free_workspace.hpp:77-99): no proxy pair reports a
+  /// negative minimum distance at p (always free without pairs).  Served by rkb_is_free.
+  bool is_free(const point_type& p) const {
+    if (mPairs.empty()) return true;
+    std::vector<point_type> one(1, p);
+    std::vector<char> out;
+    are_free(one, out);
+    return out[0] != 0;
+  }
+  /// ... for all candidate points of a planner iteration in one launch
+  void are_free(const std::vector<point_type>& pts, std::vector<char>& out) const {
+    const std::size_t n = pts.size(), nx = mSys.get_state_dimensions();
+    out.assign(n, 1);
+    if (mPairs.empty() || n == 0) return;
+    std::vector<double> x(n * nx);
+    for (std::size_t i = 0; i < n; ++i) {
+      if (pts[i].size() != nx) throw std::range_error("State vector dimension mismatch!");
+      for (std::size_t k = 0; k < nx; ++k) x[i * nx + k] = pts[i][k];
+    }
+    std::vector<int32_t> fr(n);
+    std::vector<const rkb_proxy*> pairs(mPairs.begin(), mPairs.end());
+    mSys.batch().get_is_free(pairs, n, &x[0], &fr[0]);
+    for (std::size_t i = 0; i < n; ++i) out[i] = fr[i] ? 1 : 0;
+  }
+  ~kte_steer_space() { for (std::size_t i = 0; i < mPairs.size(); ++i) rkb_proxy_destroy(mPairs[i]); }
 
   void reseed(unsigned long long seed) { mRng.seed(seed); }
   /// The inputs tried by the last steering call, [pairs][n_controls][n_inputs], and the winners' indices.
@@ -457,6 +514,80 @@ class kte_steer_space {
   mutable std::mt19937_64 mRng;
   mutable std::vector<double> mU;
   mutable std::vector<int32_t> mBest;
+  vect_n<double> mXLo, mXHi;
+  std::vector<rkb_proxy*> mPairs;
+  kte_steer_space(const kte_steer_space&);             // owns device handles: not copyable (planners hold spaces by shared_ptr)
+  kte_steer_space& operator=(const kte_steer_space&);
+};
+
+// The planners dispatch on these traits: planning_visitor::dispatched_steer_towards_position takes its
+// `space.steer_position_toward` branch only for is_steerable_space (planning_visitors.hpp:251-296; the primary
+// template is false_, steerable_space_concept.hpp:95), and get(distance_metric, space) / get(random_sampler, space)
+// exist only for is_metric_space / is_point_distribution (metric_space_concept.hpp:288-293,
+// default_random_sampler.hpp:82-88).
+template <> struct is_steerable_space<kte_steer_space> : boost::mpl::true_ {};
+template <> struct is_metric_space<kte_steer_space> : boost::mpl::true_ {};
+template <> struct is_point_distribution<kte_steer_space> : boost::mpl::true_ {};
+
+/// One planner iteration's steering, batched.  A sampling planner pulls a new node by steering from each of the
+/// nearest neighbours `Nc` of the sample towards it, one at a time, until one succeeds
+/// (rrg_node_puller::expand_to_nearest, ctrl/graph_alg/node_generators.hpp:59-75, calling
+/// planning_visitor::steer_towards_position, planning_visitors.hpp:349-360).  This visitor answers the same
+/// `steer_towards_position(p, u, g)` question, but from a table filled by ONE batched steering call over all the
+/// candidates (prepare), so the reference's own expand_to_nearest can run on top of it unchanged.  The answers are
+/// those of the one-at-a-time visitor (steer_towards_position of a fresh visitor with the same seed) as long as
+/// the candidates are asked in the order they were prepared — which is what expand_to_nearest does.
+///   Graph: g[u].position is the vertex' point; Graph::edge_bundled has `steer_record` (mg_edge_data,
+///   any_motion_graphs.hpp) and, for the optimal motion graphs, `weight`.
+template <typename Graph>
+class batched_steer_visitor {
+ public:
+  typedef kte_steer_space::point_type point_type;
+  typedef typename Graph::vertex_descriptor Vertex;
+  typedef typename Graph::edge_bundled EdgeProp;
+  typedef boost::tuple<point_type, bool, EdgeProp> ResultType;
+
+  batched_steer_visitor(const kte_steer_space& aSpace, double aProgressTolerance) : mSpace(&aSpace), mTol(aProgressTolerance) {}
+
+  /// Steer from every vertex of Nc towards p in one call (fraction 1, like steer_towards_position) and, when the
+  /// space has a collision environment, test all the end points in one more.
+  void prepare(const point_type& p, const std::vector<Vertex>& Nc, const Graph& g) {
+    std::vector<point_type> a, b(Nc.size(), p), res;
+    for (std::size_t i = 0; i < Nc.size(); ++i) a.push_back(g[Nc[i]].position);
+    std::vector<kte_steer_space::steer_record_type> rec;
+    mSpace->steer_positions_toward(a, 1.0, b, res, &rec);
+    std::vector<char> fr;
+    mSpace->are_free(res, fr);
+    mTable.clear();
+    const kte_steer_space& super = mSpace->get_super_space();
+    for (std::size_t i = 0; i < Nc.size(); ++i) {
+      ResultType r;
+      boost::get<0>(r) = res[i];
+      boost::get<2>(r).steer_record = rec[i];
+      // planning_visitors.hpp:353-357
+      const double traveled = get(distance_metric, super)(a[i], res[i], super);
+      const double best_case = get(distance_metric, super)(a[i], p, super);
+      set_weight(boost::get<2>(r), traveled, 0);
+      boost::get<1>(r) = (!std::isinf(traveled)) && (traveled < 2.0 * best_case) && (traveled > mTol * best_case) && fr[i] != 0;
+      mTable.push_back(std::make_pair(Nc[i], r));
+    }
+    mTarget = p;
+  }
+  /// NodePullingVisitorConcept: the prepared answer for vertex u.
+  ResultType steer_towards_position(const point_type& p, Vertex u, Graph&) const {
+    for (std::size_t i = 0; i < mTable.size(); ++i)
+      if (mTable[i].first == u) return mTable[i].second;
+    throw std::logic_error("batched_steer_visitor: vertex was not prepared");
+  }
+  std::size_t prepared() const { return mTable.size(); }
+
+ private:
+  template <typename E> static auto set_weight(E& e, double w, int) -> decltype(e.weight = w, void()) { e.weight = w; }
+  template <typename E> static void set_weight(E&, double, long) {}
+  const kte_steer_space* mSpace;
+  double mTol;
+  point_type mTarget;
+  std::vector<std::pair<Vertex, ResultType> > mTable;
 };
 
 }  // namespace pp

@@ -36,6 +36,7 @@
 #include <ReaK/geometry/shapes/cylinder.hpp>
 #include <ReaK/geometry/shapes/box.hpp>
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
+#include <ReaK/ctrl/graph_alg/node_generators.hpp>
 
 #include "../include/reak_b200.h"
 // libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
@@ -63,6 +64,7 @@
 #pragma weak rkb_proxy_create
 #pragma weak rkb_proxy_destroy
 #pragma weak rkb_min_distance
+#pragma weak rkb_is_free
 #include "../include/reak_b200/reak_bridge.hpp"
 #include "steer_law.h"
 
@@ -661,6 +663,188 @@ int rkref_steer_space_check(void* hv, std::size_t P, const double* a, const doub
     for (int k = 0; k < nx; ++k) err[2] = std::max(err[2], std::fabs(one.first[k] - res[0][k]));
     if (one.second.size() != rec[0].size()) throw std::runtime_error("single and batched steer records differ in length");
     if (std::fabs(space.distance(A[0], B[0]) - norm_2(A[0] - B[0])) > 0.0) throw std::runtime_error("distance is not the Euclidean one");
+    return 0;
+  } catch (std::exception& e) {
+    if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
+    return -1;
+  }
+}
+
+}  // extern "C" (reopened below)
+
+namespace {
+
+// The smallest graph the reference's node generators can walk: vertices carry `position`, edges what
+// mg_edge_data / optimal_mg_edge carry (ctrl/path_planning/any_motion_graphs.hpp): a steer record and a weight.
+struct tiny_graph {
+  typedef std::size_t vertex_descriptor;
+  typedef std::pair<std::size_t, std::size_t> edge_descriptor;
+  static const bool is_directed = false;
+  static vertex_descriptor null_vertex() { return std::size_t(-1); }
+  struct vertex_bundled { vect_n<double> position; };
+  struct edge_bundled { std::vector<vect_n<double> > steer_record; double weight; edge_bundled() : weight(0.0) {} };
+  std::vector<vertex_bundled> v;
+  vertex_bundled& operator[](vertex_descriptor u) { return v[u]; }
+  const vertex_bundled& operator[](vertex_descriptor u) const { return v[u]; }
+};
+
+// planning_visitor's steering, one candidate at a time, written with the reference's own pieces: the
+// is_steerable_space dispatch of planning_visitors.hpp:251-296 (both overloads, so that the trait decides), the
+// boost::tie / get(distance_metric, space.get_super_space()) expressions of :258-260 and the acceptance test of
+// :349-360 plus is_position_free (:242).  (planning_visitors.hpp itself needs Boost.Graph, Boost.Any, Boost.Range
+// and Boost.Random through motion_planner_base.hpp / any_motion_graphs.hpp and cannot be compiled here.)
+template <typename Space>
+struct one_at_a_time_visitor {
+  typedef typename pp::topology_traits<Space>::point_type point_type;
+  const Space* space;
+  double tol;
+  mutable int steer_branch, move_branch;
+  one_at_a_time_visitor(const Space& s, double t) : space(&s), tol(t), steer_branch(0), move_branch(0) {}
+
+  template <typename SwitchFreeSpace>
+  typename boost::enable_if<pp::is_steerable_space<SwitchFreeSpace>, double>::type dispatched_steer_towards_position(
+      const SwitchFreeSpace& sp, const point_type& p_src, const point_type& p_dest, point_type& p_result, double fraction,
+      tiny_graph::edge_bundled& ep_result) const {
+    ++steer_branch;
+    boost::tie(p_result, ep_result.steer_record) = sp.steer_position_toward(p_src, fraction, p_dest);
+    ep_result.weight = get(pp::distance_metric, sp.get_super_space())(p_src, p_result, sp.get_super_space());
+    return ep_result.weight;
+  }
+  template <typename SwitchFreeSpace>
+  typename boost::disable_if<pp::is_steerable_space<SwitchFreeSpace>, double>::type dispatched_steer_towards_position(
+      const SwitchFreeSpace& sp, const point_type& p_src, const point_type& p_dest, point_type& p_result, double fraction,
+      tiny_graph::edge_bundled& ep_result) const {
+    ++move_branch;
+    p_result = sp.move_position_toward(p_src, fraction, p_dest);
+    ep_result.weight = get(pp::distance_metric, sp.get_super_space())(p_src, p_result, sp.get_super_space());
+    return ep_result.weight;
+  }
+  boost::tuple<point_type, bool, tiny_graph::edge_bundled> steer_towards_position(const point_type& p, std::size_t u, tiny_graph& g) const {
+    boost::tuple<point_type, bool, tiny_graph::edge_bundled> result;
+    const double traveled = dispatched_steer_towards_position(*space, g[u].position, p, boost::get<0>(result), 1.0, boost::get<2>(result));
+    const double best_case = get(pp::distance_metric, space->get_super_space())(g[u].position, p, space->get_super_space());
+    boost::get<1>(result) = (!std::isinf(traveled)) && (traveled < 2.0 * best_case) && (traveled > tol * best_case) &&
+                            space->is_free(boost::get<0>(result));
+    return result;
+  }
+};
+
+shared_ptr<geom::proxy_query_model_3D> shapes_to_model(ref_model* m, const rkb_shape* in, int n, const char* name) {
+  shared_ptr<geom::proxy_query_model_3D> mdl(new geom::proxy_query_model_3D(name));
+  for (int k = 0; k < n; ++k) {
+    const rkb_shape& s = in[k];
+    shared_ptr<pose_3D<double> > anchor;
+    if (s.anchor >= 0) anchor = m->f3[s.anchor];
+    const pose_3D<double> pose(weak_ptr<pose_3D<double> >(), vect<double,3>(s.position[0], s.position[1], s.position[2]),
+                               quaternion<double>(vect<double,4>(s.quat[0], s.quat[1], s.quat[2], s.quat[3])));
+    shared_ptr<geom::shape_3D> sh;
+    switch (s.kind) {
+      case RKB_SHAPE_PLANE: sh = shared_ptr<geom::shape_3D>(new geom::plane("p", anchor, pose, vect<double,2>(s.dims[0], s.dims[1]))); break;
+      case RKB_SHAPE_SPHERE: sh = shared_ptr<geom::shape_3D>(new geom::sphere("s", anchor, pose, s.dims[0])); break;
+      case RKB_SHAPE_CCYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::capped_cylinder("cc", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_CYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::cylinder("cy", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_BOX: sh = shared_ptr<geom::shape_3D>(new geom::box("b", anchor, pose, vect<double,3>(s.dims[0], s.dims[1], s.dims[2]))); break;
+      default: throw std::runtime_error("unknown shape kind");
+    }
+    mdl->addShape(sh);
+  }
+  return mdl;
+}
+
+}  // namespace
+
+extern "C" {
+
+// SURVEY 8(f) rank 1, planner side.  ReaK::pp::kte_steer_space (reak_bridge.hpp) under the reference's own planner
+// plumbing, as far as it compiles without Boost.Graph:
+//   * the traits the planners dispatch on (is_steerable_space / is_metric_space / is_point_distribution) and the
+//     tagged get() overloads they enable (metric_space_concept.hpp:288-293, default_random_sampler.hpp:82-88);
+//   * the valid expression of SteerableSpaceConcept (steerable_space_concept.hpp:60-85);
+//   * ReaK::graph::detail::rrg_node_puller<Graph>::expand_to_nearest — the REAL one, ctrl/graph_alg/node_generators.hpp:59-75 —
+//     run twice over the same K candidate vertices: with a visitor that steers one candidate at a time (the
+//     reference's way) and with batched_steer_visitor, which steered all K in one GPU call beforehand.  Same seed,
+//     so both must pull the same vertex, the same point, the same steer record and the same edge weight.
+// x_nodes: K vertex positions, target: the sample, shapes (n1 + n2 > 0): a collision environment for is_free.
+// out: [0] vertex pulled one-at-a-time, [1] vertex pulled batched, [2] steer-branch count, [3] move-branch count,
+//      [4] candidates the batched visitor prepared;  free_flags: is_free of the K nodes (space.is_free, one by one)
+//      and of the same K nodes through are_free (K more);  p_new: the pulled point (batched run);  sample: one random_point().
+int rkref_planner_dispatch_check(void* hv, int K, const double* x_nodes, const double* target, const double* u_lo, const double* u_hi,
+                                 const double* x_lo, const double* x_hi, int n_controls, int n_intervals, int steps, double dt,
+                                 double tol, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2,
+                                 int* out, int* free_flags, double* p_new, double* sample, double* err, char* msg, int msg_len) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  try {
+    if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
+    typedef pp::kte_steer_space space_t;
+    static_assert(pp::is_steerable_space<space_t>::value, "kte_steer_space must be steerable for the planners");
+    static_assert(pp::is_metric_space<space_t>::value && pp::is_point_distribution<space_t>::value, "metric / sampling traits");
+    static_assert(!pp::is_steerable_space<tiny_graph>::value, "the primary template stays false");
+    vect_n<double> lo(nu), hi(nu), xl(nx), xh(nx), tgt(nx);
+    for (int k = 0; k < nu; ++k) { lo[k] = u_lo[k]; hi[k] = u_hi[k]; }
+    for (int k = 0; k < nx; ++k) { xl[k] = x_lo[k]; xh[k] = x_hi[k]; tgt[k] = target[k]; }
+    tiny_graph g;
+    g.v.resize(K);
+    std::vector<std::size_t> Nc;
+    for (int i = 0; i < K; ++i) {
+      g.v[i].position = vect_n<double>(nx);
+      for (int k = 0; k < nx; ++k) g.v[i].position[k] = x_nodes[i * nx + k];
+      Nc.push_back(i);
+    }
+    shared_ptr<geom::proxy_query_model_3D> mdl1, mdl2;
+    if (n1 + n2 > 0) { mdl1 = shapes_to_model(m, m1, n1, "model1"); mdl2 = shapes_to_model(m, m2, n2, "model2"); }
+    // ---- run 1: one candidate at a time -----------------------------------------------------------------
+    space_t sp1(m->sys, lo, hi, n_controls, n_intervals, steps, dt, 4321ull);
+    sp1.set_state_bounds(xl, xh);
+    if (mdl1) sp1.add_proxy_pair(*mdl1, *mdl2);
+    {  // SteerableSpaceConcept's valid expression, verbatim
+      vect_n<double> p1 = g.v[0].position, p2 = tgt;
+      pp::steerable_space_traits<space_t>::steer_record_type st_rec;
+      double d = 0.5;
+      boost::tie(p1, st_rec) = sp1.steer_position_toward(p1, d, p2);
+      if ((int)st_rec.size() != n_intervals + 1) throw std::runtime_error("steer record has the wrong length");
+      sp1.reseed(4321ull);
+    }
+    one_at_a_time_visitor<space_t> vis1(sp1, tol);
+    vect_n<double> p_a = tgt;
+    boost::tuple<std::size_t, bool, tiny_graph::edge_bundled> r1 =
+        graph::detail::rrg_node_puller<tiny_graph>::expand_to_nearest(p_a, Nc, g, vis1);
+    // ---- run 2: all candidates in one batched call, then the same node puller -----------------------------
+    space_t sp2(m->sys, lo, hi, n_controls, n_intervals, steps, dt, 4321ull);
+    sp2.set_state_bounds(xl, xh);
+    if (mdl1) sp2.add_proxy_pair(*mdl1, *mdl2);
+    pp::batched_steer_visitor<tiny_graph> vis2(sp2, tol);
+    vis2.prepare(tgt, Nc, g);
+    vect_n<double> p_b = tgt;
+    boost::tuple<std::size_t, bool, tiny_graph::edge_bundled> r2 =
+        graph::detail::rrg_node_puller<tiny_graph>::expand_to_nearest(p_b, Nc, g, vis2);
+    out[0] = boost::get<1>(r1) ? (int)boost::get<0>(r1) : -1;
+    out[1] = boost::get<1>(r2) ? (int)boost::get<0>(r2) : -1;
+    out[2] = vis1.steer_branch; out[3] = vis1.move_branch; out[4] = (int)vis2.prepared();
+    err[0] = err[1] = err[2] = 0.0;
+    if (out[0] != out[1]) throw std::runtime_error("batched and one-at-a-time node pulling chose different vertices");
+    for (int k = 0; k < nx; ++k) { err[0] = std::max(err[0], std::fabs(p_a[k] - p_b[k])); p_new[k] = p_b[k]; }
+    if (boost::get<1>(r1)) {
+      const tiny_graph::edge_bundled &e1 = boost::get<2>(r1), &e2 = boost::get<2>(r2);
+      if (e1.steer_record.size() != e2.steer_record.size()) throw std::runtime_error("steer records differ in length");
+      for (std::size_t j = 0; j < e1.steer_record.size(); ++j)
+        for (int k = 0; k < nx; ++k) err[1] = std::max(err[1], std::fabs(e1.steer_record[j][k] - e2.steer_record[j][k]));
+      err[2] = std::fabs(e1.weight - e2.weight);
+      // the weight is the reference's default_distance_metric on the super-space, i.e. space.distance
+      if (std::fabs(e2.weight - sp2.distance(g.v[out[1]].position, p_b)) > 0.0) throw std::runtime_error("edge weight is not the metric's distance");
+    }
+    // ---- is_free, one by one and batched; random_point through the reference's default_random_sampler --------
+    std::vector<vect_n<double> > pts;
+    for (int i = 0; i < K; ++i) { pts.push_back(g.v[i].position); free_flags[i] = sp2.is_free(g.v[i].position) ? 1 : 0; }
+    std::vector<char> fr;
+    sp2.are_free(pts, fr);
+    for (int i = 0; i < K; ++i) free_flags[K + i] = fr[i];
+    vect_n<double> rp = get(pp::random_sampler, sp2)(sp2);
+    for (int k = 0; k < nx; ++k) {
+      sample[k] = rp[k];
+      if (!(rp[k] >= xl[k] && rp[k] <= xh[k])) throw std::runtime_error("random_point left the state box");
+    }
     return 0;
   } catch (std::exception& e) {
     if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }

@@ -642,6 +642,60 @@ def test_reak_steer_space_cpp(oracle_built):
         assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] == 0.0, (name, err)
 
 
+def test_planner_dispatch_cpp(oracle_built):
+    """SURVEY 8(f) rank 1, planner side (oracle/ref_lib.cpp: rkref_planner_dispatch_check): kte_steer_space carries
+    the traits ReaK's planners dispatch on, models SteerableSpaceConcept, and the reference's own
+    rrg_node_puller::expand_to_nearest (ctrl/graph_alg/node_generators.hpp:59-75) pulls the same vertex, point,
+    steer record and edge weight whether the candidates are steered one at a time or all at once by
+    batched_steer_visitor; is_free of the space agrees with the reference's findMinimumDistance."""
+    import ctypes as C
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built")
+    from reak_b200 import proximity as px
+    for name, with_env, tol in (("crs6", True, 0.01), ("crs6", False, 0.01), ("crs7", False, 0.01), ("crs6", True, 1e9)):
+        s = presets.make(name)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        R = oracle_built.Reference(c)
+        fn = R.lib.rkref_planner_dispatch_check
+        fn.restype = C.c_int
+        fn.argtypes = ([C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                       C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_char_p, C.c_int])
+        K, nx, nu = 7, 2 * c.n_coords, c.n_inputs
+        nodes, _ = random_batch(c, K, seed=65, q_range=2.5)
+        rng = np.random.default_rng(66)
+        target = nodes[3] + rng.uniform(-0.05, 0.05, nx)          # a sample the tree can actually get closer to
+        lo, hi = -3.0 * np.ones(nu), 3.0 * np.ones(nu)
+        xl, xh = -2.0 * np.ones(nx), 2.0 * np.ones(nx)
+        if with_env:
+            robot, lab = presets.crs_proxy_models(s)
+            pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+            (m1, n1), (m2, n2) = robot.to_c(c.frames), lab.to_c(c.frames)
+            a1, a2 = C.cast(m1, C.c_void_p), C.cast(m2, C.c_void_p)
+        else:
+            a1 = a2 = None
+            n1 = n2 = 0
+        out, flags = np.zeros(5, dtype=np.int32), np.zeros(2 * K, dtype=np.int32)
+        p_new, sample, err = np.zeros(nx), np.zeros(nx), np.zeros(3)
+        msg = C.create_string_buffer(512)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = fn(R.h, K, vp(nodes), vp(target), vp(lo), vp(hi), vp(xl), vp(xh), 32, 2, 5, 1e-3, tol, a1, n1, a2, n2,
+                vp(out), vp(flags), vp(p_new), vp(sample), vp(err), msg, 512)
+        assert rc == 0, (name, msg.value)
+        assert out[0] == out[1] and out[3] == 0 and out[4] == K, (name, out)   # same vertex; never the move_position_toward branch
+        assert out[2] >= 1 and (out[2] == K if out[0] < 0 else out[2] == out[0] + 1), (name, out)  # stops at the first success
+        assert np.all(err == 0.0), (name, err)                                  # bit-identical point, record, weight
+        if tol > 1.0:
+            assert out[0] == -1                                                 # nothing progresses 1e9 x the distance
+        assert np.all((sample >= xl) & (sample <= xh))
+        assert np.array_equal(flags[:K], flags[K:])
+        if with_env:
+            d, _, _ = R.min_distance(pair, nodes)
+            assert np.array_equal(flags[:K] != 0, d >= 0.0), (name, flags, d)
+            assert (d < 0).any() and (d >= 0).any()
+        else:
+            assert flags.all()
+
+
 # ---- the trigonometric paths of the serial kernels -------------------------------------------------------
 @pytest.mark.parametrize("name", ["crs6", "crs7"])
 def test_large_angles_and_fast_joints(name, oracle_built):

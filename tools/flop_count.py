@@ -74,6 +74,48 @@ class Counter(object):
                 r[i] += e[i]
         return {ph: {"mul": m, "add": a, "fused": f, "flops": m + a, "instr": m + a - f} for ph, (m, a, f) in res.items()}
 
+    def depth(self, outputs):
+        """length of the longest chain of dependent FP64 instructions behind `outputs` (a product formed only for one
+        addition rides in that addition's fused multiply-add): the floor one sample's evaluation cannot go below,
+        whatever the number of lanes or warps that share it, times the ~8-cycle DFMA latency"""
+        uses, stack, seen = {}, [o for o in outputs if isinstance(o, V)], set()
+        while stack:
+            v = stack.pop()
+            if id(v) in seen:
+                continue
+            seen.add(id(v))
+            for a in v.args:
+                uses[id(a)] = uses.get(id(a), 0) + 1
+                stack.append(a)
+        memo = {}
+
+        def d(v):
+            # iterative post-order (the chains are thousands of nodes long)
+            st = [v]
+            while st:
+                n = st[-1]
+                if id(n) in memo:
+                    st.pop(); continue
+                pend = [a for a in n.args if id(a) not in memo]
+                if pend:
+                    st.extend(pend); continue
+                if n.op is None:
+                    memo[id(n)] = 0
+                elif n.op == "mul":
+                    memo[id(n)] = 1 + max(memo[id(a)] for a in n.args)
+                else:
+                    best = 0
+                    for a in n.args:
+                        if a.op == "mul" and uses.get(id(a), 0) == 1:
+                            best = max(best, max(memo[id(b)] for b in a.args))  # fused: the product costs no extra level
+                        else:
+                            best = max(best, memo[id(a)])
+                    memo[id(n)] = 1 + best
+                st.pop()
+            return memo[id(v)]
+
+        return max([d(o) for o in outputs if isinstance(o, V)] or [0])
+
 
 class V(object):
     """kind: 'z' structural zero, 'p' literal +1, 'm' literal -1, 'v' any other value; op / args: how it was formed"""
@@ -531,10 +573,14 @@ def count_chain(stages):
     c.phase = "sincos_shift"; [trig_shift(c) for _ in range(n_rev)]
     c.phase = "rk4_combine_per_step"; rk4_combine(c, 2 * N)
     out = c.count(qdd)
+    # dependent-instruction depth of one evaluation: sine / cosine first (full: 13 levels, shift: 8), then the sweeps and the solve
+    depth_f, depth_m, depth_all = c.depth(f), c.depth(list(M.values())), c.depth(qdd)
     ev = {k: sum(out[p][k] for p in ("forces_sweeps_1_2", "mass_sweep_3", "ldl_solve")) for k in ("flops", "instr")}
     step = {k: 4 * ev[k] + out["sincos_full"][k] + 3 * out["sincos_shift"][k] + out["rk4_combine_per_step"][k] for k in ("flops", "instr")}
     return {"n": N, "flop_per_evaluation": ev["flops"] + out["sincos_full"]["flops"], "instr_per_evaluation": ev["instr"] + out["sincos_full"]["instr"],
-            "flop_per_state_step": step["flops"], "instr_per_state_step": step["instr"], "breakdown": out}
+            "flop_per_state_step": step["flops"], "instr_per_state_step": step["instr"], "breakdown": out,
+            "critical_path": {"forces": depth_f, "mass": depth_m, "evaluation": depth_all, "sincos_full": 13, "sincos_shift": 8,
+                              "per_state_step": 4 * depth_all + 13 + 3 * 8 + 4 * 2}}
 
 
 def stages_of(prop):
@@ -586,6 +632,9 @@ def main(argv):
         res[name] = r
         print("%-10s n=%d  %5d flop / evaluation   %6d flop, >= %5d FP64 instructions / RK4 state-step" %
               (name, r["n"], r["flop_per_evaluation"], r["flop_per_state_step"], r["instr_per_state_step"]))
+        cp = r["critical_path"]
+        print("    critical path: forces %d, mass matrix %d, evaluation with solve %d dependent FP64 instructions; %d per RK4 state-step"
+              % (cp["forces"], cp["mass"], cp["evaluation"], cp["per_state_step"]))
         for k, v in r["breakdown"].items():
             print("    %-22s %5d mul %5d add  -> %5d flop, %5d instr" % (k, v["mul"], v["add"], v["flops"], v["instr"]))
     return res
