@@ -158,6 +158,23 @@ RKB_API const char* rkb_last_cuda_error(void);
 /* Validate `desc`, lower it to the device program and return a handle.  The descriptor is
  * copied; the caller may free it afterwards. */
 RKB_API int  rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out);
+/* ... with a say in the lowering (0 = rkb_chain_create).  The results of every entry point are the same up to
+ * rounding whatever the flags; they exist so that the kernel families can be compared with each other. */
+#define RKB_CREATE_INTERPRETER 1u  /* run on the interpreter kernels even if the chain has the serial form        */
+#define RKB_CREATE_GENERAL     2u  /* serial kernels without structural specialisation (axis / link / tensor shape) */
+RKB_API int  rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_flags, rkb_chain** out);
+
+/* Execution options of a handle (none changes results beyond rounding; all have measured defaults):
+ *   RKB_OPT_SPLIT_MAX_SAMPLES  RK4 rollouts, control sequences and steering loops of at most this many samples run with
+ *                              one sample on a PAIR of warps (forces | mass matrix + solve) instead of one thread per
+ *                              sample: ~2x faster while the batch cannot fill the GPU.  0 = never, -1 = default (8192).
+ *   RKB_OPT_FUSED_STEER        1 (default): rkb_steer_feedback on a serial chain is one launch; 0: one control-law and
+ *                              one rollout launch per interval (what interpreter chains always do)
+ *   RKB_OPT_FUSED_SEQUENCE     1 (default): rkb_rollout with the RK4 scheme on a serial chain is one launch; 0: one per interval
+ *   RKB_OPT_HOST_PIPELINE      1 (default): large RKB_MEM_HOST rollouts are cut into chunks whose copies overlap the kernels */
+enum rkb_option { RKB_OPT_SPLIT_MAX_SAMPLES = 1, RKB_OPT_FUSED_STEER = 2, RKB_OPT_FUSED_SEQUENCE = 3, RKB_OPT_HOST_PIPELINE = 4 };
+RKB_API int       rkb_chain_set_option(rkb_chain* chain, int option, long long value);
+RKB_API long long rkb_chain_get_option(const rkb_chain* chain, int option);
 RKB_API void rkb_chain_destroy(rkb_chain* chain);
 
 RKB_API int  rkb_chain_state_dim(const rkb_chain* chain);  /* kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147 */

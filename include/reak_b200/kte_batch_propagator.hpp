@@ -316,6 +316,14 @@ class kte_batch_propagator {
   }
   double last_kernel_ms() const { return rkb_last_kernel_ms(mChain); }
   rkb_chain* handle() const { return mChain; }
+  /// rkb_chain_set_option (RKB_OPT_*): execution choices that do not change results beyond rounding
+  void set_option(int option, long long value) { check(rkb_chain_set_option(mChain, option, value), "rkb_chain_set_option"); }
+  long long get_option(int option) const { return rkb_chain_get_option(mChain, option); }
+  /// A caller's std::vector is pageable memory: the library then pays the driver's synchronous staged copies (about
+  /// half the end-to-end rate).  pin() page-locks the vector's storage once (rkb_host_pin) so that every later call on
+  /// it copies by DMA, overlapped with the kernels; unpin() before the vector is resized or destroyed.
+  template <typename T> static void pin(std::vector<T>& v) { if (!v.empty()) check(rkb_host_pin(&v[0], v.size() * sizeof(T)), "rkb_host_pin"); }
+  template <typename T> static void unpin(std::vector<T>& v) { if (!v.empty()) check(rkb_host_unpin(&v[0]), "rkb_host_unpin"); }
 
  private:
   kte_batch_propagator(const kte_batch_propagator&);

@@ -63,6 +63,8 @@ class rkb_steer_opts(C.Structure):
                 ("u_lower", C.c_void_p), ("u_upper", C.c_void_p), ("du_lower", C.c_void_p), ("du_upper", C.c_void_p)]
 
 
+CREATE_INTERPRETER, CREATE_GENERAL = 1, 2
+OPT_SPLIT_MAX_SAMPLES, OPT_FUSED_STEER, OPT_FUSED_SEQUENCE, OPT_HOST_PIPELINE = 1, 2, 3, 4
 SCHEME_EULER, SCHEME_MIDPOINT, SCHEME_RK4, SCHEME_RK5 = 1, 2, 4, 5
 SCHEMES = {"euler": SCHEME_EULER, "midpoint": SCHEME_MIDPOINT, "rk4": SCHEME_RK4, "runge_kutta4": SCHEME_RK4,
            "rk5": SCHEME_RK5, "runge_kutta5": SCHEME_RK5}
@@ -81,6 +83,9 @@ SYMBOLS = {
     "rkb_strerror": (C.c_char_p, [C.c_int]),
     "rkb_last_cuda_error": (C.c_char_p, []),
     "rkb_chain_create": (C.c_int, [C.POINTER(rkb_chain_desc), C.POINTER(C.c_void_p)]),
+    "rkb_chain_create_ex": (C.c_int, [C.POINTER(rkb_chain_desc), C.c_uint, C.POINTER(C.c_void_p)]),
+    "rkb_chain_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong]),
+    "rkb_chain_get_option": (C.c_longlong, [C.c_void_p, C.c_int]),
     "rkb_chain_destroy": (None, [C.c_void_p]),
     "rkb_chain_state_dim": (C.c_int, [C.c_void_p]),
     "rkb_chain_input_dim": (C.c_int, [C.c_void_p]),

@@ -757,9 +757,8 @@ RKB_DEV double fast_rcp(double d) {
 // (:80-82) is applied to D(i) unchanged, and only one reciprocal per pivot is needed — no sqrt.
 // Row i keeps W(i,k) = L(i,k) D(k) in a scratch row while L(i,k) overwrites the matrix.
 template <int N>
-RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N]) {
+RKB_DEV int ldl_factor_packed(double (&Mp)[N * (N + 1) / 2], double (&inv)[N]) {
   int st = 0;
-  double inv[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double W[N];
@@ -777,6 +776,11 @@ RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N])
     if (!(d >= 1.0e-8)) st = RKB_STATUS_SINGULAR;
     inv[i] = fast_rcp(d);
   }
+  return st;
+}
+// ... and the two substitutions with the factors: b <- (L D L^T)^-1 b
+template <int N>
+RKB_DEV void ldl_apply_packed(const double (&Mp)[N * (N + 1) / 2], const double (&inv)[N], double (&b)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {  // L y = b
     double s = b[i];
@@ -791,6 +795,12 @@ RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N])
     for (int k = N - 1; k > i; --k) s = fma(-Mp[k * (k + 1) / 2 + i], b[k], s);
     b[i] = s;
   }
+}
+template <int N>
+RKB_DEV int cholesky_solve_packed(double (&Mp)[N * (N + 1) / 2], double (&b)[N]) {
+  double inv[N];
+  const int st = ldl_factor_packed<N>(Mp, inv);
+  ldl_apply_packed<N>(Mp, inv, b);
   return st;
 }
 
@@ -807,6 +817,52 @@ RKB_DEV int serial_accel_trig(const SerialParams& P, const SerialState<N>& X, do
   double Mp[N * (N + 1) / 2];
   serial_sweeps<N, FL, SHAPE, SMS, true, true, true>(P, X, cs, sn, qdd, Mp, sm);
   return cholesky_solve_packed<N>(Mp, qdd);
+}
+
+// ---- one sample on two warps (small batches) -----------------------------------------------------------
+// A lone warp per SM sub-partition — the situation of a batch of a few hundred to a few thousand samples — issues
+// one FP64 instruction every 2.5 cycles and spends ~2600 cycles on the ~750 FP64 instructions of a 6-coordinate
+// evaluation, while the longest chain of dependent instructions in it is only ~62 (500 cycles): the warp is bound by
+// its own issue slot, not by latency (tools/small_batch_microbench.cu, tools/flop_count.py: critical_path).  The
+// evaluation has two independent halves of almost equal size — sweeps 1-2 (the generalised forces) and sweep 3 plus
+// the factorisation (the mass matrix) — so a PAIR of warps on two sub-partitions takes one each: the "force" warp
+// hands f over through shared memory, the "mass" warp solves and hands q_ddot back, both advance their own copy of
+// the RK4 state.  Two named-barrier hand-offs per evaluation (~75 cycles each, same microbenchmark).
+struct DuoCtx {
+  double* xf;   // this sample's exchange column for f     (N doubles, stride 32)
+  double* xq;   // ...                          for q_ddot
+  int role;     // 0: forces, 1: mass matrix + solve (warp-uniform)
+  int bar_f, bar_q;  // named barrier ids of this pair
+};
+RKB_DEV void named_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+RKB_DEV void named_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int N, int FL, shape_t SHAPE, int SMS>
+RKB_DEV int duo_accel_trig(const SerialParams& P, const SerialState<N>& X, double (&cs)[N], double (&sn)[N], double (&qdd)[N], double* sm,
+                           const DuoCtx& duo) {
+  double Mp[N * (N + 1) / 2];
+  int st = 0;
+  if (duo.role == 0) {
+    serial_sweeps<N, FL, SHAPE, SMS, true, false, true>(P, X, cs, sn, qdd, Mp, sm);
+#pragma unroll
+    for (int k = 0; k < N; ++k) duo.xf[k * 32] = qdd[k];
+    named_arrive(duo.bar_f);   // f is there
+    named_sync(duo.bar_q);     // wait for q_ddot
+#pragma unroll
+    for (int k = 0; k < N; ++k) qdd[k] = duo.xq[k * 32];
+  } else {
+    double inv[N];
+    serial_sweeps<N, FL, SHAPE, SMS, false, true, true>(P, X, cs, sn, qdd, Mp, sm);
+    st = ldl_factor_packed<N>(Mp, inv);
+    named_sync(duo.bar_f);
+#pragma unroll
+    for (int k = 0; k < N; ++k) qdd[k] = duo.xf[k * 32];
+    ldl_apply_packed<N>(Mp, inv, qdd);
+#pragma unroll
+    for (int k = 0; k < N; ++k) duo.xq[k * 32] = qdd[k];
+    named_arrive(duo.bar_q);
+  }
+  return st;
 }
 
 template <int N>
@@ -1058,8 +1114,8 @@ RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long of
 
 // n_steps RK4 steps of size dt on the state in X with the inputs X.u held; returns the status bits.
 // sm is this thread's shared-memory column: w (2N), k1 + 2 k2 (2N), cos / sin at the start of the step (2N).
-template <int N, int FL, shape_t SHAPE, int SMS>
-RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n_steps, double* sm) {
+template <int N, int FL, shape_t SHAPE, int SMS, bool DUO = false>
+RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n_steps, double* sm, const DuoCtx* duo = nullptr) {
   double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
   double* sb = sa + 2 * N * SMS;    // cos, sin of the joint angles at the start of the step
@@ -1097,7 +1153,8 @@ RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n
       }
       serial_trig_fold<N, FL, SHAPE>(P, sn);
     }
-    st |= serial_accel_trig<N, FL, SHAPE, SMS>(P, X, cs, sn, qdd, sm);
+    if (DUO) st |= duo_accel_trig<N, FL, SHAPE, SMS>(P, X, cs, sn, qdd, sm, *duo);
+    else st |= serial_accel_trig<N, FL, SHAPE, SMS>(P, X, cs, sn, qdd, sm);
     // state derivative f = (qd, qdd) interleaved; the four stages of fixed_step_integrators.hpp:277-289
     if (stage == 0) {
 #pragma unroll
@@ -1316,6 +1373,227 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
   A.n_done[i] = k;
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = st;
+}
+
+// ---- the same three kernels with one sample on a pair of warps (see DuoCtx) ---------------------------------
+// CTA = 128 threads = two pairs = 64 samples; warps 2p (forces) and 2p + 1 (mass matrix, solve) of pair p sit on
+// different SM sub-partitions.  Lanes beyond the batch integrate a copy of the last sample (they must take part in the
+// pair's barriers) and store nothing.  Results are those of the one-thread-per-sample kernels bit for bit: the same
+// instruction sequences run, only on two warps.
+#define RKB_DUO_BLOCK 128
+#define RKB_SMEM_DUO(n) (6 * (n) * RKB_DUO_BLOCK + 2 * 2 * (n) * 32)  // doubles per CTA: RK4 columns + two exchange tiles
+
+template <int N>
+RKB_DEV bool duo_setup(double* smem, long long n_samples, DuoCtx& d, long long& i, bool& valid) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1;
+  const long long first = ((long long)blockIdx.x * 2 + pair) * 32;
+  if (first >= n_samples) return false;  // the whole pair has nothing to do (both of its warps leave)
+  double* x = smem + 6 * N * RKB_DUO_BLOCK + pair * (2 * N * 32);
+  d.role = warp & 1;
+  d.xf = x + lane;
+  d.xq = x + N * 32 + lane;
+  d.bar_f = 1 + 2 * pair;
+  d.bar_q = 2 + 2 * pair;
+  i = first + lane;
+  valid = i < n_samples;
+  if (!valid) i = n_samples - 1;
+  return true;
+}
+
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_DUO_BLOCK, 2) serial_rollout_duo_kernel(const __grid_constant__ SerialParams P, const RolloutArgs A) {
+  extern __shared__ double smem[];
+  DuoCtx duo;
+  long long i;
+  bool valid;
+  if (!duo_setup<N>(smem, A.n_samples, duo, i, valid)) return;
+  double* sm = smem + threadIdx.x;
+  SerialState<N> X;
+  {
+    const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
+    ConstBatchView xv = A.x0;
+    xv.p += i0 * xv.si - i * xv.si;
+    load_state<N>(P, xv, A.u, i, X);
+  }
+  int st = rk4_steps<N, FL, SHAPE, RKB_DUO_BLOCK, true>(P, X, A.dt, A.n_steps, sm, &duo);
+  if (!valid) return;
+  if (duo.role == 0) {
+    store_state<N>(P, A.xout, i * A.xout.si, X);
+    if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si, X);
+  } else {
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+    if (!finite) st |= RKB_STATUS_NONFINITE;
+    if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
+  }
+}
+
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_DUO_BLOCK, 2) serial_rollout_seq_duo_kernel(const __grid_constant__ SerialParams P, const RolloutSeqArgs A) {
+  extern __shared__ double smem[];
+  DuoCtx duo;
+  long long i;
+  bool valid;
+  if (!duo_setup<N>(smem, A.n_samples, duo, i, valid)) return;
+  double* sm = smem + threadIdx.x;
+  SerialState<N> X;
+  load_state<N>(P, A.x0, A.u, i, X);
+  int st = 0;
+#pragma unroll 1
+  for (int j = 0; j < A.n_intervals; ++j) {
+    if (j > 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int in = P.st[k].input;
+        X.u[k] = (in >= 0) ? A.u.p[i * A.u.si + j * A.u_sj + in * A.u.sk] : 0.0;
+      }
+    }
+    st |= rk4_steps<N, FL, SHAPE, RKB_DUO_BLOCK, true>(P, X, A.dt, A.n_steps, sm, &duo);
+    if (valid && duo.role == 0 && A.traj.p) store_state<N>(P, A.traj, i * A.traj.si + j * A.traj_sj, X);
+  }
+  if (!valid) return;
+  if (duo.role == 0) {
+    store_state<N>(P, A.xout, i * A.xout.si, X);
+  } else {
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+    if (!finite) st |= RKB_STATUS_NONFINITE;
+    if (A.status) A.status[i] = st;
+  }
+}
+
+// The steering loop: samples of a warp stop after different numbers of intervals, but the pair's barriers need every
+// lane, so a finished lane keeps riding along with a zero step (its state does not move) until the whole warp is done;
+// both warps of the pair hold the same states and therefore agree on when that is.
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_DUO_BLOCK, 2) serial_steer_duo_kernel(const __grid_constant__ SerialParams P, const __grid_constant__ SteerArgs A) {
+  extern __shared__ double smem[];
+  constexpr int NX = 2 * N;
+  DuoCtx duo;
+  long long i;
+  bool valid;
+  if (!duo_setup<N>(smem, A.n_samples, duo, i, valid)) return;
+  double* sm = smem + threadIdx.x;
+  const int nu = A.nu;
+  SerialState<N> X;
+  {
+    const ConstBatchView xv = {A.x0, NX, 1, A.blocked};
+    const ConstBatchView uv = {A.x0, 1, 1, 0};
+    load_state<N>(P, xv, uv, i, X);
+  }
+  const double T = A.time_step;
+  double up[N];
+  bool act[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    const int in = P.st[s].input;
+    act[s] = in >= 0 && in < nu;
+    up[s] = act[s] ? A.u_prev[i * nu + in] : 0.0;
+  }
+  int st = 0, n_done = 0;
+  bool live = true;
+#pragma unroll 1
+  for (int k = 0; k < A.max_intervals; ++k) {
+    double dx[NX];
+    double d2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      const int c = P.st[s].coord;
+      const double dq = X.q[s] - A.goal[i * NX + rkb_state_q(A.blocked, N, c)];
+      const double dd = X.qd[s] - A.goal[i * NX + rkb_state_qd(A.blocked, N, c)];
+      dx[2 * s] = dq; dx[2 * s + 1] = dd;
+      d2 = fma(dq, dq, d2); d2 = fma(dd, dd, d2);
+    }
+    if (live && !(sqrt(d2) > A.proximity)) live = false;  // MEAQR_topology.hpp:513-514
+    if (!__any_sync(0xffffffffu, live)) break;
+    double bias[N], corr[N], cur[N], un[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      bias[s] = corr[s] = cur[s] = 0.0;
+      un[s] = up[s];
+      if (!act[s]) continue;
+      const int in = P.st[s].input;
+      const double* G = A.gain + (i * nu + in) * NX;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < N; ++t) {
+        const int c = P.st[t].coord;
+        acc = fma(G[rkb_state_q(A.blocked, N, c)], dx[2 * t], acc);
+        acc = fma(G[rkb_state_qd(A.blocked, N, c)], dx[2 * t + 1], acc);
+      }
+      corr[s] = -acc;
+      bias[s] = A.u_bias[i * nu + in];
+    }
+    if (k == 0 && !A.saturate_first) {
+#pragma unroll
+      for (int s = 0; s < N; ++s) if (act[s]) un[s] = bias[s] + corr[s];
+    } else {  // IHAQR_topology.hpp:304-327
+      bool inside = true;
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        if (!act[s]) continue;
+        const int in = P.st[s].input;
+        if (A.have_u_box) { if (bias[s] < A.u_lo[in]) bias[s] = A.u_lo[in]; else if (bias[s] > A.u_hi[in]) bias[s] = A.u_hi[in]; }
+        cur[s] = bias[s] + corr[s];
+        if (A.have_u_box && ((cur[s] < A.u_lo[in]) || (cur[s] > A.u_hi[in]))) inside = false;
+      }
+      if (!inside) {
+#pragma unroll 1
+        for (int j = 0; j < 10; ++j) {
+          bool ok = true;
+#pragma unroll
+          for (int s = 0; s < N; ++s) {
+            if (!act[s]) continue;
+            const int in = P.st[s].input;
+            corr[s] *= 0.5; cur[s] -= corr[s];
+            if ((cur[s] < A.u_lo[in]) || (cur[s] > A.u_hi[in])) ok = false;
+          }
+          if (ok) {
+#pragma unroll
+            for (int s = 0; s < N; ++s) { bias[s] = cur[s]; cur[s] += corr[s]; }
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        if (!act[s]) continue;
+        const int in = P.st[s].input;
+        double du = ((inside ? cur[s] : bias[s]) - up[s]) * (1.0 / T);
+        if (A.have_du_box) { if (du < A.du_lo[in]) du = A.du_lo[in]; else if (du > A.du_hi[in]) du = A.du_hi[in]; }
+        un[s] = up[s] + T * du;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      if (live) up[s] = un[s];
+      X.u[s] = up[s];
+    }
+    const int s_k = rk4_steps<N, FL, SHAPE, RKB_DUO_BLOCK, true>(P, X, live ? A.dt : 0.0, A.substeps, sm, &duo);
+    if (live) {
+      st |= s_k;
+      n_done = k + 1;
+      if (valid && duo.role == 0 && A.traj) {
+        const BatchView tv = {A.traj + (long long)k * NX, (long long)NX * A.max_intervals, 1, A.blocked};
+        store_state<N>(P, tv, i * tv.si, X);
+      }
+    }
+  }
+  if (!valid) return;
+  if (duo.role == 0) {
+    const BatchView ov = {A.xout, NX, 1, A.blocked};
+    store_state<N>(P, ov, i * NX, X);
+#pragma unroll
+    for (int s = 0; s < N; ++s) if (act[s]) A.u_prev[i * nu + P.st[s].input] = up[s];
+    A.n_done[i] = n_done;
+  } else {
+    bool finite = true;
+#pragma unroll
+    for (int s = 0; s < N; ++s) finite = finite && isfinite(X.q[s]) && isfinite(X.qd[s]);
+    if (!finite) st |= RKB_STATUS_NONFINITE;
+    if (A.status) A.status[i] = st;
+  }
 }
 
 // Any explicit one-step scheme given as an RkTable (Euler, midpoint, RK5 — and RK4, which the kernel

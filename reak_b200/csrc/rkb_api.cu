@@ -79,7 +79,15 @@ struct rkb_chain {
   std::mutex mu;
   uint64_t launches = 0;
   DeviceCtx* last = nullptr;
+  // rkb_chain_set_option
+  long long split_max = -1;        // largest batch integrated with one sample on a pair of warps; -1: the measured default
+  bool fused_steer = true, fused_sequence = true, host_pipeline = true;
+  unsigned create_flags = 0;
 };
+
+// Below this many samples a batch cannot fill the GPU with one thread per sample (148 SMs x 4 sub-partitions x 32
+// lanes = 18944 lone warps) and the pair-of-warps kernels win; measured crossover on B200: profiles/r2_small_batch.md.
+constexpr long long kSplitMaxDefault = 8192;
 
 namespace {
 
@@ -434,7 +442,7 @@ int shape_score(unsigned long long have, int n) {
   return sc;
 }
 
-const SerialKernels* find_serial(int n, int fl, unsigned long long shape) {
+const SerialKernels* find_serial(int n, int fl, unsigned long long shape, bool no_special) {
   int count = 0;
   const SerialKernels* t = nullptr;
   switch (n) {
@@ -448,7 +456,6 @@ const SerialKernels* find_serial(int n, int fl, unsigned long long shape) {
     case 8: t = rkb_serial_table_8(&count); break;
     default: return nullptr;
   }
-  const bool no_special = std::getenv("RKB_NO_SPECIALIZE") && std::getenv("RKB_NO_SPECIALIZE")[0] == '1';
   const SerialKernels* best = nullptr;
   for (int i = 0; i < count; ++i) {
     if ((t[i].fl & fl) != fl || !shape_compatible(t[i].shape, shape, n)) continue;
@@ -617,6 +624,13 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   return RKB_OK;
 }
 
+// small batch: one sample on a pair of warps (kte_serial.cuh: DuoCtx).  Not for run-time specialised handles (the
+// NVRTC set holds the one-thread-per-sample kernels only).
+bool use_split(const rkb_chain* c, long long n_samples) {
+  const long long lim = c->split_max < 0 ? kSplitMaxDefault : c->split_max;
+  return c->serial_ok && c->sk && !c->jit && n_samples <= lim;
+}
+
 // rollout on device-resident views; used by rkb_rollout_rk4 and rkb_steer_batch
 // table == nullptr: the dedicated RK4 kernels (the fast path)
 int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, const RkTable* table, cudaStream_t s) {
@@ -625,7 +639,11 @@ int launch_rollout(rkb_chain* c, DeviceCtx* ctx, const RolloutArgs& A, const RkT
     e = table ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_RK, c->sp, &A, table, A.n_samples,
                                (2 * c->n + 2 * c->n * table->stages) * 128 * (int)sizeof(double), s)
               : rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT, c->sp, &A, nullptr, A.n_samples, 0, s);
-  else if (c->serial_ok && c->sk) e = table ? c->sk->rollout_rk(c->sp, A, *table, s) : c->sk->rollout(c->sp, A, s);
+  else if (c->serial_ok && c->sk) {
+    if (table) e = c->sk->rollout_rk(c->sp, A, *table, s);
+    else if (use_split(c, A.n_samples) && !A.active) e = c->sk->rollout_duo(c->sp, A, s);
+    else e = c->sk->rollout(c->sp, A, s);
+  }
   else if (c->generic_ok) e = rkb_generic_rollout(ctx->d_prog, c->gp, A, table, s);
   else return RKB_ERR_UNSUPPORTED;
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -656,9 +674,10 @@ const char* rkb_strerror(int code) {
 
 const char* rkb_last_cuda_error(void) { return g_cuda_err; }
 
-int rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out) {
+int rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_flags, rkb_chain** out) {
   if (!out) return RKB_ERR_INVALID;
   *out = nullptr;
+  if (create_flags & ~(RKB_CREATE_INTERPRETER | RKB_CREATE_GENERAL)) return RKB_ERR_INVALID;
   int rc = validate(desc);
   if (rc) return rc;
   rkb_chain* c = new (std::nothrow) rkb_chain();
@@ -668,17 +687,41 @@ int rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out) {
   c->desc.elements = c->elements.data();
   c->n = desc->n_coords;
   c->nu = desc->n_inputs;
+  c->create_flags = create_flags;
   c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl, c->serial_shape);
   if (c->serial_ok) {
-    c->sk = find_serial(c->n, c->serial_fl, c->serial_shape);
+    c->sk = find_serial(c->n, c->serial_fl, c->serial_shape, (create_flags & RKB_CREATE_GENERAL) != 0);
     if (!c->sk) c->serial_ok = false;
   }
-  const char* force = std::getenv("RKB_FORCE_GENERIC");
   c->generic_ok = lower_generic(c->desc, c->gp);
-  if (force && force[0] == '1' && c->generic_ok) { c->serial_ok = false; c->sk = nullptr; }
+  if ((create_flags & RKB_CREATE_INTERPRETER) && c->generic_ok) { c->serial_ok = false; c->sk = nullptr; }
   if (!c->serial_ok && !c->generic_ok) { delete c; return RKB_ERR_UNSUPPORTED; }
   *out = c;
   return RKB_OK;
+}
+
+int rkb_chain_create(const rkb_chain_desc* desc, rkb_chain** out) { return rkb_chain_create_ex(desc, 0u, out); }
+
+int rkb_chain_set_option(rkb_chain* c, int option, long long value) {
+  if (!c) return RKB_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(c->mu);
+  switch (option) {
+    case RKB_OPT_SPLIT_MAX_SAMPLES: if (value < -1) return RKB_ERR_INVALID; c->split_max = value; return RKB_OK;
+    case RKB_OPT_FUSED_STEER: c->fused_steer = value != 0; return RKB_OK;
+    case RKB_OPT_FUSED_SEQUENCE: c->fused_sequence = value != 0; return RKB_OK;
+    case RKB_OPT_HOST_PIPELINE: c->host_pipeline = value != 0; return RKB_OK;
+    default: return RKB_ERR_INVALID;
+  }
+}
+long long rkb_chain_get_option(const rkb_chain* c, int option) {
+  if (!c) return RKB_ERR_INVALID;
+  switch (option) {
+    case RKB_OPT_SPLIT_MAX_SAMPLES: return c->split_max < 0 ? kSplitMaxDefault : c->split_max;
+    case RKB_OPT_FUSED_STEER: return c->fused_steer ? 1 : 0;
+    case RKB_OPT_FUSED_SEQUENCE: return c->fused_sequence ? 1 : 0;
+    case RKB_OPT_HOST_PIPELINE: return c->host_pipeline ? 1 : 0;
+    default: return RKB_ERR_INVALID;
+  }
 }
 
 void rkb_chain_destroy(rkb_chain* c) {
@@ -1032,12 +1075,12 @@ int make_plan(const rkb_rollout_opts* o, RolloutPlan& pl) {
 //   traj: likewise with traj_sj
 int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long long n, ConstBatchView x0, ConstBatchView u, long long u_sj,
                      BatchView xout, BatchView traj, long long traj_sj, int32_t* status, cudaStream_t s) {
-  if (pl.n_intervals > 1 && !pl.use_table && c->serial_ok && c->sk &&
-      !(std::getenv("RKB_ROLLOUT_UNFUSED") && std::getenv("RKB_ROLLOUT_UNFUSED")[0] == '1')) {
+  if (pl.n_intervals > 1 && !pl.use_table && c->serial_ok && c->sk && c->fused_sequence) {
     RolloutSeqArgs A;  // RK4 on the serial kernels: the whole sequence in one launch
     A.x0 = x0; A.u = u; A.xout = xout; A.traj = traj; A.status = status;
     A.n_samples = n; A.u_sj = u_sj; A.traj_sj = traj_sj; A.dt = pl.dt; A.n_steps = pl.n_steps; A.n_intervals = pl.n_intervals;
-    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_SEQ, c->sp, &A, nullptr, A.n_samples, 0, s) : c->sk->rollout_seq(c->sp, A, s);
+    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_SEQ, c->sp, &A, nullptr, A.n_samples, 0, s)
+                    : use_split(c, A.n_samples) ? c->sk->rollout_seq_duo(c->sp, A, s) : c->sk->rollout_seq(c->sp, A, s);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     c->launches += 1;
     return RKB_OK;
@@ -1172,7 +1215,7 @@ static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, cons
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!L.device && !L.soa && N >= kPipeMinSamples && pl.n_steps > 0 && !(std::getenv("RKB_NO_PIPELINE") && std::getenv("RKB_NO_PIPELINE")[0] == '1'))
+  if (!L.device && !L.soa && N >= kPipeMinSamples && pl.n_steps > 0 && c->host_pipeline)
     return rollout_host_pipelined(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, L.blocked);
   const void *dx = nullptr, *du = nullptr;
   void *dout = nullptr, *dtraj = nullptr, *dst = nullptr;
@@ -1374,8 +1417,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   dst = (L.device && status) ? (void*)status : ctx->st.p;
   if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
   CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
-  const bool fused = n_pairs == 0 && c->serial_ok && c->sk &&
-                     !(std::getenv("RKB_STEER_UNFUSED") && std::getenv("RKB_STEER_UNFUSED")[0] == '1');
+  const bool fused = n_pairs == 0 && c->serial_ok && c->sk && c->fused_steer;
   void *dcol = nullptr, *dxn = nullptr, *dun = nullptr, *ddist = nullptr;
   if (n_pairs > 0) {
     // the interval is integrated into x_next, tested, and only then accepted (MEAQR_topology.hpp:550-559)
@@ -1401,7 +1443,8 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
       F.du_lo[r] = (o->du_lower && r < nu) ? o->du_lower[r] : 0.0; F.du_hi[r] = (o->du_upper && r < nu) ? o->du_upper[r] : 0.0;
     }
     CU(cudaEventRecord(ctx->ev0, s));
-    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_STEER, c->sp, &F, nullptr, F.n_samples, 0, s) : c->sk->steer(c->sp, F, s);
+    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_STEER, c->sp, &F, nullptr, F.n_samples, 0, s)
+                    : use_split(c, F.n_samples) ? c->sk->steer_duo(c->sp, F, s) : c->sk->steer(c->sp, F, s);
     if (e != cudaSuccess) return cuda_fail(e, "steer kernel");
     c->launches += 1;
   } else {

@@ -19,6 +19,10 @@ struct SerialKernels {
   cudaError_t (*rollout_rk)(const SerialParams&, const RolloutArgs&, const RkTable&, cudaStream_t);  // any explicit scheme
   cudaError_t (*rollout_seq)(const SerialParams&, const RolloutSeqArgs&, cudaStream_t);              // RK4, control sequence
   cudaError_t (*steer)(const SerialParams&, const SteerArgs&, cudaStream_t);                         // the whole steering loop
+  // small batches: one sample on a pair of warps (kte_serial.cuh: DuoCtx); same results bit for bit
+  cudaError_t (*rollout_duo)(const SerialParams&, const RolloutArgs&, cudaStream_t);
+  cudaError_t (*rollout_seq_duo)(const SerialParams&, const RolloutSeqArgs&, cudaStream_t);
+  cudaError_t (*steer_duo)(const SerialParams&, const SteerArgs&, cudaStream_t);
 };
 
 // defined in rkb_serial_n.cu, compiled once per N with -DRKB_N=<n>

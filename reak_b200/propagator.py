@@ -28,7 +28,8 @@ def _is_torch(a):
 
 
 class kte_batch_propagator(object):
-    def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3, blocked=False):
+    def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3, blocked=False,
+                 interpreter=False, general=False):
         if mass_calc is None and hasattr(chain, "chain"):  # a kte_system / kte_nl_system-like object
             sys_ = chain
             chain, mass_calc, dofs_gen, inputs = sys_.chain, sys_.mass_calc, sys_.dofs_gen, sys_.inputs
@@ -41,7 +42,9 @@ class kte_batch_propagator(object):
         self.blocked = bool(blocked)
         self._lib = _abi.load_library()
         h = C.c_void_p()
-        _abi.check(self._lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(h)), "rkb_chain_create")
+        # interpreter / general: which kernel family runs the chain (rkb_chain_create_ex); same results up to rounding
+        cf = (_abi.CREATE_INTERPRETER if interpreter else 0) | (_abi.CREATE_GENERAL if general else 0)
+        _abi.check(self._lib.rkb_chain_create_ex(C.byref(self.compiled.desc), cf, C.byref(h)), "rkb_chain_create_ex")
         self._h = h
         self.n = self._lib.rkb_chain_dof(h)
         self.nx = self._lib.rkb_chain_state_dim(h)
@@ -57,6 +60,18 @@ class kte_batch_propagator(object):
             self.close()
         except Exception:
             pass
+
+    def set_option(self, option, value):
+        """rkb_chain_set_option: 'split_max_samples', 'fused_steer', 'fused_sequence', 'host_pipeline' (include/reak_b200.h)"""
+        code = {"split_max_samples": _abi.OPT_SPLIT_MAX_SAMPLES, "fused_steer": _abi.OPT_FUSED_STEER,
+                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE}[option]
+        _abi.check(self._lib.rkb_chain_set_option(self._h, code, int(value)), "rkb_chain_set_option")
+        return self
+
+    def get_option(self, option):
+        code = {"split_max_samples": _abi.OPT_SPLIT_MAX_SAMPLES, "fused_steer": _abi.OPT_FUSED_STEER,
+                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE}[option]
+        return int(self._lib.rkb_chain_get_option(self._h, code))
 
     def is_serial(self):
         """True when the chain runs on the register-resident serial-chain kernels."""

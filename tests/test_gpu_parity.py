@@ -3,7 +3,8 @@
 Tolerances are BASELINE.json's: 1e-10 relative per step, 1e-8 after 1000 steps, relative error
 taken per component as |a-b| / max(1, |b|).  Evaluation outputs (xdot, f, M, Mdot) are held to
 1e-10 as well.  Every chain is run on the kernels the library picks for it and, where that is
-the register-resident serial path, once more on the interpreter kernels (RKB_FORCE_GENERIC=1).
+the register-resident serial path, once more on the interpreter kernels (RKB_CREATE_INTERPRETER) and
+with one thread per sample instead of one sample per pair of warps (RKB_OPT_SPLIT_MAX_SAMPLES = 0).
 """
 import os
 
@@ -20,25 +21,23 @@ TOL_LONG = 1e-8
 ALL = sorted(presets.PRESETS)
 
 
-def _make(name, generic=False):
+def _make(name, generic=False, split=None):
+    """generic: run the chain on the interpreter kernels (rkb_chain_create_ex, RKB_CREATE_INTERPRETER);
+    split: RKB_OPT_SPLIT_MAX_SAMPLES (0 = one thread per sample whatever the batch size)."""
     from reak_b200 import kte_batch_propagator
-    s = presets.make(name)
-    old = os.environ.get("RKB_FORCE_GENERIC")
-    os.environ["RKB_FORCE_GENERIC"] = "1" if generic else "0"
-    try:
-        p = kte_batch_propagator(s)
-    finally:
-        if old is None:
-            os.environ.pop("RKB_FORCE_GENERIC", None)
-        else:
-            os.environ["RKB_FORCE_GENERIC"] = old
+    p = kte_batch_propagator(presets.make(name), interpreter=generic)
+    if split is not None:
+        p.set_option("split_max_samples", split)
     return p
 
 
 def _variants(name):
+    """Every kernel family that can run the chain: what the library picks by itself (small batches of a serial chain:
+    one sample on a pair of warps), the one-thread-per-sample serial kernels, and the interpreter."""
     p = _make(name)
     out = [("auto", p)]
     if p.is_serial():
+        out.append(("thread-per-sample", _make(name, split=0)))
         out.append(("generic", _make(name, generic=True)))
     return out
 
@@ -925,7 +924,7 @@ def test_streams_and_threads():
 
 
 def test_steer_feedback_fused_kernel_equals_the_launch_per_interval_path():
-    """Serial chains run the whole steering loop in one launch; RKB_STEER_UNFUSED=1 selects the law-kernel +
+    """Serial chains run the whole steering loop in one launch; RKB_OPT_FUSED_STEER = 0 selects the law-kernel +
     rollout-per-interval path the interpreter chains use.  Same decisions, results within rounding."""
     p = _make("crs6_sd")
     x0, goal, u_bias, gain, u_prev = _steer_case(p, 500, seed=91)
@@ -933,11 +932,10 @@ def test_steer_feedback_fused_kernel_equals_the_launch_per_interval_path():
     goal[5:60] = x0[5:60] + 0.62 / np.sqrt(p.nx)               # these start just outside the proximity ball
     kw = dict(bounds=(-2 * np.ones(p.nu), 2 * np.ones(p.nu)), rate_bounds=(-60 * np.ones(p.nu), 60 * np.ones(p.nu)), want_traj=True)
     a = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 7, 0.6, **kw)
-    os.environ["RKB_STEER_UNFUSED"] = "1"
-    try:
-        b = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 7, 0.6, **kw)
-    finally:
-        os.environ.pop("RKB_STEER_UNFUSED", None)
+    p.set_option("fused_steer", 0)
+    assert p.get_option("fused_steer") == 0
+    b = p.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 7, 0.6, **kw)
+    p.set_option("fused_steer", 1)
     assert np.array_equal(a[2], b[2]) and len(set(a[2].tolist())) > 1
     assert rel_err(a[0], b[0]) < 1e-12 and rel_err(a[1], b[1]) < 1e-12
     for i in range(500):
@@ -945,18 +943,81 @@ def test_steer_feedback_fused_kernel_equals_the_launch_per_interval_path():
 
 
 def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
-    """RK4 control sequences on the serial kernels run in one launch; RKB_ROLLOUT_UNFUSED=1 selects one launch
+    """RK4 control sequences on the serial kernels run in one launch; RKB_OPT_FUSED_SEQUENCE = 0 selects one launch
     per interval (what the other schemes and the interpreter chains use).  Bit-identical."""
     p = _make("crs7")
     x, _ = random_batch(p.compiled, 3000, seed=93)
     u_seq = np.random.default_rng(94).uniform(-2, 2, (3000, 6, p.nu))
     a = p.rollout(x, u_seq, 1e-3, 5, scheme="rk4", want_traj=True)
-    os.environ["RKB_ROLLOUT_UNFUSED"] = "1"
-    try:
-        b = p.rollout(x, u_seq, 1e-3, 5, scheme="rk4", want_traj=True)
-    finally:
-        os.environ.pop("RKB_ROLLOUT_UNFUSED", None)
+    p.set_option("fused_sequence", 0)
+    b = p.rollout(x, u_seq, 1e-3, 5, scheme="rk4", want_traj=True)
+    p.set_option("fused_sequence", 1)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
+
+
+# ---- small batches: one sample on a pair of warps ----------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_pair_of_warps_kernels_equal_thread_per_sample(name):
+    """RKB_OPT_SPLIT_MAX_SAMPLES: rollouts, control sequences and steering loops of small batches run with the forces
+    on one warp and the mass matrix + solve on its partner.  The same instruction sequences run, so the results are
+    those of the one-thread-per-sample kernels BIT FOR BIT — for every serial preset, ragged batch sizes (lanes and
+    whole pairs beyond the batch), shared start states (steer batch), both state orders, and loops whose samples stop
+    after different numbers of intervals."""
+    from reak_b200 import kte_batch_propagator
+    duo = _make(name, split=1 << 20)
+    if not duo.is_serial():
+        pytest.skip("interpreter chain")
+    assert duo.get_option("split_max_samples") == 1 << 20 and _make(name).get_option("split_max_samples") == 8192
+    solo = _make(name, split=0)
+    rng = np.random.default_rng(101)
+    for n in (1, 31, 33, 64, 65, 1000):
+        x, u = random_batch(duo.compiled, n, seed=102 + n, q_range=2.0)
+        a, sa = duo.get_next_states(x, u, 1e-3, 9)
+        b, sb = solo.get_next_states(x, u, 1e-3, 9)
+        assert np.array_equal(a, b) and np.array_equal(sa, sb), (name, n)
+    n = 777
+    x, u = random_batch(duo.compiled, n, seed=103)
+    useq = rng.uniform(-2, 2, (n, 4, duo.nu))
+    a = duo.rollout(x, useq, 1e-3, 3, scheme="rk4", want_traj=True)
+    b = solo.rollout(x, useq, 1e-3, 3, scheme="rk4", want_traj=True)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b)), name
+    if duo.nu:
+        P, R = 9, 37
+        uu = rng.uniform(-4, 4, (P, R, duo.nu))
+        a = duo.steer_batch(x[:P], x[P:2 * P], uu, 1e-3, 6, want_status=True)
+        b = solo.steer_batch(x[:P], x[P:2 * P], uu, 1e-3, 6, want_status=True)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), name
+        x0, goal, u_bias, gain, u_prev = _steer_case(duo, 300, seed=104)
+        goal[:5] = x0[:5]
+        goal[5:40] = x0[5:40] + 0.62 / np.sqrt(duo.nx)
+        kw = dict(bounds=(-2 * np.ones(duo.nu), 2 * np.ones(duo.nu)), rate_bounds=(-60 * np.ones(duo.nu), 60 * np.ones(duo.nu)), want_traj=True)
+        for sat in (False, True):
+            a = duo.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 5, 6, 0.6, saturate_first=sat, **kw)
+            b = solo.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 5, 6, 0.6, saturate_first=sat, **kw)
+            nd = a[2]
+            assert np.array_equal(nd, b[2]) and len(set(nd.tolist())) > 1, name
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[4], b[4]), name
+            for i in range(300):
+                assert np.array_equal(a[3][i, :nd[i]], b[3][i, :nd[i]]), (name, i)
+    # the (q..., qd...) state order goes through the same kernels
+    s = presets.make(name)
+    db, sb_ = kte_batch_propagator(s, blocked=True), kte_batch_propagator(presets.make(name), blocked=True)
+    db.set_option("split_max_samples", 1 << 20)
+    sb_.set_option("split_max_samples", 0)
+    assert np.array_equal(db.get_next_states(x[:100], u[:100], 1e-3, 4)[0], sb_.get_next_states(x[:100], u[:100], 1e-3, 4)[0])
+
+
+def test_pair_of_warps_is_only_used_below_the_threshold():
+    """above RKB_OPT_SPLIT_MAX_SAMPLES the one-thread-per-sample kernel runs: same launch count, same results; the
+    threshold only moves work between two bit-identical kernels"""
+    p = _make("crs6", split=100)
+    x, u = random_batch(p.compiled, 101, seed=105)
+    big, _ = p.get_next_states(x, u, 1e-3, 3)        # 101 samples: thread per sample
+    small, _ = p.get_next_states(x[:100], u[:100], 1e-3, 3)   # 100 samples: pairs of warps
+    assert np.array_equal(big[:100], small)
+    from reak_b200 import _abi
+    assert _abi.load_library().rkb_chain_set_option(p._h, 99, 1) == _abi.ERR_INVALID
+    assert _abi.load_library().rkb_chain_set_option(p._h, _abi.OPT_SPLIT_MAX_SAMPLES, -2) == _abi.ERR_INVALID
 
 
 # ---- run-time specialisation (NVRTC) ---------------------------------------------------------------------

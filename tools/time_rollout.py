@@ -3,7 +3,7 @@
 RKB_LIB_PATH selects the library build.  (Parity is the job of tests/: nothing outside tests/, smoke() and
 bench.py's CPU legs touches oracle/.)
 
-    python tools/time_rollout.py [preset] [n_samples] [rk4_steps] [reps]
+    python tools/time_rollout.py [preset] [n_samples] [rk4_steps] [reps] [split_max_samples]
 """
 import os
 import sys
@@ -21,6 +21,8 @@ def main():
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 100
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
     p = kte_batch_propagator(presets.make(name))
+    if len(sys.argv) > 5:
+        p.set_option("split_max_samples", int(sys.argv[5]))
     rng = np.random.default_rng(1)
     x = rng.uniform(-1, 1, (n, p.nx))
     u = rng.uniform(-1, 1, (n, p.nu))
