@@ -167,7 +167,8 @@ RKB_API int  rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_fla
 /* Execution options of a handle (none changes results beyond rounding; all have measured defaults):
  *   RKB_OPT_SPLIT_MAX_SAMPLES  RK4 rollouts, control sequences and steering loops of at most this many samples run with
  *                              one sample on a PAIR of warps (forces | mass matrix + solve) instead of one thread per
- *                              sample: ~2x faster while the batch cannot fill the GPU.  0 = never, -1 = default (8192).
+ *                              sample: ~1.5x faster while the batch cannot fill the GPU.  0 = never, -1 = default (8192
+ *                              for chains of 4 or more coordinates, 0 for shorter ones, whose evaluation is too brief).
  *   RKB_OPT_FUSED_STEER        1 (default): rkb_steer_feedback on a serial chain is one launch; 0: one control-law and
  *                              one rollout launch per interval (what interpreter chains always do)
  *   RKB_OPT_FUSED_SEQUENCE     1 (default): rkb_rollout with the RK4 scheme on a serial chain is one launch; 0: one per interval
@@ -338,6 +339,15 @@ RKB_API int rkb_twist_shaping_rows(const rkb_chain* chain);
 RKB_API int rkb_twist_shaping_mcm(const rkb_chain* chain, double* Mcm);
 RKB_API int rkb_twist_shaping(rkb_chain* chain, int device, size_t n_samples,
                               const double* x, double* Tcm, double* Tcm_dot, unsigned flags, void* stream);
+
+/* Linearisation of the dynamics about (x[i], u[i]) — what a linear-quadratic steering asks its system for
+ * (get_linear_blocks in examples/misc/IHAQR_topology.hpp:240-258, MEAQR_topology.hpp): A[i] = d xdot / d x
+ * (2n x 2n, row-major) and B[i] = d xdot / d u (2n x n_inputs), by central differences of get_state_derivative with the
+ * step h = eps max(1, |component|) per state / input component (eps <= 0: 1e-6); the divisor is the difference of the
+ * perturbed values as formed in floating point.  A or B may be NULL.  status (nullable): the bits of every
+ * evaluation involved, OR-ed.  AOS, interleaved states only (RKB_LAYOUT_SOA / _BLOCKED: RKB_ERR_UNSUPPORTED). */
+RKB_API int rkb_linearize(rkb_chain* chain, int device, size_t n_samples, const double* x, const double* u, double eps,
+                          double* A, double* B, int32_t* status, unsigned flags, void* stream);
 
 /* For each of n_pairs (start, goal) pairs roll out n_rollouts constant controls for n_steps
  * RK4 steps and keep the rollout whose end state is closest to the goal (Euclidean norm over

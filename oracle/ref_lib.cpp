@@ -698,14 +698,14 @@ struct one_at_a_time_visitor {
   typedef typename pp::topology_traits<Space>::point_type point_type;
   const Space* space;
   double tol;
-  mutable int steer_branch, move_branch;
-  one_at_a_time_visitor(const Space& s, double t) : space(&s), tol(t), steer_branch(0), move_branch(0) {}
+  int* branch;  // [0] calls that took the steerable branch, [1] the move_position_toward branch (the node puller copies its visitor)
+  one_at_a_time_visitor(const Space& s, double t, int* counters) : space(&s), tol(t), branch(counters) {}
 
   template <typename SwitchFreeSpace>
   typename boost::enable_if<pp::is_steerable_space<SwitchFreeSpace>, double>::type dispatched_steer_towards_position(
       const SwitchFreeSpace& sp, const point_type& p_src, const point_type& p_dest, point_type& p_result, double fraction,
       tiny_graph::edge_bundled& ep_result) const {
-    ++steer_branch;
+    ++branch[0];
     boost::tie(p_result, ep_result.steer_record) = sp.steer_position_toward(p_src, fraction, p_dest);
     ep_result.weight = get(pp::distance_metric, sp.get_super_space())(p_src, p_result, sp.get_super_space());
     return ep_result.weight;
@@ -714,7 +714,7 @@ struct one_at_a_time_visitor {
   typename boost::disable_if<pp::is_steerable_space<SwitchFreeSpace>, double>::type dispatched_steer_towards_position(
       const SwitchFreeSpace& sp, const point_type& p_src, const point_type& p_dest, point_type& p_result, double fraction,
       tiny_graph::edge_bundled& ep_result) const {
-    ++move_branch;
+    ++branch[1];
     p_result = sp.move_position_toward(p_src, fraction, p_dest);
     ep_result.weight = get(pp::distance_metric, sp.get_super_space())(p_src, p_result, sp.get_super_space());
     return ep_result.weight;
@@ -806,7 +806,8 @@ int rkref_planner_dispatch_check(void* hv, int K, const double* x_nodes, const d
       if ((int)st_rec.size() != n_intervals + 1) throw std::runtime_error("steer record has the wrong length");
       sp1.reseed(4321ull);
     }
-    one_at_a_time_visitor<space_t> vis1(sp1, tol);
+    int branches[2] = {0, 0};
+    one_at_a_time_visitor<space_t> vis1(sp1, tol, branches);
     vect_n<double> p_a = tgt;
     boost::tuple<std::size_t, bool, tiny_graph::edge_bundled> r1 =
         graph::detail::rrg_node_puller<tiny_graph>::expand_to_nearest(p_a, Nc, g, vis1);
@@ -821,7 +822,7 @@ int rkref_planner_dispatch_check(void* hv, int K, const double* x_nodes, const d
         graph::detail::rrg_node_puller<tiny_graph>::expand_to_nearest(p_b, Nc, g, vis2);
     out[0] = boost::get<1>(r1) ? (int)boost::get<0>(r1) : -1;
     out[1] = boost::get<1>(r2) ? (int)boost::get<0>(r2) : -1;
-    out[2] = vis1.steer_branch; out[3] = vis1.move_branch; out[4] = (int)vis2.prepared();
+    out[2] = branches[0]; out[3] = branches[1]; out[4] = (int)vis2.prepared();
     err[0] = err[1] = err[2] = 0.0;
     if (out[0] != out[1]) throw std::runtime_error("batched and one-at-a-time node pulling chose different vertices");
     for (int k = 0; k < nx; ++k) { err[0] = std::max(err[0], std::fabs(p_a[k] - p_b[k])); p_new[k] = p_b[k]; }

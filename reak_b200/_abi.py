@@ -120,6 +120,8 @@ SYMBOLS = {
     "rkb_twist_shaping_rows": (C.c_int, [C.c_void_p]),
     "rkb_twist_shaping_mcm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rkb_twist_shaping": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_linearize": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_uint, C.c_void_p]),
     "rkb_steer_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_uint, C.c_void_p]),

@@ -88,6 +88,7 @@ struct rkb_chain {
 // Below this many samples a batch cannot fill the GPU with one thread per sample (148 SMs x 4 sub-partitions x 32
 // lanes = 18944 lone warps) and the pair-of-warps kernels win; measured crossover on B200: profiles/r2_small_batch.md.
 constexpr long long kSplitMaxDefault = 8192;
+constexpr int kSplitMinCoords = 4;
 
 namespace {
 
@@ -627,8 +628,11 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
 // small batch: one sample on a pair of warps (kte_serial.cuh: DuoCtx).  Not for run-time specialised handles (the
 // NVRTC set holds the one-thread-per-sample kernels only).
 bool use_split(const rkb_chain* c, long long n_samples) {
-  const long long lim = c->split_max < 0 ? kSplitMaxDefault : c->split_max;
-  return c->serial_ok && c->sk && !c->jit && n_samples <= lim;
+  if (!c->serial_ok || !c->sk || c->jit) return false;
+  if (c->split_max >= 0) return n_samples <= c->split_max;  // the caller's explicit choice
+  // default: a short evaluation does not pay for the two hand-offs (planar 2-link chain: measured 0.9x; from 6
+  // coordinates on 1.5x), and beyond ~8192 samples one thread per sample already fills the sub-partitions
+  return c->n >= kSplitMinCoords && n_samples <= kSplitMaxDefault;
 }
 
 // rollout on device-resident views; used by rkb_rollout_rk4 and rkb_steer_batch
@@ -716,7 +720,7 @@ int rkb_chain_set_option(rkb_chain* c, int option, long long value) {
 long long rkb_chain_get_option(const rkb_chain* c, int option) {
   if (!c) return RKB_ERR_INVALID;
   switch (option) {
-    case RKB_OPT_SPLIT_MAX_SAMPLES: return c->split_max < 0 ? kSplitMaxDefault : c->split_max;
+    case RKB_OPT_SPLIT_MAX_SAMPLES: return c->split_max >= 0 ? c->split_max : (c->n >= kSplitMinCoords ? kSplitMaxDefault : 0);
     case RKB_OPT_FUSED_STEER: return c->fused_steer ? 1 : 0;
     case RKB_OPT_FUSED_SEQUENCE: return c->fused_sequence ? 1 : 0;
     case RKB_OPT_HOST_PIPELINE: return c->host_pipeline ? 1 : 0;
@@ -1539,6 +1543,72 @@ int rkb_steer_feedback_checked(rkb_chain* c, int device, size_t N, const double*
   if (n_pairs <= 0) return RKB_ERR_INVALID;
   return steer_feedback_impl(c, device, N, x0, x_goal, u_bias, gain, u_prev, o, pairs, n_pairs, x_out, n_done, collided, x_traj,
                              status, flags, stream);
+}
+
+/* A = d xdot / d x (2n x 2n) and B = d xdot / d u (2n x n_inputs) about (x[i], u[i]) by central differences of
+ * get_state_derivative — the linearisation the LQR steering of examples/misc/IHAQR_topology.hpp:240-258 asks its system
+ * for (get_linear_blocks).  One perturbation kernel, the ordinary evaluation kernels on the 2 (2n + n_inputs) perturbed
+ * copies of every sample, one differencing kernel; the batch goes in slices so that the scratch stays below ~150 MB. */
+int rkb_linearize(rkb_chain* c, int device, size_t N, const double* x, const double* u, double eps, double* A, double* B,
+                  int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  const Layout L = parse_flags(flags);
+  if (L.soa || L.blocked) return RKB_ERR_UNSUPPORTED;
+  const int n = c->n, nx = 2 * n, nu = c->nu, D = nx + nu;
+  if (!x || (nu > 0 && !u) || (!A && !B) || (B && nu == 0)) return RKB_ERR_INVALID;
+  if (!(eps > 0.0) || !std::isfinite(eps)) eps = 1.0e-6;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx = nullptr, *du = nullptr;
+  void *dA = nullptr, *dB = nullptr, *dst = nullptr;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if (nu > 0 && (rc = stage_in(ctx->in_u, u, N * nu * sizeof(double), L.device, s, &du))) return rc;
+  if ((rc = stage_out(ctx->out_a, A, N * nx * nx * sizeof(double), L.device, &dA))) return rc;
+  if ((rc = stage_out(ctx->out_b, B, N * nx * (size_t)nu * sizeof(double), L.device, &dB))) return rc;
+  if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
+  const size_t slice = 1u << 14, rows = (N < slice ? N : slice) * (size_t)D * 2;
+  if ((rc = ctx->scratch_x.ensure(rows * nx * sizeof(double)))) return rc;
+  if ((rc = ctx->scratch_u.ensure(rows * (nu > 0 ? nu : 1) * sizeof(double)))) return rc;
+  if ((rc = ctx->scratch_o.ensure(rows * nx * sizeof(double)))) return rc;
+  if ((rc = ctx->scratch_s.ensure(rows * sizeof(int32_t)))) return rc;
+  if (dst) CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
+  CU(cudaEventRecord(ctx->ev0, s));
+  for (size_t lo = 0; lo < N; lo += slice) {
+    const size_t m = N - lo < slice ? N - lo : slice, r = m * (size_t)D * 2;
+    cudaError_t e = rkb_lin_perturb((long long)m, nx, nu, eps, (const double*)dx + lo * nx, nu > 0 ? (const double*)du + lo * nu : nullptr,
+                                    (double*)ctx->scratch_x.p, (double*)ctx->scratch_u.p, s);
+    if (e != cudaSuccess) return cuda_fail(e, "linearize: perturb");
+    EvalArgs E;
+    E.x = cview((const double*)ctx->scratch_x.p, (long long)r, nx, false);
+    E.u = cview((const double*)(nu > 0 ? ctx->scratch_u.p : ctx->scratch_x.p), (long long)r, nu > 0 ? nu : 1, false);
+    E.out = view((double*)ctx->scratch_o.p, (long long)r, nx, false);
+    E.out2 = view((double*)nullptr, (long long)r, nx, false);
+    E.status = (int32_t*)ctx->scratch_s.p;
+    E.n_samples = (long long)r;
+    if (c->serial_ok && c->sk) e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_EVAL, c->sp, &E, nullptr, E.n_samples, 0, s) : c->sk->eval(c->sp, E, s);
+    else if (c->generic_ok) e = rkb_generic_eval(ctx->d_prog, c->gp, E, s);
+    else return RKB_ERR_UNSUPPORTED;
+    if (e != cudaSuccess) return cuda_fail(e, "linearize: evaluation");
+    e = rkb_lin_combine((long long)m, nx, nu, (const double*)ctx->scratch_x.p, (const double*)ctx->scratch_u.p, (const double*)ctx->scratch_o.p,
+                        (const int32_t*)ctx->scratch_s.p, dA ? (double*)dA + lo * nx * nx : nullptr, dB ? (double*)dB + lo * nx * (size_t)nu : nullptr,
+                        dst ? (int32_t*)dst + lo : nullptr, s);
+    if (e != cudaSuccess) return cuda_fail(e, "linearize: differences");
+    c->launches += 3;
+  }
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(dA, A, N * nx * nx * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dB, B, N * nx * (size_t)nu * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
 }
 
 double rkb_last_kernel_ms(rkb_chain* c) {

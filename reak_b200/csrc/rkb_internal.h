@@ -67,4 +67,10 @@ cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s);
 cudaError_t rkb_steer_commit(const SteerCommitArgs& a, cudaStream_t s);
 cudaError_t rkb_free_combine(const double* dist, int n_pairs, long long n, int32_t* out, cudaStream_t s);
 
+
+// rkb_linearize.cu: perturbed batch (rows (i, d, +-)) and the central differences of its evaluation
+cudaError_t rkb_lin_perturb(long long n, int nx, int nu, double eps, const double* x, const double* u, double* xp, double* up, cudaStream_t s);
+cudaError_t rkb_lin_combine(long long n, int nx, int nu, const double* xp, const double* up, const double* fd, const int32_t* st_in, double* A,
+                            double* B, int32_t* status, cudaStream_t s);
+
 #endif

@@ -352,6 +352,22 @@ class kte_batch_propagator(object):
         _abi.check(self._lib.rkb_twist_shaping(self._h, self.device, N, ptr(x), ptr(T), ptr(Td), flags, stream), "rkb_twist_shaping")
         return (T, Mc, Td) if with_derivative else (T, Mc)
 
+    def get_linear_blocks(self, x, u=None, eps=1e-6):
+        """A = d xdot / d x [N][nx][nx] and B = d xdot / d u [N][nx][nu] about every (x, u) by central differences
+        (rkb_linearize; get_linear_blocks of the LQR steering topologies, examples/misc/IHAQR_topology.hpp:240-258).
+        Returns (A, B, status)."""
+        if self.blocked:
+            raise NotImplementedError("rkb_linearize takes interleaved states")
+        x, N = self._in(x, self.nx, np.float64)
+        u = self._u_default(x, N, False) if u is None else self._in(u, self.nu, np.float64, False, N)[0]
+        A = self._like(x, (N, self.nx, self.nx))
+        B = self._like(x, (N, self.nx, self.nu)) if self.nu else None
+        st = self._like(x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, u if self.nu else None, A, B, st], False)
+        _abi.check(self._lib.rkb_linearize(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None, float(eps), ptr(A), ptr(B), ptr(st),
+                                           flags, stream), "rkb_linearize")
+        return A, B, st
+
     def steer_batch(self, x0, goal, u, dt=None, n_steps=10, want_status=False):
         """x0, goal: [P][nx]; u: [P][R][nu].  Returns (best_idx[P], best_x[P][nx], best_cost[P])."""
         x0, P = self._in(x0, self.nx, np.float64)

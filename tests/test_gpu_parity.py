@@ -955,6 +955,63 @@ def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
 
 
+# ---- linearisation ---------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7", "planar2_act", "crs6_lin_sd", "pendulum"])
+def test_linear_blocks_by_central_differences(name, oracle_built):
+    """rkb_linearize: A = d xdot / d x, B = d xdot / d u about (x, u) by central differences with the step
+    h = eps max(1, |component|).  Checked against the same differences of the ORACLE's get_state_derivative
+    (a difference quotient amplifies the 1e-15 agreement of the evaluations by 1 / (2 h): tolerance 1e-7 at
+    eps = 1e-6), against the structure every mechanical system has (d q_dot / d q = 0, d q_dot / d q_dot = 1,
+    d q_dot / d u = 0), and against M^-1 for d q_ddot / d u of an actuated joint."""
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        n, nx, nu = 37, p.nx, p.nu
+        x, u = random_batch(p.compiled, n, seed=111, q_range=1.5)
+        eps = 1e-6
+        A, B, st = p.get_linear_blocks(x, u if nu else None, eps)
+        assert not st.any()
+        Ao, Bo = np.empty((n, nx, nx)), np.empty((n, nx, nu))
+        for d in range(nx + nu):
+            xp, xm, up_, um = x.copy(), x.copy(), u.copy(), u.copy()
+            if d < nx:
+                h = eps * np.maximum(1.0, np.abs(x[:, d]))
+                xp[:, d] += h; xm[:, d] -= h
+                den = xp[:, d] - xm[:, d]
+            else:
+                h = eps * np.maximum(1.0, np.abs(u[:, d - nx]))
+                up_[:, d - nx] += h; um[:, d - nx] -= h
+                den = up_[:, d - nx] - um[:, d - nx]
+            col = (O.eval(xp, up_)[0] - O.eval(xm, um)[0]) / den[:, None]
+            if d < nx:
+                Ao[:, :, d] = col
+            else:
+                Bo[:, :, d - nx] = col
+        assert rel_err(A, Ao) < 1e-7, (name, label)
+        # kinematic rows: q_dot does not depend on q or u, and is the identity in q_dot
+        assert np.abs(A[:, 0::2, 0::2]).max() < 1e-9 and np.abs(A[:, 0::2, 1::2] - np.eye(p.n)[None]).max() < 1e-9
+        if nu:
+            assert rel_err(B, Bo) < 1e-7, (name, label)
+            assert np.abs(B[:, 0::2, :]).max() == 0.0
+        if name == "crs7":   # the track is prismatic and first in the chain: nothing below it removes the axial part, so
+            Minv = np.linalg.inv(p.get_mass_matrices(x))                  # d q_ddot / d u_0 is column 0 of M^-1
+            assert rel_err(B[:, 1::2, 0], Minv[:, :, 0]) < 1e-6
+    # argument checks
+    import ctypes as C
+    from reak_b200 import _abi
+    p = _make("crs6")
+    lib = _abi.load_library()
+    x, u = random_batch(p.compiled, 4, seed=1)
+    A = np.empty((4, 12, 12))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.rkb_linearize(p._h, 0, 4, vp(x), vp(u), 1e-6, None, None, None, 0, None) == _abi.ERR_INVALID
+    assert lib.rkb_linearize(p._h, 0, 4, vp(x), vp(u), 1e-6, vp(A), None, None, _abi.LAYOUT_SOA, None) == _abi.ERR_UNSUPPORTED
+    assert lib.rkb_linearize(p._h, 0, 4, vp(x), vp(u), 0.0, vp(A), None, None, 0, None) == 0   # eps <= 0: the default step
+    big_x, big_u = random_batch(p.compiled, 40000, seed=2)                                  # more than one slice
+    A2, B2, st2 = p.get_linear_blocks(big_x, big_u)
+    A3, B3, _ = p.get_linear_blocks(big_x[16000:16400], big_u[16000:16400])
+    assert np.array_equal(A2[16000:16400], A3) and np.array_equal(B2[16000:16400], B3) and not st2.any()
+
+
 # ---- small batches: one sample on a pair of warps ----------------------------------------------------------
 @pytest.mark.parametrize("name", ALL)
 def test_pair_of_warps_kernels_equal_thread_per_sample(name):
@@ -967,7 +1024,7 @@ def test_pair_of_warps_kernels_equal_thread_per_sample(name):
     duo = _make(name, split=1 << 20)
     if not duo.is_serial():
         pytest.skip("interpreter chain")
-    assert duo.get_option("split_max_samples") == 1 << 20 and _make(name).get_option("split_max_samples") == 8192
+    assert duo.get_option("split_max_samples") == 1 << 20 and _make(name).get_option("split_max_samples") == (8192 if duo.n >= 4 else 0)
     solo = _make(name, split=0)
     rng = np.random.default_rng(101)
     for n in (1, 31, 33, 64, 65, 1000):

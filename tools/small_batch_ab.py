@@ -28,10 +28,13 @@ def main():
     from reak_b200 import kte_batch_propagator, presets
     rows = []
     rng = np.random.default_rng(3)
-    for name, steps in (("crs6", 1000), ("planar2", 1000), ("crs7", 200)):
-        solo = kte_batch_propagator(presets.make(name)).set_option("split_max_samples", 0)
-        duo = kte_batch_propagator(presets.make(name)).set_option("split_max_samples", 1 << 30)
-        for n in (256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 1 << 18, 1 << 20):
+    quick = "--quick" in sys.argv
+    chains = [("crs6", 1000), ("planar2", 1000), ("crs7", 200)] if not quick else [("crs3", 1000), ("crs4", 1000), ("crs5", 1000), ("crs6_sd", 500)]
+    for name, steps in chains:
+        mk = (lambda: presets.crs_chain(n_revolute=int(name[3:]))) if name in ("crs4", "crs5") else (lambda: presets.make(name))
+        solo = kte_batch_propagator(mk()).set_option("split_max_samples", 0)
+        duo = kte_batch_propagator(mk()).set_option("split_max_samples", 1 << 30)
+        for n in ((256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 1 << 18, 1 << 20) if not quick else (1024, 8192, 12288, 16384)):
             k = steps if n <= 65536 else max(10, steps // 10)
             x = torch.from_numpy(rng.uniform(-1, 1, (n, solo.nx))).cuda()
             u = torch.from_numpy(rng.uniform(-1, 1, (n, solo.nu))).cuda()
@@ -45,7 +48,7 @@ def main():
             print("%-8s rollout  n=%7d steps=%4d  thread/sample %8.3f ms   pair of warps %8.3f ms   x%.2f" % (name, n, k, t_solo, t_duo, t_solo / t_duo), flush=True)
     solo = kte_batch_propagator(presets.make("crs6")).set_option("split_max_samples", 0)
     duo = kte_batch_propagator(presets.make("crs6")).set_option("split_max_samples", 1 << 30)
-    for n in (256, 1024, 4096, 16384, 65536):
+    for n in ((256, 1024, 4096, 16384, 65536) if not quick else ()):
         J = 50
         x = torch.from_numpy(rng.uniform(-.5, .5, (n, 12))).cuda()
         goal = x + 0.3
