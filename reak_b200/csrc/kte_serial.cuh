@@ -1114,8 +1114,17 @@ RKB_DEV void store_state(const SerialParams& P, const BatchView& o, long long of
 
 // n_steps RK4 steps of size dt on the state in X with the inputs X.u held; returns the status bits.
 // sm is this thread's shared-memory column: w (2N), k1 + 2 k2 (2N), cos / sin at the start of the step (2N).
+// Inputs that vary within a step (ctrl::detail::runge_kutta4_integrate_impl, ctrl/sys_integrators/
+// runge_kutta4_integrator_sys.hpp:50-97): the input trajectory sampled at every half step; evaluation 1 of step s reads
+// node 2 s, evaluations 2 and 3 node 2 s + 1, evaluation 4 node 2 s + 2.
+struct NodeInputs {
+  const double* p;    // this sample's node 0
+  long long sj, sk;   // input k of node j at p[j * sj + k * sk]
+};
+
 template <int N, int FL, shape_t SHAPE, int SMS, bool DUO = false>
-RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n_steps, double* sm, const DuoCtx* duo = nullptr) {
+RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n_steps, double* sm, const DuoCtx* duo = nullptr,
+                      const NodeInputs* nodes = nullptr) {
   double* sw = sm;                  // state at the start of the step (w)
   double* sa = sw + 2 * N * SMS;    // k1 + 2 k2
   double* sb = sa + 2 * N * SMS;    // cos, sin of the joint angles at the start of the step
@@ -1126,6 +1135,14 @@ RKB_DEV int rk4_steps(const SerialParams& P, SerialState<N>& X, double dt, int n
   for (int it = 0; it < total; ++it) {
     const int stage = it & 3;
     double qdd[N], cs[N], sn[N];
+    if (nodes) {
+      const long long node = 2 * (long long)(it >> 2) + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int in = P.st[k].input;
+        X.u[k] = (in >= 0) ? nodes->p[node * nodes->sj + in * nodes->sk] : 0.0;
+      }
+    }
     {
       // Stage 1 evaluates sin / cos in full and keeps them; stages 2-4 sit at w + d with d = dt q_dot / 2
       // or dt q_dot, and get theirs by sincos_shift unless some |d| is not small (or not finite).
@@ -1233,17 +1250,23 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
   SerialState<N> X;
   load_state<N>(P, A.x0, A.u, i, X);
   int st = 0;
+  if (A.half_step_nodes) {  // one interval whose input is sampled at every half step
+    const NodeInputs nd = {A.u.p + i * A.u.si, A.u_sj, A.u.sk};
+    st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, sm, nullptr, &nd);
+    if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si, X);
+  } else {
 #pragma unroll 1
-  for (int j = 0; j < A.n_intervals; ++j) {
-    if (j > 0) {
+    for (int j = 0; j < A.n_intervals; ++j) {
+      if (j > 0) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const int in = P.st[k].input;
-        X.u[k] = (in >= 0) ? A.u.p[i * A.u.si + j * A.u_sj + in * A.u.sk] : 0.0;
+        for (int k = 0; k < N; ++k) {
+          const int in = P.st[k].input;
+          X.u[k] = (in >= 0) ? A.u.p[i * A.u.si + j * A.u_sj + in * A.u.sk] : 0.0;
+        }
       }
+      st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, sm);
+      if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si + j * A.traj_sj, X);
     }
-    st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, sm);
-    if (A.traj.p) store_state<N>(P, A.traj, i * A.traj.si + j * A.traj_sj, X);
   }
   bool finite = true;
 #pragma unroll

@@ -117,6 +117,7 @@ struct RolloutArgs {
   int32_t        n_steps;
   int32_t        status_or;  // != 0: OR the status bits into status[i] instead of overwriting it
   const int32_t* active;     // nullable: samples with active[i] == 0 are left untouched (closed-loop steering)
+  long long      u_node_stride;  // interpreter kernels, RK4: != 0: the input at every half step, node j at u.p[.. + j * u_node_stride]
 };
 
 // A control sequence in one launch (serial kernels, RK4): n_intervals intervals of n_steps steps
@@ -128,6 +129,8 @@ struct RolloutSeqArgs {
   long long      n_samples, u_sj, traj_sj;
   double         dt;
   int32_t        n_steps, n_intervals;
+  int32_t        half_step_nodes;  // != 0: ONE interval, u holds the input at every half step (2 n_steps + 1 nodes, stride u_sj)
+  int32_t        pad;
 };
 
 // The whole steering loop in one launch (serial kernels), all buffers device-resident AoS

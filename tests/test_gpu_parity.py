@@ -986,11 +986,14 @@ def test_linear_blocks_by_central_differences(name, oracle_built):
                 Ao[:, :, d] = col
             else:
                 Bo[:, :, d - nx] = col
-        assert rel_err(A, Ao) < 1e-7, (name, label)
+        # torsion_spring_3D: the reference's own 2 acos(w) carries ~1e-16 / |sin(q/2)| of noise (see the spring edge test),
+        # which the difference quotient amplifies as well
+        tol = 2e-6 if "_sd" in name else 1e-7
+        assert rel_err(A, Ao) < tol, (name, label)
         # kinematic rows: q_dot does not depend on q or u, and is the identity in q_dot
         assert np.abs(A[:, 0::2, 0::2]).max() < 1e-9 and np.abs(A[:, 0::2, 1::2] - np.eye(p.n)[None]).max() < 1e-9
         if nu:
-            assert rel_err(B, Bo) < 1e-7, (name, label)
+            assert rel_err(B, Bo) < tol, (name, label)
             assert np.abs(B[:, 0::2, :]).max() == 0.0
         if name == "crs7":   # the track is prismatic and first in the chain: nothing below it removes the axial part, so
             Minv = np.linalg.inv(p.get_mass_matrices(x))                  # d q_ddot / d u_0 is column 0 of M^-1
