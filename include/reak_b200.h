@@ -13,6 +13,8 @@
  *                            (ctrl/mbd_kte/manipulator_model.cpp:292-355), the state_rate_function of the legacy models
  *   rkb_rollout_rk4       <- runge_kutta4_integrator<double>::integrate (core/integrators/fixed_step_integrators.hpp:256-293)
  *                            driven through num_int_dtnl_sys::get_next_state (ctrl/ctrl_sys/num_int_dtnl_system.hpp:166-180)
+ *   rkb_rollout_rk4_inputs <- ctrl::detail::runge_kutta4_integrate_impl (ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97):
+ *                            RK4 with an input trajectory read at t, t + dt/2, t + dt
  *   rkb_rollout           <- the same with euler / midpoint / runge_kutta4 / runge_kutta5 integrators
  *                            (fixed_step_integrators.hpp:60-399) over a sequence of control intervals
  *   rkb_mass_matrix       <- mass_matrix_calc::getMassMatrix / getMassMatrixAndDerivative
@@ -172,8 +174,15 @@ RKB_API int  rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_fla
  *   RKB_OPT_FUSED_STEER        1 (default): rkb_steer_feedback on a serial chain is one launch; 0: one control-law and
  *                              one rollout launch per interval (what interpreter chains always do)
  *   RKB_OPT_FUSED_SEQUENCE     1 (default): rkb_rollout with the RK4 scheme on a serial chain is one launch; 0: one per interval
- *   RKB_OPT_HOST_PIPELINE      1 (default): large RKB_MEM_HOST rollouts are cut into chunks whose copies overlap the kernels */
-enum rkb_option { RKB_OPT_SPLIT_MAX_SAMPLES = 1, RKB_OPT_FUSED_STEER = 2, RKB_OPT_FUSED_SEQUENCE = 3, RKB_OPT_HOST_PIPELINE = 4 };
+ *   RKB_OPT_HOST_PIPELINE      1 (default): large RKB_MEM_HOST rollouts are cut into chunks whose copies overlap the kernels
+ *   RKB_OPT_AUTO_SPECIALIZE    1 (default): a serial chain whose structure the shipped kernels do not fully match gets kernels
+ *                              compiled for exactly its structure on the first call of >= 4096 samples — from the disk cache
+ *                              ($RKB_CACHE_DIR, else $XDG_CACHE_HOME/reak_b200, else ~/.cache/reak_b200; RKB_CACHE_DIR=off
+ *                              disables it) or by NVRTC on a background thread; calls made meanwhile run on the shipped
+ *                              kernels, so results may change at rounding level once the new kernels take over.  0: only on
+ *                              rkb_chain_specialize. */
+enum rkb_option { RKB_OPT_SPLIT_MAX_SAMPLES = 1, RKB_OPT_FUSED_STEER = 2, RKB_OPT_FUSED_SEQUENCE = 3, RKB_OPT_HOST_PIPELINE = 4,
+                  RKB_OPT_AUTO_SPECIALIZE = 5 };
 RKB_API int       rkb_chain_set_option(rkb_chain* chain, int option, long long value);
 RKB_API long long rkb_chain_get_option(const rkb_chain* chain, int option);
 RKB_API void rkb_chain_destroy(rkb_chain* chain);
@@ -239,6 +248,15 @@ typedef struct rkb_rollout_opts {
 RKB_API int rkb_rollout(rkb_chain* chain, int device, size_t n_samples,
                         const double* x0, const double* u, const rkb_rollout_opts* opts,
                         double* x_out, double* x_traj, int32_t* status, unsigned flags, void* stream);
+
+/* RK4 with an input TRAJECTORY instead of a held input — ctrl::detail::runge_kutta4_integrate_impl
+ * (ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97) reads u_traj at t for the first evaluation of a step, at
+ * t + dt/2 for the second and third and at t + dt for the fourth.  u_nodes holds that trajectory sampled at every half
+ * step: 2 n_steps + 1 nodes per sample, AOS [N][2 n_steps + 1][n_inputs], SOA [2 n_steps + 1][n_inputs][N].  With all
+ * nodes equal this is rkb_rollout_rk4. */
+RKB_API int rkb_rollout_rk4_inputs(rkb_chain* chain, int device, size_t n_samples,
+                                   const double* x0, const double* u_nodes, double dt, int n_steps,
+                                   double* x_out, int32_t* status, unsigned flags, void* stream);
 
 /* rkb_rollout_rk4 on HOST buffers (AoS), sharded over `n_devices` GPUs of this box from one
  * process: contiguous blocks of samples, one copy/compute pipeline per device, no inter-GPU

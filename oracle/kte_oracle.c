@@ -998,6 +998,50 @@ static void rk4_range(model* m, size_t i0, size_t i1, const double* x0, const do
   }
 }
 
+/* ctrl::detail::runge_kutta4_integrate_impl (ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97): RK4 whose
+ * input comes from a trajectory, read at t (:66, carried over from the previous step's :91), t + dt/2 (:81, used for the
+ * second and third evaluations) and t + dt (:91).  u_nodes: the trajectory sampled at every half step,
+ * [N][2 n_steps + 1][nu].  The final combination is written as the reference writes it (:93), which differs from
+ * fixed_step_integrators.hpp:289 in the order of the additions. */
+void kto_rk4_inputs(void* h, size_t N, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status) {
+  model* m = (model*)h;
+  const int nx = 2 * m->n;
+  const size_t J = 2 * (size_t)n_steps + 1;
+  double x[2 * RKB_MAX_COORDS], w[2 * RKB_MAX_COORDS], f[2 * RKB_MAX_COORDS];
+  double k1[2 * RKB_MAX_COORDS], k2[2 * RKB_MAX_COORDS], k3[2 * RKB_MAX_COORDS];
+  size_t i;
+  int s, k;
+  for (i = 0; i < N; ++i) {
+    const double* ui = u_nodes ? u_nodes + i * J * (size_t)m->nu : NULL;
+    int st = 0;
+    for (k = 0; k < nx; ++k) x[k] = x0[i * nx + k];
+    if (n_steps > 0) {
+      st |= state_derivative(m, x, ui, f);                                                             /* :68 */
+      for (s = 0; s < n_steps && !st; ++s) {
+        const double* u_mid = ui ? ui + (2 * (size_t)s + 1) * (size_t)m->nu : NULL;
+        const double* u_end = ui ? ui + (2 * (size_t)s + 2) * (size_t)m->nu : NULL;
+        for (k = 0; k < nx; ++k) { w[k] = x[k]; k1[k] = dt * f[k]; x[k] = x[k] + 0.5 * k1[k]; }        /* :75-77 */
+        st |= state_derivative(m, x, u_mid, f);                                                        /* :79-81 */
+        if (st) break;
+        for (k = 0; k < nx; ++k) { k2[k] = dt * f[k]; x[k] = w[k] + 0.5 * k2[k]; }                      /* :82-83 */
+        st |= state_derivative(m, x, u_mid, f);                                                        /* :85 */
+        if (st) break;
+        for (k = 0; k < nx; ++k) { k3[k] = dt * f[k]; x[k] = w[k] + k3[k]; }                            /* :86-87 */
+        st |= state_derivative(m, x, u_end, f);                                                        /* :89-92 */
+        if (st) break;
+        for (k = 0; k < nx; ++k)                                                                       /* :93 */
+          x[k] = x[k] + ((((1.0 / 6.0) * k1[k] + (2.0 / 6.0) * k2[k]) + (dt / 6.0) * f[k]) - (2.0 / 3.0) * k3[k]);
+        st |= state_derivative(m, x, u_end, f);                                                        /* :95 */
+      }
+    }
+    for (k = 0; k < nx; ++k) {
+      xout[i * nx + k] = x[k];
+      if (!isfinite(x[k])) st |= RKB_STATUS_NONFINITE;
+    }
+    if (status) status[i] = st;
+  }
+}
+
 /* euler_integrator<T>::integrate (fixed_step_integrators.hpp:64-84), midpoint_integrator<T>::integrate
  * (:177-202) and runge_kutta5_integrator<T>::integrate (:351-399), same conventions as rk4_range:
  * explicit step count, input held constant, the trailing rate evaluation kept for the status only. */

@@ -20,6 +20,7 @@ int    kto_gen_forces_qdd(void* h, const double* x, const double* u, const doubl
 int    kto_mass(void* h, size_t n, const double* x, double* M, double* Mdot);
 int    kto_frames(void* h, const double* x, const double* u, double* out);
 /* returns wall seconds (< 0 on failure); n_workers > 1 forks worker processes */
+void kto_rk4_inputs(void* h, size_t n, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status);
 double kto_rk4(void* h, size_t n, const double* x0, const double* u, double dt, int n_steps,
                double* xout, int32_t* status, int n_workers);
 /* the same for any scheme of enum rkb_scheme (euler, midpoint, runge_kutta4, runge_kutta5) */

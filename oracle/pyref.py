@@ -100,6 +100,19 @@ class _Checker(object):
         secs = self._rk4(self.h, N, _dp(x), _dp(u), float(dt), int(n_steps), _dp(out), _dp(st), int(n_workers))
         return out, st, secs
 
+    def rk4_inputs(self, x0, u_nodes, dt):
+        """RK4 with an input trajectory sampled at every half step, u_nodes [N][2 n_steps + 1][nu]
+        (ctrl::detail::runge_kutta4_integrate_impl).  Returns (x_out, status)."""
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        u_nodes = np.ascontiguousarray(u_nodes, dtype=np.float64).reshape(N, -1, max(self.nu, 1) if self.nu else 0) if self.nu else np.zeros((N, 1, 0))
+        n_steps = (u_nodes.shape[1] - 1) // 2
+        out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        fn = getattr(self.lib, self._prefix + "rk4_inputs")
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        fn(self.h, N, _dp(x), _dp(u_nodes), float(dt), int(n_steps), _dp(out), _dp(st))
+        return out, st
+
     def integrate(self, x0, u, scheme, dt, n_steps, n_workers=1):
         """n_steps of euler (1) / midpoint (2) / runge_kutta4 (4) / runge_kutta5 (5); returns (x_out, status, seconds)."""
         x, u, N = self._xu(x0, u)

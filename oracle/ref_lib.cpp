@@ -253,6 +253,28 @@ class rate_fn : public state_rate_function<double> {
   }
 };
 
+// The same wrapper with the input read from a sampled trajectory: node round(t / (dt / 2)).  runge_kutta4_integrator
+// asks for the rate at t, t + dt/2 (twice) and t + dt (fixed_step_integrators.hpp:273-291) — the instants at which
+// ctrl::detail::runge_kutta4_integrate_impl reads its input trajectory (runge_kutta4_integrator_sys.hpp:66-91).
+class rate_fn_nodes : public state_rate_function<double> {
+ public:
+  const ctrl::kte_nl_system* sys;
+  const double* nodes;
+  int nu;
+  long long n_nodes;
+  double half_dt;
+  rate_fn_nodes(const ctrl::kte_nl_system* s, const double* aNodes, int aNu, long long aCount, double aHalf)
+      : sys(s), nodes(aNodes), nu(aNu), n_nodes(aCount), half_dt(aHalf) {}
+  virtual void RK_CALL computeStateRate(double t, const vect_n<double>& x, vect_n<double>& xd) {
+    long long j = llround(t / half_dt);
+    if (j < 0) j = 0;
+    if (j >= n_nodes) j = n_nodes - 1;
+    vect_n<double> u(nu);
+    for (int k = 0; k < nu; ++k) u[k] = nodes[j * nu + k];
+    xd = sys->get_state_derivative(*sys, x, u, t);
+  }
+};
+
 // scheme: enum rkb_scheme (1 euler, 2 midpoint, 4 runge_kutta4, 5 runge_kutta5)
 integrator<double>* make_integrator(int scheme, const vect_n<double>& x, double dt, const shared_ptr<state_rate_function<double> >& fn) {
   switch (scheme) {
@@ -295,6 +317,34 @@ void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, c
 }  // namespace
 
 extern "C" {
+
+// RK4 with an input trajectory sampled at every half step ([N][2 n_steps + 1][nu]): the reference's own
+// runge_kutta4_integrator<double> over its kte_nl_system, the rate function reading the node that belongs to the time it is asked at.
+int rkref_rk4_inputs(void* hv, std::size_t N, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int nx = 2 * m->n, nu = m->nu;
+  const long long J = 2LL * n_steps + 1;
+  for (std::size_t i = 0; i < N; ++i) {
+    vect_n<double> x(nx);
+    for (int k = 0; k < nx; ++k) x[k] = x0[i * nx + k];
+    int32_t st = 0;
+    if (n_steps > 0) {
+      shared_ptr<state_rate_function<double> > fn(new rate_fn_nodes(&m->sys, u_nodes + i * J * nu, nu, J, 0.5 * dt));
+      runge_kutta4_integrator<double> integ("rk4", x, 0.0, dt, fn);
+      try {
+        integ.integrate((double(n_steps) - 0.5) * dt);
+      } catch (singularity_error&) { st |= RKB_STATUS_SINGULAR; }
+      int k = 0;
+      for (std::vector<double>::const_iterator it = integ.getStateBegin(); it != integ.getStateEnd(); ++it, ++k) xout[i * nx + k] = *it;
+    } else {
+      for (int k = 0; k < nx; ++k) xout[i * nx + k] = x[k];
+    }
+    for (int k = 0; k < nx; ++k) if (!std::isfinite(xout[i * nx + k])) st |= RKB_STATUS_NONFINITE;
+    if (status) status[i] = st;
+  }
+  return 0;
+}
 
 void* rkref_create(const rkb_chain_desc* d) {
   if (!d || !d->elements) return NULL;

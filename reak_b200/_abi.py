@@ -64,7 +64,7 @@ class rkb_steer_opts(C.Structure):
 
 
 CREATE_INTERPRETER, CREATE_GENERAL = 1, 2
-OPT_SPLIT_MAX_SAMPLES, OPT_FUSED_STEER, OPT_FUSED_SEQUENCE, OPT_HOST_PIPELINE = 1, 2, 3, 4
+OPT_SPLIT_MAX_SAMPLES, OPT_FUSED_STEER, OPT_FUSED_SEQUENCE, OPT_HOST_PIPELINE, OPT_AUTO_SPECIALIZE = 1, 2, 3, 4, 5
 SCHEME_EULER, SCHEME_MIDPOINT, SCHEME_RK4, SCHEME_RK5 = 1, 2, 4, 5
 SCHEMES = {"euler": SCHEME_EULER, "midpoint": SCHEME_MIDPOINT, "rk4": SCHEME_RK4, "runge_kutta4": SCHEME_RK4,
            "rk5": SCHEME_RK5, "runge_kutta5": SCHEME_RK5}
@@ -99,6 +99,8 @@ SYMBOLS = {
                            C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_rollout_rk4_inputs": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(rkb_rollout_opts),
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,

@@ -829,6 +829,10 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
         }
         continue;
       }
+      // inputs sampled at every half step (runge_kutta4_integrate_impl, runge_kutta4_integrator_sys.hpp:50-97):
+      // evaluation 1 reads node 2 step, evaluations 2 and 3 node 2 step + 1, evaluation 4 node 2 step + 2
+      const long long un = A.u_node_stride;
+      if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step) * un + k * A.u.sk];
       st |= accel(G, W);
       for (int c = 0; c < n; ++c) {
         const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
@@ -836,6 +840,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
         acc[2 * c] = kq; acc[2 * c + 1] = kv;
         W.q[c] += kq * 0.5; W.qd[c] += kv * 0.5;
       }
+      if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step + 1) * un + k * A.u.sk];
       st |= accel(G, W);
       for (int c = 0; c < n; ++c) {
         const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
@@ -848,6 +853,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
         k3[2 * c] = kq; k3[2 * c + 1] = kv;
         W.q[c] = w[2 * c] + kq; W.qd[c] = w[2 * c + 1] + kv;
       }
+      if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step + 2) * un + k * A.u.sk];
       st |= accel(G, W);
       for (int c = 0; c < n; ++c) {
         const double kq = W.qd[c] * dt, kv = W.f[c] * dt;

@@ -82,6 +82,7 @@ struct rkb_chain {
   // rkb_chain_set_option
   long long split_max = -1;        // largest batch integrated with one sample on a pair of warps; -1: the measured default
   bool fused_steer = true, fused_sequence = true, host_pipeline = true;
+  bool auto_specialize = true, auto_done = false;
   unsigned create_flags = 0;
 };
 
@@ -553,6 +554,8 @@ int unstage_out(void* dev, void* dst, size_t bytes, bool on_device, cudaStream_t
 
 enum Op { OP_EVAL, OP_FORCES, OP_MASS, OP_TMT, OP_FRAMES };
 
+void maybe_auto_specialize(rkb_chain* c, long long n_samples);  // below, next to the kernel selection
+
 int tmt_rows(const rkb_chain_desc& d) {
   int rows = 0;
   for (int e = 0; e < d.n_elements; ++e) {
@@ -579,6 +582,7 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   DeviceCtx* ctx = nullptr;
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
+  maybe_auto_specialize(c, (long long)N);
   cudaStream_t s = (cudaStream_t)stream;
   const void *dx = nullptr, *du = nullptr;
   void *dout = nullptr, *dout2 = nullptr, *dst = nullptr;
@@ -633,6 +637,30 @@ bool use_split(const rkb_chain* c, long long n_samples) {
   // default: a short evaluation does not pay for the two hand-offs (planar 2-link chain: measured 0.9x; from 6
   // coordinates on 1.5x), and beyond ~8192 samples one thread per sample already fills the sub-partitions
   return c->n >= kSplitMinCoords && n_samples <= kSplitMaxDefault;
+}
+
+// A serial chain whose structure (axis-aligned joints, links along one axis, diagonal tensors) the shipped kernels only
+// partly promise runs on more general code than it needs, at half the speed.  On the first call that is big enough to
+// care, kernels for exactly this chain's structure are requested: from the disk cache if a previous process compiled
+// them, else from NVRTC on a background thread — the call at hand (and every one until the compilation has finished)
+// runs on the shipped kernels.  Called with the handle locked and the device current.
+constexpr long long kAutoSpecializeMinSamples = 4096;
+void maybe_auto_specialize(rkb_chain* c, long long n_samples) {
+  if (!c->auto_specialize || c->auto_done || c->jit || !c->serial_ok || !c->sk) return;
+  if (c->sk->shape == c->serial_shape) { c->auto_done = true; return; }  // the shipped kernels already match
+  if (n_samples < kAutoSpecializeMinSamples) return;
+  const JitKernels* J = nullptr;
+  if (rkb_jit_poll(c->n, c->serial_fl, c->serial_shape, &J) != RKB_OK) { c->auto_done = true; return; }  // no NVRTC here: stay as we are
+  if (!J) return;  // still compiling
+  int cur = -1;
+  cudaGetDevice(&cur);
+  for (DeviceCtx* x : c->ctx) {
+    if (x->device == cur) continue;  // rkb_jit_poll prepared the kernels on the current device
+    DeviceGuard g(x->device);
+    if (rkb_jit_prepare(*J) != cudaSuccess) { cudaGetLastError(); c->auto_done = true; return; }
+  }
+  c->jit = J;
+  c->auto_done = true;
 }
 
 // rollout on device-resident views; used by rkb_rollout_rk4 and rkb_steer_batch
@@ -714,6 +742,7 @@ int rkb_chain_set_option(rkb_chain* c, int option, long long value) {
     case RKB_OPT_FUSED_STEER: c->fused_steer = value != 0; return RKB_OK;
     case RKB_OPT_FUSED_SEQUENCE: c->fused_sequence = value != 0; return RKB_OK;
     case RKB_OPT_HOST_PIPELINE: c->host_pipeline = value != 0; return RKB_OK;
+    case RKB_OPT_AUTO_SPECIALIZE: c->auto_specialize = value != 0; return RKB_OK;
     default: return RKB_ERR_INVALID;
   }
 }
@@ -724,6 +753,7 @@ long long rkb_chain_get_option(const rkb_chain* c, int option) {
     case RKB_OPT_FUSED_STEER: return c->fused_steer ? 1 : 0;
     case RKB_OPT_FUSED_SEQUENCE: return c->fused_sequence ? 1 : 0;
     case RKB_OPT_HOST_PIPELINE: return c->host_pipeline ? 1 : 0;
+    case RKB_OPT_AUTO_SPECIALIZE: return c->auto_specialize ? 1 : 0;
     default: return RKB_ERR_INVALID;
   }
 }
@@ -1083,6 +1113,7 @@ int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long l
     RolloutSeqArgs A;  // RK4 on the serial kernels: the whole sequence in one launch
     A.x0 = x0; A.u = u; A.xout = xout; A.traj = traj; A.status = status;
     A.n_samples = n; A.u_sj = u_sj; A.traj_sj = traj_sj; A.dt = pl.dt; A.n_steps = pl.n_steps; A.n_intervals = pl.n_intervals;
+    A.half_step_nodes = 0; A.pad = 0;
     cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_ROLLOUT_SEQ, c->sp, &A, nullptr, A.n_samples, 0, s)
                     : use_split(c, A.n_samples) ? c->sk->rollout_seq_duo(c->sp, A, s) : c->sk->rollout_seq(c->sp, A, s);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -1102,6 +1133,7 @@ int launch_intervals(rkb_chain* c, DeviceCtx* ctx, const RolloutPlan& pl, long l
     A.n_steps = pl.n_steps;
     A.status_or = j > 0;
     A.active = nullptr;
+    A.u_node_stride = 0;
     const int rc = launch_rollout(c, ctx, A, pl.use_table ? &pl.table : nullptr, s);
     if (rc) return rc;
   }
@@ -1218,6 +1250,7 @@ static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, cons
   DeviceCtx* ctx = nullptr;
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
+  maybe_auto_specialize(c, (long long)N);
   cudaStream_t s = (cudaStream_t)stream;
   if (!L.device && !L.soa && N >= kPipeMinSamples && pl.n_steps > 0 && c->host_pipeline)
     return rollout_host_pipelined(c, ctx, N, x0, u, pl, x_out, x_traj, status, s, L.blocked);
@@ -1264,6 +1297,64 @@ int rkb_rollout(rkb_chain* c, int device, size_t N, const double* x0, const doub
   const int rc = make_plan(opts, pl);
   if (rc) return rc;
   return do_rollout(c, device, N, x0, u, pl, x_out, x_traj, status, flags, stream);
+}
+
+/* ctrl::detail::runge_kutta4_integrate_impl (ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97): RK4 with an
+ * input TRAJECTORY — the input is read at t for the first evaluation of a step, at t + dt/2 for the second and third
+ * and at t + dt for the fourth.  The batched form takes the trajectory sampled at those instants: 2 n_steps + 1 nodes. */
+int rkb_rollout_rk4_inputs(rkb_chain* c, int device, size_t N, const double* x0, const double* u_nodes, double dt, int n_steps,
+                           double* x_out, int32_t* status, unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
+  if (c->nu == 0) return rkb_rollout_rk4(c, device, N, x0, nullptr, dt, n_steps, x_out, status, flags, stream);  // nothing to sample
+  if (N == 0) return RKB_OK;
+  if (!x0 || !x_out || !u_nodes) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n, nu = c->nu;
+  const long long J = 2LL * n_steps + 1;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!(c->serial_ok && c->sk) && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void *dx = nullptr, *du = nullptr;
+  void *dout = nullptr, *dst = nullptr;
+  if ((rc = stage_in(ctx->in_x, x0, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if ((rc = stage_in(ctx->in_u, u_nodes, N * (size_t)nu * (size_t)J * sizeof(double), L.device, s, &du))) return rc;
+  if ((rc = stage_out(ctx->out_a, x_out, N * nx * sizeof(double), L.device, &dout))) return rc;
+  if ((rc = stage_out(ctx->st, status, N * sizeof(int32_t), L.device, &dst))) return rc;
+  // AoS [N][J][nu]: sample stride J nu, node stride nu; SoA [J][nu][N]: sample stride 1, node stride nu N, input stride N
+  const ConstBatchView uv = L.soa ? ConstBatchView{(const double*)du, 1, (long long)N, 0} : ConstBatchView{(const double*)du, (long long)nu * J, 1, 0};
+  const long long u_sj = L.soa ? (long long)nu * (long long)N : (long long)nu;
+  CU(cudaEventRecord(ctx->ev0, s));
+  cudaError_t e;
+  if (c->serial_ok && c->sk) {  // (a run-time specialised set has no node kernel: the shipped one serves)
+    RolloutSeqArgs A;
+    A.x0 = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked); A.u = uv;
+    A.xout = view((double*)dout, (long long)N, nx, L.soa, L.blocked); A.traj = BatchView{nullptr, 0, 0, 0};
+    A.status = (int32_t*)dst; A.n_samples = (long long)N; A.u_sj = u_sj; A.traj_sj = 0; A.dt = dt; A.n_steps = n_steps; A.n_intervals = 1;
+    A.half_step_nodes = 1; A.pad = 0;
+    e = c->sk->rollout_seq(c->sp, A, s);
+  } else {
+    RolloutArgs A;
+    A.x0 = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked); A.u = uv;
+    A.xout = view((double*)dout, (long long)N, nx, L.soa, L.blocked); A.traj = BatchView{nullptr, 0, 0, 0};
+    A.status = (int32_t*)dst; A.n_samples = (long long)N; A.x0_div = 1; A.dt = dt; A.n_steps = n_steps; A.status_or = 0; A.active = nullptr;
+    A.u_node_stride = u_sj;
+    e = rkb_generic_rollout(ctx->d_prog, c->gp, A, nullptr, s);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  c->launches += 1;
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  if ((rc = unstage_out(dout, x_out, N * nx * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
 }
 
 /* Host-buffer rollout sharded over several GPUs of one box from one process: contiguous block
@@ -1327,6 +1418,7 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   DeviceCtx* ctx = nullptr;
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
+  maybe_auto_specialize(c, (long long)P * R);
   cudaStream_t s = (cudaStream_t)stream;
   const void *dx0 = nullptr, *dgoal = nullptr, *du = nullptr;
   void *didx = nullptr, *dbx = nullptr, *dbc = nullptr, *dst = nullptr;
@@ -1355,6 +1447,7 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   A.n_steps = n_steps;
   A.status_or = 0;
   A.active = nullptr;
+  A.u_node_stride = 0;
   if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
   e = rkb_steer_reduce(nx, (long long)P, (long long)R, (const double*)ctx->scratch_o.p, (const double*)dgoal, (int32_t*)didx,
                        (double*)dbx, (double*)dbc, s);
@@ -1403,6 +1496,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   DeviceCtx* ctx = nullptr;
   int rc = get_ctx(c, device, &ctx);
   if (rc) return rc;
+  maybe_auto_specialize(c, (long long)N);
   cudaStream_t s = (cudaStream_t)stream;
   const void *dx0 = nullptr, *dgoal = nullptr, *dbias = nullptr, *dgain = nullptr, *dup_in = nullptr;
   void *dxo = nullptr, *dnd = nullptr, *dtraj = nullptr, *dst = nullptr;
@@ -1488,6 +1582,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
     A.n_steps = o->substeps;
     A.status_or = 1;
     A.active = (const int32_t*)ctx->act.p;
+    A.u_node_stride = 0;
     if ((rc = launch_rollout(c, ctx, A, nullptr, s))) return rc;
     if (n_pairs > 0) {
       for (int p = 0; p < n_pairs; ++p) {

@@ -56,6 +56,9 @@ struct JitKernels {
   int smem[RKB_JIT_COUNT];
 };
 int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out);  // compiles on first use, cached per process
+// non-blocking: *out == NULL while a background NVRTC compilation runs (started on the first call); a disk cache of cubins
+// ($RKB_CACHE_DIR, $XDG_CACHE_HOME/reak_b200, ~/.cache/reak_b200; keyed by build id) serves later processes in milliseconds
+int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out);
 cudaError_t rkb_jit_prepare(const JitKernels& J);                                  // per-device kernel attributes (current device)
 const char* rkb_jit_log();                                                         // NVRTC log / error text of the calling thread
 // args: the kernel's second parameter (EvalArgs, RolloutArgs, ...); extra: its third (RkTable) or NULL

@@ -10,17 +10,24 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
 #include "kte_serial.cuh"
 #include "rkb_internal.h"
 #include "jit_src.inc"
+#include "build_id.h"
 
 namespace {
 
@@ -50,7 +57,7 @@ struct Nvrtc {
 };
 
 Nvrtc g_nvrtc;
-std::mutex g_mu;
+std::mutex g_mu, g_nvrtc_mu;
 std::map<std::tuple<int, int, unsigned long long>, JitKernels*> g_cache;
 thread_local std::string g_log;
 
@@ -70,13 +77,82 @@ cudaError_t rkb_jit_prepare(const JitKernels& J) {
   return cudaSuccess;
 }
 
-int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  const auto key = std::make_tuple(n, fl, shape);
-  auto it = g_cache.find(key);
-  if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
-  g_log.clear();
-  if (!g_nvrtc.load()) { g_log = "libnvrtc.so.12 not found"; return RKB_ERR_UNSUPPORTED; }
+namespace {
+
+typedef std::tuple<int, int, unsigned long long> Key;
+
+// What NVRTC produced for one (n, fl, shape): the cubin and the lowered (mangled) name of every kernel in it.
+struct Cubin {
+  std::vector<char> image;
+  std::vector<std::string> names;  // RKB_JIT_COUNT entries
+};
+
+// ---- disk cache -----------------------------------------------------------------------------------------
+// $RKB_CACHE_DIR, else $XDG_CACHE_HOME/reak_b200, else $HOME/.cache/reak_b200.  One file per (build, n, fl, shape):
+// a header line per kernel name, then the cubin.  A cubin is only valid for the sources it was compiled from, so the
+// file name carries rkb_build_id().  Failures to read or write are not errors: the kernels are compiled instead.
+std::string cache_path(const Key& key) {
+  std::string dir;
+  if (const char* d = std::getenv("RKB_CACHE_DIR")) dir = d;
+  else if (const char* x = std::getenv("XDG_CACHE_HOME")) dir = std::string(x) + "/reak_b200";
+  else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/reak_b200";
+  else return std::string();
+  if (dir.empty() || dir == "off") return std::string();
+  std::string acc;
+  for (size_t i = 0; i <= dir.size(); ++i)  // mkdir -p
+    if (i == dir.size() || (dir[i] == '/' && i > 0)) { acc = dir.substr(0, i); ::mkdir(acc.c_str(), 0755); }
+  char buf[160];
+  std::snprintf(buf, sizeof buf, "/%s-n%d-fl%d-%016llx.cubin", RKB_BUILD_ID, std::get<0>(key), std::get<1>(key), std::get<2>(key));
+  return dir + buf;
+}
+bool cache_read(const Key& key, Cubin& out) {
+  const std::string path = cache_path(key);
+  if (path.empty()) return false;
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  bool ok = true;
+  out.names.clear();
+  char line[1024];
+  unsigned long long size = 0;
+  if (!std::fgets(line, sizeof line, f) || std::sscanf(line, "RKBCUBIN %llu", &size) != 1 || size == 0 || size > (1ull << 28)) ok = false;
+  for (int k = 0; ok && k < RKB_JIT_COUNT; ++k) {
+    if (!std::fgets(line, sizeof line, f)) { ok = false; break; }
+    std::string n(line);
+    while (!n.empty() && (n.back() == '\n' || n.back() == '\r')) n.pop_back();
+    if (n.empty()) ok = false;
+    out.names.push_back(n);
+  }
+  if (ok) {
+    out.image.resize(size);
+    ok = std::fread(out.image.data(), 1, size, f) == size;
+  }
+  std::fclose(f);
+  return ok;
+}
+void cache_write(const Key& key, const Cubin& c) {
+  const std::string path = cache_path(key);
+  if (path.empty()) return;
+  char tmp[32];
+  std::snprintf(tmp, sizeof tmp, ".%d.tmp", (int)::getpid());
+  const std::string t = path + tmp;
+  FILE* f = std::fopen(t.c_str(), "wb");
+  if (!f) return;
+  std::fprintf(f, "RKBCUBIN %llu\n", (unsigned long long)c.image.size());
+  for (const auto& n : c.names) std::fprintf(f, "%s\n", n.c_str());
+  const bool ok = std::fwrite(c.image.data(), 1, c.image.size(), f) == c.image.size();
+  std::fclose(f);
+  if (ok) std::rename(t.c_str(), path.c_str());  // atomic: concurrent processes never see half a file
+  else std::remove(t.c_str());
+}
+
+// ---- NVRTC: host-only, needs no CUDA context (may run on a helper thread) ----------------------------------
+int compile_cubin(const Key& key, Cubin& out, std::string& log) {
+  const int n = std::get<0>(key), fl = std::get<1>(key);
+  const unsigned long long shape = std::get<2>(key);
+  {
+    std::lock_guard<std::mutex> lock(g_nvrtc_mu);
+    if (!g_nvrtc.load()) { log = "libnvrtc.so.12 not found"; return RKB_ERR_UNSUPPORTED; }
+  }
   // program: the kernel header plus one name expression per kernel
   std::string src = "#include \"kte_serial.cuh\"\n";
   std::vector<std::string> exprs(RKB_JIT_COUNT);
@@ -95,34 +171,44 @@ int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out)
   const char* stubs[][2] = {{"cuda_runtime.h", ""}, {"math.h", ""}, {"stddef.h", ""}, {"stdint.h", kStdint}};
   for (auto& s : stubs) { hn.push_back(s[0]); ht.push_back(s[1]); }
   nvrtcProgram prog = nullptr;
-  if (g_nvrtc.CreateProgram(&prog, src.c_str(), "rkb_jit.cu", (int)hn.size(), ht.data(), hn.data()) != 0) { g_log = "nvrtcCreateProgram failed"; return RKB_ERR_CUDA; }
+  if (g_nvrtc.CreateProgram(&prog, src.c_str(), "rkb_jit.cu", (int)hn.size(), ht.data(), hn.data()) != 0) { log = "nvrtcCreateProgram failed"; return RKB_ERR_CUDA; }
   for (auto& e : exprs) g_nvrtc.AddNameExpression(prog, e.c_str());
   // -default-device: the C-ABI prototypes of reak_b200.h carry no execution-space annotation
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
   const int rc = g_nvrtc.CompileProgram(prog, 4, opts);
   size_t ls = 0;
   g_nvrtc.GetProgramLogSize(prog, &ls);
-  if (ls > 1) { g_log.resize(ls); g_nvrtc.GetProgramLog(prog, &g_log[0]); }
+  if (ls > 1) { log.resize(ls); g_nvrtc.GetProgramLog(prog, &log[0]); }
   if (rc != 0) { g_nvrtc.DestroyProgram(&prog); return RKB_ERR_CUDA; }
   size_t cs = 0;
   g_nvrtc.GetCUBINSize(prog, &cs);
-  std::vector<char> cubin(cs);
-  g_nvrtc.GetCUBIN(prog, cubin.data());
-  JitKernels* J = new JitKernels();
-  J->n = n; J->fl = fl; J->shape = shape;
-  cudaLibrary_t lib = nullptr;
-  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  if (e != cudaSuccess) { g_log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); cudaGetLastError(); g_nvrtc.DestroyProgram(&prog); delete J; return RKB_ERR_CUDA; }
-  J->library = lib;
+  out.image.resize(cs);
+  g_nvrtc.GetCUBIN(prog, out.image.data());
+  out.names.clear();
   for (int k = 0; k < RKB_JIT_COUNT; ++k) {
     const char* low = nullptr;
-    if (g_nvrtc.GetLoweredName(prog, exprs[k].c_str(), &low) != 0 || !low) { g_log = "nvrtcGetLoweredName failed for " + exprs[k]; g_nvrtc.DestroyProgram(&prog); delete J; return RKB_ERR_CUDA; }
-    cudaKernel_t kern = nullptr;
-    e = cudaLibraryGetKernel(&kern, lib, low);
-    if (e != cudaSuccess) { g_log = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e); cudaGetLastError(); g_nvrtc.DestroyProgram(&prog); delete J; return RKB_ERR_CUDA; }
-    J->kernel[k] = (const void*)kern;
+    if (g_nvrtc.GetLoweredName(prog, exprs[k].c_str(), &low) != 0 || !low) { log = "nvrtcGetLoweredName failed for " + exprs[k]; g_nvrtc.DestroyProgram(&prog); return RKB_ERR_CUDA; }
+    out.names.push_back(low);
   }
   g_nvrtc.DestroyProgram(&prog);
+  return RKB_OK;
+}
+
+// ---- loading: needs the CUDA context of the calling thread --------------------------------------------------
+int load_cubin(const Key& key, const Cubin& c, JitKernels** out, std::string& log) {
+  const int n = std::get<0>(key);
+  JitKernels* J = new JitKernels();
+  J->n = n; J->fl = std::get<1>(key); J->shape = std::get<2>(key);
+  cudaLibrary_t lib = nullptr;
+  cudaError_t e = cudaLibraryLoadData(&lib, c.image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) { log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); cudaGetLastError(); delete J; return RKB_ERR_CUDA; }
+  J->library = lib;
+  for (int k = 0; k < RKB_JIT_COUNT; ++k) {
+    cudaKernel_t kern = nullptr;
+    e = cudaLibraryGetKernel(&kern, lib, c.names[k].c_str());
+    if (e != cudaSuccess) { log = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e); cudaGetLastError(); cudaLibraryUnload(lib); delete J; return RKB_ERR_CUDA; }
+    J->kernel[k] = (const void*)kern;
+  }
   // dynamic shared memory per CTA, as rkb_serial_n.cu sizes it
   const int B = RKB_BLOCK * (int)sizeof(double);
   J->smem[RKB_JIT_EVAL] = (1 > 2 * n + 1 ? 1 : 2 * n + 1) * B;
@@ -131,7 +217,117 @@ int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out)
   J->smem[RKB_JIT_ROLLOUT] = J->smem[RKB_JIT_ROLLOUT_SEQ] = J->smem[RKB_JIT_STEER] = RKB_SMEM_ROLLOUT(n) * B;
   J->smem[RKB_JIT_ROLLOUT_RK] = (2 * n + 2 * n * RKB_RK_MAX_STAGES) * B;
   e = rkb_jit_prepare(*J);
-  if (e != cudaSuccess) { g_log = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaGetLastError(); delete J; return RKB_ERR_CUDA; }
+  if (e != cudaSuccess) { log = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaGetLastError(); delete J; return RKB_ERR_CUDA; }
+  *out = J;
+  return RKB_OK;
+}
+
+// background compilations: key -> state
+struct Pending {
+  int state = 0;  // 0 compiling, 1 ready, -1 failed
+  Cubin cubin;
+  std::string log;
+};
+std::map<Key, std::shared_ptr<Pending> > g_pending;
+std::vector<std::thread> g_threads;
+bool g_atexit = false;
+void join_all() {
+  std::vector<std::thread> t;
+  { std::lock_guard<std::mutex> lock(g_mu); t.swap(g_threads); }
+  for (auto& x : t) if (x.joinable()) x.join();
+}
+
+}  // namespace
+
+// Synchronous: disk cache, else NVRTC now.  `from_cache` (nullable) tells which.
+int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out) {
+  const Key key = std::make_tuple(n, fl, shape);
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
+  }
+  g_log.clear();
+  Cubin c;
+  bool cached = cache_read(key, c);
+  if (!cached) {
+    const int rc = compile_cubin(key, c, g_log);
+    if (rc) return rc;
+    cache_write(key, c);
+  }
+  JitKernels* J = nullptr;
+  int rc = load_cubin(key, c, &J, g_log);
+  if (rc && cached) {  // a stale or damaged cache file: compile afresh
+    if ((rc = compile_cubin(key, c, g_log))) return rc;
+    cache_write(key, c);
+    rc = load_cubin(key, c, &J, g_log);
+  }
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) { *out = it->second; return RKB_OK; }  // (another thread was faster; the spare library stays loaded)
+  g_cache[key] = J;
+  *out = J;
+  return RKB_OK;
+}
+
+// Asynchronous: returns RKB_OK with *out set when the kernels are available (loaded before, in the disk cache, or a
+// background compilation has finished: they are loaded into the CALLER's context), RKB_OK with *out == NULL while a
+// background compilation is running (it is started on the first call), an error when it failed.
+int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out) {
+  *out = nullptr;
+  const Key key = std::make_tuple(n, fl, shape);
+  std::shared_ptr<Pending> p;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
+    auto pit = g_pending.find(key);
+    if (pit != g_pending.end()) p = pit->second;
+  }
+  Cubin from_disk;
+  const Cubin* ready = nullptr;
+  if (!p) {
+    if (cache_read(key, from_disk)) {
+      ready = &from_disk;
+    } else {
+      std::lock_guard<std::mutex> lock(g_mu);
+      if (g_pending.find(key) == g_pending.end()) {
+        p = std::make_shared<Pending>();
+        g_pending[key] = p;
+        if (!g_atexit) { std::atexit(join_all); g_atexit = true; }
+        g_threads.emplace_back([key, p]() {
+          Cubin c;
+          std::string log;
+          const int rc = compile_cubin(key, c, log);
+          if (rc == RKB_OK) cache_write(key, c);
+          std::lock_guard<std::mutex> lock2(g_mu);
+          p->cubin.image.swap(c.image);
+          p->cubin.names.swap(c.names);
+          p->log = log;
+          p->state = rc == RKB_OK ? 1 : -1;
+        });
+      }
+      return RKB_OK;
+    }
+  } else {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (p->state == 0) return RKB_OK;
+    if (p->state < 0) { g_log = p->log; return RKB_ERR_CUDA; }
+    ready = &p->cubin;
+  }
+  JitKernels* J = nullptr;
+  const int rc = load_cubin(key, *ready, &J, g_log);
+  if (rc) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto np = std::make_shared<Pending>();
+    np->state = -1; np->log = g_log;
+    g_pending[key] = np;  // do not try again
+    return rc;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
   g_cache[key] = J;
   *out = J;
   return RKB_OK;

@@ -64,13 +64,15 @@ class kte_batch_propagator(object):
     def set_option(self, option, value):
         """rkb_chain_set_option: 'split_max_samples', 'fused_steer', 'fused_sequence', 'host_pipeline' (include/reak_b200.h)"""
         code = {"split_max_samples": _abi.OPT_SPLIT_MAX_SAMPLES, "fused_steer": _abi.OPT_FUSED_STEER,
-                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE}[option]
+                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE,
+                "auto_specialize": _abi.OPT_AUTO_SPECIALIZE}[option]
         _abi.check(self._lib.rkb_chain_set_option(self._h, code, int(value)), "rkb_chain_set_option")
         return self
 
     def get_option(self, option):
         code = {"split_max_samples": _abi.OPT_SPLIT_MAX_SAMPLES, "fused_steer": _abi.OPT_FUSED_STEER,
-                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE}[option]
+                "fused_sequence": _abi.OPT_FUSED_SEQUENCE, "host_pipeline": _abi.OPT_HOST_PIPELINE,
+                "auto_specialize": _abi.OPT_AUTO_SPECIALIZE}[option]
         return int(self._lib.rkb_chain_get_option(self._h, code))
 
     def is_serial(self):
@@ -228,6 +230,24 @@ class kte_batch_propagator(object):
         flags, stream, ptr = self._prep([x, u if self.nu else None, xo, st], soa)
         _abi.check(self._lib.rkb_rollout_rk4(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
                                              dt, int(n_steps), ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4")
+        return xo, st
+
+    def get_next_states_input_trajectory(self, x, u_nodes, dt=None, out=None, status=None):
+        """RK4 with an input trajectory (ctrl::detail::runge_kutta4_integrate_impl, runge_kutta4_integrator_sys.hpp:50-97):
+        u_nodes [N][2 n_steps + 1][nu] is the trajectory sampled at every half step.  Returns (x_out, status)."""
+        x, N = self._in(x, self.nx, np.float64)
+        u_nodes = u_nodes.contiguous() if _is_torch(u_nodes) else np.ascontiguousarray(u_nodes, dtype=np.float64)
+        if len(u_nodes.shape) != 3 or u_nodes.shape[0] != N or u_nodes.shape[2] != self.nu or u_nodes.shape[1] < 1 or u_nodes.shape[1] % 2 != 1:
+            raise IndexError("Input vector dimension mismatch!")
+        n_steps = (int(u_nodes.shape[1]) - 1) // 2
+        dt = self.dt if dt is None else float(dt)
+        if dt == 0.0:
+            raise impossible_integration("dt == 0")
+        xo = self._out(out, x, x.shape)
+        st = self._out(status, x, (N,), np.int32)
+        flags, stream, ptr = self._prep([x, u_nodes if self.nu else None, xo, st], False)
+        _abi.check(self._lib.rkb_rollout_rk4_inputs(self._h, self.device, N, ptr(x), ptr(u_nodes) if self.nu else None, dt, n_steps,
+                                                    ptr(xo), ptr(st), flags, stream), "rkb_rollout_rk4_inputs")
         return xo, st
 
     def rollout(self, x, u_seq, dt=None, steps_per_interval=1, scheme="rk4", want_traj=False, out=None, status=None):

@@ -15,6 +15,7 @@ from conftest import random_batch, rel_err
 from reak_b200 import kte, presets
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL_STEP = 1e-10
 TOL_LONG = 1e-8
@@ -26,6 +27,7 @@ def _make(name, generic=False, split=None):
     split: RKB_OPT_SPLIT_MAX_SAMPLES (0 = one thread per sample whatever the batch size)."""
     from reak_b200 import kte_batch_propagator
     p = kte_batch_propagator(presets.make(name), interpreter=generic)
+    p.set_option("auto_specialize", 0)   # (kernels that change between two calls would disturb the bit-for-bit comparisons)
     if split is not None:
         p.set_option("split_max_samples", split)
     return p
@@ -955,6 +957,46 @@ def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
 
 
+# ---- RK4 with an input trajectory (a27) ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7_phys_sd", "planar2_act", "crs6_lin_sd", "planar2"])
+def test_rk4_with_an_input_trajectory(name, oracle_built):
+    """rkb_rollout_rk4_inputs = ctrl::detail::runge_kutta4_integrate_impl (runge_kutta4_integrator_sys.hpp:50-97): the
+    input is read at t, t + dt/2 (twice) and t + dt.  Against the oracle's restatement (pinned on the CPU against the
+    reference's runge_kutta4_integrator with a rate function that reads the node of the time it is asked at), on the
+    serial kernels and the interpreter, AoS and SoA, host and device buffers; equal nodes reproduce rkb_rollout_rk4."""
+    import torch
+    for label, p in _variants(name):
+        O = oracle_built.Oracle(p.compiled)
+        n, K = 301, 9
+        x, u = random_batch(p.compiled, n, seed=121)
+        nodes = np.random.default_rng(122).uniform(-2.0, 2.0, (n, 2 * K + 1, p.nu))
+        got, st = p.get_next_states_input_trajectory(x, nodes, 1e-3)
+        want, st_o = O.rk4_inputs(x, nodes, 1e-3)
+        assert not st.any() and not st_o.any() and rel_err(got, want) < TOL_STEP, (name, label)
+        if p.nu:
+            held, _ = p.get_next_states(x, nodes[:, 0, :].copy(), 1e-3, K)
+            assert rel_err(got, held) > 1e-6                         # the trajectory matters ...
+            same, _ = p.get_next_states_input_trajectory(x, np.repeat(nodes[:, :1, :], 2 * K + 1, axis=1), 1e-3)
+            assert rel_err(same, held) < 1e-13, (name, label)        # ... and equal nodes are a held input
+        dev, _ = p.get_next_states_input_trajectory(torch.from_numpy(x).cuda(), torch.from_numpy(nodes).cuda(), 1e-3)
+        assert np.array_equal(dev.cpu().numpy(), got), (name, label)
+    # SoA through the C-ABI: [2K+1][nu][N]
+    import ctypes as C
+    from reak_b200 import _abi
+    p = _make("crs6")
+    x, _ = random_batch(p.compiled, 257, seed=123)
+    nodes = np.random.default_rng(124).uniform(-1, 1, (257, 7, 6))
+    ref, _ = p.get_next_states_input_trajectory(x, nodes, 1e-3)
+    xs, us = np.ascontiguousarray(x.T), np.ascontiguousarray(nodes.transpose(1, 2, 0))
+    out = np.empty_like(xs)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib = _abi.load_library()
+    assert lib.rkb_rollout_rk4_inputs(p._h, 0, 257, vp(xs), vp(us), 1e-3, 3, vp(out), None, _abi.LAYOUT_SOA, None) == 0
+    assert np.array_equal(out.T, ref)
+    assert lib.rkb_rollout_rk4_inputs(p._h, 0, 257, vp(xs), vp(us), 0.0, 3, vp(out), None, 0, None) == _abi.ERR_INTEGRATION
+    assert lib.rkb_rollout_rk4_inputs(p._h, 0, 257, vp(xs), None, 1e-3, 3, vp(out), None, 0, None) == _abi.ERR_INVALID
+
+
 # ---- linearisation (SURVEY 8(f) rank 3) ---------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7", "planar2_act", "crs6_lin_sd", "pendulum"])
 def test_linear_blocks_by_central_differences(name, oracle_built):
@@ -1129,6 +1171,62 @@ def test_runtime_specialised_kernels(which, oracle_built):
     # a second handle of the same structure reuses the compiled kernels
     p2 = kte_batch_propagator(s).specialize()
     assert np.array_equal(p2.get_next_states(x, u, 1e-3, 12)[0], after[5])
+
+
+def test_automatic_specialisation_and_its_disk_cache(tmp_path, oracle_built):
+    """RKB_OPT_AUTO_SPECIALIZE (default on): a serial chain whose structure the shipped kernels do not match asks for
+    its own kernels on the first call of >= 4096 samples — NVRTC on a background thread, the calls made meanwhile run
+    on the shipped kernels — and leaves the cubin in the disk cache, from which a later PROCESS is served on its
+    first call.  Small calls never trigger it; results stay within rounding of the oracle throughout."""
+    import subprocess
+    import sys
+    import time
+    script = r"""
+import os, sys, time, json
+import numpy as np
+sys.path.insert(0, %r)
+from reak_b200 import kte_batch_propagator, presets
+s = presets.crs_chain(n_revolute=7, axes=presets.ERA_AXES, link_offsets=presets.ERA_LINKS, physical=True)
+p = kte_batch_propagator(s)
+rng = np.random.default_rng(5)
+x, u = rng.uniform(-1, 1, (8192, p.nx)), rng.uniform(-1, 1, (8192, p.nu))
+small, _ = p.get_next_states(x[:100], u[:100], 1e-3, 3)
+assert not p.is_specialized()
+first, _ = p.get_next_states(x, u, 1e-3, 3)
+at_first = p.is_specialized()
+t0 = time.time()
+calls = 1
+while not p.is_specialized() and time.time() - t0 < 120:
+    time.sleep(0.2)
+    p.get_next_states(x, u, 1e-3, 3)
+    calls += 1
+last, _ = p.get_next_states(x, u, 1e-3, 3)
+off = kte_batch_propagator(s).set_option("auto_specialize", 0)
+plain, _ = off.get_next_states(x, u, 1e-3, 3)
+print(json.dumps({"at_first": bool(at_first), "specialised": bool(p.is_specialized()), "calls": calls, "wait_s": time.time() - t0,
+                  "drift": float(np.abs(first - last).max()), "vs_plain": float(np.abs(plain - last).max()),
+                  "off_specialised": bool(off.is_specialized()), "shape": p.kernel_shape()}))
+""" % ROOT
+    env = dict(os.environ, RKB_CACHE_DIR=str(tmp_path / "cache"))
+
+    def run():
+        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        import json
+        return json.loads(r.stdout.strip().splitlines()[-1])
+
+    a = run()
+    assert a["specialised"] and not a["at_first"] and a["calls"] > 1, a        # compiled in the background, several calls on the shipped kernels
+    assert a["shape"] != 0 and a["drift"] < 1e-11 and a["vs_plain"] < 1e-11 and not a["off_specialised"], a
+    files = list((tmp_path / "cache").glob("*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size > 100000
+    b = run()
+    assert b["at_first"] and b["calls"] == 1 and b["wait_s"] < 1.0, b          # served from the disk cache on the first large call
+    assert b["drift"] == 0.0
+    # a damaged cache file is recompiled, not trusted
+    files[0].write_bytes(b"RKBCUBIN 12\n" + b"x\n" * 8 + b"not a cubin!")
+    c = run()
+    assert c["specialised"] and not c["at_first"], c
 
 
 def test_specialised_kernels_on_every_device():
