@@ -100,13 +100,27 @@ class _Checker(object):
         secs = self._rk4(self.h, N, _dp(x), _dp(u), float(dt), int(n_steps), _dp(out), _dp(st), int(n_workers))
         return out, st, secs
 
+    def manip_state_rate(self, x_blocked, u=None):
+        """kte::manipulator_dynamics_model::computeStateRate (ctrl/kte_models/manip_dynamics_model.cpp:152-218) on
+        blocked states (q..., qd...): returns (xdot_blocked, status).  Reference checker only."""
+        if self._prefix != "rkref_":
+            raise NotImplementedError("the legacy model is the compiled reference's")
+        x, u, N = self._xu(x_blocked, u)
+        xd, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        fn = self.lib.rkref_manip_state_rate
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+        if fn(self.h, N, _dp(x), _dp(u), _dp(xd), _dp(st)) != 0:
+            raise RuntimeError("rkref_manip_state_rate: the legacy model could not be assembled")
+        return xd, st
+
     def rk4_inputs(self, x0, u_nodes, dt):
         """RK4 with an input trajectory sampled at every half step, u_nodes [N][2 n_steps + 1][nu]
         (ctrl::detail::runge_kutta4_integrate_impl).  Returns (x_out, status)."""
         x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
         N = x.shape[0]
-        u_nodes = np.ascontiguousarray(u_nodes, dtype=np.float64).reshape(N, -1, max(self.nu, 1) if self.nu else 0) if self.nu else np.zeros((N, 1, 0))
-        n_steps = (u_nodes.shape[1] - 1) // 2
+        n_steps = (np.shape(u_nodes)[1] - 1) // 2
+        u_nodes = np.ascontiguousarray(u_nodes, dtype=np.float64).reshape(N, 2 * n_steps + 1, self.nu) if self.nu else np.zeros((N, 1, 0))
         out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
         fn = getattr(self.lib, self._prefix + "rk4_inputs")
         fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]

@@ -37,6 +37,7 @@
 #include <ReaK/geometry/shapes/box.hpp>
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
 #include <ReaK/ctrl/graph_alg/node_generators.hpp>
+#include <ReaK/ctrl/kte_models/manip_dynamics_model.hpp>
 
 #include "../include/reak_b200.h"
 // libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
@@ -92,6 +93,9 @@ struct ref_model {
   std::vector<shared_ptr<kte::kte_map> > elems;
   shared_ptr<kte::kte_map_chain> chain;
   shared_ptr<kte::mass_matrix_calc> mcalc;
+  std::vector<shared_ptr<kte::inertia_gen> > in_gen;   // in the order they were handed to mcalc
+  std::vector<shared_ptr<kte::inertia_2D> > in_2d;
+  std::vector<shared_ptr<kte::inertia_3D> > in_3d;
   ctrl::kte_nl_system sys;
   int n, nu;
 };
@@ -185,7 +189,7 @@ ref_model* build_model(const rkb_chain_desc& d) {
           if ((E.upstream >> c) & 1u) dep->add_joint(m->coords[c], m->jac3[c]);
         shared_ptr<kte::inertia_3D> in(new kte::inertia_3D(nm, dep, E.p[0],
             mat<double,mat_structure::symmetric>(E.p[1], E.p[2], E.p[3], E.p[4], E.p[5], E.p[6])));
-        *m->mcalc << in; k = in; break; }
+        *m->mcalc << in; m->in_3d.push_back(in); k = in; break; }
       case RKB_INERTIA_GEN: {
         shared_ptr<kte::joint_dependent_gen_coord> dep(new kte::joint_dependent_gen_coord(m->coords[E.coord]));
         dep->add_joint(m->coords[E.coord], shared_ptr<jacobian_gen_gen<double> >(new jacobian_gen_gen<double>(1.0, 0.0)));
@@ -213,7 +217,7 @@ ref_model* build_model(const rkb_chain_desc& d) {
           if ((E.upstream >> c) & 1u) jm[m->coords[c]] = m->jac2[c];
         shared_ptr<kte::joint_dependent_frame_2D> dep(new kte::joint_dependent_frame_2D(m->f2[E.frame_a], jm));
         shared_ptr<kte::inertia_2D> in(new kte::inertia_2D(nm, dep, E.p[0], E.p[1]));
-        *m->mcalc << in; k = in; break; }
+        *m->mcalc << in; m->in_2d.push_back(in); k = in; break; }
       case RKB_TORSION_SPRING_2D:
         k = shared_ptr<kte::kte_map>(new kte::torsion_spring_2D(nm, m->f2[E.frame_a], m->f2[E.frame_b], E.p[0], E.p[1])); break;
       case RKB_TORSION_DAMPER_2D:
@@ -230,6 +234,7 @@ ref_model* build_model(const rkb_chain_desc& d) {
   }
   // CRS_A465_models.cpp:791-822: link inertias, then motor inertias, then the coordinates.
   for (std::size_t i = 0; i < gen_inertias.size(); ++i) *m->mcalc << gen_inertias[i];
+  m->in_gen = gen_inertias;
   for (int c = 0; c < d.n_coords; ++c) *m->mcalc << m->coords[c];
 
   m->sys.dofs_gen = m->coords;
@@ -341,6 +346,42 @@ int rkref_rk4_inputs(void* hv, std::size_t N, const double* x0, const double* u_
       for (int k = 0; k < nx; ++k) xout[i * nx + k] = x[k];
     }
     for (int k = 0; k < nx; ++k) if (!std::isfinite(xout[i * nx + k])) st |= RKB_STATUS_NONFINITE;
+    if (status) status[i] = st;
+  }
+  return 0;
+}
+
+// a29: the legacy manipulator model, kte::manipulator_dynamics_model::computeStateRate (ctrl/kte_models/
+// manip_dynamics_model.cpp:152-218; the same code as ctrl/mbd_kte/manipulator_model.cpp:292-355, whose translation unit
+// g++ 13 rejects).  Its state is BLOCKED — all positions, then all velocities — and it does not zero q_ddot itself
+// (the coordinates keep the 0 they were created with).  The model is assembled over the very objects of this handle:
+// coordinates, inertias (in mass_calc order), inputs and the chain.
+int rkref_manip_state_rate(void* hv, std::size_t N, const double* x_blocked, const double* u, double* xdot_blocked, int32_t* status) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  const int n = m->n, nx = 2 * n, nu = m->nu;
+  kte::manipulator_dynamics_model mdl("legacy");
+  mdl.setModel(m->chain);
+  for (int c = 0; c < n; ++c) mdl << m->coords[c];
+  for (std::size_t i = 0; i < m->in_3d.size(); ++i) mdl << m->in_3d[i];
+  for (std::size_t i = 0; i < m->in_2d.size(); ++i) mdl << m->in_2d[i];
+  for (std::size_t i = 0; i < m->in_gen.size(); ++i) mdl << m->in_gen[i];
+  for (std::size_t i = 0; i < m->sys.inputs.size(); ++i) mdl << m->sys.inputs[i];
+  if ((int)mdl.getJointStatesCount() != nx || (int)mdl.getInputsCount() != nu) return -1;
+  for (int c = 0; c < n; ++c) m->coords[c]->q_ddot = 0.0;
+  vect_n<double> x(nx), xd(nx), uu(nu);
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) x[k] = x_blocked[i * nx + k];
+    for (int k = 0; k < nu; ++k) uu[k] = u[i * nu + k];
+    int32_t st = 0;
+    try {
+      mdl.setInput(uu);
+      mdl.computeStateRate(0.0, x, xd);
+      for (int k = 0; k < nx; ++k) xdot_blocked[i * nx + k] = xd[k];
+    } catch (singularity_error&) {
+      st |= RKB_STATUS_SINGULAR;
+      for (int k = 0; k < nx; ++k) xdot_blocked[i * nx + k] = 0.0;
+    }
     if (status) status[i] = st;
   }
   return 0;

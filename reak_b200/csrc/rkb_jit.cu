@@ -285,31 +285,39 @@ int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out
     auto pit = g_pending.find(key);
     if (pit != g_pending.end()) p = pit->second;
   }
-  Cubin from_disk;
   const Cubin* ready = nullptr;
   if (!p) {
+    Cubin from_disk;
     if (cache_read(key, from_disk)) {
-      ready = &from_disk;
-    } else {
-      std::lock_guard<std::mutex> lock(g_mu);
-      if (g_pending.find(key) == g_pending.end()) {
-        p = std::make_shared<Pending>();
-        g_pending[key] = p;
-        if (!g_atexit) { std::atexit(join_all); g_atexit = true; }
-        g_threads.emplace_back([key, p]() {
-          Cubin c;
-          std::string log;
-          const int rc = compile_cubin(key, c, log);
-          if (rc == RKB_OK) cache_write(key, c);
-          std::lock_guard<std::mutex> lock2(g_mu);
-          p->cubin.image.swap(c.image);
-          p->cubin.names.swap(c.names);
-          p->log = log;
-          p->state = rc == RKB_OK ? 1 : -1;
-        });
+      JitKernels* Jd = nullptr;
+      if (load_cubin(key, from_disk, &Jd, g_log) == RKB_OK) {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
+        g_cache[key] = Jd;
+        *out = Jd;
+        return RKB_OK;
       }
-      return RKB_OK;
+      std::remove(cache_path(key).c_str());  // stale or damaged: not trusted, compiled afresh below
     }
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_pending.find(key) == g_pending.end()) {
+      p = std::make_shared<Pending>();
+      g_pending[key] = p;
+      if (!g_atexit) { std::atexit(join_all); g_atexit = true; }
+      g_threads.emplace_back([key, p]() {
+        Cubin c;
+        std::string log;
+        const int rc = compile_cubin(key, c, log);
+        if (rc == RKB_OK) cache_write(key, c);
+        std::lock_guard<std::mutex> lock2(g_mu);
+        p->cubin.image.swap(c.image);
+        p->cubin.names.swap(c.names);
+        p->log = log;
+        p->state = rc == RKB_OK ? 1 : -1;
+      });
+    }
+    return RKB_OK;
   } else {
     std::lock_guard<std::mutex> lock(g_mu);
     if (p->state == 0) return RKB_OK;

@@ -615,6 +615,24 @@ def test_blocked_state_layout(name):
         assert rel_err(b[0], _to_blocked(a[0])) < 1e-12 and rel_err(b[1], a[1]) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7_phys_sd", "planar2_act", "crs6_lin_sd", "crs2d"])
+def test_legacy_manipulator_model_state_rate(name, oracle_built):
+    """a29: RKB_LAYOUT_BLOCKED serves kte::manipulator_dynamics_model::computeStateRate (ctrl/kte_models/
+    manip_dynamics_model.cpp:152-218; ctrl/mbd_kte/manipulator_model.cpp:292-355 is the same code) — checked against
+    that class itself, compiled from the reference and assembled over the same chain objects."""
+    from reak_b200 import kte_batch_propagator
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built")
+    for interp in (False, True):
+        pb = kte_batch_propagator(presets.make(name), blocked=True, interpreter=interp)
+        R = oracle_built.Reference(pb.compiled)
+        x, u = random_batch(pb.compiled, 200, seed=55, q_range=2.0)
+        xb = _to_blocked(x)
+        want, st_r = R.manip_state_rate(xb, u)
+        got, st = pb.get_state_derivatives(xb, u)
+        assert not st.any() and not st_r.any() and rel_err(got, want) < TOL_STEP, (name, interp)
+
+
 def test_reak_steer_space_cpp(oracle_built):
     """ReaK::pp::kte_steer_space (reak_bridge.hpp): steer_position_toward of SteerableSpaceConcept served by the
     batched propagator, checked in C++ against the unmodified reference — every candidate control is
