@@ -39,7 +39,7 @@ RK4_STEPS = 100
 DT = 1e-3
 TOL = 1e-8             # BASELINE.json: relative error per component after the config's horizon
 CPU_SUBSET = 4096      # samples of each large batch the reference integrates
-GATHER_CHUNKS = 8
+GATHER_WAVES = 2      # the rank's block is integrated and gathered in pieces of this many full waves of the rollout kernel
 # Roofline accounting:
 #   * ALGORITHMIC FP64 flops per RK4 state-step of the formulation the kernel ships — counted by running that
 #     formulation on symbolic scalars with only the kernel's structural promises known (tools/flop_count.py, live
@@ -438,6 +438,10 @@ def run_ours(args):
     dout = torch.empty_like(dx)
     dst = torch.empty((n,), dtype=torch.int32, device=dx.device)
     sp, gathered, gathered_st = None, None, None
+    # pieces of GATHER_WAVES full waves of the rollout kernel: a launch ends with a partial wave, and pieces of e.g. 1.7
+    # waves would cost 2 each (measured: 8 equal pieces of 2^17 samples = 1.73 waves cost 1.2 ms per step more)
+    wave = prop.wave_samples()
+    chunk_samples = GATHER_WAVES * wave if wave > 0 else n // 8
     if world > 1:
         sp = sharded_propagator(prop, comm_device=dx.device)
         gathered = torch.empty((world * n, nx), dtype=torch.float64, device=dx.device)
@@ -457,7 +461,7 @@ def run_ours(args):
                 kernel_ms.append(prop.last_kernel_ms())  # CUDA events recorded around the kernel on its launch stream
         else:
             # the shipped sharded path: rollout in pieces, every piece all-gathered (NCCL) while the next one integrates
-            sp.get_next_states(dx, du, DT, RK4_STEPS, local_input=True, n_total=world * n, chunks=GATHER_CHUNKS,
+            sp.get_next_states(dx, du, DT, RK4_STEPS, local_input=True, n_total=world * n, chunk_samples=chunk_samples,
                                out=gathered, status=gathered_st)
 
     def e2e_step():
@@ -650,7 +654,7 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if rollout_only_ms is not None:
-        line["gather"] = {"included_in_value": True, "chunks": GATHER_CHUNKS, "rollout_only_ms_per_step": rollout_only_ms,
+        line["gather"] = {"included_in_value": True, "piece_samples": int(chunk_samples), "pieces": int(-(-n // chunk_samples)), "rollout_only_ms_per_step": rollout_only_ms,
                           "exposed_ms_per_step": elapsed_ms / args.steps - rollout_only_ms}
     if others is not None:
         line["other_configs"] = others

@@ -288,6 +288,9 @@ RKB_API int rkb_mass_matrix(rkb_chain* chain, int device, size_t n_samples,
  * link-local coordinates and never build these frames). */
 #define RKB_FRAME_DOUBLES 25
 RKB_API int rkb_chain_frame_count(const rkb_chain* chain);
+/* Samples one full wave of the RK4 rollout kernel holds on `device` (SMs x resident CTAs x 128; 0 for interpreter
+ * chains): cut batches that are processed piecewise at multiples of it, every launch ends with a partial wave. */
+RKB_API long long rkb_chain_wave_samples(rkb_chain* chain, int device);
 RKB_API int rkb_frames(rkb_chain* chain, int device, size_t n_samples,
                        const double* x, const double* u, double* frames, unsigned flags, void* stream);
 

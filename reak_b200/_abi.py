@@ -110,6 +110,7 @@ SYMBOLS = {
     "rkb_mass_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_uint, C.c_void_p]),
     "rkb_chain_frame_count": (C.c_int, [C.c_void_p]),
+    "rkb_chain_wave_samples": (C.c_longlong, [C.c_void_p, C.c_int]),
     "rkb_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_proxy_create": (C.c_int, [C.c_void_p, C.POINTER(rkb_shape), C.c_int, C.POINTER(rkb_shape), C.c_int, C.POINTER(C.c_void_p)]),
     "rkb_proxy_destroy": (None, [C.c_void_p]),

@@ -828,6 +828,23 @@ int rkb_mass_matrix(rkb_chain* c, int device, size_t N, const double* x, double*
 
 int rkb_chain_frame_count(const rkb_chain* c) { return c ? c->desc.n_frames : RKB_ERR_INVALID; }
 
+/* Samples in one full wave of the RK4 rollout kernel on `device`: SMs x resident CTAs per SM x 128.  A caller that cuts
+ * a batch into pieces (to overlap their transfer with the integration of the next piece) should cut at multiples of it:
+ * every launch ends with a partial wave, and pieces of, say, 1.7 waves each would cost two. */
+long long rkb_chain_wave_samples(rkb_chain* c, int device) {
+  if (!c) return RKB_ERR_INVALID;
+  if (!c->serial_ok || !c->sk) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) return RKB_ERR_CUDA;
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); return RKB_ERR_CUDA; }
+  return (long long)sms * c->sk->rollout_ctas_per_sm() * c->sk->block;
+}
+
 int rkb_frames(rkb_chain* c, int device, size_t N, const double* x, const double* u, double* frames, unsigned flags, void* stream) {
   return run_eval_like(c, OP_FRAMES, device, N, x, u, frames, nullptr, nullptr, flags, stream);
 }

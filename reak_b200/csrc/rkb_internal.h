@@ -23,6 +23,7 @@ struct SerialKernels {
   cudaError_t (*rollout_duo)(const SerialParams&, const RolloutArgs&, cudaStream_t);
   cudaError_t (*rollout_seq_duo)(const SerialParams&, const RolloutSeqArgs&, cudaStream_t);
   cudaError_t (*steer_duo)(const SerialParams&, const SteerArgs&, cudaStream_t);
+  int (*rollout_ctas_per_sm)(void);  // occupancy of the RK4 rollout kernel on the current device
 };
 
 // defined in rkb_serial_n.cu, compiled once per N with -DRKB_N=<n>

@@ -94,10 +94,17 @@ struct Launch {
     serial_steer_duo_kernel<N, FL, SHAPE><<<grid_duo(A.n_samples), RKB_DUO_BLOCK, kSmemDuo, s>>>(P, A);
     return cudaGetLastError();
   }
+  // resident CTAs per SM of the RK4 rollout kernel on the current device (for sizing chunks in whole waves)
+  static int rollout_ctas_per_sm() {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, serial_rollout_kernel<N, FL, SHAPE>, RKB_BLOCK, kSmemRollout) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+  }
   static SerialKernels entry() {
     SerialKernels k;
     k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
     k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk; k.rollout_seq = &rollout_seq; k.steer = &steer;
+    k.rollout_ctas_per_sm = &rollout_ctas_per_sm;
     k.rollout_duo = &rollout_duo; k.rollout_seq_duo = &rollout_seq_duo; k.steer_duo = &steer_duo;
     return k;
   }

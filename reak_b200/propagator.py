@@ -75,6 +75,10 @@ class kte_batch_propagator(object):
                 "auto_specialize": _abi.OPT_AUTO_SPECIALIZE}[option]
         return int(self._lib.rkb_chain_get_option(self._h, code))
 
+    def wave_samples(self):
+        """samples in one full wave of the RK4 rollout kernel on this device (rkb_chain_wave_samples); 0 = unknown"""
+        return max(0, int(self._lib.rkb_chain_wave_samples(self._h, self.device)))
+
     def is_serial(self):
         """True when the chain runs on the register-resident serial-chain kernels."""
         return bool(self._lib.rkb_chain_is_serial(self._h))

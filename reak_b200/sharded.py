@@ -59,15 +59,18 @@ class sharded_propagator(object):
         t = t.to(dtype)
         return t.to(self.comm_device) if self.comm_device is not None else t
 
-    def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None, chunks=1, out=None, status=None):
+    def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None, chunks=1, out=None, status=None,
+                        chunk_samples=None):
         """Returns (x_out[n_total][nx], status[n_total]) gathered on every rank (torch tensors on the
         communication device).  `compute(x_block, u_block, dt, n_steps) -> (x_out, status)` defaults to
         the wrapped propagator's GPU rollout.
 
         chunks > 1 (and n_total divisible by world * chunks): the rank's block is integrated in `chunks` pieces and
         the all-gather of piece c is issued asynchronously right behind its rollout, so that it travels while piece
-        c + 1 integrates — only the last piece's gather is exposed.  out / status: preallocated
-        result tensors on the communication device ([n_total][nx] float64, [n_total] int32)."""
+        c + 1 integrates — only the last piece's gather is exposed.  chunk_samples: the piece size instead of
+        the piece count (the last piece takes the remainder) — use a multiple of the propagator's wave_samples(), every
+        launch ends with a partial wave.  out / status: preallocated result tensors on the communication device
+        ([n_total][nx] float64, [n_total] int32)."""
         import torch
         compute = compute or self.prop.get_next_states
         if local_input:
@@ -78,8 +81,14 @@ class sharded_propagator(object):
             n_total = x.shape[0]
             lo, hi = shard_bounds(n_total, self.rank, self.world)
             xb, ub = x[lo:hi], (u[lo:hi] if u is not None else None)
-        if chunks > 1 and n_total > 0 and n_total % (self.world * chunks) == 0:
-            return self._get_next_states_chunked(xb, ub, dt, n_steps, n_total, compute, chunks, out, status)
+        if n_total > 0 and n_total % self.world == 0:
+            n_loc = n_total // self.world
+            if chunk_samples and 0 < chunk_samples < n_loc:
+                bounds = list(range(0, n_loc, int(chunk_samples))) + [n_loc]
+                return self._get_next_states_chunked(xb, ub, dt, n_steps, n_total, compute, bounds, out, status)
+            if chunks > 1 and n_loc % chunks == 0:
+                bounds = [c * (n_loc // chunks) for c in range(chunks + 1)]
+                return self._get_next_states_chunked(xb, ub, dt, n_steps, n_total, compute, bounds, out, status)
         xo, st = compute(xb, ub, dt, n_steps)
         xo_t, st_t = self._to_comm(xo, torch.float64), self._to_comm(st, torch.int32)
         full, full_st = _all_gather_rows(xo_t, n_total, self.group), _all_gather_rows(st_t, n_total, self.group)
@@ -89,21 +98,21 @@ class sharded_propagator(object):
             status.copy_(full_st); full_st = status
         return full, full_st
 
-    def _get_next_states_chunked(self, xb, ub, dt, n_steps, n_total, compute, chunks, out, status):
+    def _get_next_states_chunked(self, xb, ub, dt, n_steps, n_total, compute, bounds, out, status):
+        """bounds: piece c covers rows bounds[c] .. bounds[c + 1] of every rank's block (all ranks cut alike)"""
         import torch
         dist = _dist()
         n_loc = n_total // self.world
-        m = n_loc // chunks
-        assert xb.shape[0] == n_loc
+        assert xb.shape[0] == n_loc and bounds[0] == 0 and bounds[-1] == n_loc
         full, st_loc, works = out, [], []
-        for c in range(chunks):
-            xo, st = compute(xb[c * m:(c + 1) * m], ub[c * m:(c + 1) * m] if ub is not None else None, dt, n_steps)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            xo, st = compute(xb[lo:hi], ub[lo:hi] if ub is not None else None, dt, n_steps)
             xo_t = self._to_comm(xo, torch.float64).contiguous()
             st_loc.append(self._to_comm(st, torch.int32))
             if full is None:
                 full = torch.empty((n_total,) + tuple(xo_t.shape[1:]), dtype=torch.float64, device=xo_t.device)
-            # rank r's piece c lands where the block partition puts it: rows r n_loc + c m ...
-            dst = [full[r * n_loc + c * m: r * n_loc + (c + 1) * m] for r in range(self.world)]
+            # rank r's piece lands where the block partition puts it: rows r n_loc + lo ...
+            dst = [full[r * n_loc + lo: r * n_loc + hi] for r in range(self.world)]
             works.append(dist.all_gather(dst, xo_t, group=self.group, async_op=True))
         st_t = torch.cat(st_loc, dim=0).contiguous()
         full_st = status if status is not None else torch.empty((n_total,), dtype=torch.int32, device=st_t.device)

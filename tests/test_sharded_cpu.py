@@ -60,6 +60,8 @@ def _worker(rank, world, port, n_total, out_dir):
     ch, st3 = sp.get_next_states(x, u, 1e-3, 5, compute=compute, chunks=4, out=pre, status=pre_st)
     assert ch is pre and st3 is pre_st
     assert np.array_equal(full.numpy(), ch.numpy()) and np.array_equal(st.numpy(), st3.numpy())
+    ch2, st4 = sp.get_next_states(x, u, 1e-3, 5, compute=compute, chunk_samples=5)   # pieces of 5, the last one shorter
+    assert np.array_equal(full.numpy(), ch2.numpy()) and np.array_equal(st.numpy(), st4.numpy())
 
     # steer: pairs are sharded, rollouts of a pair stay together
     P, R = 5, 7
