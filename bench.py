@@ -10,8 +10,10 @@ metric = state-steps/s (samples x RK4 steps per second), whole job over all rank
 
 N > 1 runs under torchrun (one rank per GPU, NCCL): the batch is sharded by sample index, every
 rank integrates its own 2^20 states (weak scaling), no data-path collective while integrating; the
-all-gather of the end states the north star names IS inside the timed step (reak_b200.sharded: the rank's
-block goes in pieces, piece c travels while piece c + 1 integrates).
+all-gather of the end states the north star names IS inside the timed step (reak_b200.sharded): by default the
+rollout kernel itself stores every end state into all ranks' copies of the batch over NVLink peer memory (no collective
+kernel at all, only a barrier); --gather nccl (and the fallback where peer mapping is unavailable) integrates the rank's
+block in pieces of whole waves and all-gathers piece c with NCCL while piece c + 1 integrates.
 
 Every BASELINE config is in the line: config 2 is the headline, configs 1, 3, 4, 5 are `other_configs`
 at BASELINE's full sizes (sharded over the ranks: strong scaling for those), and at N = 1 each of them is
@@ -453,6 +455,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     kernel_ms = []
+    gathered_now = [None, None]  # the tensors the last step's gathered batch lives in
 
     def device_step(record=False):
         if world == 1:
@@ -461,8 +464,11 @@ def run_ours(args):
                 kernel_ms.append(prop.last_kernel_ms())  # CUDA events recorded around the kernel on its launch stream
         else:
             # the shipped sharded path: rollout in pieces, every piece all-gathered (NCCL) while the next one integrates
-            sp.get_next_states(dx, du, DT, RK4_STEPS, local_input=True, n_total=world * n, chunk_samples=chunk_samples,
-                               out=gathered, status=gathered_st)
+            # (or, where the GPUs can map each other's memory, the rollout kernel stores its end states into every rank's
+            # copy of the batch itself and no collective runs at all: --gather p2p, the default)
+            res = sp.get_next_states(dx, du, DT, RK4_STEPS, local_input=True, n_total=world * n, chunk_samples=chunk_samples,
+                                     out=gathered, status=gathered_st, peer_stores=(args.gather == "p2p"))
+            gathered_now[0], gathered_now[1] = res
 
     def e2e_step():
         prop.get_next_states(px.numpy(), pu.numpy(), DT, RK4_STEPS, out=po.numpy(), status=ps.numpy())
@@ -493,7 +499,8 @@ def run_ours(args):
     elapsed_ms = float(t.item())
     rollout_only_ms = None
     if world > 1:
-        assert int(gathered_st.max().item()) == 0, "status word set in the timed region"
+        assert int(gathered_now[1].max().item()) == 0, "status word set in the timed region"
+        gather_mode = "p2p_stores" if gathered_now[0].data_ptr() != gathered.data_ptr() else "nccl_pieces"
         # the same steps without the gather, for the record (what round 1 reported as `value`)
         prop.get_next_states(dx, du, DT, RK4_STEPS, out=dout, status=dst)
         barrier()
@@ -507,7 +514,13 @@ def run_ours(args):
         t = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dx.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rollout_only_ms = float(t.item()) / args.steps
-        assert torch.equal(gathered[rank * n:(rank + 1) * n], dout), "gathered block differs from the local result"
+        assert torch.equal(gathered_now[0][rank * n:(rank + 1) * n], dout), "gathered block differs from the local result"
+        # ... and every rank holds every block: compare a checksum of the whole gathered batch across ranks
+        chk = torch.stack([gathered_now[0].sum(), gathered_now[0][::97].abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "the ranks' gathered batches differ"
     assert int(dst.max().item()) == 0, "status word set in the timed region"
 
     # ---- end-to-end leg: pinned host buffers through the public API -------------------------
@@ -654,7 +667,8 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if rollout_only_ms is not None:
-        line["gather"] = {"included_in_value": True, "piece_samples": int(chunk_samples), "pieces": int(-(-n // chunk_samples)), "rollout_only_ms_per_step": rollout_only_ms,
+        line["gather"] = {"included_in_value": True, "mode": gather_mode, "piece_samples": int(chunk_samples) if gather_mode == "nccl_pieces" else None,
+                          "peer_error": getattr(sp, "_peer_error", None), "rollout_only_ms_per_step": rollout_only_ms,
                           "exposed_ms_per_step": elapsed_ms / args.steps - rollout_only_ms}
     if others is not None:
         line["other_configs"] = others
@@ -686,6 +700,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = the rollout kernel stores into every rank's buffer over NVLink (falls back to nccl); nccl = pipelined NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()

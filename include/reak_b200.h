@@ -258,6 +258,17 @@ RKB_API int rkb_rollout_rk4_inputs(rkb_chain* chain, int device, size_t n_sample
                                    const double* x0, const double* u_nodes, double dt, int n_steps,
                                    double* x_out, int32_t* status, unsigned flags, void* stream);
 
+/* One rank's share of a sample-sharded rollout WITH its all-gather (one process per GPU): the rank
+ * integrates its n_samples states and the kernel stores every end state to row `row_offset + i` of EACH of the n_dest
+ * (<= 8) destination buffers — its own copy of the gathered batch and the other ranks' copies, mapped into this process
+ * as peer memory (CUDA IPC handles, or torch.distributed's symmetric memory).  The stores travel over NVLink while the
+ * other CTAs integrate; nothing is left to gather afterwards — the ranks only need a barrier before they read.
+ * x_out_dest[d]: [n_total][2n] AoS; status_dest (nullable, entries nullable): [n_total].  RKB_MEM_DEVICE | RKB_LAYOUT_AOS
+ * (| RKB_LAYOUT_BLOCKED) only; serial chains only (RKB_ERR_UNSUPPORTED otherwise).  Returns without synchronising. */
+RKB_API int rkb_rollout_rk4_scatter(rkb_chain* chain, int device, size_t n_samples, const double* x0, const double* u,
+                                    double dt, int n_steps, int n_dest, double* const* x_out_dest, int32_t* const* status_dest,
+                                    size_t row_offset, unsigned flags, void* stream);
+
 /* rkb_rollout_rk4 on HOST buffers (AoS), sharded over `n_devices` GPUs of this box from one
  * process: contiguous blocks of samples, one copy/compute pipeline per device, no inter-GPU
  * communication (the reference has no counterpart; per sample the semantics are unchanged). */
@@ -360,6 +371,16 @@ RKB_API int rkb_twist_shaping_rows(const rkb_chain* chain);
 RKB_API int rkb_twist_shaping_mcm(const rkb_chain* chain, double* Mcm);
 RKB_API int rkb_twist_shaping(rkb_chain* chain, int device, size_t n_samples,
                               const double* x, double* Tcm, double* Tcm_dot, unsigned flags, void* stream);
+
+/* Direct-kinematics Jacobian of ONE frame — an end effector — and its time derivative at state x[i]: what
+ * manip_kin_mdl_jac_calculator::getJacobianMatrixAndDerivative (ctrl/mbd_kte/manipulator_model_helper.hpp:342-...) stacks
+ * for the dependent frames of a manipulator, i.e. jacobian_gen_3D / _2D::get_jac_relative_to(frame) of every upstream
+ * joint (core/kinetostatics/motion_jacobians.hpp:238-279, 139-147).  `frame`: frame id of the descriptor; `upstream`: bit
+ * c set <=> coordinate c moves the frame (the joint_dependent_frame's mUpStreamJoints); other columns are zero.
+ * J, Jdot (nullable): 3D chains [N][6][n] — rows v (3) then w (3), in the frame's own coordinates — 2D chains [N][3][n];
+ * SOA [rows * n][N].  Interpreter kernels. */
+RKB_API int rkb_frame_jacobian(rkb_chain* chain, int device, size_t n_samples, const double* x, int frame, uint64_t upstream,
+                               double* J, double* Jdot, unsigned flags, void* stream);
 
 /* Linearisation of the dynamics about (x[i], u[i]) — what a linear-quadratic steering asks its system for
  * (get_linear_blocks in examples/misc/IHAQR_topology.hpp:240-258, MEAQR_topology.hpp): A[i] = d xdot / d x

@@ -103,6 +103,8 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(rkb_rollout_opts),
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_rollout_rk4_scatter": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_uint, C.c_void_p]),
     "rkb_rollout_rk4_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "rkb_gen_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -123,6 +125,7 @@ SYMBOLS = {
     "rkb_twist_shaping_rows": (C.c_int, [C.c_void_p]),
     "rkb_twist_shaping_mcm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rkb_twist_shaping": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_frame_jacobian": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_linearize": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_uint, C.c_void_p]),
     "rkb_steer_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,

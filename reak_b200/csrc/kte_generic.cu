@@ -604,6 +604,58 @@ GD void tmt(const GenericProgram* G, const Work<2, MAXF>& W, const BatchView& T,
   }
 }
 
+// Jacobian of ONE frame with respect to the coordinates (and its time derivative): the rows a 3D / 2D inertia on that
+// frame would have in Tcm — jacobian_gen_3D / _2D::get_jac_relative_to(frame) written by write_to_matrices — which is
+// what manip_kin_mdl_jac_calculator::getJacobianMatrixAndDerivative stacks for the dependent (end-effector) frames of
+// a manipulator (ctrl/mbd_kte/manipulator_model_helper.hpp:342-...).  Rows: v (3 / 2), then w (3 / 1), expressed in
+// the frame's own coordinates like every twist in ReaK.
+template <int MAXF>
+GD void frame_jac(const GenericProgram* G, const Work<3, MAXF>& W, int frame, unsigned upstream, const BatchView& T, const BatchView& Td, long long i) {
+  const int n = G->n_coords;
+  const bool want_dot = Td.p != (double*)0;
+  const Fr3& F = W.fr[frame];
+  const M3 RF = qrot(F.q);
+  for (int c = 0; c < n; ++c) {
+    double col[6] = {0, 0, 0, 0, 0, 0}, cold[6] = {0, 0, 0, 0, 0, 0};
+    if ((upstream >> c) & 1u) jac_col(G, W, c, F, RF, col, cold, want_dot);
+    for (int r = 0; r < 6; ++r) {
+      const long long k = (long long)r * n + c;
+      T.p[i * T.si + k * T.sk] = col[r];
+      if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
+    }
+  }
+}
+template <int MAXF>
+GD void frame_jac(const GenericProgram* G, const Work<2, MAXF>& W, int frame, unsigned upstream, const BatchView& T, const BatchView& Td, long long i) {
+  const int n = G->n_coords;
+  const bool want_dot = Td.p != (double*)0;
+  const Fr2& F = W.fr[frame];
+  for (int c = 0; c < n; ++c) {
+    double col[3] = {0, 0, 0}, cold[3] = {0, 0, 0};
+    if ((upstream >> c) & 1u) {
+      const GenericElement& J = G->el[G->jelem[c]];
+      const Fr2& Ej = W.fr[J.fb];
+      const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
+      const double wrel = F.w - Ej.w;
+      V2 Tv, Tvd;
+      if (J.kind == RKB_REVOLUTE_2D) {
+        Tv = rtmul(F.R, crs(1.0, dp));
+        col[2] = 1.0;
+        Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
+      } else {
+        Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
+        Tvd = v2(0, 0) - crs(wrel, Tv);
+      }
+      col[0] = Tv.x; col[1] = Tv.y; cold[0] = Tvd.x; cold[1] = Tvd.y;
+    }
+    for (int r = 0; r < 3; ++r) {
+      const long long k = (long long)r * n + c;
+      T.p[i * T.si + k * T.sk] = col[r];
+      if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
+    }
+  }
+}
+
 // linsolve_Cholesky (mat_cholesky.hpp:63-84, 160-179) on a row-major n x n matrix, in place
 GD int cholesky_solve(int n, double* A, double* b) {
   int st = 0;
@@ -792,6 +844,16 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericPro
 }
 
 template <int DIM, int MAXF>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_frame_jac_kernel(const GenericProgram* __restrict__ G, const EvalArgs A, int frame, unsigned upstream) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Work<DIM, MAXF> W;
+  load(G, W, A.x, A.u, i, i, false);
+  motion(G, W);
+  frame_jac(G, W, frame, upstream, A.out, A.out2, i);
+}
+
+template <int DIM, int MAXF>
 GD void store_state(const GenericProgram* G, const Work<DIM, MAXF>& W, const BatchView& o, long long off) {
   for (int c = 0; c < G->n_coords; ++c) {
     o.p[off + rkb_state_q(o.blocked, G->n_coords, c) * o.sk] = W.q[c];
@@ -973,6 +1035,12 @@ cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& ho
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
   DISPATCH(generic_tmt_kernel, host, prog, a);
+  return cudaGetLastError();
+}
+cudaError_t rkb_generic_frame_jac(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, int frame, unsigned upstream, cudaStream_t s) {
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  DISPATCH(generic_frame_jac_kernel, host, prog, a, frame, upstream);
   return cudaGetLastError();
 }
 cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,

@@ -1236,6 +1236,46 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
   if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }
 
+// The sample-sharded job's rollout AND its all-gather in one kernel: every CTA parks its tile of end states in shared
+// memory (the RK4 columns are free by then) and streams it, as coalesced 128-bit stores, to its place in EVERY
+// destination buffer — this GPU's copy of the gathered batch and, through NVLink peer mappings, the other GPUs'.  The
+// 96 bytes per sample and peer are nothing against the ~20 us of arithmetic behind them, so the transfer hides under
+// the integration of the other CTAs and no collective runs afterwards (only a barrier before anyone reads).
+template <int N, int FL, shape_t SHAPE>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT_K(N))) serial_rollout_scatter_kernel(const __grid_constant__ SerialParams P, const __grid_constant__ RolloutScatterArgs A) {
+  extern __shared__ double smem[];
+  constexpr int SMS = RKB_BLOCK;
+  const long long tile_first = (long long)blockIdx.x * RKB_BLOCK;
+  const long long i = tile_first + threadIdx.x;
+  const bool active = i < A.n_samples;
+  SerialState<N> X;
+  int st = 0;
+  if (active) {
+    load_state<N>(P, A.x0, A.u, i, X);
+    st = rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.n_steps, smem + threadIdx.x);
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) finite = finite && isfinite(X.q[k]) && isfinite(X.qd[k]);
+    if (!finite) st |= RKB_STATUS_NONFINITE;
+  }
+  __syncthreads();  // every thread is done with its RK4 columns
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int c = P.st[k].coord;
+      smem[threadIdx.x * (2 * N + 1) + rkb_state_q(A.blocked, N, c)] = X.q[k];
+      smem[threadIdx.x * (2 * N + 1) + rkb_state_qd(A.blocked, N, c)] = X.qd[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int d = 0; d < A.n_dest; ++d) {
+    const BatchView o = {A.xout[d] + A.row_offset * (2 * N), 2 * N, 1, A.blocked};
+    tile_write_back<2 * N>(smem, o, tile_first, A.n_samples);
+    if (active && A.status[d]) A.status[d][A.row_offset + i] = st;
+  }
+}
+
 // A piecewise-constant control sequence in one launch: interval j integrates n_steps RK4 steps with the
 // j-th input of the sample (num_int_dtnl_sys::get_next_state once per interval) and leaves its end state in
 // slot j of the trajectory.  Kept apart from serial_rollout_kernel: the interval loop around the RK4 loop

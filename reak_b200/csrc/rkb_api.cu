@@ -1073,6 +1073,49 @@ int rkb_twist_shaping_mcm(const rkb_chain* c, double* Mcm) {
   return RKB_OK;
 }
 
+/* Jacobian of one frame with respect to the coordinates and its time derivative (see kte_generic.cu: frame_jac) */
+int rkb_frame_jacobian(rkb_chain* c, int device, size_t N, const double* x, int frame, uint64_t upstream, double* J, double* Jdot,
+                       unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  if (frame < 0 || frame >= c->desc.n_frames || (c->n < 64 && (upstream >> c->n))) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  if (!x || !J) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  const int nx = 2 * c->n, rows = c->desc.dim == 3 ? 6 : 3, dim = rows * c->n;
+  if (dim == 0) return RKB_OK;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* dx = nullptr;
+  void *dJ = nullptr, *dJd = nullptr;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if ((rc = stage_out(ctx->out_a, J, N * dim * sizeof(double), L.device, &dJ))) return rc;
+  if ((rc = stage_out(ctx->out_b, Jdot, N * dim * sizeof(double), L.device, &dJd))) return rc;
+  EvalArgs A;
+  A.x = cview((const double*)dx, (long long)N, nx, L.soa, L.blocked);
+  A.u = cview((const double*)dx, (long long)N, 1, L.soa);
+  A.out = view((double*)dJ, (long long)N, dim, L.soa);
+  A.out2 = view((double*)dJd, (long long)N, dim, L.soa);
+  A.status = nullptr;
+  A.n_samples = (long long)N;
+  CU(cudaEventRecord(ctx->ev0, s));
+  const cudaError_t e = rkb_generic_frame_jac(ctx->d_prog, c->gp, A, frame, (unsigned)upstream, s);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  c->launches += 1;
+  if ((rc = unstage_out(dJ, J, N * dim * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(dJd, Jdot, N * dim * sizeof(double), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
 int rkb_twist_shaping(rkb_chain* c, int device, size_t N, const double* x, double* Tcm, double* Tcm_dot, unsigned flags, void* stream) {
   return run_eval_like(c, OP_TMT, device, N, x, nullptr, Tcm, Tcm_dot, nullptr, flags, stream);
 }
@@ -1371,6 +1414,46 @@ int rkb_rollout_rk4_inputs(rkb_chain* c, int device, size_t N, const double* x0,
   if ((rc = unstage_out(dout, x_out, N * nx * sizeof(double), L.device, s))) return rc;
   if ((rc = unstage_out(dst, status, N * sizeof(int32_t), L.device, s))) return rc;
   if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
+/* Rollout of this rank's block of a sample-sharded batch with the all-gather folded into the kernel: the end states go
+ * straight to their rows in n_dest copies of the gathered batch — the caller's own and the peers', mapped into this
+ * process (CUDA IPC / symmetric memory) — as coalesced stores over NVLink.  Device buffers, AoS, serial chains. */
+int rkb_rollout_rk4_scatter(rkb_chain* c, int device, size_t N, const double* x0, const double* u, double dt, int n_steps,
+                            int n_dest, double* const* x_out_dest, int32_t* const* status_dest, size_t row_offset,
+                            unsigned flags, void* stream) {
+  if (!c) return RKB_ERR_INVALID;
+  if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
+  if (n_dest < 1 || n_dest > RKB_MAX_DEST || !x_out_dest) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  if (!L.device || L.soa) return RKB_ERR_UNSUPPORTED;
+  if (!c->serial_ok || !c->sk) return RKB_ERR_UNSUPPORTED;
+  if (N == 0) return RKB_OK;
+  if (!x0 || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
+  for (int d = 0; d < n_dest; ++d) if (!x_out_dest[d]) return RKB_ERR_INVALID;
+  const int nx = 2 * c->n, nu = c->nu;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  RolloutScatterArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.x0 = cview(x0, (long long)N, nx, false, L.blocked);
+  A.u = cview(nu > 0 ? u : x0, (long long)N, nu > 0 ? nu : 1, false);
+  for (int d = 0; d < n_dest; ++d) { A.xout[d] = x_out_dest[d]; A.status[d] = status_dest ? status_dest[d] : nullptr; }
+  A.n_samples = (long long)N; A.row_offset = (long long)row_offset; A.dt = dt; A.n_steps = n_steps; A.n_dest = n_dest;
+  A.blocked = L.blocked ? 1 : 0;
+  CU(cudaEventRecord(ctx->ev0, s));
+  const cudaError_t e = c->sk->rollout_scatter(c->sp, A, s);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  c->launches += 1;
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
   return RKB_OK;
 }
 

@@ -23,6 +23,7 @@ struct SerialKernels {
   cudaError_t (*rollout_duo)(const SerialParams&, const RolloutArgs&, cudaStream_t);
   cudaError_t (*rollout_seq_duo)(const SerialParams&, const RolloutSeqArgs&, cudaStream_t);
   cudaError_t (*steer_duo)(const SerialParams&, const SteerArgs&, cudaStream_t);
+  cudaError_t (*rollout_scatter)(const SerialParams&, const RolloutScatterArgs&, cudaStream_t);  // rollout + all-gather by peer stores
   int (*rollout_ctas_per_sm)(void);  // occupancy of the RK4 rollout kernel on the current device
 };
 
@@ -37,6 +38,7 @@ cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram&
 cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp, cudaStream_t s);
+cudaError_t rkb_generic_frame_jac(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, int frame, unsigned upstream, cudaStream_t s);
 cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,
                                 cudaStream_t s);  // table == NULL: the reference's RK4 arithmetic

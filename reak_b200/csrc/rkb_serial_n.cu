@@ -16,6 +16,7 @@ struct Launch {
   static constexpr int kSmemForces = RKB_SMEM_FORCES_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemMass = RKB_SMEM_MASS_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemRollout = RKB_SMEM_ROLLOUT(N) * RKB_BLOCK * (int)sizeof(double);
+  static constexpr int kSmemScatter = RKB_SMEM_ROLLOUT_K(N) * RKB_BLOCK * (int)sizeof(double);
   static constexpr int kSmemDuo = RKB_SMEM_DUO(N) * (int)sizeof(double);
   static unsigned grid_duo(long long n) { return (unsigned)((n + 63) / 64); }
   static constexpr int smem_rk(int stages) { return (2 * N + 2 * N * stages) * RKB_BLOCK * (int)sizeof(double); }
@@ -28,6 +29,8 @@ struct Launch {
     e = cudaFuncSetAttribute(serial_rollout_seq_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_steer_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRollout);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(serial_rollout_scatter_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemScatter);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(serial_rollout_duo_kernel<N, FL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDuo);
     if (e != cudaSuccess) return e;
@@ -79,6 +82,11 @@ struct Launch {
     serial_steer_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemRollout, s>>>(P, A);
     return cudaGetLastError();
   }
+  static cudaError_t rollout_scatter(const SerialParams& P, const RolloutScatterArgs& A, cudaStream_t s) {
+    if (A.n_samples <= 0) return cudaSuccess;
+    serial_rollout_scatter_kernel<N, FL, SHAPE><<<grid(A.n_samples), RKB_BLOCK, kSmemScatter, s>>>(P, A);
+    return cudaGetLastError();
+  }
   static cudaError_t rollout_duo(const SerialParams& P, const RolloutArgs& A, cudaStream_t s) {
     if (A.n_samples <= 0) return cudaSuccess;
     serial_rollout_duo_kernel<N, FL, SHAPE><<<grid_duo(A.n_samples), RKB_DUO_BLOCK, kSmemDuo, s>>>(P, A);
@@ -104,7 +112,7 @@ struct Launch {
     SerialKernels k;
     k.n = N; k.fl = FL; k.shape = SHAPE; k.smem_eval = kSmemEval; k.smem_rollout = kSmemRollout; k.block = RKB_BLOCK;
     k.prepare = &prepare; k.eval = &eval; k.forces = &forces; k.mass = &mass; k.rollout = &rollout; k.rollout_rk = &rollout_rk; k.rollout_seq = &rollout_seq; k.steer = &steer;
-    k.rollout_ctas_per_sm = &rollout_ctas_per_sm;
+    k.rollout_ctas_per_sm = &rollout_ctas_per_sm; k.rollout_scatter = &rollout_scatter;
     k.rollout_duo = &rollout_duo; k.rollout_seq_duo = &rollout_seq_duo; k.steer_duo = &steer_duo;
     return k;
   }

@@ -120,6 +120,18 @@ struct RolloutArgs {
   long long      u_node_stride;  // interpreter kernels, RK4: != 0: the input at every half step, node j at u.p[.. + j * u_node_stride]
 };
 
+// Rollout whose results go to several destination buffers at once (this GPU's own and, over NVLink, the peers'
+// copies of the gathered batch): the all-gather of a sample-sharded job done by the stores of the kernel itself.
+#define RKB_MAX_DEST 8
+struct RolloutScatterArgs {
+  ConstBatchView x0, u;
+  double*   xout[RKB_MAX_DEST];    // AoS [n_total][2n] each; sample i of this launch is row row_offset + i
+  int32_t*  status[RKB_MAX_DEST];  // [n_total] each (entries may be null)
+  long long n_samples, row_offset;
+  double    dt;
+  int32_t   n_steps, n_dest, blocked, pad;
+};
+
 // A control sequence in one launch (serial kernels, RK4): n_intervals intervals of n_steps steps
 struct RolloutSeqArgs {
   ConstBatchView x0, u;    // input k of interval j of sample i: u.p[i * u.si + j * u_sj + k * u.sk]

@@ -376,6 +376,27 @@ class kte_batch_propagator(object):
         _abi.check(self._lib.rkb_twist_shaping(self._h, self.device, N, ptr(x), ptr(T), ptr(Td), flags, stream), "rkb_twist_shaping")
         return (T, Mc, Td) if with_derivative else (T, Mc)
 
+    def get_frame_jacobian(self, x, frame, upstream=None, with_derivative=True):
+        """Jacobian of one frame (a kte frame object of the chain, or its frame id) w.r.t. the coordinates and its time
+        derivative: J, Jdot [N][6][n] (3D: v then w, in the frame's own coordinates) or [N][3][n] (2D) — rkb_frame_jacobian,
+        manip_kin_mdl_jac_calculator::getJacobianMatrixAndDerivative.  upstream: iterable of coordinate indices (or
+        gen_coord objects) that move the frame; default: every coordinate."""
+        x, N = self._in(x, self.nx, np.float64)
+        fid = frame if isinstance(frame, int) else [id(f) for f in self.compiled.frames].index(id(frame))
+        if upstream is None:
+            mask = (1 << self.n) - 1
+        else:
+            ids = [id(c) for c in self.compiled.coords]
+            mask = 0
+            for c in upstream:
+                mask |= 1 << (c if isinstance(c, int) else ids.index(id(c)))
+        rows = 6 if self.compiled.desc.dim == 3 else 3
+        J = self._like(x, (N, rows, self.n))
+        Jd = self._like(x, (N, rows, self.n)) if with_derivative else None
+        flags, stream, ptr = self._prep([x, J, Jd], False)
+        _abi.check(self._lib.rkb_frame_jacobian(self._h, self.device, N, ptr(x), fid, mask, ptr(J), ptr(Jd), flags, stream), "rkb_frame_jacobian")
+        return (J, Jd) if with_derivative else J
+
     def get_linear_blocks(self, x, u=None, eps=1e-6):
         """A = d xdot / d x [N][nx][nx] and B = d xdot / d u [N][nx][nu] about every (x, u) by central differences
         (rkb_linearize; get_linear_blocks of the LQR steering topologies, examples/misc/IHAQR_topology.hpp:240-258).

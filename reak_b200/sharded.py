@@ -50,6 +50,67 @@ class sharded_propagator(object):
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.comm_device = comm_device  # torch device the collective runs from (cuda:k for NCCL, cpu for gloo)
 
+    # ---- all-gather by the rollout kernel's own stores (peer memory over NVLink) -----------------------------------
+    def _peer_buffers(self, n_total, nx, device):
+        """Symmetric result buffers [n_total][nx] float64 + [n_total] int32 on every rank, each rank's mapped into all the
+        others (torch.distributed's symmetric memory: CUDA virtual-memory handles exchanged at rendezvous).  Allocated
+        once per shape.  Returns None where peer mapping is not available (then the NCCL path is used)."""
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        key = (int(n_total), int(nx), str(device))
+        if key in cache:
+            return cache[key]
+        entry = None
+        try:
+            import torch
+            import torch.distributed._symmetric_memory as symm_mem
+            dist = _dist()
+            group = self.group if self.group is not None else dist.group.WORLD
+            x = symm_mem.empty((n_total, nx), dtype=torch.float64, device=device)
+            st = symm_mem.empty((n_total,), dtype=torch.int32, device=device)
+            hx, hs = symm_mem.rendezvous(x, group), symm_mem.rendezvous(st, group)
+            entry = {"x": x, "st": st, "hx": hx, "hs": hs, "px": [int(p) for p in hx.buffer_ptrs], "ps": [int(p) for p in hs.buffer_ptrs]}
+        except Exception as e:  # no peer access / no symmetric-memory support in this build or on this box
+            self.__dict__["_peer_error"] = "%s: %s" % (type(e).__name__, e)
+            entry = None
+        # every rank must take the same path: agree on the outcome
+        try:
+            import torch
+            dist = _dist()
+            ok = torch.tensor([1 if entry is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                entry = None
+        except Exception:
+            entry = None
+        cache[key] = entry
+        return entry
+
+    def get_next_states_peer_stores(self, xb, ub, dt, n_steps, n_total):
+        """This rank's block integrated by rkb_rollout_rk4_scatter: the kernel stores every end state into ALL ranks'
+        copies of the gathered batch (its own and, over NVLink, the peers'), so that no collective follows — only a
+        barrier.  xb, ub: this rank's block, CUDA tensors.  Returns (x_out[n_total][nx], status[n_total]) — the rank's
+        symmetric buffers, valid until the next call of the same shape — or None where peer mapping is unavailable."""
+        import ctypes as C
+        import torch
+        from . import _abi
+        prop = self.prop
+        if n_total % self.world or xb.shape[0] != n_total // self.world or not prop.is_serial():
+            return None
+        buf = self._peer_buffers(n_total, prop.nx, xb.device)
+        if buf is None:
+            return None
+        n_loc = n_total // self.world
+        px = (C.c_void_p * self.world)(*buf["px"])
+        ps = (C.c_void_p * self.world)(*buf["ps"])
+        flags = _abi.MEM_DEVICE | _abi.LAYOUT_AOS | (_abi.LAYOUT_BLOCKED if prop.blocked else 0)
+        stream = C.c_void_p(torch.cuda.current_stream(xb.device).cuda_stream)
+        buf["hx"].barrier(channel=0)   # nobody is still reading the previous call's results
+        _abi.check(prop._lib.rkb_rollout_rk4_scatter(prop._h, prop.device, n_loc, C.c_void_p(xb.data_ptr()),
+                                                     C.c_void_p(ub.data_ptr()) if prop.nu else None, float(dt), int(n_steps), self.world,
+                                                     px, ps, self.rank * n_loc, flags, stream), "rkb_rollout_rk4_scatter")
+        buf["hx"].barrier(channel=1)   # every rank's stores have landed in every copy
+        return buf["x"], buf["st"]
+
     def _to_comm(self, a, dtype):
         import torch
         if type(a).__module__.startswith("torch"):
@@ -60,7 +121,7 @@ class sharded_propagator(object):
         return t.to(self.comm_device) if self.comm_device is not None else t
 
     def get_next_states(self, x, u, dt, n_steps, local_input=False, n_total=None, compute=None, chunks=1, out=None, status=None,
-                        chunk_samples=None):
+                        chunk_samples=None, peer_stores=False):
         """Returns (x_out[n_total][nx], status[n_total]) gathered on every rank (torch tensors on the
         communication device).  `compute(x_block, u_block, dt, n_steps) -> (x_out, status)` defaults to
         the wrapped propagator's GPU rollout.
@@ -70,7 +131,12 @@ class sharded_propagator(object):
         c + 1 integrates — only the last piece's gather is exposed.  chunk_samples: the piece size instead of
         the piece count (the last piece takes the remainder) — use a multiple of the propagator's wave_samples(), every
         launch ends with a partial wave.  out / status: preallocated result tensors on the communication device
-        ([n_total][nx] float64, [n_total] int32)."""
+        ([n_total][nx] float64, [n_total] int32).
+
+        peer_stores=True (CUDA tensors, serial chain, equal blocks): no collective at all — the rollout kernel itself
+        stores every end state into all ranks' result buffers over NVLink (get_next_states_peer_stores); the returned
+        tensors are then the rank's symmetric buffers (out / status are not used).  Falls back to the NCCL paths where
+        peer mapping is unavailable."""
         import torch
         compute = compute or self.prop.get_next_states
         if local_input:
@@ -81,6 +147,10 @@ class sharded_propagator(object):
             n_total = x.shape[0]
             lo, hi = shard_bounds(n_total, self.rank, self.world)
             xb, ub = x[lo:hi], (u[lo:hi] if u is not None else None)
+        if peer_stores and n_total > 0 and compute == self.prop.get_next_states and type(xb).__module__.startswith("torch") and xb.is_cuda:
+            res = self.get_next_states_peer_stores(xb.contiguous(), ub.contiguous() if ub is not None else None, dt, n_steps, n_total)
+            if res is not None:
+                return res
         if n_total > 0 and n_total % self.world == 0:
             n_loc = n_total // self.world
             if chunk_samples and 0 < chunk_samples < n_loc:

@@ -46,6 +46,11 @@ def _worker(rank, world, port, n_total, out_dir):
     pre_st = torch.full((n_total,), -1, dtype=torch.int32, device=dev)
     ch, st2 = sp.get_next_states(xd[lo:hi].contiguous(), ud[lo:hi].contiguous(), 1e-3, 20, local_input=True, n_total=n_total,
                                  chunks=4, out=pre, status=pre_st)
+    # no collective at all: the rollout kernel stores into every rank's symmetric buffer over NVLink
+    ps = sp.get_next_states(xd[lo:hi].contiguous(), ud[lo:hi].contiguous(), 1e-3, 20, local_input=True, n_total=n_total, peer_stores=True)
+    peer_used = getattr(sp, "_peer_error", None) is None and ps[0].data_ptr() != pre.data_ptr() and (n_total % world == 0)
+    ps2 = sp.get_next_states(xd[lo:hi].contiguous(), ud[lo:hi].contiguous(), 1e-3, 20, local_input=True, n_total=n_total, peer_stores=True)
+    ps_x, ps_st = ps2[0].clone(), ps2[1].clone()
     # host (numpy) inputs through the staged path of the library
     hfull, hst = sp.get_next_states(x, u, 1e-3, 20)
     # steer batch: pairs sharded
@@ -60,7 +65,8 @@ def _worker(rank, world, port, n_total, out_dir):
         one = dict(one=o.cpu().numpy(), one_st=s1.cpu().numpy(), one_idx=i1, one_bx=b1, one_bc=c1)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), full=full.cpu().numpy(), st=st.cpu().numpy(), ch=ch.cpu().numpy(),
              st2=st2.cpu().numpy(), hfull=hfull.cpu().numpy(), idx=idx.cpu().numpy(), bx=bx.cpu().numpy(), bc=bc.cpu().numpy(),
-             is_pre=np.array(ch.data_ptr() == pre.data_ptr()), **(one or {}))
+             is_pre=np.array(ch.data_ptr() == pre.data_ptr()), ps=ps_x.cpu().numpy(), ps_st=ps_st.cpu().numpy(),
+             peer_used=np.array(bool(peer_used)), peer_error=np.array(str(getattr(sp, "_peer_error", None))), **(one or {}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,5 +86,7 @@ def test_two_rank_nccl_sharded_propagator(n_total, tmp_path):
         assert np.array_equal(g["full"], want) and np.array_equal(g["st"], want_st)
         assert np.array_equal(g["ch"], want) and np.array_equal(g["st2"], want_st) and bool(g["is_pre"])
         assert np.array_equal(g["hfull"], want)
+        assert np.array_equal(g["ps"], want) and np.array_equal(g["ps_st"], want_st)     # whichever path served it
+        assert bool(g["peer_used"]), "peer-store gather fell back to NCCL: %s" % g["peer_error"]
         assert np.array_equal(g["idx"], got[0]["one_idx"]) and np.array_equal(g["bx"], got[0]["one_bx"])
         assert np.array_equal(g["bc"], got[0]["one_bc"])
