@@ -587,8 +587,7 @@ def run_ours(args):
                 o["state_steps_per_s"] = world * o.pop("units_per_gpu") / (ms * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(torch, dist, sp, world)
         return 0
 
     state_steps_per_step = float(world) * n * RK4_STEPS
@@ -673,9 +672,22 @@ def run_ours(args):
     if others is not None:
         line["other_configs"] = others
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(torch, dist, sp, world)
     return 0
+
+
+def shutdown(torch, dist, sp, world):
+    """Orderly exit of a multi-rank run: the symmetric (peer-mapped) buffers are released while every rank is still
+    there, then the process group goes."""
+    if world <= 1:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    if sp is not None:
+        sp.release_peer_buffers()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 _JSON_OUT = None

@@ -85,6 +85,14 @@ class sharded_propagator(object):
         cache[key] = entry
         return entry
 
+    def release_peer_buffers(self):
+        """Drop the symmetric buffers (collectively: call it on every rank, before the process group is destroyed)."""
+        cache = self.__dict__.get("_peer_cache", {})
+        for entry in list(cache.values()):
+            if entry is not None:
+                entry.clear()
+        cache.clear()
+
     def get_next_states_peer_stores(self, xb, ub, dt, n_steps, n_total):
         """This rank's block integrated by rkb_rollout_rk4_scatter: the kernel stores every end state into ALL ranks'
         copies of the gathered batch (its own and, over NVLink, the peers'), so that no collective follows — only a

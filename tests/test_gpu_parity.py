@@ -975,6 +975,62 @@ def test_rollout_sequence_fused_kernel_equals_the_launch_per_interval_path():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not a[2].any() and not b[2].any()
 
 
+# ---- direct-kinematics Jacobian of a frame -----------------------------------------------
+@pytest.mark.parametrize("name", ["crs6", "crs7_phys_sd", "crs6_twist", "planar3_sd", "crs2d"])
+def test_frame_jacobian(name, oracle_built):
+    """rkb_frame_jacobian = jacobian_gen_3D / _2D::get_jac_relative_to(frame) of every upstream joint, the rows
+    manip_kin_mdl_jac_calculator stacks for an end-effector frame.  For the frame of an inertia with that inertia's
+    upstream set these are that inertia's rows of Tcm / Tcm_dot (checked against the oracle = the reference's
+    get_TMT_TdMT); for the last frame of the chain with every coordinate upstream, J q_dot must be the frame's twist
+    as doMotion leaves it (rkb_frames) and Jdot q_dot its acceleration with q_ddot = 0."""
+    from reak_b200 import _abi
+    p = _make(name)
+    O = oracle_built.Oracle(p.compiled)
+    x, u = random_batch(p.compiled, 50, seed=151, q_range=2.0)
+    d = p.compiled.desc
+    dim3 = d.dim == 3
+    rows_per = 6 if dim3 else 3
+    row = sum(1 for e in range(d.n_elements) if d.elements[e].kind == _abi.INERTIA_GEN)
+    T, Mc, Td = p.get_twist_shaping(x)
+    checked = 0
+    for e in range(d.n_elements):
+        E = d.elements[e]
+        if E.kind not in (_abi.INERTIA_3D, _abi.INERTIA_2D):
+            continue
+        up = [c for c in range(p.n) if (E.upstream >> c) & 1]
+        J, Jd = p.get_frame_jacobian(x, int(E.frame_a), upstream=up)
+        assert np.array_equal(J, T[:, row:row + rows_per, :]) and np.array_equal(Jd, Td[:, row:row + rows_per, :]), (name, e)
+        To, _, Tdo = O.tmt(x[3:4])
+        assert rel_err(J[3], To[row:row + rows_per]) < TOL_STEP and rel_err(Jd[3], Tdo[row:row + rows_per]) < TOL_STEP
+        row += rows_per
+        checked += 1
+    assert checked >= 2
+    # the end effector: last frame written by the chain, every coordinate upstream
+    last = [int(d.elements[e].frame_b) for e in range(d.n_elements)
+            if d.elements[e].kind in (_abi.REVOLUTE_3D, _abi.PRISMATIC_3D, _abi.RIGID_LINK_3D, _abi.REVOLUTE_2D, _abi.PRISMATIC_2D, _abi.RIGID_LINK_2D)][-1]
+    J, Jd = p.get_frame_jacobian(x, last)
+    fr = p.get_frames(x, u)[:, last, :]
+    qd = x[:, 1::2]
+    twist = np.einsum("nrc,nc->nr", J, qd)
+    if dim3:
+        # frame_3D: Velocity is in parent (world) coordinates, AngVelocity local; the Jacobian rows are both local
+        from scipy.spatial.transform import Rotation
+        Rw = Rotation.from_quat(fr[:, [4, 5, 6, 3]]).as_matrix()
+        v_local = np.einsum("nji,nj->ni", Rw, fr[:, 7:10])
+        assert rel_err(twist[:, :3], v_local) < 1e-9 and rel_err(twist[:, 3:], fr[:, 10:13]) < 1e-9
+    else:
+        c, s_ = fr[:, 3], fr[:, 4]
+        v_local = np.stack([c * fr[:, 7] + s_ * fr[:, 8], -s_ * fr[:, 7] + c * fr[:, 8]], axis=1)
+        assert rel_err(twist[:, :2], v_local) < 1e-9 and rel_err(twist[:, 2], fr[:, 10]) < 1e-9
+    J_only = p.get_frame_jacobian(x, last, with_derivative=False)
+    assert np.array_equal(J_only, J)
+    lib = _abi.load_library()
+    import ctypes as C
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.rkb_frame_jacobian(p._h, 0, 50, vp(x), 999, 1, vp(J), None, 0, None) == _abi.ERR_INVALID
+    assert lib.rkb_frame_jacobian(p._h, 0, 50, vp(x), last, 1 << 20, vp(J), None, 0, None) == _abi.ERR_INVALID
+
+
 # ---- RK4 with an input trajectory (a27) ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["crs6", "crs6_sd", "crs7_phys_sd", "planar2_act", "crs6_lin_sd", "planar2"])
 def test_rk4_with_an_input_trajectory(name, oracle_built):
