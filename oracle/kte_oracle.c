@@ -234,6 +234,13 @@ static frame2 f2_compose(const frame2* A, const frame2* B) {
 typedef struct { int parent; v3 qd_vel, qd_avel, qd_acc, qd_aacc; } jac3;
 typedef struct { int parent; v2 qd_vel; double qd_avel; v2 qd_acc; double qd_aacc; } jac2;
 
+/* jacobian_3D_3D as filled by free_joint_3D::doMotion (motion_jacobians.hpp:1035-1076): eight triples of vectors */
+typedef struct { int parent; v3 vel_vel[3], vel_avel[3], avel_vel[3], avel_avel[3], vel_acc[3], vel_aacc[3], avel_acc[3], avel_aacc[3]; } jac33;
+
+#define KTO_MAX_FREE 1
+#define KTO_MAX_ACC (RKB_MAX_COORDS + 6 * KTO_MAX_FREE)
+#define KTO_MAX_STATE (2 * RKB_MAX_COORDS + 13 * KTO_MAX_FREE)
+
 typedef struct {
   rkb_chain_desc d;
   rkb_element* el;
@@ -244,6 +251,10 @@ typedef struct {
   jac2* j2;
   double* u; /* inputs[k]->mDriveForce */
   int n, nu, m_rows;
+  /* free_joint_3D coordinate frames (kte_nl_system::dofs_3D): 13 states and 6 accelerations each */
+  int nfree, nx, na;
+  frame3 fc[KTO_MAX_FREE];
+  jac33 jf[KTO_MAX_FREE];
 } model;
 
 static void model_free(model* m) {
@@ -290,6 +301,11 @@ void* kto_create(const rkb_chain_desc* desc) {
         bad = E->coord < 0 || E->coord >= m->n; /* fallthrough to frame checks */
         bad |= E->frame_a < 0 || E->frame_a >= desc->n_frames || E->frame_b < 0 || E->frame_b >= desc->n_frames;
         break;
+      case RKB_FREE_3D:
+        bad = desc->dim != 3 || E->coord != m->nfree || m->nfree >= KTO_MAX_FREE;
+        bad |= E->frame_a < 0 || E->frame_a >= desc->n_frames || E->frame_b < 0 || E->frame_b >= desc->n_frames;
+        if (!bad) m->nfree += 1;
+        break;
       case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D:
       case RKB_TORSION_SPRING_3D: case RKB_TORSION_DAMPER_3D: case RKB_SPRING_3D: case RKB_DAMPER_3D:
       case RKB_TORSION_SPRING_2D: case RKB_TORSION_DAMPER_2D: case RKB_SPRING_2D: case RKB_DAMPER_2D:
@@ -331,6 +347,9 @@ void* kto_create(const rkb_chain_desc* desc) {
     }
   }
   m->m_rows = count_rows(m);
+  m->nx = 2 * m->n + 13 * m->nfree; /* kte_nl_system.hpp:145-147 */
+  m->na = m->n + 6 * m->nfree;
+  for (e = 0; e < KTO_MAX_FREE; ++e) m->fc[e].Q = Q4(1, 0, 0, 0);
   return m;
 }
 
@@ -343,6 +362,16 @@ static void apply_states_and_inputs(model* m, const double* p, const double* u) 
     m->c[j].q = p[2 * j];
     m->c[j].qd = p[2 * j + 1];
     m->c[j].qdd = 0.0;
+  }
+  for (j = 0; j < m->nfree; ++j) { /* :205-219: the quaternion is normalised by quaternion(vect<4>) */
+    const double* s = p + 2 * m->n + 13 * j;
+    frame3* F = &m->fc[j];
+    F->p = V3(s[0], s[1], s[2]);
+    F->Q = quat_unit(s[3], s[4], s[5], s[6]);
+    F->v = V3(s[7], s[8], s[9]);
+    F->w = V3(s[10], s[11], s[12]);
+    F->a = V3(0, 0, 0);
+    F->al = V3(0, 0, 0);
   }
   for (j = 0; j < m->nu; ++j) m->u[j] = u ? u[j] : 0.0;
 }
@@ -390,6 +419,17 @@ static void do_motion(model* m) {
         m->j3[E->coord].qd_avel = V3(0, 0, 0);
         m->j3[E->coord].qd_acc = V3(0, 0, 0);
         m->j3[E->coord].qd_aacc = V3(0, 0, 0);
+        break;
+      }
+      case RKB_FREE_3D: { /* free_joints.cpp:123-146: *mEnd = (*mBase) * (*mCoord); the Jacobian is two identity blocks */
+        frame3 r = f3_compose(m->f3[E->frame_a], &m->fc[E->coord]);
+        frame3* N = &m->f3[E->frame_b];
+        jac33* J = &m->jf[E->coord];
+        int k;
+        N->p = r.p; N->Q = r.Q; N->v = r.v; N->w = r.w; N->a = r.a; N->al = r.al; /* frame_3D.hpp:296-308 */
+        memset(J, 0, sizeof *J);
+        J->parent = E->frame_b;
+        for (k = 0; k < 3; ++k) { J->vel_vel[k].x[k] = 1.0; J->avel_avel[k].x[k] = 1.0; }
         break;
       }
       case RKB_RIGID_LINK_3D: { /* rigid_link.cpp:152-156: *mEnd = *mBase * mPoseOffset */
@@ -459,6 +499,7 @@ static void clear_force(model* m) {
     m->f2[i].F = V2(0, 0); m->f2[i].T = 0.0;
   }
   for (i = 0; i < m->n; ++i) m->c[i].f = 0.0;
+  for (i = 0; i < m->nfree; ++i) { m->fc[i].F = V3(0, 0, 0); m->fc[i].T = V3(0, 0, 0); } /* free_joints.cpp:184-197 */
 }
 
 /* kte_map_chain::doForce, kte_map_chain.hpp:78-83 (REVERSE order) */
@@ -487,6 +528,13 @@ static void do_force(model* m) {
         c->f += tf;
         B->F = add3(B->F, sub3(N->F, scl3(tf, axis)));
         B->T = add3(B->T, add3(N->T, cross3(scl3(c->q, axis), N->F)));
+        break;
+      }
+      case RKB_FREE_3D: { /* free_joints.cpp:164-172: the wrench at the end frame lands on the coordinate frame */
+        frame3* C = &m->fc[E->coord];
+        const frame3* N = &m->f3[E->frame_b];
+        C->F = add3(C->F, N->F);
+        C->T = add3(C->T, N->T);
         break;
       }
       case RKB_RIGID_LINK_3D: { /* rigid_link.cpp:170-177 */
@@ -701,11 +749,38 @@ static void jac2_rel(const model* m, const jac2* J, int frame, double* col, doub
   coldot[0] = acc.x[0]; coldot[1] = acc.x[1]; coldot[2] = J->qd_aacc;
 }
 
+/* jacobian_3D_3D::get_jac_relative_to + write_to_matrices, motion_jacobians.hpp:1077-1203: a 6 x 6 block, column k
+ * (k < 3) from vel_*[k], column 3 + k from avel_*[k]; rows v (3) then w (3).  blk / blkdot: row-major 6 x 6. */
+static void jac33_rel(const model* m, const jac33* J, int frame, double* blk, double* blkdot) {
+  frame3 inv = f3_inverse(&m->f3[J->parent]);
+  frame3 f2 = f3_compose(inv, &m->f3[frame]);
+  rot3 R = quat_rotmat(f2.Q);
+  int k, r;
+  for (k = 0; k < 3; ++k) {
+    v3 n_vel_avel = vmulr(J->vel_avel[k], R);
+    v3 n_vel_aacc = sub3(vmulr(J->vel_aacc[k], R), cross3(f2.w, n_vel_avel));
+    v3 n_avel_avel = vmulr(J->avel_avel[k], R);
+    v3 n_avel_aacc = sub3(vmulr(J->avel_aacc[k], R), cross3(f2.w, n_avel_avel));
+    v3 n_vel_vel = vmulr(add3(cross3(J->vel_avel[k], f2.p), J->vel_vel[k]), R);
+    v3 n_vel_acc = sub3(vmulr(add3(add3(cross3(J->vel_avel[k], f2.v), cross3(J->vel_aacc[k], f2.p)), J->vel_acc[k]), R),
+                        cross3(f2.w, n_vel_vel));
+    v3 n_avel_vel = vmulr(add3(cross3(J->avel_avel[k], f2.p), J->avel_vel[k]), R);
+    v3 n_avel_acc = sub3(vmulr(add3(add3(cross3(J->avel_avel[k], f2.v), cross3(J->avel_aacc[k], f2.p)), J->avel_acc[k]), R),
+                         cross3(f2.w, n_avel_vel));
+    for (r = 0; r < 3; ++r) {
+      blk[r * 6 + k] = n_vel_vel.x[r];        blk[(3 + r) * 6 + k] = n_vel_avel.x[r];
+      blk[r * 6 + 3 + k] = n_avel_vel.x[r];   blk[(3 + r) * 6 + 3 + k] = n_avel_avel.x[r];
+      blkdot[r * 6 + k] = n_vel_acc.x[r];     blkdot[(3 + r) * 6 + k] = n_vel_aacc.x[r];
+      blkdot[r * 6 + 3 + k] = n_avel_acc.x[r]; blkdot[(3 + r) * 6 + 3 + k] = n_avel_aacc.x[r];
+    }
+  }
+}
+
 /* mass_matrix_calc::get_TMT_TdMT, ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287.
  * Rows: gen inertias, then 2D inertias (vx, vy, w), then 3D inertias (v3, w3), each group in
  * registration (= chain) order; columns: the coordinates.  T, Td are rows x n, Mc rows x rows. */
 static void get_tmt(const model* m, double* T, double* Mc, double* Td) {
-  const int n = m->n, rows = m->m_rows;
+  const int nc = m->n, n = m->na, rows = m->m_rows; /* columns: the coordinates, then 6 per free-joint frame (:232-276) */
   int e, i, row = 0, pass;
   memset(T, 0, sizeof(double) * (size_t)rows * (size_t)n);
   memset(Td, 0, sizeof(double) * (size_t)rows * (size_t)n);
@@ -714,12 +789,12 @@ static void get_tmt(const model* m, double* T, double* Mc, double* Td) {
     for (e = 0; e < m->d.n_elements; ++e) {
       const rkb_element* E = &m->el[e];
       if (pass == 0 && E->kind == RKB_INERTIA_GEN) {
-        for (i = 0; i < n; ++i)
+        for (i = 0; i < nc; ++i)
           if ((E->upstream >> i) & 1u) { T[row * n + i] = 1.0; Td[row * n + i] = 0.0; } /* jacobian_gen_gen(1,0), motion_jacobians.hpp:49-107 */
         Mc[row * rows + row] = E->p[0];
         row += 1;
       } else if (pass == 1 && E->kind == RKB_INERTIA_2D) {
-        for (i = 0; i < n; ++i)
+        for (i = 0; i < nc; ++i)
           if ((E->upstream >> i) & 1u) {
             double c[3], cd[3];
             int k;
@@ -732,12 +807,20 @@ static void get_tmt(const model* m, double* T, double* Mc, double* Td) {
         row += 3;
       } else if (pass == 2 && E->kind == RKB_INERTIA_3D) {
         const double* I = &E->p[1];
-        for (i = 0; i < n; ++i)
+        for (i = 0; i < nc; ++i)
           if ((E->upstream >> i) & 1u) {
             double c[6], cd[6];
             int k;
             jac3_rel(m, &m->j3[i], E->frame_a, c, cd);
             for (k = 0; k < 6; ++k) { T[(row + k) * n + i] = c[k]; Td[(row + k) * n + i] = cd[k]; }
+          }
+        for (i = 0; i < m->nfree; ++i)
+          if ((E->upstream >> (32 + i)) & 1u) { /* mUpStream3DJoints, :264-274 */
+            double b[36], bd[36];
+            int k, l;
+            jac33_rel(m, &m->jf[i], E->frame_a, b, bd);
+            for (k = 0; k < 6; ++k)
+              for (l = 0; l < 6; ++l) { T[(row + k) * n + nc + 6 * i + l] = b[k * 6 + l]; Td[(row + k) * n + nc + 6 * i + l] = bd[k * 6 + l]; }
           }
         Mc[row * rows + row] = E->p[0];
         Mc[(row + 1) * rows + row + 1] = E->p[0];
@@ -759,7 +842,7 @@ static void get_tmt(const model* m, double* T, double* Mc, double* Td) {
  * mat<symmetric> converting constructor (core/lin_alg/mat_alg_symmetric.hpp:171-200);
  * Mdot = Td^T (Mc T) + its transpose. */
 static void mass_matrix(const model* m, double* M, double* Mdot) {
-  const int n = m->n, rows = m->m_rows;
+  const int n = m->na, rows = m->m_rows;
   double* T = (double*)malloc(sizeof(double) * (size_t)(rows * n + 1));
   double* Td = (double*)malloc(sizeof(double) * (size_t)(rows * n + 1));
   double* Mc = (double*)malloc(sizeof(double) * (size_t)(rows * rows + 1));
@@ -799,7 +882,7 @@ static void mass_matrix(const model* m, double* M, double* Mdot) {
 /* decompose_Cholesky_impl + backsub_Cholesky_impl, core/lin_alg/mat_cholesky.hpp:63-84, 160-179.
  * Returns 1 where the reference throws singularity_error (pivot < tol, tested BEFORE the sqrt). */
 static int cholesky_solve(int n, const double* A, double* b, int nrhs, double tol) {
-  double L[RKB_MAX_COORDS * RKB_MAX_COORDS];
+  double L[KTO_MAX_ACC * KTO_MAX_ACC];
   int i, j, k, c;
   memset(L, 0, sizeof L);
   for (i = 0; i < n; ++i) {
@@ -858,25 +941,40 @@ int kto_ldl_solve(int n, const double* Ain, double* b, int nrhs, double tol) {
   return 0;
 }
 
-/* kte_nl_system::get_state_derivative, ctrl/ctrl_sys/kte_nl_system.hpp:238-346 (gen coords only) */
+/* kte_nl_system::get_state_derivative, ctrl/ctrl_sys/kte_nl_system.hpp:238-346 (gen coords and 3D free frames) */
 static int state_derivative(model* m, const double* x, const double* u, double* xd) {
-  double M[RKB_MAX_COORDS * RKB_MAX_COORDS], f[RKB_MAX_COORDS];
-  int i, st;
+  double M[KTO_MAX_ACC * KTO_MAX_ACC], f[KTO_MAX_ACC];
+  int i, k, st;
   apply_states_and_inputs(m, x, u);
   do_motion(m);
   clear_force(m);
   do_force(m);
   for (i = 0; i < m->n; ++i) f[i] = m->c[i].f;
+  for (i = 0; i < m->nfree; ++i)                                                     /* :262-270 */
+    for (k = 0; k < 3; ++k) { f[m->n + 6 * i + k] = m->fc[i].F.x[k]; f[m->n + 6 * i + 3 + k] = m->fc[i].T.x[k]; }
   mass_matrix(m, M, NULL);
-  st = cholesky_solve(m->n, M, f, 1, 1E-8);
+  st = cholesky_solve(m->na, M, f, 1, 1E-8);
   if (st) return RKB_STATUS_SINGULAR;
   for (i = 0; i < m->n; ++i) { xd[2 * i] = m->c[i].qd; xd[2 * i + 1] = f[i]; }
+  for (i = 0; i < m->nfree; ++i) {                                                   /* :293-308 */
+    double* o = xd + 2 * m->n + 13 * i;
+    const frame3* F = &m->fc[i];
+    const double* q = F->Q.q;
+    const double* W = F->w.x;
+    for (k = 0; k < 3; ++k) o[k] = F->v.x[k];
+    /* quaternion::getQuaternionDot, rotations_3D.hpp:1206-1211 */
+    o[3] = -0.5 * (q[1] * W[0] + q[2] * W[1] + q[3] * W[2]);
+    o[4] = 0.5 * (q[0] * W[0] - q[3] * W[1] + q[2] * W[2]);
+    o[5] = 0.5 * (q[0] * W[1] + q[3] * W[0] - q[1] * W[2]);
+    o[6] = 0.5 * (q[0] * W[2] - q[2] * W[0] + q[1] * W[1]);
+    for (k = 0; k < 6; ++k) o[7 + k] = f[m->n + 6 * i + k];
+  }
   return 0;
 }
 
 int kto_eval(void* h, size_t N, const double* x, const double* u, double* xdot, int32_t* status) {
   model* m = (model*)h;
-  const int nx = 2 * m->n;
+  const int nx = m->nx;
   size_t i;
   int k;
   for (i = 0; i < N; ++i) {
@@ -889,13 +987,15 @@ int kto_eval(void* h, size_t N, const double* x, const double* u, double* xdot, 
 
 int kto_gen_forces(void* h, size_t N, const double* x, const double* u, double* f) {
   model* m = (model*)h;
-  const int nx = 2 * m->n;
+  const int nx = m->nx;
   size_t i;
   int k;
   for (i = 0; i < N; ++i) {
     apply_states_and_inputs(m, x + i * nx, u ? u + i * m->nu : NULL);
     do_motion(m); clear_force(m); do_force(m);
-    for (k = 0; k < m->n; ++k) f[i * m->n + k] = m->c[k].f;
+    for (k = 0; k < m->n; ++k) f[i * m->na + k] = m->c[k].f;
+    for (k = 0; k < 6 * m->nfree; ++k)  /* Force, Torque of the free joints' coordinate frames (kte_nl_system.hpp:262-270) */
+      f[i * m->na + m->n + k] = (k % 6 < 3) ? m->fc[k / 6].F.x[k % 6] : m->fc[k / 6].T.x[k % 6 - 3];
   }
   return 0;
 }
@@ -914,7 +1014,7 @@ int kto_gen_forces_qdd(void* h, const double* x, const double* u, const double* 
 
 int kto_mass(void* h, size_t N, const double* x, double* M, double* Mdot) {
   model* m = (model*)h;
-  const int nx = 2 * m->n, nn = m->n * m->n;
+  const int nx = m->nx, nn = m->na * m->na;
   size_t i;
   for (i = 0; i < N; ++i) {
     apply_states_and_inputs(m, x + i * nx, NULL);
@@ -964,9 +1064,9 @@ int kto_frames(void* h, const double* x, const double* u, double* out) {
  * for the status word only. */
 static void rk4_range(model* m, size_t i0, size_t i1, const double* x0, const double* u, double dt, int n_steps,
                       double* xout, int32_t* status) {
-  const int nx = 2 * m->n;
-  double x[2 * RKB_MAX_COORDS], w[2 * RKB_MAX_COORDS], f[2 * RKB_MAX_COORDS];
-  double k1[2 * RKB_MAX_COORDS], k2[2 * RKB_MAX_COORDS], k3[2 * RKB_MAX_COORDS];
+  const int nx = m->nx;
+  double x[KTO_MAX_STATE], w[KTO_MAX_STATE], f[KTO_MAX_STATE];
+  double k1[KTO_MAX_STATE], k2[KTO_MAX_STATE], k3[KTO_MAX_STATE];
   size_t i;
   int s, k;
   for (i = i0; i < i1; ++i) {
@@ -1005,10 +1105,10 @@ static void rk4_range(model* m, size_t i0, size_t i1, const double* x0, const do
  * fixed_step_integrators.hpp:289 in the order of the additions. */
 void kto_rk4_inputs(void* h, size_t N, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status) {
   model* m = (model*)h;
-  const int nx = 2 * m->n;
+  const int nx = m->nx;
   const size_t J = 2 * (size_t)n_steps + 1;
-  double x[2 * RKB_MAX_COORDS], w[2 * RKB_MAX_COORDS], f[2 * RKB_MAX_COORDS];
-  double k1[2 * RKB_MAX_COORDS], k2[2 * RKB_MAX_COORDS], k3[2 * RKB_MAX_COORDS];
+  double x[KTO_MAX_STATE], w[KTO_MAX_STATE], f[KTO_MAX_STATE];
+  double k1[KTO_MAX_STATE], k2[KTO_MAX_STATE], k3[KTO_MAX_STATE];
   size_t i;
   int s, k;
   for (i = 0; i < N; ++i) {
@@ -1047,9 +1147,9 @@ void kto_rk4_inputs(void* h, size_t N, const double* x0, const double* u_nodes, 
  * explicit step count, input held constant, the trailing rate evaluation kept for the status only. */
 static void scheme_range(model* m, int scheme, size_t i0, size_t i1, const double* x0, const double* u, double dt, int n_steps,
                          double* xout, int32_t* status) {
-  const int nx = 2 * m->n;
-  double x[2 * RKB_MAX_COORDS], w[2 * RKB_MAX_COORDS], f[2 * RKB_MAX_COORDS];
-  double k1[2 * RKB_MAX_COORDS], k2[2 * RKB_MAX_COORDS], k3[2 * RKB_MAX_COORDS], k4[2 * RKB_MAX_COORDS], k5[2 * RKB_MAX_COORDS];
+  const int nx = m->nx;
+  double x[KTO_MAX_STATE], w[KTO_MAX_STATE], f[KTO_MAX_STATE];
+  double k1[KTO_MAX_STATE], k2[KTO_MAX_STATE], k3[KTO_MAX_STATE], k4[KTO_MAX_STATE], k5[KTO_MAX_STATE];
   size_t i;
   int s, k;
   if (scheme == RKB_SCHEME_RK4) { rk4_range(m, i0, i1, x0, u, dt, n_steps, xout, status); return; }
@@ -1118,11 +1218,11 @@ int kto_steer_feedback(void* h, size_t N, const double* x0, const double* goal, 
                        const double* lo, const double* hi, const double* dlo, const double* dhi,
                        double* x_out, int32_t* n_done, double* traj, int32_t* status) {
   model* m = (model*)h;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   size_t i;
   if (nu > STEER_MAX_INPUTS) return -1;
   for (i = 0; i < N; ++i) {
-    double x[2 * RKB_MAX_COORDS], xn[2 * RKB_MAX_COORDS], u[STEER_MAX_INPUTS], up[STEER_MAX_INPUTS];
+    double x[KTO_MAX_STATE], xn[KTO_MAX_STATE], u[STEER_MAX_INPUTS], up[STEER_MAX_INPUTS];
     int k = 0, j, st = 0;
     for (j = 0; j < nx; ++j) x[j] = x0[i * nx + j];
     for (j = 0; j < nu; ++j) up[j] = u_prev[i * nu + j];
@@ -1156,7 +1256,7 @@ double kto_rk4(void* h, size_t N, const double* x0, const double* u, double dt, 
 double kto_integrate(void* h, size_t N, const double* x0, const double* u, int scheme, double dt, int n_steps,
                      double* xout, int32_t* status, int n_workers) {
   model* m = (model*)h;
-  const int nx = 2 * m->n;
+  const int nx = m->nx;
   struct timespec t0, t1;
   if (n_workers < 1) n_workers = 1;
   if ((size_t)n_workers > N && N > 0) n_workers = (int)N;

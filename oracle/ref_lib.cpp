@@ -20,6 +20,7 @@
 #include <ReaK/ctrl/mbd_kte/kte_map_chain.hpp>
 #include <ReaK/ctrl/mbd_kte/revolute_joint.hpp>
 #include <ReaK/ctrl/mbd_kte/prismatic_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/free_joints.hpp>
 #include <ReaK/ctrl/mbd_kte/rigid_link.hpp>
 #include <ReaK/ctrl/mbd_kte/inertia.hpp>
 #include <ReaK/ctrl/mbd_kte/spring.hpp>
@@ -98,6 +99,10 @@ struct ref_model {
   std::vector<shared_ptr<kte::inertia_3D> > in_3d;
   ctrl::kte_nl_system sys;
   int n, nu;
+  // free_joint_3D coordinate frames (kte_nl_system::dofs_3D) and their Jacobian holders
+  std::vector<shared_ptr<frame_3D<double> > > fcoord;
+  std::vector<shared_ptr<jacobian_3D_3D<double> > > jac33;
+  int nx, na;  // state / acceleration dimensions: 2 n + 13 n_free, n + 6 n_free
 };
 
 struct ref_handle {
@@ -120,6 +125,14 @@ ref_model* build_model(const rkb_chain_desc& d) {
     if (is3) m->jac3.push_back(shared_ptr<jacobian_gen_3D<double> >(new jacobian_gen_3D<double>()));
     else     m->jac2.push_back(shared_ptr<jacobian_gen_2D<double> >(new jacobian_gen_2D<double>()));
   }
+  for (int e = 0; e < d.n_elements; ++e)
+    if (d.elements[e].kind == RKB_FREE_3D) {
+      if (!is3 || d.elements[e].coord != (int)m->fcoord.size()) { delete m; return NULL; }
+      m->fcoord.push_back(shared_ptr<frame_3D<double> >(new frame_3D<double>()));
+      m->jac33.push_back(shared_ptr<jacobian_3D_3D<double> >(new jacobian_3D_3D<double>()));
+    }
+  m->nx = 2 * m->n + 13 * (int)m->fcoord.size();
+  m->na = m->n + 6 * (int)m->fcoord.size();
   const rkb_base_frame& b = d.base;
   if (is3) {
     frame_3D<double>& B = *m->f3[d.base_frame];
@@ -178,6 +191,9 @@ ref_model* build_model(const rkb_chain_desc& d) {
     switch (E.kind) {
       case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
         k = joint_of_elem[e]; break;
+      case RKB_FREE_3D:
+        k = shared_ptr<kte::kte_map>(new kte::free_joint_3D(nm, m->fcoord[E.coord], m->f3[E.frame_a], m->f3[E.frame_b], m->jac33[E.coord]));
+        break;
       case RKB_RIGID_LINK_3D: {
         pose_3D<double> off(weak_ptr<pose_3D<double> >(), vect<double,3>(E.p[0], E.p[1], E.p[2]),
                             quaternion<double>(vect<double,4>(E.p[3], E.p[4], E.p[5], E.p[6])));
@@ -187,6 +203,8 @@ ref_model* build_model(const rkb_chain_desc& d) {
         shared_ptr<kte::joint_dependent_frame_3D> dep(new kte::joint_dependent_frame_3D(m->f3[E.frame_a]));
         for (int c = 0; c < d.n_coords; ++c)
           if ((E.upstream >> c) & 1u) dep->add_joint(m->coords[c], m->jac3[c]);
+        for (std::size_t c = 0; c < m->fcoord.size(); ++c)
+          if ((E.upstream >> (32 + c)) & 1u) dep->add_joint(m->fcoord[c], m->jac33[c]);
         shared_ptr<kte::inertia_3D> in(new kte::inertia_3D(nm, dep, E.p[0],
             mat<double,mat_structure::symmetric>(E.p[1], E.p[2], E.p[3], E.p[4], E.p[5], E.p[6])));
         *m->mcalc << in; m->in_3d.push_back(in); k = in; break; }
@@ -236,8 +254,10 @@ ref_model* build_model(const rkb_chain_desc& d) {
   for (std::size_t i = 0; i < gen_inertias.size(); ++i) *m->mcalc << gen_inertias[i];
   m->in_gen = gen_inertias;
   for (int c = 0; c < d.n_coords; ++c) *m->mcalc << m->coords[c];
+  for (std::size_t c = 0; c < m->fcoord.size(); ++c) *m->mcalc << m->fcoord[c];
 
   m->sys.dofs_gen = m->coords;
+  m->sys.dofs_3D = m->fcoord;
   for (int i = 0; i < d.n_inputs; ++i) {
     if (!actuators[i]) { delete m; return NULL; }
     m->sys.inputs.push_back(actuators[i]);
@@ -292,7 +312,7 @@ integrator<double>* make_integrator(int scheme, const vect_n<double>& x, double 
 
 void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, const double* u,
                double dt, int n_steps, double* xout, int32_t* status, int scheme = RKB_SCHEME_RK4) {
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   for (std::size_t i = i0; i < i1; ++i) {
     vect_n<double> x(nx), uu(nu);
     for (int k = 0; k < nx; ++k) x[k] = x0[i * nx + k];
@@ -328,7 +348,7 @@ extern "C" {
 int rkref_rk4_inputs(void* hv, std::size_t N, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   const long long J = 2LL * n_steps + 1;
   for (std::size_t i = 0; i < N; ++i) {
     vect_n<double> x(nx);
@@ -407,7 +427,7 @@ void rkref_destroy(void* hv) {
 
 int rkref_eval(void* hv, std::size_t N, const double* x, const double* u, double* xdot, int32_t* status) {
   ref_model* m = static_cast<ref_handle*>(hv)->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   vect_n<double> p(nx), uu(nu);
   for (std::size_t i = 0; i < N; ++i) {
     for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
@@ -428,7 +448,7 @@ int rkref_eval(void* hv, std::size_t N, const double* x, const double* u, double
 // gen_coord::f after doMotion/clearForce/doForce with q_ddot = 0 (kte_nl_system.hpp:240-253).
 int rkref_gen_forces(void* hv, std::size_t N, const double* x, const double* u, double* f) {
   ref_model* m = static_cast<ref_handle*>(hv)->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   vect_n<double> p(nx), uu(nu);
   for (std::size_t i = 0; i < N; ++i) {
     for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
@@ -437,7 +457,12 @@ int rkref_gen_forces(void* hv, std::size_t N, const double* x, const double* u, 
     m->chain->doMotion();
     m->chain->clearForce();
     m->chain->doForce();
-    for (int k = 0; k < m->n; ++k) f[i * m->n + k] = m->coords[k]->f;
+    for (int k = 0; k < m->n; ++k) f[i * m->na + k] = m->coords[k]->f;
+    for (std::size_t c = 0; c < m->fcoord.size(); ++c)
+      for (int k = 0; k < 3; ++k) {
+        f[i * m->na + m->n + 6 * c + k] = m->fcoord[c]->Force[k];
+        f[i * m->na + m->n + 6 * c + 3 + k] = m->fcoord[c]->Torque[k];
+      }
   }
   return 0;
 }
@@ -445,7 +470,7 @@ int rkref_gen_forces(void* hv, std::size_t N, const double* x, const double* u, 
 // M (and Mdot) row-major n x n per sample (mass_matrix_calculator.cpp:80-98).
 int rkref_mass(void* hv, std::size_t N, const double* x, double* M, double* Mdot) {
   ref_model* m = static_cast<ref_handle*>(hv)->proto;
-  const int nx = 2 * m->n, nu = m->nu, n = m->n;
+  const int nx = m->nx, nu = m->nu, n = m->na;
   vect_n<double> p(nx), uu(nu, 0.0);
   for (std::size_t i = 0; i < N; ++i) {
     for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
@@ -470,7 +495,7 @@ int rkref_mass(void* hv, std::size_t N, const double* x, double* M, double* Mdot
 int rkref_frames(void* hv, const double* x, const double* u, double* out) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   vect_n<double> p(nx), uu(nu);
   for (int k = 0; k < nx; ++k) p[k] = x[k];
   for (int k = 0; k < nu; ++k) uu[k] = u[k];
@@ -506,7 +531,7 @@ int rkref_min_distance(void* hv, std::size_t N, const double* x, const rkb_shape
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
   if (h->desc.dim != 3) return -1;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   std::vector<shared_ptr<geom::shape_3D> > shapes;
   shared_ptr<geom::proxy_query_model_3D> mdl[2];
   mdl[0] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("model1"));
@@ -643,7 +668,7 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
                            double* err, char* msg, int msg_len) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   try {
     if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
     ctrl::kte_batch_system bs(m->sys, 0, dt);
@@ -682,7 +707,7 @@ int rkref_bridge_gpu_check(void* hv, std::size_t N, const double* x, const doubl
 int rkref_tmt(void* hv, const double* x, double* Tcm, double* Mcm, double* Tcm_dot) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   vect_n<double> p(nx), u(nu, 0.0);
   for (int k = 0; k < nx; ++k) p[k] = x[k];
   m->sys.apply_states_and_inputs(p, u);
@@ -709,7 +734,7 @@ int rkref_steer_space_check(void* hv, std::size_t P, const double* a, const doub
                             int msg_len) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   try {
     if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
     vect_n<double> lo(nu), hi(nu);
@@ -865,7 +890,7 @@ int rkref_planner_dispatch_check(void* hv, int K, const double* x_nodes, const d
                                  int* out, int* free_flags, double* p_new, double* sample, double* err, char* msg, int msg_len) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   try {
     if (!rkb_chain_create) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
     typedef pp::kte_steer_space space_t;
@@ -962,7 +987,7 @@ int rkref_steer_feedback(void* hv, std::size_t N, const double* x0, const double
                          double* x_out, int32_t* n_done, double* traj, int32_t* status) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   if (nu > STEER_MAX_INPUTS) return -1;
   for (std::size_t i = 0; i < N; ++i) {
     std::vector<double> x(x0 + i * nx, x0 + (i + 1) * nx), xn(nx), u(nu ? nu : 1), up(nu ? nu : 1);
@@ -998,7 +1023,7 @@ int rkref_steer_feedback_checked(void* hv, std::size_t N, const double* x0, cons
                                  double* x_out, int32_t* n_done, int32_t* collided, double* traj, int32_t* status) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n, nu = m->nu;
+  const int nx = m->nx, nu = m->nu;
   if (nu > STEER_MAX_INPUTS || h->desc.dim != 3) return -1;
   std::vector<shared_ptr<geom::proxy_query_pair_3D> > pairs;
   for (int p = 0; p < n_pairs; ++p) {
@@ -1070,7 +1095,7 @@ double rkref_integrate(void* hv, std::size_t N, const double* x0, const double* 
                        double* xout, int32_t* status, int n_workers) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
-  const int nx = 2 * m->n;
+  const int nx = m->nx;
   if (n_workers < 1) n_workers = 1;
   if (std::size_t(n_workers) > N && N > 0) n_workers = int(N);
   const auto t0 = std::chrono::steady_clock::now();

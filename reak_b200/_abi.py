@@ -8,6 +8,7 @@ import ctypes as C
 import os
 
 RKB_MAX_COORDS = 16
+RKB_MAX_FREE = 1
 
 # enum rkb_kind
 REVOLUTE_3D, PRISMATIC_3D, FREE_3D, RIGID_LINK_3D, INERTIA_3D, INERTIA_GEN, ACTUATOR_GEN = 1, 2, 3, 4, 5, 6, 7

@@ -74,6 +74,10 @@ class jacobian_gen_2D(object):
     """core/kinetostatics/motion_jacobians.hpp:108-198."""
 
 
+class jacobian_3D_3D(object):
+    """core/kinetostatics/motion_jacobians.hpp:1035-1240; the holder a free_joint_3D fills with identity blocks."""
+
+
 class jacobian_gen_gen(object):
     """core/kinetostatics/motion_jacobians.hpp:49-107."""
 
@@ -124,6 +128,15 @@ class prismatic_joint_2D(kte_map):
         self.mCoord, self.mAxis, self.mBase, self.mEnd, self.mJacobian = coord, list(axis), base, end, jacobian
 
 
+class free_joint_3D(kte_map):
+    """ctrl/mbd_kte/free_joints.hpp:205-300 / free_joints.cpp:119-208: End = Base * Coord, the coordinate being a whole
+    frame_3D (position, quaternion, velocity, angular velocity: 13 states, kte_nl_system.hpp:205-219)."""
+
+    def __init__(self, name, coord, base, end, jacobian=None):
+        kte_map.__init__(self, name)
+        self.mCoord, self.mBase, self.mEnd, self.mJacobian = coord, base, end, jacobian
+
+
 class rigid_link_3D(kte_map):
     """ctrl/mbd_kte/rigid_link.hpp:296-299 / rigid_link.cpp:152-185."""
 
@@ -144,9 +157,13 @@ class _joint_dependent(object):
     def __init__(self, frame=None, upstream=None):
         self.mFrame = frame
         self.mUpStreamJoints = dict(upstream or {})
+        self.mUpStream3DJoints = {}  # free-joint coordinate frames (jacobian_joint_map.hpp:252-331)
 
     def add_joint(self, joint_coord, joint_jacobian):
-        self.mUpStreamJoints[joint_coord] = joint_jacobian
+        if isinstance(joint_coord, frame_3D):
+            self.mUpStream3DJoints[joint_coord] = joint_jacobian
+        else:
+            self.mUpStreamJoints[joint_coord] = joint_jacobian
         return self
 
 
@@ -271,6 +288,7 @@ class mass_matrix_calc(object):
     def __init__(self, name=""):
         self.name = name
         self.mGenInertias, self.m2DInertias, self.m3DInertias, self.mCoords = [], [], [], []
+        self.mFrames3D = []
 
     def __lshift__(self, obj):
         if isinstance(obj, inertia_gen):
@@ -281,8 +299,10 @@ class mass_matrix_calc(object):
             self.m3DInertias.append(obj)
         elif isinstance(obj, gen_coord):
             self.mCoords.append(obj)
+        elif isinstance(obj, frame_3D):
+            self.mFrames3D.append(obj)   # mass_matrix_calculator.cpp:72-78: a free joint's coordinate frame
         else:
-            raise TypeError("mass_matrix_calc << %r: free-frame coordinates are not in the compiled path" % (obj,))
+            raise TypeError("mass_matrix_calc << %r: 2D free-frame coordinates are not in the compiled path" % (obj,))
         return self
 
 
@@ -297,9 +317,11 @@ class compiled_chain(object):
     def __init__(self, desc, elements, frames, coords):
         self.desc, self.elements, self.frames, self.coords = desc, elements, frames, coords
         self.n_coords, self.n_inputs, self.dim = desc.n_coords, desc.n_inputs, desc.dim
+        # free joints (free_joint_3D): 13 states and 6 accelerations each, after the generalized coordinates'
+        self.n_free, self.nx, self.n_acc = 0, 2 * desc.n_coords, desc.n_coords
 
 
-def compile_chain(chain, mass_calc, dofs_gen, inputs):
+def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
     """Flatten (chain, mass_calc, dofs_gen, inputs) — the public members of kte_nl_system —
     into an `rkb_chain_desc`.  Coordinates are numbered in `dofs_gen` order (that is the state
     layout, kte_nl_system.hpp:189-193) and inputs in `inputs` order (kte_nl_system.hpp:221-224)."""
@@ -307,6 +329,12 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
         raise UnsupportedChain("more than %d generalized coordinates" % _abi.RKB_MAX_COORDS)
     if list(mass_calc.mCoords) != list(dofs_gen):
         raise UnsupportedChain("mass_matrix_calc coordinates must be the system dofs in the same order")
+    dofs_3D = list(dofs_3D)
+    if [id(f) for f in getattr(mass_calc, "mFrames3D", [])] != [id(f) for f in dofs_3D]:
+        raise UnsupportedChain("mass_matrix_calc 3D frames must be the system's dofs_3D in the same order")
+    if len(dofs_3D) > _abi.RKB_MAX_FREE:
+        raise UnsupportedChain("more than %d free joints" % _abi.RKB_MAX_FREE)
+    free_id = {id(f): i for i, f in enumerate(dofs_3D)}
     coord_id = {id(c): i for i, c in enumerate(dofs_gen)}
     input_id = {id(a): i for i, a in enumerate(inputs)}
     frames, frame_id = [], {}
@@ -333,6 +361,10 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
         m = 0
         for c in dep.mUpStreamJoints:
             m |= 1 << cid(c)
+        for f in getattr(dep, "mUpStream3DJoints", {}):   # free-joint frames: bits 32 and up
+            if id(f) not in free_id:
+                raise UnsupportedChain("inertia depends on a free-joint frame that is not in dofs_3D")
+            m |= 1 << (32 + free_id[id(f)])
         return m
 
     recs, written, elem_index, actuator_joint = [], set(), {}, {}
@@ -359,6 +391,11 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
         elif isinstance(k, prismatic_joint_2D):
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
             rec(_abi.PRISMATIC_2D, a, b, cid(k.mCoord), p=k.mAxis)
+        elif isinstance(k, free_joint_3D):
+            if id(k.mCoord) not in free_id:
+                raise UnsupportedChain("free joint %s: its coordinate frame is not in dofs_3D" % k.name)
+            a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
+            rec(_abi.FREE_3D, a, b, free_id[id(k.mCoord)])
         elif isinstance(k, rigid_link_3D):
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
             rec(_abi.RIGID_LINK_3D, a, b, p=list(k.mPoseOffset.Position) + list(k.mPoseOffset.Quat))
@@ -419,6 +456,16 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
 
     if len(input_id) != sum(1 for e in recs if e.kind == _abi.ACTUATOR_GEN):
         raise UnsupportedChain("system inputs and chain actuators differ")
+    if dofs_3D:
+        # the reference's mass_matrix_calc dereferences a null Jacobian when a gen inertia depends on mCoords[i] for a
+        # free-frame index i (mass_matrix_calculator.cpp:226-233): there is no behaviour to match for such a model
+        n_free_used = sum(1 for e in recs if e.kind == _abi.FREE_3D)
+        if n_free_used != len(dofs_3D):
+            raise UnsupportedChain("every frame of dofs_3D needs exactly one free_joint_3D in the chain")
+        for e in recs:
+            if e.kind == _abi.INERTIA_GEN and e.coord < len(dofs_3D):
+                raise UnsupportedChain("inertia_gen on coordinate %d next to %d free joint(s): the reference itself crashes on this "
+                                       "model (mass_matrix_calculator.cpp:226-233)" % (e.coord, len(dofs_3D)))
     roots = [i for i in range(len(frames)) if i not in written]
     if len(roots) != 1:
         raise UnsupportedChain("chain must have exactly one un-driven base frame (found %d)" % len(roots))
@@ -446,4 +493,7 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs):
         d.base.ang_acceleration[0] = B.AngAcceleration
     import ctypes as C
     d.elements = C.cast(arr, C.POINTER(_abi.rkb_element))
-    return compiled_chain(d, arr, frames, list(dofs_gen))
+    cc = compiled_chain(d, arr, frames, list(dofs_gen))
+    cc.n_free = len(dofs_3D)
+    cc.nx, cc.n_acc = 2 * len(dofs_gen) + 13 * len(dofs_3D), len(dofs_gen) + 6 * len(dofs_3D)
+    return cc

@@ -16,11 +16,12 @@ class kte_system(object):
     def __init__(self, name=""):
         self.name = name
         self.dofs_gen, self.inputs = [], []
+        self.dofs_3D = []  # free-joint coordinate frames (kte_nl_system.hpp:72)
         self.chain = kte.kte_map_chain(name + "_chain")
         self.mass_calc = kte.mass_matrix_calc(name + "_mcalc")
 
     def get_state_dimensions(self):
-        return 2 * len(self.dofs_gen)
+        return 2 * len(self.dofs_gen) + 13 * len(self.dofs_3D)  # kte_nl_system.hpp:145-147
 
     def get_input_dimensions(self):
         return sum(a.getInputCount() for a in self.inputs)
@@ -139,6 +140,54 @@ def planar_chain(lengths=(0.5, 0.4), masses=(1.0, 0.8), moments=(0.1, 0.05), act
         cur = nxt
     for c in s.dofs_gen:
         s.mass_calc << c
+    return s
+
+
+def free_base_chain(n_revolute=3, actuated=True, link_rotation=False):
+    """A platform on a free_joint_3D (free_joints.cpp:119-208) carrying an arm of `n_revolute` revolute joints, the way
+    the reference builds its free-floating platforms (ctrl/kte_models/free_floating_platform.cpp, examples/robot_airship):
+    every inertia_3D depends on the free frame through the joint's jacobian_3D_3D and on the arm joints below it.  No
+    inertia_gen: the reference's mass_matrix_calc crashes on a rotor next to a free joint (mass_matrix_calculator.cpp:226-233).
+    n_revolute = 0: a single free rigid body."""
+    s = kte_system("free_base")
+    base = kte.frame_3D()
+    base.Acceleration = [0.0, 0.0, 9.81]
+    base.Position = [0.1, -0.2, 0.3]
+    base.Quat = kte.axis_angle_quat(0.4, (1.0, 1.0, 0.0))
+    coord, jac0, plat = kte.frame_3D(), kte.jacobian_3D_3D(), kte.frame_3D()
+    s.chain << kte.free_joint_3D("free_base", coord, base, plat, jac0)
+    dep0 = kte.joint_dependent_frame_3D(plat)
+    dep0.add_joint(coord, jac0)
+    body = kte.inertia_3D("platform", dep0, 5.0, (0.6, 0.02, -0.01, 0.5, 0.03, 0.4))
+    s.chain << body
+    s.mass_calc << body
+    s.dofs_3D.append(coord)
+    cur = plat
+    upstream = []
+    axes = [(0.0, 0.0, 1.0), (0.0, -1.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 1.0)]
+    for idx in range(n_revolute):
+        q, jac, end, nxt = kte.gen_coord(), kte.jacobian_gen_3D(), kte.frame_3D(), kte.frame_3D()
+        joint = kte.revolute_joint_3D("joint_%d" % idx, q, axes[idx % 4], cur, end, jac)
+        if actuated:
+            act = kte.driving_actuator_gen("joint_%d_actuator" % idx, q, joint)
+            s.chain << act
+            s.inputs.append(act)
+        s.chain << joint
+        q_off = kte.axis_angle_quat(0.2 + 0.1 * idx, (1.0, -1.0, 2.0)) if link_rotation else (1.0, 0.0, 0.0, 0.0)
+        s.chain << kte.rigid_link_3D("link_%d" % idx, end, nxt, kte.pose_3D((0.05 * idx, 0.02, 0.25 + 0.05 * idx), q_off))
+        upstream.append((q, jac))
+        dep = kte.joint_dependent_frame_3D(nxt)
+        dep.add_joint(coord, jac0)
+        for c, j in upstream:
+            dep.add_joint(c, j)
+        inertia = kte.inertia_3D("link_%d_inertia" % idx, dep, 1.5 - 0.3 * idx, (0.05, 0.001 * idx, 0.0, 0.04, 0.002, 0.03))
+        s.chain << inertia
+        s.mass_calc << inertia
+        s.dofs_gen.append(q)
+        cur = nxt
+    for q in s.dofs_gen:
+        s.mass_calc << q
+    s.mass_calc << coord
     return s
 
 
@@ -275,8 +324,16 @@ PRESETS = {
 }
 
 
+# chains with a free_joint_3D: their state is 2 n + 13 doubles (not in PRESETS, whose users assume 2 n)
+FREE_PRESETS = {
+    "free_body": lambda: free_base_chain(0),                          # one free rigid body (13 states)
+    "free_arm3": lambda: free_base_chain(3),                          # cfg 4's "free" variant, as far as the reference evaluates it
+    "free_arm2_twist": lambda: free_base_chain(2, actuated=False, link_rotation=True),
+}
+
+
 def make(name):
-    return PRESETS[name]()
+    return (PRESETS.get(name) or FREE_PRESETS[name])()
 
 
 def crs_proxy_models(system, track=False):
