@@ -34,7 +34,14 @@
  *
  * Conventions
  *   - All arithmetic is IEEE double, like the reference.
- *   - State per sample: 2n doubles interleaved (q0, qd0, q1, qd1, ...) — kte_nl_system.hpp:189-193.
+ *   - State per sample: 2n doubles interleaved (q0, qd0, q1, qd1, ...) — kte_nl_system.hpp:189-193 — followed, for a
+ *     chain with a free_joint_3D, by the 13 states of its coordinate frame: Position (3), Quat (w,x,y,z; normalised when
+ *     the state is applied, the integrators advance the raw vector), Velocity (3), AngVelocity (3) —
+ *     kte_nl_system.hpp:145-147, 205-219.  State derivative: Velocity, QuatDot, 6 accelerations (:293-308).  Generalised
+ *     forces, M, Mdot and the columns of the twist-shaping matrix then have n + 6 entries / rows / columns (the six of
+ *     the free joint last: Force, Torque / jacobian_3D_3D columns, mass_matrix_calculator.cpp:232-276).  At most one free
+ *     joint per chain; interpreter kernels; not with RKB_LAYOUT_BLOCKED.  A rotor (inertia_gen) on coordinate 0 next to
+ *     a free joint is rejected: the reference itself dereferences a null pointer there (mass_matrix_calculator.cpp:226-233).
  *     Input per sample: one double per driving_actuator_gen, in input-index order.
  *   - Buffers are caller-owned.  RKB_MEM_DEVICE pointers must be valid on `device`;
  *     RKB_MEM_HOST pointers are staged through device memory by the library
@@ -71,7 +78,7 @@ extern "C" {
 enum rkb_kind {
   RKB_REVOLUTE_3D       = 1,  /* revolute_joint_3D   (revolute_joint.cpp:121-213)  p[0..2] = axis                   */
   RKB_PRISMATIC_3D      = 2,  /* prismatic_joint_3D  (prismatic_joint.cpp:129-222) p[0..2] = axis                   */
-  RKB_FREE_3D           = 3,  /* free_joint_3D       (free_joints.cpp:123-208)     reserved, not accepted yet       */
+  RKB_FREE_3D           = 3,  /* free_joint_3D       (free_joints.cpp:123-208)     coord = index of its coordinate frame in dofs_3D */
   RKB_RIGID_LINK_3D     = 4,  /* rigid_link_3D       (rigid_link.cpp:152-185)      p[0..2] = offset, p[3..6] = quat (w,x,y,z) */
   RKB_INERTIA_3D        = 5,  /* inertia_3D          (inertia.cpp:111-121)         p[0] = mass, p[1..6] = Ixx Ixy Ixz Iyy Iyz Izz */
   RKB_INERTIA_GEN       = 6,  /* inertia_gen         (inertia.cpp:47-53)           p[0] = mass (jacobian_gen_gen(1,0))          */
@@ -100,7 +107,8 @@ typedef struct rkb_element {
   int32_t  coord;     /* generalized coordinate (joints, inertia_gen, actuator); else -1 */
   int32_t  aux;       /* actuator: input index; else 0 */
   int32_t  reserved;
-  uint64_t upstream;  /* inertias: bit c set <=> coordinate c is in mUpStreamJoints (jacobian_joint_map.hpp:252-331) */
+  uint64_t upstream;  /* inertias: bit c set <=> coordinate c is in mUpStreamJoints (jacobian_joint_map.hpp:252-331);
+                         bit 32 + i set <=> the coordinate frame of free joint i is in mUpStream3DJoints */
   double   p[12];     /* parameters, see enum rkb_kind */
 } rkb_element;
 

@@ -33,6 +33,7 @@
 #include <ReaK/ctrl/mbd_kte/kte_map_chain.hpp>
 #include <ReaK/ctrl/mbd_kte/revolute_joint.hpp>
 #include <ReaK/ctrl/mbd_kte/prismatic_joint.hpp>
+#include <ReaK/ctrl/mbd_kte/free_joints.hpp>
 #include <ReaK/ctrl/mbd_kte/rigid_link.hpp>
 #include <ReaK/ctrl/mbd_kte/inertia.hpp>
 #include <ReaK/ctrl/mbd_kte/spring.hpp>
@@ -94,9 +95,15 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
   using namespace ReaK::kte;
   using ReaK::rtti::rk_dynamic_ptr_cast;
   if (!sys.chain || !sys.mass_calc) throw unsupported_chain("kte_nl_system without chain or mass_calc");
-  if (!sys.dofs_2D.empty() || !sys.dofs_3D.empty()) throw unsupported_chain("free-frame dofs are outside the compiled path");
+  if (!sys.dofs_2D.empty()) throw unsupported_chain("2D free-frame dofs (free_joint_2D) are outside the compiled path");
   if (sys.mass_calc->Coords().size() != sys.dofs_gen.size()) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
-  detail::id_map coords, inputs, frames, elems;
+  if (sys.mass_calc->Frames3D().size() != sys.dofs_3D.size() || !sys.mass_calc->Frames2D().empty())
+    throw unsupported_chain("mass_matrix_calc free frames differ from the system dofs");
+  detail::id_map coords, inputs, frames, elems, free3;
+  for (std::size_t i = 0; i < sys.dofs_3D.size(); ++i) {  // state block 2 n + 13 i <-> dofs_3D[i] (kte_nl_system.hpp:205-219)
+    if (sys.mass_calc->Frames3D()[i] != sys.dofs_3D[i]) throw unsupported_chain("mass_matrix_calc free frames differ from the system dofs");
+    free3.ids[sys.dofs_3D[i].get()] = static_cast<int>(i);
+  }
   for (std::size_t i = 0; i < sys.dofs_gen.size(); ++i) {
     if (sys.mass_calc->Coords()[i] != sys.dofs_gen[i]) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
     coords.ids[sys.dofs_gen[i].get()] = static_cast<int>(i);
@@ -110,7 +117,8 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
   int dim = 0;
   for (std::size_t e = 0; e < ktes.size() && !dim; ++e) {
     if (rk_dynamic_ptr_cast<revolute_joint_3D>(ktes[e]) || rk_dynamic_ptr_cast<prismatic_joint_3D>(ktes[e]) ||
-        rk_dynamic_ptr_cast<rigid_link_3D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_3D>(ktes[e])) dim = 3;
+        rk_dynamic_ptr_cast<rigid_link_3D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_3D>(ktes[e]) ||
+        rk_dynamic_ptr_cast<free_joint_3D>(ktes[e])) dim = 3;
     else if (rk_dynamic_ptr_cast<revolute_joint_2D>(ktes[e]) || rk_dynamic_ptr_cast<prismatic_joint_2D>(ktes[e]) ||
              rk_dynamic_ptr_cast<rigid_link_2D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_2D>(ktes[e])) dim = 2;
   }
@@ -147,6 +155,12 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
       frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
       vect<double, 3> a = j->Axis();
       idx = b.prismatic_joint_3D(local::cid(coords, j->Coord().get()), a[0], a[1], a[2], fa, fb);
+    } else if (shared_ptr<free_joint_3D> j = rk_dynamic_ptr_cast<free_joint_3D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      const int fi = free3.lookup(j->Coord().get());
+      if (fi < 0) throw unsupported_chain("a free joint's coordinate frame is not listed in the system's dofs_3D");
+      idx = b.free_joint_3D(fi, fa, fb);
     } else if (shared_ptr<revolute_joint_2D> j = rk_dynamic_ptr_cast<revolute_joint_2D>(k)) {
       int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
       frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
@@ -173,7 +187,10 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
       frame_obj[f] = in->CenterOfMass()->mFrame.get();
       mat<double, mat_structure::symmetric> I = in->InertiaTensor();
       double t[6] = {I(0, 0), I(0, 1), I(0, 2), I(1, 1), I(1, 2), I(2, 2)};
-      idx = b.inertia_3D(f, in->Mass(), t, detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords));
+      std::uint64_t up = detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords);
+      if (!in->CenterOfMass()->mUpStream2DJoints.empty()) throw unsupported_chain("an inertia depends on a 2D free joint");
+      up |= detail::upstream_mask(in->CenterOfMass()->mUpStream3DJoints, free3) << 32;  // free-joint frames: bits 32 and up
+      idx = b.inertia_3D(f, in->Mass(), t, up);
     } else if (shared_ptr<inertia_2D> in = rk_dynamic_ptr_cast<inertia_2D>(k)) {
       int f = local::fid(b, frames, in->CenterOfMass()->mFrame.get());
       frame_obj[f] = in->CenterOfMass()->mFrame.get();

@@ -33,7 +33,10 @@ class _Checker(object):
         self.lib = C.CDLL(so_path)
         self._prefix = prefix
         self.compiled = compiled  # keeps the descriptor arrays alive
-        self.n, self.nu, self.nx = compiled.n_coords, compiled.n_inputs, 2 * compiled.n_coords
+        self.n, self.nu = compiled.n_coords, compiled.n_inputs
+        # chains with a free_joint_3D carry 13 more states and 6 more accelerations (kte_nl_system.hpp:145-147)
+        self.nx = getattr(compiled, "nx", 2 * compiled.n_coords)
+        self.na = getattr(compiled, "n_acc", compiled.n_coords)
         g = lambda name: getattr(self.lib, prefix + name)
         self._create, self._destroy = g("create"), g("destroy")
         self._eval, self._forces, self._mass, self._rk4, self._frames = g("eval"), g("gen_forces"), g("mass"), g("rk4"), g("frames")
@@ -82,14 +85,14 @@ class _Checker(object):
 
     def gen_forces(self, x, u=None):
         x, u, N = self._xu(x, u)
-        f = np.empty((N, self.n))
+        f = np.empty((N, self.na))
         self._forces(self.h, N, _dp(x), _dp(u), _dp(f))
         return f
 
     def mass(self, x, with_dot=True):
         x, _, N = self._xu(x, None)
-        M = np.empty((N, self.n, self.n))
-        Md = np.empty((N, self.n, self.n)) if with_dot else None
+        M = np.empty((N, self.na, self.na))
+        Md = np.empty((N, self.na, self.na)) if with_dot else None
         self._mass(self.h, N, _dp(x), _dp(M), _dp(Md))
         return (M, Md) if with_dot else M
 
@@ -205,7 +208,7 @@ class _Checker(object):
         fn.argtypes = [C.c_void_p] * 5
         x0 = x[0].copy()
         rows = fn(self.h, _dp(x0), None, None, None)
-        T, Mc, Td = np.zeros((rows, self.n)), np.zeros((rows, rows)), np.zeros((rows, self.n))
+        T, Mc, Td = np.zeros((rows, self.na)), np.zeros((rows, rows)), np.zeros((rows, self.na))
         fn(self.h, _dp(x0), _dp(T), _dp(Mc), _dp(Td))
         return T, Mc, Td
 

@@ -97,8 +97,13 @@ template <> struct FrameOf<2> { typedef Fr2 type; };
 template <int DIM, int MAXF>
 struct Work {
   typename FrameOf<DIM>::type fr[MAXF];
-  double q[MAXC], qd[MAXC], f[MAXC], u[MAXC];
+  // coordinate frame of the chain's free_joint_3D (kte_nl_system::dofs_3D[0]): Position, Quat (normalised), Velocity,
+  // AngVelocity from the state, zero accelerations, Force / Torque collected by doForce.  Unused by other chains.
+  typename FrameOf<DIM>::type fc;
+  double q[MAXC], qd[MAXC], f[RKB_GEN_MAX_ACC], u[MAXC];
 };
+#define MAXA RKB_GEN_MAX_ACC
+#define MAXX RKB_GEN_MAX_STATE
 
 GD void set_base(const GenericProgram* G, Fr3& B) {
   const double* b = G->base;
@@ -140,6 +145,18 @@ GD void motion(const GenericProgram* G, Work<3, MAXF>& W) {
       N.v = B.v + mul(R, cross(B.w, tp) + tv);
       N.a = B.a + mul(R, cross(B.w, cross(B.w, tp)) + 2.0 * cross(B.w, tv) + cross(B.al, tp));
       N.q = B.q; N.w = B.w; N.al = B.al;
+    } else if (E.kind == RKB_FREE_3D) {  // free_joints.cpp:123-131: *mEnd = (*mBase) * (*mCoord), frame_3D.hpp:219-234
+      const Fr3 B = W.fr[E.fa];
+      Fr3& N = W.fr[E.fb];
+      const Fr3& C = W.fc;
+      const M3 R = qrot(B.q), R2 = qrot(C.q);
+      N.p = B.p + mul(R, C.p);
+      N.v = B.v + mul(R, cross(B.w, C.p) + C.v);
+      N.a = B.a + mul(R, cross(B.w, cross(B.w, C.p)) + 2.0 * cross(B.w, C.v) + cross(B.al, C.p) + C.a);
+      N.q = qmul(B.q, C.q);
+      const V3 wt = tmul(R2, B.w);
+      N.al = tmul(R2, B.al) + cross(wt, C.w) + C.al;
+      N.w = wt + C.w;
     } else if (E.kind == RKB_RIGID_LINK_3D) {  // rigid_link.cpp:156 -> frame_3D.hpp:236-251
       const Fr3 B = W.fr[E.fa];
       Fr3& N = W.fr[E.fb];
@@ -197,6 +214,7 @@ template <int MAXF>
 GD void force(const GenericProgram* G, Work<3, MAXF>& W) {
   for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v3(0, 0, 0); W.fr[i].T = v3(0, 0, 0); }
   for (int i = 0; i < G->n_coords; ++i) W.f[i] = 0.0;
+  W.fc.F = v3(0, 0, 0); W.fc.T = v3(0, 0, 0);
   for (int e = G->n_elements - 1; e >= 0; --e) {
     const GenericElement& E = G->el[e];
     switch (E.kind) {
@@ -219,6 +237,12 @@ GD void force(const GenericProgram* G, Work<3, MAXF>& W) {
         W.f[E.coord] += tf;
         B.F = B.F + (N.F - tf * ax);
         B.T = B.T + (N.T + cross(W.q[E.coord] * ax, N.F));
+        break;
+      }
+      case RKB_FREE_3D: {  // free_joints.cpp:164-172: the end frame's wrench lands on the coordinate frame
+        const Fr3& N = W.fr[E.fb];
+        W.fc.F = W.fc.F + N.F;
+        W.fc.T = W.fc.T + N.T;
         break;
       }
       case RKB_RIGID_LINK_3D: {  // rigid_link.cpp:170-177
@@ -447,10 +471,41 @@ GD void jac_col(const GenericProgram* G, const Work<3, MAXF>& W, int c, const Fr
   Td[0] = Tvd.x; Td[1] = Tvd.y; Td[2] = Tvd.z; Td[3] = Twd.x; Td[4] = Twd.y; Td[5] = Twd.z;
 }
 
+// The six columns a free_joint_3D contributes for inertia frame F: jacobian_3D_3D::get_jac_relative_to
+// (motion_jacobians.hpp:1077-1140) on the joint's two identity blocks, with f2 = (~E) * F (E the joint's end frame)
+// in world quantities: g_k = R_E e_k,  dp = p_F - p_E,  dv = v_F - v_E,  W_E = R_E w_E,  w_rel = w_F - R_F^T W_E
+//   velocity input k        : Tv = R_F^T g_k,          Tw = 0,          Tvd = -w_rel x Tv,  Twd = 0
+//   angular-velocity input k: Tv = R_F^T (g_k x dp),   Tw = R_F^T g_k,  Tvd = R_F^T (g_k x (dv - W_E x dp)) - w_rel x Tv,  Twd = -w_rel x Tw
+// T[l] / Td[l]: column l (0-2 velocity, 3-5 angular velocity) as (v3, w3), the order write_to_matrices uses (:1142-1203).
+template <int MAXF>
+GD void jac_free_block(const GenericProgram* G, const Work<3, MAXF>& W, int fj, const Fr3& F, const M3& RF, double (*T)[6], double (*Td)[6], bool want_dot) {
+  const Fr3& E = W.fr[G->el[G->free_elem[fj]].fb];
+  const M3 RE = qrot(E.q);
+  const V3 dp = F.p - E.p, WE = mul(RE, E.w);
+  const V3 wrel = F.w - tmul(RF, WE);
+  const V3 dvr = (F.v - E.v) - cross(WE, dp);
+  for (int k = 0; k < 3; ++k) {
+    const V3 g = v3(RE.m[k], RE.m[3 + k], RE.m[6 + k]);
+    const V3 Tg = tmul(RF, g);
+    const V3 Tv = tmul(RF, cross(g, dp));
+    T[k][0] = Tg.x; T[k][1] = Tg.y; T[k][2] = Tg.z; T[k][3] = 0.0; T[k][4] = 0.0; T[k][5] = 0.0;
+    T[3 + k][0] = Tv.x; T[3 + k][1] = Tv.y; T[3 + k][2] = Tv.z; T[3 + k][3] = Tg.x; T[3 + k][4] = Tg.y; T[3 + k][5] = Tg.z;
+    if (want_dot) {
+      const V3 a = v3(0, 0, 0) - cross(wrel, Tg);
+      const V3 b = tmul(RF, cross(g, dvr)) - cross(wrel, Tv);
+      Td[k][0] = a.x; Td[k][1] = a.y; Td[k][2] = a.z; Td[k][3] = 0.0; Td[k][4] = 0.0; Td[k][5] = 0.0;
+      Td[3 + k][0] = b.x; Td[3 + k][1] = b.y; Td[3 + k][2] = b.z; Td[3 + k][3] = a.x; Td[3 + k][4] = a.y; Td[3 + k][5] = a.z;
+    }
+  }
+}
+
+// does an inertia with upstream mask `up` depend on column c of the (n_coords + 6 n_free)-column twist-shaping matrix?
+GD bool col_upstream(unsigned up, int n, int c) { return c < n ? ((up >> c) & 1u) : ((up >> (RKB_GEN_FREE_BIT + (c - n) / 6)) & 1u); }
+
 // M and (optionally) S with Mdot = S + S^T; both n x n row-major in local memory.
 template <int MAXF>
 GD void mass(const GenericProgram* G, const Work<3, MAXF>& W, double* M, double* S, bool want_dot) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 6 * G->n_free;
   for (int i = 0; i < n * n; ++i) { M[i] = 0.0; if (want_dot) S[i] = 0.0; }
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
@@ -461,19 +516,24 @@ GD void mass(const GenericProgram* G, const Work<3, MAXF>& W, double* M, double*
       const M3 RF = qrot(F.q);
       const double m = E.p[0];
       const double* I = &E.p[1];
-      double T[MAXC][6], Td[MAXC][6], MT[MAXC][6];
-      for (int c = 0; c < n; ++c) {
+      double T[MAXA][6], Td[MAXA][6], MT[MAXA][6];
+      for (int c = 0; c < nc; ++c) {
         if (!((E.upstream >> c) & 1u)) continue;
         jac_col(G, W, c, F, RF, T[c], Td[c], want_dot);
+      }
+      for (int fj = 0; fj < G->n_free; ++fj)
+        if ((E.upstream >> (RKB_GEN_FREE_BIT + fj)) & 1u) jac_free_block(G, W, fj, F, RF, &T[nc + 6 * fj], &Td[nc + 6 * fj], want_dot);
+      for (int c = 0; c < n; ++c) {
+        if (!col_upstream(E.upstream, nc, c)) continue;
         MT[c][0] = m * T[c][0]; MT[c][1] = m * T[c][1]; MT[c][2] = m * T[c][2];
         MT[c][3] = I[0] * T[c][3] + I[1] * T[c][4] + I[2] * T[c][5];
         MT[c][4] = I[1] * T[c][3] + I[3] * T[c][4] + I[4] * T[c][5];
         MT[c][5] = I[2] * T[c][3] + I[4] * T[c][4] + I[5] * T[c][5];
       }
       for (int a = 0; a < n; ++a) {
-        if (!((E.upstream >> a) & 1u)) continue;
+        if (!col_upstream(E.upstream, nc, a)) continue;
         for (int b = 0; b < n; ++b) {
-          if (!((E.upstream >> b) & 1u)) continue;
+          if (!col_upstream(E.upstream, nc, b)) continue;
           double s = 0.0, sd = 0.0;
           for (int k = 0; k < 6; ++k) { s += T[a][k] * MT[b][k]; if (want_dot) sd += Td[a][k] * MT[b][k]; }
           M[a * n + b] += s;
@@ -537,20 +597,20 @@ GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double*
 // set stay zero.
 template <int MAXF>
 GD void tmt(const GenericProgram* G, const Work<3, MAXF>& W, const BatchView& T, const BatchView& Td, long long i) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 6 * G->n_free;
   const bool want_dot = Td.p != (double*)0;
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
     if (E.kind == RKB_INERTIA_GEN) {
       for (int c = 0; c < n; ++c) {
         const long long k = (long long)E.row * n + c;
-        T.p[i * T.si + k * T.sk] = ((E.upstream >> c) & 1u) ? 1.0 : 0.0;
+        T.p[i * T.si + k * T.sk] = (c < nc && ((E.upstream >> c) & 1u)) ? 1.0 : 0.0;
         if (want_dot) Td.p[i * Td.si + k * Td.sk] = 0.0;
       }
     } else if (E.kind == RKB_INERTIA_3D) {
       const Fr3& F = W.fr[E.fa];
       const M3 RF = qrot(F.q);
-      for (int c = 0; c < n; ++c) {
+      for (int c = 0; c < nc; ++c) {
         double col[6] = {0, 0, 0, 0, 0, 0}, cold[6] = {0, 0, 0, 0, 0, 0};
         if ((E.upstream >> c) & 1u) jac_col(G, W, c, F, RF, col, cold, want_dot);
         for (int r = 0; r < 6; ++r) {
@@ -558,6 +618,17 @@ GD void tmt(const GenericProgram* G, const Work<3, MAXF>& W, const BatchView& T,
           T.p[i * T.si + k * T.sk] = col[r];
           if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
         }
+      }
+      for (int fj = 0; fj < G->n_free; ++fj) {
+        double blk[6][6], blkd[6][6];
+        const bool up = (E.upstream >> (RKB_GEN_FREE_BIT + fj)) & 1u;
+        if (up) jac_free_block(G, W, fj, F, RF, blk, blkd, want_dot);
+        for (int l = 0; l < 6; ++l)
+          for (int r = 0; r < 6; ++r) {
+            const long long k = (long long)(E.row + r) * n + nc + 6 * fj + l;
+            T.p[i * T.si + k * T.sk] = up ? blk[l][r] : 0.0;
+            if (want_dot) Td.p[i * Td.si + k * Td.sk] = up ? blkd[l][r] : 0.0;
+          }
       }
     }
   }
@@ -611,11 +682,11 @@ GD void tmt(const GenericProgram* G, const Work<2, MAXF>& W, const BatchView& T,
 // the frame's own coordinates like every twist in ReaK.
 template <int MAXF>
 GD void frame_jac(const GenericProgram* G, const Work<3, MAXF>& W, int frame, unsigned upstream, const BatchView& T, const BatchView& Td, long long i) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 6 * G->n_free;
   const bool want_dot = Td.p != (double*)0;
   const Fr3& F = W.fr[frame];
   const M3 RF = qrot(F.q);
-  for (int c = 0; c < n; ++c) {
+  for (int c = 0; c < nc; ++c) {
     double col[6] = {0, 0, 0, 0, 0, 0}, cold[6] = {0, 0, 0, 0, 0, 0};
     if ((upstream >> c) & 1u) jac_col(G, W, c, F, RF, col, cold, want_dot);
     for (int r = 0; r < 6; ++r) {
@@ -623,6 +694,17 @@ GD void frame_jac(const GenericProgram* G, const Work<3, MAXF>& W, int frame, un
       T.p[i * T.si + k * T.sk] = col[r];
       if (want_dot) Td.p[i * Td.si + k * Td.sk] = cold[r];
     }
+  }
+  for (int fj = 0; fj < G->n_free; ++fj) {  // jacobian_3D_3D columns of a free joint upstream of the frame
+    double blk[6][6], blkd[6][6];
+    const bool up = (upstream >> (RKB_GEN_FREE_BIT + fj)) & 1u;
+    if (up) jac_free_block(G, W, fj, F, RF, blk, blkd, want_dot);
+    for (int l = 0; l < 6; ++l)
+      for (int r = 0; r < 6; ++r) {
+        const long long k = (long long)r * n + nc + 6 * fj + l;
+        T.p[i * T.si + k * T.sk] = up ? blk[l][r] : 0.0;
+        if (want_dot) Td.p[i * Td.si + k * Td.sk] = up ? blkd[l][r] : 0.0;
+      }
   }
 }
 template <int MAXF>
@@ -683,21 +765,67 @@ GD int cholesky_solve(int n, double* A, double* b) {
   return st;
 }
 
-// q_ddot into W.f; returns status
+// accelerations into W.f (the coordinates', then 6 per free joint: kte_nl_system.hpp:256-273); returns status
+template <int MAXF>
+GD void pack_free_forces(const GenericProgram* G, Work<3, MAXF>& W) {
+  if (G->n_free) {
+    double* f = &W.f[G->n_coords];
+    f[0] = W.fc.F.x; f[1] = W.fc.F.y; f[2] = W.fc.F.z; f[3] = W.fc.T.x; f[4] = W.fc.T.y; f[5] = W.fc.T.z;
+  }
+}
+template <int MAXF>
+GD void pack_free_forces(const GenericProgram*, Work<2, MAXF>&) {}
+
 template <int DIM, int MAXF>
 GD int accel(const GenericProgram* G, Work<DIM, MAXF>& W) {
-  double M[MAXC * MAXC];
+  double M[MAXA * MAXA];
   motion(G, W);
   force(G, W);
+  pack_free_forces(G, W);
   mass(G, W, M, (double*)0, false);
-  return cholesky_solve(G->n_coords, M, W.f);
+  return cholesky_solve(G->n_coords + 6 * G->n_free, M, W.f);
 }
+
+// kte_nl_system::apply_states_and_inputs for the free joint's 13 states (kte_nl_system.hpp:205-219): the quaternion is
+// normalised (explicit quaternion(Vector), rotations_3D.hpp:917-920), the accelerations are zero
+template <int MAXF>
+GD void apply_free(Work<3, MAXF>& W, const double* s) {
+  Fr3& C = W.fc;
+  C.p = v3(s[0], s[1], s[2]);
+  const double nq = sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+  C.q.w = s[3] / nq; C.q.x = s[4] / nq; C.q.y = s[5] / nq; C.q.z = s[6] / nq;
+  C.v = v3(s[7], s[8], s[9]);
+  C.w = v3(s[10], s[11], s[12]);
+  C.a = v3(0, 0, 0); C.al = v3(0, 0, 0);
+}
+template <int MAXF>
+GD void apply_free(Work<2, MAXF>&, const double*) {}
+
+// the free joint's 13 state derivatives after accel(): Velocity, QuatDot (quaternion::getQuaternionDot,
+// rotations_3D.hpp:1206-1211, of the normalised quaternion), the six accelerations (kte_nl_system.hpp:293-308)
+template <int MAXF>
+GD void free_derivative(const GenericProgram* G, const Work<3, MAXF>& W, double* o) {
+  const Fr3& C = W.fc;
+  o[0] = C.v.x; o[1] = C.v.y; o[2] = C.v.z;
+  o[3] = -0.5 * (C.q.x * C.w.x + C.q.y * C.w.y + C.q.z * C.w.z);
+  o[4] = 0.5 * (C.q.w * C.w.x - C.q.z * C.w.y + C.q.y * C.w.z);
+  o[5] = 0.5 * (C.q.w * C.w.y + C.q.z * C.w.x - C.q.x * C.w.z);
+  o[6] = 0.5 * (C.q.w * C.w.z - C.q.y * C.w.x + C.q.x * C.w.y);
+  for (int k = 0; k < 6; ++k) o[7 + k] = W.f[G->n_coords + k];
+}
+template <int MAXF>
+GD void free_derivative(const GenericProgram*, const Work<2, MAXF>&, double*) {}
 
 template <int DIM, int MAXF>
 GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& x, const ConstBatchView& u, long long ix, long long iu, bool with_u) {
   for (int c = 0; c < G->n_coords; ++c) {
     W.q[c] = x.p[ix * x.si + rkb_state_q(x.blocked, G->n_coords, c) * x.sk];
     W.qd[c] = x.p[ix * x.si + rkb_state_qd(x.blocked, G->n_coords, c) * x.sk];
+  }
+  if (G->n_free) {  // the 13 states of the free joint follow the coordinates' (never blocked: rejected by the host)
+    double s[13];
+    for (int k = 0; k < 13; ++k) s[k] = x.p[ix * x.si + (2 * G->n_coords + k) * x.sk];
+    apply_free(W, s);
   }
   for (int k = 0; k < G->n_inputs; ++k) W.u[k] = with_u ? u.p[iu * u.si + k * u.sk] : 0.0;
 }
@@ -717,6 +845,14 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_eval_kernel(const GenericPr
     A.out.p[i * A.out.si + rkb_state_qd(A.out.blocked, G->n_coords, c) * A.out.sk] = W.f[c];
     finite = finite && isfinite(W.f[c]) && isfinite(W.qd[c]);
   }
+  if (G->n_free) {
+    double o[13];
+    free_derivative(G, W, o);
+    for (int k = 0; k < 13; ++k) {
+      A.out.p[i * A.out.si + (2 * G->n_coords + k) * A.out.sk] = o[k];
+      finite = finite && isfinite(o[k]);
+    }
+  }
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = st;
 }
@@ -729,7 +865,8 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_forces_kernel(const Generic
   load(G, W, A.x, A.u, i, i, true);
   motion(G, W);
   force(G, W);
-  for (int c = 0; c < G->n_coords; ++c) A.out.p[i * A.out.si + c * A.out.sk] = W.f[c];
+  pack_free_forces(G, W);
+  for (int c = 0; c < G->n_coords + 6 * G->n_free; ++c) A.out.p[i * A.out.si + c * A.out.sk] = W.f[c];
 }
 
 template <int DIM, int MAXF>
@@ -739,10 +876,10 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
   Work<DIM, MAXF> W;
   load(G, W, A.x, A.u, i, i, false);
   motion(G, W);
-  double M[MAXC * MAXC], S[MAXC * MAXC];
+  double M[MAXA * MAXA], S[MAXA * MAXA];
   const bool want_dot = A.out2.p != (double*)0;
   mass(G, W, M, S, want_dot);
-  const int n = G->n_coords;
+  const int n = G->n_coords + 6 * G->n_free;
   for (int a = 0; a < n; ++a)
     for (int b = 0; b < n; ++b) {
       // mat<symmetric> converting ctor averages the two halves (mat_alg_symmetric.hpp:171-200)
@@ -779,7 +916,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_frames_kernel(const Generic
 // motion() above, operation for operation.  The frame being built lives in registers; only the frames the
 // program marks (ProxProgram::slot_of) are written to the thread's local array.
 template <int MAXS>
-GD void motion_pose(const GenericProgram* G, const ProxProgram& P, const double* q, Pose (&slots)[MAXS]) {
+GD void motion_pose(const GenericProgram* G, const ProxProgram& P, const double* q, const Pose& freec, Pose (&slots)[MAXS]) {
   Pose cur;
   {
     const double* b = G->base;
@@ -789,7 +926,7 @@ GD void motion_pose(const GenericProgram* G, const ProxProgram& P, const double*
   if (P.slot_of[last] >= 0) slots[P.slot_of[last]] = cur;
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
-    if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D) continue;
+    if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D && E.kind != RKB_FREE_3D) continue;
     Pose B = cur;
     if (E.fa != last) B = slots[P.slot_of[E.fa]];
     if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-131
@@ -802,6 +939,9 @@ GD void motion_pose(const GenericProgram* G, const ProxProgram& P, const double*
     } else if (E.kind == RKB_PRISMATIC_3D) {  // prismatic_joint.cpp:129-140
       cur.p = B.p + mul(qrot(B.q), q[E.coord] * ldv(E.p));
       cur.q = B.q;
+    } else if (E.kind == RKB_FREE_3D) {  // free_joints.cpp:127: End = Base * Coord
+      cur.p = B.p + mul(qrot(B.q), freec.p);
+      cur.q = qmul(B.q, freec.q);
     } else {  // rigid_link.cpp:156 -> pose_3D::addBefore
       Q4 qo; qo.w = E.p[3]; qo.x = E.p[4]; qo.y = E.p[5]; qo.z = E.p[6];
       cur.p = B.p + mul(qrot(B.q), ldv(E.p));
@@ -821,8 +961,16 @@ __global__ void __launch_bounds__(GEN_BLOCK, MINB) generic_proximity_kernel(cons
   if (i >= A.n_samples) return;
   double q[MAXC];
   for (int c = 0; c < G->n_coords; ++c) q[c] = A.x.p[i * A.x.si + rkb_state_q(A.x.blocked, G->n_coords, c) * A.x.sk];
-  Pose fr[MAXS];
-  motion_pose(G, P, q, fr);
+  Pose fr[MAXS], freec;
+  freec.p = v3(0, 0, 0); freec.q.w = 1.0; freec.q.x = 0.0; freec.q.y = 0.0; freec.q.z = 0.0;
+  if (G->n_free) {  // pose states of the free joint, the quaternion normalised as apply_states_and_inputs does
+    double s[7];
+    for (int k = 0; k < 7; ++k) s[k] = A.x.p[i * A.x.si + (2 * G->n_coords + k) * A.x.sk];
+    const double nq = sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+    freec.p = v3(s[0], s[1], s[2]);
+    freec.q.w = s[3] / nq; freec.q.x = s[4] / nq; freec.q.y = s[5] / nq; freec.q.z = s[6] / nq;
+  }
+  motion_pose(G, P, q, freec, fr);
   ProxRecord bestR;
   const int best = prox_min_distance(P, fr, A.out2.p != (double*)0, bestR);
   A.out.p[i * A.out.si] = bestR.d;
@@ -853,12 +1001,34 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_frame_jac_kernel(const Gene
   frame_jac(G, W, frame, upstream, A.out, A.out2, i);
 }
 
-template <int DIM, int MAXF>
-GD void store_state(const GenericProgram* G, const Work<DIM, MAXF>& W, const BatchView& o, long long off) {
-  for (int c = 0; c < G->n_coords; ++c) {
-    o.p[off + rkb_state_q(o.blocked, G->n_coords, c) * o.sk] = W.q[c];
-    o.p[off + rkb_state_qd(o.blocked, G->n_coords, c) * o.sk] = W.qd[c];
+// The integrators work on the state VECTOR as the reference's do (vect_n<double>; a free joint's quaternion is only
+// normalised when the state is applied to the model): xs = (q0, qd0, q1, qd1, ..., then the 13 states of a free joint).
+GD void load_flat(const GenericProgram* G, const ConstBatchView& x, long long ix, double* xs) {
+  const int n = G->n_coords;
+  for (int c = 0; c < n; ++c) {
+    xs[2 * c] = x.p[ix * x.si + rkb_state_q(x.blocked, n, c) * x.sk];
+    xs[2 * c + 1] = x.p[ix * x.si + rkb_state_qd(x.blocked, n, c) * x.sk];
   }
+  for (int k = 0; k < 13 * G->n_free; ++k) xs[2 * n + k] = x.p[ix * x.si + (2 * n + k) * x.sk];
+}
+GD void store_flat(const GenericProgram* G, const double* xs, const BatchView& o, long long off) {
+  const int n = G->n_coords;
+  for (int c = 0; c < n; ++c) {
+    o.p[off + rkb_state_q(o.blocked, n, c) * o.sk] = xs[2 * c];
+    o.p[off + rkb_state_qd(o.blocked, n, c) * o.sk] = xs[2 * c + 1];
+  }
+  for (int k = 0; k < 13 * G->n_free; ++k) o.p[off + (2 * n + k) * o.sk] = xs[2 * n + k];
+}
+// apply_states_and_inputs + get_state_derivative at the state vector xs: xd = f(xs, u); returns the status bits
+template <int DIM, int MAXF>
+GD int rate(const GenericProgram* G, Work<DIM, MAXF>& W, const double* xs, double* xd) {
+  const int n = G->n_coords;
+  for (int c = 0; c < n; ++c) { W.q[c] = xs[2 * c]; W.qd[c] = xs[2 * c + 1]; }
+  if (G->n_free) apply_free(W, xs + 2 * n);
+  const int st = accel(G, W);
+  for (int c = 0; c < n; ++c) { xd[2 * c] = W.qd[c]; xd[2 * c + 1] = W.f[c]; }
+  if (G->n_free) free_derivative(G, W, xd + 2 * n);
+  return st;
 }
 
 // n_steps RK4 steps (fixed_step_integrators.hpp:277-289, the reference's own operation order) with
@@ -870,23 +1040,25 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
   if (A.active && !A.active[i]) return;
   Work<DIM, MAXF> W;
   const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
-  load(G, W, A.x0, A.u, i0, i, true);
-  const int n = G->n_coords;
+  const int nx = 2 * G->n_coords + 13 * G->n_free;
+  double xs[MAXX], xd[MAXX];
+  load_flat(G, A.x0, i0, xs);
+  for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + k * A.u.sk];
   const double dt = A.dt;
-  double w[2 * MAXC], acc[2 * MAXC], k3[2 * MAXC];
-  double ks[TABLE ? RKB_RK_MAX_STAGES : 1][2 * MAXC];
+  double w[MAXX], acc[MAXX], k3[MAXX];
+  double ks[TABLE ? RKB_RK_MAX_STAGES : 1][MAXX];
   int st = 0;
   {
     for (int step = 0; step < A.n_steps; ++step) {
       if (TABLE) {
-        for (int c = 0; c < n; ++c) { w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c]; }
+        for (int k = 0; k < nx; ++k) w[k] = xs[k];
         for (int s = 0; s < T.stages; ++s) {
-          st |= accel(G, W);
-          for (int c = 0; c < n; ++c) { ks[s][2 * c] = W.qd[c] * dt; ks[s][2 * c + 1] = W.f[c] * dt; }
-          for (int c = 0; c < n; ++c) {
-            double q = w[2 * c], qd = w[2 * c + 1];
-            for (int j = 0; j <= s; ++j) { q = fma(T.c[s][j], ks[j][2 * c], q); qd = fma(T.c[s][j], ks[j][2 * c + 1], qd); }
-            W.q[c] = q; W.qd[c] = qd;
+          st |= rate(G, W, xs, xd);
+          for (int k = 0; k < nx; ++k) ks[s][k] = xd[k] * dt;
+          for (int k = 0; k < nx; ++k) {
+            double v = w[k];
+            for (int j = 0; j <= s; ++j) v = fma(T.c[s][j], ks[j][k], v);
+            xs[k] = v;
           }
         }
         continue;
@@ -895,39 +1067,35 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
       // evaluation 1 reads node 2 step, evaluations 2 and 3 node 2 step + 1, evaluation 4 node 2 step + 2
       const long long un = A.u_node_stride;
       if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step) * un + k * A.u.sk];
-      st |= accel(G, W);
-      for (int c = 0; c < n; ++c) {
-        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-        w[2 * c] = W.q[c]; w[2 * c + 1] = W.qd[c];
-        acc[2 * c] = kq; acc[2 * c + 1] = kv;
-        W.q[c] += kq * 0.5; W.qd[c] += kv * 0.5;
+      st |= rate(G, W, xs, xd);
+      for (int k = 0; k < nx; ++k) {
+        const double kk = xd[k] * dt;
+        w[k] = xs[k];
+        acc[k] = kk;
+        xs[k] += kk * 0.5;
       }
       if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step + 1) * un + k * A.u.sk];
-      st |= accel(G, W);
-      for (int c = 0; c < n; ++c) {
-        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-        acc[2 * c] += kq * 2.0; acc[2 * c + 1] += kv * 2.0;
-        W.q[c] = w[2 * c] + kq * 0.5; W.qd[c] = w[2 * c + 1] + kv * 0.5;
+      st |= rate(G, W, xs, xd);
+      for (int k = 0; k < nx; ++k) {
+        const double kk = xd[k] * dt;
+        acc[k] += kk * 2.0;
+        xs[k] = w[k] + kk * 0.5;
       }
-      st |= accel(G, W);
-      for (int c = 0; c < n; ++c) {
-        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-        k3[2 * c] = kq; k3[2 * c + 1] = kv;
-        W.q[c] = w[2 * c] + kq; W.qd[c] = w[2 * c + 1] + kv;
+      st |= rate(G, W, xs, xd);
+      for (int k = 0; k < nx; ++k) {
+        const double kk = xd[k] * dt;
+        k3[k] = kk;
+        xs[k] = w[k] + kk;
       }
       if (un) for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + (2LL * step + 2) * un + k * A.u.sk];
-      st |= accel(G, W);
-      for (int c = 0; c < n; ++c) {
-        const double kq = W.qd[c] * dt, kv = W.f[c] * dt;
-        W.q[c] += (acc[2 * c] + kq) / 6.0 - k3[2 * c] * (2.0 / 3.0);
-        W.qd[c] += (acc[2 * c + 1] + kv) / 6.0 - k3[2 * c + 1] * (2.0 / 3.0);
-      }
+      st |= rate(G, W, xs, xd);
+      for (int k = 0; k < nx; ++k) xs[k] += (acc[k] + xd[k] * dt) / 6.0 - k3[k] * (2.0 / 3.0);
     }
   }
   bool finite = true;
-  for (int c = 0; c < n; ++c) finite = finite && isfinite(W.q[c]) && isfinite(W.qd[c]);
-  store_state(G, W, A.xout, i * A.xout.si);
-  if (A.traj.p) store_state(G, W, A.traj, i * A.traj.si);
+  for (int k = 0; k < nx; ++k) finite = finite && isfinite(xs[k]);
+  store_flat(G, xs, A.xout, i * A.xout.si);
+  if (A.traj.p) store_flat(G, xs, A.traj, i * A.traj.si);
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }

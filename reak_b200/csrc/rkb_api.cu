@@ -67,6 +67,7 @@ struct rkb_chain {
   rkb_chain_desc desc;
   std::vector<rkb_element> elements;
   int n = 0, nu = 0;
+  int n_free = 0, nx = 0, na = 0;  // free_joint_3D count; state (2 n + 13 n_free) and acceleration (n + 6 n_free) dimensions
   bool serial_ok = false;
   int serial_fl = 0;
   unsigned long long serial_shape = 0;  // structure found in the descriptor (RKB_SHAPE_*)
@@ -129,6 +130,10 @@ int validate(const rkb_chain_desc* d) {
       !finite_all(d->base.ang_velocity, 3) || !finite_all(d->base.acceleration, 3) || !finite_all(d->base.ang_acceleration, 3))
     return RKB_ERR_INVALID;
   std::vector<int> coord_joint(d->n_coords, 0), input_used(d->n_inputs, 0), written(d->n_frames, 0);
+  int n_free = 0;
+  for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_FREE_3D) ++n_free;
+  if (n_free > RKB_GEN_MAX_FREE) return RKB_ERR_UNSUPPORTED;
+  int free_seen = 0;
   for (int e = 0; e < d->n_elements; ++e) {
     const rkb_element& E = d->elements[e];
     if (!finite_all(E.p, 12)) return RKB_ERR_INVALID;
@@ -153,11 +158,19 @@ int validate(const rkb_chain_desc* d) {
         break;
       case RKB_INERTIA_3D: case RKB_INERTIA_2D:
         if (!frame_ok(E.frame_a) || (d->dim == 3) != is3) return RKB_ERR_INVALID;
-        if (d->n_coords < 64 && (E.upstream >> d->n_coords)) return RKB_ERR_INVALID;
+        {  // bits 0 .. n_coords-1: coordinates; bits 32 .. 32+n_free-1: free-joint frames (mUpStream3DJoints)
+          const uint64_t allowed = (d->n_coords >= 32 ? 0xffffffffull : ((1ull << d->n_coords) - 1ull)) | (((1ull << n_free) - 1ull) << 32);
+          if (E.upstream & ~allowed) return RKB_ERR_INVALID;
+          if (E.kind == RKB_INERTIA_2D && (E.upstream >> 32)) return RKB_ERR_UNSUPPORTED;
+        }
         break;
       case RKB_INERTIA_GEN:
         if (!coord_ok(E.coord)) return RKB_ERR_INVALID;
         if (E.upstream != (1ull << E.coord)) return RKB_ERR_UNSUPPORTED;
+        // mass_matrix_calc::get_TMT_TdMT tests mUpStreamJoints.find(mCoords[i]) with i running over the 3D FRAMES and then
+        // dereferences mUpStream3DJoints[mFrames3D[i]] (mass_matrix_calculator.cpp:226-233): a rotor on coordinate i < n_free
+        // is a null dereference in the reference; there is no behaviour to reproduce
+        if (E.coord < n_free) return RKB_ERR_UNSUPPORTED;
         break;
       case RKB_ACTUATOR_GEN: {
         if (!coord_ok(E.coord) || E.aux < 0 || E.aux >= d->n_inputs) return RKB_ERR_INVALID;
@@ -171,8 +184,11 @@ int validate(const rkb_chain_desc* d) {
       case RKB_TORSION_SPRING_2D: case RKB_TORSION_DAMPER_2D: case RKB_SPRING_2D: case RKB_DAMPER_2D:
         if (!frame_ok(E.frame_a) || !frame_ok(E.frame_b) || (d->dim == 3) != is3) return RKB_ERR_INVALID;
         break;
-      case RKB_FREE_3D:
-        return RKB_ERR_UNSUPPORTED;
+      case RKB_FREE_3D:  // coord = index of the joint's coordinate frame in kte_nl_system::dofs_3D, in chain order
+        if (d->dim != 3 || !frame_ok(E.frame_a) || !frame_ok(E.frame_b) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
+        if (E.coord != free_seen++) return RKB_ERR_INVALID;
+        if (written[E.frame_b]++ || E.frame_b == d->base_frame) return RKB_ERR_INVALID;
+        break;
       default:
         return RKB_ERR_INVALID;
     }
@@ -186,7 +202,7 @@ int validate(const rkb_chain_desc* d) {
     const rkb_element& E = d->elements[e];
     switch (E.kind) {
       case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
-      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D:
+      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D: case RKB_FREE_3D:
         if (!ready[E.frame_a]) return RKB_ERR_UNSUPPORTED;
         ready[E.frame_b] = 1;
         break;
@@ -413,7 +429,8 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
     const rkb_element& E = d.elements[e];
     GenericElement& g = G.el[e];
     g.kind = E.kind; g.fa = E.frame_a; g.fb = E.frame_b; g.coord = E.coord; g.aux = E.aux;
-    g.upstream = (uint32_t)E.upstream;
+    g.upstream = (uint32_t)(E.upstream & 0xffffull) | ((uint32_t)((E.upstream >> 32) & 0xffull) << RKB_GEN_FREE_BIT);
+    if (E.kind == RKB_FREE_3D) { G.free_elem[G.n_free] = e; G.n_free += 1; }
     std::memcpy(g.p, E.p, sizeof g.p);
     if (E.kind == RKB_RIGID_LINK_3D) unit_quat(&E.p[3], &g.p[3]);
     if (E.kind == RKB_RIGID_LINK_2D) { g.p[3] = std::cos(E.p[2]); g.p[4] = std::sin(E.p[2]); }
@@ -572,7 +589,8 @@ int run_eval_like(rkb_chain* c, Op op, int device, size_t N, const double* x, co
   if (!x || !out || (c->nu > 0 && !u && op != OP_MASS && op != OP_TMT)) return RKB_ERR_INVALID;
   if ((op == OP_TMT || op == OP_FRAMES) && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
   const Layout L = parse_flags(flags);
-  const int n = c->n, nx = 2 * n, nu = c->nu;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;  // the legacy blocked order has no place for a free joint's 13 states
+  const int n = c->na, nx = c->nx, nu = c->nu;
   const int out_dim = op == OP_EVAL ? nx : op == OP_FORCES ? n : op == OP_MASS ? n * n : op == OP_TMT ? tmt_rows(c->desc) * n
                                                                                            : RKB_FRAME_DOUBLES * c->desc.n_frames;
   if (out_dim == 0) return RKB_OK;
@@ -719,6 +737,9 @@ int rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_flags, rkb_c
   c->desc.elements = c->elements.data();
   c->n = desc->n_coords;
   c->nu = desc->n_inputs;
+  for (int e = 0; e < desc->n_elements; ++e) if (desc->elements[e].kind == RKB_FREE_3D) c->n_free += 1;
+  c->nx = 2 * c->n + 13 * c->n_free;  // kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147
+  c->na = c->n + 6 * c->n_free;
   c->create_flags = create_flags;
   c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl, c->serial_shape);
   if (c->serial_ok) {
@@ -779,7 +800,7 @@ void rkb_chain_destroy(rkb_chain* c) {
   delete c;
 }
 
-int rkb_chain_state_dim(const rkb_chain* c) { return c ? 2 * c->n : RKB_ERR_INVALID; }
+int rkb_chain_state_dim(const rkb_chain* c) { return c ? c->nx : RKB_ERR_INVALID; }
 int rkb_chain_input_dim(const rkb_chain* c) { return c ? c->nu : RKB_ERR_INVALID; }
 int rkb_chain_dof(const rkb_chain* c) { return c ? c->n : RKB_ERR_INVALID; }
 /* 1 when the chain runs on the register-resident serial kernels, 0 on the interpreter */
@@ -927,7 +948,7 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
     int last = c->gp.base_frame;
     for (int e = 0; e < c->gp.n_elements; ++e) {
       const GenericElement& E = c->gp.el[e];
-      if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D) continue;
+      if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D && E.kind != RKB_FREE_3D) continue;
       if (E.fa != last) keep[E.fa] = true;
       last = E.fb;
     }
@@ -964,7 +985,8 @@ int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, con
   if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
   if (p->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -1008,7 +1030,8 @@ int rkb_is_free(rkb_chain* c, int device, size_t N, const double* x, const rkb_p
   for (int p = 0; p < n_pairs; ++p)
     if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -1078,11 +1101,15 @@ int rkb_frame_jacobian(rkb_chain* c, int device, size_t N, const double* x, int 
                        unsigned flags, void* stream) {
   if (!c) return RKB_ERR_INVALID;
   if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
-  if (frame < 0 || frame >= c->desc.n_frames || (c->n < 64 && (upstream >> c->n))) return RKB_ERR_INVALID;
+  {  // bits 0 .. n-1: coordinates; bits 32 .. 32 + n_free - 1: free joints (as rkb_element::upstream)
+    const uint64_t allowed = (c->n >= 32 ? 0xffffffffull : ((1ull << c->n) - 1ull)) | (((1ull << c->n_free) - 1ull) << 32);
+    if (frame < 0 || frame >= c->desc.n_frames || (upstream & ~allowed)) return RKB_ERR_INVALID;
+  }
   if (N == 0) return RKB_OK;
   if (!x || !J) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n, rows = c->desc.dim == 3 ? 6 : 3, dim = rows * c->n;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx, rows = c->desc.dim == 3 ? 6 : 3, dim = rows * c->na;
   if (dim == 0) return RKB_OK;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
@@ -1104,7 +1131,7 @@ int rkb_frame_jacobian(rkb_chain* c, int device, size_t N, const double* x, int 
   A.status = nullptr;
   A.n_samples = (long long)N;
   CU(cudaEventRecord(ctx->ev0, s));
-  const cudaError_t e = rkb_generic_frame_jac(ctx->d_prog, c->gp, A, frame, (unsigned)upstream, s);
+  const cudaError_t e = rkb_generic_frame_jac(ctx->d_prog, c->gp, A, frame, (unsigned)(upstream & 0xffffull) | ((unsigned)((upstream >> 32) & 0xffull) << RKB_GEN_FREE_BIT), s);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   CU(cudaEventRecord(ctx->ev1, s));
   ctx->timed = true;
@@ -1223,7 +1250,7 @@ int ensure_pipe(DeviceCtx* ctx) {
 // and the last copy-out stay exposed.  Pinned host memory is what makes the copies asynchronous.
 int rollout_host_issue(rkb_chain* c, DeviceCtx* ctx, size_t N, const double* x0, const double* u, const RolloutPlan& pl,
                        double* x_out, double* x_traj, int32_t* status, cudaStream_t s, bool join_caller, bool blocked = false) {
-  const int nx = 2 * c->n;
+  const int nx = c->nx;
   const size_t nu = (size_t)c->nu * pl.n_intervals;  // doubles of input per sample
   const size_t nt = (size_t)nx * pl.n_intervals;     // doubles of trajectory per sample
   int rc;
@@ -1303,7 +1330,8 @@ static int do_rollout(rkb_chain* c, int device, size_t N, const double* x0, cons
   if (N == 0) return RKB_OK;
   if (!x0 || !x_out || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n, nu = c->nu, J = pl.n_intervals;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx, nu = c->nu, J = pl.n_intervals;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -1370,7 +1398,8 @@ int rkb_rollout_rk4_inputs(rkb_chain* c, int device, size_t N, const double* x0,
   if (N == 0) return RKB_OK;
   if (!x0 || !x_out || !u_nodes) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n, nu = c->nu;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx, nu = c->nu;
   const long long J = 2LL * n_steps + 1;
   std::lock_guard<std::mutex> lock(c->mu);
   if (!(c->serial_ok && c->sk) && !c->generic_ok) return RKB_ERR_UNSUPPORTED;
@@ -1427,12 +1456,13 @@ int rkb_rollout_rk4_scatter(rkb_chain* c, int device, size_t N, const double* x0
   if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
   if (n_dest < 1 || n_dest > RKB_MAX_DEST || !x_out_dest) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
   if (!L.device || L.soa) return RKB_ERR_UNSUPPORTED;
   if (!c->serial_ok || !c->sk) return RKB_ERR_UNSUPPORTED;
   if (N == 0) return RKB_OK;
   if (!x0 || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
   for (int d = 0; d < n_dest; ++d) if (!x_out_dest[d]) return RKB_ERR_INVALID;
-  const int nx = 2 * c->n, nu = c->nu;
+  const int nx = c->nx, nu = c->nu;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
   if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
@@ -1467,7 +1497,7 @@ int rkb_rollout_rk4_multi(rkb_chain* c, int n_devices, const int* devices, size_
   if (dt == 0.0 || n_steps < 0 || !std::isfinite(dt)) return RKB_ERR_INTEGRATION;
   if (N == 0) return RKB_OK;
   if (!x0 || !x_out || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
-  const int nx = 2 * c->n, nu = c->nu;
+  const int nx = c->nx, nu = c->nu;
   std::lock_guard<std::mutex> lock(c->mu);
   int prev = -1;
   cudaGetDevice(&prev);
@@ -1510,7 +1540,8 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
   if (R == 0) return RKB_ERR_INVALID;
   if (!x0 || !goal || !best_idx || !best_x || (c->nu > 0 && !u)) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
-  const int nx = 2 * c->n, nu = c->nu;
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  const int nx = c->nx, nu = c->nu;
   const size_t T = P * R;
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard guard(device);
@@ -1581,9 +1612,10 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   if (!(o->time_step > 0.0) || !std::isfinite(o->time_step) || !std::isfinite(o->goal_proximity)) return RKB_ERR_INVALID;
   if ((o->u_lower == nullptr) != (o->u_upper == nullptr) || (o->du_lower == nullptr) != (o->du_upper == nullptr)) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
   if (L.soa) return RKB_ERR_UNSUPPORTED;
   if (N == 0) return RKB_OK;
-  const int nx = 2 * c->n, nu = c->nu;
+  const int nx = c->nx, nu = c->nu;
   if (!x0 || !x_goal || !x_out || !n_done || (nu > 0 && (!u_bias || !gain || !u_prev))) return RKB_ERR_INVALID;
   for (int r = 0; r < nu; ++r) {
     if (o->u_lower && !(o->u_lower[r] < o->u_upper[r])) return RKB_ERR_INVALID;
@@ -1749,8 +1781,9 @@ int rkb_linearize(rkb_chain* c, int device, size_t N, const double* x, const dou
   if (!c) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
   const Layout L = parse_flags(flags);
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
   if (L.soa || L.blocked) return RKB_ERR_UNSUPPORTED;
-  const int n = c->n, nx = 2 * n, nu = c->nu, D = nx + nu;
+  const int nx = c->nx, nu = c->nu, D = nx + nu;
   if (!x || (nu > 0 && !u) || (!A && !B) || (B && nu == 0)) return RKB_ERR_INVALID;
   if (!(eps > 0.0) || !std::isfinite(eps)) eps = 1.0e-6;
   std::lock_guard<std::mutex> lock(c->mu);

@@ -226,6 +226,14 @@ struct ProxProgram {
 #define RKB_GEN_MAX_FRAMES 40
 #define RKB_GEN_MAX_ELEMENTS 96
 
+// free_joint_3D (free_joints.cpp:123-208): at most RKB_GEN_MAX_FREE per chain, each adding 13 states (position,
+// quaternion, velocity, angular velocity of the coordinate frame) and 6 accelerations after the generalized coordinates'
+// (kte_nl_system.hpp:145-147, 205-219, 293-308).  Interpreter kernels only.
+#define RKB_GEN_MAX_FREE 1
+#define RKB_GEN_MAX_ACC (RKB_MAX_COORDS + 6 * RKB_GEN_MAX_FREE)
+#define RKB_GEN_MAX_STATE (2 * RKB_MAX_COORDS + 13 * RKB_GEN_MAX_FREE)
+#define RKB_GEN_FREE_BIT 16  // GenericElement::upstream: bit c = coordinate c, bit 16 + i = free joint i
+
 struct GenericElement {
   int32_t kind, fa, fb, coord, aux, pad;
   uint32_t upstream;
@@ -235,6 +243,7 @@ struct GenericElement {
 
 struct GenericProgram {
   int32_t dim, n_elements, n_frames, n_coords, n_inputs, base_frame;
+  int32_t n_free, free_elem[RKB_GEN_MAX_FREE];  // free joints and the element index of each
   double  base[19];  // p3 q4 v3 w3 a3 al3 (2D: p2, -, cos, sin, -, -, v2, -, w, -, -, a2, -, al)
   int32_t jelem[RKB_MAX_COORDS];  // element index of the joint that owns each coordinate
   GenericElement el[RKB_GEN_MAX_ELEMENTS];

@@ -29,12 +29,16 @@ def _is_torch(a):
 
 class kte_batch_propagator(object):
     def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3, blocked=False,
-                 interpreter=False, general=False):
+                 interpreter=False, general=False, dofs_3D=None):
         if mass_calc is None and hasattr(chain, "chain"):  # a kte_system / kte_nl_system-like object
             sys_ = chain
             chain, mass_calc, dofs_gen, inputs = sys_.chain, sys_.mass_calc, sys_.dofs_gen, sys_.inputs
+            dofs_3D = getattr(sys_, "dofs_3D", ()) if dofs_3D is None else dofs_3D
         self.chain, self.mass_calc, self.dofs_gen, self.inputs = chain, mass_calc, list(dofs_gen), list(inputs)
-        self.compiled = kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs)
+        # coordinate frames of free_joint_3D elements (kte_nl_system::dofs_3D): 13 states and 6 accelerations each,
+        # after the generalized coordinates' (kte_nl_system.hpp:145-147)
+        self.dofs_3D = list(dofs_3D or ())
+        self.compiled = kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs, self.dofs_3D)
         self.device = int(device)
         self.dt = float(time_step)
         # True: every state-shaped buffer is (q..., qd...) like manipulator_dynamics_model::computeStateRate
@@ -48,6 +52,7 @@ class kte_batch_propagator(object):
         self._h = h
         self.n = self._lib.rkb_chain_dof(h)
         self.nx = self._lib.rkb_chain_state_dim(h)
+        self.na = self.n + 6 * len(self.dofs_3D)  # accelerations: rows / columns of M, entries of f, columns of Tcm
         self.nu = self._lib.rkb_chain_input_dim(h)
 
     def close(self):
@@ -301,7 +306,7 @@ class kte_batch_propagator(object):
     def get_gen_forces(self, x, u=None, soa=False):
         x, N = self._in(x, self.nx, np.float64, soa)
         u = self._u_default(x, N, soa) if u is None else self._in(u, self.nu, np.float64, soa, N)[0]
-        f = self._like(x, (self.n, N) if soa else (N, self.n))
+        f = self._like(x, (self.na, N) if soa else (N, self.na))
         flags, stream, ptr = self._prep([x, u if self.nu else None, f], soa)
         _abi.check(self._lib.rkb_gen_forces(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None,
                                             ptr(f), flags, stream), "rkb_gen_forces")
@@ -309,7 +314,7 @@ class kte_batch_propagator(object):
 
     def get_mass_matrices(self, x, with_derivative=False, soa=False):
         x, N = self._in(x, self.nx, np.float64, soa)
-        shape = (self.n * self.n, N) if soa else (N, self.n, self.n)
+        shape = (self.na * self.na, N) if soa else (N, self.na, self.na)
         M = self._like(x, shape)
         Md = self._like(x, shape) if with_derivative else None
         flags, stream, ptr = self._prep([x, M, Md], soa)
@@ -368,15 +373,15 @@ class kte_batch_propagator(object):
         (constant) and, with_derivative, Tcm_dot [N][rows][n]."""
         x, N = self._in(x, self.nx, np.float64)
         rows = self._lib.rkb_twist_shaping_rows(self._h)
-        T = self._like(x, (N, rows, self.n))
-        Td = self._like(x, (N, rows, self.n)) if with_derivative else None
+        T = self._like(x, (N, rows, self.na))
+        Td = self._like(x, (N, rows, self.na)) if with_derivative else None
         Mc = np.zeros((rows, rows))
         _abi.check(self._lib.rkb_twist_shaping_mcm(self._h, Mc.ctypes.data_as(C.c_void_p)), "rkb_twist_shaping_mcm")
         flags, stream, ptr = self._prep([x, T, Td], False)
         _abi.check(self._lib.rkb_twist_shaping(self._h, self.device, N, ptr(x), ptr(T), ptr(Td), flags, stream), "rkb_twist_shaping")
         return (T, Mc, Td) if with_derivative else (T, Mc)
 
-    def get_frame_jacobian(self, x, frame, upstream=None, with_derivative=True):
+    def get_frame_jacobian(self, x, frame, upstream=None, with_derivative=True, free_joints=()):
         """Jacobian of one frame (a kte frame object of the chain, or its frame id) w.r.t. the coordinates and its time
         derivative: J, Jdot [N][6][n] (3D: v then w, in the frame's own coordinates) or [N][3][n] (2D) — rkb_frame_jacobian,
         manip_kin_mdl_jac_calculator::getJacobianMatrixAndDerivative.  upstream: iterable of coordinate indices (or
@@ -384,15 +389,17 @@ class kte_batch_propagator(object):
         x, N = self._in(x, self.nx, np.float64)
         fid = frame if isinstance(frame, int) else [id(f) for f in self.compiled.frames].index(id(frame))
         if upstream is None:
-            mask = (1 << self.n) - 1
+            mask = ((1 << self.n) - 1) | (((1 << len(self.dofs_3D)) - 1) << 32)
         else:
             ids = [id(c) for c in self.compiled.coords]
             mask = 0
             for c in upstream:
                 mask |= 1 << (c if isinstance(c, int) else ids.index(id(c)))
+            for j in free_joints:  # indices into dofs_3D: six more columns each (jacobian_3D_3D), after the coordinates'
+                mask |= 1 << (32 + int(j))
         rows = 6 if self.compiled.desc.dim == 3 else 3
-        J = self._like(x, (N, rows, self.n))
-        Jd = self._like(x, (N, rows, self.n)) if with_derivative else None
+        J = self._like(x, (N, rows, self.na))
+        Jd = self._like(x, (N, rows, self.na)) if with_derivative else None
         flags, stream, ptr = self._prep([x, J, Jd], False)
         _abi.check(self._lib.rkb_frame_jacobian(self._h, self.device, N, ptr(x), fid, mask, ptr(J), ptr(Jd), flags, stream), "rkb_frame_jacobian")
         return (J, Jd) if with_derivative else J
