@@ -87,6 +87,13 @@ enum rkb_kind {
   RKB_TORSION_DAMPER_3D = 9,  /* torsion_damper_3D   (torsion_damper.cpp:93-104)   p[0] = damping                    */
   RKB_SPRING_3D         = 10, /* spring_3D           (spring.cpp:178-207)          p[0] = rest length, p[1] = stiffness, p[2] = saturation */
   RKB_DAMPER_3D         = 11, /* damper_3D           (damper.cpp:136-149)          p[0] = damping                    */
+  /* elements on generalized coordinates alone.  Their anchors are system coordinates (index < n_coords) or AUXILIARY
+   * coordinates — gen_coord objects that are not system states: fixed anchors, or the end of a rigid_link_gen — declared by
+   * RKB_COORD_GEN records with indices n_coords, n_coords + 1, ... (n_coords + auxiliaries <= RKB_MAX_COORDS). */
+  RKB_RIGID_LINK_GEN    = 12, /* rigid_link_gen      (rigid_link.cpp:34-75)        coord = base, aux = end (auxiliary), p[0] = offset */
+  RKB_SPRING_GEN        = 13, /* spring_gen          (spring.cpp:50-84)            coord = anchor 1, aux = anchor 2, p as RKB_SPRING_3D */
+  RKB_DAMPER_GEN        = 14, /* damper_gen          (damper.cpp:48-57)            coord = anchor 1, aux = anchor 2, p[0] = damping  */
+  RKB_COORD_GEN         = 15, /* an auxiliary gen_coord (gen_coord.hpp:44-178): coord = its index, p[0..2] = q, q_dot, q_ddot it holds */
   RKB_REVOLUTE_2D       = 17, /* revolute_joint_2D   (revolute_joint.cpp:32-116)                                     */
   RKB_PRISMATIC_2D      = 18, /* prismatic_joint_2D  (prismatic_joint.cpp:33-123)  p[0..1] = axis                    */
   RKB_RIGID_LINK_2D     = 20, /* rigid_link_2D       (rigid_link.cpp:87-139)       p[0..1] = offset, p[2] = angle    */
@@ -105,7 +112,7 @@ typedef struct rkb_element {
   int32_t  frame_a;   /* joint/link: base frame; spring/damper: anchor 1; inertia_2D/3D: CoM frame; else -1 */
   int32_t  frame_b;   /* joint/link: end frame;  spring/damper: anchor 2; actuator: index of the reacting joint element; else -1 */
   int32_t  coord;     /* generalized coordinate (joints, inertia_gen, actuator); else -1 */
-  int32_t  aux;       /* actuator: input index; else 0 */
+  int32_t  aux;       /* actuator: input index; _gen link / spring / damper: second coordinate; else 0 */
   int32_t  reserved;
   uint64_t upstream;  /* inertias: bit c set <=> coordinate c is in mUpStreamJoints (jacobian_joint_map.hpp:252-331);
                          bit 32 + i set <=> the coordinate frame of free joint i is in mUpStream3DJoints */

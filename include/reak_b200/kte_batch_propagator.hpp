@@ -57,7 +57,7 @@ class propagator_error : public std::runtime_error {
 /// appended in kte_map_chain order (the order `chain << element` would give).
 class chain_builder {
  public:
-  explicit chain_builder(int dim = 3) : mDim(dim), mFrames(0), mCoords(0), mInputs(0), mBaseFrame(-1) {
+  explicit chain_builder(int dim = 3) : mDim(dim), mFrames(0), mCoords(0), mInputs(0), mBaseFrame(-1), mAux(0) {
     mBase = rkb_base_frame();
     mBase.quat[0] = dim == 3 ? 1.0 : 0.0;
   }
@@ -119,6 +119,21 @@ class chain_builder {
   }
   int damper(int a1, int a2, double damping) { return push(mDim == 3 ? RKB_DAMPER_3D : RKB_DAMPER_2D, a1, a2, -1, 0, 0, vec(damping)); }
 
+  /// Elements on generalized coordinates alone (rigid_link.cpp:30-75, spring.cpp:32-96, damper.cpp:32-68).  Their anchors
+  /// are system coordinates or auxiliary ones: add_aux_coord() declares a gen_coord that is not a system state (a fixed
+  /// anchor, or the end of a rigid_link_gen) holding (q, q_dot, q_ddot), and returns its index.  Call it after every
+  /// add_coord() and before the first element that uses it.
+  int add_aux_coord(double q = 0.0, double q_dot = 0.0, double q_ddot = 0.0) {
+    const int idx = mCoords + mAux++;
+    push(RKB_COORD_GEN, -1, -1, idx, 0, 0, vec(q, q_dot, q_ddot));
+    return idx;
+  }
+  int rigid_link_gen(int base_coord, int end_aux_coord, double offset) { return push(RKB_RIGID_LINK_GEN, -1, -1, base_coord, end_aux_coord, 0, vec(offset)); }
+  int spring_gen(int c1, int c2, double rest_length, double stiffness, double saturation = 0.0) {
+    return push(RKB_SPRING_GEN, -1, -1, c1, c2, 0, vec(rest_length, stiffness, saturation));
+  }
+  int damper_gen(int c1, int c2, double damping) { return push(RKB_DAMPER_GEN, -1, -1, c1, c2, 0, vec(damping)); }
+
   /// Actuators may be appended before the joint they drive (CRS order: actuator, rotor, joint, ...).
   void set_actuator_joint(int actuator_element, int joint_element) { mElements.at(actuator_element).frame_b = joint_element; }
 
@@ -150,7 +165,7 @@ class chain_builder {
     mElements.push_back(e);
     return static_cast<int>(mElements.size()) - 1;
   }
-  int mDim, mFrames, mCoords, mInputs, mBaseFrame;
+  int mDim, mFrames, mCoords, mInputs, mBaseFrame, mAux;
   rkb_base_frame mBase;
   std::vector<rkb_element> mElements;
 };

@@ -139,6 +139,19 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
       return id;
     }
   };
+  // a generalized coordinate of a _gen element: a system dof, or an auxiliary gen_coord declared (with the values it
+  // holds) right before the first element that uses it
+  detail::id_map aux;
+  struct gen {
+    static int id(chain_builder& bb, const detail::id_map& co, detail::id_map& ax, const shared_ptr<gen_coord<double> >& c) {
+      if (!c) throw unsupported_chain("_gen element with a null coordinate");
+      int i = co.lookup(c.get());
+      if (i >= 0) return i;
+      i = ax.lookup(c.get());
+      if (i < 0) { i = bb.add_aux_coord(c->q, c->q_dot, c->q_ddot); ax.ids[c.get()] = i; }
+      return i;
+    }
+  };
   std::vector<std::pair<int, const void*> > pending_actuators;  // (element index, joint object)
   const void* base3 = NULL;
   std::map<int, const void*> frame_obj;
@@ -213,6 +226,16 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
       idx = b.torsion_damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
     } else if (shared_ptr<torsion_damper_2D> s = rk_dynamic_ptr_cast<torsion_damper_2D>(k)) {
       idx = b.torsion_damper(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->Damping());
+    } else if (shared_ptr<rigid_link_gen> l = rk_dynamic_ptr_cast<rigid_link_gen>(k)) {
+      const int ca = gen::id(b, coords, aux, l->BaseFrame()), cb = gen::id(b, coords, aux, l->EndFrame());
+      if (coords.lookup(l->EndFrame().get()) >= 0) throw unsupported_chain("rigid_link_gen ends on a system dof");
+      idx = b.rigid_link_gen(ca, cb, l->Offset());
+    } else if (shared_ptr<spring_gen> s = rk_dynamic_ptr_cast<spring_gen>(k)) {
+      const int ca = gen::id(b, coords, aux, s->Anchor1()), cb = gen::id(b, coords, aux, s->Anchor2());
+      idx = b.spring_gen(ca, cb, s->RestLength(), s->Stiffness(), s->Saturation());
+    } else if (shared_ptr<damper_gen> s = rk_dynamic_ptr_cast<damper_gen>(k)) {
+      const int ca = gen::id(b, coords, aux, s->Anchor1()), cb = gen::id(b, coords, aux, s->Anchor2());
+      idx = b.damper_gen(ca, cb, s->Damping());
     } else if (shared_ptr<spring_3D> s = rk_dynamic_ptr_cast<spring_3D>(k)) {
       idx = b.spring(local::fid(b, frames, s->Anchor1().get()), local::fid(b, frames, s->Anchor2().get()), s->RestLength(), s->Stiffness(), s->Saturation());
     } else if (shared_ptr<spring_2D> s = rk_dynamic_ptr_cast<spring_2D>(k)) {

@@ -251,6 +251,7 @@ typedef struct {
   jac2* j2;
   double* u; /* inputs[k]->mDriveForce */
   int n, nu, m_rows;
+  int n_aux; /* auxiliary gen_coords (RKB_COORD_GEN): c[n .. n + n_aux - 1], never part of the state */
   /* free_joint_3D coordinate frames (kte_nl_system::dofs_3D): 13 states and 6 accelerations each */
   int nfree, nx, na;
   frame3 fc[KTO_MAX_FREE];
@@ -288,7 +289,9 @@ void* kto_create(const rkb_chain_desc* desc) {
   m->d.elements = m->el;
   m->f3 = (frame3*)calloc((size_t)desc->n_frames, sizeof(frame3));
   m->f2 = (frame2*)calloc((size_t)desc->n_frames, sizeof(frame2));
-  m->c = (gcoord*)calloc((size_t)m->n + 1, sizeof(gcoord));
+  for (e = 0; e < desc->n_elements; ++e) if (m->el[e].kind == RKB_COORD_GEN) m->n_aux += 1;
+  if (m->n + m->n_aux > RKB_MAX_COORDS) { model_free(m); return NULL; }
+  m->c = (gcoord*)calloc((size_t)(m->n + m->n_aux) + 1, sizeof(gcoord));
   m->j3 = (jac3*)calloc((size_t)m->n + 1, sizeof(jac3));
   m->j2 = (jac2*)calloc((size_t)m->n + 1, sizeof(jac2));
   m->u = (double*)calloc((size_t)m->nu + 1, sizeof(double));
@@ -300,6 +303,16 @@ void* kto_create(const rkb_chain_desc* desc) {
       case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
         bad = E->coord < 0 || E->coord >= m->n; /* fallthrough to frame checks */
         bad |= E->frame_a < 0 || E->frame_a >= desc->n_frames || E->frame_b < 0 || E->frame_b >= desc->n_frames;
+        break;
+      case RKB_COORD_GEN: /* an auxiliary gen_coord holding constant values unless a rigid_link_gen writes it */
+        bad = E->coord < m->n || E->coord >= m->n + m->n_aux;
+        if (!bad) { m->c[E->coord].q = E->p[0]; m->c[E->coord].qd = E->p[1]; m->c[E->coord].qdd = E->p[2]; }
+        break;
+      case RKB_RIGID_LINK_GEN:
+        bad = E->coord < 0 || E->coord >= m->n + m->n_aux || E->aux < m->n || E->aux >= m->n + m->n_aux;
+        break;
+      case RKB_SPRING_GEN: case RKB_DAMPER_GEN:
+        bad = E->coord < 0 || E->coord >= m->n + m->n_aux || E->aux < 0 || E->aux >= m->n + m->n_aux;
         break;
       case RKB_FREE_3D:
         bad = desc->dim != 3 || E->coord != m->nfree || m->nfree >= KTO_MAX_FREE;
@@ -421,6 +434,14 @@ static void do_motion(model* m) {
         m->j3[E->coord].qd_aacc = V3(0, 0, 0);
         break;
       }
+      case RKB_RIGID_LINK_GEN: { /* rigid_link.cpp:34-40 */
+        const gcoord* B = &m->c[E->coord];
+        gcoord* N = &m->c[E->aux];
+        N->q = B->q + E->p[0];
+        N->qd = B->qd;
+        N->qdd = B->qdd;
+        break;
+      }
       case RKB_FREE_3D: { /* free_joints.cpp:123-146: *mEnd = (*mBase) * (*mCoord); the Jacobian is two identity blocks */
         frame3 r = f3_compose(m->f3[E->frame_a], &m->fc[E->coord]);
         frame3* N = &m->f3[E->frame_b];
@@ -498,7 +519,7 @@ static void clear_force(model* m) {
     m->f3[i].F = V3(0, 0, 0); m->f3[i].T = V3(0, 0, 0);
     m->f2[i].F = V2(0, 0); m->f2[i].T = 0.0;
   }
-  for (i = 0; i < m->n; ++i) m->c[i].f = 0.0;
+  for (i = 0; i < m->n + m->n_aux; ++i) m->c[i].f = 0.0;
   for (i = 0; i < m->nfree; ++i) { m->fc[i].F = V3(0, 0, 0); m->fc[i].T = V3(0, 0, 0); } /* free_joints.cpp:184-197 */
 }
 
@@ -528,6 +549,34 @@ static void do_force(model* m) {
         c->f += tf;
         B->F = add3(B->F, sub3(N->F, scl3(tf, axis)));
         B->T = add3(B->T, add3(N->T, cross3(scl3(c->q, axis), N->F)));
+        break;
+      }
+      case RKB_RIGID_LINK_GEN: /* rigid_link.cpp:53-57 */
+        m->c[E->coord].f += m->c[E->aux].f;
+        break;
+      case RKB_SPRING_GEN: { /* spring.cpp:50-84 */
+        gcoord* A1 = &m->c[E->coord];
+        gcoord* A2 = &m->c[E->aux];
+        double rest = E->p[0], k = E->p[1], sat = E->p[2];
+        if (A1->q > A2->q) {
+          double fm = (A1->q - A2->q - rest) * k;
+          if (sat > 0 && fabs(fm) > sat) {
+            if (fm > 0) { A1->f -= sat; A2->f += sat; } else { A1->f += sat; A2->f -= sat; }
+          } else { A1->f -= fm; A2->f += fm; }
+        } else {
+          double fm = (A2->q - A1->q - rest) * k;
+          if (sat > 0 && fabs(fm) > sat) {
+            if (fm > 0) { A1->f += sat; A2->f -= sat; } else { A1->f -= sat; A2->f += sat; }
+          } else { A1->f += fm; A2->f -= fm; }
+        }
+        break;
+      }
+      case RKB_DAMPER_GEN: { /* damper.cpp:48-57 */
+        gcoord* A1 = &m->c[E->coord];
+        gcoord* A2 = &m->c[E->aux];
+        double fm = (A1->qd - A2->qd) * E->p[0];
+        A1->f -= fm;
+        A2->f += fm;
         break;
       }
       case RKB_FREE_3D: { /* free_joints.cpp:164-172: the wrench at the end frame lands on the coordinate frame */

@@ -100,6 +100,7 @@ struct ref_model {
   ctrl::kte_nl_system sys;
   int n, nu;
   // free_joint_3D coordinate frames (kte_nl_system::dofs_3D) and their Jacobian holders
+  std::vector<shared_ptr<gen_coord<double> > > aux_coords;  // RKB_COORD_GEN: gen_coords that are not system states
   std::vector<shared_ptr<frame_3D<double> > > fcoord;
   std::vector<shared_ptr<jacobian_3D_3D<double> > > jac33;
   int nx, na;  // state / acceleration dimensions: 2 n + 13 n_free, n + 6 n_free
@@ -120,6 +121,9 @@ ref_model* build_model(const rkb_chain_desc& d) {
     if (is3) m->f3.push_back(shared_ptr<frame_3D<double> >(new frame_3D<double>()));
     else     m->f2.push_back(shared_ptr<frame_2D<double> >(new frame_2D<double>()));
   }
+  int n_aux = 0;
+  for (int e = 0; e < d.n_elements; ++e) if (d.elements[e].kind == RKB_COORD_GEN) ++n_aux;
+  std::vector<shared_ptr<gen_coord<double> > > all_coords;  // system coordinates, then the auxiliary gen_coords
   for (int i = 0; i < d.n_coords; ++i) {
     m->coords.push_back(shared_ptr<gen_coord<double> >(new gen_coord<double>()));
     if (is3) m->jac3.push_back(shared_ptr<jacobian_gen_3D<double> >(new jacobian_gen_3D<double>()));
@@ -133,6 +137,9 @@ ref_model* build_model(const rkb_chain_desc& d) {
     }
   m->nx = 2 * m->n + 13 * (int)m->fcoord.size();
   m->na = m->n + 6 * (int)m->fcoord.size();
+  all_coords = m->coords;
+  for (int i = 0; i < n_aux; ++i) all_coords.push_back(shared_ptr<gen_coord<double> >(new gen_coord<double>()));
+  m->aux_coords.assign(all_coords.begin() + d.n_coords, all_coords.end());
   const rkb_base_frame& b = d.base;
   if (is3) {
     frame_3D<double>& B = *m->f3[d.base_frame];
@@ -191,6 +198,17 @@ ref_model* build_model(const rkb_chain_desc& d) {
     switch (E.kind) {
       case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
         k = joint_of_elem[e]; break;
+      case RKB_COORD_GEN: {  // not a KTE: a free-standing gen_coord with the values it keeps
+        gen_coord<double>& g = *all_coords.at(E.coord);
+        g.q = E.p[0]; g.q_dot = E.p[1]; g.q_ddot = E.p[2];
+        m->elems.push_back(shared_ptr<kte::kte_map>());
+        continue; }
+      case RKB_RIGID_LINK_GEN:
+        k = shared_ptr<kte::kte_map>(new kte::rigid_link_gen(nm, all_coords.at(E.coord), all_coords.at(E.aux), E.p[0])); break;
+      case RKB_SPRING_GEN:
+        k = shared_ptr<kte::kte_map>(new kte::spring_gen(nm, all_coords.at(E.coord), all_coords.at(E.aux), E.p[0], E.p[1], E.p[2])); break;
+      case RKB_DAMPER_GEN:
+        k = shared_ptr<kte::kte_map>(new kte::damper_gen(nm, all_coords.at(E.coord), all_coords.at(E.aux), E.p[0])); break;
       case RKB_FREE_3D:
         k = shared_ptr<kte::kte_map>(new kte::free_joint_3D(nm, m->fcoord[E.coord], m->f3[E.frame_a], m->f3[E.frame_b], m->jac33[E.coord]));
         break;

@@ -122,7 +122,10 @@ GD void motion(const GenericProgram* G, Work<3, MAXF>& W) {
   set_base(G, W.fr[G->base_frame]);
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
-    if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-152 (q_ddot = 0)
+    if (E.kind == RKB_RIGID_LINK_GEN) {  // rigid_link.cpp:34-40
+      W.q[E.aux] = W.q[E.coord] + E.p[0];
+      W.qd[E.aux] = W.qd[E.coord];
+    } else if (E.kind == RKB_REVOLUTE_3D) {  // revolute_joint.cpp:121-152 (q_ddot = 0)
       const Fr3 B = W.fr[E.fa];
       Fr3& N = W.fr[E.fb];
       const V3 ax = ldv(E.p), an = unit_axis(ax);
@@ -177,7 +180,10 @@ GD void motion(const GenericProgram* G, Work<2, MAXF>& W) {
   set_base(G, W.fr[G->base_frame]);
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
-    if (E.kind == RKB_REVOLUTE_2D) {  // revolute_joint.cpp:32-58
+    if (E.kind == RKB_RIGID_LINK_GEN) {  // rigid_link.cpp:34-40
+      W.q[E.aux] = W.q[E.coord] + E.p[0];
+      W.qd[E.aux] = W.qd[E.coord];
+    } else if (E.kind == RKB_REVOLUTE_2D) {  // revolute_joint.cpp:32-58
       const Fr2 B = W.fr[E.fa];
       Fr2& N = W.fr[E.fb];
       R2 rq;
@@ -210,10 +216,35 @@ GD void motion(const GenericProgram* G, Work<2, MAXF>& W) {
 }
 
 // ---- clearForce + doForce ------------------------------------------------------------------------
+// elements that act on generalized coordinates alone (the same in 2D and 3D chains); f is indexed like q: system
+// coordinates, then the auxiliary gen_coords.  Returns false for any other kind.
+GD bool force_gen(const GenericElement& E, const double* q, const double* qd, double* f) {
+  switch (E.kind) {
+    case RKB_RIGID_LINK_GEN:  // rigid_link.cpp:53-57
+      f[E.coord] += f[E.aux];
+      return true;
+    case RKB_SPRING_GEN: {  // spring.cpp:50-84
+      const double rest = E.p[0], k = E.p[1], sat = E.p[2];
+      const bool first = q[E.coord] > q[E.aux];
+      const double fm = ((first ? q[E.coord] - q[E.aux] : q[E.aux] - q[E.coord]) - rest) * k;
+      double t = fm;
+      if (sat > 0.0 && fabs(fm) > sat) t = fm > 0.0 ? sat : -sat;
+      if (first) { f[E.coord] -= t; f[E.aux] += t; } else { f[E.coord] += t; f[E.aux] -= t; }
+      return true;
+    }
+    case RKB_DAMPER_GEN: {  // damper.cpp:48-57
+      const double fm = (qd[E.coord] - qd[E.aux]) * E.p[0];
+      f[E.coord] -= fm; f[E.aux] += fm;
+      return true;
+    }
+    default: return false;
+  }
+}
+
 template <int MAXF>
 GD void force(const GenericProgram* G, Work<3, MAXF>& W) {
   for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v3(0, 0, 0); W.fr[i].T = v3(0, 0, 0); }
-  for (int i = 0; i < G->n_coords; ++i) W.f[i] = 0.0;
+  for (int i = 0; i < G->n_coords + G->n_aux; ++i) W.f[i] = 0.0;
   W.fc.F = v3(0, 0, 0); W.fc.T = v3(0, 0, 0);
   for (int e = G->n_elements - 1; e >= 0; --e) {
     const GenericElement& E = G->el[e];
@@ -333,14 +364,14 @@ GD void force(const GenericProgram* G, Work<3, MAXF>& W) {
         }
         break;
       }
-      default: break;  // inertia_gen: f -= q_ddot * m with q_ddot = 0
+      default: force_gen(E, W.q, W.qd, W.f); break;  // (inertia_gen: f -= q_ddot * m with q_ddot = 0)
     }
   }
 }
 template <int MAXF>
 GD void force(const GenericProgram* G, Work<2, MAXF>& W) {
   for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v2(0, 0); W.fr[i].T = 0.0; }
-  for (int i = 0; i < G->n_coords; ++i) W.f[i] = 0.0;
+  for (int i = 0; i < G->n_coords + G->n_aux; ++i) W.f[i] = 0.0;
   for (int e = G->n_elements - 1; e >= 0; --e) {
     const GenericElement& E = G->el[e];
     switch (E.kind) {
@@ -432,7 +463,7 @@ GD void force(const GenericProgram* G, Work<2, MAXF>& W) {
         }
         break;
       }
-      default: break;
+      default: force_gen(E, W.q, W.qd, W.f); break;
     }
   }
 }
@@ -822,6 +853,7 @@ GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& 
     W.q[c] = x.p[ix * x.si + rkb_state_q(x.blocked, G->n_coords, c) * x.sk];
     W.qd[c] = x.p[ix * x.si + rkb_state_qd(x.blocked, G->n_coords, c) * x.sk];
   }
+  for (int k = 0; k < G->n_aux; ++k) { W.q[G->n_coords + k] = G->aux_q[k]; W.qd[G->n_coords + k] = G->aux_qd[k]; }
   if (G->n_free) {  // the 13 states of the free joint follow the coordinates' (never blocked: rejected by the host)
     double s[13];
     for (int k = 0; k < 13; ++k) s[k] = x.p[ix * x.si + (2 * G->n_coords + k) * x.sk];
@@ -1044,6 +1076,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
   double xs[MAXX], xd[MAXX];
   load_flat(G, A.x0, i0, xs);
   for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + k * A.u.sk];
+  for (int k = 0; k < G->n_aux; ++k) { W.q[G->n_coords + k] = G->aux_q[k]; W.qd[G->n_coords + k] = G->aux_qd[k]; }
   const double dt = A.dt;
   double w[MAXX], acc[MAXX], k3[MAXX];
   double ks[TABLE ? RKB_RK_MAX_STAGES : 1][MAXX];

@@ -130,8 +130,12 @@ int validate(const rkb_chain_desc* d) {
       !finite_all(d->base.ang_velocity, 3) || !finite_all(d->base.acceleration, 3) || !finite_all(d->base.ang_acceleration, 3))
     return RKB_ERR_INVALID;
   std::vector<int> coord_joint(d->n_coords, 0), input_used(d->n_inputs, 0), written(d->n_frames, 0);
-  int n_free = 0;
+  int n_free = 0, n_aux = 0;
   for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_FREE_3D) ++n_free;
+  for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_COORD_GEN) ++n_aux;
+  if (d->n_coords + n_aux > RKB_MAX_COORDS) return RKB_ERR_UNSUPPORTED;
+  std::vector<int> aux_declared(n_aux, 0), aux_written(n_aux, 0);
+  auto any_coord_ok = [&](int c) { return c >= 0 && c < d->n_coords + n_aux && (c < d->n_coords || aux_declared[c - d->n_coords]); };
   if (n_free > RKB_GEN_MAX_FREE) return RKB_ERR_UNSUPPORTED;
   int free_seen = 0;
   for (int e = 0; e < d->n_elements; ++e) {
@@ -183,6 +187,16 @@ int validate(const rkb_chain_desc* d) {
       case RKB_TORSION_SPRING_3D: case RKB_TORSION_DAMPER_3D: case RKB_SPRING_3D: case RKB_DAMPER_3D:
       case RKB_TORSION_SPRING_2D: case RKB_TORSION_DAMPER_2D: case RKB_SPRING_2D: case RKB_DAMPER_2D:
         if (!frame_ok(E.frame_a) || !frame_ok(E.frame_b) || (d->dim == 3) != is3) return RKB_ERR_INVALID;
+        break;
+      case RKB_COORD_GEN:  // declares auxiliary coordinate `coord` (>= n_coords), ahead of the elements that use it
+        if (E.coord < d->n_coords || E.coord >= d->n_coords + n_aux || aux_declared[E.coord - d->n_coords]++) return RKB_ERR_INVALID;
+        break;
+      case RKB_RIGID_LINK_GEN:  // the end is an auxiliary coordinate no other link writes
+        if (!any_coord_ok(E.coord) || !any_coord_ok(E.aux) || E.aux < d->n_coords || E.aux == E.coord) return RKB_ERR_INVALID;
+        if (aux_written[E.aux - d->n_coords]++) return RKB_ERR_INVALID;
+        break;
+      case RKB_SPRING_GEN: case RKB_DAMPER_GEN:
+        if (!any_coord_ok(E.coord) || !any_coord_ok(E.aux)) return RKB_ERR_INVALID;
         break;
       case RKB_FREE_3D:  // coord = index of the joint's coordinate frame in kte_nl_system::dofs_3D, in chain order
         if (d->dim != 3 || !frame_ok(E.frame_a) || !frame_ok(E.frame_b) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
@@ -431,6 +445,7 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
     g.kind = E.kind; g.fa = E.frame_a; g.fb = E.frame_b; g.coord = E.coord; g.aux = E.aux;
     g.upstream = (uint32_t)(E.upstream & 0xffffull) | ((uint32_t)((E.upstream >> 32) & 0xffull) << RKB_GEN_FREE_BIT);
     if (E.kind == RKB_FREE_3D) { G.free_elem[G.n_free] = e; G.n_free += 1; }
+    if (E.kind == RKB_COORD_GEN) { G.aux_q[E.coord - d.n_coords] = E.p[0]; G.aux_qd[E.coord - d.n_coords] = E.p[1]; G.n_aux += 1; }
     std::memcpy(g.p, E.p, sizeof g.p);
     if (E.kind == RKB_RIGID_LINK_3D) unit_quat(&E.p[3], &g.p[3]);
     if (E.kind == RKB_RIGID_LINK_2D) { g.p[3] = std::cos(E.p[2]); g.p[4] = std::sin(E.p[2]); }

@@ -266,6 +266,31 @@ class damper_2D(damper_3D):
     """ctrl/mbd_kte/damper.hpp:197-200 / damper.cpp:88-102."""
 
 
+class rigid_link_gen(kte_map):
+    """ctrl/mbd_kte/rigid_link.hpp:40-118 / rigid_link.cpp:30-75: End.q = Base.q + offset on generalized coordinates."""
+
+    def __init__(self, name, base, end, offset):
+        kte_map.__init__(self, name)
+        self.mBase, self.mEnd, self.mOffset = base, end, float(offset)
+
+
+class spring_gen(kte_map):
+    """ctrl/mbd_kte/spring.hpp:44-175 / spring.cpp:32-96: linear spring between two generalized coordinates."""
+
+    def __init__(self, name, anchor1, anchor2, rest_length, stiffness, saturation=0.0):
+        kte_map.__init__(self, name)
+        self.mAnchor1, self.mAnchor2 = anchor1, anchor2
+        self.mRestLength, self.mStiffness, self.mSaturation = float(rest_length), float(stiffness), float(saturation)
+
+
+class damper_gen(kte_map):
+    """ctrl/mbd_kte/damper.hpp:44-140 / damper.cpp:32-68: linear damper between two generalized coordinates."""
+
+    def __init__(self, name, anchor1, anchor2, damping):
+        kte_map.__init__(self, name)
+        self.mAnchor1, self.mAnchor2, self.mDamping = anchor1, anchor2, float(damping)
+
+
 class kte_map_chain(kte_map):
     """ctrl/mbd_kte/kte_map_chain.hpp:50-120: ordered list of KTEs, `chain << kte` appends."""
 
@@ -357,6 +382,22 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
             raise UnsupportedChain("element refers to a coordinate that is not a system dof")
         return coord_id[id(c)]
 
+    aux_id = {}  # gen_coords that are not system states: anchors and rigid_link_gen ends, numbered after the dofs
+
+    def gid(c):
+        """any generalized coordinate: a dof, or an auxiliary one (declared by a COORD_GEN record right before the first
+        element that uses it — the rule the C++ bridge follows too)"""
+        if not isinstance(c, gen_coord):
+            raise UnsupportedChain("a _gen element needs gen_coord anchors, got %r" % (c,))
+        if id(c) in coord_id:
+            return coord_id[id(c)]
+        if id(c) not in aux_id:
+            if len(dofs_gen) + len(aux_id) >= _abi.RKB_MAX_COORDS:
+                raise UnsupportedChain("more than %d generalized coordinates (dofs + auxiliaries)" % _abi.RKB_MAX_COORDS)
+            aux_id[id(c)] = len(dofs_gen) + len(aux_id)
+            rec(_abi.COORD_GEN, coord=aux_id[id(c)], p=[c.q, c.q_dot, c.q_ddot])
+        return aux_id[id(c)]
+
     def upstream_mask(dep):
         m = 0
         for c in dep.mUpStreamJoints:
@@ -396,6 +437,17 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
                 raise UnsupportedChain("free joint %s: its coordinate frame is not in dofs_3D" % k.name)
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
             rec(_abi.FREE_3D, a, b, free_id[id(k.mCoord)])
+        elif isinstance(k, rigid_link_gen):
+            a, b = gid(k.mBase), gid(k.mEnd)
+            if b < len(dofs_gen):
+                raise UnsupportedChain("rigid_link_gen %s ends on a system dof (the state would be overwritten)" % k.name)
+            rec(_abi.RIGID_LINK_GEN, coord=a, aux=b, p=[k.mOffset])
+        elif isinstance(k, spring_gen):
+            a, b = gid(k.mAnchor1), gid(k.mAnchor2)
+            rec(_abi.SPRING_GEN, coord=a, aux=b, p=[k.mRestLength, k.mStiffness, k.mSaturation])
+        elif isinstance(k, damper_gen):
+            a, b = gid(k.mAnchor1), gid(k.mAnchor2)
+            rec(_abi.DAMPER_GEN, coord=a, aux=b, p=[k.mDamping])
         elif isinstance(k, rigid_link_3D):
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
             rec(_abi.RIGID_LINK_3D, a, b, p=list(k.mPoseOffset.Position) + list(k.mPoseOffset.Quat))

@@ -230,6 +230,36 @@ def crs_linear_spring_chain():
     return s
 
 
+def crs_gen_elements_chain():
+    """3-joint arm with the elements that act on generalized coordinates alone (rigid_link.cpp:30-75, spring.cpp:32-96,
+    damper.cpp:32-68): a joint-space return spring and damper from joint 0 to a fixed anchor coordinate, a coupling spring
+    (saturating) and damper between joints 1 and 2, and a spring acting on an OFFSET copy of joint 2's coordinate
+    (rigid_link_gen) whose force flows back through the link."""
+    s = crs_chain(n_revolute=3, physical=True)
+    q = s.dofs_gen
+    ground = kte.gen_coord(0.25, 0.1)          # a gen_coord that is not a state: keeps q = 0.25, q_dot = 0.1
+    shifted = kte.gen_coord()                  # written by the rigid_link_gen
+    wall = kte.gen_coord(-0.4)
+    s.chain << kte.spring_gen("return_spring", q[0], ground, 0.1, 40.0)
+    s.chain << kte.damper_gen("return_damper", q[0], ground, 1.5)
+    s.chain << kte.spring_gen("coupling_spring", q[1], q[2], 0.2, 300.0, 25.0)
+    s.chain << kte.damper_gen("coupling_damper", q[2], q[1], 0.8)
+    s.chain << kte.rigid_link_gen("offset", q[2], shifted, 0.35)
+    s.chain << kte.spring_gen("offset_spring", wall, shifted, 0.0, 15.0)
+    return s
+
+
+def planar_gen_elements_chain():
+    """2-link planar arm with a joint-space spring / damper to a fixed anchor and between its two joints."""
+    s = planar_chain(actuated=True)
+    q = s.dofs_gen
+    ground = kte.gen_coord(0.3)
+    s.chain << kte.spring_gen("spring_0", ground, q[0], 0.0, 12.0, 5.0)
+    s.chain << kte.damper_gen("damper_01", q[0], q[1], 0.6)
+    s.chain << kte.spring_gen("spring_01", q[0], q[1], 0.5, 8.0)
+    return s
+
+
 def planar_linear_spring_chain():
     """3-link planar arm with spring_2D / damper_2D between the base and the tip and a saturating
     spring between link ends (spring.cpp:116-143, damper.cpp:88-102)."""
@@ -321,6 +351,8 @@ PRESETS = {
     "planar2_lin_sd": planar_linear_spring_chain,
     "planar_pr": planar_prismatic_revolute_chain,
     "crs2d": crs_2d_analog_chain,                                     # the reference's own planar dynamic model
+    "crs3_gen": crs_gen_elements_chain,                               # rigid_link_gen / spring_gen / damper_gen
+    "planar2_gen": planar_gen_elements_chain,
 }
 
 

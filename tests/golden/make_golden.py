@@ -22,13 +22,16 @@ from reak_b200 import kte, presets  # noqa: E402
 
 N = 16
 CASES = ["pendulum", "planar2", "planar3_sd", "torsion1", "crs3", "crs6", "crs6_phys", "crs6_sd", "crs6_sd_sat",
-         "crs6_twist", "crs7", "crs7_phys_sd", "crs6_passive", "planar2_act", "crs6_lin_sd", "planar2_lin_sd", "planar_pr", "crs2d"]
+         "crs6_twist", "crs7", "crs7_phys_sd", "crs6_passive", "planar2_act", "crs6_lin_sd", "planar2_lin_sd", "planar_pr", "crs2d", "crs3_gen", "planar2_gen"]
 
 
 def main():
     if not pyref.have_ref():
         raise SystemExit("oracle/_ref/libreak_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+    only = set(sys.argv[1:])  # optional: regenerate just these fixtures (the seeds depend on the position in CASES only)
     for idx, name in enumerate(CASES):
+        if only and name not in only:
+            continue
         s = presets.make(name)
         c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
         R = pyref.Reference(c)

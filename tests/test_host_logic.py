@@ -106,3 +106,34 @@ def test_inertia_registered_with_mass_calc_but_missing_from_the_chain_is_refused
     s.mass_calc << kte.inertia_3D("ghost", ghost_frame, 2.0, (0.1, 0.0, 0.0, 0.1, 0.0, 0.1))
     with pytest.raises(kte.UnsupportedChain, match="not in the chain"):
         kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+
+
+def test_gen_elements_lowering():
+    """rigid_link_gen / spring_gen / damper_gen (rigid_link.cpp:30-75, spring.cpp:32-96, damper.cpp:32-68): anchors that are
+    not system dofs become auxiliary coordinates, declared once, right before their first use, with the values they hold"""
+    s = presets.make("crs3_gen")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    kinds = [e.kind for e in c.elements]
+    decl = [e for e in c.elements if e.kind == _abi.COORD_GEN]
+    assert [e.coord for e in decl] == [3, 4, 5] and c.n_coords == 3
+    assert [list(e.p)[:2] for e in decl] == [[0.25, 0.1], [0.0, 0.0], [-0.4, 0.0]]
+    first_use = kinds.index(_abi.SPRING_GEN)
+    assert kinds[first_use - 1] == _abi.COORD_GEN and c.elements[first_use].aux == 3
+    link = [e for e in c.elements if e.kind == _abi.RIGID_LINK_GEN][0]
+    assert (link.coord, link.aux, link.p[0]) == (2, 4, 0.35)
+    # a link that ends on a state would overwrite it every doMotion: rejected
+    s.chain << kte.rigid_link_gen("bad", s.dofs_gen[0], s.dofs_gen[1], 0.1)
+    with pytest.raises(kte.UnsupportedChain):
+        kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    # the library validates the same rules on a raw descriptor
+    import ctypes as C
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    assert lib.rkb_chain_create(C.byref(c.desc), C.byref(h)) == 0
+    assert lib.rkb_chain_is_serial(h) == 0 and lib.rkb_chain_state_dim(h) == 6
+    lib.rkb_chain_destroy(h)
+    bad = [e for e in c.elements if e.kind == _abi.SPRING_GEN][0]
+    keep = bad.aux
+    bad.aux = 9  # an auxiliary coordinate nobody declared
+    assert lib.rkb_chain_create(C.byref(c.desc), C.byref(h)) == _abi.ERR_INVALID
+    bad.aux = keep
