@@ -397,6 +397,22 @@ RKB_API int rkb_twist_shaping(rkb_chain* chain, int device, size_t n_samples,
 RKB_API int rkb_frame_jacobian(rkb_chain* chain, int device, size_t n_samples, const double* x, int frame, uint64_t upstream,
                                double* J, double* Jdot, unsigned flags, void* stream);
 
+
+/* ---- model files -----------------------------------------------------------------------------------------
+ * Read a ctrl::kte_nl_system (ctrl/ctrl_sys/kte_nl_system.hpp:376-395: dofs_gen, dofs_3D, inputs, chain, mass_calc) from
+ * a ReaK XML archive — the `.rkx` files ReaK::serialization::xml_oarchive writes (core/serialization/xml_archiver.cpp,
+ * examples/robot_airship/build_P3R3R_model.cpp:78) — without any ReaK code: classes are recognised by their RTTI
+ * numbers, shared objects by their object_ID.  The descriptor is the one include/reak_b200/reak_bridge.hpp derives from
+ * the same system loaded by ReaK's own xml_iarchive (same element order, frame and coordinate numbering).  Values are
+ * what the file holds (the archiver prints 6 significant digits).
+ *   rkb_rkx_read  fills *desc and elements[0 .. n) (desc->elements = elements); returns the element count n >= 0.
+ *                 elements == NULL: count and header only.
+ *   rkb_rkx_load  reads and lowers in one go (create_flags as rkb_chain_create_ex).
+ * Errors: RKB_ERR_INVALID (file cannot be opened), RKB_ERR_UNSUPPORTED (not a kte_nl_system archive, or an element
+ * outside the compiled set), RKB_ERR_NOMEM (max_elements too small); `err` receives a message. */
+RKB_API int rkb_rkx_read(const char* path, rkb_chain_desc* desc, rkb_element* elements, int max_elements, char* err, size_t err_len);
+RKB_API int rkb_rkx_load(const char* path, unsigned create_flags, rkb_chain** out, char* err, size_t err_len);
+
 /* Linearisation of the dynamics about (x[i], u[i]) — what a linear-quadratic steering asks its system for
  * (get_linear_blocks in examples/misc/IHAQR_topology.hpp:240-258, MEAQR_topology.hpp): A[i] = d xdot / d x
  * (2n x 2n, row-major) and B[i] = d xdot / d u (2n x n_inputs), by central differences of get_state_derivative with the

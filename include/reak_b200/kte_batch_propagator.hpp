@@ -195,6 +195,14 @@ class kte_batch_propagator {
     int rc = rkb_chain_create(&d, &mChain);
     if (rc != RKB_OK) throw propagator_error(rc, "rkb_chain_create");
   }
+  /// The kte_nl_system stored in a ReaK XML archive (`.rkx`, core/serialization/xml_archiver.cpp; rkb_rkx_load).
+  struct from_rkx_t {};
+  kte_batch_propagator(from_rkx_t, const std::string& path, int device = 0, double time_step = 1e-3)
+      : mChain(NULL), mDevice(device), mDt(time_step) {
+    char err[256] = {0};
+    int rc = rkb_rkx_load(path.c_str(), 0u, &mChain, err, sizeof err);
+    if (rc != RKB_OK) throw propagator_error(rc, std::string("rkb_rkx_load: ") + err);
+  }
   ~kte_batch_propagator() { rkb_chain_destroy(mChain); }
 
   // ---- SSSystemConcept / DiscreteSSSConcept ----------------------------------------------------

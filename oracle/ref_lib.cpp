@@ -39,6 +39,7 @@
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
 #include <ReaK/ctrl/graph_alg/node_generators.hpp>
 #include <ReaK/ctrl/kte_models/manip_dynamics_model.hpp>
+#include <ReaK/core/serialization/xml_archiver.hpp>
 
 #include "../include/reak_b200.h"
 // libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
@@ -425,6 +426,26 @@ int rkref_manip_state_rate(void* hv, std::size_t N, const double* x_blocked, con
   return 0;
 }
 
+// f4: the live kte_nl_system of this handle written by the reference's own XML archiver (core/serialization/
+// xml_archiver.cpp) — the `.rkx` format of examples/robot_airship/build_P3R3R_model.cpp:78.  what: 0 = the whole
+// kte_nl_system (dofs, inputs, chain, mass_calc), 1 = the kte_map_chain alone.
+int rkref_save_rkx(void* hv, const char* path, int what) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  try {
+    serialization::xml_oarchive out(path);
+    if (what == 1) {
+      out << m->chain;
+    } else {
+      shared_ptr<ctrl::kte_nl_system> sys(new ctrl::kte_nl_system(m->sys));
+      out << sys;
+    }
+    return 0;
+  } catch (std::exception&) {
+    return -1;
+  }
+}
+
 void* rkref_create(const rkb_chain_desc* d) {
   if (!d || !d->elements) return NULL;
   ref_handle* h = new ref_handle();
@@ -664,6 +685,47 @@ int rkref_bridge_desc(void* hv, rkb_chain_desc* out, rkb_element* elems, int max
   ref_handle* h = static_cast<ref_handle*>(hv);
   try {
     reak_b200::chain_builder b = reak_b200::compile_kte_system(h->proto->sys);
+    rkb_chain_desc d = b.desc();
+    if (d.n_elements > max_elems) return -2;
+    for (int i = 0; i < d.n_elements; ++i) elems[i] = b.element(i);
+    *out = d;
+    out->elements = elems;
+    return d.n_elements;
+  } catch (std::exception& e) {
+    if (err && err_len > 0) { std::strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+    return -1;
+  }
+}
+
+// f4: a `.rkx` file read back by the reference's own xml_iarchive into a live kte_nl_system, then flattened by the
+// bridge: what a ReaK process that loads the model file and hands it to the batched path ends up with.  The product's
+// own reader (rkb_rkx_read, no ReaK code) must produce the same descriptor.  Returns the element count or -1 (err).
+int rkref_load_rkx_desc(const char* path, rkb_chain_desc* out, rkb_element* elems, int max_elems, char* err, int err_len) {
+  try {
+    // the archive creates objects through the type repository: make sure the classes of this path are registered
+    {
+      ctrl::kte_nl_system s0; kte::kte_map_chain c0; kte::mass_matrix_calc m0;
+      kte::revolute_joint_3D a1; kte::revolute_joint_2D a2; kte::prismatic_joint_3D a3; kte::prismatic_joint_2D a4; kte::free_joint_3D a5;
+      kte::rigid_link_3D b1; kte::rigid_link_2D b2; kte::rigid_link_gen b3; kte::inertia_3D c1; kte::inertia_2D c2; kte::inertia_gen c3;
+      kte::driving_actuator_gen d1; kte::torsion_spring_3D e1; kte::torsion_spring_2D e2; kte::torsion_damper_3D e3; kte::torsion_damper_2D e4;
+      kte::spring_3D f1; kte::spring_2D f2; kte::spring_gen f3; kte::damper_3D g1; kte::damper_2D g2; kte::damper_gen g3;
+      kte::joint_dependent_frame_3D h1; kte::joint_dependent_frame_2D h2; kte::joint_dependent_gen_coord h3;
+      shared_ptr<rtti::so_type> keep[] = {s0.getObjectType(), c0.getObjectType(), m0.getObjectType(), a1.getObjectType(), a2.getObjectType(),
+        a3.getObjectType(), a4.getObjectType(), a5.getObjectType(), b1.getObjectType(), b2.getObjectType(), b3.getObjectType(), c1.getObjectType(),
+        c2.getObjectType(), c3.getObjectType(), d1.getObjectType(), e1.getObjectType(), e2.getObjectType(), e3.getObjectType(), e4.getObjectType(),
+        f1.getObjectType(), f2.getObjectType(), f3.getObjectType(), g1.getObjectType(), g2.getObjectType(), g3.getObjectType(),
+        h1.getObjectType(), h2.getObjectType(), h3.getObjectType(), gen_coord<double>().getObjectType(), frame_3D<double>().getObjectType(),
+        frame_2D<double>().getObjectType(), jacobian_gen_3D<double>().getObjectType(), jacobian_gen_2D<double>().getObjectType(),
+        jacobian_gen_gen<double>().getObjectType(), jacobian_3D_3D<double>().getObjectType()};
+      (void)keep;
+    }
+    shared_ptr<ctrl::kte_nl_system> sys;
+    {
+      serialization::xml_iarchive in(path);
+      in >> sys;
+    }
+    if (!sys) throw std::runtime_error("the archive did not hold a kte_nl_system");
+    reak_b200::chain_builder b = reak_b200::compile_kte_system(*sys);
     rkb_chain_desc d = b.desc();
     if (d.n_elements > max_elems) return -2;
     for (int i = 0; i < d.n_elements; ++i) elems[i] = b.element(i);

@@ -138,6 +138,8 @@ SYMBOLS = {
     "rkb_steer_feedback_checked": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(rkb_steer_opts), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_rkx_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
+    "rkb_rkx_load": (C.c_int, [C.c_char_p, C.c_uint, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
     "rkb_host_pin": (C.c_int, [C.c_void_p, C.c_size_t]),

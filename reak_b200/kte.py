@@ -7,6 +7,7 @@ numerics: `compile_chain()` walks a kte_map_chain + mass_matrix_calc + dofs + in
 members kte_nl_system holds, ctrl/ctrl_sys/kte_nl_system.hpp:70-78) and emits the flat
 `rkb_chain_desc` the CUDA library (and the test oracles) consume.
 """
+import os
 import math
 
 from . import _abi
@@ -548,4 +549,26 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
     cc = compiled_chain(d, arr, frames, list(dofs_gen))
     cc.n_free = len(dofs_3D)
     cc.nx, cc.n_acc = 2 * len(dofs_gen) + 13 * len(dofs_3D), len(dofs_gen) + 6 * len(dofs_3D)
+    return cc
+
+
+def read_rkx(path, max_elements=512):
+    """The flat descriptor of the kte_nl_system in a ReaK XML archive (rkb_rkx_read: the library's own reader of the
+    `.rkx` files ReaK::serialization::xml_oarchive writes).  Returns a compiled_chain without Python-side objects
+    (frames / coords are None: address frames by id)."""
+    import ctypes as C
+    lib = _abi.load_library()
+    d = _abi.rkb_chain_desc()
+    arr = (_abi.rkb_element * max_elements)()
+    err = C.create_string_buffer(512)
+    n = lib.rkb_rkx_read(os.fsencode(path), C.byref(d), arr, max_elements, err, 512)
+    if n < 0:
+        raise UnsupportedChain("%s: %s" % (path, err.value.decode() or "rkb_rkx_read failed (%d)" % n))
+    own = (_abi.rkb_element * max(n, 1))()
+    C.memmove(own, arr, n * C.sizeof(_abi.rkb_element))
+    d.elements = C.cast(own, C.POINTER(_abi.rkb_element))
+    cc = compiled_chain(d, (_abi.rkb_element * n).from_buffer(own) if n else own, [None] * d.n_frames, [None] * d.n_coords)
+    cc._keep = own
+    cc.n_free = sum(1 for i in range(n) if own[i].kind == _abi.FREE_3D)
+    cc.nx, cc.n_acc = 2 * d.n_coords + 13 * cc.n_free, d.n_coords + 6 * cc.n_free
     return cc

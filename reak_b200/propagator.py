@@ -30,6 +30,11 @@ def _is_torch(a):
 class kte_batch_propagator(object):
     def __init__(self, chain, mass_calc=None, dofs_gen=None, inputs=None, device=0, time_step=1e-3, blocked=False,
                  interpreter=False, general=False, dofs_3D=None):
+        if isinstance(chain, kte.compiled_chain):  # a ready descriptor (from_rkx)
+            self.chain = self.mass_calc = None
+            self.dofs_gen, self.inputs, self.dofs_3D = [], [], [None] * chain.n_free
+            self._create(chain, device, time_step, blocked, interpreter, general)
+            return
         if mass_calc is None and hasattr(chain, "chain"):  # a kte_system / kte_nl_system-like object
             sys_ = chain
             chain, mass_calc, dofs_gen, inputs = sys_.chain, sys_.mass_calc, sys_.dofs_gen, sys_.inputs
@@ -38,7 +43,16 @@ class kte_batch_propagator(object):
         # coordinate frames of free_joint_3D elements (kte_nl_system::dofs_3D): 13 states and 6 accelerations each,
         # after the generalized coordinates' (kte_nl_system.hpp:145-147)
         self.dofs_3D = list(dofs_3D or ())
-        self.compiled = kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs, self.dofs_3D)
+        self._create(kte.compile_chain(chain, mass_calc, self.dofs_gen, self.inputs, self.dofs_3D), device, time_step, blocked, interpreter, general)
+
+    @classmethod
+    def from_rkx(cls, path, **kw):
+        """A propagator for the kte_nl_system stored in a ReaK XML archive (`.rkx`, core/serialization/xml_archiver.cpp) —
+        read by the library itself (rkb_rkx_read); no ReaK objects are involved."""
+        return cls(kte.read_rkx(path), **kw)
+
+    def _create(self, compiled, device, time_step, blocked, interpreter, general):
+        self.compiled = compiled
         self.device = int(device)
         self.dt = float(time_step)
         # True: every state-shaped buffer is (q..., qd...) like manipulator_dynamics_model::computeStateRate
@@ -52,7 +66,7 @@ class kte_batch_propagator(object):
         self._h = h
         self.n = self._lib.rkb_chain_dof(h)
         self.nx = self._lib.rkb_chain_state_dim(h)
-        self.na = self.n + 6 * len(self.dofs_3D)  # accelerations: rows / columns of M, entries of f, columns of Tcm
+        self.na = self.n + 6 * self.compiled.n_free  # accelerations: rows / columns of M, entries of f, columns of Tcm
         self.nu = self._lib.rkb_chain_input_dim(h)
 
     def close(self):
@@ -389,7 +403,7 @@ class kte_batch_propagator(object):
         x, N = self._in(x, self.nx, np.float64)
         fid = frame if isinstance(frame, int) else [id(f) for f in self.compiled.frames].index(id(frame))
         if upstream is None:
-            mask = ((1 << self.n) - 1) | (((1 << len(self.dofs_3D)) - 1) << 32)
+            mask = ((1 << self.n) - 1) | (((1 << self.compiled.n_free) - 1) << 32)
         else:
             ids = [id(c) for c in self.compiled.coords]
             mask = 0
