@@ -413,6 +413,24 @@ RKB_API int rkb_frame_jacobian(rkb_chain* chain, int device, size_t n_samples, c
 RKB_API int rkb_rkx_read(const char* path, rkb_chain_desc* desc, rkb_element* elements, int max_elements, char* err, size_t err_len);
 RKB_API int rkb_rkx_load(const char* path, unsigned create_flags, rkb_chain** out, char* err, size_t err_len);
 
+/* ---- nearest neighbours -----------------------------------------------------------------------------------
+ * The k vertices nearest to each query point, the search the planners run before every steer:
+ * ReaK::pp::linear_neighbor_search / dvp_tree (ctrl/path_planning/topological_search.hpp:91-112, 238-270, 586-596;
+ * metric_space_search.hpp, dvp_tree_detail.hpp — a vantage-point tree is an exact search, it returns what the linear scan
+ * returns) under distance(a, b) = norm_2(difference(b, a)) of vect_n points (core/lin_alg/vect_alg.hpp:2314-2333).
+ *   vertices [n_vertices][dim], queries [n_queries][dim]   row-major (the points of the motion graph / the samples)
+ *   radius   only vertices with distance < radius qualify (+inf: no limit), as min_dist_linear_search's `radius`
+ *   index    [n_queries][k]  vertex indices by ascending distance; -1 where fewer than k qualify
+ *   distance [n_queries][k]  nullable; +inf where index is -1        count [n_queries] nullable: qualifying neighbours (<= k)
+ * Distances are bit-identical to the reference's arithmetic (separately rounded multiply / add in index order, sqrt);
+ * among equal distances the lowest vertex index comes first (the element min_dist_linear_search meets first).
+ * flags: RKB_MEM_HOST or RKB_MEM_DEVICE (all buffers alike; device: asynchronous on `stream`). */
+#define RKB_NEAREST_MAX_K   16
+#define RKB_NEAREST_MAX_DIM 48
+RKB_API int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_queries, const double* queries, int dim, int k,
+                        double radius, int32_t* index, double* distance, int32_t* count, unsigned flags, void* stream);
+RKB_API const char* rkb_nearest_last_error(void);
+
 /* Linearisation of the dynamics about (x[i], u[i]) — what a linear-quadratic steering asks its system for
  * (get_linear_blocks in examples/misc/IHAQR_topology.hpp:240-258, MEAQR_topology.hpp): A[i] = d xdot / d x
  * (2n x 2n, row-major) and B[i] = d xdot / d u (2n x n_inputs), by central differences of get_state_derivative with the

@@ -1349,3 +1349,46 @@ double kto_integrate(void* h, size_t N, const double* x0, const double* u, int s
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * nearest neighbours: ReaK::pp::min_dist_linear_search (ctrl/path_planning/topological_search.hpp:91-112 and :238-270)
+ * over points of a vect_n topology, distance = norm_2(difference) (core/lin_alg/vect_alg.hpp:2314-2333: the sum of
+ * squares accumulated in index order from 0.0, then sqrt).  A candidate must compare less than the running k-th
+ * distance (initially `radius`) to enter; the output is sorted by ascending distance.  Restated as "the k smallest by
+ * (distance, index)": identical to the reference whenever no two candidate distances are bit-equal (the reference's
+ * heap leaves the order of equal keys to std::push_heap / pop_heap; its single-neighbour form :102-110 keeps the first
+ * of equal minima, as this does).
+ * ---------------------------------------------------------------------------------------- */
+int kto_nearest(size_t V, const double* vertices, size_t Q, const double* queries, int dim, int k, double radius,
+                int32_t* index, double* distance, int32_t* count) {
+  size_t i, v;
+  int c, r;
+  double* dl = (double*)malloc(sizeof(double) * (size_t)(k + 1));
+  int32_t* il = (int32_t*)malloc(sizeof(int32_t) * (size_t)(k + 1));
+  for (i = 0; i < Q; ++i) {
+    int cnt = 0;
+    double bound = radius;
+    for (v = 0; v < V; ++v) {
+      double sum = 0.0, d;
+      int pos;
+      for (c = 0; c < dim; ++c) {
+        double t = vertices[v * (size_t)dim + c] - queries[i * (size_t)dim + c];
+        sum += t * t;
+      }
+      d = sqrt(sum);
+      if (!(d < bound)) continue;
+      pos = cnt < k ? cnt : k - 1;
+      while (pos > 0 && dl[pos - 1] > d) { dl[pos] = dl[pos - 1]; il[pos] = il[pos - 1]; --pos; }
+      dl[pos] = d; il[pos] = (int32_t)v;
+      if (cnt < k) ++cnt;
+      if (cnt == k) bound = dl[k - 1];
+    }
+    for (r = 0; r < k; ++r) {
+      index[i * (size_t)k + r] = r < cnt ? il[r] : -1;
+      if (distance) distance[i * (size_t)k + r] = r < cnt ? dl[r] : INFINITY;
+    }
+    if (count) count[i] = cnt;
+  }
+  free(dl); free(il);
+  return 0;
+}

@@ -38,6 +38,10 @@ int    kto_tmt(void* h, const double* x, double* Tcm, double* Mcm, double* Tcm_d
 int    kto_cholesky_solve(int n, const double* A, double* b, int nrhs, double tol);
 int    kto_ldl_solve(int n, const double* A, double* b, int nrhs, double tol);
 
+/* k nearest vertices per query within `radius` (min_dist_linear_search, topological_search.hpp:91-112, 238-270) */
+int    kto_nearest(size_t n_vertices, const double* vertices, size_t n_queries, const double* queries, int dim, int k, double radius,
+                   int32_t* index, double* distance, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,6 +256,23 @@ class _Checker(object):
         return out
 
 
+def nearest(which, vertices, queries, k=1, radius=np.inf):
+    """k nearest vertices per query by the reference's linear scan: which = "oracle" (kto_nearest, the C restatement) or
+    "ref" (rkref_nearest: ReaK::pp::min_dist_linear_search itself).  Returns (index [Q][k], distance [Q][k], count [Q])."""
+    lib = C.CDLL(ORACLE_SO if which == "oracle" else REF_SO)
+    fn = lib.kto_nearest if which == "oracle" else lib.rkref_nearest
+    fn.argtypes = [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    q = np.ascontiguousarray(queries, dtype=np.float64)
+    dim = q.shape[1]
+    v = v.reshape(-1, dim)
+    idx = np.empty((q.shape[0], k), dtype=np.int32)
+    dist = np.empty((q.shape[0], k))
+    cnt = np.empty(q.shape[0], dtype=np.int32)
+    fn(v.shape[0], _dp(v), q.shape[0], _dp(q), dim, int(k), float(radius), _dp(idx), _dp(dist), _dp(cnt))
+    return idx, dist, cnt
+
+
 _PRODUCT_SO = os.path.join(os.path.dirname(_HERE), "reak_b200", "lib", "libreak_b200.so")
 _preloaded = []
 

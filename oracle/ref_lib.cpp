@@ -40,6 +40,7 @@
 #include <ReaK/ctrl/graph_alg/node_generators.hpp>
 #include <ReaK/ctrl/kte_models/manip_dynamics_model.hpp>
 #include <ReaK/core/serialization/xml_archiver.hpp>
+#include <ReaK/ctrl/path_planning/topological_search.hpp>
 
 #include "../include/reak_b200.h"
 // libreak_b200.so is only needed by rkref_bridge_gpu_check: keep its symbols weak so that this
@@ -444,6 +445,43 @@ int rkref_save_rkx(void* hv, const char* path, int what) {
   } catch (std::exception&) {
     return -1;
   }
+}
+
+// f4: nearest neighbours by the reference's own linear scan — ReaK::pp::min_dist_linear_search
+// (ctrl/path_planning/topological_search.hpp:91-112 for k == 1 without a radius, :238-270 otherwise) over vect_n points
+// with the metric of the vect_n topologies, norm_2(difference) (core/lin_alg/vect_alg.hpp:2314-2333).
+namespace {
+struct nn_distance {  // distance from the query to vertex number v
+  const std::vector<vect_n<double> >* pts;
+  const vect_n<double>* q;
+  double operator()(std::size_t v) const { return norm_2((*pts)[v] - *q); }
+};
+}
+int rkref_nearest(std::size_t V, const double* vertices, std::size_t Q, const double* queries, int dim, int k, double radius,
+                  int32_t* index, double* distance, int32_t* count) {
+  std::vector<vect_n<double> > pts(V, vect_n<double>(dim));
+  std::vector<std::size_t> ids(V);
+  for (std::size_t i = 0; i < V; ++i) { ids[i] = i; for (int c = 0; c < dim; ++c) pts[i][c] = vertices[i * dim + c]; }
+  vect_n<double> q(dim);
+  for (std::size_t i = 0; i < Q; ++i) {
+    for (int c = 0; c < dim; ++c) q[c] = queries[i * dim + c];
+    nn_distance dist; dist.pts = &pts; dist.q = &q;
+    for (int r = 0; r < k; ++r) { index[i * k + r] = -1; if (distance) distance[i * k + r] = std::numeric_limits<double>::infinity(); }
+    int found = 0;
+    if (k == 1 && radius == std::numeric_limits<double>::infinity()) {
+      std::vector<std::size_t>::iterator it = pp::min_dist_linear_search<double>(ids.begin(), ids.end(), dist);
+      if (it != ids.end()) { index[i] = int32_t(*it); if (distance) distance[i] = dist(*it); found = 1; }
+    } else {
+      std::vector<std::size_t> out(k);
+      std::vector<std::size_t>::iterator last = pp::min_dist_linear_search<double>(ids.begin(), ids.end(), out.begin(), dist, std::size_t(k), radius);
+      for (std::vector<std::size_t>::iterator o = out.begin(); o != last; ++o, ++found) {
+        index[i * k + found] = int32_t(*o);
+        if (distance) distance[i * k + found] = dist(*o);
+      }
+    }
+    if (count) count[i] = found;
+  }
+  return 0;
 }
 
 void* rkref_create(const rkb_chain_desc* d) {

@@ -140,6 +140,9 @@ SYMBOLS = {
                                              C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_rkx_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
     "rkb_rkx_load": (C.c_int, [C.c_char_p, C.c_uint, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
+    "rkb_nearest": (C.c_int, [C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_uint, C.c_void_p]),
+    "rkb_nearest_last_error": (C.c_char_p, []),
     "rkb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "rkb_launch_count": (C.c_uint64, [C.c_void_p]),
     "rkb_host_pin": (C.c_int, [C.c_void_p, C.c_size_t]),

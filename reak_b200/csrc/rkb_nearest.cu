@@ -1,0 +1,275 @@
+// rkb_nearest.cu — batched nearest-neighbour queries over a set of state-space points.
+//
+// What the planners ask right before they steer: the vertices of the motion graph nearest to a sample, under the
+// topology's metric — ReaK::pp::linear_neighbor_search / dvp_tree (ctrl/path_planning/topological_search.hpp:91-112,
+// 238-270, 586-596; metric_space_search.hpp; dvp_tree_detail.hpp) with distance(a, b) = norm_2(difference(b, a)) on
+// vect_n points (core/lin_alg/vect_alg.hpp:2314-2333: sum += v[i] * v[i] in index order from 0.0, then sqrt).  A
+// vantage-point tree returns the same neighbours as the linear scan (it is an exact search); here the scan itself is
+// done for a whole batch of queries at once.
+//
+// Exactness: the squared distance is accumulated with separately rounded multiply and add (__dmul_rn / __dadd_rn, never
+// contracted to an FMA) in the reference's order, and candidates are compared on d = sqrt(s) like the reference compares
+// them, so distances are bit-identical to the CPU scan and so are the chosen vertices; among equal distances the lowest
+// vertex index wins (the first one met by min_dist_linear_search).  The sqrt is only taken for the rare candidate that
+// beats the current k-th squared distance (sqrt is monotonic: s >= s_k implies d >= d_k).
+//
+// Mapping: one thread per query, its coordinates in registers (dimension padded to a multiple of 4 with zeros, which add
+// +0.0 to a non-negative sum: exact); vertices stream through shared memory in tiles and are read by broadcast, four
+// vertices per thread in flight.  When the queries alone cannot fill the GPU the vertex set is split over blockIdx.y and
+// the per-chunk lists are merged by a second kernel.  Bound: the FP64 pipe (3 instructions per coordinate and pair).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+
+#include "../../include/reak_b200.h"
+#include "rkb_internal.h"
+
+namespace {
+
+constexpr int NN_BLOCK = 128;   // queries per CTA
+constexpr int NN_TILE = 64;     // vertices per shared-memory tile
+constexpr int NN_MAX_K = RKB_NEAREST_MAX_K;
+
+struct NearestArgs {
+  const double* vertices;  // [V][dim]
+  const double* queries;   // [Q][dim]
+  long long n_vertices, n_queries;
+  int dim, k;
+  double radius;           // candidates need d < radius
+  long long chunk;         // vertices per blockIdx.y
+  int32_t* part_idx;       // [Q][n_chunks][k]
+  double*  part_dist;      // [Q][n_chunks][k]
+  int n_chunks;
+};
+
+// sorted insertion of (d, s, idx) into the thread's list of at most k entries (ascending d; a new entry goes behind
+// entries of equal d, which have lower indices)
+__device__ __forceinline__ void nn_insert(double* dl, double* sl, int32_t* il, int& cnt, int k, double d, double s, int32_t idx) {
+  int pos = cnt < k ? cnt : k - 1;
+  while (pos > 0 && dl[pos - 1] > d) {
+    dl[pos] = dl[pos - 1]; sl[pos] = sl[pos - 1]; il[pos] = il[pos - 1];
+    --pos;
+  }
+  dl[pos] = d; sl[pos] = s; il[pos] = idx;
+  if (cnt < k) ++cnt;
+}
+
+template <int DIMP>
+__global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArgs A) {
+  __shared__ __align__(16) double tile[NN_TILE * DIMP];
+  const long long qi = (long long)blockIdx.x * NN_BLOCK + threadIdx.x;
+  const bool live = qi < A.n_queries;
+  double q[DIMP];
+#pragma unroll
+  for (int c = 0; c < DIMP; ++c) q[c] = (live && c < A.dim) ? A.queries[qi * A.dim + c] : 0.0;
+
+  double dl[NN_MAX_K], sl[NN_MAX_K];
+  int32_t il[NN_MAX_K];
+  int cnt = 0;
+  const int k = A.k;
+  // squared-distance gate: anything at or above it is rejected without a sqrt.  Until the list is full the gate is the
+  // radius squared, widened by a few ulps so that no candidate with sqrt(s) < radius is lost to rounding.
+  const double gate0 = isinf(A.radius) ? A.radius : A.radius * A.radius * (1.0 + 8.0 * 2.220446049250313e-16);
+  double gate_s = gate0, gate_d = A.radius;
+
+  const long long v0 = (long long)blockIdx.y * A.chunk;
+  const long long v1 = v0 + A.chunk < A.n_vertices ? v0 + A.chunk : A.n_vertices;
+  for (long long base = v0; base < v1; base += NN_TILE) {
+    const int nt = (int)(v1 - base < NN_TILE ? v1 - base : NN_TILE);
+    __syncthreads();
+    // tile load: nt * dim consecutive doubles, coalesced; padded coordinates are zero
+    if (A.dim == DIMP) {
+      for (int e = threadIdx.x; e < nt * DIMP; e += NN_BLOCK) tile[e] = A.vertices[base * DIMP + e];
+    } else {
+      for (int e = threadIdx.x; e < nt * DIMP; e += NN_BLOCK) {
+        const int v = e / DIMP, c = e - v * DIMP;
+        tile[e] = c < A.dim ? A.vertices[(base + v) * A.dim + c] : 0.0;
+      }
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int j = 0; j < nt; j += 4) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double* t0 = &tile[(j + 0) * DIMP];
+      const double* t1 = &tile[(j + 1 < nt ? j + 1 : j) * DIMP];
+      const double* t2 = &tile[(j + 2 < nt ? j + 2 : j) * DIMP];
+      const double* t3 = &tile[(j + 3 < nt ? j + 3 : j) * DIMP];
+#pragma unroll
+      for (int c = 0; c < DIMP; c += 2) {
+        const double2 a0 = *reinterpret_cast<const double2*>(t0 + c), a1 = *reinterpret_cast<const double2*>(t1 + c);
+        const double2 a2 = *reinterpret_cast<const double2*>(t2 + c), a3 = *reinterpret_cast<const double2*>(t3 + c);
+        double d;
+        d = __dsub_rn(a0.x, q[c]); s0 = __dadd_rn(s0, __dmul_rn(d, d));
+        d = __dsub_rn(a1.x, q[c]); s1 = __dadd_rn(s1, __dmul_rn(d, d));
+        d = __dsub_rn(a2.x, q[c]); s2 = __dadd_rn(s2, __dmul_rn(d, d));
+        d = __dsub_rn(a3.x, q[c]); s3 = __dadd_rn(s3, __dmul_rn(d, d));
+        d = __dsub_rn(a0.y, q[c + 1]); s0 = __dadd_rn(s0, __dmul_rn(d, d));
+        d = __dsub_rn(a1.y, q[c + 1]); s1 = __dadd_rn(s1, __dmul_rn(d, d));
+        d = __dsub_rn(a2.y, q[c + 1]); s2 = __dadd_rn(s2, __dmul_rn(d, d));
+        d = __dsub_rn(a3.y, q[c + 1]); s3 = __dadd_rn(s3, __dmul_rn(d, d));
+      }
+      const double ss[4] = {s0, s1, s2, s3};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (j + r < nt && ss[r] < gate_s) {  // rare
+          const double d = sqrt(ss[r]);
+          if (d < gate_d) {
+            nn_insert(dl, sl, il, cnt, k, d, ss[r], (int32_t)(base + j + r));
+            if (cnt == k) { gate_d = dl[k - 1]; gate_s = sl[k - 1]; }
+          }
+        }
+      }
+    }
+  }
+  if (!live) return;
+  int32_t* oi = A.part_idx + (qi * A.n_chunks + blockIdx.y) * k;
+  double* od = A.part_dist + (qi * A.n_chunks + blockIdx.y) * k;
+  for (int r = 0; r < k; ++r) {
+    oi[r] = r < cnt ? il[r] : -1;
+    od[r] = r < cnt ? dl[r] : INFINITY;
+  }
+}
+
+// the k best of n_chunks sorted lists per query, by (distance, vertex index)
+__global__ void __launch_bounds__(128) nearest_merge_kernel(long long n_queries, int n_chunks, int k, const int32_t* __restrict__ part_idx,
+                                                             const double* __restrict__ part_dist, int32_t* __restrict__ idx,
+                                                             double* __restrict__ dist, int32_t* __restrict__ count) {
+  const long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= n_queries) return;
+  double dl[NN_MAX_K];
+  int32_t il[NN_MAX_K];
+  int cnt = 0;
+  for (int c = 0; c < n_chunks; ++c) {  // chunks in vertex order: equal distances keep the lower index in front
+    const int32_t* pi = part_idx + (qi * n_chunks + c) * k;
+    const double* pd = part_dist + (qi * n_chunks + c) * k;
+    for (int r = 0; r < k; ++r) {
+      const int32_t id = pi[r];
+      if (id < 0) break;
+      const double d = pd[r];
+      if (cnt == k && !(d < dl[k - 1])) break;  // the rest of this list is no better
+      int pos = cnt < k ? cnt : k - 1;
+      while (pos > 0 && dl[pos - 1] > d) { dl[pos] = dl[pos - 1]; il[pos] = il[pos - 1]; --pos; }
+      dl[pos] = d; il[pos] = id;
+      if (cnt < k) ++cnt;
+    }
+  }
+  for (int r = 0; r < k; ++r) {
+    idx[qi * k + r] = r < cnt ? il[r] : -1;
+    if (dist) dist[qi * k + r] = r < cnt ? dl[r] : INFINITY;
+  }
+  if (count) count[qi] = cnt;
+}
+
+template <int DIMP>
+cudaError_t launch_scan(const NearestArgs& A, dim3 grid, cudaStream_t s) {
+  nearest_scan_kernel<DIMP><<<grid, NN_BLOCK, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+thread_local char g_nn_err[160] = "";
+
+}  // namespace
+
+extern "C" {
+
+const char* rkb_nearest_last_error(void) { return g_nn_err; }
+
+int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_queries, const double* queries, int dim, int k,
+                double radius, int32_t* index, double* distance, int32_t* count, unsigned flags, void* stream) {
+  g_nn_err[0] = 0;
+  if (dim < 1 || dim > RKB_NEAREST_MAX_DIM || k < 1 || k > RKB_NEAREST_MAX_K || !(radius > 0.0)) return RKB_ERR_INVALID;
+  if (n_queries == 0) return RKB_OK;
+  if (!queries || !index || (n_vertices > 0 && !vertices) || n_vertices > 0x7fffffffull) return RKB_ERR_INVALID;
+  if (flags & ~RKB_MEM_DEVICE) return RKB_ERR_UNSUPPORTED;  // AoS only
+  const bool on_device = (flags & RKB_MEM_DEVICE) != 0;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    snprintf(g_nn_err, sizeof g_nn_err, "cudaSetDevice(%d) failed", device);
+    return RKB_ERR_CUDA;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  const long long gx = (long long)((n_queries + NN_BLOCK - 1) / NN_BLOCK);
+  // enough CTAs for every SM several times over, but no chunk shorter than a few tiles
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  long long want = (4LL * sms + gx - 1) / gx;
+  const long long max_chunks = (long long)((n_vertices + 4 * NN_TILE - 1) / (4 * NN_TILE));
+  if (want > max_chunks) want = max_chunks;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  long long chunk = ((long long)n_vertices + want - 1) / want;
+  chunk = (chunk + NN_TILE - 1) / NN_TILE * NN_TILE;
+  if (chunk < NN_TILE) chunk = NN_TILE;
+  const int n_chunks = n_vertices ? (int)(((long long)n_vertices + chunk - 1) / chunk) : 1;
+
+  void *dv = nullptr, *dq = nullptr, *dpi = nullptr, *dpd = nullptr, *di = nullptr, *dd = nullptr, *dc = nullptr;
+  const size_t bv = n_vertices * (size_t)dim * sizeof(double), bq = n_queries * (size_t)dim * sizeof(double);
+  const size_t bo = n_queries * (size_t)k;
+  auto fail = [&](const char* where) {
+    snprintf(g_nn_err, sizeof g_nn_err, "%s: %s", where, cudaGetErrorString(e));
+    cudaGetLastError();
+    void* all[] = {on_device ? nullptr : dv, on_device ? nullptr : dq, dpi, dpd, on_device ? nullptr : di, on_device ? nullptr : dd,
+                   on_device ? nullptr : dc};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return RKB_ERR_CUDA;
+  };
+  if (on_device) {
+    dv = const_cast<double*>(vertices); dq = const_cast<double*>(queries); di = index; dd = distance; dc = count;
+  } else {
+    if (bv && (e = cudaMallocAsync(&dv, bv, s)) != cudaSuccess) return fail("cudaMallocAsync");
+    if ((e = cudaMallocAsync(&dq, bq, s)) != cudaSuccess) return fail("cudaMallocAsync");
+    if ((e = cudaMallocAsync(&di, bo * sizeof(int32_t), s)) != cudaSuccess) return fail("cudaMallocAsync");
+    if (distance && (e = cudaMallocAsync(&dd, bo * sizeof(double), s)) != cudaSuccess) return fail("cudaMallocAsync");
+    if (count && (e = cudaMallocAsync(&dc, n_queries * sizeof(int32_t), s)) != cudaSuccess) return fail("cudaMallocAsync");
+    if (bv && (e = cudaMemcpyAsync(dv, vertices, bv, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("cudaMemcpyAsync");
+    if ((e = cudaMemcpyAsync(dq, queries, bq, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("cudaMemcpyAsync");
+  }
+  if ((e = cudaMallocAsync(&dpi, bo * n_chunks * sizeof(int32_t), s)) != cudaSuccess) return fail("cudaMallocAsync");
+  if ((e = cudaMallocAsync(&dpd, bo * n_chunks * sizeof(double), s)) != cudaSuccess) return fail("cudaMallocAsync");
+
+  NearestArgs A;
+  A.vertices = (const double*)dv; A.queries = (const double*)dq;
+  A.n_vertices = (long long)n_vertices; A.n_queries = (long long)n_queries;
+  A.dim = dim; A.k = k; A.radius = radius; A.chunk = chunk;
+  A.part_idx = (int32_t*)dpi; A.part_dist = (double*)dpd; A.n_chunks = n_chunks;
+  const dim3 grid((unsigned)gx, (unsigned)n_chunks);
+  const int dimp = (dim + 3) / 4 * 4;
+  switch (dimp) {
+    case 4: e = launch_scan<4>(A, grid, s); break;
+    case 8: e = launch_scan<8>(A, grid, s); break;
+    case 12: e = launch_scan<12>(A, grid, s); break;
+    case 16: e = launch_scan<16>(A, grid, s); break;
+    case 20: e = launch_scan<20>(A, grid, s); break;
+    case 24: e = launch_scan<24>(A, grid, s); break;
+    case 28: e = launch_scan<28>(A, grid, s); break;
+    case 32: e = launch_scan<32>(A, grid, s); break;
+    case 36: e = launch_scan<36>(A, grid, s); break;
+    case 40: e = launch_scan<40>(A, grid, s); break;
+    case 44: e = launch_scan<44>(A, grid, s); break;
+    default: e = launch_scan<48>(A, grid, s); break;
+  }
+  if (e != cudaSuccess) return fail("nearest_scan_kernel");
+  nearest_merge_kernel<<<(unsigned)((n_queries + 127) / 128), 128, 0, s>>>((long long)n_queries, n_chunks, k, (const int32_t*)dpi,
+                                                                           (const double*)dpd, (int32_t*)di, (double*)dd, (int32_t*)dc);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("nearest_merge_kernel");
+  if (!on_device) {
+    if ((e = cudaMemcpyAsync(index, di, bo * sizeof(int32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail("cudaMemcpyAsync");
+    if (distance && (e = cudaMemcpyAsync(distance, dd, bo * sizeof(double), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail("cudaMemcpyAsync");
+    if (count && (e = cudaMemcpyAsync(count, dc, n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail("cudaMemcpyAsync");
+    if (dv) cudaFreeAsync(dv, s);
+    cudaFreeAsync(dq, s); cudaFreeAsync(di, s);
+    if (dd) cudaFreeAsync(dd, s);
+    if (dc) cudaFreeAsync(dc, s);
+  }
+  cudaFreeAsync(dpi, s); cudaFreeAsync(dpd, s);
+  if (!on_device && (e = cudaStreamSynchronize(s)) != cudaSuccess) { dv = dq = di = dd = dc = dpi = dpd = nullptr; return fail("cudaStreamSynchronize"); }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return RKB_OK;
+}
+
+}  // extern "C"
