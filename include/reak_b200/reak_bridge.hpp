@@ -21,6 +21,8 @@
 #define REAK_B200_REAK_BRIDGE_HPP
 
 #include <cmath>
+#include <limits>
+#include <iterator>
 #include <map>
 #include <random>
 #include <stdexcept>
@@ -628,6 +630,69 @@ class batched_steer_visitor {
   double mTol;
   point_type mTarget;
   std::vector<std::pair<Vertex, ResultType> > mTable;
+};
+
+/// Batched counterpart of linear_neighbor_search's iterator forms (ctrl/path_planning/topological_search.hpp:647-692)
+/// and of what a dvp_tree answers (metric_space_search.hpp): the nearest candidates of [first, last) to EVERY point of a
+/// batch — all the samples of one planner iteration — in one rkb_nearest call.  Points are vect_n-like (size(),
+/// operator[]); the metric is the one the vect_n topologies use, norm_2(difference) (vect_alg.hpp:2314-2333), and the
+/// distances are bit-identical to it.  Among candidates at equal distance the first of the range wins.
+class batched_neighbor_search {
+ public:
+  explicit batched_neighbor_search(int device = 0) : mDevice(device) {}
+
+  /// nearest candidate to each point; `last` for every point when the range is empty
+  template <typename Point, typename ForwardIter, typename Topology, typename PositionMap>
+  std::vector<ForwardIter> operator()(const std::vector<Point>& ps, ForwardIter first, ForwardIter last, const Topology&,
+                                      PositionMap position) const {
+    std::vector<ForwardIter> cand;
+    std::vector<int32_t> idx;
+    std::vector<double> dist;
+    search(ps, first, last, position, 1, std::numeric_limits<double>::infinity(), cand, idx, dist);
+    std::vector<ForwardIter> out(ps.size(), last);
+    for (std::size_t i = 0; i < ps.size(); ++i) if (idx[i] >= 0) out[i] = cand[idx[i]];
+    return out;
+  }
+
+  /// out[i]: up to max_neighbors candidates strictly closer than `radius` to ps[i], by ascending distance
+  template <typename Point, typename ForwardIter, typename Topology, typename PositionMap>
+  void operator()(const std::vector<Point>& ps, ForwardIter first, ForwardIter last,
+                  std::vector<std::vector<typename std::iterator_traits<ForwardIter>::value_type> >& out, const Topology&,
+                  PositionMap position, std::size_t max_neighbors = 1, double radius = std::numeric_limits<double>::infinity()) const {
+    std::vector<ForwardIter> cand;
+    std::vector<int32_t> idx;
+    std::vector<double> dist;
+    if (max_neighbors > RKB_NEAREST_MAX_K) throw std::range_error("batched_neighbor_search: at most RKB_NEAREST_MAX_K neighbours per query");
+    search(ps, first, last, position, static_cast<int>(max_neighbors), radius, cand, idx, dist);
+    out.assign(ps.size(), std::vector<typename std::iterator_traits<ForwardIter>::value_type>());
+    for (std::size_t i = 0; i < ps.size(); ++i)
+      for (std::size_t r = 0; r < max_neighbors && idx[i * max_neighbors + r] >= 0; ++r) out[i].push_back(*cand[idx[i * max_neighbors + r]]);
+  }
+
+ private:
+  template <typename Point, typename ForwardIter, typename PositionMap>
+  void search(const std::vector<Point>& ps, ForwardIter first, ForwardIter last, PositionMap position, int k, double radius,
+              std::vector<ForwardIter>& cand, std::vector<int32_t>& idx, std::vector<double>& dist) const {
+    idx.assign(ps.size() * k, -1);
+    dist.assign(ps.size() * k, std::numeric_limits<double>::infinity());
+    if (ps.empty()) return;
+    const std::size_t dim = ps[0].size();
+    std::vector<double> v, q(ps.size() * dim);
+    for (; first != last; ++first) {
+      cand.push_back(first);
+      const Point& pt = get(position, *first);
+      if (pt.size() != dim) throw std::range_error("Point dimension mismatch!");
+      for (std::size_t c = 0; c < dim; ++c) v.push_back(pt[c]);
+    }
+    for (std::size_t i = 0; i < ps.size(); ++i) {
+      if (ps[i].size() != dim) throw std::range_error("Point dimension mismatch!");
+      for (std::size_t c = 0; c < dim; ++c) q[i * dim + c] = ps[i][c];
+    }
+    const int rc = rkb_nearest(mDevice, cand.size(), v.empty() ? NULL : &v[0], ps.size(), &q[0], static_cast<int>(dim), k, radius, &idx[0],
+                               &dist[0], NULL, RKB_MEM_HOST, NULL);
+    if (rc != RKB_OK) throw reak_b200::propagator_error(rc, "rkb_nearest");
+  }
+  int mDevice;
 };
 
 }  // namespace pp

@@ -69,6 +69,7 @@
 #pragma weak rkb_proxy_destroy
 #pragma weak rkb_min_distance
 #pragma weak rkb_is_free
+#pragma weak rkb_nearest
 #include "../include/reak_b200/reak_bridge.hpp"
 #include "steer_law.h"
 
@@ -482,6 +483,49 @@ int rkref_nearest(std::size_t V, const double* vertices, std::size_t Q, const do
     if (count) count[i] = found;
   }
   return 0;
+}
+
+// GPU drop-in check of ReaK::pp::batched_neighbor_search (reak_bridge.hpp): a batch of query points against a range of
+// vertex ids with a position map, both forms, compared in C++ with ReaK::pp::min_dist_linear_search run point by point.
+// Needs libreak_b200.so loaded first (RTLD_GLOBAL) and a GPU.  Returns the number of mismatches, or -1 (msg).
+namespace {
+struct nn_position_map {
+  typedef vect_n<double> value_type;
+  typedef std::size_t key_type;
+  typedef const vect_n<double>& reference;
+  const std::vector<vect_n<double> >* pts;
+};
+inline const vect_n<double>& get(const nn_position_map& m, std::size_t v) { return (*m.pts)[v]; }
+struct nn_space {};
+}
+int rkref_nn_bridge_check(std::size_t V, const double* vertices, std::size_t Q, const double* queries, int dim, int k, double radius,
+                          char* msg, int msg_len) {
+  try {
+    if (!rkb_nearest) throw std::runtime_error("libreak_b200.so is not loaded (load it with RTLD_GLOBAL first)");
+    std::vector<vect_n<double> > pts(V, vect_n<double>(dim)), qs(Q, vect_n<double>(dim));
+    std::vector<std::size_t> ids(V);
+    for (std::size_t i = 0; i < V; ++i) { ids[i] = i; for (int c = 0; c < dim; ++c) pts[i][c] = vertices[i * dim + c]; }
+    for (std::size_t i = 0; i < Q; ++i) for (int c = 0; c < dim; ++c) qs[i][c] = queries[i * dim + c];
+    nn_position_map pm; pm.pts = &pts;
+    pp::batched_neighbor_search nn(0);
+    int bad = 0;
+    std::vector<std::vector<std::size_t>::iterator> one = nn(qs, ids.begin(), ids.end(), nn_space(), pm);
+    std::vector<std::vector<std::size_t> > many;
+    nn(qs, ids.begin(), ids.end(), many, nn_space(), pm, std::size_t(k), radius);
+    for (std::size_t i = 0; i < Q; ++i) {
+      nn_distance dist; dist.pts = &pts; dist.q = &qs[i];
+      std::vector<std::size_t>::iterator it = pp::min_dist_linear_search<double>(ids.begin(), ids.end(), dist);
+      if (it != one[i]) ++bad;
+      std::vector<std::size_t> out(k);
+      std::vector<std::size_t>::iterator last = pp::min_dist_linear_search<double>(ids.begin(), ids.end(), out.begin(), dist, std::size_t(k), radius);
+      out.erase(last, out.end());
+      if (out != many[i]) ++bad;
+    }
+    return bad;
+  } catch (std::exception& e) {
+    if (msg && msg_len > 0) { std::strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
+    return -1;
+  }
 }
 
 void* rkref_create(const rkb_chain_desc* d) {

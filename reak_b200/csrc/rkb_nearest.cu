@@ -55,23 +55,47 @@ __device__ __forceinline__ void nn_insert(double* dl, double* sl, int32_t* il, i
   if (cnt < k) ++cnt;
 }
 
-template <int DIMP>
-__global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArgs A) {
-  __shared__ __align__(16) double tile[NN_TILE * DIMP];
-  const long long qi = (long long)blockIdx.x * NN_BLOCK + threadIdx.x;
-  const bool live = qi < A.n_queries;
-  double q[DIMP];
-#pragma unroll
-  for (int c = 0; c < DIMP; ++c) q[c] = (live && c < A.dim) ? A.queries[qi * A.dim + c] : 0.0;
-
+// the thread's sorted list of at most k candidates for one query, and the gates that spare the sqrt
+struct NnList {
   double dl[NN_MAX_K], sl[NN_MAX_K];
   int32_t il[NN_MAX_K];
-  int cnt = 0;
+  int cnt;
+  double gate_s, gate_d;
+};
+
+__device__ __forceinline__ void nn_offer(NnList& L, int k, double s, int32_t idx) {
+  if (s < L.gate_s) {  // rare
+    const double d = sqrt(s);
+    if (d < L.gate_d) {
+      nn_insert(L.dl, L.sl, L.il, L.cnt, k, d, s, idx);
+      if (L.cnt == k) { L.gate_d = L.dl[k - 1]; L.gate_s = L.sl[k - 1]; }
+    }
+  }
+}
+
+// RQ queries per thread: a vertex coordinate fetched from shared memory (a broadcast read, but still 16 bytes written
+// to every lane's registers — the LSU's return path, not the FP64 pipe, bounds the kernel at RQ = 1) feeds 3 RQ FP64
+// instructions.
+template <int DIMP, int RQ>
+__global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArgs A) {
+  __shared__ __align__(16) double tile[NN_TILE * DIMP];
+  long long qi[RQ];
+  bool live[RQ];
+  double q[RQ][DIMP];
+#pragma unroll
+  for (int r = 0; r < RQ; ++r) {
+    qi[r] = ((long long)blockIdx.x * RQ + r) * NN_BLOCK + threadIdx.x;
+    live[r] = qi[r] < A.n_queries;
+#pragma unroll
+    for (int c = 0; c < DIMP; ++c) q[r][c] = (live[r] && c < A.dim) ? A.queries[qi[r] * A.dim + c] : 0.0;
+  }
   const int k = A.k;
+  NnList L[RQ];
   // squared-distance gate: anything at or above it is rejected without a sqrt.  Until the list is full the gate is the
   // radius squared, widened by a few ulps so that no candidate with sqrt(s) < radius is lost to rounding.
   const double gate0 = isinf(A.radius) ? A.radius : A.radius * A.radius * (1.0 + 8.0 * 2.220446049250313e-16);
-  double gate_s = gate0, gate_d = A.radius;
+#pragma unroll
+  for (int r = 0; r < RQ; ++r) { L[r].cnt = 0; L[r].gate_s = gate0; L[r].gate_d = A.radius; }
 
   const long long v0 = (long long)blockIdx.y * A.chunk;
   const long long v1 = v0 + A.chunk < A.n_vertices ? v0 + A.chunk : A.n_vertices;
@@ -88,9 +112,11 @@ __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArg
       }
     }
     __syncthreads();
-    if (!live) continue;
+    if (!live[0]) continue;  // (queries of a thread are live front to back)
     for (int j = 0; j < nt; j += 4) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      double s[RQ][4];
+#pragma unroll
+      for (int r = 0; r < RQ; ++r) { s[r][0] = 0.0; s[r][1] = 0.0; s[r][2] = 0.0; s[r][3] = 0.0; }
       const double* t0 = &tile[(j + 0) * DIMP];
       const double* t1 = &tile[(j + 1 < nt ? j + 1 : j) * DIMP];
       const double* t2 = &tile[(j + 2 < nt ? j + 2 : j) * DIMP];
@@ -99,35 +125,37 @@ __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArg
       for (int c = 0; c < DIMP; c += 2) {
         const double2 a0 = *reinterpret_cast<const double2*>(t0 + c), a1 = *reinterpret_cast<const double2*>(t1 + c);
         const double2 a2 = *reinterpret_cast<const double2*>(t2 + c), a3 = *reinterpret_cast<const double2*>(t3 + c);
-        double d;
-        d = __dsub_rn(a0.x, q[c]); s0 = __dadd_rn(s0, __dmul_rn(d, d));
-        d = __dsub_rn(a1.x, q[c]); s1 = __dadd_rn(s1, __dmul_rn(d, d));
-        d = __dsub_rn(a2.x, q[c]); s2 = __dadd_rn(s2, __dmul_rn(d, d));
-        d = __dsub_rn(a3.x, q[c]); s3 = __dadd_rn(s3, __dmul_rn(d, d));
-        d = __dsub_rn(a0.y, q[c + 1]); s0 = __dadd_rn(s0, __dmul_rn(d, d));
-        d = __dsub_rn(a1.y, q[c + 1]); s1 = __dadd_rn(s1, __dmul_rn(d, d));
-        d = __dsub_rn(a2.y, q[c + 1]); s2 = __dadd_rn(s2, __dmul_rn(d, d));
-        d = __dsub_rn(a3.y, q[c + 1]); s3 = __dadd_rn(s3, __dmul_rn(d, d));
-      }
-      const double ss[4] = {s0, s1, s2, s3};
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (j + r < nt && ss[r] < gate_s) {  // rare
-          const double d = sqrt(ss[r]);
-          if (d < gate_d) {
-            nn_insert(dl, sl, il, cnt, k, d, ss[r], (int32_t)(base + j + r));
-            if (cnt == k) { gate_d = dl[k - 1]; gate_s = sl[k - 1]; }
-          }
+        for (int r = 0; r < RQ; ++r) {
+          double d;
+          d = __dsub_rn(a0.x, q[r][c]); s[r][0] = __dadd_rn(s[r][0], __dmul_rn(d, d));
+          d = __dsub_rn(a1.x, q[r][c]); s[r][1] = __dadd_rn(s[r][1], __dmul_rn(d, d));
+          d = __dsub_rn(a2.x, q[r][c]); s[r][2] = __dadd_rn(s[r][2], __dmul_rn(d, d));
+          d = __dsub_rn(a3.x, q[r][c]); s[r][3] = __dadd_rn(s[r][3], __dmul_rn(d, d));
+          d = __dsub_rn(a0.y, q[r][c + 1]); s[r][0] = __dadd_rn(s[r][0], __dmul_rn(d, d));
+          d = __dsub_rn(a1.y, q[r][c + 1]); s[r][1] = __dadd_rn(s[r][1], __dmul_rn(d, d));
+          d = __dsub_rn(a2.y, q[r][c + 1]); s[r][2] = __dadd_rn(s[r][2], __dmul_rn(d, d));
+          d = __dsub_rn(a3.y, q[r][c + 1]); s[r][3] = __dadd_rn(s[r][3], __dmul_rn(d, d));
         }
+      }
+#pragma unroll
+      for (int r = 0; r < RQ; ++r) {
+        if (!live[r]) continue;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (j + m < nt) nn_offer(L[r], k, s[r][m], (int32_t)(base + j + m));
       }
     }
   }
-  if (!live) return;
-  int32_t* oi = A.part_idx + (qi * A.n_chunks + blockIdx.y) * k;
-  double* od = A.part_dist + (qi * A.n_chunks + blockIdx.y) * k;
-  for (int r = 0; r < k; ++r) {
-    oi[r] = r < cnt ? il[r] : -1;
-    od[r] = r < cnt ? dl[r] : INFINITY;
+#pragma unroll
+  for (int r = 0; r < RQ; ++r) {
+    if (!live[r]) continue;
+    int32_t* oi = A.part_idx + (qi[r] * A.n_chunks + blockIdx.y) * k;
+    double* od = A.part_dist + (qi[r] * A.n_chunks + blockIdx.y) * k;
+    for (int m = 0; m < k; ++m) {
+      oi[m] = m < L[r].cnt ? L[r].il[m] : -1;
+      od[m] = m < L[r].cnt ? L[r].dl[m] : INFINITY;
+    }
   }
 }
 
@@ -161,9 +189,13 @@ __global__ void __launch_bounds__(128) nearest_merge_kernel(long long n_queries,
   if (count) count[qi] = cnt;
 }
 
+// two queries per thread while their coordinates fit comfortably in registers and there are queries enough
 template <int DIMP>
-cudaError_t launch_scan(const NearestArgs& A, dim3 grid, cudaStream_t s) {
-  nearest_scan_kernel<DIMP><<<grid, NN_BLOCK, 0, s>>>(A);
+cudaError_t launch_scan(const NearestArgs& A, int rq, unsigned n_chunks, cudaStream_t s) {
+  const long long per_cta = (long long)NN_BLOCK * rq;
+  const dim3 grid((unsigned)((A.n_queries + per_cta - 1) / per_cta), n_chunks);
+  if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1)><<<grid, NN_BLOCK, 0, s>>>(A);
+  else nearest_scan_kernel<DIMP, 1><<<grid, NN_BLOCK, 0, s>>>(A);
   return cudaGetLastError();
 }
 
@@ -191,7 +223,21 @@ int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_
   }
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  const long long gx = (long long)((n_queries + NN_BLOCK - 1) / NN_BLOCK);
+  {  // keep the stream-ordered pool's memory across calls (by default it goes back to the driver at every synchronisation)
+    static bool pool_set[64] = {};
+    if (device >= 0 && device < 64 && !pool_set[device]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_set[device] = true;
+    }
+  }
+  const int dimp = (dim + 3) / 4 * 4;
+  const int rq = (dimp <= 24 && n_queries > (size_t)NN_BLOCK) ? 2 : 1;
+  const long long gx = (long long)((n_queries + (size_t)NN_BLOCK * rq - 1) / ((size_t)NN_BLOCK * rq));
   // enough CTAs for every SM several times over, but no chunk shorter than a few tiles
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -237,21 +283,19 @@ int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_
   A.n_vertices = (long long)n_vertices; A.n_queries = (long long)n_queries;
   A.dim = dim; A.k = k; A.radius = radius; A.chunk = chunk;
   A.part_idx = (int32_t*)dpi; A.part_dist = (double*)dpd; A.n_chunks = n_chunks;
-  const dim3 grid((unsigned)gx, (unsigned)n_chunks);
-  const int dimp = (dim + 3) / 4 * 4;
   switch (dimp) {
-    case 4: e = launch_scan<4>(A, grid, s); break;
-    case 8: e = launch_scan<8>(A, grid, s); break;
-    case 12: e = launch_scan<12>(A, grid, s); break;
-    case 16: e = launch_scan<16>(A, grid, s); break;
-    case 20: e = launch_scan<20>(A, grid, s); break;
-    case 24: e = launch_scan<24>(A, grid, s); break;
-    case 28: e = launch_scan<28>(A, grid, s); break;
-    case 32: e = launch_scan<32>(A, grid, s); break;
-    case 36: e = launch_scan<36>(A, grid, s); break;
-    case 40: e = launch_scan<40>(A, grid, s); break;
-    case 44: e = launch_scan<44>(A, grid, s); break;
-    default: e = launch_scan<48>(A, grid, s); break;
+    case 4: e = launch_scan<4>(A, rq, (unsigned)n_chunks, s); break;
+    case 8: e = launch_scan<8>(A, rq, (unsigned)n_chunks, s); break;
+    case 12: e = launch_scan<12>(A, rq, (unsigned)n_chunks, s); break;
+    case 16: e = launch_scan<16>(A, rq, (unsigned)n_chunks, s); break;
+    case 20: e = launch_scan<20>(A, rq, (unsigned)n_chunks, s); break;
+    case 24: e = launch_scan<24>(A, rq, (unsigned)n_chunks, s); break;
+    case 28: e = launch_scan<28>(A, rq, (unsigned)n_chunks, s); break;
+    case 32: e = launch_scan<32>(A, rq, (unsigned)n_chunks, s); break;
+    case 36: e = launch_scan<36>(A, rq, (unsigned)n_chunks, s); break;
+    case 40: e = launch_scan<40>(A, rq, (unsigned)n_chunks, s); break;
+    case 44: e = launch_scan<44>(A, rq, (unsigned)n_chunks, s); break;
+    default: e = launch_scan<48>(A, rq, (unsigned)n_chunks, s); break;
   }
   if (e != cudaSuccess) return fail("nearest_scan_kernel");
   nearest_merge_kernel<<<(unsigned)((n_queries + 127) / 128), 128, 0, s>>>((long long)n_queries, n_chunks, k, (const int32_t*)dpi,

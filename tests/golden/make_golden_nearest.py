@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/nearest.npz from the REAL reference: ReaK::pp::min_dist_linear_search
+"""Regenerates tests/golden/nearest/nearest.npz from the REAL reference: ReaK::pp::min_dist_linear_search
 (ctrl/path_planning/topological_search.hpp:91-112, 238-270) compiled into oracle/_ref/libreak_ref.so (rkref_nearest).
 Build container only:   make -C oracle ref && python tests/golden/make_golden_nearest.py"""
 import os
@@ -26,7 +26,7 @@ def main():
         out.update({"v%d" % n: v, "q%d" % n: q, "idx%d" % n: idx, "dist%d" % n: dist, "cnt%d" % n: cnt,
                     "par%d" % n: np.array([dim, k, radius])})
         print(dim, k, radius, "neighbours found:", int(cnt.sum()))
-    np.savez(os.path.join(HERE, "nearest.npz"), n_cases=len(CASES), **out)
+    np.savez(os.path.join(HERE, "nearest", "nearest.npz"), n_cases=len(CASES), **out)
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
 metric_space_search.hpp) — for a batch of query points at once.
 
 Oracle: kto_nearest (oracle/kte_oracle.c), pinned bit for bit against ReaK::pp::min_dist_linear_search compiled from the
-reference (rkref_nearest) and against tests/golden/nearest.npz generated from it.  GPU: indices AND distances must be
+reference (rkref_nearest) and against tests/golden/nearest/nearest.npz generated from it.  GPU: indices AND distances must be
 bit-identical to the oracle (index work: exact)."""
 import os
 
@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _golden():
-    g = np.load(os.path.join(HERE, "golden", "nearest.npz"))
+    g = np.load(os.path.join(HERE, "golden", "nearest", "nearest.npz"))
     for n in range(int(g["n_cases"])):
         dim, k, radius = g["par%d" % n]
         yield g["v%d" % n], g["q%d" % n], int(k), float(radius), g["idx%d" % n], g["dist%d" % n], g["cnt%d" % n]
@@ -120,3 +120,22 @@ def test_gpu_ties_empty_and_device_buffers(oracle_built):
     c = oracle_built.nearest("oracle", big_v, big_q, 3)
     assert np.array_equal(a[0].cpu().numpy(), b[0]) and np.array_equal(a[1].cpu().numpy(), b[1])
     assert np.array_equal(b[0], c[0]) and np.array_equal(b[1], c[1]) and np.array_equal(b[2], c[2])
+
+
+@pytest.mark.gpu
+def test_gpu_reak_side_batched_neighbor_search(oracle_built):
+    """ReaK::pp::batched_neighbor_search (reak_bridge.hpp) — the batched form of linear_neighbor_search's iterator calls
+    (topological_search.hpp:647-692) — compared in C++ with ReaK::pp::min_dist_linear_search, point by point"""
+    import ctypes as C
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref/libreak_ref.so not built")
+    C.CDLL(_abi.LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(oracle_built.REF_SO)
+    fn = lib.rkref_nn_bridge_check
+    fn.argtypes = [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    rng = np.random.default_rng(21)
+    for dim, V, Q, k, radius in ((12, 4000, 200, 5, np.inf), (19, 1500, 64, 16, 2.2), (2, 300, 33, 3, 0.2), (6, 0, 5, 2, np.inf)):
+        v = rng.uniform(-1.0, 1.0, (V, dim))
+        q = rng.uniform(-1.0, 1.0, (Q, dim))
+        msg = C.create_string_buffer(256)
+        assert fn(V, v.ctypes.data, Q, q.ctypes.data, dim, k, radius, msg, 256) == 0, (dim, V, msg.value)
