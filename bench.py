@@ -375,6 +375,45 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
     t7 = best(steer, p6)
     out.append({"config": "steer_checked", "workload": "closed-loop steering with collision test: %d tuples x <= %d intervals x 10 RK4 steps per GPU"
                 % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": int(done[0].sum().item()) * 10})
+    # the nearest-neighbour search that precedes every steer (linear_neighbor_search / dvp_tree), for
+    # a batch of 4096 samples against 2^20 motion-graph vertices of the 6-DOF state space (12 coordinates)
+    from reak_b200.nearest import nearest_neighbors
+    nv, nq, nd = 1 << 20, 4096, 12
+    vv, qq = uniform((nv, nd), -1, 1), uniform((nq, nd), -1, 1)
+    res = [None]
+
+    def nn():
+        res[0] = nearest_neighbors(vv, qq, 1)
+
+    nn()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms_nn = []
+    for _ in range(3):
+        ev[0].record()
+        nn()
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        ms_nn.append(ev[0].elapsed_time(ev[1]))
+    t8 = min(ms_nn)
+    e8 = {"config": "nearest", "workload": "nearest vertex (k = 1) of %d query points among %d vertices, %d coordinates, per GPU" % (nq, nv, nd),
+          "nearest_ms": t8, "pairs_per_s": float(nv) * nq / (t8 * 1e-3),
+          "roofline": {"bound": "fp64", "algorithmic_flop_per_pair": 3 * nd, "achieved": float(nv) * nq * 3 * nd / (t8 * 1e-3) * 1e-12,
+                       "unit": "TFLOP/s", "note": "sub, mul, add per coordinate and pair as the reference computes; the scan issues sub + fma "
+                                                  "(ceiling 3/4 of the DFMA peak), exact arithmetic only for the candidates"}}
+    if check:
+        from oracle import pyref
+        sub = strided(nq, 16)
+        which = "ref" if pyref.have_ref() else "oracle"
+        t0 = time.perf_counter()
+        ri, rd, _ = pyref.nearest(which, vv.cpu().numpy(), qq[torch.from_numpy(sub).to(dev)].cpu().numpy(), 1)
+        secs_n = time.perf_counter() - t0
+        gi, gd = res[0][0].cpu().numpy()[sub], res[0][1].cpu().numpy()[sub]
+        assert np.array_equal(gi, ri) and np.array_equal(gd, rd), "GPU nearest neighbours differ from the reference's linear scan"
+        e8["exact_match"] = True
+        e8["cpu_baseline"] = {"value": float(nv) * sub.size / secs_n, "unit": "pairs/s", "cores": 1,
+                              "kind": "reference" if which == "ref" else "port",
+                              "sample": "%d of the queries, min_dist_linear_search over all %d vertices" % (sub.size, nv)}
+    out.append(e8)
     return out
 
 

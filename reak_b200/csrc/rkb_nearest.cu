@@ -7,16 +7,17 @@
 // vantage-point tree returns the same neighbours as the linear scan (it is an exact search); here the scan itself is
 // done for a whole batch of queries at once.
 //
-// Exactness: the squared distance is accumulated with separately rounded multiply and add (__dmul_rn / __dadd_rn, never
-// contracted to an FMA) in the reference's order, and candidates are compared on d = sqrt(s) like the reference compares
-// them, so distances are bit-identical to the CPU scan and so are the chosen vertices; among equal distances the lowest
-// vertex index wins (the first one met by min_dist_linear_search).  The sqrt is only taken for the rare candidate that
-// beats the current k-th squared distance (sqrt is monotonic: s >= s_k implies d >= d_k).
+// Exactness: every vertex that can possibly enter a query's list (a fused-multiply-add scan with a proven error margin
+// finds them) has its squared distance accumulated with separately rounded multiply and add (__dmul_rn / __dadd_rn) in
+// the reference's order, and is compared on d = sqrt(s) like the reference compares, so distances are bit-identical to
+// the CPU scan and so are the chosen vertices; among equal distances the lowest vertex index wins (the first one met by
+// min_dist_linear_search).  The sqrt is only taken for the rare candidate that beats the current k-th squared distance
+// (sqrt is monotonic: s >= s_k implies d >= d_k).
 //
 // Mapping: one thread per query, its coordinates in registers (dimension padded to a multiple of 4 with zeros, which add
 // +0.0 to a non-negative sum: exact); vertices stream through shared memory in tiles and are read by broadcast, four
 // vertices per thread in flight.  When the queries alone cannot fill the GPU the vertex set is split over blockIdx.y and
-// the per-chunk lists are merged by a second kernel.  Bound: the FP64 pipe (3 instructions per coordinate and pair).
+// the per-chunk lists are merged by a second kernel.  Bound: the FP64 pipe (2 instructions per coordinate and pair).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -74,28 +75,47 @@ __device__ __forceinline__ void nn_offer(NnList& L, int k, double s, int32_t idx
 }
 
 // RQ queries per thread: a vertex coordinate fetched from shared memory (a broadcast read, but still 16 bytes written
-// to every lane's registers — the LSU's return path, not the FP64 pipe, bounds the kernel at RQ = 1) feeds 3 RQ FP64
+// to every lane's registers — the LSU's return path, not the FP64 pipe, bounds the kernel at RQ = 1) feeds 2 RQ FP64
 // instructions.
-template <int DIMP, int RQ>
+//
+// Two-stage test.  The scan itself forms s~ = sum fma(d, d, .) (2 instructions per coordinate); the reference's sum s
+// (separately rounded multiply and add, 3 instructions) differs from it by at most 2 (dim + 2) ulps relative — both
+// approximate the same sum of non-negative terms — so only a vertex with s~ below the gate widened by that bound can
+// beat the current k-th neighbour.  For those (a handful per query) the exact s is recomputed from the tile in the
+// reference's arithmetic and offered to the list: the result is bit-identical, the scan 1.5x shorter.
+// the rare path, out of line so that it costs the scan neither registers nor instruction-cache space: the exact squared
+// distance of one (query, vertex) pair in the reference's arithmetic, offered to the query's list.  Returns the list's
+// squared-distance gate afterwards.
+__device__ __noinline__ double nn_exact_offer(const double* __restrict__ query, const double* __restrict__ vertex, int dim, NnList* L, int k,
+                                              int32_t idx) {
+  double se = 0.0;
+  for (int c = 0; c < dim; ++c) { const double d = __dsub_rn(vertex[c], query[c]); se = __dadd_rn(se, __dmul_rn(d, d)); }
+  nn_offer(*L, k, se, idx);
+  return L->gate_s;
+}
+
+template <int DIMP, int RQ, int RV>
 __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArgs A) {
   __shared__ __align__(16) double tile[NN_TILE * DIMP];
-  long long qi[RQ];
   bool live[RQ];
   double q[RQ][DIMP];
+  const long long q_first = (long long)blockIdx.x * RQ * NN_BLOCK + threadIdx.x;  // query r of this thread: q_first + r NN_BLOCK
 #pragma unroll
   for (int r = 0; r < RQ; ++r) {
-    qi[r] = ((long long)blockIdx.x * RQ + r) * NN_BLOCK + threadIdx.x;
-    live[r] = qi[r] < A.n_queries;
+    const long long qi = q_first + (long long)r * NN_BLOCK;
+    live[r] = qi < A.n_queries;
 #pragma unroll
-    for (int c = 0; c < DIMP; ++c) q[r][c] = (live[r] && c < A.dim) ? A.queries[qi[r] * A.dim + c] : 0.0;
+    for (int c = 0; c < DIMP; ++c) q[r][c] = (live[r] && c < A.dim) ? A.queries[qi * A.dim + c] : 0.0;
   }
   const int k = A.k;
   NnList L[RQ];
   // squared-distance gate: anything at or above it is rejected without a sqrt.  Until the list is full the gate is the
   // radius squared, widened by a few ulps so that no candidate with sqrt(s) < radius is lost to rounding.
   const double gate0 = isinf(A.radius) ? A.radius : A.radius * A.radius * (1.0 + 8.0 * 2.220446049250313e-16);
+  const double widen = 1.0 + 4.0 * (DIMP + 2) * 2.220446049250313e-16;
+  double fast[RQ];  // gate of the fused scan: the list's exact gate, widened
 #pragma unroll
-  for (int r = 0; r < RQ; ++r) { L[r].cnt = 0; L[r].gate_s = gate0; L[r].gate_d = A.radius; }
+  for (int r = 0; r < RQ; ++r) { L[r].cnt = 0; L[r].gate_s = gate0; L[r].gate_d = A.radius; fast[r] = live[r] ? gate0 * widen : -1.0; }
 
   const long long v0 = (long long)blockIdx.y * A.chunk;
   const long long v1 = v0 + A.chunk < A.n_vertices ? v0 + A.chunk : A.n_vertices;
@@ -113,45 +133,51 @@ __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArg
     }
     __syncthreads();
     if (!live[0]) continue;  // (queries of a thread are live front to back)
-    for (int j = 0; j < nt; j += 4) {
-      double s[RQ][4];
+    for (int j = 0; j < nt; j += RV) {
+      double s[RQ][RV];
+      const double* t[RV];
 #pragma unroll
-      for (int r = 0; r < RQ; ++r) { s[r][0] = 0.0; s[r][1] = 0.0; s[r][2] = 0.0; s[r][3] = 0.0; }
-      const double* t0 = &tile[(j + 0) * DIMP];
-      const double* t1 = &tile[(j + 1 < nt ? j + 1 : j) * DIMP];
-      const double* t2 = &tile[(j + 2 < nt ? j + 2 : j) * DIMP];
-      const double* t3 = &tile[(j + 3 < nt ? j + 3 : j) * DIMP];
+      for (int m = 0; m < RV; ++m) t[m] = &tile[(j + m < nt ? j + m : j) * DIMP];
+#pragma unroll
+      for (int r = 0; r < RQ; ++r)
+#pragma unroll
+        for (int m = 0; m < RV; ++m) s[r][m] = 0.0;
 #pragma unroll
       for (int c = 0; c < DIMP; c += 2) {
-        const double2 a0 = *reinterpret_cast<const double2*>(t0 + c), a1 = *reinterpret_cast<const double2*>(t1 + c);
-        const double2 a2 = *reinterpret_cast<const double2*>(t2 + c), a3 = *reinterpret_cast<const double2*>(t3 + c);
+        double2 a[RV];
+#pragma unroll
+        for (int m = 0; m < RV; ++m) a[m] = *reinterpret_cast<const double2*>(t[m] + c);
 #pragma unroll
         for (int r = 0; r < RQ; ++r) {
-          double d;
-          d = __dsub_rn(a0.x, q[r][c]); s[r][0] = __dadd_rn(s[r][0], __dmul_rn(d, d));
-          d = __dsub_rn(a1.x, q[r][c]); s[r][1] = __dadd_rn(s[r][1], __dmul_rn(d, d));
-          d = __dsub_rn(a2.x, q[r][c]); s[r][2] = __dadd_rn(s[r][2], __dmul_rn(d, d));
-          d = __dsub_rn(a3.x, q[r][c]); s[r][3] = __dadd_rn(s[r][3], __dmul_rn(d, d));
-          d = __dsub_rn(a0.y, q[r][c + 1]); s[r][0] = __dadd_rn(s[r][0], __dmul_rn(d, d));
-          d = __dsub_rn(a1.y, q[r][c + 1]); s[r][1] = __dadd_rn(s[r][1], __dmul_rn(d, d));
-          d = __dsub_rn(a2.y, q[r][c + 1]); s[r][2] = __dadd_rn(s[r][2], __dmul_rn(d, d));
-          d = __dsub_rn(a3.y, q[r][c + 1]); s[r][3] = __dadd_rn(s[r][3], __dmul_rn(d, d));
+#pragma unroll
+          for (int m = 0; m < RV; ++m) { const double d = a[m].x - q[r][c]; s[r][m] = fma(d, d, s[r][m]); }
+#pragma unroll
+          for (int m = 0; m < RV; ++m) { const double d = a[m].y - q[r][c + 1]; s[r][m] = fma(d, d, s[r][m]); }
         }
       }
+      unsigned hits = 0;  // bit r RV + m: vertex j + m may enter the list of query r
 #pragma unroll
-      for (int r = 0; r < RQ; ++r) {
-        if (!live[r]) continue;
+      for (int r = 0; r < RQ; ++r)
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (j + m < nt) nn_offer(L[r], k, s[r][m], (int32_t)(base + j + m));
+        for (int m = 0; m < RV; ++m) hits |= (s[r][m] < fast[r] ? 1u : 0u) << (r * RV + m);
+      while (hits) {  // rare: the reference's own arithmetic decides, vertex by vertex in index order per query
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int r = b / RV, m = b - r * RV;
+        if (j + m >= nt) continue;
+        const long long qi = q_first + (long long)r * NN_BLOCK;
+        const double g = nn_exact_offer(A.queries + qi * A.dim, &tile[(j + m) * DIMP], A.dim, &L[r], k, (int32_t)(base + j + m)) * widen;
+#pragma unroll
+        for (int r2 = 0; r2 < RQ; ++r2) if (r2 == r) fast[r2] = g;
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < RQ; ++r) {
     if (!live[r]) continue;
-    int32_t* oi = A.part_idx + (qi[r] * A.n_chunks + blockIdx.y) * k;
-    double* od = A.part_dist + (qi[r] * A.n_chunks + blockIdx.y) * k;
+    const long long qi = q_first + (long long)r * NN_BLOCK;
+    int32_t* oi = A.part_idx + (qi * A.n_chunks + blockIdx.y) * k;
+    double* od = A.part_dist + (qi * A.n_chunks + blockIdx.y) * k;
     for (int m = 0; m < k; ++m) {
       oi[m] = m < L[r].cnt ? L[r].il[m] : -1;
       od[m] = m < L[r].cnt ? L[r].dl[m] : INFINITY;
@@ -189,13 +215,13 @@ __global__ void __launch_bounds__(128) nearest_merge_kernel(long long n_queries,
   if (count) count[qi] = cnt;
 }
 
-// two queries per thread while their coordinates fit comfortably in registers and there are queries enough
+// one or two queries per thread (rkb_nearest decides)
 template <int DIMP>
 cudaError_t launch_scan(const NearestArgs& A, int rq, unsigned n_chunks, cudaStream_t s) {
   const long long per_cta = (long long)NN_BLOCK * rq;
   const dim3 grid((unsigned)((A.n_queries + per_cta - 1) / per_cta), n_chunks);
-  if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1)><<<grid, NN_BLOCK, 0, s>>>(A);
-  else nearest_scan_kernel<DIMP, 1><<<grid, NN_BLOCK, 0, s>>>(A);
+  if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1), 4><<<grid, NN_BLOCK, 0, s>>>(A);
+  else nearest_scan_kernel<DIMP, 1, 4><<<grid, NN_BLOCK, 0, s>>>(A);
   return cudaGetLastError();
 }
 
@@ -236,13 +262,18 @@ int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_
     }
   }
   const int dimp = (dim + 3) / 4 * 4;
-  const int rq = (dimp <= 24 && n_queries > (size_t)NN_BLOCK) ? 2 : 1;
+  // queries per thread: as many as their coordinates leave registers for, while every thread still gets work
+  // (measured, profiles/r2_nearest.md: 2 queries per thread reach the rate 4 reach, at 5 instead of 3 CTAs per SM; with
+  // k > 1 a warp takes the exact path whenever ANY of its 32 RQ lists accepts a vertex, which favours 1)
+  const int rq = (k == 1 && dimp <= 24 && n_queries > (size_t)NN_BLOCK) ? 2 : 1;
   const long long gx = (long long)((n_queries + (size_t)NN_BLOCK * rq - 1) / ((size_t)NN_BLOCK * rq));
   // enough CTAs for every SM several times over, but no chunk shorter than a few tiles
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   long long want = (4LL * sms + gx - 1) / gx;
-  const long long max_chunks = (long long)((n_vertices + 4 * NN_TILE - 1) / (4 * NN_TILE));
+  // every chunk starts with empty lists and accepts ~k (1 + ln(chunk / k)) vertices per query before its gates are tight
+  const long long cmin = k == 1 ? 4 * NN_TILE : 16384;
+  const long long max_chunks = (long long)((n_vertices + cmin - 1) / cmin);
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
