@@ -367,6 +367,17 @@ RKB_API int rkb_min_distance(rkb_chain* chain, const rkb_proxy* proxy, int devic
                              const double* x, double* distance, int32_t* finder, double* points,
                              unsigned flags, void* stream);
 
+
+/* proxy_query_pair_3D::gatherCollisionPoints (geometry/proximity/proxy_query_model.cpp:402-421) at the pose of every state:
+ * each finder of the pair (createProxFinderList order) whose bounding spheres overlap is evaluated and every one that
+ * reports a NEGATIVE distance contributes a record.
+ *   count   [N]                    colliding finders of the state (can exceed max_records: only the first are stored)
+ *   finder  [N][max_records]       nullable: finder index of each stored record, -1 beyond count
+ *   records [N][max_records][7]    mDistance, mPoint1 (3), mPoint2 (3) in world coordinates; distance +inf beyond count
+ * 3D chains, RKB_LAYOUT_AOS. */
+RKB_API int rkb_collision_points(rkb_chain* chain, const rkb_proxy* proxy, int device, size_t n_samples, const double* x, int max_records,
+                                 int32_t* count, int32_t* finder, double* records, unsigned flags, void* stream);
+
 /* manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99) and the is_free_impl of the
  * steering topologies (examples/misc/MEAQR_topology.hpp:921-940) for every state: is_free[i] = 1 unless some proxy
  * pair's findMinimumDistance reports a negative distance at x[i] (a pair without finders never objects), else 0.

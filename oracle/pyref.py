@@ -232,6 +232,24 @@ class _Checker(object):
             raise RuntimeError("rkref_min_distance failed")
         return d, f, pts
 
+    def collision_points(self, pair, x, max_records):
+        """proxy_query_pair_3D::gatherCollisionPoints of the live reference after doMotion at every state:
+        (count [N], records [N][max_records][7]).  Reference checker only."""
+        if self._prefix != "rkref_":
+            raise NotImplementedError("proximity is checked against the compiled reference only")
+        x, _, N = self._xu(x, None)
+        m1, n1 = pair.model1.to_c(self.compiled.frames)
+        m2, n2 = pair.model2.to_c(self.compiled.frames)
+        cnt = np.zeros(N, dtype=np.int32)
+        rec = np.zeros((N, max_records, 7))
+        fn = self.lib.rkref_collision_points
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        xc = np.ascontiguousarray(x)
+        if fn(self.h, N, _dp(xc), C.cast(m1, C.c_void_p), n1, C.cast(m2, C.c_void_p), n2, int(max_records), _dp(cnt), None, _dp(rec)) != 0:
+            raise RuntimeError("rkref_collision_points failed")
+        return cnt, rec
+
     def bridge_proxy(self, model):
         """include/reak_b200/reak_bridge.hpp's compile_proxy_model on live geom:: shapes built from `model`:
         returns the rkb_shape array it derives and, per shape, the anchor translated back to this descriptor's

@@ -716,6 +716,62 @@ int rkref_min_distance(void* hv, std::size_t N, const double* x, const rkb_shape
   return (int)order.size();
 }
 
+// proxy_query_pair_3D::gatherCollisionPoints of the live reference (proxy_query_model.cpp:402-421) after doMotion at
+// each state: count[i] records, the first max_records of them in records[i][r][7] (mDistance, mPoint1, mPoint2) with the
+// finder index (createProxFinderList order, recovered through the record's position in a full scan) in finder[i][r].
+int rkref_collision_points(void* hv, std::size_t N, const double* x, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2,
+                           int max_records, int32_t* count, int32_t* finder, double* records) {
+  ref_handle* h = static_cast<ref_handle*>(hv);
+  ref_model* m = h->proto;
+  if (h->desc.dim != 3) return -1;
+  const int nx = m->nx, nu = m->nu;
+  std::vector<shared_ptr<geom::shape_3D> > shapes;
+  shared_ptr<geom::proxy_query_model_3D> mdl[2];
+  mdl[0] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("model1"));
+  mdl[1] = shared_ptr<geom::proxy_query_model_3D>(new geom::proxy_query_model_3D("model2"));
+  for (int k = 0; k < n1 + n2; ++k) {
+    const rkb_shape& s = k < n1 ? m1[k] : m2[k - n1];
+    shared_ptr<pose_3D<double> > anchor;
+    if (s.anchor >= 0) anchor = m->f3[s.anchor];
+    const pose_3D<double> pose(weak_ptr<pose_3D<double> >(), vect<double,3>(s.position[0], s.position[1], s.position[2]),
+                               quaternion<double>(vect<double,4>(s.quat[0], s.quat[1], s.quat[2], s.quat[3])));
+    shared_ptr<geom::shape_3D> sh;
+    switch (s.kind) {
+      case RKB_SHAPE_PLANE: sh = shared_ptr<geom::shape_3D>(new geom::plane("p", anchor, pose, vect<double,2>(s.dims[0], s.dims[1]))); break;
+      case RKB_SHAPE_SPHERE: sh = shared_ptr<geom::shape_3D>(new geom::sphere("s", anchor, pose, s.dims[0])); break;
+      case RKB_SHAPE_CCYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::capped_cylinder("cc", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_CYLINDER: sh = shared_ptr<geom::shape_3D>(new geom::cylinder("cy", anchor, pose, s.dims[0], s.dims[1])); break;
+      case RKB_SHAPE_BOX: sh = shared_ptr<geom::shape_3D>(new geom::box("b", anchor, pose, vect<double,3>(s.dims[0], s.dims[1], s.dims[2]))); break;
+      default: return -1;
+    }
+    shapes.push_back(sh);
+    mdl[k < n1 ? 0 : 1]->addShape(sh);
+  }
+  geom::proxy_query_pair_3D pair("pair", mdl[0], mdl[1]);
+  vect_n<double> p(nx), uu(nu);
+  for (int k = 0; k < nu; ++k) uu[k] = 0.0;
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    std::vector<geom::proximity_record_3D> out;
+    pair.gatherCollisionPoints(out);
+    count[i] = int32_t(out.size());
+    for (int r = 0; r < max_records; ++r) {
+      double* o = records + (i * max_records + r) * 7;
+      if (r < int(out.size())) {
+        o[0] = out[r].mDistance;
+        for (int k = 0; k < 3; ++k) { o[1 + k] = out[r].mPoint1[k]; o[4 + k] = out[r].mPoint2[k]; }
+      } else {
+        o[0] = std::numeric_limits<double>::infinity();
+        for (int k = 1; k < 7; ++k) o[k] = 0.0;
+      }
+      if (finder) finder[i * max_records + r] = -1;  // (the records do not say which finder made them)
+    }
+  }
+  return 0;
+}
+
 // reak_bridge.hpp's compile_proxy_model on live geom:: shapes riding on this model's frames: builds the shapes
 // from `in` (as rkref_min_distance does), compiles the system and the model through the bridge and hands the
 // shape list it derives back, so that a test can check rkb_shape -> ReaK shapes -> rkb_shape is the identity

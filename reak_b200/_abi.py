@@ -124,6 +124,8 @@ SYMBOLS = {
     "rkb_is_free": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_min_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint, C.c_void_p]),
+    "rkb_collision_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_uint, C.c_void_p]),
     "rkb_twist_shaping_rows": (C.c_int, [C.c_void_p]),
     "rkb_twist_shaping_mcm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rkb_twist_shaping": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),

@@ -1013,6 +1013,42 @@ __global__ void __launch_bounds__(GEN_BLOCK, MINB) generic_proximity_kernel(cons
   }
 }
 
+// proxy_query_pair_3D::gatherCollisionPoints at the chain's pose for state x[i]: count into status[i], records into out
+// ([N][max_records][7]: distance, point 1, point 2) and the finder index of each into out2's int view ([N][max_records])
+template <int DIM, int MAXS>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_collision_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
+                                                                       const __grid_constant__ ProxProgram P, int max_records,
+                                                                       int32_t* __restrict__ finder) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  double q[MAXC];
+  for (int c = 0; c < G->n_coords; ++c) q[c] = A.x.p[i * A.x.si + rkb_state_q(A.x.blocked, G->n_coords, c) * A.x.sk];
+  Pose fr[MAXS], freec;
+  freec.p = v3(0, 0, 0); freec.q.w = 1.0; freec.q.x = 0.0; freec.q.y = 0.0; freec.q.z = 0.0;
+  if (G->n_free) {
+    double s[7];
+    for (int k = 0; k < 7; ++k) s[k] = A.x.p[i * A.x.si + (2 * G->n_coords + k) * A.x.sk];
+    const double nq = sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+    freec.p = v3(s[0], s[1], s[2]);
+    freec.q.w = s[3] / nq; freec.q.x = s[4] / nq; freec.q.y = s[5] / nq; freec.q.z = s[6] / nq;
+  }
+  motion_pose(G, P, q, freec, fr);
+  double* rec = A.out.p + i * (long long)max_records * 7;
+  int32_t* fnd = finder ? finder + i * (long long)max_records : (int32_t*)0;
+  const int n = prox_gather_collisions(P, fr, max_records, [&](int r, int f, const ProxRecord& R) {
+    double* o = rec + 7 * r;
+    o[0] = R.d; o[1] = R.p1.x; o[2] = R.p1.y; o[3] = R.p1.z; o[4] = R.p2.x; o[5] = R.p2.y; o[6] = R.p2.z;
+    if (fnd) fnd[r] = f;
+  });
+  for (int r = n; r < max_records; ++r) {
+    double* o = rec + 7 * r;
+    o[0] = INFINITY;
+    for (int k = 1; k < 7; ++k) o[k] = 0.0;
+    if (fnd) fnd[r] = -1;
+  }
+  A.status[i] = n;
+}
+
 template <int DIM, int MAXF>
 __global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
@@ -1232,6 +1268,17 @@ cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgr
   else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES, 4><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   return cudaGetLastError();
 }
+cudaError_t rkb_generic_collisions(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp,
+                                   int max_records, int32_t* finder, cudaStream_t s) {
+  (void)host;
+  const long long n = a.n_samples;
+  if (n <= 0) return cudaSuccess;
+  if (pp.n_slots <= 8) generic_collision_kernel<3, 8><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
+  else if (pp.n_slots <= 16) generic_collision_kernel<3, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
+  else generic_collision_kernel<3, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
+  return cudaGetLastError();
+}
+
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;

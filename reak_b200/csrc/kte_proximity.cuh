@@ -492,3 +492,31 @@ GD int prox_min_distance(const ProxProgram& P, const Pose* slots, bool want_poin
   }
   return best;
 }
+
+// proxy_query_pair_3D::gatherCollisionPoints (proxy_query_model.cpp:402-421): every finder, in createProxFinderList
+// order, whose bounding spheres overlap (origin distance minus the two radii not above 0) is evaluated, and the record
+// of each one that reports a negative distance is kept.  rec[r] (r < max_records): d, p1 (3), p2 (3); fnd[r]: the finder
+// index.  Returns the number of colliding finders (all of them are counted, the first max_records are stored).
+template <class Store>
+GD int prox_gather_collisions(const ProxProgram& P, const Pose* slots, int max_records, Store store) {
+  int f = 0, n = 0;
+  for (int a = 0; a < P.n1; ++a) {
+    const ProxShape& Sa = P.s[a];
+    const SPose Pa = prox_shape_pose(P, Sa, slots);
+    for (int b = 0; b < P.n2; ++b) {
+      const ProxShape& Sb = P.s[P.n1 + b];
+      if (!prox_has_finder(Sa.kind, Sb.kind)) continue;
+      const SPose Pb = prox_shape_pose(P, Sb, slots);
+      if (!(norm3(Pb.p - Pa.p) - Sa.brad - Sb.brad > 0.0)) {
+        const ProxRecord R = prox_compute<true>(Sa, Pa, Sb, Pb);
+        if (R.d < 0.0) {
+          if (n < max_records) store(n, f, R);
+          ++n;
+        }
+      }
+      ++f;
+    }
+  }
+  return n;
+}
+

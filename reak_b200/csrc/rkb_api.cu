@@ -1036,6 +1036,53 @@ int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, con
   return RKB_OK;
 }
 
+int rkb_collision_points(rkb_chain* c, const rkb_proxy* p, int device, size_t N, const double* x, int max_records, int32_t* count,
+                         int32_t* finder, double* records, unsigned flags, void* stream) {
+  if (!c || !p) return RKB_ERR_INVALID;
+  if (max_records < 1 || max_records > 2 * RKB_PROX_MAX_SHAPES * RKB_PROX_MAX_SHAPES) return RKB_ERR_INVALID;
+  if (N == 0) return RKB_OK;
+  if (!x || !count || !records) return RKB_ERR_INVALID;
+  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  if (p->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+  const Layout L = parse_flags(flags);
+  if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
+  if (L.soa) return RKB_ERR_UNSUPPORTED;  // records are per state: AoS only
+  const int nx = c->nx;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(c, device, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* dx = nullptr;
+  void *dr = nullptr, *df = nullptr, *dc = nullptr;
+  const size_t M = (size_t)max_records;
+  if ((rc = stage_in(ctx->in_x, x, N * nx * sizeof(double), L.device, s, &dx))) return rc;
+  if ((rc = stage_out(ctx->out_a, records, N * M * 7 * sizeof(double), L.device, &dr))) return rc;
+  if ((rc = stage_out(ctx->out_b, finder, N * M * sizeof(int32_t), L.device, &df))) return rc;
+  if ((rc = stage_out(ctx->st, count, N * sizeof(int32_t), L.device, &dc))) return rc;
+  EvalArgs A;
+  A.x = cview((const double*)dx, (long long)N, nx, false, L.blocked);
+  A.u = cview((const double*)dx, (long long)N, 1, false);
+  A.out = view((double*)dr, (long long)N, (int)(M * 7), false);
+  A.out2 = view((double*)nullptr, (long long)N, 1, false);
+  A.status = (int32_t*)dc;
+  A.n_samples = (long long)N;
+  CU(cudaEventRecord(ctx->ev0, s));
+  const cudaError_t e = rkb_generic_collisions(ctx->d_prog, c->gp, A, p->prog, max_records, (int32_t*)df, s);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->timed = true;
+  c->last = ctx;
+  c->launches += 1;
+  if ((rc = unstage_out(dr, records, N * M * 7 * sizeof(double), L.device, s))) return rc;
+  if ((rc = unstage_out(df, finder, N * M * sizeof(int32_t), L.device, s))) return rc;
+  if ((rc = unstage_out(dc, count, N * sizeof(int32_t), L.device, s))) return rc;
+  if (!L.device) CU(cudaStreamSynchronize(s));
+  return RKB_OK;
+}
+
 int rkb_is_free(rkb_chain* c, int device, size_t N, const double* x, const rkb_proxy* const* pairs, int n_pairs, int32_t* is_free,
                 unsigned flags, void* stream) {
   if (!c || n_pairs < 1 || !pairs) return RKB_ERR_INVALID;

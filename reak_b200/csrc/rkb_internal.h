@@ -38,6 +38,8 @@ cudaError_t rkb_generic_forces(const GenericProgram* prog, const GenericProgram&
 cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_tmt(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp, cudaStream_t s);
+cudaError_t rkb_generic_collisions(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp, int max_records,
+                                   int32_t* finder, cudaStream_t s);
 cudaError_t rkb_generic_frame_jac(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, int frame, unsigned upstream, cudaStream_t s);
 cudaError_t rkb_generic_mass(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s);
 cudaError_t rkb_generic_rollout(const GenericProgram* prog, const GenericProgram& host, const RolloutArgs& a, const RkTable* table,

@@ -364,6 +364,25 @@ class kte_batch_propagator(object):
                    "rkb_min_distance")
         return (d, f, pts) if with_points else (d, f)
 
+    def gather_collision_points(self, pair, x, max_records=None):
+        """proxy_query_pair_3D::gatherCollisionPoints at every state (rkb_collision_points): count [N] of finders reporting
+        a negative distance, their finder indices [N][M] (-1 beyond count) and records [N][M][7] (distance, point 1,
+        point 2; +inf beyond count).  M = max_records, default: the pair's finder count (nothing is ever dropped)."""
+        from . import proximity
+        h = getattr(pair, "_rkb_handle", None)
+        if h is None or getattr(pair, "_rkb_owner", None) is not self:
+            h = proximity.ProxyHandle(self._lib, self._h, pair, self.compiled.frames)
+            pair._rkb_handle, pair._rkb_owner = h, self
+        M = int(max_records) if max_records is not None else max(1, int(self._lib.rkb_proxy_finder_count(h._h)))
+        x, N = self._in(x, self.nx, np.float64)
+        cnt = self._like(x, (N,), np.int32)
+        fnd = self._like(x, (N, M), np.int32)
+        rec = self._like(x, (N, M, 7))
+        flags, stream, ptr = self._prep([x, cnt, fnd, rec], False)
+        _abi.check(self._lib.rkb_collision_points(self._h, h._h, self.device, N, ptr(x), M, ptr(cnt), ptr(fnd), ptr(rec), flags, stream),
+                   "rkb_collision_points")
+        return cnt, fnd, rec
+
     def is_free(self, pairs, x):
         """manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99): no proxy pair reports
         a negative minimum distance.  Returns a bool array [N]."""

@@ -47,3 +47,20 @@ extern "C" int prox_host_min_distance(const ProxProgram* P, const double* frames
   return best;
 }
 extern "C" int prox_host_program_size(void) { return (int)sizeof(ProxProgram); }
+
+// proxy_query_pair_3D::gatherCollisionPoints through the same device source: records [max_records][7], finder [max_records]
+extern "C" int prox_host_gather(const ProxProgram* P, const double* frames, int n_frames, int max_records, double* records, int32_t* finder) {
+  Pose fr[RKB_GEN_MAX_FRAMES];
+  for (int f = 0; f < n_frames && f < RKB_GEN_MAX_FRAMES; ++f) {
+    if (P->slot_of[f] < 0) continue;
+    const double* v = frames + 7 * f;
+    Pose& S = fr[P->slot_of[f]];
+    S.p = v3(v[0], v[1], v[2]);
+    S.q.w = v[3]; S.q.x = v[4]; S.q.y = v[5]; S.q.z = v[6];
+  }
+  return prox_gather_collisions(*P, fr, max_records, [&](int r, int f, const ProxRecord& R) {
+    double* o = records + 7 * r;
+    o[0] = R.d; o[1] = R.p1.x; o[2] = R.p1.y; o[3] = R.p1.z; o[4] = R.p2.x; o[5] = R.p2.y; o[6] = R.p2.z;
+    finder[r] = f;
+  });
+}

@@ -105,6 +105,22 @@ class HostProximity(object):
             d[i] = di.value
         return d, f, p
 
+    def gather(self, frames, max_records):
+        """frames [N][n_frames][>=7] -> (count [N], finder [N][M], records [N][M][7]) of gatherCollisionPoints"""
+        N = frames.shape[0]
+        cnt = np.zeros(N, dtype=np.int32)
+        fnd = np.full((N, max_records), -1, dtype=np.int32)
+        rec = np.zeros((N, max_records, 7))
+        rec[:, :, 0] = np.inf
+        fn = self.host.prox_host_gather
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        for i in range(N):
+            fr = np.ascontiguousarray(frames[i][:, :7])
+            cnt[i] = fn(self.blob, fr.ctypes.data_as(C.c_void_p), fr.shape[0], max_records, rec[i].ctypes.data_as(C.c_void_p),
+                        fnd[i].ctypes.data_as(C.c_void_p))
+        return cnt, fnd, rec
+
     def close(self):
         self.proxy.close()
         self.lib.rkb_chain_destroy(self.h)
@@ -611,3 +627,55 @@ def test_gpu_is_free_two_pairs_vs_reference(oracle_built):
     assert np.array_equal(P.is_free([pair], x), ~(d1 < 0)) and P.is_free([none], x).all()
     got_d = P.is_free([pair, extra, none], torch.from_numpy(x).cuda())
     assert np.array_equal(got_d.cpu().numpy(), want)
+
+
+# ---- gatherCollisionPoints ------------------------------------------------------------------------
+def _gather_agree(cnt, rec, want_cnt, want_rec, tol):
+    assert np.array_equal(cnt, want_cnt)
+    live = np.isfinite(want_rec[:, :, 0])
+    assert np.array_equal(live, np.isfinite(rec[:, :, 0]))
+    assert np.max(np.abs(rec[live] - want_rec[live]), initial=0.0) < tol
+
+
+def test_gather_collision_points_host_vs_reference(host_lib, oracle_built):
+    """proxy_query_pair_3D::gatherCollisionPoints (proxy_query_model.cpp:402-421): the device source compiled for the host
+    against the live reference — which finders collide, in which order, distance and both points of each"""
+    need_ref(oracle_built)
+    s = presets.make("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    H = HostProximity(host_lib, s, pair)
+    R = oracle_built.Reference(H.compiled)
+    x, _ = random_batch(H.compiled, 400, seed=31, q_range=3.1)
+    want_cnt, want_rec = R.collision_points(pair, x, 25)
+    cnt, fnd, rec = H.gather(ref_frames(R, x), 25)
+    _gather_agree(cnt, rec, want_cnt, want_rec, 1e-12)
+    assert want_cnt.max() >= 2 and (want_cnt == 0).any()
+    assert all((np.diff(fnd[i, :cnt[i]]) > 0).all() for i in range(len(cnt)))   # createProxFinderList order
+    # a record buffer shorter than the number of collisions: all are counted, the first are kept
+    cnt2, fnd2, rec2 = H.gather(ref_frames(R, x), 1)
+    assert np.array_equal(cnt2, want_cnt) and np.array_equal(rec2[:, 0], rec[:, 0])
+    H.close()
+
+
+@pytest.mark.gpu
+def test_gpu_gather_collision_points_vs_reference(oracle_built):
+    need_ref(oracle_built)
+    for preset, track in (("crs6", False), ("crs7", True)):
+        s, P = _gpu_prop(preset)
+        robot, lab = presets.crs_proxy_models(s, track=track)
+        pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+        R = oracle_built.Reference(P.compiled)
+        x, _ = random_batch(P.compiled, 3000, seed=32, q_range=3.1)
+        cnt, fnd, rec = P.gather_collision_points(pair, x)       # one slot per finder of the pair: nothing is dropped
+        want_cnt, want_rec = R.collision_points(pair, x, rec.shape[1])
+        _gather_agree(cnt, rec, want_cnt, want_rec, TOL)
+        # consistent with the minimum-distance query: a state collides iff its minimum distance is negative
+        d = P.get_min_distances(pair, x, with_points=False)[0]
+        assert np.array_equal(cnt > 0, d < 0.0)
+        hit = cnt > 0
+        assert np.allclose(rec[hit, :, 0].min(axis=1), d[hit], rtol=0, atol=TOL)
+        # device buffers, short record buffer
+        import torch
+        c2, f2, r2 = P.gather_collision_points(pair, torch.from_numpy(x).cuda(), max_records=2)
+        assert np.array_equal(c2.cpu().numpy(), cnt) and np.array_equal(r2.cpu().numpy(), rec[:, :2])
