@@ -396,7 +396,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
         ms_nn.append(ev[0].elapsed_time(ev[1]))
     t8 = min(ms_nn)
     e8 = {"config": "nearest", "workload": "nearest vertex (k = 1) of %d query points among %d vertices, %d coordinates, per GPU" % (nq, nv, nd),
-          "nearest_ms": t8, "pairs_per_s": float(nv) * nq / (t8 * 1e-3),
+          "nearest_ms": t8, "pairs_per_gpu": float(nv) * nq,
           "roofline": {"bound": "fp64", "algorithmic_flop_per_pair": 3 * nd, "achieved": float(nv) * nq * 3 * nd / (t8 * 1e-3) * 1e-12,
                        "unit": "TFLOP/s", "note": "sub, mul, add per coordinate and pair as the reference computes; the scan issues sub + fma "
                                                   "(ceiling 3/4 of the DFMA peak), exact arithmetic only for the candidates"}}
@@ -622,6 +622,8 @@ def run_ours(args):
                 o["states_per_s"] = world * o.pop("states_per_gpu") / (ms * 1e-3)
             elif "units_total" in o:
                 o["state_steps_per_s"] = o.pop("units_total") / (ms * 1e-3)
+            elif "pairs_per_gpu" in o:  # nearest neighbours: every rank searches its own queries
+                o["pairs_per_s"] = world * o.pop("pairs_per_gpu") / (ms * 1e-3)
             else:
                 o["state_steps_per_s"] = world * o.pop("units_per_gpu") / (ms * 1e-3)
 
