@@ -670,13 +670,10 @@ def test_gpu_gather_collision_points_vs_reference(oracle_built):
         cnt, fnd, rec = P.gather_collision_points(pair, x)       # one slot per finder of the pair: nothing is dropped
         want_cnt, want_rec = R.collision_points(pair, x, rec.shape[1])
         _gather_agree(cnt, rec, want_cnt, want_rec, TOL)
-        # against the minimum-distance query: a negative minimum distance is among the records; the converse need not hold
-        # (findMinimumDistance culls a finder whose bounding spheres are farther apart than the running minimum, and a
-        # plane's "bounding radius" does not bound what its finders measure — DESIGN.md 4.4)
-        d = P.get_min_distances(pair, x, with_points=False)[0]
-        assert not ((d < 0.0) & (cnt == 0)).any()
-        hit = d < 0.0
-        assert (rec[hit, :, 0].min(axis=1) <= d[hit] + TOL).all()
+        # (no simple relation to findMinimumDistance holds: that query evaluates its first finder unconditionally and culls
+        # the others against the running minimum, this one culls every finder against 0 — and a plane's "bounding radius"
+        # does not bound what its finders measure, DESIGN.md 4.4.  Both are held to the reference separately.)
+        assert (cnt > 0).any() and (cnt == 0).any()
         # device buffers, short record buffer
         import torch
         c2, f2, r2 = P.gather_collision_points(pair, torch.from_numpy(x).cuda(), max_records=2)
