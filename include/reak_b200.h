@@ -39,8 +39,10 @@
  *     the state is applied, the integrators advance the raw vector), Velocity (3), AngVelocity (3) —
  *     kte_nl_system.hpp:145-147, 205-219.  State derivative: Velocity, QuatDot, 6 accelerations (:293-308).  Generalised
  *     forces, M, Mdot and the columns of the twist-shaping matrix then have n + 6 entries / rows / columns (the six of
- *     the free joint last: Force, Torque / jacobian_3D_3D columns, mass_matrix_calculator.cpp:232-276).  At most one free
- *     joint per chain; interpreter kernels; not with RKB_LAYOUT_BLOCKED.  A rotor (inertia_gen) on coordinate 0 next to
+ *     the free joint last: Force, Torque / jacobian_3D_3D columns, mass_matrix_calculator.cpp:232-276).  A planar chain
+ *     with a free_joint_2D carries 7 states — Position (2), Rotation (cos, sin; normalised when applied), Velocity (2),
+ *     AngVelocity — and 3 accelerations instead (kte_nl_system.hpp:194-204, 282-291; jacobian_2D_2D columns).  At most one
+ *     free joint per chain; interpreter kernels; not with RKB_LAYOUT_BLOCKED.  A rotor (inertia_gen) on coordinate 0 next to
  *     a free joint is rejected: the reference itself dereferences a null pointer there (mass_matrix_calculator.cpp:226-233).
  *     Input per sample: one double per driving_actuator_gen, in input-index order.
  *   - Buffers are caller-owned.  RKB_MEM_DEVICE pointers must be valid on `device`;
@@ -96,6 +98,7 @@ enum rkb_kind {
   RKB_COORD_GEN         = 15, /* an auxiliary gen_coord (gen_coord.hpp:44-178): coord = its index, p[0..2] = q, q_dot, q_ddot it holds */
   RKB_REVOLUTE_2D       = 17, /* revolute_joint_2D   (revolute_joint.cpp:32-116)                                     */
   RKB_PRISMATIC_2D      = 18, /* prismatic_joint_2D  (prismatic_joint.cpp:33-123)  p[0..1] = axis                    */
+  RKB_FREE_2D           = 19, /* free_joint_2D       (free_joints.cpp:33-117)      coord = index of its coordinate frame in dofs_2D */
   RKB_RIGID_LINK_2D     = 20, /* rigid_link_2D       (rigid_link.cpp:87-139)       p[0..1] = offset, p[2] = angle    */
   RKB_INERTIA_2D        = 21, /* inertia_2D          (inertia.cpp:77-86)           p[0] = mass, p[1] = moment of inertia */
   RKB_TORSION_SPRING_2D = 24, /* torsion_spring_2D   (torsion_spring.cpp:50-71)    p[0] = stiffness, p[1] = saturation */

@@ -78,6 +78,8 @@ class chain_builder {
   /// free_joint_3D (free_joints.cpp:119-208): `free_index` = position of its coordinate frame in kte_nl_system::dofs_3D;
   /// adds 13 states and 6 accelerations after the generalized coordinates' (kte_nl_system.hpp:145-147)
   int free_joint_3D(int free_index, int base, int end) { return push(RKB_FREE_3D, base, end, free_index, 0, 0, std::vector<double>()); }
+  /// free_joint_2D (free_joints.cpp:33-117): 7 states and 3 accelerations (kte_nl_system.hpp:194-204, 282-291)
+  int free_joint_2D(int free_index, int base, int end) { return push(RKB_FREE_2D, base, end, free_index, 0, 0, std::vector<double>()); }
   int prismatic_joint_3D(int coord, double ax, double ay, double az, int base, int end) {
     return push(RKB_PRISMATIC_3D, base, end, coord, 0, 0, vec(ax, ay, az));
   }

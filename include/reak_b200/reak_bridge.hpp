@@ -97,14 +97,18 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
   using namespace ReaK::kte;
   using ReaK::rtti::rk_dynamic_ptr_cast;
   if (!sys.chain || !sys.mass_calc) throw unsupported_chain("kte_nl_system without chain or mass_calc");
-  if (!sys.dofs_2D.empty()) throw unsupported_chain("2D free-frame dofs (free_joint_2D) are outside the compiled path");
+  if (!sys.dofs_2D.empty() && !sys.dofs_3D.empty()) throw unsupported_chain("2D and 3D free-frame dofs in one system");
   if (sys.mass_calc->Coords().size() != sys.dofs_gen.size()) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
-  if (sys.mass_calc->Frames3D().size() != sys.dofs_3D.size() || !sys.mass_calc->Frames2D().empty())
+  if (sys.mass_calc->Frames3D().size() != sys.dofs_3D.size() || sys.mass_calc->Frames2D().size() != sys.dofs_2D.size())
     throw unsupported_chain("mass_matrix_calc free frames differ from the system dofs");
-  detail::id_map coords, inputs, frames, elems, free3;
+  detail::id_map coords, inputs, frames, elems, free3;  // free3: the coordinate frames of the free joints, 2D or 3D
   for (std::size_t i = 0; i < sys.dofs_3D.size(); ++i) {  // state block 2 n + 13 i <-> dofs_3D[i] (kte_nl_system.hpp:205-219)
     if (sys.mass_calc->Frames3D()[i] != sys.dofs_3D[i]) throw unsupported_chain("mass_matrix_calc free frames differ from the system dofs");
     free3.ids[sys.dofs_3D[i].get()] = static_cast<int>(i);
+  }
+  for (std::size_t i = 0; i < sys.dofs_2D.size(); ++i) {  // state block 2 n + 7 i <-> dofs_2D[i] (kte_nl_system.hpp:194-204)
+    if (sys.mass_calc->Frames2D()[i] != sys.dofs_2D[i]) throw unsupported_chain("mass_matrix_calc free frames differ from the system dofs");
+    free3.ids[sys.dofs_2D[i].get()] = static_cast<int>(i);
   }
   for (std::size_t i = 0; i < sys.dofs_gen.size(); ++i) {
     if (sys.mass_calc->Coords()[i] != sys.dofs_gen[i]) throw unsupported_chain("mass_matrix_calc coordinates differ from the system dofs");
@@ -122,7 +126,8 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
         rk_dynamic_ptr_cast<rigid_link_3D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_3D>(ktes[e]) ||
         rk_dynamic_ptr_cast<free_joint_3D>(ktes[e])) dim = 3;
     else if (rk_dynamic_ptr_cast<revolute_joint_2D>(ktes[e]) || rk_dynamic_ptr_cast<prismatic_joint_2D>(ktes[e]) ||
-             rk_dynamic_ptr_cast<rigid_link_2D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_2D>(ktes[e])) dim = 2;
+             rk_dynamic_ptr_cast<rigid_link_2D>(ktes[e]) || rk_dynamic_ptr_cast<inertia_2D>(ktes[e]) ||
+             rk_dynamic_ptr_cast<free_joint_2D>(ktes[e])) dim = 2;
   }
   if (!dim) throw unsupported_chain("chain has no 2D or 3D element");
   chain_builder b(dim);
@@ -176,6 +181,12 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
       const int fi = free3.lookup(j->Coord().get());
       if (fi < 0) throw unsupported_chain("a free joint's coordinate frame is not listed in the system's dofs_3D");
       idx = b.free_joint_3D(fi, fa, fb);
+    } else if (shared_ptr<free_joint_2D> j = rk_dynamic_ptr_cast<free_joint_2D>(k)) {
+      int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
+      frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
+      const int fi = free3.lookup(j->Coord().get());
+      if (fi < 0) throw unsupported_chain("a free joint's coordinate frame is not listed in the system's dofs_2D");
+      idx = b.free_joint_2D(fi, fa, fb);
     } else if (shared_ptr<revolute_joint_2D> j = rk_dynamic_ptr_cast<revolute_joint_2D>(k)) {
       int fa = local::fid(b, frames, j->BaseFrame().get()), fb = local::fid(b, frames, j->EndFrame().get());
       frame_obj[fa] = j->BaseFrame().get(); written[fb] = 1;
@@ -209,7 +220,10 @@ inline chain_builder compile_kte_system(const ReaK::ctrl::kte_nl_system& sys) {
     } else if (shared_ptr<inertia_2D> in = rk_dynamic_ptr_cast<inertia_2D>(k)) {
       int f = local::fid(b, frames, in->CenterOfMass()->mFrame.get());
       frame_obj[f] = in->CenterOfMass()->mFrame.get();
-      idx = b.inertia_2D(f, in->Mass(), in->MomentOfInertia(), detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords));
+      std::uint64_t up = detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords);
+      if (!in->CenterOfMass()->mUpStream3DJoints.empty()) throw unsupported_chain("a 2D inertia depends on a 3D free joint");
+      up |= detail::upstream_mask(in->CenterOfMass()->mUpStream2DJoints, free3) << 32;  // free-joint frames: bits 32 and up
+      idx = b.inertia_2D(f, in->Mass(), in->MomentOfInertia(), up);
     } else if (shared_ptr<inertia_gen> in = rk_dynamic_ptr_cast<inertia_gen>(k)) {
       int c = local::cid(coords, in->CenterOfMass()->mFrame.get());
       if (detail::upstream_mask(in->CenterOfMass()->mUpStreamJoints, coords) != (std::uint64_t(1) << c))

@@ -234,6 +234,9 @@ static frame2 f2_compose(const frame2* A, const frame2* B) {
 typedef struct { int parent; v3 qd_vel, qd_avel, qd_acc, qd_aacc; } jac3;
 typedef struct { int parent; v2 qd_vel; double qd_avel; v2 qd_acc; double qd_aacc; } jac2;
 
+/* jacobian_2D_2D as filled by free_joint_2D::doMotion (motion_jacobians.hpp:411-446) */
+typedef struct { int parent; v2 vel_vel[2]; double vel_avel[2]; v2 avel_vel; double avel_avel; v2 vel_acc[2]; double vel_aacc[2]; v2 avel_acc; double avel_aacc; } jac22;
+
 /* jacobian_3D_3D as filled by free_joint_3D::doMotion (motion_jacobians.hpp:1035-1076): eight triples of vectors */
 typedef struct { int parent; v3 vel_vel[3], vel_avel[3], avel_vel[3], avel_avel[3], vel_acc[3], vel_aacc[3], avel_acc[3], avel_aacc[3]; } jac33;
 
@@ -254,8 +257,13 @@ typedef struct {
   int n_aux; /* auxiliary gen_coords (RKB_COORD_GEN): c[n .. n + n_aux - 1], never part of the state */
   /* free_joint_3D coordinate frames (kte_nl_system::dofs_3D): 13 states and 6 accelerations each */
   int nfree, nx, na;
+  int free_states, free_acc; /* per free joint: 13 / 6 (free_joint_3D), 7 / 3 (free_joint_2D) */
   frame3 fc[KTO_MAX_FREE];
   jac33 jf[KTO_MAX_FREE];
+  /* free_joint_2D: coordinate frames (kte_nl_system::dofs_2D), the raw (cos, sin) of the state, jacobian_2D_2D */
+  frame2 fc2[KTO_MAX_FREE];
+  double fc2_raw[KTO_MAX_FREE][2];
+  jac22 jf2[KTO_MAX_FREE];
 } model;
 
 static void model_free(model* m) {
@@ -314,6 +322,11 @@ void* kto_create(const rkb_chain_desc* desc) {
       case RKB_SPRING_GEN: case RKB_DAMPER_GEN:
         bad = E->coord < 0 || E->coord >= m->n + m->n_aux || E->aux < 0 || E->aux >= m->n + m->n_aux;
         break;
+      case RKB_FREE_2D:
+        bad = desc->dim != 2 || E->coord != m->nfree || m->nfree >= KTO_MAX_FREE;
+        bad |= E->frame_a < 0 || E->frame_a >= desc->n_frames || E->frame_b < 0 || E->frame_b >= desc->n_frames;
+        if (!bad) m->nfree += 1;
+        break;
       case RKB_FREE_3D:
         bad = desc->dim != 3 || E->coord != m->nfree || m->nfree >= KTO_MAX_FREE;
         bad |= E->frame_a < 0 || E->frame_a >= desc->n_frames || E->frame_b < 0 || E->frame_b >= desc->n_frames;
@@ -360,9 +373,11 @@ void* kto_create(const rkb_chain_desc* desc) {
     }
   }
   m->m_rows = count_rows(m);
-  m->nx = 2 * m->n + 13 * m->nfree; /* kte_nl_system.hpp:145-147 */
-  m->na = m->n + 6 * m->nfree;
-  for (e = 0; e < KTO_MAX_FREE; ++e) m->fc[e].Q = Q4(1, 0, 0, 0);
+  m->free_states = desc->dim == 3 ? 13 : 7;
+  m->free_acc = desc->dim == 3 ? 6 : 3;
+  m->nx = 2 * m->n + m->free_states * m->nfree; /* kte_nl_system.hpp:145-147 */
+  m->na = m->n + m->free_acc * m->nfree;
+  for (e = 0; e < KTO_MAX_FREE; ++e) { m->fc[e].Q = Q4(1, 0, 0, 0); m->fc2[e].R.q[0] = 1.0; }
   return m;
 }
 
@@ -376,7 +391,19 @@ static void apply_states_and_inputs(model* m, const double* p, const double* u) 
     m->c[j].qd = p[2 * j + 1];
     m->c[j].qdd = 0.0;
   }
-  for (j = 0; j < m->nfree; ++j) { /* :205-219: the quaternion is normalised by quaternion(vect<4>) */
+  for (j = 0; j < m->nfree && m->d.dim == 2; ++j) { /* :194-204: rotation_type(vect<2>) normalises (rotations_2D.hpp:119-123) */
+    const double* s = p + 2 * m->n + 7 * j;
+    frame2* F = &m->fc2[j];
+    double nrm = sqrt(s[2] * s[2] + s[3] * s[3]);
+    F->p = V2(s[0], s[1]);
+    F->R.q[0] = s[2] / nrm; F->R.q[1] = s[3] / nrm;
+    m->fc2_raw[j][0] = s[2]; m->fc2_raw[j][1] = s[3];
+    F->v = V2(s[4], s[5]);
+    F->w = s[6];
+    F->a = V2(0, 0);
+    F->al = 0.0;
+  }
+  for (j = 0; j < m->nfree && m->d.dim == 3; ++j) { /* :205-219: the quaternion is normalised by quaternion(vect<4>) */
     const double* s = p + 2 * m->n + 13 * j;
     frame3* F = &m->fc[j];
     F->p = V3(s[0], s[1], s[2]);
@@ -460,6 +487,16 @@ static void do_motion(model* m) {
         N->p = r.p; N->Q = r.Q; N->v = r.v; N->w = r.w; N->a = r.a; N->al = r.al; /* frame_3D.hpp:296-308 */
         break;
       }
+      case RKB_FREE_2D: { /* free_joints.cpp:33-56: *mEnd = (*mBase) * (*mCoord); the Jacobian is the identity */
+        frame2 r = f2_compose(&m->f2[E->frame_a], &m->fc2[E->coord]);
+        frame2* N = &m->f2[E->frame_b];
+        jac22* J = &m->jf2[E->coord];
+        N->p = r.p; N->R = r.R; N->v = r.v; N->w = r.w; N->a = r.a; N->al = r.al;
+        memset(J, 0, sizeof *J);
+        J->parent = E->frame_b;
+        J->vel_vel[0] = V2(1, 0); J->vel_vel[1] = V2(0, 1); J->avel_avel = 1.0;
+        break;
+      }
       case RKB_REVOLUTE_2D: { /* revolute_joint.cpp:32-58 */
         const frame2* B = &m->f2[E->frame_a];
         frame2* N = &m->f2[E->frame_b];
@@ -521,6 +558,7 @@ static void clear_force(model* m) {
   }
   for (i = 0; i < m->n + m->n_aux; ++i) m->c[i].f = 0.0;
   for (i = 0; i < m->nfree; ++i) { m->fc[i].F = V3(0, 0, 0); m->fc[i].T = V3(0, 0, 0); } /* free_joints.cpp:184-197 */
+  for (i = 0; i < m->nfree; ++i) { m->fc2[i].F = V2(0, 0); m->fc2[i].T = 0.0; }                  /* free_joints.cpp:93-106 */
 }
 
 /* kte_map_chain::doForce, kte_map_chain.hpp:78-83 (REVERSE order) */
@@ -686,6 +724,13 @@ static void do_force(model* m) {
         }
         break;
       }
+      case RKB_FREE_2D: { /* free_joints.cpp:75-85 */
+        frame2* C = &m->fc2[E->coord];
+        const frame2* N = &m->f2[E->frame_b];
+        C->F = add2(C->F, N->F);
+        C->T += N->T;
+        break;
+      }
       case RKB_REVOLUTE_2D: { /* revolute_joint.cpp:78-90; the torque is NOT passed to the base */
         frame2* B = &m->f2[E->frame_a];
         const frame2* N = &m->f2[E->frame_b];
@@ -825,6 +870,26 @@ static void jac33_rel(const model* m, const jac33* J, int frame, double* blk, do
   }
 }
 
+/* jacobian_2D_2D::get_jac_relative_to + write_to_matrices, motion_jacobians.hpp:448-502: a 3 x 3 block, column k (k < 2)
+ * from vel_*[k], column 2 from avel_*; rows v (2) then w.  blk / blkdot: row-major 3 x 3. */
+static void jac22_rel(const model* m, const jac22* J, int frame, double* blk, double* blkdot) {
+  frame2 inv = f2_inverse(&m->f2[J->parent]);
+  frame2 f2 = f2_compose(&inv, &m->f2[frame]);
+  v2 n_avel_vel = v2mulr(add2(cross_s2(J->avel_avel, f2.p), J->avel_vel), f2.R);
+  v2 n_avel_acc = sub2(v2mulr(add2(add2(cross_s2(J->avel_avel, f2.v), cross_s2(J->avel_aacc, f2.p)), J->avel_acc), f2.R),
+                       cross_s2(f2.w, n_avel_vel));
+  int k;
+  for (k = 0; k < 2; ++k) {
+    v2 n_vel_vel = v2mulr(add2(cross_s2(J->vel_avel[k], f2.p), J->vel_vel[k]), f2.R);
+    v2 n_vel_acc = sub2(v2mulr(add2(add2(cross_s2(J->vel_avel[k], f2.v), cross_s2(J->vel_aacc[k], f2.p)), J->vel_acc[k]), f2.R),
+                        cross_s2(f2.w, n_vel_vel));
+    blk[0 * 3 + k] = n_vel_vel.x[0]; blk[1 * 3 + k] = n_vel_vel.x[1]; blk[2 * 3 + k] = J->vel_avel[k];
+    blkdot[0 * 3 + k] = n_vel_acc.x[0]; blkdot[1 * 3 + k] = n_vel_acc.x[1]; blkdot[2 * 3 + k] = J->vel_aacc[k];
+  }
+  blk[0 * 3 + 2] = n_avel_vel.x[0]; blk[1 * 3 + 2] = n_avel_vel.x[1]; blk[2 * 3 + 2] = J->avel_avel;
+  blkdot[0 * 3 + 2] = n_avel_acc.x[0]; blkdot[1 * 3 + 2] = n_avel_acc.x[1]; blkdot[2 * 3 + 2] = J->avel_aacc;
+}
+
 /* mass_matrix_calc::get_TMT_TdMT, ctrl/mbd_kte/mass_matrix_calculator.cpp:100-287.
  * Rows: gen inertias, then 2D inertias (vx, vy, w), then 3D inertias (v3, w3), each group in
  * registration (= chain) order; columns: the coordinates.  T, Td are rows x n, Mc rows x rows. */
@@ -849,6 +914,14 @@ static void get_tmt(const model* m, double* T, double* Mc, double* Td) {
             int k;
             jac2_rel(m, &m->j2[i], E->frame_a, c, cd);
             for (k = 0; k < 3; ++k) { T[(row + k) * n + i] = c[k]; Td[(row + k) * n + i] = cd[k]; }
+          }
+        for (i = 0; i < m->nfree; ++i)
+          if ((E->upstream >> (32 + i)) & 1u) { /* mUpStream2DJoints, :184-196 */
+            double b[9], bd[9];
+            int k, l;
+            jac22_rel(m, &m->jf2[i], E->frame_a, b, bd);
+            for (k = 0; k < 3; ++k)
+              for (l = 0; l < 3; ++l) { T[(row + k) * n + nc + 3 * i + l] = b[k * 3 + l]; Td[(row + k) * n + nc + 3 * i + l] = bd[k * 3 + l]; }
           }
         Mc[row * rows + row] = E->p[0];
         Mc[(row + 1) * rows + row + 1] = E->p[0];
@@ -999,13 +1072,24 @@ static int state_derivative(model* m, const double* x, const double* u, double* 
   clear_force(m);
   do_force(m);
   for (i = 0; i < m->n; ++i) f[i] = m->c[i].f;
-  for (i = 0; i < m->nfree; ++i)                                                     /* :262-270 */
+  for (i = 0; i < m->nfree && m->d.dim == 3; ++i)                                    /* :262-270 */
     for (k = 0; k < 3; ++k) { f[m->n + 6 * i + k] = m->fc[i].F.x[k]; f[m->n + 6 * i + 3 + k] = m->fc[i].T.x[k]; }
+  for (i = 0; i < m->nfree && m->d.dim == 2; ++i) {                                  /* :255-260 */
+    f[m->n + 3 * i] = m->fc2[i].F.x[0]; f[m->n + 3 * i + 1] = m->fc2[i].F.x[1]; f[m->n + 3 * i + 2] = m->fc2[i].T;
+  }
   mass_matrix(m, M, NULL);
   st = cholesky_solve(m->na, M, f, 1, 1E-8);
   if (st) return RKB_STATUS_SINGULAR;
   for (i = 0; i < m->n; ++i) { xd[2 * i] = m->c[i].qd; xd[2 * i + 1] = f[i]; }
-  for (i = 0; i < m->nfree; ++i) {                                                   /* :293-308 */
+  for (i = 0; i < m->nfree && m->d.dim == 2; ++i) {                                  /* :282-291: (cos, sin)' from the RAW state */
+    double* o = xd + 2 * m->n + 7 * i;
+    const frame2* F = &m->fc2[i];
+    o[0] = F->v.x[0]; o[1] = F->v.x[1];
+    o[2] = -m->fc2_raw[i][1] * F->w;
+    o[3] = m->fc2_raw[i][0] * F->w;
+    for (k = 0; k < 3; ++k) o[4 + k] = f[m->n + 3 * i + k];
+  }
+  for (i = 0; i < m->nfree && m->d.dim == 3; ++i) {                                  /* :293-308 */
     double* o = xd + 2 * m->n + 13 * i;
     const frame3* F = &m->fc[i];
     const double* q = F->Q.q;
@@ -1043,8 +1127,10 @@ int kto_gen_forces(void* h, size_t N, const double* x, const double* u, double* 
     apply_states_and_inputs(m, x + i * nx, u ? u + i * m->nu : NULL);
     do_motion(m); clear_force(m); do_force(m);
     for (k = 0; k < m->n; ++k) f[i * m->na + k] = m->c[k].f;
-    for (k = 0; k < 6 * m->nfree; ++k)  /* Force, Torque of the free joints' coordinate frames (kte_nl_system.hpp:262-270) */
+    for (k = 0; k < 6 * m->nfree && m->d.dim == 3; ++k)  /* Force, Torque of the free joints' coordinate frames (kte_nl_system.hpp:262-270) */
       f[i * m->na + m->n + k] = (k % 6 < 3) ? m->fc[k / 6].F.x[k % 6] : m->fc[k / 6].T.x[k % 6 - 3];
+    for (k = 0; k < 3 * m->nfree && m->d.dim == 2; ++k)
+      f[i * m->na + m->n + k] = (k % 3 < 2) ? m->fc2[k / 3].F.x[k % 3] : m->fc2[k / 3].T;
   }
   return 0;
 }

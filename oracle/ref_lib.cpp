@@ -106,6 +106,8 @@ struct ref_model {
   std::vector<shared_ptr<gen_coord<double> > > aux_coords;  // RKB_COORD_GEN: gen_coords that are not system states
   std::vector<shared_ptr<frame_3D<double> > > fcoord;
   std::vector<shared_ptr<jacobian_3D_3D<double> > > jac33;
+  std::vector<shared_ptr<frame_2D<double> > > fcoord2;   // free_joint_2D coordinate frames (kte_nl_system::dofs_2D)
+  std::vector<shared_ptr<jacobian_2D_2D<double> > > jac22;
   int nx, na;  // state / acceleration dimensions: 2 n + 13 n_free, n + 6 n_free
 };
 
@@ -138,8 +140,14 @@ ref_model* build_model(const rkb_chain_desc& d) {
       m->fcoord.push_back(shared_ptr<frame_3D<double> >(new frame_3D<double>()));
       m->jac33.push_back(shared_ptr<jacobian_3D_3D<double> >(new jacobian_3D_3D<double>()));
     }
-  m->nx = 2 * m->n + 13 * (int)m->fcoord.size();
-  m->na = m->n + 6 * (int)m->fcoord.size();
+  for (int e = 0; e < d.n_elements; ++e)
+    if (d.elements[e].kind == RKB_FREE_2D) {
+      if (is3 || d.elements[e].coord != (int)m->fcoord2.size()) { delete m; return NULL; }
+      m->fcoord2.push_back(shared_ptr<frame_2D<double> >(new frame_2D<double>()));
+      m->jac22.push_back(shared_ptr<jacobian_2D_2D<double> >(new jacobian_2D_2D<double>()));
+    }
+  m->nx = 2 * m->n + 13 * (int)m->fcoord.size() + 7 * (int)m->fcoord2.size();
+  m->na = m->n + 6 * (int)m->fcoord.size() + 3 * (int)m->fcoord2.size();
   all_coords = m->coords;
   for (int i = 0; i < n_aux; ++i) all_coords.push_back(shared_ptr<gen_coord<double> >(new gen_coord<double>()));
   m->aux_coords.assign(all_coords.begin() + d.n_coords, all_coords.end());
@@ -212,6 +220,9 @@ ref_model* build_model(const rkb_chain_desc& d) {
         k = shared_ptr<kte::kte_map>(new kte::spring_gen(nm, all_coords.at(E.coord), all_coords.at(E.aux), E.p[0], E.p[1], E.p[2])); break;
       case RKB_DAMPER_GEN:
         k = shared_ptr<kte::kte_map>(new kte::damper_gen(nm, all_coords.at(E.coord), all_coords.at(E.aux), E.p[0])); break;
+      case RKB_FREE_2D:
+        k = shared_ptr<kte::kte_map>(new kte::free_joint_2D(nm, m->fcoord2[E.coord], m->f2[E.frame_a], m->f2[E.frame_b], m->jac22[E.coord]));
+        break;
       case RKB_FREE_3D:
         k = shared_ptr<kte::kte_map>(new kte::free_joint_3D(nm, m->fcoord[E.coord], m->f3[E.frame_a], m->f3[E.frame_b], m->jac33[E.coord]));
         break;
@@ -255,6 +266,8 @@ ref_model* build_model(const rkb_chain_desc& d) {
         for (int c = 0; c < d.n_coords; ++c)
           if ((E.upstream >> c) & 1u) jm[m->coords[c]] = m->jac2[c];
         shared_ptr<kte::joint_dependent_frame_2D> dep(new kte::joint_dependent_frame_2D(m->f2[E.frame_a], jm));
+        for (std::size_t c = 0; c < m->fcoord2.size(); ++c)
+          if ((E.upstream >> (32 + c)) & 1u) dep->add_joint(m->fcoord2[c], m->jac22[c]);
         shared_ptr<kte::inertia_2D> in(new kte::inertia_2D(nm, dep, E.p[0], E.p[1]));
         *m->mcalc << in; m->in_2d.push_back(in); k = in; break; }
       case RKB_TORSION_SPRING_2D:
@@ -275,10 +288,12 @@ ref_model* build_model(const rkb_chain_desc& d) {
   for (std::size_t i = 0; i < gen_inertias.size(); ++i) *m->mcalc << gen_inertias[i];
   m->in_gen = gen_inertias;
   for (int c = 0; c < d.n_coords; ++c) *m->mcalc << m->coords[c];
+  for (std::size_t c = 0; c < m->fcoord2.size(); ++c) *m->mcalc << m->fcoord2[c];
   for (std::size_t c = 0; c < m->fcoord.size(); ++c) *m->mcalc << m->fcoord[c];
 
   m->sys.dofs_gen = m->coords;
   m->sys.dofs_3D = m->fcoord;
+  m->sys.dofs_2D = m->fcoord2;
   for (int i = 0; i < d.n_inputs; ++i) {
     if (!actuators[i]) { delete m; return NULL; }
     m->sys.inputs.push_back(actuators[i]);
@@ -584,6 +599,11 @@ int rkref_gen_forces(void* hv, std::size_t N, const double* x, const double* u, 
         f[i * m->na + m->n + 6 * c + k] = m->fcoord[c]->Force[k];
         f[i * m->na + m->n + 6 * c + 3 + k] = m->fcoord[c]->Torque[k];
       }
+    for (std::size_t c = 0; c < m->fcoord2.size(); ++c) {
+      f[i * m->na + m->n + 3 * c] = m->fcoord2[c]->Force[0];
+      f[i * m->na + m->n + 3 * c + 1] = m->fcoord2[c]->Force[1];
+      f[i * m->na + m->n + 3 * c + 2] = m->fcoord2[c]->Torque;
+    }
   }
   return 0;
 }
@@ -843,13 +863,13 @@ int rkref_load_rkx_desc(const char* path, rkb_chain_desc* out, rkb_element* elem
     // the archive creates objects through the type repository: make sure the classes of this path are registered
     {
       ctrl::kte_nl_system s0; kte::kte_map_chain c0; kte::mass_matrix_calc m0;
-      kte::revolute_joint_3D a1; kte::revolute_joint_2D a2; kte::prismatic_joint_3D a3; kte::prismatic_joint_2D a4; kte::free_joint_3D a5;
+      kte::revolute_joint_3D a1; kte::revolute_joint_2D a2; kte::prismatic_joint_3D a3; kte::prismatic_joint_2D a4; kte::free_joint_3D a5; kte::free_joint_2D a6;
       kte::rigid_link_3D b1; kte::rigid_link_2D b2; kte::rigid_link_gen b3; kte::inertia_3D c1; kte::inertia_2D c2; kte::inertia_gen c3;
       kte::driving_actuator_gen d1; kte::torsion_spring_3D e1; kte::torsion_spring_2D e2; kte::torsion_damper_3D e3; kte::torsion_damper_2D e4;
       kte::spring_3D f1; kte::spring_2D f2; kte::spring_gen f3; kte::damper_3D g1; kte::damper_2D g2; kte::damper_gen g3;
       kte::joint_dependent_frame_3D h1; kte::joint_dependent_frame_2D h2; kte::joint_dependent_gen_coord h3;
       shared_ptr<rtti::so_type> keep[] = {s0.getObjectType(), c0.getObjectType(), m0.getObjectType(), a1.getObjectType(), a2.getObjectType(),
-        a3.getObjectType(), a4.getObjectType(), a5.getObjectType(), b1.getObjectType(), b2.getObjectType(), b3.getObjectType(), c1.getObjectType(),
+        a3.getObjectType(), a4.getObjectType(), a5.getObjectType(), a6.getObjectType(), jacobian_2D_2D<double>().getObjectType(), b1.getObjectType(), b2.getObjectType(), b3.getObjectType(), c1.getObjectType(),
         c2.getObjectType(), c3.getObjectType(), d1.getObjectType(), e1.getObjectType(), e2.getObjectType(), e3.getObjectType(), e4.getObjectType(),
         f1.getObjectType(), f2.getObjectType(), f3.getObjectType(), g1.getObjectType(), g2.getObjectType(), g3.getObjectType(),
         h1.getObjectType(), h2.getObjectType(), h3.getObjectType(), gen_coord<double>().getObjectType(), frame_3D<double>().getObjectType(),

@@ -14,7 +14,7 @@ RKB_MAX_FREE = 1
 REVOLUTE_3D, PRISMATIC_3D, FREE_3D, RIGID_LINK_3D, INERTIA_3D, INERTIA_GEN, ACTUATOR_GEN = 1, 2, 3, 4, 5, 6, 7
 TORSION_SPRING_3D, TORSION_DAMPER_3D, SPRING_3D, DAMPER_3D = 8, 9, 10, 11
 RIGID_LINK_GEN, SPRING_GEN, DAMPER_GEN, COORD_GEN = 12, 13, 14, 15
-REVOLUTE_2D, PRISMATIC_2D, RIGID_LINK_2D, INERTIA_2D = 17, 18, 20, 21
+REVOLUTE_2D, PRISMATIC_2D, FREE_2D, RIGID_LINK_2D, INERTIA_2D = 17, 18, 19, 20, 21
 TORSION_SPRING_2D, TORSION_DAMPER_2D, SPRING_2D, DAMPER_2D = 24, 25, 26, 27
 
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -100,6 +100,7 @@ struct Work {
   // coordinate frame of the chain's free_joint_3D (kte_nl_system::dofs_3D[0]): Position, Quat (normalised), Velocity,
   // AngVelocity from the state, zero accelerations, Force / Torque collected by doForce.  Unused by other chains.
   typename FrameOf<DIM>::type fc;
+  double fraw[2];  // free_joint_2D: (cos, sin) of the state as given (its derivative uses the raw values)
   double q[MAXC], qd[MAXC], f[RKB_GEN_MAX_ACC], u[MAXC];
 };
 #define MAXA RKB_GEN_MAX_ACC
@@ -183,6 +184,16 @@ GD void motion(const GenericProgram* G, Work<2, MAXF>& W) {
     if (E.kind == RKB_RIGID_LINK_GEN) {  // rigid_link.cpp:34-40
       W.q[E.aux] = W.q[E.coord] + E.p[0];
       W.qd[E.aux] = W.qd[E.coord];
+    } else if (E.kind == RKB_FREE_2D) {  // free_joints.cpp:33-41: *mEnd = (*mBase) * (*mCoord), frame_2D.hpp:288-300
+      const Fr2 B = W.fr[E.fa];
+      Fr2& N = W.fr[E.fb];
+      const Fr2& C = W.fc;
+      N.p = B.p + rmul(B.R, C.p);
+      N.v = B.v + rmul(B.R, crs(B.w, C.p) + C.v);
+      N.a = B.a + rmul(B.R, (-B.w * B.w) * C.p + crs(2.0 * B.w, C.v) + crs(B.al, C.p) + C.a);
+      N.R = rr(B.R, C.R);
+      N.w = B.w + C.w;
+      N.al = B.al + C.al;
     } else if (E.kind == RKB_REVOLUTE_2D) {  // revolute_joint.cpp:32-58
       const Fr2 B = W.fr[E.fa];
       Fr2& N = W.fr[E.fb];
@@ -372,9 +383,16 @@ template <int MAXF>
 GD void force(const GenericProgram* G, Work<2, MAXF>& W) {
   for (int i = 0; i < G->n_frames; ++i) { W.fr[i].F = v2(0, 0); W.fr[i].T = 0.0; }
   for (int i = 0; i < G->n_coords + G->n_aux; ++i) W.f[i] = 0.0;
+  W.fc.F = v2(0, 0); W.fc.T = 0.0;
   for (int e = G->n_elements - 1; e >= 0; --e) {
     const GenericElement& E = G->el[e];
     switch (E.kind) {
+      case RKB_FREE_2D: {  // free_joints.cpp:75-85
+        const Fr2& N = W.fr[E.fb];
+        W.fc.F = W.fc.F + N.F;
+        W.fc.T += N.T;
+        break;
+      }
       case RKB_REVOLUTE_2D: {  // revolute_joint.cpp:78-90 (torque is not passed to the base)
         const Fr2& N = W.fr[E.fb];
         Fr2& B = W.fr[E.fa];
@@ -531,7 +549,7 @@ GD void jac_free_block(const GenericProgram* G, const Work<3, MAXF>& W, int fj, 
 }
 
 // does an inertia with upstream mask `up` depend on column c of the (n_coords + 6 n_free)-column twist-shaping matrix?
-GD bool col_upstream(unsigned up, int n, int c) { return c < n ? ((up >> c) & 1u) : ((up >> (RKB_GEN_FREE_BIT + (c - n) / 6)) & 1u); }
+GD bool col_upstream(unsigned up, int n, int c, int per_free = 6) { return c < n ? ((up >> c) & 1u) : ((up >> (RKB_GEN_FREE_BIT + (c - n) / per_free)) & 1u); }
 
 // M and (optionally) S with Mdot = S + S^T; both n x n row-major in local memory.
 template <int MAXF>
@@ -576,10 +594,38 @@ GD void mass(const GenericProgram* G, const Work<3, MAXF>& W, double* M, double*
 }
 // 2D: jacobian_gen_2D::get_jac_relative_to (motion_jacobians.hpp:139-147) with f2 = (~E) * F
 // (frame_2D.hpp:288-300, 350-360): f2.p = R_E^T dp, f2.R = R_E^T R_F, f2.w = w_F - w_E,
-// f2.v = R_E^T (dv - w_E % dp).
+// f2.v = R_E^T (dv - w_E % dp).  Column c of the twist-shaping matrix seen from the inertia frame F: a joint's column for
+// c < n_coords; else column (c - n_coords) % 3 of a free_joint_2D (jacobian_2D_2D::get_jac_relative_to on the identity,
+// motion_jacobians.hpp:448-470): a velocity input e_k gives Tv = R_F^T R_E e_k, Tw = 0, Tvd = -w_rel % Tv; the
+// angular-velocity input gives what a revolute joint at E gives.
+template <int MAXF>
+GD void jac_col2(const GenericProgram* G, const Work<2, MAXF>& W, int c, const Fr2& F, double* col, double* cold) {
+  const int nc = G->n_coords;
+  const bool is_free = c >= nc;
+  const int l = is_free ? (c - nc) % 3 : 0;
+  const GenericElement& J = G->el[is_free ? G->free_elem[(c - nc) / 3] : G->jelem[c]];
+  const Fr2& Ej = W.fr[J.fb];
+  const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
+  const double wrel = F.w - Ej.w;
+  V2 Tv, Tvd;
+  double Tw;
+  if (is_free ? (l == 2) : (J.kind == RKB_REVOLUTE_2D)) {
+    Tv = rtmul(F.R, crs(1.0, dp));
+    Tw = 1.0;
+    Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
+  } else {
+    const V2 ax = is_free ? (l == 0 ? v2(1.0, 0.0) : v2(0.0, 1.0)) : v2(J.p[0], J.p[1]);
+    Tv = rtmul(F.R, rmul(Ej.R, ax));
+    Tw = 0.0;
+    Tvd = v2(0, 0) - crs(wrel, Tv);
+  }
+  col[0] = Tv.x; col[1] = Tv.y; col[2] = Tw;
+  cold[0] = Tvd.x; cold[1] = Tvd.y; cold[2] = 0.0;
+}
+
 template <int MAXF>
 GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double* S, bool want_dot) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 3 * G->n_free;
   for (int i = 0; i < n * n; ++i) { M[i] = 0.0; if (want_dot) S[i] = 0.0; }
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
@@ -587,32 +633,14 @@ GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double*
       M[E.coord * n + E.coord] += E.p[0];
     } else if (E.kind == RKB_INERTIA_2D) {
       const Fr2& F = W.fr[E.fa];
-      double T[MAXC][3], Td[MAXC][3];
-      for (int c = 0; c < n; ++c) {
-        if (!((E.upstream >> c) & 1u)) continue;
-        const GenericElement& J = G->el[G->jelem[c]];
-        const Fr2& Ej = W.fr[J.fb];
-        const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
-        const double wrel = F.w - Ej.w;
-        V2 Tv, Tvd;
-        double Tw;
-        if (J.kind == RKB_REVOLUTE_2D) {
-          Tv = rtmul(F.R, crs(1.0, dp));
-          Tw = 1.0;
-          Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
-        } else {
-          Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
-          Tw = 0.0;
-          Tvd = v2(0, 0) - crs(wrel, Tv);
-        }
-        T[c][0] = Tv.x; T[c][1] = Tv.y; T[c][2] = Tw;
-        Td[c][0] = Tvd.x; Td[c][1] = Tvd.y; Td[c][2] = 0.0;
-      }
+      double T[MAXA][3], Td[MAXA][3];
+      for (int c = 0; c < n; ++c)
+        if (col_upstream(E.upstream, nc, c, 3)) jac_col2(G, W, c, F, T[c], Td[c]);
       const double mc[3] = {E.p[0], E.p[0], E.p[1]};
       for (int a = 0; a < n; ++a) {
-        if (!((E.upstream >> a) & 1u)) continue;
+        if (!col_upstream(E.upstream, nc, a, 3)) continue;
         for (int b = 0; b < n; ++b) {
-          if (!((E.upstream >> b) & 1u)) continue;
+          if (!col_upstream(E.upstream, nc, b, 3)) continue;
           double s = 0.0, sd = 0.0;
           for (int k = 0; k < 3; ++k) { s += T[a][k] * mc[k] * T[b][k]; if (want_dot) sd += Td[a][k] * mc[k] * T[b][k]; }
           M[a * n + b] += s;
@@ -666,36 +694,21 @@ GD void tmt(const GenericProgram* G, const Work<3, MAXF>& W, const BatchView& T,
 }
 template <int MAXF>
 GD void tmt(const GenericProgram* G, const Work<2, MAXF>& W, const BatchView& T, const BatchView& Td, long long i) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 3 * G->n_free;
   const bool want_dot = Td.p != (double*)0;
   for (int e = 0; e < G->n_elements; ++e) {
     const GenericElement& E = G->el[e];
     if (E.kind == RKB_INERTIA_GEN) {
       for (int c = 0; c < n; ++c) {
         const long long k = (long long)E.row * n + c;
-        T.p[i * T.si + k * T.sk] = ((E.upstream >> c) & 1u) ? 1.0 : 0.0;
+        T.p[i * T.si + k * T.sk] = (c < nc && ((E.upstream >> c) & 1u)) ? 1.0 : 0.0;
         if (want_dot) Td.p[i * Td.si + k * Td.sk] = 0.0;
       }
     } else if (E.kind == RKB_INERTIA_2D) {
       const Fr2& F = W.fr[E.fa];
       for (int c = 0; c < n; ++c) {
         double col[3] = {0, 0, 0}, cold[3] = {0, 0, 0};
-        if ((E.upstream >> c) & 1u) {
-          const GenericElement& J = G->el[G->jelem[c]];
-          const Fr2& Ej = W.fr[J.fb];
-          const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
-          const double wrel = F.w - Ej.w;
-          V2 Tv, Tvd;
-          if (J.kind == RKB_REVOLUTE_2D) {
-            Tv = rtmul(F.R, crs(1.0, dp));
-            col[2] = 1.0;
-            Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
-          } else {
-            Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
-            Tvd = v2(0, 0) - crs(wrel, Tv);
-          }
-          col[0] = Tv.x; col[1] = Tv.y; cold[0] = Tvd.x; cold[1] = Tvd.y;
-        }
+        if (col_upstream(E.upstream, nc, c, 3)) jac_col2(G, W, c, F, col, cold);
         for (int r = 0; r < 3; ++r) {
           const long long k = (long long)(E.row + r) * n + c;
           T.p[i * T.si + k * T.sk] = col[r];
@@ -740,27 +753,12 @@ GD void frame_jac(const GenericProgram* G, const Work<3, MAXF>& W, int frame, un
 }
 template <int MAXF>
 GD void frame_jac(const GenericProgram* G, const Work<2, MAXF>& W, int frame, unsigned upstream, const BatchView& T, const BatchView& Td, long long i) {
-  const int n = G->n_coords;
+  const int nc = G->n_coords, n = nc + 3 * G->n_free;
   const bool want_dot = Td.p != (double*)0;
   const Fr2& F = W.fr[frame];
   for (int c = 0; c < n; ++c) {
     double col[3] = {0, 0, 0}, cold[3] = {0, 0, 0};
-    if ((upstream >> c) & 1u) {
-      const GenericElement& J = G->el[G->jelem[c]];
-      const Fr2& Ej = W.fr[J.fb];
-      const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
-      const double wrel = F.w - Ej.w;
-      V2 Tv, Tvd;
-      if (J.kind == RKB_REVOLUTE_2D) {
-        Tv = rtmul(F.R, crs(1.0, dp));
-        col[2] = 1.0;
-        Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
-      } else {
-        Tv = rtmul(F.R, rmul(Ej.R, v2(J.p[0], J.p[1])));
-        Tvd = v2(0, 0) - crs(wrel, Tv);
-      }
-      col[0] = Tv.x; col[1] = Tv.y; cold[0] = Tvd.x; cold[1] = Tvd.y;
-    }
+    if (col_upstream(upstream, nc, c, 3)) jac_col2(G, W, c, F, col, cold);
     for (int r = 0; r < 3; ++r) {
       const long long k = (long long)r * n + c;
       T.p[i * T.si + k * T.sk] = col[r];
@@ -805,7 +803,12 @@ GD void pack_free_forces(const GenericProgram* G, Work<3, MAXF>& W) {
   }
 }
 template <int MAXF>
-GD void pack_free_forces(const GenericProgram*, Work<2, MAXF>&) {}
+GD void pack_free_forces(const GenericProgram* G, Work<2, MAXF>& W) {
+  if (G->n_free) {
+    double* f = &W.f[G->n_coords];
+    f[0] = W.fc.F.x; f[1] = W.fc.F.y; f[2] = W.fc.T;
+  }
+}
 
 template <int DIM, int MAXF>
 GD int accel(const GenericProgram* G, Work<DIM, MAXF>& W) {
@@ -814,7 +817,7 @@ GD int accel(const GenericProgram* G, Work<DIM, MAXF>& W) {
   force(G, W);
   pack_free_forces(G, W);
   mass(G, W, M, (double*)0, false);
-  return cholesky_solve(G->n_coords + 6 * G->n_free, M, W.f);
+  return cholesky_solve(G->n_coords + G->free_acc * G->n_free, M, W.f);
 }
 
 // kte_nl_system::apply_states_and_inputs for the free joint's 13 states (kte_nl_system.hpp:205-219): the quaternion is
@@ -829,8 +832,18 @@ GD void apply_free(Work<3, MAXF>& W, const double* s) {
   C.w = v3(s[10], s[11], s[12]);
   C.a = v3(0, 0, 0); C.al = v3(0, 0, 0);
 }
+// ... and for a free_joint_2D's 7 states (kte_nl_system.hpp:194-204): rot_mat_2D(vect<2>) normalises (rotations_2D.hpp:119-123)
 template <int MAXF>
-GD void apply_free(Work<2, MAXF>&, const double*) {}
+GD void apply_free(Work<2, MAXF>& W, const double* s) {
+  Fr2& C = W.fc;
+  C.p = v2(s[0], s[1]);
+  const double nr = sqrt(s[2] * s[2] + s[3] * s[3]);
+  C.R.c = s[2] / nr; C.R.s = s[3] / nr;
+  W.fraw[0] = s[2]; W.fraw[1] = s[3];
+  C.v = v2(s[4], s[5]);
+  C.w = s[6];
+  C.a = v2(0, 0); C.al = 0.0;
+}
 
 // the free joint's 13 state derivatives after accel(): Velocity, QuatDot (quaternion::getQuaternionDot,
 // rotations_3D.hpp:1206-1211, of the normalised quaternion), the six accelerations (kte_nl_system.hpp:293-308)
@@ -844,8 +857,15 @@ GD void free_derivative(const GenericProgram* G, const Work<3, MAXF>& W, double*
   o[6] = 0.5 * (C.q.w * C.w.z - C.q.y * C.w.x + C.q.x * C.w.y);
   for (int k = 0; k < 6; ++k) o[7 + k] = W.f[G->n_coords + k];
 }
+// free_joint_2D (kte_nl_system.hpp:282-291): Velocity, (-sin, cos) AngVelocity from the RAW state, three accelerations
 template <int MAXF>
-GD void free_derivative(const GenericProgram*, const Work<2, MAXF>&, double*) {}
+GD void free_derivative(const GenericProgram* G, const Work<2, MAXF>& W, double* o) {
+  const Fr2& C = W.fc;
+  o[0] = C.v.x; o[1] = C.v.y;
+  o[2] = -W.fraw[1] * C.w;
+  o[3] = W.fraw[0] * C.w;
+  for (int k = 0; k < 3; ++k) o[4 + k] = W.f[G->n_coords + k];
+}
 
 template <int DIM, int MAXF>
 GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& x, const ConstBatchView& u, long long ix, long long iu, bool with_u) {
@@ -856,7 +876,7 @@ GD void load(const GenericProgram* G, Work<DIM, MAXF>& W, const ConstBatchView& 
   for (int k = 0; k < G->n_aux; ++k) { W.q[G->n_coords + k] = G->aux_q[k]; W.qd[G->n_coords + k] = G->aux_qd[k]; }
   if (G->n_free) {  // the 13 states of the free joint follow the coordinates' (never blocked: rejected by the host)
     double s[13];
-    for (int k = 0; k < 13; ++k) s[k] = x.p[ix * x.si + (2 * G->n_coords + k) * x.sk];
+    for (int k = 0; k < G->free_states; ++k) s[k] = x.p[ix * x.si + (2 * G->n_coords + k) * x.sk];
     apply_free(W, s);
   }
   for (int k = 0; k < G->n_inputs; ++k) W.u[k] = with_u ? u.p[iu * u.si + k * u.sk] : 0.0;
@@ -880,7 +900,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_eval_kernel(const GenericPr
   if (G->n_free) {
     double o[13];
     free_derivative(G, W, o);
-    for (int k = 0; k < 13; ++k) {
+    for (int k = 0; k < G->free_states; ++k) {
       A.out.p[i * A.out.si + (2 * G->n_coords + k) * A.out.sk] = o[k];
       finite = finite && isfinite(o[k]);
     }
@@ -898,7 +918,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_forces_kernel(const Generic
   motion(G, W);
   force(G, W);
   pack_free_forces(G, W);
-  for (int c = 0; c < G->n_coords + 6 * G->n_free; ++c) A.out.p[i * A.out.si + c * A.out.sk] = W.f[c];
+  for (int c = 0; c < G->n_coords + G->free_acc * G->n_free; ++c) A.out.p[i * A.out.si + c * A.out.sk] = W.f[c];
 }
 
 template <int DIM, int MAXF>
@@ -911,7 +931,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_mass_kernel(const GenericPr
   double M[MAXA * MAXA], S[MAXA * MAXA];
   const bool want_dot = A.out2.p != (double*)0;
   mass(G, W, M, S, want_dot);
-  const int n = G->n_coords + 6 * G->n_free;
+  const int n = G->n_coords + G->free_acc * G->n_free;
   for (int a = 0; a < n; ++a)
     for (int b = 0; b < n; ++b) {
       // mat<symmetric> converting ctor averages the two halves (mat_alg_symmetric.hpp:171-200)
@@ -1077,7 +1097,7 @@ GD void load_flat(const GenericProgram* G, const ConstBatchView& x, long long ix
     xs[2 * c] = x.p[ix * x.si + rkb_state_q(x.blocked, n, c) * x.sk];
     xs[2 * c + 1] = x.p[ix * x.si + rkb_state_qd(x.blocked, n, c) * x.sk];
   }
-  for (int k = 0; k < 13 * G->n_free; ++k) xs[2 * n + k] = x.p[ix * x.si + (2 * n + k) * x.sk];
+  for (int k = 0; k < G->free_states * G->n_free; ++k) xs[2 * n + k] = x.p[ix * x.si + (2 * n + k) * x.sk];
 }
 GD void store_flat(const GenericProgram* G, const double* xs, const BatchView& o, long long off) {
   const int n = G->n_coords;
@@ -1085,7 +1105,7 @@ GD void store_flat(const GenericProgram* G, const double* xs, const BatchView& o
     o.p[off + rkb_state_q(o.blocked, n, c) * o.sk] = xs[2 * c];
     o.p[off + rkb_state_qd(o.blocked, n, c) * o.sk] = xs[2 * c + 1];
   }
-  for (int k = 0; k < 13 * G->n_free; ++k) o.p[off + (2 * n + k) * o.sk] = xs[2 * n + k];
+  for (int k = 0; k < G->free_states * G->n_free; ++k) o.p[off + (2 * n + k) * o.sk] = xs[2 * n + k];
 }
 // apply_states_and_inputs + get_state_derivative at the state vector xs: xd = f(xs, u); returns the status bits
 template <int DIM, int MAXF>
@@ -1108,7 +1128,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
   if (A.active && !A.active[i]) return;
   Work<DIM, MAXF> W;
   const long long i0 = A.x0_div > 1 ? i / A.x0_div : i;
-  const int nx = 2 * G->n_coords + 13 * G->n_free;
+  const int nx = 2 * G->n_coords + G->free_states * G->n_free;
   double xs[MAXX], xd[MAXX];
   load_flat(G, A.x0, i0, xs);
   for (int k = 0; k < G->n_inputs; ++k) W.u[k] = A.u.p[i * A.u.si + k * A.u.sk];

@@ -131,7 +131,7 @@ int validate(const rkb_chain_desc* d) {
     return RKB_ERR_INVALID;
   std::vector<int> coord_joint(d->n_coords, 0), input_used(d->n_inputs, 0), written(d->n_frames, 0);
   int n_free = 0, n_aux = 0;
-  for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_FREE_3D) ++n_free;
+  for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_FREE_3D || d->elements[e].kind == RKB_FREE_2D) ++n_free;
   for (int e = 0; e < d->n_elements; ++e) if (d->elements[e].kind == RKB_COORD_GEN) ++n_aux;
   if (d->n_coords + n_aux > RKB_MAX_COORDS) return RKB_ERR_UNSUPPORTED;
   std::vector<int> aux_declared(n_aux, 0), aux_written(n_aux, 0);
@@ -165,7 +165,6 @@ int validate(const rkb_chain_desc* d) {
         {  // bits 0 .. n_coords-1: coordinates; bits 32 .. 32+n_free-1: free-joint frames (mUpStream3DJoints)
           const uint64_t allowed = (d->n_coords >= 32 ? 0xffffffffull : ((1ull << d->n_coords) - 1ull)) | (((1ull << n_free) - 1ull) << 32);
           if (E.upstream & ~allowed) return RKB_ERR_INVALID;
-          if (E.kind == RKB_INERTIA_2D && (E.upstream >> 32)) return RKB_ERR_UNSUPPORTED;
         }
         break;
       case RKB_INERTIA_GEN:
@@ -198,8 +197,8 @@ int validate(const rkb_chain_desc* d) {
       case RKB_SPRING_GEN: case RKB_DAMPER_GEN:
         if (!any_coord_ok(E.coord) || !any_coord_ok(E.aux)) return RKB_ERR_INVALID;
         break;
-      case RKB_FREE_3D:  // coord = index of the joint's coordinate frame in kte_nl_system::dofs_3D, in chain order
-        if (d->dim != 3 || !frame_ok(E.frame_a) || !frame_ok(E.frame_b) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
+      case RKB_FREE_3D: case RKB_FREE_2D:  // coord = index of the joint's coordinate frame in dofs_3D / dofs_2D, in chain order
+        if ((d->dim == 3) != (E.kind == RKB_FREE_3D) || !frame_ok(E.frame_a) || !frame_ok(E.frame_b) || E.frame_a == E.frame_b) return RKB_ERR_INVALID;
         if (E.coord != free_seen++) return RKB_ERR_INVALID;
         if (written[E.frame_b]++ || E.frame_b == d->base_frame) return RKB_ERR_INVALID;
         break;
@@ -216,7 +215,7 @@ int validate(const rkb_chain_desc* d) {
     const rkb_element& E = d->elements[e];
     switch (E.kind) {
       case RKB_REVOLUTE_3D: case RKB_PRISMATIC_3D: case RKB_REVOLUTE_2D: case RKB_PRISMATIC_2D:
-      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D: case RKB_FREE_3D:
+      case RKB_RIGID_LINK_3D: case RKB_RIGID_LINK_2D: case RKB_FREE_3D: case RKB_FREE_2D:
         if (!ready[E.frame_a]) return RKB_ERR_UNSUPPORTED;
         ready[E.frame_b] = 1;
         break;
@@ -416,6 +415,7 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
   std::memset(&G, 0, sizeof G);
   G.dim = d.dim; G.n_elements = d.n_elements; G.n_frames = d.n_frames;
   G.n_coords = d.n_coords; G.n_inputs = d.n_inputs; G.base_frame = d.base_frame;
+  G.free_states = d.dim == 3 ? 13 : 7; G.free_acc = d.dim == 3 ? 6 : 3;
   if (d.dim == 3) {
     double q[4];
     unit_quat(d.base.quat, q);
@@ -444,7 +444,7 @@ bool lower_generic(const rkb_chain_desc& d, GenericProgram& G) {
     GenericElement& g = G.el[e];
     g.kind = E.kind; g.fa = E.frame_a; g.fb = E.frame_b; g.coord = E.coord; g.aux = E.aux;
     g.upstream = (uint32_t)(E.upstream & 0xffffull) | ((uint32_t)((E.upstream >> 32) & 0xffull) << RKB_GEN_FREE_BIT);
-    if (E.kind == RKB_FREE_3D) { G.free_elem[G.n_free] = e; G.n_free += 1; }
+    if (E.kind == RKB_FREE_3D || E.kind == RKB_FREE_2D) { G.free_elem[G.n_free] = e; G.n_free += 1; }
     if (E.kind == RKB_COORD_GEN) { G.aux_q[E.coord - d.n_coords] = E.p[0]; G.aux_qd[E.coord - d.n_coords] = E.p[1]; G.n_aux += 1; }
     std::memcpy(g.p, E.p, sizeof g.p);
     if (E.kind == RKB_RIGID_LINK_3D) unit_quat(&E.p[3], &g.p[3]);
@@ -752,9 +752,9 @@ int rkb_chain_create_ex(const rkb_chain_desc* desc, unsigned create_flags, rkb_c
   c->desc.elements = c->elements.data();
   c->n = desc->n_coords;
   c->nu = desc->n_inputs;
-  for (int e = 0; e < desc->n_elements; ++e) if (desc->elements[e].kind == RKB_FREE_3D) c->n_free += 1;
-  c->nx = 2 * c->n + 13 * c->n_free;  // kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147
-  c->na = c->n + 6 * c->n_free;
+  for (int e = 0; e < desc->n_elements; ++e) if (desc->elements[e].kind == RKB_FREE_3D || desc->elements[e].kind == RKB_FREE_2D) c->n_free += 1;
+  c->nx = 2 * c->n + (desc->dim == 3 ? 13 : 7) * c->n_free;  // kte_nl_system::get_state_dimensions, kte_nl_system.hpp:145-147
+  c->na = c->n + (desc->dim == 3 ? 6 : 3) * c->n_free;
   c->create_flags = create_flags;
   c->serial_ok = lower_serial(c->desc, c->sp, c->serial_fl, c->serial_shape);
   if (c->serial_ok) {

@@ -146,7 +146,7 @@ void quat(const Node* n, double* out) {
 unsigned long class_of(const Node* n) { return n ? std::strtoul(n->type.c_str(), nullptr, 10) : 0ul; }
 enum : unsigned long {
   T_NL_SYSTEM = 0xC2300002ul, T_CHAIN = 0xC2100002ul, T_MASS_CALC = 0xC2000001ul,
-  T_REV_2D = 0xC2100003ul, T_REV_3D = 0xC2100004ul, T_PRI_2D = 0xC2100005ul, T_PRI_3D = 0xC2100006ul, T_FREE_3D = 0xC2100042ul,
+  T_REV_2D = 0xC2100003ul, T_REV_3D = 0xC2100004ul, T_PRI_2D = 0xC2100005ul, T_PRI_3D = 0xC2100006ul, T_FREE_2D = 0xC2100041ul, T_FREE_3D = 0xC2100042ul,
   T_LINK_GEN = 0xC2100007ul, T_LINK_2D = 0xC2100008ul, T_LINK_3D = 0xC2100009ul,
   T_IN_GEN = 0xC210000Aul, T_IN_2D = 0xC210000Bul, T_IN_3D = 0xC210000Cul,
   T_SPRING_GEN = 0xC210000Dul, T_SPRING_2D = 0xC210000Eul, T_SPRING_3D = 0xC210000Ful,
@@ -207,12 +207,15 @@ struct Builder {
     uint64_t m = 0;
     const long n = count_of(dep, "mUpStreamJoints");
     for (long k = 0; k < n; ++k) m |= uint64_t(1) << cid(dep->kid("mUpStreamJoints_key[" + std::to_string(k) + "]"), "mUpStreamJoints");
-    if (count_of(dep, "mUpStream2DJoints") != 0) throw fail("an inertia depends on a 2D free joint");
-    const long n3 = count_of(dep, "mUpStream3DJoints");
-    for (long k = 0; k < n3; ++k) {
-      std::map<long, int>::const_iterator it = free3.find(oid(dep->kid("mUpStream3DJoints_key[" + std::to_string(k) + "]"), "mUpStream3DJoints"));
-      if (it == free3.end()) throw fail("an inertia depends on a free-joint frame that is not in dofs_3D");
-      m |= uint64_t(1) << (32 + it->second);
+    // the free joints of a chain are all 2D or all 3D (read_system): one index space
+    const char* maps[2] = {"mUpStream2DJoints", "mUpStream3DJoints"};
+    for (int w = 0; w < 2; ++w) {
+      const long n3 = count_of(dep, maps[w]);
+      for (long k = 0; k < n3; ++k) {
+        std::map<long, int>::const_iterator it = free3.find(oid(dep->kid(std::string(maps[w]) + "_key[" + std::to_string(k) + "]"), maps[w]));
+        if (it == free3.end()) throw fail("an inertia depends on a free-joint frame that is not among the system's free-frame dofs");
+        m |= uint64_t(1) << (32 + it->second);
+      }
     }
     return m;
   }
@@ -220,23 +223,25 @@ struct Builder {
 
 void read_system(const Archive& A, const Node* sys, Builder& B, rkb_chain_desc& d) {
   if (class_of(sys) != T_NL_SYSTEM) throw fail("the archive's first object is not a kte_nl_system (type " + sys->type + ")");
-  if (count_of(sys, "dofs_2D") != 0) throw fail("2D free-frame dofs (free_joint_2D) are outside the compiled path");
-  const long n = count_of(sys, "dofs_gen"), nf = count_of(sys, "dofs_3D"), nu = count_of(sys, "inputs");
+  const long n = count_of(sys, "dofs_gen"), nf3 = count_of(sys, "dofs_3D"), nf2 = count_of(sys, "dofs_2D"), nu = count_of(sys, "inputs");
+  if (nf3 != 0 && nf2 != 0) throw fail("2D and 3D free-frame dofs in one system");
+  const long nf = nf3 + nf2;
+  const std::string fdofs = nf2 ? "dofs_2D" : "dofs_3D", fcalc = nf2 ? "mFrames2D" : "mFrames3D";
   if (n > RKB_MAX_COORDS) throw fail("more generalized coordinates than RKB_MAX_COORDS");
   for (long i = 0; i < n; ++i) B.coords[B.oid(sys->kid("dofs_gen_q[" + std::to_string(i) + "]"), "dofs_gen")] = (int)i;
-  for (long i = 0; i < nf; ++i) B.free3[B.oid(sys->kid("dofs_3D_q[" + std::to_string(i) + "]"), "dofs_3D")] = (int)i;
+  for (long i = 0; i < nf; ++i) B.free3[B.oid(sys->kid(fdofs + "_q[" + std::to_string(i) + "]"), "free-frame dofs")] = (int)i;
   for (long i = 0; i < nu; ++i) B.inputs[B.oid(sys->kid("inputs_q[" + std::to_string(i) + "]"), "inputs")] = (int)i;
   B.n_coords = (int)n;
   const Node* chain = A.deref(sys->kid("chain"));
   const Node* mcalc = A.deref(sys->kid("mass_calc"));
   if (!chain || class_of(chain) != T_CHAIN || !mcalc || class_of(mcalc) != T_MASS_CALC) throw fail("kte_nl_system without chain or mass_calc");
   // mass_matrix_calc must list the system's coordinates and free frames in the system's order (kte_nl_system.hpp:271)
-  if (count_of(mcalc, "mCoords") != n || count_of(mcalc, "mFrames3D") != nf || count_of(mcalc, "mFrames2D") != 0)
+  if (count_of(mcalc, "mCoords") != n || count_of(mcalc, "mFrames3D") != nf3 || count_of(mcalc, "mFrames2D") != nf2)
     throw fail("mass_matrix_calc coordinates differ from the system dofs");
   for (long i = 0; i < n; ++i)
     if (B.cid(mcalc->kid("mCoords_q[" + std::to_string(i) + "]"), "mCoords") != (int)i) throw fail("mass_matrix_calc coordinates differ from the system dofs");
   for (long i = 0; i < nf; ++i) {
-    std::map<long, int>::const_iterator it = B.free3.find(B.oid(mcalc->kid("mFrames3D_q[" + std::to_string(i) + "]"), "mFrames3D"));
+    std::map<long, int>::const_iterator it = B.free3.find(B.oid(mcalc->kid(fcalc + "_q[" + std::to_string(i) + "]"), "mass_calc free frames"));
     if (it == B.free3.end() || it->second != (int)i) throw fail("mass_matrix_calc free frames differ from the system dofs");
   }
   const long nk = count_of(chain, "mKTEs");
@@ -249,7 +254,7 @@ void read_system(const Archive& A, const Node* sys, Builder& B, rkb_chain_desc& 
   for (const Node* f : ktes) {  // 2D or 3D: decided by the first joint / link / inertia, as the bridge does
     const unsigned long t = class_of(f);
     if (t == T_REV_3D || t == T_PRI_3D || t == T_LINK_3D || t == T_IN_3D || t == T_FREE_3D) { B.dim = 3; break; }
-    if (t == T_REV_2D || t == T_PRI_2D || t == T_LINK_2D || t == T_IN_2D) { B.dim = 2; break; }
+    if (t == T_REV_2D || t == T_PRI_2D || t == T_LINK_2D || t == T_IN_2D || t == T_FREE_2D) { B.dim = 2; break; }
   }
   if (!B.dim) throw fail("chain has no 2D or 3D element");
   std::vector<std::pair<int, long> > pending;  // (actuator element, object id of its joint)
@@ -269,12 +274,12 @@ void read_system(const Archive& A, const Node* sys, Builder& B, rkb_chain_desc& 
                      fa, fb, c, 0, 0, p, 3);
         break;
       }
-      case T_FREE_3D: {
+      case T_FREE_3D: case T_FREE_2D: {
         const int fa = B.fid(k->kid("mBase"), "mBase"), fb = B.fid(k->kid("mEnd"), "mEnd");
         B.written[fb] = 1;
         std::map<long, int>::const_iterator it = B.free3.find(B.oid(k->kid("mCoord"), "mCoord"));
-        if (it == B.free3.end()) throw fail("a free joint's coordinate frame is not listed in the system's dofs_3D");
-        idx = B.push(RKB_FREE_3D, fa, fb, it->second, 0, 0, p, 0);
+        if (it == B.free3.end()) throw fail("a free joint's coordinate frame is not listed in the system's free-frame dofs");
+        idx = B.push(t == T_FREE_3D ? RKB_FREE_3D : RKB_FREE_2D, fa, fb, it->second, 0, 0, p, 0);
         break;
       }
       case T_LINK_3D: {

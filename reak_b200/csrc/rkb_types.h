@@ -244,6 +244,7 @@ struct GenericElement {
 struct GenericProgram {
   int32_t dim, n_elements, n_frames, n_coords, n_inputs, base_frame;
   int32_t n_free, free_elem[RKB_GEN_MAX_FREE];  // free joints and the element index of each
+  int32_t free_states, free_acc;                // per free joint: 13 / 6 (free_joint_3D), 7 / 3 (free_joint_2D)
   int32_t n_aux;  // auxiliary gen_coords (RKB_COORD_GEN), indexed n_coords .. n_coords + n_aux - 1 like the coordinates
   double  aux_q[RKB_MAX_COORDS], aux_qd[RKB_MAX_COORDS];  // the values they hold unless a rigid_link_gen writes them
   double  base[19];  // p3 q4 v3 w3 a3 al3 (2D: p2, -, cos, sin, -, -, v2, -, w, -, -, a2, -, al)

@@ -79,6 +79,10 @@ class jacobian_3D_3D(object):
     """core/kinetostatics/motion_jacobians.hpp:1035-1240; the holder a free_joint_3D fills with identity blocks."""
 
 
+class jacobian_2D_2D(object):
+    """core/kinetostatics/motion_jacobians.hpp:411-520; the holder a free_joint_2D fills with identity blocks."""
+
+
 class jacobian_gen_gen(object):
     """core/kinetostatics/motion_jacobians.hpp:49-107."""
 
@@ -138,6 +142,15 @@ class free_joint_3D(kte_map):
         self.mCoord, self.mBase, self.mEnd, self.mJacobian = coord, base, end, jacobian
 
 
+class free_joint_2D(kte_map):
+    """ctrl/mbd_kte/free_joints.hpp:46-130 / free_joints.cpp:33-117: End = Base * Coord, the coordinate being a whole
+    frame_2D (position, rotation as (cos, sin), velocity, angular velocity: 7 states, kte_nl_system.hpp:194-204)."""
+
+    def __init__(self, name, coord, base, end, jacobian=None):
+        kte_map.__init__(self, name)
+        self.mCoord, self.mBase, self.mEnd, self.mJacobian = coord, base, end, jacobian
+
+
 class rigid_link_3D(kte_map):
     """ctrl/mbd_kte/rigid_link.hpp:296-299 / rigid_link.cpp:152-185."""
 
@@ -161,7 +174,7 @@ class _joint_dependent(object):
         self.mUpStream3DJoints = {}  # free-joint coordinate frames (jacobian_joint_map.hpp:252-331)
 
     def add_joint(self, joint_coord, joint_jacobian):
-        if isinstance(joint_coord, frame_3D):
+        if isinstance(joint_coord, (frame_3D, frame_2D)):   # (mUpStream3DJoints / mUpStream2DJoints: one kind per chain)
             self.mUpStream3DJoints[joint_coord] = joint_jacobian
         else:
             self.mUpStreamJoints[joint_coord] = joint_jacobian
@@ -325,10 +338,10 @@ class mass_matrix_calc(object):
             self.m3DInertias.append(obj)
         elif isinstance(obj, gen_coord):
             self.mCoords.append(obj)
-        elif isinstance(obj, frame_3D):
-            self.mFrames3D.append(obj)   # mass_matrix_calculator.cpp:72-78: a free joint's coordinate frame
+        elif isinstance(obj, (frame_3D, frame_2D)):
+            self.mFrames3D.append(obj)   # mass_matrix_calculator.cpp:64-78: a free joint's coordinate frame (mFrames2D / mFrames3D)
         else:
-            raise TypeError("mass_matrix_calc << %r: 2D free-frame coordinates are not in the compiled path" % (obj,))
+            raise TypeError("mass_matrix_calc << %r" % (obj,))
         return self
 
 
@@ -433,11 +446,11 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
         elif isinstance(k, prismatic_joint_2D):
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
             rec(_abi.PRISMATIC_2D, a, b, cid(k.mCoord), p=k.mAxis)
-        elif isinstance(k, free_joint_3D):
+        elif isinstance(k, (free_joint_3D, free_joint_2D)):
             if id(k.mCoord) not in free_id:
-                raise UnsupportedChain("free joint %s: its coordinate frame is not in dofs_3D" % k.name)
+                raise UnsupportedChain("free joint %s: its coordinate frame is not among the system's free-frame dofs" % k.name)
             a, b = fid(k.mBase), fid(k.mEnd); written.add(b)
-            rec(_abi.FREE_3D, a, b, free_id[id(k.mCoord)])
+            rec(_abi.FREE_3D if isinstance(k, free_joint_3D) else _abi.FREE_2D, a, b, free_id[id(k.mCoord)])
         elif isinstance(k, rigid_link_gen):
             a, b = gid(k.mBase), gid(k.mEnd)
             if b < len(dofs_gen):
@@ -512,7 +525,7 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
     if dofs_3D:
         # the reference's mass_matrix_calc dereferences a null Jacobian when a gen inertia depends on mCoords[i] for a
         # free-frame index i (mass_matrix_calculator.cpp:226-233): there is no behaviour to match for such a model
-        n_free_used = sum(1 for e in recs if e.kind == _abi.FREE_3D)
+        n_free_used = sum(1 for e in recs if e.kind in (_abi.FREE_3D, _abi.FREE_2D))
         if n_free_used != len(dofs_3D):
             raise UnsupportedChain("every frame of dofs_3D needs exactly one free_joint_3D in the chain")
         for e in recs:
@@ -548,7 +561,8 @@ def compile_chain(chain, mass_calc, dofs_gen, inputs, dofs_3D=()):
     d.elements = C.cast(arr, C.POINTER(_abi.rkb_element))
     cc = compiled_chain(d, arr, frames, list(dofs_gen))
     cc.n_free = len(dofs_3D)
-    cc.nx, cc.n_acc = 2 * len(dofs_gen) + 13 * len(dofs_3D), len(dofs_gen) + 6 * len(dofs_3D)
+    fs, fa = (13, 6) if d.dim == 3 else (7, 3)   # states / accelerations per free joint (kte_nl_system.hpp:145-147)
+    cc.nx, cc.n_acc = 2 * len(dofs_gen) + fs * len(dofs_3D), len(dofs_gen) + fa * len(dofs_3D)
     return cc
 
 
@@ -569,6 +583,7 @@ def read_rkx(path, max_elements=512):
     d.elements = C.cast(own, C.POINTER(_abi.rkb_element))
     cc = compiled_chain(d, (_abi.rkb_element * n).from_buffer(own) if n else own, [None] * d.n_frames, [None] * d.n_coords)
     cc._keep = own
-    cc.n_free = sum(1 for i in range(n) if own[i].kind == _abi.FREE_3D)
-    cc.nx, cc.n_acc = 2 * d.n_coords + 13 * cc.n_free, d.n_coords + 6 * cc.n_free
+    cc.n_free = sum(1 for i in range(n) if own[i].kind in (_abi.FREE_3D, _abi.FREE_2D))
+    fs, fa = (13, 6) if d.dim == 3 else (7, 3)
+    cc.nx, cc.n_acc = 2 * d.n_coords + fs * cc.n_free, d.n_coords + fa * cc.n_free
     return cc

@@ -191,6 +191,48 @@ def free_base_chain(n_revolute=3, actuated=True, link_rotation=False):
     return s
 
 
+def free_planar_chain(n_revolute=2, actuated=True):
+    """A planar platform on a free_joint_2D (free_joints.cpp:33-117) carrying `n_revolute` links: 7 states for the
+    platform (position, (cos, sin), velocity, angular velocity) after the joints' (q, qd) pairs.  The system's free
+    frames are listed in dofs_3D whatever their dimension (kte_nl_system keeps dofs_2D / dofs_3D apart; a chain has one kind)."""
+    s = kte_system("free_planar")
+    base = kte.frame_2D()
+    base.Acceleration = [0.0, 9.81]
+    base.Position = [0.2, -0.1]
+    coord, jac0, plat = kte.frame_2D(), kte.jacobian_2D_2D(), kte.frame_2D()
+    s.chain << kte.free_joint_2D("free_base", coord, base, plat, jac0)
+    dep0 = kte.joint_dependent_frame_2D(plat)
+    dep0.add_joint(coord, jac0)
+    body = kte.inertia_2D("platform", dep0, 3.0, 0.4)
+    s.chain << body
+    s.mass_calc << body
+    s.dofs_3D.append(coord)
+    cur, upstream = plat, []
+    for idx in range(n_revolute):
+        q, jac, end, nxt = kte.gen_coord(), kte.jacobian_gen_2D(), kte.frame_2D(), kte.frame_2D()
+        joint = kte.revolute_joint_2D("joint_%d" % idx, q, cur, end, jac)
+        if actuated:
+            act = kte.driving_actuator_gen("actuator_%d" % idx, q, joint)
+            s.chain << act
+            s.inputs.append(act)
+        s.chain << joint
+        s.chain << kte.rigid_link_2D("link_%d" % idx, end, nxt, kte.pose_2D((0.4 - 0.1 * idx, 0.05), 0.2 * idx))
+        upstream.append((q, jac))
+        dep = kte.joint_dependent_frame_2D(nxt)
+        dep.add_joint(coord, jac0)
+        for c, j in upstream:
+            dep.add_joint(c, j)
+        inertia = kte.inertia_2D("mass_%d" % idx, dep, 1.0 - 0.3 * idx, 0.05)
+        s.chain << inertia
+        s.mass_calc << inertia
+        s.dofs_gen.append(q)
+        cur = nxt
+    for q in s.dofs_gen:
+        s.mass_calc << q
+    s.mass_calc << coord
+    return s
+
+
 def pendulum_chain():
     """ctrl/mbd_kte/test_bm.cpp:46-72: 0.5 m massless rod, 1 kg point mass, gravity (0, 9.81)."""
     return planar_chain(lengths=(0.5,), masses=(1.0,), moments=(0.0,))
@@ -361,6 +403,8 @@ FREE_PRESETS = {
     "free_body": lambda: free_base_chain(0),                          # one free rigid body (13 states)
     "free_arm3": lambda: free_base_chain(3),                          # cfg 4's "free" variant, as far as the reference evaluates it
     "free_arm2_twist": lambda: free_base_chain(2, actuated=False, link_rotation=True),
+    "free_planar_body": lambda: free_planar_chain(0),                 # free_joint_2D: one planar rigid body (7 states)
+    "free_planar2": lambda: free_planar_chain(2),
 }
 
 

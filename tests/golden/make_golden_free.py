@@ -25,16 +25,20 @@ N = 16
 
 def free_batch(compiled, n_samples, seed, q_range=2.5):
     """states of a chain with free joints: (q, qd) pairs, then per free joint position, quaternion (norm 0.8 .. 1.25),
-    velocity, angular velocity"""
+    velocity, angular velocity (free_joint_2D: position, (cos, sin) of norm 0.8 .. 1.25, velocity, angular velocity)"""
     rng = np.random.default_rng(seed)
     n, nu = compiled.n_coords, compiled.n_inputs
     x = rng.uniform(-1.0, 1.0, (n_samples, compiled.nx))
     x[:, 0:2 * n:2] *= q_range
+    planar = compiled.desc.dim == 2   # free_joint_2D: 7 states, the rotation as (cos, sin) at 2..3
     for j in range(compiled.n_free):
-        o = 2 * n + 13 * j
-        q = rng.normal(size=(n_samples, 4))
+        o = 2 * n + (7 if planar else 13) * j
+        q = rng.normal(size=(n_samples, 2 if planar else 4))
         q *= (rng.uniform(0.8, 1.25, (n_samples, 1)) / np.linalg.norm(q, axis=1, keepdims=True))
-        x[:, o + 3:o + 7] = q
+        if planar:
+            x[:, o + 2:o + 4] = q
+        else:
+            x[:, o + 3:o + 7] = q
     u = rng.uniform(-1.0, 1.0, (n_samples, nu))
     return x, u
 

@@ -264,3 +264,45 @@ def test_gpu_reak_bridge_drop_in_with_free_joint(oracle_built):
     rc = fn(R.h, 64, x.ctypes.data, u.ctypes.data, 1e-3, 20, err.ctypes.data, msg, 512)
     assert rc == 0, msg.value
     assert err[0] < TOL_STEP and err[1] < TOL_STEP and err[2] < TOL_LONG, err
+
+
+@pytest.mark.gpu
+def test_gpu_free_chain_steer_batch_and_linearisation(oracle_built):
+    """the entry points built on top of the evaluation / rollout kernels carry the longer state of a free chain through:
+    rkb_steer_batch (arg-min over constant-control rollouts) and rkb_linearize (A, B by central differences)"""
+    p = _prop("free_arm3")
+    O = oracle_built.Oracle(p.compiled)
+    rng = np.random.default_rng(5)
+    P, R, K = 5, 23, 8
+    x0, _ = _batch(p.compiled, P, 41)
+    goal, _ = _batch(p.compiled, P, 42)
+    u = rng.uniform(-3, 3, (P, R, p.nu))
+    idx, bx, bc, st = p.steer_batch(x0, goal, u, 1e-3, K, want_status=True)
+    xe, _, _ = O.rk4(np.repeat(x0, R, axis=0), u.reshape(P * R, -1), 1e-3, K)
+    cost = np.linalg.norm(xe.reshape(P, R, -1) - goal[:, None, :], axis=2)
+    assert np.array_equal(idx, cost.argmin(axis=1)) and not st.any()
+    assert rel_err(bx, xe.reshape(P, R, -1)[np.arange(P), idx]) < TOL_STEP and rel_err(bc, cost.min(axis=1)) < TOL_STEP
+    # linearisation against the same central differences of the oracle
+    n, nx, nu, eps = 11, p.nx, p.nu, 1e-6
+    x, uu = _batch(p.compiled, n, 43)
+    A, B, st = p.get_linear_blocks(x, uu, eps)
+    assert not st.any() and A.shape == (n, nx, nx) and B.shape == (n, nx, nu)
+    for d in range(nx + nu):
+        xp, xm, up_, um = x.copy(), x.copy(), uu.copy(), uu.copy()
+        if d < nx:
+            h = eps * np.maximum(1.0, np.abs(x[:, d]))
+            xp[:, d] += h; xm[:, d] -= h
+            den = xp[:, d] - xm[:, d]
+        else:
+            h = eps * np.maximum(1.0, np.abs(uu[:, d - nx]))
+            up_[:, d - nx] += h; um[:, d - nx] -= h
+            den = up_[:, d - nx] - um[:, d - nx]
+        col = (O.eval(xp, up_)[0] - O.eval(xm, um)[0]) / den[:, None]
+        got = A[:, :, d] if d < nx else B[:, :, d - nx]
+        assert rel_err(got, col) < 1e-7, d
+    # control sequences with waypoints (one launch per interval on the interpreter)
+    J = 4
+    useq = rng.uniform(-2, 2, (n, J, nu))
+    xo, traj, st = p.rollout(x, useq, 1e-3, 5, scheme="rk4", want_traj=True)
+    xr, tr, sr = O.rollout(x, useq, 4, 1e-3, 5)
+    assert not st.any() and rel_err(xo, xr) < TOL_LONG and rel_err(traj, tr) < TOL_LONG

@@ -44,7 +44,7 @@ def test_unsupported_chains_raise():
     with pytest.raises(kte.UnsupportedChain):
         kte.compile_chain(s3.chain, s3.mass_calc, s3.dofs_gen, s3.inputs)
     with pytest.raises(TypeError):
-        kte.mass_matrix_calc() << kte.frame_2D()   # 2D free-frame coordinates (free_joint_2D) are not compiled
+        kte.mass_matrix_calc() << kte.pose_3D()    # only inertias, generalized coordinates and free-joint frames register
 
 
 def test_axis_angle_quaternion():
