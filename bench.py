@@ -299,6 +299,20 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
     out.append(e4)
     del x4, u4, o4, s4
     torch.cuda.empty_cache()
+    # cfg 4, "free" variant: a six-joint arm on a free-floating base (free_joint_3D: 25 states, 12 accelerations) — the model
+    # the reference evaluates (no rotors next to a free joint).  Interpreter kernels: the compatibility path.
+    p4f = kte_batch_propagator(presets.make("free_arm6"), device=local)
+    n4f = (1 << 18) // world
+    x4f, u4f = uniform((n4f, p4f.nx), -1, 1), uniform((n4f, p4f.nu), -1, 1)
+    o4f = torch.empty_like(x4f)
+    s4f = torch.empty((n4f,), dtype=torch.int32, device=dev)
+    t4f = best(lambda: p4f.get_next_states(x4f, u4f, DT, 10, out=o4f, status=s4f), p4f)
+    e4f = {"config": "4-free", "workload": "6-joint arm on a free_joint_3D base (25 states): 2^18 extensions over %d GPU(s) x 10 RK4 steps" % world,
+           "rollout_ms": t4f, "serial_kernels": bool(p4f.is_serial()), "units_total": (1 << 18) * 10, "scaling": "strong"}
+    if check:
+        cpu_check(e4f, p4f, x4f, u4f, 10, o4f, "one control interval of 10 steps")
+    out.append(e4f)
+    del x4f, u4f, o4f, s4f
     # cfg 5: steer batch, 4096 pairs x 256 controls x 100 steps over all GPUs, pairs sharded
     p5 = kte_batch_propagator(presets.make(PRESET), device=local)
     P, R = max(1, 4096 // world), 256

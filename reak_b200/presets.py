@@ -403,6 +403,7 @@ FREE_PRESETS = {
     "free_body": lambda: free_base_chain(0),                          # one free rigid body (13 states)
     "free_arm3": lambda: free_base_chain(3),                          # cfg 4's "free" variant, as far as the reference evaluates it
     "free_arm2_twist": lambda: free_base_chain(2, actuated=False, link_rotation=True),
+    "free_arm6": lambda: free_base_chain(6),                          # six-joint arm on a free-floating base: 25 states, 12 accelerations
     "free_planar_body": lambda: free_planar_chain(0),                 # free_joint_2D: one planar rigid body (7 states)
     "free_planar2": lambda: free_planar_chain(2),
 }

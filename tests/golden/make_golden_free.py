@@ -46,7 +46,12 @@ def free_batch(compiled, n_samples, seed, q_range=2.5):
 def main():
     if not pyref.have_ref():
         raise SystemExit("oracle/_ref/libreak_ref.so missing: run `make -C oracle ref` where /root/reference exists")
-    for idx, name in enumerate(sorted(presets.FREE_PRESETS)):
+    only = set(sys.argv[1:])  # optional: regenerate just these fixtures
+    order = ["free_arm2_twist", "free_arm3", "free_body", "free_planar2", "free_planar_body", "free_arm6"]  # seeds follow this order
+    assert sorted(order) == sorted(presets.FREE_PRESETS)
+    for idx, name in enumerate(order):
+        if only and name not in only:
+            continue
         s = presets.make(name)
         c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs, s.dofs_3D)
         R = pyref.Reference(c)
