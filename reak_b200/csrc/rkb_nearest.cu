@@ -94,7 +94,7 @@ __device__ __noinline__ double nn_exact_offer(const double* __restrict__ query, 
   return L->gate_s;
 }
 
-template <int DIMP, int RQ, int RV>
+template <int DIMP, int RQ, int RV, bool DEFER>
 __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArgs A) {
   __shared__ __align__(16) double tile[NN_TILE * DIMP];
   bool live[RQ];
@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArg
     }
     __syncthreads();
     if (!live[0]) continue;  // (queries of a thread are live front to back)
+    unsigned long long hits[RQ];  // bit j: vertex j of the tile may enter the list of query r
+#pragma unroll
+    for (int r = 0; r < RQ; ++r) hits[r] = 0ull;
     for (int j = 0; j < nt; j += RV) {
       double s[RQ][RV];
       const double* t[RV];
@@ -155,20 +158,45 @@ __global__ void __launch_bounds__(NN_BLOCK) nearest_scan_kernel(const NearestArg
           for (int m = 0; m < RV; ++m) { const double d = a[m].y - q[r][c + 1]; s[r][m] = fma(d, d, s[r][m]); }
         }
       }
-      unsigned hits = 0;  // bit r RV + m: vertex j + m may enter the list of query r
+      if (DEFER) {
 #pragma unroll
-      for (int r = 0; r < RQ; ++r)
+        for (int r = 0; r < RQ; ++r)
 #pragma unroll
-        for (int m = 0; m < RV; ++m) hits |= (s[r][m] < fast[r] ? 1u : 0u) << (r * RV + m);
-      while (hits) {  // rare: the reference's own arithmetic decides, vertex by vertex in index order per query
-        const int b = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int r = b / RV, m = b - r * RV;
-        if (j + m >= nt) continue;
+          for (int m = 0; m < RV; ++m) hits[r] |= (unsigned long long)(s[r][m] < fast[r] ? 1u : 0u) << (j + m);
+      } else {  // k = 1: a query accepts ~ln(chunk) vertices in all; they are handled where they are met
+        unsigned now = 0;
+#pragma unroll
+        for (int r = 0; r < RQ; ++r)
+#pragma unroll
+          for (int m = 0; m < RV; ++m) now |= (s[r][m] < fast[r] ? 1u : 0u) << (r * RV + m);
+        while (now) {
+          const int b = __ffs(now) - 1;
+          now &= now - 1;
+          const int r = b / RV, m = b - r * RV;
+          if (j + m >= nt) continue;
+          const long long qi = q_first + (long long)r * NN_BLOCK;
+          const double g = nn_exact_offer(A.queries + qi * A.dim, &tile[(j + m) * DIMP], A.dim, &L[r], k, (int32_t)(base + j + m)) * widen;
+#pragma unroll
+          for (int r2 = 0; r2 < RQ; ++r2) if (r2 == r) fast[r2] = g;
+        }
+      }
+    }
+    // k > 1: the candidates of the tile, per query in vertex order, decided by the reference's own arithmetic.  Collected
+    // per tile rather than handled where they are met: a warp leaves the scan once per tile instead of once per accepting
+    // lane (some list of the warp accepts a vertex in most groups of four).  The gate a candidate was admitted by may be
+    // stale by then; the exact test inside nn_offer uses the current one.
+#pragma unroll
+    for (int r = 0; r < RQ && DEFER; ++r) {
+      unsigned long long h = hits[r] & (nt < 64 ? ((1ull << nt) - 1ull) : ~0ull);
+      if (h) {
         const long long qi = q_first + (long long)r * NN_BLOCK;
-        const double g = nn_exact_offer(A.queries + qi * A.dim, &tile[(j + m) * DIMP], A.dim, &L[r], k, (int32_t)(base + j + m)) * widen;
-#pragma unroll
-        for (int r2 = 0; r2 < RQ; ++r2) if (r2 == r) fast[r2] = g;
+        double g = fast[r];
+        while (h) {
+          const int j = __ffsll((long long)h) - 1;
+          h &= h - 1;
+          g = nn_exact_offer(A.queries + qi * A.dim, &tile[j * DIMP], A.dim, &L[r], k, (int32_t)(base + j)) * widen;
+        }
+        fast[r] = g;
       }
     }
   }
@@ -220,8 +248,13 @@ template <int DIMP>
 cudaError_t launch_scan(const NearestArgs& A, int rq, unsigned n_chunks, cudaStream_t s) {
   const long long per_cta = (long long)NN_BLOCK * rq;
   const dim3 grid((unsigned)((A.n_queries + per_cta - 1) / per_cta), n_chunks);
-  if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1), 4><<<grid, NN_BLOCK, 0, s>>>(A);
-  else nearest_scan_kernel<DIMP, 1, 4><<<grid, NN_BLOCK, 0, s>>>(A);
+  if (A.k == 1) {
+    if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1), 4, false><<<grid, NN_BLOCK, 0, s>>>(A);
+    else nearest_scan_kernel<DIMP, 1, 4, false><<<grid, NN_BLOCK, 0, s>>>(A);
+  } else {
+    if (rq == 2) nearest_scan_kernel<DIMP, (DIMP <= 24 ? 2 : 1), 4, true><<<grid, NN_BLOCK, 0, s>>>(A);
+    else nearest_scan_kernel<DIMP, 1, 4, true><<<grid, NN_BLOCK, 0, s>>>(A);
+  }
   return cudaGetLastError();
 }
 
@@ -263,9 +296,8 @@ int rkb_nearest(int device, size_t n_vertices, const double* vertices, size_t n_
   }
   const int dimp = (dim + 3) / 4 * 4;
   // queries per thread: as many as their coordinates leave registers for, while every thread still gets work
-  // (measured, profiles/r2_nearest.md: 2 queries per thread reach the rate 4 reach, at 5 instead of 3 CTAs per SM; with
-  // k > 1 a warp takes the exact path whenever ANY of its 32 RQ lists accepts a vertex, which favours 1)
-  const int rq = (k == 1 && dimp <= 24 && n_queries > (size_t)NN_BLOCK) ? 2 : 1;
+  // (measured, profiles/r2_nearest.md: 2 queries per thread reach the rate 4 reach, at 5 instead of 3 CTAs per SM)
+  const int rq = (dimp <= 24 && n_queries > (size_t)NN_BLOCK) ? 2 : 1;
   const long long gx = (long long)((n_queries + (size_t)NN_BLOCK * rq - 1) / ((size_t)NN_BLOCK * rq));
   // enough CTAs for every SM several times over, but no chunk shorter than a few tiles
   int sms = 148;

@@ -66,7 +66,7 @@ class kte_batch_propagator(object):
         self._h = h
         self.n = self._lib.rkb_chain_dof(h)
         self.nx = self._lib.rkb_chain_state_dim(h)
-        self.na = self.n + 6 * self.compiled.n_free  # accelerations: rows / columns of M, entries of f, columns of Tcm
+        self.na = self.compiled.n_acc  # accelerations: rows / columns of M, entries of f, columns of Tcm
         self.nu = self._lib.rkb_chain_input_dim(h)
 
     def close(self):
