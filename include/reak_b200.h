@@ -357,6 +357,9 @@ RKB_API int  rkb_proxy_finder(const rkb_proxy* proxy, int k, int* i1, int* i2);
  * returns its size in bytes, or RKB_ERR_INVALID when `size` is too small.  tests/host_build uses it to run the
  * device source of the finders on the host against the compiled reference. */
 RKB_API int  rkb_proxy_program(const rkb_proxy* proxy, void* out, size_t size);
+/* Test hook: the interpreter program the descriptor was lowered to (an internal structure of this build, rkb_types.h:
+ * GenericProgram), for tests/host_build/generic_host.cpp which runs the device source of the interpreter on the host. */
+RKB_API int  rkb_chain_program(const rkb_chain* chain, void* out, size_t size);
 
 /* proxy_query_pair_3D::findMinimumDistance (proxy_query_model.cpp:388-412) after the chain's doMotion at state
  * x[i], including its bounding-sphere culling, for every sample:

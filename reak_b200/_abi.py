@@ -121,6 +121,7 @@ SYMBOLS = {
     "rkb_proxy_finder_count": (C.c_int, [C.c_void_p]),
     "rkb_proxy_finder": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rkb_proxy_program": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rkb_chain_program": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rkb_is_free": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_min_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint, C.c_void_p]),

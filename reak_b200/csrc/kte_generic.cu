@@ -601,20 +601,30 @@ GD void mass(const GenericProgram* G, const Work<3, MAXF>& W, double* M, double*
 template <int MAXF>
 GD void jac_col2(const GenericProgram* G, const Work<2, MAXF>& W, int c, const Fr2& F, double* col, double* cold) {
   const int nc = G->n_coords;
-  const bool is_free = c >= nc;
-  const int l = is_free ? (c - nc) % 3 : 0;
-  const GenericElement& J = G->el[is_free ? G->free_elem[(c - nc) / 3] : G->jelem[c]];
-  const Fr2& Ej = W.fr[J.fb];
+  // kind of column: 0 = a rotation about E (revolute joint, angular velocity of a free joint), 1 = a translation along
+  // `ax` expressed in E (prismatic joint, velocity component of a free joint)
+  int elem, translation;
+  V2 ax = v2(0.0, 0.0);
+  if (c < nc) {
+    elem = G->jelem[c];
+    translation = G->el[elem].kind == RKB_REVOLUTE_2D ? 0 : 1;
+    if (translation) ax = v2(G->el[elem].p[0], G->el[elem].p[1]);
+  } else {
+    const int l = (c - nc) % 3;
+    elem = G->free_elem[(c - nc) / 3];
+    translation = l == 2 ? 0 : 1;
+    if (translation) ax = l == 0 ? v2(1.0, 0.0) : v2(0.0, 1.0);
+  }
+  const Fr2 Ej = W.fr[G->el[elem].fb];
   const V2 dp = F.p - Ej.p, dv = F.v - Ej.v;
   const double wrel = F.w - Ej.w;
   V2 Tv, Tvd;
   double Tw;
-  if (is_free ? (l == 2) : (J.kind == RKB_REVOLUTE_2D)) {
+  if (!translation) {
     Tv = rtmul(F.R, crs(1.0, dp));
     Tw = 1.0;
     Tvd = rtmul(F.R, crs(1.0, dv - crs(Ej.w, dp))) - crs(wrel, Tv);
   } else {
-    const V2 ax = is_free ? (l == 0 ? v2(1.0, 0.0) : v2(0.0, 1.0)) : v2(J.p[0], J.p[1]);
     Tv = rtmul(F.R, rmul(Ej.R, ax));
     Tw = 0.0;
     Tvd = v2(0, 0) - crs(wrel, Tv);
@@ -632,17 +642,19 @@ GD void mass(const GenericProgram* G, const Work<2, MAXF>& W, double* M, double*
     if (E.kind == RKB_INERTIA_GEN) {
       M[E.coord * n + E.coord] += E.p[0];
     } else if (E.kind == RKB_INERTIA_2D) {
-      const Fr2& F = W.fr[E.fa];
-      double T[MAXA][3], Td[MAXA][3];
-      for (int c = 0; c < n; ++c)
+      const Fr2 F = W.fr[E.fa];
+      double T[MAXA][3], Td[MAXA][3], MT[MAXA][3];
+      for (int c = 0; c < n; ++c) {
+        T[c][0] = 0.0; T[c][1] = 0.0; T[c][2] = 0.0; Td[c][0] = 0.0; Td[c][1] = 0.0; Td[c][2] = 0.0;
         if (col_upstream(E.upstream, nc, c, 3)) jac_col2(G, W, c, F, T[c], Td[c]);
-      const double mc[3] = {E.p[0], E.p[0], E.p[1]};
+        MT[c][0] = E.p[0] * T[c][0]; MT[c][1] = E.p[0] * T[c][1]; MT[c][2] = E.p[1] * T[c][2];
+      }
       for (int a = 0; a < n; ++a) {
         if (!col_upstream(E.upstream, nc, a, 3)) continue;
         for (int b = 0; b < n; ++b) {
           if (!col_upstream(E.upstream, nc, b, 3)) continue;
           double s = 0.0, sd = 0.0;
-          for (int k = 0; k < 3; ++k) { s += T[a][k] * mc[k] * T[b][k]; if (want_dot) sd += Td[a][k] * mc[k] * T[b][k]; }
+          for (int k = 0; k < 3; ++k) { s += T[a][k] * MT[b][k]; if (want_dot) sd += Td[a][k] * MT[b][k]; }
           M[a * n + b] += s;
           if (want_dot) S[a * n + b] += sd;
         }
@@ -1189,6 +1201,7 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_rollout_kernel(const Generi
   if (A.status) A.status[i] = A.status_or ? (A.status[i] | st) : st;
 }
 
+#ifndef RKB_HOST_TEST  // (tests/host_build/generic_host.cpp compiles everything above for the host: no launches there)
 unsigned grid_of(long long n) { return (unsigned)((n + GEN_BLOCK - 1) / GEN_BLOCK); }
 
 #define DISPATCH(kernel, host, ...)                                                              \
@@ -1252,8 +1265,11 @@ __global__ void __launch_bounds__(256) steer_reduce_kernel(int nx, long long n_r
   }
   for (int k = threadIdx.x; k < nx; k += blockDim.x) best_x[pair * nx + k] = xend[(pair * n_rollouts + win) * nx + k];
 }
+#endif  // RKB_HOST_TEST
 
 }  // namespace
+
+#ifndef RKB_HOST_TEST
 
 cudaError_t rkb_generic_eval(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, cudaStream_t s) {
   const long long n = a.n_samples;
@@ -1327,3 +1343,4 @@ cudaError_t rkb_steer_reduce(int nx, long long n_pairs, long long n_rollouts, co
   steer_reduce_kernel<<<(unsigned)n_pairs, 256, 0, s>>>(nx, n_rollouts, xend, goal, best_idx, best_x, best_cost);
   return cudaGetLastError();
 }
+#endif  // RKB_HOST_TEST

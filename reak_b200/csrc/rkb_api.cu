@@ -986,6 +986,13 @@ int rkb_proxy_finder(const rkb_proxy* p, int k, int* i1, int* i2) {
   return RKB_OK;
 }
 
+int rkb_chain_program(const rkb_chain* c, void* out, size_t size) {
+  if (!c || !out || size < sizeof(GenericProgram)) return RKB_ERR_INVALID;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  std::memcpy(out, &c->gp, sizeof(GenericProgram));
+  return (int)sizeof(GenericProgram);
+}
+
 int rkb_proxy_program(const rkb_proxy* p, void* out, size_t size) {
   if (!p || !out || size < sizeof(ProxProgram)) return RKB_ERR_INVALID;
   std::memcpy(out, &p->prog, sizeof(ProxProgram));
