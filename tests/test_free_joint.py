@@ -187,8 +187,9 @@ def test_gpu_free_chain_against_oracle(name, oracle_built):
     M, Md = p.get_mass_matrices(x, with_derivative=True)
     Mo, Mdo = O.mass(x)
     assert rel_err(M, Mo) < TOL_STEP and rel_err(Md, Mdo) < TOL_STEP
-    xo, st = p.get_next_states(x, u, 1e-3, 200)
-    xr, sr, _ = O.rk4(x, u, 1e-3, 200, n_workers=min(8, os.cpu_count() or 1))
+    steps = 200 if p.n < 4 else 60   # (the six-joint arm on a free base under random unit torques leaves the finite range after ~150 ms)
+    xo, st = p.get_next_states(x, u, 1e-3, steps)
+    xr, sr, _ = O.rk4(x, u, 1e-3, steps, n_workers=min(8, os.cpu_count() or 1))
     assert not st.any() and not sr.any() and rel_err(xo, xr) < TOL_LONG
     # SoA buffers and device-resident tensors give the same bits as host AoS
     import torch
