@@ -5,8 +5,10 @@ tag=r2_final
 out=gpurun_out
 mkdir -p $out
 set -o pipefail
+if [ "$1" != "notests" ]; then
 echo "== pytest -m gpu"
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+fi
 echo "== bench (ours)"
 timeout 900 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err || { echo "bench failed"; tail -5 $out/bench_$tag.err; }
 head -c 1200 $out/bench_$tag.json; echo
