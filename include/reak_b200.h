@@ -350,6 +350,22 @@ RKB_API int  rkb_proxy_create(const rkb_chain* chain, const rkb_shape* model1, i
                               const rkb_shape* model2, int n2, rkb_proxy** out);
 RKB_API void rkb_proxy_destroy(rkb_proxy* proxy);
 /* number of finders; finder k pairs shape *i1 of model 1 with shape *i2 of model 2 */
+/* Run-time specialisation of a pair's query (rkb_min_distance, rkb_is_free, rkb_steer_feedback_checked).  The library
+ * ships an interpreter kernel that reads the chain and the shape list at run time; rkb_proxy_specialize writes the query of
+ * THIS chain and pair as straight-line CUDA (forward kinematics with the chain's constants, world-fixed shapes as literals,
+ * every finder of createProxFinderList with its argument order resolved), compiles it with NVRTC (a few seconds; cubins
+ * are cached on disk like those of rkb_chain_specialize) and routes the pair's launches to it: ~2x the interpreter.
+ * Results agree with the interpreter kernel to rounding.  By default (RKB_PROXY_OPT_AUTO_SPECIALIZE = 1) the same happens
+ * on a background thread from the first query of >= 4096 states on; queries made meanwhile run on the interpreter.
+ * RKB_ERR_UNSUPPORTED: libnvrtc.so.12 is not installed. */
+enum rkb_proxy_option { RKB_PROXY_OPT_AUTO_SPECIALIZE = 1, RKB_PROXY_OPT_MIN_BLOCKS = 2 /* CTAs per SM compiled for, 1..8 */ };
+RKB_API int  rkb_proxy_set_option(rkb_proxy* proxy, int option, long long value);
+RKB_API int  rkb_proxy_specialize(rkb_proxy* proxy, int device);
+RKB_API int  rkb_proxy_is_specialized(const rkb_proxy* proxy);
+/* test hook: the CUDA source rkb_proxy_specialize compiles (NUL-terminated); returns its size including the NUL,
+ * out may be NULL to ask for the size */
+RKB_API int  rkb_proxy_source(const rkb_proxy* proxy, char* out, size_t size);
+
 RKB_API int  rkb_proxy_finder_count(const rkb_proxy* proxy);
 RKB_API int  rkb_proxy_finder(const rkb_proxy* proxy, int k, int* i1, int* i2);
 

@@ -118,6 +118,10 @@ SYMBOLS = {
     "rkb_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "rkb_proxy_create": (C.c_int, [C.c_void_p, C.POINTER(rkb_shape), C.c_int, C.POINTER(rkb_shape), C.c_int, C.POINTER(C.c_void_p)]),
     "rkb_proxy_destroy": (None, [C.c_void_p]),
+    "rkb_proxy_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong]),
+    "rkb_proxy_specialize": (C.c_int, [C.c_void_p, C.c_int]),
+    "rkb_proxy_is_specialized": (C.c_int, [C.c_void_p]),
+    "rkb_proxy_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rkb_proxy_finder_count": (C.c_int, [C.c_void_p]),
     "rkb_proxy_finder": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rkb_proxy_program": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -419,29 +419,32 @@ GD bool prox_has_finder(int ka, int kb) {
 }
 
 template <bool PTS>
-GD ProxRecord prox_compute(const ProxShape& a, const SPose& Pa, const ProxShape& b, const SPose& Pb) {
+GD ProxRecord prox_compute_kd(int ka, V3 da, const SPose& Pa, int kb, V3 db, const SPose& Pb) {
   // first = the shape whose kind is listed first; on equal kinds model 1's shape
-  const bool swap = b.kind < a.kind;
-  const ProxShape& s1 = swap ? b : a;
-  const ProxShape& s2 = swap ? a : b;
+  const bool swap = kb < ka;
+  const int k1 = swap ? kb : ka, k2 = swap ? ka : kb;
   const SPose& P1 = swap ? Pb : Pa;
   const SPose& P2 = swap ? Pa : Pb;
-  const V3 d1 = v3(s1.dims[0], s1.dims[1], s1.dims[2]), d2 = v3(s2.dims[0], s2.dims[1], s2.dims[2]);
-  if (s1.kind == RKB_SHAPE_PLANE) {
-    if (s2.kind == RKB_SHAPE_PLANE) return prox_plane_plane<PTS>(P1, d1, P2, d2);
-    if (s2.kind == RKB_SHAPE_SPHERE) return prox_plane_sphere<PTS>(P1, P2, d2.x);
-    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_plane_ccylinder<PTS>(P1, P2, d2.x, d2.y);
-    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_plane_cylinder<PTS>(P1, P2, d2.x, d2.y);
+  const V3 d1 = swap ? db : da, d2 = swap ? da : db;
+  if (k1 == RKB_SHAPE_PLANE) {
+    if (k2 == RKB_SHAPE_PLANE) return prox_plane_plane<PTS>(P1, d1, P2, d2);
+    if (k2 == RKB_SHAPE_SPHERE) return prox_plane_sphere<PTS>(P1, P2, d2.x);
+    if (k2 == RKB_SHAPE_CCYLINDER) return prox_plane_ccylinder<PTS>(P1, P2, d2.x, d2.y);
+    if (k2 == RKB_SHAPE_CYLINDER) return prox_plane_cylinder<PTS>(P1, P2, d2.x, d2.y);
     return prox_plane_box<PTS>(P1, P2, d2);
   }
-  if (s1.kind == RKB_SHAPE_SPHERE) {
-    if (s2.kind == RKB_SHAPE_SPHERE) return prox_sphere_sphere<PTS>(P1, d1.x, P2, d2.x);
-    if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_sphere_ccylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
-    if (s2.kind == RKB_SHAPE_CYLINDER) return prox_sphere_cylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
+  if (k1 == RKB_SHAPE_SPHERE) {
+    if (k2 == RKB_SHAPE_SPHERE) return prox_sphere_sphere<PTS>(P1, d1.x, P2, d2.x);
+    if (k2 == RKB_SHAPE_CCYLINDER) return prox_sphere_ccylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
+    if (k2 == RKB_SHAPE_CYLINDER) return prox_sphere_cylinder<PTS>(P1, d1.x, P2, d2.x, d2.y);
     return prox_sphere_box<PTS>(P1, d1.x, P2, d2);
   }
-  if (s2.kind == RKB_SHAPE_CCYLINDER) return prox_ccylinder_ccylinder<PTS>(P1, d1.x, d1.y, P2, d2.x, d2.y);
+  if (k2 == RKB_SHAPE_CCYLINDER) return prox_ccylinder_ccylinder<PTS>(P1, d1.x, d1.y, P2, d2.x, d2.y);
   return prox_ccylinder_box<PTS>(P1, d1.x, d1.y, P2, d2);
+}
+template <bool PTS>
+GD ProxRecord prox_compute(const ProxShape& a, const SPose& Pa, const ProxShape& b, const SPose& Pb) {
+  return prox_compute_kd<PTS>(a.kind, v3(a.dims[0], a.dims[1], a.dims[2]), Pa, b.kind, v3(b.dims[0], b.dims[1], b.dims[2]), Pb);
 }
 
 // world pose of a shape riding on a frame with pose F: pose_3D::getGlobalPose, pose_3D.hpp:102-110

@@ -888,13 +888,46 @@ int rkb_frames(rkb_chain* c, int device, size_t N, const double* x, const double
 /* ---- proximity (kte_proximity.cuh) ---------------------------------------------------------------- */
 }  // extern "C"
 
+// CTAs of 128 threads per SM the generated proximity kernels are compiled for (measured: profiles/r2_proximity.md)
+constexpr int kProxSpecMinBlocks = 6;
+
 struct rkb_proxy {
   ProxProgram prog;
   std::vector<std::pair<int, int> > finders;
   int n_frames;
+  // run-time specialisation (rkb_prox_jit.cu): the chain's program is kept to write the kernel source from
+  GenericProgram gp;
+  int min_blocks = kProxSpecMinBlocks;
+  bool auto_specialize = true;
+  mutable std::mutex mu;
+  mutable const SourceKernels* spec = nullptr;
+  mutable bool auto_done = false;
 };
 
 namespace {
+const char* const kProxSpecNames[2] = {"rkb_prox_spec_d", "rkb_prox_spec_p"};
+
+// The proximity query of one pair at every state of A: the kernels compiled for this chain and pair when they are
+// there (rkb_proxy_specialize, or in the background from the first call of >= 4096 states on), else the interpreter.
+cudaError_t launch_proximity(const rkb_chain* c, const DeviceCtx* ctx, const rkb_proxy* p, const EvalArgs& A, cudaStream_t s) {
+  const SourceKernels* K = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (!p->spec && p->auto_specialize && !p->auto_done && A.n_samples >= 4096) {
+      const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
+      const SourceKernels* J = nullptr;
+      if (src.empty() || rkb_jit_source_poll("prox", src, kProxSpecNames, 2, &J) != RKB_OK) p->auto_done = true;  // no NVRTC here: stay as we are
+      else if (J) { p->spec = J; p->auto_done = true; }
+    }
+    K = p->spec;
+  }
+  if (!K) return rkb_generic_proximity(ctx->d_prog, c->gp, A, p->prog, s);
+  if (A.n_samples <= 0) return cudaSuccess;
+  void* argv[1] = {const_cast<EvalArgs*>(&A)};
+  const unsigned grid = (unsigned)((A.n_samples + 127) / 128);
+  return cudaLaunchKernel(K->kernel[A.out2.p ? 1 : 0], dim3(grid), dim3(128), argv, 0, s);
+}
+
 bool prox_pair_has_finder(int ka, int kb) {  // proxy_query_model.cpp:212-384
   const int lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
   if (lo == RKB_SHAPE_PLANE || lo == RKB_SHAPE_SPHERE) return true;
@@ -949,6 +982,7 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
   p->prog.n1 = n1;
   p->prog.n2 = n2;
   p->n_frames = c->desc.n_frames;
+  p->gp = c->gp;
   for (int k = 0; k < n1 + n2; ++k) {
     const rkb_shape& in = k < n1 ? m1[k] : m2[k - n1];
     if (!lower_shape(in, c->desc.n_frames, &p->prog.s[k])) { delete p; return RKB_ERR_INVALID; }
@@ -976,6 +1010,48 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
 }
 
 void rkb_proxy_destroy(rkb_proxy* p) { delete p; }
+
+int rkb_proxy_set_option(rkb_proxy* p, int option, long long value) {
+  if (!p) return RKB_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(p->mu);
+  switch (option) {
+    case RKB_PROXY_OPT_AUTO_SPECIALIZE: p->auto_specialize = value != 0; return RKB_OK;
+    case RKB_PROXY_OPT_MIN_BLOCKS:
+      if (value < 1 || value > 8) return RKB_ERR_INVALID;
+      p->min_blocks = (int)value;
+      return RKB_OK;
+    default: return RKB_ERR_INVALID;
+  }
+}
+
+int rkb_proxy_specialize(rkb_proxy* p, int device) {
+  if (!p) return RKB_ERR_INVALID;
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(p->mu);
+  const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
+  if (src.empty()) return RKB_ERR_UNSUPPORTED;
+  const SourceKernels* J = nullptr;
+  const int rc = rkb_jit_source_get("prox", src, kProxSpecNames, 2, &J);
+  if (rc) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "run-time compilation failed: %.200s", rkb_jit_log()); return rc; }
+  p->spec = J;
+  return RKB_OK;
+}
+
+int rkb_proxy_is_specialized(const rkb_proxy* p) {
+  if (!p) return 0;
+  std::lock_guard<std::mutex> lock(p->mu);
+  return p->spec ? 1 : 0;
+}
+
+int rkb_proxy_source(const rkb_proxy* p, char* out, size_t size) {
+  if (!p) return RKB_ERR_INVALID;
+  const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
+  if (src.empty()) return RKB_ERR_UNSUPPORTED;
+  if (out && size > src.size()) std::memcpy(out, src.c_str(), src.size() + 1);
+  else if (out) return RKB_ERR_INVALID;
+  return (int)src.size() + 1;
+}
 
 int rkb_proxy_finder_count(const rkb_proxy* p) { return p ? (int)p->finders.size() : RKB_ERR_INVALID; }
 
@@ -1030,7 +1106,7 @@ int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, con
   A.status = (int32_t*)df;
   A.n_samples = (long long)N;
   CU(cudaEventRecord(ctx->ev0, s));
-  const cudaError_t e = rkb_generic_proximity(ctx->d_prog, c->gp, A, p->prog, s);
+  const cudaError_t e = launch_proximity(c, ctx, p, A, s);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   CU(cudaEventRecord(ctx->ev1, s));
   ctx->timed = true;
@@ -1122,7 +1198,7 @@ int rkb_is_free(rkb_chain* c, int device, size_t N, const double* x, const rkb_p
     E.out2 = view((double*)nullptr, (long long)N, 6, false);
     E.status = nullptr;
     E.n_samples = (long long)N;
-    const cudaError_t e = rkb_generic_proximity(ctx->d_prog, c->gp, E, pairs[p]->prog, s);
+    const cudaError_t e = launch_proximity(c, ctx, pairs[p], E, s);
     if (e != cudaSuccess) return cuda_fail(e, "proximity kernel");
     c->launches += 1;
   }
@@ -1794,7 +1870,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
         E.out2 = view((double*)nullptr, (long long)N, 6, false);
         E.status = nullptr;
         E.n_samples = (long long)N;
-        const cudaError_t pe = rkb_generic_proximity(ctx->d_prog, c->gp, E, pairs[p]->prog, s);
+        const cudaError_t pe = launch_proximity(c, ctx, pairs[p], E, s);
         if (pe != cudaSuccess) return cuda_fail(pe, "proximity kernel");
         c->launches += 1;
       }

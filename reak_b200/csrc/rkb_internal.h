@@ -70,6 +70,21 @@ const char* rkb_jit_log();                                                      
 cudaError_t rkb_jit_launch(const JitKernels& J, int which, const SerialParams& P, const void* args, const void* extra, long long n_samples,
                            int smem_override, cudaStream_t s);
 
+// kernels compiled at run time from a generated source (extern "C" names), keyed by a hash of the text; same disk cache
+#define RKB_SRC_MAX_KERNELS 4
+struct SourceKernels {
+  void* library;                            // cudaLibrary_t
+  const void* kernel[RKB_SRC_MAX_KERNELS];  // cudaKernel_t in the order of `names`
+};
+#ifdef __cplusplus
+#include <string>
+int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out);
+int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out);
+// rkb_prox_jit.cu: the source of the proximity kernels (rkb_prox_spec_d: distance and finder, rkb_prox_spec_p: with the two
+// points) of one chain and one proxy pair; empty when the chain cannot be written as straight-line code
+std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int min_blocks);
+#endif
+
 // steering law between two control intervals (rkb_steer.cu)
 cudaError_t rkb_steer_law(const SteerLawArgs& a, cudaStream_t s);
 cudaError_t rkb_steer_commit(const SteerCommitArgs& a, cudaStream_t s);

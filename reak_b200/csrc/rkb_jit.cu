@@ -91,7 +91,7 @@ struct Cubin {
 // $RKB_CACHE_DIR, else $XDG_CACHE_HOME/reak_b200, else $HOME/.cache/reak_b200.  One file per (build, n, fl, shape):
 // a header line per kernel name, then the cubin.  A cubin is only valid for the sources it was compiled from, so the
 // file name carries rkb_build_id().  Failures to read or write are not errors: the kernels are compiled instead.
-std::string cache_path(const Key& key) {
+std::string cache_path(const std::string& stem) {
   std::string dir;
   if (const char* d = std::getenv("RKB_CACHE_DIR")) dir = d;
   else if (const char* x = std::getenv("XDG_CACHE_HOME")) dir = std::string(x) + "/reak_b200";
@@ -101,12 +101,15 @@ std::string cache_path(const Key& key) {
   std::string acc;
   for (size_t i = 0; i <= dir.size(); ++i)  // mkdir -p
     if (i == dir.size() || (dir[i] == '/' && i > 0)) { acc = dir.substr(0, i); ::mkdir(acc.c_str(), 0755); }
-  char buf[160];
-  std::snprintf(buf, sizeof buf, "/%s-n%d-fl%d-%016llx.cubin", RKB_BUILD_ID, std::get<0>(key), std::get<1>(key), std::get<2>(key));
-  return dir + buf;
+  return dir + "/" + RKB_BUILD_ID + "-" + stem + ".cubin";
 }
-bool cache_read(const Key& key, Cubin& out) {
-  const std::string path = cache_path(key);
+std::string stem_of(const Key& key) {
+  char buf[96];
+  std::snprintf(buf, sizeof buf, "n%d-fl%d-%016llx", std::get<0>(key), std::get<1>(key), std::get<2>(key));
+  return buf;
+}
+bool cache_read(const std::string& stem, int n_names, Cubin& out) {
+  const std::string path = cache_path(stem);
   if (path.empty()) return false;
   FILE* f = std::fopen(path.c_str(), "rb");
   if (!f) return false;
@@ -115,7 +118,7 @@ bool cache_read(const Key& key, Cubin& out) {
   char line[1024];
   unsigned long long size = 0;
   if (!std::fgets(line, sizeof line, f) || std::sscanf(line, "RKBCUBIN %llu", &size) != 1 || size == 0 || size > (1ull << 28)) ok = false;
-  for (int k = 0; ok && k < RKB_JIT_COUNT; ++k) {
+  for (int k = 0; ok && k < n_names; ++k) {
     if (!std::fgets(line, sizeof line, f)) { ok = false; break; }
     std::string n(line);
     while (!n.empty() && (n.back() == '\n' || n.back() == '\r')) n.pop_back();
@@ -129,8 +132,8 @@ bool cache_read(const Key& key, Cubin& out) {
   std::fclose(f);
   return ok;
 }
-void cache_write(const Key& key, const Cubin& c) {
-  const std::string path = cache_path(key);
+void cache_write(const std::string& stem, const Cubin& c) {
+  const std::string path = cache_path(stem);
   if (path.empty()) return;
   char tmp[32];
   std::snprintf(tmp, sizeof tmp, ".%d.tmp", (int)::getpid());
@@ -146,23 +149,34 @@ void cache_write(const Key& key, const Cubin& c) {
 }
 
 // ---- NVRTC: host-only, needs no CUDA context (may run on a helper thread) ----------------------------------
-int compile_cubin(const Key& key, Cubin& out, std::string& log) {
+// One compilation: the program text, the kernels wanted from it (C++ name expressions when `lowered`, else the
+// extern "C" names themselves) and the file stem of its disk-cache entry.
+struct Job {
+  std::string stem, src;
+  std::vector<std::string> exprs;
+  bool lowered = true;
+};
+Job chain_job(const Key& key) {
   const int n = std::get<0>(key), fl = std::get<1>(key);
   const unsigned long long shape = std::get<2>(key);
-  {
-    std::lock_guard<std::mutex> lock(g_nvrtc_mu);
-    if (!g_nvrtc.load()) { log = "libnvrtc.so.12 not found"; return RKB_ERR_UNSUPPORTED; }
-  }
-  // program: the kernel header plus one name expression per kernel
-  std::string src = "#include \"kte_serial.cuh\"\n";
-  std::vector<std::string> exprs(RKB_JIT_COUNT);
+  Job j;
+  j.stem = stem_of(key);
+  j.src = "#include \"kte_serial.cuh\"\n";
+  j.exprs.resize(RKB_JIT_COUNT);
   char buf[256];
   for (int k = 0; k < RKB_JIT_COUNT; ++k) {
     if (k == RKB_JIT_MASS || k == RKB_JIT_MASSDOT)
       std::snprintf(buf, sizeof buf, "rkb::%s<%d, %d, %lluull, %s>", kKernelNames[k], n, fl, shape, k == RKB_JIT_MASSDOT ? "true" : "false");
     else
       std::snprintf(buf, sizeof buf, "rkb::%s<%d, %d, %lluull>", kKernelNames[k], n, fl, shape);
-    exprs[k] = buf;
+    j.exprs[k] = buf;
+  }
+  return j;
+}
+int compile_cubin(const Job& job, Cubin& out, std::string& log) {
+  {
+    std::lock_guard<std::mutex> lock(g_nvrtc_mu);
+    if (!g_nvrtc.load()) { log = "libnvrtc.so.12 not found"; return RKB_ERR_UNSUPPORTED; }
   }
   std::vector<const char*> hn, ht;
   for (const auto& h : kJitHeaders) { hn.push_back(h.name); ht.push_back(h.text); }
@@ -171,8 +185,9 @@ int compile_cubin(const Key& key, Cubin& out, std::string& log) {
   const char* stubs[][2] = {{"cuda_runtime.h", ""}, {"math.h", ""}, {"stddef.h", ""}, {"stdint.h", kStdint}};
   for (auto& s : stubs) { hn.push_back(s[0]); ht.push_back(s[1]); }
   nvrtcProgram prog = nullptr;
-  if (g_nvrtc.CreateProgram(&prog, src.c_str(), "rkb_jit.cu", (int)hn.size(), ht.data(), hn.data()) != 0) { log = "nvrtcCreateProgram failed"; return RKB_ERR_CUDA; }
-  for (auto& e : exprs) g_nvrtc.AddNameExpression(prog, e.c_str());
+  if (g_nvrtc.CreateProgram(&prog, job.src.c_str(), "rkb_jit.cu", (int)hn.size(), ht.data(), hn.data()) != 0) { log = "nvrtcCreateProgram failed"; return RKB_ERR_CUDA; }
+  if (job.lowered)
+    for (auto& e : job.exprs) g_nvrtc.AddNameExpression(prog, e.c_str());
   // -default-device: the C-ABI prototypes of reak_b200.h carry no execution-space annotation
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
   const int rc = g_nvrtc.CompileProgram(prog, 4, opts);
@@ -185,9 +200,10 @@ int compile_cubin(const Key& key, Cubin& out, std::string& log) {
   out.image.resize(cs);
   g_nvrtc.GetCUBIN(prog, out.image.data());
   out.names.clear();
-  for (int k = 0; k < RKB_JIT_COUNT; ++k) {
+  for (const auto& e : job.exprs) {
+    if (!job.lowered) { out.names.push_back(e); continue; }
     const char* low = nullptr;
-    if (g_nvrtc.GetLoweredName(prog, exprs[k].c_str(), &low) != 0 || !low) { log = "nvrtcGetLoweredName failed for " + exprs[k]; g_nvrtc.DestroyProgram(&prog); return RKB_ERR_CUDA; }
+    if (g_nvrtc.GetLoweredName(prog, e.c_str(), &low) != 0 || !low) { log = "nvrtcGetLoweredName failed for " + e; g_nvrtc.DestroyProgram(&prog); return RKB_ERR_CUDA; }
     out.names.push_back(low);
   }
   g_nvrtc.DestroyProgram(&prog);
@@ -249,17 +265,18 @@ int rkb_jit_get(int n, int fl, unsigned long long shape, const JitKernels** out)
   }
   g_log.clear();
   Cubin c;
-  bool cached = cache_read(key, c);
+  const Job job = chain_job(key);
+  bool cached = cache_read(job.stem, RKB_JIT_COUNT, c);
   if (!cached) {
-    const int rc = compile_cubin(key, c, g_log);
+    const int rc = compile_cubin(job, c, g_log);
     if (rc) return rc;
-    cache_write(key, c);
+    cache_write(job.stem, c);
   }
   JitKernels* J = nullptr;
   int rc = load_cubin(key, c, &J, g_log);
   if (rc && cached) {  // a stale or damaged cache file: compile afresh
-    if ((rc = compile_cubin(key, c, g_log))) return rc;
-    cache_write(key, c);
+    if ((rc = compile_cubin(job, c, g_log))) return rc;
+    cache_write(job.stem, c);
     rc = load_cubin(key, c, &J, g_log);
   }
   if (rc) return rc;
@@ -288,7 +305,7 @@ int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out
   const Cubin* ready = nullptr;
   if (!p) {
     Cubin from_disk;
-    if (cache_read(key, from_disk)) {
+    if (cache_read(stem_of(key), RKB_JIT_COUNT, from_disk)) {
       JitKernels* Jd = nullptr;
       if (load_cubin(key, from_disk, &Jd, g_log) == RKB_OK) {
         std::lock_guard<std::mutex> lock(g_mu);
@@ -298,7 +315,7 @@ int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out
         *out = Jd;
         return RKB_OK;
       }
-      std::remove(cache_path(key).c_str());  // stale or damaged: not trusted, compiled afresh below
+      std::remove(cache_path(stem_of(key)).c_str());  // stale or damaged: not trusted, compiled afresh below
     }
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_pending.find(key) == g_pending.end()) {
@@ -308,8 +325,9 @@ int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out
       g_threads.emplace_back([key, p]() {
         Cubin c;
         std::string log;
-        const int rc = compile_cubin(key, c, log);
-        if (rc == RKB_OK) cache_write(key, c);
+        const Job job = chain_job(key);
+        const int rc = compile_cubin(job, c, log);
+        if (rc == RKB_OK) cache_write(job.stem, c);
         std::lock_guard<std::mutex> lock2(g_mu);
         p->cubin.image.swap(c.image);
         p->cubin.names.swap(c.names);
@@ -338,6 +356,147 @@ int rkb_jit_poll(int n, int fl, unsigned long long shape, const JitKernels** out
   if (it != g_cache.end()) { *out = it->second; return RKB_OK; }
   g_cache[key] = J;
   *out = J;
+  return RKB_OK;
+}
+
+// ---- kernels from a generated source (rkb_prox_jit.cu): extern "C" kernels, cached by a hash of the text ---------
+namespace {
+struct SrcPending {
+  int state = 0;  // 0 compiling, 1 ready, -1 failed
+  Cubin cubin;
+  std::string log;
+};
+std::map<std::string, SourceKernels*> g_src_cache;
+std::map<std::string, std::shared_ptr<SrcPending> > g_src_pending;
+
+std::string source_stem(const char* prefix, const std::string& src) {
+  unsigned long long h = 1469598103934665603ull;  // FNV-1a
+  for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
+  char buf[96];
+  std::snprintf(buf, sizeof buf, "%s-%016llx", prefix, h);
+  return buf;
+}
+Job source_job(const std::string& stem, const std::string& src, const char* const* names, int n_names) {
+  Job j;
+  j.stem = stem;
+  j.src = src;
+  j.lowered = false;
+  for (int k = 0; k < n_names; ++k) j.exprs.push_back(names[k]);
+  return j;
+}
+int load_source(const Cubin& c, int n_names, SourceKernels** out, std::string& log) {
+  cudaLibrary_t lib = nullptr;
+  cudaError_t e = cudaLibraryLoadData(&lib, c.image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) { log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); cudaGetLastError(); return RKB_ERR_CUDA; }
+  SourceKernels* S = new SourceKernels();
+  S->library = lib;
+  for (int k = 0; k < n_names && k < RKB_SRC_MAX_KERNELS; ++k) {
+    cudaKernel_t kern = nullptr;
+    e = cudaLibraryGetKernel(&kern, lib, c.names[k].c_str());
+    if (e != cudaSuccess) { log = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e); cudaGetLastError(); cudaLibraryUnload(lib); delete S; return RKB_ERR_CUDA; }
+    S->kernel[k] = (const void*)kern;
+  }
+  *out = S;
+  return RKB_OK;
+}
+const SourceKernels* src_publish(const std::string& stem, SourceKernels* S) {  // g_mu held
+  auto it = g_src_cache.find(stem);
+  if (it != g_src_cache.end()) return it->second;  // (another thread was faster; the spare library stays loaded)
+  g_src_cache[stem] = S;
+  return S;
+}
+}  // namespace
+
+// Synchronous: this process's table, else the disk cache, else NVRTC now.
+int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out) {
+  if (n_names < 1 || n_names > RKB_SRC_MAX_KERNELS) return RKB_ERR_INVALID;
+  const std::string stem = source_stem(prefix, src);
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_src_cache.find(stem);
+    if (it != g_src_cache.end()) { *out = it->second; return RKB_OK; }
+  }
+  g_log.clear();
+  const Job job = source_job(stem, src, names, n_names);
+  Cubin c;
+  bool cached = cache_read(stem, n_names, c);
+  if (!cached) {
+    const int rc = compile_cubin(job, c, g_log);
+    if (rc) return rc;
+    cache_write(stem, c);
+  }
+  SourceKernels* S = nullptr;
+  int rc = load_source(c, n_names, &S, g_log);
+  if (rc && cached) {  // a stale or damaged cache file: compile afresh
+    if ((rc = compile_cubin(job, c, g_log))) return rc;
+    cache_write(stem, c);
+    rc = load_source(c, n_names, &S, g_log);
+  }
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(g_mu);
+  *out = src_publish(stem, S);
+  return RKB_OK;
+}
+
+// Asynchronous, like rkb_jit_poll: *out == NULL while a background compilation (started by the first call) runs.
+int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out) {
+  *out = nullptr;
+  if (n_names < 1 || n_names > RKB_SRC_MAX_KERNELS) return RKB_ERR_INVALID;
+  const std::string stem = source_stem(prefix, src);
+  std::shared_ptr<SrcPending> p;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_src_cache.find(stem);
+    if (it != g_src_cache.end()) { *out = it->second; return RKB_OK; }
+    auto pit = g_src_pending.find(stem);
+    if (pit != g_src_pending.end()) p = pit->second;
+  }
+  if (!p) {
+    Cubin from_disk;
+    if (cache_read(stem, n_names, from_disk)) {
+      SourceKernels* S = nullptr;
+      if (load_source(from_disk, n_names, &S, g_log) == RKB_OK) {
+        std::lock_guard<std::mutex> lock(g_mu);
+        *out = src_publish(stem, S);
+        return RKB_OK;
+      }
+      std::remove(cache_path(stem).c_str());
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_src_pending.find(stem) == g_src_pending.end()) {
+      p = std::make_shared<SrcPending>();
+      g_src_pending[stem] = p;
+      if (!g_atexit) { std::atexit(join_all); g_atexit = true; }
+      const Job job = source_job(stem, src, names, n_names);
+      g_threads.emplace_back([job, p]() {
+        Cubin c;
+        std::string log;
+        const int rc = compile_cubin(job, c, log);
+        if (rc == RKB_OK) cache_write(job.stem, c);
+        std::lock_guard<std::mutex> lock2(g_mu);
+        p->cubin.image.swap(c.image);
+        p->cubin.names.swap(c.names);
+        p->log = log;
+        p->state = rc == RKB_OK ? 1 : -1;
+      });
+    }
+    return RKB_OK;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (p->state == 0) return RKB_OK;
+    if (p->state < 0) { g_log = p->log; return RKB_ERR_CUDA; }
+  }
+  SourceKernels* S = nullptr;
+  const int rc = load_source(p->cubin, n_names, &S, g_log);
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (rc) {
+    auto np = std::make_shared<SrcPending>();
+    np->state = -1; np->log = g_log;
+    g_src_pending[stem] = np;  // do not try again
+    return rc;
+  }
+  *out = src_publish(stem, S);
   return RKB_OK;
 }
 

@@ -346,6 +346,15 @@ class kte_batch_propagator(object):
         _abi.check(self._lib.rkb_frames(self._h, self.device, N, ptr(x), ptr(u) if self.nu else None, ptr(fr), flags, stream), "rkb_frames")
         return fr
 
+    def proxy_handle(self, pair):
+        """the rkb_proxy of `pair` for this chain (built once, cached on the pair)"""
+        from . import proximity
+        h = getattr(pair, "_rkb_handle", None)
+        if h is None or getattr(pair, "_rkb_owner", None) is not self:
+            h = proximity.ProxyHandle(self._lib, self._h, pair, self.compiled.frames)
+            pair._rkb_handle, pair._rkb_owner = h, self
+        return h
+
     def get_min_distances(self, pair, x, with_points=True):
         """proxy_query_pair_3D::findMinimumDistance at every state (rkb_min_distance): distance [N], finder index [N]
         and, with_points, (mPoint1, mPoint2) [N][6].  `pair` is a reak_b200.proximity.proxy_query_pair_3D; its device

@@ -144,6 +144,26 @@ class ProxyHandle:
         _abi.check(self._lib.rkb_proxy_finder(self._h, int(k), C.byref(a), C.byref(b)), "rkb_proxy_finder")
         return a.value, b.value
 
+    # run-time specialisation of the pair's query (rkb_proxy_specialize)
+    OPT_AUTO_SPECIALIZE, OPT_MIN_BLOCKS = 1, 2
+
+    def set_option(self, option, value):
+        _abi.check(self._lib.rkb_proxy_set_option(self._h, int(option), int(value)), "rkb_proxy_set_option")
+
+    def specialize(self, device=0):
+        _abi.check(self._lib.rkb_proxy_specialize(self._h, int(device)), "rkb_proxy_specialize")
+
+    def is_specialized(self):
+        return bool(self._lib.rkb_proxy_is_specialized(self._h))
+
+    def source(self):
+        """the CUDA source rkb_proxy_specialize compiles (test hook)"""
+        n = self._lib.rkb_proxy_source(self._h, None, 0)
+        _abi.check(min(n, 0), "rkb_proxy_source")
+        buf = C.create_string_buffer(n)
+        _abi.check(min(self._lib.rkb_proxy_source(self._h, buf, n), 0), "rkb_proxy_source")
+        return buf.value.decode()
+
     def close(self):
         if self._h:
             self._lib.rkb_proxy_destroy(self._h)

@@ -327,6 +327,124 @@ def test_proxy_create_rejects():
     lib.rkb_chain_destroy(h2)
 
 
+# ---- the generated (run-time specialised) source, compiled for the host -------------------------------
+class SpecHost(object):
+    """rkb_proxy_source() of a chain + pair — the text rkb_proxy_specialize gives NVRTC — compiled by g++ with
+    tests/host_build/prox_spec_host.h and run on the coordinates themselves (its own forward kinematics)."""
+
+    def __init__(self, tmp, system, pair, min_blocks=None):
+        self.compiled = kte.compile_chain(system.chain, system.mass_calc, system.dofs_gen, system.inputs)
+        lib = _abi.load_library()
+        h = C.c_void_p()
+        _abi.check(lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(h)), "rkb_chain_create")
+        proxy = px.ProxyHandle(lib, h, pair, self.compiled.frames)
+        if min_blocks:
+            proxy.set_option(px.ProxyHandle.OPT_MIN_BLOCKS, min_blocks)
+        self.source = proxy.source()
+        proxy.close()
+        lib.rkb_chain_destroy(h)
+        SpecHost.count = getattr(SpecHost, "count", 0) + 1
+        cu, so = os.path.join(tmp, "spec%d.cu" % SpecHost.count), os.path.join(tmp, "libspec%d.so" % SpecHost.count)
+        with open(cu, "w") as f:
+            f.write(self.source)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-include", os.path.join(HERE, "host_build", "prox_spec_host.h"),
+                        "-I", os.path.join(HERE, "..", "reak_b200", "csrc"), "-x", "c++", cu, "-o", so], check=True)
+        self.lib = C.CDLL(so)
+        self.lib.prox_spec_host.restype = C.c_int
+        self.lib.prox_spec_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+
+    def min_distance(self, x, with_points=True):
+        n = self.compiled.n_coords
+        N = x.shape[0]
+        d, f, p = np.zeros(N), np.zeros(N, dtype=np.int32), np.zeros((N, 6))
+        for i in range(N):
+            q = np.ascontiguousarray(x[i, 0:2 * n:2])
+            fc = np.ascontiguousarray(x[i, 2 * n:2 * n + 7]) if x.shape[1] > 2 * n else np.zeros(7)
+            di = C.c_double()
+            f[i] = self.lib.prox_spec_host(q.ctypes.data_as(C.c_void_p), fc.ctypes.data_as(C.c_void_p), int(with_points), C.byref(di),
+                                           p[i].ctypes.data_as(C.c_void_p))
+            d[i] = di.value
+        return d, f, p
+
+
+@pytest.fixture(scope="module")
+def spec_tmp(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("prox_spec"))
+
+
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True), ("crs6_twist", False)])
+def test_generated_source_crs_lab_vs_reference(preset, track, spec_tmp, oracle_built):
+    """the straight-line kernel source of the CRS arm against the MD148 lab: forward kinematics with axis-aligned joints
+    and links, world-fixed shapes as literals; crs6_twist has rotated links (the general quaternion product)"""
+    need_ref(oracle_built)
+    s = presets.make(preset)
+    robot, lab = presets.crs_proxy_models(s, track=track)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    H = SpecHost(spec_tmp, s, pair)
+    assert "rkb_prox_spec" not in H.source.split("RKB_PROX_SPEC_KERNELS")[0] and "RKB_PROX_SPEC_KERNELS(%d, 0, " % H.compiled.n_coords in H.source
+    R = oracle_built.Reference(H.compiled)
+    x, _ = random_batch(H.compiled, 256, seed=11, q_range=3.1)
+    want = R.min_distance(pair, x)
+    agree(H.min_distance(x), want, TOL)
+    d0, f0, _ = H.min_distance(x, with_points=False)   # the distance-only kernel's path
+    assert np.max(np.abs(d0 - want[0])) < TOL and np.all((f0 == want[1]) | (np.abs(d0 - want[0]) < TOL))
+    assert (want[0] < 0).any() and (want[0] > 0).any()
+
+
+def test_generated_source_mixed_models_vs_reference(spec_tmp, oracle_built):
+    """every shape kind on both sides, rotated local poses, pairs without a finder, the culling test"""
+    need_ref(oracle_built)
+    s = presets.make("crs7")
+    for seed in range(4):
+        pair = mixed_models(s, np.random.default_rng(100 + seed))
+        H = SpecHost(spec_tmp, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 64, seed=seed, q_range=2.0)
+        agree(H.min_distance(x), R.min_distance(pair, x), TOL_SEARCH)
+
+
+def test_generated_source_general_axes_and_moving_second_model(spec_tmp, oracle_built):
+    """joint axes that are not unit vectors of the frame (physical CRS), shapes of BOTH models riding on the chain"""
+    need_ref(oracle_built)
+    s = presets.make("crs6_phys")
+    rng = np.random.default_rng(7)
+    m1, m2 = px.proxy_query_model_3D("upper"), px.proxy_query_model_3D("lower")
+    kinds = sorted(KINDS)
+    for k in range(4):
+        m1.addShape(random_shape(rng, kinds[(k + 1) % 5], s.joint_end_frames[3 + k % 3], spread=0.3))
+        m2.addShape(random_shape(rng, kinds[(k + 3) % 5], s.joint_end_frames[k % 2] if k < 3 else None, spread=0.4))
+    pair = px.proxy_query_pair_3D("self", m1, m2)
+    H = SpecHost(spec_tmp, s, pair)
+    R = oracle_built.Reference(H.compiled)
+    x, _ = random_batch(H.compiled, 96, seed=3, q_range=3.0)
+    agree(H.min_distance(x), R.min_distance(pair, x), TOL_SEARCH)
+
+
+def test_generated_source_vs_golden(spec_tmp):
+    """committed outputs of the reference; runs without oracle/_ref (the golden file stores the states)"""
+    g = np.load(GOLDEN)
+    for tag, preset in (("crs_lab", "crs6"), ("mixed", "crs7")):
+        if tag + "_x" not in g.files:
+            pytest.skip("golden file without states")
+        s = presets.make(preset)
+        sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        H = SpecHost(spec_tmp, s, golden_pair(s, sub))
+        agree(H.min_distance(sub["x"]), (sub["distance"], sub["finder"], sub["points"]), TOL_SEARCH if tag == "mixed" else TOL)
+
+
+def test_generated_source_is_keyed_by_its_constants(spec_tmp):
+    """two pairs that differ in one dimension give different texts (the cubin cache is keyed by a hash of the text);
+    the same pair gives the same text twice; min_blocks lands in the kernel's launch bounds"""
+    s = presets.make("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    a = SpecHost(spec_tmp, s, px.proxy_query_pair_3D("a", robot, lab))
+    b = SpecHost(spec_tmp, s, px.proxy_query_pair_3D("b", robot, lab))
+    assert a.source == b.source
+    lab.mShapeList[3].dims = tuple(np.array(lab.mShapeList[3].dims) * [1.0, 1.5, 1.0][:len(lab.mShapeList[3].dims)])
+    c = SpecHost(spec_tmp, s, px.proxy_query_pair_3D("c", robot, lab), min_blocks=5)
+    assert c.source != a.source and "RKB_PROX_SPEC_KERNELS(6, 0, 5)" in c.source
+
+
 # ---- GPU ------------------------------------------------------------------------------------------
 def _gpu_prop(preset):
     from reak_b200.propagator import kte_batch_propagator
@@ -392,6 +510,98 @@ def test_gpu_vs_golden():
         sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
         pair = golden_pair(s, sub)
         agree(P.get_min_distances(pair, sub["x"]), (sub["distance"], sub["finder"], sub["points"]), TOL_SEARCH if tag == "mixed" else TOL)
+
+
+def _same(got, want, tol):
+    """interpreter kernel against generated kernel: same finder unless a tie, distances and points to rounding"""
+    agree(tuple(np.asarray(a) for a in got), tuple(np.asarray(a) for a in want), tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True), ("crs6_twist", False), ("crs6_phys", False)])
+def test_gpu_specialized_crs_lab(preset, track, oracle_built):
+    """rkb_proxy_specialize: the query of this chain and pair as generated straight-line CUDA (NVRTC) — against the
+    compiled reference and against the interpreter kernel; is_free served by it"""
+    need_ref(oracle_built)
+    s, P = _gpu_prop(preset)
+    robot, lab = presets.crs_proxy_models(s, track=track)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    h = P.proxy_handle(pair)
+    h.set_option(h.OPT_AUTO_SPECIALIZE, 0)
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 4096 + 77, seed=5, q_range=3.1)
+    want = R.min_distance(pair, x)
+    before = P.get_min_distances(pair, x)
+    free_before = P.is_free([pair], x)
+    assert not h.is_specialized()
+    h.specialize()
+    assert h.is_specialized()
+    got = P.get_min_distances(pair, x)
+    agree(got, want, TOL)
+    _same(got, before, 1e-12)
+    d_only, f_only = P.get_min_distances(pair, x, with_points=False)
+    assert np.max(np.abs(d_only - got[0])) < 1e-12 and np.array_equal(f_only, got[1])   # two kernels, the same search
+    assert np.array_equal(P.is_free([pair], x), free_before) and np.array_equal(free_before, ~(want[0] < 0.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_gpu_specialized_mixed_models(seed, oracle_built):
+    need_ref(oracle_built)
+    s, P = _gpu_prop("crs7")
+    pair = mixed_models(s, np.random.default_rng(100 + seed))
+    P.proxy_handle(pair).specialize()
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 1024, seed=seed, q_range=2.0)
+    agree(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL_SEARCH)
+
+
+@pytest.mark.gpu
+def test_gpu_specialized_free_base_and_layouts():
+    """a free-floating base in front of the arm (the pose states of free_joint_3D feed the kinematics), device-resident
+    and structure-of-arrays buffers: generated kernel against the interpreter kernel"""
+    import torch
+    s, P = _gpu_prop("free_arm6")
+    rng = np.random.default_rng(9)
+    m1, m2 = px.proxy_query_model_3D("arm"), px.proxy_query_model_3D("world")
+    kinds = sorted(KINDS)
+    frames = [f for f in P.compiled.frames][-4:]
+    for k in range(4):
+        m1.addShape(random_shape(rng, kinds[k % 5], frames[k % len(frames)], spread=0.3))
+        m2.addShape(random_shape(rng, kinds[(k + 2) % 5], None, spread=1.0))
+    pair = px.proxy_query_pair_3D("free", m1, m2)
+    h = P.proxy_handle(pair)
+    h.set_option(h.OPT_AUTO_SPECIALIZE, 0)
+    x = rng.uniform(-1.0, 1.0, (3000, P.nx))
+    before = P.get_min_distances(pair, x)
+    dx = torch.from_numpy(x).cuda()
+    h.specialize()
+    _same(P.get_min_distances(pair, x), before, 1e-6)
+    d, f, pts = P.get_min_distances(pair, dx)
+    _same((d.cpu().numpy(), f.cpu().numpy(), pts.cpu().numpy()), before, 1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_proxy_auto_specialize():
+    """default behaviour: the first query of >= 4096 states starts the compilation in the background, queries made
+    meanwhile run on the interpreter, later ones on the generated kernel — same answers throughout"""
+    import time
+    s, P = _gpu_prop("crs6")
+    robot, lab = presets.crs_proxy_models(s)
+    lab.mShapeList[0].pose.position = (0.013, 0.0, 0.0)   # a pair no other test has put into the cubin cache
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    h = P.proxy_handle(pair)
+    x, _ = random_batch(P.compiled, 8192, seed=2, q_range=3.0)
+    small = P.get_min_distances(pair, x[:100])
+    assert not h.is_specialized()
+    first = P.get_min_distances(pair, x)
+    t0 = time.time()
+    while not h.is_specialized() and time.time() - t0 < 180:
+        time.sleep(0.2)
+        P.get_min_distances(pair, x)
+    assert h.is_specialized(), "no generated kernel after 180 s"
+    _same(P.get_min_distances(pair, x), first, 1e-12)
+    _same(P.get_min_distances(pair, x[:100]), small, 1e-12)
 
 
 @pytest.mark.gpu

@@ -23,12 +23,28 @@ def main():
     rng = np.random.default_rng(1)
     x = rng.uniform(-3, 3, (n, p.nx))
     dx = torch.from_numpy(x).cuda()
-    ms = []
-    for k in range(7):
-        d, f = p.get_min_distances(pair, dx, with_points=False)
-        ms.append(p.last_kernel_ms())
-    t = min(ms[2:])
-    print("%s min_distance (25 finders) n=%d  %.3f ms  %.3g states/s  colliding %.1f %%" % (name, n, t, n / t * 1e3, 100.0 * (d < 0).double().mean().item()))
+    h = p.proxy_handle(pair)
+    h.set_option(h.OPT_AUTO_SPECIALIZE, 0)
+
+    def timed(label):
+        ms = []
+        for k in range(7):
+            d, f = p.get_min_distances(pair, dx, with_points=False)
+            ms.append(p.last_kernel_ms())
+        t = min(ms[2:])
+        print("%s min_distance (25 finders) %s n=%d  %.3f ms  %.3g states/s  colliding %.1f %%" % (name, label, n, t, n / t * 1e3, 100.0 * (d < 0).double().mean().item()))
+        return d, f
+
+    d0, f0 = timed("interpreter")
+    blocks = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+    for b in blocks:   # generated kernels (rkb_proxy_specialize), compiled for b CTAs per SM (0: the library's default)
+        if b:
+            h.set_option(h.OPT_MIN_BLOCKS, b)
+        t0 = time.perf_counter()
+        h.specialize()
+        tc = time.perf_counter() - t0
+        d, f = timed("generated, min_blocks %s (NVRTC %.1f s)" % (b or "default", tc))
+        print("   max |d - d_interpreter| %.2e, finder differs on %d states" % ((d - d0).abs().max().item(), int((f != f0).sum().item())))
     d, f, pts = p.get_min_distances(pair, dx)
     print("%s with points               n=%d  %.3f ms" % (name, n, p.last_kernel_ms()))
     t0 = time.perf_counter()
