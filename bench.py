@@ -359,9 +359,18 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
     def prox6():
         d6[0] = p6.get_min_distances(pair, x6, with_points=False)[0]
 
+    # interpreter kernel first (no background compilation while it is timed), then the kernel generated for this chain and pair
+    h6 = p6.proxy_handle(pair)
+    h6.set_option(h6.OPT_AUTO_SPECIALIZE, 0)
+    t6i = best(prox6, p6)
+    kernel6 = "generated for this chain and pair (rkb_proxy_specialize, NVRTC)"
+    try:
+        h6.specialize(local)
+    except Exception as e:  # no libnvrtc on this box: the interpreter kernel is what runs
+        kernel6 = "interpreter (%s)" % e
     t6 = best(prox6, p6)
     e6 = {"config": "proximity", "workload": "findMinimumDistance, CRS arm vs MD148 lab (25 finders): %d states per GPU" % n6,
-          "min_distance_ms": t6, "states_per_gpu": n6}
+          "min_distance_ms": t6, "states_per_gpu": n6, "kernel": kernel6, "interpreter_kernel_ms": t6i}
     if check:
         from oracle import pyref
         if pyref.have_ref():
@@ -386,9 +395,24 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
     def steer():
         done[0] = p6.steer_feedback(xs6, gl, ub, g6, up, 1e-2, DT, 10, J6, 0.25, proxy_pairs=[pair])[2]
 
+    p6.set_option("auto_specialize", 0)
+    t7i = best(steer, p6)   # interval by interval: law, rollout, proximity, commit launches
+    kernel7 = "one launch: steering kernel compiled with the pair's collision test (rkb_steer_checked_specialize, NVRTC)"
+    try:
+        p6.specialize_checked_steering([pair])
+    except Exception as e:
+        kernel7 = "interval by interval (%s)" % e
     t7 = best(steer, p6)
+    units7 = int(done[0].sum().item()) * 10
+
+    def steer_unchecked():
+        done[0] = p6.steer_feedback(xs6, gl, ub, g6, up, 1e-2, DT, 10, J6, 0.25)[2]
+
+    t7u = best(steer_unchecked, p6)
     out.append({"config": "steer_checked", "workload": "closed-loop steering with collision test: %d tuples x <= %d intervals x 10 RK4 steps per GPU"
-                % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": int(done[0].sum().item()) * 10})
+                % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": units7, "kernel": kernel7, "interval_by_interval_ms": t7i,
+                "unchecked": {"ms": t7u, "state_steps": int(done[0].sum().item()) * 10,
+                              "note": "the same tuples without the test (they run on where the checked loop stops at a collision)"}})
     # the nearest-neighbour search that precedes every steer (linear_neighbor_search / dvp_tree), for
     # a batch of 4096 samples against 2^20 motion-graph vertices of the 6-DOF state space (12 coordinates)
     from reak_b200.nearest import nearest_neighbors

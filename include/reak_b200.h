@@ -355,8 +355,9 @@ RKB_API void rkb_proxy_destroy(rkb_proxy* proxy);
  * THIS chain and pair as straight-line CUDA (forward kinematics with the chain's constants, world-fixed shapes as literals,
  * every finder of createProxFinderList with its argument order resolved), compiles it with NVRTC (a few seconds; cubins
  * are cached on disk like those of rkb_chain_specialize) and routes the pair's launches to it: ~2x the interpreter.
- * Results agree with the interpreter kernel to rounding.  By default (RKB_PROXY_OPT_AUTO_SPECIALIZE = 1) the same happens
- * on a background thread from the first query of >= 4096 states on; queries made meanwhile run on the interpreter.
+ * Results agree with the interpreter kernel to rounding.  By default (RKB_PROXY_OPT_AUTO_SPECIALIZE = 1, and the chain's
+ * RKB_OPT_AUTO_SPECIALIZE on) the same happens on a background thread from the first query of >= 4096 states on; queries
+ * made meanwhile run on the interpreter.
  * RKB_ERR_UNSUPPORTED: libnvrtc.so.12 is not installed. */
 enum rkb_proxy_option { RKB_PROXY_OPT_AUTO_SPECIALIZE = 1, RKB_PROXY_OPT_MIN_BLOCKS = 2 /* CTAs per SM compiled for, 1..8 */ };
 RKB_API int  rkb_proxy_set_option(rkb_proxy* proxy, int option, long long value);
@@ -536,6 +537,19 @@ RKB_API int rkb_steer_feedback_checked(rkb_chain* chain, int device, size_t n_sa
                                        const rkb_proxy* const* pairs, int n_pairs,
                                        double* x_out, int32_t* n_done, int32_t* collided, double* x_traj, int32_t* status,
                                        unsigned flags, void* stream);
+
+/* Checked steering in ONE launch.  For a serial chain the library can compile its steering kernel with the collision
+ * test of a given set of proxy pairs built in (the generated query of rkb_proxy_specialize inside the loop: integrate an
+ * interval, test the state it ends on, accept or stop — no state round trips between four kernels per interval).
+ * rkb_steer_checked_specialize does it now (NVRTC, a few seconds, cubin cached on disk); by default it happens in the
+ * background from the first rkb_steer_feedback_checked call of >= 4096 tuples on (while every pair and the chain have
+ * their AUTO_SPECIALIZE option on), calls made meanwhile run interval by interval.  Results: those of the interval-by-
+ * interval path up to rounding.  RKB_ERR_UNSUPPORTED: interpreter chain, RKB_OPT_FUSED_STEER off, or no libnvrtc.so.12. */
+RKB_API int rkb_steer_checked_specialize(rkb_chain* chain, int device, const rkb_proxy* const* pairs, int n_pairs);
+RKB_API int rkb_steer_checked_is_specialized(rkb_chain* chain, const rkb_proxy* const* pairs, int n_pairs);
+/* test hook: the CUDA source rkb_steer_checked_specialize compiles, its last line naming the kernel instantiated from it
+ * ("// kernel: <name expression>"); returns its size including the NUL, out may be NULL to ask for the size */
+RKB_API int rkb_steer_checked_source(rkb_chain* chain, const rkb_proxy* const* pairs, int n_pairs, char* out, size_t size);
 
 /* Device-side timing of the last compute launch issued through `chain` on the calling
  * thread, in milliseconds (CUDA events on the launch stream); < 0 if none. Blocks until

@@ -122,6 +122,9 @@ SYMBOLS = {
     "rkb_proxy_specialize": (C.c_int, [C.c_void_p, C.c_int]),
     "rkb_proxy_is_specialized": (C.c_int, [C.c_void_p]),
     "rkb_proxy_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rkb_steer_checked_specialize": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "rkb_steer_checked_is_specialized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "rkb_steer_checked_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "rkb_proxy_finder_count": (C.c_int, [C.c_void_p]),
     "rkb_proxy_finder": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rkb_proxy_program": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

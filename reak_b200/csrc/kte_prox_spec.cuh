@@ -61,11 +61,13 @@ GD SPose spose_lit(double px, double py, double pz, double m0, double m1, double
 }  // namespace
 
 #ifndef RKB_PROX_SPEC_HOST
-// The two kernels of a generated source: NC coordinates, NFREE free joints (0 or 1), the search in prox_spec<PTS>.
-// Same buffers as generic_proximity_kernel.
+// The kernel of a generated source: NC coordinates, NFREE free joints (0 or 1), the search in prox_spec<false> — distance
+// and finder index, the buffers of generic_proximity_kernel.  (A query that also wants the two points runs on the
+// interpreter kernel: every thread of a warp may hold a different winner, and evaluating its record needs the shapes picked
+// by index — measured 0.61 ms there against 0.70 ms (a switch over all finders) and 6 ms (poses in a per-thread array) here.
+// prox_spec<true> is what the host build of the CPU suite checks the points of.)
 #define RKB_PROX_SPEC_KERNELS(NC, NFREE, MINB)                                                                          \
-  template <bool PTS>                                                                                                   \
-  __device__ __forceinline__ void prox_spec_body(const EvalArgs& A) {                                                   \
+  extern "C" __global__ void __launch_bounds__(128, MINB) rkb_prox_spec_d(const EvalArgs A) {                           \
     const long long i = (long long)blockIdx.x * 128 + threadIdx.x;                                                      \
     if (i >= A.n_samples) return;                                                                                       \
     double q[NC > 0 ? NC : 1];                                                                                          \
@@ -78,14 +80,8 @@ GD SPose spose_lit(double px, double py, double pz, double m0, double m1, double
       freec = pose_of(v3(s[0], s[1], s[2]), q4(s[3] / nq, s[4] / nq, s[5] / nq, s[6] / nq));                            \
     }                                                                                                                   \
     ProxRecord R;                                                                                                       \
-    const int best = prox_spec<PTS>(q, freec, R);                                                                       \
+    const int best = prox_spec<false>(q, freec, R);                                                                     \
     A.out.p[i * A.out.si] = R.d;                                                                                        \
     if (A.status) A.status[i] = best;                                                                                   \
-    if (PTS) {                                                                                                          \
-      const double v[6] = {R.p1.x, R.p1.y, R.p1.z, R.p2.x, R.p2.y, R.p2.z};                                             \
-      _Pragma("unroll") for (int k = 0; k < 6; ++k) A.out2.p[i * A.out2.si + k * A.out2.sk] = v[k];                     \
-    }                                                                                                                   \
-  }                                                                                                                     \
-  extern "C" __global__ void __launch_bounds__(128, MINB) rkb_prox_spec_d(const EvalArgs A) { prox_spec_body<false>(A); } \
-  extern "C" __global__ void __launch_bounds__(128, MINB) rkb_prox_spec_p(const EvalArgs A) { prox_spec_body<true>(A); }
+  }
 #endif

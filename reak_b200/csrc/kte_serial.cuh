@@ -1321,8 +1321,17 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
 // control interval the goal-proximity test, the state feedback u = u_bias - G (x - x_goal) through
 // get_bounded_input (IHAQR_topology.hpp:304-327, see rkb_steer.cu for the same law as a separate pass), then
 // `substeps` RK4 steps with that input.  A sample whose loop has ended leaves; its warp carries on.
-template <int N, int FL, shape_t SHAPE>
-__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N))) serial_steer_kernel(const __grid_constant__ SerialParams P, const __grid_constant__ SteerArgs A) {
+// CHK: the collision test of `with_collision_check = true` (MEAQR_topology.hpp:550-559: the interval is integrated, the
+// state it ends on is tested, and only a free state is accepted — else the loop stops on the last free state).  The
+// shipped kernels carry none; rkb_prox_jit.cu generates one per chain and set of proxy pairs (straight-line forward
+// kinematics and finders, kte_prox_spec.cuh) and NVRTC compiles this kernel with it: checked steering in one launch.
+struct NoSteerCheck {
+  static constexpr bool enabled = false;
+  static constexpr int fewer_blocks = 0;  // CTAs per SM given up for the test's registers
+  template <int N> RKB_DEV static bool is_free(const SerialState<N>&) { return true; }
+};
+template <int N, int FL, shape_t SHAPE, class CHK = NoSteerCheck>
+__global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_ROLLOUT(N)) - CHK::fewer_blocks) serial_steer_kernel(const __grid_constant__ SerialParams P, const __grid_constant__ SteerArgs A) {
   extern __shared__ double smem[];
   constexpr int SMS = RKB_BLOCK;
   constexpr int NX = 2 * N;
@@ -1346,9 +1355,14 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
     act[s] = in >= 0 && in < nu;
     up[s] = act[s] ? A.u_prev[i * nu + in] : 0.0;
   }
-  int st = 0, k = 0;
+  int st = 0, k = 0, collided = 0;
 #pragma unroll 1
   for (; k < A.max_intervals; ++k) {
+    double up_old[CHK::enabled ? N : 1];
+    if (CHK::enabled) {
+#pragma unroll
+      for (int s = 0; s < N; ++s) up_old[s] = up[s];
+    }
     // ---- the law: x - x_goal, distance, correction -G (x - x_goal), get_bounded_input ----------------------
     double dx[NX];
     double d2 = 0.0;
@@ -1420,7 +1434,18 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
 #pragma unroll
     for (int s = 0; s < N; ++s) X.u[s] = up[s];
     // ---- one control interval -----------------------------------------------------------------------------
+    double q0[CHK::enabled ? N : 1], qd0[CHK::enabled ? N : 1];
+    if (CHK::enabled) {
+#pragma unroll
+      for (int s = 0; s < N; ++s) { q0[s] = X.q[s]; qd0[s] = X.qd[s]; }
+    }
     st |= rk4_steps<N, FL, SHAPE, SMS>(P, X, A.dt, A.substeps, sm);
+    if (CHK::enabled && !CHK::is_free(X)) {  // rejected: back on the last free state, with the input that led to it
+#pragma unroll
+      for (int s = 0; s < N; ++s) { X.q[s] = q0[s]; X.qd[s] = qd0[s]; up[s] = up_old[s]; }
+      collided = 1;
+      break;
+    }
     if (A.traj) {
       const BatchView tv = {A.traj + (long long)k * NX, (long long)NX * A.max_intervals, 1, A.blocked};
       store_state<N>(P, tv, i * tv.si, X);
@@ -1434,6 +1459,7 @@ __global__ void __launch_bounds__(RKB_BLOCK, RKB_MINBLOCKS(SHAPE, N, RKB_SMEM_RO
 #pragma unroll
   for (int s = 0; s < N; ++s) if (act[s]) A.u_prev[i * nu + P.st[s].input] = up[s];  // u_prev = u_current (MEAQR_topology.hpp:553)
   A.n_done[i] = k;
+  if (CHK::enabled && A.collided) A.collided[i] = collided;
   if (!finite) st |= RKB_STATUS_NONFINITE;
   if (A.status) A.status[i] = st;
 }

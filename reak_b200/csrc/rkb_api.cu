@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -85,6 +86,9 @@ struct rkb_chain {
   bool fused_steer = true, fused_sequence = true, host_pipeline = true;
   bool auto_specialize = true, auto_done = false;
   unsigned create_flags = 0;
+  // checked steering in one launch: kernels generated per set of proxy pairs (rkb_steer_checked_source)
+  struct CheckedSteer { std::vector<unsigned long long> key; const SourceKernels* K; bool done; };
+  std::vector<CheckedSteer> checked;
 };
 
 // Below this many samples a batch cannot fill the GPU with one thread per sample (148 SMs x 4 sub-partitions x 32
@@ -902,10 +906,12 @@ struct rkb_proxy {
   mutable std::mutex mu;
   mutable const SourceKernels* spec = nullptr;
   mutable bool auto_done = false;
+  unsigned long long serial = 0;  // identity for the chain's table of checked-steering kernels (a pointer can be reused)
 };
+std::atomic<unsigned long long> g_proxy_serial{1};
 
 namespace {
-const char* const kProxSpecNames[2] = {"rkb_prox_spec_d", "rkb_prox_spec_p"};
+const char* const kProxSpecNames[1] = {"rkb_prox_spec_d"};
 
 // The proximity query of one pair at every state of A: the kernels compiled for this chain and pair when they are
 // there (rkb_proxy_specialize, or in the background from the first call of >= 4096 states on), else the interpreter.
@@ -913,19 +919,19 @@ cudaError_t launch_proximity(const rkb_chain* c, const DeviceCtx* ctx, const rkb
   const SourceKernels* K = nullptr;
   {
     std::lock_guard<std::mutex> lock(p->mu);
-    if (!p->spec && p->auto_specialize && !p->auto_done && A.n_samples >= 4096) {
+    if (!p->spec && p->auto_specialize && c->auto_specialize && !p->auto_done && A.n_samples >= 4096) {
       const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
       const SourceKernels* J = nullptr;
-      if (src.empty() || rkb_jit_source_poll("prox", src, kProxSpecNames, 2, &J) != RKB_OK) p->auto_done = true;  // no NVRTC here: stay as we are
+      if (src.empty() || rkb_jit_source_poll("prox", src, kProxSpecNames, 1, false, &J) != RKB_OK) p->auto_done = true;  // no NVRTC here: stay as we are
       else if (J) { p->spec = J; p->auto_done = true; }
     }
     K = p->spec;
   }
-  if (!K) return rkb_generic_proximity(ctx->d_prog, c->gp, A, p->prog, s);
+  if (!K || A.out2.p) return rkb_generic_proximity(ctx->d_prog, c->gp, A, p->prog, s);  // (the two points: interpreter, see kte_prox_spec.cuh)
   if (A.n_samples <= 0) return cudaSuccess;
   void* argv[1] = {const_cast<EvalArgs*>(&A)};
   const unsigned grid = (unsigned)((A.n_samples + 127) / 128);
-  return cudaLaunchKernel(K->kernel[A.out2.p ? 1 : 0], dim3(grid), dim3(128), argv, 0, s);
+  return cudaLaunchKernel(K->kernel[0], dim3(grid), dim3(128), argv, 0, s);
 }
 
 bool prox_pair_has_finder(int ka, int kb) {  // proxy_query_model.cpp:212-384
@@ -983,6 +989,7 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
   p->prog.n2 = n2;
   p->n_frames = c->desc.n_frames;
   p->gp = c->gp;
+  p->serial = g_proxy_serial.fetch_add(1);
   for (int k = 0; k < n1 + n2; ++k) {
     const rkb_shape& in = k < n1 ? m1[k] : m2[k - n1];
     if (!lower_shape(in, c->desc.n_frames, &p->prog.s[k])) { delete p; return RKB_ERR_INVALID; }
@@ -1032,7 +1039,7 @@ int rkb_proxy_specialize(rkb_proxy* p, int device) {
   const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
   if (src.empty()) return RKB_ERR_UNSUPPORTED;
   const SourceKernels* J = nullptr;
-  const int rc = rkb_jit_source_get("prox", src, kProxSpecNames, 2, &J);
+  const int rc = rkb_jit_source_get("prox", src, kProxSpecNames, 1, false, &J);
   if (rc) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "run-time compilation failed: %.200s", rkb_jit_log()); return rc; }
   p->spec = J;
   return RKB_OK;
@@ -1743,6 +1750,39 @@ int rkb_steer_batch(rkb_chain* c, int device, size_t P, size_t R, const double* 
 }  // extern "C"
 
 namespace {
+// The steering kernel with the collision test of `pairs` compiled in (c->mu held).  sync: compile now if need be; else
+// from the first call of >= 4096 tuples on in the background, NULL until it is there (the caller runs interval by interval).
+const SourceKernels* checked_steer_kernel(rkb_chain* c, const rkb_proxy* const* pairs, int n_pairs, long long n_samples, bool sync, int* rc_out) {
+  if (rc_out) *rc_out = RKB_OK;
+  if (!c->serial_ok || !c->sk || c->n_free || n_pairs < 1) { if (rc_out) *rc_out = RKB_ERR_UNSUPPORTED; return nullptr; }
+  std::vector<unsigned long long> key;
+  bool may_auto = c->auto_specialize;
+  for (int p = 0; p < n_pairs; ++p) {
+    key.push_back(pairs[p]->serial);
+    std::lock_guard<std::mutex> lock(pairs[p]->mu);
+    may_auto = may_auto && pairs[p]->auto_specialize;
+  }
+  rkb_chain::CheckedSteer* entry = nullptr;
+  for (auto& e : c->checked)
+    if (e.key == key) entry = &e;
+  if (entry && (entry->K || (entry->done && !sync))) return entry->K;
+  if (!sync && (!may_auto || n_samples < 4096)) return nullptr;
+  if (!entry) { c->checked.push_back(rkb_chain::CheckedSteer{key, nullptr, false}); entry = &c->checked.back(); }
+  int coords[RKB_SERIAL_MAX_DOF];
+  for (int s = 0; s < c->n; ++s) coords[s] = c->sp.st[s].coord;
+  std::vector<const ProxProgram*> progs;
+  for (int p = 0; p < n_pairs; ++p) progs.push_back(&pairs[p]->prog);
+  std::string expr;
+  const std::string src = rkb_steer_checked_source(c->n, c->serial_fl, c->serial_shape, coords, c->gp, progs.data(), n_pairs, &expr);
+  if (src.empty()) { entry->done = true; if (rc_out) *rc_out = RKB_ERR_UNSUPPORTED; return nullptr; }
+  const char* names[1] = {expr.c_str()};
+  const SourceKernels* K = nullptr;
+  const int rc = sync ? rkb_jit_source_get("steerchk", src, names, 1, true, &K) : rkb_jit_source_poll("steerchk", src, names, 1, true, &K);
+  if (rc != RKB_OK) { entry->done = true; if (rc_out) *rc_out = rc; return nullptr; }  // no NVRTC here, or it failed: stay as we are
+  if (K) { entry->K = K; entry->done = true; }
+  return K;
+}
+
 int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, const double* x_goal, const double* u_bias,
                         const double* gain, double* u_prev, const rkb_steer_opts* o, const rkb_proxy* const* pairs, int n_pairs,
                         double* x_out, int32_t* n_done, int32_t* collided, double* x_traj, int32_t* status, unsigned flags,
@@ -1792,9 +1832,12 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   dst = (L.device && status) ? (void*)status : ctx->st.p;
   if ((rc = ctx->act.ensure(N * sizeof(int32_t)))) return rc;
   CU(cudaMemsetAsync(dst, 0, N * sizeof(int32_t), s));
-  const bool fused = n_pairs == 0 && c->serial_ok && c->sk && c->fused_steer;
+  const SourceKernels* CK = (n_pairs > 0 && c->fused_steer) ? checked_steer_kernel(c, pairs, n_pairs, (long long)N, false, nullptr) : nullptr;
+  const bool fused = (n_pairs == 0 || CK) && c->serial_ok && c->sk && c->fused_steer;
   void *dcol = nullptr, *dxn = nullptr, *dun = nullptr, *ddist = nullptr;
-  if (n_pairs > 0) {
+  if (CK) {
+    if ((rc = stage_out(ctx->out_idx, collided, N * sizeof(int32_t), L.device, &dcol))) return rc;
+  } else if (n_pairs > 0) {
     // the interval is integrated into x_next, tested, and only then accepted (MEAQR_topology.hpp:550-559)
     if ((rc = stage_out(ctx->out_idx, collided, N * sizeof(int32_t), L.device, &dcol))) return rc;
     if ((rc = ctx->scratch_x.ensure(bx))) return rc;
@@ -1813,12 +1856,14 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
     F.n_samples = (long long)N; F.nu = nu; F.max_intervals = J; F.substeps = o->substeps; F.saturate_first = o->saturate_first ? 1 : 0;
     F.have_u_box = o->u_lower ? 1 : 0; F.have_du_box = o->du_lower ? 1 : 0; F.blocked = L.blocked ? 1 : 0; F.pad = 0;
     F.time_step = o->time_step; F.dt = o->dt; F.proximity = o->goal_proximity;
+    F.collided = (int32_t*)dcol;
     for (int r = 0; r < RKB_MAX_COORDS; ++r) {
       F.u_lo[r] = (o->u_lower && r < nu) ? o->u_lower[r] : 0.0; F.u_hi[r] = (o->u_upper && r < nu) ? o->u_upper[r] : 0.0;
       F.du_lo[r] = (o->du_lower && r < nu) ? o->du_lower[r] : 0.0; F.du_hi[r] = (o->du_upper && r < nu) ? o->du_upper[r] : 0.0;
     }
     CU(cudaEventRecord(ctx->ev0, s));
-    cudaError_t e = c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_STEER, c->sp, &F, nullptr, F.n_samples, 0, s)
+    cudaError_t e = CK ? rkb_jit_launch_source_rollout(*CK, 0, c->sp, &F, F.n_samples, c->n, s)
+                    : c->jit ? rkb_jit_launch(*c->jit, RKB_JIT_STEER, c->sp, &F, nullptr, F.n_samples, 0, s)
                     : use_split(c, F.n_samples) ? c->sk->steer_duo(c->sp, F, s) : c->sk->steer(c->sp, F, s);
     if (e != cudaSuccess) return cuda_fail(e, "steer kernel");
     c->launches += 1;
@@ -1915,6 +1960,48 @@ int rkb_steer_feedback_checked(rkb_chain* c, int device, size_t N, const double*
   if (n_pairs <= 0) return RKB_ERR_INVALID;
   return steer_feedback_impl(c, device, N, x0, x_goal, u_bias, gain, u_prev, o, pairs, n_pairs, x_out, n_done, collided, x_traj,
                              status, flags, stream);
+}
+
+int rkb_steer_checked_specialize(rkb_chain* c, int device, const rkb_proxy* const* pairs, int n_pairs) {
+  if (!c || !pairs || n_pairs < 1) return RKB_ERR_INVALID;
+  for (int p = 0; p < n_pairs; ++p)
+    if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard guard(device);
+  if (!guard.ok) { std::snprintf(g_cuda_err, sizeof g_cuda_err, "cudaSetDevice(%d) failed", device); return RKB_ERR_CUDA; }
+  int rc = RKB_OK;
+  const SourceKernels* K = checked_steer_kernel(c, pairs, n_pairs, 0, true, &rc);
+  if (!K && rc == RKB_OK) rc = RKB_ERR_UNSUPPORTED;
+  if (rc && rc != RKB_ERR_UNSUPPORTED) std::snprintf(g_cuda_err, sizeof g_cuda_err, "run-time compilation failed: %.200s", rkb_jit_log());
+  return rc;
+}
+
+int rkb_steer_checked_source(rkb_chain* c, const rkb_proxy* const* pairs, int n_pairs, char* out, size_t size) {
+  if (!c || !pairs || n_pairs < 1) return RKB_ERR_INVALID;
+  for (int p = 0; p < n_pairs; ++p)
+    if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
+  if (!c->serial_ok || !c->sk || c->n_free) return RKB_ERR_UNSUPPORTED;
+  int coords[RKB_SERIAL_MAX_DOF];
+  for (int s = 0; s < c->n; ++s) coords[s] = c->sp.st[s].coord;
+  std::vector<const ProxProgram*> progs;
+  for (int p = 0; p < n_pairs; ++p) progs.push_back(&pairs[p]->prog);
+  std::string expr;
+  std::string src = rkb_steer_checked_source(c->n, c->serial_fl, c->serial_shape, coords, c->gp, progs.data(), n_pairs, &expr);
+  if (src.empty()) return RKB_ERR_UNSUPPORTED;
+  src += "// kernel: " + expr + "\n";
+  if (out && size > src.size()) std::memcpy(out, src.c_str(), src.size() + 1);
+  else if (out) return RKB_ERR_INVALID;
+  return (int)src.size() + 1;
+}
+
+int rkb_steer_checked_is_specialized(rkb_chain* c, const rkb_proxy* const* pairs, int n_pairs) {
+  if (!c || !pairs || n_pairs < 1) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  std::vector<unsigned long long> key;
+  for (int p = 0; p < n_pairs; ++p) { if (!pairs[p]) return 0; key.push_back(pairs[p]->serial); }
+  for (const auto& e : c->checked)
+    if (e.key == key && e.K) return 1;
+  return 0;
 }
 
 /* A = d xdot / d x (2n x 2n) and B = d xdot / d u (2n x n_inputs) about (x[i], u[i]) by central differences of

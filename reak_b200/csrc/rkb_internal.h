@@ -78,11 +78,18 @@ struct SourceKernels {
 };
 #ifdef __cplusplus
 #include <string>
-int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out);
-int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out);
+// lowered: `names` are C++ name expressions of templates to instantiate (else the extern "C" names themselves)
+int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, bool lowered, const SourceKernels** out);
+int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, bool lowered, const SourceKernels** out);
+cudaError_t rkb_jit_launch_source_rollout(const SourceKernels& K, int which, const SerialParams& P, const void* args, long long n_samples, int n,
+                                          cudaStream_t s);
 // rkb_prox_jit.cu: the source of the proximity kernels (rkb_prox_spec_d: distance and finder, rkb_prox_spec_p: with the two
 // points) of one chain and one proxy pair; empty when the chain cannot be written as straight-line code
 std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int min_blocks);
+// the source of serial_steer_kernel<n, fl, shape, RkbSteerCheck>: the steering loop with the collision test of the pairs
+// compiled in; *expr: the kernel's name expression
+std::string rkb_steer_checked_source(int n, int fl, unsigned long long shape, const int* coord_of_stage, const GenericProgram& G,
+                                     const ProxProgram* const* pairs, int n_pairs, std::string* expr);
 #endif
 
 // steering law between two control intervals (rkb_steer.cu)

@@ -376,11 +376,11 @@ std::string source_stem(const char* prefix, const std::string& src) {
   std::snprintf(buf, sizeof buf, "%s-%016llx", prefix, h);
   return buf;
 }
-Job source_job(const std::string& stem, const std::string& src, const char* const* names, int n_names) {
+Job source_job(const std::string& stem, const std::string& src, const char* const* names, int n_names, bool lowered) {
   Job j;
   j.stem = stem;
   j.src = src;
-  j.lowered = false;
+  j.lowered = lowered;
   for (int k = 0; k < n_names; ++k) j.exprs.push_back(names[k]);
   return j;
 }
@@ -408,7 +408,7 @@ const SourceKernels* src_publish(const std::string& stem, SourceKernels* S) {  /
 }  // namespace
 
 // Synchronous: this process's table, else the disk cache, else NVRTC now.
-int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out) {
+int rkb_jit_source_get(const char* prefix, const std::string& src, const char* const* names, int n_names, bool lowered, const SourceKernels** out) {
   if (n_names < 1 || n_names > RKB_SRC_MAX_KERNELS) return RKB_ERR_INVALID;
   const std::string stem = source_stem(prefix, src);
   {
@@ -417,7 +417,7 @@ int rkb_jit_source_get(const char* prefix, const std::string& src, const char* c
     if (it != g_src_cache.end()) { *out = it->second; return RKB_OK; }
   }
   g_log.clear();
-  const Job job = source_job(stem, src, names, n_names);
+  const Job job = source_job(stem, src, names, n_names, lowered);
   Cubin c;
   bool cached = cache_read(stem, n_names, c);
   if (!cached) {
@@ -439,7 +439,7 @@ int rkb_jit_source_get(const char* prefix, const std::string& src, const char* c
 }
 
 // Asynchronous, like rkb_jit_poll: *out == NULL while a background compilation (started by the first call) runs.
-int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, const SourceKernels** out) {
+int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* const* names, int n_names, bool lowered, const SourceKernels** out) {
   *out = nullptr;
   if (n_names < 1 || n_names > RKB_SRC_MAX_KERNELS) return RKB_ERR_INVALID;
   const std::string stem = source_stem(prefix, src);
@@ -467,7 +467,7 @@ int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* 
       p = std::make_shared<SrcPending>();
       g_src_pending[stem] = p;
       if (!g_atexit) { std::atexit(join_all); g_atexit = true; }
-      const Job job = source_job(stem, src, names, n_names);
+      const Job job = source_job(stem, src, names, n_names, lowered);
       g_threads.emplace_back([job, p]() {
         Cubin c;
         std::string log;
@@ -498,6 +498,19 @@ int rkb_jit_source_poll(const char* prefix, const std::string& src, const char* 
   }
   *out = src_publish(stem, S);
   return RKB_OK;
+}
+
+// a generated serial-chain kernel taking (SerialParams, args) with the rollout kernels' shared-memory layout
+cudaError_t rkb_jit_launch_source_rollout(const SourceKernels& K, int which, const SerialParams& P, const void* args, long long n_samples, int n,
+                                          cudaStream_t s) {
+  if (n_samples <= 0) return cudaSuccess;
+  const int smem = RKB_SMEM_ROLLOUT(n) * RKB_BLOCK * (int)sizeof(double);
+  // (per device and cheap: the opt-in to more than 48 KB of dynamic shared memory)
+  const cudaError_t e = cudaFuncSetAttribute(K.kernel[which], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  void* argv[2] = {const_cast<SerialParams*>(&P), const_cast<void*>(args)};
+  const unsigned grid = (unsigned)((n_samples + RKB_BLOCK - 1) / RKB_BLOCK);
+  return cudaLaunchKernel(K.kernel[which], dim3(grid), dim3(RKB_BLOCK), argv, smem, s);
 }
 
 cudaError_t rkb_jit_launch(const JitKernels& J, int which, const SerialParams& P, const void* args, const void* extra, long long n_samples,

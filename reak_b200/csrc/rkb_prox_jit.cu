@@ -129,9 +129,10 @@ bool has_finder(int ka, int kb) {  // proxy_query_model.cpp:212-384
 
 }  // namespace
 
-// min_blocks: CTAs of 128 threads per SM the kernels are compiled for (register budget 65536 / (128 min_blocks))
-std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int min_blocks) {
-  std::lock_guard<std::mutex> lock(g_gen_mu);
+namespace {
+// `namespace <ns> { tables, prox_spec<PTS>(q, freec, bestR) }` of one chain and pair (inside the caller's anonymous
+// namespace); empty when the chain cannot be written as straight-line code.  g_gen_mu held.
+std::string prox_body(const GenericProgram& G, const ProxProgram& P, const char* ns) {
   std::vector<double> pool;
   g_pool = &pool;
   struct Reset { ~Reset() { g_pool = nullptr; } } reset;
@@ -226,11 +227,10 @@ std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int m
     e.f("    bestR = prox_compute_kd<true>(KIND[a], v3(DIMS[3 * a], DIMS[3 * a + 1], DIMS[3 * a + 2]), SP[a], KIND[b], "
         "v3(DIMS[3 * b], DIMS[3 * b + 1], DIMS[3 * b + 2]), SP[b]);\n  }\n");
   }
-  e.f("  return best;\n}\n}  // namespace\n");
-  e.f("RKB_PROX_SPEC_KERNELS(%d, %d, %d)\n", G.n_coords, G.n_free > 0 ? 1 : 0, min_blocks);
+  e.f("  return best;\n}\n}  // namespace %s\n", ns);
   Emit h;
-  h.f("// generated by reak_b200 (rkb_prox_jit.cu): %d elements, %d + %d shapes\n", G.n_elements, P.n1, P.n2);
-  h.f("#include \"kte_prox_spec.cuh\"\nnamespace {\nRKB_PROX_SPEC_TABLE double C[%d] = {", (int)(pool.size() ? pool.size() : 1));
+  h.f("// %d elements, %d + %d shapes\nnamespace %s {\n", G.n_elements, P.n1, P.n2, ns);
+  h.f("RKB_PROX_SPEC_TABLE double C[%d] = {", (int)(pool.size() ? pool.size() : 1));
   for (size_t k = 0; k < pool.size(); ++k) h.f("%s%a", k ? ", " : "", pool[k]);
   if (pool.empty()) h.f("0.0");
   h.f("};\n");
@@ -244,4 +244,57 @@ std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int m
     h.f("};\n");
   }
   return h.s + e.s;
+}
+}  // namespace
+
+// The two query kernels (kte_prox_spec.cuh: RKB_PROX_SPEC_KERNELS) of one chain and pair.
+// min_blocks: CTAs of 128 threads per SM the kernels are compiled for (register budget 65536 / (128 min_blocks))
+std::string rkb_prox_source(const GenericProgram& G, const ProxProgram& P, int min_blocks) {
+  std::lock_guard<std::mutex> lock(g_gen_mu);
+  const std::string body = prox_body(G, P, "pair0");
+  if (body.empty()) return body;
+  Emit e;
+  e.f("// generated by reak_b200 (rkb_prox_jit.cu)\n#include \"kte_prox_spec.cuh\"\nnamespace {\n");
+  e.s += body;
+  e.f("using pair0::prox_spec;\n}  // namespace\nRKB_PROX_SPEC_KERNELS(%d, %d, %d)\n", G.n_coords, G.n_free > 0 ? 1 : 0, min_blocks);
+  return e.s;
+}
+
+// serial_steer_kernel<n, fl, shape, RkbSteerCheck> (kte_serial.cuh) with the collision test of `n_pairs` proxy pairs
+// compiled in: the whole checked steering loop in one launch.  coord_of_stage: SerialParams::st[s].coord.  `expr` receives
+// the name expression of the kernel.  Serial chains have no free joint.
+std::string rkb_steer_checked_source(int n, int fl, unsigned long long shape, const int* coord_of_stage, const GenericProgram& G,
+                                     const ProxProgram* const* pairs, int n_pairs, std::string* expr) {
+  std::lock_guard<std::mutex> lock(g_gen_mu);
+  if (G.n_free > 0 || G.n_coords != n || n_pairs < 1) return std::string();
+  Emit e;
+  e.f("// generated by reak_b200 (rkb_prox_jit.cu): checked steering, %d proxy pair(s)\n", n_pairs);
+  e.f("#include \"kte_serial.cuh\"\n#include \"kte_prox_spec.cuh\"\nnamespace {\n");
+  for (int p = 0; p < n_pairs; ++p) {
+    char ns[16];
+    std::snprintf(ns, sizeof ns, "pair%d", p);
+    const std::string body = prox_body(G, *pairs[p], ns);
+    if (body.empty()) return body;
+    e.s += body;
+  }
+  // fewer_blocks = 1: the kernel gives up one CTA per SM (4 -> 3 for the 6- and 7-joint arms) so that the test's forward
+  // kinematics and finders get their registers.  Measured on the CRS arm against the MD148 lab, 2^18 tuples x 10 intervals
+  // (unchecked loop 5.29 ms): inlined at the rollout kernel's occupancy 7.55 ms, as a real call 8.24, inlined with one CTA
+  // fewer 6.81, a real call with one CTA fewer 7.44; interval by interval (four launches each) 7.08.  Chains of 7 and 8
+  // coordinates already run at 3 CTAs per SM and keep them (7-joint arm: 8.20 ms against 8.41 interval by interval).
+  e.f("}  // namespace\nstruct RkbSteerCheck {\n  static constexpr bool enabled = true;\n  static constexpr int fewer_blocks = %d;\n", n <= 6 ? 1 : 0);
+  e.f("  template <int N> __device__ __forceinline__ static bool is_free(");
+  e.f("const rkb::SerialState<N>& X) {\n    double q[%d];\n", n);
+  for (int s = 0; s < n; ++s) {
+    if (coord_of_stage[s] < 0 || coord_of_stage[s] >= n) return std::string();
+    e.f("    q[%d] = X.q[%d];\n", coord_of_stage[s], s);
+  }
+  e.f("    const Pose freec = pose_of(v3(0.0, 0.0, 0.0), q4(1.0, 0.0, 0.0, 0.0));\n    ProxRecord R;\n");
+  // is_free_impl (MEAQR_topology.hpp:921-940): no pair with a negative minimum distance
+  for (int p = 0; p < n_pairs; ++p) e.f("    pair%d::prox_spec<false>(q, freec, R);\n    if (R.d < 0.0) return false;\n", p);
+  e.f("    return true;\n  }\n};\n");
+  char buf[160];
+  std::snprintf(buf, sizeof buf, "rkb::serial_steer_kernel<%d, %d, %lluull, RkbSteerCheck>", n, fl, shape);
+  *expr = buf;
+  return e.s;
 }

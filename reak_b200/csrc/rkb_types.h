@@ -160,6 +160,7 @@ struct SteerArgs {
   int32_t       nu, max_intervals, substeps, saturate_first, have_u_box, have_du_box, blocked, pad;
   double        time_step, dt, proximity;
   double        u_lo[RKB_MAX_COORDS], u_hi[RKB_MAX_COORDS], du_lo[RKB_MAX_COORDS], du_hi[RKB_MAX_COORDS];
+  int32_t*      collided;  // [N], kernels generated with a collision test only (else unused): 1 when the loop stopped on a state that was not free
 };
 
 // One pass of the steering loop head (rkb_steer.cu), all buffers device-resident AoS

@@ -546,6 +546,30 @@ class kte_batch_propagator(object):
             return xo, up, nd, tr[:, :int(max_intervals)], st
         return xo, up, nd, st
 
+    # ---- checked steering in one launch (rkb_steer_checked_specialize) ----------------------------
+    def _pair_array(self, proxy_pairs):
+        hs = [self.proxy_handle(pair)._h for pair in proxy_pairs]
+        return (C.c_void_p * len(hs))(*hs), len(hs)
+
+    def specialize_checked_steering(self, proxy_pairs):
+        """compile the steering kernel with the collision test of these pairs built in (NVRTC, now)"""
+        arr, n = self._pair_array(proxy_pairs)
+        _abi.check(self._lib.rkb_steer_checked_specialize(self._h, self.device, arr, n), "rkb_steer_checked_specialize")
+        return self
+
+    def checked_steering_is_specialized(self, proxy_pairs):
+        arr, n = self._pair_array(proxy_pairs)
+        return bool(self._lib.rkb_steer_checked_is_specialized(self._h, arr, n))
+
+    def checked_steering_source(self, proxy_pairs):
+        """the CUDA source rkb_steer_checked_specialize compiles; its last line names the kernel (test hook)"""
+        arr, n = self._pair_array(proxy_pairs)
+        size = self._lib.rkb_steer_checked_source(self._h, arr, n, None, 0)
+        _abi.check(min(size, 0), "rkb_steer_checked_source")
+        buf = C.create_string_buffer(size)
+        _abi.check(min(self._lib.rkb_steer_checked_source(self._h, arr, n, buf, size), 0), "rkb_steer_checked_source")
+        return buf.value.decode()
+
     # ---- instrumentation ----------------------------------------------------------------------
     def last_kernel_ms(self):
         return self._lib.rkb_last_kernel_ms(self._h)

@@ -445,11 +445,48 @@ def test_generated_source_is_keyed_by_its_constants(spec_tmp):
     assert c.source != a.source and "RKB_PROX_SPEC_KERNELS(6, 0, 5)" in c.source
 
 
+def test_checked_steering_source_builds_for_sm_100a(spec_tmp):
+    """the source rkb_steer_checked_specialize hands to NVRTC — kte_serial.cuh's steering kernel with the generated collision
+    test of two pairs as its CHK parameter — compiles with nvcc for sm_100a (cross-compilation, no GPU needed)"""
+    import shutil
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    from reak_b200.propagator import kte_batch_propagator
+    s = presets.make("crs7")
+    P = kte_batch_propagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    robot, lab = presets.crs_proxy_models(s, track=True)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    extra = px.proxy_query_pair_3D("tool-obstacle", px.proxy_query_model_3D("tool").addShape(px.sphere("tool", s.joint_end_frames[-1], None, 0.12)),
+                                   px.proxy_query_model_3D("obstacle").addShape(px.box("crate", None, px.pose_3D((0.3, -3.0, 0.9)), (0.5, 0.5, 0.5))))
+    src = P.checked_steering_source([pair, extra])
+    expr = src.strip().splitlines()[-1].split("// kernel: ")[1]
+    assert expr.startswith("rkb::serial_steer_kernel<7, ") and expr.endswith("RkbSteerCheck>")
+    assert "pair0::prox_spec<false>" in src and "pair1::prox_spec<false>" in src
+    cu = os.path.join(spec_tmp, "steerchk.cu")
+    with open(cu, "w") as f:
+        f.write(src + "template __global__ void %s(const __grid_constant__ SerialParams, const __grid_constant__ SteerArgs);\n" % expr)
+    r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-cubin", "-I", os.path.join(HERE, "..", "reak_b200", "csrc"),
+                        "-o", os.path.join(spec_tmp, "steerchk.cubin"), cu], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # an interpreter chain has no steering kernel to build the test into
+    s2 = presets.make("crs6_lin_sd")
+    P2 = kte_batch_propagator(s2.chain, s2.mass_calc, s2.dofs_gen, s2.inputs)
+    if not P2.is_serial():
+        robot2, lab2 = presets.crs_proxy_models(s2)
+        with pytest.raises(Exception):
+            P2.checked_steering_source([px.proxy_query_pair_3D("robot-lab", robot2, lab2)])
+
+
 # ---- GPU ------------------------------------------------------------------------------------------
-def _gpu_prop(preset):
+def _gpu_prop(preset, auto=False):
+    """auto = False: no kernels compiled in the background (they would take over between two calls of a test that compares
+    results bit for bit); the tests of the generated kernels ask for them explicitly"""
     from reak_b200.propagator import kte_batch_propagator
     s = presets.make(preset)
-    return s, kte_batch_propagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    P = kte_batch_propagator(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    if not auto:
+        P.set_option("auto_specialize", 0)
+    return s, P
 
 
 @pytest.mark.gpu
@@ -536,11 +573,12 @@ def test_gpu_specialized_crs_lab(preset, track, oracle_built):
     assert not h.is_specialized()
     h.specialize()
     assert h.is_specialized()
-    got = P.get_min_distances(pair, x)
+    d_only, f_only = P.get_min_distances(pair, x, with_points=False)   # the generated kernel
+    fin = np.isfinite(want[0])
+    assert np.max(np.abs(d_only[fin] - want[0][fin])) < TOL and np.all((f_only == want[1]) | (np.abs(d_only - want[0]) < TOL))
+    assert np.max(np.abs(d_only - before[0])) < 1e-12 and np.all((f_only == before[1]) | (np.abs(d_only - before[0]) < 1e-12))
+    got = P.get_min_distances(pair, x)                                 # with the two points: the interpreter kernel
     agree(got, want, TOL)
-    _same(got, before, 1e-12)
-    d_only, f_only = P.get_min_distances(pair, x, with_points=False)
-    assert np.max(np.abs(d_only - got[0])) < 1e-12 and np.array_equal(f_only, got[1])   # two kernels, the same search
     assert np.array_equal(P.is_free([pair], x), free_before) and np.array_equal(free_before, ~(want[0] < 0.0))
 
 
@@ -561,7 +599,9 @@ def test_gpu_specialized_free_base_and_layouts():
     """a free-floating base in front of the arm (the pose states of free_joint_3D feed the kinematics), device-resident
     and structure-of-arrays buffers: generated kernel against the interpreter kernel"""
     import torch
-    s, P = _gpu_prop("free_arm6")
+    from reak_b200.propagator import kte_batch_propagator
+    s = presets.make("free_arm6")
+    P = kte_batch_propagator(s).set_option("auto_specialize", 0)
     rng = np.random.default_rng(9)
     m1, m2 = px.proxy_query_model_3D("arm"), px.proxy_query_model_3D("world")
     kinds = sorted(KINDS)
@@ -573,12 +613,12 @@ def test_gpu_specialized_free_base_and_layouts():
     h = P.proxy_handle(pair)
     h.set_option(h.OPT_AUTO_SPECIALIZE, 0)
     x = rng.uniform(-1.0, 1.0, (3000, P.nx))
-    before = P.get_min_distances(pair, x)
+    d0, f0 = P.get_min_distances(pair, x, with_points=False)
     dx = torch.from_numpy(x).cuda()
     h.specialize()
-    _same(P.get_min_distances(pair, x), before, 1e-6)
-    d, f, pts = P.get_min_distances(pair, dx)
-    _same((d.cpu().numpy(), f.cpu().numpy(), pts.cpu().numpy()), before, 1e-6)
+    for d, f in (P.get_min_distances(pair, x, with_points=False), tuple(a.cpu().numpy() for a in P.get_min_distances(pair, dx, with_points=False))):
+        assert np.max(np.abs(d - d0)) < 1e-6 and np.all((f == f0) | (np.abs(d - d0) < 1e-6))
+    assert (d0 < 0).any() and (d0 > 0).any()
 
 
 @pytest.mark.gpu
@@ -586,22 +626,22 @@ def test_gpu_proxy_auto_specialize():
     """default behaviour: the first query of >= 4096 states starts the compilation in the background, queries made
     meanwhile run on the interpreter, later ones on the generated kernel — same answers throughout"""
     import time
-    s, P = _gpu_prop("crs6")
+    s, P = _gpu_prop("crs6", auto=True)
     robot, lab = presets.crs_proxy_models(s)
     lab.mShapeList[0].pose.position = (0.013, 0.0, 0.0)   # a pair no other test has put into the cubin cache
     pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
     h = P.proxy_handle(pair)
     x, _ = random_batch(P.compiled, 8192, seed=2, q_range=3.0)
-    small = P.get_min_distances(pair, x[:100])
+    small = P.get_min_distances(pair, x[:100], with_points=False)
     assert not h.is_specialized()
-    first = P.get_min_distances(pair, x)
+    first = P.get_min_distances(pair, x, with_points=False)
     t0 = time.time()
     while not h.is_specialized() and time.time() - t0 < 180:
         time.sleep(0.2)
-        P.get_min_distances(pair, x)
+        P.get_min_distances(pair, x, with_points=False)
     assert h.is_specialized(), "no generated kernel after 180 s"
-    _same(P.get_min_distances(pair, x), first, 1e-12)
-    _same(P.get_min_distances(pair, x[:100]), small, 1e-12)
+    for got, was in ((P.get_min_distances(pair, x, with_points=False), first), (P.get_min_distances(pair, x[:100], with_points=False), small)):
+        assert np.max(np.abs(got[0] - was[0])) < 1e-12 and np.all((got[1] == was[1]) | (np.abs(got[0] - was[0]) < 1e-12))
 
 
 @pytest.mark.gpu
@@ -684,6 +724,68 @@ def test_gpu_steer_feedback_checked_vs_reference(preset, track, oracle_built):
     b = P.steer_feedback(*args, want_traj=True, **kw)
     assert not a[5].any() and np.array_equal(a[2], b[2])
     assert np.max(np.abs(a[0] - b[0])) < 1e-10 and np.max(np.abs(a[1] - b[1])) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True), ("crs6_sd", False)])
+def test_gpu_steer_checked_one_launch_vs_reference(preset, track, oracle_built):
+    """rkb_steer_checked_specialize: the steering kernel compiled with the collision test of the pairs built in — against
+    the live reference's checked loop and against the interval-by-interval path"""
+    need_ref(oracle_built)
+    s, P = _gpu_prop(preset)
+    robot, lab = presets.crs_proxy_models(s, track=track)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    je = s.joint_end_frames
+    extra = px.proxy_query_pair_3D("tool-obstacle", px.proxy_query_model_3D("tool").addShape(px.sphere("tool", je[-1], None, 0.12)),
+                                   px.proxy_query_model_3D("obstacle").addShape(px.box("crate", None, px.pose_3D((0.3, -3.0, 0.9)), (0.5, 0.5, 0.5))))
+    R = oracle_built.Reference(P.compiled)
+    n, J = 500, 8
+    x0, goal, u_bias, gain, u_prev = _steer_case(P, n, seed=9)
+    kw = dict(bounds=(-2 * np.ones(P.nu), 2 * np.ones(P.nu)), rate_bounds=(-60 * np.ones(P.nu), 60 * np.ones(P.nu)))
+    args = (x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, J, 0.25)
+    for pairs in ([pair], [pair, extra]):
+        before = P.steer_feedback(*args, want_traj=True, proxy_pairs=pairs, **kw)
+        n_launch = P.launch_count()
+        assert not P.checked_steering_is_specialized(pairs)
+        P.specialize_checked_steering(pairs)
+        assert P.checked_steering_is_specialized(pairs)
+        l0 = P.launch_count()
+        got = P.steer_feedback(*args, want_traj=True, proxy_pairs=pairs, **kw)
+        assert P.launch_count() - l0 == 1 and n_launch > 1, "checked steering is not one launch"
+        _same_loop(got, R.steer_feedback(*args, proxy_pairs=pairs, **kw), J)
+        _same_loop(got, before, J)
+        assert np.array_equal(got[4], before[4])   # status words
+        nd, col = got[2], got[5]
+        assert (col == 1).any() and (col == 0).any() and ((col == 1) & (nd > 0)).any()
+    # without a steer record, and J = 0
+    a = P.steer_feedback(*args, proxy_pairs=[pair], **kw)
+    b = P.steer_feedback(*args, want_traj=True, proxy_pairs=[pair], **kw)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[5])
+    z = P.steer_feedback(x0, goal, u_bias, gain, u_prev, 1e-2, 1e-3, 10, 0, 0.25, proxy_pairs=[pair], **kw)
+    assert np.array_equal(z[0], x0) and not z[2].any() and not z[4].any()
+
+
+@pytest.mark.gpu
+def test_gpu_steer_checked_auto_specialize():
+    """default behaviour: the first checked call of >= 4096 tuples starts the compilation, calls made meanwhile run
+    interval by interval, later ones in one launch — same loops throughout"""
+    import time
+    s, P = _gpu_prop("crs6", auto=True)
+    robot, lab = presets.crs_proxy_models(s)
+    lab.mShapeList[0].pose.position = (0.017, 0.0, 0.0)   # a pair no other test has put into the cubin cache
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    n, J = 4200, 4
+    args = _steer_case(P, n, seed=4) + (1e-2, 1e-3, 10, J, 0.25)
+    first = P.steer_feedback(*args, want_traj=True, proxy_pairs=[pair])
+    t0 = time.time()
+    while not P.checked_steering_is_specialized([pair]) and time.time() - t0 < 180:
+        time.sleep(0.2)
+        P.steer_feedback(*args, want_traj=True, proxy_pairs=[pair])
+    assert P.checked_steering_is_specialized([pair]), "no generated kernel after 180 s"
+    l0 = P.launch_count()
+    later = P.steer_feedback(*args, want_traj=True, proxy_pairs=[pair])
+    assert P.launch_count() - l0 == 1
+    _same_loop(later, first, J)
 
 
 @pytest.mark.gpu
