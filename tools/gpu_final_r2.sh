@@ -31,6 +31,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:near
   python tools/time_nearest.py 12 1048576 4096 1 > $out/ncu_nn_$tag.log 2>&1
 echo "rc=$?"
 for a in "12 1048576 256 1" "12 1048576 65536 1" "12 1048576 4096 8" "19 1048576 4096 1" "6 1048576 4096 1" "25 1048576 4096 1"; do timeout 120 python tools/time_nearest.py $a 2>&1 | tail -1; done
+echo "== proximity: interpreter and generated kernels, checked steering"
+timeout 150 python tools/time_proximity.py crs6 $((1<<20)) 0 2>&1 | tail -6
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rkb_prox_spec_d -s 2 -c 1 -f -o $out/prof_prox_$tag \
+  python tools/time_proximity.py crs6 > $out/ncu_prox_$tag.log 2>&1
+echo "rc=$?"
+timeout 200 python tools/time_steer_checked.py crs6 2>&1 | tail -5
+timeout 200 python tools/time_steer_checked.py crs7 2>&1 | tail -5
 echo "== other entry points"
 for p in crs6 crs6_sd crs7; do timeout 300 python tools/time_ops.py $p 2>&1 | tail -8; done
 timeout 300 python tools/time_rollout.py free_arm6 $((1<<18)) 10 3 2>&1 | tail -1
