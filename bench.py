@@ -370,7 +370,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
         kernel6 = "interpreter (%s)" % e
     t6 = best(prox6, p6)
     e6 = {"config": "proximity", "workload": "findMinimumDistance, CRS arm vs MD148 lab (25 finders): %d states per GPU" % n6,
-          "min_distance_ms": t6, "states_per_gpu": n6, "kernel": kernel6, "interpreter_kernel_ms": t6i}
+          "min_distance_ms": t6, "states_per_gpu": n6, "kernel": kernel6, "interpreter_kernel": {"ms": t6i}}
     if check:
         from oracle import pyref
         if pyref.have_ref():
@@ -410,7 +410,7 @@ def other_configs(torch, presets, kte_batch_propagator, local, world, rank, chec
 
     t7u = best(steer_unchecked, p6)
     out.append({"config": "steer_checked", "workload": "closed-loop steering with collision test: %d tuples x <= %d intervals x 10 RK4 steps per GPU"
-                % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": units7, "kernel": kernel7, "interval_by_interval_ms": t7i,
+                % (m6, J6), "steer_checked_ms": t7, "units_per_gpu": units7, "kernel": kernel7, "interval_by_interval": {"ms": t7i},
                 "unchecked": {"ms": t7u, "state_steps": int(done[0].sum().item()) * 10,
                               "note": "the same tuples without the test (they run on where the checked loop stops at a collision)"}})
     # the nearest-neighbour search that precedes every steer (linear_neighbor_search / dvp_tree), for
