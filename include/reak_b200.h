@@ -328,13 +328,21 @@ RKB_API int rkb_frames(rkb_chain* chain, int device, size_t n_samples,
  * each riding on a frame of the chain (geometry_3D::mAnchor) or fixed in the world, with its own pose relative to
  * that anchor (geometry_3D::mPose).  rkb_proxy pairs two models the way proxy_query_pair_3D does
  * (geometry/proximity/proxy_query_model.hpp): one finder per (shape of model 1, shape of model 2) the reference has
- * a finder for, in createProxFinderList order (proxy_query_model.cpp:212-384).  3D chains only. */
+ * a finder for, in createProxFinderList order (proxy_query_model.cpp:212-384; planar chains with planar shapes:
+ * proxy_query_pair_2D, :73-160). */
 enum rkb_shape_kind {
   RKB_SHAPE_PLANE     = 1,   /* dims: x, y extents (only the culling test looks at them)  plane.hpp      */
   RKB_SHAPE_SPHERE    = 2,   /* dims: radius                                              sphere.hpp     */
   RKB_SHAPE_CCYLINDER = 3,   /* dims: length, radius; axis = local z                      capped_cylinder.hpp */
   RKB_SHAPE_CYLINDER  = 4,   /* dims: length, radius; axis = local z                      cylinder.hpp   */
-  RKB_SHAPE_BOX       = 5    /* dims: x, y, z extents                                     box.hpp        */
+  RKB_SHAPE_BOX       = 5,   /* dims: x, y, z extents                                     box.hpp        */
+  /* planar shapes, for planar chains (proxy_query_pair_2D, proxy_query_model.cpp:73-212): position[0..1] and
+   * quat[0..1] = (cos, sin) of the shape's own rotation (pose_2D: Position, rot_mat_2D), the rest ignored; every pair of
+   * planar shapes has a finder (prox_circle_circle / circle_crect / circle_rectangle / crect_crect / crect_rectangle /
+   * rectangle_rectangle.cpp).  Points come back as (x, y, 0). */
+  RKB_SHAPE_CIRCLE    = 6,   /* dims: radius                                              circle.hpp     */
+  RKB_SHAPE_CRECT     = 7,   /* dims: length along x, width (= diameter of the round caps)  capped_rectangle.hpp */
+  RKB_SHAPE_RECTANGLE = 8    /* dims: x, y extents                                        rectangle.hpp  */
 };
 typedef struct rkb_shape {
   int32_t kind;          /* rkb_shape_kind */

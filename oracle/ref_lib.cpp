@@ -36,6 +36,9 @@
 #include <ReaK/geometry/shapes/capped_cylinder.hpp>
 #include <ReaK/geometry/shapes/cylinder.hpp>
 #include <ReaK/geometry/shapes/box.hpp>
+#include <ReaK/geometry/shapes/circle.hpp>
+#include <ReaK/geometry/shapes/capped_rectangle.hpp>
+#include <ReaK/geometry/shapes/rectangle.hpp>
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
 #include <ReaK/ctrl/graph_alg/node_generators.hpp>
 #include <ReaK/ctrl/kte_models/manip_dynamics_model.hpp>
@@ -663,6 +666,105 @@ int rkref_frames(void* hv, const double* x, const double* u, double* out) {
   return 0;
 }
 
+// ---- planar models (proxy_query_pair_2D, proxy_query_model.cpp:73-212) -----------------------------------------
+namespace {
+struct planar_pair {
+  std::vector<shared_ptr<geom::shape_2D> > shapes;
+  shared_ptr<geom::proxy_query_model_2D> mdl[2];
+  shared_ptr<geom::proxy_query_pair_2D> pair;
+};
+// rkb_shape of a planar shape: position[0..1], quat[0..1] = (cos, sin) of its own rotation
+bool build_planar_pair(ref_model* m, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2, planar_pair& P) {
+  P.mdl[0] = shared_ptr<geom::proxy_query_model_2D>(new geom::proxy_query_model_2D("model1"));
+  P.mdl[1] = shared_ptr<geom::proxy_query_model_2D>(new geom::proxy_query_model_2D("model2"));
+  for (int k = 0; k < n1 + n2; ++k) {
+    const rkb_shape& s = k < n1 ? m1[k] : m2[k - n1];
+    shared_ptr<pose_2D<double> > anchor;
+    if (s.anchor >= 0) anchor = m->f2[s.anchor];
+    const pose_2D<double> pose(weak_ptr<pose_2D<double> >(), vect<double,2>(s.position[0], s.position[1]),
+                               rot_mat_2D<double>(vect<double,2>(s.quat[0], s.quat[1])));
+    shared_ptr<geom::shape_2D> sh;
+    switch (s.kind) {
+      case RKB_SHAPE_CIRCLE: sh = shared_ptr<geom::shape_2D>(new geom::circle("ci", anchor, pose, s.dims[0])); break;
+      case RKB_SHAPE_CRECT: sh = shared_ptr<geom::shape_2D>(new geom::capped_rectangle("cr", anchor, pose, vect<double,2>(s.dims[0], s.dims[1]))); break;
+      case RKB_SHAPE_RECTANGLE: sh = shared_ptr<geom::shape_2D>(new geom::rectangle("re", anchor, pose, vect<double,2>(s.dims[0], s.dims[1]))); break;
+      default: return false;
+    }
+    P.shapes.push_back(sh);
+    P.mdl[k < n1 ? 0 : 1]->addShape(sh);
+  }
+  P.pair = shared_ptr<geom::proxy_query_pair_2D>(new geom::proxy_query_pair_2D("pair", P.mdl[0], P.mdl[1]));
+  return true;
+}
+int min_distance_2d(ref_model* m, std::size_t N, const double* x, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2,
+                    double* dist, int32_t* finder, double* points) {
+  planar_pair P;
+  if (!build_planar_pair(m, m1, n1, m2, n2, P)) return -1;
+  const int nx = m->nx, nu = m->nu;
+  vect_n<double> p(nx), uu(nu);
+  for (int k = 0; k < nu; ++k) uu[k] = 0.0;
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    shared_ptr<geom::proximity_finder_2D> f = P.pair->findMinimumDistance();
+    if (!f) {
+      dist[i] = std::numeric_limits<double>::infinity();
+      if (finder) finder[i] = -1;
+      if (points) for (int k = 0; k < 6; ++k) points[6 * i + k] = 0.0;
+      continue;
+    }
+    const geom::proximity_record_2D r = f->getLastResult();
+    dist[i] = r.mDistance;
+    if (points) {
+      points[6 * i + 0] = r.mPoint1[0]; points[6 * i + 1] = r.mPoint1[1]; points[6 * i + 2] = 0.0;
+      points[6 * i + 3] = r.mPoint2[0]; points[6 * i + 4] = r.mPoint2[1]; points[6 * i + 5] = 0.0;
+    }
+    if (finder) {  // every pair of planar shapes has a finder: index a * n2 + b, found through the finder's two shapes
+      finder[i] = -2;
+      const geom::shape_2D* s1 = f->getShape1().get();
+      const geom::shape_2D* s2 = f->getShape2().get();
+      for (int a = 0; a < n1 && finder[i] < 0; ++a)
+        for (int b = 0; b < n2; ++b) {
+          const geom::shape_2D* sa = P.shapes[a].get();
+          const geom::shape_2D* sb = P.shapes[n1 + b].get();
+          if ((sa == s1 && sb == s2) || (sa == s2 && sb == s1)) { finder[i] = (int32_t)(a * n2 + b); break; }
+        }
+    }
+  }
+  return n1 * n2;
+}
+int collision_points_2d(ref_model* m, std::size_t N, const double* x, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2,
+                        int max_records, int32_t* count, int32_t* finder, double* records) {
+  planar_pair P;
+  if (!build_planar_pair(m, m1, n1, m2, n2, P)) return -1;
+  const int nx = m->nx, nu = m->nu;
+  vect_n<double> p(nx), uu(nu);
+  for (int k = 0; k < nu; ++k) uu[k] = 0.0;
+  for (std::size_t i = 0; i < N; ++i) {
+    for (int k = 0; k < nx; ++k) p[k] = x[i * nx + k];
+    m->sys.apply_states_and_inputs(p, uu);
+    m->chain->doMotion();
+    std::vector<geom::proximity_record_2D> out;
+    P.pair->gatherCollisionPoints(out);
+    count[i] = int32_t(out.size());
+    for (int r = 0; r < max_records; ++r) {
+      double* o = records + (i * max_records + r) * 7;
+      if (r < int(out.size())) {
+        o[0] = out[r].mDistance;
+        o[1] = out[r].mPoint1[0]; o[2] = out[r].mPoint1[1]; o[3] = 0.0;
+        o[4] = out[r].mPoint2[0]; o[5] = out[r].mPoint2[1]; o[6] = 0.0;
+      } else {
+        o[0] = std::numeric_limits<double>::infinity();
+        for (int k = 1; k < 7; ++k) o[k] = 0.0;
+      }
+      if (finder) finder[i * max_records + r] = -1;
+    }
+  }
+  return 0;
+}
+}  // namespace
+
 // proxy_query_pair_3D::findMinimumDistance of the live reference (geometry/proximity/proxy_query_model.cpp)
 // for two proximity models given as rkb_shape lists, the shapes of either riding on frames of this model
 // (anchor = frame id) or fixed in the world (-1), after kte_map_chain::doMotion at each state x[i].
@@ -671,6 +773,7 @@ int rkref_min_distance(void* hv, std::size_t N, const double* x, const rkb_shape
                        double* dist, int32_t* finder, double* points) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
+  if (h->desc.dim == 2) return min_distance_2d(m, N, x, m1, n1, m2, n2, dist, finder, points);
   if (h->desc.dim != 3) return -1;
   const int nx = m->nx, nu = m->nu;
   std::vector<shared_ptr<geom::shape_3D> > shapes;
@@ -743,6 +846,7 @@ int rkref_collision_points(void* hv, std::size_t N, const double* x, const rkb_s
                            int max_records, int32_t* count, int32_t* finder, double* records) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
+  if (h->desc.dim == 2) return collision_points_2d(m, N, x, m1, n1, m2, n2, max_records, count, finder, records);
   if (h->desc.dim != 3) return -1;
   const int nx = m->nx, nu = m->nu;
   std::vector<shared_ptr<geom::shape_3D> > shapes;

@@ -51,6 +51,7 @@ class rkb_shape(C.Structure):
 
 
 SHAPE_PLANE, SHAPE_SPHERE, SHAPE_CCYLINDER, SHAPE_CYLINDER, SHAPE_BOX = 1, 2, 3, 4, 5
+SHAPE_CIRCLE, SHAPE_CRECT, SHAPE_RECTANGLE = 6, 7, 8   # planar shapes (planar chains)
 PROXY_MAX_SHAPES = 16
 
 

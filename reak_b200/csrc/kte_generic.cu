@@ -24,18 +24,6 @@ namespace {
 #include "kte_math.cuh"
 
 struct Fr3 { V3 p; Q4 q; V3 v, w, a, al, F, T; };
-struct V2 { double x, y; };
-GD V2 v2(double x, double y) { V2 r; r.x = x; r.y = y; return r; }
-GD V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
-GD V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
-GD V2 operator*(double s, V2 a) { return v2(s * a.x, s * a.y); }
-GD double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
-GD double cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }   // vect_alg.hpp:1142
-GD V2 crs(double s, V2 v) { return v2(-v.y * s, v.x * s); }     // vect_alg.hpp:1171
-struct R2 { double c, s; };
-GD V2 rmul(R2 R, V2 v) { return v2(v.x * R.c - v.y * R.s, v.x * R.s + v.y * R.c); }    // rotations_2D.hpp:292
-GD V2 rtmul(R2 R, V2 v) { return v2(v.x * R.c + v.y * R.s, v.y * R.c - v.x * R.s); }   // rotations_2D.hpp:300 (v * R)
-GD R2 rr(R2 a, R2 b) { R2 r; r.c = a.c * b.c - a.s * b.s; r.s = a.s * b.c + a.c * b.s; return r; }
 struct Fr2 { V2 p; R2 R; V2 v; double w; V2 a; double al; V2 F; double T; };
 
 template <int DIM> struct FrameOf;
@@ -1029,6 +1017,104 @@ __global__ void __launch_bounds__(GEN_BLOCK) generic_collision_kernel(const Gene
   A.status[i] = n;
 }
 
+#include "kte_proximity2d.cuh"
+
+// doMotion of a planar chain at position level (revolute_joint.cpp:32-58, prismatic_joint.cpp:33-67, free_joints.cpp:33-41,
+// rigid_link.cpp:87-99: the Position / Rotation lines of motion() above), frames kept as motion_pose keeps them
+template <int MAXS>
+GD void motion_pose2(const GenericProgram* G, const ProxProgram& P, const double* q, const Pose2& freec, Pose2 (&slots)[MAXS]) {
+  Pose2 cur;
+  {
+    const double* b = G->base;
+    cur.p = v2(b[0], b[1]); cur.R.c = b[3]; cur.R.s = b[4];
+  }
+  int last = G->base_frame;
+  if (P.slot_of[last] >= 0) slots[P.slot_of[last]] = cur;
+  for (int e = 0; e < G->n_elements; ++e) {
+    const GenericElement& E = G->el[e];
+    if (E.kind != RKB_REVOLUTE_2D && E.kind != RKB_PRISMATIC_2D && E.kind != RKB_RIGID_LINK_2D && E.kind != RKB_FREE_2D) continue;
+    Pose2 B = cur;
+    if (E.fa != last) B = slots[P.slot_of[E.fa]];
+    if (E.kind == RKB_REVOLUTE_2D) {
+      R2 rq;
+      sincos(q[E.coord], &rq.s, &rq.c);
+      cur.p = B.p;
+      cur.R = rr(B.R, rq);
+    } else if (E.kind == RKB_PRISMATIC_2D) {
+      cur.p = B.p + rmul(B.R, q[E.coord] * v2(E.p[0], E.p[1]));
+      cur.R = B.R;
+    } else if (E.kind == RKB_FREE_2D) {
+      cur.p = B.p + rmul(B.R, freec.p);
+      cur.R = rr(B.R, freec.R);
+    } else {
+      R2 ro; ro.c = E.p[3]; ro.s = E.p[4];
+      cur.p = B.p + rmul(B.R, v2(E.p[0], E.p[1]));
+      cur.R = rr(B.R, ro);
+    }
+    last = E.fb;
+    if (P.slot_of[last] >= 0) slots[P.slot_of[last]] = cur;
+  }
+}
+
+template <int MAXS>
+GD void prox_load2(const GenericProgram* G, const ProxProgram& P, const EvalArgs& A, long long i, Pose2 (&fr)[MAXS]) {
+  double q[MAXC];
+  for (int c = 0; c < G->n_coords; ++c) q[c] = A.x.p[i * A.x.si + rkb_state_q(A.x.blocked, G->n_coords, c) * A.x.sk];
+  Pose2 freec;
+  freec.p = v2(0, 0); freec.R.c = 1.0; freec.R.s = 0.0;
+  if (G->n_free) {  // position and (cos, sin) states of the free_joint_2D, normalised as apply_free does
+    double s[4];
+    for (int k = 0; k < 4; ++k) s[k] = A.x.p[i * A.x.si + (2 * G->n_coords + k) * A.x.sk];
+    const double nr = sqrt(s[2] * s[2] + s[3] * s[3]);
+    freec.p = v2(s[0], s[1]);
+    freec.R.c = s[2] / nr; freec.R.s = s[3] / nr;
+  }
+  motion_pose2(G, P, q, freec, fr);
+}
+
+// proxy_query_pair_2D::findMinimumDistance (proxy_query_model.cpp:163-190) at the pose of state x[i]; points as (x, y, 0)
+template <int MAXS>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_proximity2d_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
+                                                                         const __grid_constant__ ProxProgram P) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Pose2 fr[MAXS];
+  prox_load2(G, P, A, i, fr);
+  ProxRecord2 R;
+  const int best = prox_min_distance2(P, fr, R);
+  A.out.p[i * A.out.si] = R.d;
+  if (A.status) A.status[i] = best;
+  if (A.out2.p) {
+    const double v[6] = {R.p1.x, R.p1.y, 0.0, R.p2.x, R.p2.y, 0.0};
+    for (int k = 0; k < 6; ++k) A.out2.p[i * A.out2.si + k * A.out2.sk] = v[k];
+  }
+}
+
+// proxy_query_pair_2D::gatherCollisionPoints (proxy_query_model.cpp:192-212); buffers as generic_collision_kernel
+template <int MAXS>
+__global__ void __launch_bounds__(GEN_BLOCK) generic_collision2d_kernel(const GenericProgram* __restrict__ G, const EvalArgs A,
+                                                                         const __grid_constant__ ProxProgram P, int max_records,
+                                                                         int32_t* __restrict__ finder) {
+  const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
+  if (i >= A.n_samples) return;
+  Pose2 fr[MAXS];
+  prox_load2(G, P, A, i, fr);
+  double* rec = A.out.p + i * (long long)max_records * 7;
+  int32_t* fnd = finder ? finder + i * (long long)max_records : (int32_t*)0;
+  const int n = prox_gather_collisions2(P, fr, max_records, [&](int r, int f, const ProxRecord2& R) {
+    double* o = rec + 7 * r;
+    o[0] = R.d; o[1] = R.p1.x; o[2] = R.p1.y; o[3] = 0.0; o[4] = R.p2.x; o[5] = R.p2.y; o[6] = 0.0;
+    if (fnd) fnd[r] = f;
+  });
+  for (int r = n; r < max_records; ++r) {
+    double* o = rec + 7 * r;
+    o[0] = INFINITY;
+    for (int k = 1; k < 7; ++k) o[k] = 0.0;
+    if (fnd) fnd[r] = -1;
+  }
+  A.status[i] = n;
+}
+
 template <int DIM, int MAXF>
 __global__ void __launch_bounds__(GEN_BLOCK) generic_tmt_kernel(const GenericProgram* __restrict__ G, const EvalArgs A) {
   const long long i = (long long)blockIdx.x * GEN_BLOCK + threadIdx.x;
@@ -1246,7 +1332,11 @@ cudaError_t rkb_generic_frames(const GenericProgram* prog, const GenericProgram&
 cudaError_t rkb_generic_proximity(const GenericProgram* prog, const GenericProgram& host, const EvalArgs& a, const ProxProgram& pp, cudaStream_t s) {
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
-  if (host.dim != 3) return cudaErrorInvalidValue;
+  if (host.dim == 2) {  // planar models (kte_proximity2d.cuh)
+    if (pp.n_slots <= 16) generic_proximity2d_kernel<16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+    else generic_proximity2d_kernel<RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
+    return cudaGetLastError();
+  }
   // 6 resident CTAs per SM (80 registers): measured best of 3 / 4 / 5 / 6
   if (pp.n_slots <= 8) generic_proximity_kernel<3, 8, 6><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
   else generic_proximity_kernel<3, RKB_GEN_MAX_FRAMES, 4><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp);
@@ -1257,6 +1347,11 @@ cudaError_t rkb_generic_collisions(const GenericProgram* prog, const GenericProg
   (void)host;
   const long long n = a.n_samples;
   if (n <= 0) return cudaSuccess;
+  if (host.dim == 2) {
+    if (pp.n_slots <= 16) generic_collision2d_kernel<16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
+    else generic_collision2d_kernel<RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
+    return cudaGetLastError();
+  }
   if (pp.n_slots <= 8) generic_collision_kernel<3, 8><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
   else if (pp.n_slots <= 16) generic_collision_kernel<3, 16><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);
   else generic_collision_kernel<3, RKB_GEN_MAX_FRAMES><<<grid_of(n), GEN_BLOCK, 0, s>>>(prog, a, pp, max_records, finder);

@@ -56,3 +56,17 @@ GD M3 aa_rot(double angle, V3 a) {  // axis_angle::getRotMat, rotations_3D.hpp:2
   R.m[6] = t13 - t02; R.m[7] = t23 + t01; R.m[8] = ca + omc * a.z * a.z;
   return R;
 }
+
+// planar vectors and rotations
+struct V2 { double x, y; };
+GD V2 v2(double x, double y) { V2 r; r.x = x; r.y = y; return r; }
+GD V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+GD V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+GD V2 operator*(double s, V2 a) { return v2(s * a.x, s * a.y); }
+GD double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+GD double cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }   // vect_alg.hpp:1142
+GD V2 crs(double s, V2 v) { return v2(-v.y * s, v.x * s); }     // vect_alg.hpp:1171
+struct R2 { double c, s; };
+GD V2 rmul(R2 R, V2 v) { return v2(v.x * R.c - v.y * R.s, v.x * R.s + v.y * R.c); }    // rotations_2D.hpp:292
+GD V2 rtmul(R2 R, V2 v) { return v2(v.x * R.c + v.y * R.s, v.y * R.c - v.x * R.s); }   // rotations_2D.hpp:300 (v * R)
+GD R2 rr(R2 a, R2 b) { R2 r; r.c = a.c * b.c - a.s * b.s; r.s = a.s * b.c + a.c * b.s; return r; }

@@ -940,6 +940,24 @@ bool prox_pair_has_finder(int ka, int kb) {  // proxy_query_model.cpp:212-384
   if (lo == RKB_SHAPE_CCYLINDER) return hi == RKB_SHAPE_CCYLINDER || hi == RKB_SHAPE_BOX;
   return false;
 }
+bool lower_shape_2d(const rkb_shape& in, int n_frames, ProxShape* out) {
+  if (in.kind < RKB_SHAPE_CIRCLE || in.kind > RKB_SHAPE_RECTANGLE) return false;
+  if (in.anchor < -1 || in.anchor >= n_frames) return false;
+  const int nd = in.kind == RKB_SHAPE_CIRCLE ? 1 : 2;
+  for (int k = 0; k < nd; ++k)
+    if (!(in.dims[k] > 0.0) || !std::isfinite(in.dims[k])) return false;
+  if (!std::isfinite(in.position[0]) || !std::isfinite(in.position[1]) || !std::isfinite(in.quat[0]) || !std::isfinite(in.quat[1])) return false;
+  if (std::fabs(in.quat[0] * in.quat[0] + in.quat[1] * in.quat[1] - 1.0) > 1e-6) return false;
+  std::memset(out, 0, sizeof *out);
+  out->kind = in.kind;
+  out->anchor = in.anchor;
+  out->pos[0] = in.position[0]; out->pos[1] = in.position[1];
+  out->quat[0] = in.quat[0]; out->quat[1] = in.quat[1];  // (cos, sin) as rot_mat_2D holds them
+  for (int k = 0; k < nd; ++k) out->dims[k] = in.dims[k];
+  // getBoundingRadius: circle.cpp:31, capped_rectangle.cpp:31, rectangle.cpp:31
+  out->brad = in.kind == RKB_SHAPE_CIRCLE ? in.dims[0] : std::sqrt(in.dims[0] * in.dims[0] + in.dims[1] * in.dims[1]) * 0.5;
+  return true;
+}
 bool lower_shape(const rkb_shape& in, int n_frames, ProxShape* out) {
   if (in.kind < RKB_SHAPE_PLANE || in.kind > RKB_SHAPE_BOX) return false;
   if (in.anchor < -1 || in.anchor >= n_frames) return false;
@@ -981,7 +999,12 @@ extern "C" {
 int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_shape* m2, int n2, rkb_proxy** out) {
   if (!c || !out || n1 < 0 || n2 < 0 || (n1 > 0 && !m1) || (n2 > 0 && !m2)) return RKB_ERR_INVALID;
   if (n1 > RKB_PROX_MAX_SHAPES || n2 > RKB_PROX_MAX_SHAPES) return RKB_ERR_UNSUPPORTED;
-  if (c->desc.dim != 3 || !c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
+  const bool planar = c->desc.dim == 2;
+  for (int k = 0; k < n1 + n2; ++k) {  // planar shapes ride on planar chains, spatial shapes on spatial ones
+    const int kind = (k < n1 ? m1[k] : m2[k - n1]).kind;
+    if (kind >= RKB_SHAPE_PLANE && kind <= RKB_SHAPE_RECTANGLE && (kind >= RKB_SHAPE_CIRCLE) != planar) return RKB_ERR_UNSUPPORTED;
+  }
   rkb_proxy* p = new (std::nothrow) rkb_proxy();
   if (!p) return RKB_ERR_NOMEM;
   std::memset(&p->prog, 0, sizeof p->prog);
@@ -992,11 +1015,11 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
   p->serial = g_proxy_serial.fetch_add(1);
   for (int k = 0; k < n1 + n2; ++k) {
     const rkb_shape& in = k < n1 ? m1[k] : m2[k - n1];
-    if (!lower_shape(in, c->desc.n_frames, &p->prog.s[k])) { delete p; return RKB_ERR_INVALID; }
+    if (!(planar ? lower_shape_2d(in, c->desc.n_frames, &p->prog.s[k]) : lower_shape(in, c->desc.n_frames, &p->prog.s[k]))) { delete p; return RKB_ERR_INVALID; }
   }
   for (int a = 0; a < n1; ++a)
     for (int b = 0; b < n2; ++b)
-      if (prox_pair_has_finder(m1[a].kind, m2[b].kind)) p->finders.push_back(std::make_pair(a, b));
+      if (planar || prox_pair_has_finder(m1[a].kind, m2[b].kind)) p->finders.push_back(std::make_pair(a, b));
   {  // which frames outlive the element after their writer (motion_pose in kte_generic.cu walks the same loop)
     bool keep[RKB_GEN_MAX_FRAMES] = {};
     for (int k = 0; k < n1 + n2; ++k)
@@ -1004,7 +1027,8 @@ int rkb_proxy_create(const rkb_chain* c, const rkb_shape* m1, int n1, const rkb_
     int last = c->gp.base_frame;
     for (int e = 0; e < c->gp.n_elements; ++e) {
       const GenericElement& E = c->gp.el[e];
-      if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D && E.kind != RKB_FREE_3D) continue;
+      if (E.kind != RKB_REVOLUTE_3D && E.kind != RKB_PRISMATIC_3D && E.kind != RKB_RIGID_LINK_3D && E.kind != RKB_FREE_3D &&
+          E.kind != RKB_REVOLUTE_2D && E.kind != RKB_PRISMATIC_2D && E.kind != RKB_RIGID_LINK_2D && E.kind != RKB_FREE_2D) continue;
       if (E.fa != last) keep[E.fa] = true;
       last = E.fb;
     }
@@ -1087,7 +1111,7 @@ int rkb_min_distance(rkb_chain* c, const rkb_proxy* p, int device, size_t N, con
   if (!c || !p) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
   if (!x || !distance) return RKB_ERR_INVALID;
-  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
   if (p->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
   if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
@@ -1132,7 +1156,7 @@ int rkb_collision_points(rkb_chain* c, const rkb_proxy* p, int device, size_t N,
   if (max_records < 1 || max_records > 2 * RKB_PROX_MAX_SHAPES * RKB_PROX_MAX_SHAPES) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
   if (!x || !count || !records) return RKB_ERR_INVALID;
-  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
   if (p->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
   if (L.blocked && c->n_free) return RKB_ERR_UNSUPPORTED;
@@ -1178,7 +1202,7 @@ int rkb_is_free(rkb_chain* c, int device, size_t N, const double* x, const rkb_p
   if (!c || n_pairs < 1 || !pairs) return RKB_ERR_INVALID;
   if (N == 0) return RKB_OK;
   if (!x || !is_free) return RKB_ERR_INVALID;
-  if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+  if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
   for (int p = 0; p < n_pairs; ++p)
     if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
   const Layout L = parse_flags(flags);
@@ -1791,7 +1815,7 @@ int steer_feedback_impl(rkb_chain* c, int device, size_t N, const double* x0, co
   if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !collided))) return RKB_ERR_INVALID;
   for (int p = 0; p < n_pairs; ++p) {
     if (!pairs[p] || pairs[p]->n_frames != c->desc.n_frames) return RKB_ERR_INVALID;
-    if (!c->generic_ok || c->desc.dim != 3) return RKB_ERR_UNSUPPORTED;
+    if (!c->generic_ok) return RKB_ERR_UNSUPPORTED;
   }
   if (o->dt == 0.0 || !std::isfinite(o->dt) || o->substeps < 1 || o->max_intervals < 0) return RKB_ERR_INTEGRATION;
   if (!(o->time_step > 0.0) || !std::isfinite(o->time_step) || !std::isfinite(o->goal_proximity)) return RKB_ERR_INVALID;

@@ -133,6 +133,7 @@ namespace {
 // `namespace <ns> { tables, prox_spec<PTS>(q, freec, bestR) }` of one chain and pair (inside the caller's anonymous
 // namespace); empty when the chain cannot be written as straight-line code.  g_gen_mu held.
 std::string prox_body(const GenericProgram& G, const ProxProgram& P, const char* ns) {
+  if (G.dim != 3) return std::string();  // planar models run on the interpreter kernel (kte_proximity2d.cuh)
   std::vector<double> pool;
   g_pool = &pool;
   struct Reset { ~Reset() { g_pool = nullptr; } } reset;

@@ -94,6 +94,47 @@ class box(shape_3D):
         super().__init__(name, anchor, pose, dims)
 
 
+class pose_2D:
+    """Position + rotation angle relative to the anchor (core/kinetostatics/pose_2D.hpp: Position, rot_mat_2D(angle))."""
+
+    def __init__(self, position=(0.0, 0.0), angle=0.0):
+        self.position = tuple(float(v) for v in position)
+        self.angle = float(angle)
+
+
+class shape_2D(shape_3D):
+    """planar shapes ride on planar chains; rkb_shape carries position[0..1] and quat[0..1] = (cos, sin)"""
+
+    def __init__(self, name="", anchor=None, pose=None, dims=()):
+        self.name = name
+        self.anchor = anchor
+        self.pose2 = pose if pose is not None else pose_2D()
+        # rot_mat_2D(angle) stores cos(angle), sin(angle) (rotations_2D.hpp:104-109)
+        self.pose = pose_3D(self.pose2.position + (0.0,), (np.cos(self.pose2.angle), np.sin(self.pose2.angle), 0.0, 0.0))
+        self.dims = tuple(float(v) for v in dims) + (0.0,) * (3 - len(dims))
+
+
+class circle(shape_2D):
+    kind = _abi.SHAPE_CIRCLE
+
+    def __init__(self, name="", anchor=None, pose=None, radius=1.0):
+        super().__init__(name, anchor, pose, (radius,))
+
+
+class capped_rectangle(shape_2D):
+    kind = _abi.SHAPE_CRECT
+
+    def __init__(self, name="", anchor=None, pose=None, dims=(1.0, 1.0)):
+        super().__init__(name, anchor, pose, dims)
+
+
+class rectangle(shape_2D):
+    kind = _abi.SHAPE_RECTANGLE
+
+    def __init__(self, name="", anchor=None, pose=None, dims=(1.0, 1.0)):
+        super().__init__(name, anchor, pose, dims)
+
+
 class proxy_query_model_3D:
     def __init__(self, name=""):
         self.name = name
@@ -126,6 +167,17 @@ class proxy_query_pair_3D:
                 if lo in (_abi.SHAPE_PLANE, _abi.SHAPE_SPHERE) or (lo == _abi.SHAPE_CCYLINDER and hi in (_abi.SHAPE_CCYLINDER, _abi.SHAPE_BOX)):
                     out.append((a, b))
         return out
+
+
+class proxy_query_model_2D(proxy_query_model_3D):
+    pass
+
+
+class proxy_query_pair_2D(proxy_query_pair_3D):
+    """Two planar models; every pair of planar shapes has a finder (proxy_query_model.cpp:73-160)."""
+
+    def finder_pairs(self):
+        return [(a, b) for a in range(len(self.model1.mShapeList)) for b in range(len(self.model2.mShapeList))]
 
 
 class ProxyHandle:

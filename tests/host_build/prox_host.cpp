@@ -8,26 +8,11 @@
 #include "../../reak_b200/csrc/rkb_types.h"
 
 #define GD static inline
-// the helpers kte_generic.cu defines ahead of including the header
-struct V3 { double x, y, z; };
-GD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-GD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-GD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-GD V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-GD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-struct Q4 { double w, x, y, z; };
-GD Q4 qmul(Q4 a, Q4 b) {
-  Q4 r;
-  r.w = b.w * a.w - b.x * a.x - b.y * a.y - b.z * a.z;
-  r.x = b.w * a.x + b.z * a.y - b.y * a.z + b.x * a.w;
-  r.y = b.w * a.y - b.z * a.x + b.x * a.z + b.y * a.w;
-  r.z = b.w * a.z + b.y * a.x - b.x * a.y + b.z * a.w;
-  return r;
-}
-GD Q4 qconj(Q4 a) { Q4 r; r.w = a.w; r.x = -a.x; r.y = -a.y; r.z = -a.z; return r; }
 using std::fabs;
 using std::sqrt;
+#include "../../reak_b200/csrc/kte_math.cuh"   // the helpers kte_generic.cu has ahead of the two headers
 #include "../../reak_b200/csrc/kte_proximity.cuh"
+#include "../../reak_b200/csrc/kte_proximity2d.cuh"
 
 // program: the ProxProgram rkb_proxy_create lowers (read back through rkb_proxy_program, a test hook of the
 // product library); frames: [n_frames][7] world position + quaternion of the chain frames.
@@ -61,6 +46,35 @@ extern "C" int prox_host_gather(const ProxProgram* P, const double* frames, int 
   return prox_gather_collisions(*P, fr, max_records, [&](int r, int f, const ProxRecord& R) {
     double* o = records + 7 * r;
     o[0] = R.d; o[1] = R.p1.x; o[2] = R.p1.y; o[3] = R.p1.z; o[4] = R.p2.x; o[5] = R.p2.y; o[6] = R.p2.z;
+    finder[r] = f;
+  });
+}
+
+// ---- planar models: frames [n_frames][7] = (x, y, -, cos, sin, -, -) as rkb_frames / the reference report them ----
+static void load_slots2(const ProxProgram* P, const double* frames, int n_frames, Pose2* fr) {
+  for (int f = 0; f < n_frames && f < RKB_GEN_MAX_FRAMES; ++f) {
+    if (P->slot_of[f] < 0) continue;
+    const double* v = frames + 7 * f;
+    Pose2& S = fr[P->slot_of[f]];
+    S.p = v2(v[0], v[1]);
+    S.R.c = v[3]; S.R.s = v[4];
+  }
+}
+extern "C" int prox2d_host_min_distance(const ProxProgram* P, const double* frames, int n_frames, double* dist, double* pts) {
+  Pose2 fr[RKB_GEN_MAX_FRAMES];
+  load_slots2(P, frames, n_frames, fr);
+  ProxRecord2 R;
+  const int best = prox_min_distance2(*P, fr, R);
+  *dist = R.d;
+  pts[0] = R.p1.x; pts[1] = R.p1.y; pts[2] = 0.0; pts[3] = R.p2.x; pts[4] = R.p2.y; pts[5] = 0.0;
+  return best;
+}
+extern "C" int prox2d_host_gather(const ProxProgram* P, const double* frames, int n_frames, int max_records, double* records, int32_t* finder) {
+  Pose2 fr[RKB_GEN_MAX_FRAMES];
+  load_slots2(P, frames, n_frames, fr);
+  return prox_gather_collisions2(*P, fr, max_records, [&](int r, int f, const ProxRecord2& R) {
+    double* o = records + 7 * r;
+    o[0] = R.d; o[1] = R.p1.x; o[2] = R.p1.y; o[3] = 0.0; o[4] = R.p2.x; o[5] = R.p2.y; o[6] = 0.0;
     finder[r] = f;
   });
 }

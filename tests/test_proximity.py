@@ -98,10 +98,13 @@ class HostProximity(object):
         """frames [N][n_frames][>=7] world poses -> (distance, finder, points)."""
         N = frames.shape[0]
         d, f, p = np.zeros(N), np.zeros(N, dtype=np.int32), np.zeros((N, 6))
+        fn = self.host.prox2d_host_min_distance if self.compiled.dim == 2 else self.host.prox_host_min_distance
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         for i in range(N):
             fr = np.ascontiguousarray(frames[i][:, :7])
             di = C.c_double()
-            f[i] = self.host.prox_host_min_distance(self.blob, fr.ctypes.data_as(C.c_void_p), fr.shape[0], C.byref(di), p[i].ctypes.data_as(C.c_void_p))
+            f[i] = fn(self.blob, fr.ctypes.data_as(C.c_void_p), fr.shape[0], C.byref(di), p[i].ctypes.data_as(C.c_void_p))
             d[i] = di.value
         return d, f, p
 
@@ -112,7 +115,7 @@ class HostProximity(object):
         fnd = np.full((N, max_records), -1, dtype=np.int32)
         rec = np.zeros((N, max_records, 7))
         rec[:, :, 0] = np.inf
-        fn = self.host.prox_host_gather
+        fn = self.host.prox2d_host_gather if self.compiled.dim == 2 else self.host.prox_host_gather
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for i in range(N):
@@ -325,6 +328,171 @@ def test_proxy_create_rejects():
     out = C.c_void_p()
     assert lib.rkb_proxy_create(h2, arr, 1, arr, 1, C.byref(out)) == _abi.ERR_UNSUPPORTED
     lib.rkb_chain_destroy(h2)
+
+
+# ---- planar models (proxy_query_pair_2D): circle, capped rectangle, rectangle on planar chains -------------
+KINDS2 = {"circle": px.circle, "crect": px.capped_rectangle, "rectangle": px.rectangle}
+
+
+def agree2(got, want, tol, pair=None):
+    """as agree(); crossing centre lines make the reference divide 0 by 0 for the two points (prox_crect_crect.cpp:121-124,
+    prox_crect_rectangle.cpp:198-203): NaN there is the expected answer, in the same places"""
+    (d, f, p), (dr, fr, pr) = got, want
+    p, pr = p.copy(), pr.copy()
+    if pair is not None:
+        # ... and centre lines that cross up to rounding (distance between them ~1e-17) give two points in a direction made
+        # of rounding noise, in the reference as here: only the distance is defined for those
+        n2 = len(pair.model2.mShapeList)
+        for i in range(len(dr)):
+            if fr[i] < 0 or f[i] != fr[i]:
+                continue
+            sa, sb = pair.model1.mShapeList[fr[i] // n2], pair.model2.mShapeList[fr[i] % n2]
+            if sa.kind == _abi.SHAPE_CRECT and sb.kind == _abi.SHAPE_CRECT and abs(dr[i] + 0.5 * sa.dims[1] + 0.5 * sb.dims[1]) < 1e-9:
+                p[i] = pr[i] = 0.0
+    assert np.array_equal(np.isnan(p), np.isnan(pr)) and np.array_equal(np.isnan(d), np.isnan(dr))
+    agree((d, f, np.nan_to_num(p, nan=0.0)), (dr, fr, np.nan_to_num(pr, nan=0.0)), tol)
+
+
+def random_shape2(rng, kind, anchor=None, spread=1.0, angle=None):
+    pose = px.pose_2D(rng.uniform(-spread, spread, size=2), rng.uniform(-np.pi, np.pi) if angle is None else angle)
+    if kind == "circle":
+        return px.circle("ci", anchor, pose, rng.uniform(0.05, 0.5))
+    if kind == "crect":
+        return px.capped_rectangle("cr", anchor, pose, (rng.uniform(0.2, 1.2), rng.uniform(0.05, 0.4)))
+    return px.rectangle("re", anchor, pose, rng.uniform(0.2, 1.2, size=2))
+
+
+def mixed_models2(compiled, rng, n1=5, n2=6):
+    kinds = sorted(KINDS2)
+    m1, m2 = px.proxy_query_model_2D("robot"), px.proxy_query_model_2D("world")
+    nf = compiled.desc.n_frames
+    for k in range(n1):
+        m1.addShape(random_shape2(rng, kinds[k % 3], int(rng.integers(1, nf)), spread=0.3))
+    for k in range(n2):
+        m2.addShape(random_shape2(rng, kinds[(k + 1) % 3], None, spread=1.5))
+    return px.proxy_query_pair_2D("mixed2", m1, m2)
+
+
+@pytest.mark.parametrize("k2", sorted(KINDS2))
+@pytest.mark.parametrize("k1", sorted(KINDS2))
+def test_planar_single_finder_host_vs_reference(k1, k2, host_lib, oracle_built):
+    """every (kind, kind) combination of planar shapes, both model orders: one fixed in the world, one on the arm"""
+    need_ref(oracle_built)
+    rng = np.random.default_rng(sum(ord(c) for c in k1) * 17 + sum(ord(c) for c in k2))
+    s = presets.make("planar3_sd")
+    for trial in range(24):
+        probe = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        a = random_shape2(rng, k1, (1 + trial % (probe.desc.n_frames - 1)) if trial % 2 else None, spread=0.6 if trial % 2 else 1.2)
+        b = random_shape2(rng, k2, None)
+        pair = px.proxy_query_pair_2D("t", px.proxy_query_model_2D("a").addShape(a), px.proxy_query_model_2D("b").addShape(b))
+        H = HostProximity(host_lib, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 4, seed=trial, q_range=3.0)
+        agree2(H.min_distance(ref_frames(R, x)), R.min_distance(pair, x), TOL)
+        H.close()
+
+
+def planar_special_pairs():
+    """axis-parallel configurations (the 1e-5 tests on the tangent) and containment"""
+    out = []
+    P = px.pose_2D
+    out.append(("crect_parallel", px.capped_rectangle("a", None, P((0, 0), 0.0), (1.0, 0.2)), px.capped_rectangle("b", None, P((0.3, 0.5), 0.0), (0.6, 0.3))))
+    out.append(("crect_parallel_far", px.capped_rectangle("a", None, P((0, 0), 0.0), (1.0, 0.2)), px.capped_rectangle("b", None, P((3.0, 0.5), np.pi), (0.6, 0.3))))
+    out.append(("crect_rect_vertical", px.capped_rectangle("a", None, P((0.9, 0.1), np.pi / 2), (1.0, 0.2)), px.rectangle("b", None, P((0, 0), 0.0), (1.0, 0.8))))
+    out.append(("crect_rect_horizontal", px.capped_rectangle("a", None, P((0.1, -0.9), 0.0), (1.0, 0.2)), px.rectangle("b", None, P((0, 0), 0.0), (1.0, 0.8))))
+    out.append(("crect_rect_end_in_slab", px.capped_rectangle("a", None, P((1.2, 0.1), 0.3), (0.8, 0.1)), px.rectangle("b", None, P((0, 0), 0.0), (1.0, 0.8))))
+    out.append(("crect_rect_crossing", px.capped_rectangle("a", None, P((0.1, 0.1), 0.7), (2.0, 0.1)), px.rectangle("b", None, P((0, 0), 0.2), (1.0, 0.8))))
+    out.append(("circle_in_rect", px.circle("a", None, P((0.1, 0.25)), 0.05), px.rectangle("b", None, P((0, 0), 0.4), (1.0, 0.8))))
+    out.append(("circle_in_crect", px.circle("a", None, P((0.1, 0.02)), 0.05), px.capped_rectangle("b", None, P((0, 0), 0.4), (1.0, 0.3))))
+    out.append(("circle_crect_cap", px.circle("a", None, P((0.9, 0.2)), 0.1), px.capped_rectangle("b", None, P((0, 0), 0.0), (1.0, 0.3))))
+    out.append(("rect_rect_overlap", px.rectangle("a", None, P((0.2, 0.1), 0.3), (1.0, 0.6)), px.rectangle("b", None, P((0, 0), 0.0), (1.0, 0.8))))
+    out.append(("circle_circle_in", px.circle("a", None, P((0.1, 0.0)), 0.3), px.circle("b", None, P((0.3, 0.1)), 0.2)))
+    return out
+
+
+@pytest.mark.parametrize("case", planar_special_pairs(), ids=[c[0] for c in planar_special_pairs()])
+def test_planar_special_branches_host_vs_reference(case, host_lib, oracle_built):
+    need_ref(oracle_built)
+    _, a, b = case
+    s = presets.make("planar2")
+    for first, second in ((a, b), (b, a)):
+        pair = px.proxy_query_pair_2D("t", px.proxy_query_model_2D("a").addShape(first), px.proxy_query_model_2D("b").addShape(second))
+        H = HostProximity(host_lib, s, pair)
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 1, seed=1)
+        agree2(H.min_distance(ref_frames(R, x)), R.min_distance(pair, x), TOL)
+        H.close()
+
+
+@pytest.mark.parametrize("preset", ["planar3_sd", "crs2d", "planar_pr"])
+def test_planar_mixed_models_host_vs_reference(preset, host_lib, oracle_built):
+    """several shapes per model on revolute / prismatic planar chains: the culling test, gatherCollisionPoints"""
+    need_ref(oracle_built)
+    s = presets.make(preset)
+    for seed in range(3):
+        probe = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        pair = mixed_models2(probe, np.random.default_rng(40 + seed))
+        H = HostProximity(host_lib, s, pair)
+        assert H.proxy.n_finders == 30
+        R = oracle_built.Reference(H.compiled)
+        x, _ = random_batch(H.compiled, 64, seed=seed, q_range=2.5)
+        fr = ref_frames(R, x)
+        want = R.min_distance(pair, x)
+        agree2(H.min_distance(fr), want, TOL, pair)
+        assert (want[0] < 0).any() and (want[0] > 0).any()
+        cnt, fnd, rec = H.gather(fr, 30)
+        cr, recr = R.collision_points(pair, x, 30)
+        assert np.array_equal(cnt, cr) and cnt.max() > 1
+        # (distances of the records; their points are the finders' own, checked above, and undefined for crossing centre lines)
+        dg, dw = rec[:, :, 0], recr[:, :, 0]
+        assert np.array_equal(np.isfinite(dg), np.isfinite(dw)) and np.max(np.abs(dg[np.isfinite(dw)] - dw[np.isfinite(dw)])) < 1e-9
+        H.close()
+
+
+GOLDEN2 = os.path.join(HERE, "golden", "proximity", "proximity_2d.npz")
+
+
+def golden_pair2(g):
+    m = [px.proxy_query_model_2D("m1"), px.proxy_query_model_2D("m2")]
+    for which, key in enumerate(("shapes1", "shapes2")):
+        for row in g[key]:
+            kind, anchor = int(row[0]), int(row[1])
+            sh = px.shape_2D("g", None if anchor < 0 else anchor, px.pose_2D(row[2:4], np.arctan2(row[6], row[5])), row[9:12])
+            sh.kind = kind
+            sh.pose = px.pose_3D(tuple(row[2:5]), tuple(row[5:9]))   # the stored (cos, sin), bit for bit
+            m[which].addShape(sh)
+    return px.proxy_query_pair_2D("golden2", m[0], m[1])
+
+
+def test_planar_host_vs_golden(host_lib):
+    """committed outputs of the reference (tests/golden/proximity/make_golden_proximity_2d.py); runs without oracle/_ref"""
+    g = np.load(GOLDEN2)
+    for tag, preset in (("arm3", "planar3_sd"), ("crs2d", "crs2d")):
+        s = presets.make(preset)
+        sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        pair = golden_pair2(sub)
+        H = HostProximity(host_lib, s, pair)
+        agree2(H.min_distance(sub["frames"]), (sub["distance"], sub["finder"], sub["points"]), TOL, pair)
+        H.close()
+
+
+def test_planar_proxy_create_rejects():
+    """planar shapes need a planar chain and the other way round; a planar rotation must be a unit (cos, sin)"""
+    lib = _abi.load_library()
+    for preset, shape, want in (("planar2", px.circle("c", None, None, 0.1), 0), ("planar2", px.sphere("s", None, None, 0.1), _abi.ERR_UNSUPPORTED),
+                                ("crs6", px.circle("c", None, None, 0.1), _abi.ERR_UNSUPPORTED), ("planar2", px.rectangle("r", None, None, (0.1, -1.0)), _abi.ERR_INVALID)):
+        s = presets.make(preset)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        h = C.c_void_p()
+        _abi.check(lib.rkb_chain_create(C.byref(c.desc), C.byref(h)), "rkb_chain_create")
+        arr = (_abi.rkb_shape * 1)()
+        arr[0] = shape.to_c(c.frames)
+        out = C.c_void_p()
+        rc = lib.rkb_proxy_create(h, arr, 1, arr, 1, C.byref(out))
+        assert rc == want, (preset, shape.kind, rc)
+        if rc == 0:
+            lib.rkb_proxy_destroy(out)
+        lib.rkb_chain_destroy(h)
 
 
 # ---- the generated (run-time specialised) source, compiled for the host -------------------------------
@@ -642,6 +810,55 @@ def test_gpu_proxy_auto_specialize():
     assert h.is_specialized(), "no generated kernel after 180 s"
     for got, was in ((P.get_min_distances(pair, x, with_points=False), first), (P.get_min_distances(pair, x[:100], with_points=False), small)):
         assert np.max(np.abs(got[0] - was[0])) < 1e-12 and np.all((got[1] == was[1]) | (np.abs(got[0] - was[0]) < 1e-12))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["planar3_sd", "crs2d", "planar_pr", "free_planar2"])
+def test_gpu_planar_models_vs_reference(preset, oracle_built):
+    """proxy_query_pair_2D on planar chains (revolute, prismatic, free_joint_2D): findMinimumDistance, is_free and
+    gatherCollisionPoints through the C-ABI against the live reference"""
+    need_ref(oracle_built)
+    from reak_b200.propagator import kte_batch_propagator
+    s = presets.make(preset)
+    P = kte_batch_propagator(s).set_option("auto_specialize", 0)
+    R = oracle_built.Reference(P.compiled)
+    for seed in range(2):
+        pair = mixed_models2(P.compiled, np.random.default_rng(60 + seed))
+        x, _ = random_batch(P.compiled, 1500, seed=seed, q_range=2.5)
+        if P.nx > x.shape[1]:  # free_joint_2D: position, (cos, sin) not normalised, velocity, angular velocity
+            rng = np.random.default_rng(seed)
+            ang, scale = rng.uniform(-np.pi, np.pi, 1500), rng.uniform(0.8, 1.2, 1500)
+            x = np.hstack([x, rng.uniform(-0.5, 0.5, (1500, 2)), (scale * np.cos(ang))[:, None], (scale * np.sin(ang))[:, None],
+                           rng.uniform(-1, 1, (1500, 3))])
+        want = R.min_distance(pair, x)
+        got = P.get_min_distances(pair, x)
+        agree2(got, want, TOL, pair)
+        assert (want[0] < 0).any() and (want[0] > 0).any()
+        assert np.array_equal(P.is_free([pair], x), ~(want[0] < 0.0))
+        cnt, fnd, rec = P.gather_collision_points(pair, x[:300])
+        cr, recr = R.collision_points(pair, x[:300], rec.shape[1])
+        dg, dw = rec[:, :, 0], recr[:, :, 0]
+        assert np.array_equal(cnt, cr) and np.array_equal(np.isfinite(dg), np.isfinite(dw))
+        assert np.max(np.abs(dg[np.isfinite(dw)] - dw[np.isfinite(dw)]), initial=0.0) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_planar_vs_golden_and_special_branches(oracle_built):
+    g = np.load(GOLDEN2)
+    for tag, preset in (("arm3", "planar3_sd"), ("crs2d", "crs2d")):
+        s, P = _gpu_prop(preset)
+        sub = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        pair = golden_pair2(sub)
+        agree2(P.get_min_distances(pair, sub["x"]), (sub["distance"], sub["finder"], sub["points"]), TOL, pair)
+    if not oracle_built.have_ref():
+        return
+    s, P = _gpu_prop("planar2")
+    R = oracle_built.Reference(P.compiled)
+    x, _ = random_batch(P.compiled, 2, seed=1)
+    for _, a, b in planar_special_pairs():
+        for first, second in ((a, b), (b, a)):
+            pair = px.proxy_query_pair_2D("t", px.proxy_query_model_2D("a").addShape(first), px.proxy_query_model_2D("b").addShape(second))
+            agree2(P.get_min_distances(pair, x), R.min_distance(pair, x), TOL)
 
 
 @pytest.mark.gpu
