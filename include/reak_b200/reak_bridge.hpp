@@ -50,6 +50,9 @@
 #include <ReaK/geometry/shapes/capped_cylinder.hpp>
 #include <ReaK/geometry/shapes/cylinder.hpp>
 #include <ReaK/geometry/shapes/box.hpp>
+#include <ReaK/geometry/shapes/circle.hpp>
+#include <ReaK/geometry/shapes/capped_rectangle.hpp>
+#include <ReaK/geometry/shapes/rectangle.hpp>
 #include <ReaK/geometry/proximity/proxy_query_model.hpp>
 #include <ReaK/ctrl/topologies/metric_space_concept.hpp>
 #include <ReaK/ctrl/topologies/subspace_concept.hpp>
@@ -346,6 +349,44 @@ inline std::vector<rkb_shape> compile_proxy_model(const ReaK::geom::proxy_query_
   return out;
 }
 
+/// The planar counterpart (proxy_query_model_2D: circle / capped_rectangle / rectangle riding on frame_2D's of a planar
+/// chain): rkb_shape carries position[0..1] and quat[0..1] = the (cos, sin) rot_mat_2D holds.
+inline std::vector<rkb_shape> compile_proxy_model(const ReaK::geom::proxy_query_model_2D& mdl, const chain_builder& builder) {
+  using namespace ReaK;
+  using ReaK::rtti::rk_dynamic_ptr_cast;
+  std::vector<rkb_shape> out;
+  for (std::size_t i = 0; i < mdl.mShapeList.size(); ++i) {
+    const shared_ptr<geom::shape_2D>& sh = mdl.mShapeList[i];
+    if (!sh) continue;  // createProxFinderList skips null shapes (proxy_query_model.cpp:81-82)
+    rkb_shape s = rkb_shape();
+    if (shared_ptr<geom::circle> p = rk_dynamic_ptr_cast<geom::circle>(sh)) {
+      s.kind = RKB_SHAPE_CIRCLE; s.dims[0] = p->getRadius();
+    } else if (shared_ptr<geom::capped_rectangle> p = rk_dynamic_ptr_cast<geom::capped_rectangle>(sh)) {
+      s.kind = RKB_SHAPE_CRECT; s.dims[0] = p->getDimensions()[0]; s.dims[1] = p->getDimensions()[1];
+    } else if (shared_ptr<geom::rectangle> p = rk_dynamic_ptr_cast<geom::rectangle>(sh)) {
+      s.kind = RKB_SHAPE_RECTANGLE; s.dims[0] = p->getDimensions()[0]; s.dims[1] = p->getDimensions()[1];
+    } else {
+      throw unsupported_chain("planar proximity shape outside circle / capped_rectangle / rectangle");
+    }
+    const shared_ptr<pose_2D<double> >& anchor = sh->getAnchor();
+    if (!anchor) s.anchor = -1;
+    else {
+      std::map<const void*, int>::const_iterator it = builder.frame_ids.find(static_cast<const void*>(anchor.get()));
+      if (it == builder.frame_ids.end()) {
+        for (it = builder.frame_ids.begin(); it != builder.frame_ids.end(); ++it)
+          if (static_cast<const pose_2D<double>*>(static_cast<const frame_2D<double>*>(it->first)) == anchor.get()) break;
+      }
+      if (it == builder.frame_ids.end()) throw unsupported_chain("proximity shape anchored to a pose that is not a frame of the chain");
+      s.anchor = it->second;
+    }
+    const pose_2D<double>& P = sh->getPose();
+    s.position[0] = P.Position[0]; s.position[1] = P.Position[1];
+    s.quat[0] = P.Rotation(0, 0); s.quat[1] = P.Rotation(1, 0);  // rot_mat_2D: [[c, -s], [s, c]]
+    out.push_back(s);
+  }
+  return out;
+}
+
 }  // namespace reak_b200
 
 namespace ReaK {
@@ -395,6 +436,9 @@ class kte_batch_system {
   /// manip_dk_proxy_env_impl::is_free (ctrl/topologies/manip_free_workspace.hpp:77-99).  Owned by the caller
   /// (rkb_proxy_destroy).
   rkb_proxy* make_proxy_pair(const geom::proxy_query_model_3D& aModel1, const geom::proxy_query_model_3D& aModel2) const {
+    return mProp.make_proxy_pair(reak_b200::compile_proxy_model(aModel1, mBuilder), reak_b200::compile_proxy_model(aModel2, mBuilder));
+  }
+  rkb_proxy* make_proxy_pair(const geom::proxy_query_model_2D& aModel1, const geom::proxy_query_model_2D& aModel2) const {
     return mProp.make_proxy_pair(reak_b200::compile_proxy_model(aModel1, mBuilder), reak_b200::compile_proxy_model(aModel2, mBuilder));
   }
   const reak_b200::chain_builder& descriptor() const { return mBuilder; }

@@ -903,6 +903,28 @@ int rkref_collision_points(void* hv, std::size_t N, const double* x, const rkb_s
 int rkref_bridge_proxy(void* hv, const rkb_shape* in, int n, rkb_shape* out, int* anchor_frame_of_desc, char* err, int err_len) {
   ref_handle* h = static_cast<ref_handle*>(hv);
   ref_model* m = h->proto;
+  if (h->desc.dim == 2) {  // planar models: the 2D overload of compile_proxy_model
+    try {
+      planar_pair P;
+      if (!build_planar_pair(m, in, n, in, 0, P)) throw std::runtime_error("not a planar shape");
+      reak_b200::chain_builder b = reak_b200::compile_kte_system(m->sys);
+      std::vector<rkb_shape> shapes = reak_b200::compile_proxy_model(*P.mdl[0], b);
+      if ((int)shapes.size() != n) throw std::runtime_error("shape count differs");
+      for (int k = 0; k < n; ++k) {
+        out[k] = shapes[k];
+        anchor_frame_of_desc[k] = -1;
+        if (shapes[k].anchor >= 0)
+          for (std::size_t f = 0; f < m->f2.size(); ++f) {
+            std::map<const void*, int>::const_iterator it = b.frame_ids.find(static_cast<const void*>(m->f2[f].get()));
+            if (it != b.frame_ids.end() && it->second == shapes[k].anchor) anchor_frame_of_desc[k] = (int)f;
+          }
+      }
+      return n;
+    } catch (std::exception& e) {
+      if (err && err_len > 0) { std::strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+      return -1;
+    }
+  }
   try {
     geom::proxy_query_model_3D mdl("m");
     for (int k = 0; k < n; ++k) {

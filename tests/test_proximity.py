@@ -292,6 +292,23 @@ def test_reference_side_binding_round_trip(oracle_built):
             assert np.allclose(list(out[k].dims), list(src[k].dims), rtol=0, atol=0)
 
 
+def test_reference_side_binding_round_trip_planar(oracle_built):
+    """the planar overload of reak_bridge.hpp's compile_proxy_model on live geom::circle / capped_rectangle / rectangle
+    riding on live frame_2D's"""
+    need_ref(oracle_built)
+    s = presets.make("crs2d")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    R = oracle_built.Reference(c)
+    pair = mixed_models2(c, np.random.default_rng(5))
+    for model in (pair.model1, pair.model2):
+        src, out, anchors = R.bridge_proxy(model)
+        for k in range(len(model.mShapeList)):
+            assert out[k].kind == src[k].kind and anchors[k] == src[k].anchor
+            assert np.allclose(list(out[k].position)[:2], list(src[k].position)[:2], rtol=0, atol=0)
+            assert np.allclose(list(out[k].quat)[:2], list(src[k].quat)[:2], rtol=0, atol=1e-15)
+            assert np.allclose(list(out[k].dims), list(src[k].dims), rtol=0, atol=0)
+
+
 def test_proxy_create_rejects():
     lib = _abi.load_library()
     s = presets.make("crs6")
