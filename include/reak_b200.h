@@ -364,8 +364,8 @@ RKB_API void rkb_proxy_destroy(rkb_proxy* proxy);
  * every finder of createProxFinderList with its argument order resolved), compiles it with NVRTC (a few seconds; cubins
  * are cached on disk like those of rkb_chain_specialize) and routes the pair's launches to it: ~2x the interpreter.
  * Results agree with the interpreter kernel to rounding.  By default (RKB_PROXY_OPT_AUTO_SPECIALIZE = 1, and the chain's
- * RKB_OPT_AUTO_SPECIALIZE on) the same happens on a background thread from the first query of >= 4096 states on; queries
- * made meanwhile run on the interpreter.
+ * RKB_OPT_AUTO_SPECIALIZE on) the same happens on a background thread once 4096 states have been queried (in one call or
+ * over many small ones); queries made meanwhile run on the interpreter.
  * RKB_ERR_UNSUPPORTED: libnvrtc.so.12 is not installed. */
 enum rkb_proxy_option { RKB_PROXY_OPT_AUTO_SPECIALIZE = 1, RKB_PROXY_OPT_MIN_BLOCKS = 2 /* CTAs per SM compiled for, 1..8 */ };
 RKB_API int  rkb_proxy_set_option(rkb_proxy* proxy, int option, long long value);
@@ -550,8 +550,8 @@ RKB_API int rkb_steer_feedback_checked(rkb_chain* chain, int device, size_t n_sa
  * test of a given set of proxy pairs built in (the generated query of rkb_proxy_specialize inside the loop: integrate an
  * interval, test the state it ends on, accept or stop — no state round trips between four kernels per interval).
  * rkb_steer_checked_specialize does it now (NVRTC, a few seconds, cubin cached on disk); by default it happens in the
- * background from the first rkb_steer_feedback_checked call of >= 4096 tuples on (while every pair and the chain have
- * their AUTO_SPECIALIZE option on), calls made meanwhile run interval by interval.  Results: those of the interval-by-
+ * background once 4096 tuples have been steered with these pairs (in one call or over many; while every pair and the chain
+ * have their AUTO_SPECIALIZE option on), calls made meanwhile run interval by interval.  Results: those of the interval-by-
  * interval path up to rounding.  RKB_ERR_UNSUPPORTED: interpreter chain, RKB_OPT_FUSED_STEER off, or no libnvrtc.so.12. */
 RKB_API int rkb_steer_checked_specialize(rkb_chain* chain, int device, const rkb_proxy* const* pairs, int n_pairs);
 RKB_API int rkb_steer_checked_is_specialized(rkb_chain* chain, const rkb_proxy* const* pairs, int n_pairs);

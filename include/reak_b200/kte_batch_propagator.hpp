@@ -304,6 +304,23 @@ class kte_batch_propagator {
                          double* points = NULL, unsigned flags = 0, void* stream = NULL) const {
     check(rkb_min_distance(mChain, pair, mDevice, n, x, distance, finder, points, flags, stream), "rkb_min_distance");
   }
+  /// Compiles the query of this chain and pair as straight-line CUDA now (rkb_proxy_specialize: NVRTC, a few seconds, cubin
+  /// cached on disk) instead of waiting for the background compilation that starts once 4096 states have been queried.
+  /// False when libnvrtc.so.12 is not installed (the interpreter kernel keeps serving the pair).
+  bool specialize_proxy_pair(rkb_proxy* pair) const {
+    const int rc = rkb_proxy_specialize(pair, mDevice);
+    if (rc == RKB_ERR_UNSUPPORTED) return false;
+    check(rc, "rkb_proxy_specialize");
+    return true;
+  }
+  /// The steering kernel with the collision test of `pairs` built in (rkb_steer_checked_specialize): the steering loops with
+  /// with_collision_check = true (MEAQR_topology.hpp:550-559) become one launch.  False for interpreter chains / no NVRTC.
+  bool specialize_checked_steering(const std::vector<const rkb_proxy*>& pairs) const {
+    const int rc = rkb_steer_checked_specialize(mChain, mDevice, pairs.empty() ? NULL : &pairs[0], static_cast<int>(pairs.size()));
+    if (rc == RKB_ERR_UNSUPPORTED) return false;
+    check(rc, "rkb_steer_checked_specialize");
+    return true;
+  }
   /// manip_dk_proxy_env_impl::is_free for every state: is_free[i] = 1 unless some pair reports a negative distance
   void get_is_free(const std::vector<const rkb_proxy*>& pairs, std::size_t n, const double* x, int32_t* is_free,
                    unsigned flags = 0, void* stream = NULL) const {

@@ -87,7 +87,7 @@ struct rkb_chain {
   bool auto_specialize = true, auto_done = false;
   unsigned create_flags = 0;
   // checked steering in one launch: kernels generated per set of proxy pairs (rkb_steer_checked_source)
-  struct CheckedSteer { std::vector<unsigned long long> key; const SourceKernels* K; bool done; };
+  struct CheckedSteer { std::vector<unsigned long long> key; const SourceKernels* K; bool done; long long seen; };
   std::vector<CheckedSteer> checked;
 };
 
@@ -906,6 +906,7 @@ struct rkb_proxy {
   mutable std::mutex mu;
   mutable const SourceKernels* spec = nullptr;
   mutable bool auto_done = false;
+  mutable long long seen = 0;  // states queried so far: the background compilation starts once 4096 have gone by
   unsigned long long serial = 0;  // identity for the chain's table of checked-steering kernels (a pointer can be reused)
 };
 std::atomic<unsigned long long> g_proxy_serial{1};
@@ -919,7 +920,8 @@ cudaError_t launch_proximity(const rkb_chain* c, const DeviceCtx* ctx, const rkb
   const SourceKernels* K = nullptr;
   {
     std::lock_guard<std::mutex> lock(p->mu);
-    if (!p->spec && p->auto_specialize && c->auto_specialize && !p->auto_done && A.n_samples >= 4096) {
+    if (!p->spec && !p->auto_done) p->seen += A.n_samples;  // a planner's many small queries count like one large one
+    if (!p->spec && p->auto_specialize && c->auto_specialize && !p->auto_done && p->seen >= 4096) {
       const std::string src = rkb_prox_source(p->gp, p->prog, p->min_blocks);
       const SourceKernels* J = nullptr;
       if (src.empty() || rkb_jit_source_poll("prox", src, kProxSpecNames, 1, false, &J) != RKB_OK) p->auto_done = true;  // no NVRTC here: stay as we are
@@ -1790,8 +1792,9 @@ const SourceKernels* checked_steer_kernel(rkb_chain* c, const rkb_proxy* const* 
   for (auto& e : c->checked)
     if (e.key == key) entry = &e;
   if (entry && (entry->K || (entry->done && !sync))) return entry->K;
-  if (!sync && (!may_auto || n_samples < 4096)) return nullptr;
-  if (!entry) { c->checked.push_back(rkb_chain::CheckedSteer{key, nullptr, false}); entry = &c->checked.back(); }
+  if (!entry) { c->checked.push_back(rkb_chain::CheckedSteer{key, nullptr, false, 0}); entry = &c->checked.back(); }
+  entry->seen += n_samples;  // many small calls count like one large one
+  if (!sync && (!may_auto || entry->seen < 4096)) return nullptr;
   int coords[RKB_SERIAL_MAX_DOF];
   for (int s = 0; s < c->n; ++s) coords[s] = c->sp.st[s].coord;
   std::vector<const ProxProgram*> progs;
