@@ -33,6 +33,7 @@ echo "rc=$?"
 for a in "12 1048576 256 1" "12 1048576 65536 1" "12 1048576 4096 8" "19 1048576 4096 1" "6 1048576 4096 1" "25 1048576 4096 1"; do timeout 120 python tools/time_nearest.py $a 2>&1 | tail -1; done
 echo "== proximity: interpreter and generated kernels, checked steering"
 timeout 150 python tools/time_proximity.py crs6 $((1<<20)) 0 2>&1 | tail -6
+for n in 1024 16384; do timeout 100 python tools/time_proximity.py crs6 $n 0 2>&1 | grep min_distance; done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rkb_prox_spec_d -s 2 -c 1 -f -o $out/prof_prox_$tag \
   python tools/time_proximity.py crs6 > $out/ncu_prox_$tag.log 2>&1
 echo "rc=$?"
