@@ -710,6 +710,23 @@ def run_ours(args):
                          "executed_source": "profiles/roofline_constants.json <- " + str(rc.get("source"))})
     else:
         roofline["executed_source"] = "none: profiles/roofline_constants.json is of build %s, this library is %s" % (rc.get("build_id"), build)
+    # ... and of the generated proximity kernel: executed FP64 flops per state of this build's capture (the
+    # count is data-dependent: the bounding-sphere test skips finders), against the same measured DFMA peak
+    if others:
+        try:
+            with open(os.path.join(ROOT, "profiles", "proximity_constants.json")) as f:
+                pc = json.load(f)
+        except Exception:
+            pc = {}
+        for o in others:
+            if o.get("config") == "proximity" and str(o.get("kernel", "")).startswith("generated") and pc.get("build_id") == build:
+                sps = o["states_per_s"] / world
+                o["roofline"] = {"bound": "fp64", "achieved": pc["flop_per_state_step"] * sps / 1e12, "peak": tf.value, "unit": "TFLOP/s",
+                                 "frac": pc["flop_per_state_step"] * sps / 1e12 / tf.value,
+                                 "executed_flop_per_state": pc["flop_per_state_step"], "executed_fp64_instr_per_state": pc["fp64_instr_per_state_step"],
+                                 "fp64_pipe_active_pct": pc["fp64_pipe_active_pct"], "traffic": pc["dram_traffic_bytes_per_launch"],
+                                 "algorithmic_bytes": 108 * pc["units_per_launch"], "kernel": pc["kernel"],
+                                 "source": "profiles/proximity_constants.json <- " + str(pc.get("source"))}
     roofline_hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                     "frac": achieved_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src, "bytes_per_sample": BYTES_PER_SAMPLE}
 
