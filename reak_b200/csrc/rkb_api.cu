@@ -1792,7 +1792,11 @@ const SourceKernels* checked_steer_kernel(rkb_chain* c, const rkb_proxy* const* 
   for (auto& e : c->checked)
     if (e.key == key) entry = &e;
   if (entry && (entry->K || (entry->done && !sync))) return entry->K;
-  if (!entry) { c->checked.push_back(rkb_chain::CheckedSteer{key, nullptr, false, 0}); entry = &c->checked.back(); }
+  if (!entry) {
+    if (c->checked.size() >= 64) c->checked.erase(c->checked.begin());  // (pairs come and go: the table stays small; the kernels themselves are cached by rkb_jit.cu)
+    c->checked.push_back(rkb_chain::CheckedSteer{key, nullptr, false, 0});
+    entry = &c->checked.back();
+  }
   entry->seen += n_samples;  // many small calls count like one large one
   if (!sync && (!may_auto || entry->seen < 4096)) return nullptr;
   int coords[RKB_SERIAL_MAX_DOF];

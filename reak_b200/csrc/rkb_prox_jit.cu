@@ -20,13 +20,20 @@ namespace {
 
 struct Emit {
   std::string s;
-  void f(const char* fmt, ...) {
+  void f(const char* fmt, ...) {  // (any length: a line is never cut short)
     char buf[1024];
-    va_list ap;
+    va_list ap, ap2;
     va_start(ap, fmt);
-    std::vsnprintf(buf, sizeof buf, fmt, ap);
+    va_copy(ap2, ap);
+    const int n = std::vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    s += buf;
+    if (n >= 0 && n < (int)sizeof buf) s += buf;
+    else if (n > 0) {
+      std::vector<char> big((size_t)n + 1);
+      std::vsnprintf(big.data(), big.size(), fmt, ap2);
+      s += big.data();
+    }
+    va_end(ap2);
   }
 };
 
