@@ -557,7 +557,7 @@ def spec_tmp(tmp_path_factory):
     return str(tmp_path_factory.mktemp("prox_spec"))
 
 
-@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True), ("crs6_twist", False)])
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True), ("crs6_twist", False), ("crs7_phys_sd", True), ("crs6_sd_sat", False)])
 def test_generated_source_crs_lab_vs_reference(preset, track, spec_tmp, oracle_built):
     """the straight-line kernel source of the CRS arm against the MD148 lab: forward kinematics with axis-aligned joints
     and links, world-fixed shapes as literals; crs6_twist has rotated links (the general quaternion product)"""
