@@ -1346,6 +1346,17 @@ static void scheme_range(model* m, int scheme, size_t i0, size_t i1, const doubl
 
 #include "steer_law.h"
 
+/* test hook: steer_bounded_input for `count` (u_prev, u_bias, u_correction) triples — what tests/test_oracle.py holds against
+ * IHAQR_topology::get_bounded_input itself (oracle/ref_steer_law.cpp) */
+int kto_bounded_input(int nu, double T, const double* lo, const double* hi, const double* dlo, const double* dhi, int count,
+                      const double* u_prev, const double* u_bias, const double* u_corr, double* u_out) {
+  int i;
+  if (nu < 1 || nu > STEER_MAX_INPUTS) return -1;
+  for (i = 0; i < count; ++i)
+    steer_bounded_input(nu, T, lo, hi, dlo, dhi, u_prev + (size_t)i * nu, u_bias + (size_t)i * nu, u_corr + (size_t)i * nu, u_out + (size_t)i * nu);
+  return 0;
+}
+
 /* The steering loop of MEAQR_topology.hpp:503-561 / IHAQR_topology.hpp:349-378 for each sample (see
  * steer_law.h for the feedback law); one control interval = `substeps` RK4 steps of `dt`. */
 int kto_steer_feedback(void* h, size_t N, const double* x0, const double* goal, const double* u_bias, const double* gain,

@@ -26,6 +26,9 @@ double kto_rk4(void* h, size_t n, const double* x0, const double* u, double dt, 
 /* the same for any scheme of enum rkb_scheme (euler, midpoint, runge_kutta4, runge_kutta5) */
 double kto_integrate(void* h, size_t n, const double* x0, const double* u, int scheme, double dt, int n_steps,
                      double* xout, int32_t* status, int n_workers);
+/* steer_bounded_input of oracle/steer_law.h for `count` triples (test hook: pinned against IHAQR_topology::get_bounded_input) */
+int    kto_bounded_input(int nu, double T, const double* lo, const double* hi, const double* dlo, const double* dhi, int count,
+                         const double* u_prev, const double* u_bias, const double* u_corr, double* u_out);
 /* closed-loop steering (oracle/steer_law.h); lo/hi/dlo/dhi may be NULL */
 int    kto_steer_feedback(void* h, size_t n, const double* x0, const double* goal, const double* u_bias, const double* gain,
                           double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,

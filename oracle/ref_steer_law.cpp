@@ -1,0 +1,80 @@
+// TEST INFRASTRUCTURE — pins oracle/steer_law.h's restatement of IHAQR_topology::get_bounded_input against the member
+// function itself: the UNMODIFIED examples/misc/IHAQR_topology.hpp is instantiated on ReaK's own hyperbox_topology and a
+// stand-in system type (only its typedefs are read: get_bounded_input touches m_input_space, m_input_rate_space and
+// m_time_step), and the protected member is reached through a derived class.
+//
+// everything the two integrator headers include, first and unharmed
+#include <ReaK/core/base/named_object.hpp>
+#include <ReaK/ctrl/ctrl_sys/state_space_sys_concept.hpp>
+#include <ReaK/ctrl/topologies/metric_space_concept.hpp>
+#include <ReaK/ctrl/topologies/temporal_space_concept.hpp>
+#include <ReaK/ctrl/interpolation/spatial_trajectory_concept.hpp>
+#include <ReaK/core/integrators/integration_exceptions.hpp>
+#include <ReaK/core/lin_alg/vect_alg.hpp>
+#include <ReaK/core/lin_alg/arithmetic_tuple.hpp>
+// The two headers IHAQR_topology.hpp includes next have a *_factory::load that hands its iarchive to named_object::save
+// (runge_kutta4_integrator_sys.hpp:267, dormand_prince45_integrator_sys.hpp:385); g++ rejects that statement even though
+// the factories are never instantiated.  They are read with the parameter type spelled as the output archive, which makes
+// that one statement well-formed; nothing of theirs is used here.
+#define iarchive oarchive
+#include <ReaK/ctrl/sys_integrators/dormand_prince45_integrator_sys.hpp>
+#include <ReaK/ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp>
+#undef iarchive
+#include <ReaK/examples/misc/IHAQR_topology.hpp>
+
+namespace {
+using namespace ReaK;
+
+struct law_system : public named_object {   // the typedefs ss_system_traits / linear_ss_system_traits read
+  typedef vect_n<double> point_type;
+  typedef vect_n<double> point_difference_type;
+  typedef vect_n<double> point_derivative_type;
+  typedef double time_type;
+  typedef double time_difference_type;
+  typedef vect_n<double> input_type;
+  typedef vect_n<double> output_type;
+  typedef mat<double, mat_structure::rectangular> matrixA_type;
+  typedef mat<double, mat_structure::rectangular> matrixB_type;
+  typedef mat<double, mat_structure::rectangular> matrixC_type;
+  typedef mat<double, mat_structure::rectangular> matrixD_type;
+  BOOST_STATIC_CONSTANT(std::size_t, dimensions = 0);
+  BOOST_STATIC_CONSTANT(std::size_t, input_dimensions = 0);
+  BOOST_STATIC_CONSTANT(std::size_t, output_dimensions = 0);
+  virtual void RK_CALL save(serialization::oarchive& A, unsigned int) const { named_object::save(A, named_object::getStaticObjectType()->TypeVersion()); }
+  virtual void RK_CALL load(serialization::iarchive& A, unsigned int) { named_object::load(A, named_object::getStaticObjectType()->TypeVersion()); }
+  RK_RTTI_MAKE_CONCRETE_1BASE(law_system, 0xC23FFF01, 1, "rkb_law_system", named_object)
+};
+struct law_sampler : public named_object {
+  virtual void RK_CALL save(serialization::oarchive& A, unsigned int) const { named_object::save(A, named_object::getStaticObjectType()->TypeVersion()); }
+  virtual void RK_CALL load(serialization::iarchive& A, unsigned int) { named_object::load(A, named_object::getStaticObjectType()->TypeVersion()); }
+  RK_RTTI_MAKE_CONCRETE_1BASE(law_sampler, 0xC23FFF02, 1, "rkb_law_sampler", named_object)
+};
+typedef pp::hyperbox_topology<vect_n<double> > law_space;
+typedef pp::IHAQR_topology<law_space, law_system, law_sampler> law_topology;
+
+struct law_access : public law_topology {
+  law_access(const vect_n<double>& lo, const vect_n<double>& hi, const vect_n<double>& bw, double T)
+      : law_topology("law", shared_ptr<law_system>(), law_space(), lo, hi, bw, mat<double, mat_structure::diagonal>(),
+                     mat<double, mat_structure::diagonal>(), T) {}
+  vect_n<double> bounded(const vect_n<double>& u_prev, const vect_n<double>& u_bias, const vect_n<double>& u_corr) const {
+    return this->get_bounded_input(u_prev, u_bias, u_corr);
+  }
+};
+}  // namespace
+
+// u_out = IHAQR_topology::get_bounded_input(u_prev, u_bias, u_correction) (IHAQR_topology.hpp:304-327) for `count` triples;
+// input box [lo, hi], rate box [-bandwidth, bandwidth] (the constructor's aInputBandwidth, :440), time step T.
+extern "C" int rkref_ihaqr_bounded_input(int nu, const double* lo, const double* hi, const double* bandwidth, double T, int count,
+                                         const double* u_prev, const double* u_bias, const double* u_corr, double* u_out) {
+  try {
+    vect_n<double> vlo(nu), vhi(nu), vbw(nu), a(nu), b(nu), c(nu);
+    for (int k = 0; k < nu; ++k) { vlo[k] = lo[k]; vhi[k] = hi[k]; vbw[k] = bandwidth[k]; }
+    law_access topo(vlo, vhi, vbw, T);
+    for (int i = 0; i < count; ++i) {
+      for (int k = 0; k < nu; ++k) { a[k] = u_prev[i * nu + k]; b[k] = u_bias[i * nu + k]; c[k] = u_corr[i * nu + k]; }
+      const vect_n<double> r = topo.bounded(a, b, c);
+      for (int k = 0; k < nu; ++k) u_out[i * nu + k] = r[k];
+    }
+    return 0;
+  } catch (...) { return -1; }
+}

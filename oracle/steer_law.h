@@ -7,10 +7,13 @@
  *   the loop around them                         examples/misc/MEAQR_topology.hpp:503-561 (steer_with_constant_control),
  *                                                examples/misc/IHAQR_topology.hpp:349-378 (move_position_toward_impl)
  *
- * PARITY UNPINNED for this file: IHAQR_topology / MEAQR_topology cannot be instantiated here (they
- * need geometry/proximity, the ARE solvers and a linearisable system, and the concept-based
- * runge_kutta4_integrate_impl they call does not compile with g++ 13:
- * ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:267 passes an iarchive to named_object::save).
+ * PARITY: steer_bounded_input is PINNED against IHAQR_topology::get_bounded_input itself — oracle/ref_steer_law.cpp
+ * instantiates the unmodified examples/misc/IHAQR_topology.hpp on ReaK's hyperbox_topology and calls the member through a
+ * derived class; tests/test_oracle.py::test_bounded_input_law_matches_the_reference_member_function holds the two against
+ * each other bit for bit over every regime (request inside / outside the box, bias outside, rate limit acting or not,
+ * values on the faces of the box).  The few lines AROUND it (goal-proximity test, correction = -G (x - x_goal), MEAQR's
+ * unsaturated first interval: steer_next_input below) remain a restatement: move_position_toward_impl /
+ * steer_with_constant_control need a linearisable system with its ARE solution and a collision environment to run.
  * The dynamics and the RK4 integration inside the loop are the pinned ones.
  */
 #ifndef RKB_ORACLE_STEER_LAW_H
