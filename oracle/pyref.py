@@ -130,6 +130,24 @@ class _Checker(object):
         fn(self.h, N, _dp(x), _dp(u_nodes), float(dt), int(n_steps), _dp(out), _dp(st))
         return out, st
 
+    def rk4_inputs_concept(self, x0, u_nodes, dt):
+        """The same through ctrl::detail::runge_kutta4_integrate_impl ITSELF (runge_kutta4_integrator_sys.hpp:50-97, compiled in
+        oracle/ref_steer_law.cpp) over the live kte_nl_system.  Reference checker only."""
+        if self._prefix != "rkref_" or not hasattr(self.lib, "rkref_rk4_inputs_concept"):
+            raise NotImplementedError("needs oracle/_ref/libreak_ref.so with ref_steer_law.cpp")
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        n_steps = (np.shape(u_nodes)[1] - 1) // 2
+        u_nodes = np.ascontiguousarray(u_nodes, dtype=np.float64).reshape(N, 2 * n_steps + 1, self.nu) if self.nu else np.zeros((N, 1, 0))
+        out, st = np.empty_like(x), np.zeros(N, dtype=np.int32)
+        self.lib.rkref_kte_nl_system.restype = C.c_void_p
+        self.lib.rkref_kte_nl_system.argtypes = [C.c_void_p]
+        fn = self.lib.rkref_rk4_inputs_concept
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        fn(self.lib.rkref_kte_nl_system(self.h), self.nx, self.nu, N, _dp(x), _dp(u_nodes), float(dt), int(n_steps), _dp(out), _dp(st))
+        return out, st
+
     def integrate(self, x0, u, scheme, dt, n_steps, n_workers=1):
         """n_steps of euler (1) / midpoint (2) / runge_kutta4 (4) / runge_kutta5 (5); returns (x_out, status, seconds)."""
         x, u, N = self._xu(x0, u)

@@ -382,6 +382,9 @@ void rk4_range(ref_model* m, std::size_t i0, std::size_t i1, const double* x0, c
 
 extern "C" {
 
+// the live kte_nl_system of a handle, for the units that drive it through other reference code (ref_steer_law.cpp)
+const void* rkref_kte_nl_system(void* hv) { return &static_cast<ref_handle*>(hv)->proto->sys; }
+
 // RK4 with an input trajectory sampled at every half step ([N][2 n_steps + 1][nu]): the reference's own
 // runge_kutta4_integrator<double> over its kte_nl_system, the rate function reading the node that belongs to the time it is asked at.
 int rkref_rk4_inputs(void* hv, std::size_t N, const double* x0, const double* u_nodes, double dt, int n_steps, double* xout, int32_t* status) {

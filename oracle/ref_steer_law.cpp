@@ -1,5 +1,8 @@
-// TEST INFRASTRUCTURE — pins oracle/steer_law.h's restatement of IHAQR_topology::get_bounded_input against the member
-// function itself: the UNMODIFIED examples/misc/IHAQR_topology.hpp is instantiated on ReaK's own hyperbox_topology and a
+// TEST INFRASTRUCTURE — two pieces of reference code that sit behind headers g++ 13 rejects, compiled all the same:
+//   (1) IHAQR_topology::get_bounded_input (examples/misc/IHAQR_topology.hpp:304-327), what oracle/steer_law.h restates;
+//   (2) ctrl::detail::runge_kutta4_integrate_impl (ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97), RK4 with an
+//       input trajectory, what kto_rk4_inputs / rkb_rollout_rk4_inputs restate — run over the live kte_nl_system.
+// For (1) the UNMODIFIED examples/misc/IHAQR_topology.hpp is instantiated on ReaK's own hyperbox_topology and a
 // stand-in system type (only its typedefs are read: get_bounded_input touches m_input_space, m_input_rate_space and
 // m_time_step), and the protected member is reached through a derived class.
 //
@@ -15,12 +18,48 @@
 // The two headers IHAQR_topology.hpp includes next have a *_factory::load that hands its iarchive to named_object::save
 // (runge_kutta4_integrator_sys.hpp:267, dormand_prince45_integrator_sys.hpp:385); g++ rejects that statement even though
 // the factories are never instantiated.  They are read with the parameter type spelled as the output archive, which makes
-// that one statement well-formed; nothing of theirs is used here.
+// that one statement well-formed; the integrate_impl function templates above the factories are not touched by the spelling.
 #define iarchive oarchive
 #include <ReaK/ctrl/sys_integrators/dormand_prince45_integrator_sys.hpp>
 #include <ReaK/ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp>
 #undef iarchive
 #include <ReaK/examples/misc/IHAQR_topology.hpp>
+#include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
+
+#include <cmath>
+#include <cstddef>
+#include <stdint.h>
+
+// ---- an input trajectory given by its values at every half step (what rkb_rollout_rk4_inputs takes) --------------------
+namespace {
+struct node_traj {
+  struct point_type { ReaK::vect_n<double> pt; double time; };   // (the integrator reads .pt, like a temporal_point)
+  typedef long long const_waypoint_descriptor;
+  const double* nodes;
+  int nu;
+  long long n_nodes;
+  double half_dt;
+  std::pair<long long, point_type> at(long long j) const {
+    if (j < 0) j = 0;
+    if (j >= n_nodes) j = n_nodes - 1;
+    point_type p;
+    p.pt = ReaK::vect_n<double>(nu);
+    for (int k = 0; k < nu; ++k) p.pt[k] = nodes[j * nu + k];
+    p.time = double(j) * half_dt;
+    return std::make_pair(j, p);
+  }
+  std::pair<long long, point_type> get_waypoint_at_time(double t) const { return at(llround(t / half_dt)); }
+  std::pair<long long, point_type> move_time_diff_from(const std::pair<long long, point_type>& wp, double dt) const {
+    return at(wp.first + llround(dt / half_dt));
+  }
+};
+}  // namespace
+namespace ReaK { namespace pp {
+template <> struct spatial_trajectory_traits<node_traj> {   // the two typedefs runge_kutta4_integrate_impl asks for
+  typedef node_traj::point_type point_type;
+  typedef node_traj::const_waypoint_descriptor const_waypoint_descriptor;
+};
+}}
 
 namespace {
 using namespace ReaK;
@@ -77,4 +116,30 @@ extern "C" int rkref_ihaqr_bounded_input(int nu, const double* lo, const double*
     }
     return 0;
   } catch (...) { return -1; }
+}
+
+// ctrl::detail::runge_kutta4_integrate_impl ITSELF (runge_kutta4_integrator_sys.hpp:50-97) over the live kte_nl_system
+// `sys` (rkref_kte_nl_system of a handle of ref_lib.cpp) with the input read from the node trajectory: n_steps steps of dt
+// from x0[i]; u_nodes [N][2 n_steps + 1][nu].  status: bit 0 singular mass matrix, bit 1 non-finite (as the batch API).
+extern "C" int rkref_rk4_inputs_concept(const void* sys, int nx, int nu, std::size_t N, const double* x0, const double* u_nodes, double dt,
+                                        int n_steps, double* xout, int32_t* status) {
+  const ctrl::kte_nl_system& S = *static_cast<const ctrl::kte_nl_system*>(sys);
+  const law_space space;
+  const long long J = 2LL * n_steps + 1;
+  for (std::size_t i = 0; i < N; ++i) {
+    vect_n<double> a(nx), b(nx);
+    for (int k = 0; k < nx; ++k) a[k] = b[k] = x0[i * nx + k];
+    int32_t st = 0;
+    if (n_steps > 0) {
+      node_traj traj;
+      traj.nodes = u_nodes + i * J * nu; traj.nu = nu; traj.n_nodes = J; traj.half_dt = 0.5 * dt;
+      try {
+        // the loop is time-driven (:72-73): an end time half a step short of n_steps dt makes it run exactly n_steps steps
+        ctrl::detail::runge_kutta4_integrate_impl(space, S, a, b, traj, 0.0, (double(n_steps) - 0.5) * dt, dt);
+      } catch (singularity_error&) { st |= 1; }
+    }
+    for (int k = 0; k < nx; ++k) { xout[i * nx + k] = b[k]; if (!std::isfinite(b[k])) st |= 2; }
+    if (status) status[i] = st;
+  }
+  return 0;
 }
