@@ -148,6 +148,57 @@ class _Checker(object):
         fn(self.lib.rkref_kte_nl_system(self.h), self.nx, self.nu, N, _dp(x), _dp(u_nodes), float(dt), int(n_steps), _dp(out), _dp(st))
         return out, st
 
+    def ihaqr_move_toward(self, x0, goal, u_bias, gain, u_prev, T, horizon, proximity, bounds, bandwidth):
+        """IHAQR_topology::move_position_toward_impl ITSELF (examples/misc/IHAQR_topology.hpp:337-381, no collision check,
+        fraction 1) over the live kte_nl_system, the points' linearisation / gain payloads filled in from the arguments
+        (oracle/ref_steer_law.cpp).  Integrates each interval with steps of T * 1e-2, time-driven, as the reference does.
+        Returns the state the loop ended on.  Reference checker only."""
+        if self._prefix != "rkref_" or not hasattr(self.lib, "rkref_ihaqr_move_toward"):
+            raise NotImplementedError("needs oracle/_ref/libreak_ref.so with ref_steer_law.cpp")
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(N, self.nx)
+        u_bias = np.ascontiguousarray(u_bias, dtype=np.float64).reshape(N, self.nu)
+        gain = np.ascontiguousarray(gain, dtype=np.float64).reshape(N, self.nu, self.nx)
+        up = np.ascontiguousarray(u_prev, dtype=np.float64).reshape(N, self.nu)
+        lo, hi = (np.ascontiguousarray(b, dtype=np.float64).reshape(self.nu) for b in bounds)
+        bw = np.ascontiguousarray(bandwidth, dtype=np.float64).reshape(self.nu)
+        out = np.empty_like(x)
+        self.lib.rkref_kte_nl_system.restype = C.c_void_p
+        self.lib.rkref_kte_nl_system.argtypes = [C.c_void_p]
+        fn = self.lib.rkref_ihaqr_move_toward
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t] + [C.c_void_p] * 6
+        if fn(self.lib.rkref_kte_nl_system(self.h), self.nx, self.nu, _dp(lo), _dp(hi), _dp(bw), float(T), float(horizon), float(proximity), N,
+              _dp(x), _dp(goal), _dp(up), _dp(u_bias), _dp(gain), _dp(out)) != 0:
+            raise RuntimeError("rkref_ihaqr_move_toward failed")
+        return out
+
+    def meaqr_steer(self, x0, goal, u_bias, gain, u_prev, T, time_limit, proximity, bounds, bandwidth):
+        """MEAQR_topology::steer_with_constant_control ITSELF (examples/misc/MEAQR_topology.hpp:503-561, no collision check) over
+        the live kte_nl_system, with H = I and eta = 0 so that u0 = u_bias and K = gain (oracle/ref_steer_law.cpp).  Each
+        interval is integrated with steps of T * 1e-1, time-driven.  Returns (x_end, u_last, time reached)."""
+        if self._prefix != "rkref_" or not hasattr(self.lib, "rkref_meaqr_steer"):
+            raise NotImplementedError("needs oracle/_ref/libreak_ref.so with ref_steer_law.cpp")
+        x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        N = x.shape[0]
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(N, self.nx)
+        u_bias = np.ascontiguousarray(u_bias, dtype=np.float64).reshape(N, self.nu)
+        gain = np.ascontiguousarray(gain, dtype=np.float64).reshape(N, self.nu, self.nx)
+        up = np.ascontiguousarray(u_prev, dtype=np.float64).reshape(N, self.nu)
+        lo, hi = (np.ascontiguousarray(b, dtype=np.float64).reshape(self.nu) for b in bounds)
+        bw = np.ascontiguousarray(bandwidth, dtype=np.float64).reshape(self.nu)
+        out, uo, to = np.empty_like(x), np.empty((N, self.nu)), np.zeros(N)
+        self.lib.rkref_kte_nl_system.restype = C.c_void_p
+        self.lib.rkref_kte_nl_system.argtypes = [C.c_void_p]
+        fn = self.lib.rkref_meaqr_steer
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t] + [C.c_void_p] * 8
+        if fn(self.lib.rkref_kte_nl_system(self.h), self.nx, self.nu, _dp(lo), _dp(hi), _dp(bw), float(T), float(time_limit), float(proximity), N,
+              _dp(x), _dp(goal), _dp(up), _dp(u_bias), _dp(gain), _dp(out), _dp(uo), _dp(to)) != 0:
+            raise RuntimeError("rkref_meaqr_steer failed")
+        return out, uo, to
+
     def integrate(self, x0, u, scheme, dt, n_steps, n_workers=1):
         """n_steps of euler (1) / midpoint (2) / runge_kutta4 (4) / runge_kutta5 (5); returns (x_out, status, seconds)."""
         x, u, N = self._xu(x0, u)

@@ -1347,7 +1347,7 @@ double rkref_integrate(void* hv, std::size_t N, const double* x0, const double* 
                        double* xout, int32_t* status, int n_workers);
 
 // The steering loop with the reference's own dynamics and runge_kutta4_integrator inside; the feedback
-// law is the restatement of oracle/steer_law.h (its get_bounded_input pinned against IHAQR_topology's own: ref_steer_law.cpp).
+// law is the restatement of oracle/steer_law.h, itself pinned against IHAQR_topology / MEAQR_topology's own members (ref_steer_law.cpp).
 int rkref_steer_feedback(void* hv, std::size_t N, const double* x0, const double* goal, const double* u_bias, const double* gain,
                          double* u_prev, double T, double dt, int substeps, int max_intervals, double proximity, int saturate_first,
                          const double* lo, const double* hi, const double* dlo, const double* dhi,

@@ -24,6 +24,8 @@
 #include <ReaK/ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp>
 #undef iarchive
 #include <ReaK/examples/misc/IHAQR_topology.hpp>
+#include <ReaK/examples/misc/MEAQR_topology.hpp>
+#include <ReaK/ctrl/topologies/hyperball_topology.hpp>
 #include <ReaK/ctrl/ctrl_sys/kte_nl_system.hpp>
 
 #include <cmath>
@@ -79,6 +81,20 @@ struct law_system : public named_object {   // the typedefs ss_system_traits / l
   BOOST_STATIC_CONSTANT(std::size_t, dimensions = 0);
   BOOST_STATIC_CONSTANT(std::size_t, input_dimensions = 0);
   BOOST_STATIC_CONSTANT(std::size_t, output_dimensions = 0);
+  // the dynamics are the live kte_nl_system's (set for the steering loop below; get_bounded_input never asks)
+  const ctrl::kte_nl_system* live;
+  law_system() : live(NULL) {}
+  template <typename Space>
+  vect_n<double> get_state_derivative(const Space&, const vect_n<double>& x, const vect_n<double>& u, double t) const {
+    return live->get_state_derivative(*live, x, u, t);
+  }
+  // compute_linearization_data / compute_IHAQR_data are compiled with move_position_toward_impl but never run here: the
+  // points arrive with their linearisation and gains filled in
+  template <typename Space>
+  void get_linear_blocks(matrixA_type&, matrixB_type&, matrixC_type&, matrixD_type&, const Space&, double, const vect_n<double>&,
+                         const vect_n<double>&) const {
+    throw std::logic_error("law_system: not linearisable");
+  }
   virtual void RK_CALL save(serialization::oarchive& A, unsigned int) const { named_object::save(A, named_object::getStaticObjectType()->TypeVersion()); }
   virtual void RK_CALL load(serialization::iarchive& A, unsigned int) { named_object::load(A, named_object::getStaticObjectType()->TypeVersion()); }
   RK_RTTI_MAKE_CONCRETE_1BASE(law_system, 0xC23FFF01, 1, "rkb_law_system", named_object)
@@ -88,13 +104,17 @@ struct law_sampler : public named_object {
   virtual void RK_CALL load(serialization::iarchive& A, unsigned int) { named_object::load(A, named_object::getStaticObjectType()->TypeVersion()); }
   RK_RTTI_MAKE_CONCRETE_1BASE(law_sampler, 0xC23FFF02, 1, "rkb_law_sampler", named_object)
 };
-typedef pp::hyperbox_topology<vect_n<double> > law_space;
+typedef pp::hyperball_topology<vect_n<double> > law_space;   // vector space with the Euclidean distance() member the loop asks for
 typedef pp::IHAQR_topology<law_space, law_system, law_sampler> law_topology;
 
 struct law_access : public law_topology {
-  law_access(const vect_n<double>& lo, const vect_n<double>& hi, const vect_n<double>& bw, double T)
-      : law_topology("law", shared_ptr<law_system>(), law_space(), lo, hi, bw, mat<double, mat_structure::diagonal>(),
-                     mat<double, mat_structure::diagonal>(), T) {}
+  law_access(const vect_n<double>& lo, const vect_n<double>& hi, const vect_n<double>& bw, double T,
+             const shared_ptr<law_system>& sys = shared_ptr<law_system>(), double horizon = 10.0, double threshold = 1.0)
+      : law_topology("law", sys, law_space(), lo, hi, bw, mat<double, mat_structure::diagonal>(),
+                     mat<double, mat_structure::diagonal>(), T, horizon, threshold) {}
+  law_topology::point_type move(const law_topology::point_type& a, double fraction, const law_topology::point_type& b) const {
+    return this->move_position_toward_impl(a, fraction, b, false);
+  }
   vect_n<double> bounded(const vect_n<double>& u_prev, const vect_n<double>& u_bias, const vect_n<double>& u_corr) const {
     return this->get_bounded_input(u_prev, u_bias, u_corr);
   }
@@ -142,4 +162,88 @@ extern "C" int rkref_rk4_inputs_concept(const void* sys, int nx, int nu, std::si
     if (status) status[i] = st;
   }
   return 0;
+}
+
+// IHAQR_topology::move_position_toward_impl ITSELF (IHAQR_topology.hpp:337-381, with_collision_check = false) over the live
+// kte_nl_system `sys`: per tuple the loop `while (t < horizon && |x - goal| > threshold) { u = get_bounded_input(u_prev,
+// u_bias, -K (x - goal)); runge_kutta4_integrate_impl over [t, t + T] with step T * 1e-2; accept }`.  The two points arrive
+// with their payloads filled in (a: u_prev0 as lin_data->u with a zero bias; b: u_bias as lin_data->u with a zero bias, the
+// gain K [nu][nx]) so that neither the linearisation nor the ARE solver runs.  fraction = 1: the goal is
+// m_space.move_position_toward(a.x, 1.0, b.x).  x_out: the state the loop ended on.
+extern "C" int rkref_ihaqr_move_toward(const void* sys, int nx, int nu, const double* lo, const double* hi, const double* bandwidth, double T,
+                                       double horizon, double threshold, std::size_t N, const double* x0, const double* goal,
+                                       const double* u_prev0, const double* u_bias, const double* gain, double* x_out) {
+  try {
+    vect_n<double> vlo(nu), vhi(nu), vbw(nu);
+    for (int k = 0; k < nu; ++k) { vlo[k] = lo[k]; vhi[k] = hi[k]; vbw[k] = bandwidth[k]; }
+    shared_ptr<law_system> S(new law_system());
+    S->live = static_cast<const ctrl::kte_nl_system*>(sys);
+    law_access topo(vlo, vhi, vbw, T, S, horizon, threshold);
+    typedef law_topology::point_type point;
+    for (std::size_t i = 0; i < N; ++i) {
+      vect_n<double> xa(nx), xb(nx), ua(nu), ub(nu), zero(nu);
+      for (int k = 0; k < nx; ++k) { xa[k] = x0[i * nx + k]; xb[k] = goal[i * nx + k]; }
+      for (int k = 0; k < nu; ++k) { ua[k] = u_prev0[i * nu + k]; ub[k] = u_bias[i * nu + k]; zero[k] = 0.0; }
+      point a(xa), b(xb);
+      a.lin_data = shared_ptr<point::linearization_payload>(new point::linearization_payload());
+      b.lin_data = shared_ptr<point::linearization_payload>(new point::linearization_payload());
+      a.IHAQR_data = shared_ptr<point::IHAQR_payload>(new point::IHAQR_payload());
+      b.IHAQR_data = shared_ptr<point::IHAQR_payload>(new point::IHAQR_payload());
+      a.lin_data->u = ua; a.IHAQR_data->u_bias = zero;
+      b.lin_data->u = ub; b.IHAQR_data->u_bias = zero;
+      b.IHAQR_data->K = mat<double, mat_structure::rectangular>(nu, nx);
+      for (int r = 0; r < nu; ++r)
+        for (int c = 0; c < nx; ++c) b.IHAQR_data->K(r, c) = gain[(i * nu + r) * nx + c];
+      const point res = topo.move(a, 1.0, b);
+      for (int k = 0; k < nx; ++k) x_out[i * nx + k] = res.x[k];
+    }
+    return 0;
+  } catch (std::exception& e) { return -1; }
+}
+
+// MEAQR_topology::steer_with_constant_control ITSELF (examples/misc/MEAQR_topology.hpp:503-561, with_collision_check = false,
+// no steer record) over the live kte_nl_system: `while (t < time_limit && |x - goal| > threshold) { u = t < T ? u0 - K eta -
+// K H^-1 (x - goal) : get_bounded_input(u_prev, u0 - K eta, -K H^-1 (x - goal)); runge_kutta4_integrate_impl over [t, t + T]
+// with step T * 1e-1; accept }`.  Called with H = I (its Cholesky factor is I: the back-substitution returns x - goal) and
+// eta = 0, so that u0 is the batch call's u_bias and K its gain.  Out: the end state, the last input, the time reached.
+namespace {
+typedef pp::MEAQR_topology<law_space, law_system, law_sampler> meaqr_topology;
+struct meaqr_access : public meaqr_topology {
+  explicit meaqr_access(const shared_ptr<law_topology>& s) : meaqr_topology("meaqr", s) {}
+  bool steer(const mat<double, mat_structure::square>& H, const mat<double, mat_structure::rectangular>& K, const vect_n<double>& eta,
+             const vect_n<double>& u0, vect_n<double>& u_prev, vect_n<double>& x, const vect_n<double>& goal, double& t, double limit) const {
+    return this->steer_with_constant_control(H, K, eta, u0, u_prev, x, goal, t, limit, false, NULL);
+  }
+};
+}  // namespace
+extern "C" int rkref_meaqr_steer(const void* sys, int nx, int nu, const double* lo, const double* hi, const double* bandwidth, double T,
+                                 double time_limit, double threshold, std::size_t N, const double* x0, const double* goal,
+                                 const double* u_prev0, const double* u_bias, const double* gain, double* x_out, double* u_out, double* t_out) {
+  try {
+    vect_n<double> vlo(nu), vhi(nu), vbw(nu);
+    for (int k = 0; k < nu; ++k) { vlo[k] = lo[k]; vhi[k] = hi[k]; vbw[k] = bandwidth[k]; }
+    shared_ptr<law_system> S(new law_system());
+    S->live = static_cast<const ctrl::kte_nl_system*>(sys);
+    shared_ptr<law_topology> ih(new law_access(vlo, vhi, vbw, T, S, 1e30, threshold));
+    meaqr_access topo(ih);
+    mat<double, mat_structure::square> H(nx);
+    for (int r = 0; r < nx; ++r)
+      for (int c = 0; c < nx; ++c) H(r, c) = r == c ? 1.0 : 0.0;
+    vect_n<double> eta(nx);
+    for (int k = 0; k < nx; ++k) eta[k] = 0.0;
+    for (std::size_t i = 0; i < N; ++i) {
+      vect_n<double> x(nx), g(nx), up(nu), u0(nu);
+      for (int k = 0; k < nx; ++k) { x[k] = x0[i * nx + k]; g[k] = goal[i * nx + k]; }
+      for (int k = 0; k < nu; ++k) { up[k] = u_prev0[i * nu + k]; u0[k] = u_bias[i * nu + k]; }
+      mat<double, mat_structure::rectangular> K(nu, nx);
+      for (int r = 0; r < nu; ++r)
+        for (int c = 0; c < nx; ++c) K(r, c) = gain[(i * nu + r) * nx + c];
+      double t = 0.0;
+      topo.steer(H, K, eta, u0, up, x, g, t, time_limit);
+      for (int k = 0; k < nx; ++k) x_out[i * nx + k] = x[k];
+      for (int k = 0; k < nu; ++k) u_out[i * nu + k] = up[k];
+      t_out[i] = t;
+    }
+    return 0;
+  } catch (std::exception& e) { return -1; }
 }

@@ -7,14 +7,17 @@
  *   the loop around them                         examples/misc/MEAQR_topology.hpp:503-561 (steer_with_constant_control),
  *                                                examples/misc/IHAQR_topology.hpp:349-378 (move_position_toward_impl)
  *
- * PARITY: steer_bounded_input is PINNED against IHAQR_topology::get_bounded_input itself — oracle/ref_steer_law.cpp
- * instantiates the unmodified examples/misc/IHAQR_topology.hpp on ReaK's hyperbox_topology and calls the member through a
- * derived class; tests/test_oracle.py::test_bounded_input_law_matches_the_reference_member_function holds the two against
- * each other bit for bit over every regime (request inside / outside the box, bias outside, rate limit acting or not,
- * values on the faces of the box).  The few lines AROUND it (goal-proximity test, correction = -G (x - x_goal), MEAQR's
- * unsaturated first interval: steer_next_input below) remain a restatement: move_position_toward_impl /
- * steer_with_constant_control need a linearisable system with its ARE solution and a collision environment to run.
- * The dynamics and the RK4 integration inside the loop are the pinned ones.
+ * PARITY: PINNED against the reference's own classes (oracle/ref_steer_law.cpp instantiates the unmodified
+ * examples/misc/IHAQR_topology.hpp and MEAQR_topology.hpp over the live kte_nl_system and reaches their protected members
+ * through derived classes; tests/test_oracle.py):
+ *   steer_bounded_input  == IHAQR_topology::get_bounded_input, bit for bit over every regime (request inside / outside the
+ *                           box, bias outside, bisection, rate limit acting or not, values on the faces of the box);
+ *   the loop, every interval saturated      == IHAQR_topology::move_position_toward_impl (end state, 1e-16);
+ *   the loop, first interval unsaturated    == MEAQR_topology::steer_with_constant_control with H = I, eta = 0
+ *                                              (end state, last input, number of intervals).
+ * The reference integrates an interval with a time-driven loop (T / 100 resp. T / 10 steps, 100 or 101 resp. 10 or 11 of
+ * them depending on rounding); the batch call takes the step count explicitly, and the tests use a T for which the
+ * reference's count is the same in every interval.
  */
 #ifndef RKB_ORACLE_STEER_LAW_H
 #define RKB_ORACLE_STEER_LAW_H
