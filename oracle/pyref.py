@@ -174,10 +174,12 @@ class _Checker(object):
             raise RuntimeError("rkref_ihaqr_move_toward failed")
         return out
 
-    def meaqr_steer(self, x0, goal, u_bias, gain, u_prev, T, time_limit, proximity, bounds, bandwidth):
+    def meaqr_steer(self, x0, goal, u_bias, gain, u_prev, T, time_limit, proximity, bounds, bandwidth, is_free=None):
         """MEAQR_topology::steer_with_constant_control ITSELF (examples/misc/MEAQR_topology.hpp:503-561, no collision check) over
         the live kte_nl_system, with H = I and eta = 0 so that u0 = u_bias and K = gain (oracle/ref_steer_law.cpp).  Each
-        interval is integrated with steps of T * 1e-1, time-driven.  Returns (x_end, u_last, time reached)."""
+        interval is integrated with steps of T * 1e-1, time-driven.  is_free: a function of one state (numpy [nx]) the loop's
+        virtual is_free_impl is answered by (with_collision_check = true); then `collided` is appended.
+        Returns (x_end, u_last, time reached[, collided])."""
         if self._prefix != "rkref_" or not hasattr(self.lib, "rkref_meaqr_steer"):
             raise NotImplementedError("needs oracle/_ref/libreak_ref.so with ref_steer_law.cpp")
         x = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
@@ -193,11 +195,14 @@ class _Checker(object):
         self.lib.rkref_kte_nl_system.argtypes = [C.c_void_p]
         fn = self.lib.rkref_meaqr_steer
         fn.restype = C.c_int
-        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t] + [C.c_void_p] * 8
+        CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t] + [C.c_void_p] * 8 + [CB, C.c_void_p, C.c_void_p]
+        col = np.zeros(N, dtype=np.int32)
+        cb = CB(lambda px, n, ctx: int(bool(is_free(np.array([px[k] for k in range(n)]))))) if is_free is not None else C.cast(None, CB)
         if fn(self.lib.rkref_kte_nl_system(self.h), self.nx, self.nu, _dp(lo), _dp(hi), _dp(bw), float(T), float(time_limit), float(proximity), N,
-              _dp(x), _dp(goal), _dp(up), _dp(u_bias), _dp(gain), _dp(out), _dp(uo), _dp(to)) != 0:
+              _dp(x), _dp(goal), _dp(up), _dp(u_bias), _dp(gain), _dp(out), _dp(uo), _dp(to), cb, None, _dp(col)) != 0:
             raise RuntimeError("rkref_meaqr_steer failed")
-        return out, uo, to
+        return (out, uo, to, col) if is_free is not None else (out, uo, to)
 
     def integrate(self, x0, u, scheme, dt, n_steps, n_workers=1):
         """n_steps of euler (1) / midpoint (2) / runge_kutta4 (4) / runge_kutta5 (5); returns (x_out, status, seconds)."""

@@ -201,24 +201,34 @@ extern "C" int rkref_ihaqr_move_toward(const void* sys, int nx, int nu, const do
   } catch (std::exception& e) { return -1; }
 }
 
-// MEAQR_topology::steer_with_constant_control ITSELF (examples/misc/MEAQR_topology.hpp:503-561, with_collision_check = false,
-// no steer record) over the live kte_nl_system: `while (t < time_limit && |x - goal| > threshold) { u = t < T ? u0 - K eta -
+// MEAQR_topology::steer_with_constant_control ITSELF (examples/misc/MEAQR_topology.hpp:503-561, no steer record; with
+// `is_free` given, with_collision_check = true and the virtual is_free_impl answers through it) over the live kte_nl_system: `while (t < time_limit && |x - goal| > threshold) { u = t < T ? u0 - K eta -
 // K H^-1 (x - goal) : get_bounded_input(u_prev, u0 - K eta, -K H^-1 (x - goal)); runge_kutta4_integrate_impl over [t, t + T]
 // with step T * 1e-1; accept }`.  Called with H = I (its Cholesky factor is I: the back-substitution returns x - goal) and
 // eta = 0, so that u0 is the batch call's u_bias and K its gain.  Out: the end state, the last input, the time reached.
 namespace {
 typedef pp::MEAQR_topology<law_space, law_system, law_sampler> meaqr_topology;
+typedef int (*is_free_fn)(const double* x, int nx, void* ctx);
 struct meaqr_access : public meaqr_topology {
-  explicit meaqr_access(const shared_ptr<law_topology>& s) : meaqr_topology("meaqr", s) {}
+  is_free_fn free_fn;   // the collision environment: MEAQR_topology::is_free_impl (:416) is virtual, "always free" in the base class
+  void* free_ctx;
+  explicit meaqr_access(const shared_ptr<law_topology>& s) : meaqr_topology("meaqr", s), free_fn(NULL), free_ctx(NULL) {}
+  virtual bool is_free_impl(const vect_n<double>& a) const {
+    if (!free_fn) return true;
+    std::vector<double> x(a.size());
+    for (std::size_t k = 0; k < a.size(); ++k) x[k] = a[k];
+    return free_fn(&x[0], (int)x.size(), free_ctx) != 0;
+  }
   bool steer(const mat<double, mat_structure::square>& H, const mat<double, mat_structure::rectangular>& K, const vect_n<double>& eta,
              const vect_n<double>& u0, vect_n<double>& u_prev, vect_n<double>& x, const vect_n<double>& goal, double& t, double limit) const {
-    return this->steer_with_constant_control(H, K, eta, u0, u_prev, x, goal, t, limit, false, NULL);
+    return this->steer_with_constant_control(H, K, eta, u0, u_prev, x, goal, t, limit, free_fn != NULL, NULL);
   }
 };
 }  // namespace
 extern "C" int rkref_meaqr_steer(const void* sys, int nx, int nu, const double* lo, const double* hi, const double* bandwidth, double T,
                                  double time_limit, double threshold, std::size_t N, const double* x0, const double* goal,
-                                 const double* u_prev0, const double* u_bias, const double* gain, double* x_out, double* u_out, double* t_out) {
+                                 const double* u_prev0, const double* u_bias, const double* gain, double* x_out, double* u_out, double* t_out,
+                                 is_free_fn is_free, void* ctx, int32_t* collided) {
   try {
     vect_n<double> vlo(nu), vhi(nu), vbw(nu);
     for (int k = 0; k < nu; ++k) { vlo[k] = lo[k]; vhi[k] = hi[k]; vbw[k] = bandwidth[k]; }
@@ -226,6 +236,8 @@ extern "C" int rkref_meaqr_steer(const void* sys, int nx, int nu, const double* 
     S->live = static_cast<const ctrl::kte_nl_system*>(sys);
     shared_ptr<law_topology> ih(new law_access(vlo, vhi, vbw, T, S, 1e30, threshold));
     meaqr_access topo(ih);
+    topo.free_fn = is_free;   // NULL: with_collision_check = false; else the loop asks it about every x_next (:550)
+    topo.free_ctx = ctx;
     mat<double, mat_structure::square> H(nx);
     for (int r = 0; r < nx; ++r)
       for (int c = 0; c < nx; ++c) H(r, c) = r == c ? 1.0 : 0.0;
@@ -239,7 +251,8 @@ extern "C" int rkref_meaqr_steer(const void* sys, int nx, int nu, const double* 
       for (int r = 0; r < nu; ++r)
         for (int c = 0; c < nx; ++c) K(r, c) = gain[(i * nu + r) * nx + c];
       double t = 0.0;
-      topo.steer(H, K, eta, u0, up, x, g, t, time_limit);
+      const bool was_free = topo.steer(H, K, eta, u0, up, x, g, t, time_limit);
+      if (collided) collided[i] = was_free ? 0 : 1;
       for (int k = 0; k < nx; ++k) x_out[i * nx + k] = x[k];
       for (int k = 0; k < nu; ++k) u_out[i * nu + k] = up[k];
       t_out[i] = t;

@@ -14,7 +14,9 @@
  *                           box, bias outside, bisection, rate limit acting or not, values on the faces of the box);
  *   the loop, every interval saturated      == IHAQR_topology::move_position_toward_impl (end state, 1e-16);
  *   the loop, first interval unsaturated    == MEAQR_topology::steer_with_constant_control with H = I, eta = 0
- *                                              (end state, last input, number of intervals).
+ *                                              (end state, last input, number of intervals; with_collision_check = true
+ *                                              as well, its virtual is_free_impl answered by the reference's proxy pairs:
+ *                                              collision flag and the state the loop stops on).
  * The reference integrates an interval with a time-driven loop (T / 100 resp. T / 10 steps, 100 or 101 resp. 10 or 11 of
  * them depending on rounding); the batch call takes the step count explicitly, and the tests use a T for which the
  * reference's count is the same in every interval.

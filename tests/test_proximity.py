@@ -309,6 +309,44 @@ def test_reference_side_binding_round_trip_planar(oracle_built):
             assert np.allclose(list(out[k].dims), list(src[k].dims), rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("preset,track", [("crs6", False), ("crs7", True)])
+def test_checked_steering_loop_matches_meaqr_steer_with_constant_control_itself(preset, track, oracle_built):
+    """The checked steering loop the GPU path is held against (rkref_steer_feedback_checked: restated loop, the reference's
+    proximity query) against MEAQR_topology::steer_with_constant_control ITSELF with with_collision_check = true — the
+    unmodified class over the live kte_nl_system (oracle/ref_steer_law.cpp), its virtual is_free_impl answered by the same
+    proxy pairs (findMinimumDistance >= 0 after doMotion, MEAQR_topology.hpp:921-940).  End state, last accepted input,
+    number of accepted intervals and the collision flag."""
+    need_ref(oracle_built)
+    s = presets.make(preset)
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    R = oracle_built.Reference(c)
+    robot, lab = presets.crs_proxy_models(s, track=track)
+    pair = px.proxy_query_pair_3D("robot-lab", robot, lab)
+    nu, nx = c.n_inputs, 2 * c.n_coords
+    n, J, T = 40, 6, 0.05
+    rng = np.random.default_rng(21)
+    x0 = np.zeros((n, nx))
+    x0[:, 0::2] = rng.uniform(-2.5, 2.5, (n, c.n_coords))
+    x0[:, 1::2] = rng.uniform(-2.0, 2.0, (n, c.n_coords))
+    x0 = x0[R.min_distance(pair, x0)[0] >= 0.0][:16]            # free start states
+    n = x0.shape[0]
+    goal = x0 + rng.uniform(-1.0, 1.0, (n, nx))
+    u_bias = rng.uniform(-1.0, 1.0, (n, nu))
+    gain = rng.uniform(-2.0, 2.0, (n, nu, nx))
+    u_prev = rng.uniform(-0.5, 0.5, (n, nu))
+    lo, hi, bw = -2.0 * np.ones(nu), 2.0 * np.ones(nu), 60.0 * np.ones(nu)
+    try:
+        xw, uw, tw, cw = R.meaqr_steer(x0, goal, u_bias, gain, u_prev, T, (J - 0.5) * T, 0.25, (lo, hi), bw,
+                                       is_free=lambda x: R.min_distance(pair, x[None, :])[0][0] >= 0.0)
+    except NotImplementedError:
+        pytest.skip("prebuilt libreak_ref.so without the MEAQR unit")
+    xg, ug, nd, _, st, cg = R.steer_feedback(x0, goal, u_bias, gain, u_prev, T, T * 1e-1, 10, J, 0.25, saturate_first=False,
+                                             bounds=(lo, hi), rate_bounds=(-bw, bw), proxy_pairs=[pair])
+    assert np.array_equal(cg, cw) and (cw == 1).any() and (cw == 0).any()
+    assert np.array_equal(nd, np.rint(tw / T).astype(np.int32)) and ((cw == 1) & (nd > 0)).any()
+    assert np.max(np.abs(xg - xw)) < 1e-12 and np.max(np.abs(ug - uw)) < 1e-12
+
+
 def test_proxy_create_rejects():
     lib = _abi.load_library()
     s = presets.make("crs6")
