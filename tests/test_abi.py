@@ -179,3 +179,52 @@ def test_specialize_needs_a_gpu_and_a_serial_chain():
         if not torch.cuda.is_available() or want == _abi.ERR_UNSUPPORTED:
             assert lib.rkb_chain_specialize(h, 0) == want
         lib.rkb_chain_destroy(h)
+
+
+def test_proxy_specialize_error_paths():
+    """rkb_proxy_specialize / rkb_steer_checked_specialize fail loudly, never silently: no GPU -> RKB_ERR_CUDA (there is no CPU
+    path), an interpreter chain has no steering kernel to build a collision test into -> RKB_ERR_UNSUPPORTED, options are
+    range-checked, NULL handles are refused"""
+    import ctypes as C
+    import torch
+    from reak_b200 import proximity as px
+    lib = _abi.load_library()
+    s = presets.make("crs6")
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    rc, h = _create(c.desc)
+    assert rc == 0
+    robot, lab = presets.crs_proxy_models(s)
+    pair = px.ProxyHandle(lib, h, px.proxy_query_pair_3D("robot-lab", robot, lab), c.frames)
+    assert lib.rkb_proxy_is_specialized(pair._h) == 0
+    assert lib.rkb_proxy_set_option(pair._h, px.ProxyHandle.OPT_MIN_BLOCKS, 0) == _abi.ERR_INVALID
+    assert lib.rkb_proxy_set_option(pair._h, px.ProxyHandle.OPT_MIN_BLOCKS, 9) == _abi.ERR_INVALID
+    assert lib.rkb_proxy_set_option(pair._h, px.ProxyHandle.OPT_MIN_BLOCKS, 5) == 0
+    assert lib.rkb_proxy_set_option(pair._h, 77, 1) == _abi.ERR_INVALID
+    assert lib.rkb_proxy_set_option(None, px.ProxyHandle.OPT_AUTO_SPECIALIZE, 0) == _abi.ERR_INVALID
+    assert lib.rkb_proxy_specialize(None, 0) == _abi.ERR_INVALID
+    arr = (C.c_void_p * 1)(pair._h)
+    assert lib.rkb_steer_checked_specialize(h, 0, None, 1) == _abi.ERR_INVALID
+    assert lib.rkb_steer_checked_specialize(h, 0, arr, 0) == _abi.ERR_INVALID
+    assert lib.rkb_steer_checked_is_specialized(h, arr, 1) == 0
+    if not torch.cuda.is_available():
+        assert lib.rkb_proxy_specialize(pair._h, 0) == _abi.ERR_CUDA
+        assert lib.rkb_steer_checked_specialize(h, 0, arr, 1) == _abi.ERR_CUDA
+        assert lib.rkb_proxy_is_specialized(pair._h) == 0
+    n = lib.rkb_proxy_source(pair._h, None, 0)
+    assert n > 1000
+    small = C.create_string_buffer(16)
+    assert lib.rkb_proxy_source(pair._h, small, 16) == _abi.ERR_INVALID       # too small a buffer is refused, not overrun
+    pair.close()
+    lib.rkb_chain_destroy(h)
+    # an interpreter chain (two-anchor linear springs): no serial steering kernel
+    s2 = presets.make("crs6_lin_sd")
+    c2 = kte.compile_chain(s2.chain, s2.mass_calc, s2.dofs_gen, s2.inputs)
+    rc, h2 = _create(c2.desc)
+    assert rc == 0 and lib.rkb_chain_is_serial(h2) == 0
+    robot2, lab2 = presets.crs_proxy_models(s2)
+    pair2 = px.ProxyHandle(lib, h2, px.proxy_query_pair_3D("robot-lab", robot2, lab2), c2.frames)
+    arr2 = (C.c_void_p * 1)(pair2._h)
+    assert lib.rkb_steer_checked_source(h2, arr2, 1, None, 0) == _abi.ERR_UNSUPPORTED
+    assert lib.rkb_proxy_source(pair2._h, None, 0) > 1000                      # (the query itself can still be generated)
+    pair2.close()
+    lib.rkb_chain_destroy(h2)
