@@ -643,6 +643,39 @@ def test_generated_source_general_axes_and_moving_second_model(spec_tmp, oracle_
     agree(H.min_distance(x), R.min_distance(pair, x), TOL_SEARCH)
 
 
+def _spatial_presets():
+    out = []
+    for n in sorted(presets.PRESETS):
+        s = presets.make(n)
+        if kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs).dim == 3:
+            out.append(n)
+    return out
+
+
+ALL_3D = _spatial_presets()
+
+
+@pytest.mark.parametrize("preset", ALL_3D)
+def test_generated_source_every_spatial_preset_vs_reference(preset, spec_tmp, oracle_built):
+    """the generator on every 3D preset chain (springs, dampers, rotors, generalized-coordinate elements, rotated links,
+    prismatic tracks, physical axes): shapes of every kind on random frames of the chain against world-fixed ones — the
+    text compiles, and its forward kinematics and finder sequence give the reference's distances"""
+    need_ref(oracle_built)
+    s = presets.make(preset)
+    c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+    rng = np.random.default_rng(sum(ord(ch) for ch in preset))
+    kinds = sorted(KINDS)
+    m1, m2 = px.proxy_query_model_3D("robot"), px.proxy_query_model_3D("world")
+    for k in range(5):
+        m1.addShape(random_shape(rng, kinds[k % 5], int(rng.integers(0, c.desc.n_frames)), spread=0.3))
+        m2.addShape(random_shape(rng, kinds[(k + 2) % 5], None, spread=1.0))
+    pair = px.proxy_query_pair_3D("any", m1, m2)
+    H = SpecHost(spec_tmp, s, pair)
+    R = oracle_built.Reference(H.compiled)
+    x, _ = random_batch(H.compiled, 48, seed=5, q_range=2.5)
+    agree(H.min_distance(x), R.min_distance(pair, x), TOL_SEARCH)
+
+
 def test_generated_source_vs_golden(spec_tmp):
     """committed outputs of the reference; runs without oracle/_ref (the golden file stores the states)"""
     g = np.load(GOLDEN)
