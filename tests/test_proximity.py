@@ -556,7 +556,7 @@ class SpecHost(object):
     tests/host_build/prox_spec_host.h and run on the coordinates themselves (its own forward kinematics)."""
 
     def __init__(self, tmp, system, pair, min_blocks=None):
-        self.compiled = kte.compile_chain(system.chain, system.mass_calc, system.dofs_gen, system.inputs)
+        self.compiled = kte.compile_chain(system.chain, system.mass_calc, system.dofs_gen, system.inputs, getattr(system, "dofs_3D", ()))
         lib = _abi.load_library()
         h = C.c_void_p()
         _abi.check(lib.rkb_chain_create(C.byref(self.compiled.desc), C.byref(h)), "rkb_chain_create")
@@ -674,6 +674,35 @@ def test_generated_source_every_spatial_preset_vs_reference(preset, spec_tmp, or
     R = oracle_built.Reference(H.compiled)
     x, _ = random_batch(H.compiled, 48, seed=5, q_range=2.5)
     agree(H.min_distance(x), R.min_distance(pair, x), TOL_SEARCH)
+
+
+@pytest.mark.parametrize("preset", ["free_arm3", "free_arm2_twist", "free_body"])
+def test_generated_source_free_base_vs_reference(preset, spec_tmp, oracle_built):
+    """a free_joint_3D in front of the arm: the generated kinematics read the joint's pose states (position; quaternion,
+    normalised as apply_states_and_inputs does) — against the reference's doMotion + findMinimumDistance"""
+    need_ref(oracle_built)
+    s = presets.make(preset)
+    probe = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs, s.dofs_3D)
+    rng = np.random.default_rng(11)
+    kinds = sorted(KINDS)
+    m1, m2 = px.proxy_query_model_3D("robot"), px.proxy_query_model_3D("world")
+    for k in range(4):
+        m1.addShape(random_shape(rng, kinds[k % 5], int(rng.integers(1, probe.desc.n_frames)), spread=0.3))
+        m2.addShape(random_shape(rng, kinds[(k + 2) % 5], None, spread=1.0))
+    pair = px.proxy_query_pair_3D("free", m1, m2)
+    H = SpecHost(spec_tmp, s, pair)
+    assert "RKB_PROX_SPEC_KERNELS(%d, 1, " % probe.n_coords in H.source and "freec.q" in H.source
+    R = oracle_built.Reference(H.compiled)
+    n, nq = 64, probe.n_coords
+    x = np.zeros((n, 2 * nq + 13))
+    x[:, :2 * nq] = rng.uniform(-2.0, 2.0, (n, 2 * nq))
+    x[:, 2 * nq:2 * nq + 3] = rng.uniform(-0.6, 0.6, (n, 3))
+    quat = rng.normal(size=(n, 4))
+    x[:, 2 * nq + 3:2 * nq + 7] = quat / np.linalg.norm(quat, axis=1, keepdims=True) * rng.uniform(0.7, 1.3, (n, 1))   # not normalised
+    x[:, 2 * nq + 7:] = rng.uniform(-1.0, 1.0, (n, 6))
+    want = R.min_distance(pair, x)
+    agree(H.min_distance(x), want, TOL_SEARCH)
+    assert np.ptp(want[0]) > 0.1 and len(set(want[1].tolist())) > 1   # the states matter, and more than one finder wins
 
 
 def test_generated_source_vs_golden(spec_tmp):
