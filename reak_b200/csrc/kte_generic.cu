@@ -19,6 +19,11 @@
 namespace {
 
 #define GD __device__ __forceinline__
+#ifdef RKB_HOST_TEST
+#define GNI static                    // (tests/host_build: an ordinary function)
+#else
+#define GNI __device__ __noinline__   // a real call on the device: see rate()
+#endif
 #define MAXC RKB_MAX_COORDS
 
 #include "kte_math.cuh"
@@ -1154,8 +1159,12 @@ GD void store_flat(const GenericProgram* G, const double* xs, const BatchView& o
   for (int k = 0; k < G->free_states * G->n_free; ++k) o.p[off + (2 * n + k) * o.sk] = xs[2 * n + k];
 }
 // apply_states_and_inputs + get_state_derivative at the state vector xs: xd = f(xs, u); returns the status bits
+// A real call, not inlined: the RK4 loop evaluates the chain four times per step, and four inlined copies of the whole
+// interpreter (motion, force, mass matrix, solve) made the kernel's code four times as large and cost it a CTA per SM
+// (160 -> 126 registers).  Measured on B200, 2^18 samples x 10 steps: free-base arm 139.6 -> 86.8 ms, arm with two-anchor
+// springs 52.7 -> 25.9 ms (profiles/r2_interpreter.md).  Same arithmetic: the body is compiled once instead of four times.
 template <int DIM, int MAXF>
-GD int rate(const GenericProgram* G, Work<DIM, MAXF>& W, const double* xs, double* xd) {
+GNI int rate(const GenericProgram* G, Work<DIM, MAXF>& W, const double* xs, double* xd) {
   const int n = G->n_coords;
   for (int c = 0; c < n; ++c) { W.q[c] = xs[2 * c]; W.qd[c] = xs[2 * c + 1]; }
   if (G->n_free) apply_free(W, xs + 2 * n);
