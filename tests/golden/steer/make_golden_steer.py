@@ -1,7 +1,8 @@
 """Generates tests/golden/steer/steer_loops.npz from the UNMODIFIED reference (oracle/_ref/libreak_ref.so, the unit
 oracle/ref_steer_law.cpp): IHAQR_topology::move_position_toward_impl and MEAQR_topology::steer_with_constant_control
 (examples/misc/IHAQR_topology.hpp:337-381, MEAQR_topology.hpp:503-561) run over the live kte_nl_system of two preset chains,
-and IHAQR_topology::get_bounded_input on random triples.  Run from the repo root:
+IHAQR_topology::get_bounded_input on random triples, and ctrl::detail::runge_kutta4_integrate_impl
+(ctrl/sys_integrators/runge_kutta4_integrator_sys.hpp:50-97) with an input trajectory.  Run from the repo root:
 
     python tests/golden/steer/make_golden_steer.py
 """
@@ -56,6 +57,19 @@ def main():
         assert fn(nu, p(lo), p(hi), p(bw), 0.02, n, p(up), p(ub), p(uc), p(res)) == 0
         for k, v in (("lo", lo), ("hi", hi), ("bw", bw), ("u_prev", up), ("u_bias", ub), ("u_corr", uc), ("u_out", res)):
             out["law%d_%s" % (nu, k)] = v
+    # ctrl::detail::runge_kutta4_integrate_impl itself (runge_kutta4_integrator_sys.hpp:50-97) with an input trajectory
+    for name in ("crs6", "crs7_phys_sd"):
+        s = presets.make(name)
+        c = kte.compile_chain(s.chain, s.mass_calc, s.dofs_gen, s.inputs)
+        R = pyref.Reference(c)
+        rng = np.random.default_rng(53)
+        K = 9
+        x = np.zeros((8, 2 * c.n_coords))
+        x[:, 0::2], x[:, 1::2] = rng.uniform(-1, 1, (8, c.n_coords)), rng.uniform(-1, 1, (8, c.n_coords))
+        nodes = rng.uniform(-2, 2, (8, 2 * K + 1, c.n_inputs))
+        xo, st = R.rk4_inputs_concept(x, nodes, 1e-3)
+        assert not st.any()
+        out["rk4c_%s_x0" % name], out["rk4c_%s_nodes" % name], out["rk4c_%s_xout" % name] = x, nodes, xo
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "steer", "steer_loops.npz"), **out)
 
 
