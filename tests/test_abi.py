@@ -146,6 +146,23 @@ def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
     assert r.returncode == 1 and "-> -4" in r.stderr, (r.returncode, r.stdout, r.stderr)
 
 
+def test_proximity_demo_is_c99_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/proximity_demo.c (planar and spatial proximity models, rkb_proxy_specialize, rkb_is_free) is C99 against
+    include/reak_b200.h only, -Wall -Wextra -Werror; without a CUDA device the first query returns RKB_ERR_CUDA"""
+    import subprocess
+    import torch
+    exe = os.path.join(str(tmp_path), "proximity_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "proximity_demo.c"), "-L" + os.path.dirname(_abi.LIB_PATH), "-lreak_b200", "-lm",
+                           "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_abi.LIB_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout, r.stderr)
+    else:
+        assert r.returncode == 1 and "rkb_min_distance" in r.stderr and "-> -4" in r.stderr, (r.returncode, r.stdout, r.stderr)
+
+
 def _build_cpp_demo(tmp_path):
     import subprocess
     exe = os.path.join(str(tmp_path), "cpp_host_demo")
